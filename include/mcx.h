@@ -1,0 +1,252 @@
+/* mcx.h — C ABI of libmcx, the B200-native replacement for MCell4's per-timestep
+ * diffuse-and-react hot path (DiffuseReactEvent).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * mcellteam/mcell tree).  Signatures are plain C: pointers, sizes, POD structs; no torch,
+ * no C++ types.  All lengths are MCell internal length units (1/sqrt(surface_grid_density)
+ * um, libmcell/api/mcell4_converter.cpp:243-247), all times are iterations
+ * (mcell4_converter.cpp:237).
+ *
+ * Threading: a handle is NOT re-entrant; one host thread per handle (the reference is
+ * single threaded, src4/diffuse_react_event.cpp:54).  Errors never exit()/throw across the
+ * ABI (cf. World::fatal_error, src4/world.cpp:561-565): functions return MCX_OK or a
+ * negative code and mcx_last_error() returns the text.
+ */
+#ifndef MCX_H
+#define MCX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCX_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------- */
+#define MCX_OK 0
+#define MCX_ERR_INVALID_ARG (-1)
+#define MCX_ERR_CUDA (-2)        /* CUDA runtime failure or no CUDA device: there is NO CPU fallback */
+#define MCX_ERR_CAPACITY (-3)    /* molecule / product / pending buffers exhausted */
+#define MCX_ERR_ESCAPED (-4)     /* molecule left the partition (diffuse_react_event.cpp:592-612) */
+#define MCX_ERR_STATE (-5)       /* call order violated (e.g. step before upload) */
+#define MCX_ERR_OVERFLOW (-6)    /* per-molecule subpartition set overflowed */
+#define MCX_ERR_COMM (-7)        /* NCCL failure */
+
+#define MCX_NONE 0xFFFFFFFFu
+#define MCX_MAX_PRODUCTS 4
+#define MCX_TRACE_K 4
+
+/* Pseudo species for surface-class rules (libmcell/api/model.cpp:95, rxn_utils.inl:192-203) */
+#define MCX_ALL_MOLECULES 0xFFFFFFF0u
+#define MCX_ALL_VOLUME_MOLECULES 0xFFFFFFF1u
+
+/* time sentinels (src4/defines.h:178-179) */
+#define MCX_TIME_INVALID (-256.0)
+#define MCX_TIME_FOREVER (1e20)
+
+typedef struct mcx_handle mcx_handle;
+
+/* ---- configuration: SimulationConfig (src4/simulation_config.h:28-135) + BNGConfig scalars */
+enum { MCX_RNG_PHILOX = 0, MCX_RNG_TAPE = 1 };
+
+typedef struct mcx_config {
+  uint32_t abi_version;            /* MCX_ABI_VERSION */
+  int32_t  device;                 /* CUDA device ordinal */
+  uint64_t seed;                   /* Config.seed; Philox key */
+  double   origin[3];              /* Partition::origin_corner (partition.h:248-251) */
+  double   partition_edge_length;  /* SimulationConfig::partition_edge_length */
+  uint32_t num_subparts_per_edge;  /* num_subparts_per_partition_edge (<= 300, defines.h:159) */
+  uint32_t use_expanded_list;      /* config.use_expanded_list (mcell4_converter.cpp:84-87) */
+  double   rxn_radius_3d;          /* BNGConfig::rxn_radius_3d, length units */
+  double   cell_edge;              /* neighbour-cell edge of the device grid; 0 = auto */
+  double   active_llf[3];          /* box that bounds every molecule position (e.g. geometry bbox) */
+  double   active_urb[3];          /*   llf == urb == 0 -> whole partition */
+  uint64_t max_molecules;          /* slot capacity per device (incl. products and ghosts) */
+  uint32_t max_resolve_rounds;     /* conflict-resolution rounds per iteration; 0 = default 8 */
+  uint32_t rng_mode;               /* MCX_RNG_PHILOX | MCX_RNG_TAPE (replay) */
+  int32_t  rank;                   /* slab decomposition: this process' rank ...           */
+  int32_t  world_size;             /* ... of world_size (1 = single GPU)                    */
+  uint64_t initial_iteration;      /* Config.initial_iteration (checkpoint resume) */
+} mcx_config;
+
+/* ---- species: BNG::Species subset (src/mcell_species.c:207-300) --------- */
+enum {
+  MCX_SP_VOL = 1u << 0,            /* volume molecule */
+  MCX_SP_CAN_DIFFUSE = 1u << 1,    /* D != 0 */
+  MCX_SP_CANT_INITIATE = 1u << 2   /* TARGET_ONLY */
+};
+typedef struct mcx_species {
+  double   space_step;             /* sqrt(4*1e8*D*time_unit)/length_unit */
+  double   time_step;              /* in iterations (1.0 unless custom time step) */
+  uint32_t flags;                  /* MCX_SP_* */
+  uint32_t reserved;
+} mcx_species;
+
+/* ---- reactions: RxnClass / pathway tables ------------------------------ */
+enum { MCX_RXN_UNIMOL = 1, MCX_RXN_BIMOL_VOLVOL = 2 };
+typedef struct mcx_rxn_class {
+  uint32_t kind;                   /* MCX_RXN_* */
+  uint32_t reactants[2];           /* species ids in rule order; [1] = MCX_NONE for unimol */
+  uint32_t first_pathway;          /* index into the pathway array */
+  uint32_t n_pathways;
+  uint32_t reserved;
+  double   max_fixed_p;            /* RxnClass::get_max_fixed_p() = cum_probs[last] */
+} mcx_rxn_class;
+typedef struct mcx_pathway {
+  double   cum_prob;               /* cumulative probability (src/mcell_reactions.c:2932-2933) */
+  uint32_t n_products;             /* newly created products (kept reactants are NOT listed) */
+  uint32_t products[MCX_MAX_PRODUCTS];
+  uint32_t keep_reactant_mask;     /* bit r: rule reactant r appears unchanged on both sides */
+  uint32_t rxn_rule_id;            /* slot of the per-reaction occurrence counter */
+  uint32_t reserved;
+} mcx_pathway;
+
+/* ---- surface classes (mcell4_converter.cpp:515-622; rxn_utils.inl:263-287) ----------- */
+enum { MCX_SURF_REFLECTIVE = 0, MCX_SURF_TRANSPARENT = 1, MCX_SURF_ABSORPTIVE = 2 };
+typedef struct mcx_surf_class_rxn {
+  uint32_t species;                /* species id, MCX_ALL_MOLECULES or MCX_ALL_VOLUME_MOLECULES */
+  uint32_t surf_class;             /* value used in wall_surf_class[] */
+  int32_t  orientation;            /* 0: both sides; +1: hits on the FRONT only; -1: BACK only */
+  uint32_t type;                   /* MCX_SURF_* */
+} mcx_surf_class_rxn;
+
+/* ---- molecules: SoA view of Partition::molecules (src4/molecule.h:52-260) ------------ */
+enum {
+  MCX_MOL_DEFUNCT = 1u << 0,          /* MOLECULE_FLAG_DEFUNCT */
+  MCX_MOL_SCHEDULE_UNIMOL = 1u << 1,  /* MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN: lifetime not drawn yet */
+  MCX_MOL_PARTIAL = 1u << 2           /* diffusion_time is fractional (born mid-iteration) */
+};
+typedef struct mcx_mol_soa {
+  uint64_t  n;
+  double   *x, *y, *z;             /* Molecule::v.pos */
+  uint32_t *id;                    /* Molecule::id (unique, persistent) */
+  uint32_t *species;               /* Molecule::species_id */
+  uint32_t *flags;                 /* MCX_MOL_* */
+  double   *diffusion_time;        /* Molecule::diffusion_time; NULL = all at current iteration */
+  double   *unimol_rxn_time;       /* Molecule::unimol_rxn_time; NULL = MCX_TIME_INVALID */
+} mcx_mol_soa;
+
+/* ---- per-call statistics: SimulationStats mirror (src4/simulation_stats.h:46-83) ----- */
+typedef struct mcx_step_stats {
+  uint64_t iterations;
+  uint64_t molecule_steps;         /* sum over iterations of molecules diffused (the bench metric) */
+  uint64_t n_live;                 /* live molecules after the call */
+  uint64_t ray_polygon_tests;
+  uint64_t ray_polygon_colls;
+  uint64_t mol_wall_reflections;
+  uint64_t mol_wall_transparent;
+  uint64_t mol_wall_absorptions;
+  uint64_t vol_mol_vol_mol_collisions;
+  uint64_t bimol_rxns;
+  uint64_t unimol_rxns;
+  uint64_t wall_redos;
+  uint64_t resolve_retries;        /* molecules re-evaluated after losing a reaction conflict */
+  uint64_t unresolved_conflicts;   /* proposals dropped after max_resolve_rounds */
+  uint64_t products_created;
+  double   device_ms;              /* CUDA-event time of the iteration loop */
+} mcx_step_stats;
+
+/* ---- replay trace (kernel-level parity; mirrors the reference's DEBUG_* dumps,
+ *      include/debug_config.h:153-245) ------------------------------------------------- */
+enum {
+  MCX_OUT_NONE = 0, MCX_OUT_MOVED = 1, MCX_OUT_REACTED = 2, MCX_OUT_ABSORBED = 3,
+  MCX_OUT_UNIMOL = 4, MCX_OUT_CONSUMED = 5, MCX_OUT_STATIC = 6
+};
+typedef struct mcx_trace_rec {
+  uint32_t id;
+  uint32_t outcome;                /* MCX_OUT_* */
+  uint32_t n_words;                /* random words consumed by this molecule this iteration */
+  uint32_t n_wall_hits;            /* walls processed (reflect + transparent + absorb) */
+  uint32_t n_collisions;           /* vol-vol collisions evaluated in time order */
+  uint32_t n_redo;
+  uint32_t wall[MCX_TRACE_K];      /* first K wall indices hit, in order */
+  uint32_t wall_side[MCX_TRACE_K]; /* 1 = FRONT, 2 = BACK */
+  uint32_t partner[MCX_TRACE_K];   /* first K collision partner ids, in evaluation order */
+  uint32_t rxn_class;              /* MCX_NONE if no reaction */
+  uint32_t rxn_pathway;
+  uint32_t rxn_partner;            /* partner id for bimolecular, MCX_NONE otherwise */
+  uint32_t rounds;                 /* evaluation passes (1 + conflict retries) */
+  uint64_t event_hash;             /* hash over the complete ordered event sequence */
+  double   pos[3];                 /* final position (reaction position if consumed as initiator) */
+  double   t_event;                /* absolute time of the reaction / absorption, else 0 */
+} mcx_trace_rec;
+
+/* ---- lifecycle ----------------------------------------------------------------------- */
+/* Replaces: DiffuseReactEvent construction in World::init_simulation (src4/world.cpp:279-282)
+ * plus the Partition constructor's grid set-up (src4/partition.cpp:36-77). */
+int mcx_create(const mcx_config* cfg, mcx_handle** out);
+/* Replaces: Scheduler deleting the event (src4/scheduler.h:124-126). */
+void mcx_destroy(mcx_handle* h);
+/* Replaces: World::fatal_error message path (src4/world.cpp:561-565). h may be NULL (create errors). */
+const char* mcx_last_error(const mcx_handle* h);
+int mcx_abi_version(void);
+
+/* ---- one-time immutable tables -------------------------------------------------------- */
+/* Replaces: Partition::add_geometry_vertex / add_uninitialized_wall,
+ * Wall::initialize_wall_constants (src4/wall.cpp:281-342) and Partition::finalize_walls
+ * (src4/partition.cpp:91-118 -> geometry_utils.inl:110-207 -> wall_utils.inl:326-504).
+ * vertices: 3*n_vertices doubles; tri: 3*n_walls vertex indices;
+ * wall_surf_class: n_walls entries or NULL (MCX_NONE = default reflective). */
+int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
+                     const uint32_t* tri, uint64_t n_walls,
+                     const uint32_t* wall_surf_class, const uint32_t* wall_object);
+/* Replaces: p.get_species(id) lookups (src4/partition.h:989-997; libbng Species). */
+int mcx_set_species(mcx_handle* h, const mcx_species* species, uint32_t n_species);
+/* Replaces: RxnContainer::get_bimol_rxn_class / get_unimol_rxn_class and
+ * RxnClass::{get_max_fixed_p,get_pathway_index_for_probability} (libbng; call sites
+ * src4/collision_utils.inl:537-538, src4/rxn_utils.inl:353-412,712-782). */
+int mcx_set_reactions(mcx_handle* h, const mcx_rxn_class* classes, uint32_t n_classes,
+                      const mcx_pathway* pathways, uint32_t n_pathways);
+/* Replaces: RxnUtils::trigger_intersect table walk (src4/rxn_utils.inl:263-287). */
+int mcx_set_surface_classes(mcx_handle* h, const mcx_surf_class_rxn* rules, uint32_t n_rules);
+
+/* ---- molecule state ------------------------------------------------------------------- */
+/* Replaces: Partition::add_volume_molecule for a batch (src4/partition.h:555-611);
+ * HOST pointers. Resets the device population. */
+int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* mols);
+/* Replaces: Partition::get_molecules() read access (src4/partition.h:648-666) for viz,
+ * checkpoint and API introspection.  capacity = arrays' length; out->n = live count. */
+int mcx_download_molecules(mcx_handle* h, mcx_mol_soa* out, uint64_t capacity);
+uint64_t mcx_num_molecules(mcx_handle* h);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* Replaces: DiffuseReactEvent::step() (src4/diffuse_react_event.cpp:53-64) called
+ * n_iterations times in a row; the scheduler's barrier contract allows up to
+ * time_up_to_next_barrier iterations per call (src4/diffuse_react_event.h:37,142-150).
+ * Also folds SortMolsBySubpartEvent::step (sort_mols_by_subpart_event.cpp:62-98) and
+ * DefragmentationEvent::step (defragmentation_event.cpp:31-114) into every iteration. */
+int mcx_step(mcx_handle* h, uint32_t n_iterations, mcx_step_stats* stats_out);
+/* One iteration in which molecule `id` consumes words[offset_by_id[id] ...] instead of its
+ * Philox stream (requires rng_mode == MCX_RNG_TAPE); trace_out[id] receives the per-molecule
+ * event trace.  Replaces the reference's lock-step DEBUG_DIFFUSION/DEBUG_COLLISIONS/DEBUG_RXNS
+ * trace method (include/debug_config.h:153-245).  n_ids = number of trace slots. */
+int mcx_replay_step(mcx_handle* h, const uint32_t* words, uint64_t n_words,
+                    const uint64_t* offset_by_id, uint64_t n_ids,
+                    mcx_trace_rec* trace_out, mcx_step_stats* stats_out);
+/* Like mcx_step for one iteration with the Philox streams, but also returns the trace. */
+int mcx_trace_step(mcx_handle* h, uint64_t n_ids, mcx_trace_rec* trace_out,
+                   mcx_step_stats* stats_out);
+
+/* ---- observables ---------------------------------------------------------------------- */
+/* Replaces: MolOrRxnCountEvent::compute_counts world-count fast path
+ * (src4/mol_or_rxn_count_event.cpp:622-653) and rxn occurrence counters
+ * (src4/partition.h:1036-1077).  Arrays may be NULL.  Multi-GPU: summed over ranks. */
+int mcx_counts(mcx_handle* h, uint64_t* per_species, uint32_t n_species,
+               uint64_t* per_rxn_rule, uint32_t n_rxn_rules);
+
+/* ---- multi-GPU (new: the reference has a single partition, world.cpp:147,277) --------- */
+/* nccl_unique_id: the 128-byte ncclUniqueId created by rank 0 and broadcast by the host
+ * plumbing (torch.distributed).  Must be called after mcx_create on every rank. */
+int mcx_comm_init(mcx_handle* h, const void* nccl_unique_id, uint32_t id_bytes);
+
+/* ---- host helpers that need no device (also exported for the CPU test tier) ----------- */
+/* Philox4x32-10 block for (seed, molecule id, iteration, block index); the device stream
+ * of molecule `id` is the concatenation of blocks 0,1,2,... */
+void mcx_philox_block(uint64_t seed, uint32_t mol_id, uint64_t iteration, uint32_t block,
+                      uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCX_H */

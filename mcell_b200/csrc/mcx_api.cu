@@ -1,0 +1,588 @@
+// mcx_api.cu — the C ABI of libmcx (include/mcx.h): handle, device memory, table upload, step driver.
+// There is no CPU fallback: every compute entry point needs a CUDA device and returns MCX_ERR_CUDA
+// (with text) when none is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mcx_internal.h"
+#include "mcx_philox.h"
+#include "mcx_geom.h"
+#include "mcx_comm.h"
+
+void mcx_set_scan_scratch(unsigned int* ptr);
+
+static thread_local std::string g_create_error;
+
+struct mcx_handle {
+  mcx_config cfg{};
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+  DevParams p{};
+  StepPlan plan{};
+  std::vector<void*> allocs;       // everything cudaMalloc'ed, freed in destroy
+  // host copies of tables
+  std::vector<mcx_species> species;
+  std::vector<mcx_rxn_class> classes;
+  std::vector<mcx_pathway> pathways;
+  std::vector<mcx_surf_class_rxn> surf_rules;
+  std::vector<uint32_t> wall_class_host;
+  uint32_t n_surf_classes = 0;
+  bool has_geometry = false, has_species = false, uploaded = false;
+  uint64_t iteration = 0;
+  uint32_t *cs[2] = {nullptr, nullptr};
+  int cs_cur = 0;
+  unsigned int* scan_sums = nullptr;
+  unsigned int* d_n_out = nullptr;
+  // table device pointers that get replaced on re-set
+  void *d_species = nullptr, *d_bimol = nullptr, *d_unimol = nullptr, *d_classes = nullptr, *d_pathways = nullptr,
+       *d_surf = nullptr, *d_walls = nullptr, *d_tri = nullptr, *d_verts = nullptr, *d_wclass = nullptr,
+       *d_spw_start = nullptr, *d_spw_list = nullptr;
+  McxComm* comm = nullptr;
+};
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+      return MCX_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+template <typename T>
+static int dev_alloc(mcx_handle* h, T** out, size_t count) {
+  void* ptr = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CK(cudaMalloc(&ptr, bytes));
+  CK(cudaMemset(ptr, 0, bytes));
+  h->allocs.push_back(ptr);
+  *out = (T*)ptr;
+  return MCX_OK;
+}
+template <typename T>
+static int dev_replace(mcx_handle* h, void** slot, const T* src, size_t count) {
+  if (*slot) {
+    cudaFree(*slot);
+    h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), *slot), h->allocs.end());
+    *slot = nullptr;
+  }
+  T* d = nullptr;
+  int rc = dev_alloc(h, &d, count);
+  if (rc) return rc;
+  if (count) CK(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  *slot = d;
+  return MCX_OK;
+}
+
+extern "C" {
+
+int mcx_abi_version(void) { return MCX_ABI_VERSION; }
+
+const char* mcx_last_error(const mcx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void mcx_philox_block(uint64_t seed, uint32_t mol_id, uint64_t iteration, uint32_t block, uint32_t out[4]) {
+  philox4x32_10(block, (uint32_t)iteration, (uint32_t)(iteration >> 32), mol_id, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+}
+
+int mcx_create(const mcx_config* cfg, mcx_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return MCX_ERR_INVALID_ARG; }
+  if (cfg->abi_version != MCX_ABI_VERSION) { g_create_error = "ABI version mismatch"; return MCX_ERR_INVALID_ARG; }
+  if (cfg->num_subparts_per_edge == 0 || cfg->num_subparts_per_edge > 300 || !(cfg->partition_edge_length > 0) ||
+      cfg->max_molecules == 0 || cfg->max_molecules > 0xFFFFFFF0ull) {
+    g_create_error = "invalid configuration (subpartitions, partition size or max_molecules)";
+    return MCX_ERR_INVALID_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device available (libmcx has no CPU fallback): ") + cudaGetErrorString(e);
+    return MCX_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return MCX_ERR_INVALID_ARG; }
+  mcx_handle* h = new mcx_handle();
+  h->cfg = *cfg;
+  auto fail = [&](int rc) { g_create_error = h->err; mcx_destroy(h); return rc; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(MCX_ERR_CUDA); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+    h->err = "stream/event creation failed"; return fail(MCX_ERR_CUDA);
+  }
+  DevParams& p = h->p;
+  p.ox = cfg->origin[0]; p.oy = cfg->origin[1]; p.oz = cfg->origin[2];
+  p.part_len = cfg->partition_edge_length;
+  p.n_sp = (int)cfg->num_subparts_per_edge;
+  p.sp_len = cfg->partition_edge_length / cfg->num_subparts_per_edge;  // simulation_config.cpp:48
+  p.sp_rcp = 1.0 / p.sp_len;                                          // simulation_config.cpp:63
+  p.R = cfg->rxn_radius_3d;
+  p.use_expanded = cfg->use_expanded_list ? 1 : 0;
+  p.seed = cfg->seed;
+  p.rng_mode = (int)cfg->rng_mode;
+  p.capacity = (unsigned int)cfg->max_molecules;
+  p.max_rounds = cfg->max_resolve_rounds ? cfg->max_resolve_rounds : 8;
+  h->iteration = cfg->initial_iteration;
+
+  // device neighbour-cell grid over the active box
+  double lo[3], hi[3];
+  bool whole = true;
+  for (int k = 0; k < 3; k++) whole = whole && cfg->active_llf[k] == 0 && cfg->active_urb[k] == 0;
+  for (int k = 0; k < 3; k++) {
+    lo[k] = whole ? cfg->origin[k] : cfg->active_llf[k];
+    hi[k] = whole ? cfg->origin[k] + cfg->partition_edge_length : cfg->active_urb[k];
+    if (!(hi[k] > lo[k])) { h->err = "empty active box"; return fail(MCX_ERR_INVALID_ARG); }
+  }
+  double vol = (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+  double edge = cfg->cell_edge;
+  if (!(edge > 0)) edge = std::cbrt(vol * 8.0 / (double)cfg->max_molecules);
+  const double max_cells = 2.0e8;
+  for (;;) {
+    double nc = std::ceil((hi[0] - lo[0]) / edge + 1) * std::ceil((hi[1] - lo[1]) / edge + 1) * std::ceil((hi[2] - lo[2]) / edge + 1);
+    if (nc <= max_cells) break;
+    edge *= 1.26;
+  }
+  p.cell_rcp = 1.0 / edge;
+  p.cgx = lo[0] - 0.5 * edge; p.cgy = lo[1] - 0.5 * edge; p.cgz = lo[2] - 0.5 * edge;
+  p.ncx = (int)std::ceil((hi[0] - p.cgx) / edge) + 1;
+  p.ncy = (int)std::ceil((hi[1] - p.cgy) / edge) + 1;
+  p.ncz = (int)std::ceil((hi[2] - p.cgz) / edge) + 1;
+  p.n_cells = (unsigned int)((size_t)p.ncx * p.ncy * p.ncz);
+  p.zc_lo = 0; p.zc_hi = p.ncz;
+
+  const size_t cap = p.capacity;
+  int rc = MCX_OK;
+  rc |= dev_alloc(h, &p.recA, cap); rc |= dev_alloc(h, &p.recB, cap);
+  rc |= dev_alloc(h, &p.tschedA, cap); rc |= dev_alloc(h, &p.tschedB, cap);
+  rc |= dev_alloc(h, &p.tuniA, cap); rc |= dev_alloc(h, &p.tuniB, cap);
+  rc |= dev_alloc(h, &p.rank, cap);
+  rc |= dev_alloc(h, &p.claim, cap);
+  rc |= dev_alloc(h, &p.prop_partner, cap); rc |= dev_alloc(h, &p.prop_info, cap); rc |= dev_alloc(h, &p.prop_t, cap);
+  rc |= dev_alloc(h, &p.pend[0], cap); rc |= dev_alloc(h, &p.pend[1], cap);
+  rc |= dev_alloc(h, &h->cs[0], (size_t)p.n_cells + 8); rc |= dev_alloc(h, &h->cs[1], (size_t)p.n_cells + 8);
+  rc |= dev_alloc(h, &h->scan_sums, (size_t)(p.n_cells + 1) / 4096 + 16);
+  rc |= dev_alloc(h, &p.ctr, 1);
+  rc |= dev_alloc(h, &h->d_n_out, 4);
+  if (rc) return fail(MCX_ERR_CUDA);
+  // empty wall tables until geometry arrives
+  std::vector<uint32_t> zero_start((size_t)p.n_sp * p.n_sp * p.n_sp + 1, 0);
+  if (dev_replace(h, &h->d_spw_start, zero_start.data(), zero_start.size())) return fail(MCX_ERR_CUDA);
+  p.spw_start = (const uint32_t*)h->d_spw_start;
+  h->plan.sm_count = h->sm_count;
+  *out = h;
+  return MCX_OK;
+}
+
+void mcx_destroy(mcx_handle* h) {
+  if (!h) return;
+  if (h->comm) mcx_comm_destroy(h->comm);
+  for (void* a : h->allocs) cudaFree(a);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices, const uint32_t* tri, uint64_t n_walls,
+                     const uint32_t* wall_surf_class, const uint32_t* wall_object) {
+  (void)wall_object;
+  if (!h) return MCX_ERR_INVALID_ARG;
+  if ((n_walls && (!vertices || !tri)) || n_walls > 0xFFFFFFF0ull) { h->err = "bad geometry arrays"; return MCX_ERR_INVALID_ARG; }
+  for (uint64_t i = 0; i < 3 * n_walls; i++)
+    if (tri[i] >= n_vertices) { h->err = "triangle vertex index out of range"; return MCX_ERR_INVALID_ARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<DevWall> walls;
+  mcxg::wall_constants(vertices, tri, n_walls, walls);
+  mcxg::GridSpec g{h->p.ox, h->p.oy, h->p.oz, h->p.sp_len, h->p.sp_rcp, h->p.R, h->p.n_sp, h->p.use_expanded != 0};
+  std::vector<uint32_t> start, list;
+  mcxg::bin_walls(g, vertices, tri, walls, start, list);
+  h->wall_class_host.assign(n_walls, MCX_NONE);
+  if (wall_surf_class) h->wall_class_host.assign(wall_surf_class, wall_surf_class + n_walls);
+  int rc = MCX_OK;
+  rc |= dev_replace(h, &h->d_walls, walls.data(), walls.size());
+  rc |= dev_replace(h, &h->d_tri, tri, 3 * n_walls);
+  rc |= dev_replace(h, &h->d_verts, vertices, 3 * n_vertices);
+  rc |= dev_replace(h, &h->d_wclass, h->wall_class_host.data(), h->wall_class_host.size());
+  rc |= dev_replace(h, &h->d_spw_start, start.data(), start.size());
+  rc |= dev_replace(h, &h->d_spw_list, list.data(), list.size());
+  if (rc) return MCX_ERR_CUDA;
+  DevParams& p = h->p;
+  p.walls = (const DevWall*)h->d_walls; p.wall_tri = (const uint32_t*)h->d_tri; p.verts = (const double*)h->d_verts;
+  p.wall_class = (const uint32_t*)h->d_wclass; p.spw_start = (const uint32_t*)h->d_spw_start;
+  p.spw_list = (const uint32_t*)h->d_spw_list; p.n_walls = (int)n_walls;
+  h->has_geometry = true;
+  return MCX_OK;
+}
+
+// (re)build every table that depends on species x reactions x surface classes
+static int rebuild_tables(mcx_handle* h) {
+  const size_t ns = h->species.size();
+  if (ns == 0) return MCX_OK;
+  if (ns > 256) { h->err = "more than 256 species are not supported by the device counters"; return MCX_ERR_INVALID_ARG; }
+  std::vector<int> bimol(ns * ns, -1), unimol(ns, -1);
+  std::vector<DevClass> dc(h->classes.size());
+  std::vector<DevPathway> dp(h->pathways.size());
+  for (size_t c = 0; c < h->classes.size(); c++) {
+    const mcx_rxn_class& rc = h->classes[c];
+    if (rc.first_pathway + rc.n_pathways > h->pathways.size() || rc.n_pathways == 0 || rc.n_pathways > 4095) {
+      h->err = "reaction class pathway range invalid"; return MCX_ERR_INVALID_ARG;
+    }
+    if (rc.reactants[0] >= ns || (rc.kind == MCX_RXN_BIMOL_VOLVOL && rc.reactants[1] >= ns)) {
+      h->err = "reaction class references an unknown species"; return MCX_ERR_INVALID_ARG;
+    }
+    dc[c] = DevClass{rc.max_fixed_p, rc.kind, rc.reactants[0], rc.reactants[1], rc.first_pathway, rc.n_pathways, 0};
+    if (rc.kind == MCX_RXN_BIMOL_VOLVOL) {
+      bimol[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
+      bimol[rc.reactants[1] * ns + rc.reactants[0]] = (int)c;
+    } else if (rc.kind == MCX_RXN_UNIMOL) unimol[rc.reactants[0]] = (int)c;
+    else { h->err = "unknown reaction kind"; return MCX_ERR_INVALID_ARG; }
+  }
+  for (size_t k = 0; k < h->pathways.size(); k++) {
+    const mcx_pathway& pw = h->pathways[k];
+    if (pw.n_products > MCX_MAX_PRODUCTS) { h->err = "too many products"; return MCX_ERR_INVALID_ARG; }
+    DevPathway d{};
+    d.cum_prob = pw.cum_prob; d.n_products = pw.n_products; d.keep_mask = pw.keep_reactant_mask; d.rule_id = pw.rxn_rule_id;
+    for (uint32_t q = 0; q < pw.n_products; q++) {
+      if (pw.products[q] >= ns) { h->err = "product references an unknown species"; return MCX_ERR_INVALID_ARG; }
+      d.products[q] = pw.products[q];
+    }
+    dp[k] = d;
+  }
+  std::vector<DevSpecies> ds(ns);
+  for (size_t a = 0; a < ns; a++) {
+    bool any = false;
+    for (size_t b = 0; b < ns; b++) any = any || bimol[a * ns + b] >= 0;
+    ds[a] = DevSpecies{h->species[a].space_step, h->species[a].time_step, h->species[a].flags,
+                       (any && !(h->species[a].flags & MCX_SP_CANT_INITIATE)) ? 1u : 0u};
+  }
+  // surface-class action table; lookup order as in find_mol_reactions_with_surf_classes
+  // (rxn_utils.inl:182-244): species-specific, ALL_MOLECULES, ALL_VOLUME_MOLECULES
+  uint32_t nsc = 0;
+  for (const auto& r : h->surf_rules) nsc = std::max(nsc, r.surf_class + 1);
+  for (uint32_t c : h->wall_class_host) if (c != MCX_NONE) nsc = std::max(nsc, c + 1);
+  h->n_surf_classes = nsc;
+  std::vector<uint8_t> act(std::max<size_t>(1, ns * nsc * 2), MCX_SURF_REFLECTIVE);
+  bool absorbing = false;
+  for (size_t a = 0; a < ns; a++)
+    for (uint32_t c = 0; c < nsc; c++)
+      for (int side = 0; side < 2; side++) {
+        const int orient = side == 0 ? 1 : -1;
+        const uint32_t order[3] = {(uint32_t)a, MCX_ALL_MOLECULES, MCX_ALL_VOLUME_MOLECULES};
+        bool done = false;
+        for (int o = 0; o < 3 && !done; o++)
+          for (const auto& r : h->surf_rules)
+            if (r.species == order[o] && r.surf_class == c && (r.orientation == 0 || r.orientation == orient)) {
+              act[(a * nsc + c) * 2 + side] = (uint8_t)r.type;
+              absorbing = absorbing || r.type == MCX_SURF_ABSORPTIVE;
+              done = true;
+              break;
+            }
+      }
+  int rc = MCX_OK;
+  rc |= dev_replace(h, &h->d_species, ds.data(), ds.size());
+  rc |= dev_replace(h, &h->d_bimol, bimol.data(), bimol.size());
+  rc |= dev_replace(h, &h->d_unimol, unimol.data(), unimol.size());
+  rc |= dev_replace(h, &h->d_classes, dc.data(), dc.size());
+  rc |= dev_replace(h, &h->d_pathways, dp.data(), dp.size());
+  rc |= dev_replace(h, &h->d_surf, act.data(), act.size());
+  if (rc) return MCX_ERR_CUDA;
+  DevParams& p = h->p;
+  p.species = (const DevSpecies*)h->d_species; p.bimol = (const int*)h->d_bimol; p.unimol = (const int*)h->d_unimol;
+  p.classes = (const DevClass*)h->d_classes; p.pathways = (const DevPathway*)h->d_pathways;
+  p.surf_action = (const uint8_t*)h->d_surf; p.n_species = (int)ns; p.n_surf_classes = (int)nsc;
+  h->plan.has_claims = !h->classes.empty() || absorbing;
+  return MCX_OK;
+}
+
+int mcx_set_species(mcx_handle* h, const mcx_species* species, uint32_t n_species) {
+  if (!h || !species || n_species == 0) { if (h) h->err = "no species"; return MCX_ERR_INVALID_ARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  h->species.assign(species, species + n_species);
+  h->has_species = true;
+  return rebuild_tables(h);
+}
+
+int mcx_set_reactions(mcx_handle* h, const mcx_rxn_class* classes, uint32_t n_classes, const mcx_pathway* pathways,
+                      uint32_t n_pathways) {
+  if (!h || (n_classes && (!classes || !pathways))) { if (h) h->err = "bad reaction arrays"; return MCX_ERR_INVALID_ARG; }
+  if (!h->has_species) { h->err = "mcx_set_species must precede mcx_set_reactions"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  h->classes.assign(classes, classes + n_classes);
+  h->pathways.assign(pathways, pathways + n_pathways);
+  for (const auto& pw : h->pathways)
+    if (pw.rxn_rule_id >= 256) { h->err = "rxn_rule_id >= 256 not supported by the device counters"; return MCX_ERR_INVALID_ARG; }
+  return rebuild_tables(h);
+}
+
+int mcx_set_surface_classes(mcx_handle* h, const mcx_surf_class_rxn* rules, uint32_t n_rules) {
+  if (!h || (n_rules && !rules)) { if (h) h->err = "bad surface class arrays"; return MCX_ERR_INVALID_ARG; }
+  if (!h->has_species) { h->err = "mcx_set_species must precede mcx_set_surface_classes"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  h->surf_rules.assign(rules, rules + n_rules);
+  for (const auto& r : h->surf_rules)
+    if (r.surf_class >= 4096 || r.type > MCX_SURF_ABSORPTIVE) { h->err = "bad surface class rule"; return MCX_ERR_INVALID_ARG; }
+  return rebuild_tables(h);
+}
+
+static void bind_iteration(mcx_handle* h) {
+  h->p.cs_cur = h->cs[h->cs_cur];
+  h->p.cs_next = h->cs[h->cs_cur ^ 1];
+  h->p.iteration = h->iteration;
+}
+
+static int check_device_error(mcx_handle* h, Counters* host_ctr) {
+  CK(cudaMemcpyAsync(host_ctr, h->p.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (host_ctr->error) {
+    char buf[256];
+    const char* what = host_ctr->error == MCX_ERR_ESCAPED ? "escaped the simulation area defined by partition size"
+                     : host_ctr->error == MCX_ERR_CAPACITY ? "could not be stored: max_molecules exhausted"
+                     : host_ctr->error == MCX_ERR_OVERFLOW ? "crossed more subpartitions than the device set holds"
+                     : "raised a device error";
+    snprintf(buf, sizeof(buf), "molecule (id: %u) %s", host_ctr->error_id, what);
+    h->err = buf;
+    return host_ctr->error;
+  }
+  return MCX_OK;
+}
+
+int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
+  if (!h || !m) return MCX_ERR_INVALID_ARG;
+  if (!h->has_species) { h->err = "species table missing"; return MCX_ERR_STATE; }
+  if (m->n > h->p.capacity) { h->err = "more molecules than max_molecules"; return MCX_ERR_CAPACITY; }
+  if (m->n && (!m->x || !m->y || !m->z || !m->id || !m->species)) { h->err = "null molecule arrays"; return MCX_ERR_INVALID_ARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t n = m->n;
+  // stage through scratch device arrays carved from buffers that are idle during upload:
+  // prop_t (8B), claim (8B), tschedA (8B), tuniA (8B), tschedB/tuniB are targets -> use separate scratch
+  double *dx = nullptr, *dy = nullptr, *dz = nullptr, *dts = nullptr, *dtu = nullptr;
+  uint32_t *did = nullptr, *dsp = nullptr, *dfl = nullptr;
+  auto tmp = [&](void** q, size_t bytes) { return cudaMalloc(q, std::max<size_t>(bytes, 8)); };
+  CK(tmp((void**)&dx, n * 8)); CK(tmp((void**)&dy, n * 8)); CK(tmp((void**)&dz, n * 8));
+  CK(tmp((void**)&did, n * 4)); CK(tmp((void**)&dsp, n * 4));
+  if (m->flags) CK(tmp((void**)&dfl, n * 4));
+  if (m->diffusion_time) CK(tmp((void**)&dts, n * 8));
+  if (m->unimol_rxn_time) CK(tmp((void**)&dtu, n * 8));
+  uint32_t max_id = 0;
+  for (size_t i = 0; i < n; i++) {
+    max_id = std::max(max_id, m->id[i]);
+    if (m->species[i] >= h->species.size()) { h->err = "molecule references an unknown species"; return MCX_ERR_INVALID_ARG; }
+  }
+  cudaStream_t s = h->stream;
+  CK(cudaMemcpyAsync(dx, m->x, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dy, m->y, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dz, m->z, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(did, m->id, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dsp, m->species, n * 4, cudaMemcpyHostToDevice, s));
+  if (dfl) CK(cudaMemcpyAsync(dfl, m->flags, n * 4, cudaMemcpyHostToDevice, s));
+  if (dts) CK(cudaMemcpyAsync(dts, m->diffusion_time, n * 8, cudaMemcpyHostToDevice, s));
+  if (dtu) CK(cudaMemcpyAsync(dtu, m->unimol_rxn_time, n * 8, cudaMemcpyHostToDevice, s));
+  Counters zero;
+  memset(&zero, 0, sizeof(zero));
+  zero.n_slots = (unsigned int)n;
+  zero.next_id = n ? max_id + 1 : 0;
+  CK(cudaMemcpyAsync(h->p.ctr, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
+  bind_iteration(h);
+  mcx_set_scan_scratch(h->scan_sums);
+  mcx_launch_pack_soa(h->p, dx, dy, dz, did, dsp, dfl, dts, dtu, (unsigned int)n, s);
+  mcx_launch_initial_sort(h->p, h->plan, s);
+  h->cs_cur ^= 1;
+  Counters hc;
+  int rc = check_device_error(h, &hc);
+  cudaFree(dx); cudaFree(dy); cudaFree(dz); cudaFree(did); cudaFree(dsp);
+  if (dfl) cudaFree(dfl);
+  if (dts) cudaFree(dts);
+  if (dtu) cudaFree(dtu);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  h->uploaded = true;
+  return MCX_OK;
+}
+
+uint64_t mcx_num_molecules(mcx_handle* h) {
+  if (!h || !h->uploaded) return 0;
+  cudaSetDevice(h->cfg.device);
+  Counters hc;
+  if (cudaMemcpy(&hc, h->p.ctr, sizeof(hc), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  uint64_t n = 0;
+  for (size_t i = 0; i < h->species.size(); i++) n += hc.species_count[i];
+  return n;
+}
+
+int mcx_download_molecules(mcx_handle* h, mcx_mol_soa* out, uint64_t capacity) {
+  if (!h || !out) return MCX_ERR_INVALID_ARG;
+  if (!h->uploaded) { h->err = "nothing uploaded"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  Counters hc;
+  CK(cudaMemcpy(&hc, h->p.ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  const size_t n = hc.n_slots;
+  double *dx, *dy, *dz, *dts, *dtu; uint32_t *did, *dsp, *dfl;
+  auto tmp = [&](void** q, size_t bytes) { return cudaMalloc(q, std::max<size_t>(bytes, 8)); };
+  CK(tmp((void**)&dx, n * 8)); CK(tmp((void**)&dy, n * 8)); CK(tmp((void**)&dz, n * 8));
+  CK(tmp((void**)&dts, n * 8)); CK(tmp((void**)&dtu, n * 8));
+  CK(tmp((void**)&did, n * 4)); CK(tmp((void**)&dsp, n * 4)); CK(tmp((void**)&dfl, n * 4));
+  bind_iteration(h);
+  mcx_launch_unpack_soa(h->p, dx, dy, dz, did, dsp, dfl, dts, dtu, h->d_n_out, h->stream);
+  unsigned int live = 0;
+  CK(cudaMemcpyAsync(&live, h->d_n_out, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  int rc = MCX_OK;
+  if (live > capacity) { h->err = "download capacity too small"; rc = MCX_ERR_CAPACITY; }
+  else {
+    CK(cudaMemcpy(out->x, dx, live * 8ull, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->y, dy, live * 8ull, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->z, dz, live * 8ull, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->id, did, live * 4ull, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->species, dsp, live * 4ull, cudaMemcpyDeviceToHost));
+    if (out->flags) CK(cudaMemcpy(out->flags, dfl, live * 4ull, cudaMemcpyDeviceToHost));
+    if (out->diffusion_time) CK(cudaMemcpy(out->diffusion_time, dts, live * 8ull, cudaMemcpyDeviceToHost));
+    if (out->unimol_rxn_time) CK(cudaMemcpy(out->unimol_rxn_time, dtu, live * 8ull, cudaMemcpyDeviceToHost));
+    out->n = live;
+  }
+  cudaFree(dx); cudaFree(dy); cudaFree(dz); cudaFree(dts); cudaFree(dtu); cudaFree(did); cudaFree(dsp); cudaFree(dfl);
+  return rc;
+}
+
+static void fill_stats(const Counters& a, const Counters& b, uint64_t iters, float ms, size_t ns, mcx_step_stats* s) {
+  if (!s) return;
+  memset(s, 0, sizeof(*s));
+  s->iterations = iters;
+  s->molecule_steps = b.molecule_steps - a.molecule_steps;
+  for (size_t i = 0; i < ns; i++) s->n_live += b.species_count[i];
+  s->ray_polygon_tests = b.ray_polygon_tests - a.ray_polygon_tests;
+  s->ray_polygon_colls = b.ray_polygon_colls - a.ray_polygon_colls;
+  s->mol_wall_reflections = b.reflections - a.reflections;
+  s->mol_wall_transparent = b.transparent - a.transparent;
+  s->mol_wall_absorptions = b.absorptions - a.absorptions;
+  s->vol_mol_vol_mol_collisions = b.volvol_collisions - a.volvol_collisions;
+  s->bimol_rxns = b.bimol_rxns - a.bimol_rxns;
+  s->unimol_rxns = b.unimol_rxns - a.unimol_rxns;
+  s->wall_redos = b.redos - a.redos;
+  s->resolve_retries = b.retries - a.retries;
+  s->unresolved_conflicts = b.unresolved - a.unresolved;
+  s->products_created = b.products - a.products;
+  s->device_ms = ms;
+}
+
+static int run_iterations(mcx_handle* h, uint32_t n_iterations, mcx_step_stats* stats_out) {
+  if (!h->uploaded) { h->err = "mcx_upload_molecules must precede stepping"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  Counters before;
+  CK(cudaMemcpyAsync(&before, h->p.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  mcx_set_scan_scratch(h->scan_sums);
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (uint32_t k = 0; k < n_iterations; k++) {
+    bind_iteration(h);
+    if (h->comm) {
+      int rc = mcx_comm_iteration(h->comm, h->p, h->plan, h->stream);
+      if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+    } else {
+      mcx_launch_iteration(h->p, h->plan, h->stream);
+    }
+    h->cs_cur ^= 1;
+    h->iteration++;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  Counters after;
+  int rc = check_device_error(h, &after);
+  CK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  fill_stats(before, after, n_iterations, ms, h->species.size(), stats_out);
+  return rc;
+}
+
+int mcx_step(mcx_handle* h, uint32_t n_iterations, mcx_step_stats* stats_out) {
+  if (!h) return MCX_ERR_INVALID_ARG;
+  if (h->p.rng_mode != MCX_RNG_PHILOX) { h->err = "mcx_step needs rng_mode == MCX_RNG_PHILOX (use mcx_replay_step)"; return MCX_ERR_STATE; }
+  h->p.trace = nullptr; h->p.n_trace = 0; h->plan.trace = false;
+  return run_iterations(h, n_iterations, stats_out);
+}
+
+static int traced_iteration(mcx_handle* h, uint64_t n_ids, mcx_trace_rec* trace_out, mcx_step_stats* stats_out) {
+  mcx_trace_rec* d_trace = nullptr;
+  CK(cudaMalloc((void**)&d_trace, std::max<uint64_t>(n_ids, 1) * sizeof(mcx_trace_rec)));
+  CK(cudaMemset(d_trace, 0, std::max<uint64_t>(n_ids, 1) * sizeof(mcx_trace_rec)));
+  h->p.trace = d_trace; h->p.n_trace = n_ids; h->plan.trace = true;
+  int rc = run_iterations(h, 1, stats_out);
+  h->p.trace = nullptr; h->p.n_trace = 0; h->plan.trace = false;
+  if (rc == MCX_OK && trace_out) {
+    cudaError_t e = cudaMemcpy(trace_out, d_trace, n_ids * sizeof(mcx_trace_rec), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = MCX_ERR_CUDA; }
+  }
+  cudaFree(d_trace);
+  return rc;
+}
+
+int mcx_replay_step(mcx_handle* h, const uint32_t* words, uint64_t n_words, const uint64_t* offset_by_id, uint64_t n_ids,
+                    mcx_trace_rec* trace_out, mcx_step_stats* stats_out) {
+  if (!h || !words || !offset_by_id) return MCX_ERR_INVALID_ARG;
+  if (h->p.rng_mode != MCX_RNG_TAPE) { h->err = "mcx_replay_step needs rng_mode == MCX_RNG_TAPE"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  uint32_t* d_words = nullptr; unsigned long long* d_off = nullptr;
+  CK(cudaMalloc((void**)&d_words, std::max<uint64_t>(n_words, 1) * 4));
+  CK(cudaMalloc((void**)&d_off, std::max<uint64_t>(n_ids, 1) * 8));
+  CK(cudaMemcpy(d_words, words, n_words * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_off, offset_by_id, n_ids * 8, cudaMemcpyHostToDevice));
+  h->p.tape = d_words; h->p.n_words = n_words; h->p.tape_off = d_off; h->p.n_ids = n_ids;
+  int rc = traced_iteration(h, n_ids, trace_out, stats_out);
+  h->p.tape = nullptr; h->p.tape_off = nullptr; h->p.n_words = 0; h->p.n_ids = 0;
+  cudaFree(d_words); cudaFree(d_off);
+  return rc;
+}
+
+int mcx_trace_step(mcx_handle* h, uint64_t n_ids, mcx_trace_rec* trace_out, mcx_step_stats* stats_out) {
+  if (!h) return MCX_ERR_INVALID_ARG;
+  if (h->p.rng_mode != MCX_RNG_PHILOX) { h->err = "mcx_trace_step needs rng_mode == MCX_RNG_PHILOX"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  return traced_iteration(h, n_ids, trace_out, stats_out);
+}
+
+int mcx_counts(mcx_handle* h, uint64_t* per_species, uint32_t n_species, uint64_t* per_rxn_rule, uint32_t n_rxn_rules) {
+  if (!h) return MCX_ERR_INVALID_ARG;
+  if (!h->uploaded) { h->err = "nothing uploaded"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  Counters hc;
+  CK(cudaMemcpy(&hc, h->p.ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> buf(512, 0);
+  for (uint32_t i = 0; i < 256; i++) { buf[i] = hc.species_count[i]; buf[256 + i] = hc.rxn_count[i]; }
+  if (h->comm) {
+    int rc = mcx_comm_allreduce_u64(h->comm, buf.data(), 512, h->stream);
+    if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+  }
+  for (uint32_t i = 0; i < n_species && per_species; i++) per_species[i] = i < 256 ? buf[i] : 0;
+  for (uint32_t i = 0; i < n_rxn_rules && per_rxn_rule; i++) per_rxn_rule[i] = i < 256 ? buf[256 + i] : 0;
+  return MCX_OK;
+}
+
+int mcx_comm_init(mcx_handle* h, const void* nccl_unique_id, uint32_t id_bytes) {
+  if (!h || !nccl_unique_id) return MCX_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->cfg.device));
+  std::string err;
+  h->comm = mcx_comm_create(nccl_unique_id, id_bytes, h->cfg.rank, h->cfg.world_size, h->p, err);
+  if (!h->comm) { h->err = err; return MCX_ERR_COMM; }
+  return MCX_OK;
+}
+
+// sizeof table for the binding-side layout check (tests/test_abi.py)
+int mcx_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(mcx_config);
+    case 1: return (int)sizeof(mcx_species);
+    case 2: return (int)sizeof(mcx_rxn_class);
+    case 3: return (int)sizeof(mcx_pathway);
+    case 4: return (int)sizeof(mcx_surf_class_rxn);
+    case 5: return (int)sizeof(mcx_mol_soa);
+    case 6: return (int)sizeof(mcx_step_stats);
+    case 7: return (int)sizeof(mcx_trace_rec);
+    default: return -1;
+  }
+}
+
+}  // extern "C"

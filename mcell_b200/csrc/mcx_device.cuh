@@ -1,0 +1,677 @@
+// mcx_device.cuh — per-molecule evaluation for sm_100a: displacement sampling, subpartition DDA,
+// wall ray tracing, neighbour-cell partner search, reaction tests.  fp64 throughout, compiled with
+// -fmad=false so every expression rounds like the reference's -march=core2 build (no FMA).
+//
+// Reference functions realised here (src4/): compute_vol_displacement (diffusion_utils.inl:366-432),
+// rng_gauss (src/rng.c:173-218), collect_crossed_subparts / collect_neighboring_subparts
+// (collision_utils_subparts.inl:38-300), get_closest_wall_collision / collide_wall / jump_away_line
+// (collision_utils.inl:568-914), collide_mol (:464-515), sort_collisions_by_time
+// (diffuse_react_event.cpp:341-364), test_bimolecular (rxn_utils.inl:336-414), reflect_from_wall
+// (collision_utils.inl:1711-1747), cross_transparent_wall (diffuse_react_event.cpp:3007-3099),
+// diffuse_single_molecule / get_max_time (:164-337), unimolecular scheduling (:1731-1826).
+#pragma once
+#include <cfloat>
+#include "mcx_internal.h"
+#include "zig_tables.inc"
+
+#define MCX_EPS 1e-12
+#define MCX_SQRT_EPS 1e-6
+#define MCX_POS_SQRT2 1.41421356238  /* src4/defines.h:182 */
+#define MCX_MAX_SP_WALLS 40
+#define MCX_MAX_SP_MOLS 64
+
+__device__ const double d_zig_y[128] = MCX_ZIG_YTAB_INIT;
+__device__ const double d_zig_w[128] = MCX_ZIG_WTAB_INIT;
+__device__ const unsigned int d_zig_k[128] = MCX_ZIG_KTAB_INIT;
+
+struct ZigShared { double y[128]; double w[128]; unsigned int k[128]; };
+
+__device__ __forceinline__ void zig_load(ZigShared* z) {
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) { z->y[i] = d_zig_y[i]; z->w[i] = d_zig_w[i]; z->k[i] = d_zig_k[i]; }
+}
+
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ double dot3(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double max3d(double a, double b, double c) { return fmax(fmax(a, b), c); }
+__device__ __forceinline__ double abs_max_2vec(D3 a, D3 b) {
+  return max3d(fmax(fabs(a.x), fabs(b.x)), fmax(fabs(a.y), fabs(b.y)), fmax(fabs(a.z), fabs(b.z)));
+}
+__device__ __forceinline__ bool cmp_eq_d(double a, double b, double eps) { return fabs(a - b) < eps; }
+__device__ __forceinline__ bool distinguishable_d(double a, double b, double eps) {  // src/util.c:449-463
+  double c = fabs(a - b);
+  a = fabs(a);
+  if (a < 1) a = 1;
+  b = fabs(b);
+  if (b < a) eps *= a; else eps *= b;
+  return c > eps;
+}
+
+#include "mcx_philox.h"
+
+// ---- per-molecule word stream: Philox (production) or tape slice (replay) ----------------------
+struct Stream {
+  const uint32_t* tape; unsigned long long tape_left;
+  uint32_t k0, k1, it_lo, it_hi, id;
+  uint32_t buf[4];
+  uint32_t used;
+  const ZigShared* zig;
+
+  __device__ __forceinline__ void init(const DevParams& p, uint32_t mol_id, const ZigShared* z) {
+    zig = z; used = 0; id = mol_id;
+    if (p.rng_mode == MCX_RNG_TAPE) {
+      unsigned long long off = mol_id < p.n_ids ? p.tape_off[mol_id] : p.n_words;
+      if (off > p.n_words) off = p.n_words;
+      tape = p.tape + off; tape_left = p.n_words - off;
+    } else {
+      tape = nullptr; tape_left = 0;
+      k0 = (uint32_t)p.seed; k1 = (uint32_t)(p.seed >> 32);
+      it_lo = (uint32_t)p.iteration; it_hi = (uint32_t)(p.iteration >> 32);
+    }
+  }
+  __device__ __forceinline__ uint32_t next() {
+    uint32_t w;
+    if (tape) w = used < tape_left ? tape[used] : 0u;
+    else {
+      if ((used & 3u) == 0u) philox4x32_10(used >> 2, it_lo, it_hi, id, k0, k1, buf);
+      w = buf[used & 3u];
+    }
+    used++;
+    return w;
+  }
+  __device__ __forceinline__ double dbl() { return 2.3283064365386962890625e-10 * (double)next(); }
+  // src/rng.c:173-218
+  __device__ double gauss() {
+    double x, y, sign;
+    for (;;) {
+      uint32_t bits = next();
+      sign = (bits & 0x80u) ? -1.0 : 1.0;
+      uint32_t region = bits & 0x7fu;
+      uint32_t pos_within_region = bits & 0xffffff00u;
+      x = (double)pos_within_region * zig->w[region];
+      if (pos_within_region < zig->k[region]) break;
+      if (region != 0) {
+        double yB = zig->y[region];
+        double yR = zig->y[region - 1] - yB;
+        y = yB + yR * dbl();
+      } else {
+        const double R = MCX_ZIG_R;
+        x = R - log1p(-dbl()) * (1.0 / R);
+        y = exp(-R * (x - 0.5 * R)) * dbl();
+      }
+      if (!(y >= exp(-0.5 * x * x))) break;
+    }
+    return sign * x;
+  }
+};
+
+// ---- evaluation result ----------------------------------------------------------------------------
+struct Outcome {
+  int kind;               // MCX_OUT_*
+  D3 pos;
+  double t_now, unimol_time, t_event;
+  uint32_t flags;         // device flag bits (DF_*)
+  int rxn_class, pathway;
+  uint32_t partner_slot, partner_id;
+};
+
+struct Tracer {
+  mcx_trace_rec* tr;
+  unsigned long long h;
+  __device__ __forceinline__ void ev(uint32_t a, uint32_t b) {
+    h = (h ^ a) * 0x100000001b3ULL;
+    h = (h ^ b) * 0x100000001b3ULL;
+  }
+};
+enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
+       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u };
+
+struct LocalStats {
+  unsigned int ray_polygon_tests, ray_polygon_colls, reflections, transparent, volvol_collisions, redos;
+};
+
+// ---- subpartition index math (src4/partition.h:248-309) -------------------------------------------------
+__device__ __forceinline__ bool in_partition(const DevParams& p, D3 q) {
+  return q.x >= p.ox && q.y >= p.oy && q.z >= p.oz && q.x < p.ox + p.part_len && q.y < p.oy + p.part_len &&
+         q.z < p.oz + p.part_len;
+}
+__device__ __forceinline__ void subpart_3d(const DevParams& p, D3 q, int idx[3]) {
+  idx[0] = (int)((q.x - p.ox) * p.sp_rcp);
+  idx[1] = (int)((q.y - p.oy) * p.sp_rcp);
+  idx[2] = (int)((q.z - p.oz) * p.sp_rcp);
+}
+__device__ __forceinline__ uint32_t subpart_from_3d(const DevParams& p, int x, int y, int z) {
+  return (uint32_t)(x + y * p.n_sp + z * p.n_sp * p.n_sp);
+}
+__device__ __forceinline__ uint32_t subpart_index(const DevParams& p, D3 q) {
+  int i[3]; subpart_3d(p, q, i); return subpart_from_3d(p, i[0], i[1], i[2]);
+}
+__device__ __forceinline__ bool idx_in_range(const DevParams& p, int i) { return i >= 0 && i < p.n_sp; }
+
+// ---- device neighbour-cell grid --------------------------------------------------------------------------
+__device__ __forceinline__ int cell_coord(double v, double origin, double rcp, int n) {
+  int c = (int)floor((v - origin) * rcp);
+  return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+__device__ __forceinline__ uint32_t cell_of(const DevParams& p, double x, double y, double z) {
+  int cx = cell_coord(x, p.cgx, p.cell_rcp, p.ncx);
+  int cy = cell_coord(y, p.cgy, p.cell_rcp, p.ncy);
+  int cz = cell_coord(z, p.cgz, p.cell_rcp, p.ncz);
+  return (uint32_t)(cx + p.ncx * (cy + p.ncy * cz));
+}
+
+struct SpSet { uint32_t v[MCX_MAX_SP_MOLS]; int n; bool overflow; };
+struct SpList { uint32_t v[MCX_MAX_SP_WALLS]; int n; };
+
+__device__ __forceinline__ void spset_insert(SpSet& s, uint32_t sp) {
+  for (int i = 0; i < s.n; i++) if (s.v[i] == sp) return;
+  if (s.n < MCX_MAX_SP_MOLS) s.v[s.n++] = sp; else s.overflow = true;
+}
+__device__ __forceinline__ bool spset_has(const SpSet& s, uint32_t sp) {
+  for (int i = 0; i < s.n; i++) if (s.v[i] == sp) return true;
+  return false;
+}
+
+// collect_neighboring_subparts, collision_utils_subparts.inl:38-122
+__device__ void collect_neighboring_subparts(const DevParams& p, D3 pos, const int si[3], double rr, SpSet& out) {
+  const double sp_len = p.sp_len, part_len = p.part_len;
+  D3 rel = {pos.x - p.ox, pos.y - p.oy, pos.z - p.oz};
+  D3 plus = {rel.x + rr, rel.y + rr, rel.z + rr};
+  D3 minus = {rel.x - rr, rel.y - rr, rel.z - rr};
+  D3 boundary = {si[0] * sp_len, si[1] * sp_len, si[2] * sp_len};
+  int xd = 0, yd = 0, zd = 0;
+  if (minus.x < boundary.x && minus.x > 0.0) { spset_insert(out, subpart_from_3d(p, si[0] - 1, si[1], si[2])); xd = -1; }
+  else if (plus.x > boundary.x + sp_len && plus.x < part_len) { spset_insert(out, subpart_from_3d(p, si[0] + 1, si[1], si[2])); xd = 1; }
+  if (minus.y < boundary.y && minus.y > 0.0) { spset_insert(out, subpart_from_3d(p, si[0], si[1] - 1, si[2])); yd = -1; }
+  else if (plus.y > boundary.y + sp_len && plus.y < part_len) { spset_insert(out, subpart_from_3d(p, si[0], si[1] + 1, si[2])); yd = 1; }
+  if (minus.z < boundary.z && minus.z > 0.0) { spset_insert(out, subpart_from_3d(p, si[0], si[1], si[2] - 1)); zd = -1; }
+  else if (plus.z > boundary.z + sp_len && plus.z < part_len) { spset_insert(out, subpart_from_3d(p, si[0], si[1], si[2] + 1)); zd = 1; }
+  if (xd && yd) spset_insert(out, subpart_from_3d(p, si[0] + xd, si[1] + yd, si[2]));
+  if (xd && zd) spset_insert(out, subpart_from_3d(p, si[0] + xd, si[1], si[2] + zd));
+  if (yd && zd) spset_insert(out, subpart_from_3d(p, si[0], si[1] + yd, si[2] + zd));
+  if (xd && yd && zd) spset_insert(out, subpart_from_3d(p, si[0] + xd, si[1] + yd, si[2] + zd));
+}
+
+// collect_crossed_subparts, collision_utils_subparts.inl:127-300
+__device__ uint32_t collect_crossed_subparts(const DevParams& p, D3 pos, uint32_t cur_subpart, D3 disp,
+                                             bool for_mols, bool for_walls, SpList& spw, SpSet& spm) {
+  const double sp_len = p.sp_len;
+  if (for_walls) { spw.n = 0; spw.v[spw.n++] = cur_subpart; }
+  if (for_mols) spset_insert(spm, cur_subpart);
+  D3 dest = pos + disp;
+  D3 dnz = disp;
+  if (dnz.x == 0) dnz.x = FLT_MIN;
+  if (dnz.y == 0) dnz.y = FLT_MIN;
+  if (dnz.z == 0) dnz.z = FLT_MIN;
+  int dir[3] = {dnz.x > 0 ? 1 : 0, dnz.y > 0 ? 1 : 0, dnz.z > 0 ? 1 : 0};
+  int src[3], dst[3];
+  src[0] = cur_subpart % p.n_sp; src[1] = (cur_subpart / p.n_sp) % p.n_sp; src[2] = (cur_subpart / (p.n_sp * p.n_sp)) % p.n_sp;
+  subpart_3d(p, dest, dst);
+  const double rr = p.R * MCX_POS_SQRT2;
+  const bool expanded = p.use_expanded != 0;
+  if (for_mols && expanded) collect_neighboring_subparts(p, pos, src, rr, spm);
+  uint32_t dest_subpart = subpart_from_3d(p, dst[0], dst[1], dst[2]);
+  if (cur_subpart != dest_subpart) {
+    int add[3] = {dir[0] ? 1 : -1, dir[1] ? 1 : -1, dir[2] ? 1 : -1};
+    D3 cur = pos;
+    int ci[3] = {src[0], src[1], src[2]};
+    uint32_t cs;
+    D3 rcp = {1.0 / dnz.x, 1.0 / dnz.y, 1.0 / dnz.z};
+    int guard = 0;
+    do {
+      D3 edges = {p.ox + ci[0] * sp_len + dir[0] * sp_len, p.oy + ci[1] * sp_len + dir[1] * sp_len,
+                  p.oz + ci[2] * sp_len + dir[2] * sp_len};
+      D3 diff = edges - cur;
+      D3 ct = {diff.x * rcp.x, diff.y * rcp.y, diff.z * rcp.z};
+      if (ct.x < ct.y && ct.x <= ct.z) {
+        cur = cur + disp * ct.x; ci[0] += add[0];
+        if (!idx_in_range(p, ci[0])) break;
+      } else if (ct.y <= ct.z) {
+        cur = cur + disp * ct.y; ci[1] += add[1];
+        if (!idx_in_range(p, ci[1])) break;
+      } else {
+        cur = cur + disp * ct.z; ci[2] += add[2];
+        if (!idx_in_range(p, ci[2])) break;
+      }
+      cs = subpart_from_3d(p, ci[0], ci[1], ci[2]);
+      if (for_walls) { if (spw.n < MCX_MAX_SP_WALLS) spw.v[spw.n++] = cs; else spm.overflow = true; }
+      if (for_mols) spset_insert(spm, cs);
+      if (for_mols && expanded) collect_neighboring_subparts(p, cur, ci, rr, spm);
+      if (++guard > 4096) break;
+    } while (cs != dest_subpart);
+  }
+  if (for_mols && expanded) collect_neighboring_subparts(p, dest, dst, rr, spm);
+  return dest_subpart;
+}
+
+// get_displacement_up_to_partition_boundary, collision_utils.inl:48-114
+__device__ D3 displacement_up_to_partition_boundary(const DevParams& p, D3 pos, D3 disp) {
+  D3 dnz = disp;
+  if (dnz.x == 0) dnz.x = FLT_MIN;
+  if (dnz.y == 0) dnz.y = FLT_MIN;
+  if (dnz.z == 0) dnz.z = FLT_MIN;
+  D3 edges = {p.ox + (dnz.x > 0 ? 1.0 : 0.0) * p.part_len, p.oy + (dnz.y > 0 ? 1.0 : 0.0) * p.part_len,
+              p.oz + (dnz.z > 0 ? 1.0 : 0.0) * p.part_len};
+  D3 diff = edges - pos;
+  double hit_time = 1;
+  if (fabs(diff.x) < MCX_EPS || fabs(diff.y) < MCX_EPS || fabs(diff.z) < MCX_EPS) return {0, 0, 0};
+  D3 ct = {diff.x / dnz.x, diff.y / dnz.y, diff.z / dnz.z};
+  if (ct.x >= 0 && ct.x < ct.y && ct.x <= ct.z) hit_time = ct.x;
+  else if (ct.y >= 0 && ct.y <= ct.z) hit_time = ct.y;
+  else if (ct.z >= 0) hit_time = ct.z;
+  return disp * (hit_time - MCX_EPS);
+}
+
+enum { W_MISS = 0, W_FRONT = 1, W_BACK = 2, W_REDO = 3 };
+
+__device__ __forceinline__ D3 wall_vertex(const DevParams& p, uint32_t wi, int k) {
+  uint32_t v = p.wall_tri[3 * wi + k];
+  return {p.verts[3 * v], p.verts[3 * v + 1], p.verts[3 * v + 2]};
+}
+
+// jump_away_line, collision_utils.inl:568-603
+__device__ void jump_away_line(D3 pt, double k, D3 A, D3 B, D3 n, Stream& rs, D3& v) {
+  D3 e = B - A;
+  double le_1 = 1.0 / sqrt(dot3(e, e));
+  e = e * le_1;
+  D3 f = {n.y * e.z - n.z * e.y, n.z * e.x - n.x * e.z, n.x * e.y - n.y * e.x};
+  double tiny = MCX_EPS * (abs_max_2vec(pt, v) + 1.0) / (k * max3d(fabs(f.x), fabs(f.y), fabs(f.z)));
+  if ((rs.next() & 1u) == 0u) tiny = -tiny;
+  v.x -= tiny * f.x; v.y -= tiny * f.y; v.z -= tiny * f.z;
+}
+
+// collide_wall, collision_utils.inl:629-812 (update_move = true)
+__device__ int collide_wall(const DevParams& p, D3 pos, uint32_t wi, Stream& rs, D3& move, double& t, D3& hit) {
+  const DevWall& f = p.walls[wi];
+  const D3 n = {f.nx, f.ny, f.nz};
+  double dp = dot3(n, pos), dv = dot3(n, move), dd = dp - f.dist, d_eps;
+  if (dd > 0) {
+    d_eps = MCX_EPS;
+    if (dd < d_eps) d_eps = 0.5 * dd;
+    if (dd + dv > d_eps) return W_MISS;
+  } else {
+    d_eps = -MCX_EPS;
+    if (dd > d_eps) d_eps = 0.5 * dd;
+    if (dd < 0 && dd + dv < d_eps) return W_MISS;
+  }
+  double a;
+  if (dd == 0) {
+    if (dv != 0) return W_MISS;
+    a = (abs_max_2vec(pos, move) + 1.0) * MCX_EPS;
+    if ((rs.next() & 1u) == 0u) a = -a;
+    move = move - n * a;
+    return W_REDO;
+  }
+  a = 1.0 / dv;
+  a *= -dd;
+  t = a;
+  hit = pos + move * a;
+  D3 v0 = {f.v0x, f.v0y, f.v0z};
+  D3 local = hit - v0;
+  double b = dot3(local, D3{f.ux, f.uy, f.uz}), c = dot3(local, D3{f.vx, f.vy, f.vz}), ff;
+  if (f.uv2v < 0) { c = -c; ff = -f.uv2v; } else ff = f.uv2v;
+  if (c > 0) {
+    double g = b * ff, hh = c * f.uv2u;
+    if (g > hh) {
+      if (c * f.uv1u + g < hh + f.uv1u * f.uv2v) return dv > 0 ? W_BACK : W_FRONT;
+      else if (!distinguishable_d(c * f.uv1u + g, hh + f.uv1u * f.uv2v, MCX_EPS)) {
+        jump_away_line(pos, a, wall_vertex(p, wi, 1), wall_vertex(p, wi, 2), n, rs, move);
+        return W_REDO;
+      } else return W_MISS;
+    } else if (!distinguishable_d(g, hh, MCX_EPS)) {
+      jump_away_line(pos, a, wall_vertex(p, wi, 2), v0, n, rs, move);
+      return W_REDO;
+    } else return W_MISS;
+  } else if (!distinguishable_d(c, 0.0, MCX_EPS)) {
+    jump_away_line(pos, a, v0, wall_vertex(p, wi, 1), n, rs, move);
+    return W_REDO;
+  }
+  return W_MISS;
+}
+
+struct WallHit { int side; double t; D3 pos; uint32_t wall; };
+
+// get_closest_wall_collision, collision_utils.inl:819-914
+__device__ bool closest_wall_collision(const DevParams& p, D3 pos, uint32_t subpart, uint32_t last_hit_wall,
+                                       Stream& rs, D3& disp, D3& up_to_wall, WallHit& best, LocalStats& ls, Tracer& tc) {
+  const uint32_t w0 = p.spw_start[subpart], w1 = p.spw_start[subpart + 1];
+  if (w0 == w1) return false;
+  int guard = 0;
+restart:
+  bool found = false;
+  double closest = MCX_TIME_FOREVER;
+  for (uint32_t k = w0; k < w1; k++) {
+    uint32_t wi = p.spw_list[k];
+    if (wi == last_hit_wall) continue;
+    double t; D3 hit;
+    ls.ray_polygon_tests++;
+    int ct = collide_wall(p, pos, wi, rs, disp, t, hit);
+    if (ct == W_REDO) {
+      ls.redos++; tc.ev(EV_REDO, wi);
+      if (tc.tr) tc.tr->n_redo++;
+      if (++guard > 64) return false;
+      goto restart;
+    } else if (ct != W_MISS) {
+      ls.ray_polygon_colls++;
+      if (subpart_index(p, hit) != subpart) continue;
+      if (t < closest) { found = true; closest = t; best.side = ct; best.t = t; best.pos = hit; best.wall = wi; }
+    }
+  }
+  if (found) up_to_wall = best.pos - pos;
+  return found;
+}
+
+// test_bimolecular, rxn_utils.inl:336-414 (local_prob_factor == 0)
+__device__ int test_bimolecular(const DevParams& p, const DevClass& rc, double scaling, Stream& rs) {
+  double max_fixed_p = rc.max_fixed_p, prob;
+  if (max_fixed_p < scaling) {
+    prob = rs.dbl() * scaling;
+    if (prob >= max_fixed_p) return -1;
+  } else {
+    float max_p = (float)rc.max_fixed_p;  // sic (rxn_utils.inl:369)
+    if (max_p >= scaling) prob = rs.dbl() * max_p;
+    else {
+      prob = rs.dbl() * scaling;
+      if (prob >= max_p) return -1;
+    }
+  }
+  // binary_search_double, rxn_utils.inl:301-320
+  int min_idx = 0, max_idx = (int)rc.n_pathways - 1;
+  const DevPathway* A = p.pathways + rc.first_pathway;
+  while (max_idx - min_idx > 1) {
+    int mid = (max_idx + min_idx) / 2;
+    if (prob > A[mid].cum_prob) min_idx = mid; else max_idx = mid;
+  }
+  return prob > A[min_idx].cum_prob ? max_idx : min_idx;
+}
+
+__device__ __forceinline__ MolRec load_rec(const MolRec* a, uint32_t i) {
+  // two 128-bit loads of one 32-byte sector
+  const double2* q = reinterpret_cast<const double2*>(a + i);
+  double2 lo = __ldg(q);
+  double2 hi = __ldg(q + 1);
+  MolRec r; r.x = lo.x; r.y = lo.y; r.z = hi.x;
+  unsigned long long m = (unsigned long long)__double_as_longlong(hi.y);
+  r.id = (uint32_t)m; r.sf = (uint32_t)(m >> 32);
+  return r;
+}
+// snapshot records may receive DEAD flags while retry kernels run: read through L2, not the nc path
+__device__ __forceinline__ MolRec load_rec_volatile(const MolRec* a, uint32_t i) {
+  const double2* q = reinterpret_cast<const double2*>(a + i);
+  double2 lo = __ldcg(q);
+  double2 hi = __ldcg(q + 1);
+  MolRec r; r.x = lo.x; r.y = lo.y; r.z = hi.x;
+  unsigned long long m = (unsigned long long)__double_as_longlong(hi.y);
+  r.id = (uint32_t)m; r.sf = (uint32_t)(m >> 32);
+  return r;
+}
+__device__ __forceinline__ void store_rec(MolRec* a, uint32_t i, D3 pos, uint32_t id, uint32_t sf) {
+  double2* q = reinterpret_cast<double2*>(a + i);
+  unsigned long long m = ((unsigned long long)sf << 32) | id;
+  q[0] = make_double2(pos.x, pos.y);
+  q[1] = make_double2(pos.z, __longlong_as_double((long long)m));
+}
+
+// Partner scan: one pass over the neighbour cells overlapped by the swept volume (segment inflated by R).
+// Finds the earliest eligible collision strictly after (t_last, id_last) in (time asc, id desc) order and
+// strictly before t_limit, counting how many eligible collisions remain.
+struct PartnerHit { double t; uint32_t slot, id, species; int rxn_class; };
+
+template <bool VOLATILE_SNAPSHOT>
+__device__ int scan_partners(const DevParams& p, D3 pos, D3 disp, uint32_t self_id, uint32_t self_species,
+                             const SpSet& spm, bool need_sp_filter, double t_last, uint32_t id_last, double t_limit,
+                             PartnerHit& best) {
+  const double R = p.R;
+  const double pad = R * (1.0 + 1e-9) + 1e-9;
+  double lox = fmin(pos.x, pos.x + disp.x) - pad, hix = fmax(pos.x, pos.x + disp.x) + pad;
+  double loy = fmin(pos.y, pos.y + disp.y) - pad, hiy = fmax(pos.y, pos.y + disp.y) + pad;
+  double loz = fmin(pos.z, pos.z + disp.z) - pad, hiz = fmax(pos.z, pos.z + disp.z) + pad;
+  int cx0 = cell_coord(lox, p.cgx, p.cell_rcp, p.ncx), cx1 = cell_coord(hix, p.cgx, p.cell_rcp, p.ncx);
+  int cy0 = cell_coord(loy, p.cgy, p.cell_rcp, p.ncy), cy1 = cell_coord(hiy, p.cgy, p.cell_rcp, p.ncy);
+  int cz0 = cell_coord(loz, p.cgz, p.cell_rcp, p.ncz), cz1 = cell_coord(hiz, p.cgz, p.cell_rcp, p.ncz);
+  const double movelen2 = dot3(disp, disp);
+  const double sigma2 = R * R;
+  const double rhs = movelen2 * sigma2;
+  const int* bimol_row = p.bimol + self_species * p.n_species;
+  int count = 0;
+  best.t = MCX_TIME_FOREVER; best.id = 0; best.slot = MCX_NONE;
+  for (int cz = cz0; cz <= cz1; cz++) {
+    for (int cy = cy0; cy <= cy1; cy++) {
+      const uint32_t row = (uint32_t)(p.ncx * (cy + p.ncy * cz));
+      const uint32_t j0 = p.cs_cur[row + cx0], j1 = p.cs_cur[row + cx1 + 1];
+      for (uint32_t j = j0; j < j1; j++) {
+        MolRec c = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j) : load_rec(p.recA, j);
+        // collide_mol, collision_utils.inl:464-515
+        D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
+        double d = dot3(dir, disp);
+        if (d < 0) continue;
+        if (d > movelen2) continue;
+        double dirlen2 = dot3(dir, dir);
+        if (movelen2 * dirlen2 - d * d > rhs) continue;
+        if (c.id == self_id) continue;
+        if (c.sf & DF_DEAD) continue;
+        uint32_t csp = c.sf & SF_SPECIES_MASK;
+        int rc = bimol_row[csp];
+        if (rc < 0) continue;
+        if (need_sp_filter && !spset_has(spm, subpart_index(p, D3{c.x, c.y, c.z}))) continue;
+        double t = d / movelen2;
+        if (!(t < t_limit)) continue;
+        // strictly after (t_last, id_last): later time, or same time and smaller id
+        if (t < t_last || (t == t_last && c.id >= id_last)) continue;
+        count++;
+        if (t < best.t || (t == best.t && c.id > best.id)) {
+          best.t = t; best.id = c.id; best.slot = j; best.species = csp; best.rxn_class = rc;
+        }
+      }
+    }
+  }
+  return count;
+}
+
+// ===================================================================================================
+// One molecule, (the rest of) one iteration.  `forced` = last conflict round: no partner search.
+// ===================================================================================================
+template <bool RETRY>
+__device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t_sched, double t_unimol_in,
+                                   Stream& rs, bool forced, Outcome& out, LocalStats& ls, Tracer& tc, int& err) {
+  const uint32_t species = m.sf & SF_SPECIES_MASK;
+  const DevSpecies sp = p.species[species];
+  const double it = (double)p.iteration, t_end = it + 1;
+  uint32_t flags = m.sf & ~SF_SPECIES_MASK;
+  D3 pos = {m.x, m.y, m.z};
+  uint32_t subpart = subpart_index(p, pos);
+  double t_now = (flags & DF_PARTIAL) ? t_sched : it;
+  double unimol_time = (flags & DF_HAS_UNIMOL) ? t_unimol_in : MCX_TIME_INVALID;
+  const bool can_diffuse = (sp.flags & MCX_SP_CAN_DIFFUSE) != 0;
+  const bool can_vol_react = sp.can_vol_react != 0 && !forced;
+  out.rxn_class = -1; out.pathway = -1; out.partner_slot = MCX_NONE; out.partner_id = MCX_NONE; out.t_event = 0;
+
+  for (int sub_guard = 0; sub_guard < 1000; sub_guard++) {
+    // -- unimolecular firing (diffuse_react_event.cpp:215-223, :1764-1826)
+    if (unimol_time != MCX_TIME_INVALID && unimol_time <= t_now) {
+      int rc = p.unimol[species];
+      const DevClass& cl = p.classes[rc];
+      int pathway = 0;
+      if (cl.n_pathways > 1) {  // which_unimolecular, rxn_utils.inl:774-783
+        double match = rs.dbl() * cl.max_fixed_p;
+        int min_idx = 0, max_idx = (int)cl.n_pathways - 1;
+        const DevPathway* A = p.pathways + cl.first_pathway;
+        while (max_idx - min_idx > 1) {
+          int mid = (max_idx + min_idx) / 2;
+          if (match > A[mid].cum_prob) min_idx = mid; else max_idx = mid;
+        }
+        pathway = match > A[min_idx].cum_prob ? max_idx : min_idx;
+      }
+      tc.ev(EV_UNIMOL | (uint32_t)pathway, (uint32_t)rc);
+      if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->t_event = unimol_time; }
+      out.kind = MCX_OUT_UNIMOL; out.pos = pos; out.rxn_class = rc; out.pathway = pathway; out.t_event = unimol_time;
+      out.t_now = t_now; out.flags = flags; out.unimol_time = unimol_time;
+      return;
+    }
+    // -- newbie lifetime (:232-236 -> pick_unimol_rxn_class_and_set_rxn_time :1731-1758, time_of_unimol)
+    if (flags & DF_SCHED_UNIMOL) {
+      flags &= ~DF_SCHED_UNIMOL;
+      int rc = p.unimol[species];
+      if (rc < 0) unimol_time = MCX_TIME_INVALID;
+      else {
+        double k_tot = p.classes[rc].max_fixed_p;
+        double pr = rs.dbl();
+        double from_now = (k_tot <= 0 || !distinguishable_d(pr, 0, MCX_EPS)) ? MCX_TIME_FOREVER : -log(pr) / k_tot;
+        unimol_time = t_now + from_now;
+      }
+    }
+    // -- get_max_time (:164-198)
+    double max_time = t_end - t_now;
+    if (unimol_time != MCX_TIME_INVALID && unimol_time < t_now + max_time) max_time = unimol_time - t_now;
+
+    if (can_diffuse) {
+      // ---- compute_vol_displacement (diffusion_utils.inl:366-432)
+      double steps = 1.0, t_steps = steps * sp.time_step, r_rate_factor, scale;
+      if (t_steps > max_time) { t_steps = max_time; steps = max_time / sp.time_step; }
+      if (steps < MCX_EPS) { steps = MCX_EPS; t_steps = MCX_EPS * sp.time_step; }
+      if (steps == 1.0) { scale = sp.space_step; r_rate_factor = 1.0; }
+      else { double rate_factor = sqrt(steps); r_rate_factor = 1.0 / rate_factor; scale = rate_factor * sp.space_step; }
+      D3 remaining;
+      remaining.x = scale * rs.gauss() * 0.70710678118654752440;
+      remaining.y = scale * rs.gauss() * 0.70710678118654752440;
+      remaining.z = scale * rs.gauss() * 0.70710678118654752440;
+      max_time = t_steps;
+
+      uint32_t last_hit_wall = MCX_NONE;
+      double elapsed = t_now;
+      // ---- diffuse_vol_molecule loop (:423-572)
+      for (int trace_guard = 0;; trace_guard++) {
+        if (trace_guard > 100000) { err = MCX_ERR_STATE; break; }
+        // ---- ray_trace_vol (:627-780)
+        D3 part_disp = remaining;
+        if (!in_partition(p, pos + remaining)) part_disp = displacement_up_to_partition_boundary(p, pos, remaining);
+        SpList spw; SpSet spm; spm.n = 0; spm.overflow = false;
+        uint32_t last_subpart = collect_crossed_subparts(p, pos, subpart, part_disp, can_vol_react, true, spw, spm);
+        D3 up_to_wall = remaining;
+        bool hit = false, hit_in_last = false;
+        WallHit wh;
+        for (int k = 0; k < spw.n; k++) {
+          if (closest_wall_collision(p, pos, spw.v[k], last_hit_wall, rs, remaining, up_to_wall, wh, ls, tc)) {
+            hit = true; hit_in_last = last_subpart == spw.v[k];
+            break;
+          }
+        }
+        bool reacted = false;
+        if (can_vol_react) {
+          if (hit && !hit_in_last) {
+            spm.n = 0;
+            collect_crossed_subparts(p, pos, subpart, up_to_wall, true, false, spw, spm);
+          }
+          if (spm.overflow) err = MCX_ERR_OVERFLOW;
+          const bool need_filter = !(spm.n == 1);  // single subpart: every partner in reach shares it unless...
+          // ... it sits across a subpart face: the filter is still required then, so only skip when the swept
+          // box lies strictly inside the own subpart
+          bool filter = true;
+          if (!need_filter) {
+            int si[3] = {(int)(subpart % p.n_sp), (int)((subpart / p.n_sp) % p.n_sp), (int)(subpart / (p.n_sp * p.n_sp))};
+            const double pad = p.R * 1.000001 + 1e-6;
+            double lx = p.ox + si[0] * p.sp_len, ly = p.oy + si[1] * p.sp_len, lz = p.oz + si[2] * p.sp_len;
+            D3 e = pos + remaining;
+            filter = !(fmin(pos.x, e.x) - pad > lx && fmax(pos.x, e.x) + pad < lx + p.sp_len &&
+                       fmin(pos.y, e.y) - pad > ly && fmax(pos.y, e.y) + pad < ly + p.sp_len &&
+                       fmin(pos.z, e.z) - pad > lz && fmax(pos.z, e.z) + pad < lz + p.sp_len);
+          }
+          // sort_collisions_by_time (:341-364) realised as repeated selection of the next collision
+          const double t_limit = hit ? wh.t : MCX_TIME_FOREVER;
+          double t_last = -1.0; uint32_t id_last = 0;
+          for (;;) {
+            PartnerHit ph;
+            int cnt = scan_partners<RETRY>(p, pos, remaining, m.id, species, spm, filter, t_last, id_last, t_limit, ph);
+            if (cnt == 0) break;
+            t_last = ph.t; id_last = ph.id;
+            ls.volvol_collisions++;
+            if (!(ph.t < MCX_EPS)) {  // is_immediate_collision
+              // collide_and_react_with_vol_mol (:786-829); exact_disk factor := 1 (documented gap)
+              double factor = 1.0;
+              double abs_t = elapsed + t_steps * ph.t;
+              double scaling = factor * r_rate_factor;
+              tc.ev(EV_COLL, ph.id);
+              if (tc.tr) { if (tc.tr->n_collisions < MCX_TRACE_K) tc.tr->partner[tc.tr->n_collisions] = ph.id; tc.tr->n_collisions++; }
+              int pathway = test_bimolecular(p, p.classes[ph.rxn_class], scaling, rs);
+              if (pathway >= 0) {
+                tc.ev(EV_RXN | (uint32_t)pathway, (uint32_t)ph.rxn_class);
+                if (tc.tr) { tc.tr->rxn_class = ph.rxn_class; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = ph.id; tc.tr->t_event = abs_t; }
+                out.kind = MCX_OUT_REACTED; out.pos = pos + remaining * ph.t;
+                out.rxn_class = ph.rxn_class; out.pathway = pathway; out.partner_slot = ph.slot; out.partner_id = ph.id;
+                out.t_event = abs_t; out.t_now = t_now; out.flags = flags; out.unimol_time = unimol_time;
+                reacted = true;
+                break;
+              }
+            }
+            if (cnt == 1) break;
+          }
+        }
+        if (reacted) return;
+        if (!hit) {  // RayTraceState::FINISHED
+          pos = pos + remaining;
+          if (!in_partition(p, pos)) { err = MCX_ERR_ESCAPED; out.kind = MCX_OUT_NONE; out.pos = pos; return; }
+          subpart = subpart_index(p, pos);
+          break;
+        }
+        // ---- wall collision (:476-567)
+        const int side = wh.side;  // W_FRONT / W_BACK
+        const uint32_t wclass = p.wall_class[wh.wall];
+        int action = MCX_SURF_REFLECTIVE;
+        if (wclass != MCX_NONE) action = p.surf_action[(species * p.n_surf_classes + wclass) * 2 + (side == W_FRONT ? 0 : 1)];
+        if (tc.tr) {
+          if (tc.tr->n_wall_hits < MCX_TRACE_K) { tc.tr->wall[tc.tr->n_wall_hits] = wh.wall; tc.tr->wall_side[tc.tr->n_wall_hits] = side; }
+          tc.tr->n_wall_hits++;
+        }
+        if (action == MCX_SURF_TRANSPARENT) {  // cross_transparent_wall (:3007-3099)
+          tc.ev(EV_TRANSP | (uint32_t)side, wh.wall);
+          ls.transparent++;
+          pos = wh.pos; subpart = subpart_index(p, pos);
+          remaining = remaining * (1.0 - wh.t);
+          elapsed += t_steps * wh.t;
+          t_steps *= (1.0 - wh.t);
+          if (t_steps < MCX_EPS) t_steps = MCX_EPS;
+          last_hit_wall = wh.wall;
+        } else if (action == MCX_SURF_ABSORPTIVE) {  // test_intersect: two draws (rxn_utils.inl:593-626)
+          double abs_t = elapsed + t_steps * wh.t;
+          (void)rs.dbl(); (void)rs.dbl();
+          tc.ev(EV_ABSORB | (uint32_t)side, wh.wall);
+          if (tc.tr) tc.tr->t_event = abs_t;
+          out.kind = MCX_OUT_ABSORBED; out.pos = wh.pos; out.t_event = abs_t; out.t_now = t_now; out.flags = flags;
+          out.unimol_time = unimol_time;
+          return;
+        } else {  // reflect_from_wall, collision_utils.inl:1711-1747
+          tc.ev(EV_WALL | (uint32_t)side, wh.wall);
+          ls.reflections++;
+          elapsed += t_steps * wh.t;
+          pos = wh.pos; subpart = subpart_index(p, pos);
+          t_steps *= (1.0 - wh.t);
+          last_hit_wall = wh.wall;
+          const DevWall& f = p.walls[wh.wall];
+          D3 n = {f.nx, f.ny, f.nz};
+          double reflect_factor = -2.0 * dot3(remaining, n);
+          remaining = (remaining + n * reflect_factor) * (1.0 - wh.t);
+        }
+      }
+    }
+    // -- reschedule (:283-336)
+    bool again = false;
+    if (can_diffuse) {
+      t_now += max_time;
+      if ((unimol_time != MCX_TIME_INVALID && unimol_time < t_end) || (t_now < t_end && !cmp_eq_d(t_now, t_end, MCX_EPS))) again = true;
+      else {
+        double r = round(t_now);
+        if (cmp_eq_d(t_now, r, MCX_SQRT_EPS)) t_now = r;
+      }
+    } else {
+      if (unimol_time != MCX_TIME_INVALID) {
+        t_now = unimol_time;
+        if (unimol_time < t_end) again = true;
+      } else t_now = MCX_TIME_FOREVER;
+    }
+    if (!again) break;
+  }
+  out.kind = can_diffuse ? MCX_OUT_MOVED : MCX_OUT_STATIC;
+  out.pos = pos; out.t_now = t_now; out.flags = flags & ~DF_PARTIAL; out.unimol_time = unimol_time;
+}

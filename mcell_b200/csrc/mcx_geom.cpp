@@ -1,0 +1,170 @@
+// mcx_geom.cpp — host-side, init-time geometry preparation of libmcx:
+//   * per-triangle constants           (replaces Wall::initialize_wall_constants, src4/wall.cpp:281-342)
+//   * wall -> subpartition binning      (replaces Partition::finalize_walls, src4/partition.cpp:91-118,
+//                                        GeometryUtils::wall_subparts_collision_test, geometry_utils.inl:110-207,
+//                                        WallUtils::wall_in_box, wall_utils.inl:326-504)
+// The binning decides which walls a molecule can ever see, so it keeps the reference's exact tests and
+// floating-point expression order; the output is a CSR (spw_start / spw_list) with ascending wall indices
+// per subpartition (the iteration order of the reference's uint_set<wall_index_t>).
+#include <cmath>
+#include <cstdint>
+#include <vector>
+#include "mcx_geom.h"
+
+namespace mcxg {
+
+struct P3 { double x, y, z; };
+static inline P3 sub(P3 a, P3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline P3 scale(P3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+static inline double dotp(P3 a, P3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline P3 crossp(P3 x, P3 y) { return {x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y}; }
+static inline double len2(P3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+
+static inline bool distinguishable(double a, double b, double eps) {
+  double c = std::fabs(a - b);
+  a = std::fabs(a);
+  if (a < 1) a = 1;
+  b = std::fabs(b);
+  if (b < a) eps *= a; else eps *= b;
+  return c > eps;
+}
+
+void wall_constants(const double* verts, const uint32_t* tri, uint64_t n_walls, std::vector<DevWall>& out) {
+  out.resize(n_walls);
+  for (uint64_t i = 0; i < n_walls; i++) {
+    const double* a = verts + 3 * tri[3 * i];
+    const double* b = verts + 3 * tri[3 * i + 1];
+    const double* c = verts + 3 * tri[3 * i + 2];
+    P3 v0 = {a[0], a[1], a[2]}, v1 = {b[0], b[1], b[2]}, v2 = {c[0], c[1], c[2]};
+    DevWall w{};
+    w.v0x = v0.x; w.v0y = v0.y; w.v0z = v0.z;
+    P3 e1 = sub(v1, v0), e2 = sub(v2, v0);
+    double area = 0.5 * std::sqrt(len2(crossp(e1, e2)));
+    if (distinguishable(area, 0, 1e-12)) {
+      double inv_len = 1 / std::sqrt(len2(e1));
+      P3 uu = scale(e1, inv_len);
+      P3 nn = crossp(uu, e2);
+      double inv_n = 1 / std::sqrt(len2(nn));
+      nn = scale(nn, inv_n);
+      P3 vv = crossp(nn, uu);
+      w.nx = nn.x; w.ny = nn.y; w.nz = nn.z;
+      w.dist = dotp(v0, nn);
+      w.ux = uu.x; w.uy = uu.y; w.uz = uu.z;
+      w.vx = vv.x; w.vy = vv.y; w.vz = vv.z;
+      w.uv1u = dotp(e1, uu);
+      w.uv2u = dotp(e2, uu);
+      w.uv2v = dotp(e2, vv);
+    }
+    out[i] = w;
+  }
+}
+
+namespace {
+struct Box { P3 lo, hi; };
+
+inline bool inside(const Box& b, P3 p) {
+  return p.x >= b.lo.x && p.x <= b.hi.x && p.y >= b.lo.y && p.y <= b.hi.y && p.z >= b.lo.z && p.z <= b.hi.z;
+}
+inline double comp(P3 p, int k) { return k == 0 ? p.x : (k == 1 ? p.y : p.z); }
+
+// does the segment p->q pierce the box face {axis = plane} within the face rectangle?
+inline bool edge_hits_face(P3 p, P3 q, const Box& b, int axis, double plane, int o1, int o2) {
+  double pa = comp(p, axis), qa = comp(q, axis);
+  if (!((pa <= plane && plane < qa) || (pa > plane && plane >= qa))) return false;
+  double r = (plane - pa) / (qa - pa);
+  double c1 = comp(p, o1) + r * (comp(q, o1) - comp(p, o1));
+  double c2 = comp(p, o2) + r * (comp(q, o2) - comp(p, o2));
+  return comp(b.lo, o1) <= c1 && c1 <= comp(b.hi, o1) && comp(b.lo, o2) <= c2 && c2 <= comp(b.hi, o2);
+}
+
+// triangle vs axis-aligned box, same decision sequence as wall_in_box
+bool triangle_touches_box(const P3 tv[3], const DevWall& w, const Box& b) {
+  for (int k = 0; k < 3; k++) if (inside(b, tv[k])) return true;
+  for (int k = 0; k < 3; k++) {
+    P3 q = tv[k], p = tv[k == 0 ? 2 : k - 1];
+    if (edge_hits_face(p, q, b, 0, b.lo.x, 1, 2) || edge_hits_face(p, q, b, 0, b.hi.x, 1, 2)) return true;
+    if (edge_hits_face(p, q, b, 1, b.lo.y, 0, 2) || edge_hits_face(p, q, b, 1, b.hi.y, 0, 2)) return true;
+    if (edge_hits_face(p, q, b, 2, b.lo.z, 1, 0) || edge_hits_face(p, q, b, 2, b.hi.z, 1, 0)) return true;
+  }
+  // box edges against the triangle: the 12 edges in the reference's visiting order (corner bit k of
+  // a/b selects hi (1) or lo (0) for x,y,z)
+  static const unsigned char A[12][3] = {{0,0,0},{0,0,1},{0,1,1},{0,1,0},{1,1,0},{1,1,1},{1,0,1},{1,0,0},{0,0,0},{0,0,1},{0,1,1},{1,0,0}};
+  static const unsigned char Bc[12][3] = {{0,0,1},{0,1,1},{0,1,0},{1,1,0},{1,1,1},{1,0,1},{1,0,0},{0,0,0},{0,1,0},{1,0,1},{1,1,1},{0,1,0}};
+  P3 n = {w.nx, w.ny, w.nz};
+  double d = w.dist;
+  P3 u = sub(tv[1], tv[0]);
+  double r_u = 1 / std::sqrt(len2(u));
+  u = scale(u, r_u);
+  P3 v = crossp(n, u);
+  double tu[3], tw[3];
+  for (int j = 0; j < 3; j++) { tu[j] = dotp(tv[j], u); tw[j] = dotp(tv[j], v); }
+  auto corner = [&](const unsigned char s[3]) { return P3{s[0] ? b.hi.x : b.lo.x, s[1] ? b.hi.y : b.lo.y, s[2] ? b.hi.z : b.lo.z}; };
+  for (int e = 0; e < 12; e++) {
+    P3 ba = corner(A[e]), bb = corner(Bc[e]);
+    double a1 = dotp(ba, n), a2 = dotp(bb, n);
+    if ((a1 - d < 0 && a2 - d < 0) || (a1 - d > 0 && a2 - d > 0)) continue;
+    double r = (d - a1) / (a2 - a1);
+    P3 c = {ba.x + r * (bb.x - ba.x), ba.y + r * (bb.y - ba.y), ba.z + r * (bb.z - ba.z)};
+    double cu = dotp(c, u), cv = dotp(c, v);
+    int crossings = 0;
+    for (int j = 0; j < 3; j++) {
+      int k = j == 0 ? 2 : j - 1;
+      if ((tu[k] < cu && cu <= tu[j]) || (tu[k] >= cu && cu > tu[j])) {
+        double rr = (cu - tu[k]) / (tu[j] - tu[k]);
+        if ((tw[k] + rr * (tw[j] - tw[k])) > cv) crossings++;
+      }
+    }
+    if (crossings & 1) return true;
+  }
+  return false;
+}
+}  // namespace
+
+void bin_walls(const GridSpec& g, const double* verts, const uint32_t* tri, const std::vector<DevWall>& walls,
+               std::vector<uint32_t>& start, std::vector<uint32_t>& list) {
+  const size_t ns3 = (size_t)g.n_sp * g.n_sp * g.n_sp;
+  std::vector<std::vector<uint32_t>> per(ns3);
+  auto idx = [&](double v, double o) { return (int)((v - o) * g.sp_rcp); };
+  for (uint32_t wi = 0; wi < walls.size(); wi++) {
+    P3 tv[3];
+    for (int k = 0; k < 3; k++) { const double* q = verts + 3 * tri[3 * wi + k]; tv[k] = {q[0], q[1], q[2]}; }
+    P3 lo = tv[0], hi = tv[0];
+    for (int k = 1; k < 3; k++) {
+      if (tv[k].x < lo.x) lo.x = tv[k].x; else if (tv[k].x > hi.x) hi.x = tv[k].x;
+      if (tv[k].y < lo.y) lo.y = tv[k].y; else if (tv[k].y > hi.y) hi.y = tv[k].y;
+      if (tv[k].z < lo.z) lo.z = tv[k].z; else if (tv[k].z > hi.z) hi.z = tv[k].z;
+    }
+    double leeway = 1;
+    if (lo.x < -leeway) leeway = -lo.x;
+    if (lo.y < -leeway) leeway = -lo.y;
+    if (lo.z < -leeway) leeway = -lo.z;
+    if (hi.x > leeway) leeway = hi.x;
+    if (hi.y > leeway) leeway = hi.y;
+    if (hi.z > leeway) leeway = hi.z;
+    leeway = 1e-12 + leeway * 1e-12;
+    if (g.use_expanded) leeway += g.R;
+    lo = {lo.x - leeway, lo.y - leeway, lo.z - leeway};
+    hi = {hi.x + leeway, hi.y + leeway, hi.z + leeway};
+    int x0 = idx(lo.x, g.ox), y0 = idx(lo.y, g.oy), z0 = idx(lo.z, g.oz);
+    int x1 = idx(hi.x, g.ox), y1 = idx(hi.y, g.oy), z1 = idx(hi.z, g.oz);
+    for (int x = x0; x <= x1; x++)
+      for (int y = y0; y <= y1; y++)
+        for (int z = z0; z <= z1; z++) {
+          if (x < 0 || y < 0 || z < 0 || x >= g.n_sp || y >= g.n_sp || z >= g.n_sp) continue;
+          Box b;
+          b.lo = {g.ox + x * g.sp_len, g.oy + y * g.sp_len, g.oz + z * g.sp_len};
+          b.hi = {b.lo.x + g.sp_len, b.lo.y + g.sp_len, b.lo.z + g.sp_len};
+          b.lo = {b.lo.x - leeway, b.lo.y - leeway, b.lo.z - leeway};
+          b.hi = {b.hi.x + leeway, b.hi.y + leeway, b.hi.z + leeway};
+          if (triangle_touches_box(tv, walls[wi], b)) per[(size_t)x + (size_t)y * g.n_sp + (size_t)z * g.n_sp * g.n_sp].push_back(wi);
+        }
+  }
+  start.assign(ns3 + 1, 0);
+  size_t total = 0;
+  for (size_t s = 0; s < ns3; s++) { start[s] = (uint32_t)total; total += per[s].size(); }
+  start[ns3] = (uint32_t)total;
+  list.clear(); list.reserve(total);
+  for (size_t s = 0; s < ns3; s++) list.insert(list.end(), per[s].begin(), per[s].end());
+}
+
+}  // namespace mcxg

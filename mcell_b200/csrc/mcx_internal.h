@@ -1,0 +1,122 @@
+// mcx_internal.h — device/host shared layouts of libmcx (not part of the C ABI).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/mcx.h"
+
+// ---- HBM layout ------------------------------------------------------------------------------
+// Hot molecule record: 32 bytes = exactly one DRAM/L2 sector, so a neighbour gather costs one
+// sector per candidate and the streaming pass is perfectly coalesced (32 lanes x 32 B = 1 KiB).
+// sf = species (low 16 bits) | device flags (high 16 bits).
+struct __align__(32) MolRec {
+  double x, y, z;
+  uint32_t id;
+  uint32_t sf;
+};
+static_assert(sizeof(MolRec) == 32, "MolRec must be one 32-byte sector");
+
+enum : uint32_t {
+  DF_DEAD = 1u << 16,        // consumed / defunct (tombstone until the next sort drops it)
+  DF_SCHED_UNIMOL = 1u << 17,  // MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN
+  DF_PARTIAL = 1u << 18,     // cold t_sched[] holds a fractional diffusion_time
+  DF_HAS_UNIMOL = 1u << 19,  // cold t_unimol[] holds a scheduled unimolecular time
+  DF_GHOST = 1u << 20,       // multi-GPU halo copy: visible as partner, never evaluated here
+  SF_SPECIES_MASK = 0xFFFFu
+};
+
+struct DevSpecies { double space_step, time_step; uint32_t flags; uint32_t can_vol_react; };
+struct DevClass { double max_fixed_p; uint32_t kind, r0, r1, first_pathway, n_pathways, pad; };
+struct DevPathway { double cum_prob; uint32_t n_products, products[MCX_MAX_PRODUCTS], keep_mask, rule_id, pad; };
+
+// per-wall constants (Wall::initialize_wall_constants, src4/wall.cpp:281-342), 128 B/wall
+struct __align__(16) DevWall {
+  double nx, ny, nz, dist;        // WallCollisionRejectionData (partition.h:1157-1159)
+  double ux, uy, uz;              // unit_u
+  double vx, vy, vz;              // unit_v
+  double uv1u, uv2u, uv2v;        // uv_vert1_u, uv_vert2
+  double v0x, v0y, v0z;           // vertex 0
+};
+
+struct Counters {
+  // population
+  unsigned int n_slots;        // records in the current snapshot buffer (incl. tombstones/ghosts)
+  unsigned int n_prod;         // products appended behind n_slots this iteration
+  unsigned int n_pend[2];      // pending-proposal list sizes (ping-pong)
+  unsigned int n_next;         // records binned for the next snapshot
+  int error;                   // first MCX_ERR_* raised on the device
+  unsigned int error_id;       // molecule id that raised it
+  unsigned int next_id;        // fresh molecule ids
+  unsigned int n_emigrants[2]; // multi-GPU: records leaving through the low/high slab face
+  unsigned int pad[5];
+  // statistics (SimulationStats mirror)
+  unsigned long long molecule_steps, ray_polygon_tests, ray_polygon_colls, reflections, transparent,
+      absorptions, volvol_collisions, bimol_rxns, unimol_rxns, redos, retries, unresolved, products;
+  unsigned long long species_count[256];
+  unsigned long long rxn_count[256];
+};
+
+struct DevParams {
+  // partition / subpartition grid (reference semantics)
+  double ox, oy, oz, part_len, sp_len, sp_rcp, R;
+  int n_sp, use_expanded;
+  // device neighbour-cell grid
+  double cgx, cgy, cgz, cell_rcp;
+  int ncx, ncy, ncz;
+  unsigned int n_cells;
+  // immutable tables
+  const DevWall* walls;
+  const uint32_t* wall_tri;
+  const double* verts;
+  const uint32_t* wall_class;
+  const uint32_t* spw_start;
+  const uint32_t* spw_list;
+  const DevSpecies* species;
+  const int* bimol;
+  const int* unimol;
+  const DevClass* classes;
+  const DevPathway* pathways;
+  const uint8_t* surf_action;   // [species][surf_class][side(0 front,1 back)]
+  int n_species, n_surf_classes, n_walls;
+  // rng
+  unsigned long long seed, iteration;
+  int rng_mode;
+  const uint32_t* tape;
+  unsigned long long n_words;
+  const unsigned long long* tape_off;
+  unsigned long long n_ids;
+  // molecule state
+  MolRec* recA;      // snapshot (sorted by cell), read by everyone
+  MolRec* recB;      // results of this iteration (same slot), products appended
+  double* tschedA; double* tschedB;
+  double* tuniA; double* tuniB;
+  uint32_t* rank;    // rank inside the destination cell, MCX_NONE = not carried over
+  uint32_t* cs_cur;  // cell_start of snapshot A (n_cells + 1)
+  uint32_t* cs_next; // histogram -> cell_start of the next snapshot
+  unsigned long long* claim;   // per slot: (epoch << 32) | ~priority
+  uint32_t* prop_partner;      // per slot: partner slot of the pending proposal
+  uint32_t* prop_info;         // per slot: kind(4) | pathway(12) | class(16)
+  double* prop_t;              // per slot: absolute event time
+  uint32_t* pend[2];           // pending lists (slot indices)
+  unsigned int capacity;
+  unsigned int max_rounds;
+  Counters* ctr;
+  mcx_trace_rec* trace;
+  unsigned long long n_trace;
+  // slab decomposition (multi-GPU): owned z-range in cell rows [zc_lo, zc_hi)
+  int zc_lo, zc_hi;
+};
+
+// kernels / launchers implemented in mcx_kernels.cu
+struct StepPlan {
+  int sm_count;
+  bool has_claims;   // model can produce reactions / absorptions (conflict rounds needed)
+  bool trace;
+};
+void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t s);
+void mcx_launch_initial_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
+void mcx_launch_pack_soa(const DevParams& p, const double* x, const double* y, const double* z,
+                         const uint32_t* id, const uint32_t* species, const uint32_t* flags,
+                         const double* tsched, const double* tuni, unsigned int n, cudaStream_t s);
+void mcx_launch_unpack_soa(const DevParams& p, double* x, double* y, double* z, uint32_t* id,
+                           uint32_t* species, uint32_t* flags, double* tsched, double* tuni,
+                           unsigned int* n_out, cudaStream_t s);

@@ -1,0 +1,452 @@
+// mcx_kernels.cu — the per-iteration kernel pipeline of libmcx (sm_100a).
+//
+//   k_diffuse      every live molecule: evaluate against snapshot A, write result to B, bin it for the
+//                  next snapshot (histogram atomics -> rank); claiming events become proposals
+//   k_resolve/k_retry  synchronous conflict-resolution rounds over the (small) pending list
+//   k_scan_*       exclusive scan of the cell histogram -> cell_start of the next snapshot
+//   k_scatter      counting-sort scatter B -> A (drops consumed molecules: folds
+//                  SortMolsBySubpartEvent + DefragmentationEvent into every iteration)
+//
+// All population sizes live in device memory (Counters); kernels are grid-stride over them so that an
+// iteration needs no host round trip.
+#include <cstdio>
+#include "mcx_device.cuh"
+
+#define TPB 256
+
+__device__ __forceinline__ unsigned long long claim_key(unsigned int epoch, uint32_t id) {
+  return ((unsigned long long)epoch << 32) | (unsigned long long)(~id);
+}
+__device__ __forceinline__ unsigned int round_epoch(const DevParams& p, unsigned int round) {
+  return (unsigned int)(p.iteration * (unsigned long long)(p.max_rounds + 1) + round + 1);
+}
+
+__device__ __forceinline__ void flush_stats(const DevParams& p, const LocalStats& ls, unsigned int msteps) {
+  // warp-aggregate, one atomic per warp per counter
+  unsigned int v[7] = {ls.ray_polygon_tests, ls.ray_polygon_colls, ls.reflections, ls.transparent,
+                       ls.volvol_collisions, ls.redos, msteps};
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    unsigned int s = v[k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    v[k] = s;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    Counters* c = p.ctr;
+    if (v[0]) atomicAdd(&c->ray_polygon_tests, (unsigned long long)v[0]);
+    if (v[1]) atomicAdd(&c->ray_polygon_colls, (unsigned long long)v[1]);
+    if (v[2]) atomicAdd(&c->reflections, (unsigned long long)v[2]);
+    if (v[3]) atomicAdd(&c->transparent, (unsigned long long)v[3]);
+    if (v[4]) atomicAdd(&c->volvol_collisions, (unsigned long long)v[4]);
+    if (v[5]) atomicAdd(&c->redos, (unsigned long long)v[5]);
+    if (v[6]) atomicAdd(&c->molecule_steps, (unsigned long long)v[6]);
+  }
+}
+
+__device__ __forceinline__ void raise_error(const DevParams& p, int err, uint32_t id) {
+  if (atomicCAS(&p.ctr->error, 0, err) == 0) p.ctr->error_id = id;
+}
+
+// result record of a molecule that stays alive: write to B and bin it for the next snapshot
+__device__ __forceinline__ void finalize_alive(const DevParams& p, uint32_t slot, D3 pos, uint32_t id, uint32_t species,
+                                               uint32_t flags, double t_now, double unimol_time) {
+  uint32_t sf = species | (flags & ~(DF_HAS_UNIMOL | DF_DEAD));
+  if (unimol_time != MCX_TIME_INVALID) { sf |= DF_HAS_UNIMOL; p.tuniB[slot] = unimol_time; }
+  if (sf & DF_PARTIAL) p.tschedB[slot] = t_now;
+  store_rec(p.recB, slot, pos, id, sf);
+  uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
+  p.rank[slot] = atomicAdd(&p.cs_next[cell], 1u);
+}
+
+__device__ __forceinline__ bool partner_is_consumed(const DevParams& p, int kind, int rxn_class, int pathway,
+                                                    uint32_t self_species) {
+  if (kind != MCX_OUT_REACTED) return false;
+  const DevClass& c = p.classes[rxn_class];
+  const DevPathway& pw = p.pathways[c.first_pathway + pathway];
+  bool a_is_r0 = self_species == c.r0;
+  return !((pw.keep_mask >> (a_is_r0 ? 1 : 0)) & 1u);
+}
+
+// accepted claiming event: consume reactants, create products, count
+__device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rxn_class, int pathway, uint32_t partner_slot,
+                             double t_event, D3 pos, uint32_t id, uint32_t species, uint32_t flags, double t_now,
+                             double unimol_time) {
+  Counters* c = p.ctr;
+  if (kind == MCX_OUT_ABSORBED) {
+    atomicOr(&p.recA[slot].sf, DF_DEAD);
+    atomicAdd(&c->absorptions, 1ull);
+    atomicAdd(&c->species_count[species], (unsigned long long)-1ll);
+    return;
+  }
+  const DevClass& cl = p.classes[rxn_class];
+  const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
+  atomicAdd(&c->rxn_count[pw.rule_id & 255u], 1ull);
+  bool keepA, keepB = true;
+  uint32_t reuse[2]; int n_reuse = 0;
+  if (kind == MCX_OUT_REACTED) {
+    atomicAdd(&c->bimol_rxns, 1ull);
+    bool a_is_r0 = species == cl.r0;
+    keepA = (pw.keep_mask >> (a_is_r0 ? 0 : 1)) & 1u;
+    keepB = (pw.keep_mask >> (a_is_r0 ? 1 : 0)) & 1u;
+  } else {
+    atomicAdd(&c->unimol_rxns, 1ull);
+    keepA = pw.keep_mask & 1u;
+  }
+  if (!keepA) {
+    atomicOr(&p.recA[slot].sf, DF_DEAD);
+    atomicAdd(&c->species_count[species], (unsigned long long)-1ll);
+    reuse[n_reuse++] = id;
+  }
+  if (!keepB) {
+    uint32_t old = atomicOr(&p.recA[partner_slot].sf, DF_DEAD);
+    atomicOr(&p.recB[partner_slot].sf, DF_DEAD);
+    atomicAdd(&c->species_count[old & SF_SPECIES_MASK], (unsigned long long)-1ll);
+    uint32_t pid = p.recA[partner_slot].id;
+    reuse[n_reuse++] = pid;
+    if (p.trace && pid < p.n_trace) p.trace[pid].outcome = MCX_OUT_CONSUMED;
+  }
+  for (uint32_t k = 0; k < pw.n_products; k++) {
+    uint32_t ns = c->n_slots + atomicAdd(&c->n_prod, 1u);
+    if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
+    uint32_t nid = (int)k < n_reuse ? reuse[k] : atomicAdd(&c->next_id, 1u);
+    uint32_t psp = pw.products[k];
+    p.tschedB[ns] = t_event;
+    store_rec(p.recB, ns, pos, nid, psp | DF_SCHED_UNIMOL | DF_PARTIAL);
+    uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
+    p.rank[ns] = atomicAdd(&p.cs_next[cell], 1u);
+    atomicAdd(&c->species_count[psp], 1ull);
+    atomicAdd(&c->products, 1ull);
+  }
+  if (keepA) {
+    // kept initiator stops at the event and takes the rest of its step lazily next iteration
+    uint32_t f = flags | DF_PARTIAL;
+    double ut = unimol_time;
+    if (cl.kind == MCX_RXN_UNIMOL) { f |= DF_SCHED_UNIMOL; ut = MCX_TIME_INVALID; }
+    finalize_alive(p, slot, pos, id, species, f, t_event, ut);
+  }
+}
+
+__device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot, const Outcome& o, uint32_t id,
+                                               uint32_t species, unsigned int epoch, int list) {
+  store_rec(p.recB, slot, o.pos, id, species | (o.flags & ~DF_DEAD));
+  p.tschedB[slot] = o.t_now;
+  p.tuniB[slot] = o.unimol_time;
+  p.prop_partner[slot] = o.partner_slot;
+  p.prop_info[slot] = (uint32_t)o.kind | ((uint32_t)o.pathway << 4) | ((uint32_t)o.rxn_class << 16);
+  p.prop_t[slot] = o.t_event;
+  p.rank[slot] = MCX_NONE;
+  unsigned long long key = claim_key(epoch, id);
+  atomicMax(&p.claim[slot], key);
+  if (partner_is_consumed(p, o.kind, o.rxn_class, o.pathway, species)) atomicMax(&p.claim[o.partner_slot], key);
+  uint32_t k = atomicAdd(&p.ctr->n_pend[list], 1u);
+  p.pend[list][k] = slot;
+}
+
+__device__ __forceinline__ void trace_begin(const DevParams& p, Tracer& tc, uint32_t id) {
+  tc.h = 0xcbf29ce484222325ULL; tc.tr = nullptr;
+  if (p.trace && id < p.n_trace) {
+    mcx_trace_rec* t = p.trace + id;
+    uint32_t rounds = t->rounds;
+    mcx_trace_rec z;
+    memset(&z, 0, sizeof(z));
+    z.id = id; z.rxn_class = z.rxn_pathway = z.rxn_partner = MCX_NONE; z.rounds = rounds + 1;
+    *t = z;
+    tc.tr = t;
+  }
+}
+__device__ __forceinline__ void trace_end(Tracer& tc, const Outcome& o, const Stream& rs) {
+  if (!tc.tr) return;
+  tc.tr->outcome = o.kind; tc.tr->n_words = rs.used; tc.tr->event_hash = tc.h;
+  tc.tr->pos[0] = o.pos.x; tc.tr->pos[1] = o.pos.y; tc.tr->pos[2] = o.pos.z;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_diffuse(const __grid_constant__ DevParams p) {
+  __shared__ ZigShared zig;
+  zig_load(&zig);
+  __syncthreads();
+  const unsigned int n = p.ctr->n_slots;
+  const unsigned int epoch = round_epoch(p, 0);
+  LocalStats ls = {0, 0, 0, 0, 0, 0};
+  unsigned int msteps = 0;
+  // all lanes of a warp iterate together so the warp-level stat flush sees full warps
+  for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    unsigned int i = base + threadIdx.x;
+    if (i >= n) continue;
+    MolRec m = load_rec(p.recA, i);
+    if (m.sf & (DF_DEAD | DF_GHOST)) { p.rank[i] = MCX_NONE; continue; }
+    const uint32_t species = m.sf & SF_SPECIES_MASK;
+    double t_sched = (m.sf & DF_PARTIAL) ? p.tschedA[i] : 0.0;
+    double t_uni = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;
+    Stream rs; rs.init(p, m.id, &zig);
+    Tracer tc; trace_begin(p, tc, m.id);
+    Outcome o; int err = 0;
+    if (p.species[species].flags & MCX_SP_CAN_DIFFUSE) msteps++;
+    evaluate_iteration<false>(p, m, t_sched, t_uni, rs, false, o, ls, tc, err);
+    trace_end(tc, o, rs);
+    if (err) raise_error(p, err, m.id);
+    if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time);
+    else if (o.kind == MCX_OUT_NONE) p.rank[i] = MCX_NONE;
+    else write_proposal(p, i, o, m.id, species, epoch, 0);
+  }
+  flush_stats(p, ls, msteps);
+}
+
+// round r: decide every pending proposal on the claims as they stand
+__global__ void __launch_bounds__(TPB) k_resolve(const __grid_constant__ DevParams p, unsigned int round) {
+  const int cur = 0, nxt = 1;  // list 0: proposals, list 1: rejected
+  const unsigned int n = p.ctr->n_pend[cur];
+  const unsigned int epoch = round_epoch(p, round);
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    uint32_t slot = p.pend[cur][k];
+    MolRec e = load_rec_volatile(p.recB, slot);  // event position + identity
+    uint32_t species = e.sf & SF_SPECIES_MASK;
+    uint32_t info = p.prop_info[slot];
+    int kind = info & 15, pathway = (info >> 4) & 0xFFF, rxn_class = info >> 16;
+    uint32_t partner = p.prop_partner[slot];
+    unsigned long long key = claim_key(epoch, e.id);
+    bool ok = p.claim[slot] == key;
+    if (ok && partner_is_consumed(p, kind, rxn_class, pathway, species)) ok = p.claim[partner] == key;
+    if (ok) {
+      commit_event(p, slot, kind, rxn_class, pathway, partner, p.prop_t[slot], D3{e.x, e.y, e.z}, e.id, species,
+                   e.sf & ~SF_SPECIES_MASK, p.tschedB[slot], p.tuniB[slot]);
+    } else {
+      uint32_t q = atomicAdd(&p.ctr->n_pend[nxt], 1u);
+      p.pend[nxt][q] = slot;
+    }
+  }
+}
+
+// losers of round r are re-evaluated against the updated snapshot flags; their new proposals go back
+// to list `cur` for round r+1
+__global__ void __launch_bounds__(TPB) k_retry(const __grid_constant__ DevParams p, unsigned int round, int forced) {
+  __shared__ ZigShared zig;
+  zig_load(&zig);
+  __syncthreads();
+  const int cur = 0, nxt = 1;
+  const unsigned int n = p.ctr->n_pend[nxt];
+  const unsigned int epoch = round_epoch(p, round + 1);
+  LocalStats ls = {0, 0, 0, 0, 0, 0};
+  for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    unsigned int k = base + threadIdx.x;
+    if (k >= n) continue;
+    uint32_t i = p.pend[nxt][k];
+    MolRec m = load_rec_volatile(p.recA, i);
+    if (m.sf & DF_DEAD) {  // consumed as somebody's partner in this round
+      p.rank[i] = MCX_NONE;
+      if (p.trace && m.id < p.n_trace) p.trace[m.id].outcome = MCX_OUT_CONSUMED;
+      continue;
+    }
+    atomicAdd(&p.ctr->retries, 1ull);
+    if (forced) atomicAdd(&p.ctr->unresolved, 1ull);
+    const uint32_t species = m.sf & SF_SPECIES_MASK;
+    double t_sched = (m.sf & DF_PARTIAL) ? p.tschedA[i] : 0.0;
+    double t_uni = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;
+    Stream rs; rs.init(p, m.id, &zig);
+    Tracer tc; trace_begin(p, tc, m.id);
+    Outcome o; int err = 0;
+    evaluate_iteration<true>(p, m, t_sched, t_uni, rs, forced != 0, o, ls, tc, err);
+    trace_end(tc, o, rs);
+    if (err) raise_error(p, err, m.id);
+    if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time);
+    else if (o.kind == MCX_OUT_NONE) p.rank[i] = MCX_NONE;
+    else if (forced) {  // only self-claims can occur without partners: commit directly
+      p.rank[i] = MCX_NONE;
+      commit_event(p, i, o.kind, o.rxn_class, o.pathway, o.partner_slot, o.t_event, o.pos, m.id, species, o.flags, o.t_now,
+                   o.unimol_time);
+    } else write_proposal(p, i, o, m.id, species, epoch, cur);
+  }
+  flush_stats(p, ls, 0);
+}
+
+__global__ void k_round_begin(const __grid_constant__ DevParams p, unsigned int round) {
+  // before k_resolve(round): the list it fills (nxt) must be empty
+  p.ctr->n_pend[1] = 0;
+}
+__global__ void k_round_mid(const __grid_constant__ DevParams p, unsigned int round) {
+  // before k_retry(round): list cur was consumed by k_resolve and is refilled by k_retry
+  p.ctr->n_pend[0] = 0;
+}
+
+// ---- exclusive scan of the cell histogram (3 phases, 4096 cells per block) ---------------------------
+#define SCAN_TPB 1024
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_TPB * SCAN_ITEMS)
+
+__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* total, unsigned int* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned int x = v;
+  for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) smem[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned int s = lane < (blockDim.x >> 5) ? smem[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    smem[lane] = s;
+  }
+  __syncthreads();
+  unsigned int prefix = warp ? smem[warp - 1] : 0;
+  *total = smem[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return prefix + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_reduce(const uint32_t* __restrict__ cnt, unsigned int n, unsigned int* __restrict__ sums) {
+  __shared__ unsigned int smem[32];
+  unsigned int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  unsigned int s = 0;
+  if (base + SCAN_ITEMS <= n) { uint4 v = *reinterpret_cast<const uint4*>(cnt + base); s = v.x + v.y + v.z + v.w; }
+  else for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) s += cnt[base + k];
+  unsigned int total;
+  block_exclusive_scan(s, &total, smem);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_sums(unsigned int* sums, unsigned int nblocks, uint32_t* out_total, Counters* ctr) {
+  __shared__ unsigned int smem[32];
+  __shared__ unsigned int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (unsigned int base = 0; base < nblocks; base += SCAN_TPB) {
+    unsigned int i = base + threadIdx.x;
+    unsigned int v = i < nblocks ? sums[i] : 0;
+    unsigned int total;
+    unsigned int ex = block_exclusive_scan(v, &total, smem);
+    if (i < nblocks) sums[i] = ex + carry;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *out_total = carry; ctr->n_next = carry; }
+}
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_apply(uint32_t* __restrict__ cnt, unsigned int n, const unsigned int* __restrict__ sums) {
+  __shared__ unsigned int smem[32];
+  unsigned int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  unsigned int v[SCAN_ITEMS];
+  unsigned int s = 0;
+  if (base + SCAN_ITEMS <= n) { uint4 q = *reinterpret_cast<const uint4*>(cnt + base); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+  else for (int k = 0; k < SCAN_ITEMS; k++) v[k] = base + k < n ? cnt[base + k] : 0;
+  for (int k = 0; k < SCAN_ITEMS; k++) s += v[k];
+  unsigned int total;
+  unsigned int ex = block_exclusive_scan(s, &total, smem) + sums[blockIdx.x];
+  unsigned int o[SCAN_ITEMS];
+  for (int k = 0; k < SCAN_ITEMS; k++) { o[k] = ex; ex += v[k]; }
+  if (base + SCAN_ITEMS <= n) *reinterpret_cast<uint4*>(cnt + base) = make_uint4(o[0], o[1], o[2], o[3]);
+  else for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) cnt[base + k] = o[k];
+}
+
+// ---- counting-sort scatter B -> A ------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_scatter(const __grid_constant__ DevParams p) {
+  const unsigned int n = p.ctr->n_slots + p.ctr->n_prod;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t r = p.rank[i];
+    if (r == MCX_NONE) continue;
+    const double2* q = reinterpret_cast<const double2*>(p.recB + i);
+    double2 lo = q[0], hi = q[1];
+    uint32_t sf = (uint32_t)((unsigned long long)__double_as_longlong(hi.y) >> 32);
+    uint32_t cell = cell_of(p, lo.x, lo.y, hi.x);
+    uint32_t dst = p.cs_next[cell] + r;
+    double2* d = reinterpret_cast<double2*>(p.recA + dst);
+    d[0] = lo; d[1] = hi;
+    if (sf & DF_PARTIAL) p.tschedA[dst] = p.tschedB[i];
+    if (sf & DF_HAS_UNIMOL) p.tuniA[dst] = p.tuniB[i];
+  }
+}
+__global__ void k_end_iteration(const __grid_constant__ DevParams p) {
+  Counters* c = p.ctr;
+  c->n_slots = c->n_next;
+  c->n_prod = 0; c->n_pend[0] = 0; c->n_pend[1] = 0;
+}
+
+// initial binning of uploaded records (they sit in B, slots [0, n_slots))
+__global__ void __launch_bounds__(TPB) k_bin_initial(const __grid_constant__ DevParams p) {
+  const unsigned int n = p.ctr->n_slots;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    MolRec m = load_rec_volatile(p.recB, i);
+    if (m.sf & DF_DEAD) { p.rank[i] = MCX_NONE; continue; }
+    if (!in_partition(p, D3{m.x, m.y, m.z})) { raise_error(p, MCX_ERR_ESCAPED, m.id); p.rank[i] = MCX_NONE; continue; }
+    p.rank[i] = atomicAdd(&p.cs_next[cell_of(p, m.x, m.y, m.z)], 1u);
+    atomicAdd(&p.ctr->species_count[m.sf & SF_SPECIES_MASK], 1ull);
+  }
+}
+
+// ---- SoA <-> record conversion at the ABI boundary ---------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_pack_soa(const __grid_constant__ DevParams p, const double* x, const double* y, const double* z,
+                                                  const uint32_t* id, const uint32_t* species, const uint32_t* flags,
+                                                  const double* tsched, const double* tuni, unsigned int n) {
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t hf = flags ? flags[i] : 0;
+    uint32_t sf = species[i] & SF_SPECIES_MASK;
+    if (hf & MCX_MOL_DEFUNCT) sf |= DF_DEAD;
+    if (hf & MCX_MOL_SCHEDULE_UNIMOL) sf |= DF_SCHED_UNIMOL;
+    if ((hf & MCX_MOL_PARTIAL) && tsched) { sf |= DF_PARTIAL; p.tschedB[i] = tsched[i]; }
+    if (tuni && tuni[i] != MCX_TIME_INVALID) { sf |= DF_HAS_UNIMOL; p.tuniB[i] = tuni[i]; }
+    store_rec(p.recB, i, D3{x[i], y[i], z[i]}, id[i], sf);
+  }
+}
+__global__ void __launch_bounds__(TPB) k_unpack_soa(const __grid_constant__ DevParams p, double* x, double* y, double* z, uint32_t* id,
+                                                    uint32_t* species, uint32_t* flags, double* tsched, double* tuni,
+                                                    unsigned int* n_out) {
+  const unsigned int n = p.ctr->n_slots;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    MolRec m = load_rec_volatile(p.recA, i);
+    if (m.sf & (DF_DEAD | DF_GHOST)) continue;
+    unsigned int k = atomicAdd(n_out, 1u);
+    x[k] = m.x; y[k] = m.y; z[k] = m.z; id[k] = m.id; species[k] = m.sf & SF_SPECIES_MASK;
+    uint32_t hf = 0;
+    if (m.sf & DF_SCHED_UNIMOL) hf |= MCX_MOL_SCHEDULE_UNIMOL;
+    if (m.sf & DF_PARTIAL) hf |= MCX_MOL_PARTIAL;
+    if (flags) flags[k] = hf;
+    if (tsched) tsched[k] = (m.sf & DF_PARTIAL) ? p.tschedA[i] : (double)p.iteration;
+    if (tuni) tuni[k] = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;
+  }
+}
+
+// ---- launchers -----------------------------------------------------------------------------------------------
+static void launch_sort(const DevParams& p, const StepPlan& plan, unsigned int* scan_sums, cudaStream_t s) {
+  const unsigned int n = p.n_cells + 1;  // last entry receives the total
+  const unsigned int nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_reduce<<<nblocks, SCAN_TPB, 0, s>>>(p.cs_next, n, scan_sums);
+  k_scan_sums<<<1, SCAN_TPB, 0, s>>>(scan_sums, nblocks, scan_sums + nblocks, p.ctr);
+  k_scan_apply<<<nblocks, SCAN_TPB, 0, s>>>(p.cs_next, n, scan_sums);
+  k_scatter<<<plan.sm_count * 8, TPB, 0, s>>>(p);
+  k_end_iteration<<<1, 1, 0, s>>>(p);
+}
+
+// scan scratch lives behind the pending lists' allocation; passed via a file-static set by the API layer
+static unsigned int* g_scan_sums = nullptr;
+void mcx_set_scan_scratch(unsigned int* ptr) { g_scan_sums = ptr; }
+
+void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
+  cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
+  k_diffuse<<<plan.sm_count * 8, TPB, 0, s>>>(p);
+  if (plan.has_claims) {
+    const int small_grid = plan.sm_count * 2;
+    for (unsigned int r = 0; r < p.max_rounds; r++) {
+      k_round_begin<<<1, 1, 0, s>>>(p, r);
+      k_resolve<<<small_grid, TPB, 0, s>>>(p, r);
+      k_round_mid<<<1, 1, 0, s>>>(p, r);
+      k_retry<<<small_grid, TPB, 0, s>>>(p, r, r + 1 == p.max_rounds ? 1 : 0);
+    }
+  }
+  launch_sort(p, plan, g_scan_sums, s);
+}
+
+void mcx_launch_initial_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
+  cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
+  k_bin_initial<<<plan.sm_count * 8, TPB, 0, s>>>(p);
+  launch_sort(p, plan, g_scan_sums, s);
+}
+
+void mcx_launch_pack_soa(const DevParams& p, const double* x, const double* y, const double* z, const uint32_t* id,
+                         const uint32_t* species, const uint32_t* flags, const double* tsched, const double* tuni,
+                         unsigned int n, cudaStream_t s) {
+  unsigned int grid = (n + TPB - 1) / TPB;
+  if (grid == 0) grid = 1;
+  if (grid > 65535u * 16u) grid = 65535u * 16u;
+  k_pack_soa<<<grid, TPB, 0, s>>>(p, x, y, z, id, species, flags, tsched, tuni, n);
+}
+void mcx_launch_unpack_soa(const DevParams& p, double* x, double* y, double* z, uint32_t* id, uint32_t* species,
+                           uint32_t* flags, double* tsched, double* tuni, unsigned int* n_out, cudaStream_t s) {
+  cudaMemsetAsync(n_out, 0, sizeof(unsigned int), s);
+  k_unpack_soa<<<148 * 8, TPB, 0, s>>>(p, x, y, z, id, species, flags, tsched, tuni, n_out);
+}

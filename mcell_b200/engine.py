@@ -1,0 +1,150 @@
+"""Host-side binding of libmcx (ctypes over the C ABI in include/mcx.h).
+
+The library is built in-tree (mcell_b200/build.py).  Importing works without a GPU (so the CPU
+test tier can check the ABI); every compute entry point fails loudly with McxError when no CUDA
+device is usable — there is no CPU fallback and nothing here touches oracle/."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .model import MolArrays
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcx.so")
+_lib = None
+
+
+class McxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libmcx error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise McxError(abi.MCX_ERR_STATE, "libmcx.so is not built: run `python -m mcell_b200.build` "
+                       "(__graft_entry__.build()); the CUDA extension is mandatory")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    L.mcx_create.argtypes = [C.POINTER(abi.mcx_config), C.POINTER(H)]
+    L.mcx_destroy.argtypes = [H]
+    L.mcx_destroy.restype = None
+    L.mcx_last_error.argtypes = [H]
+    L.mcx_last_error.restype = C.c_char_p
+    L.mcx_set_geometry.argtypes = [H, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.mcx_set_species.argtypes = [H, C.c_void_p, C.c_uint32]
+    L.mcx_set_reactions.argtypes = [H, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.mcx_set_surface_classes.argtypes = [H, C.c_void_p, C.c_uint32]
+    L.mcx_upload_molecules.argtypes = [H, C.POINTER(abi.mcx_mol_soa)]
+    L.mcx_download_molecules.argtypes = [H, C.POINTER(abi.mcx_mol_soa), C.c_uint64]
+    L.mcx_num_molecules.argtypes = [H]
+    L.mcx_num_molecules.restype = C.c_uint64
+    L.mcx_step.argtypes = [H, C.c_uint32, C.POINTER(abi.mcx_step_stats)]
+    L.mcx_replay_step.argtypes = [H, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(abi.mcx_step_stats)]
+    L.mcx_trace_step.argtypes = [H, C.c_uint64, C.c_void_p, C.POINTER(abi.mcx_step_stats)]
+    L.mcx_counts.argtypes = [H, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.mcx_comm_init.argtypes = [H, C.c_void_p, C.c_uint32]
+    L.mcx_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
+    L.mcx_philox_block.restype = None
+    _lib = L
+    return L
+
+
+def _vp(a):
+    return C.c_void_p(a.ctypes.data) if a is not None and a.size else None
+
+
+class Engine:
+    """One libmcx handle = the device-resident replacement of one DiffuseReactEvent + Partition."""
+
+    def __init__(self, tables):
+        self.L = load_library()
+        self.t = tables
+        self.h = C.c_void_p()
+        rc = self.L.mcx_create(C.byref(tables.cfg), C.byref(self.h))
+        if rc:
+            msg = self.L.mcx_last_error(None).decode()
+            self.h = None
+            raise McxError(rc, msg)
+        t = tables
+        self._ck(self.L.mcx_set_species(self.h, C.cast(t.species, C.c_void_p), t.n_species))
+        self._ck(self.L.mcx_set_reactions(self.h, C.cast(t.classes, C.c_void_p), t.n_classes,
+                                          C.cast(t.pathways, C.c_void_p), t.n_pathways))
+        self._ck(self.L.mcx_set_surface_classes(self.h, C.cast(t.surf_rules, C.c_void_p), t.n_surf_rules))
+        self._ck(self.L.mcx_set_geometry(self.h, _vp(t.vertices), len(t.vertices), _vp(t.tri), len(t.tri),
+                                         _vp(t.wall_surf_class), None))
+
+    def _ck(self, rc):
+        if rc:
+            raise McxError(rc, self.L.mcx_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mcx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def comm_init(self, unique_id_bytes):
+        buf = C.create_string_buffer(bytes(unique_id_bytes), len(unique_id_bytes))
+        self._ck(self.L.mcx_comm_init(self.h, C.cast(buf, C.c_void_p), len(unique_id_bytes)))
+
+    def upload(self, mols):
+        v = mols.view()
+        self._ck(self.L.mcx_upload_molecules(self.h, C.byref(v)))
+
+    def num_molecules(self):
+        return int(self.L.mcx_num_molecules(self.h))
+
+    def download(self, capacity=None):
+        cap = int(capacity if capacity is not None else self.num_molecules() + 16)
+        m = MolArrays(cap)
+        v = m.view()
+        self._ck(self.L.mcx_download_molecules(self.h, C.byref(v), cap))
+        return m.truncated(int(v.n))
+
+    def download_into(self, mols):
+        v = mols.view()
+        self._ck(self.L.mcx_download_molecules(self.h, C.byref(v), len(mols.x)))
+        mols.n = int(v.n)
+        return mols.n
+
+    def step(self, n_iterations=1):
+        st = abi.mcx_step_stats()
+        self._ck(self.L.mcx_step(self.h, n_iterations, C.byref(st)))
+        return st
+
+    def trace_step(self, n_ids):
+        tr = np.zeros(n_ids, dtype=abi.TRACE_DTYPE)
+        st = abi.mcx_step_stats()
+        self._ck(self.L.mcx_trace_step(self.h, n_ids, _vp(tr), C.byref(st)))
+        return tr, st
+
+    def replay_step(self, words, offsets):
+        words = np.ascontiguousarray(words, np.uint32)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        tr = np.zeros(len(offsets), dtype=abi.TRACE_DTYPE)
+        st = abi.mcx_step_stats()
+        self._ck(self.L.mcx_replay_step(self.h, _vp(words), len(words), _vp(offsets), len(offsets), _vp(tr), C.byref(st)))
+        return tr, st
+
+    def counts(self):
+        s = np.zeros(max(1, self.t.n_species), np.uint64)
+        r = np.zeros(max(1, self.t.n_rules), np.uint64)
+        self._ck(self.L.mcx_counts(self.h, _vp(s), self.t.n_species, _vp(r), self.t.n_rules))
+        return s[:self.t.n_species], r[:self.t.n_rules]
+
+
+def philox_block(seed, mol_id, iteration, block):
+    out = np.zeros(4, np.uint32)
+    load_library().mcx_philox_block(seed, mol_id, iteration, block, _vp(out))
+    return out

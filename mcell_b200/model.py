@@ -1,0 +1,376 @@
+"""Host-side model description and table builder.
+
+Mirrors the part of pymcell4's Model/Config/Species/ReactionRule vocabulary that feeds the
+diffuse-and-react hot path, and derives the flat tables the C ABI takes, with the arithmetic the
+reference keeps in libbng / MCell3:
+
+* units            libmcell/api/mcell4_converter.cpp:237-256  (length_unit = 1/sqrt(grid_density),
+                   time_unit = time_step, default interaction radius 1/sqrt(pi*density) um)
+* partition        mcell4_converter.cpp:280-390 (centred origin aligned to subpartition length)
+* space_step       src/mcell_species.c:270-273   sqrt(4*1e8*D*time_unit)/length_unit
+* bimol pb_factor  src/react_util.c:163-181       1e15/N_AV / (2*sqrt(pi)*R_um^2*eff_vel)
+* unimol           src/react_util.c:74-78         k * time_unit
+* cum_probs        src/mcell_reactions.c:2932-2933
+* create_box / create_icosphere  libmcell/api/geometry_utils.cpp:32-91,124-262
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import abi
+
+N_AV = 6.0221417930e23  # src/mcell_structs_shared.h:18
+MY_PI = 3.14159265358979323846
+MAX_SUBPARTS_PER_PARTITION = 300  # src4/defines.h:159
+
+
+@dataclass
+class Config:
+    """libmcell/definition/simulation_setup.yaml defaults."""
+    seed: int = 1
+    time_step: float = 1e-6
+    surface_grid_density: float = 10000.0
+    interaction_radius: float = None
+    partition_dimension: float = 10.0
+    subpartition_dimension: float = 0.5
+    initial_partition_origin: tuple = None
+
+
+@dataclass
+class Species:
+    name: str
+    diffusion_constant_3d: float = 0.0
+    target_only: bool = False
+
+
+@dataclass
+class ReactionRule:
+    """reactants/products are species names; fwd_rate in 1/s (unimol) or 1/(M*s) (bimol)."""
+    reactants: list
+    products: list
+    fwd_rate: float
+    name: str = ""
+
+
+@dataclass
+class SurfaceProperty:
+    surf_class: int
+    type: int                      # abi.MCX_SURF_*
+    species: str = None            # None = ALL_MOLECULES
+    orientation: int = 0           # 0 any, +1 front, -1 back
+
+
+def create_box(edge_um):
+    """Vertex/face tables of geometry_utils.create_box (same order as CellBlender)."""
+    h = edge_um / 2
+    v = np.array([[-h, -h, -h], [-h, -h, h], [-h, h, -h], [-h, h, h],
+                  [h, -h, -h], [h, -h, h], [h, h, -h], [h, h, h]], dtype=np.float64)
+    f = np.array([[1, 2, 0], [3, 6, 2], [7, 4, 6], [5, 0, 4], [6, 0, 2], [3, 5, 7],
+                  [1, 3, 2], [3, 7, 6], [7, 5, 4], [5, 1, 0], [6, 4, 0], [3, 1, 5]], dtype=np.uint32)
+    return v, f
+
+
+def create_icosphere(radius_um, subdivisions):
+    """geometry_utils.create_icosphere: 20*4^(subdivisions-1) faces, watertight."""
+    if not 1 <= subdivisions <= 8:
+        raise ValueError("subdivisions must be in [1, 8]")
+    t = (1.0 + math.sqrt(5.0)) / 2.0
+
+    def norm(a):
+        l = 1.0 / math.sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2])
+        return (a[0] * l, a[1] * l, a[2] * l)
+
+    verts = [norm(p) for p in [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t),
+                               (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]]
+    faces = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2),
+             (10, 7, 6), (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5),
+             (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    for _ in range(subdivisions - 1):
+        div = {}
+        out = []
+
+        def mid(a, b):
+            key = (a, b) if a < b else (b, a)
+            if key in div:
+                return div[key]
+            va, vb = verts[a], verts[b]
+            verts.append(norm((0.5 * (va[0] + vb[0]), 0.5 * (va[1] + vb[1]), 0.5 * (va[2] + vb[2]))))
+            div[key] = len(verts) - 1
+            return div[key]
+
+        for f0, f1, f2 in faces:
+            f3, f4, f5 = mid(f0, f1), mid(f1, f2), mid(f2, f0)
+            out += [(f0, f3, f5), (f3, f1, f4), (f4, f2, f5), (f3, f4, f5)]
+        faces = out
+    v = np.array(verts, dtype=np.float64) * radius_um
+    return v, np.array(faces, dtype=np.uint32)
+
+
+@dataclass
+class Tables:
+    """Flat tables in ABI form; the same object drives libmcx and (in tests) the oracle."""
+    cfg: abi.mcx_config
+    species: object
+    classes: object
+    pathways: object
+    surf_rules: object
+    vertices: np.ndarray       # (nv,3) length units
+    tri: np.ndarray            # (nw,3)
+    wall_surf_class: np.ndarray
+    species_names: list = field(default_factory=list)
+    rule_names: list = field(default_factory=list)
+    length_unit: float = 0.01
+    time_unit: float = 1e-6
+
+
+class Model:
+    def __init__(self, config=None):
+        self.config = config or Config()
+        self.species = []
+        self.rules = []
+        self.surface_properties = []
+        self._verts = []
+        self._tris = []
+        self._wall_class = []
+
+    # -- subsystem ------------------------------------------------------------------------
+    def add_species(self, name, D, target_only=False):
+        self.species.append(Species(name, D, target_only))
+        return len(self.species) - 1
+
+    def add_reaction_rule(self, reactants, products, fwd_rate, name=""):
+        self.rules.append(ReactionRule(list(reactants), list(products), fwd_rate, name or
+                                       ("+".join(reactants) + "->" + "+".join(products))))
+
+    def add_surface_property(self, surf_class, type_, species=None, orientation=0):
+        self.surface_properties.append(SurfaceProperty(surf_class, type_, species, orientation))
+
+    # -- instantiation --------------------------------------------------------------------
+    def add_geometry_object(self, vertices_um, faces, surf_class=abi.MCX_NONE):
+        """surf_class: scalar or per-face array."""
+        base = sum(len(v) for v in self._verts)
+        self._verts.append(np.asarray(vertices_um, dtype=np.float64))
+        self._tris.append(np.asarray(faces, dtype=np.uint32) + np.uint32(base))
+        sc = np.broadcast_to(np.asarray(surf_class, dtype=np.uint32), (len(faces),)).copy()
+        self._wall_class.append(sc)
+
+    # -- derived units ----------------------------------------------------------------------
+    @property
+    def length_unit(self):
+        return 1.0 / math.sqrt(self.config.surface_grid_density)
+
+    @property
+    def rxn_radius_um(self):
+        c = self.config
+        return c.interaction_radius if c.interaction_radius is not None else 1.0 / math.sqrt(MY_PI * c.surface_grid_density)
+
+    def space_step(self, D):
+        return math.sqrt(4.0 * 1.0e8 * D * self.config.time_step) / self.length_unit
+
+    def _partition(self):
+        """mcell4_converter.cpp:280-390 (no explicit origin; geometry bbox + 0.01 um margin)."""
+        c, lu = self.config, self.length_unit
+        edge = c.partition_dimension / lu
+        origin = np.array([-edge / 2] * 3)
+        if self._verts:
+            allv = np.concatenate(self._verts)
+            llf, urb = allv.min(0) - 0.01, allv.max(0) + 0.01
+            auto_dim = float(urb.max() - llf.min())
+            if c.initial_partition_origin is None and auto_dim > c.partition_dimension:
+                edge = auto_dim / lu
+                origin = llf / lu
+        if c.initial_partition_origin is not None:
+            origin = np.array(c.initial_partition_origin, dtype=np.float64) / lu
+        sp_len = c.subpartition_dimension / lu
+        if int(edge / sp_len) > MAX_SUBPARTS_PER_PARTITION:
+            sp_len = edge / MAX_SUBPARTS_PER_PARTITION
+        eps = 1e-12
+
+        def floor_mult(v):
+            if v >= 0:
+                return float(int((v + eps) / sp_len)) * sp_len
+            return float(int((v + eps - sp_len) / sp_len)) * sp_len
+
+        new_origin = np.array([floor_mult(v) for v in origin])
+        edge_enlarged = edge + float((origin - new_origin).max())
+        res = float(int((edge_enlarged + eps) / sp_len)) * sp_len
+        if not abs(edge_enlarged - res) < eps:
+            res += sp_len
+        n = int(round(res / sp_len))
+        return new_origin, res, n
+
+    def build(self, max_molecules=0, device=0, rng_mode=abi.MCX_RNG_PHILOX, cell_edge=0.0,
+              rank=0, world_size=1, max_resolve_rounds=0):
+        c, lu = self.config, self.length_unit
+        names = [s.name for s in self.species]
+        idx = {n: i for i, n in enumerate(names)}
+        origin, edge, n_sub = self._partition()
+
+        sp = (abi.mcx_species * max(1, len(self.species)))()
+        for i, s in enumerate(self.species):
+            sp[i].space_step = self.space_step(s.diffusion_constant_3d)
+            sp[i].time_step = 1.0
+            sp[i].flags = abi.MCX_SP_VOL | (abi.MCX_SP_CAN_DIFFUSE if s.diffusion_constant_3d > 0 else 0) | \
+                (abi.MCX_SP_CANT_INITIATE if s.target_only else 0)
+
+        # group rules into reaction classes (same reactant set), cumulative probabilities
+        groups = {}
+        for r_id, r in enumerate(self.rules):
+            key = tuple(sorted(idx[x] for x in r.reactants))
+            groups.setdefault(key, []).append((r_id, r))
+        classes = (abi.mcx_rxn_class * max(1, len(groups)))()
+        n_path = sum(len(v) for v in groups.values())
+        pathways = (abi.mcx_pathway * max(1, n_path))()
+        pi = 0
+        has_bimol = False
+        for ci, (key, rules) in enumerate(groups.items()):
+            rc = classes[ci]
+            first = rules[0][1]
+            r_idx = [idx[x] for x in first.reactants]
+            if len(key) == 1:
+                rc.kind = abi.MCX_RXN_UNIMOL
+                rc.reactants[0], rc.reactants[1] = r_idx[0], abi.MCX_NONE
+                pb_factor = c.time_step
+            else:
+                has_bimol = True
+                rc.kind = abi.MCX_RXN_BIMOL_VOLVOL
+                rc.reactants[0], rc.reactants[1] = r_idx[0], r_idx[1]
+                sa, sb = self.species[r_idx[0]], self.species[r_idx[1]]
+                eff_a = self.space_step(sa.diffusion_constant_3d) / 1.0
+                eff_b = self.space_step(sb.diffusion_constant_3d) / 1.0
+                if sa.target_only and sb.target_only:
+                    raise ValueError("both reactants TARGET_ONLY")
+                if sa.target_only:
+                    eff_a = 0
+                elif sb.target_only:
+                    eff_b = 0
+                if eff_a + eff_b > 0:
+                    eff_vel = (eff_a + eff_b) * lu / c.time_step
+                    R = self.rxn_radius_um
+                    pb_factor = 1.0 / (2.0 * math.sqrt(MY_PI) * R * R * eff_vel)
+                    pb_factor *= 1.0e15 / N_AV
+                else:
+                    pb_factor = 0.0
+            rc.first_pathway, rc.n_pathways = pi, len(rules)
+            cum = 0.0
+            for r_id, r in rules:
+                pw = pathways[pi]
+                cum += pb_factor * r.fwd_rate
+                pw.cum_prob = cum
+                # kept reactants: rule reactant that re-appears unchanged among the products
+                prods = [idx[x] for x in r.products]
+                this_r = [idx[x] for x in r.reactants]
+                if len(this_r) == 2 and this_r != r_idx:  # pathway written in the other order
+                    this_r = this_r[::-1]
+                keep = 0
+                for k, rs in enumerate(r_idx):
+                    if rs in prods:
+                        prods.remove(rs)
+                        keep |= 1 << k
+                if len(prods) > abi.MCX_MAX_PRODUCTS:
+                    raise ValueError("too many products")
+                pw.n_products = len(prods)
+                for k, p in enumerate(prods):
+                    pw.products[k] = p
+                pw.keep_reactant_mask = keep
+                pw.rxn_rule_id = r_id
+                pi += 1
+            rc.max_fixed_p = cum
+
+        rules = (abi.mcx_surf_class_rxn * max(1, len(self.surface_properties)))()
+        for i, s in enumerate(self.surface_properties):
+            rules[i].species = abi.MCX_ALL_MOLECULES if s.species is None else idx[s.species]
+            rules[i].surf_class, rules[i].orientation, rules[i].type = s.surf_class, s.orientation, s.type
+
+        if self._verts:
+            verts = np.concatenate(self._verts) / lu   # mcell4_converter.cpp:921-923
+            tri = np.concatenate(self._tris)
+            wsc = np.concatenate(self._wall_class)
+        else:
+            verts, tri, wsc = np.zeros((0, 3)), np.zeros((0, 3), np.uint32), np.zeros((0,), np.uint32)
+
+        cfg = abi.mcx_config()
+        cfg.abi_version = abi.MCX_ABI_VERSION
+        cfg.device = device
+        cfg.seed = c.seed
+        for k in range(3):
+            cfg.origin[k] = origin[k]
+        cfg.partition_edge_length = edge
+        cfg.num_subparts_per_edge = n_sub
+        cfg.use_expanded_list = 1 if has_bimol else 0      # mcell4_converter.cpp:84-87
+        cfg.rxn_radius_3d = self.rxn_radius_um / lu
+        cfg.cell_edge = cell_edge
+        if len(verts):
+            llf, urb = verts.min(0), verts.max(0)
+            for k in range(3):
+                cfg.active_llf[k], cfg.active_urb[k] = llf[k], urb[k]
+        cfg.max_molecules = max_molecules
+        cfg.max_resolve_rounds = max_resolve_rounds
+        cfg.rng_mode = rng_mode
+        cfg.rank, cfg.world_size = rank, world_size
+        # guard of mcell4_converter.cpp:121-127
+        if has_bimol and cfg.rxn_radius_3d * math.sqrt(2.0) >= (edge / n_sub) / 2:
+            raise ValueError("reaction radius too large for the subpartition size")
+        t = Tables(cfg, sp, classes, pathways, rules, np.ascontiguousarray(verts, np.float64),
+                   np.ascontiguousarray(tri, np.uint32), np.ascontiguousarray(wsc, np.uint32),
+                   names, [r.name for r in self.rules], lu, c.time_step)
+        t.n_species, t.n_classes, t.n_pathways = len(self.species), len(groups), n_path
+        t.n_surf_rules = len(self.surface_properties)
+        t.n_rules = len(self.rules)
+        return t
+
+
+def release_uniform_box(rng, n, edge_um, length_unit, margin=0.0):
+    """Uniform release inside a centred cube (release_event.cpp:904-1003 semantics: three uniform
+    draws per molecule).  rng: numpy Generator.  Returns (n,3) positions in length units."""
+    h = (edge_um / 2 - margin) / length_unit
+    return rng.uniform(-h, h, size=(n, 3))
+
+
+class MolArrays:
+    """Owning numpy SoA + the ctypes view (mcx_mol_soa)."""
+
+    def __init__(self, n, with_times=True):
+        self.x = np.zeros(n); self.y = np.zeros(n); self.z = np.zeros(n)
+        self.id = np.zeros(n, np.uint32); self.species = np.zeros(n, np.uint32); self.flags = np.zeros(n, np.uint32)
+        self.diffusion_time = np.zeros(n) if with_times else None
+        self.unimol_rxn_time = np.full(n, abi.MCX_TIME_INVALID) if with_times else None
+        self.n = n
+
+    @classmethod
+    def from_positions(cls, pos, species, first_id=0, schedule_unimol=False, iteration=0):
+        n = len(pos)
+        m = cls(n)
+        m.x[:], m.y[:], m.z[:] = pos[:, 0], pos[:, 1], pos[:, 2]
+        m.id[:] = np.arange(first_id, first_id + n, dtype=np.uint32)
+        m.species[:] = species
+        m.diffusion_time[:] = iteration
+        if schedule_unimol:
+            m.flags[:] = abi.MCX_MOL_SCHEDULE_UNIMOL
+        return m
+
+    def view(self, n=None):
+        s = abi.mcx_mol_soa()
+        s.n = self.n if n is None else n
+        s.x, s.y, s.z = abi.ptr(self.x, C.c_double), abi.ptr(self.y, C.c_double), abi.ptr(self.z, C.c_double)
+        s.id, s.species, s.flags = abi.ptr(self.id, C.c_uint32), abi.ptr(self.species, C.c_uint32), abi.ptr(self.flags, C.c_uint32)
+        s.diffusion_time = abi.ptr(self.diffusion_time, C.c_double)
+        s.unimol_rxn_time = abi.ptr(self.unimol_rxn_time, C.c_double)
+        return s
+
+    def truncated(self, n):
+        m = MolArrays(0)
+        for k in ("x", "y", "z", "id", "species", "flags", "diffusion_time", "unimol_rxn_time"):
+            setattr(m, k, getattr(self, k)[:n].copy())
+        m.n = n
+        return m
+
+    def sorted_by_id(self):
+        o = np.argsort(self.id[:self.n], kind="stable")
+        m = MolArrays(0)
+        for k in ("x", "y", "z", "id", "species", "flags", "diffusion_time", "unimol_rxn_time"):
+            setattr(m, k, getattr(self, k)[:self.n][o].copy())
+        m.n = self.n
+        return m

@@ -1,0 +1,1409 @@
+// oracle/oracle.cpp — TEST INFRASTRUCTURE: CPU restatement of MCell4's per-timestep
+// diffuse-and-react hot path (DiffuseReactEvent) for volume molecules.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load this library; the product (libmcx.so) never does.
+//
+// PARITY STATUS: "parity unpinned" for the geometry/collision/reaction arithmetic — the
+// reference tree holds no golden vectors for this path and cannot be built here (SURVEY §0.4,
+// §8c).  What IS pinned: the RNG (ISAAC64 + Ziggurat) against the reference's own rng.c
+// compiled into oracle/_ref/librefrng.so and the known-answer vectors in tests/golden/.
+// Everything else is a line-by-line restatement of the cited reference functions plus analytic
+// checks (MSD, uniform density, mass action) in tests/.
+//
+// Absent third-party arithmetic: libbng (github.com/mcellteam/libbng, version unpinned —
+// consumed as sibling checkout, CMakeLists.txt:146-148).  Restated from MCell3 originals:
+// cmp_eq(a,b,eps) := fabs(a-b) < eps (ASSUMPTION, not in tree); distinguishable() src/util.c:449-463;
+// get_pathway_index_for_probability := binary_search_double over cum_probs, src/react_cond.c:80-97.
+//
+// Two execution modes:
+//   SEQUENTIAL — reference semantics: molecules one after another, one global ISAAC64 stream,
+//                reactions applied immediately, products diffused from a FIFO in the same
+//                iteration (diffuse_react_event.cpp:67-161).  Used for CPU timing and ensembles.
+//   SNAPSHOT   — the parallel semantics the GPU implements: every molecule is evaluated against
+//                the start-of-iteration state with its own word stream (tape or Philox);
+//                reactions are proposals resolved in synchronous rounds.
+//
+// Not restated yet (documented gaps, identical in the product): exact_disk occlusion factor
+// (exact_disk_utils.inl:840-1145; factor := 1), surface molecules, counted volumes.
+#include <algorithm>
+#include <cassert>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../include/mcx.h"
+#include "oracle_rng.h"
+
+namespace orc {
+
+// ---- constants (src/mcell_structs.h:238-241, src4/defines.h:178-182) -------------------
+static const double EPS = 1e-12;
+static const double SQRT_EPS = 1e-6;
+static const double POS_EPS = EPS, STIME_EPS = EPS;
+static const double POS_SQRT2 = 1.41421356238;  // src4/defines.h:182 (truncated on purpose)
+static const double TIME_INVALID = -256, TIME_FOREVER = 1e20;
+
+struct V3 { double x, y, z; };
+static inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+static inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline V3 operator*(V3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+static inline V3 mul(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+// glm::dot for dvec3: tmp = a*b; tmp.x + tmp.y + tmp.z  (libs/glm/detail/func_geometric.inl:48-55)
+static inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// glm::cross (func_geometric.inl:68-79)
+static inline V3 cross(V3 x, V3 y) {
+  return {x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y};
+}
+static inline double len3_squared(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+static inline double fabs_p(double x) { return x < 0 ? -x : x; }
+static inline double max3(V3 v) { return std::max(std::max(v.x, v.y), v.z); }
+static inline double abs_max_2vec(V3 a, V3 b) {  // defines.h abs_max_2vec
+  V3 m = {std::max(fabs(a.x), fabs(b.x)), std::max(fabs(a.y), fabs(b.y)), std::max(fabs(a.z), fabs(b.z))};
+  return max3(m);
+}
+static inline bool cmp_eq(double a, double b, double eps = EPS) { return fabs(a - b) < eps; }  // ASSUMPTION
+static inline bool cmp_lt(double a, double b, double eps) { return a < b && !cmp_eq(a, b, eps); }
+static inline bool distinguishable(double a, double b, double eps) {  // src/util.c:449-463
+  double c = fabs(a - b);
+  a = fabs(a);
+  if (a < 1) a = 1;
+  b = fabs(b);
+  if (b < a) eps *= a; else eps *= b;
+  return c > eps;
+}
+static inline void guard_zero_div(V3& v) {  // defines.h guard_zero_div
+  if (v.x == 0) v.x = FLT_MIN;
+  if (v.y == 0) v.y = FLT_MIN;
+  if (v.z == 0) v.z = FLT_MIN;
+}
+
+// ---- data ------------------------------------------------------------------------------
+struct Wall {  // src4/wall.h Wall subset; constants per Wall::initialize_wall_constants (wall.cpp:281-342)
+  uint32_t vi[3];
+  V3 normal, unit_u, unit_v;
+  double distance_to_origin, uv_vert1_u, uv_vert2_u, uv_vert2_v, area;
+  uint32_t surf_class, object;
+};
+
+struct Mol {  // src4/molecule.h:52-260 (volume part)
+  V3 pos;
+  uint32_t id, species, flags;
+  double diffusion_time, unimol_rxn_time;
+  uint32_t subpart;       // v.subpart_index
+  uint32_t list_slot;     // position inside its reactant list (sequential mode)
+  uint32_t reg_subpart;   // v.reactant_subpart_index
+};
+
+enum { COLL_VOLMOL = 0, COLL_WALL_FRONT = 1, COLL_WALL_BACK = 2 };
+struct Collision {  // src4/collision_structs.h:29-243
+  int type; double time; V3 pos; uint32_t partner_id; uint32_t partner_index; int rxn_class; uint32_t wall;
+};
+
+enum { WALL_MISS, WALL_FRONT, WALL_BACK, WALL_REDO };
+
+static inline uint64_t hash_ev(uint64_t h, uint32_t a, uint32_t b) {
+  h = (h ^ a) * 0x100000001b3ULL;
+  h = (h ^ b) * 0x100000001b3ULL;
+  return h;
+}
+enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
+       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u };
+
+struct Stats {
+  uint64_t molecule_steps = 0, ray_polygon_tests = 0, ray_polygon_colls = 0, reflections = 0,
+           transparent = 0, absorptions = 0, volvol_collisions = 0, bimol_rxns = 0, unimol_rxns = 0,
+           redos = 0, retries = 0, unresolved = 0, products = 0, collide_mol_tests = 0;
+};
+
+// Result of evaluating one molecule for (the rest of) one iteration.
+struct Outcome {
+  int kind = MCX_OUT_NONE;        // MCX_OUT_*
+  V3 pos;                         // final position, or event position
+  double t_now = 0;               // diffusion_time after evaluation
+  double unimol_time = TIME_INVALID;
+  uint32_t flags = 0;
+  // claiming events
+  int rxn_class = -1, pathway = -1;
+  uint32_t partner_index = MCX_NONE, partner_id = MCX_NONE;
+  double t_event = 0;
+  bool initiator_is_reactant0 = true;
+};
+
+struct World {
+  mcx_config cfg;
+  double sp_len, sp_rcp;
+  uint32_t n_sp;  // subparts per edge
+  std::vector<V3> verts;
+  std::vector<Wall> walls;
+  std::vector<std::vector<uint32_t>> walls_per_subpart;  // ascending wall indices (uint_set order)
+  std::vector<mcx_species> species;
+  std::vector<mcx_rxn_class> classes;
+  std::vector<mcx_pathway> pathways;
+  std::vector<int> bimol;        // [a*ns+b] -> class or -1
+  std::vector<int> unimol;       // [a] -> class or -1
+  std::vector<uint8_t> can_vol_react;
+  std::vector<mcx_surf_class_rxn> surf_rules;
+  std::vector<Mol> mols;
+  std::vector<uint32_t> id_to_index;  // molecule_id_to_index_mapping
+  std::vector<uint32_t> sched_ids;    // schedulable_molecule_ids
+  // per (species, subpart) id lists: volume_molecule_reactants_per_reactant_class (partition.h:1125-1143)
+  std::unordered_map<uint64_t, std::vector<uint32_t>> lists;
+  uint32_t next_id = 0;
+  uint64_t iteration = 0;
+  Isaac64 rng;
+  Stats stats;
+  std::vector<uint64_t> species_count, rxn_count;
+  std::vector<mcx_trace_rec> trace;  // by id, when tracing
+  bool tracing = false;
+  std::string err;
+  // replay tape recorded in sequential mode: words per molecule id for the last iteration
+  std::vector<uint32_t> tape_words; std::vector<uint64_t> tape_off; std::vector<uint32_t> tape_len;
+  bool record_tape = false;
+
+  // -- subpart index math (partition.h:248-309)
+  inline bool in_this_partition(V3 p) const {
+    double e = cfg.partition_edge_length;
+    return p.x >= cfg.origin[0] && p.y >= cfg.origin[1] && p.z >= cfg.origin[2] &&
+           p.x < cfg.origin[0] + e && p.y < cfg.origin[1] + e && p.z < cfg.origin[2] + e;
+  }
+  inline void subpart_3d(V3 p, int idx[3]) const {
+    idx[0] = (int)((p.x - cfg.origin[0]) * sp_rcp);
+    idx[1] = (int)((p.y - cfg.origin[1]) * sp_rcp);
+    idx[2] = (int)((p.z - cfg.origin[2]) * sp_rcp);
+  }
+  inline uint32_t subpart_from_3d(const int idx[3]) const {
+    return (uint32_t)(idx[0] + idx[1] * (int)n_sp + idx[2] * (int)(n_sp * n_sp));
+  }
+  inline uint32_t subpart_index(V3 p) const { int i[3]; subpart_3d(p, i); return subpart_from_3d(i); }
+  inline void subpart_3d_from_index(uint32_t s, int idx[3]) const {
+    idx[0] = s % n_sp; idx[1] = (s / n_sp) % n_sp; idx[2] = (s / (n_sp * n_sp)) % n_sp;
+  }
+  inline bool idx_in_range(int i) const { return i >= 0 && i < (int)n_sp; }
+};
+
+// ---- geometry set-up ---------------------------------------------------------------------
+// Wall::initialize_wall_constants, src4/wall.cpp:281-342
+static void init_wall_constants(const World& w, Wall& f) {
+  V3 v0 = w.verts[f.vi[0]], v1 = w.verts[f.vi[1]], v2 = w.verts[f.vi[2]];
+  V3 vA = v1 - v0, vB = v2 - v0, vX = cross(vA, vB);
+  f.area = 0.5 * sqrt(len3_squared(vX));
+  if (!distinguishable(f.area, 0, EPS)) {
+    f.normal = f.unit_u = f.unit_v = {0, 0, 0};
+    f.uv_vert1_u = f.uv_vert2_u = f.uv_vert2_v = f.distance_to_origin = 0;
+    return;
+  }
+  V3 f1 = v1 - v0;
+  double inv_f1_len = 1 / sqrt(len3_squared(f1));
+  f.unit_u = f1 * inv_f1_len;
+  V3 f2 = v2 - v0;
+  f.normal = cross(f.unit_u, f2);
+  double inv_norm_len = 1 / sqrt(len3_squared(f.normal));
+  f.normal = f.normal * inv_norm_len;
+  f.unit_v = cross(f.normal, f.unit_u);
+  f.distance_to_origin = dot(v0, f.normal);
+  f.uv_vert1_u = dot(f1, f.unit_u);
+  f.uv_vert2_u = dot(f2, f.unit_u);
+  f.uv_vert2_v = dot(f2, f.unit_v);
+}
+
+static inline bool point_in_box(V3 p, V3 llf, V3 urb) {
+  return p.x >= llf.x && p.x <= urb.x && p.y >= llf.y && p.y <= urb.y && p.z >= llf.z && p.z <= urb.z;
+}
+
+// WallUtils::wall_in_box, src4/wall_utils.inl:326-504
+static int wall_in_box(const World& w, const Wall& f, V3 llf, V3 urb) {
+  const V3 vert[3] = {w.verts[f.vi[0]], w.verts[f.vi[1]], w.verts[f.vi[2]]};
+  for (int i = 0; i < 3; i++)
+    if (point_in_box(vert[i], llf, urb)) return 1;
+  // any wall edge through a box face
+  for (int i = 0; i < 3; i++) {
+    const V3& v2 = vert[i];
+    const V3& v1 = vert[i == 0 ? 2 : i - 1];
+    double r, a3, a4;
+    const double lo[3] = {llf.x, llf.y, llf.z}, hi[3] = {urb.x, urb.y, urb.z};
+    const double p1[3] = {v1.x, v1.y, v1.z}, p2[3] = {v2.x, v2.y, v2.z};
+    // axis order and the (a3,a4) pairing follow the reference: x:(y,z) y:(x,z) z:(y,x)
+    const int oa[3][2] = {{1, 2}, {0, 2}, {1, 0}};
+    for (int ax = 0; ax < 3; ax++) {
+      for (int side = 0; side < 2; side++) {
+        double pl = side == 0 ? lo[ax] : hi[ax];
+        if ((p1[ax] <= pl && pl < p2[ax]) || (p1[ax] > pl && pl >= p2[ax])) {
+          r = (pl - p1[ax]) / (p2[ax] - p1[ax]);
+          int b = oa[ax][0], c = oa[ax][1];
+          a3 = p1[b] + r * (p2[b] - p1[b]);
+          a4 = p1[c] + r * (p2[c] - p1[c]);
+          if (lo[b] <= a3 && a3 <= hi[b] && lo[c] <= a4 && a4 <= hi[c]) return 2 + ax * 2 + side;
+        }
+      }
+    }
+  }
+  // any box edge through the wall
+  static const int which_x1[12] = {0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 1};
+  static const int which_y1[12] = {0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 0};
+  static const int which_z1[12] = {0, 1, 1, 0, 0, 1, 1, 0, 0, 1, 1, 0};
+  static const int which_x2[12] = {0, 0, 0, 1, 1, 1, 1, 0, 0, 1, 1, 0};
+  static const int which_y2[12] = {0, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 1};
+  static const int which_z2[12] = {1, 1, 0, 0, 1, 1, 0, 0, 0, 1, 1, 0};
+  static const int edge1_vt[12] = {0, 1, 3, 2, 6, 7, 5, 4, 0, 1, 3, 4};
+  static const int edge2_vt[12] = {1, 3, 2, 6, 7, 5, 4, 0, 2, 5, 7, 2};
+  V3 n = f.normal;
+  double d = f.distance_to_origin;
+  double vu_[3], vv_[3];
+  V3 u = vert[1] - vert[0];
+  double r_u = 1 / sqrt(len3_squared(u));
+  u = u * r_u;
+  V3 v = cross(n, u);
+  for (int j = 0; j < 3; j++) { vu_[j] = dot(vert[j], u); vv_[j] = dot(vert[j], v); }
+  V3 bb = llf, ba = llf;
+  double d_box[8];
+  d_box[0] = dot(bb, n);
+  for (int i = 0; i < 12; i++) {
+    double a1, a2;
+    if (i < 7) {
+      ba = bb;
+      bb.x = which_x2[i] ? urb.x : llf.x;
+      bb.y = which_y2[i] ? urb.y : llf.y;
+      bb.z = which_z2[i] ? urb.z : llf.z;
+      a2 = d_box[edge2_vt[i]] = dot(bb, n);
+      a1 = d_box[edge1_vt[i]];
+      if ((a1 - d < 0 && a2 - d < 0) || (a1 - d > 0 && a2 - d > 0)) continue;
+    } else {
+      a1 = d_box[edge1_vt[i]];
+      a2 = d_box[edge2_vt[i]];
+      if ((a1 - d < 0 && a2 - d < 0) || (a1 - d > 0 && a2 - d > 0)) continue;
+      ba.x = which_x1[i] ? urb.x : llf.x;
+      ba.y = which_y1[i] ? urb.y : llf.y;
+      ba.z = which_z1[i] ? urb.z : llf.z;
+      bb.x = which_x2[i] ? urb.x : llf.x;
+      bb.y = which_y2[i] ? urb.y : llf.y;
+      bb.z = which_z2[i] ? urb.z : llf.z;
+    }
+    double r = (d - a1) / (a2 - a1);
+    V3 c = ba + (bb - ba) * r;
+    double cu = dot(c, u), cv = dot(c, v);
+    int temp = 0;
+    for (int j = 0; j < 3; j++) {
+      int k = j == 0 ? 2 : j - 1;
+      if ((vu_[k] < cu && cu <= vu_[j]) || (vu_[k] >= cu && cu > vu_[j])) {
+        double rr = (cu - vu_[k]) / (vu_[j] - vu_[k]);
+        if ((vv_[k] + rr * (vv_[j] - vv_[k])) > cv) temp++;
+      }
+    }
+    if (temp & 1) return 8 + i;
+  }
+  return 0;
+}
+
+// GeometryUtils::wall_subparts_collision_test (geometry_utils.inl:110-207) +
+// Partition::finalize_walls (partition.cpp:91-118)
+static void finalize_walls(World& w) {
+  size_t ns3 = (size_t)w.n_sp * w.n_sp * w.n_sp;
+  w.walls_per_subpart.assign(ns3, {});
+  V3 origin = {w.cfg.origin[0], w.cfg.origin[1], w.cfg.origin[2]};
+  for (uint32_t wi = 0; wi < w.walls.size(); wi++) {
+    const Wall& f = w.walls[wi];
+    V3 p[3] = {w.verts[f.vi[0]], w.verts[f.vi[1]], w.verts[f.vi[2]]};
+    V3 llf = p[0], urb = p[0];
+    for (int k = 1; k < 3; k++) {
+      if (p[k].x < llf.x) llf.x = p[k].x; else if (p[k].x > urb.x) urb.x = p[k].x;
+      if (p[k].y < llf.y) llf.y = p[k].y; else if (p[k].y > urb.y) urb.y = p[k].y;
+      if (p[k].z < llf.z) llf.z = p[k].z; else if (p[k].z > urb.z) urb.z = p[k].z;
+    }
+    double leeway = 1;
+    if (llf.x < -leeway) leeway = -llf.x;
+    if (llf.y < -leeway) leeway = -llf.y;
+    if (llf.z < -leeway) leeway = -llf.z;
+    if (urb.x > leeway) leeway = urb.x;
+    if (urb.y > leeway) leeway = urb.y;
+    if (urb.z > leeway) leeway = urb.z;
+    leeway = POS_EPS + leeway * POS_EPS;
+    if (w.cfg.use_expanded_list) leeway += w.cfg.rxn_radius_3d;
+    V3 lw = {leeway, leeway, leeway};
+    llf = llf - lw; urb = urb + lw;
+    int mn[3], mx[3];
+    w.subpart_3d(llf, mn); w.subpart_3d(urb, mx);
+    for (int x = mn[0]; x <= mx[0]; x++)
+      for (int y = mn[1]; y <= mx[1]; y++)
+        for (int z = mn[2]; z <= mx[2]; z++) {
+          if (!w.idx_in_range(x) || !w.idx_in_range(y) || !w.idx_in_range(z)) continue;
+          int idx[3] = {x, y, z};
+          uint32_t s = w.subpart_from_3d(idx);
+          V3 sl = origin + V3{(double)x, (double)y, (double)z} * w.sp_len;  // get_subpart_llf_point
+          V3 su = sl + V3{w.sp_len, w.sp_len, w.sp_len};
+          sl = sl - lw; su = su + lw;
+          if (wall_in_box(w, f, sl, su) != 0) w.walls_per_subpart[s].push_back(wi);
+        }
+  }
+}
+
+// ---- reactant lists (sequential mode) -------------------------------------------------------
+static inline uint64_t list_key(uint32_t species, uint32_t subpart) { return ((uint64_t)species << 32) | subpart; }
+static void list_insert(World& w, Mol& m) {
+  auto& v = w.lists[list_key(m.species, m.subpart)];
+  m.list_slot = (uint32_t)v.size(); m.reg_subpart = m.subpart;
+  v.push_back(m.id);
+}
+static void list_erase(World& w, Mol& m) {
+  auto& v = w.lists[list_key(m.species, m.reg_subpart)];
+  uint32_t last = v.back();
+  v[m.list_slot] = last;
+  w.mols[w.id_to_index[last]].list_slot = m.list_slot;
+  v.pop_back();
+}
+
+// ---- model table helpers ------------------------------------------------------------------
+static void build_lookups(World& w) {
+  size_t ns = w.species.size();
+  w.bimol.assign(ns * ns, -1);
+  w.unimol.assign(ns, -1);
+  w.can_vol_react.assign(ns, 0);
+  for (size_t c = 0; c < w.classes.size(); c++) {
+    const mcx_rxn_class& rc = w.classes[c];
+    if (rc.kind == MCX_RXN_BIMOL_VOLVOL) {
+      w.bimol[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
+      w.bimol[rc.reactants[1] * ns + rc.reactants[0]] = (int)c;
+    } else if (rc.kind == MCX_RXN_UNIMOL) {
+      w.unimol[rc.reactants[0]] = (int)c;
+    }
+  }
+  // Species::can_vol_react(): has a vol-vol reaction and may initiate it
+  for (size_t a = 0; a < ns; a++) {
+    bool any = false;
+    for (size_t b = 0; b < ns; b++) any |= w.bimol[a * ns + b] >= 0;
+    w.can_vol_react[a] = any && !(w.species[a].flags & MCX_SP_CANT_INITIATE);
+  }
+  uint32_t max_rule = 0;
+  for (auto& p : w.pathways) max_rule = std::max(max_rule, p.rxn_rule_id + 1);
+  w.rxn_count.assign(max_rule, 0);
+  w.species_count.assign(ns, 0);
+}
+
+// surface class lookup: first matching rule in the reference's order
+// (species-specific, then ALL_MOLECULES, then ALL_VOLUME_MOLECULES; rxn_utils.inl:182-244)
+static int surf_action(const World& w, uint32_t species, uint32_t surf_class, int side /*COLL_WALL_*/) {
+  if (surf_class == MCX_NONE) return MCX_SURF_REFLECTIVE;
+  int orient = side == COLL_WALL_FRONT ? 1 : -1;  // FRONT -> ORIENTATION_UP (diffuse_react_event.cpp:1009)
+  const uint32_t order[3] = {species, MCX_ALL_MOLECULES, MCX_ALL_VOLUME_MOLECULES};
+  for (int o = 0; o < 3; o++)
+    for (const auto& r : w.surf_rules)
+      if (r.species == order[o] && r.surf_class == surf_class && (r.orientation == 0 || r.orientation == orient))
+        return (int)r.type;
+  return MCX_SURF_REFLECTIVE;
+}
+
+// binary_search_double, src4/rxn_utils.inl:301-320 (== src/react_cond.c:80-97)
+static int pathway_for_probability(const World& w, const mcx_rxn_class& rc, double match) {
+  int min_idx = 0, max_idx = (int)rc.n_pathways - 1;
+  const mcx_pathway* A = &w.pathways[rc.first_pathway];
+  while (max_idx - min_idx > 1) {
+    int mid = (max_idx + min_idx) / 2;
+    if (match > A[mid].cum_prob) min_idx = mid; else max_idx = mid;
+  }
+  if (match > A[min_idx].cum_prob) return max_idx;
+  return min_idx;
+}
+
+// ---- the evaluation context ---------------------------------------------------------------
+struct Eval {
+  World& w;
+  WordSource& rs;
+  bool snapshot;                     // true: read-only against frozen state, return proposals
+  const std::vector<Mol>* frozen;    // snapshot mode: start-of-iteration molecules (w.mols itself)
+  const std::vector<uint8_t>* dead;  // snapshot mode: consumed flags by index
+  bool no_partners = false;          // forced-final pass
+  mcx_trace_rec* tr = nullptr;
+  uint32_t words_base = 0;
+  uint64_t h = 0xcbf29ce484222325ULL;
+
+  Eval(World& w_, WordSource& r) : w(w_), rs(r), snapshot(false), frozen(nullptr), dead(nullptr) {}
+
+  void ev(uint32_t a, uint32_t b) { h = hash_ev(h, a, b); }
+
+  // CollisionUtils::collect_neighboring_subparts, collision_utils_subparts.inl:38-122
+  void collect_neighboring_subparts(V3 pos, const int si[3], double rxn_radius, double sp_len,
+                                    std::vector<uint32_t>& out) {
+    const double part_len = w.cfg.partition_edge_length;
+    V3 rel = pos - V3{w.cfg.origin[0], w.cfg.origin[1], w.cfg.origin[2]};
+    V3 plus = rel + V3{rxn_radius, rxn_radius, rxn_radius};
+    V3 minus = rel - V3{rxn_radius, rxn_radius, rxn_radius};
+    V3 boundary = {si[0] * sp_len, si[1] * sp_len, si[2] * sp_len};
+    auto ins = [&](int x, int y, int z) {
+      int idx[3] = {x, y, z};
+      uint32_t s = w.subpart_from_3d(idx);
+      if (std::find(out.begin(), out.end(), s) == out.end()) out.push_back(s);
+    };
+    int xd = 0, yd = 0, zd = 0;
+    if (minus.x < boundary.x && minus.x > 0.0) { ins(si[0] - 1, si[1], si[2]); xd = -1; }
+    else if (plus.x > boundary.x + sp_len && plus.x < part_len) { ins(si[0] + 1, si[1], si[2]); xd = +1; }
+    if (minus.y < boundary.y && minus.y > 0.0) { ins(si[0], si[1] - 1, si[2]); yd = -1; }
+    else if (plus.y > boundary.y + sp_len && plus.y < part_len) { ins(si[0], si[1] + 1, si[2]); yd = +1; }
+    if (minus.z < boundary.z && minus.z > 0.0) { ins(si[0], si[1], si[2] - 1); zd = -1; }
+    else if (plus.z > boundary.z + sp_len && plus.z < part_len) { ins(si[0], si[1], si[2] + 1); zd = +1; }
+    if (xd && yd) ins(si[0] + xd, si[1] + yd, si[2]);
+    if (xd && zd) ins(si[0] + xd, si[1], si[2] + zd);
+    if (yd && zd) ins(si[0], si[1] + yd, si[2] + zd);
+    if (xd && yd && zd) ins(si[0] + xd, si[1] + yd, si[2] + zd);
+  }
+
+  // CollisionUtils::collect_crossed_subparts, collision_utils_subparts.inl:127-300
+  uint32_t collect_crossed_subparts(V3 pos, uint32_t cur_subpart, V3 displacement, bool for_mols, bool for_walls,
+                                    std::vector<uint32_t>& sp_walls, std::vector<uint32_t>& sp_mols) {
+    const double sp_len = w.sp_len;
+    auto ins_m = [&](uint32_t s) { if (std::find(sp_mols.begin(), sp_mols.end(), s) == sp_mols.end()) sp_mols.push_back(s); };
+    if (for_walls) sp_walls.push_back(cur_subpart);
+    if (for_mols) ins_m(cur_subpart);
+    V3 dest = pos + displacement;
+    V3 dnz = displacement; guard_zero_div(dnz);
+    int dir[3] = {dnz.x > 0 ? 1 : 0, dnz.y > 0 ? 1 : 0, dnz.z > 0 ? 1 : 0};
+    int src[3], dst[3];
+    w.subpart_3d_from_index(cur_subpart, src);
+    w.subpart_3d(dest, dst);
+    double rr = w.cfg.rxn_radius_3d * POS_SQRT2;
+    bool expanded = w.cfg.use_expanded_list != 0;
+    if (for_mols && expanded) collect_neighboring_subparts(pos, src, rr, sp_len, sp_mols);
+    uint32_t dest_subpart = w.subpart_from_3d(dst);
+    if (cur_subpart != dest_subpart) {
+      int add[3] = {dir[0] ? 1 : -1, dir[1] ? 1 : -1, dir[2] ? 1 : -1};
+      V3 cur = pos;
+      int ci[3] = {src[0], src[1], src[2]};
+      uint32_t cs;
+      V3 rcp = {1.0 / dnz.x, 1.0 / dnz.y, 1.0 / dnz.z};
+      int guard = 0;
+      do {
+        V3 edges = {w.cfg.origin[0] + ci[0] * sp_len + dir[0] * sp_len,
+                    w.cfg.origin[1] + ci[1] * sp_len + dir[1] * sp_len,
+                    w.cfg.origin[2] + ci[2] * sp_len + dir[2] * sp_len};
+        V3 diff = edges - cur;
+        V3 ct = mul(diff, rcp);
+        if (ct.x < ct.y && ct.x <= ct.z) {
+          cur = cur + displacement * ct.x; ci[0] += add[0];
+          if (!w.idx_in_range(ci[0])) break;
+        } else if (ct.y <= ct.z) {
+          cur = cur + displacement * ct.y; ci[1] += add[1];
+          if (!w.idx_in_range(ci[1])) break;
+        } else {
+          cur = cur + displacement * ct.z; ci[2] += add[2];
+          if (!w.idx_in_range(ci[2])) break;
+        }
+        cs = w.subpart_from_3d(ci);
+        if (for_walls) sp_walls.push_back(cs);
+        if (for_mols) ins_m(cs);
+        if (for_mols && expanded) collect_neighboring_subparts(cur, ci, rr, sp_len, sp_mols);
+        if (++guard > 4096) break;  // safety net (not in the reference)
+      } while (cs != dest_subpart);
+    }
+    if (for_mols && expanded) collect_neighboring_subparts(dest, dst, rr, sp_len, sp_mols);
+    return dest_subpart;
+  }
+
+  // CollisionUtils::get_displacement_up_to_partition_boundary, collision_utils.inl:48-114
+  V3 displacement_up_to_partition_boundary(V3 pos, V3 displacement) {
+    V3 dnz = displacement; guard_zero_div(dnz);
+    double e = w.cfg.partition_edge_length;
+    V3 edges = {w.cfg.origin[0] + (dnz.x > 0 ? 1.0 : 0.0) * e, w.cfg.origin[1] + (dnz.y > 0 ? 1.0 : 0.0) * e,
+                w.cfg.origin[2] + (dnz.z > 0 ? 1.0 : 0.0) * e};
+    V3 diff = edges - pos;
+    double hit_time = 1;
+    if (fabs(diff.x) < POS_EPS || fabs(diff.y) < POS_EPS || fabs(diff.z) < POS_EPS) return {0, 0, 0};
+    V3 ct = {diff.x / dnz.x, diff.y / dnz.y, diff.z / dnz.z};
+    if (ct.x >= 0 && ct.x < ct.y && ct.x <= ct.z) hit_time = ct.x;
+    else if (ct.y >= 0 && ct.y <= ct.z) hit_time = ct.y;
+    else if (ct.z >= 0) hit_time = ct.z;
+    return displacement * (hit_time - STIME_EPS);
+  }
+
+  // CollisionUtils::jump_away_line, collision_utils.inl:568-603
+  void jump_away_line(V3 p, double k, V3 A, V3 B, V3 n, V3& v) {
+    V3 e = B - A;
+    double le_1 = 1.0 / sqrt(dot(e, e));
+    e = e * le_1;
+    V3 f = {n.y * e.z - n.z * e.y, n.z * e.x - n.x * e.z, n.x * e.y - n.y * e.x};
+    double tiny = POS_EPS * (abs_max_2vec(p, v) + 1.0) / (k * max3(V3{fabs(f.x), fabs(f.y), fabs(f.z)}));
+    if ((rs.next() & 1) == 0) tiny = -tiny;
+    v.x -= tiny * f.x; v.y -= tiny * f.y; v.z -= tiny * f.z;
+  }
+
+  // CollisionUtils::collide_wall, collision_utils.inl:629-812 (update_move = true)
+  int collide_wall(V3 pos, uint32_t wi, V3& move, double& t, V3& hit) {
+    w.stats.ray_polygon_tests++;
+    const Wall& f = w.walls[wi];
+    double dp = dot(f.normal, pos), dv = dot(f.normal, move), dd = dp - f.distance_to_origin, d_eps;
+    if (dd > 0) {
+      d_eps = POS_EPS;
+      if (dd < d_eps) d_eps = 0.5 * dd;
+      if (dd + dv > d_eps) return WALL_MISS;
+    } else {
+      d_eps = -POS_EPS;
+      if (dd > d_eps) d_eps = 0.5 * dd;
+      if (dd < 0 && dd + dv < d_eps) return WALL_MISS;
+    }
+    double a;
+    if (dd == 0) {
+      if (dv != 0) return WALL_MISS;
+      a = (abs_max_2vec(pos, move) + 1.0) * POS_EPS;
+      if ((rs.next() & 1) == 0) a = -a;
+      move = move - f.normal * a;  // dd == 0.0 branch
+      return WALL_REDO;
+    }
+    a = 1.0 / dv;
+    a *= -dd;
+    t = a;
+    hit = pos + move * a;
+    V3 v0 = w.verts[f.vi[0]];
+    V3 local = hit - v0;
+    double b = dot(local, f.unit_u), c = dot(local, f.unit_v), ff;
+    if (f.uv_vert2_v < 0) { c = -c; ff = -f.uv_vert2_v; } else ff = f.uv_vert2_v;
+    if (c > 0) {
+      double g = b * ff, hh = c * f.uv_vert2_u;
+      if (g > hh) {
+        if (c * f.uv_vert1_u + g < hh + f.uv_vert1_u * f.uv_vert2_v) return dv > 0 ? WALL_BACK : WALL_FRONT;
+        else if (!distinguishable(c * f.uv_vert1_u + g, hh + f.uv_vert1_u * f.uv_vert2_v, POS_EPS)) {
+          jump_away_line(pos, a, w.verts[f.vi[1]], w.verts[f.vi[2]], f.normal, move);
+          return WALL_REDO;
+        } else return WALL_MISS;
+      } else if (!distinguishable(g, hh, POS_EPS)) {
+        jump_away_line(pos, a, w.verts[f.vi[2]], v0, f.normal, move);
+        return WALL_REDO;
+      } else return WALL_MISS;
+    } else if (!distinguishable(c, 0.0, POS_EPS)) {
+      jump_away_line(pos, a, v0, w.verts[f.vi[1]], f.normal, move);
+      return WALL_REDO;
+    }
+    return WALL_MISS;
+  }
+
+  // CollisionUtils::get_closest_wall_collision, collision_utils.inl:819-914
+  bool closest_wall_collision(V3 pos, uint32_t subpart, uint32_t last_hit_wall, V3& displacement,
+                              V3& disp_up_to_wall, Collision& best) {
+    int guard = 0;
+  restart:
+    bool found = false;
+    double closest = TIME_FOREVER;
+    for (uint32_t wi : w.walls_per_subpart[subpart]) {
+      if (wi == last_hit_wall) continue;
+      double t; V3 hit;
+      int ct = collide_wall(pos, wi, displacement, t, hit);
+      if (ct == WALL_REDO) {
+        w.stats.redos++; ev(EV_REDO, wi);
+        if (tr) tr->n_redo++;
+        if (++guard > 64) return false;  // safety net (not in the reference)
+        goto restart;
+      } else if (ct != WALL_MISS) {
+        w.stats.ray_polygon_colls++;
+        if (w.subpart_index(hit) != subpart) continue;
+        if (t < closest) {
+          found = true; closest = t;
+          best.type = ct == WALL_FRONT ? COLL_WALL_FRONT : COLL_WALL_BACK;
+          best.time = t; best.pos = hit; best.wall = wi; best.partner_id = MCX_NONE; best.rxn_class = -1;
+        }
+      }
+    }
+    if (found) disp_up_to_wall = best.pos - pos;
+    return found;
+  }
+
+  // CollisionUtils::collide_mol, collision_utils.inl:464-515
+  inline bool collide_mol(V3 mpos, uint32_t mid, V3 disp, const Mol& c, double R, double& t, V3& cpos) {
+    w.stats.collide_mol_tests++;
+    V3 dir = c.pos - mpos;
+    double d = dot(dir, disp);
+    if (d < 0) return false;
+    double movelen2 = dot(disp, disp);
+    if (d > movelen2) return false;
+    double dirlen2 = dot(dir, dir);
+    double sigma2 = R * R;
+    if (movelen2 * dirlen2 - d * d > movelen2 * sigma2) return false;
+    if (mid == c.id) return false;
+    t = d / movelen2;
+    cpos = mpos + disp * t;
+    return true;
+  }
+
+  // ray_trace_vol, diffuse_react_event.cpp:627-780.  Returns true if a wall was hit.
+  // pos/subpart are the molecule's current position; on FINISHED the caller moves it.
+  bool ray_trace_vol(V3 pos, uint32_t subpart, uint32_t self_id, uint32_t species, bool can_vol_react,
+                     uint32_t last_hit_wall, V3& remaining, std::vector<Collision>& colls) {
+    colls.clear();
+    double R = w.cfg.rxn_radius_3d;
+    V3 part_disp = remaining;
+    if (!w.in_this_partition(pos + remaining)) part_disp = displacement_up_to_partition_boundary(pos, remaining);
+    std::vector<uint32_t> sp_walls, sp_mols;
+    uint32_t last_subpart = collect_crossed_subparts(pos, subpart, part_disp, can_vol_react, true, sp_walls, sp_mols);
+    V3 up_to_wall = remaining;
+    bool hit_wall = false, hit_in_last = false;
+    Collision closest;
+    for (uint32_t s : sp_walls) {
+      if (closest_wall_collision(pos, s, last_hit_wall, remaining, up_to_wall, closest)) {
+        colls.push_back(closest);
+        hit_wall = true;
+        hit_in_last = last_subpart == s;
+        break;
+      }
+    }
+    if (can_vol_react && !no_partners) {
+      if (hit_wall && !hit_in_last) {
+        sp_mols.clear(); sp_walls.clear();
+        collect_crossed_subparts(pos, subpart, up_to_wall, true, false, sp_walls, sp_mols);
+      }
+      size_t ns = w.species.size();
+      for (uint32_t s : sp_mols) {
+        for (size_t b = 0; b < ns; b++) {
+          int rc = w.bimol[species * ns + b];
+          if (rc < 0) continue;
+          auto it = w.lists.find(list_key((uint32_t)b, s));
+          if (it == w.lists.end()) continue;
+          for (uint32_t cid : it->second) {
+            uint32_t cidx = w.id_to_index[cid];
+            const Mol& c = w.mols[cidx];
+            if (snapshot ? (*dead)[cidx] : (c.flags & MCX_MOL_DEFUNCT)) continue;
+            double t; V3 cp;
+            if (collide_mol(pos, self_id, remaining, c, R, t, cp)) {
+              Collision k; k.type = COLL_VOLMOL; k.time = t; k.pos = cp; k.partner_id = cid; k.partner_index = cidx;
+              k.rxn_class = rc; k.wall = MCX_NONE;
+              colls.push_back(k);
+            }
+          }
+        }
+      }
+    }
+    return hit_wall;
+  }
+
+  // RxnUtils::test_bimolecular, rxn_utils.inl:336-414 (local_prob_factor == 0)
+  int test_bimolecular(const mcx_rxn_class& rc, double scaling) {
+    double max_fixed_p = rc.max_fixed_p, prob;
+    if (max_fixed_p < scaling) {
+      prob = rs.dbl() * scaling;
+      if (prob >= max_fixed_p) return -1;
+    } else {
+      float max_p = (float)rc.max_fixed_p;  // sic: float in the reference (rxn_utils.inl:369)
+      if (max_p >= scaling) {
+        prob = rs.dbl() * max_p;  // skipped-reaction accounting omitted (stats only)
+      } else {
+        prob = rs.dbl() * scaling;
+        if (prob >= max_p) return -1;
+      }
+    }
+    return pathway_for_probability(w, rc, prob);
+  }
+
+  // compute_vol_displacement + pick_vol_displacement, diffusion_utils.inl:366-432,113-119
+  void compute_vol_displacement(const mcx_species& sp, double& max_time, V3& disp, double& r_rate_factor,
+                                double& t_steps) {
+    double steps = 1.0, rate_factor;
+    t_steps = steps * sp.time_step;
+    if (t_steps > max_time) { t_steps = max_time; steps = max_time / sp.time_step; }
+    if (steps < EPS) { steps = EPS; t_steps = EPS * sp.time_step; }
+    double scale;
+    if (steps == 1.0) { scale = sp.space_step; r_rate_factor = rate_factor = 1.0; }
+    else { rate_factor = sqrt(steps); r_rate_factor = 1.0 / rate_factor; scale = rate_factor * sp.space_step; }
+    disp.x = scale * rs.gauss() * 0.70710678118654752440;
+    disp.y = scale * rs.gauss() * 0.70710678118654752440;
+    disp.z = scale * rs.gauss() * 0.70710678118654752440;
+    max_time = t_steps;
+  }
+
+  // pick_unimol_rxn_class_and_set_rxn_time (diffuse_react_event.cpp:1731-1758) +
+  // time_of_unimol (rxn_utils.inl:721-736)
+  double pick_unimol_time(uint32_t species, double current_time) {
+    int rc = w.unimol[species];
+    if (rc < 0) return TIME_INVALID;
+    double k_tot = w.classes[rc].max_fixed_p;
+    double p = rs.dbl();
+    double from_now;
+    if (k_tot <= 0 || !distinguishable(p, 0, EPS)) from_now = TIME_FOREVER;
+    else from_now = -log(p) / k_tot;
+    return current_time + from_now;
+  }
+};
+
+// ================================================================================================
+// One call of diffuse_single_molecule (diffuse_react_event.cpp:201-337) incl. diffuse_vol_molecule
+// (:367-618) for one molecule: one sub-step of the iteration.  `again` reports that the reference would
+// push a new DiffuseAction for the same iteration (:299-308, :326-329).
+//
+// apply == true  (SEQUENTIAL): reactions mutate the world immediately (reference semantics).
+// apply == false (SNAPSHOT):   the first claiming event (bimolecular reaction, absorption, unimolecular
+//                 firing) ends the evaluation and is returned as a proposal.
+// ================================================================================================
+static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
+                            bool& a_destroyed);
+static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, bool& destroyed);
+static void seq_set_defunct(World& w, Mol& m);
+
+struct MolState { V3 pos; uint32_t subpart; double t_now; uint32_t flags; double unimol_time; };
+
+static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply, bool& again) {
+  World& w = E.w;
+  Outcome out;
+  again = false;
+  const uint32_t m_id = w.mols[index].id, m_species = w.mols[index].species;
+  const double it = (double)w.iteration, t_end = it + 1;
+  std::vector<Collision> colls;
+  mcx_trace_rec* tr = E.tr;
+  const mcx_species sp = w.species[m_species];
+  auto fill_event = [&](Outcome& o) { o.t_now = s.t_now; o.flags = s.flags; o.unimol_time = s.unimol_time; };
+
+  // -- unimolecular firing (diffuse_single_molecule :215-223 -> react_unimol_single_molecule :1764-1826)
+  if (s.unimol_time != TIME_INVALID && s.unimol_time <= s.t_now) {
+    int rc = w.unimol[m_species];
+    int pathway = 0;
+    if (w.classes[rc].n_pathways > 1) {  // which_unimolecular, rxn_utils.inl:774-783
+      double match = E.rs.dbl() * w.classes[rc].max_fixed_p;
+      pathway = pathway_for_probability(w, w.classes[rc], match);
+    }
+    E.ev(EV_UNIMOL | (uint32_t)pathway, (uint32_t)rc);
+    if (tr) { tr->rxn_class = rc; tr->rxn_pathway = pathway; tr->t_event = s.unimol_time; }
+    if (!apply) {
+      out.kind = MCX_OUT_UNIMOL; out.pos = s.pos; out.rxn_class = rc; out.pathway = pathway;
+      out.t_event = s.unimol_time; fill_event(out);
+      return out;
+    }
+    bool destroyed = false;
+    w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart;
+    seq_apply_unimol(w, index, rc, pathway, s.unimol_time, destroyed);
+    if (destroyed) { out.kind = MCX_OUT_UNIMOL; out.pos = s.pos; out.t_event = s.unimol_time; return out; }
+    s.flags |= MCX_MOL_SCHEDULE_UNIMOL;  // survivor re-draws its lifetime (outcome_unimolecular :2999)
+  }
+  // -- newbie lifetime (diffuse_single_molecule :232-236)
+  if (s.flags & MCX_MOL_SCHEDULE_UNIMOL) {
+    s.flags &= ~MCX_MOL_SCHEDULE_UNIMOL;
+    s.unimol_time = E.pick_unimol_time(m_species, s.t_now);
+  }
+  // -- get_max_time (:164-198); barrier = end of this iteration; species.time_step == 1
+  double max_time = t_end - s.t_now;
+  if (s.unimol_time != TIME_INVALID && s.unimol_time < s.t_now + max_time) max_time = s.unimol_time - s.t_now;
+
+  bool destroyed = false;
+  if (sp.flags & MCX_SP_CAN_DIFFUSE) {
+    // ---- diffuse_vol_molecule (:367-618)
+    V3 remaining; double r_rate_factor, t_steps;
+    E.compute_vol_displacement(sp, max_time, remaining, r_rate_factor, t_steps);
+    uint32_t last_hit_wall = MCX_NONE;
+    double elapsed = s.t_now;
+    bool can_vol_react = w.can_vol_react[m_species] != 0;
+    bool hit;
+    int trace_guard = 0;
+    do {
+      hit = E.ray_trace_vol(s.pos, s.subpart, m_id, m_species, can_vol_react, last_hit_wall, remaining, colls);
+      if (colls.size() > 1) {  // sort_collisions_by_time (:341-364)
+        std::stable_sort(colls.begin(), colls.end(), [](const Collision& a, const Collision& b) {
+          if (a.time < b.time) return true;
+          if (a.time > b.time) return false;
+          if (a.type == COLL_VOLMOL && b.type == COLL_VOLMOL) return a.partner_id > b.partner_id;
+          return false;
+        });
+      }
+      for (Collision& c : colls) {
+        if (c.type == COLL_VOLMOL) {
+          w.stats.volvol_collisions++;
+          if (c.time < STIME_EPS) continue;  // is_immediate_collision, collision_utils.inl:814-816
+          if (apply && (w.mols[c.partner_index].flags & MCX_MOL_DEFUNCT)) continue;
+          // collide_and_react_with_vol_mol (:786-829); exact_disk factor := 1 (gap, see header)
+          double factor = 1.0;
+          double abs_t = elapsed + t_steps * c.time;
+          double scaling = factor * r_rate_factor;
+          E.ev(EV_COLL, c.partner_id);
+          if (tr) { if (tr->n_collisions < MCX_TRACE_K) tr->partner[tr->n_collisions] = c.partner_id; tr->n_collisions++; }
+          int pathway = E.test_bimolecular(w.classes[c.rxn_class], scaling);
+          if (pathway < 0) continue;
+          E.ev(EV_RXN | (uint32_t)pathway, (uint32_t)c.rxn_class);
+          if (tr) { tr->rxn_class = c.rxn_class; tr->rxn_pathway = pathway; tr->rxn_partner = c.partner_id; tr->t_event = abs_t; }
+          if (!apply) {
+            out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.rxn_class = c.rxn_class; out.pathway = pathway;
+            out.partner_index = c.partner_index; out.partner_id = c.partner_id; out.t_event = abs_t; fill_event(out);
+            return out;
+          }
+          bool a_destroyed = false;
+          w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart;
+          seq_apply_bimol(w, index, c.partner_index, c.rxn_class, pathway, c.pos, abs_t, a_destroyed);
+          if (a_destroyed) { destroyed = true; out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.t_event = abs_t; break; }
+        } else {
+          // ---- wall collision (:476-567)
+          const Wall& wall = w.walls[c.wall];
+          int action = surf_action(w, m_species, wall.surf_class, c.type);
+          if (tr) {
+            if (tr->n_wall_hits < MCX_TRACE_K) { tr->wall[tr->n_wall_hits] = c.wall; tr->wall_side[tr->n_wall_hits] = c.type; }
+            tr->n_wall_hits++;
+          }
+          if (action == MCX_SURF_TRANSPARENT) {
+            // cross_transparent_wall (:3007-3099), non-compartment branch
+            E.ev(EV_TRANSP | (uint32_t)c.type, c.wall);
+            w.stats.transparent++;
+            s.pos = c.pos; s.subpart = w.subpart_index(s.pos);
+            double t_smash = c.time;
+            remaining = remaining * (1.0 - t_smash);
+            elapsed += t_steps * t_smash;
+            t_steps *= (1.0 - t_smash);
+            if (t_steps < EPS) t_steps = EPS;
+            last_hit_wall = c.wall;
+          } else if (action == MCX_SURF_ABSORPTIVE) {
+            // collide_and_react_with_walls (:991-1067) -> test_intersect (rxn_utils.inl:593-626):
+            // max_fixed_p = GIGANTIC > scaling: two draws, always reacts -> outcome_intersect destroys
+            double abs_t = elapsed + t_steps * c.time;
+            (void)E.rs.dbl(); (void)E.rs.dbl();
+            E.ev(EV_ABSORB | (uint32_t)c.type, c.wall);
+            if (tr) tr->t_event = abs_t;
+            if (!apply) {
+              out.kind = MCX_OUT_ABSORBED; out.pos = c.pos; out.t_event = abs_t; fill_event(out);
+              return out;
+            }
+            w.stats.absorptions++;
+            destroyed = true; out.kind = MCX_OUT_ABSORBED; out.pos = c.pos; out.t_event = abs_t;
+            seq_set_defunct(w, w.mols[index]);
+          } else {
+            // reflect_from_wall, collision_utils.inl:1711-1747
+            E.ev(EV_WALL | (uint32_t)c.type, c.wall);
+            w.stats.reflections++;
+            elapsed += t_steps * c.time;
+            s.pos = c.pos; s.subpart = w.subpart_index(s.pos);
+            t_steps *= (1.0 - c.time);
+            last_hit_wall = c.wall;
+            double reflect_factor = -2.0 * dot(remaining, wall.normal);
+            remaining = (remaining + wall.normal * reflect_factor) * (1.0 - c.time);
+          }
+          break;  // exactly one wall per trace, then re-trace (:566)
+        }
+      }
+      if (!hit && !destroyed) {  // RayTraceState::FINISHED (ray_trace_vol :774-777)
+        s.pos = s.pos + remaining;
+        if (!w.in_this_partition(s.pos)) {  // :592-612
+          w.err = "molecule " + std::to_string(m_id) + " escaped the partition";
+          out.kind = MCX_OUT_NONE; out.pos = s.pos; return out;
+        }
+        s.subpart = w.subpart_index(s.pos);
+      }
+      if (++trace_guard > 100000) { w.err = "ray trace did not terminate"; break; }
+    } while (hit && !destroyed);
+  }
+  if (destroyed) return out;
+
+  // -- reschedule (diffuse_single_molecule :283-336)
+  if (sp.flags & MCX_SP_CAN_DIFFUSE) {
+    s.t_now += max_time;
+    if ((s.unimol_time != TIME_INVALID && s.unimol_time < t_end) || cmp_lt(s.t_now, t_end, EPS)) again = true;
+    else {
+      double r = round(s.t_now);
+      if (cmp_eq(s.t_now, r, SQRT_EPS)) s.t_now = r;
+    }
+  } else {
+    if (s.unimol_time != TIME_INVALID) {
+      s.t_now = s.unimol_time;
+      if (s.unimol_time < t_end) again = true;
+    } else s.t_now = TIME_FOREVER;
+  }
+  out.kind = (sp.flags & MCX_SP_CAN_DIFFUSE) ? MCX_OUT_MOVED : MCX_OUT_STATIC;
+  out.pos = s.pos; fill_event(out);
+  return out;
+}
+
+static MolState load_state(const World& w, const Mol& m) {
+  MolState s;
+  s.pos = m.pos; s.subpart = w.subpart_index(m.pos);
+  s.t_now = (m.flags & MCX_MOL_PARTIAL) ? m.diffusion_time : (double)w.iteration;
+  s.flags = m.flags; s.unimol_time = m.unimol_rxn_time;
+  return s;
+}
+
+// SNAPSHOT: all sub-steps of the iteration back to back (the product's kernel loop)
+static Outcome evaluate_iteration(Eval& E, uint32_t index) {
+  MolState s = load_state(E.w, E.w.mols[index]);
+  Outcome o; bool again = false; int guard = 0;
+  do {
+    o = evaluate_substep(E, index, s, false, again);
+    if (o.kind != MCX_OUT_MOVED && o.kind != MCX_OUT_STATIC) return o;
+  } while (again && ++guard < 1000);
+  o.flags &= ~MCX_MOL_PARTIAL;
+  return o;
+}
+
+// ---- sequential-mode world mutation --------------------------------------------------------------
+static void seq_set_defunct(World& w, Mol& m) {  // Partition::set_molecule_as_defunct, partition.h:612-628
+  if (m.flags & MCX_MOL_DEFUNCT) return;
+  m.flags |= MCX_MOL_DEFUNCT;
+  list_erase(w, m);
+  w.species_count[m.species]--;
+}
+static uint32_t seq_add_molecule(World& w, uint32_t species, V3 pos, double t) {  // add_volume_molecule
+  Mol n{};
+  n.pos = pos; n.id = w.next_id++; n.species = species;
+  n.flags = MCX_MOL_SCHEDULE_UNIMOL | MCX_MOL_PARTIAL;
+  n.diffusion_time = t; n.unimol_rxn_time = TIME_INVALID;
+  n.subpart = w.subpart_index(pos);
+  w.mols.push_back(n);
+  if (w.id_to_index.size() <= n.id) w.id_to_index.resize(n.id + 1, MCX_NONE);
+  w.id_to_index[n.id] = (uint32_t)w.mols.size() - 1;
+  w.sched_ids.push_back(n.id);
+  list_insert(w, w.mols.back());
+  w.species_count[species]++;
+  w.stats.products++;
+  return n.id;
+}
+static std::vector<uint32_t>* g_new_actions = nullptr;  // new_diffuse_actions FIFO of the running step
+
+// outcome_bimolecular / outcome_products_random for two volume reactants (:1833-1895, :2446-2933)
+static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
+                            bool& a_destroyed) {
+  const mcx_rxn_class& c = w.classes[rc];
+  const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
+  w.rxn_count[pw.rxn_rule_id]++;
+  w.stats.bimol_rxns++;
+  // reactant ordering vs rule (:2541-2554)
+  bool a_is_r0 = w.mols[a_index].species == c.reactants[0];
+  bool keepA = (pw.keep_reactant_mask >> (a_is_r0 ? 0 : 1)) & 1;
+  bool keepB = (pw.keep_reactant_mask >> (a_is_r0 ? 1 : 0)) & 1;
+  for (uint32_t k = 0; k < pw.n_products; k++) {
+    uint32_t nid = seq_add_molecule(w, pw.products[k], pos, t);
+    if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
+  }
+  if (!keepA) seq_set_defunct(w, w.mols[a_index]);
+  if (!keepB) seq_set_defunct(w, w.mols[b_index]);
+  a_destroyed = !keepA;
+}
+// outcome_unimolecular (:2939-3003)
+static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, bool& destroyed) {
+  const mcx_rxn_class& c = w.classes[rc];
+  const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
+  w.rxn_count[pw.rxn_rule_id]++;
+  w.stats.unimol_rxns++;
+  V3 pos = w.mols[index].pos;
+  for (uint32_t k = 0; k < pw.n_products; k++) {
+    uint32_t nid = seq_add_molecule(w, pw.products[k], pos, t);
+    if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
+  }
+  bool keep = pw.keep_reactant_mask & 1;
+  if (!keep) seq_set_defunct(w, w.mols[index]);
+  destroyed = !keep;
+}
+
+static void trace_begin(World& w, Eval& E, const Mol& m) {
+  if (!w.tracing) return;
+  if (w.trace.size() <= m.id) {
+    mcx_trace_rec z{}; z.rxn_class = z.rxn_pathway = z.rxn_partner = MCX_NONE;
+    w.trace.resize(m.id + 1, z);
+  }
+  mcx_trace_rec& t = w.trace[m.id];
+  if (!E.snapshot && t.rounds > 0) {  // sequential mode: later sub-step of the same iteration accumulates
+    t.rounds++; E.tr = &t; E.h = t.event_hash; E.words_base = t.n_words;
+    return;
+  }
+  uint32_t rounds = t.rounds;
+  memset(&t, 0, sizeof(t));
+  t.id = m.id; t.rxn_class = t.rxn_pathway = t.rxn_partner = MCX_NONE; t.rounds = rounds + 1;
+  E.tr = &t;
+}
+static void trace_end(World& w, Eval& E, const Outcome& o) {
+  (void)w;
+  if (!E.tr) return;
+  E.tr->outcome = o.kind; E.tr->n_words = E.words_base + E.rs.used; E.tr->event_hash = E.h;
+  E.tr->pos[0] = o.pos.x; E.tr->pos[1] = o.pos.y; E.tr->pos[2] = o.pos.z;
+}
+
+// ---- SEQUENTIAL iteration: DiffuseReactEvent::step + diffuse_molecules (:53-161) -----------------------
+static void step_sequential(World& w) {
+  std::vector<uint32_t> ready;  // get_molecules_ready_for_diffusion, partition.h:232-246
+  double t_end = (double)w.iteration + 1;
+  for (uint32_t id : w.sched_ids) {
+    const Mol& m = w.mols[w.id_to_index[id]];
+    if (!(m.flags & MCX_MOL_DEFUNCT) && cmp_lt((m.flags & MCX_MOL_PARTIAL) ? m.diffusion_time : (double)w.iteration, t_end, EPS))
+      { ready.push_back(id); if (w.species[m.species].flags & MCX_SP_CAN_DIFFUSE) w.stats.molecule_steps++; }
+  }
+  std::vector<uint32_t> actions;
+  g_new_actions = &actions;
+  if (w.record_tape) {
+    w.tape_words.clear();
+    w.tape_off.assign(w.next_id, 0); w.tape_len.assign(w.next_id, 0);
+  }
+  auto run_one = [&](uint32_t id) {
+    uint32_t index = w.id_to_index[id];
+    if (w.mols[index].flags & MCX_MOL_DEFUNCT) return;
+    WordSource rs; rs.kind = WordSource::ISAAC; rs.isaac = &w.rng;
+    size_t tape_start = w.tape_words.size();
+    if (w.record_tape) rs.record = &w.tape_words;
+    Eval E(w, rs);
+    trace_begin(w, E, w.mols[index]);
+    MolState s = load_state(w, w.mols[index]);
+    bool again = false;
+    Outcome o = evaluate_substep(E, index, s, true, again);
+    trace_end(w, E, o);
+    if (w.record_tape && id < w.tape_off.size()) {
+      if (w.tape_len[id] == 0) { w.tape_off[id] = tape_start; w.tape_len[id] = rs.used; }
+      else w.tape_len[id] = 0xFFFFFFFFu;  // split step: words are not contiguous in the global stream
+    }
+    Mol& m = w.mols[w.id_to_index[id]];
+    if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) {
+      m.pos = o.pos; m.subpart = w.subpart_index(o.pos);
+      m.flags = again ? (o.flags | MCX_MOL_PARTIAL) : (o.flags & ~MCX_MOL_PARTIAL);
+      m.diffusion_time = o.t_now; m.unimol_rxn_time = o.unimol_time;
+      // Partition::update_molecule_reactants_map, partition.h:406-418
+      if (m.subpart != m.reg_subpart) { list_erase(w, m); list_insert(w, m); }
+      if (again) actions.push_back(id);  // new_diffuse_actions (:305-308)
+    }
+  };
+  // phase 1: existing molecules in schedulable order; phase 3: FIFO of products
+  // (phase 2, delayed releases, does not occur: releases happen at iteration starts)
+  for (uint32_t id : ready) {
+    const Mol& m = w.mols[w.id_to_index[id]];
+    if (m.flags & MCX_MOL_PARTIAL) { actions.push_back(id); continue; }
+    run_one(id);
+  }
+  for (size_t i = 0; i < actions.size(); i++) run_one(actions[i]);
+  g_new_actions = nullptr;
+  w.iteration++;
+}
+
+// DefragmentationEvent::step, defragmentation_event.cpp:31-114
+static void defragment(World& w) {
+  std::vector<Mol> keep; keep.reserve(w.mols.size());
+  for (auto& m : w.mols) if (!(m.flags & MCX_MOL_DEFUNCT)) keep.push_back(m);
+  w.mols.swap(keep);
+  std::fill(w.id_to_index.begin(), w.id_to_index.end(), MCX_NONE);
+  for (uint32_t i = 0; i < w.mols.size(); i++) w.id_to_index[w.mols[i].id] = i;
+  std::vector<uint32_t> s; s.reserve(w.mols.size());
+  for (uint32_t id : w.sched_ids) if (id < w.id_to_index.size() && w.id_to_index[id] != MCX_NONE) s.push_back(id);
+  w.sched_ids.swap(s);
+}
+
+// ---- SNAPSHOT iteration: the parallel semantics of the product ---------------------------
+struct SnapStreams { int kind; const uint32_t* words; uint64_t n_words; const uint64_t* off; uint64_t n_ids; };
+
+static void step_snapshot(World& w, const SnapStreams& st) {
+  const size_t n0 = w.mols.size();
+  const uint32_t max_rounds = w.cfg.max_resolve_rounds ? w.cfg.max_resolve_rounds : 8;
+  std::vector<uint8_t> dead(n0, 0);
+  for (size_t i = 0; i < n0; i++) {
+    dead[i] = (w.mols[i].flags & MCX_MOL_DEFUNCT) ? 1 : 0;
+    if (!dead[i] && (w.species[w.mols[i].species].flags & MCX_SP_CAN_DIFFUSE)) w.stats.molecule_steps++;
+  }
+  std::vector<Outcome> outs(n0);
+  std::vector<uint32_t> claim(n0, MCX_NONE);
+  std::vector<uint32_t> pending;
+  struct NewMol { uint32_t species; V3 pos; double t; uint32_t id; };
+  std::vector<NewMol> born;
+
+  auto eval_one = [&](uint32_t i, bool forced) {
+    const Mol& m = w.mols[i];
+    WordSource rs;
+    if (st.kind == MCX_RNG_TAPE) {
+      rs.kind = WordSource::TAPE;
+      uint64_t off = m.id < st.n_ids ? st.off[m.id] : st.n_words;
+      rs.tape = st.words + off; rs.tape_len = st.n_words - off;
+    } else {
+      rs.kind = WordSource::PHILOX; rs.seed = w.cfg.seed; rs.mol_id = m.id; rs.iteration = w.iteration;
+    }
+    Eval E(w, rs);
+    E.snapshot = true; E.dead = &dead; E.no_partners = forced;
+    trace_begin(w, E, m);
+    outs[i] = evaluate_iteration(E, i);
+    trace_end(w, E, outs[i]);
+  };
+  auto is_claiming = [](const Outcome& o) {
+    return o.kind == MCX_OUT_REACTED || o.kind == MCX_OUT_ABSORBED || o.kind == MCX_OUT_UNIMOL;
+  };
+  // does the claiming event consume the partner? (kept reactants are not claimed)
+  auto partner_consumed = [&](uint32_t i) {
+    const Outcome& o = outs[i];
+    if (o.kind != MCX_OUT_REACTED) return false;
+    const mcx_rxn_class& c = w.classes[o.rxn_class];
+    const mcx_pathway& pw = w.pathways[c.first_pathway + o.pathway];
+    bool a_is_r0 = w.mols[i].species == c.reactants[0];
+    return !((pw.keep_reactant_mask >> (a_is_r0 ? 1 : 0)) & 1);
+  };
+  auto make_claims = [&](uint32_t i) {
+    uint32_t prio = w.mols[i].id;
+    claim[i] = std::min(claim[i], prio);
+    if (partner_consumed(i)) { uint32_t j = outs[i].partner_index; claim[j] = std::min(claim[j], prio); }
+  };
+  auto commit = [&](uint32_t i) {  // accepted claiming event
+    Outcome& o = outs[i];
+    const Mol& m = w.mols[i];
+    if (o.kind == MCX_OUT_ABSORBED) { dead[i] = 1; w.stats.absorptions++; w.species_count[m.species]--; return; }
+    const mcx_rxn_class& c = w.classes[o.rxn_class];
+    const mcx_pathway& pw = w.pathways[c.first_pathway + o.pathway];
+    w.rxn_count[pw.rxn_rule_id]++;
+    bool keepA, keepB = true;
+    uint32_t reuse[2]; int n_reuse = 0;
+    if (o.kind == MCX_OUT_REACTED) {
+      w.stats.bimol_rxns++;
+      bool a_is_r0 = m.species == c.reactants[0];
+      keepA = (pw.keep_reactant_mask >> (a_is_r0 ? 0 : 1)) & 1;
+      keepB = (pw.keep_reactant_mask >> (a_is_r0 ? 1 : 0)) & 1;
+    } else {
+      w.stats.unimol_rxns++;
+      keepA = pw.keep_reactant_mask & 1;
+    }
+    if (!keepA) { dead[i] = 1; w.species_count[m.species]--; reuse[n_reuse++] = m.id; }
+    if (!keepB) { uint32_t j = o.partner_index; dead[j] = 1; w.species_count[w.mols[j].species]--; reuse[n_reuse++] = w.mols[j].id; }
+    // product ids: consumed reactants' ids are recycled first (initiator, then partner), then fresh ids
+    for (uint32_t k = 0; k < pw.n_products; k++) {
+      NewMol nm; nm.species = pw.products[k]; nm.pos = o.pos; nm.t = o.t_event;
+      nm.id = (int)k < n_reuse ? reuse[k] : MCX_NONE;
+      born.push_back(nm);
+      w.species_count[nm.species]++;
+      w.stats.products++;
+    }
+    if (keepA) {
+      // kept initiator: evaluation stopped at the event; it resumes from there next iteration
+      // (catalytic initiators are rare; documented deviation: remaining sub-step is taken lazily)
+      o.kind = MCX_OUT_MOVED; o.t_now = o.t_event; o.flags |= MCX_MOL_PARTIAL;
+      if (c.kind == MCX_RXN_UNIMOL) { o.flags |= MCX_MOL_SCHEDULE_UNIMOL; o.unimol_time = TIME_INVALID; }
+    }
+  };
+
+  // round 0: everyone
+  for (uint32_t i = 0; i < n0; i++) {
+    if (dead[i]) { outs[i].kind = MCX_OUT_NONE; continue; }
+    eval_one(i, false);
+    if (is_claiming(outs[i])) { pending.push_back(i); make_claims(i); }
+  }
+  for (uint32_t round = 0; round < max_rounds && !pending.empty(); round++) {
+    // resolve: decisions use the claims as they stand; commits become visible afterwards
+    std::vector<uint32_t> still, accepted;
+    for (uint32_t i : pending) {
+      uint32_t prio = w.mols[i].id;
+      bool ok = claim[i] == prio;
+      if (ok && partner_consumed(i)) ok = claim[outs[i].partner_index] == prio;
+      (ok ? accepted : still).push_back(i);
+    }
+    for (uint32_t i : accepted) commit(i);
+    // reset claims of the losers, then re-evaluate them against the updated dead set
+    for (uint32_t i : still) { claim[i] = MCX_NONE; if (partner_consumed(i)) claim[outs[i].partner_index] = MCX_NONE; }
+    pending.clear();
+    bool last = round + 1 == max_rounds;
+    for (uint32_t i : still) {
+      if (dead[i]) { outs[i].kind = MCX_OUT_CONSUMED; if (w.tracing) w.trace[w.mols[i].id].outcome = MCX_OUT_CONSUMED; continue; }
+      w.stats.retries++;
+      eval_one(i, last);
+      if (last) w.stats.unresolved++;
+      if (is_claiming(outs[i])) {
+        if (last) commit(i);  // forced pass: only self-claims (absorption, unimolecular) can occur
+        else { pending.push_back(i); make_claims(i); }
+      }
+    }
+    // claims of re-evaluated molecules compete only among themselves and with accepted ones (consumed)
+  }
+  // finalize survivors
+  for (uint32_t i = 0; i < n0; i++) {
+    if (dead[i]) {
+      if (!(w.mols[i].flags & MCX_MOL_DEFUNCT)) {
+        w.mols[i].flags |= MCX_MOL_DEFUNCT;
+        if (w.tracing && outs[i].kind != MCX_OUT_REACTED && outs[i].kind != MCX_OUT_ABSORBED && outs[i].kind != MCX_OUT_UNIMOL)
+          w.trace[w.mols[i].id].outcome = MCX_OUT_CONSUMED;
+      }
+      continue;
+    }
+    const Outcome& o = outs[i];
+    Mol& m = w.mols[i];
+    m.pos = o.pos; m.flags = o.flags; m.diffusion_time = o.t_now; m.unimol_rxn_time = o.unimol_time;
+    m.subpart = w.subpart_index(m.pos);
+  }
+  // compaction + products (the product's per-iteration sort does both)
+  std::vector<Mol> keep; keep.reserve(w.mols.size() + born.size());
+  for (auto& m : w.mols) if (!(m.flags & MCX_MOL_DEFUNCT)) keep.push_back(m);
+  for (auto& nm : born) {
+    Mol n{};
+    n.pos = nm.pos; n.species = nm.species; n.id = nm.id != MCX_NONE ? nm.id : w.next_id++;
+    n.flags = MCX_MOL_SCHEDULE_UNIMOL | MCX_MOL_PARTIAL;
+    n.diffusion_time = nm.t; n.unimol_rxn_time = TIME_INVALID; n.subpart = w.subpart_index(nm.pos);
+    keep.push_back(n);
+  }
+  w.mols.swap(keep);
+  w.lists.clear();
+  if (w.id_to_index.size() < w.next_id) w.id_to_index.resize(w.next_id, MCX_NONE);
+  std::fill(w.id_to_index.begin(), w.id_to_index.end(), MCX_NONE);
+  w.sched_ids.clear();
+  for (uint32_t i = 0; i < w.mols.size(); i++) {
+    w.id_to_index[w.mols[i].id] = i; w.sched_ids.push_back(w.mols[i].id);
+    list_insert(w, w.mols[i]);
+  }
+  w.iteration++;
+}
+
+}  // namespace orc
+
+// ================================================================================================
+// C interface for ctypes (tests / bench only)
+// ================================================================================================
+using namespace orc;
+extern "C" {
+
+void* orc_create(const mcx_config* cfg) {
+  World* w = new World();
+  w->cfg = *cfg;
+  w->n_sp = cfg->num_subparts_per_edge;
+  w->sp_len = cfg->partition_edge_length / cfg->num_subparts_per_edge;  // simulation_config.cpp:48
+  w->sp_rcp = 1.0 / w->sp_len;                                         // :63
+  w->rng.init((uint32_t)cfg->seed);
+  w->iteration = cfg->initial_iteration;
+  w->walls_per_subpart.assign((size_t)w->n_sp * w->n_sp * w->n_sp, {});
+  return w;
+}
+void orc_destroy(void* h) { delete (World*)h; }
+const char* orc_last_error(void* h) { return ((World*)h)->err.c_str(); }
+
+int orc_set_geometry(void* h, const double* v, uint64_t nv, const uint32_t* tri, uint64_t nw,
+                     const uint32_t* surf_class, const uint32_t* object) {
+  World& w = *(World*)h;
+  w.verts.resize(nv);
+  for (uint64_t i = 0; i < nv; i++) w.verts[i] = {v[3 * i], v[3 * i + 1], v[3 * i + 2]};
+  w.walls.resize(nw);
+  for (uint64_t i = 0; i < nw; i++) {
+    Wall& f = w.walls[i];
+    f.vi[0] = tri[3 * i]; f.vi[1] = tri[3 * i + 1]; f.vi[2] = tri[3 * i + 2];
+    f.surf_class = surf_class ? surf_class[i] : MCX_NONE;
+    f.object = object ? object[i] : 0;
+    init_wall_constants(w, f);
+  }
+  finalize_walls(w);
+  return 0;
+}
+int orc_set_species(void* h, const mcx_species* s, uint32_t n) {
+  World& w = *(World*)h; w.species.assign(s, s + n); build_lookups(w); return 0;
+}
+int orc_set_reactions(void* h, const mcx_rxn_class* c, uint32_t nc, const mcx_pathway* p, uint32_t np) {
+  World& w = *(World*)h; w.classes.assign(c, c + nc); w.pathways.assign(p, p + np); build_lookups(w); return 0;
+}
+int orc_set_surface_classes(void* h, const mcx_surf_class_rxn* r, uint32_t n) {
+  World& w = *(World*)h; w.surf_rules.assign(r, r + n); return 0;
+}
+int orc_upload_molecules(void* h, const mcx_mol_soa* s) {
+  World& w = *(World*)h;
+  w.mols.clear(); w.lists.clear(); w.sched_ids.clear(); w.id_to_index.clear();
+  std::fill(w.species_count.begin(), w.species_count.end(), 0);
+  uint32_t max_id = 0;
+  for (uint64_t i = 0; i < s->n; i++) max_id = std::max(max_id, s->id[i]);
+  w.id_to_index.assign((size_t)max_id + 1, MCX_NONE);
+  w.mols.reserve(s->n);
+  for (uint64_t i = 0; i < s->n; i++) {
+    Mol m{};
+    m.pos = {s->x[i], s->y[i], s->z[i]}; m.id = s->id[i]; m.species = s->species[i];
+    m.flags = s->flags ? s->flags[i] : 0;
+    m.diffusion_time = s->diffusion_time ? s->diffusion_time[i] : (double)w.iteration;
+    m.unimol_rxn_time = s->unimol_rxn_time ? s->unimol_rxn_time[i] : TIME_INVALID;
+    if (!w.in_this_partition(m.pos)) { w.err = "molecule outside partition"; return MCX_ERR_ESCAPED; }
+    m.subpart = w.subpart_index(m.pos);
+    w.mols.push_back(m);
+    w.id_to_index[m.id] = (uint32_t)i;
+    if (!(m.flags & MCX_MOL_DEFUNCT)) { w.sched_ids.push_back(m.id); list_insert(w, w.mols.back()); w.species_count[m.species]++; }
+  }
+  w.next_id = max_id + 1;
+  return 0;
+}
+uint64_t orc_num_molecules(void* h) {
+  World& w = *(World*)h; uint64_t n = 0;
+  for (auto& m : w.mols) n += !(m.flags & MCX_MOL_DEFUNCT);
+  return n;
+}
+int orc_download_molecules(void* h, mcx_mol_soa* o, uint64_t cap) {
+  World& w = *(World*)h; uint64_t n = 0;
+  for (auto& m : w.mols) {
+    if (m.flags & MCX_MOL_DEFUNCT) continue;
+    if (n >= cap) return MCX_ERR_CAPACITY;
+    o->x[n] = m.pos.x; o->y[n] = m.pos.y; o->z[n] = m.pos.z; o->id[n] = m.id; o->species[n] = m.species;
+    if (o->flags) o->flags[n] = m.flags;
+    if (o->diffusion_time) o->diffusion_time[n] = (m.flags & MCX_MOL_PARTIAL) ? m.diffusion_time : (double)w.iteration;
+    if (o->unimol_rxn_time) o->unimol_rxn_time[n] = m.unimol_rxn_time;
+    n++;
+  }
+  o->n = n;
+  return 0;
+}
+static void fill_stats(World& w, mcx_step_stats* s, uint64_t iters, double ms) {
+  if (!s) return;
+  memset(s, 0, sizeof(*s));
+  s->iterations = iters; s->molecule_steps = w.stats.molecule_steps; s->n_live = orc_num_molecules(&w);
+  s->ray_polygon_tests = w.stats.ray_polygon_tests; s->ray_polygon_colls = w.stats.ray_polygon_colls;
+  s->mol_wall_reflections = w.stats.reflections; s->mol_wall_transparent = w.stats.transparent;
+  s->mol_wall_absorptions = w.stats.absorptions; s->vol_mol_vol_mol_collisions = w.stats.volvol_collisions;
+  s->bimol_rxns = w.stats.bimol_rxns; s->unimol_rxns = w.stats.unimol_rxns; s->wall_redos = w.stats.redos;
+  s->resolve_retries = w.stats.retries; s->unresolved_conflicts = w.stats.unresolved;
+  s->products_created = w.stats.products; s->device_ms = ms;
+}
+// mode 0 = sequential (reference semantics, global ISAAC64), 1 = snapshot with Philox streams
+int orc_step(void* h, uint32_t n_iterations, int mode, mcx_step_stats* stats) {
+  World& w = *(World*)h;
+  w.stats = Stats();
+  auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t k = 0; k < n_iterations; k++) {
+    if (mode == 0) {
+      step_sequential(w);
+      if (w.iteration % 100 == 0) defragment(w);  // DEFRAGMENTATION_PERIODICITY, defines.h
+    } else {
+      SnapStreams st{MCX_RNG_PHILOX, nullptr, 0, nullptr, 0};
+      step_snapshot(w, st);
+    }
+    if (!w.err.empty()) return MCX_ERR_ESCAPED;
+  }
+  double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  fill_stats(w, stats, n_iterations, ms);
+  return 0;
+}
+// One traced iteration.  mode 0: sequential, also records the per-molecule ISAAC tape;
+// mode 1: snapshot+Philox; mode 2: snapshot replaying words[off[id]...].
+int orc_trace_step(void* h, int mode, const uint32_t* words, uint64_t n_words, const uint64_t* off, uint64_t n_ids,
+                   mcx_trace_rec* trace_out, uint64_t n_trace, mcx_step_stats* stats) {
+  World& w = *(World*)h;
+  w.stats = Stats();
+  w.tracing = true; w.trace.clear();
+  mcx_trace_rec z{}; z.rxn_class = z.rxn_pathway = z.rxn_partner = MCX_NONE;
+  w.trace.assign(std::max<uint64_t>(n_trace, w.next_id), z);
+  if (mode == 0) { w.record_tape = true; step_sequential(w); w.record_tape = false; }
+  else {
+    SnapStreams st{mode == 2 ? MCX_RNG_TAPE : MCX_RNG_PHILOX, words, n_words, off, n_ids};
+    step_snapshot(w, st);
+  }
+  w.tracing = false;
+  for (uint64_t i = 0; i < n_trace && i < w.trace.size(); i++) trace_out[i] = w.trace[i];
+  fill_stats(w, stats, 1, 0);
+  return w.err.empty() ? 0 : MCX_ERR_ESCAPED;
+}
+// tape recorded by the last sequential traced iteration
+uint64_t orc_tape_size(void* h) { return ((World*)h)->tape_words.size(); }
+int orc_tape_get(void* h, uint32_t* words, uint64_t* off, uint32_t* len, uint64_t n_ids) {
+  World& w = *(World*)h;
+  memcpy(words, w.tape_words.data(), w.tape_words.size() * 4);
+  for (uint64_t i = 0; i < n_ids; i++) { off[i] = i < w.tape_off.size() ? w.tape_off[i] : 0; len[i] = i < w.tape_len.size() ? w.tape_len[i] : 0; }
+  return 0;
+}
+int orc_counts(void* h, uint64_t* per_species, uint32_t ns, uint64_t* per_rule, uint32_t nr) {
+  World& w = *(World*)h;
+  for (uint32_t i = 0; i < ns && per_species; i++) per_species[i] = i < w.species_count.size() ? w.species_count[i] : 0;
+  for (uint32_t i = 0; i < nr && per_rule; i++) per_rule[i] = i < w.rxn_count.size() ? w.rxn_count[i] : 0;
+  return 0;
+}
+// geometry set-up introspection for parity of the wall tables
+uint64_t orc_subpart_wall_count(void* h, uint32_t subpart) { return ((World*)h)->walls_per_subpart[subpart].size(); }
+int orc_subpart_walls(void* h, uint32_t subpart, uint32_t* out) {
+  auto& v = ((World*)h)->walls_per_subpart[subpart];
+  std::copy(v.begin(), v.end(), out); return 0;
+}
+int orc_wall_constants(void* h, uint32_t wi, double out[16]) {
+  const Wall& f = ((World*)h)->walls[wi];
+  double t[16] = {f.normal.x, f.normal.y, f.normal.z, f.distance_to_origin, f.unit_u.x, f.unit_u.y, f.unit_u.z,
+                  f.unit_v.x, f.unit_v.y, f.unit_v.z, f.uv_vert1_u, f.uv_vert2_u, f.uv_vert2_v, f.area, 0, 0};
+  memcpy(out, t, sizeof(t)); return 0;
+}
+// RNG restatement entry points (pinned against oracle/_ref/librefrng.so)
+void* orc_rng_new(uint32_t seed) { Isaac64* r = new Isaac64(); r->init(seed); return r; }
+void orc_rng_free(void* r) { delete (Isaac64*)r; }
+uint32_t orc_rng_uint(void* r) { return ((Isaac64*)r)->next32(); }
+double orc_rng_dbl(void* r) { WordSource s; s.isaac = (Isaac64*)r; return s.dbl(); }
+double orc_rng_gauss(void* r) { WordSource s; s.isaac = (Isaac64*)r; return s.gauss(); }
+void orc_rng_fill_uint(void* r, uint32_t* out, long n) { for (long i = 0; i < n; i++) out[i] = ((Isaac64*)r)->next32(); }
+void orc_rng_fill_gauss(void* r, double* out, long n) { WordSource s; s.isaac = (Isaac64*)r; for (long i = 0; i < n; i++) out[i] = s.gauss(); }
+long long orc_rng_uses(void* r) { return ((Isaac64*)r)->uses(); }
+void orc_philox_block(uint64_t seed, uint32_t id, uint64_t it, uint32_t block, uint32_t out[4]) { philox_block(seed, id, it, block, out); }
+// gaussians from a tape (device Ziggurat parity)
+void orc_tape_gauss(const uint32_t* words, uint64_t n_words, double* out, long n, uint32_t* used) {
+  WordSource s; s.kind = WordSource::TAPE; s.tape = words; s.tape_len = n_words;
+  for (long i = 0; i < n; i++) out[i] = s.gauss();
+  *used = s.used;
+}
+}

@@ -1,0 +1,170 @@
+"""ctypes driver of the CPU oracle (oracle/liboracle.so) — TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  It takes the same Tables object (mcell_b200.model.Model.build()) as the product
+so both sides see identical inputs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from mcell_b200 import abi
+from mcell_b200.model import MolArrays
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(native=False):
+    target = "liboracle_native.so" if native else "liboracle.so"
+    subprocess.run(["make", "-s", "-C", _HERE, target], check=True)
+    if os.path.isdir("/root/reference/src"):
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+    return os.path.join(_HERE, target)
+
+
+def lib(native=False):
+    global _LIB
+    key = "native" if native else "core2"
+    if _LIB is None:
+        _LIB = {}
+    if key not in _LIB:
+        path = os.path.join(_HERE, "liboracle_native.so" if native else "liboracle.so")
+        if not os.path.exists(path):
+            build(native)
+        L = C.CDLL(path)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.POINTER(abi.mcx_config)]
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_last_error.argtypes = [C.c_void_p]
+        L.orc_num_molecules.restype = C.c_uint64
+        L.orc_num_molecules.argtypes = [C.c_void_p]
+        L.orc_tape_size.restype = C.c_uint64
+        L.orc_tape_size.argtypes = [C.c_void_p]
+        L.orc_subpart_wall_count.restype = C.c_uint64
+        L.orc_subpart_wall_count.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_rng_new.restype = C.c_void_p
+        L.orc_rng_dbl.restype = C.c_double
+        L.orc_rng_gauss.restype = C.c_double
+        L.orc_rng_uint.restype = C.c_uint32
+        L.orc_rng_uses.restype = C.c_longlong
+        for f in ("orc_rng_free", "orc_rng_uint", "orc_rng_dbl", "orc_rng_gauss", "orc_rng_uses"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_rng_fill_uint.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+        L.orc_rng_fill_gauss.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+        _LIB[key] = L
+    return _LIB[key]
+
+
+def ref_rng_lib():
+    """The reference's own RNG (src/rng.c) compiled into oracle/_ref/ (build container only,
+    travels prebuilt to the GPU box)."""
+    path = os.path.join(_HERE, "_ref", "librefrng.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_rng_new.restype = C.c_void_p
+    L.ref_rng_dbl.restype = C.c_double
+    L.ref_rng_gauss.restype = C.c_double
+    L.ref_rng_uint.restype = C.c_uint32
+    L.ref_rng_uses.restype = C.c_longlong
+    for f in ("ref_rng_free", "ref_rng_uint", "ref_rng_dbl", "ref_rng_gauss", "ref_rng_uses"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.ref_rng_fill_uint.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+    L.ref_rng_fill_gauss.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+    return L
+
+
+class Oracle:
+    SEQUENTIAL, SNAPSHOT = 0, 1
+
+    def __init__(self, tables, native=False):
+        self.L = lib(native)
+        self.t = tables
+        self.h = C.c_void_p(self.L.orc_create(C.byref(tables.cfg)))
+        t = tables
+        self._v = lambda x: C.c_void_p(x.ctypes.data) if x is not None and x.size else None
+        self.L.orc_set_species(self.h, t.species, C.c_uint32(t.n_species))
+        self.L.orc_set_reactions(self.h, t.classes, C.c_uint32(t.n_classes), t.pathways, C.c_uint32(t.n_pathways))
+        self.L.orc_set_surface_classes(self.h, t.surf_rules, C.c_uint32(t.n_surf_rules))
+        self.L.orc_set_geometry(self.h, self._v(t.vertices), C.c_uint64(len(t.vertices)), self._v(t.tri),
+                                C.c_uint64(len(t.tri)), self._v(t.wall_surf_class), None)
+
+    def close(self):
+        if self.h:
+            self.L.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def error(self):
+        return self.L.orc_last_error(self.h).decode()
+
+    def upload(self, mols):
+        v = mols.view()
+        rc = self.L.orc_upload_molecules(self.h, C.byref(v))
+        if rc:
+            raise RuntimeError(self.error())
+
+    def num_molecules(self):
+        return int(self.L.orc_num_molecules(self.h))
+
+    def download(self):
+        n = self.num_molecules()
+        m = MolArrays(n)
+        v = m.view()
+        rc = self.L.orc_download_molecules(self.h, C.byref(v), C.c_uint64(n))
+        assert rc == 0
+        m.n = int(v.n)
+        return m
+
+    def step(self, n_iterations=1, mode=0):
+        st = abi.mcx_step_stats()
+        rc = self.L.orc_step(self.h, C.c_uint32(n_iterations), C.c_int(mode), C.byref(st))
+        if rc:
+            raise RuntimeError(self.error())
+        return st
+
+    def trace_step(self, mode, n_trace, words=None, offsets=None):
+        """mode 0 sequential(+tape recording), 1 snapshot/Philox, 2 snapshot replaying a tape."""
+        tr = np.zeros(n_trace, dtype=abi.TRACE_DTYPE)
+        st = abi.mcx_step_stats()
+        nw = 0 if words is None else len(words)
+        ni = 0 if offsets is None else len(offsets)
+        rc = self.L.orc_trace_step(self.h, C.c_int(mode), self._v(words), C.c_uint64(nw), self._v(offsets),
+                                   C.c_uint64(ni), C.c_void_p(tr.ctypes.data), C.c_uint64(n_trace), C.byref(st))
+        if rc:
+            raise RuntimeError(self.error())
+        return tr, st
+
+    def tape(self, n_ids):
+        n = int(self.L.orc_tape_size(self.h))
+        words = np.zeros(max(n, 1), np.uint32)
+        off = np.zeros(n_ids, np.uint64)
+        ln = np.zeros(n_ids, np.uint32)
+        self.L.orc_tape_get(self.h, C.c_void_p(words.ctypes.data), C.c_void_p(off.ctypes.data),
+                            C.c_void_p(ln.ctypes.data), C.c_uint64(n_ids))
+        return words[:n], off, ln
+
+    def counts(self):
+        s = np.zeros(max(1, self.t.n_species), np.uint64)
+        r = np.zeros(max(1, self.t.n_rules), np.uint64)
+        self.L.orc_counts(self.h, C.c_void_p(s.ctypes.data), C.c_uint32(self.t.n_species),
+                          C.c_void_p(r.ctypes.data), C.c_uint32(self.t.n_rules))
+        return s[:self.t.n_species], r[:self.t.n_rules]
+
+    def subpart_walls(self, subpart):
+        n = int(self.L.orc_subpart_wall_count(self.h, C.c_uint32(subpart)))
+        out = np.zeros(max(n, 1), np.uint32)
+        self.L.orc_subpart_walls(self.h, C.c_uint32(subpart), C.c_void_p(out.ctypes.data))
+        return out[:n]
+
+    def wall_constants(self, wi):
+        out = np.zeros(16)
+        self.L.orc_wall_constants(self.h, C.c_uint32(wi), C.c_void_p(out.ctypes.data))
+        return out

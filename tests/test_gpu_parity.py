@@ -1,0 +1,204 @@
+"""GPU parity tests (run on the B200 box): libmcx through its C ABI against the CPU oracle on the same
+seeded inputs.  Bit-exact on event sequences / partner lists / reaction choices (integers), 1e-12 relative
+on positions and event times (fp64), as BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+
+import common as cm
+from mcell_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-12  # relative, north_star
+
+
+def _engine(t):
+    from mcell_b200 import Engine
+    return Engine(t)
+
+
+def _oracle(t):
+    from oracle import oracle_py as O
+    return O.Oracle(t)
+
+
+def _assert_same_population(a, b):
+    """a, b: MolArrays sorted by id."""
+    assert a.n == b.n
+    assert (a.id == b.id).all()
+    assert (a.species == b.species).all()
+    for k in ("x", "y", "z"):
+        assert cm.rel_close(getattr(a, k), getattr(b, k), POS_TOL).all(), k
+    assert (a.flags == b.flags).all()
+    assert cm.rel_close(a.diffusion_time, b.diffusion_time, POS_TOL).all()
+    assert cm.rel_close(a.unimol_rxn_time, b.unimol_rxn_time, POS_TOL).all()
+
+
+def test_replay_reference_stream_free_diffusion():
+    """The sequential oracle draws from ONE global ISAAC64 stream (reference semantics); the GPU replays
+    each molecule's slice of that stream and must reproduce wall-hit sequences and positions."""
+    n = 20000
+    t, mols = cm.free_diffusion_box(n=n, rng_mode=abi.MCX_RNG_TAPE)
+    o = _oracle(t)
+    o.upload(mols)
+    e = _engine(t)
+    e.upload(mols)
+    for it in range(3):
+        tr_o, st_o = o.trace_step(0, n)
+        words, off, ln = o.tape(n)
+        tr_g, st_g = e.replay_step(words, off)
+        ids = np.arange(n)
+        bad = cm.compare_traces(tr_o, tr_g, ids)
+        assert not bad, bad
+        assert (tr_g["n_words"] == ln).all()
+        assert st_g.mol_wall_reflections == st_o.mol_wall_reflections
+        assert st_g.ray_polygon_tests == st_o.ray_polygon_tests
+        assert st_g.molecule_steps == n
+    assert st_o.mol_wall_reflections > 100
+    _assert_same_population(o.download().sorted_by_id(), e.download().sorted_by_id())
+
+
+@pytest.mark.parametrize("subpart_um,cell_edge", [(0.5, 0.0), (0.05, 0.0), (0.5, 1.3), (0.05, 7.0)])
+def test_replay_reactive_box_snapshot(subpart_um, cell_edge):
+    """A + B -> C: per-molecule ISAAC64 tape slices; partner lists, reaction choices, conflict rounds."""
+    n = 16000
+    t, mols = cm.reactive_box(n=n, edge_um=0.4, p_target=0.5, rng_mode=abi.MCX_RNG_TAPE,
+                              subpartition_dimension=subpart_um, cell_edge=cell_edge)
+    o = _oracle(t)
+    o.upload(mols)
+    e = _engine(t)
+    e.upload(mols)
+    n_ids = n
+    total_rxn = 0
+    for it in range(4):
+        words, off = cm.isaac_slices(100 + it, n_ids, 48)
+        tr_o, st_o = o.trace_step(2, n_ids, words, off)
+        tr_g, st_g = e.replay_step(words, off)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all()
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, bad
+        for k in ("bimol_rxns", "vol_mol_vol_mol_collisions", "resolve_retries", "unresolved_conflicts",
+                  "products_created", "mol_wall_reflections", "molecule_steps", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), k
+        total_rxn += st_g.bimol_rxns
+        assert (e.counts()[0] == o.counts()[0]).all()
+        assert (e.counts()[1] == o.counts()[1]).all()
+    assert total_rxn > 300
+    _assert_same_population(o.download().sorted_by_id(), e.download().sorted_by_id())
+
+
+def test_philox_multi_iteration_reactive():
+    """Production RNG path: per-molecule Philox streams, 12 iterations with products carried over."""
+    n = 16000
+    t, mols = cm.reactive_box(n=n, edge_um=0.4, p_target=0.4, seed=7)
+    o = _oracle(t)
+    o.upload(mols)
+    e = _engine(t)
+    e.upload(mols)
+    for it in range(12):
+        st_o = o.step(1, 1)
+        st_g = e.step(1)
+        assert st_g.bimol_rxns == st_o.bimol_rxns, it
+        assert st_g.vol_mol_vol_mol_collisions == st_o.vol_mol_vol_mol_collisions, it
+        assert st_g.molecule_steps == st_o.molecule_steps, it
+    assert (e.counts()[0] == o.counts()[0]).all()
+    _assert_same_population(o.download().sorted_by_id(), e.download().sorted_by_id())
+
+
+def test_philox_surface_classes_icosphere():
+    """Absorptive / transparent / reflective faces of an icosphere (config 3 without receptors)."""
+    n = 20000
+    t, mols = cm.sphere_classes(n=n, seed=3)
+    o = _oracle(t)
+    o.upload(mols)
+    e = _engine(t)
+    e.upload(mols)
+    tot = {"mol_wall_absorptions": 0, "mol_wall_transparent": 0, "mol_wall_reflections": 0}
+    for it in range(10):
+        tr_o, st_o = o.trace_step(1, n)
+        tr_g, st_g = e.trace_step(n)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all()
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in tot:
+            assert getattr(st_g, k) == getattr(st_o, k), k
+            tot[k] += getattr(st_g, k)
+    assert tot["mol_wall_absorptions"] > 50 and tot["mol_wall_transparent"] > 100 and tot["mol_wall_reflections"] > 1000
+    assert (e.counts()[0] == o.counts()[0]).all()
+    _assert_same_population(o.download().sorted_by_id(), e.download().sorted_by_id())
+
+
+def test_philox_reversible_binding_unimolecular():
+    """Ca + CB <-> CaCB: unimolecular lifetimes, split steps, two-product unimolecular firing.
+    Fresh ids of second products are allocated by atomics on the device, so populations are compared
+    as (species, position) multisets rather than by id."""
+    n = 9000
+    t, mols = cm.reversible_box(n=n, seed=5)
+    o = _oracle(t)
+    o.upload(mols)
+    e = _engine(t)
+    e.upload(mols)
+    for it in range(1):
+        st_o = o.step(1, 1)
+        st_g = e.step(1)
+        for k in ("bimol_rxns", "unimol_rxns", "products_created", "molecule_steps", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+    a, b = o.download(), e.download()
+    assert a.n == b.n
+
+    def key(m):
+        arr = np.c_[m.species.astype(float), m.x, m.y, m.z, m.diffusion_time, m.unimol_rxn_time]
+        return arr[np.lexsort(arr.T[::-1])]
+
+    ka, kb = key(a), key(b)
+    assert (ka[:, 0] == kb[:, 0]).all()
+    assert cm.rel_close(ka[:, 1:], kb[:, 1:], POS_TOL).all()
+    # statistical agreement over more iterations (ids diverge after the first fresh allocation)
+    for it in range(30):
+        o.step(1, 1)
+        e.step(1)
+    co, cg = o.counts()[0].astype(float), e.counts()[0].astype(float)
+    assert np.all(np.abs(co - cg) < 6 * np.sqrt(co + 1)), (co, cg)
+
+
+def test_full_size_properties_free_diffusion():
+    """BASELINE config 1 at full size (1e5 molecules, 1 um cube): size-independent properties —
+    conservation, containment, uniform density, mean-square displacement 3*space_step^2/2 per step
+    for molecules that did not touch a wall."""
+    n = 100000
+    t, mols = cm.free_diffusion_box(n=n, seed=11)
+    e = _engine(t)
+    e.upload(mols)
+    before = mols.sorted_by_id()
+    st = e.step(1)
+    assert st.molecule_steps == n and st.n_live == n
+    after = e.download().sorted_by_id()
+    assert (after.id == before.id).all()
+    d2 = (after.x - before.x) ** 2 + (after.y - before.y) ** 2 + (after.z - before.z) ** 2
+    inner = (np.abs(before.x) < 30) & (np.abs(before.y) < 30) & (np.abs(before.z) < 30)
+    msd = d2[inner].mean()
+    expect = 1.5 * t.species[0].space_step ** 2
+    assert abs(msd - expect) < 5 * expect * np.sqrt(2.0 / 3.0 / inner.sum()) * 1.5, (msd, expect)
+    st = e.step(199)
+    assert st.molecule_steps == 199 * n
+    after = e.download().sorted_by_id()
+    assert after.n == n
+    for k in ("x", "y", "z"):
+        v = getattr(after, k)
+        assert v.min() >= -50.0 and v.max() <= 50.0
+        hist, _ = np.histogram(v, bins=10, range=(-50, 50))
+        assert np.all(np.abs(hist - n / 10) < 6 * np.sqrt(n / 10))
+
+
+def test_errors_are_reported_not_fatal():
+    from mcell_b200 import McxError
+    t, mols = cm.free_diffusion_box(n=100)
+    e = _engine(t)
+    with pytest.raises(McxError):
+        e.step(1)  # nothing uploaded
+    mols.x[0] = 1e6  # outside the partition
+    with pytest.raises(McxError) as ei:
+        e.upload(mols)
+    assert ei.value.code == abi.MCX_ERR_ESCAPED
