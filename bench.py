@@ -1,0 +1,387 @@
+#!/usr/bin/env python3
+"""bench.py — molecule-steps/sec of the diffuse-and-react hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # libmcx on N B200s (torchrun for N>1)
+  python bench.py --impl reference --gpus N ...            # CPU arm: the mcell4-equivalent oracle
+
+Workload (config.workload): BASELINE.json configs[4] — the reactive box with 4 species and
+6 reactions at config 2's number density (125 molecules/um^3), 1e8 molecules, which fits one B200.
+A "step" is one iteration (one DiffuseReactEvent::step) over every molecule.  At N>1 the same box is
+slab-decomposed along z (strong scaling).  Inputs (3.2 GB of records + cell tables) are far larger
+than the 126 MB L2, so no explicit L2 flush is needed between timed iterations.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DENSITY_PER_LU3 = 1.0e6 / 200.0 ** 3     # config 2: 1e6 molecules in a (2 um)^3 = (200 lu)^3 box
+ITERS_PER_CALL = 10                      # "counts every 10 iterations": barrier window of one plugin call
+B_ALG_DIFFUSE = 92.0                     # 32 read + 32 write + 28 neighbour staging
+B_ALG_STEP = 160.0                       # + 68 B per-step sort
+
+
+def build_model(n_total, seed=1, rank=0, world=1, cap_factor=1.25):
+    """4 species, 6 reactions (4 bimolecular incl. a same-species one, 2 unimolecular)."""
+    from mcell_b200.model import Model, Config, create_box, N_AV, MY_PI
+    edge_lu = (n_total / DENSITY_PER_LU3) ** (1.0 / 3.0)
+    edge_um = edge_lu * 0.01
+    part_dim = max(10.0, math.ceil(edge_um + 1.0))
+    m = Model(Config(seed=seed, partition_dimension=part_dim))
+    for name in "ABCD":
+        m.add_species(name, 1e-6)
+    lu, ts = m.length_unit, m.config.time_step
+    eff = 2 * m.space_step(1e-6) * lu / ts
+    R = m.rxn_radius_um
+    pb = 1.0 / (2.0 * math.sqrt(MY_PI) * R * R * eff) * 1.0e15 / N_AV
+    k_bi = 0.1 / pb                      # max_fixed_p = 0.1
+    m.add_reaction_rule(["A", "B"], ["C"], k_bi)
+    m.add_reaction_rule(["C"], ["A", "B"], 1.0e4)
+    m.add_reaction_rule(["A", "C"], ["D"], k_bi)
+    m.add_reaction_rule(["D"], ["A", "C"], 1.0e4)
+    m.add_reaction_rule(["B", "D"], ["C", "C"], k_bi)
+    m.add_reaction_rule(["C", "C"], ["B", "D"], k_bi)
+    v, f = create_box(edge_um)
+    m.add_geometry_object(v, f)
+    per_rank = int(n_total / world * cap_factor * (1.6 if world > 1 else 1.0)) + 1024
+    t = m.build(max_molecules=per_rank, rank=rank, world_size=world)
+    return t, edge_um
+
+
+def make_molecules(n_total, edge_um, length_unit, seed, rank=0, world=1, pinned=True):
+    """Uniform positions; species in fixed proportions A:B:C:D = 4:4:1:1. For world > 1 each rank
+    generates only the molecules of its own z-slab (same global id space)."""
+    from mcell_b200.model import MolArrays
+    h = (edge_um / 2) / length_unit * (1 - 1e-9)
+    n = n_total // world + (1 if rank < n_total % world else 0)
+    first_id = rank * (n_total // world) + min(rank, n_total % world)
+    rng = np.random.default_rng(seed * 1000 + rank)
+    m = MolArrays(0)
+    alloc = _pinned_alloc if pinned else (lambda shape, dt: np.zeros(shape, dt))
+    m.x, m.y, m.z = alloc(n, np.float64), alloc(n, np.float64), alloc(n, np.float64)
+    m.id, m.species, m.flags = alloc(n, np.uint32), alloc(n, np.uint32), alloc(n, np.uint32)
+    m.diffusion_time, m.unimol_rxn_time = alloc(n, np.float64), alloc(n, np.float64)
+    chunk = 1 << 22
+    z_lo = -h + 2 * h * rank / world
+    z_hi = -h + 2 * h * (rank + 1) / world
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        m.x[s:e] = rng.uniform(-h, h, e - s)
+        m.y[s:e] = rng.uniform(-h, h, e - s)
+        m.z[s:e] = rng.uniform(z_lo, z_hi, e - s)
+        r = rng.integers(0, 10, e - s)
+        m.species[s:e] = np.select([r < 4, r < 8, r < 9], [0, 1, 2], 3)
+    m.id[:] = np.arange(first_id, first_id + n, dtype=np.uint32)
+    m.flags[:] = 2                         # MCX_MOL_SCHEDULE_UNIMOL: lifetimes drawn on first diffusion
+    m.diffusion_time[:] = 0
+    m.unimol_rxn_time[:] = -256.0
+    m.n = n
+    return m
+
+
+_PINNED_KEEP = []
+
+
+def _pinned_alloc(n, dtype):
+    """numpy view of pinned host memory (torch is plumbing for allocation only)."""
+    import torch
+    tdt = {np.float64: torch.float64, np.uint32: torch.int32}[dtype]
+    try:
+        tt = torch.empty(max(n, 1), dtype=tdt, pin_memory=True)
+    except Exception:
+        tt = torch.empty(max(n, 1), dtype=tdt)
+    _PINNED_KEEP.append(tt)
+    a = tt.numpy()[:n]
+    return a.view(np.uint32) if dtype is np.uint32 else a
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle-reason sampling during the timed region (NVML)."""
+
+    def __init__(self, index=0, period=0.2):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    """One independent seed of the bounded CPU sample (the reference's only scaling mode:
+    utils/mcell4_runner/mcell4_runner.py:203-212)."""
+    n_sample, seed, iters = args
+    from oracle import oracle_py as O
+    t, edge_um = build_model(n_sample, seed=seed)
+    mols = make_molecules(n_sample, edge_um, t.length_unit, seed, pinned=False)
+    o = O.Oracle(t)
+    o.upload(mols)
+    t0 = time.perf_counter()
+    st = o.step(iters, 0)
+    dt = time.perf_counter() - t0
+    return st.molecule_steps, dt
+
+
+def cpu_sample(n_sample, iters, cores):
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(n_sample, 100 + i, iters) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return steps / busy, steps, busy, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_py as O
+    O.build()
+    cores = os.cpu_count() or 1
+    n_sample, iters = args.cpu_sample, 1
+    vals = []
+    for _ in range(args.warmup_cpu):
+        cpu_sample(n_sample, iters, cores)
+    t_all = 0.0
+    for _ in range(args.steps_cpu):
+        v, steps, busy, wall = cpu_sample(n_sample, iters, cores)
+        vals.append(v)
+        t_all += busy
+    value = float(np.mean(vals))
+    sample = ("%d independent seeds x %d molecules x %d iteration(s) of the same reactive-box "
+              "chemistry and density, default 0.5 um subpartitions, sequential reference semantics" % (cores, n_sample, iters))
+    line = {
+        "impl": "reference", "metric": "molecule_steps_per_sec", "value": value, "unit": "molecule-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps_cpu, "warmup": args.warmup_cpu,
+        "ms_per_step": 1e3 * t_all / max(1, args.steps_cpu), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "reactive box, 4 species / 6 reactions, 125 molecules/um^3 (BASELINE configs[4])",
+                   "molecules": args.molecules, "cpu_sample_molecules_per_core": n_sample},
+        "cpu_baseline": {"value": value, "unit": "molecule-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "molecule-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "mcell4-equivalent CPU oracle (oracle/), not the upstream binary: the reference cannot be built here",
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libmcx has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from mcell_b200 import Engine, build as mb
+    if rank == 0:
+        mb.build()
+    if dist:
+        dist.barrier()
+
+    n_total = args.molecules
+    t, edge_um = build_model(n_total, seed=1, rank=rank, world=world)
+    t.cfg.device = local_rank
+    mols = make_molecules(n_total, edge_um, t.length_unit, 1, rank, world)
+    eng = Engine(t)
+    if world > 1:
+        import ctypes
+        from mcell_b200 import comm as mcomm
+        uid = mcomm.unique_id() if rank == 0 else bytes(128)
+        buf = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
+        dist.broadcast(buf, 0)
+        eng.comm_init(bytes(buf.cpu().tolist()))
+    eng.upload(mols)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing: inputs already in HBM
+    eng.set_profiling(True)
+    sync_all()
+    if args.warmup:
+        eng.step(args.warmup)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sync_all()
+    st = eng.step(args.steps)
+    sync_all()
+    ms = torch.tensor([st.device_ms], dtype=torch.float64, device="cuda")
+    steps_done = torch.tensor([float(st.molecule_steps)], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(steps_done, op=dist.ReduceOp.SUM)
+    ms_total = float(ms.item())
+    mol_steps = float(steps_done.item())
+    value = mol_steps / (ms_total * 1e-3)
+    launches = int(st.kernel_launches)
+    prof_it = max(1, int(st.profiled_iterations))
+    diffuse_ms = st.ms_diffuse / prof_it
+    mol_per_launch = float(st.molecule_steps) / max(1, args.steps)
+    peak, peak_src = _peaks()
+    achieved = mol_per_launch * B_ALG_DIFFUSE / (diffuse_ms * 1e-3) / 1e9 if diffuse_ms > 0 else 0.0
+
+    # ---- end to end through the C ABI with HOST buffers: upload -> ITERS_PER_CALL iterations -> download
+    eng.set_profiling(False)
+    e2e_steps = 0.0
+    cap = int(t.cfg.max_molecules)
+    from mcell_b200.model import MolArrays
+    out = MolArrays(0)
+    out.x, out.y, out.z = _pinned_alloc(cap, np.float64), _pinned_alloc(cap, np.float64), _pinned_alloc(cap, np.float64)
+    out.id, out.species, out.flags = _pinned_alloc(cap, np.uint32), _pinned_alloc(cap, np.uint32), _pinned_alloc(cap, np.uint32)
+    out.diffusion_time, out.unimol_rxn_time = _pinned_alloc(cap, np.float64), _pinned_alloc(cap, np.float64)
+    out.n = cap
+    cur = mols
+    h2d = d2h = 0
+    e2e_calls = max(1, args.e2e_calls)
+    eng.upload(cur)
+    eng.step(ITERS_PER_CALL)  # warm the path once
+    n_live = eng.download_into(out)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_calls):
+        src = _view(out, n_live)
+        eng.upload(src)
+        h2d += n_live * 52
+        s2 = eng.step(ITERS_PER_CALL)
+        e2e_steps += s2.molecule_steps
+        n_live = eng.download_into(out)
+        counts = eng.counts()
+        d2h += n_live * 52 + 8 * (len(counts[0]) + len(counts[1]))
+    sync_all()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    e2e_total = torch.tensor([e2e_steps], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.SUM)
+    e2e_value = float(e2e_total.item()) / float(dt.item())
+    clocks = sampler.result()
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle_py as O
+            O.build()
+            cores = os.cpu_count() or 1
+            v, steps, busy, wall = cpu_sample(args.cpu_sample, 1, cores)
+            cpu = {"value": v, "unit": "molecule-steps/s", "cores": cores, "kind": "port",
+                   "sample": "%d independent seeds x %d molecules x 1 iteration (2x2x2 full default subpartitions), same chemistry/density, "
+                             "sequential reference semantics, %.1f s of CPU work per core" % (cores, args.cpu_sample, busy)}
+        line = {
+            "metric": "molecule_steps_per_sec", "value": value, "unit": "molecule-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / max(1, args.steps),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "reactive box, 4 species / 6 reactions, 125 molecules/um^3 (BASELINE configs[4])",
+                       "molecules": n_total, "box_edge_um": edge_um, "iterations_per_plugin_call": ITERS_PER_CALL,
+                       "l2": "inputs (>=3 GB at 1e8 molecules) larger than L2; no flush",
+                       "parallelism": "z-slabs x%d" % world, "rng": "philox4x32-10 per molecule"},
+            "roofline": {"bound": "hbm", "kernel": "k_diffuse", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_per_molecule": B_ALG_DIFFUSE, "kernel_ms": diffuse_ms,
+                         "kernel_share_of_step": diffuse_ms / (ms_total / max(1, args.steps)),
+                         "whole_step_frac_at_160B": value / world * B_ALG_STEP / 1e9 / peak,
+                         "ms_resolve": st.ms_resolve / prof_it, "ms_sort": st.ms_sort / prof_it},
+            "e2e": {"value": e2e_value, "unit": "molecule-steps/s", "h2d_bytes_per_step": h2d / e2e_calls,
+                    "d2h_bytes_per_step": d2h / e2e_calls, "iterations_per_call": ITERS_PER_CALL},
+            "gpu_launches": launches, "clocks": clocks,
+            "stats": {k: int(getattr(st, k)) for k in ("bimol_rxns", "unimol_rxns", "vol_mol_vol_mol_collisions",
+                                                        "mol_wall_reflections", "resolve_retries", "unresolved_conflicts", "n_live")},
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _view(m, n):
+    from mcell_b200.model import MolArrays
+    v = MolArrays(0)
+    for k in ("x", "y", "z", "id", "species", "flags", "diffusion_time", "unimol_rxn_time"):
+        setattr(v, k, getattr(m, k)[:n])
+    v.n = n
+    return v
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--molecules", type=int, default=100_000_000)
+    ap.add_argument("--e2e-calls", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=125_000, help="molecules per CPU core in the bounded CPU sample")
+    ap.add_argument("--steps-cpu", type=int, default=2)
+    ap.add_argument("--warmup-cpu", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,7 +144,12 @@ typedef struct mcx_step_stats {
   uint64_t resolve_retries;        /* molecules re-evaluated after losing a reaction conflict */
   uint64_t unresolved_conflicts;   /* proposals dropped after max_resolve_rounds */
   uint64_t products_created;
+  uint64_t kernel_launches;        /* libmcx kernels launched by this call */
   double   device_ms;              /* CUDA-event time of the iteration loop */
+  double   ms_diffuse;             /* with mcx_set_profiling: summed CUDA-event time of the diffuse kernel */
+  double   ms_resolve;             /*   ... of the conflict-resolution rounds */
+  double   ms_sort;                /*   ... of histogram scan + scatter */
+  uint64_t profiled_iterations;    /*   iterations covered by the three sums above */
 } mcx_step_stats;
 
 /* ---- replay trace (kernel-level parity; mirrors the reference's DEBUG_* dumps,
@@ -227,6 +232,9 @@ int mcx_replay_step(mcx_handle* h, const uint32_t* words, uint64_t n_words,
 /* Like mcx_step for one iteration with the Philox streams, but also returns the trace. */
 int mcx_trace_step(mcx_handle* h, uint64_t n_ids, mcx_trace_rec* trace_out,
                    mcx_step_stats* stats_out);
+
+/* Per-kernel CUDA-event timing inside mcx_step (events on the launching stream). Off by default. */
+int mcx_set_profiling(mcx_handle* h, int enabled);
 
 /* ---- observables ---------------------------------------------------------------------- */
 /* Replaces: MolOrRxnCountEvent::compute_counts world-count fast path

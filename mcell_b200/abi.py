@@ -66,7 +66,9 @@ class mcx_step_stats(C.Structure):
         "iterations", "molecule_steps", "n_live", "ray_polygon_tests", "ray_polygon_colls",
         "mol_wall_reflections", "mol_wall_transparent", "mol_wall_absorptions",
         "vol_mol_vol_mol_collisions", "bimol_rxns", "unimol_rxns", "wall_redos",
-        "resolve_retries", "unresolved_conflicts", "products_created")] + [("device_ms", c_f64)]
+        "resolve_retries", "unresolved_conflicts", "products_created", "kernel_launches")] + [("device_ms", c_f64), ("ms_diffuse", c_f64),
+                                                    ("ms_resolve", c_f64), ("ms_sort", c_f64),
+                                                    ("profiled_iterations", c_u64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -96,7 +98,7 @@ EXPORTED_SYMBOLS = [
     "mcx_create", "mcx_destroy", "mcx_last_error", "mcx_abi_version", "mcx_set_geometry",
     "mcx_set_species", "mcx_set_reactions", "mcx_set_surface_classes", "mcx_upload_molecules",
     "mcx_download_molecules", "mcx_num_molecules", "mcx_step", "mcx_replay_step", "mcx_trace_step",
-    "mcx_counts", "mcx_comm_init", "mcx_philox_block",
+    "mcx_counts", "mcx_comm_init", "mcx_philox_block", "mcx_set_profiling",
 ]
 
 

@@ -44,6 +44,11 @@ struct mcx_handle {
        *d_surf = nullptr, *d_walls = nullptr, *d_tri = nullptr, *d_verts = nullptr, *d_wclass = nullptr,
        *d_spw_start = nullptr, *d_spw_list = nullptr;
   McxComm* comm = nullptr;
+  double *st_x = nullptr, *st_y = nullptr, *st_z = nullptr, *st_ts = nullptr, *st_tu = nullptr;
+  uint32_t *st_id = nullptr, *st_sp = nullptr, *st_fl = nullptr;
+  unsigned long long launches = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
 };
 
 #define CK(call)                                                                        \
@@ -174,6 +179,7 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   if (dev_replace(h, &h->d_spw_start, zero_start.data(), zero_start.size())) return fail(MCX_ERR_CUDA);
   p.spw_start = (const uint32_t*)h->d_spw_start;
   h->plan.sm_count = h->sm_count;
+  h->plan.launches = &h->launches;
   *out = h;
   return MCX_OK;
 }
@@ -182,6 +188,7 @@ void mcx_destroy(mcx_handle* h) {
   if (!h) return;
   if (h->comm) mcx_comm_destroy(h->comm);
   for (void* a : h->allocs) cudaFree(a);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -351,54 +358,48 @@ static int check_device_error(mcx_handle* h, Counters* host_ctr) {
   return MCX_OK;
 }
 
+// staging SoA on the device (allocated once, sized by capacity): the ABI boundary is SoA, HBM is records
+static int ensure_staging(mcx_handle* h) {
+  if (h->st_x) return MCX_OK;
+  const size_t cap = h->p.capacity;
+  int rc = MCX_OK;
+  rc |= dev_alloc(h, &h->st_x, cap); rc |= dev_alloc(h, &h->st_y, cap); rc |= dev_alloc(h, &h->st_z, cap);
+  rc |= dev_alloc(h, &h->st_ts, cap); rc |= dev_alloc(h, &h->st_tu, cap);
+  rc |= dev_alloc(h, &h->st_id, cap); rc |= dev_alloc(h, &h->st_sp, cap); rc |= dev_alloc(h, &h->st_fl, cap);
+  return rc ? MCX_ERR_CUDA : MCX_OK;
+}
+
 int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
   if (!h || !m) return MCX_ERR_INVALID_ARG;
   if (!h->has_species) { h->err = "species table missing"; return MCX_ERR_STATE; }
   if (m->n > h->p.capacity) { h->err = "more molecules than max_molecules"; return MCX_ERR_CAPACITY; }
   if (m->n && (!m->x || !m->y || !m->z || !m->id || !m->species)) { h->err = "null molecule arrays"; return MCX_ERR_INVALID_ARG; }
   CK(cudaSetDevice(h->cfg.device));
+  if (ensure_staging(h)) return MCX_ERR_CUDA;
   const size_t n = m->n;
-  // stage through scratch device arrays carved from buffers that are idle during upload:
-  // prop_t (8B), claim (8B), tschedA (8B), tuniA (8B), tschedB/tuniB are targets -> use separate scratch
-  double *dx = nullptr, *dy = nullptr, *dz = nullptr, *dts = nullptr, *dtu = nullptr;
-  uint32_t *did = nullptr, *dsp = nullptr, *dfl = nullptr;
-  auto tmp = [&](void** q, size_t bytes) { return cudaMalloc(q, std::max<size_t>(bytes, 8)); };
-  CK(tmp((void**)&dx, n * 8)); CK(tmp((void**)&dy, n * 8)); CK(tmp((void**)&dz, n * 8));
-  CK(tmp((void**)&did, n * 4)); CK(tmp((void**)&dsp, n * 4));
-  if (m->flags) CK(tmp((void**)&dfl, n * 4));
-  if (m->diffusion_time) CK(tmp((void**)&dts, n * 8));
-  if (m->unimol_rxn_time) CK(tmp((void**)&dtu, n * 8));
-  uint32_t max_id = 0;
-  for (size_t i = 0; i < n; i++) {
-    max_id = std::max(max_id, m->id[i]);
-    if (m->species[i] >= h->species.size()) { h->err = "molecule references an unknown species"; return MCX_ERR_INVALID_ARG; }
-  }
   cudaStream_t s = h->stream;
-  CK(cudaMemcpyAsync(dx, m->x, n * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(dy, m->y, n * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(dz, m->z, n * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(did, m->id, n * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(dsp, m->species, n * 4, cudaMemcpyHostToDevice, s));
-  if (dfl) CK(cudaMemcpyAsync(dfl, m->flags, n * 4, cudaMemcpyHostToDevice, s));
-  if (dts) CK(cudaMemcpyAsync(dts, m->diffusion_time, n * 8, cudaMemcpyHostToDevice, s));
-  if (dtu) CK(cudaMemcpyAsync(dtu, m->unimol_rxn_time, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->st_x, m->x, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->st_y, m->y, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->st_z, m->z, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->st_id, m->id, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->st_sp, m->species, n * 4, cudaMemcpyHostToDevice, s));
+  if (m->flags) CK(cudaMemcpyAsync(h->st_fl, m->flags, n * 4, cudaMemcpyHostToDevice, s));
+  if (m->diffusion_time) CK(cudaMemcpyAsync(h->st_ts, m->diffusion_time, n * 8, cudaMemcpyHostToDevice, s));
+  if (m->unimol_rxn_time) CK(cudaMemcpyAsync(h->st_tu, m->unimol_rxn_time, n * 8, cudaMemcpyHostToDevice, s));
   Counters zero;
   memset(&zero, 0, sizeof(zero));
   zero.n_slots = (unsigned int)n;
-  zero.next_id = n ? max_id + 1 : 0;
   CK(cudaMemcpyAsync(h->p.ctr, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
   bind_iteration(h);
   mcx_set_scan_scratch(h->scan_sums);
-  mcx_launch_pack_soa(h->p, dx, dy, dz, did, dsp, dfl, dts, dtu, (unsigned int)n, s);
+  mcx_launch_pack_soa(h->p, h->st_x, h->st_y, h->st_z, h->st_id, h->st_sp, m->flags ? h->st_fl : nullptr,
+                      m->diffusion_time ? h->st_ts : nullptr, m->unimol_rxn_time ? h->st_tu : nullptr, (unsigned int)n, s);
+  h->launches += 1;
   mcx_launch_initial_sort(h->p, h->plan, s);
   h->cs_cur ^= 1;
   Counters hc;
   int rc = check_device_error(h, &hc);
-  cudaFree(dx); cudaFree(dy); cudaFree(dz); cudaFree(did); cudaFree(dsp);
-  if (dfl) cudaFree(dfl);
-  if (dts) cudaFree(dts);
-  if (dtu) cudaFree(dtu);
-  if (rc) return rc;
+  if (rc) { if (rc == MCX_ERR_INVALID_ARG) h->err += " (unknown species)"; return rc; }
   CK(cudaGetLastError());
   h->uploaded = true;
   return MCX_OK;
@@ -418,34 +419,26 @@ int mcx_download_molecules(mcx_handle* h, mcx_mol_soa* out, uint64_t capacity) {
   if (!h || !out) return MCX_ERR_INVALID_ARG;
   if (!h->uploaded) { h->err = "nothing uploaded"; return MCX_ERR_STATE; }
   CK(cudaSetDevice(h->cfg.device));
-  Counters hc;
-  CK(cudaMemcpy(&hc, h->p.ctr, sizeof(hc), cudaMemcpyDeviceToHost));
-  const size_t n = hc.n_slots;
-  double *dx, *dy, *dz, *dts, *dtu; uint32_t *did, *dsp, *dfl;
-  auto tmp = [&](void** q, size_t bytes) { return cudaMalloc(q, std::max<size_t>(bytes, 8)); };
-  CK(tmp((void**)&dx, n * 8)); CK(tmp((void**)&dy, n * 8)); CK(tmp((void**)&dz, n * 8));
-  CK(tmp((void**)&dts, n * 8)); CK(tmp((void**)&dtu, n * 8));
-  CK(tmp((void**)&did, n * 4)); CK(tmp((void**)&dsp, n * 4)); CK(tmp((void**)&dfl, n * 4));
+  if (ensure_staging(h)) return MCX_ERR_CUDA;
+  cudaStream_t s = h->stream;
   bind_iteration(h);
-  mcx_launch_unpack_soa(h->p, dx, dy, dz, did, dsp, dfl, dts, dtu, h->d_n_out, h->stream);
+  mcx_launch_unpack_soa(h->p, h->st_x, h->st_y, h->st_z, h->st_id, h->st_sp, h->st_fl, h->st_ts, h->st_tu, h->d_n_out, s);
+  h->launches += 1;
   unsigned int live = 0;
-  CK(cudaMemcpyAsync(&live, h->d_n_out, 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  int rc = MCX_OK;
-  if (live > capacity) { h->err = "download capacity too small"; rc = MCX_ERR_CAPACITY; }
-  else {
-    CK(cudaMemcpy(out->x, dx, live * 8ull, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out->y, dy, live * 8ull, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out->z, dz, live * 8ull, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out->id, did, live * 4ull, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out->species, dsp, live * 4ull, cudaMemcpyDeviceToHost));
-    if (out->flags) CK(cudaMemcpy(out->flags, dfl, live * 4ull, cudaMemcpyDeviceToHost));
-    if (out->diffusion_time) CK(cudaMemcpy(out->diffusion_time, dts, live * 8ull, cudaMemcpyDeviceToHost));
-    if (out->unimol_rxn_time) CK(cudaMemcpy(out->unimol_rxn_time, dtu, live * 8ull, cudaMemcpyDeviceToHost));
-    out->n = live;
-  }
-  cudaFree(dx); cudaFree(dy); cudaFree(dz); cudaFree(dts); cudaFree(dtu); cudaFree(did); cudaFree(dsp); cudaFree(dfl);
-  return rc;
+  CK(cudaMemcpyAsync(&live, h->d_n_out, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (live > capacity) { h->err = "download capacity too small"; return MCX_ERR_CAPACITY; }
+  CK(cudaMemcpyAsync(out->x, h->st_x, live * 8ull, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->y, h->st_y, live * 8ull, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->z, h->st_z, live * 8ull, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->id, h->st_id, live * 4ull, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out->species, h->st_sp, live * 4ull, cudaMemcpyDeviceToHost, s));
+  if (out->flags) CK(cudaMemcpyAsync(out->flags, h->st_fl, live * 4ull, cudaMemcpyDeviceToHost, s));
+  if (out->diffusion_time) CK(cudaMemcpyAsync(out->diffusion_time, h->st_ts, live * 8ull, cudaMemcpyDeviceToHost, s));
+  if (out->unimol_rxn_time) CK(cudaMemcpyAsync(out->unimol_rxn_time, h->st_tu, live * 8ull, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  out->n = live;
+  return MCX_OK;
 }
 
 static void fill_stats(const Counters& a, const Counters& b, uint64_t iters, float ms, size_t ns, mcx_step_stats* s) {
@@ -472,13 +465,21 @@ static void fill_stats(const Counters& a, const Counters& b, uint64_t iters, flo
 static int run_iterations(mcx_handle* h, uint32_t n_iterations, mcx_step_stats* stats_out) {
   if (!h->uploaded) { h->err = "mcx_upload_molecules must precede stepping"; return MCX_ERR_STATE; }
   CK(cudaSetDevice(h->cfg.device));
+  const unsigned long long launches_before = h->launches;
   Counters before;
   CK(cudaMemcpyAsync(&before, h->p.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   mcx_set_scan_scratch(h->scan_sums);
   CK(cudaEventRecord(h->ev0, h->stream));
+  const uint32_t n_prof = h->profiling ? std::min<uint32_t>(n_iterations, 256) : 0;
+  if (h->prof_events.size() < 4ull * n_prof) {
+    size_t old = h->prof_events.size();
+    h->prof_events.resize(4ull * n_prof);
+    for (size_t q = old; q < h->prof_events.size(); q++) CK(cudaEventCreate(&h->prof_events[q]));
+  }
   for (uint32_t k = 0; k < n_iterations; k++) {
     bind_iteration(h);
+    h->plan.prof = k < n_prof ? &h->prof_events[4ull * k] : nullptr;
     if (h->comm) {
       int rc = mcx_comm_iteration(h->comm, h->p, h->plan, h->stream);
       if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
@@ -495,6 +496,17 @@ static int run_iterations(mcx_handle* h, uint32_t n_iterations, mcx_step_stats* 
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   fill_stats(before, after, n_iterations, ms, h->species.size(), stats_out);
+  h->plan.prof = nullptr;
+  if (stats_out) {
+    stats_out->kernel_launches = h->launches - launches_before;
+    for (uint32_t k = 0; k < n_prof && rc == MCX_OK; k++) {
+      float a = 0, b = 0, c = 0;
+      cudaEvent_t* e = &h->prof_events[4ull * k];
+      cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]);
+      stats_out->ms_diffuse += a; stats_out->ms_resolve += b; stats_out->ms_sort += c;
+    }
+    stats_out->profiled_iterations = n_prof;
+  }
   return rc;
 }
 
@@ -567,6 +579,12 @@ int mcx_comm_init(mcx_handle* h, const void* nccl_unique_id, uint32_t id_bytes) 
   std::string err;
   h->comm = mcx_comm_create(nccl_unique_id, id_bytes, h->cfg.rank, h->cfg.world_size, h->p, err);
   if (!h->comm) { h->err = err; return MCX_ERR_COMM; }
+  return MCX_OK;
+}
+
+int mcx_set_profiling(mcx_handle* h, int enabled) {
+  if (!h) return MCX_ERR_INVALID_ARG;
+  h->profiling = enabled != 0;
   return MCX_OK;
 }
 

@@ -109,6 +109,8 @@ struct DevParams {
 // kernels / launchers implemented in mcx_kernels.cu
 struct StepPlan {
   int sm_count;
+  unsigned long long* launches;  // host-side counter of kernels launched (may be null)
+  cudaEvent_t* prof;             // 4 events for this iteration (null = no per-kernel timing)
   bool has_claims;   // model can produce reactions / absorptions (conflict rounds needed)
   bool trace;
 };

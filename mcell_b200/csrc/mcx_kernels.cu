@@ -376,6 +376,8 @@ __global__ void __launch_bounds__(TPB) k_pack_soa(const __grid_constant__ DevPar
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t hf = flags ? flags[i] : 0;
     uint32_t sf = species[i] & SF_SPECIES_MASK;
+    if (species[i] >= (uint32_t)p.n_species) raise_error(p, MCX_ERR_INVALID_ARG, id[i]);
+    atomicMax(&p.ctr->next_id, id[i] + 1u);
     if (hf & MCX_MOL_DEFUNCT) sf |= DF_DEAD;
     if (hf & MCX_MOL_SCHEDULE_UNIMOL) sf |= DF_SCHED_UNIMOL;
     if ((hf & MCX_MOL_PARTIAL) && tsched) { sf |= DF_PARTIAL; p.tschedB[i] = tsched[i]; }
@@ -402,7 +404,10 @@ __global__ void __launch_bounds__(TPB) k_unpack_soa(const __grid_constant__ DevP
 }
 
 // ---- launchers -----------------------------------------------------------------------------------------------
+static inline void count_launches(const StepPlan& plan, unsigned int n) { if (plan.launches) *plan.launches += n; }
+
 static void launch_sort(const DevParams& p, const StepPlan& plan, unsigned int* scan_sums, cudaStream_t s) {
+  count_launches(plan, 5);
   const unsigned int n = p.n_cells + 1;  // last entry receives the total
   const unsigned int nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
   k_scan_reduce<<<nblocks, SCAN_TPB, 0, s>>>(p.cs_next, n, scan_sums);
@@ -418,8 +423,12 @@ void mcx_set_scan_scratch(unsigned int* ptr) { g_scan_sums = ptr; }
 
 void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
   cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
+  if (plan.prof) cudaEventRecord(plan.prof[0], s);
   k_diffuse<<<plan.sm_count * 8, TPB, 0, s>>>(p);
+  if (plan.prof) cudaEventRecord(plan.prof[1], s);
+  count_launches(plan, 1);
   if (plan.has_claims) {
+    count_launches(plan, 4 * p.max_rounds);
     const int small_grid = plan.sm_count * 2;
     for (unsigned int r = 0; r < p.max_rounds; r++) {
       k_round_begin<<<1, 1, 0, s>>>(p, r);
@@ -428,12 +437,15 @@ void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t
       k_retry<<<small_grid, TPB, 0, s>>>(p, r, r + 1 == p.max_rounds ? 1 : 0);
     }
   }
+  if (plan.prof) cudaEventRecord(plan.prof[2], s);
   launch_sort(p, plan, g_scan_sums, s);
+  if (plan.prof) cudaEventRecord(plan.prof[3], s);
 }
 
 void mcx_launch_initial_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
   cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
   k_bin_initial<<<plan.sm_count * 8, TPB, 0, s>>>(p);
+  count_launches(plan, 1);
   launch_sort(p, plan, g_scan_sums, s);
 }
 
