@@ -1,0 +1,189 @@
+"""CPU tier: the oracle (restatement of the reference algorithm) against analytic expectations and structural
+identities (the reference tree holds no golden vectors for the geometry/collision/reaction path),
+and the oracle's two execution modes against each other."""
+import math
+
+import numpy as np
+import pytest
+
+import common as cm
+from mcell_b200 import abi
+from mcell_b200.model import N_AV
+from oracle import oracle_py as O
+
+
+def test_wall_constants_of_a_box():
+    t, _ = cm.free_diffusion_box(n=10)
+    o = O.Oracle(t)
+    for wi in range(12):
+        c = o.wall_constants(wi)
+        n, d, u, v = c[0:3], c[3], c[4:7], c[7:10]
+        assert np.linalg.norm(n) == pytest.approx(1.0, abs=1e-14)
+        assert sorted(np.abs(n)) == pytest.approx([0, 0, 1], abs=1e-14)     # axis-aligned faces
+        assert abs(d) == pytest.approx(50.0, abs=1e-12)
+        assert d > 0                                                         # outward normals (create_box order)
+        assert abs(np.dot(u, v)) < 1e-14 and abs(np.dot(u, n)) < 1e-14
+        assert np.allclose(np.cross(n, u), v, atol=1e-14)
+        assert c[13] == pytest.approx(0.5 * 100 * 100)                       # area
+
+
+def test_walls_per_subpart_of_a_box():
+    """Config 1: the 1 um cube fills 2x2x2 default subpartitions; its faces lie exactly on subpartition
+    boundaries, so with the leeway of wall_subparts_collision_test (geometry_utils.inl:110-207) the walls are also
+    registered in the touching outer layer: 4x4x4 subpartitions hold walls."""
+    t, _ = cm.free_diffusion_box(n=10)
+    o = O.Oracle(t)
+    n = t.cfg.num_subparts_per_edge
+    occupied = {}
+    for s in range(n ** 3):
+        w = o.subpart_walls(s)
+        if len(w):
+            occupied[s] = w
+    assert len(occupied) == 64
+    for s, w in occupied.items():
+        x, y, z = s % n, (s // n) % n, s // (n * n)
+        assert 8 <= x <= 11 and 8 <= y <= 11 and 8 <= z <= 11
+        if x in (9, 10) and y in (9, 10) and z in (9, 10):
+            assert 3 <= len(w) <= 6                                          # the three faces of a corner octant
+        assert (np.diff(w.astype(int)) > 0).all()                            # ascending (uint_set order)
+    allw = np.unique(np.concatenate(list(occupied.values())))
+    assert (allw == np.arange(12)).all()
+
+
+def test_free_diffusion_msd_and_containment():
+    n = 40000
+    t, mols = cm.free_diffusion_box(n=n, seed=5)
+    o = O.Oracle(t)
+    o.upload(mols)
+    before = mols.sorted_by_id()
+    st = o.step(1, 0)
+    assert st.molecule_steps == n
+    after = o.download().sorted_by_id()
+    d2 = (after.x - before.x) ** 2 + (after.y - before.y) ** 2 + (after.z - before.z) ** 2
+    inner = (np.abs(before.x) < 30) & (np.abs(before.y) < 30) & (np.abs(before.z) < 30)
+    expect = 1.5 * t.species[0].space_step ** 2                              # 3*space_step^2/2 = 6 D dt
+    assert abs(d2[inner].mean() - expect) < 5 * expect * math.sqrt(2.0 / 3.0 / inner.sum())
+    st = o.step(60, 0)
+    assert st.mol_wall_reflections > 1000
+    a = o.download()
+    assert a.n == n
+    for k in ("x", "y", "z"):
+        v = getattr(a, k)
+        assert v.min() >= -50 and v.max() <= 50
+        h, _ = np.histogram(v, bins=10, range=(-50, 50))
+        assert np.all(np.abs(h - n / 10) < 6 * math.sqrt(n / 10))
+
+
+def test_snapshot_replay_of_the_sequential_tape_is_identical_without_reactions():
+    """Without reactions a molecule's outcome depends only on its own random words: the sequential mode
+    (ONE global ISAAC64 stream, reference semantics) and the snapshot mode replaying each molecule's slice
+    of that stream must agree bit for bit."""
+    n = 6000
+    t, mols = cm.free_diffusion_box(n=n, rng_mode=abi.MCX_RNG_TAPE, seed=2)
+    a, b = O.Oracle(t), O.Oracle(t)
+    a.upload(mols); b.upload(mols)
+    for _ in range(3):
+        tr_a, st_a = a.trace_step(0, n)
+        words, off, ln = a.tape(n)
+        tr_b, st_b = b.trace_step(2, n, words, off)
+        assert not cm.compare_traces(tr_a, tr_b, np.arange(n))
+        assert (tr_b["n_words"] == ln).all()
+        assert st_a.mol_wall_reflections == st_b.mol_wall_reflections
+    x, y = a.download().sorted_by_id(), b.download().sorted_by_id()
+    assert (x.x == y.x).all() and (x.y == y.y).all() and (x.z == y.z).all()
+
+
+def _mass_action_expected(t, n_a, n_b, edge_um, k):
+    v_litres = (edge_um * 1e-5) ** 3             # 1 um = 1e-5 dm; dm^3 = litre
+    return k * n_a * n_b / (N_AV * v_litres) * t.time_unit
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bimolecular_rate_matches_mass_action(mode):
+    """A + B -> C in a well-mixed reflective box: reactions per iteration = k [A][B] V dt (SURVEY §8c golden (2))."""
+    n, edge = 40000, 0.5
+    t, mols = cm.reactive_box(n=n, edge_um=edge, p_target=0.05, seed=9)
+    k = 0.05 / cm._pb_factor(_two_species_model(), 0, 1)
+    o = O.Oracle(t)
+    o.upload(mols)
+    got = expect = 0.0
+    for _ in range(6):
+        c, _r = o.counts()
+        expect += _mass_action_expected(t, float(c[0]), float(c[1]), edge, k)
+        st = o.step(1, mode)
+        got += st.bimol_rxns
+    assert got > 1500
+    assert abs(got - expect) < 4 * math.sqrt(expect) + 0.03 * expect, (got, expect)
+
+
+def _two_species_model():
+    from mcell_b200.model import Model, Config
+    m = Model(Config())
+    m.add_species("A", 1e-6); m.add_species("B", 1e-6)
+    return m
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_unimolecular_decay_is_exponential(mode):
+    from mcell_b200.model import Model, Config, MolArrays, create_box, release_uniform_box
+    m = Model(Config(seed=4))
+    m.add_species("C", 1e-6); m.add_species("A", 1e-6)
+    k = 5e4
+    m.add_reaction_rule(["C"], ["A"], k)
+    v, f = create_box(0.5)
+    m.add_geometry_object(v, f)
+    n = 30000
+    t = m.build(max_molecules=2 * n)
+    pos = release_uniform_box(np.random.default_rng(1), n, 0.5, t.length_unit, margin=1e-4)
+    mols = MolArrays.from_positions(pos, 0, schedule_unimol=True)
+    o = O.Oracle(t)
+    o.upload(mols)
+    iters = 10
+    o.step(iters, mode)
+    c, r = o.counts()
+    surv = n * math.exp(-k * t.time_unit * iters)
+    assert abs(c[0] - surv) < 5 * math.sqrt(n * (surv / n) * (1 - surv / n))
+    assert c[0] + c[1] == n and r[0] == c[1]
+
+
+def test_snapshot_and_sequential_semantics_agree_statistically():
+    """The parallel (snapshot + conflict rounds) semantics must not bias reaction counts against the
+    reference's sequential semantics: 3 sigma over seeds (north_star ensemble criterion, reduced size)."""
+    seq, snap = [], []
+    for seed in range(1, 9):
+        t, mols = cm.reactive_box(n=8000, edge_um=0.3, p_target=0.3, seed=seed)
+        for mode, acc in ((0, seq), (1, snap)):
+            o = O.Oracle(t)
+            o.upload(mols)
+            o.step(15, mode)
+            acc.append(float(o.counts()[0][2]))
+    seq, snap = np.array(seq), np.array(snap)
+    se = math.sqrt(seq.var(ddof=1) / len(seq) + snap.var(ddof=1) / len(snap))
+    assert abs(seq.mean() - snap.mean()) < 3 * se + 0.005 * seq.mean(), (seq.mean(), snap.mean(), se)
+
+
+def test_surface_classes_conserve_and_act():
+    n = 12000
+    t, mols = cm.sphere_classes(n=n, seed=3)
+    for mode in (0, 1):
+        o = O.Oracle(t)
+        o.upload(mols)
+        tot_abs = tot_tr = 0
+        for _ in range(12):
+            st = o.step(1, mode)
+            tot_abs += st.mol_wall_absorptions
+            tot_tr += st.mol_wall_transparent
+        c, _ = o.counts()
+        assert tot_abs > 30 and tot_tr > 60
+        assert c[0] == n // 2 - tot_abs       # only L is absorbed
+        assert c[1] == n // 2
+
+
+def test_conflict_rounds_resolve_everything_at_default_depth():
+    t, mols = cm.reactive_box(n=8000, edge_um=0.3, p_target=0.5, seed=3)
+    o = O.Oracle(t)
+    o.upload(mols)
+    st = o.step(3, 1)
+    assert st.bimol_rxns > 500 and st.resolve_retries > 0 and st.unresolved_conflicts == 0
+    c, r = o.counts()
+    assert c[0] + c[2] == 4000 and c[1] + c[2] == 4000 and r[0] == c[2]
