@@ -4,12 +4,20 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library; the product (libmcx.so) never does.
 //
-// PARITY STATUS: "parity unpinned" for the geometry/collision/reaction arithmetic — the
-// reference tree holds no golden vectors for this path and cannot be built here (SURVEY §0.4,
-// §8c).  What IS pinned: the RNG (ISAAC64 + Ziggurat) against the reference's own rng.c
-// compiled into oracle/_ref/librefrng.so and the known-answer vectors in tests/golden/.
-// Everything else is a line-by-line restatement of the cited reference functions plus analytic
-// checks (MSD, uniform density, mass action) in tests/.
+// PARITY STATUS: pinned at function level, unpinned at whole-step level.
+//   PINNED bit-for-bit against the reference's own compiled code (oracle/_ref, built by `make ref` from the
+//   sources where they lie; golden outputs committed in tests/golden/):
+//     * RNG: ISAAC64 + Ziggurat vs src/rng.c, src/isaac64.c           (tests/test_oracle_rng.py)
+//     * init_wall_constants, collide_wall incl. every REDO / jump_away_line path, collide_mol, wall_in_box,
+//       test_bimolecular, binary search of pathways, distinguishable, and the table builder's pb_factor vs
+//       MCell3's src/wall_util.c, react_cond.c, react_util.c, util.c — the originals MCell4's src4/*.inl
+//       functions were derived from and kept identical to (include/debug_config.h:36-37)
+//                                                                       (tests/test_oracle_vs_reference.py)
+//   UNPINNED: the composition of those functions into a whole diffuse_vol_molecule step (ray_trace_vol,
+//   subpartition DDA, collision ordering, rescheduling).  The reference tree holds no golden vectors for it and
+//   src4/ cannot be built here (absent libbng/nfsim/boost); it is a line-by-line restatement
+//   of the cited src4 functions, checked by analytic expectations (MSD, uniform density, mass action,
+//   exponential decay) in tests/test_oracle_physics.py.
 //
 // Absent third-party arithmetic: libbng (github.com/mcellteam/libbng, version unpinned —
 // consumed as sibling checkout, CMakeLists.txt:146-148).  Restated from MCell3 originals:
@@ -1405,5 +1413,74 @@ void orc_tape_gauss(const uint32_t* words, uint64_t n_words, double* out, long n
   WordSource s; s.kind = WordSource::TAPE; s.tape = words; s.tape_len = n_words;
   for (long i = 0; i < n; i++) out[i] = s.gauss();
   *used = s.used;
+}
+// ---- unit entry points: one reference function each, for pinning against oracle/_ref/libmcell3ref.so
+//      (the reference's own compiled arithmetic) in tests/test_oracle_vs_reference.py -------------------------
+static void unit_world(World& w, const double* v9) {
+  w.cfg = mcx_config{};
+  w.cfg.partition_edge_length = 1000; w.cfg.num_subparts_per_edge = 1;
+  w.n_sp = 1; w.sp_len = 1000; w.sp_rcp = 1e-3;
+  w.verts = {{v9[0], v9[1], v9[2]}, {v9[3], v9[4], v9[5]}, {v9[6], v9[7], v9[8]}};
+  w.walls.resize(1);
+  w.walls[0].vi[0] = 0; w.walls[0].vi[1] = 1; w.walls[0].vi[2] = 2;
+  w.walls[0].surf_class = MCX_NONE; w.walls[0].object = 0;
+  init_wall_constants(w, w.walls[0]);
+}
+void orc_unit_wall_constants(const double* v9, double* out16) {
+  World w; unit_world(w, v9);
+  const Wall& f = w.walls[0];
+  double t[16] = {f.normal.x, f.normal.y, f.normal.z, f.distance_to_origin, f.unit_u.x, f.unit_u.y, f.unit_u.z,
+                  f.unit_v.x, f.unit_v.y, f.unit_v.z, f.uv_vert1_u, f.uv_vert2_u, f.uv_vert2_v, f.area, 0, 0};
+  memcpy(out16, t, sizeof(t));
+}
+// returns the reference's codes: COLLIDE_REDO -1, COLLIDE_MISS 0, COLLIDE_FRONT 1, COLLIDE_BACK 2
+// (src/mcell_structs.h); words = the 32-bit words the RNG would deliver next
+int orc_unit_collide_wall(const double* point3, double* move3, const double* v9, const uint32_t* words,
+                          uint64_t n_words, double* t, double* hit3, long long* words_used) {
+  World w; unit_world(w, v9);
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  Eval E(w, rs);
+  V3 move = {move3[0], move3[1], move3[2]}, hit = {0, 0, 0};
+  double tt = 0;
+  int r = E.collide_wall(V3{point3[0], point3[1], point3[2]}, 0, move, tt, hit);
+  move3[0] = move.x; move3[1] = move.y; move3[2] = move.z;
+  *t = tt; hit3[0] = hit.x; hit3[1] = hit.y; hit3[2] = hit.z;
+  *words_used = rs.used;
+  return r == WALL_MISS ? 0 : r == WALL_FRONT ? 1 : r == WALL_BACK ? 2 : -1;
+}
+// returns COLLIDE_VOL_M (3) on hit, COLLIDE_MISS (0) otherwise
+int orc_unit_collide_mol(const double* point3, const double* move3, const double* target3, double R, double* t,
+                         double* hit3) {
+  World w; w.cfg = mcx_config{};
+  WordSource rs; Eval E(w, rs);
+  Mol c{}; c.pos = {target3[0], target3[1], target3[2]}; c.id = 1;
+  V3 cp = {0, 0, 0}; double tt = 0;
+  bool hit = E.collide_mol(V3{point3[0], point3[1], point3[2]}, 0, V3{move3[0], move3[1], move3[2]}, c, R, tt, cp);
+  *t = tt; hit3[0] = cp.x; hit3[1] = cp.y; hit3[2] = cp.z;
+  return hit ? 3 : 0;
+}
+int orc_unit_wall_in_box(const double* v9, const double* llf3, const double* urb3) {
+  World w; unit_world(w, v9);
+  return wall_in_box(w, w.walls[0], V3{llf3[0], llf3[1], llf3[2]}, V3{urb3[0], urb3[1], urb3[2]}) != 0 ? 1 : 0;
+}
+int orc_unit_distinguishable(double a, double b, double eps) { return distinguishable(a, b, eps) ? 1 : 0; }
+// returns the pathway index or -1 (no reaction)
+int orc_unit_test_bimolecular(const double* cum_probs, int n, double scaling, const uint32_t* words, uint64_t n_words,
+                              long long* words_used) {
+  World w; w.cfg = mcx_config{};
+  w.pathways.resize(n);
+  for (int i = 0; i < n; i++) { w.pathways[i] = mcx_pathway{}; w.pathways[i].cum_prob = cum_probs[i]; }
+  mcx_rxn_class rc{}; rc.kind = MCX_RXN_BIMOL_VOLVOL; rc.first_pathway = 0; rc.n_pathways = n; rc.max_fixed_p = cum_probs[n - 1];
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  Eval E(w, rs);
+  int r = E.test_bimolecular(rc, scaling);
+  *words_used = rs.used;
+  return r;
+}
+int orc_unit_pathway_for_probability(const double* cum_probs, int n, double match) {
+  World w; w.pathways.resize(n);
+  for (int i = 0; i < n; i++) { w.pathways[i] = mcx_pathway{}; w.pathways[i].cum_prob = cum_probs[i]; }
+  mcx_rxn_class rc{}; rc.first_pathway = 0; rc.n_pathways = n;
+  return pathway_for_probability(w, rc, match);
 }
 }

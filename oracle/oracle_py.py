@@ -168,3 +168,35 @@ class Oracle:
         out = np.zeros(16)
         self.L.orc_wall_constants(self.h, C.c_uint32(wi), C.c_void_p(out.ctypes.data))
         return out
+
+
+def ref_mcell3_lib():
+    """The reference's own wall/collision/reaction arithmetic (MCell3 originals of the MCell4 hot-path
+    functions) compiled into oracle/_ref/libmcell3ref.so by `make -C oracle ref` (build container only;
+    the .so travels prebuilt to the GPU box)."""
+    path = os.path.join(_HERE, "_ref", "libmcell3ref.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref3_compute_pb_factor_volvol.restype = C.c_double
+    L.ref3_compute_pb_factor_volvol.argtypes = [C.c_double] * 8 + [C.c_int, C.c_int]
+    L.ref3_distinguishable.argtypes = [C.c_double, C.c_double, C.c_double]
+    L.ref3_collide_mol.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    L.ref3_collide_wall.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref3_test_bimolecular.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint, C.c_uint, C.c_void_p]
+    L.ref3_test_intersect.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint, C.c_uint, C.c_void_p]
+    L.ref3_binary_search_double.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double]
+    return L
+
+
+def unit_lib():
+    """Typed access to the oracle's single-function entry points (orc_unit_*)."""
+    L = lib()
+    L.orc_unit_collide_mol.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    L.orc_unit_collide_wall.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_unit_distinguishable.argtypes = [C.c_double, C.c_double, C.c_double]
+    L.orc_unit_test_bimolecular.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.orc_unit_pathway_for_probability.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.orc_unit_wall_in_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_unit_wall_constants.argtypes = [C.c_void_p, C.c_void_p]
+    return L

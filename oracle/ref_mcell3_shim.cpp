@@ -1,0 +1,154 @@
+// oracle/ref_mcell3_shim.cpp — oracle/_ref build only (TEST INFRASTRUCTURE).
+//
+// Thin extern "C" entry points around the REFERENCE's own arithmetic for the hot path, compiled from the
+// sources where they lie under /root/reference/src (MCell3 originals; MCell4's src4/*.inl versions were derived
+// from them and kept MCell3-identical, include/debug_config.h:36-37):
+//   init_tri_wall      src/wall_util.c:1214   (== Wall::initialize_wall_constants, src4/wall.cpp:281-342)
+//   collide_wall       src/wall_util.c:825    (== CollisionUtils::collide_wall, src4/collision_utils.inl:629-812)
+//   jump_away_line     src/wall_util.c:771    (== src4/collision_utils.inl:568-603)
+//   collide_mol        src/wall_util.c:967    (== src4/collision_utils.inl:464-515)
+//   wall_in_box        src/wall_util.c:1025   (== WallUtils::wall_in_box, src4/wall_utils.inl:326-504)
+//   test_bimolecular / test_intersect / binary_search_double / timeof_unimolecular   src/react_cond.c
+//   compute_pb_factor  src/react_util.c:45
+//   distinguishable    src/util.c:449
+// Nothing from the reference is copied into this repository: this file #includes the reference translation
+// unit at build time (wall_util.c must be included, not linked, because wall_in_box is static).
+// Unused reference functions are dropped by -ffunction-sections/--gc-sections, so their NFsim/MDL dependencies
+// never need to resolve.
+#include "wall_util.c"
+#include "react_util.h"
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+struct RefWall {
+  struct geom_object obj;
+  struct wall w;
+  struct vector3 v[3];
+  RefWall(const double* vv) {
+    memset(&obj, 0, sizeof(obj));
+    memset(&w, 0, sizeof(w));
+    for (int k = 0; k < 3; k++) { v[k].x = vv[3 * k]; v[k].y = vv[3 * k + 1]; v[k].z = vv[3 * k + 2]; }
+    obj.walls = &w;
+    obj.n_walls = 1;
+    init_tri_wall(&obj, 0, &v[0], &v[1], &v[2]);
+  }
+};
+void seed_rng(struct rng_state* r, unsigned seed, unsigned skip) {
+  rng_init(r, seed);
+  for (unsigned i = 0; i < skip; i++) (void)rng_uint(r);
+}
+}  // namespace
+
+EXPORT void ref3_init_tri_wall(const double* v9, double* out16) {
+  RefWall rw(v9);
+  const struct wall& w = rw.w;
+  double t[16] = {w.normal.x, w.normal.y, w.normal.z, w.d, w.unit_u.x, w.unit_u.y, w.unit_u.z,
+                  w.unit_v.x, w.unit_v.y, w.unit_v.z, w.uv_vert1_u, w.uv_vert2.u, w.uv_vert2.v, w.area, 0, 0};
+  memcpy(out16, t, sizeof(t));
+}
+
+// returns the reference's COLLIDE_REDO(-1)/MISS(0)/FRONT(1)/BACK(2) (src/mcell_structs.h:201-206); move is in/out
+EXPORT int ref3_collide_wall(const double* point3, double* move3, const double* v9, unsigned seed, unsigned skip,
+                             double* t, double* hit3, long long* rng_words_used) {
+  RefWall rw(v9);
+  struct rng_state rng;
+  seed_rng(&rng, seed, skip);
+  long long before = rng_uses(&rng);
+  struct notifications notify;
+  memset(&notify, 0, sizeof(notify));
+  long long tests = 0;
+  struct vector3 p = {point3[0], point3[1], point3[2]}, m = {move3[0], move3[1], move3[2]}, h = {0, 0, 0};
+  double tt = 0;
+  int r = collide_wall(&p, &m, &rw.w, &tt, &h, 1, &rng, &notify, &tests);
+  move3[0] = m.x; move3[1] = m.y; move3[2] = m.z;
+  *t = tt; hit3[0] = h.x; hit3[1] = h.y; hit3[2] = h.z;
+  *rng_words_used = rng_uses(&rng) - before;
+  return r;
+}
+
+EXPORT int ref3_collide_mol(const double* point3, const double* move3, const double* target3, double rx_radius_3d,
+                            double* t, double* hit3) {
+  struct species sp;
+  memset(&sp, 0, sizeof(sp));
+  struct volume_molecule vm;
+  memset(&vm, 0, sizeof(vm));
+  vm.properties = &sp;
+  vm.pos.x = target3[0]; vm.pos.y = target3[1]; vm.pos.z = target3[2];
+  struct vector3 p = {point3[0], point3[1], point3[2]}, m = {move3[0], move3[1], move3[2]}, h = {0, 0, 0};
+  double tt = 0;
+  int r = collide_mol(&p, &m, (struct abstract_molecule*)&vm, &tt, &h, rx_radius_3d);
+  *t = tt; hit3[0] = h.x; hit3[1] = h.y; hit3[2] = h.z;
+  return r;
+}
+
+EXPORT int ref3_wall_in_box(const double* v9, const double* llf3, const double* urb3) {
+  RefWall rw(v9);
+  struct vector3 b0 = {llf3[0], llf3[1], llf3[2]}, b1 = {urb3[0], urb3[1], urb3[2]};
+  return wall_in_box(rw.w.vert, &rw.w.normal, rw.w.d, &b0, &b1);
+}
+
+EXPORT int ref3_distinguishable(double a, double b, double eps) { return distinguishable(a, b, eps); }
+
+static void make_rxn(struct rxn* rx, double* cum_probs, int n) {
+  memset(rx, 0, sizeof(*rx));
+  rx->n_pathways = n;
+  rx->cum_probs = cum_probs;
+  rx->max_fixed_p = cum_probs[n - 1];
+  rx->min_noreaction_p = cum_probs[n - 1];
+}
+
+// returns RX_NO_RX (-2... see src/mcell_structs_shared.h) or the pathway index
+EXPORT int ref3_test_bimolecular(double* cum_probs, int n, double scaling, unsigned seed, unsigned skip,
+                                 long long* rng_words_used) {
+  struct rxn rx;
+  make_rxn(&rx, cum_probs, n);
+  struct rng_state rng;
+  seed_rng(&rng, seed, skip);
+  long long before = rng_uses(&rng);
+  int r = test_bimolecular(&rx, scaling, 0.0, NULL, NULL, &rng);
+  *rng_words_used = rng_uses(&rng) - before;
+  return r;
+}
+EXPORT int ref3_test_intersect(double* cum_probs, int n, double scaling, unsigned seed, unsigned skip,
+                               long long* rng_words_used) {
+  struct rxn rx;
+  make_rxn(&rx, cum_probs, n);
+  struct rng_state rng;
+  seed_rng(&rng, seed, skip);
+  long long before = rng_uses(&rng);
+  int r = test_intersect(&rx, scaling, &rng);
+  *rng_words_used = rng_uses(&rng) - before;
+  return r;
+}
+EXPORT int ref3_binary_search_double(double* A, double match, int max_idx, double mult) {
+  return binary_search_double(A, match, max_idx, mult);
+}
+EXPORT int ref3_rx_no_rx(void) { return RX_NO_RX; }
+
+// volume-volume pb_factor for two volume reactants with the given D (cm^2/s); returns pb_factor
+EXPORT double ref3_compute_pb_factor_volvol(double time_unit, double length_unit, double grid_density,
+                                            double rx_radius_3d, double space_step_a, double time_step_a,
+                                            double space_step_b, double time_step_b, int a_cant_initiate,
+                                            int b_cant_initiate) {
+  struct species sa, sb;
+  memset(&sa, 0, sizeof(sa)); memset(&sb, 0, sizeof(sb));
+  sa.space_step = space_step_a; sa.time_step = time_step_a; sa.D = 1;
+  sb.space_step = space_step_b; sb.time_step = time_step_b; sb.D = 1;
+  if (a_cant_initiate) sa.flags |= CANT_INITIATE;
+  if (b_cant_initiate) sb.flags |= CANT_INITIATE;
+  struct species* players[2] = {&sa, &sb};
+  short geom[2] = {0, 0};
+  struct rxn rx;
+  memset(&rx, 0, sizeof(rx));
+  rx.n_reactants = 2;
+  rx.players = players;
+  rx.geometries = geom;
+  rx.get_reactant_diffusion = rxn_get_standard_diffusion;
+  rx.get_reactant_time_step = rxn_get_standard_time_step;
+  rx.get_reactant_space_step = rxn_get_standard_space_step;
+  struct reaction_flags rf;
+  memset(&rf, 0, sizeof(rf));
+  int shared = 0;
+  return compute_pb_factor(time_unit, length_unit, grid_density, rx_radius_3d, &rf, &shared, &rx, 0);
+}
