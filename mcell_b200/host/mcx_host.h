@@ -1,0 +1,180 @@
+// mcx_host.h — C++ host side of libmcx: the reference-shaped adapter above the C ABI (include/mcx.h).
+//
+// It mirrors the part of MCell4's engine interface that DiffuseReactEvent lives behind, with the reference's
+// names, argument meaning and error behaviour, so that a maintainer can drop GpuDiffuseReactEvent into
+// World::init_simulation (src4/world.cpp:279-282) in place of DiffuseReactEvent:
+//
+//   MCell::BaseEvent                src4/base_event.h:63-139    (same virtuals, fields, type_index ordering)
+//   MCell::Molecule                 src4/molecule.h:52-260      (80-byte AoS record, flag values frozen :30-47)
+//   MCell::PartitionMolecules       src4/partition.h:648-666,1125-1143  (molecules vector + id->index map)
+//   MCell::GpuDiffuseReactEvent     src4/diffuse_react_event.h:108-154  (step, barrier contract, type_index 500)
+//
+// The adapter owns no arithmetic: it marshals AoS Molecule records <-> the ABI's SoA view and calls mcx_*.
+// The device owns the population between calls; the host vector is a cache with a dirty flag in each direction.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mcx.h"
+
+namespace MCell {
+
+typedef uint32_t molecule_id_t;
+typedef uint32_t species_id_t;
+typedef uint32_t subpart_index_t;
+typedef uint32_t wall_index_t;
+typedef uint32_t counted_volume_index_t;
+typedef uint16_t event_type_index_t;
+
+const double TIME_INVALID = -256;        // src4/defines.h:178
+const double TIME_FOREVER = 1e20;        // src4/defines.h:179
+const molecule_id_t MOLECULE_ID_INVALID = 0xFFFFFFFFu;
+const uint32_t INDEX_INVALID32 = 0xFFFFFFFFu;
+const event_type_index_t EVENT_TYPE_INDEX_DIFFUSE_REACT = 500;  // src4/base_event.h:33-56
+const double DIFFUSE_REACT_EVENT_PERIODICITY = 1.0;             // src4/diffuse_react_event.h:36
+const double DIFFUSION_TIME_UPPER_LIMIT = 100.0;                // src4/diffuse_react_event.h:37
+
+// src4/molecule.h:30-47 — values are frozen (checkpoints store them)
+enum molecule_flag_t {
+  MOLECULE_FLAG_SURF = 1 << 0,
+  MOLECULE_FLAG_VOL = 1 << 1,
+  MOLECULE_FLAG_MATURE = 1 << 2,
+  MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN = 1 << 4,
+  MOLECULE_FLAG_NO_NEED_TO_SCHEDULE = 1 << 14,
+  MOLECULE_FLAG_DEFUNCT = 1 << 15,
+};
+
+struct Vec3 { double x, y, z; };
+struct Vec2 { double u, v; };
+
+// src4/molecule.h:52-260: "data is ordered to avoid alignment holes"
+struct Molecule {
+  molecule_id_t id;
+  species_id_t species_id;
+  uint32_t flags;
+  uint32_t pad_;
+  double diffusion_time;
+  double unimol_rxn_time;
+  double birthday;
+  union {
+    struct {
+      Vec3 pos;
+      subpart_index_t subpart_index;
+      subpart_index_t reactant_subpart_index;
+      counted_volume_index_t counted_volume_index;
+      wall_index_t previous_wall_index;
+    } v;
+    struct {
+      Vec2 pos;
+      int32_t orientation;
+      wall_index_t wall_index;
+      uint32_t grid_tile_index;
+    } s;
+  };
+  Molecule() { memset(this, 0, sizeof(*this)); id = MOLECULE_ID_INVALID; diffusion_time = TIME_INVALID; unimol_rxn_time = TIME_FOREVER; birthday = TIME_INVALID; }
+  Molecule(molecule_id_t id_, species_id_t sp, const Vec3& pos_, double birthday_) {
+    memset(this, 0, sizeof(*this));
+    id = id_; species_id = sp; flags = MOLECULE_FLAG_VOL;
+    diffusion_time = TIME_INVALID; unimol_rxn_time = TIME_INVALID; birthday = birthday_;
+    v.pos = pos_; v.subpart_index = v.reactant_subpart_index = v.counted_volume_index = v.previous_wall_index = INDEX_INVALID32;
+  }
+  bool is_vol() const { return (flags & MOLECULE_FLAG_VOL) != 0; }
+  bool is_defunct() const { return (flags & MOLECULE_FLAG_DEFUNCT) != 0; }
+};
+static_assert(sizeof(Molecule) == 80, "sizeof(Molecule) must stay 80 bytes (SURVEY A.5)");
+
+// src4/base_event.h:63-139
+class BaseEvent {
+public:
+  explicit BaseEvent(event_type_index_t t) : event_time(TIME_INVALID), periodicity_interval(0), type_index(t) {}
+  virtual ~BaseEvent() {}
+  virtual void step() = 0;
+  virtual bool update_event_time_for_next_scheduled_time() {
+    if (periodicity_interval == 0) return false;
+    event_time = event_time + periodicity_interval;
+    return true;
+  }
+  virtual bool is_barrier() const { return false; }
+  virtual bool may_be_blocked_by_barrier_and_needs_set_time_step() const { return false; }
+  virtual double get_max_time_up_to_next_barrier() const { return 0; }
+  virtual void set_barrier_time_for_next_execution(const double) {}
+  double event_time;
+  double periodicity_interval;
+  event_type_index_t type_index;
+};
+
+// The molecule containers of Partition that the event reads and writes (partition.h:1125-1143)
+struct PartitionMolecules {
+  std::vector<Molecule> molecules;
+  std::vector<uint32_t> molecule_id_to_index_mapping;
+  molecule_id_t next_molecule_id = 0;
+
+  // Partition::add_volume_molecule (partition.h:555-611): assigns the id, marks a newborn
+  Molecule& add_volume_molecule(species_id_t species, const Vec3& pos, double birthday);
+  // Partition::get_m (partition.h:210-219)
+  Molecule& get_m(molecule_id_t id) { return molecules[molecule_id_to_index_mapping[id]]; }
+  void rebuild_mapping();
+};
+
+// World::fatal_error equivalent for this seam: the ABI never exits; the adapter throws and the host decides
+struct McxFatalError : std::runtime_error {
+  int code;
+  McxFatalError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+// Immutable model tables in ABI form (filled by the host from World/BNGEngine/Partition)
+struct GpuModelTables {
+  mcx_config cfg{};
+  std::vector<mcx_species> species;
+  std::vector<mcx_rxn_class> rxn_classes;
+  std::vector<mcx_pathway> pathways;
+  std::vector<mcx_surf_class_rxn> surf_class_rxns;
+  std::vector<double> vertices;        // 3 per vertex, length units
+  std::vector<uint32_t> wall_vertex_indices;  // 3 per wall
+  std::vector<uint32_t> wall_surf_class;      // per wall or empty
+};
+
+// Drop-in for DiffuseReactEvent (src4/diffuse_react_event.h:108-154) running on the GPU through libmcx.
+class GpuDiffuseReactEvent : public BaseEvent {
+public:
+  GpuDiffuseReactEvent(const GpuModelTables& tables, PartitionMolecules* partition);
+  ~GpuDiffuseReactEvent() override;
+
+  // one scheduler slot: runs round(time_up_to_next_barrier) iterations on the device (the barrier contract of
+  // diffuse_react_event.h:142-150 passes whole numbers <= DIFFUSION_TIME_UPPER_LIMIT)
+  void step() override;
+  bool update_event_time_for_next_scheduled_time() override {
+    event_time = event_time + iterations_last_step;  // = min(time_up_to_next_barrier, window) whole iterations
+    return true;
+  }
+  bool may_be_blocked_by_barrier_and_needs_set_time_step() const override { return true; }
+  double get_max_time_up_to_next_barrier() const override { return DIFFUSION_TIME_UPPER_LIMIT; }
+  void set_barrier_time_for_next_execution(const double t) override;
+
+  // host <-> device population sync (dirty flags): the host calls mark_host_modified() after releases or API
+  // edits; viz/checkpoint/introspection paths call sync_to_host() before reading Partition::get_molecules()
+  void mark_host_modified() { host_dirty = true; }
+  void sync_to_host();
+  // MolOrRxnCountEvent world-count fast path (mol_or_rxn_count_event.cpp:622-653)
+  void get_counts(std::vector<uint64_t>& per_species, std::vector<uint64_t>& per_rxn_rule);
+  const mcx_step_stats& last_stats() const { return stats; }
+
+private:
+  void upload_from_host();
+  void check(int rc, const char* what);
+  mcx_handle* h = nullptr;
+  PartitionMolecules* p;
+  size_t n_species, n_rules;
+  double time_up_to_next_barrier;
+  double iterations_last_step = 1;
+  bool host_dirty = true, device_dirty = false;
+  mcx_step_stats stats{};
+  // SoA staging (host side of the ABI)
+  std::vector<double> x, y, z, tdiff, tuni;
+  std::vector<uint32_t> id, species, flags;
+};
+
+}  // namespace MCell

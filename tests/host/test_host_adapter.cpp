@@ -1,0 +1,120 @@
+// tests/host/test_host_adapter.cpp — drives libmcx the way MCell4's scheduler would, through the C++ adapter
+// (mcell_b200/host/mcx_host.h): BASELINE config 1 shape (free diffusion in a reflective 1 um cube) plus an
+// A + B -> C run, with a count "barrier" every 10 iterations.
+// Without a CUDA device it must fail loudly (McxFatalError, MCX_ERR_CUDA) — exit code 3.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+#include "../../mcell_b200/host/mcx_host.h"
+
+using namespace MCell;
+
+static GpuModelTables box_model(double half_lu, bool reactive, uint64_t max_mols) {
+  GpuModelTables t;
+  t.cfg.abi_version = MCX_ABI_VERSION;
+  t.cfg.device = 0;
+  t.cfg.seed = 1;
+  t.cfg.origin[0] = t.cfg.origin[1] = t.cfg.origin[2] = -500;
+  t.cfg.partition_edge_length = 1000;
+  t.cfg.num_subparts_per_edge = 20;
+  t.cfg.use_expanded_list = reactive ? 1 : 0;
+  t.cfg.rxn_radius_3d = 0.5641895835477563;
+  for (int k = 0; k < 3; k++) { t.cfg.active_llf[k] = -half_lu; t.cfg.active_urb[k] = half_lu; }
+  t.cfg.max_molecules = max_mols;
+  t.cfg.rng_mode = MCX_RNG_PHILOX;
+  t.cfg.world_size = 1;
+  const double h = half_lu;
+  const double v[8][3] = {{-h, -h, -h}, {-h, -h, h}, {-h, h, -h}, {-h, h, h}, {h, -h, -h}, {h, -h, h}, {h, h, -h}, {h, h, h}};
+  const uint32_t f[12][3] = {{1, 2, 0}, {3, 6, 2}, {7, 4, 6}, {5, 0, 4}, {6, 0, 2}, {3, 5, 7},
+                             {1, 3, 2}, {3, 7, 6}, {7, 5, 4}, {5, 1, 0}, {6, 4, 0}, {3, 1, 5}};
+  for (auto& p : v) for (double c : p) t.vertices.push_back(c);
+  for (auto& q : f) for (uint32_t c : q) t.wall_vertex_indices.push_back(c);
+  const int ns = reactive ? 3 : 1;
+  for (int i = 0; i < ns; i++) t.species.push_back(mcx_species{2.0, 1.0, MCX_SP_VOL | MCX_SP_CAN_DIFFUSE, 0});
+  if (reactive) {
+    mcx_rxn_class rc{};
+    rc.kind = MCX_RXN_BIMOL_VOLVOL; rc.reactants[0] = 0; rc.reactants[1] = 1; rc.first_pathway = 0; rc.n_pathways = 1;
+    rc.max_fixed_p = 0.3;
+    mcx_pathway pw{};
+    pw.cum_prob = 0.3; pw.n_products = 1; pw.products[0] = 2; pw.keep_reactant_mask = 0; pw.rxn_rule_id = 0;
+    t.rxn_classes.push_back(rc);
+    t.pathways.push_back(pw);
+  }
+  return t;
+}
+
+int main() {
+  const int n = 20000;
+  const double half = 50.0;
+  std::mt19937_64 gen(7);
+  std::uniform_real_distribution<double> U(-half * 0.999, half * 0.999);
+  try {
+    // ---- config 1 shape: free diffusion, barrier every 10 iterations
+    PartitionMolecules part;
+    for (int i = 0; i < n; i++) part.add_volume_molecule(0, Vec3{U(gen), U(gen), U(gen)}, 0.0);
+    std::vector<Molecule> before = part.molecules;
+    GpuModelTables t = box_model(half, false, 2 * n);
+    GpuDiffuseReactEvent ev(t, &part);
+    ev.event_time = 0;
+    if (ev.type_index != 500 || !ev.may_be_blocked_by_barrier_and_needs_set_time_step()) return 1;
+    // one iteration: MSD = 3*space_step^2/2 for molecules away from the walls
+    ev.set_barrier_time_for_next_execution(1);
+    ev.step();
+    ev.update_event_time_for_next_scheduled_time();
+    ev.sync_to_host();
+    if (part.molecules.size() != (size_t)n) { printf("lost molecules: %zu\n", part.molecules.size()); return 1; }
+    double msd = 0; int cnt = 0;
+    for (const Molecule& b : before) {
+      if (std::fabs(b.v.pos.x) > 30 || std::fabs(b.v.pos.y) > 30 || std::fabs(b.v.pos.z) > 30) continue;
+      const Molecule& a = part.get_m(b.id);
+      double dx = a.v.pos.x - b.v.pos.x, dy = a.v.pos.y - b.v.pos.y, dz = a.v.pos.z - b.v.pos.z;
+      msd += dx * dx + dy * dy + dz * dz; cnt++;
+    }
+    msd /= cnt;
+    if (std::fabs(msd - 6.0) > 6.0 * 5 * std::sqrt(2.0 / 3.0 / cnt)) { printf("MSD %g, expected 6\n", msd); return 1; }
+    for (int window = 0; window < 3; window++) {
+      ev.set_barrier_time_for_next_execution(10);   // a count event every 10 iterations
+      ev.step();
+      ev.update_event_time_for_next_scheduled_time();
+    }
+    if (ev.event_time != 31) { printf("event_time %g\n", ev.event_time); return 1; }
+    ev.sync_to_host();
+    for (const Molecule& m : part.molecules)
+      if (std::fabs(m.v.pos.x) > half || std::fabs(m.v.pos.y) > half || std::fabs(m.v.pos.z) > half) { printf("escaped\n"); return 1; }
+    if (ev.last_stats().molecule_steps != (uint64_t)10 * n) return 1;
+
+    // ---- A + B -> C with counts at every barrier
+    PartitionMolecules p2;
+    for (int i = 0; i < n; i++) p2.add_volume_molecule(i & 1, Vec3{U(gen) * 0.3, U(gen) * 0.3, U(gen) * 0.3}, 0.0);
+    GpuModelTables t2 = box_model(half * 0.3, true, 2 * n);
+    GpuDiffuseReactEvent ev2(t2, &p2);
+    ev2.event_time = 0;
+    std::vector<uint64_t> sp, rx;
+    uint64_t last_c = 0;
+    for (int window = 0; window < 3; window++) {
+      ev2.set_barrier_time_for_next_execution(10);
+      ev2.step();
+      ev2.update_event_time_for_next_scheduled_time();
+      ev2.get_counts(sp, rx);
+      if (sp[0] + sp[2] != (uint64_t)n / 2 || sp[1] + sp[2] != (uint64_t)n / 2 || rx[0] != sp[2] || sp[2] < last_c) { printf("count identity broken\n"); return 1; }
+      last_c = sp[2];
+    }
+    if (last_c < 100) { printf("too few reactions: %llu\n", (unsigned long long)last_c); return 1; }
+    ev2.sync_to_host();
+    if (p2.molecules.size() != sp[0] + sp[1] + sp[2]) return 1;
+    // host edits the population (a "release"), marks it dirty, continues
+    for (int i = 0; i < 100; i++) p2.add_volume_molecule(0, Vec3{0, 0, 0}, ev2.event_time);
+    ev2.mark_host_modified();
+    ev2.set_barrier_time_for_next_execution(1);
+    ev2.step();
+    ev2.get_counts(sp, rx);
+    if (sp[0] + sp[2] != (uint64_t)n / 2 + 100) { printf("release not seen\n"); return 1; }
+    printf("host adapter ok: MSD %.4f, C after 30 iterations %llu\n", msd, (unsigned long long)last_c);
+    return 0;
+  } catch (const McxFatalError& e) {
+    printf("McxFatalError %d: %s\n", e.code, e.what());
+    return e.code == MCX_ERR_CUDA ? 3 : 2;
+  }
+}
