@@ -146,11 +146,24 @@ typedef struct mcx_step_stats {
   uint64_t products_created;
   uint64_t kernel_launches;        /* libmcx kernels launched by this call */
   double   device_ms;              /* CUDA-event time of the iteration loop */
-  double   ms_diffuse;             /* with mcx_set_profiling: summed CUDA-event time of the diffuse kernel */
+  double   ms_diffuse;             /* with mcx_set_profiling: summed CUDA-event time of k_diffuse_fast */
   double   ms_resolve;             /*   ... of the conflict-resolution rounds */
   double   ms_sort;                /*   ... of histogram scan + scatter */
-  uint64_t profiled_iterations;    /*   iterations covered by the three sums above */
+  uint64_t profiled_iterations;    /*   iterations covered by the sums above */
+  double   ms_diffuse_slow;        /*   ... of k_diffuse_slow (deferred molecules, generic evaluation) */
+  uint64_t deferred_molecules;     /* molecules the fast diffuse pass handed to the generic evaluation */
+  uint64_t deferred_by_reason[8];  /* ... split by MCX_DEFER_* */
 } mcx_step_stats;
+
+/* why k_diffuse_fast handed a molecule to the generic evaluation (diagnostics) */
+enum {
+  MCX_DEFER_TIMING = 0,       /* partial step, newborn, unimolecular event inside the iteration, non-diffusing */
+  MCX_DEFER_GEOMETRY = 1,     /* leaves the partition or crosses several subpartition faces near walls */
+  MCX_DEFER_WALL = 2,         /* a wall of the start/end subpartition is not rejected by the plane test */
+  MCX_DEFER_PROBE_SHAPE = 3,  /* swept box overlaps more than 2x2 cell rows */
+  MCX_DEFER_MULTI_HIT = 4,    /* more than one collision partner */
+  MCX_DEFER_FOREIGN_HIT = 5   /* single partner outside the molecule's own subpartition */
+};
 
 /* ---- replay trace (kernel-level parity; mirrors the reference's DEBUG_* dumps,
  *      include/debug_config.h:153-245) ------------------------------------------------- */

@@ -68,10 +68,11 @@ class mcx_step_stats(C.Structure):
         "vol_mol_vol_mol_collisions", "bimol_rxns", "unimol_rxns", "wall_redos",
         "resolve_retries", "unresolved_conflicts", "products_created", "kernel_launches")] + [("device_ms", c_f64), ("ms_diffuse", c_f64),
                                                     ("ms_resolve", c_f64), ("ms_sort", c_f64),
-                                                    ("profiled_iterations", c_u64)]
+                                                    ("profiled_iterations", c_u64), ("ms_diffuse_slow", c_f64),
+                                                    ("deferred_molecules", c_u64), ("deferred_by_reason", c_u64 * 8)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n == "deferred_by_reason" else getattr(self, n)) for n, _ in self._fields_}
 
 
 class mcx_trace_rec(C.Structure):

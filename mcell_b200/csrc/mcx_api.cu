@@ -42,7 +42,7 @@ struct mcx_handle {
   // table device pointers that get replaced on re-set
   void *d_species = nullptr, *d_bimol = nullptr, *d_unimol = nullptr, *d_classes = nullptr, *d_pathways = nullptr,
        *d_surf = nullptr, *d_walls = nullptr, *d_tri = nullptr, *d_verts = nullptr, *d_wclass = nullptr,
-       *d_spw_start = nullptr, *d_spw_list = nullptr;
+       *d_spw_start = nullptr, *d_spw_list = nullptr, *d_sp_flags = nullptr;
   McxComm* comm = nullptr;
   double *st_x = nullptr, *st_y = nullptr, *st_z = nullptr, *st_ts = nullptr, *st_tu = nullptr;
   uint32_t *st_id = nullptr, *st_sp = nullptr, *st_fl = nullptr;
@@ -145,18 +145,25 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   }
   double vol = (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
   double edge = cfg->cell_edge;
-  if (!(edge > 0)) edge = std::cbrt(vol * 8.0 / (double)cfg->max_molecules);
+  // default: about one molecule slot per cell — the candidate walk then touches ~1-2 records per molecule
+  if (!(edge > 0)) edge = std::cbrt(vol * 1.0 / (double)cfg->max_molecules);
+  if (edge < 4.0 * cfg->rxn_radius_3d) edge = 4.0 * cfg->rxn_radius_3d;
+  // Anisotropic cells of volume edge^3: the records of one x-row of cells are contiguous in the sorted snapshot,
+  // so a swept box costs one [start,end) lookup per (y,z) row whatever the x resolution.  Short x cells keep the
+  // x-range tight; long y/z cells keep the box within 2x2 rows (the fast pass enumerates at most 4 rows).
   const double max_cells = 2.0e8;
+  double ex, ey, ez;
   for (;;) {
-    double nc = std::ceil((hi[0] - lo[0]) / edge + 1) * std::ceil((hi[1] - lo[1]) / edge + 1) * std::ceil((hi[2] - lo[2]) / edge + 1);
+    ex = edge / 2.25; ey = ez = edge * 1.5;
+    double nc = std::ceil((hi[0] - lo[0]) / ex + 2) * std::ceil((hi[1] - lo[1]) / ey + 2) * std::ceil((hi[2] - lo[2]) / ez + 2);
     if (nc <= max_cells) break;
     edge *= 1.26;
   }
-  p.cell_rcp = 1.0 / edge;
-  p.cgx = lo[0] - 0.5 * edge; p.cgy = lo[1] - 0.5 * edge; p.cgz = lo[2] - 0.5 * edge;
-  p.ncx = (int)std::ceil((hi[0] - p.cgx) / edge) + 1;
-  p.ncy = (int)std::ceil((hi[1] - p.cgy) / edge) + 1;
-  p.ncz = (int)std::ceil((hi[2] - p.cgz) / edge) + 1;
+  p.cell_rcp_x = 1.0 / ex; p.cell_rcp_y = 1.0 / ey; p.cell_rcp_z = 1.0 / ez;
+  p.cgx = lo[0] - 0.5 * ex; p.cgy = lo[1] - 0.5 * ey; p.cgz = lo[2] - 0.5 * ez;
+  p.ncx = (int)std::ceil((hi[0] - p.cgx) / ex) + 1;
+  p.ncy = (int)std::ceil((hi[1] - p.cgy) / ey) + 1;
+  p.ncz = (int)std::ceil((hi[2] - p.cgz) / ez) + 1;
   p.n_cells = (unsigned int)((size_t)p.ncx * p.ncy * p.ncz);
   p.zc_lo = 0; p.zc_hi = p.ncz;
 
@@ -169,6 +176,7 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   rc |= dev_alloc(h, &p.claim, cap);
   rc |= dev_alloc(h, &p.prop_partner, cap); rc |= dev_alloc(h, &p.prop_info, cap); rc |= dev_alloc(h, &p.prop_t, cap);
   rc |= dev_alloc(h, &p.pend[0], cap); rc |= dev_alloc(h, &p.pend[1], cap);
+  rc |= dev_alloc(h, &p.slow_list, cap);
   rc |= dev_alloc(h, &h->cs[0], (size_t)p.n_cells + 8); rc |= dev_alloc(h, &h->cs[1], (size_t)p.n_cells + 8);
   rc |= dev_alloc(h, &h->scan_sums, (size_t)(p.n_cells + 1) / 4096 + 16);
   rc |= dev_alloc(h, &p.ctr, 1);
@@ -178,6 +186,9 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   std::vector<uint32_t> zero_start((size_t)p.n_sp * p.n_sp * p.n_sp + 1, 0);
   if (dev_replace(h, &h->d_spw_start, zero_start.data(), zero_start.size())) return fail(MCX_ERR_CUDA);
   p.spw_start = (const uint32_t*)h->d_spw_start;
+  std::vector<uint8_t> zero_flags(zero_start.size(), 0);
+  if (dev_replace(h, &h->d_sp_flags, zero_flags.data(), zero_flags.size())) return fail(MCX_ERR_CUDA);
+  p.sp_flags = (const uint8_t*)h->d_sp_flags;
   h->plan.sm_count = h->sm_count;
   h->plan.launches = &h->launches;
   *out = h;
@@ -217,11 +228,32 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   rc |= dev_replace(h, &h->d_wclass, h->wall_class_host.data(), h->wall_class_host.size());
   rc |= dev_replace(h, &h->d_spw_start, start.data(), start.size());
   rc |= dev_replace(h, &h->d_spw_list, list.data(), list.size());
+  // per-subpartition wall flags for the fast diffuse pass: bit0 = holds walls, bit1 = 3x3x3 neighbourhood does
+  {
+    const int n = h->p.n_sp;
+    std::vector<uint8_t> flags((size_t)n * n * n + 1, 0);
+    auto at = [&](int x, int y, int z) { return (size_t)x + (size_t)y * n + (size_t)z * n * n; };
+    for (size_t sidx = 0; sidx + 1 < start.size(); sidx++)
+      if (start[sidx + 1] > start[sidx]) flags[sidx] |= 1;
+    for (int z = 0; z < n; z++)
+      for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++) {
+          if (!(flags[at(x, y, z)] & 1)) continue;
+          for (int dz = -1; dz <= 1; dz++)
+            for (int dy = -1; dy <= 1; dy++)
+              for (int dx = -1; dx <= 1; dx++) {
+                int X = x + dx, Y = y + dy, Z = z + dz;
+                if (X < 0 || Y < 0 || Z < 0 || X >= n || Y >= n || Z >= n) continue;
+                flags[at(X, Y, Z)] |= 2;
+              }
+        }
+    rc |= dev_replace(h, &h->d_sp_flags, flags.data(), flags.size());
+  }
   if (rc) return MCX_ERR_CUDA;
   DevParams& p = h->p;
   p.walls = (const DevWall*)h->d_walls; p.wall_tri = (const uint32_t*)h->d_tri; p.verts = (const double*)h->d_verts;
   p.wall_class = (const uint32_t*)h->d_wclass; p.spw_start = (const uint32_t*)h->d_spw_start;
-  p.spw_list = (const uint32_t*)h->d_spw_list; p.n_walls = (int)n_walls;
+  p.spw_list = (const uint32_t*)h->d_spw_list; p.n_walls = (int)n_walls; p.sp_flags = (const uint8_t*)h->d_sp_flags;
   h->has_geometry = true;
   return MCX_OK;
 }
@@ -459,6 +491,8 @@ static void fill_stats(const Counters& a, const Counters& b, uint64_t iters, flo
   s->resolve_retries = b.retries - a.retries;
   s->unresolved_conflicts = b.unresolved - a.unresolved;
   s->products_created = b.products - a.products;
+  s->deferred_molecules = b.deferred - a.deferred;
+  for (int k = 0; k < 8; k++) s->deferred_by_reason[k] = b.defer_reason[k] - a.defer_reason[k];
   s->device_ms = ms;
 }
 
@@ -472,14 +506,14 @@ static int run_iterations(mcx_handle* h, uint32_t n_iterations, mcx_step_stats* 
   mcx_set_scan_scratch(h->scan_sums);
   CK(cudaEventRecord(h->ev0, h->stream));
   const uint32_t n_prof = h->profiling ? std::min<uint32_t>(n_iterations, 256) : 0;
-  if (h->prof_events.size() < 4ull * n_prof) {
+  if (h->prof_events.size() < 5ull * n_prof) {
     size_t old = h->prof_events.size();
-    h->prof_events.resize(4ull * n_prof);
+    h->prof_events.resize(5ull * n_prof);
     for (size_t q = old; q < h->prof_events.size(); q++) CK(cudaEventCreate(&h->prof_events[q]));
   }
   for (uint32_t k = 0; k < n_iterations; k++) {
     bind_iteration(h);
-    h->plan.prof = k < n_prof ? &h->prof_events[4ull * k] : nullptr;
+    h->plan.prof = k < n_prof ? &h->prof_events[5ull * k] : nullptr;
     if (h->comm) {
       int rc = mcx_comm_iteration(h->comm, h->p, h->plan, h->stream);
       if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
@@ -500,10 +534,11 @@ static int run_iterations(mcx_handle* h, uint32_t n_iterations, mcx_step_stats* 
   if (stats_out) {
     stats_out->kernel_launches = h->launches - launches_before;
     for (uint32_t k = 0; k < n_prof && rc == MCX_OK; k++) {
-      float a = 0, b = 0, c = 0;
-      cudaEvent_t* e = &h->prof_events[4ull * k];
-      cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]);
-      stats_out->ms_diffuse += a; stats_out->ms_resolve += b; stats_out->ms_sort += c;
+      float a = 0, a2 = 0, b = 0, c = 0;
+      cudaEvent_t* e = &h->prof_events[5ull * k];
+      cudaEventElapsedTime(&a, e[0], e[4]); cudaEventElapsedTime(&a2, e[4], e[1]);
+      cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]);
+      stats_out->ms_diffuse += a; stats_out->ms_diffuse_slow += a2; stats_out->ms_resolve += b; stats_out->ms_sort += c;
     }
     stats_out->profiled_iterations = n_prof;
   }

@@ -55,7 +55,7 @@ __device__ __forceinline__ bool distinguishable_d(double a, double b, double eps
 struct Stream {
   const uint32_t* tape; unsigned long long tape_left;
   uint32_t k0, k1, it_lo, it_hi, id;
-  uint32_t buf[4];
+  uint32_t b0, b1, b2, b3;  // current Philox block (scalars, not an array: dynamic indexing would put it in local memory)
   uint32_t used;
   const ZigShared* zig;
 
@@ -75,8 +75,9 @@ struct Stream {
     uint32_t w;
     if (tape) w = used < tape_left ? tape[used] : 0u;
     else {
-      if ((used & 3u) == 0u) philox4x32_10(used >> 2, it_lo, it_hi, id, k0, k1, buf);
-      w = buf[used & 3u];
+      const uint32_t k = used & 3u;
+      if (k == 0u) { uint32_t o[4]; philox4x32_10(used >> 2, it_lo, it_hi, id, k0, k1, o); b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3]; }
+      w = k == 0u ? b0 : (k == 1u ? b1 : (k == 2u ? b2 : b3));
     }
     used++;
     return w;
@@ -156,9 +157,9 @@ __device__ __forceinline__ int cell_coord(double v, double origin, double rcp, i
   return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 __device__ __forceinline__ uint32_t cell_of(const DevParams& p, double x, double y, double z) {
-  int cx = cell_coord(x, p.cgx, p.cell_rcp, p.ncx);
-  int cy = cell_coord(y, p.cgy, p.cell_rcp, p.ncy);
-  int cz = cell_coord(z, p.cgz, p.cell_rcp, p.ncz);
+  int cx = cell_coord(x, p.cgx, p.cell_rcp_x, p.ncx);
+  int cy = cell_coord(y, p.cgy, p.cell_rcp_y, p.ncy);
+  int cz = cell_coord(z, p.cgz, p.cell_rcp_z, p.ncz);
   return (uint32_t)(cx + p.ncx * (cy + p.ncy * cz));
 }
 
@@ -414,65 +415,199 @@ __device__ __forceinline__ void store_rec(MolRec* a, uint32_t i, D3 pos, uint32_
   q[1] = make_double2(pos.z, __longlong_as_double((long long)m));
 }
 
+// Cell range overlapped by the swept volume of a move (segment inflated by R, padded against rounding).
+struct CellBox { int cx0, cx1, cy0, cy1, cz0, cz1; };
+__device__ __forceinline__ CellBox swept_cells(const DevParams& p, D3 pos, D3 disp) {
+  const double pad = p.R * (1.0 + 1e-9) + 1e-9;
+  CellBox b;
+  b.cx0 = cell_coord(fmin(pos.x, pos.x + disp.x) - pad, p.cgx, p.cell_rcp_x, p.ncx);
+  b.cx1 = cell_coord(fmax(pos.x, pos.x + disp.x) + pad, p.cgx, p.cell_rcp_x, p.ncx);
+  b.cy0 = cell_coord(fmin(pos.y, pos.y + disp.y) - pad, p.cgy, p.cell_rcp_y, p.ncy);
+  b.cy1 = cell_coord(fmax(pos.y, pos.y + disp.y) + pad, p.cgy, p.cell_rcp_y, p.ncy);
+  b.cz0 = cell_coord(fmin(pos.z, pos.z + disp.z) - pad, p.cgz, p.cell_rcp_z, p.ncz);
+  b.cz1 = cell_coord(fmax(pos.z, pos.z + disp.z) + pad, p.cgz, p.cell_rcp_z, p.ncz);
+  return b;
+}
+
+// Flattened walk over the candidate records of a CellBox: cells of one x-row are contiguous in the sorted
+// snapshot, so a row is ONE [j, jend) range.  A single loop with a uniform body (advance-row step, then test
+// step) keeps the lanes of a warp converged even though their row/candidate counts differ; the nested
+// cz/cy/j loops this replaces serialised the lanes of different cells (profiles/r01_a_*: 5.5 of 32 lanes active).
+template <bool SKIP_2X2>
+struct CandWalkT {
+  int ny, nrows, row, ry, rz, cx0, cx1, cy0, cz0;
+  uint32_t j, jend;
+  // enabled == false gives an empty walk (lanes that have nothing to probe stay in lock step with the warp)
+  __device__ __forceinline__ void init(const CellBox& b, bool enabled = true) {
+    ny = b.cy1 - b.cy0 + 1; nrows = enabled ? ny * (b.cz1 - b.cz0 + 1) : 0; row = 0; ry = 0; rz = 0;
+    cx0 = b.cx0; cx1 = b.cx1; cy0 = b.cy0; cz0 = b.cz0; j = 0; jend = 0;
+  }
+  __device__ __forceinline__ void next_row() { row++; if (++ry == ny) { ry = 0; rz++; } }
+  // returns false when exhausted; on true, `has` tells whether slot j is a candidate to test this round
+  __device__ __forceinline__ bool step(const DevParams& p, bool& has, uint32_t& slot) {
+    if (j >= jend) {
+      if (SKIP_2X2) { while (row < nrows && ry < 2 && rz < 2) next_row(); }  // rows the 2x2 probe already covered
+      if (row >= nrows) return false;
+      const uint32_t base = (uint32_t)(p.ncx * ((cy0 + ry) + p.ncy * (cz0 + rz)));
+      j = __ldg(p.cs_cur + base + cx0);
+      jend = __ldg(p.cs_cur + base + cx1 + 1);
+      next_row();
+    }
+    has = j < jend;
+    slot = j;
+    if (has) j++;
+    return true;
+  }
+};
+typedef CandWalkT<false> CandWalk;
+
 // Partner scan: one pass over the neighbour cells overlapped by the swept volume (segment inflated by R).
 // Finds the earliest eligible collision strictly after (t_last, id_last) in (time asc, id desc) order and
 // strictly before t_limit, counting how many eligible collisions remain.
-struct PartnerHit { double t; uint32_t slot, id, species; int rxn_class; };
+struct PartnerHit { double t; uint32_t slot, id, species; int rxn_class; bool in_own_subpart; };
 
 template <bool VOLATILE_SNAPSHOT>
 __device__ int scan_partners(const DevParams& p, D3 pos, D3 disp, uint32_t self_id, uint32_t self_species,
                              const SpSet& spm, bool need_sp_filter, double t_last, uint32_t id_last, double t_limit,
                              PartnerHit& best) {
-  const double R = p.R;
-  const double pad = R * (1.0 + 1e-9) + 1e-9;
-  double lox = fmin(pos.x, pos.x + disp.x) - pad, hix = fmax(pos.x, pos.x + disp.x) + pad;
-  double loy = fmin(pos.y, pos.y + disp.y) - pad, hiy = fmax(pos.y, pos.y + disp.y) + pad;
-  double loz = fmin(pos.z, pos.z + disp.z) - pad, hiz = fmax(pos.z, pos.z + disp.z) + pad;
-  int cx0 = cell_coord(lox, p.cgx, p.cell_rcp, p.ncx), cx1 = cell_coord(hix, p.cgx, p.cell_rcp, p.ncx);
-  int cy0 = cell_coord(loy, p.cgy, p.cell_rcp, p.ncy), cy1 = cell_coord(hiy, p.cgy, p.cell_rcp, p.ncy);
-  int cz0 = cell_coord(loz, p.cgz, p.cell_rcp, p.ncz), cz1 = cell_coord(hiz, p.cgz, p.cell_rcp, p.ncz);
   const double movelen2 = dot3(disp, disp);
-  const double sigma2 = R * R;
-  const double rhs = movelen2 * sigma2;
+  const double rhs = movelen2 * (p.R * p.R);
   const int* bimol_row = p.bimol + self_species * p.n_species;
   int count = 0;
   best.t = MCX_TIME_FOREVER; best.id = 0; best.slot = MCX_NONE;
-  for (int cz = cz0; cz <= cz1; cz++) {
-    for (int cy = cy0; cy <= cy1; cy++) {
-      const uint32_t row = (uint32_t)(p.ncx * (cy + p.ncy * cz));
-      const uint32_t j0 = p.cs_cur[row + cx0], j1 = p.cs_cur[row + cx1 + 1];
-      for (uint32_t j = j0; j < j1; j++) {
-        MolRec c = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j) : load_rec(p.recA, j);
-        // collide_mol, collision_utils.inl:464-515
-        D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
-        double d = dot3(dir, disp);
-        if (d < 0) continue;
-        if (d > movelen2) continue;
-        double dirlen2 = dot3(dir, dir);
-        if (movelen2 * dirlen2 - d * d > rhs) continue;
-        if (c.id == self_id) continue;
-        if (c.sf & DF_DEAD) continue;
-        uint32_t csp = c.sf & SF_SPECIES_MASK;
-        int rc = bimol_row[csp];
-        if (rc < 0) continue;
-        if (need_sp_filter && !spset_has(spm, subpart_index(p, D3{c.x, c.y, c.z}))) continue;
-        double t = d / movelen2;
-        if (!(t < t_limit)) continue;
-        // strictly after (t_last, id_last): later time, or same time and smaller id
-        if (t < t_last || (t == t_last && c.id >= id_last)) continue;
-        count++;
-        if (t < best.t || (t == best.t && c.id > best.id)) {
-          best.t = t; best.id = c.id; best.slot = j; best.species = csp; best.rxn_class = rc;
-        }
-      }
+  CandWalk cw; cw.init(swept_cells(p, pos, disp));
+  bool has; uint32_t j;
+  while (cw.step(p, has, j)) {
+    if (!has) continue;
+    MolRec c = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j) : load_rec(p.recA, j);
+    // collide_mol, collision_utils.inl:464-515
+    D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
+    double d = dot3(dir, disp);
+    if (d < 0) continue;
+    if (d > movelen2) continue;
+    double dirlen2 = dot3(dir, dir);
+    if (movelen2 * dirlen2 - d * d > rhs) continue;
+    if (c.id == self_id) continue;
+    if (c.sf & DF_DEAD) continue;
+    uint32_t csp = c.sf & SF_SPECIES_MASK;
+    int rc = bimol_row[csp];
+    if (rc < 0) continue;
+    if (need_sp_filter && !spset_has(spm, subpart_index(p, D3{c.x, c.y, c.z}))) continue;
+    double t = d / movelen2;
+    if (!(t < t_limit)) continue;
+    // strictly after (t_last, id_last): later time, or same time and smaller id
+    if (t < t_last || (t == t_last && c.id >= id_last)) continue;
+    count++;
+    if (t < best.t || (t == best.t && c.id > best.id)) {
+      best.t = t; best.id = c.id; best.slot = j; best.species = csp; best.rxn_class = rc;
     }
   }
   return count;
 }
 
+// Fast-path probe: every live partner with a reaction that passes collide_mol for this move (no subpartition
+// filter, no ordering).  Returns their number and remembers one; 0 => the generic evaluation would find no
+// collision either (its candidate set is a subset of this one).
+//
+// Shape: the swept box overlaps at most 3x2 (or 2x3) cell rows, else `overflow` (generic path).  The six
+// row ranges are fetched up front (12 independent loads in flight), then ONE loop runs over the concatenated
+// candidates, two per trip with both record loads issued before any arithmetic: no row-advance branch inside
+// the loop, half the trips, and the L1/L2 latency of a record overlaps the test of the previous one.
+__device__ __forceinline__ bool collide_mol_hit(const MolRec& c, D3 pos, D3 disp, double movelen2, double rhs, uint32_t self_id,
+                                                double& d_out) {
+  D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
+  double d = dot3(dir, disp);
+  double dirlen2 = dot3(dir, dir);
+  d_out = d;
+  return !(d < 0) && !(d > movelen2) && !(movelen2 * dirlen2 - d * d > rhs) && c.id != self_id && !(c.sf & DF_DEAD);
+}
+__device__ __forceinline__ int probe_partners(const DevParams& p, bool enabled, D3 pos, D3 disp, uint32_t self_id,
+                                              uint32_t self_species, PartnerHit& first, bool& overflow) {
+  const double movelen2 = dot3(disp, disp);
+  const double rhs = movelen2 * (p.R * p.R);
+  const int* bimol_row = p.bimol + self_species * p.n_species;
+  const CellBox b = swept_cells(p, pos, disp);
+  const int ny = b.cy1 - b.cy0 + 1, nz = b.cz1 - b.cz0 + 1;
+  // six row slots: 3 (y) x 2 (z), or 2 (y) x 3 (z) for a box that is tall in z; anything wider -> generic path
+  const bool tall = nz > 2;
+  overflow = enabled && (ny * nz > 6 || ny > 3 || nz > 3);
+  const bool en = enabled && !overflow;
+  uint32_t lo[6], cum[6];
+  uint32_t total = 0;
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    const int ry = tall ? (r & 1) : (r % 3), rz = tall ? (r >> 1) : (r / 3);
+    const bool valid = en && ry < ny && rz < nz;
+    const uint32_t base = (uint32_t)(p.ncx * ((b.cy0 + ry) + p.ncy * (b.cz0 + rz)));
+    const uint32_t a = __ldg(p.cs_cur + (valid ? base + b.cx0 : 0u));
+    const uint32_t e = __ldg(p.cs_cur + (valid ? base + b.cx1 + 1 : 0u));
+    lo[r] = a - total;   // slot of candidate k in row r is lo[r] + k  (k counted over the concatenation)
+    total += e - a;
+    cum[r] = total;
+  }
+  int found = 0;
+  first.slot = MCX_NONE; first.in_own_subpart = false; first.t = 0; first.id = 0; first.species = 0; first.rxn_class = 0;
+  for (uint32_t k = 0; k < total; k += 2) {
+    const uint32_t k1 = k + 1 < total ? k + 1 : k;
+    const uint32_t oa = k < cum[2] ? (k < cum[0] ? lo[0] : (k < cum[1] ? lo[1] : lo[2])) : (k < cum[3] ? lo[3] : (k < cum[4] ? lo[4] : lo[5]));
+    const uint32_t ob = k1 < cum[2] ? (k1 < cum[0] ? lo[0] : (k1 < cum[1] ? lo[1] : lo[2])) : (k1 < cum[3] ? lo[3] : (k1 < cum[4] ? lo[4] : lo[5]));
+    const uint32_t ja = oa + k, jb = ob + k1;
+    const MolRec ca = load_rec(p.recA, ja);
+    const MolRec cb = load_rec(p.recA, jb);
+    double da, db;
+    const bool ha = collide_mol_hit(ca, pos, disp, movelen2, rhs, self_id, da);
+    const bool hb = collide_mol_hit(cb, pos, disp, movelen2, rhs, self_id, db) && k1 != k;
+    if (ha) {
+      const uint32_t csp = ca.sf & SF_SPECIES_MASK;
+      const int rc = bimol_row[csp];
+      if (rc >= 0) { first.t = da / movelen2; first.slot = ja; first.id = ca.id; first.species = csp; first.rxn_class = rc; found++; }
+    }
+    if (hb) {
+      const uint32_t csp = cb.sf & SF_SPECIES_MASK;
+      const int rc = bimol_row[csp];
+      if (rc >= 0) { first.t = db / movelen2; first.slot = jb; first.id = cb.id; first.species = csp; first.rxn_class = rc; found++; }
+    }
+  }
+  if (found == 1) {  // is the partner in the molecule's own subpartition (always a collected one)?
+    const MolRec c = load_rec(p.recA, first.slot);
+    first.in_own_subpart = subpart_index(p, D3{c.x, c.y, c.z}) == subpart_index(p, pos);
+  }
+  return found;
+}
+
+// Plane-rejection stage of collide_wall (collision_utils.inl:664-683) for every wall of one subpartition:
+// true when each wall is a COLLIDE_MISS already there (no random draw, no REDO can occur).
+__device__ __forceinline__ bool all_walls_plane_rejected(const DevParams& p, bool enabled, uint32_t subpart, D3 pos, D3 move,
+                                                         unsigned int& n_tests) {
+  const uint32_t w0 = __ldg(p.spw_start + subpart), w1 = enabled ? __ldg(p.spw_start + subpart + 1) : w0;
+  bool all = true;
+  for (uint32_t k = w0; k < w1; k++) {
+    const DevWall& f = p.walls[__ldg(p.spw_list + k)];
+    const D3 n = {f.nx, f.ny, f.nz};
+    const double dp = dot3(n, pos), dv = dot3(n, move), dd = dp - f.dist;
+    double d_eps;
+    bool miss;
+    if (dd > 0) {
+      d_eps = MCX_EPS;
+      if (dd < d_eps) d_eps = 0.5 * dd;
+      miss = dd + dv > d_eps;
+    } else {
+      d_eps = -MCX_EPS;
+      if (dd > d_eps) d_eps = 0.5 * dd;
+      miss = dd < 0 && dd + dv < d_eps;
+    }
+    all = all && miss;
+  }
+  n_tests = w1 - w0;
+  return all;
+}
+
 // ===================================================================================================
 // One molecule, (the rest of) one iteration.  `forced` = last conflict round: no partner search.
 // ===================================================================================================
+// Control flow note: no early `return` / `goto` — the outcome is carried in `decided` and every loop has a single
+// exit condition, so that the lanes of a warp (32 different molecules) re-converge at the loop headers and run
+// the common stages (DDA, wall tests, partner scan) together.
 template <bool RETRY>
 __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t_sched, double t_unimol_in,
                                    Stream& rs, bool forced, Outcome& out, LocalStats& ls, Tracer& tc, int& err) {
@@ -487,8 +622,12 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
   const bool can_diffuse = (sp.flags & MCX_SP_CAN_DIFFUSE) != 0;
   const bool can_vol_react = sp.can_vol_react != 0 && !forced;
   out.rxn_class = -1; out.pathway = -1; out.partner_slot = MCX_NONE; out.partner_id = MCX_NONE; out.t_event = 0;
+  out.kind = MCX_OUT_NONE;
+  bool decided = false;  // a claiming event or an error ended the evaluation; `out` is complete
 
-  for (int sub_guard = 0; sub_guard < 1000; sub_guard++) {
+  bool again = true;
+  for (int sub_guard = 0; again && !decided && sub_guard < 1000; sub_guard++) {
+    again = false;
     // -- unimolecular firing (diffuse_react_event.cpp:215-223, :1764-1826)
     if (unimol_time != MCX_TIME_INVALID && unimol_time <= t_now) {
       int rc = p.unimol[species];
@@ -508,170 +647,176 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
       if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->t_event = unimol_time; }
       out.kind = MCX_OUT_UNIMOL; out.pos = pos; out.rxn_class = rc; out.pathway = pathway; out.t_event = unimol_time;
       out.t_now = t_now; out.flags = flags; out.unimol_time = unimol_time;
-      return;
+      decided = true;
     }
-    // -- newbie lifetime (:232-236 -> pick_unimol_rxn_class_and_set_rxn_time :1731-1758, time_of_unimol)
-    if (flags & DF_SCHED_UNIMOL) {
-      flags &= ~DF_SCHED_UNIMOL;
-      int rc = p.unimol[species];
-      if (rc < 0) unimol_time = MCX_TIME_INVALID;
-      else {
-        double k_tot = p.classes[rc].max_fixed_p;
-        double pr = rs.dbl();
-        double from_now = (k_tot <= 0 || !distinguishable_d(pr, 0, MCX_EPS)) ? MCX_TIME_FOREVER : -log(pr) / k_tot;
-        unimol_time = t_now + from_now;
-      }
-    }
-    // -- get_max_time (:164-198)
-    double max_time = t_end - t_now;
-    if (unimol_time != MCX_TIME_INVALID && unimol_time < t_now + max_time) max_time = unimol_time - t_now;
-
-    if (can_diffuse) {
-      // ---- compute_vol_displacement (diffusion_utils.inl:366-432)
-      double steps = 1.0, t_steps = steps * sp.time_step, r_rate_factor, scale;
-      if (t_steps > max_time) { t_steps = max_time; steps = max_time / sp.time_step; }
-      if (steps < MCX_EPS) { steps = MCX_EPS; t_steps = MCX_EPS * sp.time_step; }
-      if (steps == 1.0) { scale = sp.space_step; r_rate_factor = 1.0; }
-      else { double rate_factor = sqrt(steps); r_rate_factor = 1.0 / rate_factor; scale = rate_factor * sp.space_step; }
-      D3 remaining;
-      remaining.x = scale * rs.gauss() * 0.70710678118654752440;
-      remaining.y = scale * rs.gauss() * 0.70710678118654752440;
-      remaining.z = scale * rs.gauss() * 0.70710678118654752440;
-      max_time = t_steps;
-
-      uint32_t last_hit_wall = MCX_NONE;
-      double elapsed = t_now;
-      // ---- diffuse_vol_molecule loop (:423-572)
-      for (int trace_guard = 0;; trace_guard++) {
-        if (trace_guard > 100000) { err = MCX_ERR_STATE; break; }
-        // ---- ray_trace_vol (:627-780)
-        D3 part_disp = remaining;
-        if (!in_partition(p, pos + remaining)) part_disp = displacement_up_to_partition_boundary(p, pos, remaining);
-        SpList spw; SpSet spm; spm.n = 0; spm.overflow = false;
-        uint32_t last_subpart = collect_crossed_subparts(p, pos, subpart, part_disp, can_vol_react, true, spw, spm);
-        D3 up_to_wall = remaining;
-        bool hit = false, hit_in_last = false;
-        WallHit wh;
-        for (int k = 0; k < spw.n; k++) {
-          if (closest_wall_collision(p, pos, spw.v[k], last_hit_wall, rs, remaining, up_to_wall, wh, ls, tc)) {
-            hit = true; hit_in_last = last_subpart == spw.v[k];
-            break;
-          }
+    if (!decided) {
+      // -- newbie lifetime (:232-236 -> pick_unimol_rxn_class_and_set_rxn_time :1731-1758, time_of_unimol)
+      if (flags & DF_SCHED_UNIMOL) {
+        flags &= ~DF_SCHED_UNIMOL;
+        int rc = p.unimol[species];
+        if (rc < 0) unimol_time = MCX_TIME_INVALID;
+        else {
+          double k_tot = p.classes[rc].max_fixed_p;
+          double pr = rs.dbl();
+          double from_now = (k_tot <= 0 || !distinguishable_d(pr, 0, MCX_EPS)) ? MCX_TIME_FOREVER : -log(pr) / k_tot;
+          unimol_time = t_now + from_now;
         }
-        bool reacted = false;
-        if (can_vol_react) {
-          if (hit && !hit_in_last) {
-            spm.n = 0;
-            collect_crossed_subparts(p, pos, subpart, up_to_wall, true, false, spw, spm);
+      }
+      // -- get_max_time (:164-198)
+      double max_time = t_end - t_now;
+      if (unimol_time != MCX_TIME_INVALID && unimol_time < t_now + max_time) max_time = unimol_time - t_now;
+
+      if (can_diffuse) {
+        // ---- compute_vol_displacement (diffusion_utils.inl:366-432)
+        double steps = 1.0, t_steps = steps * sp.time_step, r_rate_factor, scale;
+        if (t_steps > max_time) { t_steps = max_time; steps = max_time / sp.time_step; }
+        if (steps < MCX_EPS) { steps = MCX_EPS; t_steps = MCX_EPS * sp.time_step; }
+        if (steps == 1.0) { scale = sp.space_step; r_rate_factor = 1.0; }
+        else { double rate_factor = sqrt(steps); r_rate_factor = 1.0 / rate_factor; scale = rate_factor * sp.space_step; }
+        D3 remaining;
+        remaining.x = scale * rs.gauss() * 0.70710678118654752440;
+        remaining.y = scale * rs.gauss() * 0.70710678118654752440;
+        remaining.z = scale * rs.gauss() * 0.70710678118654752440;
+        max_time = t_steps;
+
+        uint32_t last_hit_wall = MCX_NONE;
+        double elapsed = t_now;
+        // ---- diffuse_vol_molecule loop (:423-572)
+        bool tracing = true;
+        for (int trace_guard = 0; tracing; trace_guard++) {
+          if (trace_guard > 100000) { err = MCX_ERR_STATE; tracing = false; }
+          // ---- ray_trace_vol (:627-780)
+          D3 part_disp = remaining;
+          if (!in_partition(p, pos + remaining)) part_disp = displacement_up_to_partition_boundary(p, pos, remaining);
+          SpList spw; SpSet spm; spm.n = 0; spm.overflow = false;
+          uint32_t last_subpart = collect_crossed_subparts(p, pos, subpart, part_disp, can_vol_react, true, spw, spm);
+          D3 up_to_wall = remaining;
+          bool hit = false, hit_in_last = false;
+          WallHit wh;
+          for (int k = 0; k < spw.n && !hit; k++) {
+            if (closest_wall_collision(p, pos, spw.v[k], last_hit_wall, rs, remaining, up_to_wall, wh, ls, tc)) {
+              hit = true; hit_in_last = last_subpart == spw.v[k];
+            }
           }
-          if (spm.overflow) err = MCX_ERR_OVERFLOW;
-          const bool need_filter = !(spm.n == 1);  // single subpart: every partner in reach shares it unless...
-          // ... it sits across a subpart face: the filter is still required then, so only skip when the swept
-          // box lies strictly inside the own subpart
-          bool filter = true;
-          if (!need_filter) {
-            int si[3] = {(int)(subpart % p.n_sp), (int)((subpart / p.n_sp) % p.n_sp), (int)(subpart / (p.n_sp * p.n_sp))};
-            const double pad = p.R * 1.000001 + 1e-6;
-            double lx = p.ox + si[0] * p.sp_len, ly = p.oy + si[1] * p.sp_len, lz = p.oz + si[2] * p.sp_len;
-            D3 e = pos + remaining;
-            filter = !(fmin(pos.x, e.x) - pad > lx && fmax(pos.x, e.x) + pad < lx + p.sp_len &&
-                       fmin(pos.y, e.y) - pad > ly && fmax(pos.y, e.y) + pad < ly + p.sp_len &&
-                       fmin(pos.z, e.z) - pad > lz && fmax(pos.z, e.z) + pad < lz + p.sp_len);
-          }
-          // sort_collisions_by_time (:341-364) realised as repeated selection of the next collision
-          const double t_limit = hit ? wh.t : MCX_TIME_FOREVER;
-          double t_last = -1.0; uint32_t id_last = 0;
-          for (;;) {
-            PartnerHit ph;
-            int cnt = scan_partners<RETRY>(p, pos, remaining, m.id, species, spm, filter, t_last, id_last, t_limit, ph);
-            if (cnt == 0) break;
-            t_last = ph.t; id_last = ph.id;
-            ls.volvol_collisions++;
-            if (!(ph.t < MCX_EPS)) {  // is_immediate_collision
-              // collide_and_react_with_vol_mol (:786-829); exact_disk factor := 1 (documented gap)
-              double factor = 1.0;
-              double abs_t = elapsed + t_steps * ph.t;
-              double scaling = factor * r_rate_factor;
-              tc.ev(EV_COLL, ph.id);
-              if (tc.tr) { if (tc.tr->n_collisions < MCX_TRACE_K) tc.tr->partner[tc.tr->n_collisions] = ph.id; tc.tr->n_collisions++; }
-              int pathway = test_bimolecular(p, p.classes[ph.rxn_class], scaling, rs);
-              if (pathway >= 0) {
-                tc.ev(EV_RXN | (uint32_t)pathway, (uint32_t)ph.rxn_class);
-                if (tc.tr) { tc.tr->rxn_class = ph.rxn_class; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = ph.id; tc.tr->t_event = abs_t; }
-                out.kind = MCX_OUT_REACTED; out.pos = pos + remaining * ph.t;
-                out.rxn_class = ph.rxn_class; out.pathway = pathway; out.partner_slot = ph.slot; out.partner_id = ph.id;
-                out.t_event = abs_t; out.t_now = t_now; out.flags = flags; out.unimol_time = unimol_time;
-                reacted = true;
-                break;
+          bool reacted = false;
+          if (can_vol_react) {
+            if (hit && !hit_in_last) {
+              spm.n = 0;
+              collect_crossed_subparts(p, pos, subpart, up_to_wall, true, false, spw, spm);
+            }
+            if (spm.overflow) err = MCX_ERR_OVERFLOW;
+            // the subpartition filter can be skipped only when the swept box lies strictly inside the own subpart
+            bool filter = true;
+            if (spm.n == 1) {
+              int si[3] = {(int)(subpart % p.n_sp), (int)((subpart / p.n_sp) % p.n_sp), (int)(subpart / (p.n_sp * p.n_sp))};
+              const double pad = p.R * 1.000001 + 1e-6;
+              double lx = p.ox + si[0] * p.sp_len, ly = p.oy + si[1] * p.sp_len, lz = p.oz + si[2] * p.sp_len;
+              D3 e = pos + remaining;
+              filter = !(fmin(pos.x, e.x) - pad > lx && fmax(pos.x, e.x) + pad < lx + p.sp_len &&
+                         fmin(pos.y, e.y) - pad > ly && fmax(pos.y, e.y) + pad < ly + p.sp_len &&
+                         fmin(pos.z, e.z) - pad > lz && fmax(pos.z, e.z) + pad < lz + p.sp_len);
+            }
+            // sort_collisions_by_time (:341-364) realised as repeated selection of the next collision
+            const double t_limit = hit ? wh.t : MCX_TIME_FOREVER;
+            double t_last = -1.0; uint32_t id_last = 0;
+            bool scanning = true;
+            while (scanning) {
+              PartnerHit ph;
+              int cnt = scan_partners<RETRY>(p, pos, remaining, m.id, species, spm, filter, t_last, id_last, t_limit, ph);
+              if (cnt == 0) scanning = false;
+              else {
+                t_last = ph.t; id_last = ph.id;
+                ls.volvol_collisions++;
+                if (!(ph.t < MCX_EPS)) {  // is_immediate_collision
+                  // collide_and_react_with_vol_mol (:786-829); exact_disk factor := 1 (documented gap)
+                  double factor = 1.0;
+                  double abs_t = elapsed + t_steps * ph.t;
+                  double scaling = factor * r_rate_factor;
+                  tc.ev(EV_COLL, ph.id);
+                  if (tc.tr) { if (tc.tr->n_collisions < MCX_TRACE_K) tc.tr->partner[tc.tr->n_collisions] = ph.id; tc.tr->n_collisions++; }
+                  int pathway = test_bimolecular(p, p.classes[ph.rxn_class], scaling, rs);
+                  if (pathway >= 0) {
+                    tc.ev(EV_RXN | (uint32_t)pathway, (uint32_t)ph.rxn_class);
+                    if (tc.tr) { tc.tr->rxn_class = ph.rxn_class; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = ph.id; tc.tr->t_event = abs_t; }
+                    out.kind = MCX_OUT_REACTED; out.pos = pos + remaining * ph.t;
+                    out.rxn_class = ph.rxn_class; out.pathway = pathway; out.partner_slot = ph.slot; out.partner_id = ph.id;
+                    out.t_event = abs_t; out.t_now = t_now; out.flags = flags; out.unimol_time = unimol_time;
+                    reacted = true;
+                    scanning = false;
+                  }
+                }
+                if (cnt == 1) scanning = false;
               }
             }
-            if (cnt == 1) break;
+          }
+          if (reacted) { decided = true; tracing = false; }
+          else if (!hit) {  // RayTraceState::FINISHED
+            pos = pos + remaining;
+            if (!in_partition(p, pos)) { err = MCX_ERR_ESCAPED; out.kind = MCX_OUT_NONE; out.pos = pos; decided = true; }
+            else subpart = subpart_index(p, pos);
+            tracing = false;
+          } else {
+            // ---- wall collision (:476-567)
+            const int side = wh.side;  // W_FRONT / W_BACK
+            const uint32_t wclass = p.wall_class[wh.wall];
+            int action = MCX_SURF_REFLECTIVE;
+            if (wclass != MCX_NONE) action = p.surf_action[(species * p.n_surf_classes + wclass) * 2 + (side == W_FRONT ? 0 : 1)];
+            if (tc.tr) {
+              if (tc.tr->n_wall_hits < MCX_TRACE_K) { tc.tr->wall[tc.tr->n_wall_hits] = wh.wall; tc.tr->wall_side[tc.tr->n_wall_hits] = side; }
+              tc.tr->n_wall_hits++;
+            }
+            if (action == MCX_SURF_TRANSPARENT) {  // cross_transparent_wall (:3007-3099)
+              tc.ev(EV_TRANSP | (uint32_t)side, wh.wall);
+              ls.transparent++;
+              pos = wh.pos; subpart = subpart_index(p, pos);
+              remaining = remaining * (1.0 - wh.t);
+              elapsed += t_steps * wh.t;
+              t_steps *= (1.0 - wh.t);
+              if (t_steps < MCX_EPS) t_steps = MCX_EPS;
+              last_hit_wall = wh.wall;
+            } else if (action == MCX_SURF_ABSORPTIVE) {  // test_intersect: two draws (rxn_utils.inl:593-626)
+              double abs_t = elapsed + t_steps * wh.t;
+              (void)rs.dbl(); (void)rs.dbl();
+              tc.ev(EV_ABSORB | (uint32_t)side, wh.wall);
+              if (tc.tr) tc.tr->t_event = abs_t;
+              out.kind = MCX_OUT_ABSORBED; out.pos = wh.pos; out.t_event = abs_t; out.t_now = t_now; out.flags = flags;
+              out.unimol_time = unimol_time;
+              decided = true; tracing = false;
+            } else {  // reflect_from_wall, collision_utils.inl:1711-1747
+              tc.ev(EV_WALL | (uint32_t)side, wh.wall);
+              ls.reflections++;
+              elapsed += t_steps * wh.t;
+              pos = wh.pos; subpart = subpart_index(p, pos);
+              t_steps *= (1.0 - wh.t);
+              last_hit_wall = wh.wall;
+              const DevWall& f = p.walls[wh.wall];
+              D3 n = {f.nx, f.ny, f.nz};
+              double reflect_factor = -2.0 * dot3(remaining, n);
+              remaining = (remaining + n * reflect_factor) * (1.0 - wh.t);
+            }
           }
         }
-        if (reacted) return;
-        if (!hit) {  // RayTraceState::FINISHED
-          pos = pos + remaining;
-          if (!in_partition(p, pos)) { err = MCX_ERR_ESCAPED; out.kind = MCX_OUT_NONE; out.pos = pos; return; }
-          subpart = subpart_index(p, pos);
-          break;
-        }
-        // ---- wall collision (:476-567)
-        const int side = wh.side;  // W_FRONT / W_BACK
-        const uint32_t wclass = p.wall_class[wh.wall];
-        int action = MCX_SURF_REFLECTIVE;
-        if (wclass != MCX_NONE) action = p.surf_action[(species * p.n_surf_classes + wclass) * 2 + (side == W_FRONT ? 0 : 1)];
-        if (tc.tr) {
-          if (tc.tr->n_wall_hits < MCX_TRACE_K) { tc.tr->wall[tc.tr->n_wall_hits] = wh.wall; tc.tr->wall_side[tc.tr->n_wall_hits] = side; }
-          tc.tr->n_wall_hits++;
-        }
-        if (action == MCX_SURF_TRANSPARENT) {  // cross_transparent_wall (:3007-3099)
-          tc.ev(EV_TRANSP | (uint32_t)side, wh.wall);
-          ls.transparent++;
-          pos = wh.pos; subpart = subpart_index(p, pos);
-          remaining = remaining * (1.0 - wh.t);
-          elapsed += t_steps * wh.t;
-          t_steps *= (1.0 - wh.t);
-          if (t_steps < MCX_EPS) t_steps = MCX_EPS;
-          last_hit_wall = wh.wall;
-        } else if (action == MCX_SURF_ABSORPTIVE) {  // test_intersect: two draws (rxn_utils.inl:593-626)
-          double abs_t = elapsed + t_steps * wh.t;
-          (void)rs.dbl(); (void)rs.dbl();
-          tc.ev(EV_ABSORB | (uint32_t)side, wh.wall);
-          if (tc.tr) tc.tr->t_event = abs_t;
-          out.kind = MCX_OUT_ABSORBED; out.pos = wh.pos; out.t_event = abs_t; out.t_now = t_now; out.flags = flags;
-          out.unimol_time = unimol_time;
-          return;
-        } else {  // reflect_from_wall, collision_utils.inl:1711-1747
-          tc.ev(EV_WALL | (uint32_t)side, wh.wall);
-          ls.reflections++;
-          elapsed += t_steps * wh.t;
-          pos = wh.pos; subpart = subpart_index(p, pos);
-          t_steps *= (1.0 - wh.t);
-          last_hit_wall = wh.wall;
-          const DevWall& f = p.walls[wh.wall];
-          D3 n = {f.nx, f.ny, f.nz};
-          double reflect_factor = -2.0 * dot3(remaining, n);
-          remaining = (remaining + n * reflect_factor) * (1.0 - wh.t);
+      }
+      if (!decided) {
+        // -- reschedule (:283-336)
+        if (can_diffuse) {
+          t_now += max_time;
+          if ((unimol_time != MCX_TIME_INVALID && unimol_time < t_end) || (t_now < t_end && !cmp_eq_d(t_now, t_end, MCX_EPS))) again = true;
+          else {
+            double r = round(t_now);
+            if (cmp_eq_d(t_now, r, MCX_SQRT_EPS)) t_now = r;
+          }
+        } else {
+          if (unimol_time != MCX_TIME_INVALID) {
+            t_now = unimol_time;
+            if (unimol_time < t_end) again = true;
+          } else t_now = MCX_TIME_FOREVER;
         }
       }
     }
-    // -- reschedule (:283-336)
-    bool again = false;
-    if (can_diffuse) {
-      t_now += max_time;
-      if ((unimol_time != MCX_TIME_INVALID && unimol_time < t_end) || (t_now < t_end && !cmp_eq_d(t_now, t_end, MCX_EPS))) again = true;
-      else {
-        double r = round(t_now);
-        if (cmp_eq_d(t_now, r, MCX_SQRT_EPS)) t_now = r;
-      }
-    } else {
-      if (unimol_time != MCX_TIME_INVALID) {
-        t_now = unimol_time;
-        if (unimol_time < t_end) again = true;
-      } else t_now = MCX_TIME_FOREVER;
-    }
-    if (!again) break;
   }
-  out.kind = can_diffuse ? MCX_OUT_MOVED : MCX_OUT_STATIC;
-  out.pos = pos; out.t_now = t_now; out.flags = flags & ~DF_PARTIAL; out.unimol_time = unimol_time;
+  if (!decided) {
+    out.kind = can_diffuse ? MCX_OUT_MOVED : MCX_OUT_STATIC;
+    out.pos = pos; out.t_now = t_now; out.flags = flags & ~DF_PARTIAL; out.unimol_time = unimol_time;
+  }
 }

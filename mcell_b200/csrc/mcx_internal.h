@@ -47,10 +47,12 @@ struct Counters {
   unsigned int error_id;       // molecule id that raised it
   unsigned int next_id;        // fresh molecule ids
   unsigned int n_emigrants[2]; // multi-GPU: records leaving through the low/high slab face
-  unsigned int pad[5];
+  unsigned int n_slow;         // entries of slow_list this iteration
+  unsigned int pad[4];
   // statistics (SimulationStats mirror)
   unsigned long long molecule_steps, ray_polygon_tests, ray_polygon_colls, reflections, transparent,
-      absorptions, volvol_collisions, bimol_rxns, unimol_rxns, redos, retries, unresolved, products;
+      absorptions, volvol_collisions, bimol_rxns, unimol_rxns, redos, retries, unresolved, products, deferred;
+  unsigned long long defer_reason[8];  // why the fast pass deferred a molecule (MCX_DEFER_*)
   unsigned long long species_count[256];
   unsigned long long rxn_count[256];
 };
@@ -60,7 +62,7 @@ struct DevParams {
   double ox, oy, oz, part_len, sp_len, sp_rcp, R;
   int n_sp, use_expanded;
   // device neighbour-cell grid
-  double cgx, cgy, cgz, cell_rcp;
+  double cgx, cgy, cgz, cell_rcp_x, cell_rcp_y, cell_rcp_z;  // cells are short in x (rows are contiguous), long in y/z
   int ncx, ncy, ncz;
   unsigned int n_cells;
   // immutable tables
@@ -70,6 +72,7 @@ struct DevParams {
   const uint32_t* wall_class;
   const uint32_t* spw_start;
   const uint32_t* spw_list;
+  const uint8_t* sp_flags;      // per subpartition: bit0 = holds walls, bit1 = any of its 3x3x3 neighbours holds walls
   const DevSpecies* species;
   const int* bimol;
   const int* unimol;
@@ -97,6 +100,7 @@ struct DevParams {
   uint32_t* prop_info;         // per slot: kind(4) | pathway(12) | class(16)
   double* prop_t;              // per slot: absolute event time
   uint32_t* pend[2];           // pending lists (slot indices)
+  uint32_t* slow_list;         // slots the fast diffuse pass deferred to the generic evaluation
   unsigned int capacity;
   unsigned int max_rounds;
   Counters* ctr;
@@ -110,7 +114,7 @@ struct DevParams {
 struct StepPlan {
   int sm_count;
   unsigned long long* launches;  // host-side counter of kernels launched (may be null)
-  cudaEvent_t* prof;             // 4 events for this iteration (null = no per-kernel timing)
+  cudaEvent_t* prof;             // 5 events for this iteration (null = no per-kernel timing)
   bool has_claims;   // model can produce reactions / absorptions (conflict rounds needed)
   bool trace;
 };

@@ -1,7 +1,9 @@
 // mcx_kernels.cu — the per-iteration kernel pipeline of libmcx (sm_100a).
 //
-//   k_diffuse      every live molecule: evaluate against snapshot A, write result to B, bin it for the
-//                  next snapshot (histogram atomics -> rank); claiming events become proposals
+//   k_diffuse_fast every live molecule: the common no-wall / no-partner whole step, converged control flow;
+//                  writes the result to B and bins it for the next snapshot (histogram atomics -> rank)
+//   k_diffuse_slow the deferred rest (walls, collisions, split steps): generic evaluation; claiming events
+//                  become proposals
 //   k_resolve/k_retry  synchronous conflict-resolution rounds over the (small) pending list
 //   k_scan_*       exclusive scan of the cell histogram -> cell_start of the next snapshot
 //   k_scatter      counting-sort scatter B -> A (drops consumed molecules: folds
@@ -17,6 +19,37 @@
 __device__ __forceinline__ unsigned long long claim_key(unsigned int epoch, uint32_t id) {
   return ((unsigned long long)epoch << 32) | (unsigned long long)(~id);
 }
+// ---- warp-aggregated atomics: lanes of the (possibly divergent) warp that target the same address combine
+// into one atomic.  Counters and list cursors are hit by every committing thread; without this the L2 atomic
+// unit serialises them (profiles/r01_a: k_resolve 0.5 ms for 1.4e5 proposals).
+__device__ __forceinline__ void agg_add(unsigned long long* addr, unsigned int v) {
+  const unsigned int peers = __match_any_sync(__activemask(), (unsigned long long)addr);
+  const unsigned int total = __reduce_add_sync(peers, v);
+  if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(addr, (unsigned long long)total);
+}
+__device__ __forceinline__ void agg_sub(unsigned long long* addr, unsigned int v) {
+  const unsigned int peers = __match_any_sync(__activemask(), (unsigned long long)addr);
+  const unsigned int total = __reduce_add_sync(peers, v);
+  if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(addr, (unsigned long long)(-(long long)total));
+}
+// reserve `v` consecutive indices at *addr for this lane; returns the first
+__device__ __forceinline__ unsigned int agg_reserve(unsigned int* addr, unsigned int v) {
+  const unsigned int peers = __match_any_sync(__activemask(), (unsigned long long)addr);
+  const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  // exclusive prefix of v over the peers below this lane
+  unsigned int before = 0, total = 0;
+  for (unsigned int rest = peers; rest; rest &= rest - 1) {
+    const int src = __ffs(rest) - 1;
+    const unsigned int x = __shfl_sync(peers, v, src);
+    if (src < lane) before += x;
+    total += x;
+  }
+  unsigned int base = 0;
+  if (lane == leader) base = atomicAdd(addr, total);
+  base = __shfl_sync(peers, base, leader);
+  return base + before;
+}
+
 __device__ __forceinline__ unsigned int round_epoch(const DevParams& p, unsigned int round) {
   return (unsigned int)(p.iteration * (unsigned long long)(p.max_rounds + 1) + round + 1);
 }
@@ -74,39 +107,40 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
   Counters* c = p.ctr;
   if (kind == MCX_OUT_ABSORBED) {
     atomicOr(&p.recA[slot].sf, DF_DEAD);
-    atomicAdd(&c->absorptions, 1ull);
-    atomicAdd(&c->species_count[species], (unsigned long long)-1ll);
+    agg_add(&c->absorptions, 1u);
+    agg_sub(&c->species_count[species], 1u);
     return;
   }
   const DevClass& cl = p.classes[rxn_class];
   const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
-  atomicAdd(&c->rxn_count[pw.rule_id & 255u], 1ull);
+  agg_add(&c->rxn_count[pw.rule_id & 255u], 1u);
   bool keepA, keepB = true;
   uint32_t reuse[2]; int n_reuse = 0;
   if (kind == MCX_OUT_REACTED) {
-    atomicAdd(&c->bimol_rxns, 1ull);
+    agg_add(&c->bimol_rxns, 1u);
     bool a_is_r0 = species == cl.r0;
     keepA = (pw.keep_mask >> (a_is_r0 ? 0 : 1)) & 1u;
     keepB = (pw.keep_mask >> (a_is_r0 ? 1 : 0)) & 1u;
   } else {
-    atomicAdd(&c->unimol_rxns, 1ull);
+    agg_add(&c->unimol_rxns, 1u);
     keepA = pw.keep_mask & 1u;
   }
   if (!keepA) {
     atomicOr(&p.recA[slot].sf, DF_DEAD);
-    atomicAdd(&c->species_count[species], (unsigned long long)-1ll);
+    agg_sub(&c->species_count[species], 1u);
     reuse[n_reuse++] = id;
   }
   if (!keepB) {
     uint32_t old = atomicOr(&p.recA[partner_slot].sf, DF_DEAD);
     atomicOr(&p.recB[partner_slot].sf, DF_DEAD);
-    atomicAdd(&c->species_count[old & SF_SPECIES_MASK], (unsigned long long)-1ll);
+    agg_sub(&c->species_count[old & SF_SPECIES_MASK], 1u);
     uint32_t pid = p.recA[partner_slot].id;
     reuse[n_reuse++] = pid;
     if (p.trace && pid < p.n_trace) p.trace[pid].outcome = MCX_OUT_CONSUMED;
   }
+  const uint32_t first_slot = pw.n_products ? c->n_slots + agg_reserve(&c->n_prod, pw.n_products) : 0u;
   for (uint32_t k = 0; k < pw.n_products; k++) {
-    uint32_t ns = c->n_slots + atomicAdd(&c->n_prod, 1u);
+    uint32_t ns = first_slot + k;
     if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
     uint32_t nid = (int)k < n_reuse ? reuse[k] : atomicAdd(&c->next_id, 1u);
     uint32_t psp = pw.products[k];
@@ -114,8 +148,8 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
     store_rec(p.recB, ns, pos, nid, psp | DF_SCHED_UNIMOL | DF_PARTIAL);
     uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
     p.rank[ns] = atomicAdd(&p.cs_next[cell], 1u);
-    atomicAdd(&c->species_count[psp], 1ull);
-    atomicAdd(&c->products, 1ull);
+    agg_add(&c->species_count[psp], 1u);
+    agg_add(&c->products, 1u);
   }
   if (keepA) {
     // kept initiator stops at the event and takes the rest of its step lazily next iteration
@@ -138,7 +172,7 @@ __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot
   unsigned long long key = claim_key(epoch, id);
   atomicMax(&p.claim[slot], key);
   if (partner_is_consumed(p, o.kind, o.rxn_class, o.pathway, species)) atomicMax(&p.claim[o.partner_slot], key);
-  uint32_t k = atomicAdd(&p.ctr->n_pend[list], 1u);
+  uint32_t k = agg_reserve(&p.ctr->n_pend[list], 1u);
   p.pend[list][k] = slot;
 }
 
@@ -161,20 +195,149 @@ __device__ __forceinline__ void trace_end(Tracer& tc, const Outcome& o, const St
 }
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_diffuse(const __grid_constant__ DevParams p) {
+// k_diffuse_fast: every live molecule.  The common case — a whole time step, no pending unimolecular event,
+// no wall in reach, no partner in reach — is finished here with converged control flow: 3 Gaussians, one
+// subpartition flag lookup, one flattened candidate walk, store + bin.  Everything else (wall hits, collisions,
+// split steps, newborn molecules, subpartition-set filtering) is appended to slow_list and evaluated by
+// k_diffuse_slow with the generic code, restarting the molecule's random stream from its first word, so both
+// kernels together compute exactly evaluate_iteration() for every molecule.
+//
+// Why the fast test is exact (reference semantics):
+//  * walls are only tested in subpartitions the segment crosses (ray_trace_vol :698); those lie in the index
+//    block spanned by the start and end subpartitions, so "no wall in the start subpartition" (segment stays
+//    inside) or "no wall in its 3x3x3 neighbourhood" (|index step| <= 1) means no wall collision;
+//  * partners are the molecules of collected subpartitions that pass collide_mol; probing ALL molecules that
+//    pass collide_mol (no subpartition filter) is a superset, so an empty probe means no collision.
+//
+// The body is written flat: every lane of the warp executes the same instruction stream with predicates
+// (`simple` narrows as tests fail; lanes that dropped out run empty loops), because nested `if (simple) {...}`
+// blocks made the compiler split the warp into independently scheduled groups that each ran the whole
+// candidate walk (profiles/r01_b: 7 of 32 lanes active).
+#ifndef MCX_FAST_MINBLOCKS
+#define MCX_FAST_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const __grid_constant__ DevParams p) {
   __shared__ ZigShared zig;
   zig_load(&zig);
   __syncthreads();
   const unsigned int n = p.ctr->n_slots;
+  const double t_end = (double)p.iteration + 1.0;
+  const int lane = threadIdx.x & 31;
+  unsigned int msteps = 0, n_tests = 0, n_coll = 0;
+  for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const unsigned int i = base + threadIdx.x;
+    const bool in_range = i < n;
+    const unsigned int ii = in_range ? i : base;  // a valid slot for every lane
+    const MolRec m = load_rec(p.recA, ii);
+    const bool live = in_range && !(m.sf & (DF_DEAD | DF_GHOST));
+    const uint32_t species = m.sf & SF_SPECIES_MASK;
+    const uint32_t flags = m.sf & ~SF_SPECIES_MASK;
+    const DevSpecies sp = p.species[species];
+    bool simple = live && !(m.sf & (DF_PARTIAL | DF_SCHED_UNIMOL)) && (sp.flags & MCX_SP_CAN_DIFFUSE) && sp.time_step == 1.0;
+    // scheduled unimolecular time: a predicated index keeps the load unconditional (no warp split) without
+    // touching the cold array for molecules that have none
+    const bool has_uni = (m.sf & DF_HAS_UNIMOL) != 0;
+    const double t_uni_raw = __ldg(p.tuniA + ((simple && has_uni) ? ii : 0u));
+    const double t_uni = has_uni ? t_uni_raw : MCX_TIME_INVALID;
+    simple = simple && !(has_uni && t_uni < t_end);  // fires or splits the step inside this iteration -> generic path
+    int reason = simple ? -1 : MCX_DEFER_TIMING;
+
+    // compute_vol_displacement with steps == 1 (diffusion_utils.inl:366-432); drawn by every lane
+    Stream rs; rs.init(p, m.id, &zig);
+    D3 disp;
+    disp.x = sp.space_step * rs.gauss() * 0.70710678118654752440;
+    disp.y = sp.space_step * rs.gauss() * 0.70710678118654752440;
+    disp.z = sp.space_step * rs.gauss() * 0.70710678118654752440;
+    const D3 pos = {m.x, m.y, m.z};
+    const D3 dest = pos + disp;
+    simple = simple && in_partition(p, dest);
+    if (!simple && reason < 0) reason = MCX_DEFER_GEOMETRY;
+    int s0[3], s1[3];
+    subpart_3d(p, pos, s0);
+    subpart_3d(p, dest, s1);
+    const int dx = s1[0] - s0[0], dy = s1[1] - s0[1], dz = s1[2] - s0[2];
+    const uint32_t own = simple ? subpart_from_3d(p, s0[0], s0[1], s0[2]) : 0u;
+    const uint8_t f = __ldg(p.sp_flags + own);
+    const bool same = (dx | dy | dz) == 0;
+    const bool near = dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1;
+    // one subpartition face crossed: the DDA visits exactly {start, end} (collision_utils_subparts.inl:127-300)
+    const bool single = near && ((dx != 0) + (dy != 0) + (dz != 0)) == 1;
+    const uint32_t dest_sp = (simple && single) ? subpart_from_3d(p, s1[0], s1[1], s1[2]) : 0u;
+    const uint8_t fd = __ldg(p.sp_flags + dest_sp);
+    unsigned int n_wall_tests = 0, n_wall_tests_dest = 0;
+    const bool walls_own = simple && (same || single) && (f & 1);
+    const bool walls_dest = simple && single && (fd & 1);
+    const bool rejected_own = all_walls_plane_rejected(p, walls_own, own, pos, disp, n_wall_tests);
+    const bool rejected_dest = all_walls_plane_rejected(p, walls_dest, dest_sp, pos, disp, n_wall_tests_dest);
+    n_wall_tests += n_wall_tests_dest;
+    simple = simple && ((same || single) ? ((!walls_own || rejected_own) && (!walls_dest || rejected_dest)) : (near && !(f & 2)));
+    if (!simple && reason < 0) reason = (same || single) ? MCX_DEFER_WALL : MCX_DEFER_GEOMETRY;
+
+    // partner probe: none -> move; exactly one, in the molecule's own subpartition (always a collected one)
+    // -> the single collision is evaluated below; anything else -> generic path
+    PartnerHit ph;
+    const bool probing = simple && sp.can_vol_react;
+    bool overflow;
+    const int n_hits = probe_partners(p, probing, pos, disp, m.id, species, ph, overflow);
+    simple = simple && !overflow && (n_hits == 0 || (n_hits == 1 && ph.in_own_subpart));
+    if (!simple && reason < 0) reason = overflow ? MCX_DEFER_PROBE_SHAPE : (n_hits > 1 ? MCX_DEFER_MULTI_HIT : MCX_DEFER_FOREIGN_HIT);
+
+    if (simple) {
+      Tracer tc; trace_begin(p, tc, m.id);
+      Outcome o; o.kind = MCX_OUT_MOVED; o.pos = dest;
+      if (n_hits == 1) {
+        n_coll++;
+        if (!(ph.t < MCX_EPS)) {  // is_immediate_collision (collision_utils.inl:814-816)
+          // collide_and_react_with_vol_mol (:786-829) with scaling = factor(1) * r_rate_factor(1)
+          tc.ev(EV_COLL, ph.id);
+          if (tc.tr) { tc.tr->partner[0] = ph.id; tc.tr->n_collisions = 1; }
+          const int pathway = test_bimolecular(p, p.classes[ph.rxn_class], 1.0, rs);
+          if (pathway >= 0) {
+            const double abs_t = (double)p.iteration + 1.0 * ph.t;
+            tc.ev(EV_RXN | (uint32_t)pathway, (uint32_t)ph.rxn_class);
+            if (tc.tr) { tc.tr->rxn_class = ph.rxn_class; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = ph.id; tc.tr->t_event = abs_t; }
+            o.kind = MCX_OUT_REACTED; o.pos = pos + disp * ph.t;
+            o.rxn_class = ph.rxn_class; o.pathway = pathway; o.partner_slot = ph.slot; o.partner_id = ph.id;
+            o.t_event = abs_t; o.t_now = (double)p.iteration; o.flags = flags; o.unimol_time = t_uni;
+          }
+        }
+      }
+      trace_end(tc, o, rs);
+      if (o.kind == MCX_OUT_MOVED) finalize_alive(p, i, dest, m.id, species, flags, t_end, t_uni);
+      else write_proposal(p, i, o, m.id, species, round_epoch(p, 0), 0);
+      msteps++;
+      n_tests += n_wall_tests;
+    }
+    if (in_range && !live) p.rank[i] = MCX_NONE;
+    const bool slow = live && !simple;
+    // warp-aggregated append of the deferred slots (loop bounds are warp-uniform: all 32 lanes arrive here)
+    const unsigned int bal = __ballot_sync(0xffffffffu, slow);
+    if (bal) {
+      unsigned int at = 0;
+      if (lane == 0) { at = atomicAdd(&p.ctr->n_slow, (unsigned int)__popc(bal)); atomicAdd(&p.ctr->deferred, (unsigned long long)__popc(bal)); }
+      at = __shfl_sync(0xffffffffu, at, 0);
+      if (slow) { p.slow_list[at + __popc(bal & ((1u << lane) - 1u))] = i; agg_add(&p.ctr->defer_reason[reason & 7], 1u); }
+    }
+  }
+  LocalStats ls = {n_tests, 0, 0, 0, n_coll, 0};
+  flush_stats(p, ls, msteps);
+}
+
+// k_diffuse_slow: the generic evaluation (evaluate_iteration) for the slots k_diffuse_fast deferred
+__global__ void __launch_bounds__(TPB, 2) k_diffuse_slow(const __grid_constant__ DevParams p) {
+  __shared__ ZigShared zig;
+  zig_load(&zig);
+  __syncthreads();
+  const unsigned int n = p.ctr->n_slow;
   const unsigned int epoch = round_epoch(p, 0);
   LocalStats ls = {0, 0, 0, 0, 0, 0};
   unsigned int msteps = 0;
   // all lanes of a warp iterate together so the warp-level stat flush sees full warps
   for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    unsigned int i = base + threadIdx.x;
-    if (i >= n) continue;
+    const unsigned int k = base + threadIdx.x;
+    if (k >= n) continue;
+    const unsigned int i = p.slow_list[k];
     MolRec m = load_rec(p.recA, i);
-    if (m.sf & (DF_DEAD | DF_GHOST)) { p.rank[i] = MCX_NONE; continue; }
     const uint32_t species = m.sf & SF_SPECIES_MASK;
     double t_sched = (m.sf & DF_PARTIAL) ? p.tschedA[i] : 0.0;
     double t_uni = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;
@@ -211,7 +374,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(const __grid_constant__ DevPara
       commit_event(p, slot, kind, rxn_class, pathway, partner, p.prop_t[slot], D3{e.x, e.y, e.z}, e.id, species,
                    e.sf & ~SF_SPECIES_MASK, p.tschedB[slot], p.tuniB[slot]);
     } else {
-      uint32_t q = atomicAdd(&p.ctr->n_pend[nxt], 1u);
+      uint32_t q = agg_reserve(&p.ctr->n_pend[nxt], 1u);
       p.pend[nxt][q] = slot;
     }
   }
@@ -219,7 +382,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(const __grid_constant__ DevPara
 
 // losers of round r are re-evaluated against the updated snapshot flags; their new proposals go back
 // to list `cur` for round r+1
-__global__ void __launch_bounds__(TPB) k_retry(const __grid_constant__ DevParams p, unsigned int round, int forced) {
+__global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevParams p, unsigned int round, int forced) {
   __shared__ ZigShared zig;
   zig_load(&zig);
   __syncthreads();
@@ -237,8 +400,8 @@ __global__ void __launch_bounds__(TPB) k_retry(const __grid_constant__ DevParams
       if (p.trace && m.id < p.n_trace) p.trace[m.id].outcome = MCX_OUT_CONSUMED;
       continue;
     }
-    atomicAdd(&p.ctr->retries, 1ull);
-    if (forced) atomicAdd(&p.ctr->unresolved, 1ull);
+    agg_add(&p.ctr->retries, 1u);
+    if (forced) agg_add(&p.ctr->unresolved, 1u);
     const uint32_t species = m.sf & SF_SPECIES_MASK;
     double t_sched = (m.sf & DF_PARTIAL) ? p.tschedA[i] : 0.0;
     double t_uni = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;
@@ -354,7 +517,7 @@ __global__ void __launch_bounds__(TPB) k_scatter(const __grid_constant__ DevPara
 __global__ void k_end_iteration(const __grid_constant__ DevParams p) {
   Counters* c = p.ctr;
   c->n_slots = c->n_next;
-  c->n_prod = 0; c->n_pend[0] = 0; c->n_pend[1] = 0;
+  c->n_prod = 0; c->n_pend[0] = 0; c->n_pend[1] = 0; c->n_slow = 0;
 }
 
 // initial binning of uploaded records (they sit in B, slots [0, n_slots))
@@ -365,7 +528,10 @@ __global__ void __launch_bounds__(TPB) k_bin_initial(const __grid_constant__ Dev
     if (m.sf & DF_DEAD) { p.rank[i] = MCX_NONE; continue; }
     if (!in_partition(p, D3{m.x, m.y, m.z})) { raise_error(p, MCX_ERR_ESCAPED, m.id); p.rank[i] = MCX_NONE; continue; }
     p.rank[i] = atomicAdd(&p.cs_next[cell_of(p, m.x, m.y, m.z)], 1u);
-    atomicAdd(&p.ctr->species_count[m.sf & SF_SPECIES_MASK], 1ull);
+    // one atomic per (warp, species) instead of one per molecule on a handful of addresses
+    const uint32_t spc = m.sf & SF_SPECIES_MASK;
+    const unsigned int peers = __match_any_sync(__activemask(), spc);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.ctr->species_count[spc], (unsigned long long)__popc(peers));
   }
 }
 
@@ -424,9 +590,11 @@ void mcx_set_scan_scratch(unsigned int* ptr) { g_scan_sums = ptr; }
 void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
   cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
   if (plan.prof) cudaEventRecord(plan.prof[0], s);
-  k_diffuse<<<plan.sm_count * 8, TPB, 0, s>>>(p);
+  k_diffuse_fast<<<plan.sm_count * 2 * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
+  if (plan.prof) cudaEventRecord(plan.prof[4], s);
+  k_diffuse_slow<<<plan.sm_count * 4, TPB, 0, s>>>(p);
   if (plan.prof) cudaEventRecord(plan.prof[1], s);
-  count_launches(plan, 1);
+  count_launches(plan, 2);
   if (plan.has_claims) {
     count_launches(plan, 4 * p.max_rounds);
     const int small_grid = plan.sm_count * 2;
