@@ -57,13 +57,23 @@ def build_model(n_total, seed=1, rank=0, world=1, cap_factor=1.25, cell_edge=0.0
     return t, edge_um
 
 
-def make_molecules(n_total, edge_um, length_unit, seed, rank=0, world=1, pinned=True):
-    """Uniform positions; species in fixed proportions A:B:C:D = 4:4:1:1. For world > 1 each rank
-    generates only the molecules of its own z-slab (same global id space)."""
+def make_molecules(n_total, edge_um, length_unit, seed, slab=None, pinned=True):
+    """Uniform positions; species in fixed proportions A:B:C:D = 4:4:1:1.  With a slab layout (mcx_slab_info of
+    this rank) each rank generates only the molecules of its own z-slab, in one global id space; slab faces are
+    the device's own layer boundaries (mcell_b200.comm mirrors the arithmetic)."""
     from mcell_b200.model import MolArrays
+    from mcell_b200 import comm
     h = (edge_um / 2) / length_unit * (1 - 1e-9)
-    n = n_total // world + (1 if rank < n_total % world else 0)
-    first_id = rank * (n_total // world) + min(rank, n_total % world)
+    rank, world = (slab.rank, slab.world_size) if slab is not None else (0, 1)
+    # z-interval and molecule share of every rank (identical on all ranks, no communication)
+    edges = [-h]
+    for r in range(world - 1):
+        hi_layer = comm.layer_range(slab.n_layers, r, world)[1]
+        edges.append(min(h, max(-h, slab.grid_origin_z + hi_layer / slab.layer_rcp)))
+    edges.append(h)
+    cum = [int(round(n_total * (e + h) / (2 * h))) for e in edges]
+    n, first_id = cum[rank + 1] - cum[rank], cum[rank]
+    z_lo, z_hi = edges[rank], edges[rank + 1]
     rng = np.random.default_rng(seed * 1000 + rank)
     m = MolArrays(0)
     alloc = _pinned_alloc if pinned else (lambda shape, dt: np.zeros(shape, dt))
@@ -71,13 +81,15 @@ def make_molecules(n_total, edge_um, length_unit, seed, rank=0, world=1, pinned=
     m.id, m.species, m.flags = alloc(n, np.uint32), alloc(n, np.uint32), alloc(n, np.uint32)
     m.diffusion_time, m.unimol_rxn_time = alloc(n, np.float64), alloc(n, np.float64)
     chunk = 1 << 22
-    z_lo = -h + 2 * h * rank / world
-    z_hi = -h + 2 * h * (rank + 1) / world
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         m.x[s:e] = rng.uniform(-h, h, e - s)
         m.y[s:e] = rng.uniform(-h, h, e - s)
-        m.z[s:e] = rng.uniform(z_lo, z_hi, e - s)
+        z = rng.uniform(z_lo, z_hi, e - s)
+        if slab is not None:  # a draw within rounding of a face could fall into the neighbour's layer
+            bad = comm.rank_of(z, slab) != rank
+            z[bad] = 0.5 * (z_lo + z_hi)
+        m.z[s:e] = z
         r = rng.integers(0, 10, e - s)
         m.species[s:e] = np.select([r < 4, r < 8, r < 9], [0, 1, 2], 3)
     m.id[:] = np.arange(first_id, first_id + n, dtype=np.uint32)
@@ -162,7 +174,7 @@ def _cpu_worker(args):
     n_sample, seed, iters = args
     from oracle import oracle_py as O
     t, edge_um = build_model(n_sample, seed=seed)
-    mols = make_molecules(n_sample, edge_um, t.length_unit, seed, pinned=False)
+    mols = make_molecules(n_sample, edge_um, t.length_unit, seed, None, pinned=False)
     o = O.Oracle(t)
     o.upload(mols)
     t0 = time.perf_counter()
@@ -207,7 +219,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps_cpu, "warmup": args.warmup_cpu,
         "ms_per_step": 1e3 * t_all / max(1, args.steps_cpu), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "reactive box, 4 species / 6 reactions, 125 molecules/um^3 (BASELINE configs[4])",
+        "config": {"workload": "reactive box, 4 species / 6 reactions, 1.25e5 molecules/um^3 = config 2's density (BASELINE configs[4])",
                    "molecules": args.molecules, "cpu_sample_molecules_per_core": n_sample},
         "cpu_baseline": {"value": value, "unit": "molecule-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "molecule-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -239,15 +251,13 @@ def run_ours(args):
     n_total = args.molecules
     t, edge_um = build_model(n_total, seed=1, rank=rank, world=world, cell_edge=args.cell_edge)
     t.cfg.device = local_rank
-    mols = make_molecules(n_total, edge_um, t.length_unit, 1, rank, world)
     eng = Engine(t)
+    slab = None
     if world > 1:
-        import ctypes
         from mcell_b200 import comm as mcomm
-        uid = mcomm.unique_id() if rank == 0 else bytes(128)
-        buf = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
-        dist.broadcast(buf, 0)
-        eng.comm_init(bytes(buf.cpu().tolist()))
+        eng.comm_init(mcomm.broadcast_unique_id(dist, rank, device="cuda"))
+        slab = eng.slab_info()
+    mols = make_molecules(n_total, edge_um, t.length_unit, 1, slab)
     eng.upload(mols)
 
     def sync_all():
@@ -342,10 +352,10 @@ def run_ours(args):
             "metric": "molecule_steps_per_sec", "value": value, "unit": "molecule-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / max(1, args.steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "reactive box, 4 species / 6 reactions, 125 molecules/um^3 (BASELINE configs[4])",
+            "config": {"workload": "reactive box, 4 species / 6 reactions, 1.25e5 molecules/um^3 = config 2's density (BASELINE configs[4])",
                        "molecules": n_total, "box_edge_um": edge_um, "iterations_per_plugin_call": ITERS_PER_CALL,
                        "l2": "inputs (>=3 GB at 1e8 molecules) larger than L2; no flush",
-                       "parallelism": "z-slabs x%d" % world, "rng": "philox4x32-10 per molecule"},
+                       "parallelism": "z-slabs x%d, NCCL halo refresh per iteration" % world, "rng": "philox4x32-10 per molecule"},
             "roofline": {"bound": "hbm", "kernel": top_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
                          "alg_bytes_per_launch": top_bytes, "kernel_ms": diffuse_ms,

@@ -68,6 +68,7 @@ typedef struct mcx_config {
   int32_t  rank;                   /* slab decomposition: this process' rank ...           */
   int32_t  world_size;             /* ... of world_size (1 = single GPU)                    */
   uint64_t initial_iteration;      /* Config.initial_iteration (checkpoint resume) */
+  double   halo_width;             /* multi-GPU: width of the redundantly evaluated halo, length units; 0 = auto */
 } mcx_config;
 
 /* ---- species: BNG::Species subset (src/mcell_species.c:207-300) --------- */
@@ -258,8 +259,26 @@ int mcx_counts(mcx_handle* h, uint64_t* per_species, uint32_t n_species,
 
 /* ---- multi-GPU (new: the reference has a single partition, world.cpp:147,277) --------- */
 /* nccl_unique_id: the 128-byte ncclUniqueId created by rank 0 and broadcast by the host
- * plumbing (torch.distributed).  Must be called after mcx_create on every rank. */
+ * plumbing (torch.distributed).  Call order on every rank: mcx_create (rank/world_size in the config),
+ * mcx_set_species/..., mcx_comm_init, mcx_upload_molecules (each rank may upload any superset of its own slab:
+ * molecules of other slabs are dropped), mcx_step.  Slabs are z-layers of the device cell grid. */
 int mcx_comm_init(mcx_handle* h, const void* nccl_unique_id, uint32_t id_bytes);
+/* Slab layout of this rank after mcx_comm_init: z-layers of the global device cell grid.  A position z belongs to
+ * layer clamp(floor((z - grid_origin_z) * layer_rcp), 0, n_layers - 1); rank r owns layers
+ * [n_layers * r / world, n_layers * (r + 1) / world).  Hosts that distribute molecules use exactly this
+ * arithmetic (IEEE double) so that host and device agree on every molecule. */
+typedef struct mcx_slab_info {
+  double   grid_origin_z;          /* length units */
+  double   layer_rcp;              /* 1 / layer thickness */
+  uint32_t n_layers;               /* global */
+  uint32_t layer_lo, layer_hi;     /* owned by this rank: [layer_lo, layer_hi) */
+  uint32_t halo_layers;
+  int32_t  rank, world_size;
+} mcx_slab_info;
+int mcx_slab_info_get(mcx_handle* h, mcx_slab_info* out);
+/* Rank 0 creates the id (ncclGetUniqueId) that every rank passes to mcx_comm_init; returns the number of bytes
+ * written (<= bytes) or a negative error. */
+int mcx_comm_unique_id(void* out, uint32_t bytes);
 
 /* ---- host helpers that need no device (also exported for the CPU test tier) ----------- */
 /* Philox4x32-10 block for (seed, molecule id, iteration, block index); the device stream

@@ -33,8 +33,13 @@ class mcx_config(C.Structure):
         ("rxn_radius_3d", c_f64), ("cell_edge", c_f64),
         ("active_llf", c_f64 * 3), ("active_urb", c_f64 * 3),
         ("max_molecules", c_u64), ("max_resolve_rounds", c_u32), ("rng_mode", c_u32),
-        ("rank", c_i32), ("world_size", c_i32), ("initial_iteration", c_u64),
+        ("rank", c_i32), ("world_size", c_i32), ("initial_iteration", c_u64), ("halo_width", c_f64),
     ]
+
+
+class mcx_slab_info(C.Structure):
+    _fields_ = [("grid_origin_z", c_f64), ("layer_rcp", c_f64), ("n_layers", c_u32), ("layer_lo", c_u32),
+                ("layer_hi", c_u32), ("halo_layers", c_u32), ("rank", c_i32), ("world_size", c_i32)]
 
 
 class mcx_species(C.Structure):
@@ -99,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "mcx_create", "mcx_destroy", "mcx_last_error", "mcx_abi_version", "mcx_set_geometry",
     "mcx_set_species", "mcx_set_reactions", "mcx_set_surface_classes", "mcx_upload_molecules",
     "mcx_download_molecules", "mcx_num_molecules", "mcx_step", "mcx_replay_step", "mcx_trace_step",
-    "mcx_counts", "mcx_comm_init", "mcx_philox_block", "mcx_set_profiling",
+    "mcx_counts", "mcx_comm_init", "mcx_comm_unique_id", "mcx_slab_info_get", "mcx_philox_block", "mcx_set_profiling",
 ]
 
 

@@ -13,7 +13,6 @@
 #include "mcx_geom.h"
 #include "mcx_comm.h"
 
-void mcx_set_scan_scratch(unsigned int* ptr);
 
 static thread_local std::string g_create_error;
 
@@ -44,6 +43,7 @@ struct mcx_handle {
        *d_surf = nullptr, *d_walls = nullptr, *d_tri = nullptr, *d_verts = nullptr, *d_wclass = nullptr,
        *d_spw_start = nullptr, *d_spw_list = nullptr, *d_sp_flags = nullptr;
   McxComm* comm = nullptr;
+  int ncz_global = 0;
   double *st_x = nullptr, *st_y = nullptr, *st_z = nullptr, *st_ts = nullptr, *st_tu = nullptr;
   uint32_t *st_id = nullptr, *st_sp = nullptr, *st_fl = nullptr;
   unsigned long long launches = 0;
@@ -146,7 +146,8 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   double vol = (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
   double edge = cfg->cell_edge;
   // default: about one molecule slot per cell — the candidate walk then touches ~1-2 records per molecule
-  if (!(edge > 0)) edge = std::cbrt(vol * 1.0 / (double)cfg->max_molecules);
+  // (multi-GPU: max_molecules is the per-rank capacity, the active box is global)
+  if (!(edge > 0)) edge = std::cbrt(vol * 1.0 / ((double)cfg->max_molecules * std::max(1, cfg->world_size)));
   if (edge < 4.0 * cfg->rxn_radius_3d) edge = 4.0 * cfg->rxn_radius_3d;
   // Anisotropic cells of volume edge^3: the records of one x-row of cells are contiguous in the sorted snapshot,
   // so a swept box costs one [start,end) lookup per (y,z) row whatever the x resolution.  Short x cells keep the
@@ -165,7 +166,8 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   p.ncy = (int)std::ceil((hi[1] - p.cgy) / ey) + 1;
   p.ncz = (int)std::ceil((hi[2] - p.cgz) / ez) + 1;
   p.n_cells = (unsigned int)((size_t)p.ncx * p.ncy * p.ncz);
-  p.zc_lo = 0; p.zc_hi = p.ncz;
+  p.own_lo = 0; p.own_hi = p.ncz; p.world = 1; p.halo_layers = 0; p.z_off = 0; p.has_low = 0; p.has_high = 0;
+  h->ncz_global = p.ncz;
 
   const size_t cap = p.capacity;
   int rc = MCX_OK;
@@ -179,6 +181,7 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   rc |= dev_alloc(h, &p.slow_list, cap);
   rc |= dev_alloc(h, &h->cs[0], (size_t)p.n_cells + 8); rc |= dev_alloc(h, &h->cs[1], (size_t)p.n_cells + 8);
   rc |= dev_alloc(h, &h->scan_sums, (size_t)(p.n_cells + 1) / 4096 + 16);
+  p.scan_sums = h->scan_sums;
   rc |= dev_alloc(h, &p.ctr, 1);
   rc |= dev_alloc(h, &h->d_n_out, 4);
   if (rc) return fail(MCX_ERR_CUDA);
@@ -423,12 +426,17 @@ int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
   zero.n_slots = (unsigned int)n;
   CK(cudaMemcpyAsync(h->p.ctr, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
   bind_iteration(h);
-  mcx_set_scan_scratch(h->scan_sums);
   mcx_launch_pack_soa(h->p, h->st_x, h->st_y, h->st_z, h->st_id, h->st_sp, m->flags ? h->st_fl : nullptr,
                       m->diffusion_time ? h->st_ts : nullptr, m->unimol_rxn_time ? h->st_tu : nullptr, (unsigned int)n, s);
   h->launches += 1;
   mcx_launch_initial_sort(h->p, h->plan, s);
   h->cs_cur ^= 1;
+  if (h->comm) {  // fetch the neighbours' boundary molecules before the first iteration
+    bind_iteration(h);
+    int rcc = mcx_comm_refresh(h->comm, h->p, h->plan, s);
+    if (rcc) { h->err = mcx_comm_error(h->comm); return rcc; }
+    h->cs_cur ^= 1;
+  }
   Counters hc;
   int rc = check_device_error(h, &hc);
   if (rc) { if (rc == MCX_ERR_INVALID_ARG) h->err += " (unknown species)"; return rc; }
@@ -498,12 +506,12 @@ static void fill_stats(const Counters& a, const Counters& b, uint64_t iters, flo
 
 static int run_iterations(mcx_handle* h, uint32_t n_iterations, mcx_step_stats* stats_out) {
   if (!h->uploaded) { h->err = "mcx_upload_molecules must precede stepping"; return MCX_ERR_STATE; }
+  if (h->cfg.world_size > 1 && !h->comm) { h->err = "world_size > 1 needs mcx_comm_init before stepping"; return MCX_ERR_STATE; }
   CK(cudaSetDevice(h->cfg.device));
   const unsigned long long launches_before = h->launches;
   Counters before;
   CK(cudaMemcpyAsync(&before, h->p.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  mcx_set_scan_scratch(h->scan_sums);
   CK(cudaEventRecord(h->ev0, h->stream));
   const uint32_t n_prof = h->profiling ? std::min<uint32_t>(n_iterations, 256) : 0;
   if (h->prof_events.size() < 5ull * n_prof) {
@@ -608,12 +616,52 @@ int mcx_counts(mcx_handle* h, uint64_t* per_species, uint32_t n_species, uint64_
   return MCX_OK;
 }
 
+// Slab layout of this rank: owned z-layers of the GLOBAL cell grid plus halo layers towards each neighbour.
+// halo width: cfg.halo_width, or 3x the hard reach of one step (R + 6.993 * max space_step: |gauss| < 9.89,
+// src/rng.c:198,212) — one reach makes the first evaluation of every owned molecule exact, the rest covers the
+// conflict chains that cross the face.
+static int configure_slab(mcx_handle* h) {
+  DevParams& p = h->p;
+  const int world = h->cfg.world_size, rank = h->cfg.rank;
+  double max_step = 0;
+  for (const auto& sp : h->species) max_step = std::max(max_step, sp.space_step);
+  const double reach = p.R * (1.0 + 1e-9) + 1e-9 + 6.993 * max_step;
+  const double width = h->cfg.halo_width > 0 ? h->cfg.halo_width : 3.0 * reach;
+  if (width < reach) { h->err = "halo_width smaller than the reach of one step (R + 6.993 * max space_step)"; return MCX_ERR_INVALID_ARG; }
+  const double ez = 1.0 / p.cell_rcp_z;
+  const int H = (int)std::ceil(width / ez);
+  const int g = h->ncz_global;
+  const int g_lo = (int)((long long)g * rank / world), g_hi = (int)((long long)g * (rank + 1) / world);
+  if (g_hi - g_lo < H) { h->err = "slab thinner than the halo: fewer ranks or a narrower halo_width"; return MCX_ERR_INVALID_ARG; }
+  const int z_off = std::max(0, g_lo - H), z_end = std::min(g, g_hi + H);
+  p.z_off = z_off; p.ncz = z_end - z_off;
+  p.own_lo = g_lo - z_off; p.own_hi = g_hi - z_off;
+  p.world = world; p.halo_layers = H;
+  p.has_low = rank > 0; p.has_high = rank < world - 1;
+  p.n_cells = (unsigned int)((size_t)p.ncx * p.ncy * p.ncz);
+  return MCX_OK;
+}
+
 int mcx_comm_init(mcx_handle* h, const void* nccl_unique_id, uint32_t id_bytes) {
   if (!h || !nccl_unique_id) return MCX_ERR_INVALID_ARG;
+  if (!h->has_species) { h->err = "mcx_set_species must precede mcx_comm_init (the halo width depends on the step lengths)"; return MCX_ERR_STATE; }
+  if (h->uploaded) { h->err = "mcx_comm_init must precede mcx_upload_molecules"; return MCX_ERR_STATE; }
   CK(cudaSetDevice(h->cfg.device));
+  int rc = configure_slab(h);
+  if (rc) return rc;
   std::string err;
-  h->comm = mcx_comm_create(nccl_unique_id, id_bytes, h->cfg.rank, h->cfg.world_size, h->p, err);
+  const unsigned int halo_cap = std::max<unsigned int>(1u << 16, h->p.capacity / 3);
+  h->comm = mcx_comm_create(nccl_unique_id, id_bytes, h->cfg.rank, h->cfg.world_size, halo_cap, err);
   if (!h->comm) { h->err = err; return MCX_ERR_COMM; }
+  return MCX_OK;
+}
+
+int mcx_slab_info_get(mcx_handle* h, mcx_slab_info* out) {
+  if (!h || !out) return MCX_ERR_INVALID_ARG;
+  const DevParams& p = h->p;
+  out->grid_origin_z = p.cgz; out->layer_rcp = p.cell_rcp_z; out->n_layers = (uint32_t)h->ncz_global;
+  out->layer_lo = (uint32_t)(p.own_lo + p.z_off); out->layer_hi = (uint32_t)(p.own_hi + p.z_off);
+  out->halo_layers = (uint32_t)p.halo_layers; out->rank = h->cfg.rank; out->world_size = p.world;
   return MCX_OK;
 }
 
@@ -634,6 +682,7 @@ int mcx_sizeof(int which) {
     case 5: return (int)sizeof(mcx_mol_soa);
     case 6: return (int)sizeof(mcx_step_stats);
     case 7: return (int)sizeof(mcx_trace_rec);
+    case 8: return (int)sizeof(mcx_slab_info);
     default: return -1;
   }
 }

@@ -1,11 +1,146 @@
-// mcx_comm.cu — placeholder until the slab exchange lands (single-GPU build path).
+// mcx_comm.cu — multi-GPU slab decomposition of the diffuse-and-react step (the reference has a single partition:
+// src4/world.cpp:147,277; this is new).  One process per GPU; z-slabs of the device cell grid.
+//
+// Scheme: every rank holds its owned z-layers plus `halo_layers` of its neighbours' molecules and
+// evaluates ALL of them.  Because a molecule's random stream is keyed by (seed, molecule id, iteration) and the
+// conflict rule is deterministic, a halo molecule is evaluated on the neighbour exactly as on its owner, so
+// reactions across a slab face are decided identically on both sides without any mid-iteration message.
+// After the evaluation each rank keeps the records whose NEW position it owns (this also moves emigrants: the
+// receiving rank computed them itself) and the only exchange per iteration is the halo refresh: every kept
+// record within halo_layers of a face is sent to that neighbour (grouped ncclSend/ncclRecv over NVLink), the
+// neighbour bins it into its next snapshot together with its own results.
 #include "mcx_comm.h"
-struct McxComm { std::string err; };
-McxComm* mcx_comm_create(const void*, uint32_t, int, int, DevParams&, std::string& err) {
-  err = "multi-GPU slab exchange not available in this build";
-  return nullptr;
+
+#include <nccl.h>
+
+struct McxComm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  std::string err;
+  HaloRec* send[2] = {nullptr, nullptr};
+  HaloRec* recv[2] = {nullptr, nullptr};
+  unsigned int cap = 0;
+  unsigned int* d_counts = nullptr;   // [0..1] send counts (low, high), [2..3] receive counts
+  unsigned int* h_counts = nullptr;   // pinned mirror
+  unsigned long long* d_red = nullptr;
+  int red_cap = 0;
+};
+
+#define NCK(call)                                                                         \
+  do {                                                                                    \
+    ncclResult_t r_ = (call);                                                             \
+    if (r_ != ncclSuccess) { c->err = std::string(#call) + ": " + ncclGetErrorString(r_); return MCX_ERR_COMM; } \
+  } while (0)
+#define CCK(call)                                                                         \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e_); return MCX_ERR_CUDA; } \
+  } while (0)
+
+extern "C" int mcx_comm_unique_id(void* out, uint32_t bytes) {
+  if (!out || bytes < sizeof(ncclUniqueId)) return MCX_ERR_INVALID_ARG;
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return MCX_ERR_COMM;
+  memcpy(out, &id, sizeof(id));
+  return (int)sizeof(id);
 }
-void mcx_comm_destroy(McxComm* c) { delete c; }
+
+McxComm* mcx_comm_create(const void* nccl_unique_id, uint32_t id_bytes, int rank, int world_size, unsigned int halo_capacity,
+                         std::string& err) {
+  if (id_bytes < sizeof(ncclUniqueId)) { err = "ncclUniqueId too short"; return nullptr; }
+  if (world_size < 2 || rank < 0 || rank >= world_size) { err = "mcx_comm_init needs world_size >= 2 and 0 <= rank < world_size"; return nullptr; }
+  McxComm* c = new McxComm();
+  c->rank = rank; c->world = world_size; c->cap = halo_capacity;
+  ncclUniqueId id;
+  memcpy(&id, nccl_unique_id, sizeof(id));
+  ncclResult_t r = ncclCommInitRank(&c->comm, world_size, id, rank);
+  if (r != ncclSuccess) { err = std::string("ncclCommInitRank: ") + ncclGetErrorString(r); delete c; return nullptr; }
+  bool ok = true;
+  for (int k = 0; k < 2; k++) {
+    ok = ok && cudaMalloc((void**)&c->send[k], sizeof(HaloRec) * (size_t)halo_capacity) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&c->recv[k], sizeof(HaloRec) * (size_t)halo_capacity) == cudaSuccess;
+  }
+  ok = ok && cudaMalloc((void**)&c->d_counts, 4 * sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&c->h_counts, 4 * sizeof(unsigned int)) == cudaSuccess;
+  c->red_cap = 1024;
+  ok = ok && cudaMalloc((void**)&c->d_red, sizeof(unsigned long long) * c->red_cap) == cudaSuccess;
+  if (!ok) { err = "halo buffer allocation failed"; mcx_comm_destroy(c); return nullptr; }
+  cudaMemset(c->d_counts, 0, 4 * sizeof(unsigned int));
+  return c;
+}
+
+void mcx_comm_destroy(McxComm* c) {
+  if (!c) return;
+  for (int k = 0; k < 2; k++) { if (c->send[k]) cudaFree(c->send[k]); if (c->recv[k]) cudaFree(c->recv[k]); }
+  if (c->d_counts) cudaFree(c->d_counts);
+  if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->d_red) cudaFree(c->d_red);
+  if (c->comm) ncclCommDestroy(c->comm);
+  delete c;
+}
 const char* mcx_comm_error(McxComm* c) { return c ? c->err.c_str() : ""; }
-int mcx_comm_iteration(McxComm*, DevParams&, const StepPlan&, cudaStream_t) { return MCX_ERR_COMM; }
-int mcx_comm_allreduce_u64(McxComm*, unsigned long long*, int, cudaStream_t) { return MCX_ERR_COMM; }
+
+// halo refresh: pack -> counts -> payload -> unpack (appended behind the local results in B)
+static int exchange_halo(McxComm* c, DevParams& p, cudaStream_t s) {
+  const bool lo = p.has_low != 0, hi = p.has_high != 0;
+  mcx_launch_pack_halo(p, c->send[0], c->send[1], c->cap, s);
+  CCK(cudaMemcpyAsync(c->d_counts, &p.ctr->n_send[0], 2 * sizeof(unsigned int), cudaMemcpyDeviceToDevice, s));
+  CCK(cudaMemsetAsync(c->d_counts + 2, 0, 2 * sizeof(unsigned int), s));
+  NCK(ncclGroupStart());
+  if (lo) { NCK(ncclSend(c->d_counts + 0, 1, ncclUint32, c->rank - 1, c->comm, s)); NCK(ncclRecv(c->d_counts + 2, 1, ncclUint32, c->rank - 1, c->comm, s)); }
+  if (hi) { NCK(ncclSend(c->d_counts + 1, 1, ncclUint32, c->rank + 1, c->comm, s)); NCK(ncclRecv(c->d_counts + 3, 1, ncclUint32, c->rank + 1, c->comm, s)); }
+  NCK(ncclGroupEnd());
+  CCK(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+  CCK(cudaStreamSynchronize(s));
+  const unsigned int ns0 = c->h_counts[0], ns1 = c->h_counts[1], nr0 = c->h_counts[2], nr1 = c->h_counts[3];
+  if (ns0 > c->cap || ns1 > c->cap || nr0 > c->cap || nr1 > c->cap) { c->err = "halo buffer capacity exceeded (raise max_molecules)"; return MCX_ERR_CAPACITY; }
+  NCK(ncclGroupStart());
+  if (lo && ns0) NCK(ncclSend(c->send[0], sizeof(HaloRec) * (size_t)ns0, ncclChar, c->rank - 1, c->comm, s));
+  if (lo && nr0) NCK(ncclRecv(c->recv[0], sizeof(HaloRec) * (size_t)nr0, ncclChar, c->rank - 1, c->comm, s));
+  if (hi && ns1) NCK(ncclSend(c->send[1], sizeof(HaloRec) * (size_t)ns1, ncclChar, c->rank + 1, c->comm, s));
+  if (hi && nr1) NCK(ncclRecv(c->recv[1], sizeof(HaloRec) * (size_t)nr1, ncclChar, c->rank + 1, c->comm, s));
+  NCK(ncclGroupEnd());
+  mcx_launch_unpack_halo(p, c->recv[0], nr0, 0, s);
+  mcx_launch_unpack_halo(p, c->recv[1], nr1, nr0, s);
+  mcx_launch_add_received(p, nr0 + nr1, s);
+  return MCX_OK;
+}
+
+int mcx_comm_iteration(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_t s) {
+  mcx_launch_evaluate(p, plan, s);
+  int rc = exchange_halo(c, p, s);
+  if (rc) return rc;
+  if (plan.launches) *plan.launches += 4;
+  mcx_launch_sort(p, plan, s);
+  if (plan.prof) cudaEventRecord(plan.prof[3], s);
+  return MCX_OK;
+}
+
+int mcx_comm_refresh(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_t s) {
+  // fresh molecule ids: rank r hands out ids congruent to r modulo world above the global maximum
+  unsigned int next_id = 0;
+  CCK(cudaMemcpyAsync(&next_id, &p.ctr->next_id, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+  CCK(cudaStreamSynchronize(s));
+  unsigned long long v = next_id;
+  CCK(cudaMemcpyAsync(c->d_red, &v, sizeof(v), cudaMemcpyHostToDevice, s));
+  NCK(ncclAllReduce(c->d_red, c->d_red, 1, ncclUint64, ncclMax, c->comm, s));
+  CCK(cudaMemcpyAsync(&v, c->d_red, sizeof(v), cudaMemcpyDeviceToHost, s));
+  CCK(cudaStreamSynchronize(s));
+  const unsigned long long w = (unsigned long long)c->world;
+  next_id = (unsigned int)(((v + w - 1) / w) * w + (unsigned long long)c->rank);
+  CCK(cudaMemcpyAsync(&p.ctr->next_id, &next_id, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+  mcx_launch_rebin(p, plan, s);
+  int rc = exchange_halo(c, p, s);
+  if (rc) return rc;
+  mcx_launch_sort(p, plan, s);
+  return MCX_OK;
+}
+
+int mcx_comm_allreduce_u64(McxComm* c, unsigned long long* host_buf, int n, cudaStream_t s) {
+  if (n > c->red_cap) { c->err = "allreduce buffer too small"; return MCX_ERR_INVALID_ARG; }
+  CCK(cudaMemcpyAsync(c->d_red, host_buf, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, s));
+  NCK(ncclAllReduce(c->d_red, c->d_red, n, ncclUint64, ncclSum, c->comm, s));
+  CCK(cudaMemcpyAsync(host_buf, c->d_red, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, s));
+  CCK(cudaStreamSynchronize(s));
+  return MCX_OK;
+}

@@ -156,11 +156,21 @@ __device__ __forceinline__ int cell_coord(double v, double origin, double rcp, i
   int c = (int)floor((v - origin) * rcp);
   return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
+// local z-layer of a position: global layer (same expression on every rank) minus this rank's offset
+__device__ __forceinline__ int cell_z(const DevParams& p, double z) {
+  int c = (int)floor((z - p.cgz) * p.cell_rcp_z) - p.z_off;
+  return c < 0 ? 0 : (c >= p.ncz ? p.ncz - 1 : c);
+}
 __device__ __forceinline__ uint32_t cell_of(const DevParams& p, double x, double y, double z) {
   int cx = cell_coord(x, p.cgx, p.cell_rcp_x, p.ncx);
   int cy = cell_coord(y, p.cgy, p.cell_rcp_y, p.ncy);
-  int cz = cell_coord(z, p.cgz, p.cell_rcp_z, p.ncz);
+  int cz = cell_z(p, z);
   return (uint32_t)(cx + p.ncx * (cy + p.ncy * cz));
+}
+// multi-GPU ownership: a position belongs to the rank whose owned z-layers contain it
+__device__ __forceinline__ bool owned_z(const DevParams& p, double z) {
+  const int cz = cell_z(p, z);
+  return cz >= p.own_lo && cz < p.own_hi;
 }
 
 struct SpSet { uint32_t v[MCX_MAX_SP_MOLS]; int n; bool overflow; };
@@ -424,8 +434,8 @@ __device__ __forceinline__ CellBox swept_cells(const DevParams& p, D3 pos, D3 di
   b.cx1 = cell_coord(fmax(pos.x, pos.x + disp.x) + pad, p.cgx, p.cell_rcp_x, p.ncx);
   b.cy0 = cell_coord(fmin(pos.y, pos.y + disp.y) - pad, p.cgy, p.cell_rcp_y, p.ncy);
   b.cy1 = cell_coord(fmax(pos.y, pos.y + disp.y) + pad, p.cgy, p.cell_rcp_y, p.ncy);
-  b.cz0 = cell_coord(fmin(pos.z, pos.z + disp.z) - pad, p.cgz, p.cell_rcp_z, p.ncz);
-  b.cz1 = cell_coord(fmax(pos.z, pos.z + disp.z) + pad, p.cgz, p.cell_rcp_z, p.ncz);
+  b.cz0 = cell_z(p, fmin(pos.z, pos.z + disp.z) - pad);
+  b.cz1 = cell_z(p, fmax(pos.z, pos.z + disp.z) + pad);
   return b;
 }
 

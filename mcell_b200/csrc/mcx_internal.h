@@ -20,7 +20,7 @@ enum : uint32_t {
   DF_SCHED_UNIMOL = 1u << 17,  // MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN
   DF_PARTIAL = 1u << 18,     // cold t_sched[] holds a fractional diffusion_time
   DF_HAS_UNIMOL = 1u << 19,  // cold t_unimol[] holds a scheduled unimolecular time
-  DF_GHOST = 1u << 20,       // multi-GPU halo copy: visible as partner, never evaluated here
+  DF_GHOST = 1u << 20,       // reserved
   SF_SPECIES_MASK = 0xFFFFu
 };
 
@@ -48,12 +48,14 @@ struct Counters {
   unsigned int next_id;        // fresh molecule ids
   unsigned int n_emigrants[2]; // multi-GPU: records leaving through the low/high slab face
   unsigned int n_slow;         // entries of slow_list this iteration
-  unsigned int pad[4];
+  unsigned int n_send[2];      // multi-GPU: halo records packed for the low / high neighbour
+  unsigned int pad[2];
   // statistics (SimulationStats mirror)
   unsigned long long molecule_steps, ray_polygon_tests, ray_polygon_colls, reflections, transparent,
       absorptions, volvol_collisions, bimol_rxns, unimol_rxns, redos, retries, unresolved, products, deferred;
   unsigned long long defer_reason[8];  // why the fast pass deferred a molecule (MCX_DEFER_*)
   unsigned long long species_count[256];
+  unsigned long long species_next[256];  // multi-GPU: recount of owned molecules during the scatter
   unsigned long long rxn_count[256];
 };
 
@@ -95,6 +97,7 @@ struct DevParams {
   uint32_t* rank;    // rank inside the destination cell, MCX_NONE = not carried over
   uint32_t* cs_cur;  // cell_start of snapshot A (n_cells + 1)
   uint32_t* cs_next; // histogram -> cell_start of the next snapshot
+  unsigned int* scan_sums;  // scratch of the cell-histogram scan
   unsigned long long* claim;   // per slot: (epoch << 32) | ~priority
   uint32_t* prop_partner;      // per slot: partner slot of the pending proposal
   uint32_t* prop_info;         // per slot: kind(4) | pathway(12) | class(16)
@@ -106,9 +109,17 @@ struct DevParams {
   Counters* ctr;
   mcx_trace_rec* trace;
   unsigned long long n_trace;
-  // slab decomposition (multi-GPU): owned z-range in cell rows [zc_lo, zc_hi)
-  int zc_lo, zc_hi;
+  // slab decomposition (multi-GPU): the local cell grid covers the owned z-layers [own_lo, own_hi) plus halo
+  // layers on each side that has a neighbour; world == 1: everything is owned
+  int own_lo, own_hi, world, halo_layers;
+  int z_off;                    // global z-layer index of local layer 0 (cgz stays the GLOBAL grid origin, so every
+                                // rank computes the same global layer for a position before subtracting its offset)
+  int has_low, has_high;        // a neighbour rank exists below / above
 };
+
+// multi-GPU halo record: what a neighbour needs to evaluate a molecule exactly like its owner does
+struct HaloRec { MolRec rec; double tsched, tuni, pad_[2]; };  // 64 B (MolRec is 32-byte aligned)
+static_assert(sizeof(HaloRec) == 64, "HaloRec layout");
 
 // kernels / launchers implemented in mcx_kernels.cu
 struct StepPlan {
@@ -120,6 +131,13 @@ struct StepPlan {
 };
 void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t s);
 void mcx_launch_initial_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
+// multi-GPU pieces of an iteration (mcx_comm.cu drives them around the NCCL exchange)
+void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t s);   // memset + diffuse + resolve rounds
+void mcx_launch_rebin(const DevParams& p, const StepPlan& plan, cudaStream_t s);      // A -> B unchanged (halo refresh without a step)
+void mcx_launch_pack_halo(const DevParams& p, HaloRec* send_low, HaloRec* send_high, unsigned int cap, cudaStream_t s);
+void mcx_launch_unpack_halo(const DevParams& p, const HaloRec* recv, unsigned int n, unsigned int offset, cudaStream_t s);
+void mcx_launch_add_received(const DevParams& p, unsigned int n, cudaStream_t s);
+void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
 void mcx_launch_pack_soa(const DevParams& p, const double* x, const double* y, const double* z,
                          const uint32_t* id, const uint32_t* species, const uint32_t* flags,
                          const double* tsched, const double* tuni, unsigned int n, cudaStream_t s);

@@ -83,6 +83,7 @@ __device__ __forceinline__ void raise_error(const DevParams& p, int err, uint32_
 // result record of a molecule that stays alive: write to B and bin it for the next snapshot
 __device__ __forceinline__ void finalize_alive(const DevParams& p, uint32_t slot, D3 pos, uint32_t id, uint32_t species,
                                                uint32_t flags, double t_now, double unimol_time) {
+  if (!owned_z(p, pos.z)) { p.rank[slot] = MCX_NONE; return; }  // multi-GPU: the rank owning the new position keeps it
   uint32_t sf = species | (flags & ~(DF_HAS_UNIMOL | DF_DEAD));
   if (unimol_time != MCX_TIME_INVALID) { sf |= DF_HAS_UNIMOL; p.tuniB[slot] = unimol_time; }
   if (sf & DF_PARTIAL) p.tschedB[slot] = t_now;
@@ -105,50 +106,55 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
                              double t_event, D3 pos, uint32_t id, uint32_t species, uint32_t flags, double t_now,
                              double unimol_time) {
   Counters* c = p.ctr;
+  // multi-GPU: halo molecules are evaluated redundantly (identically on both sides); an event is counted and its
+  // products are created by the rank owning the event position; reactants are marked DEAD everywhere
+  const bool own_event = owned_z(p, pos.z);
+  const bool track = p.world == 1;  // incremental species counts (multi-GPU recounts during the scatter)
   if (kind == MCX_OUT_ABSORBED) {
     atomicOr(&p.recA[slot].sf, DF_DEAD);
-    agg_add(&c->absorptions, 1u);
-    agg_sub(&c->species_count[species], 1u);
+    if (own_event) agg_add(&c->absorptions, 1u);
+    if (track) agg_sub(&c->species_count[species], 1u);
     return;
   }
   const DevClass& cl = p.classes[rxn_class];
   const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
-  agg_add(&c->rxn_count[pw.rule_id & 255u], 1u);
+  if (own_event) agg_add(&c->rxn_count[pw.rule_id & 255u], 1u);
   bool keepA, keepB = true;
   uint32_t reuse[2]; int n_reuse = 0;
   if (kind == MCX_OUT_REACTED) {
-    agg_add(&c->bimol_rxns, 1u);
+    if (own_event) agg_add(&c->bimol_rxns, 1u);
     bool a_is_r0 = species == cl.r0;
     keepA = (pw.keep_mask >> (a_is_r0 ? 0 : 1)) & 1u;
     keepB = (pw.keep_mask >> (a_is_r0 ? 1 : 0)) & 1u;
   } else {
-    agg_add(&c->unimol_rxns, 1u);
+    if (own_event) agg_add(&c->unimol_rxns, 1u);
     keepA = pw.keep_mask & 1u;
   }
   if (!keepA) {
     atomicOr(&p.recA[slot].sf, DF_DEAD);
-    agg_sub(&c->species_count[species], 1u);
+    if (track) agg_sub(&c->species_count[species], 1u);
     reuse[n_reuse++] = id;
   }
   if (!keepB) {
     uint32_t old = atomicOr(&p.recA[partner_slot].sf, DF_DEAD);
     atomicOr(&p.recB[partner_slot].sf, DF_DEAD);
-    agg_sub(&c->species_count[old & SF_SPECIES_MASK], 1u);
+    if (track) agg_sub(&c->species_count[old & SF_SPECIES_MASK], 1u);
     uint32_t pid = p.recA[partner_slot].id;
     reuse[n_reuse++] = pid;
     if (p.trace && pid < p.n_trace) p.trace[pid].outcome = MCX_OUT_CONSUMED;
   }
-  const uint32_t first_slot = pw.n_products ? c->n_slots + agg_reserve(&c->n_prod, pw.n_products) : 0u;
-  for (uint32_t k = 0; k < pw.n_products; k++) {
+  const uint32_t n_new = own_event ? pw.n_products : 0u;
+  const uint32_t first_slot = n_new ? c->n_slots + agg_reserve(&c->n_prod, n_new) : 0u;
+  for (uint32_t k = 0; k < n_new; k++) {
     uint32_t ns = first_slot + k;
     if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
-    uint32_t nid = (int)k < n_reuse ? reuse[k] : atomicAdd(&c->next_id, 1u);
+    uint32_t nid = (int)k < n_reuse ? reuse[k] : atomicAdd(&c->next_id, (unsigned int)p.world) ;  // fresh ids: strided by rank
     uint32_t psp = pw.products[k];
     p.tschedB[ns] = t_event;
     store_rec(p.recB, ns, pos, nid, psp | DF_SCHED_UNIMOL | DF_PARTIAL);
     uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
     p.rank[ns] = atomicAdd(&p.cs_next[cell], 1u);
-    agg_add(&c->species_count[psp], 1u);
+    if (track) agg_add(&c->species_count[psp], 1u);
     agg_add(&c->products, 1u);
   }
   if (keepA) {
@@ -286,7 +292,6 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       Tracer tc; trace_begin(p, tc, m.id);
       Outcome o; o.kind = MCX_OUT_MOVED; o.pos = dest;
       if (n_hits == 1) {
-        n_coll++;
         if (!(ph.t < MCX_EPS)) {  // is_immediate_collision (collision_utils.inl:814-816)
           // collide_and_react_with_vol_mol (:786-829) with scaling = factor(1) * r_rate_factor(1)
           tc.ev(EV_COLL, ph.id);
@@ -305,8 +310,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       trace_end(tc, o, rs);
       if (o.kind == MCX_OUT_MOVED) finalize_alive(p, i, dest, m.id, species, flags, t_end, t_uni);
       else write_proposal(p, i, o, m.id, species, round_epoch(p, 0), 0);
-      msteps++;
-      n_tests += n_wall_tests;
+      if (owned_z(p, pos.z)) { msteps++; n_tests += n_wall_tests; n_coll += n_hits == 1 ? 1u : 0u; }
     }
     if (in_range && !live) p.rank[i] = MCX_NONE;
     const bool slow = live && !simple;
@@ -344,10 +348,12 @@ __global__ void __launch_bounds__(TPB, 2) k_diffuse_slow(const __grid_constant__
     Stream rs; rs.init(p, m.id, &zig);
     Tracer tc; trace_begin(p, tc, m.id);
     Outcome o; int err = 0;
-    if (p.species[species].flags & MCX_SP_CAN_DIFFUSE) msteps++;
-    evaluate_iteration<false>(p, m, t_sched, t_uni, rs, false, o, ls, tc, err);
+    const bool own_start = owned_z(p, m.z);
+    if (own_start && (p.species[species].flags & MCX_SP_CAN_DIFFUSE)) msteps++;
+    LocalStats halo_ls = {0, 0, 0, 0, 0, 0};  // statistics of redundantly evaluated halo molecules are not counted
+    evaluate_iteration<false>(p, m, t_sched, t_uni, rs, false, o, own_start ? ls : halo_ls, tc, err);
     trace_end(tc, o, rs);
-    if (err) raise_error(p, err, m.id);
+    if (err && (own_start || err != MCX_ERR_ESCAPED)) raise_error(p, err, m.id);
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time);
     else if (o.kind == MCX_OUT_NONE) p.rank[i] = MCX_NONE;
     else write_proposal(p, i, o, m.id, species, epoch, 0);
@@ -400,15 +406,17 @@ __global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevPar
       if (p.trace && m.id < p.n_trace) p.trace[m.id].outcome = MCX_OUT_CONSUMED;
       continue;
     }
-    agg_add(&p.ctr->retries, 1u);
-    if (forced) agg_add(&p.ctr->unresolved, 1u);
+    const bool own_start = owned_z(p, m.z);  // statistics of redundantly evaluated halo molecules are not counted
+    if (own_start) agg_add(&p.ctr->retries, 1u);
+    if (forced && own_start) agg_add(&p.ctr->unresolved, 1u);
     const uint32_t species = m.sf & SF_SPECIES_MASK;
     double t_sched = (m.sf & DF_PARTIAL) ? p.tschedA[i] : 0.0;
     double t_uni = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;
     Stream rs; rs.init(p, m.id, &zig);
     Tracer tc; trace_begin(p, tc, m.id);
     Outcome o; int err = 0;
-    evaluate_iteration<true>(p, m, t_sched, t_uni, rs, forced != 0, o, ls, tc, err);
+    LocalStats halo_ls = {0, 0, 0, 0, 0, 0};
+    evaluate_iteration<true>(p, m, t_sched, t_uni, rs, forced != 0, o, own_start ? ls : halo_ls, tc, err);
     trace_end(tc, o, rs);
     if (err) raise_error(p, err, m.id);
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time);
@@ -512,12 +520,17 @@ __global__ void __launch_bounds__(TPB) k_scatter(const __grid_constant__ DevPara
     d[0] = lo; d[1] = hi;
     if (sf & DF_PARTIAL) p.tschedA[dst] = p.tschedB[i];
     if (sf & DF_HAS_UNIMOL) p.tuniA[dst] = p.tuniB[i];
+    // multi-GPU: recount the owned population (halo copies are not this rank's molecules)
+    if (p.world > 1 && !(sf & DF_DEAD) && owned_z(p, hi.x)) agg_add(&p.ctr->species_next[sf & SF_SPECIES_MASK], 1u);
   }
 }
 __global__ void k_end_iteration(const __grid_constant__ DevParams p) {
   Counters* c = p.ctr;
-  c->n_slots = c->n_next;
-  c->n_prod = 0; c->n_pend[0] = 0; c->n_pend[1] = 0; c->n_slow = 0;
+  if (threadIdx.x == 0) {
+    c->n_slots = c->n_next;
+    c->n_prod = 0; c->n_pend[0] = 0; c->n_pend[1] = 0; c->n_slow = 0; c->n_send[0] = 0; c->n_send[1] = 0;
+  }
+  if (p.world > 1) { c->species_count[threadIdx.x] = c->species_next[threadIdx.x]; c->species_next[threadIdx.x] = 0; }
 }
 
 // initial binning of uploaded records (they sit in B, slots [0, n_slots))
@@ -527,13 +540,70 @@ __global__ void __launch_bounds__(TPB) k_bin_initial(const __grid_constant__ Dev
     MolRec m = load_rec_volatile(p.recB, i);
     if (m.sf & DF_DEAD) { p.rank[i] = MCX_NONE; continue; }
     if (!in_partition(p, D3{m.x, m.y, m.z})) { raise_error(p, MCX_ERR_ESCAPED, m.id); p.rank[i] = MCX_NONE; continue; }
+    if (!owned_z(p, m.z)) { p.rank[i] = MCX_NONE; continue; }  // multi-GPU: another rank's slab
     p.rank[i] = atomicAdd(&p.cs_next[cell_of(p, m.x, m.y, m.z)], 1u);
     // one atomic per (warp, species) instead of one per molecule on a handful of addresses
     const uint32_t spc = m.sf & SF_SPECIES_MASK;
     const unsigned int peers = __match_any_sync(__activemask(), spc);
-    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.ctr->species_count[spc], (unsigned long long)__popc(peers));
+    if (p.world == 1 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.ctr->species_count[spc], (unsigned long long)__popc(peers));
   }
 }
+
+// ---- multi-GPU halo refresh (driven by mcx_comm.cu) --------------------------------------------------------------
+// A -> B unchanged: lets the halo refresh run without an evaluation step (after an upload)
+__global__ void __launch_bounds__(TPB) k_rebin(const __grid_constant__ DevParams p) {
+  const unsigned int n = p.ctr->n_slots;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    MolRec m = load_rec_volatile(p.recA, i);
+    if ((m.sf & DF_DEAD) || !owned_z(p, m.z)) { p.rank[i] = MCX_NONE; continue; }
+    store_rec(p.recB, i, D3{m.x, m.y, m.z}, m.id, m.sf);
+    if (m.sf & DF_PARTIAL) p.tschedB[i] = p.tschedA[i];
+    if (m.sf & DF_HAS_UNIMOL) p.tuniB[i] = p.tuniA[i];
+    p.rank[i] = atomicAdd(&p.cs_next[cell_of(p, m.x, m.y, m.z)], 1u);
+  }
+}
+// every record this rank keeps (new position owned) that lies within halo_layers of a slab face is copied to the
+// neighbour, with its cold fields: the neighbour evaluates it next iteration exactly like the owner does
+__global__ void __launch_bounds__(TPB) k_pack_halo(const __grid_constant__ DevParams p, HaloRec* send_low, HaloRec* send_high,
+                                                   unsigned int cap) {
+  const unsigned int n = p.ctr->n_slots + p.ctr->n_prod;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (p.rank[i] == MCX_NONE) continue;
+    MolRec m = load_rec_volatile(p.recB, i);
+    if (m.sf & DF_DEAD) continue;  // tombstone of a consumed partner: dropped by everybody next iteration
+    const int cz = cell_z(p, m.z);
+    const bool to_low = p.has_low && cz < p.own_lo + p.halo_layers;
+    const bool to_high = p.has_high && cz >= p.own_hi - p.halo_layers;
+    if (!to_low && !to_high) continue;
+    HaloRec h;
+    h.rec = m;
+    h.tsched = (m.sf & DF_PARTIAL) ? p.tschedB[i] : 0.0;
+    h.tuni = (m.sf & DF_HAS_UNIMOL) ? p.tuniB[i] : MCX_TIME_INVALID;
+    if (to_low) {
+      unsigned int k = agg_reserve(&p.ctr->n_send[0], 1u);
+      if (k < cap) send_low[k] = h; else raise_error(p, MCX_ERR_CAPACITY, m.id);
+    }
+    if (to_high) {
+      unsigned int k = agg_reserve(&p.ctr->n_send[1], 1u);
+      if (k < cap) send_high[k] = h; else raise_error(p, MCX_ERR_CAPACITY, m.id);
+    }
+  }
+}
+// received halo records are appended behind the local results and binned like products
+__global__ void __launch_bounds__(TPB) k_unpack_halo(const __grid_constant__ DevParams p, const HaloRec* recv, unsigned int n,
+                                                     unsigned int offset) {
+  const unsigned int base = p.ctr->n_slots + p.ctr->n_prod + offset;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const unsigned int i = base + k;
+    if (i >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, recv[k].rec.id); continue; }
+    const HaloRec h = recv[k];
+    store_rec(p.recB, i, D3{h.rec.x, h.rec.y, h.rec.z}, h.rec.id, h.rec.sf);
+    if (h.rec.sf & DF_PARTIAL) p.tschedB[i] = h.tsched;
+    if (h.rec.sf & DF_HAS_UNIMOL) p.tuniB[i] = h.tuni;
+    p.rank[i] = atomicAdd(&p.cs_next[cell_of(p, h.rec.x, h.rec.y, h.rec.z)], 1u);
+  }
+}
+__global__ void k_add_received(const __grid_constant__ DevParams p, unsigned int n) { p.ctr->n_prod += n; }
 
 // ---- SoA <-> record conversion at the ABI boundary ---------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_pack_soa(const __grid_constant__ DevParams p, const double* x, const double* y, const double* z,
@@ -557,7 +627,7 @@ __global__ void __launch_bounds__(TPB) k_unpack_soa(const __grid_constant__ DevP
   const unsigned int n = p.ctr->n_slots;
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     MolRec m = load_rec_volatile(p.recA, i);
-    if (m.sf & (DF_DEAD | DF_GHOST)) continue;
+    if ((m.sf & DF_DEAD) || !owned_z(p, m.z)) continue;  // halo copies belong to the neighbour rank
     unsigned int k = atomicAdd(n_out, 1u);
     x[k] = m.x; y[k] = m.y; z[k] = m.z; id[k] = m.id; species[k] = m.sf & SF_SPECIES_MASK;
     uint32_t hf = 0;
@@ -572,22 +642,19 @@ __global__ void __launch_bounds__(TPB) k_unpack_soa(const __grid_constant__ DevP
 // ---- launchers -----------------------------------------------------------------------------------------------
 static inline void count_launches(const StepPlan& plan, unsigned int n) { if (plan.launches) *plan.launches += n; }
 
-static void launch_sort(const DevParams& p, const StepPlan& plan, unsigned int* scan_sums, cudaStream_t s) {
+void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
   count_launches(plan, 5);
   const unsigned int n = p.n_cells + 1;  // last entry receives the total
   const unsigned int nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
-  k_scan_reduce<<<nblocks, SCAN_TPB, 0, s>>>(p.cs_next, n, scan_sums);
-  k_scan_sums<<<1, SCAN_TPB, 0, s>>>(scan_sums, nblocks, scan_sums + nblocks, p.ctr);
-  k_scan_apply<<<nblocks, SCAN_TPB, 0, s>>>(p.cs_next, n, scan_sums);
+  k_scan_reduce<<<nblocks, SCAN_TPB, 0, s>>>(p.cs_next, n, p.scan_sums);
+  k_scan_sums<<<1, SCAN_TPB, 0, s>>>(p.scan_sums, nblocks, p.scan_sums + nblocks, p.ctr);
+  k_scan_apply<<<nblocks, SCAN_TPB, 0, s>>>(p.cs_next, n, p.scan_sums);
   k_scatter<<<plan.sm_count * 8, TPB, 0, s>>>(p);
-  k_end_iteration<<<1, 1, 0, s>>>(p);
+  k_end_iteration<<<1, 256, 0, s>>>(p);
 }
 
-// scan scratch lives behind the pending lists' allocation; passed via a file-static set by the API layer
-static unsigned int* g_scan_sums = nullptr;
-void mcx_set_scan_scratch(unsigned int* ptr) { g_scan_sums = ptr; }
-
-void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
+// cell histogram reset + fast/slow diffuse + conflict rounds: results sit in B with their ranks
+void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
   cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
   if (plan.prof) cudaEventRecord(plan.prof[0], s);
   k_diffuse_fast<<<plan.sm_count * 2 * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
@@ -606,7 +673,11 @@ void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t
     }
   }
   if (plan.prof) cudaEventRecord(plan.prof[2], s);
-  launch_sort(p, plan, g_scan_sums, s);
+}
+
+void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
+  mcx_launch_evaluate(p, plan, s);
+  mcx_launch_sort(p, plan, s);
   if (plan.prof) cudaEventRecord(plan.prof[3], s);
 }
 
@@ -614,8 +685,24 @@ void mcx_launch_initial_sort(const DevParams& p, const StepPlan& plan, cudaStrea
   cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
   k_bin_initial<<<plan.sm_count * 8, TPB, 0, s>>>(p);
   count_launches(plan, 1);
-  launch_sort(p, plan, g_scan_sums, s);
+  mcx_launch_sort(p, plan, s);
 }
+
+void mcx_launch_rebin(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
+  cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
+  k_rebin<<<plan.sm_count * 8, TPB, 0, s>>>(p);
+  count_launches(plan, 1);
+}
+void mcx_launch_pack_halo(const DevParams& p, HaloRec* send_low, HaloRec* send_high, unsigned int cap, cudaStream_t s) {
+  k_pack_halo<<<148 * 8, TPB, 0, s>>>(p, send_low, send_high, cap);
+}
+void mcx_launch_unpack_halo(const DevParams& p, const HaloRec* recv, unsigned int n, unsigned int offset, cudaStream_t s) {
+  if (n == 0) return;
+  unsigned int grid = (n + TPB - 1) / TPB;
+  if (grid > 148u * 16u) grid = 148u * 16u;
+  k_unpack_halo<<<grid, TPB, 0, s>>>(p, recv, n, offset);
+}
+void mcx_launch_add_received(const DevParams& p, unsigned int n, cudaStream_t s) { k_add_received<<<1, 1, 0, s>>>(p, n); }
 
 void mcx_launch_pack_soa(const DevParams& p, const double* x, const double* y, const double* z, const uint32_t* id,
                          const uint32_t* species, const uint32_t* flags, const double* tsched, const double* tuni,

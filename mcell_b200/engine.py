@@ -49,6 +49,8 @@ def load_library():
     L.mcx_trace_step.argtypes = [H, C.c_uint64, C.c_void_p, C.POINTER(abi.mcx_step_stats)]
     L.mcx_counts.argtypes = [H, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
     L.mcx_comm_init.argtypes = [H, C.c_void_p, C.c_uint32]
+    L.mcx_comm_unique_id.argtypes = [C.c_void_p, C.c_uint32]
+    L.mcx_slab_info_get.argtypes = [H, C.POINTER(abi.mcx_slab_info)]
     L.mcx_set_profiling.argtypes = [H, C.c_int]
     L.mcx_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
     L.mcx_philox_block.restype = None
@@ -98,6 +100,11 @@ class Engine:
     def comm_init(self, unique_id_bytes):
         buf = C.create_string_buffer(bytes(unique_id_bytes), len(unique_id_bytes))
         self._ck(self.L.mcx_comm_init(self.h, C.cast(buf, C.c_void_p), len(unique_id_bytes)))
+
+    def slab_info(self):
+        info = abi.mcx_slab_info()
+        self._ck(self.L.mcx_slab_info_get(self.h, C.byref(info)))
+        return info
 
     def set_profiling(self, enabled=True):
         self._ck(self.L.mcx_set_profiling(self.h, 1 if enabled else 0))

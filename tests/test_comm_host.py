@@ -1,0 +1,78 @@
+"""CPU tier: host-side logic of the multi-GPU slab decomposition with torch.distributed (gloo, world_size 2):
+unique-id distribution, the numpy mirror of the device's slab-ownership arithmetic, count reduction."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from mcell_b200 import abi, comm
+from mcell_b200.model import MolArrays
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        blob = bytes((7 * i + 3) % 256 for i in range(comm.NCCL_UNIQUE_ID_BYTES))
+        got = comm.broadcast_unique_id(dist, rank, make_id=lambda: blob)
+        assert got == blob
+        # every rank sees the same global population and keeps what its device would own
+        rng = np.random.default_rng(5)
+        n = 20000
+        m = MolArrays(n)
+        m.x[:], m.y[:], m.z[:] = rng.uniform(-50, 50, (3, n))
+        m.z[:7] = [-50.0, 50.0, -1e9, 1e9, 0.0, -0.5 * 3.39, 3.39 * 14.5]     # faces, out of range, layer boundaries
+        m.id[:] = np.arange(n)
+        info = abi.mcx_slab_info()
+        info.grid_origin_z, info.layer_rcp, info.n_layers = -50.0 - 0.5 * 3.39, 1.0 / 3.39, 31
+        info.rank, info.world_size = rank, world
+        info.layer_lo, info.layer_hi = comm.layer_range(info.n_layers, rank, world)
+        mine = comm.select_owned(m, info)
+        lay = comm.layer_of(mine.z, info.grid_origin_z, info.layer_rcp, info.n_layers)
+        assert ((lay >= info.layer_lo) & (lay < info.layer_hi)).all()
+        z_lo, z_hi = comm.owned_z_interval(info)
+        inner = (mine.z > z_lo + 1e-9) & (mine.z < z_hi - 1e-9)
+        assert inner.sum() >= mine.n - 4
+        tot = comm.allreduce_sum(dist, [mine.n, float(mine.id.sum())])
+        assert tot[0] == n and tot[1] == n * (n - 1) / 2          # disjoint cover of the population
+        out_q.put((rank, mine.n))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_ownership_and_plumbing_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = dict(q.get(timeout=5) for _ in range(2))
+    assert got[0] > 0 and got[1] > 0 and got[0] + got[1] == 20000
+
+
+def test_layer_ranges_tile_the_grid():
+    for n_layers in (7, 31, 2738):
+        for world in (1, 2, 4, 8):
+            edges = [comm.layer_range(n_layers, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n_layers
+            for a, b in zip(edges, edges[1:]):
+                assert a[1] == b[0]
+    z = np.array([-1e30, -3.0, 0.0, 2.999, 3.0, 1e30])
+    assert comm.layer_of(z, 0.0, 1.0 / 3.0, 10).tolist() == [0, 0, 0, 0, 1, 9]
+    assert comm.rank_of(z, (0.0, 1.0 / 3.0, 10), world=2).tolist() == [0, 0, 0, 0, 0, 1]

@@ -1,0 +1,87 @@
+"""GPU tier (needs 2 devices; skipped otherwise): two ranks with NCCL halo exchange reproduce the single-GPU run
+molecule for molecule.  The ranks run as two host threads of this process (one libmcx handle per device; ctypes
+releases the GIL during the calls), which is the same C ABI sequence bench.py issues under torchrun."""
+import threading
+
+import numpy as np
+import pytest
+
+import common as cm
+from mcell_b200 import abi, comm
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_devices():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _run_ranks(tables_fn, mols, n_iter, world=2, halo_width=0.0):
+    from mcell_b200 import Engine
+    uid = comm.unique_id()
+    out, errs = [None] * world, []
+    barrier = threading.Barrier(world)
+
+    def work(rank):
+        try:
+            t = tables_fn()
+            t.cfg.device, t.cfg.rank, t.cfg.world_size, t.cfg.halo_width = rank, rank, world, halo_width
+            e = Engine(t)
+            barrier.wait()
+            e.comm_init(uid)
+            e.upload(mols)                      # every rank uploads everything; foreign slabs are dropped
+            stats = [e.step(1) for _ in range(n_iter)]
+            out[rank] = (e.download(), stats, e.counts(), e.slab_info())
+            e.close()
+        except Exception as ex:                 # noqa: BLE001
+            errs.append((rank, ex))
+            try:
+                barrier.abort()
+            except Exception:
+                pass
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join(600)
+    assert not errs, errs
+    return out
+
+
+@pytest.mark.skipif(_n_devices() < 2, reason="needs 2 CUDA devices")
+@pytest.mark.parametrize("scenario", ["reactive", "free"])
+def test_two_ranks_match_single_gpu(scenario):
+    from mcell_b200 import Engine
+    n, n_iter = 40000, 6
+    if scenario == "reactive":
+        make = lambda: cm.reactive_box(n=n, edge_um=1.0, p_target=0.5, seed=4, cap_factor=3)  # noqa: E731
+    else:
+        make = lambda: cm.free_diffusion_box(n=n, edge_um=1.0, seed=4, cap_factor=3)          # noqa: E731
+    t, mols = make()
+    single = Engine(t)
+    single.upload(mols)
+    st1 = [single.step(1) for _ in range(n_iter)]
+    ref = single.download().sorted_by_id()
+    ref_counts = single.counts()
+    res = _run_ranks(lambda: make()[0], mols, n_iter, halo_width=45.0)
+    parts = [r[0] for r in res]
+    ids = np.concatenate([p.id[:p.n] for p in parts])
+    assert len(ids) == ref.n and len(np.unique(ids)) == ref.n          # disjoint ownership, nothing lost
+    o = np.argsort(ids, kind="stable")
+    for k in ("id", "species", "x", "y", "z", "flags", "diffusion_time", "unimol_rxn_time"):
+        got = np.concatenate([getattr(p, k)[:p.n] for p in parts])[o]
+        assert (got == getattr(ref, k)[:ref.n]).all(), k               # bit for bit
+    # ownership agrees with the host-side mirror of the slab arithmetic
+    for p, r in zip(parts, res):
+        assert (comm.rank_of(p.z[:p.n], r[3]) == r[3].rank).all()
+    # counts: summed over ranks by the library; per-iteration statistics add up to the single-GPU ones
+    assert (res[0][2][0] == ref_counts[0]).all() and (res[1][2][0] == ref_counts[0]).all()
+    assert (res[0][2][1] == ref_counts[1]).all()
+    for it in range(n_iter):
+        for k in ("molecule_steps", "bimol_rxns", "mol_wall_reflections", "vol_mol_vol_mol_collisions"):
+            assert sum(getattr(r[1][it], k) for r in res) == getattr(st1[it], k), (it, k)
