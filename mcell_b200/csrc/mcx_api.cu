@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -148,7 +149,11 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   // default: about one molecule slot per cell — the candidate walk then touches ~1-2 records per molecule
   // (multi-GPU: max_molecules is the per-rank capacity, the active box is global)
   if (!(edge > 0)) edge = std::cbrt(vol * 1.0 / ((double)cfg->max_molecules * std::max(1, cfg->world_size)));
-  if (edge < 4.0 * cfg->rxn_radius_3d) edge = 4.0 * cfg->rxn_radius_3d;
+  {
+    double clamp_r = 4.0;
+    if (const char* e = getenv("MCX_CELL_CLAMP_R")) clamp_r = atof(e);  // tuning knob (profiles/)
+    if (edge < clamp_r * cfg->rxn_radius_3d) edge = clamp_r * cfg->rxn_radius_3d;
+  }
   // Anisotropic cells of volume edge^3: the records of one x-row of cells are contiguous in the sorted snapshot,
   // so a swept box costs one [start,end) lookup per (y,z) row whatever the x resolution.  Short x cells keep the
   // x-range tight; long y/z cells keep the box within 2x2 rows (the fast pass enumerates at most 4 rows).

@@ -468,9 +468,33 @@ struct CandWalkT {
     if (has) j++;
     return true;
   }
+  // up to two candidates of the current row per trip (slot1 == slot0 when only one is left)
+  __device__ __forceinline__ bool step2(const DevParams& p, bool& has0, uint32_t& slot0, bool& has1, uint32_t& slot1) {
+    if (j >= jend) {
+      if (row >= nrows) return false;
+      const uint32_t base = (uint32_t)(p.ncx * ((cy0 + ry) + p.ncy * (cz0 + rz)));
+      j = __ldg(p.cs_cur + base + cx0);
+      jend = __ldg(p.cs_cur + base + cx1 + 1);
+      next_row();
+    }
+    has0 = j < jend;
+    has1 = j + 1 < jend;
+    slot0 = j;
+    slot1 = has1 ? j + 1 : j;
+    j += has1 ? 2u : (has0 ? 1u : 0u);
+    return true;
+  }
 };
 typedef CandWalkT<false> CandWalk;
 
+__device__ __forceinline__ bool collide_mol_hit(const MolRec& c, D3 pos, D3 disp, double movelen2, double rhs, uint32_t self_id,
+                                                double& d_out) {
+  D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
+  double d = dot3(dir, disp);
+  double dirlen2 = dot3(dir, dir);
+  d_out = d;
+  return !(d < 0) && !(d > movelen2) && !(movelen2 * dirlen2 - d * d > rhs) && c.id != self_id && !(c.sf & DF_DEAD);
+}
 // Partner scan: one pass over the neighbour cells overlapped by the swept volume (segment inflated by R).
 // Finds the earliest eligible collision strictly after (t_last, id_last) in (time asc, id desc) order and
 // strictly before t_limit, counting how many eligible collisions remain.
@@ -485,32 +509,32 @@ __device__ int scan_partners(const DevParams& p, D3 pos, D3 disp, uint32_t self_
   const int* bimol_row = p.bimol + self_species * p.n_species;
   int count = 0;
   best.t = MCX_TIME_FOREVER; best.id = 0; best.slot = MCX_NONE;
-  CandWalk cw; cw.init(swept_cells(p, pos, disp));
-  bool has; uint32_t j;
-  while (cw.step(p, has, j)) {
-    if (!has) continue;
-    MolRec c = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j) : load_rec(p.recA, j);
-    // collide_mol, collision_utils.inl:464-515
-    D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
-    double d = dot3(dir, disp);
-    if (d < 0) continue;
-    if (d > movelen2) continue;
-    double dirlen2 = dot3(dir, dir);
-    if (movelen2 * dirlen2 - d * d > rhs) continue;
-    if (c.id == self_id) continue;
-    if (c.sf & DF_DEAD) continue;
-    uint32_t csp = c.sf & SF_SPECIES_MASK;
-    int rc = bimol_row[csp];
-    if (rc < 0) continue;
-    if (need_sp_filter && !spset_has(spm, subpart_index(p, D3{c.x, c.y, c.z}))) continue;
-    double t = d / movelen2;
-    if (!(t < t_limit)) continue;
+  // one candidate: collide_mol (collision_utils.inl:464-515) + eligibility + (time asc, id desc) selection
+  auto consider = [&](const MolRec& c, uint32_t j) {
+    double d;
+    if (!collide_mol_hit(c, pos, disp, movelen2, rhs, self_id, d)) return;
+    const uint32_t csp = c.sf & SF_SPECIES_MASK;
+    const int rc = bimol_row[csp];
+    if (rc < 0) return;
+    if (need_sp_filter && !spset_has(spm, subpart_index(p, D3{c.x, c.y, c.z}))) return;
+    const double t = d / movelen2;
+    if (!(t < t_limit)) return;
     // strictly after (t_last, id_last): later time, or same time and smaller id
-    if (t < t_last || (t == t_last && c.id >= id_last)) continue;
+    if (t < t_last || (t == t_last && c.id >= id_last)) return;
     count++;
     if (t < best.t || (t == best.t && c.id > best.id)) {
       best.t = t; best.id = c.id; best.slot = j; best.species = csp; best.rxn_class = rc;
     }
+  };
+  CandWalk cw; cw.init(swept_cells(p, pos, disp));
+  bool has0, has1; uint32_t j0, j1;
+  // two candidates per trip, both record loads issued before any arithmetic (the walk is latency bound)
+  while (cw.step2(p, has0, j0, has1, j1)) {
+    if (!has0) continue;
+    const MolRec c0 = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j0) : load_rec(p.recA, j0);
+    const MolRec c1 = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j1) : load_rec(p.recA, j1);
+    consider(c0, j0);
+    if (has1) consider(c1, j1);
   }
   return count;
 }
@@ -523,14 +547,6 @@ __device__ int scan_partners(const DevParams& p, D3 pos, D3 disp, uint32_t self_
 // row ranges are fetched up front (12 independent loads in flight), then ONE loop runs over the concatenated
 // candidates, two per trip with both record loads issued before any arithmetic: no row-advance branch inside
 // the loop, half the trips, and the L1/L2 latency of a record overlaps the test of the previous one.
-__device__ __forceinline__ bool collide_mol_hit(const MolRec& c, D3 pos, D3 disp, double movelen2, double rhs, uint32_t self_id,
-                                                double& d_out) {
-  D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
-  double d = dot3(dir, disp);
-  double dirlen2 = dot3(dir, dir);
-  d_out = d;
-  return !(d < 0) && !(d > movelen2) && !(movelen2 * dirlen2 - d * d > rhs) && c.id != self_id && !(c.sf & DF_DEAD);
-}
 __device__ __forceinline__ int probe_partners(const DevParams& p, bool enabled, D3 pos, D3 disp, uint32_t self_id,
                                               uint32_t self_species, PartnerHit& first, bool& overflow) {
   const double movelen2 = dot3(disp, disp);

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 
 namespace MCell {
 
@@ -116,6 +117,80 @@ void GpuDiffuseReactEvent::get_counts(std::vector<uint64_t>& per_species, std::v
   per_rxn_rule.assign(n_rules, 0);
   check(mcx_counts(h, per_species.data(), (uint32_t)n_species, per_rxn_rule.empty() ? nullptr : per_rxn_rule.data(),
                    (uint32_t)n_rules), "mcx_counts");
+}
+
+// ---- CountBuffer --------------------------------------------------------------------------------------------
+std::string CountBuffer::format_dat_row(const CountItem& item) {
+  char buf[96];
+  snprintf(buf, sizeof(buf), "%g %g\n", item.time, item.value);  // == operator<<(double) with default precision 6
+  return buf;
+}
+
+std::string CountBuffer::format_gdat_value(double d) {
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%.8e", d);  // 14-wide column: d.dddddddde+XX, exponent padded to two digits by printf
+  return buf;
+}
+
+std::string CountBuffer::format_gdat_header() const {
+  const size_t width = 14;
+  std::string line = "#";
+  line += std::string(width - 4, ' ') + "time";
+  for (const std::string& name : column_names) {
+    if (name.size() < width) line += std::string(width - name.size() + 2, ' ') + name;
+    else line += " " + name;
+  }
+  line += "\n";
+  return line;
+}
+
+bool CountBuffer::open() {
+  if (fout) return true;
+  fout = fopen(filename.c_str(), append ? "a" : "w");
+  if (!fout) return false;
+  if (output_format == CountOutputFormat::GDAT && !append) fputs(format_gdat_header().c_str(), (FILE*)fout);
+  return true;
+}
+
+void CountBuffer::add(size_t column_index, const CountItem& item) {
+  columns.at(column_index).push_back(item);
+  if (columns[column_index].size() >= buffer_size && column_index + 1 == columns.size()) flush();
+}
+
+void CountBuffer::flush() {
+  if (!open()) throw McxFatalError(MCX_ERR_STATE, "Could not open file " + filename + " for writing.");
+  FILE* f = (FILE*)fout;
+  if (output_format == CountOutputFormat::DAT) {
+    for (const CountItem& it : columns[0]) fputs(format_dat_row(it).c_str(), f);
+  } else {
+    const size_t rows = columns[0].size();
+    for (size_t r = 0; r < rows; r++) {
+      std::string line = " " + format_gdat_value(columns[0][r].time);
+      for (const auto& col : columns) line += "  " + format_gdat_value(col.at(r).value);
+      line += "\n";
+      fputs(line.c_str(), f);
+    }
+  }
+  fflush(f);
+  for (auto& col : columns) col.clear();
+}
+
+void CountBuffer::flush_and_close() {
+  if (!columns.empty() && !columns[0].empty()) flush();
+  if (fout) { fclose((FILE*)fout); fout = nullptr; }
+}
+
+void GpuMolOrRxnCountEvent::step() {
+  std::vector<uint64_t> per_species, per_rxn;
+  diffuse->get_counts(per_species, per_rxn);
+  for (const MolOrRxnCountItem& item : items) {
+    double v = 0;
+    for (const MolOrRxnCountTerm& t : item.terms) {
+      const std::vector<uint64_t>& src = t.is_rxn ? per_rxn : per_species;
+      if (t.index < src.size()) v += t.multiplier * (double)src[t.index];
+    }
+    buffers.at(item.buffer)->add(item.column, CountItem{event_time * time_unit, v});
+  }
 }
 
 }  // namespace MCell

@@ -177,4 +177,60 @@ private:
   std::vector<uint32_t> id, species, flags;
 };
 
+// ---- observables output: CountBuffer / CountItem (src4/count_buffer.h:24-123, count_buffer.cpp:30-129) -----------
+// Rows of (time, value) per column, buffered and flushed as text that is byte-identical to the reference's
+// react_data files: ".dat" = one column, "time value" per line in default stream formatting (%g, 6 significant
+// digits); ".gdat" = '#' header with 14-wide right-aligned names, then " t  v1  v2 ..." in scientific notation
+// with 8 fractional digits and an exponent of at least two digits.
+enum class CountOutputFormat { DAT, GDAT };
+
+struct CountItem {
+  double time;    // seconds: iteration * time_unit (mol_or_rxn_count_event.cpp:707-716)
+  double value;
+};
+
+class CountBuffer {
+public:
+  CountBuffer(const std::string& filename_, const std::vector<std::string>& column_names_, size_t buffer_size_,
+              CountOutputFormat fmt, bool append_ = false)
+    : filename(filename_), column_names(column_names_), buffer_size(buffer_size_), output_format(fmt), append(append_),
+      columns(column_names_.empty() ? 1 : column_names_.size()) {}
+  ~CountBuffer() { flush_and_close(); }
+  // CountBuffer::add (count_buffer.h:70-76): flushes when a column holds buffer_size rows
+  void add(size_t column_index, const CountItem& item);
+  void flush();
+  void flush_and_close();
+  static std::string format_dat_row(const CountItem& item);
+  static std::string format_gdat_value(double d);
+  std::string format_gdat_header() const;
+private:
+  bool open();
+  std::string filename;
+  std::vector<std::string> column_names;
+  size_t buffer_size;
+  CountOutputFormat output_format;
+  bool append;
+  std::vector<std::vector<CountItem>> columns;
+  void* fout = nullptr;  // FILE*
+};
+
+// The world-count part of MolOrRxnCountEvent (mol_or_rxn_count_event.cpp:622-653): every `periodicity` iterations
+// one row per observable; species counts and reaction counts come from the device (mcx_counts), so a count
+// iteration costs no molecule download.
+struct MolOrRxnCountTerm { bool is_rxn; uint32_t index; double multiplier; };   // species id or rxn rule id
+struct MolOrRxnCountItem { size_t buffer, column; std::vector<MolOrRxnCountTerm> terms; };
+
+class GpuMolOrRxnCountEvent : public BaseEvent {
+public:
+  GpuMolOrRxnCountEvent(GpuDiffuseReactEvent* diffuse_, double time_unit_)
+    : BaseEvent(290 /* EVENT_TYPE_INDEX_MOL_OR_RXN_COUNT, base_event.h:33-56 */), diffuse(diffuse_), time_unit(time_unit_) {}
+  bool is_barrier() const override { return true; }
+  void step() override;
+  std::vector<CountBuffer*> buffers;
+  std::vector<MolOrRxnCountItem> items;
+private:
+  GpuDiffuseReactEvent* diffuse;
+  double time_unit;
+};
+
 }  // namespace MCell

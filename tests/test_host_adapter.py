@@ -23,6 +23,20 @@ def _build():
                    ["-L" + libdir, "-l:libmcx.so", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
 
 
+def test_count_buffer_text_formats(tmp_path):
+    """CountBuffer .dat / .gdat writer of the host adapter: byte-identical to the reference's stream formatting."""
+    exe = os.path.join(ROOT, "tests", "host", "test_count_buffer")
+    srcs = [os.path.join(ROOT, "tests", "host", "test_count_buffer.cpp"), os.path.join(ROOT, "mcell_b200", "host", "mcx_host.cpp")]
+    from mcell_b200 import build as b
+    b.build()
+    libdir = os.path.join(ROOT, "mcell_b200")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-o", exe] + srcs +
+                   ["-L" + libdir, "-l:libmcx.so", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "count buffer ok" in r.stdout
+
+
 def _has_gpu():
     try:
         import torch
