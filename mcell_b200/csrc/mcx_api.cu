@@ -159,8 +159,11 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   // x-range tight; long y/z cells keep the box within 2x2 rows (the fast pass enumerates at most 4 rows).
   const double max_cells = 2.0e8;
   double ex, ey, ez;
+  double ax = 2.25, ayz = 1.5;   // tuning knobs (profiles/): x divisor and y/z multiplier of the cell edge
+  if (const char* e = getenv("MCX_CELL_AX")) ax = atof(e);
+  if (const char* e = getenv("MCX_CELL_AYZ")) ayz = atof(e);
   for (;;) {
-    ex = edge / 2.25; ey = ez = edge * 1.5;
+    ex = edge / ax; ey = ez = edge * ayz;
     double nc = std::ceil((hi[0] - lo[0]) / ex + 2) * std::ceil((hi[1] - lo[1]) / ey + 2) * std::ceil((hi[2] - lo[2]) / ez + 2);
     if (nc <= max_cells) break;
     edge *= 1.26;

@@ -601,6 +601,99 @@ __device__ __forceinline__ int probe_partners(const DevParams& p, bool enabled, 
   return found;
 }
 
+// Warp-flattened variant of probe_partners (same result).  Per-lane candidate counts differ by 3x between the
+// lanes of a warp (box shape x Poisson occupancy): with one lane per molecule the warp ran max-over-lanes trips at
+// 8-12 active lanes (profiles/r01_d: 60 % of k_diffuse_fast's instructions).  Here the (molecule, candidate)
+// pairs of the warp's 32 molecules are concatenated and dealt to the lanes 32 at a time, so the trip count is
+// ceil(sum / 32): every lane tests one candidate of SOME lane's molecule per trip, the owner's move is read from
+// shared memory, and the (rare) hits are reported back through shared-memory atomics.  Warp-collective.
+struct __align__(16) WarpProbe {
+  double4 a[32];          // pos.x, pos.y, pos.z, movelen2
+  double4 b[32];          // disp.x, disp.y, disp.z, bits(id | species << 32)
+  uint32_t cum[32][8];    // inclusive row ends over the concatenation of the owner's rows (6 used)
+  uint32_t lo[32][8];     // slot of candidate k in row r = lo[r] + k
+  uint32_t off[32];       // compacted owners: first pair index
+  uint32_t owner[32];     // compacted owners: lane
+  uint32_t hits[32];      // per owner lane: number of eligible collisions
+  uint32_t hit_slot[32];  // per owner lane: slot of one of them
+};
+__device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enabled, D3 pos, D3 disp, uint32_t self_id,
+                                                   uint32_t self_species, PartnerHit& first, bool& overflow, WarpProbe* sm) {
+  const int lane = threadIdx.x & 31;
+  const double movelen2 = dot3(disp, disp);
+  const double R2 = p.R * p.R;
+  const CellBox bx = swept_cells(p, pos, disp);
+  const int ny = bx.cy1 - bx.cy0 + 1, nz = bx.cz1 - bx.cz0 + 1;
+  const bool tall = nz > 2;
+  overflow = enabled && (ny * nz > 6 || ny > 3 || nz > 3);
+  const bool en = enabled && !overflow;
+  uint32_t total = 0;
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    const int ry = tall ? (r & 1) : (r % 3), rz = tall ? (r >> 1) : (r / 3);
+    const bool valid = en && ry < ny && rz < nz;
+    const uint32_t base = (uint32_t)(p.ncx * ((bx.cy0 + ry) + p.ncy * (bx.cz0 + rz)));
+    const uint32_t a = __ldg(p.cs_cur + (valid ? base + bx.cx0 : 0u));
+    const uint32_t e = __ldg(p.cs_cur + (valid ? base + bx.cx1 + 1 : 0u));
+    sm->lo[lane][r] = a - total;
+    total += e - a;
+    sm->cum[lane][r] = total;
+  }
+  sm->a[lane] = make_double4(pos.x, pos.y, pos.z, movelen2);
+  sm->b[lane] = make_double4(disp.x, disp.y, disp.z,
+                             __longlong_as_double((long long)(((unsigned long long)self_species << 32) | self_id)));
+  sm->hits[lane] = 0;
+  // exclusive prefix of the totals; owners with candidates are compacted so that their offsets strictly increase
+  uint32_t incl = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  const uint32_t W = __shfl_sync(0xffffffffu, incl, 31);
+  const unsigned int ne = __ballot_sync(0xffffffffu, total > 0);
+  if (total > 0) { const int k = __popc(ne & ((1u << lane) - 1u)); sm->off[k] = incl - total; sm->owner[k] = lane; }
+  __syncwarp();
+  const uint32_t my_off = lane < __popc(ne) ? sm->off[lane] : 0xFFFFFFFFu;
+  for (uint32_t B = 0; B < W; B += 32) {
+    const uint32_t q = B + lane;
+    const unsigned int below = __ballot_sync(0xffffffffu, my_off <= B);
+    const unsigned int bit = (my_off > B && my_off - B < 32u) ? (1u << (my_off - B)) : 0u;
+    const unsigned int mask = __reduce_or_sync(0xffffffffu, bit);
+    const int k = __popc(below) - 1 + __popc(mask & ((2u << lane) - 1u));
+    if (q < W) {
+      const uint32_t o = sm->owner[k];
+      const uint32_t kk = q - sm->off[k];
+      const uint4 c03 = *reinterpret_cast<const uint4*>(&sm->cum[o][0]);
+      const uint2 c45 = *reinterpret_cast<const uint2*>(&sm->cum[o][4]);
+      const uint4 l03 = *reinterpret_cast<const uint4*>(&sm->lo[o][0]);
+      const uint2 l45 = *reinterpret_cast<const uint2*>(&sm->lo[o][4]);
+      const uint32_t lo_r = kk < c03.z ? (kk < c03.x ? l03.x : (kk < c03.y ? l03.y : l03.z))
+                                       : (kk < c03.w ? l03.w : (kk < c45.x ? l45.x : l45.y));
+      const uint32_t j = lo_r + kk;
+      const MolRec c = load_rec(p.recA, j);
+      const double4 oa = sm->a[o], ob = sm->b[o];
+      const unsigned long long ids = (unsigned long long)__double_as_longlong(ob.w);
+      double d;
+      if (collide_mol_hit(c, D3{oa.x, oa.y, oa.z}, D3{ob.x, ob.y, ob.z}, oa.w, oa.w * R2, (uint32_t)ids, d)) {
+        const int rc = p.bimol[(uint32_t)(ids >> 32) * p.n_species + (c.sf & SF_SPECIES_MASK)];
+        if (rc >= 0) { atomicAdd(&sm->hits[o], 1u); sm->hit_slot[o] = j; }
+      }
+    }
+  }
+  __syncwarp();
+  const int found = (int)sm->hits[lane];
+  first.slot = MCX_NONE; first.in_own_subpart = false; first.t = 0; first.id = 0; first.species = 0; first.rxn_class = 0;
+  if (found == 1) {
+    const uint32_t j = sm->hit_slot[lane];
+    const MolRec c = load_rec(p.recA, j);
+    const D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
+    const uint32_t csp = c.sf & SF_SPECIES_MASK;
+    first.t = dot3(dir, disp) / movelen2; first.slot = j; first.id = c.id; first.species = csp;
+    first.rxn_class = p.bimol[self_species * p.n_species + csp];
+    first.in_own_subpart = subpart_index(p, D3{c.x, c.y, c.z}) == subpart_index(p, pos);
+  }
+  __syncwarp();  // the buffers are reused by the next trip of the caller's loop
+  return found;
+}
+
 // Plane-rejection stage of collide_wall (collision_utils.inl:664-683) for every wall of one subpartition:
 // true when each wall is a COLLIDE_MISS already there (no random draw, no REDO can occur).
 __device__ __forceinline__ bool all_walls_plane_rejected(const DevParams& p, bool enabled, uint32_t subpart, D3 pos, D3 move,

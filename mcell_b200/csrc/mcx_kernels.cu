@@ -50,6 +50,40 @@ __device__ __forceinline__ unsigned int agg_reserve(unsigned int* addr, unsigned
   return base + before;
 }
 
+
+// ---- per-warp staging of slot indices appended to a global list --------------------------------------------------
+// Every warp of k_diffuse_fast used to reserve its deferred slots with one RETURNING atomicAdd on a single
+// address (Counters::n_slow): 2.4e5 same-address round trips per iteration at 1e7 molecules, 55 % of the
+// kernel's stall samples (profiles/r01_d).  Slots are now staged in a 64-entry shared-memory buffer per warp and
+// flushed with one atomic per >32 entries.  push()/flush() are warp-collective: all 32 lanes must call them.
+#define WL_CAP 64
+struct WarpList {
+  uint32_t* buf;       // this warp's WL_CAP entries of shared memory
+  unsigned int n;      // staged entries (warp-uniform)
+  unsigned int total;  // entries appended so far (warp-uniform)
+  __device__ __forceinline__ void init(uint32_t* b) { buf = b; n = 0; total = 0; }
+  __device__ __forceinline__ void flush(unsigned int* ctr, uint32_t* list) {
+    if (n == 0) return;
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    unsigned int at = 0;
+    if (lane == 0) at = atomicAdd(ctr, n);
+    at = __shfl_sync(0xffffffffu, at, 0);
+    for (unsigned int k = lane; k < n; k += 32) list[at + k] = buf[k];
+    __syncwarp();
+    total += n;
+    n = 0;
+  }
+  __device__ __forceinline__ void push(bool pred, uint32_t v, unsigned int* ctr, uint32_t* list) {
+    const unsigned int bal = __ballot_sync(0xffffffffu, pred);
+    if (bal == 0) return;
+    const int lane = threadIdx.x & 31;
+    if (pred) buf[n + __popc(bal & ((1u << lane) - 1u))] = v;
+    n += __popc(bal);
+    if (n > WL_CAP - 32) flush(ctr, list);
+  }
+};
+
 __device__ __forceinline__ unsigned int round_epoch(const DevParams& p, unsigned int round) {
   return (unsigned int)(p.iteration * (unsigned long long)(p.max_rounds + 1) + round + 1);
 }
@@ -166,6 +200,7 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
   }
 }
 
+// list < 0: the caller appends the slot to the pending list itself (WarpList)
 __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot, const Outcome& o, uint32_t id,
                                                uint32_t species, unsigned int epoch, int list) {
   store_rec(p.recB, slot, o.pos, id, species | (o.flags & ~DF_DEAD));
@@ -178,8 +213,10 @@ __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot
   unsigned long long key = claim_key(epoch, id);
   atomicMax(&p.claim[slot], key);
   if (partner_is_consumed(p, o.kind, o.rxn_class, o.pathway, species)) atomicMax(&p.claim[o.partner_slot], key);
-  uint32_t k = agg_reserve(&p.ctr->n_pend[list], 1u);
-  p.pend[list][k] = slot;
+  if (list >= 0) {
+    uint32_t k = agg_reserve(&p.ctr->n_pend[list], 1u);
+    p.pend[list][k] = slot;
+  }
 }
 
 __device__ __forceinline__ void trace_begin(const DevParams& p, Tracer& tc, uint32_t id) {
@@ -224,11 +261,18 @@ __device__ __forceinline__ void trace_end(Tracer& tc, const Outcome& o, const St
 #endif
 __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const __grid_constant__ DevParams p) {
   __shared__ ZigShared zig;
+  __shared__ uint32_t s_slow[TPB / 32][WL_CAP], s_prop[TPB / 32][WL_CAP];
+  __shared__ unsigned int s_reason[TPB / 32][8];
+  __shared__ WarpProbe s_probe[TPB / 32];
   zig_load(&zig);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < 8) s_reason[warp][lane] = 0;
   __syncthreads();
+  WarpList slow_wl, prop_wl;
+  slow_wl.init(s_slow[warp]);
+  prop_wl.init(s_prop[warp]);
   const unsigned int n = p.ctr->n_slots;
   const double t_end = (double)p.iteration + 1.0;
-  const int lane = threadIdx.x & 31;
   unsigned int msteps = 0, n_tests = 0, n_coll = 0;
   for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const unsigned int i = base + threadIdx.x;
@@ -284,10 +328,11 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
     PartnerHit ph;
     const bool probing = simple && sp.can_vol_react;
     bool overflow;
-    const int n_hits = probe_partners(p, probing, pos, disp, m.id, species, ph, overflow);
+    const int n_hits = probe_partners_flat(p, probing, pos, disp, m.id, species, ph, overflow, &s_probe[warp]);
     simple = simple && !overflow && (n_hits == 0 || (n_hits == 1 && ph.in_own_subpart));
     if (!simple && reason < 0) reason = overflow ? MCX_DEFER_PROBE_SHAPE : (n_hits > 1 ? MCX_DEFER_MULTI_HIT : MCX_DEFER_FOREIGN_HIT);
 
+    bool proposed = false;
     if (simple) {
       Tracer tc; trace_begin(p, tc, m.id);
       Outcome o; o.kind = MCX_OUT_MOVED; o.pos = dest;
@@ -309,20 +354,21 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       }
       trace_end(tc, o, rs);
       if (o.kind == MCX_OUT_MOVED) finalize_alive(p, i, dest, m.id, species, flags, t_end, t_uni);
-      else write_proposal(p, i, o, m.id, species, round_epoch(p, 0), 0);
+      else { write_proposal(p, i, o, m.id, species, round_epoch(p, 0), -1); proposed = true; }
       if (owned_z(p, pos.z)) { msteps++; n_tests += n_wall_tests; n_coll += n_hits == 1 ? 1u : 0u; }
     }
     if (in_range && !live) p.rank[i] = MCX_NONE;
     const bool slow = live && !simple;
-    // warp-aggregated append of the deferred slots (loop bounds are warp-uniform: all 32 lanes arrive here)
-    const unsigned int bal = __ballot_sync(0xffffffffu, slow);
-    if (bal) {
-      unsigned int at = 0;
-      if (lane == 0) { at = atomicAdd(&p.ctr->n_slow, (unsigned int)__popc(bal)); atomicAdd(&p.ctr->deferred, (unsigned long long)__popc(bal)); }
-      at = __shfl_sync(0xffffffffu, at, 0);
-      if (slow) { p.slow_list[at + __popc(bal & ((1u << lane) - 1u))] = i; agg_add(&p.ctr->defer_reason[reason & 7], 1u); }
-    }
+    // staged appends (loop bounds are warp-uniform: all 32 lanes arrive here)
+    if (slow) atomicAdd(&s_reason[warp][reason & 7], 1u);
+    slow_wl.push(slow, i, &p.ctr->n_slow, p.slow_list);
+    prop_wl.push(proposed, i, &p.ctr->n_pend[0], p.pend[0]);
   }
+  slow_wl.flush(&p.ctr->n_slow, p.slow_list);
+  prop_wl.flush(&p.ctr->n_pend[0], p.pend[0]);
+  __syncwarp();
+  if (lane == 0 && slow_wl.total) atomicAdd(&p.ctr->deferred, (unsigned long long)slow_wl.total);
+  if (lane < 8 && s_reason[warp][lane]) atomicAdd(&p.ctr->defer_reason[lane], (unsigned long long)s_reason[warp][lane]);
   LocalStats ls = {n_tests, 0, 0, 0, n_coll, 0};
   flush_stats(p, ls, msteps);
 }
