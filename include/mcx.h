@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MCX_ABI_VERSION 1
+#define MCX_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define MCX_OK 0
@@ -73,7 +73,7 @@ typedef struct mcx_config {
 
 /* ---- species: BNG::Species subset (src/mcell_species.c:207-300) --------- */
 enum {
-  MCX_SP_VOL = 1u << 0,            /* volume molecule */
+  MCX_SP_VOL = 1u << 0,            /* volume molecule; clear = surface molecule living on a wall tile */
   MCX_SP_CAN_DIFFUSE = 1u << 1,    /* D != 0 */
   MCX_SP_CANT_INITIATE = 1u << 2   /* TARGET_ONLY */
 };
@@ -85,7 +85,8 @@ typedef struct mcx_species {
 } mcx_species;
 
 /* ---- reactions: RxnClass / pathway tables ------------------------------ */
-enum { MCX_RXN_UNIMOL = 1, MCX_RXN_BIMOL_VOLVOL = 2 };
+enum { MCX_RXN_UNIMOL = 1, MCX_RXN_BIMOL_VOLVOL = 2,
+       MCX_RXN_BIMOL_VOLSURF = 3 /* reactants[0] = volume species, reactants[1] = surface species */ };
 typedef struct mcx_rxn_class {
   uint32_t kind;                   /* MCX_RXN_* */
   uint32_t reactants[2];           /* species ids in rule order; [1] = MCX_NONE for unimol */
@@ -93,6 +94,7 @@ typedef struct mcx_rxn_class {
   uint32_t n_pathways;
   uint32_t reserved;
   double   max_fixed_p;            /* RxnClass::get_max_fixed_p() = cum_probs[last] */
+  int32_t  reactant_orientation[2];/* RxnClass::get_reactant_orientation (rxn_utils.inl:58-84): +1 ', -1 , and 0 = none */
 } mcx_rxn_class;
 typedef struct mcx_pathway {
   double   cum_prob;               /* cumulative probability (src/mcell_reactions.c:2932-2933) */
@@ -101,6 +103,8 @@ typedef struct mcx_pathway {
   uint32_t keep_reactant_mask;     /* bit r: rule reactant r appears unchanged on both sides */
   uint32_t rxn_rule_id;            /* slot of the per-reaction occurrence counter */
   uint32_t reserved;
+  int32_t  product_orientation[MCX_MAX_PRODUCTS]; /* rule orientation of products[k]; 0 = none: one random bit
+                                      when a surface is involved (diffuse_react_event.cpp:2622-2627) */
 } mcx_pathway;
 
 /* ---- surface classes (mcell4_converter.cpp:515-622; rxn_utils.inl:263-287) ----------- */
@@ -126,6 +130,12 @@ typedef struct mcx_mol_soa {
   uint32_t *flags;                 /* MCX_MOL_* */
   double   *diffusion_time;        /* Molecule::diffusion_time; NULL = all at current iteration */
   double   *unimol_rxn_time;       /* Molecule::unimol_rxn_time; NULL = MCX_TIME_INVALID */
+  /* Molecule::s for surface molecules (src4/molecule.h); all NULL = volume molecules only.
+   * For a surface molecule x,y,z are ignored on upload and returned as uv2xyz(u,v) on download. */
+  uint32_t *wall;                  /* s.wall_index; MCX_NONE for a volume molecule */
+  uint32_t *tile;                  /* s.grid_tile_index on that wall's grid */
+  int32_t  *orientation;           /* s.orientation: +1 up / -1 down */
+  double   *u, *v;                 /* s.pos in the wall's uv frame */
 } mcx_mol_soa;
 
 /* ---- per-call statistics: SimulationStats mirror (src4/simulation_stats.h:46-83) ----- */
@@ -281,6 +291,13 @@ int mcx_slab_info_get(mcx_handle* h, mcx_slab_info* out);
 int mcx_comm_unique_id(void* out, uint32_t bytes);
 
 /* ---- host helpers that need no device (also exported for the CPU test tier) ----------- */
+/* Surface grid of one triangle for host-side placement of surface molecules (release stays on the host):
+ * v9 = three vertices; returns num_tiles = ceil(sqrt(area))^2 (Grid::initialize, src4/wall.cpp:38-74). */
+uint32_t mcx_grid_num_tiles(const double* v9);
+/* Centre of a tile in the wall's uv frame (GridUtils::grid2uv, src4/grid_utils.inl:233-253). */
+void mcx_grid2uv(const double* v9, uint32_t tile, double* uv2);
+/* Tile under a point of the wall (GridUtils::xyz2grid_tile_index, src4/grid_utils.inl:48-118). */
+uint32_t mcx_xyz2grid(const double* v9, const double* xyz3);
 /* Philox4x32-10 block for (seed, molecule id, iteration, block index); the device stream
  * of molecule `id` is the concatenation of blocks 0,1,2,... */
 void mcx_philox_block(uint64_t seed, uint32_t mol_id, uint64_t iteration, uint32_t block,

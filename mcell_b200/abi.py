@@ -2,7 +2,7 @@
 field for field; tests/test_abi.py checks sizes against the library's own sizeof table."""
 import ctypes as C
 
-MCX_ABI_VERSION = 1
+MCX_ABI_VERSION = 2
 MCX_OK = 0
 MCX_ERR_INVALID_ARG, MCX_ERR_CUDA, MCX_ERR_CAPACITY, MCX_ERR_ESCAPED = -1, -2, -3, -4
 MCX_ERR_STATE, MCX_ERR_OVERFLOW, MCX_ERR_COMM = -5, -6, -7
@@ -15,7 +15,7 @@ MCX_TIME_INVALID = -256.0
 MCX_TIME_FOREVER = 1e20
 MCX_RNG_PHILOX, MCX_RNG_TAPE = 0, 1
 MCX_SP_VOL, MCX_SP_CAN_DIFFUSE, MCX_SP_CANT_INITIATE = 1, 2, 4
-MCX_RXN_UNIMOL, MCX_RXN_BIMOL_VOLVOL = 1, 2
+MCX_RXN_UNIMOL, MCX_RXN_BIMOL_VOLVOL, MCX_RXN_BIMOL_VOLSURF = 1, 2, 3
 MCX_SURF_REFLECTIVE, MCX_SURF_TRANSPARENT, MCX_SURF_ABSORPTIVE = 0, 1, 2
 MCX_MOL_DEFUNCT, MCX_MOL_SCHEDULE_UNIMOL, MCX_MOL_PARTIAL = 1, 2, 4
 MCX_OUT_NONE, MCX_OUT_MOVED, MCX_OUT_REACTED, MCX_OUT_ABSORBED = 0, 1, 2, 3
@@ -48,12 +48,14 @@ class mcx_species(C.Structure):
 
 class mcx_rxn_class(C.Structure):
     _fields_ = [("kind", c_u32), ("reactants", c_u32 * 2), ("first_pathway", c_u32),
-                ("n_pathways", c_u32), ("reserved", c_u32), ("max_fixed_p", c_f64)]
+                ("n_pathways", c_u32), ("reserved", c_u32), ("max_fixed_p", c_f64),
+                ("reactant_orientation", c_i32 * 2)]
 
 
 class mcx_pathway(C.Structure):
     _fields_ = [("cum_prob", c_f64), ("n_products", c_u32), ("products", c_u32 * MCX_MAX_PRODUCTS),
-                ("keep_reactant_mask", c_u32), ("rxn_rule_id", c_u32), ("reserved", c_u32)]
+                ("keep_reactant_mask", c_u32), ("rxn_rule_id", c_u32), ("reserved", c_u32),
+                ("product_orientation", c_i32 * MCX_MAX_PRODUCTS)]
 
 
 class mcx_surf_class_rxn(C.Structure):
@@ -63,7 +65,8 @@ class mcx_surf_class_rxn(C.Structure):
 class mcx_mol_soa(C.Structure):
     _fields_ = [("n", c_u64), ("x", P(c_f64)), ("y", P(c_f64)), ("z", P(c_f64)),
                 ("id", P(c_u32)), ("species", P(c_u32)), ("flags", P(c_u32)),
-                ("diffusion_time", P(c_f64)), ("unimol_rxn_time", P(c_f64))]
+                ("diffusion_time", P(c_f64)), ("unimol_rxn_time", P(c_f64)),
+                ("wall", P(c_u32)), ("tile", P(c_u32)), ("orientation", P(c_i32)), ("u", P(c_f64)), ("v", P(c_f64))]
 
 
 class mcx_step_stats(C.Structure):
@@ -105,6 +108,7 @@ EXPORTED_SYMBOLS = [
     "mcx_set_species", "mcx_set_reactions", "mcx_set_surface_classes", "mcx_upload_molecules",
     "mcx_download_molecules", "mcx_num_molecules", "mcx_step", "mcx_replay_step", "mcx_trace_step",
     "mcx_counts", "mcx_comm_init", "mcx_comm_unique_id", "mcx_slab_info_get", "mcx_philox_block", "mcx_set_profiling",
+    "mcx_grid_num_tiles", "mcx_grid2uv", "mcx_xyz2grid",
 ]
 
 

@@ -42,7 +42,10 @@ struct mcx_handle {
   // table device pointers that get replaced on re-set
   void *d_species = nullptr, *d_bimol = nullptr, *d_unimol = nullptr, *d_classes = nullptr, *d_pathways = nullptr,
        *d_surf = nullptr, *d_walls = nullptr, *d_tri = nullptr, *d_verts = nullptr, *d_wclass = nullptr,
-       *d_spw_start = nullptr, *d_spw_list = nullptr, *d_sp_flags = nullptr;
+       *d_spw_start = nullptr, *d_spw_list = nullptr, *d_sp_flags = nullptr, *d_grids = nullptr, *d_volsurf = nullptr,
+       *d_tile_slot = nullptr;
+  bool has_surf = false, surf_allocated = false;
+  uint32_t *st_wall = nullptr, *st_tile = nullptr; int32_t* st_orient = nullptr; double *st_u = nullptr, *st_v = nullptr;
   McxComm* comm = nullptr;
   int ncz_global = 0;
   double *st_x = nullptr, *st_y = nullptr, *st_z = nullptr, *st_ts = nullptr, *st_tu = nullptr;
@@ -89,6 +92,9 @@ static int dev_replace(mcx_handle* h, void** slot, const T* src, size_t count) {
 extern "C" {
 
 int mcx_abi_version(void) { return MCX_ABI_VERSION; }
+uint32_t mcx_grid_num_tiles(const double* v9) { return mcxg::tri_num_tiles(v9); }
+void mcx_grid2uv(const double* v9, uint32_t tile, double* uv2) { mcxg::tri_grid2uv(v9, tile, uv2); }
+uint32_t mcx_xyz2grid(const double* v9, const double* xyz3) { return mcxg::tri_xyz2grid(v9, xyz3); }
 
 const char* mcx_last_error(const mcx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -239,6 +245,16 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   rc |= dev_replace(h, &h->d_wclass, h->wall_class_host.data(), h->wall_class_host.size());
   rc |= dev_replace(h, &h->d_spw_start, start.data(), start.size());
   rc |= dev_replace(h, &h->d_spw_list, list.data(), list.size());
+  // surface grids of every wall and the tile table (Grid::molecules_per_tile, one entry per tile of every wall)
+  std::vector<DevGrid> grids;
+  const uint64_t n_tiles = mcxg::grid_constants(vertices, tri, walls, grids);
+  if (n_tiles > 0xFFFFFFF0ull) { h->err = "too many surface tiles"; return MCX_ERR_INVALID_ARG; }
+  rc |= dev_replace(h, &h->d_grids, grids.data(), grids.size());
+  {
+    std::vector<uint32_t> vacant(std::max<uint64_t>(n_tiles, 1), MCX_NONE);
+    rc |= dev_replace(h, &h->d_tile_slot, vacant.data(), vacant.size());
+  }
+  h->p.grids = (const DevGrid*)h->d_grids; h->p.tile_slot = (uint32_t*)h->d_tile_slot; h->p.n_tiles = (unsigned int)n_tiles;
   // per-subpartition wall flags for the fast diffuse pass: bit0 = holds walls, bit1 = 3x3x3 neighbourhood does
   {
     const int n = h->p.n_sp;
@@ -274,7 +290,9 @@ static int rebuild_tables(mcx_handle* h) {
   const size_t ns = h->species.size();
   if (ns == 0) return MCX_OK;
   if (ns > 256) { h->err = "more than 256 species are not supported by the device counters"; return MCX_ERR_INVALID_ARG; }
-  std::vector<int> bimol(ns * ns, -1), unimol(ns, -1);
+  std::vector<int> bimol(ns * ns, -1), unimol(ns, -1), volsurf(ns * ns, -1);
+  bool any_surf = false;
+  for (size_t a = 0; a < ns; a++) any_surf = any_surf || !(h->species[a].flags & MCX_SP_VOL);
   std::vector<DevClass> dc(h->classes.size());
   std::vector<DevPathway> dp(h->pathways.size());
   for (size_t c = 0; c < h->classes.size(); c++) {
@@ -282,15 +300,42 @@ static int rebuild_tables(mcx_handle* h) {
     if (rc.first_pathway + rc.n_pathways > h->pathways.size() || rc.n_pathways == 0 || rc.n_pathways > 4095) {
       h->err = "reaction class pathway range invalid"; return MCX_ERR_INVALID_ARG;
     }
-    if (rc.reactants[0] >= ns || (rc.kind == MCX_RXN_BIMOL_VOLVOL && rc.reactants[1] >= ns)) {
+    if (rc.reactants[0] >= ns || (rc.kind != MCX_RXN_UNIMOL && rc.reactants[1] >= ns)) {
       h->err = "reaction class references an unknown species"; return MCX_ERR_INVALID_ARG;
     }
-    dc[c] = DevClass{rc.max_fixed_p, rc.kind, rc.reactants[0], rc.reactants[1], rc.first_pathway, rc.n_pathways, 0};
+    if (rc.n_pathways > 255) { h->err = "more than 255 pathways in one reaction class"; return MCX_ERR_INVALID_ARG; }
+    dc[c] = DevClass{rc.max_fixed_p, rc.kind, rc.reactants[0], rc.reactants[1], rc.first_pathway, rc.n_pathways,
+                     rc.reactant_orientation[0], rc.reactant_orientation[1], 0};
+    auto is_vol = [&](uint32_t sp) { return (h->species[sp].flags & MCX_SP_VOL) != 0; };
     if (rc.kind == MCX_RXN_BIMOL_VOLVOL) {
+      if (!is_vol(rc.reactants[0]) || !is_vol(rc.reactants[1])) { h->err = "vol-vol class with a surface reactant"; return MCX_ERR_INVALID_ARG; }
       bimol[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
       bimol[rc.reactants[1] * ns + rc.reactants[0]] = (int)c;
+    } else if (rc.kind == MCX_RXN_BIMOL_VOLSURF) {
+      if (!is_vol(rc.reactants[0]) || is_vol(rc.reactants[1])) { h->err = "vol-surf class: reactants must be (volume, surface)"; return MCX_ERR_INVALID_ARG; }
+      volsurf[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
+      any_surf = true;
     } else if (rc.kind == MCX_RXN_UNIMOL) unimol[rc.reactants[0]] = (int)c;
     else { h->err = "unknown reaction kind"; return MCX_ERR_INVALID_ARG; }
+    // supported product placement (SURVEY A.2 fast cases; the general find_surf_product_positions branch is not built)
+    const bool surf_reactant = rc.kind == MCX_RXN_BIMOL_VOLSURF || (rc.kind == MCX_RXN_UNIMOL && !is_vol(rc.reactants[0]));
+    for (uint32_t q = 0; q < rc.n_pathways; q++) {
+      const mcx_pathway& pw = h->pathways[rc.first_pathway + q];
+      uint32_t n_surf_products = 0;
+      for (uint32_t k = 0; k < pw.n_products && k < MCX_MAX_PRODUCTS; k++)
+        if (pw.products[k] < ns && !is_vol(pw.products[k])) n_surf_products++;
+      if (!surf_reactant && n_surf_products) { h->err = "surface product without a surface reactant"; return MCX_ERR_INVALID_ARG; }
+      if (surf_reactant) {
+        const int surf_idx = rc.kind == MCX_RXN_BIMOL_VOLSURF ? 1 : 0;
+        const bool surf_kept = (pw.keep_reactant_mask >> surf_idx) & 1u;
+        if (n_surf_products > 1 || (n_surf_products == 1 && surf_kept)) {
+          h->err = "surface products beyond the recycled tile of the surface reactant are not supported"; return MCX_ERR_INVALID_ARG;
+        }
+        if (rc.kind == MCX_RXN_BIMOL_VOLSURF && (pw.keep_reactant_mask & 1u)) {
+          h->err = "vol-surf pathways that keep the volume reactant (RX_FLIP / catalytic) are not supported"; return MCX_ERR_INVALID_ARG;
+        }
+      }
+    }
   }
   for (size_t k = 0; k < h->pathways.size(); k++) {
     const mcx_pathway& pw = h->pathways[k];
@@ -300,6 +345,7 @@ static int rebuild_tables(mcx_handle* h) {
     for (uint32_t q = 0; q < pw.n_products; q++) {
       if (pw.products[q] >= ns) { h->err = "product references an unknown species"; return MCX_ERR_INVALID_ARG; }
       d.products[q] = pw.products[q];
+      d.prod_orient[q] = pw.product_orientation[q];
     }
     dp[k] = d;
   }
@@ -307,8 +353,10 @@ static int rebuild_tables(mcx_handle* h) {
   for (size_t a = 0; a < ns; a++) {
     bool any = false;
     for (size_t b = 0; b < ns; b++) any = any || bimol[a * ns + b] >= 0;
+    bool vs = false;
+    for (size_t b = 0; b < ns; b++) vs = vs || volsurf[a * ns + b] >= 0;
     ds[a] = DevSpecies{h->species[a].space_step, h->species[a].time_step, h->species[a].flags,
-                       (any && !(h->species[a].flags & MCX_SP_CANT_INITIATE)) ? 1u : 0u};
+                       (any && !(h->species[a].flags & MCX_SP_CANT_INITIATE)) ? 1u : 0u, vs ? 1u : 0u, 0u};
   }
   // surface-class action table; lookup order as in find_mol_reactions_with_surf_classes
   // (rxn_utils.inl:182-244): species-specific, ALL_MOLECULES, ALL_VOLUME_MOLECULES
@@ -340,8 +388,11 @@ static int rebuild_tables(mcx_handle* h) {
   rc |= dev_replace(h, &h->d_classes, dc.data(), dc.size());
   rc |= dev_replace(h, &h->d_pathways, dp.data(), dp.size());
   rc |= dev_replace(h, &h->d_surf, act.data(), act.size());
+  rc |= dev_replace(h, &h->d_volsurf, volsurf.data(), volsurf.size());
   if (rc) return MCX_ERR_CUDA;
   DevParams& p = h->p;
+  p.volsurf = (const int*)h->d_volsurf;
+  h->has_surf = any_surf;
   p.species = (const DevSpecies*)h->d_species; p.bimol = (const int*)h->d_bimol; p.unimol = (const int*)h->d_unimol;
   p.classes = (const DevClass*)h->d_classes; p.pathways = (const DevPathway*)h->d_pathways;
   p.surf_action = (const uint8_t*)h->d_surf; p.n_species = (int)ns; p.n_surf_classes = (int)nsc;
@@ -412,15 +463,45 @@ static int ensure_staging(mcx_handle* h) {
   return rc ? MCX_ERR_CUDA : MCX_OK;
 }
 
+// cold per-slot surface fields and their staging: only models with surface species pay for them
+static int ensure_surface_arrays(mcx_handle* h) {
+  h->p.has_surf = h->has_surf ? 1 : 0;
+  if (!h->has_surf || h->surf_allocated) return MCX_OK;
+  if (h->cfg.world_size > 1) { h->err = "surface molecules are not supported with world_size > 1 yet"; return MCX_ERR_INVALID_ARG; }
+  const size_t cap = h->p.capacity;
+  DevParams& p = h->p;
+  int rc = MCX_OK;
+  rc |= dev_alloc(h, &p.swallA, cap); rc |= dev_alloc(h, &p.swallB, cap);
+  rc |= dev_alloc(h, &p.stileA, cap); rc |= dev_alloc(h, &p.stileB, cap);
+  rc |= dev_alloc(h, &p.suvA, cap); rc |= dev_alloc(h, &p.suvB, cap);
+  rc |= dev_alloc(h, &h->st_wall, cap); rc |= dev_alloc(h, &h->st_tile, cap); rc |= dev_alloc(h, &h->st_orient, cap);
+  rc |= dev_alloc(h, &h->st_u, cap); rc |= dev_alloc(h, &h->st_v, cap);
+  if (rc) return MCX_ERR_CUDA;
+  h->surf_allocated = true;
+  return MCX_OK;
+}
+
 int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
   if (!h || !m) return MCX_ERR_INVALID_ARG;
   if (!h->has_species) { h->err = "species table missing"; return MCX_ERR_STATE; }
+  if (h->has_surf && !h->has_geometry) { h->err = "surface species need mcx_set_geometry before the upload"; return MCX_ERR_STATE; }
   if (m->n > h->p.capacity) { h->err = "more molecules than max_molecules"; return MCX_ERR_CAPACITY; }
   if (m->n && (!m->x || !m->y || !m->z || !m->id || !m->species)) { h->err = "null molecule arrays"; return MCX_ERR_INVALID_ARG; }
   CK(cudaSetDevice(h->cfg.device));
   if (ensure_staging(h)) return MCX_ERR_CUDA;
+  { int rcs = ensure_surface_arrays(h); if (rcs) return rcs; }
   const size_t n = m->n;
   cudaStream_t s = h->stream;
+  SurfSoa sv{nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (h->has_surf && m->wall) {
+    if (!m->tile || !m->orientation || !m->u || !m->v) { h->err = "incomplete surface molecule arrays"; return MCX_ERR_INVALID_ARG; }
+    CK(cudaMemcpyAsync(h->st_wall, m->wall, n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->st_tile, m->tile, n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->st_orient, m->orientation, n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->st_u, m->u, n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->st_v, m->v, n * 8, cudaMemcpyHostToDevice, s));
+    sv = SurfSoa{h->st_wall, h->st_tile, h->st_orient, h->st_u, h->st_v};
+  }
   CK(cudaMemcpyAsync(h->st_x, m->x, n * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(h->st_y, m->y, n * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(h->st_z, m->z, n * 8, cudaMemcpyHostToDevice, s));
@@ -435,7 +516,7 @@ int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
   CK(cudaMemcpyAsync(h->p.ctr, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
   bind_iteration(h);
   mcx_launch_pack_soa(h->p, h->st_x, h->st_y, h->st_z, h->st_id, h->st_sp, m->flags ? h->st_fl : nullptr,
-                      m->diffusion_time ? h->st_ts : nullptr, m->unimol_rxn_time ? h->st_tu : nullptr, (unsigned int)n, s);
+                      m->diffusion_time ? h->st_ts : nullptr, m->unimol_rxn_time ? h->st_tu : nullptr, sv, (unsigned int)n, s);
   h->launches += 1;
   mcx_launch_initial_sort(h->p, h->plan, s);
   h->cs_cur ^= 1;
@@ -470,7 +551,10 @@ int mcx_download_molecules(mcx_handle* h, mcx_mol_soa* out, uint64_t capacity) {
   if (ensure_staging(h)) return MCX_ERR_CUDA;
   cudaStream_t s = h->stream;
   bind_iteration(h);
-  mcx_launch_unpack_soa(h->p, h->st_x, h->st_y, h->st_z, h->st_id, h->st_sp, h->st_fl, h->st_ts, h->st_tu, h->d_n_out, s);
+  SurfSoaOut sv{nullptr, nullptr, nullptr, nullptr, nullptr};
+  const bool want_surf = h->surf_allocated && out->wall && out->tile && out->orientation && out->u && out->v;
+  if (want_surf) sv = SurfSoaOut{h->st_wall, h->st_tile, h->st_orient, h->st_u, h->st_v};
+  mcx_launch_unpack_soa(h->p, h->st_x, h->st_y, h->st_z, h->st_id, h->st_sp, h->st_fl, h->st_ts, h->st_tu, sv, h->d_n_out, s);
   h->launches += 1;
   unsigned int live = 0;
   CK(cudaMemcpyAsync(&live, h->d_n_out, 4, cudaMemcpyDeviceToHost, s));
@@ -484,6 +568,15 @@ int mcx_download_molecules(mcx_handle* h, mcx_mol_soa* out, uint64_t capacity) {
   if (out->flags) CK(cudaMemcpyAsync(out->flags, h->st_fl, live * 4ull, cudaMemcpyDeviceToHost, s));
   if (out->diffusion_time) CK(cudaMemcpyAsync(out->diffusion_time, h->st_ts, live * 8ull, cudaMemcpyDeviceToHost, s));
   if (out->unimol_rxn_time) CK(cudaMemcpyAsync(out->unimol_rxn_time, h->st_tu, live * 8ull, cudaMemcpyDeviceToHost, s));
+  if (want_surf) {
+    CK(cudaMemcpyAsync(out->wall, h->st_wall, live * 4ull, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->tile, h->st_tile, live * 4ull, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->orientation, h->st_orient, live * 4ull, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->u, h->st_u, live * 8ull, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->v, h->st_v, live * 8ull, cudaMemcpyDeviceToHost, s));
+  } else if (out->wall) {
+    for (uint64_t i = 0; i < live && i < capacity; i++) out->wall[i] = MCX_NONE;  // no surface species: all volume
+  }
   CK(cudaStreamSynchronize(s));
   out->n = live;
   return MCX_OK;

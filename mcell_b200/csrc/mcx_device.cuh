@@ -116,6 +116,7 @@ struct Outcome {
   uint32_t flags;         // device flag bits (DF_*)
   int rxn_class, pathway;
   uint32_t partner_slot, partner_id;
+  uint32_t orient_bits;   // bit k: random orientation drawn for products[k] (1 = up)
 };
 
 struct Tracer {
@@ -127,7 +128,7 @@ struct Tracer {
   }
 };
 enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
-       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u };
+       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u };
 
 struct LocalStats {
   unsigned int ray_polygon_tests, ray_polygon_colls, reflections, transparent, volvol_collisions, redos;
@@ -721,19 +722,76 @@ __device__ __forceinline__ bool all_walls_plane_rejected(const DevParams& p, boo
   return all;
 }
 
+// ---- surface molecules ------------------------------------------------------------------------------------
+// distinguishable_vec3, src4/defines.h:766-806
+__device__ __forceinline__ bool distinguishable_vec3_d(D3 a, D3 b, double eps) {
+  double c = fabs(a.x), cc, d;
+  d = fabs(a.y); if (d > c) c = d;
+  d = fabs(a.z); if (d > c) c = d;
+  d = fabs(b.x); if (d > c) c = d;
+  d = fabs(b.y); if (d > c) c = d;
+  d = fabs(b.z); if (d > c) c = d;
+  cc = fabs(a.x - b.x);
+  d = fabs(a.y - b.y); if (d > cc) cc = d;
+  d = fabs(a.z - b.z); if (d > cc) cc = d;
+  if (c < eps) c = eps;
+  return c * eps < cc;
+}
+// GridUtils::xyz2grid_tile_index, src4/grid_utils.inl:48-118
+__device__ uint32_t xyz2grid(const DevParams& p, D3 v, uint32_t wi) {
+  const DevGrid& g = p.grids[wi];
+  const DevWall& f = p.walls[wi];
+  const uint32_t n_tiles = (uint32_t)(g.n_axis * g.n_axis);
+  if (n_tiles == 1) return 0;
+  if (!distinguishable_vec3_d(v, wall_vertex(p, wi, 0), MCX_EPS)) return n_tiles - 2 * (uint32_t)g.n_axis + 1;
+  if (!distinguishable_vec3_d(v, wall_vertex(p, wi, 1), MCX_EPS)) return n_tiles - 1;
+  if (!distinguishable_vec3_d(v, wall_vertex(p, wi, 2), MCX_EPS)) return 0;
+  const double i = dot3(v, D3{f.ux, f.uy, f.uz}) - g.vert0_u;
+  const double j = dot3(v, D3{f.vx, f.vy, f.vz}) - g.vert0_v;
+  const double striploc = j * g.strip_width_rcp;
+  int strip = (int)striploc;
+  const double striprem = striploc - strip;
+  strip = g.n_axis - strip - 1;
+  const double u0 = j * g.vert2_slope;
+  const double u1_u0 = f.uv1u - j * g.fullslope;
+  const double stripeloc = ((i - u0) / u1_u0) * (strip + (1 - striprem));
+  const int stripe = (int)stripeloc;
+  const double striperem = stripeloc - stripe;
+  const int flip = (striperem < 1 - striprem) ? 0 : 1;
+  int idx = strip * strip + 2 * stripe + flip;
+  if (idx < 0) idx = 0;
+  if ((uint32_t)idx >= n_tiles) idx = (int)n_tiles - 1;
+  return (uint32_t)idx;
+}
+// RxnUtils::trigger_bimolecular orientation test, src4/rxn_utils.inl:58-84
+__device__ __forceinline__ bool orientations_match(const DevClass& rc, int orientA, int orientB) {
+  const int geomA = rc.geom0, geomB = rc.geom1;
+  if (geomA == 0 || geomB == 0 || (geomA + geomB) * (geomA - geomB) != 0) return true;
+  return orientA != 0 && orientA * orientB * geomA * geomB > 0;
+}
+// one random bit per product with rule orientation NONE (outcome_products_random, diffuse_react_event.cpp:2618-2627)
+__device__ __forceinline__ uint32_t draw_orientation_bits(const DevPathway& pw, Stream& rs) {
+  uint32_t bits = 0;
+  for (uint32_t k = 0; k < pw.n_products; k++)
+    if (pw.prod_orient[k] == 0 && (rs.next() & 1u)) bits |= 1u << k;
+  return bits;
+}
+
 // ===================================================================================================
 // One molecule, (the rest of) one iteration.  `forced` = last conflict round: no partner search.
 // ===================================================================================================
 // Control flow note: no early `return` / `goto` — the outcome is carried in `decided` and every loop has a single
 // exit condition, so that the lanes of a warp (32 different molecules) re-converge at the loop headers and run
 // the common stages (DDA, wall tests, partner scan) together.
+// created_wall / created_tile: where a DF_CREATED_ON_SURF volume product was created (MCX_NONE otherwise).
 template <bool RETRY>
 __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t_sched, double t_unimol_in,
+                                   uint32_t created_wall, uint32_t created_tile,
                                    Stream& rs, bool forced, Outcome& out, LocalStats& ls, Tracer& tc, int& err) {
   const uint32_t species = m.sf & SF_SPECIES_MASK;
   const DevSpecies sp = p.species[species];
   const double it = (double)p.iteration, t_end = it + 1;
-  uint32_t flags = m.sf & ~SF_SPECIES_MASK;
+  uint32_t flags = (m.sf & ~SF_SPECIES_MASK) & ~DF_CREATED_ON_SURF;  // the guard below lives for this iteration only
   D3 pos = {m.x, m.y, m.z};
   uint32_t subpart = subpart_index(p, pos);
   double t_now = (flags & DF_PARTIAL) ? t_sched : it;
@@ -741,7 +799,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
   const bool can_diffuse = (sp.flags & MCX_SP_CAN_DIFFUSE) != 0;
   const bool can_vol_react = sp.can_vol_react != 0 && !forced;
   out.rxn_class = -1; out.pathway = -1; out.partner_slot = MCX_NONE; out.partner_id = MCX_NONE; out.t_event = 0;
-  out.kind = MCX_OUT_NONE;
+  out.kind = MCX_OUT_NONE; out.orient_bits = 0;
   bool decided = false;  // a claiming event or an error ended the evaluation; `out` is complete
 
   bool again = true;
@@ -762,6 +820,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
         }
         pathway = match > A[min_idx].cum_prob ? max_idx : min_idx;
       }
+      if (flags & DF_SURF) out.orient_bits = draw_orientation_bits(p.pathways[cl.first_pathway + pathway], rs);
       tc.ev(EV_UNIMOL | (uint32_t)pathway, (uint32_t)rc);
       if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->t_event = unimol_time; }
       out.kind = MCX_OUT_UNIMOL; out.pos = pos; out.rxn_class = rc; out.pathway = pathway; out.t_event = unimol_time;
@@ -884,7 +943,47 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
               if (tc.tr->n_wall_hits < MCX_TRACE_K) { tc.tr->wall[tc.tr->n_wall_hits] = wh.wall; tc.tr->wall_side[tc.tr->n_wall_hits] = side; }
               tc.tr->n_wall_hits++;
             }
-            if (action == MCX_SURF_TRANSPARENT) {  // cross_transparent_wall (:3007-3099)
+            // ---- collide_and_react_with_surf_mol (:845-975): the surface molecule on the tile under the hit point
+            bool surf_reacted = false;
+            if (sp.can_vol_surf && p.n_tiles) {
+              const DevGrid& g = p.grids[wh.wall];
+              const uint32_t j = xyz2grid(p, wh.pos, wh.wall);
+              const uint32_t occ = p.tile_slot[g.tile_start + j];
+              bool occupied = false;
+              MolRec sm;
+              if (occ != MCX_NONE) {
+                sm = RETRY ? load_rec_volatile(p.recA, occ) : load_rec(p.recA, occ);
+                occupied = !(sm.sf & DF_DEAD);
+              }
+              if (occupied && created_wall == wh.wall && created_tile == j) {
+                created_wall = created_tile = MCX_NONE;  // no rebinding where it was just created; next time yes
+                occupied = false;
+              }
+              if (occupied) {
+                const uint32_t ssp = sm.sf & SF_SPECIES_MASK;
+                const int rc = p.volsurf[species * p.n_species + ssp];
+                const int coll_orient = side == W_FRONT ? 1 : -1;
+                const int surf_orient = (sm.sf & DF_ORIENT_UP) ? 1 : -1;
+                if (rc >= 0 && orientations_match(p.classes[rc], coll_orient, surf_orient)) {
+                  const double scaling = r_rate_factor / g.binding_factor;
+                  const double abs_t = elapsed + t_steps * wh.t;
+                  tc.ev(EV_SURFMOL | (uint32_t)side, sm.id);
+                  if (tc.tr) { if (tc.tr->n_collisions < MCX_TRACE_K) tc.tr->partner[tc.tr->n_collisions] = sm.id; tc.tr->n_collisions++; }
+                  const int pathway = test_bimolecular(p, p.classes[rc], scaling, rs);
+                  if (pathway >= 0) {
+                    out.orient_bits = draw_orientation_bits(p.pathways[p.classes[rc].first_pathway + pathway], rs);
+                    tc.ev(EV_RXN | (uint32_t)pathway, (uint32_t)rc);
+                    if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = sm.id; tc.tr->t_event = abs_t; }
+                    out.kind = MCX_OUT_REACTED; out.pos = wh.pos;
+                    out.rxn_class = rc; out.pathway = pathway; out.partner_slot = occ; out.partner_id = sm.id;
+                    out.t_event = abs_t; out.t_now = t_now; out.flags = flags; out.unimol_time = unimol_time;
+                    surf_reacted = true; decided = true; tracing = false;
+                  }
+                }
+              }
+            }
+            if (surf_reacted) {
+            } else if (action == MCX_SURF_TRANSPARENT) {  // cross_transparent_wall (:3007-3099)
               tc.ev(EV_TRANSP | (uint32_t)side, wh.wall);
               ls.transparent++;
               pos = wh.pos; subpart = subpart_index(p, pos);
@@ -916,6 +1015,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
           }
         }
       }
+      created_wall = created_tile = MCX_NONE;  // the guard belongs to the first DiffuseAction only (:116-129)
       if (!decided) {
         // -- reschedule (:283-336)
         if (can_diffuse) {

@@ -167,4 +167,100 @@ void bin_walls(const GridSpec& g, const double* verts, const uint32_t* tri, cons
   for (size_t s = 0; s < ns3; s++) list.insert(list.end(), per[s].begin(), per[s].end());
 }
 
+
+// ---- surface grids ------------------------------------------------------------------------------------------
+static double tri_area(const double* a, const double* b, const double* c) {
+  P3 v0 = {a[0], a[1], a[2]}, v1 = {b[0], b[1], b[2]}, v2 = {c[0], c[1], c[2]};
+  return 0.5 * std::sqrt(len2(crossp(sub(v1, v0), sub(v2, v0))));
+}
+static void one_grid(const DevWall& w, double area, DevGrid& g) {
+  g.n_axis = (int)std::ceil(std::sqrt(area));
+  if (g.n_axis < 1) g.n_axis = 1;
+  const uint32_t n_tiles = (uint32_t)(g.n_axis * g.n_axis);
+  g.strip_width_rcp = 1 / (w.uv2v / ((double)g.n_axis));
+  g.vert2_slope = w.uv2u / w.uv2v;
+  g.fullslope = w.uv1u / w.uv2v;
+  g.binding_factor = ((double)n_tiles) / area;
+  P3 v0 = {w.v0x, w.v0y, w.v0z};
+  g.vert0_u = dotp(v0, P3{w.ux, w.uy, w.uz});
+  g.vert0_v = dotp(v0, P3{w.vx, w.vy, w.vz});
+}
+uint64_t grid_constants(const double* verts, const uint32_t* tri, const std::vector<DevWall>& walls, std::vector<DevGrid>& out) {
+  out.resize(walls.size());
+  uint64_t total = 0;
+  for (size_t i = 0; i < walls.size(); i++) {
+    DevGrid g{};
+    one_grid(walls[i], tri_area(verts + 3 * tri[3 * i], verts + 3 * tri[3 * i + 1], verts + 3 * tri[3 * i + 2]), g);
+    g.tile_start = (uint32_t)total;
+    total += (uint64_t)g.n_axis * g.n_axis;
+    out[i] = g;
+  }
+  return total;
+}
+static void one_triangle(const double* v9, DevWall& w, DevGrid& g) {
+  const uint32_t t[3] = {0, 1, 2};
+  std::vector<DevWall> ws;
+  wall_constants(v9, t, 1, ws);
+  w = ws[0];
+  one_grid(w, tri_area(v9, v9 + 3, v9 + 6), g);
+}
+uint32_t tri_num_tiles(const double* v9) {
+  DevWall w; DevGrid g{};
+  one_triangle(v9, w, g);
+  return (uint32_t)(g.n_axis * g.n_axis);
+}
+// GridUtils::grid2uv, src4/grid_utils.inl:233-253
+void tri_grid2uv(const double* v9, uint32_t index, double* uv2) {
+  DevWall w; DevGrid g{};
+  one_triangle(v9, w, g);
+  int root = (int)(std::sqrt((double)index));
+  int rootrem = (int)index - root * root;
+  int k = g.n_axis - root - 1;
+  int j = rootrem / 2;
+  int i = rootrem - 2 * j;
+  double over3n = 1 / (double)(3 * g.n_axis);
+  uv2[0] = ((double)(3 * j + i + 1)) * over3n * w.uv1u + ((double)(3 * k + i + 1)) * over3n * w.uv2u;
+  uv2[1] = ((double)(3 * k + i + 1)) * over3n * w.uv2v;
+}
+static bool distinguishable_vec3(P3 a, P3 b, double eps) {  // src4/defines.h:766-806
+  double c = std::fabs(a.x), cc, d;
+  d = std::fabs(a.y); if (d > c) c = d;
+  d = std::fabs(a.z); if (d > c) c = d;
+  d = std::fabs(b.x); if (d > c) c = d;
+  d = std::fabs(b.y); if (d > c) c = d;
+  d = std::fabs(b.z); if (d > c) c = d;
+  cc = std::fabs(a.x - b.x);
+  d = std::fabs(a.y - b.y); if (d > cc) cc = d;
+  d = std::fabs(a.z - b.z); if (d > cc) cc = d;
+  if (c < eps) c = eps;
+  return c * eps < cc;
+}
+// GridUtils::xyz2grid_tile_index, src4/grid_utils.inl:48-118
+uint32_t tri_xyz2grid(const double* v9, const double* xyz3) {
+  DevWall w; DevGrid g{};
+  one_triangle(v9, w, g);
+  const uint32_t n_tiles = (uint32_t)(g.n_axis * g.n_axis);
+  if (n_tiles == 1) return 0;
+  P3 v = {xyz3[0], xyz3[1], xyz3[2]};
+  if (!distinguishable_vec3(v, P3{v9[0], v9[1], v9[2]}, 1e-12)) return n_tiles - 2 * (uint32_t)g.n_axis + 1;
+  if (!distinguishable_vec3(v, P3{v9[3], v9[4], v9[5]}, 1e-12)) return n_tiles - 1;
+  if (!distinguishable_vec3(v, P3{v9[6], v9[7], v9[8]}, 1e-12)) return 0;
+  double i = dotp(v, P3{w.ux, w.uy, w.uz}) - g.vert0_u;
+  double j = dotp(v, P3{w.vx, w.vy, w.vz}) - g.vert0_v;
+  double striploc = j * g.strip_width_rcp;
+  int strip = (int)striploc;
+  double striprem = striploc - strip;
+  strip = g.n_axis - strip - 1;
+  double u0 = j * g.vert2_slope;
+  double u1_u0 = w.uv1u - j * g.fullslope;
+  double stripeloc = ((i - u0) / u1_u0) * (strip + (1 - striprem));
+  int stripe = (int)stripeloc;
+  double striperem = stripeloc - stripe;
+  int flip = (striperem < 1 - striprem) ? 0 : 1;
+  int idx = strip * strip + 2 * stripe + flip;
+  if (idx < 0) idx = 0;
+  if ((uint32_t)idx >= n_tiles) idx = (int)n_tiles - 1;
+  return (uint32_t)idx;
+}
+
 }  // namespace mcxg

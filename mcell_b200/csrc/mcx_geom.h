@@ -7,6 +7,12 @@
 namespace mcxg {
 struct GridSpec { double ox, oy, oz, sp_len, sp_rcp, R; int n_sp; bool use_expanded; };
 void wall_constants(const double* verts, const uint32_t* tri, uint64_t n_walls, std::vector<DevWall>& out);
+// surface grids (Grid::initialize, src4/wall.cpp:38-74); tile_start = exclusive prefix of num_tiles; returns the total
+uint64_t grid_constants(const double* verts, const uint32_t* tri, const std::vector<DevWall>& walls, std::vector<DevGrid>& out);
+// host helpers behind mcx_grid_num_tiles / mcx_grid2uv / mcx_xyz2grid (one triangle given by its 9 coordinates)
+uint32_t tri_num_tiles(const double* v9);
+void tri_grid2uv(const double* v9, uint32_t tile, double* uv2);
+uint32_t tri_xyz2grid(const double* v9, const double* xyz3);
 void bin_walls(const GridSpec& g, const double* verts, const uint32_t* tri, const std::vector<DevWall>& walls,
                std::vector<uint32_t>& start, std::vector<uint32_t>& list);
 }  // namespace mcxg

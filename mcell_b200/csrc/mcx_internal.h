@@ -21,12 +21,23 @@ enum : uint32_t {
   DF_PARTIAL = 1u << 18,     // cold t_sched[] holds a fractional diffusion_time
   DF_HAS_UNIMOL = 1u << 19,  // cold t_unimol[] holds a scheduled unimolecular time
   DF_GHOST = 1u << 20,       // reserved
+  DF_SURF = 1u << 21,        // surface molecule: cold swall/stile/suv hold Molecule::s (src4/molecule.h)
+  DF_ORIENT_UP = 1u << 22,   // s.orientation == ORIENTATION_UP (else DOWN)
+  DF_CREATED_ON_SURF = 1u << 23,  // volume product of a surface reaction: cold swall/stile hold where it was created
+                                  // (DiffuseAction::where_created_this_iteration, diffuse_react_event.cpp:877-885)
   SF_SPECIES_MASK = 0xFFFFu
 };
 
-struct DevSpecies { double space_step, time_step; uint32_t flags; uint32_t can_vol_react; };
-struct DevClass { double max_fixed_p; uint32_t kind, r0, r1, first_pathway, n_pathways, pad; };
-struct DevPathway { double cum_prob; uint32_t n_products, products[MCX_MAX_PRODUCTS], keep_mask, rule_id, pad; };
+struct DevSpecies { double space_step, time_step; uint32_t flags; uint32_t can_vol_react; uint32_t can_vol_surf; uint32_t pad; };
+struct DevClass { double max_fixed_p; uint32_t kind, r0, r1, first_pathway, n_pathways; int geom0, geom1; uint32_t pad; };
+struct DevPathway { double cum_prob; uint32_t n_products, products[MCX_MAX_PRODUCTS], keep_mask, rule_id; int prod_orient[MCX_MAX_PRODUCTS]; uint32_t pad; };
+
+// per-wall surface grid (Grid::initialize, src4/wall.cpp:38-74) + the wall's first entry in the tile table
+struct __align__(16) DevGrid {
+  double strip_width_rcp, vert2_slope, fullslope, binding_factor, vert0_u, vert0_v;
+  int n_axis;
+  uint32_t tile_start;
+};
 
 // per-wall constants (Wall::initialize_wall_constants, src4/wall.cpp:281-342), 128 B/wall
 struct __align__(16) DevWall {
@@ -82,6 +93,15 @@ struct DevParams {
   const DevPathway* pathways;
   const uint8_t* surf_action;   // [species][surf_class][side(0 front,1 back)]
   int n_species, n_surf_classes, n_walls;
+  // surface molecules: tile table of the current snapshot and per-slot cold fields
+  const DevGrid* grids;         // per wall
+  const int* volsurf;           // [volume species][surface species] -> class or -1
+  uint32_t* tile_slot;          // per tile: slot in recA of the occupant, MCX_NONE = vacant (rebuilt by the scatter)
+  unsigned int n_tiles;
+  int has_surf;                 // any surface species / vol-surf class: the cold surface arrays exist
+  uint32_t *swallA, *swallB;    // s.wall_index (or creation wall of a DF_CREATED_ON_SURF volume product)
+  uint32_t *stileA, *stileB;    // s.grid_tile_index (or creation tile)
+  double2 *suvA, *suvB;         // s.pos
   // rng
   unsigned long long seed, iteration;
   int rng_mode;
@@ -138,9 +158,12 @@ void mcx_launch_pack_halo(const DevParams& p, HaloRec* send_low, HaloRec* send_h
 void mcx_launch_unpack_halo(const DevParams& p, const HaloRec* recv, unsigned int n, unsigned int offset, cudaStream_t s);
 void mcx_launch_add_received(const DevParams& p, unsigned int n, cudaStream_t s);
 void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
+// device staging of the surface part of mcx_mol_soa (all null: volume molecules only)
+struct SurfSoa { const uint32_t* wall; const uint32_t* tile; const int32_t* orientation; const double* u; const double* v; };
+struct SurfSoaOut { uint32_t* wall; uint32_t* tile; int32_t* orientation; double* u; double* v; };
 void mcx_launch_pack_soa(const DevParams& p, const double* x, const double* y, const double* z,
                          const uint32_t* id, const uint32_t* species, const uint32_t* flags,
-                         const double* tsched, const double* tuni, unsigned int n, cudaStream_t s);
+                         const double* tsched, const double* tuni, SurfSoa sv, unsigned int n, cudaStream_t s);
 void mcx_launch_unpack_soa(const DevParams& p, double* x, double* y, double* z, uint32_t* id,
-                           uint32_t* species, uint32_t* flags, double* tsched, double* tuni,
+                           uint32_t* species, uint32_t* flags, double* tsched, double* tuni, SurfSoaOut sv,
                            unsigned int* n_out, cudaStream_t s);

@@ -121,6 +121,7 @@ __device__ __forceinline__ void finalize_alive(const DevParams& p, uint32_t slot
   uint32_t sf = species | (flags & ~(DF_HAS_UNIMOL | DF_DEAD));
   if (unimol_time != MCX_TIME_INVALID) { sf |= DF_HAS_UNIMOL; p.tuniB[slot] = unimol_time; }
   if (sf & DF_PARTIAL) p.tschedB[slot] = t_now;
+  if (sf & DF_SURF) { p.swallB[slot] = p.swallA[slot]; p.stileB[slot] = p.stileA[slot]; p.suvB[slot] = p.suvA[slot]; }
   store_rec(p.recB, slot, pos, id, sf);
   uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
   p.rank[slot] = atomicAdd(&p.cs_next[cell], 1u);
@@ -138,7 +139,7 @@ __device__ __forceinline__ bool partner_is_consumed(const DevParams& p, int kind
 // accepted claiming event: consume reactants, create products, count
 __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rxn_class, int pathway, uint32_t partner_slot,
                              double t_event, D3 pos, uint32_t id, uint32_t species, uint32_t flags, double t_now,
-                             double unimol_time) {
+                             double unimol_time, uint32_t orient_bits) {
   Counters* c = p.ctr;
   // multi-GPU: halo molecules are evaluated redundantly (identically on both sides); an event is counted and its
   // products are created by the rank owning the event position; reactants are marked DEAD everywhere
@@ -177,15 +178,44 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
     reuse[n_reuse++] = pid;
     if (p.trace && pid < p.n_trace) p.trace[pid].outcome = MCX_OUT_CONSUMED;
   }
+  // the surface reactant of the event, if any: the partner of a volume initiator, or the initiator itself
+  // (outcome_products_random :2446-2933, cases of SURVEY A.2: a surface product recycles its tile and uv; a volume
+  // product is bumped 2*16*EPS off the wall to the side its orientation names and remembers where it was created)
+  uint32_t surf_slot = MCX_NONE, surf_sf = 0;
+  if (p.has_surf) {
+    if (kind == MCX_OUT_REACTED) { surf_sf = p.recA[partner_slot].sf; if (surf_sf & DF_SURF) surf_slot = partner_slot; }
+    else if (flags & DF_SURF) { surf_slot = slot; surf_sf = flags; }
+  }
   const uint32_t n_new = own_event ? pw.n_products : 0u;
   const uint32_t first_slot = n_new ? c->n_slots + agg_reserve(&c->n_prod, n_new) : 0u;
+  const D3 event_pos = pos;
   for (uint32_t k = 0; k < n_new; k++) {
     uint32_t ns = first_slot + k;
     if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
     uint32_t nid = (int)k < n_reuse ? reuse[k] : atomicAdd(&c->next_id, (unsigned int)p.world) ;  // fresh ids: strided by rank
     uint32_t psp = pw.products[k];
+    uint32_t pflags = DF_SCHED_UNIMOL | DF_PARTIAL;
+    pos = event_pos;
+    if (surf_slot != MCX_NONE) {
+      int o = pw.prod_orient[k];
+      if (o == 0) o = ((orient_bits >> k) & 1u) ? 1 : -1;
+      else if (cl.kind == MCX_RXN_BIMOL_VOLSURF && cl.geom1 != 0 && ((surf_sf & DF_ORIENT_UP) ? 1 : -1) != cl.geom1) o = -o;
+      const uint32_t wi = p.swallA[surf_slot];
+      p.swallB[ns] = wi; p.stileB[ns] = p.stileA[surf_slot];
+      if (!(p.species[psp].flags & MCX_SP_VOL)) {
+        pflags |= DF_SURF | (o > 0 ? DF_ORIENT_UP : 0u);
+        p.suvB[ns] = p.suvA[surf_slot];
+        const MolRec sr = load_rec_volatile(p.recA, surf_slot);
+        pos = D3{sr.x, sr.y, sr.z};
+      } else {
+        const DevWall& f = p.walls[wi];
+        const double bump = (o > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
+        pos = D3{event_pos.x + (2 * bump) * f.nx, event_pos.y + (2 * bump) * f.ny, event_pos.z + (2 * bump) * f.nz};
+        pflags |= DF_CREATED_ON_SURF;
+      }
+    }
     p.tschedB[ns] = t_event;
-    store_rec(p.recB, ns, pos, nid, psp | DF_SCHED_UNIMOL | DF_PARTIAL);
+    store_rec(p.recB, ns, pos, nid, psp | pflags);
     uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
     p.rank[ns] = atomicAdd(&p.cs_next[cell], 1u);
     if (track) agg_add(&c->species_count[psp], 1u);
@@ -196,7 +226,7 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
     uint32_t f = flags | DF_PARTIAL;
     double ut = unimol_time;
     if (cl.kind == MCX_RXN_UNIMOL) { f |= DF_SCHED_UNIMOL; ut = MCX_TIME_INVALID; }
-    finalize_alive(p, slot, pos, id, species, f, t_event, ut);
+    finalize_alive(p, slot, event_pos, id, species, f, t_event, ut);
   }
 }
 
@@ -207,7 +237,8 @@ __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot
   p.tschedB[slot] = o.t_now;
   p.tuniB[slot] = o.unimol_time;
   p.prop_partner[slot] = o.partner_slot;
-  p.prop_info[slot] = (uint32_t)o.kind | ((uint32_t)o.pathway << 4) | ((uint32_t)o.rxn_class << 16);
+  p.prop_info[slot] = (uint32_t)o.kind | (((uint32_t)o.pathway & 0xFFu) << 4) | ((o.orient_bits & 0xFu) << 12) |
+                      ((uint32_t)o.rxn_class << 16);
   p.prop_t[slot] = o.t_event;
   p.rank[slot] = MCX_NONE;
   unsigned long long key = claim_key(epoch, id);
@@ -287,9 +318,13 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
     // scheduled unimolecular time: a predicated index keeps the load unconditional (no warp split) without
     // touching the cold array for molecules that have none
     const bool has_uni = (m.sf & DF_HAS_UNIMOL) != 0;
-    const double t_uni_raw = __ldg(p.tuniA + ((simple && has_uni) ? ii : 0u));
+    const bool idle_candidate = live && !(sp.flags & MCX_SP_CAN_DIFFUSE) && !(m.sf & (DF_PARTIAL | DF_SCHED_UNIMOL));
+    const double t_uni_raw = __ldg(p.tuniA + (((simple || idle_candidate) && has_uni) ? ii : 0u));
     const double t_uni = has_uni ? t_uni_raw : MCX_TIME_INVALID;
     simple = simple && !(has_uni && t_uni < t_end);  // fires or splits the step inside this iteration -> generic path
+    // a non-diffusing molecule with nothing scheduled inside this iteration (receptors, pumps): the generic
+    // evaluation would return MCX_OUT_STATIC without drawing a number (diffuse_react_event.cpp:318-335)
+    const bool idle = idle_candidate && !(has_uni && t_uni < t_end);
     int reason = simple ? -1 : MCX_DEFER_TIMING;
 
     // compute_vol_displacement with steps == 1 (diffusion_utils.inl:366-432); drawn by every lane
@@ -358,7 +393,16 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       if (owned_z(p, pos.z)) { msteps++; n_tests += n_wall_tests; n_coll += n_hits == 1 ? 1u : 0u; }
     }
     if (in_range && !live) p.rank[i] = MCX_NONE;
-    const bool slow = live && !simple;
+    if (idle) {
+      if (p.trace && m.id < p.n_trace) {
+        Tracer tc; trace_begin(p, tc, m.id);
+        Outcome o; o.kind = MCX_OUT_STATIC; o.pos = pos;
+        trace_end(tc, o, rs);
+        tc.tr->n_words = 0;
+      }
+      finalize_alive(p, i, pos, m.id, species, flags, 0.0, t_uni);
+    }
+    const bool slow = live && !simple && !idle;
     // staged appends (loop bounds are warp-uniform: all 32 lanes arrive here)
     if (slow) atomicAdd(&s_reason[warp][reason & 7], 1u);
     slow_wl.push(slow, i, &p.ctr->n_slow, p.slow_list);
@@ -397,7 +441,9 @@ __global__ void __launch_bounds__(TPB, 2) k_diffuse_slow(const __grid_constant__
     const bool own_start = owned_z(p, m.z);
     if (own_start && (p.species[species].flags & MCX_SP_CAN_DIFFUSE)) msteps++;
     LocalStats halo_ls = {0, 0, 0, 0, 0, 0};  // statistics of redundantly evaluated halo molecules are not counted
-    evaluate_iteration<false>(p, m, t_sched, t_uni, rs, false, o, own_start ? ls : halo_ls, tc, err);
+    const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
+    evaluate_iteration<false>(p, m, t_sched, t_uni, guard ? p.swallA[i] : MCX_NONE, guard ? p.stileA[i] : MCX_NONE,
+                              rs, false, o, own_start ? ls : halo_ls, tc, err);
     trace_end(tc, o, rs);
     if (err && (own_start || err != MCX_ERR_ESCAPED)) raise_error(p, err, m.id);
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time);
@@ -417,14 +463,15 @@ __global__ void __launch_bounds__(TPB) k_resolve(const __grid_constant__ DevPara
     MolRec e = load_rec_volatile(p.recB, slot);  // event position + identity
     uint32_t species = e.sf & SF_SPECIES_MASK;
     uint32_t info = p.prop_info[slot];
-    int kind = info & 15, pathway = (info >> 4) & 0xFFF, rxn_class = info >> 16;
+    int kind = info & 15, pathway = (info >> 4) & 0xFF, rxn_class = info >> 16;
+    const uint32_t orient_bits = (info >> 12) & 0xFu;
     uint32_t partner = p.prop_partner[slot];
     unsigned long long key = claim_key(epoch, e.id);
     bool ok = p.claim[slot] == key;
     if (ok && partner_is_consumed(p, kind, rxn_class, pathway, species)) ok = p.claim[partner] == key;
     if (ok) {
       commit_event(p, slot, kind, rxn_class, pathway, partner, p.prop_t[slot], D3{e.x, e.y, e.z}, e.id, species,
-                   e.sf & ~SF_SPECIES_MASK, p.tschedB[slot], p.tuniB[slot]);
+                   e.sf & ~SF_SPECIES_MASK, p.tschedB[slot], p.tuniB[slot], orient_bits);
     } else {
       uint32_t q = agg_reserve(&p.ctr->n_pend[nxt], 1u);
       p.pend[nxt][q] = slot;
@@ -462,7 +509,9 @@ __global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevPar
     Tracer tc; trace_begin(p, tc, m.id);
     Outcome o; int err = 0;
     LocalStats halo_ls = {0, 0, 0, 0, 0, 0};
-    evaluate_iteration<true>(p, m, t_sched, t_uni, rs, forced != 0, o, own_start ? ls : halo_ls, tc, err);
+    const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
+    evaluate_iteration<true>(p, m, t_sched, t_uni, guard ? p.swallA[i] : MCX_NONE, guard ? p.stileA[i] : MCX_NONE,
+                             rs, forced != 0, o, own_start ? ls : halo_ls, tc, err);
     trace_end(tc, o, rs);
     if (err) raise_error(p, err, m.id);
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time);
@@ -470,7 +519,7 @@ __global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevPar
     else if (forced) {  // only self-claims can occur without partners: commit directly
       p.rank[i] = MCX_NONE;
       commit_event(p, i, o.kind, o.rxn_class, o.pathway, o.partner_slot, o.t_event, o.pos, m.id, species, o.flags, o.t_now,
-                   o.unimol_time);
+                   o.unimol_time, o.orient_bits);
     } else write_proposal(p, i, o, m.id, species, epoch, cur);
   }
   flush_stats(p, ls, 0);
@@ -566,6 +615,14 @@ __global__ void __launch_bounds__(TPB) k_scatter(const __grid_constant__ DevPara
     d[0] = lo; d[1] = hi;
     if (sf & DF_PARTIAL) p.tschedA[dst] = p.tschedB[i];
     if (sf & DF_HAS_UNIMOL) p.tuniA[dst] = p.tuniB[i];
+    if (sf & (DF_SURF | DF_CREATED_ON_SURF)) {
+      const uint32_t wi = p.swallB[i], ti = p.stileB[i];
+      p.swallA[dst] = wi; p.stileA[dst] = ti;
+      if (sf & DF_SURF) {
+        p.suvA[dst] = p.suvB[i];
+        if (!(sf & DF_DEAD)) p.tile_slot[p.grids[wi].tile_start + ti] = dst;  // Grid::molecules_per_tile of the next snapshot
+      }
+    }
     // multi-GPU: recount the owned population (halo copies are not this rank's molecules)
     if (p.world > 1 && !(sf & DF_DEAD) && owned_z(p, hi.x)) agg_add(&p.ctr->species_next[sf & SF_SPECIES_MASK], 1u);
   }
@@ -654,22 +711,35 @@ __global__ void k_add_received(const __grid_constant__ DevParams p, unsigned int
 // ---- SoA <-> record conversion at the ABI boundary ---------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_pack_soa(const __grid_constant__ DevParams p, const double* x, const double* y, const double* z,
                                                   const uint32_t* id, const uint32_t* species, const uint32_t* flags,
-                                                  const double* tsched, const double* tuni, unsigned int n) {
+                                                  const double* tsched, const double* tuni, SurfSoa sv, unsigned int n) {
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t hf = flags ? flags[i] : 0;
     uint32_t sf = species[i] & SF_SPECIES_MASK;
-    if (species[i] >= (uint32_t)p.n_species) raise_error(p, MCX_ERR_INVALID_ARG, id[i]);
+    if (species[i] >= (uint32_t)p.n_species) { raise_error(p, MCX_ERR_INVALID_ARG, id[i]); continue; }
+    D3 pos = {x[i], y[i], z[i]};
+    const bool is_surf = !(p.species[species[i]].flags & MCX_SP_VOL);
+    if (is_surf) {  // Partition::add_surface_molecule: position from the wall's uv frame (uv2xyz, geometry_utils.h:29-35)
+      const uint32_t wi = sv.wall ? sv.wall[i] : MCX_NONE;
+      if (!p.has_surf || wi >= (uint32_t)p.n_walls || sv.tile[i] >= (uint32_t)(p.grids[wi].n_axis * p.grids[wi].n_axis)) {
+        raise_error(p, MCX_ERR_INVALID_ARG, id[i]); continue;
+      }
+      const DevWall& f = p.walls[wi];
+      const double u = sv.u[i], v = sv.v[i];
+      pos = D3{u * f.ux + v * f.vx + f.v0x, u * f.uy + v * f.vy + f.v0y, u * f.uz + v * f.vz + f.v0z};
+      sf |= DF_SURF | (sv.orientation[i] > 0 ? DF_ORIENT_UP : 0u);
+      p.swallB[i] = wi; p.stileB[i] = sv.tile[i]; p.suvB[i] = make_double2(u, v);
+    }
     atomicMax(&p.ctr->next_id, id[i] + 1u);
     if (hf & MCX_MOL_DEFUNCT) sf |= DF_DEAD;
     if (hf & MCX_MOL_SCHEDULE_UNIMOL) sf |= DF_SCHED_UNIMOL;
     if ((hf & MCX_MOL_PARTIAL) && tsched) { sf |= DF_PARTIAL; p.tschedB[i] = tsched[i]; }
     if (tuni && tuni[i] != MCX_TIME_INVALID) { sf |= DF_HAS_UNIMOL; p.tuniB[i] = tuni[i]; }
-    store_rec(p.recB, i, D3{x[i], y[i], z[i]}, id[i], sf);
+    store_rec(p.recB, i, pos, id[i], sf);
   }
 }
 __global__ void __launch_bounds__(TPB) k_unpack_soa(const __grid_constant__ DevParams p, double* x, double* y, double* z, uint32_t* id,
                                                     uint32_t* species, uint32_t* flags, double* tsched, double* tuni,
-                                                    unsigned int* n_out) {
+                                                    SurfSoaOut sv, unsigned int* n_out) {
   const unsigned int n = p.ctr->n_slots;
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     MolRec m = load_rec_volatile(p.recA, i);
@@ -682,6 +752,14 @@ __global__ void __launch_bounds__(TPB) k_unpack_soa(const __grid_constant__ DevP
     if (flags) flags[k] = hf;
     if (tsched) tsched[k] = (m.sf & DF_PARTIAL) ? p.tschedA[i] : (double)p.iteration;
     if (tuni) tuni[k] = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;
+    if (sv.wall) {
+      const bool is_surf = (m.sf & DF_SURF) != 0;
+      sv.wall[k] = is_surf ? p.swallA[i] : MCX_NONE;
+      sv.tile[k] = is_surf ? p.stileA[i] : MCX_NONE;
+      sv.orientation[k] = is_surf ? ((m.sf & DF_ORIENT_UP) ? 1 : -1) : 0;
+      const double2 uv = is_surf ? p.suvA[i] : make_double2(0.0, 0.0);
+      sv.u[k] = uv.x; sv.v[k] = uv.y;
+    }
   }
 }
 
@@ -695,6 +773,7 @@ void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
   k_scan_reduce<<<nblocks, SCAN_TPB, 0, s>>>(p.cs_next, n, p.scan_sums);
   k_scan_sums<<<1, SCAN_TPB, 0, s>>>(p.scan_sums, nblocks, p.scan_sums + nblocks, p.ctr);
   k_scan_apply<<<nblocks, SCAN_TPB, 0, s>>>(p.cs_next, n, p.scan_sums);
+  if (p.has_surf && p.n_tiles) cudaMemsetAsync(p.tile_slot, 0xFF, sizeof(uint32_t) * (size_t)p.n_tiles, s);
   k_scatter<<<plan.sm_count * 8, TPB, 0, s>>>(p);
   k_end_iteration<<<1, 256, 0, s>>>(p);
 }
@@ -752,14 +831,14 @@ void mcx_launch_add_received(const DevParams& p, unsigned int n, cudaStream_t s)
 
 void mcx_launch_pack_soa(const DevParams& p, const double* x, const double* y, const double* z, const uint32_t* id,
                          const uint32_t* species, const uint32_t* flags, const double* tsched, const double* tuni,
-                         unsigned int n, cudaStream_t s) {
+                         SurfSoa sv, unsigned int n, cudaStream_t s) {
   unsigned int grid = (n + TPB - 1) / TPB;
   if (grid == 0) grid = 1;
   if (grid > 65535u * 16u) grid = 65535u * 16u;
-  k_pack_soa<<<grid, TPB, 0, s>>>(p, x, y, z, id, species, flags, tsched, tuni, n);
+  k_pack_soa<<<grid, TPB, 0, s>>>(p, x, y, z, id, species, flags, tsched, tuni, sv, n);
 }
 void mcx_launch_unpack_soa(const DevParams& p, double* x, double* y, double* z, uint32_t* id, uint32_t* species,
-                           uint32_t* flags, double* tsched, double* tuni, unsigned int* n_out, cudaStream_t s) {
+                           uint32_t* flags, double* tsched, double* tuni, SurfSoaOut sv, unsigned int* n_out, cudaStream_t s) {
   cudaMemsetAsync(n_out, 0, sizeof(unsigned int), s);
-  k_unpack_soa<<<148 * 8, TPB, 0, s>>>(p, x, y, z, id, species, flags, tsched, tuni, n_out);
+  k_unpack_soa<<<148 * 8, TPB, 0, s>>>(p, x, y, z, id, species, flags, tsched, tuni, sv, n_out);
 }

@@ -10,6 +10,8 @@ reference keeps in libbng / MCell3:
 * space_step       src/mcell_species.c:270-273   sqrt(4*1e8*D*time_unit)/length_unit
 * bimol pb_factor  src/react_util.c:163-181       1e15/N_AV / (2*sqrt(pi)*R_um^2*eff_vel)
 * unimol           src/react_util.c:74-78         k * time_unit
+* vol-surf         src/react_util.c:111-157       1e11*grid_density/(2*N_AV)*sqrt(pi*t_step/D), x2 when both
+                   reactants carry orientations of the same class
 * cum_probs        src/mcell_reactions.c:2932-2933
 * create_box / create_icosphere  libmcell/api/geometry_utils.cpp:32-91,124-262
 """
@@ -43,6 +45,16 @@ class Species:
     name: str
     diffusion_constant_3d: float = 0.0
     target_only: bool = False
+    surface: bool = False          # surface molecule (diffusion_constant_2d = 0: receptors, pumps)
+
+
+def _parse_oriented(name):
+    """MCell3 orientation marks on a species name: "L'" = up (+1), "R," = down (-1), none = 0."""
+    if name.endswith("'"):
+        return name[:-1], 1
+    if name.endswith(","):
+        return name[:-1], -1
+    return name, 0
 
 
 @dataclass
@@ -136,8 +148,10 @@ class Model:
         self._wall_class = []
 
     # -- subsystem ------------------------------------------------------------------------
-    def add_species(self, name, D, target_only=False):
-        self.species.append(Species(name, D, target_only))
+    def add_species(self, name, D, target_only=False, surface=False):
+        if surface and D != 0:
+            raise ValueError("surface diffusion is not built: surface species must have D = 0")
+        self.species.append(Species(name, D, target_only, surface))
         return len(self.species) - 1
 
     def add_reaction_rule(self, reactants, products, fwd_rate, name=""):
@@ -212,13 +226,13 @@ class Model:
         for i, s in enumerate(self.species):
             sp[i].space_step = self.space_step(s.diffusion_constant_3d)
             sp[i].time_step = 1.0
-            sp[i].flags = abi.MCX_SP_VOL | (abi.MCX_SP_CAN_DIFFUSE if s.diffusion_constant_3d > 0 else 0) | \
+            sp[i].flags = (0 if s.surface else abi.MCX_SP_VOL) | (abi.MCX_SP_CAN_DIFFUSE if s.diffusion_constant_3d > 0 else 0) | \
                 (abi.MCX_SP_CANT_INITIATE if s.target_only else 0)
 
         # group rules into reaction classes (same reactant set), cumulative probabilities
         groups = {}
         for r_id, r in enumerate(self.rules):
-            key = tuple(sorted(idx[x] for x in r.reactants))
+            key = tuple(sorted(idx[_parse_oriented(x)[0]] for x in r.reactants))
             groups.setdefault(key, []).append((r_id, r))
         classes = (abi.mcx_rxn_class * max(1, len(groups)))()
         n_path = sum(len(v) for v in groups.values())
@@ -228,8 +242,25 @@ class Model:
         for ci, (key, rules) in enumerate(groups.items()):
             rc = classes[ci]
             first = rules[0][1]
-            r_idx = [idx[x] for x in first.reactants]
-            if len(key) == 1:
+            parsed = [_parse_oriented(x) for x in first.reactants]
+            r_idx = [idx[n] for n, _ in parsed]
+            r_orient = [o for _, o in parsed]
+            n_surf_reactants = sum(1 for k in r_idx if self.species[k].surface)
+            if len(key) == 2 and n_surf_reactants == 1:
+                # class order is (volume, surface) whatever order the rule was written in
+                if self.species[r_idx[0]].surface:
+                    r_idx, r_orient = r_idx[::-1], r_orient[::-1]
+                rc.kind = abi.MCX_RXN_BIMOL_VOLSURF
+                rc.reactants[0], rc.reactants[1] = r_idx[0], r_idx[1]
+                rc.reactant_orientation[0], rc.reactant_orientation[1] = r_orient[0], r_orient[1]
+                D_tot = self.species[r_idx[0]].diffusion_constant_3d
+                t_step = 1.0 * c.time_step
+                pb_factor = 0.0 if D_tot <= 0 else 1.0e11 * c.surface_grid_density / (2.0 * N_AV) * math.sqrt(MY_PI * t_step / D_tot)
+                if (r_orient[0] + r_orient[1]) * (r_orient[0] - r_orient[1]) == 0 and r_orient[0] * r_orient[1] != 0:
+                    pb_factor *= 2.0
+            elif len(key) == 2 and n_surf_reactants == 2:
+                raise ValueError("surface-surface reactions are not built")
+            elif len(key) == 1:
                 rc.kind = abi.MCX_RXN_UNIMOL
                 rc.reactants[0], rc.reactants[1] = r_idx[0], abi.MCX_NONE
                 pb_factor = c.time_step
@@ -260,20 +291,22 @@ class Model:
                 cum += pb_factor * r.fwd_rate
                 pw.cum_prob = cum
                 # kept reactants: rule reactant that re-appears unchanged among the products
-                prods = [idx[x] for x in r.products]
-                this_r = [idx[x] for x in r.reactants]
-                if len(this_r) == 2 and this_r != r_idx:  # pathway written in the other order
-                    this_r = this_r[::-1]
+                pparsed = [_parse_oriented(x) for x in r.products]
+                prods = [idx[n] for n, _ in pparsed]
+                porient = [o for _, o in pparsed]
                 keep = 0
                 for k, rs in enumerate(r_idx):
                     if rs in prods:
-                        prods.remove(rs)
+                        at = prods.index(rs)
+                        prods.pop(at)
+                        porient.pop(at)
                         keep |= 1 << k
                 if len(prods) > abi.MCX_MAX_PRODUCTS:
                     raise ValueError("too many products")
                 pw.n_products = len(prods)
                 for k, p in enumerate(prods):
                     pw.products[k] = p
+                    pw.product_orientation[k] = porient[k]
                 pw.keep_reactant_mask = keep
                 pw.rxn_rule_id = r_id
                 pi += 1
@@ -329,14 +362,52 @@ def release_uniform_box(rng, n, edge_um, length_unit, margin=0.0):
     return rng.uniform(-h, h, size=(n, 3))
 
 
+def release_on_walls(rng, tables, walls, n, species, orientation=1, first_id=0, schedule_unimol=True):
+    """Host-side placement of n surface molecules on distinct random tiles of the given walls, one per tile, at the
+    tile centres (release_event.cpp:1063-1197 places by density on vacant tiles; the device path is "next" row f3).
+    Uses libmcx's host helpers for the grid arithmetic (Grid::initialize, GridUtils::grid2uv).  rng: numpy Generator."""
+    from . import engine
+    L = engine.load_library()
+    L.mcx_grid_num_tiles.argtypes = [C.c_void_p]
+    L.mcx_grid_num_tiles.restype = C.c_uint32
+    L.mcx_grid2uv.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.mcx_grid2uv.restype = None
+    walls = np.asarray(walls, np.uint32)
+    v9 = np.ascontiguousarray(tables.vertices[tables.tri[walls]].reshape(len(walls), 9))
+    counts = np.array([L.mcx_grid_num_tiles(C.c_void_p(v9[k].ctypes.data)) for k in range(len(walls))], np.int64)
+    total = int(counts.sum())
+    if n > total:
+        raise ValueError("more surface molecules than tiles")
+    pick = np.sort(rng.choice(total, size=n, replace=False))
+    start = np.concatenate([[0], np.cumsum(counts)])
+    wi = np.searchsorted(start, pick, side="right") - 1
+    m = MolArrays(n)
+    uv = np.zeros(2)
+    for k in range(n):
+        t = int(pick[k] - start[wi[k]])
+        L.mcx_grid2uv(C.c_void_p(v9[wi[k]].ctypes.data), t, C.c_void_p(uv.ctypes.data))
+        m.wall[k], m.tile[k], m.u[k], m.v[k] = walls[wi[k]], t, uv[0], uv[1]
+    m.orientation[:] = orientation
+    m.species[:] = species
+    m.id[:] = np.arange(first_id, first_id + n, dtype=np.uint32)
+    if schedule_unimol:
+        m.flags[:] = abi.MCX_MOL_SCHEDULE_UNIMOL
+    return m
+
+
 class MolArrays:
     """Owning numpy SoA + the ctypes view (mcx_mol_soa)."""
+    FIELDS = ("x", "y", "z", "id", "species", "flags", "diffusion_time", "unimol_rxn_time",
+              "wall", "tile", "orientation", "u", "v")
 
     def __init__(self, n, with_times=True):
         self.x = np.zeros(n); self.y = np.zeros(n); self.z = np.zeros(n)
         self.id = np.zeros(n, np.uint32); self.species = np.zeros(n, np.uint32); self.flags = np.zeros(n, np.uint32)
         self.diffusion_time = np.zeros(n) if with_times else None
         self.unimol_rxn_time = np.full(n, abi.MCX_TIME_INVALID) if with_times else None
+        # Molecule::s of surface molecules (wall == MCX_NONE: volume molecule)
+        self.wall = np.full(n, abi.MCX_NONE, np.uint32); self.tile = np.full(n, abi.MCX_NONE, np.uint32)
+        self.orientation = np.zeros(n, np.int32); self.u = np.zeros(n); self.v = np.zeros(n)
         self.n = n
 
     @classmethod
@@ -358,11 +429,16 @@ class MolArrays:
         s.id, s.species, s.flags = abi.ptr(self.id, C.c_uint32), abi.ptr(self.species, C.c_uint32), abi.ptr(self.flags, C.c_uint32)
         s.diffusion_time = abi.ptr(self.diffusion_time, C.c_double)
         s.unimol_rxn_time = abi.ptr(self.unimol_rxn_time, C.c_double)
+        # surface arrays are optional in the ABI: views assembled by hand (bench.py) may not carry them
+        if self.wall is not None and len(self.wall) >= len(self.x) and len(self.wall) > 0:
+            s.wall, s.tile = abi.ptr(self.wall, C.c_uint32), abi.ptr(self.tile, C.c_uint32)
+            s.orientation = abi.ptr(self.orientation, C.c_int32)
+            s.u, s.v = abi.ptr(self.u, C.c_double), abi.ptr(self.v, C.c_double)
         return s
 
     def truncated(self, n):
         m = MolArrays(0)
-        for k in ("x", "y", "z", "id", "species", "flags", "diffusion_time", "unimol_rxn_time"):
+        for k in self.FIELDS:
             setattr(m, k, getattr(self, k)[:n].copy())
         m.n = n
         return m
@@ -370,7 +446,16 @@ class MolArrays:
     def sorted_by_id(self):
         o = np.argsort(self.id[:self.n], kind="stable")
         m = MolArrays(0)
-        for k in ("x", "y", "z", "id", "species", "flags", "diffusion_time", "unimol_rxn_time"):
+        for k in self.FIELDS:
             setattr(m, k, getattr(self, k)[:self.n][o].copy())
         m.n = self.n
+        return m
+
+    @classmethod
+    def concat(cls, parts):
+        """One population from several (ids must already be distinct)."""
+        m = cls(0)
+        for k in cls.FIELDS:
+            setattr(m, k, np.concatenate([getattr(q, k)[:q.n] for q in parts]))
+        m.n = sum(q.n for q in parts)
         return m

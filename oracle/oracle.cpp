@@ -100,13 +100,24 @@ struct Wall {  // src4/wall.h Wall subset; constants per Wall::initialize_wall_c
   uint32_t surf_class, object;
 };
 
-struct Mol {  // src4/molecule.h:52-260 (volume part)
-  V3 pos;
+struct Mol {  // src4/molecule.h:52-260
+  V3 pos;                 // v.pos; for a surface molecule uv2xyz(s.pos)
   uint32_t id, species, flags;
   double diffusion_time, unimol_rxn_time;
   uint32_t subpart;       // v.subpart_index
   uint32_t list_slot;     // position inside its reactant list (sequential mode)
   uint32_t reg_subpart;   // v.reactant_subpart_index
+  // surface part (s.*): wall == MCX_NONE for a volume molecule
+  uint32_t wall = MCX_NONE, tile = MCX_NONE;
+  int orient = 0;
+  double u = 0, v = 0;
+  // DiffuseAction::where_created_this_iteration of a volume product of a surface reaction (:877-885)
+  uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE;
+};
+
+struct Grid {  // src4/wall.h:101-193, constants per Grid::initialize (wall.cpp:38-74)
+  int n_axis; uint32_t n_tiles;
+  double strip_width_rcp, vert2_slope, fullslope, binding_factor, vert0_u, vert0_v;
 };
 
 enum { COLL_VOLMOL = 0, COLL_WALL_FRONT = 1, COLL_WALL_BACK = 2 };
@@ -122,7 +133,7 @@ static inline uint64_t hash_ev(uint64_t h, uint32_t a, uint32_t b) {
   return h;
 }
 enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
-       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u };
+       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u };
 
 struct Stats {
   uint64_t molecule_steps = 0, ray_polygon_tests = 0, ray_polygon_colls = 0, reflections = 0,
@@ -142,6 +153,7 @@ struct Outcome {
   uint32_t partner_index = MCX_NONE, partner_id = MCX_NONE;
   double t_event = 0;
   bool initiator_is_reactant0 = true;
+  uint32_t orient_bits = 0;       // bit k: random orientation drawn for products[k] (1 = up)
 };
 
 struct World {
@@ -157,6 +169,11 @@ struct World {
   std::vector<int> bimol;        // [a*ns+b] -> class or -1
   std::vector<int> unimol;       // [a] -> class or -1
   std::vector<uint8_t> can_vol_react;
+  std::vector<int> volsurf;      // [vol*ns+surf] -> class or -1
+  std::vector<uint8_t> can_vol_surf;   // SPECIES_FLAG_CAN_VOLSURF
+  std::vector<Grid> grids;       // per wall
+  std::vector<std::vector<uint32_t>> tiles;  // per wall: molecule id per tile (Grid::molecules_per_tile); empty =
+                                             // grid not initialized (wall.h:339-346)
   std::vector<mcx_surf_class_rxn> surf_rules;
   std::vector<Mol> mols;
   std::vector<uint32_t> id_to_index;  // molecule_id_to_index_mapping
@@ -194,6 +211,7 @@ struct World {
     idx[0] = s % n_sp; idx[1] = (s / n_sp) % n_sp; idx[2] = (s / (n_sp * n_sp)) % n_sp;
   }
   inline bool idx_in_range(int i) const { return i >= 0 && i < (int)n_sp; }
+  inline bool is_surf(uint32_t species) const { return !(this->species[species].flags & MCX_SP_VOL); }
 };
 
 // ---- geometry set-up ---------------------------------------------------------------------
@@ -219,6 +237,75 @@ static void init_wall_constants(const World& w, Wall& f) {
   f.uv_vert1_u = dot(f1, f.unit_u);
   f.uv_vert2_u = dot(f2, f.unit_u);
   f.uv_vert2_v = dot(f2, f.unit_v);
+}
+
+// Grid::initialize, src4/wall.cpp:38-74
+static void grid_init(const World& w, const Wall& f, Grid& g) {
+  g.n_axis = (int)ceil(sqrt(f.area));
+  if (g.n_axis < 1) g.n_axis = 1;
+  g.n_tiles = (uint32_t)(g.n_axis * g.n_axis);
+  g.strip_width_rcp = 1 / (f.uv_vert2_v / ((double)g.n_axis));
+  g.vert2_slope = f.uv_vert2_u / f.uv_vert2_v;
+  g.fullslope = f.uv_vert1_u / f.uv_vert2_v;
+  g.binding_factor = ((double)g.n_tiles) / f.area;
+  V3 v0 = w.verts[f.vi[0]];
+  g.vert0_u = dot(v0, f.unit_u);
+  g.vert0_v = dot(v0, f.unit_v);
+}
+// distinguishable_vec3, src4/defines.h:766-806
+static bool distinguishable_vec3(V3 a, V3 b, double eps) {
+  double c = fabs(a.x), cc, d;
+  d = fabs(a.y); if (d > c) c = d;
+  d = fabs(a.z); if (d > c) c = d;
+  d = fabs(b.x); if (d > c) c = d;
+  d = fabs(b.y); if (d > c) c = d;
+  d = fabs(b.z); if (d > c) c = d;
+  cc = fabs(a.x - b.x);
+  d = fabs(a.y - b.y); if (d > cc) cc = d;
+  d = fabs(a.z - b.z); if (d > cc) cc = d;
+  if (c < eps) c = eps;
+  return c * eps < cc;
+}
+// GridUtils::xyz2grid_tile_index, src4/grid_utils.inl:48-118 (== xyz2grid, src/grid_util.c:74-128)
+static uint32_t xyz2grid(const World& w, V3 v, const Wall& f, const Grid& g) {
+  if (g.n_tiles == 1) return 0;
+  uint32_t tile_idx_mid = g.n_tiles - 2 * (uint32_t)g.n_axis + 1, tile_idx_last = g.n_tiles - 1;
+  if (!distinguishable_vec3(v, w.verts[f.vi[0]], POS_EPS)) return tile_idx_mid;
+  if (!distinguishable_vec3(v, w.verts[f.vi[1]], POS_EPS)) return tile_idx_last;
+  if (!distinguishable_vec3(v, w.verts[f.vi[2]], POS_EPS)) return 0;
+  double i = dot(v, f.unit_u) - g.vert0_u;
+  double j = dot(v, f.unit_v) - g.vert0_v;
+  double striploc = j * g.strip_width_rcp;
+  int strip = (int)striploc;
+  double striprem = striploc - strip;
+  strip = g.n_axis - strip - 1;
+  double u0 = j * g.vert2_slope;
+  double u1_u0 = f.uv_vert1_u - j * g.fullslope;
+  double stripeloc = ((i - u0) / u1_u0) * (strip + (1 - striprem));
+  int stripe = (int)stripeloc;
+  double striperem = stripeloc - stripe;
+  int flip = (striperem < 1 - striprem) ? 0 : 1;
+  int idx = strip * strip + 2 * stripe + flip;
+  if (idx < 0) idx = 0;                                   // the reference raises an internal error here
+  if ((uint32_t)idx >= g.n_tiles) idx = (int)g.n_tiles - 1;
+  return (uint32_t)idx;
+}
+// GridUtils::grid2uv, src4/grid_utils.inl:233-253
+static void grid2uv(const Wall& f, const Grid& g, uint32_t index, double& u, double& v) {
+  int root = (int)(sqrt((double)index));
+  int rootrem = (int)index - root * root;
+  int k = g.n_axis - root - 1;
+  int j = rootrem / 2;
+  int i = rootrem - 2 * j;
+  double over3n = 1 / (double)(3 * g.n_axis);
+  u = ((double)(3 * j + i + 1)) * over3n * f.uv_vert1_u + ((double)(3 * k + i + 1)) * over3n * f.uv_vert2_u;
+  v = ((double)(3 * k + i + 1)) * over3n * f.uv_vert2_v;
+}
+// GeometryUtils::uv2xyz, src4/geometry_utils.h:29-35
+static V3 uv2xyz(const World& w, const Wall& f, double u, double v) {
+  V3 v0 = w.verts[f.vi[0]];
+  return {u * f.unit_u.x + v * f.unit_v.x + v0.x, u * f.unit_u.y + v * f.unit_v.y + v0.y,
+          u * f.unit_u.z + v * f.unit_v.z + v0.z};
 }
 
 static inline bool point_in_box(V3 p, V3 llf, V3 urb) {
@@ -354,11 +441,13 @@ static void finalize_walls(World& w) {
 // ---- reactant lists (sequential mode) -------------------------------------------------------
 static inline uint64_t list_key(uint32_t species, uint32_t subpart) { return ((uint64_t)species << 32) | subpart; }
 static void list_insert(World& w, Mol& m) {
+  if (m.wall != MCX_NONE) return;  // only volume molecules are reactants of the per-subpartition lists
   auto& v = w.lists[list_key(m.species, m.subpart)];
   m.list_slot = (uint32_t)v.size(); m.reg_subpart = m.subpart;
   v.push_back(m.id);
 }
 static void list_erase(World& w, Mol& m) {
+  if (m.wall != MCX_NONE) return;
   auto& v = w.lists[list_key(m.species, m.reg_subpart)];
   uint32_t last = v.back();
   v[m.list_slot] = last;
@@ -372,9 +461,16 @@ static void build_lookups(World& w) {
   w.bimol.assign(ns * ns, -1);
   w.unimol.assign(ns, -1);
   w.can_vol_react.assign(ns, 0);
+  w.volsurf.assign(ns * ns, -1);
+  w.can_vol_surf.assign(ns, 0);
   for (size_t c = 0; c < w.classes.size(); c++) {
     const mcx_rxn_class& rc = w.classes[c];
-    if (rc.kind == MCX_RXN_BIMOL_VOLVOL) {
+    if (rc.kind == MCX_RXN_BIMOL_VOLSURF) {
+      if (rc.reactants[0] < ns && rc.reactants[1] < ns) {
+        w.volsurf[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
+        w.can_vol_surf[rc.reactants[0]] = 1;
+      }
+    } else if (rc.kind == MCX_RXN_BIMOL_VOLVOL) {
       w.bimol[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
       w.bimol[rc.reactants[1] * ns + rc.reactants[0]] = (int)c;
     } else if (rc.kind == MCX_RXN_UNIMOL) {
@@ -416,6 +512,57 @@ static int pathway_for_probability(const World& w, const mcx_rxn_class& rc, doub
   }
   if (match > A[min_idx].cum_prob) return max_idx;
   return min_idx;
+}
+
+// ---- surface reactions: orientation algebra and product placement -----------------------------------
+// RxnUtils::trigger_bimolecular, src4/rxn_utils.inl:58-84: does the (volume, surface) pair match the class?
+static bool orientations_match(const mcx_rxn_class& rc, int orientA, int orientB) {
+  int geomA = rc.reactant_orientation[0], geomB = rc.reactant_orientation[1];
+  if (geomA == 0 || geomB == 0 || (geomA + geomB) * (geomA - geomB) != 0) return true;
+  return orientA != 0 && orientA * orientB * geomA * geomB > 0;
+}
+// one random bit per product whose rule orientation is NONE, drawn from the main stream right after the pathway
+// is chosen (outcome_products_random, diffuse_react_event.cpp:2618-2627); only when a surface is involved
+template <class RS>
+static uint32_t draw_orientation_bits(const mcx_pathway& pw, RS& rs) {
+  uint32_t bits = 0;
+  for (uint32_t k = 0; k < pw.n_products; k++)
+    if (pw.product_orientation[k] == 0 && (rs.next() & 1)) bits |= 1u << k;
+  return bits;
+}
+struct ProductSpec {
+  uint32_t species; V3 pos;
+  uint32_t wall = MCX_NONE, tile = MCX_NONE; int orient = 0; double u = 0, v = 0;
+  uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE;
+};
+// Where and how product k of a pathway is created (outcome_products_random :2446-2933, the cases of SURVEY A.2):
+//  * no surface reactant: volume product at the event position;
+//  * surface product: takes the surface reactant's tile and uv (find_surf_product_positions :2145-2155);
+//  * volume product of a surface reaction: event position bumped 2*16*EPS off the wall to the side its
+//    orientation names (update_vol_mol_after_rxn_with_surf_mol :2291-2320; the wall test of tiny_diffuse_3D is
+//    omitted: another wall within 3.2e-11 length units of the position), remembered for the rebinding guard.
+static ProductSpec product_spec(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw, uint32_t k, V3 pos,
+                                uint32_t orient_bits, const Mol* surf) {
+  ProductSpec ps;
+  ps.species = pw.products[k]; ps.pos = pos;
+  if (!surf) return ps;
+  int o = pw.product_orientation[k];
+  if (o == 0) o = ((orient_bits >> k) & 1) ? 1 : -1;
+  else if (c.kind == MCX_RXN_BIMOL_VOLSURF) {  // :2634-2652: flip when the reactant's orientation differs from the rule's
+    int gB = c.reactant_orientation[1];
+    if (gB != 0 && surf->orient != gB) o = -o;
+  }
+  const Wall& f = w.walls[surf->wall];
+  if (w.is_surf(ps.species)) {
+    ps.wall = surf->wall; ps.tile = surf->tile; ps.u = surf->u; ps.v = surf->v; ps.orient = o;
+    ps.pos = uv2xyz(w, f, ps.u, ps.v);
+  } else {
+    double bump = (o > 0) ? 16 * POS_EPS : -16 * POS_EPS;
+    V3 d = {(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
+    ps.pos = pos + d;
+    ps.created_wall = surf->wall; ps.created_tile = surf->tile;
+  }
+  return ps;
 }
 
 // ---- the evaluation context ---------------------------------------------------------------
@@ -742,11 +889,12 @@ struct Eval {
 //                 firing) ends the evaluation and is returned as a proposal.
 // ================================================================================================
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
-                            bool& a_destroyed);
-static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, bool& destroyed);
+                            uint32_t orient_bits, bool& a_destroyed);
+static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed);
 static void seq_set_defunct(World& w, Mol& m);
 
-struct MolState { V3 pos; uint32_t subpart; double t_now; uint32_t flags; double unimol_time; };
+struct MolState { V3 pos; uint32_t subpart; double t_now; uint32_t flags; double unimol_time;
+                  uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE; };
 
 static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply, bool& again) {
   World& w = E.w;
@@ -767,16 +915,19 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
       double match = E.rs.dbl() * w.classes[rc].max_fixed_p;
       pathway = pathway_for_probability(w, w.classes[rc], match);
     }
+    uint32_t obits = 0;
+    if (w.mols[index].wall != MCX_NONE)  // is_orientable: the reactant is a surface molecule (:2569)
+      obits = draw_orientation_bits(w.pathways[w.classes[rc].first_pathway + pathway], E.rs);
     E.ev(EV_UNIMOL | (uint32_t)pathway, (uint32_t)rc);
     if (tr) { tr->rxn_class = rc; tr->rxn_pathway = pathway; tr->t_event = s.unimol_time; }
     if (!apply) {
       out.kind = MCX_OUT_UNIMOL; out.pos = s.pos; out.rxn_class = rc; out.pathway = pathway;
-      out.t_event = s.unimol_time; fill_event(out);
+      out.t_event = s.unimol_time; out.orient_bits = obits; fill_event(out);
       return out;
     }
     bool destroyed = false;
     w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart;
-    seq_apply_unimol(w, index, rc, pathway, s.unimol_time, destroyed);
+    seq_apply_unimol(w, index, rc, pathway, s.unimol_time, obits, destroyed);
     if (destroyed) { out.kind = MCX_OUT_UNIMOL; out.pos = s.pos; out.t_event = s.unimol_time; return out; }
     s.flags |= MCX_MOL_SCHEDULE_UNIMOL;  // survivor re-draws its lifetime (outcome_unimolecular :2999)
   }
@@ -831,7 +982,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
           }
           bool a_destroyed = false;
           w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart;
-          seq_apply_bimol(w, index, c.partner_index, c.rxn_class, pathway, c.pos, abs_t, a_destroyed);
+          seq_apply_bimol(w, index, c.partner_index, c.rxn_class, pathway, c.pos, abs_t, 0, a_destroyed);
           if (a_destroyed) { destroyed = true; out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.t_event = abs_t; break; }
         } else {
           // ---- wall collision (:476-567)
@@ -840,6 +991,48 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
           if (tr) {
             if (tr->n_wall_hits < MCX_TRACE_K) { tr->wall[tr->n_wall_hits] = c.wall; tr->wall_side[tr->n_wall_hits] = c.type; }
             tr->n_wall_hits++;
+          }
+          // ---- collide_and_react_with_surf_mol (:845-975): the surface molecule on the tile under the hit point
+          if (w.can_vol_surf[m_species] && !w.tiles[c.wall].empty()) {
+            const Grid& g = w.grids[c.wall];
+            uint32_t j = xyz2grid(w, c.pos, wall, g);
+            uint32_t occ_id = w.tiles[c.wall][j];
+            uint32_t occ_index = occ_id != MCX_NONE ? w.id_to_index[occ_id] : MCX_NONE;
+            bool occupied = occ_index != MCX_NONE &&
+                            !(E.snapshot ? (*E.dead)[occ_index] != 0 : (w.mols[occ_index].flags & MCX_MOL_DEFUNCT) != 0);
+            if (occupied && s.created_wall == c.wall && s.created_tile == j) {
+              s.created_wall = s.created_tile = MCX_NONE;  // no rebinding where it was just created; next time yes (:877-885)
+              occupied = false;
+            }
+            if (occupied) {
+              const Mol& sm = w.mols[occ_index];
+              int rc = w.volsurf[m_species * w.species.size() + sm.species];
+              int coll_orient = c.type == COLL_WALL_FRONT ? 1 : -1;
+              if (rc >= 0 && orientations_match(w.classes[rc], coll_orient, sm.orient)) {
+                double scaling = r_rate_factor / g.binding_factor;
+                double abs_t = elapsed + t_steps * c.time;
+                E.ev(EV_SURFMOL | (uint32_t)c.type, sm.id);
+                if (tr) { if (tr->n_collisions < MCX_TRACE_K) tr->partner[tr->n_collisions] = sm.id; tr->n_collisions++; }
+                int pathway = E.test_bimolecular(w.classes[rc], scaling);
+                if (pathway >= 0) {
+                  uint32_t obits = draw_orientation_bits(w.pathways[w.classes[rc].first_pathway + pathway], E.rs);
+                  E.ev(EV_RXN | (uint32_t)pathway, (uint32_t)rc);
+                  if (tr) { tr->rxn_class = rc; tr->rxn_pathway = pathway; tr->rxn_partner = sm.id; tr->t_event = abs_t; }
+                  if (!apply) {
+                    out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.rxn_class = rc; out.pathway = pathway;
+                    out.partner_index = occ_index; out.partner_id = sm.id; out.t_event = abs_t; out.orient_bits = obits;
+                    fill_event(out);
+                    return out;
+                  }
+                  bool a_destroyed = false;
+                  w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart;
+                  seq_apply_bimol(w, index, occ_index, rc, pathway, c.pos, abs_t, obits, a_destroyed);
+                  // kept volume initiators are rejected at table set-up: the molecule is gone (collide_res == 1)
+                  destroyed = true; out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.t_event = abs_t;
+                  break;
+                }
+              }
+            }
           }
           if (action == MCX_SURF_TRANSPARENT) {
             // cross_transparent_wall (:3007-3099), non-compartment branch
@@ -917,6 +1110,7 @@ static MolState load_state(const World& w, const Mol& m) {
   s.pos = m.pos; s.subpart = w.subpart_index(m.pos);
   s.t_now = (m.flags & MCX_MOL_PARTIAL) ? m.diffusion_time : (double)w.iteration;
   s.flags = m.flags; s.unimol_time = m.unimol_rxn_time;
+  s.created_wall = m.created_wall; s.created_tile = m.created_tile;
   return s;
 }
 
@@ -927,6 +1121,7 @@ static Outcome evaluate_iteration(Eval& E, uint32_t index) {
   do {
     o = evaluate_substep(E, index, s, false, again);
     if (o.kind != MCX_OUT_MOVED && o.kind != MCX_OUT_STATIC) return o;
+    s.created_wall = s.created_tile = MCX_NONE;  // the guard belongs to the first DiffuseAction only (:116-129)
   } while (again && ++guard < 1000);
   o.flags &= ~MCX_MOL_PARTIAL;
   return o;
@@ -937,28 +1132,34 @@ static void seq_set_defunct(World& w, Mol& m) {  // Partition::set_molecule_as_d
   if (m.flags & MCX_MOL_DEFUNCT) return;
   m.flags |= MCX_MOL_DEFUNCT;
   list_erase(w, m);
+  // Grid::reset_molecule_tile: a recycled tile already belongs to the product
+  if (m.wall != MCX_NONE && w.tiles[m.wall][m.tile] == m.id) w.tiles[m.wall][m.tile] = MCX_NONE;
   w.species_count[m.species]--;
 }
-static uint32_t seq_add_molecule(World& w, uint32_t species, V3 pos, double t) {  // add_volume_molecule
+static uint32_t seq_add_molecule(World& w, const ProductSpec& ps, double t) {  // add_volume_molecule / add_surface_molecule
   Mol n{};
-  n.pos = pos; n.id = w.next_id++; n.species = species;
+  n.pos = ps.pos; n.id = w.next_id++; n.species = ps.species;
   n.flags = MCX_MOL_SCHEDULE_UNIMOL | MCX_MOL_PARTIAL;
   n.diffusion_time = t; n.unimol_rxn_time = TIME_INVALID;
-  n.subpart = w.subpart_index(pos);
+  n.subpart = w.subpart_index(ps.pos);
+  n.wall = ps.wall; n.tile = ps.tile; n.orient = ps.orient; n.u = ps.u; n.v = ps.v;
+  n.created_wall = ps.created_wall; n.created_tile = ps.created_tile;
   w.mols.push_back(n);
   if (w.id_to_index.size() <= n.id) w.id_to_index.resize(n.id + 1, MCX_NONE);
   w.id_to_index[n.id] = (uint32_t)w.mols.size() - 1;
   w.sched_ids.push_back(n.id);
   list_insert(w, w.mols.back());
-  w.species_count[species]++;
+  if (n.wall != MCX_NONE) w.tiles[n.wall][n.tile] = n.id;  // Grid::set_molecule_tile (:2899)
+  w.species_count[ps.species]++;
   w.stats.products++;
   return n.id;
 }
 static std::vector<uint32_t>* g_new_actions = nullptr;  // new_diffuse_actions FIFO of the running step
 
-// outcome_bimolecular / outcome_products_random for two volume reactants (:1833-1895, :2446-2933)
+// outcome_bimolecular / outcome_products_random (:1833-1895, :2446-2933): two volume reactants, or a volume
+// initiator and the surface molecule it hit
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
-                            bool& a_destroyed) {
+                            uint32_t orient_bits, bool& a_destroyed) {
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
@@ -967,8 +1168,13 @@ static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc
   bool a_is_r0 = w.mols[a_index].species == c.reactants[0];
   bool keepA = (pw.keep_reactant_mask >> (a_is_r0 ? 0 : 1)) & 1;
   bool keepB = (pw.keep_reactant_mask >> (a_is_r0 ? 1 : 0)) & 1;
+  const bool surf_rxn = w.mols[b_index].wall != MCX_NONE;
+  const Mol surf_copy = w.mols[b_index];  // adding molecules may reallocate w.mols
+  // tiles that are going to be reused are freed first (:2606-2615)
+  if (surf_rxn && !keepB) w.tiles[surf_copy.wall][surf_copy.tile] = MCX_NONE;
   for (uint32_t k = 0; k < pw.n_products; k++) {
-    uint32_t nid = seq_add_molecule(w, pw.products[k], pos, t);
+    ProductSpec ps = product_spec(w, c, pw, k, pos, orient_bits, surf_rxn ? &surf_copy : nullptr);
+    uint32_t nid = seq_add_molecule(w, ps, t);
     if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
   }
   if (!keepA) seq_set_defunct(w, w.mols[a_index]);
@@ -976,17 +1182,21 @@ static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc
   a_destroyed = !keepA;
 }
 // outcome_unimolecular (:2939-3003)
-static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, bool& destroyed) {
+static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed) {
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
   w.stats.unimol_rxns++;
   V3 pos = w.mols[index].pos;
+  bool keep = pw.keep_reactant_mask & 1;
+  const bool surf_rxn = w.mols[index].wall != MCX_NONE;
+  const Mol surf_copy = w.mols[index];
+  if (surf_rxn && !keep) w.tiles[surf_copy.wall][surf_copy.tile] = MCX_NONE;
   for (uint32_t k = 0; k < pw.n_products; k++) {
-    uint32_t nid = seq_add_molecule(w, pw.products[k], pos, t);
+    ProductSpec ps = product_spec(w, c, pw, k, pos, orient_bits, surf_rxn ? &surf_copy : nullptr);
+    uint32_t nid = seq_add_molecule(w, ps, t);
     if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
   }
-  bool keep = pw.keep_reactant_mask & 1;
   if (!keep) seq_set_defunct(w, w.mols[index]);
   destroyed = !keep;
 }
@@ -1046,6 +1256,7 @@ static void step_sequential(World& w) {
       else w.tape_len[id] = 0xFFFFFFFFu;  // split step: words are not contiguous in the global stream
     }
     Mol& m = w.mols[w.id_to_index[id]];
+    m.created_wall = m.created_tile = MCX_NONE;  // the pair travels with the first DiffuseAction only
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) {
       m.pos = o.pos; m.subpart = w.subpart_index(o.pos);
       m.flags = again ? (o.flags | MCX_MOL_PARTIAL) : (o.flags & ~MCX_MOL_PARTIAL);
@@ -1093,7 +1304,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
   std::vector<Outcome> outs(n0);
   std::vector<uint32_t> claim(n0, MCX_NONE);
   std::vector<uint32_t> pending;
-  struct NewMol { uint32_t species; V3 pos; double t; uint32_t id; };
+  struct NewMol { ProductSpec ps; double t; uint32_t id; };
   std::vector<NewMol> born;
 
   auto eval_one = [&](uint32_t i, bool forced) {
@@ -1149,12 +1360,16 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     }
     if (!keepA) { dead[i] = 1; w.species_count[m.species]--; reuse[n_reuse++] = m.id; }
     if (!keepB) { uint32_t j = o.partner_index; dead[j] = 1; w.species_count[w.mols[j].species]--; reuse[n_reuse++] = w.mols[j].id; }
+    // the surface reactant of the event, if any: the partner of a volume initiator, or the initiator itself
+    const Mol* surf = nullptr;
+    if (o.kind == MCX_OUT_REACTED && w.mols[o.partner_index].wall != MCX_NONE) surf = &w.mols[o.partner_index];
+    else if (o.kind == MCX_OUT_UNIMOL && m.wall != MCX_NONE) surf = &m;
     // product ids: consumed reactants' ids are recycled first (initiator, then partner), then fresh ids
     for (uint32_t k = 0; k < pw.n_products; k++) {
-      NewMol nm; nm.species = pw.products[k]; nm.pos = o.pos; nm.t = o.t_event;
+      NewMol nm; nm.ps = product_spec(w, c, pw, k, o.pos, o.orient_bits, surf); nm.t = o.t_event;
       nm.id = (int)k < n_reuse ? reuse[k] : MCX_NONE;
       born.push_back(nm);
-      w.species_count[nm.species]++;
+      w.species_count[nm.ps.species]++;
       w.stats.products++;
     }
     if (keepA) {
@@ -1211,18 +1426,24 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     Mol& m = w.mols[i];
     m.pos = o.pos; m.flags = o.flags; m.diffusion_time = o.t_now; m.unimol_rxn_time = o.unimol_time;
     m.subpart = w.subpart_index(m.pos);
+    m.created_wall = m.created_tile = MCX_NONE;
   }
   // compaction + products (the product's per-iteration sort does both)
   std::vector<Mol> keep; keep.reserve(w.mols.size() + born.size());
   for (auto& m : w.mols) if (!(m.flags & MCX_MOL_DEFUNCT)) keep.push_back(m);
   for (auto& nm : born) {
     Mol n{};
-    n.pos = nm.pos; n.species = nm.species; n.id = nm.id != MCX_NONE ? nm.id : w.next_id++;
+    n.pos = nm.ps.pos; n.species = nm.ps.species; n.id = nm.id != MCX_NONE ? nm.id : w.next_id++;
     n.flags = MCX_MOL_SCHEDULE_UNIMOL | MCX_MOL_PARTIAL;
-    n.diffusion_time = nm.t; n.unimol_rxn_time = TIME_INVALID; n.subpart = w.subpart_index(nm.pos);
+    n.diffusion_time = nm.t; n.unimol_rxn_time = TIME_INVALID; n.subpart = w.subpart_index(nm.ps.pos);
+    n.wall = nm.ps.wall; n.tile = nm.ps.tile; n.orient = nm.ps.orient; n.u = nm.ps.u; n.v = nm.ps.v;
+    n.created_wall = nm.ps.created_wall; n.created_tile = nm.ps.created_tile;
     keep.push_back(n);
   }
   w.mols.swap(keep);
+  // tile occupancy of the next snapshot (the product's scatter rebuilds it the same way)
+  for (auto& t : w.tiles) std::fill(t.begin(), t.end(), MCX_NONE);
+  for (auto& m : w.mols) if (m.wall != MCX_NONE) w.tiles[m.wall][m.tile] = m.id;
   w.lists.clear();
   if (w.id_to_index.size() < w.next_id) w.id_to_index.resize(w.next_id, MCX_NONE);
   std::fill(w.id_to_index.begin(), w.id_to_index.end(), MCX_NONE);
@@ -1269,6 +1490,9 @@ int orc_set_geometry(void* h, const double* v, uint64_t nv, const uint32_t* tri,
     f.object = object ? object[i] : 0;
     init_wall_constants(w, f);
   }
+  w.grids.resize(nw);
+  for (uint64_t i = 0; i < nw; i++) grid_init(w, w.walls[i], w.grids[i]);
+  w.tiles.assign(nw, {});
   finalize_walls(w);
   return 0;
 }
@@ -1284,6 +1508,7 @@ int orc_set_surface_classes(void* h, const mcx_surf_class_rxn* r, uint32_t n) {
 int orc_upload_molecules(void* h, const mcx_mol_soa* s) {
   World& w = *(World*)h;
   w.mols.clear(); w.lists.clear(); w.sched_ids.clear(); w.id_to_index.clear();
+  w.tiles.assign(w.walls.size(), {});
   std::fill(w.species_count.begin(), w.species_count.end(), 0);
   uint32_t max_id = 0;
   for (uint64_t i = 0; i < s->n; i++) max_id = std::max(max_id, s->id[i]);
@@ -1295,6 +1520,13 @@ int orc_upload_molecules(void* h, const mcx_mol_soa* s) {
     m.flags = s->flags ? s->flags[i] : 0;
     m.diffusion_time = s->diffusion_time ? s->diffusion_time[i] : (double)w.iteration;
     m.unimol_rxn_time = s->unimol_rxn_time ? s->unimol_rxn_time[i] : TIME_INVALID;
+    if (s->wall && s->wall[i] != MCX_NONE) {  // Partition::add_surface_molecule + Grid::set_molecule_tile
+      m.wall = s->wall[i]; m.tile = s->tile[i]; m.orient = s->orientation[i]; m.u = s->u[i]; m.v = s->v[i];
+      if (m.wall >= w.walls.size() || m.tile >= w.grids[m.wall].n_tiles) { w.err = "bad wall / tile of a surface molecule"; return MCX_ERR_INVALID_ARG; }
+      m.pos = uv2xyz(w, w.walls[m.wall], m.u, m.v);
+      if (w.tiles[m.wall].empty()) w.tiles[m.wall].assign(w.grids[m.wall].n_tiles, MCX_NONE);
+      if (!(m.flags & MCX_MOL_DEFUNCT)) w.tiles[m.wall][m.tile] = m.id;
+    }
     if (!w.in_this_partition(m.pos)) { w.err = "molecule outside partition"; return MCX_ERR_ESCAPED; }
     m.subpart = w.subpart_index(m.pos);
     w.mols.push_back(m);
@@ -1318,6 +1550,9 @@ int orc_download_molecules(void* h, mcx_mol_soa* o, uint64_t cap) {
     if (o->flags) o->flags[n] = m.flags;
     if (o->diffusion_time) o->diffusion_time[n] = (m.flags & MCX_MOL_PARTIAL) ? m.diffusion_time : (double)w.iteration;
     if (o->unimol_rxn_time) o->unimol_rxn_time[n] = m.unimol_rxn_time;
+    if (o->wall) {
+      o->wall[n] = m.wall; o->tile[n] = m.tile; o->orientation[n] = m.orient; o->u[n] = m.u; o->v[n] = m.v;
+    }
     n++;
   }
   o->n = n;

@@ -2,7 +2,7 @@
 import numpy as np
 
 from mcell_b200 import abi
-from mcell_b200.model import Model, Config, MolArrays, create_box, create_icosphere, release_uniform_box
+from mcell_b200.model import Model, Config, MolArrays, create_box, create_icosphere, release_uniform_box, release_on_walls
 
 
 def free_diffusion_box(n=20000, edge_um=1.0, seed=1, D=1e-6, rng_mode=abi.MCX_RNG_PHILOX, cap_factor=2):
@@ -84,6 +84,49 @@ def reversible_box(n=20000, edge_um=0.5, seed=1, rng_mode=abi.MCX_RNG_PHILOX, k_
     pos = release_uniform_box(rng, n, edge_um, t.length_unit, margin=1e-4)
     species = (np.arange(n) % 3).astype(np.uint32)
     return t, MolArrays.from_positions(pos, species, schedule_unimol=True)
+
+
+def ligand_receptor_sphere(n_lig=6000, n_rec=1500, n_pump=600, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8,
+                           rng_mode=abi.MCX_RNG_PHILOX, p_bind=0.5, k_off=1e5, k_pump=2e5, release_products=True):
+    """BASELINE config 3/4 surface chemistry on an icosphere inside a reflective box:
+       L' + R' -> LR'        ligand binds receptors from the outside (front) only
+       LR'     -> L' + R'    unbinding releases the ligand on the outside
+       Ca, + P' -> CaP'      pumps take calcium from the inside (back) ...
+       CaP'    -> P' + Ca'   ... and release it outside."""
+    import math
+    from mcell_b200.model import N_AV, MY_PI
+    m = Model(Config(seed=seed))
+    L = m.add_species("L", 1e-6)
+    Ca = m.add_species("Ca", 2e-6)
+    R = m.add_species("R", 0.0, surface=True)
+    LR = m.add_species("LR", 0.0, surface=True)
+    P = m.add_species("P", 0.0, surface=True)
+    CaP = m.add_species("CaP", 0.0, surface=True)
+
+    def k_for(p, D):  # vol-surf pb_factor with both orientations in one class (src/react_util.c:145-157)
+        pb = 2.0 * 1.0e11 * m.config.surface_grid_density / (2.0 * N_AV) * math.sqrt(MY_PI * m.config.time_step / D)
+        return p / pb
+
+    # release_products=False: the bound ligand / pumped calcium is degraded, so every reaction has one product and
+    # molecule ids stay deterministic (fresh ids of second products come from device atomics)
+    m.add_reaction_rule(["L'", "R'"], ["LR'"], k_for(p_bind, 1e-6))
+    m.add_reaction_rule(["LR'"], ["L'", "R'"] if release_products else ["R'"], k_off)
+    m.add_reaction_rule(["Ca,", "P'"], ["CaP'"], k_for(p_bind, 2e-6))
+    m.add_reaction_rule(["CaP'"], ["P'", "Ca'"] if release_products else ["P'"], k_pump)
+    sv, sf = create_icosphere(radius_um, subdivisions)
+    m.add_geometry_object(sv, sf)
+    bv, bf = create_box(box_um)
+    m.add_geometry_object(bv, bf)
+    n_total = n_lig + n_rec + n_pump
+    t = m.build(max_molecules=2 * n_total + 64, rng_mode=rng_mode)
+    rng = np.random.default_rng(seed)
+    pos = release_uniform_box(rng, n_lig, box_um, t.length_unit, margin=1e-3)
+    vol = MolArrays.from_positions(pos, (np.arange(n_lig) % 2).astype(np.uint32) * Ca + (1 - np.arange(n_lig) % 2).astype(np.uint32) * L,
+                                   schedule_unimol=True)
+    sphere_walls = np.arange(len(sf), dtype=np.uint32)
+    surf = release_on_walls(rng, t, sphere_walls, n_rec + n_pump, R, orientation=1, first_id=n_lig)
+    surf.species[n_rec:] = P
+    return t, MolArrays.concat([vol, surf])
 
 
 def isaac_slices(seed, n_ids, words_per_mol):

@@ -32,6 +32,9 @@ def _assert_same_population(a, b):
     assert (a.flags == b.flags).all()
     assert cm.rel_close(a.diffusion_time, b.diffusion_time, POS_TOL).all()
     assert cm.rel_close(a.unimol_rxn_time, b.unimol_rxn_time, POS_TOL).all()
+    # surface part (Molecule::s): wall, tile, orientation exact; uv to 1e-12
+    assert (a.wall == b.wall).all() and (a.tile == b.tile).all() and (a.orientation == b.orientation).all()
+    assert cm.rel_close(a.u, b.u, POS_TOL).all() and cm.rel_close(a.v, b.v, POS_TOL).all()
 
 
 def test_replay_reference_stream_free_diffusion():
@@ -128,6 +131,78 @@ def test_philox_surface_classes_icosphere():
     assert tot["mol_wall_absorptions"] > 50 and tot["mol_wall_transparent"] > 100 and tot["mol_wall_reflections"] > 1000
     assert (e.counts()[0] == o.counts()[0]).all()
     _assert_same_population(o.download().sorted_by_id(), e.download().sorted_by_id())
+
+
+def test_philox_ligand_receptor_surface_molecules():
+    """BASELINE configs 3/4 surface chemistry: volume ligands binding receptors on the tiles of an icosphere
+    (collide_and_react_with_surf_mol, orientation classes, tile recycling), pumps taking calcium from the inside,
+    unimolecular unbinding of surface complexes.  Single-product pathways keep ids deterministic: traces, counts
+    and the whole population (incl. wall / tile / orientation / uv) are compared over many iterations."""
+    t, mols = cm.ligand_receptor_sphere(n_lig=24000, n_rec=3000, n_pump=1500, seed=4, release_products=False)
+    n = mols.n
+    o = _oracle(t)
+    o.upload(mols)
+    e = _engine(t)
+    e.upload(mols)
+    tot_bi = tot_uni = 0
+    for it in range(12):
+        tr_o, st_o = o.trace_step(1, n)
+        tr_g, st_g = e.trace_step(n)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "unimol_rxns", "products_created", "mol_wall_reflections", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        tot_bi += st_g.bimol_rxns
+        tot_uni += st_g.unimol_rxns
+        assert (e.counts()[0] == o.counts()[0]).all(), it
+    assert tot_bi > 100 and tot_uni > 20, (tot_bi, tot_uni)
+    a, b = o.download().sorted_by_id(), e.download().sorted_by_id()
+    _assert_same_population(a, b)
+    assert (a.wall != abi.MCX_NONE).sum() == 4500      # every receptor / pump still owns its tile
+    c = e.counts()[0]
+    assert c[2] + c[3] == 3000 and c[4] + c[5] == 1500
+
+
+def test_philox_surface_unbinding_two_products():
+    """LR' -> L' + R' and CaP' -> P' + Ca': the volume product is placed 2*16*EPS off the wall on the side its
+    orientation names, remembers where it was created (no immediate rebinding) and the surface product recycles the
+    tile.  Second products take fresh ids from device atomics, so one iteration is compared as a multiset and the
+    following ones statistically."""
+    t, mols = cm.ligand_receptor_sphere(n_lig=24000, n_rec=3000, n_pump=1500, seed=6, k_off=4e5, k_pump=6e5)
+    o = _oracle(t)
+    o.upload(mols)
+    e = _engine(t)
+    e.upload(mols)
+    # run until some complexes exist, comparing statistically; then one exact iteration from a common state
+    for it in range(6):
+        o.step(1, 1)
+        e.step(1)
+    co, cg = o.counts()[0].astype(float), e.counts()[0].astype(float)
+    assert np.all(np.abs(co - cg) < 6 * np.sqrt(co + 1)), (co, cg)
+    state = o.download()
+    o2, e2 = _oracle(t), _engine(t)
+    o2.upload(state)
+    e2.upload(state)
+    for _ in range(3):
+        st_o = o2.step(1, 1)
+        st_g = e2.step(1)
+        for k in ("bimol_rxns", "unimol_rxns", "products_created", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), k
+        if st_o.unimol_rxns:
+            break
+    assert st_o.unimol_rxns > 0
+    a, b = o2.download(), e2.download()
+    assert a.n == b.n
+
+    def key(m):
+        arr = np.c_[m.species.astype(float), m.x, m.y, m.z, m.wall.astype(float), m.tile.astype(float), m.orientation]
+        return arr[np.lexsort(arr.T[::-1])]
+
+    ka, kb = key(a), key(b)
+    assert (ka[:, 0] == kb[:, 0]).all() and (ka[:, 4:] == kb[:, 4:]).all()
+    assert cm.rel_close(ka[:, 1:4], kb[:, 1:4], POS_TOL).all()
 
 
 def test_philox_reversible_binding_unimolecular():

@@ -187,3 +187,88 @@ def test_conflict_rounds_resolve_everything_at_default_depth():
     assert st.bimol_rxns > 500 and st.resolve_retries > 0 and st.unresolved_conflicts == 0
     c, r = o.counts()
     assert c[0] + c[2] == 4000 and c[1] + c[2] == 4000 and r[0] == c[2]
+
+
+# ---- surface molecules (collide_and_react_with_surf_mol, surface unimolecular) ---------------
+def _surf_state(o, t):
+    m = o.download()
+    return m, m.wall != 0xFFFFFFFF
+
+
+def _inside_sphere(t, m, n_faces=320):
+    """Exact inside test for the (convex) icosphere made of the first n_faces walls."""
+    v = t.vertices[t.tri[:n_faces]]
+    nrm = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
+    nrm *= np.sign((nrm * v.mean(1)).sum(1))[:, None]     # outward
+    p = np.c_[m.x, m.y, m.z]
+    d = (p[:, None, :] - v[None, :, 0, :]) * nrm[None]
+    return (d.sum(2) < 0).all(1)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_surface_binding_conserves_tiles_and_respects_orientation(mode):
+    """L' + R' -> LR' only from the front (outside), Ca, + P' -> CaP' only from the back (inside)."""
+    t, mols = cm.ligand_receptor_sphere(n_lig=16000, n_rec=3000, n_pump=1500, seed=2, release_products=False,
+                                        k_off=0.0, k_pump=0.0)
+    inside = _inside_sphere(t, mols)
+    n_L_in = int(((mols.species == 0) & inside).sum())
+    n_Ca_out = int(((mols.species == 1) & ~inside).sum())
+    o = O.Oracle(t)
+    o.upload(mols)
+    tot = 0
+    for _ in range(25):
+        tot += o.step(1, mode).bimol_rxns
+    c, r = o.counts()
+    assert tot > 150 and r[0] + r[2] == tot
+    assert c[2] + c[3] == 3000 and c[4] + c[5] == 1500          # receptors / pumps are conserved on their tiles
+    assert c[0] + c[3] == 8000 and c[1] + c[5] == 8000          # ligand / calcium only move into complexes
+    m, is_surf = _surf_state(o, t)
+    assert is_surf.sum() == 4500
+    tiles = np.stack([m.wall[is_surf], m.tile[is_surf]], 1)
+    assert len(np.unique(tiles, axis=0)) == 4500                   # one molecule per tile
+    # ligands bind from the outside only, calcium from the inside only: the populations on the other side are intact
+    assert c[3] > 50 and c[5] > 20
+    ins = _inside_sphere(t, m)
+    assert int(((m.species == 0) & ins).sum()) == n_L_in
+    assert int(((m.species == 1) & ~ins).sum()) == n_Ca_out
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_surface_unbinding_places_products_on_the_named_side(mode):
+    """LR' -> L' + R': L appears just outside the wall (2*16*EPS along the normal) and R keeps the tile;
+    CaP' -> P' + Ca': calcium that was taken from the inside is released outside."""
+    t, mols = cm.ligand_receptor_sphere(n_lig=16000, n_rec=3000, n_pump=1500, seed=3, k_off=3e5, k_pump=3e5)
+    ins0 = _inside_sphere(t, mols)
+    ca_in0 = int(((mols.species == 1) & ins0).sum())
+    l_in0 = int(((mols.species == 0) & ins0).sum())
+    o = O.Oracle(t)
+    o.upload(mols)
+    uni = 0
+    for _ in range(30):
+        uni += o.step(1, mode).unimol_rxns
+    c, r = o.counts()
+    assert uni > 60 and r[1] + r[3] == uni
+    assert c[2] + c[3] == 3000 and c[4] + c[5] == 1500
+    assert c[0] + c[3] == 8000 and c[1] + c[5] == 8000
+    m, is_surf = _surf_state(o, t)
+    ins = _inside_sphere(t, m)
+    ca_in = int(((m.species == 1) & ins).sum())
+    # every calcium taken by a pump came from the inside and none was released there
+    assert ca_in == ca_in0 - int(r[2]), (ca_in, ca_in0, r[2], r[3])
+    # unbound ligands reappear outside
+    assert int(((m.species == 0) & ins).sum()) == l_in0
+
+
+def test_surface_snapshot_and_sequential_agree_statistically():
+    seq, snap = [], []
+    for seed in range(1, 9):
+        t, mols = cm.ligand_receptor_sphere(n_lig=8000, n_rec=2500, n_pump=1000, seed=seed)
+        for mode, acc in ((0, seq), (1, snap)):
+            o = O.Oracle(t)
+            o.upload(mols)
+            o.step(25, mode)
+            acc.append([float(x) for x in o.counts()[1]])
+    seq, snap = np.array(seq), np.array(snap)
+    for k in range(4):
+        se = math.sqrt(seq[:, k].var(ddof=1) / 8 + snap[:, k].var(ddof=1) / 8)
+        assert abs(seq[:, k].mean() - snap[:, k].mean()) < 3 * se + 0.02 * seq[:, k].mean() + 1, (k, seq[:, k].mean(), snap[:, k].mean())
