@@ -173,7 +173,8 @@ enum {
   MCX_DEFER_WALL = 2,         /* a wall of the start/end subpartition is not rejected by the plane test */
   MCX_DEFER_PROBE_SHAPE = 3,  /* swept box overlaps more than 2x2 cell rows */
   MCX_DEFER_MULTI_HIT = 4,    /* more than one collision partner */
-  MCX_DEFER_FOREIGN_HIT = 5   /* single partner outside the molecule's own subpartition */
+  MCX_DEFER_FOREIGN_HIT = 5,  /* single partner outside the molecule's own subpartition */
+  MCX_DEFER_DISK = 6          /* collision next to walls: the exact_disk occlusion factor is needed */
 };
 
 /* ---- replay trace (kernel-level parity; mirrors the reference's DEBUG_* dumps,

@@ -43,7 +43,7 @@ struct mcx_handle {
   void *d_species = nullptr, *d_bimol = nullptr, *d_unimol = nullptr, *d_classes = nullptr, *d_pathways = nullptr,
        *d_surf = nullptr, *d_walls = nullptr, *d_tri = nullptr, *d_verts = nullptr, *d_wclass = nullptr,
        *d_spw_start = nullptr, *d_spw_list = nullptr, *d_sp_flags = nullptr, *d_grids = nullptr, *d_volsurf = nullptr,
-       *d_tile_slot = nullptr;
+       *d_tile_slot = nullptr, *d_exd_skip = nullptr;
   bool has_surf = false, surf_allocated = false;
   uint32_t *st_wall = nullptr, *st_tile = nullptr; int32_t* st_orient = nullptr; double *st_u = nullptr, *st_v = nullptr;
   McxComm* comm = nullptr;
@@ -381,7 +381,23 @@ static int rebuild_tables(mcx_handle* h) {
               break;
             }
       }
+  // exact_disk ignores walls the moving molecule travels through (exact_disk_utils.inl:957-975): trigger_intersect
+  // with ORIENTATION_NONE matches the orientation-independent classes (rxn_utils.inl:149-158); the wall is ignored
+  // when there is at least one and all of them are transparent
+  std::vector<uint8_t> exd_skip(std::max<size_t>(1, ns * nsc), 0);
+  for (size_t a = 0; a < ns; a++)
+    for (uint32_t c = 0; c < nsc; c++) {
+      bool any = false, all_transparent = true;
+      for (const auto& r : h->surf_rules) {
+        if (r.surf_class != c || r.orientation != 0) continue;
+        if (r.species != (uint32_t)a && r.species != MCX_ALL_MOLECULES && r.species != MCX_ALL_VOLUME_MOLECULES) continue;
+        any = true;
+        all_transparent = all_transparent && r.type == MCX_SURF_TRANSPARENT;
+      }
+      exd_skip[a * nsc + c] = (any && all_transparent) ? 1 : 0;
+    }
   int rc = MCX_OK;
+  rc |= dev_replace(h, &h->d_exd_skip, exd_skip.data(), exd_skip.size());
   rc |= dev_replace(h, &h->d_species, ds.data(), ds.size());
   rc |= dev_replace(h, &h->d_bimol, bimol.data(), bimol.size());
   rc |= dev_replace(h, &h->d_unimol, unimol.data(), unimol.size());
@@ -392,6 +408,7 @@ static int rebuild_tables(mcx_handle* h) {
   if (rc) return MCX_ERR_CUDA;
   DevParams& p = h->p;
   p.volsurf = (const int*)h->d_volsurf;
+  p.exd_skip = (const uint8_t*)h->d_exd_skip;
   h->has_surf = any_surf;
   p.species = (const DevSpecies*)h->d_species; p.bimol = (const int*)h->d_bimol; p.unimol = (const int*)h->d_unimol;
   p.classes = (const DevClass*)h->d_classes; p.pathways = (const DevPathway*)h->d_pathways;

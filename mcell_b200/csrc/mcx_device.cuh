@@ -128,7 +128,7 @@ struct Tracer {
   }
 };
 enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
-       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u };
+       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u, EV_BLOCKED = 0xB10C0000u, EV_DISK = 0xD1500000u };
 
 struct LocalStats {
   unsigned int ray_polygon_tests, ray_polygon_colls, reflections, transparent, volvol_collisions, redos;
@@ -697,8 +697,10 @@ __device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enab
 
 // Plane-rejection stage of collide_wall (collision_utils.inl:664-683) for every wall of one subpartition:
 // true when each wall is a COLLIDE_MISS already there (no random draw, no REDO can occur).
+// min_dist: smallest distance of the segment's end points to any of the planes; for a rejected wall the whole
+// segment stays on one side, so no point of it is closer (used to decide whether exact_disk can see a wall).
 __device__ __forceinline__ bool all_walls_plane_rejected(const DevParams& p, bool enabled, uint32_t subpart, D3 pos, D3 move,
-                                                         unsigned int& n_tests) {
+                                                         unsigned int& n_tests, double& min_dist) {
   const uint32_t w0 = __ldg(p.spw_start + subpart), w1 = enabled ? __ldg(p.spw_start + subpart + 1) : w0;
   bool all = true;
   for (uint32_t k = w0; k < w1; k++) {
@@ -717,6 +719,7 @@ __device__ __forceinline__ bool all_walls_plane_rejected(const DevParams& p, boo
       miss = dd < 0 && dd + dv < d_eps;
     }
     all = all && miss;
+    min_dist = fmin(min_dist, fmin(fabs(dd), fabs(dd + dv)));
   }
   n_tests = w1 - w0;
   return all;
@@ -777,6 +780,8 @@ __device__ __forceinline__ uint32_t draw_orientation_bits(const DevPathway& pw, 
   return bits;
 }
 
+#include "mcx_exact_disk.cuh"
+
 // ===================================================================================================
 // One molecule, (the rest of) one iteration.  `forced` = last conflict round: no partner search.
 // ===================================================================================================
@@ -784,7 +789,12 @@ __device__ __forceinline__ uint32_t draw_orientation_bits(const DevPathway& pw, 
 // exit condition, so that the lanes of a warp (32 different molecules) re-converge at the loop headers and run
 // the common stages (DDA, wall tests, partner scan) together.
 // created_wall / created_tile: where a DF_CREATED_ON_SURF volume product was created (MCX_NONE otherwise).
-template <bool RETRY>
+// WITH_DISK == false: the evaluation stops with err = MCX_INTERNAL_NEEDS_DISK at the first collision whose
+// interaction disk is cut by a wall; the caller hands the molecule to the WITH_DISK == true instantiation.  Keeping
+// exact_disk (3.5 KB of per-thread pool, 300 more bytes of spills) out of the common generic pass saves a third of
+// its run time (profiles/r01_g).
+#define MCX_INTERNAL_NEEDS_DISK 1000
+template <bool RETRY, bool WITH_DISK>
 __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t_sched, double t_unimol_in,
                                    uint32_t created_wall, uint32_t created_tile,
                                    Stream& rs, bool forced, Outcome& out, LocalStats& ls, Tracer& tc, int& err) {
@@ -876,7 +886,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
               hit = true; hit_in_last = last_subpart == spw.v[k];
             }
           }
-          bool reacted = false;
+          bool reacted = false, aborted = false;
           if (can_vol_react) {
             if (hit && !hit_in_last) {
               spm.n = 0;
@@ -905,9 +915,20 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
               else {
                 t_last = ph.t; id_last = ph.id;
                 ls.volvol_collisions++;
-                if (!(ph.t < MCX_EPS)) {  // is_immediate_collision
-                  // collide_and_react_with_vol_mol (:786-829); exact_disk factor := 1 (documented gap)
-                  double factor = 1.0;
+                // collide_and_react_with_vol_mol (:786-829): the walls of the collision subpartition may hide part
+                // of the interaction disk or block the reaction altogether
+                double factor = 1.0;
+                if (!(ph.t < MCX_EPS) && (__ldg(p.sp_flags + subpart_index(p, pos + remaining * ph.t)) & 1)) {
+                  if (WITH_DISK) {
+                    const MolRec tg = RETRY ? load_rec_volatile(p.recA, ph.slot) : load_rec(p.recA, ph.slot);
+                    factor = exact_disk(p, pos + remaining * ph.t, remaining, species, D3{tg.x, tg.y, tg.z}, err);
+                    if (factor < 0) tc.ev(EV_BLOCKED, ph.id);
+                    else if (factor != 1.0) tc.ev(EV_DISK, (uint32_t)llrint(factor * 1073741824.0));  // 2^-30 resolution
+                  } else if (exd_any_wall_in_reach(p, pos + remaining * ph.t, remaining)) {
+                    aborted = true; scanning = false; factor = -1.0;
+                  }
+                }
+                if (!(ph.t < MCX_EPS) && !(factor < 0)) {  // is_immediate_collision; blocked by a wall
                   double abs_t = elapsed + t_steps * ph.t;
                   double scaling = factor * r_rate_factor;
                   tc.ev(EV_COLL, ph.id);
@@ -927,7 +948,8 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
               }
             }
           }
-          if (reacted) { decided = true; tracing = false; }
+          if (aborted) { err = MCX_INTERNAL_NEEDS_DISK; out.kind = MCX_OUT_NONE; decided = true; tracing = false; }
+          else if (reacted) { decided = true; tracing = false; }
           else if (!hit) {  // RayTraceState::FINISHED
             pos = pos + remaining;
             if (!in_partition(p, pos)) { err = MCX_ERR_ESCAPED; out.kind = MCX_OUT_NONE; out.pos = pos; decided = true; }

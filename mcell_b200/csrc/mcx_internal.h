@@ -92,6 +92,7 @@ struct DevParams {
   const DevClass* classes;
   const DevPathway* pathways;
   const uint8_t* surf_action;   // [species][surf_class][side(0 front,1 back)]
+  const uint8_t* exd_skip;      // [species][surf_class]: exact_disk ignores the wall (the species travels through it)
   int n_species, n_surf_classes, n_walls;
   // surface molecules: tile table of the current snapshot and per-slot cold fields
   const DevGrid* grids;         // per wall

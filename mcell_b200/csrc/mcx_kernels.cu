@@ -352,8 +352,9 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
     unsigned int n_wall_tests = 0, n_wall_tests_dest = 0;
     const bool walls_own = simple && (same || single) && (f & 1);
     const bool walls_dest = simple && single && (fd & 1);
-    const bool rejected_own = all_walls_plane_rejected(p, walls_own, own, pos, disp, n_wall_tests);
-    const bool rejected_dest = all_walls_plane_rejected(p, walls_dest, dest_sp, pos, disp, n_wall_tests_dest);
+    double wall_dist = 1e300;
+    const bool rejected_own = all_walls_plane_rejected(p, walls_own, own, pos, disp, n_wall_tests, wall_dist);
+    const bool rejected_dest = all_walls_plane_rejected(p, walls_dest, dest_sp, pos, disp, n_wall_tests_dest, wall_dist);
     n_wall_tests += n_wall_tests_dest;
     simple = simple && ((same || single) ? ((!walls_own || rejected_own) && (!walls_dest || rejected_dest)) : (near && !(f & 2)));
     if (!simple && reason < 0) reason = (same || single) ? MCX_DEFER_WALL : MCX_DEFER_GEOMETRY;
@@ -364,8 +365,12 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
     const bool probing = simple && sp.can_vol_react;
     bool overflow;
     const int n_hits = probe_partners_flat(p, probing, pos, disp, m.id, species, ph, overflow, &s_probe[warp]);
-    simple = simple && !overflow && (n_hits == 0 || (n_hits == 1 && ph.in_own_subpart));
-    if (!simple && reason < 0) reason = overflow ? MCX_DEFER_PROBE_SHAPE : (n_hits > 1 ? MCX_DEFER_MULTI_HIT : MCX_DEFER_FOREIGN_HIT);
+    // a collision next to walls needs exact_disk (walls of the collision subpartition): generic path
+    // (every wall plane of the crossed subpartitions farther than R from the whole segment: the factor is 1)
+    const bool disk_walls = n_hits == 1 && wall_dist < p.R;
+    simple = simple && !overflow && (n_hits == 0 || (n_hits == 1 && ph.in_own_subpart && !disk_walls));
+    if (!simple && reason < 0)
+      reason = overflow ? MCX_DEFER_PROBE_SHAPE : (n_hits > 1 ? MCX_DEFER_MULTI_HIT : (disk_walls ? MCX_DEFER_DISK : MCX_DEFER_FOREIGN_HIT));
 
     bool proposed = false;
     if (simple) {
@@ -417,12 +422,16 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
   flush_stats(p, ls, msteps);
 }
 
-// k_diffuse_slow: the generic evaluation (evaluate_iteration) for the slots k_diffuse_fast deferred
+// k_diffuse_slow: the generic evaluation (evaluate_iteration) for the slots k_diffuse_fast deferred.
+// WITH_DISK == false reads slow_list and hands the few molecules whose collision disk is cut by a wall on to the
+// WITH_DISK == true launch through pend[1] (free until the conflict rounds start).
+template <bool WITH_DISK>
 __global__ void __launch_bounds__(TPB, 2) k_diffuse_slow(const __grid_constant__ DevParams p) {
   __shared__ ZigShared zig;
   zig_load(&zig);
   __syncthreads();
-  const unsigned int n = p.ctr->n_slow;
+  const unsigned int n = WITH_DISK ? p.ctr->n_pend[1] : p.ctr->n_slow;
+  const uint32_t* list = WITH_DISK ? p.pend[1] : p.slow_list;
   const unsigned int epoch = round_epoch(p, 0);
   LocalStats ls = {0, 0, 0, 0, 0, 0};
   unsigned int msteps = 0;
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(TPB, 2) k_diffuse_slow(const __grid_constant__
   for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const unsigned int k = base + threadIdx.x;
     if (k >= n) continue;
-    const unsigned int i = p.slow_list[k];
+    const unsigned int i = list[k];
     MolRec m = load_rec(p.recA, i);
     const uint32_t species = m.sf & SF_SPECIES_MASK;
     double t_sched = (m.sf & DF_PARTIAL) ? p.tschedA[i] : 0.0;
@@ -439,11 +448,21 @@ __global__ void __launch_bounds__(TPB, 2) k_diffuse_slow(const __grid_constant__
     Tracer tc; trace_begin(p, tc, m.id);
     Outcome o; int err = 0;
     const bool own_start = owned_z(p, m.z);
-    if (own_start && (p.species[species].flags & MCX_SP_CAN_DIFFUSE)) msteps++;
-    LocalStats halo_ls = {0, 0, 0, 0, 0, 0};  // statistics of redundantly evaluated halo molecules are not counted
+    LocalStats mls = {0, 0, 0, 0, 0, 0};  // statistics of redundantly evaluated halo molecules are not counted
     const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
-    evaluate_iteration<false>(p, m, t_sched, t_uni, guard ? p.swallA[i] : MCX_NONE, guard ? p.stileA[i] : MCX_NONE,
-                              rs, false, o, own_start ? ls : halo_ls, tc, err);
+    evaluate_iteration<false, WITH_DISK>(p, m, t_sched, t_uni, guard ? p.swallA[i] : MCX_NONE, guard ? p.stileA[i] : MCX_NONE,
+                                         rs, false, o, mls, tc, err);
+    if (!WITH_DISK && err == MCX_INTERNAL_NEEDS_DISK) {  // re-evaluated from scratch by the WITH_DISK launch
+      if (tc.tr) tc.tr->rounds--;
+      p.pend[1][agg_reserve(&p.ctr->n_pend[1], 1u)] = i;
+      continue;
+    }
+    if (own_start) {
+      if (p.species[species].flags & MCX_SP_CAN_DIFFUSE) msteps++;
+      ls.ray_polygon_tests += mls.ray_polygon_tests; ls.ray_polygon_colls += mls.ray_polygon_colls;
+      ls.reflections += mls.reflections; ls.transparent += mls.transparent;
+      ls.volvol_collisions += mls.volvol_collisions; ls.redos += mls.redos;
+    }
     trace_end(tc, o, rs);
     if (err && (own_start || err != MCX_ERR_ESCAPED)) raise_error(p, err, m.id);
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time);
@@ -510,8 +529,8 @@ __global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevPar
     Outcome o; int err = 0;
     LocalStats halo_ls = {0, 0, 0, 0, 0, 0};
     const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
-    evaluate_iteration<true>(p, m, t_sched, t_uni, guard ? p.swallA[i] : MCX_NONE, guard ? p.stileA[i] : MCX_NONE,
-                             rs, forced != 0, o, own_start ? ls : halo_ls, tc, err);
+    evaluate_iteration<true, true>(p, m, t_sched, t_uni, guard ? p.swallA[i] : MCX_NONE, guard ? p.stileA[i] : MCX_NONE,
+                                   rs, forced != 0, o, own_start ? ls : halo_ls, tc, err);
     trace_end(tc, o, rs);
     if (err) raise_error(p, err, m.id);
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time);
@@ -784,9 +803,10 @@ void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t 
   if (plan.prof) cudaEventRecord(plan.prof[0], s);
   k_diffuse_fast<<<plan.sm_count * 2 * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
   if (plan.prof) cudaEventRecord(plan.prof[4], s);
-  k_diffuse_slow<<<plan.sm_count * 4, TPB, 0, s>>>(p);
+  k_diffuse_slow<false><<<plan.sm_count * 4, TPB, 0, s>>>(p);
+  k_diffuse_slow<true><<<plan.sm_count, TPB, 0, s>>>(p);
   if (plan.prof) cudaEventRecord(plan.prof[1], s);
-  count_launches(plan, 2);
+  count_launches(plan, 3);
   if (plan.has_claims) {
     count_launches(plan, 4 * p.max_rounds);
     const int small_grid = plan.sm_count * 2;

@@ -48,6 +48,7 @@
 
 #include "../include/mcx.h"
 #include "oracle_rng.h"
+#include "oracle_exact_disk.h"
 
 namespace orc {
 
@@ -133,7 +134,7 @@ static inline uint64_t hash_ev(uint64_t h, uint32_t a, uint32_t b) {
   return h;
 }
 enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
-       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u };
+       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u, EV_BLOCKED = 0xB10C0000u, EV_DISK = 0xD1500000u };
 
 struct Stats {
   uint64_t molecule_steps = 0, ray_polygon_tests = 0, ray_polygon_colls = 0, reflections = 0,
@@ -502,6 +503,21 @@ static int surf_action(const World& w, uint32_t species, uint32_t surf_class, in
   return MCX_SURF_REFLECTIVE;
 }
 
+// exact_disk ignores a wall the moving molecule can travel through (exact_disk_utils.inl:957-975):
+// trigger_intersect with ORIENTATION_NONE matches the classes that do not depend on orientation
+// (rxn_utils.inl:149-158); the wall is ignored when there is at least one and all of them are transparent
+static bool exd_passes_through(const World& w, uint32_t species, uint32_t surf_class) {
+  if (surf_class == MCX_NONE) return false;
+  bool any = false;
+  for (const auto& r : w.surf_rules) {
+    if (r.surf_class != surf_class || r.orientation != 0) continue;
+    if (r.species != species && r.species != MCX_ALL_MOLECULES && r.species != MCX_ALL_VOLUME_MOLECULES) continue;
+    if (r.type != MCX_SURF_TRANSPARENT) return false;
+    any = true;
+  }
+  return any;
+}
+
 // binary_search_double, src4/rxn_utils.inl:301-320 (== src/react_cond.c:80-97)
 static int pathway_for_probability(const World& w, const mcx_rxn_class& rc, double match) {
   int min_idx = 0, max_idx = (int)rc.n_pathways - 1;
@@ -831,6 +847,24 @@ struct Eval {
     return hit_wall;
   }
 
+  // ExactDiskUtils::exact_disk (exact_disk_utils.inl:840-1145) for a collision at `loc` of the molecule moving by
+  // `mv` with the molecule at `target`: walls of the collision subpartition (:921-925)
+  double exact_disk_factor(V3 loc, V3 mv, uint32_t species, V3 target) {
+    const std::vector<uint32_t>& wl = w.walls_per_subpart[w.subpart_index(loc)];
+    if (wl.empty()) return 1;
+    std::vector<double> tri(9 * wl.size()), plane(4 * wl.size());
+    std::vector<unsigned char> skip(wl.size(), 0);
+    for (size_t k = 0; k < wl.size(); k++) {
+      const Wall& f = w.walls[wl[k]];
+      for (int q = 0; q < 3; q++) { V3 p = w.verts[f.vi[q]]; tri[9 * k + 3 * q] = p.x; tri[9 * k + 3 * q + 1] = p.y; tri[9 * k + 3 * q + 2] = p.z; }
+      plane[4 * k] = f.normal.x; plane[4 * k + 1] = f.normal.y; plane[4 * k + 2] = f.normal.z; plane[4 * k + 3] = f.distance_to_origin;
+      skip[k] = exd_passes_through(w, species, f.surf_class) ? 1 : 0;
+    }
+    bool same = !distinguishable_vec3(loc, target, POS_EPS);
+    return orc_exd::exact_disk({loc.x, loc.y, loc.z}, {mv.x, mv.y, mv.z}, w.cfg.rxn_radius_3d, {target.x, target.y, target.z},
+                               same, (int)wl.size(), tri.data(), plane.data(), skip.data());
+  }
+
   // RxnUtils::test_bimolecular, rxn_utils.inl:336-414 (local_prob_factor == 0)
   int test_bimolecular(const mcx_rxn_class& rc, double scaling) {
     double max_fixed_p = rc.max_fixed_p, prob;
@@ -965,8 +999,10 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
           w.stats.volvol_collisions++;
           if (c.time < STIME_EPS) continue;  // is_immediate_collision, collision_utils.inl:814-816
           if (apply && (w.mols[c.partner_index].flags & MCX_MOL_DEFUNCT)) continue;
-          // collide_and_react_with_vol_mol (:786-829); exact_disk factor := 1 (gap, see header)
-          double factor = 1.0;
+          // collide_and_react_with_vol_mol (:786-829)
+          double factor = E.exact_disk_factor(c.pos, remaining, m_species, w.mols[c.partner_index].pos);
+          if (factor < 0) { E.ev(EV_BLOCKED, c.partner_id); continue; }  // reaction blocked by a wall
+          if (factor != 1.0) E.ev(EV_DISK, (uint32_t)llrint(factor * 1073741824.0));  // 2^-30 resolution
           double abs_t = elapsed + t_steps * c.time;
           double scaling = factor * r_rate_factor;
           E.ev(EV_COLL, c.partner_id);
@@ -1717,5 +1753,43 @@ int orc_unit_pathway_for_probability(const double* cum_probs, int n, double matc
   for (int i = 0; i < n; i++) { w.pathways[i] = mcx_pathway{}; w.pathways[i].cum_prob = cum_probs[i]; }
   mcx_rxn_class rc{}; rc.first_pathway = 0; rc.n_pathways = n;
   return pathway_for_probability(w, rc, match);
+}
+
+// surface grid arithmetic of one triangle (pinned against src/grid_util.c through oracle/_ref)
+void orc_unit_grid_constants(const double* v9, double* out8) {
+  World w; unit_world(w, v9);
+  Grid g; grid_init(w, w.walls[0], g);
+  double t[8] = {(double)g.n_axis, g.strip_width_rcp, g.vert2_slope, g.fullslope, g.binding_factor, g.vert0_u, g.vert0_v, (double)g.n_tiles};
+  memcpy(out8, t, sizeof(t));
+}
+int orc_unit_xyz2grid(const double* v9, const double* xyz3) {
+  World w; unit_world(w, v9);
+  Grid g; grid_init(w, w.walls[0], g);
+  return (int)xyz2grid(w, V3{xyz3[0], xyz3[1], xyz3[2]}, w.walls[0], g);
+}
+void orc_unit_grid2uv(const double* v9, int idx, double* uv2) {
+  World w; unit_world(w, v9);
+  Grid g; grid_init(w, w.walls[0], g);
+  grid2uv(w.walls[0], g, (uint32_t)idx, uv2[0], uv2[1]);
+}
+void orc_unit_uv2xyz(const double* v9, const double* uv2, double* xyz3) {
+  World w; unit_world(w, v9);
+  V3 r = uv2xyz(w, w.walls[0], uv2[0], uv2[1]);
+  xyz3[0] = r.x; xyz3[1] = r.y; xyz3[2] = r.z;
+}
+int orc_unit_exact_disk_max_pool(void) { return orc_exd::g_max_pool; }
+// exact_disk over an explicit wall list (pinned against src/diffuse.c:1365 through oracle/_ref)
+double orc_unit_exact_disk(const double* loc3, const double* mv3, double R, const double* target3, int n_walls,
+                           const double* tri9) {
+  std::vector<double> plane(4 * (size_t)std::max(n_walls, 1));
+  for (int k = 0; k < n_walls; k++) {
+    World w; unit_world(w, tri9 + 9 * k);
+    const Wall& f = w.walls[0];
+    plane[4 * k] = f.normal.x; plane[4 * k + 1] = f.normal.y; plane[4 * k + 2] = f.normal.z; plane[4 * k + 3] = f.distance_to_origin;
+  }
+  V3 loc = {loc3[0], loc3[1], loc3[2]}, tg = {target3[0], target3[1], target3[2]};
+  bool same = !distinguishable_vec3(loc, tg, POS_EPS);
+  return orc_exd::exact_disk({loc.x, loc.y, loc.z}, {mv3[0], mv3[1], mv3[2]}, R, {tg.x, tg.y, tg.z}, same, n_walls, tri9,
+                             plane.data(), nullptr);
 }
 }

@@ -186,6 +186,13 @@ def ref_mcell3_lib():
     L.ref3_test_bimolecular.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint, C.c_uint, C.c_void_p]
     L.ref3_test_intersect.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint, C.c_uint, C.c_void_p]
     L.ref3_binary_search_double.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double]
+    if hasattr(L, "ref3_exact_disk"):
+        L.ref3_exact_disk.restype = C.c_double
+        L.ref3_exact_disk.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref3_grid_constants.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref3_xyz2grid.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref3_grid2uv.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref3_uv2xyz.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -199,4 +206,10 @@ def unit_lib():
     L.orc_unit_pathway_for_probability.argtypes = [C.c_void_p, C.c_int, C.c_double]
     L.orc_unit_wall_in_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_unit_wall_constants.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_unit_exact_disk.restype = C.c_double
+    L.orc_unit_exact_disk.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_unit_grid_constants.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_unit_xyz2grid.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_unit_grid2uv.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_unit_uv2xyz.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     return L

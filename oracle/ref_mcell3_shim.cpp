@@ -152,3 +152,79 @@ EXPORT double ref3_compute_pb_factor_volvol(double time_unit, double length_unit
   int shared = 0;
   return compute_pb_factor(time_unit, length_unit, grid_density, rx_radius_3d, &rf, &shared, &rx, 0);
 }
+
+// ---- surface grids: src/grid_util.c (== Grid::initialize src4/wall.cpp:38-74, GridUtils::xyz2grid_tile_index /
+// grid2uv src4/grid_utils.inl:48-118,233-253) -------------------------------------------------------------------
+#include "grid_util.h"
+namespace {
+struct RefGrid {
+  RefWall rw;
+  struct surface_grid g;
+  RefGrid(const double* v9) : rw(v9) {
+    memset(&g, 0, sizeof(g));
+    // the allocation-free part of create_grid (src/grid_util.c:305-365)
+    g.surface = &rw.w;
+    g.n = (int)ceil(sqrt(rw.w.area));
+    if (g.n < 1) g.n = 1;
+    g.n_tiles = g.n * g.n;
+    g.binding_factor = ((double)g.n_tiles) / rw.w.area;
+    init_grid_geometry(&g);
+    rw.w.grid = &g;
+  }
+};
+}  // namespace
+EXPORT void ref3_grid_constants(const double* v9, double* out8) {
+  RefGrid rg(v9);
+  double t[8] = {(double)rg.g.n, rg.g.inv_strip_wid, rg.g.vert2_slope, rg.g.fullslope, rg.g.binding_factor,
+                 rg.g.vert0.u, rg.g.vert0.v, (double)rg.g.n_tiles};
+  memcpy(out8, t, sizeof(t));
+}
+EXPORT int ref3_xyz2grid(const double* v9, const double* xyz3) {
+  RefGrid rg(v9);
+  struct vector3 v = {xyz3[0], xyz3[1], xyz3[2]};
+  return xyz2grid(&v, &rg.g);
+}
+EXPORT void ref3_grid2uv(const double* v9, int idx, double* uv2) {
+  RefGrid rg(v9);
+  struct vector2 r;
+  grid2uv(&rg.g, idx, &r);
+  uv2[0] = r.u; uv2[1] = r.v;
+}
+EXPORT void ref3_uv2xyz(const double* v9, const double* uv2, double* xyz3) {
+  RefWall rw(v9);
+  struct vector2 a = {uv2[0], uv2[1]};
+  struct vector3 b;
+  uv2xyz(&a, &rw.w, &b);
+  xyz3[0] = b.x; xyz3[1] = b.y; xyz3[2] = b.z;
+}
+
+// ---- exact_disk: src/diffuse.c:1365 (== ExactDiskUtils::exact_disk, src4/exact_disk_utils.inl:840-1145) ----------
+#include "diffuse.h"
+#include <vector>
+// n walls (9 coordinates each) form the wall list of the subvolume; the moving species has no surface-class
+// reactions (CAN_VOLWALL clear) and the expanded list is on, as in every MCell4 run with volume-volume reactions
+EXPORT double ref3_exact_disk(const double* loc3, const double* mv3, double R, const double* target3, int n_walls,
+                              const double* tri9) {
+  std::vector<RefWall*> walls;
+  std::vector<struct wall_list> wl(n_walls > 0 ? n_walls : 1);
+  for (int i = 0; i < n_walls; i++) walls.push_back(new RefWall(tri9 + 9 * i));
+  for (int i = 0; i < n_walls; i++) { wl[i].this_wall = &walls[i]->w; wl[i].next = i + 1 < n_walls ? &wl[i + 1] : NULL; }
+  struct storage st;
+  memset(&st, 0, sizeof(st));
+  st.exdv = create_mem(sizeof(struct exd_vertex), 64);
+  struct subvolume sv;
+  memset(&sv, 0, sizeof(sv));
+  sv.wall_head = n_walls ? &wl[0] : NULL;
+  sv.local_storage = &st;
+  struct species sp;
+  memset(&sp, 0, sizeof(sp));
+  struct volume_molecule moving, target;
+  memset(&moving, 0, sizeof(moving)); memset(&target, 0, sizeof(target));
+  moving.properties = &sp; target.properties = &sp;
+  target.pos.x = target3[0]; target.pos.y = target3[1]; target.pos.z = target3[2];
+  struct vector3 loc = {loc3[0], loc3[1], loc3[2]}, mv = {mv3[0], mv3[1], mv3[2]};
+  double r = exact_disk(NULL, &loc, &mv, R, &sv, &moving, &target, 1, NULL, NULL, NULL);
+  delete_mem(st.exdv);
+  for (auto* w : walls) delete w;
+  return r;
+}

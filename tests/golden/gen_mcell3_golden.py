@@ -71,7 +71,26 @@ dist_cases = np.array([[1.0, 1.0 + 1e-13, 1e-12], [1.0, 1.0 + 3e-12, 1e-12], [1e
                        [0.0, 1e-13, 1e-12], [0.0, 2e-12, 1e-12], [-5.0, 5.0, 1e-12], [1e-20, -1e-20, 1e-12], [0.3, 0.3, 1e-12]])
 dist_out = np.array([R3.ref3_distinguishable(a, b, e) for a, b, e in dist_cases], np.int32)
 
-np.savez_compressed(os.path.join(HERE, "mcell3_ref_vectors.npz"), wall_constants=consts, ray_out=ray_out, mol_out=mol_out,
+# exact_disk (src/diffuse.c:1365) and the surface-grid arithmetic (src/grid_util.c)
+R3.ref3_exact_disk.restype = C.c_double
+R3.ref3_exact_disk.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
+dc, Rd = mc.disk_cases()
+disk_out = np.array([R3.ref3_exact_disk(vp(loc), vp(mv), Rd, vp(tg), len(walls), vp(walls)) for loc, mv, tg, walls in dc])
+grid_tris = [i for i in range(len(tris)) if np.linalg.norm(np.cross(tris[i][3:6] - tris[i][0:3], tris[i][6:9] - tris[i][0:3])) > 0]
+grid_consts = np.zeros((len(tris), 8))
+for i in grid_tris:
+    R3.ref3_grid_constants(vp(tris[i]), vp(grid_consts[i]))
+gp = mc.grid_points(tris)
+grid_idx = np.array([R3.ref3_xyz2grid(vp(tris[ti]), vp(pt)) for ti, pt in gp], np.int64)
+grid_uv = np.zeros((len(gp), 2)); grid_xyz = np.zeros((len(gp), 3))
+for k, (ti, pt) in enumerate(gp):
+    R3.ref3_grid2uv(vp(tris[ti]), int(grid_idx[k]), vp(grid_uv[k]))
+    R3.ref3_uv2xyz(vp(tris[ti]), vp(grid_uv[k]), vp(grid_xyz[k]))
+print("disk: blocked %d full %d partial %d" % ((disk_out < 0).sum(), (disk_out == 1).sum(), ((disk_out >= 0) & (disk_out != 1)).sum()),
+      " grid points:", len(gp), "max tiles", int(grid_consts[:, 7].max()))
+
+np.savez_compressed(os.path.join(HERE, "mcell3_ref_vectors.npz"), disk_out=disk_out, grid_consts=grid_consts, grid_idx=grid_idx,
+                    grid_uv=grid_uv, grid_xyz=grid_xyz, wall_constants=consts, ray_out=ray_out, mol_out=mol_out,
                     box_out=box_out, rxn_out=rxn_out, pb_factor=np.array(pb), dist_cases=dist_cases, dist_out=dist_out)
 codes, cnt = np.unique(ray_out[:, 0], return_counts=True)
 print("rays:", dict(zip(codes.tolist(), cnt.tolist())), " mol hits:", int(mol_out[:, 0].sum()), "/", len(mol_out),

@@ -91,3 +91,56 @@ def rxn_cases(seed=15):
     cases.append((np.array([1e140]), 1.0, 5, 0))                 # absorptive surface class: rate GIGANTIC
     cases.append((np.array([0.1]), 0.1, 6, 3))                   # max_fixed_p == scaling
     return cases
+
+
+def box_triangles(h):
+    """The 12 triangles of a centred cube with half edge h (create_box face order), 9 coordinates each."""
+    v = np.array([[-h, -h, -h], [-h, -h, h], [-h, h, -h], [-h, h, h], [h, -h, -h], [h, -h, h], [h, h, -h], [h, h, h]], float)
+    f = np.array([[1, 2, 0], [3, 6, 2], [7, 4, 6], [5, 0, 4], [6, 0, 2], [3, 5, 7], [1, 3, 2], [3, 7, 6], [7, 5, 4], [5, 1, 0],
+                  [6, 4, 0], [3, 1, 5]])
+    return np.ascontiguousarray(v[f].reshape(12, 9))
+
+
+def disk_cases(n=3000, seed=16, R=0.5641895835477563):
+    """(loc, mv, target, walls) for exact_disk: collisions next to the faces / edges / corners of a box and inside
+    random triangle soups (multi-edge sweeps, crossings, parallel chords), targets inside the interaction disk."""
+    rng = np.random.default_rng(seed)
+    out = []
+    box = box_triangles(10.0)
+    for k in range(n):
+        kind = k % 4
+        if kind < 2:
+            walls = box
+            near = rng.uniform(0.01, 0.8, 3)
+            far = np.array([1.0, float(rng.integers(0, 2)) + (0.0 if kind else 8 * rng.random()),
+                            float(rng.integers(0, 2)) + (0.0 if kind else 8 * rng.random())])
+            loc = np.array([10.0, 10.0, 10.0]) - near * far
+        else:
+            walls = np.ascontiguousarray(rng.uniform(-1.5, 1.5, (int(rng.integers(1, 7)), 9)))
+            loc = rng.uniform(-0.5, 0.5, 3)
+        mv = rng.normal(0, 1.4, 3)
+        d = rng.normal(0, 1, 3)
+        d -= d.dot(mv) / mv.dot(mv) * mv
+        d *= rng.uniform(0, R) / np.linalg.norm(d)
+        target = loc + d + mv * rng.uniform(-1e-3, 1e-3)
+        if k % 97 == 0:
+            target = loc.copy()                                  # hit the target exactly
+        out.append((np.ascontiguousarray(loc), np.ascontiguousarray(mv), np.ascontiguousarray(target), walls))
+    return out, R
+
+
+def grid_points(tris, per_tri=12, seed=17):
+    """(tri index, point on the triangle) incl. the three vertices, for xyz2grid."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for ti, t in enumerate(tris):
+        v0, v1, v2 = t[0:3], t[3:6], t[6:9]
+        if np.linalg.norm(np.cross(v1 - v0, v2 - v0)) == 0:
+            continue
+        for k in range(per_tri):
+            a, b = rng.uniform(0.001, 0.998, 2)
+            if a + b > 0.999:
+                a, b = (1 - a) * 0.999, (1 - b) * 0.999
+            out.append((ti, np.ascontiguousarray(v0 + a * (v1 - v0) + b * (v2 - v0))))
+        out += [(ti, np.ascontiguousarray(v0.copy())), (ti, np.ascontiguousarray(v1.copy())), (ti, np.ascontiguousarray(v2.copy()))]
+    return out

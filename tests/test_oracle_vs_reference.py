@@ -137,6 +137,62 @@ def test_distinguishable_and_pb_factor():
 
 # ------------------------------------------------------------------ live against the compiled reference
 R3 = O.ref_mcell3_lib()
+def test_exact_disk_bit_exact():
+    """exact_disk (src4/exact_disk_utils.inl:840-1145 == src/diffuse.c:1365): occlusion factor of the interaction disk
+    next to box faces / edges / corners and inside random triangle soups, incl. blocked targets."""
+    U = O.unit_lib()
+    cases, R = mc.disk_cases()
+    ref = G["disk_out"]
+    assert len(cases) == len(ref)
+    for i, (loc, mv, tg, walls) in enumerate(cases):
+        got = U.orc_unit_exact_disk(vp(loc), vp(mv), R, vp(tg), len(walls), vp(walls))
+        assert same(got, ref[i]), (i, got, ref[i])
+    assert (ref < 0).sum() > 300 and ((ref > 0) & (ref < 1)).sum() > 800 and (ref == 1).sum() > 300
+
+
+def test_surface_grid_bit_exact():
+    """Grid::initialize, xyz2grid_tile_index, grid2uv, uv2xyz (src4/wall.cpp:38-74, grid_utils.inl:48-118,233-253 ==
+    src/grid_util.c) on random and box triangles, incl. points on the three vertices."""
+    U = O.unit_lib()
+    tris = mc.triangles()
+    out = np.zeros(8)
+    n_checked = 0
+    for i in range(len(tris)):
+        if G["grid_consts"][i, 7] == 0:
+            continue                                             # degenerate triangle: no grid
+        U.orc_unit_grid_constants(vp(tris[i]), vp(out))
+        assert (out == G["grid_consts"][i]).all(), i
+        n_checked += 1
+    assert n_checked > 300
+    gp = mc.grid_points(tris)
+    uv, xyz = np.zeros(2), np.zeros(3)
+    for k, (ti, pt) in enumerate(gp):
+        idx = U.orc_unit_xyz2grid(vp(tris[ti]), vp(pt))
+        assert idx == G["grid_idx"][k], (k, ti)
+        U.orc_unit_grid2uv(vp(tris[ti]), idx, vp(uv))
+        assert (uv == G["grid_uv"][k]).all(), k
+        U.orc_unit_uv2xyz(vp(tris[ti]), vp(uv), vp(xyz))
+        assert (xyz == G["grid_xyz"][k]).all(), k
+
+
+def test_libmcx_host_grid_helpers_match_reference():
+    """The product's host helpers for surface placement (mcx_grid_num_tiles / mcx_grid2uv / mcx_xyz2grid)."""
+    from mcell_b200 import engine
+    L = engine.load_library()
+    L.mcx_grid_num_tiles.argtypes = [C.c_void_p]; L.mcx_grid_num_tiles.restype = C.c_uint32
+    L.mcx_grid2uv.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; L.mcx_grid2uv.restype = None
+    L.mcx_xyz2grid.argtypes = [C.c_void_p, C.c_void_p]; L.mcx_xyz2grid.restype = C.c_uint32
+    tris = mc.triangles()
+    gp = mc.grid_points(tris)
+    uv = np.zeros(2)
+    for k, (ti, pt) in enumerate(gp):
+        assert L.mcx_grid_num_tiles(vp(tris[ti])) == int(G["grid_consts"][ti, 7])
+        idx = L.mcx_xyz2grid(vp(tris[ti]), vp(pt))
+        assert idx == G["grid_idx"][k], k
+        L.mcx_grid2uv(vp(tris[ti]), idx, vp(uv))
+        assert (uv == G["grid_uv"][k]).all(), k
+
+
 needs_ref = pytest.mark.skipif(R3 is None, reason="oracle/_ref/libmcell3ref.so not present on this box")
 
 
@@ -190,3 +246,16 @@ def test_live_random_collide_mol_and_boxes():
     for i, (ti, lo, hi) in enumerate(mc.boxes(tris, per_tri=30, seed=6)):
         lo = np.ascontiguousarray(lo, dtype=np.float64); hi = np.ascontiguousarray(hi, dtype=np.float64)
         assert (R3.ref3_wall_in_box(vp(tris[ti]), vp(lo), vp(hi)) != 0) == bool(U.orc_unit_wall_in_box(vp(tris[ti]), vp(lo), vp(hi)))
+
+
+@needs_ref
+def test_live_random_exact_disk_against_compiled_reference():
+    U = O.unit_lib()
+    cases, R = mc.disk_cases(n=6000, seed=4242)
+    n_partial = 0
+    for loc, mv, tg, walls in cases:
+        a = U.orc_unit_exact_disk(vp(loc), vp(mv), R, vp(tg), len(walls), vp(walls))
+        b = R3.ref3_exact_disk(vp(loc), vp(mv), R, vp(tg), len(walls), vp(walls))
+        assert same(a, b), (a, b)
+        n_partial += 0 < b < 1
+    assert n_partial > 1500

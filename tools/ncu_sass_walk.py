@@ -2,7 +2,7 @@
 """Walk the SASS of one kernel in an ncu report with source lines and per-instruction active threads:
 python tools/ncu_sass_walk.py rep.ncu-rep <mangled-symbol> [kernel-name-substring]"""
 import collections, csv, os, re, subprocess, sys, tempfile
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.environ.get("WALK_ROOT", os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 rep, symbol = sys.argv[1], sys.argv[2]
 sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source=sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(sass.splitlines()))
