@@ -136,6 +136,7 @@ typedef struct mcx_mol_soa {
   uint32_t *tile;                  /* s.grid_tile_index on that wall's grid */
   int32_t  *orientation;           /* s.orientation: +1 up / -1 down */
   double   *u, *v;                 /* s.pos in the wall's uv frame */
+  uint32_t *counted_volume;        /* v.counted_volume_index (< 256); NULL = 0 = outside every counted object */
 } mcx_mol_soa;
 
 /* ---- per-call statistics: SimulationStats mirror (src4/simulation_stats.h:46-83) ----- */
@@ -267,6 +268,20 @@ int mcx_set_profiling(mcx_handle* h, int enabled);
  * (src4/partition.h:1036-1077).  Arrays may be NULL.  Multi-GPU: summed over ranks. */
 int mcx_counts(mcx_handle* h, uint64_t* per_species, uint32_t n_species,
                uint64_t* per_rxn_rule, uint32_t n_rxn_rules);
+
+/* Counted volumes (Partition::counted_volumes, World::init_counted_volumes src4/world.cpp:146-155; the host owns
+ * the geometry analysis, as the reference's VtkUtils does).  A counted volume is one distinct set of enclosing
+ * counted objects; index 0 = outside all (defines.h:290).  Per wall: the counted volume on its front (normal) side
+ * and on its back side — for a wall of a non-counted object both are the volume that object lies in.  A molecule
+ * crossing a transparent wall takes the index of the side it arrives on
+ * (CollisionUtils::update_counted_volume_id_when_crossing_wall, collision_utils.inl:1637-1694, non-intersecting
+ * objects); products inherit it.  Call after mcx_set_geometry; n_counted_volumes <= 256. */
+int mcx_set_counted_volumes(mcx_handle* h, uint32_t n_counted_volumes, const uint8_t* wall_cv_front,
+                            const uint8_t* wall_cv_back);
+/* Replaces: MolOrRxnCountEvent::compute_counts terms restricted to a volume (mol_or_rxn_count_event.cpp:607-716)
+ * and Partition::inc_rxn_in_volume_occured_count (partition.h:1036-1077).
+ * mol_counts[species * n_counted_volumes + cv], rxn_counts[rxn_rule * n_counted_volumes + cv]; either may be NULL. */
+int mcx_counts_by_volume(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_counts);
 
 /* ---- multi-GPU (new: the reference has a single partition, world.cpp:147,277) --------- */
 /* nccl_unique_id: the 128-byte ncclUniqueId created by rank 0 and broadcast by the host

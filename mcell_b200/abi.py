@@ -66,7 +66,8 @@ class mcx_mol_soa(C.Structure):
     _fields_ = [("n", c_u64), ("x", P(c_f64)), ("y", P(c_f64)), ("z", P(c_f64)),
                 ("id", P(c_u32)), ("species", P(c_u32)), ("flags", P(c_u32)),
                 ("diffusion_time", P(c_f64)), ("unimol_rxn_time", P(c_f64)),
-                ("wall", P(c_u32)), ("tile", P(c_u32)), ("orientation", P(c_i32)), ("u", P(c_f64)), ("v", P(c_f64))]
+                ("wall", P(c_u32)), ("tile", P(c_u32)), ("orientation", P(c_i32)), ("u", P(c_f64)), ("v", P(c_f64)),
+                ("counted_volume", P(c_u32))]
 
 
 class mcx_step_stats(C.Structure):
@@ -108,7 +109,7 @@ EXPORTED_SYMBOLS = [
     "mcx_set_species", "mcx_set_reactions", "mcx_set_surface_classes", "mcx_upload_molecules",
     "mcx_download_molecules", "mcx_num_molecules", "mcx_step", "mcx_replay_step", "mcx_trace_step",
     "mcx_counts", "mcx_comm_init", "mcx_comm_unique_id", "mcx_slab_info_get", "mcx_philox_block", "mcx_set_profiling",
-    "mcx_grid_num_tiles", "mcx_grid2uv", "mcx_xyz2grid",
+    "mcx_grid_num_tiles", "mcx_grid2uv", "mcx_xyz2grid", "mcx_set_counted_volumes", "mcx_counts_by_volume",
 ]
 
 

@@ -43,7 +43,10 @@ struct mcx_handle {
   void *d_species = nullptr, *d_bimol = nullptr, *d_unimol = nullptr, *d_classes = nullptr, *d_pathways = nullptr,
        *d_surf = nullptr, *d_walls = nullptr, *d_tri = nullptr, *d_verts = nullptr, *d_wclass = nullptr,
        *d_spw_start = nullptr, *d_spw_list = nullptr, *d_sp_flags = nullptr, *d_grids = nullptr, *d_volsurf = nullptr,
-       *d_tile_slot = nullptr, *d_exd_skip = nullptr;
+       *d_tile_slot = nullptr, *d_exd_skip = nullptr, *d_wall_cv = nullptr, *d_rxn_count_cv = nullptr,
+       *d_mol_count_cv = nullptr;
+  uint32_t n_cv = 1; uint32_t* st_cv = nullptr;
+  uint64_t n_walls_host = 0;
   bool has_surf = false, surf_allocated = false;
   uint32_t *st_wall = nullptr, *st_tile = nullptr; int32_t* st_orient = nullptr; double *st_u = nullptr, *st_v = nullptr;
   McxComm* comm = nullptr;
@@ -281,6 +284,7 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   p.walls = (const DevWall*)h->d_walls; p.wall_tri = (const uint32_t*)h->d_tri; p.verts = (const double*)h->d_verts;
   p.wall_class = (const uint32_t*)h->d_wclass; p.spw_start = (const uint32_t*)h->d_spw_start;
   p.spw_list = (const uint32_t*)h->d_spw_list; p.n_walls = (int)n_walls; p.sp_flags = (const uint8_t*)h->d_sp_flags;
+  h->n_walls_host = n_walls;
   h->has_geometry = true;
   return MCX_OK;
 }
@@ -447,6 +451,49 @@ int mcx_set_surface_classes(mcx_handle* h, const mcx_surf_class_rxn* rules, uint
   return rebuild_tables(h);
 }
 
+int mcx_set_counted_volumes(mcx_handle* h, uint32_t n_counted_volumes, const uint8_t* wall_cv_front, const uint8_t* wall_cv_back) {
+  if (!h || !wall_cv_front || !wall_cv_back) { if (h) h->err = "null counted-volume arrays"; return MCX_ERR_INVALID_ARG; }
+  if (!h->has_geometry) { h->err = "mcx_set_geometry must precede mcx_set_counted_volumes"; return MCX_ERR_STATE; }
+  if (n_counted_volumes == 0 || n_counted_volumes > MCX_MAX_CV) { h->err = "1..256 counted volumes are supported"; return MCX_ERR_INVALID_ARG; }
+  if (h->cfg.world_size > 1) { h->err = "counted volumes are not supported with world_size > 1 yet"; return MCX_ERR_INVALID_ARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<uint16_t> cv(std::max<uint64_t>(h->n_walls_host, 1), 0);
+  for (uint64_t i = 0; i < h->n_walls_host; i++) {
+    if (wall_cv_front[i] >= n_counted_volumes || wall_cv_back[i] >= n_counted_volumes) { h->err = "counted volume index out of range"; return MCX_ERR_INVALID_ARG; }
+    cv[i] = (uint16_t)(wall_cv_front[i] | (wall_cv_back[i] << 8));
+  }
+  std::vector<unsigned long long> zero_r((size_t)256 * n_counted_volumes, 0), zero_m((size_t)256 * n_counted_volumes, 0);
+  int rc = MCX_OK;
+  rc |= dev_replace(h, &h->d_wall_cv, cv.data(), cv.size());
+  rc |= dev_replace(h, &h->d_rxn_count_cv, zero_r.data(), zero_r.size());
+  rc |= dev_replace(h, &h->d_mol_count_cv, zero_m.data(), zero_m.size());
+  if (rc) return MCX_ERR_CUDA;
+  h->n_cv = n_counted_volumes;
+  h->p.wall_cv = (const uint16_t*)h->d_wall_cv; h->p.rxn_count_cv = (unsigned long long*)h->d_rxn_count_cv;
+  h->p.mol_count_cv = (unsigned long long*)h->d_mol_count_cv; h->p.n_cv = n_counted_volumes;
+  return MCX_OK;
+}
+
+int mcx_counts_by_volume(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_counts) {
+  if (!h) return MCX_ERR_INVALID_ARG;
+  if (!h->uploaded) { h->err = "nothing uploaded"; return MCX_ERR_STATE; }
+  if (!h->p.wall_cv) { h->err = "mcx_set_counted_volumes was not called"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  h->p.cs_cur = h->cs[h->cs_cur]; h->p.cs_next = h->cs[h->cs_cur ^ 1]; h->p.iteration = h->iteration;
+  if (mol_counts) {
+    mcx_launch_count_by_volume(h->p, h->stream);
+    h->launches += 1;
+    CK(cudaMemcpyAsync(mol_counts, h->p.mol_count_cv, sizeof(uint64_t) * h->species.size() * h->n_cv, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (rxn_counts) {
+    uint32_t n_rules = 0;
+    for (const auto& pw : h->pathways) n_rules = std::max(n_rules, pw.rxn_rule_id + 1);
+    CK(cudaMemcpyAsync(rxn_counts, h->p.rxn_count_cv, sizeof(uint64_t) * (size_t)n_rules * h->n_cv, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return MCX_OK;
+}
+
 static void bind_iteration(mcx_handle* h) {
   h->p.cs_cur = h->cs[h->cs_cur];
   h->p.cs_next = h->cs[h->cs_cur ^ 1];
@@ -477,6 +524,7 @@ static int ensure_staging(mcx_handle* h) {
   rc |= dev_alloc(h, &h->st_x, cap); rc |= dev_alloc(h, &h->st_y, cap); rc |= dev_alloc(h, &h->st_z, cap);
   rc |= dev_alloc(h, &h->st_ts, cap); rc |= dev_alloc(h, &h->st_tu, cap);
   rc |= dev_alloc(h, &h->st_id, cap); rc |= dev_alloc(h, &h->st_sp, cap); rc |= dev_alloc(h, &h->st_fl, cap);
+  rc |= dev_alloc(h, &h->st_cv, cap);
   return rc ? MCX_ERR_CUDA : MCX_OK;
 }
 
@@ -509,7 +557,11 @@ int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
   { int rcs = ensure_surface_arrays(h); if (rcs) return rcs; }
   const size_t n = m->n;
   cudaStream_t s = h->stream;
-  SurfSoa sv{nullptr, nullptr, nullptr, nullptr, nullptr};
+  SurfSoa sv{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (m->counted_volume && h->p.wall_cv) {
+    CK(cudaMemcpyAsync(h->st_cv, m->counted_volume, n * 4, cudaMemcpyHostToDevice, s));
+    sv.cv = h->st_cv;
+  }
   if (h->has_surf && m->wall) {
     if (!m->tile || !m->orientation || !m->u || !m->v) { h->err = "incomplete surface molecule arrays"; return MCX_ERR_INVALID_ARG; }
     CK(cudaMemcpyAsync(h->st_wall, m->wall, n * 4, cudaMemcpyHostToDevice, s));
@@ -517,7 +569,7 @@ int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
     CK(cudaMemcpyAsync(h->st_orient, m->orientation, n * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(h->st_u, m->u, n * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(h->st_v, m->v, n * 8, cudaMemcpyHostToDevice, s));
-    sv = SurfSoa{h->st_wall, h->st_tile, h->st_orient, h->st_u, h->st_v};
+    sv.wall = h->st_wall; sv.tile = h->st_tile; sv.orientation = h->st_orient; sv.u = h->st_u; sv.v = h->st_v;
   }
   CK(cudaMemcpyAsync(h->st_x, m->x, n * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(h->st_y, m->y, n * 8, cudaMemcpyHostToDevice, s));
@@ -568,9 +620,10 @@ int mcx_download_molecules(mcx_handle* h, mcx_mol_soa* out, uint64_t capacity) {
   if (ensure_staging(h)) return MCX_ERR_CUDA;
   cudaStream_t s = h->stream;
   bind_iteration(h);
-  SurfSoaOut sv{nullptr, nullptr, nullptr, nullptr, nullptr};
+  SurfSoaOut sv{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const bool want_surf = h->surf_allocated && out->wall && out->tile && out->orientation && out->u && out->v;
-  if (want_surf) sv = SurfSoaOut{h->st_wall, h->st_tile, h->st_orient, h->st_u, h->st_v};
+  if (want_surf) { sv.wall = h->st_wall; sv.tile = h->st_tile; sv.orientation = h->st_orient; sv.u = h->st_u; sv.v = h->st_v; }
+  if (out->counted_volume) sv.cv = h->st_cv;
   mcx_launch_unpack_soa(h->p, h->st_x, h->st_y, h->st_z, h->st_id, h->st_sp, h->st_fl, h->st_ts, h->st_tu, sv, h->d_n_out, s);
   h->launches += 1;
   unsigned int live = 0;
@@ -585,6 +638,7 @@ int mcx_download_molecules(mcx_handle* h, mcx_mol_soa* out, uint64_t capacity) {
   if (out->flags) CK(cudaMemcpyAsync(out->flags, h->st_fl, live * 4ull, cudaMemcpyDeviceToHost, s));
   if (out->diffusion_time) CK(cudaMemcpyAsync(out->diffusion_time, h->st_ts, live * 8ull, cudaMemcpyDeviceToHost, s));
   if (out->unimol_rxn_time) CK(cudaMemcpyAsync(out->unimol_rxn_time, h->st_tu, live * 8ull, cudaMemcpyDeviceToHost, s));
+  if (out->counted_volume) CK(cudaMemcpyAsync(out->counted_volume, h->st_cv, live * 4ull, cudaMemcpyDeviceToHost, s));
   if (want_surf) {
     CK(cudaMemcpyAsync(out->wall, h->st_wall, live * 4ull, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out->tile, h->st_tile, live * 4ull, cudaMemcpyDeviceToHost, s));

@@ -1009,6 +1009,10 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
               tc.ev(EV_TRANSP | (uint32_t)side, wh.wall);
               ls.transparent++;
               pos = wh.pos; subpart = subpart_index(p, pos);
+              if (p.wall_cv) {  // update_counted_volume_id_when_crossing_wall (collision_utils.inl:1637-1694)
+                const uint32_t cv = __ldg(p.wall_cv + wh.wall);
+                flags = (flags & ~SF_CVI_MASK) | ((side == W_FRONT ? (cv >> 8) : (cv & 0xFFu)) << SF_CVI_SHIFT);
+              }
               remaining = remaining * (1.0 - wh.t);
               elapsed += t_steps * wh.t;
               t_steps *= (1.0 - wh.t);

@@ -25,7 +25,9 @@ enum : uint32_t {
   DF_ORIENT_UP = 1u << 22,   // s.orientation == ORIENTATION_UP (else DOWN)
   DF_CREATED_ON_SURF = 1u << 23,  // volume product of a surface reaction: cold swall/stile hold where it was created
                                   // (DiffuseAction::where_created_this_iteration, diffuse_react_event.cpp:877-885)
-  SF_SPECIES_MASK = 0xFFFFu
+  SF_SPECIES_MASK = 0xFFFFu,
+  SF_CVI_SHIFT = 24,         // bits 24..31: v.counted_volume_index (rides along in the flags of every evaluation)
+  SF_CVI_MASK = 0xFF000000u
 };
 
 struct DevSpecies { double space_step, time_step; uint32_t flags; uint32_t can_vol_react; uint32_t can_vol_surf; uint32_t pad; };
@@ -69,6 +71,7 @@ struct Counters {
   unsigned long long species_next[256];  // multi-GPU: recount of owned molecules during the scatter
   unsigned long long rxn_count[256];
 };
+#define MCX_MAX_CV 256
 
 struct DevParams {
   // partition / subpartition grid (reference semantics)
@@ -93,6 +96,10 @@ struct DevParams {
   const DevPathway* pathways;
   const uint8_t* surf_action;   // [species][surf_class][side(0 front,1 back)]
   const uint8_t* exd_skip;      // [species][surf_class]: exact_disk ignores the wall (the species travels through it)
+  const uint16_t* wall_cv;      // per wall: counted volume on the front side | on the back side << 8; null = none
+  unsigned long long* rxn_count_cv;  // [rule * n_cv + cv]
+  unsigned long long* mol_count_cv;  // [species * n_cv + cv], filled by mcx_counts_by_volume
+  unsigned int n_cv;
   int n_species, n_surf_classes, n_walls;
   // surface molecules: tile table of the current snapshot and per-slot cold fields
   const DevGrid* grids;         // per wall
@@ -159,9 +166,10 @@ void mcx_launch_pack_halo(const DevParams& p, HaloRec* send_low, HaloRec* send_h
 void mcx_launch_unpack_halo(const DevParams& p, const HaloRec* recv, unsigned int n, unsigned int offset, cudaStream_t s);
 void mcx_launch_add_received(const DevParams& p, unsigned int n, cudaStream_t s);
 void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
+void mcx_launch_count_by_volume(const DevParams& p, cudaStream_t s);
 // device staging of the surface part of mcx_mol_soa (all null: volume molecules only)
-struct SurfSoa { const uint32_t* wall; const uint32_t* tile; const int32_t* orientation; const double* u; const double* v; };
-struct SurfSoaOut { uint32_t* wall; uint32_t* tile; int32_t* orientation; double* u; double* v; };
+struct SurfSoa { const uint32_t* wall; const uint32_t* tile; const int32_t* orientation; const double* u; const double* v; const uint32_t* cv; };
+struct SurfSoaOut { uint32_t* wall; uint32_t* tile; int32_t* orientation; double* u; double* v; uint32_t* cv; };
 void mcx_launch_pack_soa(const DevParams& p, const double* x, const double* y, const double* z,
                          const uint32_t* id, const uint32_t* species, const uint32_t* flags,
                          const double* tsched, const double* tuni, SurfSoa sv, unsigned int n, cudaStream_t s);

@@ -154,6 +154,7 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
   const DevClass& cl = p.classes[rxn_class];
   const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
   if (own_event) agg_add(&c->rxn_count[pw.rule_id & 255u], 1u);
+  if (own_event && p.wall_cv) agg_add(&p.rxn_count_cv[(pw.rule_id & 255u) * p.n_cv + (flags >> SF_CVI_SHIFT)], 1u);
   bool keepA, keepB = true;
   uint32_t reuse[2]; int n_reuse = 0;
   if (kind == MCX_OUT_REACTED) {
@@ -194,7 +195,7 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
     if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
     uint32_t nid = (int)k < n_reuse ? reuse[k] : atomicAdd(&c->next_id, (unsigned int)p.world) ;  // fresh ids: strided by rank
     uint32_t psp = pw.products[k];
-    uint32_t pflags = DF_SCHED_UNIMOL | DF_PARTIAL;
+    uint32_t pflags = DF_SCHED_UNIMOL | DF_PARTIAL | (flags & SF_CVI_MASK);  // products inherit the counted volume
     pos = event_pos;
     if (surf_slot != MCX_NONE) {
       int o = pw.prod_orient[k];
@@ -203,7 +204,7 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
       const uint32_t wi = p.swallA[surf_slot];
       p.swallB[ns] = wi; p.stileB[ns] = p.stileA[surf_slot];
       if (!(p.species[psp].flags & MCX_SP_VOL)) {
-        pflags |= DF_SURF | (o > 0 ? DF_ORIENT_UP : 0u);
+        pflags = (pflags & ~SF_CVI_MASK) | DF_SURF | (o > 0 ? DF_ORIENT_UP : 0u);
         p.suvB[ns] = p.suvA[surf_slot];
         const MolRec sr = load_rec_volatile(p.recA, surf_slot);
         pos = D3{sr.x, sr.y, sr.z};
@@ -212,6 +213,10 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
         const double bump = (o > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
         pos = D3{event_pos.x + (2 * bump) * f.nx, event_pos.y + (2 * bump) * f.ny, event_pos.z + (2 * bump) * f.nz};
         pflags |= DF_CREATED_ON_SURF;
+        if (p.wall_cv) {  // released to the front (up) or to the back side of the wall
+          const uint32_t cv = __ldg(p.wall_cv + wi);
+          pflags = (pflags & ~SF_CVI_MASK) | ((o > 0 ? (cv & 0xFFu) : (cv >> 8)) << SF_CVI_SHIFT);
+        } else pflags &= ~SF_CVI_MASK;
       }
     }
     p.tschedB[ns] = t_event;
@@ -671,6 +676,23 @@ __global__ void __launch_bounds__(TPB) k_bin_initial(const __grid_constant__ Dev
   }
 }
 
+// MolOrRxnCountEvent::compute_counts restricted to volumes (mol_or_rxn_count_event.cpp:607-716): molecules per
+// (species, counted volume), one pass over the snapshot with per-warp aggregation of equal keys
+__global__ void __launch_bounds__(TPB) k_count_by_volume(const __grid_constant__ DevParams p) {
+  const unsigned int n = p.ctr->n_slots;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const MolRec m = load_rec_volatile(p.recA, i);
+    if ((m.sf & DF_DEAD) || !owned_z(p, m.z)) continue;
+    const unsigned int key = (m.sf & SF_SPECIES_MASK) * p.n_cv + (m.sf >> SF_CVI_SHIFT);
+    const unsigned int peers = __match_any_sync(__activemask(), key);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.mol_count_cv[key], (unsigned long long)__popc(peers));
+  }
+}
+void mcx_launch_count_by_volume(const DevParams& p, cudaStream_t s) {
+  cudaMemsetAsync(p.mol_count_cv, 0, sizeof(unsigned long long) * (size_t)p.n_species * p.n_cv, s);
+  k_count_by_volume<<<148 * 8, TPB, 0, s>>>(p);
+}
+
 // ---- multi-GPU halo refresh (driven by mcx_comm.cu) --------------------------------------------------------------
 // A -> B unchanged: lets the halo refresh run without an evaluation step (after an upload)
 __global__ void __launch_bounds__(TPB) k_rebin(const __grid_constant__ DevParams p) {
@@ -749,6 +771,10 @@ __global__ void __launch_bounds__(TPB) k_pack_soa(const __grid_constant__ DevPar
       p.swallB[i] = wi; p.stileB[i] = sv.tile[i]; p.suvB[i] = make_double2(u, v);
     }
     atomicMax(&p.ctr->next_id, id[i] + 1u);
+    if (sv.cv && !is_surf) {
+      if (sv.cv[i] >= p.n_cv) { raise_error(p, MCX_ERR_INVALID_ARG, id[i]); continue; }
+      sf |= sv.cv[i] << SF_CVI_SHIFT;
+    }
     if (hf & MCX_MOL_DEFUNCT) sf |= DF_DEAD;
     if (hf & MCX_MOL_SCHEDULE_UNIMOL) sf |= DF_SCHED_UNIMOL;
     if ((hf & MCX_MOL_PARTIAL) && tsched) { sf |= DF_PARTIAL; p.tschedB[i] = tsched[i]; }
@@ -771,6 +797,7 @@ __global__ void __launch_bounds__(TPB) k_unpack_soa(const __grid_constant__ DevP
     if (flags) flags[k] = hf;
     if (tsched) tsched[k] = (m.sf & DF_PARTIAL) ? p.tschedA[i] : (double)p.iteration;
     if (tuni) tuni[k] = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;
+    if (sv.cv) sv.cv[k] = m.sf >> SF_CVI_SHIFT;
     if (sv.wall) {
       const bool is_surf = (m.sf & DF_SURF) != 0;
       sv.wall[k] = is_surf ? p.swallA[i] : MCX_NONE;

@@ -54,6 +54,8 @@ def load_library():
     L.mcx_set_profiling.argtypes = [H, C.c_int]
     L.mcx_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
     L.mcx_philox_block.restype = None
+    L.mcx_set_counted_volumes.argtypes = [H, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.mcx_counts_by_volume.argtypes = [H, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -81,6 +83,8 @@ class Engine:
         self._ck(self.L.mcx_set_surface_classes(self.h, C.cast(t.surf_rules, C.c_void_p), t.n_surf_rules))
         self._ck(self.L.mcx_set_geometry(self.h, _vp(t.vertices), len(t.vertices), _vp(t.tri), len(t.tri),
                                          _vp(t.wall_surf_class), None))
+        if getattr(t, "n_counted_volumes", 0) > 1:
+            self._ck(self.L.mcx_set_counted_volumes(self.h, t.n_counted_volumes, _vp(t.wall_cv_front), _vp(t.wall_cv_back)))
 
     def _ck(self, rc):
         if rc:
@@ -153,6 +157,18 @@ class Engine:
         r = np.zeros(max(1, self.t.n_rules), np.uint64)
         self._ck(self.L.mcx_counts(self.h, _vp(s), self.t.n_species, _vp(r), self.t.n_rules))
         return s[:self.t.n_species], r[:self.t.n_rules]
+
+
+def _counts_by_volume(self):
+    """(molecules[species, counted volume], reactions[rule, counted volume]) — count terms restricted to a volume."""
+    ncv = max(1, getattr(self.t, "n_counted_volumes", 1))
+    m = np.zeros((max(1, self.t.n_species), ncv), np.uint64)
+    r = np.zeros((max(1, self.t.n_rules), ncv), np.uint64)
+    self._ck(self.L.mcx_counts_by_volume(self.h, _vp(m), _vp(r)))
+    return m, r
+
+
+Engine.counts_by_volume = _counts_by_volume
 
 
 def philox_block(seed, mol_id, iteration, block):

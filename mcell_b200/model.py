@@ -135,6 +135,12 @@ class Tables:
     rule_names: list = field(default_factory=list)
     length_unit: float = 0.01
     time_unit: float = 1e-6
+    # counted volumes (World::init_counted_volumes): index 0 = outside every counted object
+    n_counted_volumes: int = 1
+    wall_cv_front: np.ndarray = None
+    wall_cv_back: np.ndarray = None
+    wall_object: np.ndarray = None
+    counted_volume_sets: list = field(default_factory=lambda: [frozenset()])
 
 
 class Model:
@@ -146,6 +152,7 @@ class Model:
         self._verts = []
         self._tris = []
         self._wall_class = []
+        self._counted = []
 
     # -- subsystem ------------------------------------------------------------------------
     def add_species(self, name, D, target_only=False, surface=False):
@@ -162,8 +169,10 @@ class Model:
         self.surface_properties.append(SurfaceProperty(surf_class, type_, species, orientation))
 
     # -- instantiation --------------------------------------------------------------------
-    def add_geometry_object(self, vertices_um, faces, surf_class=abi.MCX_NONE):
-        """surf_class: scalar or per-face array."""
+    def add_geometry_object(self, vertices_um, faces, surf_class=abi.MCX_NONE, counted=False):
+        """surf_class: scalar or per-face array.  counted: the (closed) object is a counted volume
+        (GeometryObject::is_counted_volume_or_compartment)."""
+        self._counted.append(bool(counted))
         base = sum(len(v) for v in self._verts)
         self._verts.append(np.asarray(vertices_um, dtype=np.float64))
         self._tris.append(np.asarray(faces, dtype=np.uint32) + np.uint32(base))
@@ -349,10 +358,84 @@ class Model:
         t = Tables(cfg, sp, classes, pathways, rules, np.ascontiguousarray(verts, np.float64),
                    np.ascontiguousarray(tri, np.uint32), np.ascontiguousarray(wsc, np.uint32),
                    names, [r.name for r in self.rules], lu, c.time_step)
+        t.wall_object = np.concatenate([np.full(len(f), k, np.uint32) for k, f in enumerate(self._tris)]) if self._tris else np.zeros(0, np.uint32)
+        if any(self._counted):
+            _assign_counted_volumes(t, self._counted)
         t.n_species, t.n_classes, t.n_pathways = len(self.species), len(groups), n_path
         t.n_surf_rules = len(self.surface_properties)
         t.n_rules = len(self.rules)
         return t
+
+
+def points_inside_mesh(points, tri_xyz):
+    """Parity ray cast along +x with a fixed irrational skew (closed meshes): boolean per point.  Host-side
+    stand-in for VtkUtils::is_point_inside_counted_volume (vtk_utils.cpp:285-570)."""
+    p = np.asarray(points, np.float64)
+    d = np.array([1.0, 0.0137131, 0.0071393])
+    v0, v1, v2 = tri_xyz[:, 0], tri_xyz[:, 1], tri_xyz[:, 2]
+    e1, e2 = v1 - v0, v2 - v0
+    h = np.cross(d, e2)
+    a = (e1 * h).sum(1)
+    inside = np.zeros(len(p), bool)
+    ok = np.abs(a) > 1e-300
+    f = np.where(ok, 1.0 / np.where(ok, a, 1.0), 0.0)
+    for s0 in range(0, len(p), 4096):
+        q = p[s0:s0 + 4096]
+        sv = q[:, None, :] - v0[None]
+        u = f[None] * (sv * h[None]).sum(2)
+        qq = np.cross(sv, e1[None])
+        v = f[None] * (qq * d[None, None]).sum(2)
+        tt = f[None] * (qq * e2[None]).sum(2)
+        hit = ok[None] & (u >= 0) & (v >= 0) & (u + v <= 1) & (tt > 0)
+        inside[s0:s0 + 4096] = hit.sum(1) % 2 == 1
+    return inside
+
+
+def _assign_counted_volumes(t, counted):
+    """Counted volumes of non-intersecting closed objects: every distinct set of enclosing counted objects is one
+    volume (index 0 = none).  Per wall: the volume in front of it and behind it, probed a small step off the
+    centroid along the normal."""
+    tri = t.vertices[t.tri]
+    cen = tri.mean(1)
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    ln = np.linalg.norm(nrm, axis=1)
+    nrm = nrm / np.where(ln > 0, ln, 1.0)[:, None]
+    step = 1e-3 * np.sqrt(np.maximum(ln, 1e-30))[:, None]
+
+    def sets_of(points):
+        member = np.zeros((len(points), len(counted)), bool)
+        for k, c in enumerate(counted):
+            if c:
+                member[:, k] = points_inside_mesh(points, tri[t.wall_object == k])
+        return [frozenset(np.flatnonzero(row).tolist()) for row in member]
+
+    fs, bs = sets_of(cen + nrm * step), sets_of(cen - nrm * step)
+    sets = [frozenset()]
+    for s_ in fs + bs:
+        if s_ not in sets:
+            sets.append(s_)
+    if len(sets) > 256:
+        raise ValueError("more than 256 counted volumes")
+    index = {s_: i for i, s_ in enumerate(sets)}
+    t.counted_volume_sets = sets
+    t.n_counted_volumes = len(sets)
+    t.wall_cv_front = np.array([index[s_] for s_ in fs], np.uint8)
+    t.wall_cv_back = np.array([index[s_] for s_ in bs], np.uint8)
+
+
+def counted_volume_of(t, positions):
+    """Counted volume index of each position (Partition::add_volume_molecule computes it by a ray cast,
+    collision_utils.inl:1515-1566)."""
+    if t.n_counted_volumes <= 1:
+        return np.zeros(len(positions), np.uint32)
+    tri = t.vertices[t.tri]
+    n_obj = int(t.wall_object.max()) + 1
+    member = np.zeros((len(positions), n_obj), bool)
+    used = set().union(*t.counted_volume_sets)
+    for k in used:
+        member[:, k] = points_inside_mesh(positions, tri[t.wall_object == k])
+    index = {s_: i for i, s_ in enumerate(t.counted_volume_sets)}
+    return np.array([index[frozenset(np.flatnonzero(row).tolist())] for row in member], np.uint32)
 
 
 def release_uniform_box(rng, n, edge_um, length_unit, margin=0.0):
@@ -398,7 +481,7 @@ def release_on_walls(rng, tables, walls, n, species, orientation=1, first_id=0, 
 class MolArrays:
     """Owning numpy SoA + the ctypes view (mcx_mol_soa)."""
     FIELDS = ("x", "y", "z", "id", "species", "flags", "diffusion_time", "unimol_rxn_time",
-              "wall", "tile", "orientation", "u", "v")
+              "wall", "tile", "orientation", "u", "v", "counted_volume")
 
     def __init__(self, n, with_times=True):
         self.x = np.zeros(n); self.y = np.zeros(n); self.z = np.zeros(n)
@@ -408,6 +491,7 @@ class MolArrays:
         # Molecule::s of surface molecules (wall == MCX_NONE: volume molecule)
         self.wall = np.full(n, abi.MCX_NONE, np.uint32); self.tile = np.full(n, abi.MCX_NONE, np.uint32)
         self.orientation = np.zeros(n, np.int32); self.u = np.zeros(n); self.v = np.zeros(n)
+        self.counted_volume = np.zeros(n, np.uint32)
         self.n = n
 
     @classmethod
@@ -434,6 +518,7 @@ class MolArrays:
             s.wall, s.tile = abi.ptr(self.wall, C.c_uint32), abi.ptr(self.tile, C.c_uint32)
             s.orientation = abi.ptr(self.orientation, C.c_int32)
             s.u, s.v = abi.ptr(self.u, C.c_double), abi.ptr(self.v, C.c_double)
+            s.counted_volume = abi.ptr(self.counted_volume, C.c_uint32)
         return s
 
     def truncated(self, n):

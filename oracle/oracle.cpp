@@ -99,6 +99,7 @@ struct Wall {  // src4/wall.h Wall subset; constants per Wall::initialize_wall_c
   V3 normal, unit_u, unit_v;
   double distance_to_origin, uv_vert1_u, uv_vert2_u, uv_vert2_v, area;
   uint32_t surf_class, object;
+  uint8_t cv_front = 0, cv_back = 0;  // counted volume on the normal side / on the other side
 };
 
 struct Mol {  // src4/molecule.h:52-260
@@ -114,6 +115,7 @@ struct Mol {  // src4/molecule.h:52-260
   double u = 0, v = 0;
   // DiffuseAction::where_created_this_iteration of a volume product of a surface reaction (:877-885)
   uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE;
+  uint32_t cvi = 0;       // v.counted_volume_index
 };
 
 struct Grid {  // src4/wall.h:101-193, constants per Grid::initialize (wall.cpp:38-74)
@@ -155,6 +157,7 @@ struct Outcome {
   double t_event = 0;
   bool initiator_is_reactant0 = true;
   uint32_t orient_bits = 0;       // bit k: random orientation drawn for products[k] (1 = up)
+  uint32_t cvi = 0;               // counted volume of the molecule at the end of the evaluation / at the event
 };
 
 struct World {
@@ -186,6 +189,8 @@ struct World {
   Isaac64 rng;
   Stats stats;
   std::vector<uint64_t> species_count, rxn_count;
+  uint32_t n_cv = 1;                       // counted volumes (index 0 = outside all)
+  std::vector<uint64_t> rxn_count_cv;      // [rule * n_cv + cv] (inc_rxn_in_volume_occured_count)
   std::vector<mcx_trace_rec> trace;  // by id, when tracing
   bool tracing = false;
   std::string err;
@@ -487,6 +492,7 @@ static void build_lookups(World& w) {
   uint32_t max_rule = 0;
   for (auto& p : w.pathways) max_rule = std::max(max_rule, p.rxn_rule_id + 1);
   w.rxn_count.assign(max_rule, 0);
+  w.rxn_count_cv.assign((size_t)max_rule * w.n_cv, 0);
   w.species_count.assign(ns, 0);
 }
 
@@ -550,6 +556,7 @@ struct ProductSpec {
   uint32_t species; V3 pos;
   uint32_t wall = MCX_NONE, tile = MCX_NONE; int orient = 0; double u = 0, v = 0;
   uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE;
+  uint32_t cvi = 0;
 };
 // Where and how product k of a pathway is created (outcome_products_random :2446-2933, the cases of SURVEY A.2):
 //  * no surface reactant: volume product at the event position;
@@ -557,10 +564,12 @@ struct ProductSpec {
 //  * volume product of a surface reaction: event position bumped 2*16*EPS off the wall to the side its
 //    orientation names (update_vol_mol_after_rxn_with_surf_mol :2291-2320; the wall test of tiny_diffuse_3D is
 //    omitted: another wall within 3.2e-11 length units of the position), remembered for the rebinding guard.
+// cvi: counted volume of the initiator at the event; a volume product of a surface reaction takes the volume on the
+// side of the wall it is released to (outcome_products_random :2757-2760)
 static ProductSpec product_spec(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw, uint32_t k, V3 pos,
-                                uint32_t orient_bits, const Mol* surf) {
+                                uint32_t orient_bits, const Mol* surf, uint32_t cvi) {
   ProductSpec ps;
-  ps.species = pw.products[k]; ps.pos = pos;
+  ps.species = pw.products[k]; ps.pos = pos; ps.cvi = cvi;
   if (!surf) return ps;
   int o = pw.product_orientation[k];
   if (o == 0) o = ((orient_bits >> k) & 1) ? 1 : -1;
@@ -572,7 +581,9 @@ static ProductSpec product_spec(const World& w, const mcx_rxn_class& c, const mc
   if (w.is_surf(ps.species)) {
     ps.wall = surf->wall; ps.tile = surf->tile; ps.u = surf->u; ps.v = surf->v; ps.orient = o;
     ps.pos = uv2xyz(w, f, ps.u, ps.v);
+    ps.cvi = 0;
   } else {
+    ps.cvi = o > 0 ? f.cv_front : f.cv_back;
     double bump = (o > 0) ? 16 * POS_EPS : -16 * POS_EPS;
     V3 d = {(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
     ps.pos = pos + d;
@@ -928,7 +939,7 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
 static void seq_set_defunct(World& w, Mol& m);
 
 struct MolState { V3 pos; uint32_t subpart; double t_now; uint32_t flags; double unimol_time;
-                  uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE; };
+                  uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE; uint32_t cvi = 0; };
 
 static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply, bool& again) {
   World& w = E.w;
@@ -939,7 +950,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
   std::vector<Collision> colls;
   mcx_trace_rec* tr = E.tr;
   const mcx_species sp = w.species[m_species];
-  auto fill_event = [&](Outcome& o) { o.t_now = s.t_now; o.flags = s.flags; o.unimol_time = s.unimol_time; };
+  auto fill_event = [&](Outcome& o) { o.t_now = s.t_now; o.flags = s.flags; o.unimol_time = s.unimol_time; o.cvi = s.cvi; };
 
   // -- unimolecular firing (diffuse_single_molecule :215-223 -> react_unimol_single_molecule :1764-1826)
   if (s.unimol_time != TIME_INVALID && s.unimol_time <= s.t_now) {
@@ -960,7 +971,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
       return out;
     }
     bool destroyed = false;
-    w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart;
+    w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart; w.mols[index].cvi = s.cvi;
     seq_apply_unimol(w, index, rc, pathway, s.unimol_time, obits, destroyed);
     if (destroyed) { out.kind = MCX_OUT_UNIMOL; out.pos = s.pos; out.t_event = s.unimol_time; return out; }
     s.flags |= MCX_MOL_SCHEDULE_UNIMOL;  // survivor re-draws its lifetime (outcome_unimolecular :2999)
@@ -1017,7 +1028,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
             return out;
           }
           bool a_destroyed = false;
-          w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart;
+          w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart; w.mols[index].cvi = s.cvi;
           seq_apply_bimol(w, index, c.partner_index, c.rxn_class, pathway, c.pos, abs_t, 0, a_destroyed);
           if (a_destroyed) { destroyed = true; out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.t_event = abs_t; break; }
         } else {
@@ -1061,7 +1072,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
                     return out;
                   }
                   bool a_destroyed = false;
-                  w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart;
+                  w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart; w.mols[index].cvi = s.cvi;
                   seq_apply_bimol(w, index, occ_index, rc, pathway, c.pos, abs_t, obits, a_destroyed);
                   // kept volume initiators are rejected at table set-up: the molecule is gone (collide_res == 1)
                   destroyed = true; out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.t_event = abs_t;
@@ -1075,6 +1086,8 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
             E.ev(EV_TRANSP | (uint32_t)c.type, c.wall);
             w.stats.transparent++;
             s.pos = c.pos; s.subpart = w.subpart_index(s.pos);
+            // update_counted_volume_id_when_crossing_wall (collision_utils.inl:1637-1694): a FRONT hit goes inside
+            s.cvi = c.type == COLL_WALL_FRONT ? wall.cv_back : wall.cv_front;
             double t_smash = c.time;
             remaining = remaining * (1.0 - t_smash);
             elapsed += t_steps * t_smash;
@@ -1146,7 +1159,7 @@ static MolState load_state(const World& w, const Mol& m) {
   s.pos = m.pos; s.subpart = w.subpart_index(m.pos);
   s.t_now = (m.flags & MCX_MOL_PARTIAL) ? m.diffusion_time : (double)w.iteration;
   s.flags = m.flags; s.unimol_time = m.unimol_rxn_time;
-  s.created_wall = m.created_wall; s.created_tile = m.created_tile;
+  s.created_wall = m.created_wall; s.created_tile = m.created_tile; s.cvi = m.cvi;
   return s;
 }
 
@@ -1179,7 +1192,7 @@ static uint32_t seq_add_molecule(World& w, const ProductSpec& ps, double t) {  /
   n.diffusion_time = t; n.unimol_rxn_time = TIME_INVALID;
   n.subpart = w.subpart_index(ps.pos);
   n.wall = ps.wall; n.tile = ps.tile; n.orient = ps.orient; n.u = ps.u; n.v = ps.v;
-  n.created_wall = ps.created_wall; n.created_tile = ps.created_tile;
+  n.created_wall = ps.created_wall; n.created_tile = ps.created_tile; n.cvi = ps.cvi;
   w.mols.push_back(n);
   if (w.id_to_index.size() <= n.id) w.id_to_index.resize(n.id + 1, MCX_NONE);
   w.id_to_index[n.id] = (uint32_t)w.mols.size() - 1;
@@ -1199,6 +1212,7 @@ static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
+  w.rxn_count_cv[pw.rxn_rule_id * w.n_cv + w.mols[a_index].cvi]++;
   w.stats.bimol_rxns++;
   // reactant ordering vs rule (:2541-2554)
   bool a_is_r0 = w.mols[a_index].species == c.reactants[0];
@@ -1209,7 +1223,7 @@ static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc
   // tiles that are going to be reused are freed first (:2606-2615)
   if (surf_rxn && !keepB) w.tiles[surf_copy.wall][surf_copy.tile] = MCX_NONE;
   for (uint32_t k = 0; k < pw.n_products; k++) {
-    ProductSpec ps = product_spec(w, c, pw, k, pos, orient_bits, surf_rxn ? &surf_copy : nullptr);
+    ProductSpec ps = product_spec(w, c, pw, k, pos, orient_bits, surf_rxn ? &surf_copy : nullptr, w.mols[a_index].cvi);
     uint32_t nid = seq_add_molecule(w, ps, t);
     if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
   }
@@ -1222,6 +1236,7 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
+  w.rxn_count_cv[pw.rxn_rule_id * w.n_cv + w.mols[index].cvi]++;
   w.stats.unimol_rxns++;
   V3 pos = w.mols[index].pos;
   bool keep = pw.keep_reactant_mask & 1;
@@ -1229,7 +1244,7 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
   const Mol surf_copy = w.mols[index];
   if (surf_rxn && !keep) w.tiles[surf_copy.wall][surf_copy.tile] = MCX_NONE;
   for (uint32_t k = 0; k < pw.n_products; k++) {
-    ProductSpec ps = product_spec(w, c, pw, k, pos, orient_bits, surf_rxn ? &surf_copy : nullptr);
+    ProductSpec ps = product_spec(w, c, pw, k, pos, orient_bits, surf_rxn ? &surf_copy : nullptr, w.mols[index].cvi);
     uint32_t nid = seq_add_molecule(w, ps, t);
     if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
   }
@@ -1296,7 +1311,7 @@ static void step_sequential(World& w) {
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) {
       m.pos = o.pos; m.subpart = w.subpart_index(o.pos);
       m.flags = again ? (o.flags | MCX_MOL_PARTIAL) : (o.flags & ~MCX_MOL_PARTIAL);
-      m.diffusion_time = o.t_now; m.unimol_rxn_time = o.unimol_time;
+      m.diffusion_time = o.t_now; m.unimol_rxn_time = o.unimol_time; m.cvi = o.cvi;
       // Partition::update_molecule_reactants_map, partition.h:406-418
       if (m.subpart != m.reg_subpart) { list_erase(w, m); list_insert(w, m); }
       if (again) actions.push_back(id);  // new_diffuse_actions (:305-308)
@@ -1383,6 +1398,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     const mcx_rxn_class& c = w.classes[o.rxn_class];
     const mcx_pathway& pw = w.pathways[c.first_pathway + o.pathway];
     w.rxn_count[pw.rxn_rule_id]++;
+    w.rxn_count_cv[pw.rxn_rule_id * w.n_cv + o.cvi]++;
     bool keepA, keepB = true;
     uint32_t reuse[2]; int n_reuse = 0;
     if (o.kind == MCX_OUT_REACTED) {
@@ -1402,7 +1418,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     else if (o.kind == MCX_OUT_UNIMOL && m.wall != MCX_NONE) surf = &m;
     // product ids: consumed reactants' ids are recycled first (initiator, then partner), then fresh ids
     for (uint32_t k = 0; k < pw.n_products; k++) {
-      NewMol nm; nm.ps = product_spec(w, c, pw, k, o.pos, o.orient_bits, surf); nm.t = o.t_event;
+      NewMol nm; nm.ps = product_spec(w, c, pw, k, o.pos, o.orient_bits, surf, o.cvi); nm.t = o.t_event;
       nm.id = (int)k < n_reuse ? reuse[k] : MCX_NONE;
       born.push_back(nm);
       w.species_count[nm.ps.species]++;
@@ -1462,7 +1478,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     Mol& m = w.mols[i];
     m.pos = o.pos; m.flags = o.flags; m.diffusion_time = o.t_now; m.unimol_rxn_time = o.unimol_time;
     m.subpart = w.subpart_index(m.pos);
-    m.created_wall = m.created_tile = MCX_NONE;
+    m.created_wall = m.created_tile = MCX_NONE; m.cvi = o.cvi;
   }
   // compaction + products (the product's per-iteration sort does both)
   std::vector<Mol> keep; keep.reserve(w.mols.size() + born.size());
@@ -1473,7 +1489,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     n.flags = MCX_MOL_SCHEDULE_UNIMOL | MCX_MOL_PARTIAL;
     n.diffusion_time = nm.t; n.unimol_rxn_time = TIME_INVALID; n.subpart = w.subpart_index(nm.ps.pos);
     n.wall = nm.ps.wall; n.tile = nm.ps.tile; n.orient = nm.ps.orient; n.u = nm.ps.u; n.v = nm.ps.v;
-    n.created_wall = nm.ps.created_wall; n.created_tile = nm.ps.created_tile;
+    n.created_wall = nm.ps.created_wall; n.created_tile = nm.ps.created_tile; n.cvi = nm.ps.cvi;
     keep.push_back(n);
   }
   w.mols.swap(keep);
@@ -1541,6 +1557,22 @@ int orc_set_reactions(void* h, const mcx_rxn_class* c, uint32_t nc, const mcx_pa
 int orc_set_surface_classes(void* h, const mcx_surf_class_rxn* r, uint32_t n) {
   World& w = *(World*)h; w.surf_rules.assign(r, r + n); return 0;
 }
+int orc_set_counted_volumes(void* h, uint32_t n_cv, const uint8_t* front, const uint8_t* back) {
+  World& w = *(World*)h;
+  w.n_cv = n_cv ? n_cv : 1;
+  for (size_t i = 0; i < w.walls.size(); i++) { w.walls[i].cv_front = front[i]; w.walls[i].cv_back = back[i]; }
+  build_lookups(w);
+  return 0;
+}
+int orc_counts_by_volume(void* h, uint64_t* mol_counts, uint64_t* rxn_counts) {
+  World& w = *(World*)h;
+  if (mol_counts) {
+    std::fill(mol_counts, mol_counts + w.species.size() * w.n_cv, 0);
+    for (auto& m : w.mols) if (!(m.flags & MCX_MOL_DEFUNCT)) mol_counts[m.species * w.n_cv + m.cvi]++;
+  }
+  if (rxn_counts) std::copy(w.rxn_count_cv.begin(), w.rxn_count_cv.end(), rxn_counts);
+  return 0;
+}
 int orc_upload_molecules(void* h, const mcx_mol_soa* s) {
   World& w = *(World*)h;
   w.mols.clear(); w.lists.clear(); w.sched_ids.clear(); w.id_to_index.clear();
@@ -1556,6 +1588,8 @@ int orc_upload_molecules(void* h, const mcx_mol_soa* s) {
     m.flags = s->flags ? s->flags[i] : 0;
     m.diffusion_time = s->diffusion_time ? s->diffusion_time[i] : (double)w.iteration;
     m.unimol_rxn_time = s->unimol_rxn_time ? s->unimol_rxn_time[i] : TIME_INVALID;
+    m.cvi = s->counted_volume ? s->counted_volume[i] : 0;
+    if (m.cvi >= w.n_cv) { w.err = "counted volume index out of range"; return MCX_ERR_INVALID_ARG; }
     if (s->wall && s->wall[i] != MCX_NONE) {  // Partition::add_surface_molecule + Grid::set_molecule_tile
       m.wall = s->wall[i]; m.tile = s->tile[i]; m.orient = s->orientation[i]; m.u = s->u[i]; m.v = s->v[i];
       if (m.wall >= w.walls.size() || m.tile >= w.grids[m.wall].n_tiles) { w.err = "bad wall / tile of a surface molecule"; return MCX_ERR_INVALID_ARG; }
@@ -1586,6 +1620,7 @@ int orc_download_molecules(void* h, mcx_mol_soa* o, uint64_t cap) {
     if (o->flags) o->flags[n] = m.flags;
     if (o->diffusion_time) o->diffusion_time[n] = (m.flags & MCX_MOL_PARTIAL) ? m.diffusion_time : (double)w.iteration;
     if (o->unimol_rxn_time) o->unimol_rxn_time[n] = m.unimol_rxn_time;
+    if (o->counted_volume) o->counted_volume[n] = m.cvi;
     if (o->wall) {
       o->wall[n] = m.wall; o->tile[n] = m.tile; o->orientation[n] = m.orient; o->u[n] = m.u; o->v[n] = m.v;
     }

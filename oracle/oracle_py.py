@@ -90,6 +90,8 @@ class Oracle:
         self.L.orc_set_surface_classes(self.h, t.surf_rules, C.c_uint32(t.n_surf_rules))
         self.L.orc_set_geometry(self.h, self._v(t.vertices), C.c_uint64(len(t.vertices)), self._v(t.tri),
                                 C.c_uint64(len(t.tri)), self._v(t.wall_surf_class), None)
+        if getattr(t, "n_counted_volumes", 0) > 1:
+            self.L.orc_set_counted_volumes(self.h, C.c_uint32(t.n_counted_volumes), self._v(t.wall_cv_front), self._v(t.wall_cv_back))
 
     def close(self):
         if self.h:
@@ -157,6 +159,14 @@ class Oracle:
         self.L.orc_counts(self.h, C.c_void_p(s.ctypes.data), C.c_uint32(self.t.n_species),
                           C.c_void_p(r.ctypes.data), C.c_uint32(self.t.n_rules))
         return s[:self.t.n_species], r[:self.t.n_rules]
+
+    def counts_by_volume(self):
+        """(molecules[species, counted volume], reactions[rule, counted volume])"""
+        ncv = max(1, getattr(self.t, "n_counted_volumes", 1))
+        m = np.zeros((max(1, self.t.n_species), ncv), np.uint64)
+        r = np.zeros((max(1, self.t.n_rules), ncv), np.uint64)
+        self.L.orc_counts_by_volume(self.h, C.c_void_p(m.ctypes.data), C.c_void_p(r.ctypes.data))
+        return m, r
 
     def subpart_walls(self, subpart):
         n = int(self.L.orc_subpart_wall_count(self.h, C.c_uint32(subpart)))

@@ -2,7 +2,8 @@
 import numpy as np
 
 from mcell_b200 import abi
-from mcell_b200.model import Model, Config, MolArrays, create_box, create_icosphere, release_uniform_box, release_on_walls
+from mcell_b200.model import (Model, Config, MolArrays, create_box, create_icosphere, release_uniform_box, release_on_walls,
+                              counted_volume_of)
 
 
 def free_diffusion_box(n=20000, edge_um=1.0, seed=1, D=1e-6, rng_mode=abi.MCX_RNG_PHILOX, cap_factor=2):
@@ -127,6 +128,30 @@ def ligand_receptor_sphere(n_lig=6000, n_rec=1500, n_pump=600, radius_um=0.25, s
     surf = release_on_walls(rng, t, sphere_walls, n_rec + n_pump, R, orientation=1, first_id=n_lig)
     surf.species[n_rec:] = P
     return t, MolArrays.concat([vol, surf])
+
+
+def counted_spheres(n=12000, seed=1, box_um=0.8, rng_mode=abi.MCX_RNG_PHILOX, p_target=0.4):
+    """Counted volumes: two nested transparent icospheres, both counted, inside a counted
+    reflective box; A + B -> C everywhere.  Volumes: {box}, {box, outer}, {box, outer, inner} (+ the empty set)."""
+    m = Model(Config(seed=seed))
+    m.add_species("A", 1e-6)
+    m.add_species("B", 1e-6)
+    m.add_species("C", 0.5e-6)
+    pb = _pb_factor(m, 0, 1)
+    m.add_reaction_rule(["A", "B"], ["C"], p_target / pb)
+    ov, of = create_icosphere(0.3, 3)
+    iv, if_ = create_icosphere(0.15, 2)
+    m.add_geometry_object(ov, of, surf_class=0, counted=True)
+    m.add_geometry_object(iv + 0.02, if_, surf_class=0, counted=True)
+    bv, bf = create_box(box_um)
+    m.add_geometry_object(bv, bf, counted=True)
+    m.add_surface_property(0, abi.MCX_SURF_TRANSPARENT, species=None)
+    t = m.build(max_molecules=2 * n + 64, rng_mode=rng_mode)
+    rng = np.random.default_rng(seed)
+    pos = release_uniform_box(rng, n, box_um, t.length_unit, margin=1e-3)
+    mols = MolArrays.from_positions(pos, (np.arange(n) % 2).astype(np.uint32))
+    mols.counted_volume[:] = counted_volume_of(t, pos)
+    return t, mols
 
 
 def isaac_slices(seed, n_ids, words_per_mol):

@@ -33,6 +33,7 @@ def _assert_same_population(a, b):
     assert cm.rel_close(a.diffusion_time, b.diffusion_time, POS_TOL).all()
     assert cm.rel_close(a.unimol_rxn_time, b.unimol_rxn_time, POS_TOL).all()
     # surface part (Molecule::s): wall, tile, orientation exact; uv to 1e-12
+    assert (a.counted_volume == b.counted_volume).all()
     assert (a.wall == b.wall).all() and (a.tile == b.tile).all() and (a.orientation == b.orientation).all()
     assert cm.rel_close(a.u, b.u, POS_TOL).all() and cm.rel_close(a.v, b.v, POS_TOL).all()
 
@@ -203,6 +204,31 @@ def test_philox_surface_unbinding_two_products():
     ka, kb = key(a), key(b)
     assert (ka[:, 0] == kb[:, 0]).all() and (ka[:, 4:] == kb[:, 4:]).all()
     assert cm.rel_close(ka[:, 1:4], kb[:, 1:4], POS_TOL).all()
+
+
+def test_philox_counted_volumes_nested_spheres():
+    """Counted volumes: the index switches on transparent crossings of two nested counted spheres, products inherit
+    it, and per-volume molecule / reaction counts (MolOrRxnCountEvent terms restricted to a volume) match."""
+    t, mols = cm.counted_spheres(n=16000, seed=3)
+    n = mols.n
+    o = _oracle(t)
+    o.upload(mols)
+    e = _engine(t)
+    e.upload(mols)
+    crossings = 0
+    for it in range(10):
+        tr_o, st_o = o.trace_step(1, n)
+        tr_g, st_g = e.trace_step(n)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        assert st_g.mol_wall_transparent == st_o.mol_wall_transparent and st_g.bimol_rxns == st_o.bimol_rxns
+        crossings += st_g.mol_wall_transparent
+        mo, ro = o.counts_by_volume()
+        mg, rg = e.counts_by_volume()
+        assert (mo == mg).all() and (ro == rg).all(), it
+    assert crossings > 1000 and ro[0, 1:].min() > 0
+    _assert_same_population(o.download().sorted_by_id(), e.download().sorted_by_id())
 
 
 def test_philox_reversible_binding_unimolecular():

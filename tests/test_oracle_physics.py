@@ -272,3 +272,29 @@ def test_surface_snapshot_and_sequential_agree_statistically():
     for k in range(4):
         se = math.sqrt(seq[:, k].var(ddof=1) / 8 + snap[:, k].var(ddof=1) / 8)
         assert abs(seq[:, k].mean() - snap[:, k].mean()) < 3 * se + 0.02 * seq[:, k].mean() + 1, (k, seq[:, k].mean(), snap[:, k].mean())
+
+
+# ---- counted volumes ---------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1])
+def test_counted_volume_index_follows_the_geometry(mode):
+    """update_counted_volume_id_when_crossing_wall: after many transparent crossings of two nested counted
+    spheres the index every molecule carries equals the one a fresh ray cast gives for its position; products
+    inherit it; per-volume molecule and reaction counts add up to the world counts."""
+    from mcell_b200.model import counted_volume_of
+    t, mols = cm.counted_spheres(n=12000, seed=2)
+    assert t.n_counted_volumes == 4 and sorted(len(s) for s in t.counted_volume_sets) == [0, 1, 2, 3]
+    o = O.Oracle(t)
+    o.upload(mols)
+    tr = 0
+    for _ in range(15):
+        tr += o.step(1, mode).mol_wall_transparent
+    assert tr > 1500
+    m = o.download()
+    want = counted_volume_of(t, np.c_[m.x, m.y, m.z])
+    assert (m.counted_volume == want).all(), int((m.counted_volume != want).sum())
+    mc, rc = o.counts_by_volume()
+    c, r = o.counts()
+    assert (mc.sum(1) == c).all() and (rc.sum(1) == r).all() and r[0] > 300
+    assert (mc[:, 1:] > 0).all() and (rc[0, 1:] > 0).all() and mc[:, 0].sum() == 0
+    for cv in range(t.n_counted_volumes):
+        assert (np.bincount(m.species[m.counted_volume == cv], minlength=3) == mc[:, cv]).all()
