@@ -182,7 +182,8 @@ enum {
  *      include/debug_config.h:153-245) ------------------------------------------------- */
 enum {
   MCX_OUT_NONE = 0, MCX_OUT_MOVED = 1, MCX_OUT_REACTED = 2, MCX_OUT_ABSORBED = 3,
-  MCX_OUT_UNIMOL = 4, MCX_OUT_CONSUMED = 5, MCX_OUT_STATIC = 6
+  MCX_OUT_UNIMOL = 4, MCX_OUT_CONSUMED = 5, MCX_OUT_STATIC = 6,
+  MCX_OUT_SURFMOVE = 7  /* surface molecule took a new tile (move_sm_on_same_triangle / move_sm_to_new_triangle) */
 };
 typedef struct mcx_trace_rec {
   uint32_t id;

@@ -19,7 +19,7 @@ MCX_RXN_UNIMOL, MCX_RXN_BIMOL_VOLVOL, MCX_RXN_BIMOL_VOLSURF = 1, 2, 3
 MCX_SURF_REFLECTIVE, MCX_SURF_TRANSPARENT, MCX_SURF_ABSORPTIVE = 0, 1, 2
 MCX_MOL_DEFUNCT, MCX_MOL_SCHEDULE_UNIMOL, MCX_MOL_PARTIAL = 1, 2, 4
 MCX_OUT_NONE, MCX_OUT_MOVED, MCX_OUT_REACTED, MCX_OUT_ABSORBED = 0, 1, 2, 3
-MCX_OUT_UNIMOL, MCX_OUT_CONSUMED, MCX_OUT_STATIC = 4, 5, 6
+MCX_OUT_UNIMOL, MCX_OUT_CONSUMED, MCX_OUT_STATIC, MCX_OUT_SURFMOVE = 4, 5, 6, 7
 
 c_u32, c_u64, c_i32, c_f64 = C.c_uint32, C.c_uint64, C.c_int32, C.c_double
 P = C.POINTER

@@ -44,7 +44,7 @@ struct mcx_handle {
        *d_surf = nullptr, *d_walls = nullptr, *d_tri = nullptr, *d_verts = nullptr, *d_wclass = nullptr,
        *d_spw_start = nullptr, *d_spw_list = nullptr, *d_sp_flags = nullptr, *d_grids = nullptr, *d_volsurf = nullptr,
        *d_tile_slot = nullptr, *d_exd_skip = nullptr, *d_wall_cv = nullptr, *d_rxn_count_cv = nullptr,
-       *d_mol_count_cv = nullptr;
+       *d_mol_count_cv = nullptr, *d_edges = nullptr, *d_tile_claim = nullptr;
   uint32_t n_cv = 1; uint32_t* st_cv = nullptr;
   uint64_t n_walls_host = 0;
   bool has_surf = false, surf_allocated = false;
@@ -228,7 +228,6 @@ void mcx_destroy(mcx_handle* h) {
 
 int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices, const uint32_t* tri, uint64_t n_walls,
                      const uint32_t* wall_surf_class, const uint32_t* wall_object) {
-  (void)wall_object;
   if (!h) return MCX_ERR_INVALID_ARG;
   if ((n_walls && (!vertices || !tri)) || n_walls > 0xFFFFFFF0ull) { h->err = "bad geometry arrays"; return MCX_ERR_INVALID_ARG; }
   for (uint64_t i = 0; i < 3 * n_walls; i++)
@@ -258,6 +257,14 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
     rc |= dev_replace(h, &h->d_tile_slot, vacant.data(), vacant.size());
   }
   h->p.grids = (const DevGrid*)h->d_grids; h->p.tile_slot = (uint32_t*)h->d_tile_slot; h->p.n_tiles = (unsigned int)n_tiles;
+  {
+    std::vector<DevEdge> edges;
+    mcxg::edge_constants(vertices, tri, walls, wall_object, edges);
+    rc |= dev_replace(h, &h->d_edges, edges.data(), edges.size());
+    std::vector<unsigned long long> zero(std::max<uint64_t>(n_tiles, 1), 0ull);
+    rc |= dev_replace(h, &h->d_tile_claim, zero.data(), zero.size());
+    h->p.edges = (const DevEdge*)h->d_edges; h->p.tile_claim = (unsigned long long*)h->d_tile_claim;
+  }
   // per-subpartition wall flags for the fast diffuse pass: bit0 = holds walls, bit1 = 3x3x3 neighbourhood does
   {
     const int n = h->p.n_sp;

@@ -51,6 +51,11 @@ __device__ __forceinline__ bool distinguishable_d(double a, double b, double eps
 
 #include "mcx_philox.h"
 
+// conflict-round epochs of an iteration: round r has epoch iteration * (max_rounds + 1) + r + 1
+__device__ __forceinline__ unsigned int round_epoch0(const DevParams& p) {
+  return (unsigned int)(p.iteration * (unsigned long long)(p.max_rounds + 1) + 1);
+}
+
 // ---- per-molecule word stream: Philox (production) or tape slice (replay) ----------------------
 struct Stream {
   const uint32_t* tape; unsigned long long tape_left;
@@ -117,7 +122,11 @@ struct Outcome {
   int rxn_class, pathway;
   uint32_t partner_slot, partner_id;
   uint32_t orient_bits;   // bit k: random orientation drawn for products[k] (1 = up)
+  uint32_t s_wall, s_tile; double s_u, s_v;  // surface molecule that diffused: where it is now (Molecule::s)
+  bool surf_moved;        // the surface fields above differ from the snapshot's
 };
+// surface part of a molecule's state handed to the evaluation (MCX_NONE wall: volume molecule)
+struct SurfState { uint32_t wall, tile; double u, v; };
 
 struct Tracer {
   mcx_trace_rec* tr;
@@ -128,7 +137,8 @@ struct Tracer {
   }
 };
 enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
-       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u, EV_BLOCKED = 0xB10C0000u, EV_DISK = 0xD1500000u };
+       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u, EV_BLOCKED = 0xB10C0000u, EV_DISK = 0xD1500000u,
+       EV_SURFMOVE = 0x3E000000u };
 
 struct LocalStats {
   unsigned int ray_polygon_tests, ray_polygon_colls, reflections, transparent, volvol_collisions, redos;
@@ -780,6 +790,131 @@ __device__ __forceinline__ uint32_t draw_orientation_bits(const DevPathway& pw, 
   return bits;
 }
 
+// ---- surface diffusion -------------------------------------------------------------------------------------------
+// distinguishable_vec2, src4/defines.h:733-764
+__device__ __forceinline__ bool distinguishable_vec2_d(double au, double av, double bu, double bv, double eps) {
+  double c = fabs(au), cc, d;
+  d = fabs(av); if (d > c) c = d;
+  d = fabs(bu); if (d > c) c = d;
+  d = fabs(bv); if (d > c) c = d;
+  cc = fabs(au - bu);
+  d = fabs(av - bv); if (d > cc) cc = d;
+  if (c < eps) c = eps;
+  return c * eps < cc;
+}
+// GridUtils::uv2grid_tile_index, src4/grid_utils.inl:119-190 (MCX_NONE where the reference raises an internal error)
+__device__ uint32_t uv2grid(const DevParams& p, uint32_t wi, double u, double v) {
+  const DevGrid& g = p.grids[wi];
+  const DevWall& f = p.walls[wi];
+  const uint32_t n_tiles = (uint32_t)(g.n_axis * g.n_axis);
+  if (n_tiles == 1) return 0;
+  if (!distinguishable_vec2_d(u, v, 0, 0, MCX_EPS)) return n_tiles - 2 * (uint32_t)g.n_axis + 1;
+  if (!distinguishable_vec2_d(u, v, f.uv1u, 0, MCX_EPS)) return 0;
+  if (!distinguishable_vec2_d(u, v, f.uv2u, f.uv2v, MCX_EPS)) return n_tiles - 1;
+  const double striploc = v * g.strip_width_rcp;
+  int strip = (int)striploc;
+  const double striprem = striploc - strip;
+  strip = g.n_axis - strip - 1;
+  const double u0 = v * g.vert2_slope;
+  const double u1_u0 = f.uv1u - v * g.fullslope;
+  const double stripeloc = ((u - u0) / u1_u0) * (strip + (1 - striprem));
+  const int stripe = (int)stripeloc;
+  const double striperem = stripeloc - stripe;
+  const int flip = (striperem < 1 - striprem) ? 0 : 1;
+  const int idx = strip * strip + 2 * stripe + flip;
+  if (idx < 0 || (uint32_t)idx >= n_tiles) return MCX_NONE;
+  return (uint32_t)idx;
+}
+// GeometryUtils::find_edge_point, src4/geometry_utils.inl:222-291.  0,1,2: side hit; 3: stays within the wall; 4: cannot tell
+__device__ int find_edge_point(const DevWall& here, double lu, double lv, double du, double dv, double& eu, double& ev) {
+  const double lxd = lu * dv - lv * du;
+  const double lxc1 = -lv * here.uv1u;
+  const double dxc1 = -dv * here.uv1u;
+  double f, s, t;
+  if (dxc1 < -MCX_EPS || dxc1 > MCX_EPS) {
+    f = 1 / dxc1;
+    s = -lxd * f;
+    if (0 < s && s < 1 && f > 0) {
+      t = -lxc1 * f;
+      if (MCX_EPS < t && t < 1) { eu = lu + t * du; ev = lv + t * dv; return 0; }
+      else if (t > 1 + MCX_EPS) return 3;
+    }
+  }
+  const double lxc2 = lu * here.uv2v - lv * here.uv2u;
+  const double dxc2 = du * here.uv2v - dv * here.uv2u;
+  if (dxc2 < -MCX_EPS || dxc2 > MCX_EPS) {
+    f = 1 / dxc2;
+    s = 1 + lxd * f;
+    if (0 < s && s < 1 && f < 0) {
+      t = -lxc2 * f;
+      if (MCX_EPS < t && t < 1) { eu = lu + t * du; ev = lv + t * dv; return 2; }
+      else if (t > 1 + MCX_EPS) return 3;
+    }
+  }
+  f = dxc2 - dxc1;
+  if (f < -MCX_EPS || f > MCX_EPS) {
+    f = 1 / f;
+    s = -(lxd + dxc1) * f;
+    if (0 < s && s < 1 && f > 0) {
+      t = (here.uv1u * here.uv2v + lxc1 - lxc2) * f;
+      if (MCX_EPS < t && t < 1) { eu = lu + t * du; ev = lv + t * dv; return 1; }
+      else if (t > 1 + MCX_EPS) return 3;
+    }
+  }
+  return 4;
+}
+// GeometryUtils::traverse_surface, src4/geometry_utils.inl:305-342
+__device__ __forceinline__ uint32_t traverse_surface(const DevParams& p, uint32_t wi, double lu, double lv, int which,
+                                                     double& nu, double& nv) {
+  const DevEdge e = p.edges[3 * wi + which];
+  if (e.nb_wall == MCX_NONE) return MCX_NONE;
+  if (e.forward) {
+    const double ru = e.cos_t * lu + e.sin_t * lv, rv = -e.sin_t * lu + e.cos_t * lv;
+    nu = ru + e.tu; nv = rv + e.tv;
+  } else {
+    const double ru = lu - e.tu, rv = lv - e.tv;
+    nu = e.cos_t * ru - e.sin_t * rv;
+    nv = e.sin_t * ru + e.cos_t * rv;
+  }
+  return e.nb_wall;
+}
+// ray_trace_surf, src4/diffuse_react_event.cpp:1578-1725 (no region borders).  Returns the wall the move ends on
+// (MCX_NONE: ambiguous side hit) and the end point in that wall's frame.
+__device__ uint32_t ray_trace_surf(const DevParams& p, uint32_t wall_index, double pu, double pv, double du, double dv,
+                                   double& out_u, double& out_v) {
+  uint32_t this_index = wall_index;
+  double this_u = pu, this_v = pv, disp_u = du, disp_v = dv;
+  for (int guard = 0; guard < 10000; guard++) {
+    const DevWall& tw = p.walls[this_index];
+    double bu = 0, bv = 0;
+    const int edge = find_edge_point(tw, this_u, this_v, disp_u, disp_v, bu, bv);
+    if (edge == 4) return MCX_NONE;
+    if (edge == 3) { out_u = this_u + disp_u; out_v = this_v + disp_v; return this_index; }
+    const double old_u = this_u, old_v = this_v;
+    double nu, nv;
+    const uint32_t target = traverse_surface(p, this_index, old_u, old_v, edge, nu, nv);
+    if (target != MCX_NONE) {
+      this_u = nu; this_v = nv;
+      double tu2, tv2;
+      traverse_surface(p, this_index, old_u + disp_u, old_v + disp_v, edge, tu2, tv2);
+      disp_u = tu2 - this_u; disp_v = tv2 - this_v;
+      this_index = target;
+      continue;
+    }
+    double ndu = disp_u - (bu - old_u), ndv = disp_v - (bv - old_v);  // free side: reflect
+    if (edge == 0) ndv *= -1.0;
+    else {
+      double ru = edge == 1 ? -tw.uv2v : tw.uv2v, rv = edge == 1 ? tw.uv2u - tw.uv1u : -tw.uv2u;
+      double f = 1.0 / sqrt(ru * ru + rv * rv);
+      ru *= f; rv *= f;
+      f = 2.0 * (ndu * ru + ndv * rv);
+      ndu -= f * ru; ndv -= f * rv;
+    }
+    this_u = bu; this_v = bv; disp_u = ndu; disp_v = ndv;
+  }
+  return MCX_NONE;
+}
+
 #include "mcx_exact_disk.cuh"
 
 // ===================================================================================================
@@ -796,7 +931,7 @@ __device__ __forceinline__ uint32_t draw_orientation_bits(const DevPathway& pw, 
 #define MCX_INTERNAL_NEEDS_DISK 1000
 template <bool RETRY, bool WITH_DISK>
 __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t_sched, double t_unimol_in,
-                                   uint32_t created_wall, uint32_t created_tile,
+                                   uint32_t created_wall, uint32_t created_tile, SurfState ss, unsigned int epoch,
                                    Stream& rs, bool forced, Outcome& out, LocalStats& ls, Tracer& tc, int& err) {
   const uint32_t species = m.sf & SF_SPECIES_MASK;
   const DevSpecies sp = p.species[species];
@@ -810,6 +945,8 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
   const bool can_vol_react = sp.can_vol_react != 0 && !forced;
   out.rxn_class = -1; out.pathway = -1; out.partner_slot = MCX_NONE; out.partner_id = MCX_NONE; out.t_event = 0;
   out.kind = MCX_OUT_NONE; out.orient_bits = 0;
+  out.surf_moved = false; out.s_wall = ss.wall; out.s_tile = ss.tile; out.s_u = ss.u; out.s_v = ss.v;
+  bool surf_tile_changed = false;
   bool decided = false;  // a claiming event or an error ended the evaluation; `out` is complete
 
   bool again = true;
@@ -854,7 +991,68 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
       double max_time = t_end - t_now;
       if (unimol_time != MCX_TIME_INVALID && unimol_time < t_now + max_time) max_time = unimol_time - t_now;
 
-      if (can_diffuse) {
+      if (can_diffuse && (flags & DF_SURF)) {
+        // ---- diffuse_surf_molecule (:1071-1246)
+        double t_steps = sp.time_step > max_time ? max_time : sp.time_step;
+        double steps;
+        if (sp.time_step > max_time) {
+          steps = max_time / sp.time_step;
+          if (steps < MCX_EPS) { t_steps = MCX_EPS * sp.time_step; steps = MCX_EPS; }
+        } else steps = 1.0;
+        const double space_factor = steps == 1.0 ? sp.space_step : sp.space_step * sqrt(steps);
+        const uint32_t original_wall = ss.wall;
+        const unsigned int epoch_first = round_epoch0(p);
+        bool placed = false;
+        for (int find_new_position = 11; find_new_position > 0 && !placed; find_new_position--) {  // SURFACE_DIFFUSION_RETRIES + 1
+          // pick_surf_displacement (diffusion_utils.inl:60-96)
+          double au, av, f;
+          do {
+            const uint32_t n = rs.next();
+            au = 2 * 1.52587890625e-5 * (n & 0xFFFFu) - 1;
+            av = 2 * 1.52587890625e-5 * (n >> 16) - 1;
+            f = au * au + av * av;
+          } while ((f < MCX_EPS) || (f > 1));
+          const double normal_factor = sqrt(-log(f) / f);
+          const double du = au * (normal_factor * space_factor), dv = av * (normal_factor * space_factor);
+          double nu, nv;
+          const uint32_t new_wall = ray_trace_surf(p, ss.wall, ss.u, ss.v, du, dv, nu, nv);
+          bool ok = new_wall != MCX_NONE;
+          uint32_t new_tile = MCX_NONE;
+          if (ok) { new_tile = uv2grid(p, new_wall, nu, nv); ok = new_tile != MCX_NONE; }
+          bool changes_tile = false;
+          if (ok && (new_wall != ss.wall || new_tile != ss.tile)) {
+            // move_sm_on_same_triangle / move_sm_to_new_triangle (diffusion_utils.inl:453-548): the tile must be vacant
+            // in the snapshot and not claimed by a mover of an earlier conflict round; none in the forced pass
+            const uint32_t gt = p.grids[new_wall].tile_start + new_tile;
+            const unsigned int ce = (unsigned int)(RETRY ? (__ldcg(p.tile_claim + gt) >> 32) : 0ull);
+            ok = !forced && p.tile_slot[gt] == MCX_NONE && !(RETRY && ce >= epoch_first && ce < epoch);
+            changes_tile = true;
+          }
+          if (ok) {
+            if (changes_tile) surf_tile_changed = true;
+            if (new_wall != ss.wall) {  // reschedule the unimolecular reaction of a molecule that changed wall (:1170-1186)
+              double time_until_unimol = unimol_time - t_steps - t_now;
+              time_until_unimol = (time_until_unimol < 0) ? 0 : time_until_unimol;
+              if (unimol_time == MCX_TIME_INVALID || (time_until_unimol > MCX_EPS || time_until_unimol > MCX_EPS * (t_now + t_steps))) {
+                unimol_time = MCX_TIME_INVALID;
+                flags |= DF_SCHED_UNIMOL;
+              }
+            }
+            ss.wall = new_wall; ss.tile = new_tile; ss.u = nu; ss.v = nv;
+            const DevWall& fw = p.walls[new_wall];
+            pos = D3{nu * fw.ux + nv * fw.vx + fw.v0x, nu * fw.uy + nv * fw.vy + fw.v0y, nu * fw.uz + nv * fw.vz + fw.v0z};
+            subpart = subpart_index(p, pos);
+            out.surf_moved = true;
+            placed = true;
+          }
+        }
+        if (ss.wall != original_wall && unimol_time >= t_end) {  // MCell3 compatibility rule (:1226-1236)
+          unimol_time = MCX_TIME_INVALID;
+          flags |= DF_SCHED_UNIMOL;
+        }
+        max_time = t_steps;
+        out.s_wall = ss.wall; out.s_tile = ss.tile; out.s_u = ss.u; out.s_v = ss.v;
+      } else if (can_diffuse) {
         // ---- compute_vol_displacement (diffusion_utils.inl:366-432)
         double steps = 1.0, t_steps = steps * sp.time_step, r_rate_factor, scale;
         if (t_steps > max_time) { t_steps = max_time; steps = max_time / sp.time_step; }
@@ -1056,6 +1254,14 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
             t_now = unimol_time;
             if (unimol_time < t_end) again = true;
           } else t_now = MCX_TIME_FOREVER;
+        }
+        if (surf_tile_changed) {
+          // taking a new tile is a claiming event: the evaluation ends here, what is left of the iteration is taken
+          // lazily next iteration (like a kept initiator)
+          out.kind = MCX_OUT_SURFMOVE; out.pos = pos; out.t_now = t_now; out.unimol_time = unimol_time;
+          out.flags = again ? (flags | DF_PARTIAL) : (flags & ~DF_PARTIAL);
+          tc.ev(EV_SURFMOVE | (ss.tile & 0xFFFFFFu), ss.wall);
+          decided = true; again = false;
         }
       }
     }

@@ -8,6 +8,8 @@
 // per subpartition (the iteration order of the reference's uint_set<wall_index_t>).
 #include <cmath>
 #include <cstdint>
+#include <algorithm>
+#include <map>
 #include <vector>
 #include "mcx_geom.h"
 
@@ -261,6 +263,64 @@ uint32_t tri_xyz2grid(const double* v9, const double* xyz3) {
   if (idx < 0) idx = 0;
   if ((uint32_t)idx >= n_tiles) idx = (int)n_tiles - 1;
   return (uint32_t)idx;
+}
+
+
+// ---- triangle sides ---------------------------------------------------------------------------------------------
+void edge_constants(const double* verts, const uint32_t* tri, const std::vector<DevWall>& walls, const uint32_t* wall_object,
+                    std::vector<DevEdge>& out) {
+  const size_t nw = walls.size();
+  out.assign(3 * nw, DevEdge{0, 0, 0, 0, 0xFFFFFFFFu, 0, {0, 0}});
+  auto vert = [&](size_t w, int k) { const double* q = verts + 3 * tri[3 * w + k]; return P3{q[0], q[1], q[2]}; };
+  auto same = [](P3 a, P3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; };
+  struct Key { double a[6]; bool operator<(const Key& o) const { return std::lexicographical_compare(a, a + 6, o.a, o.a + 6); } };
+  for (size_t first = 0; first < nw;) {
+    size_t last = first;
+    while (last < nw && (!wall_object || wall_object[last] == wall_object[first])) last++;
+    std::map<Key, std::pair<size_t, int>> open_edges;  // undirected edge -> (face, side) of the first face that has it
+    for (size_t fi = first; fi < last; fi++) {
+      for (int j = 0; j < 3; j++) {
+        const int k = j + 1 < 3 ? j + 1 : 0;
+        const P3 pj = vert(fi, j), pk = vert(fi, k);
+        const double a[3] = {pj.x, pj.y, pj.z}, b[3] = {pk.x, pk.y, pk.z};
+        const bool swap = std::lexicographical_compare(b, b + 3, a, a + 3);
+        Key key;
+        for (int q = 0; q < 3; q++) { key.a[q] = swap ? b[q] : a[q]; key.a[3 + q] = swap ? a[q] : b[q]; }
+        auto it = open_edges.find(key);
+        if (it == open_edges.end()) { open_edges[key] = {fi, j}; continue; }
+        const size_t f0 = it->second.first; const int e0 = it->second.second;
+        // compatible_edges: opposite directions, different third vertices, two different faces
+        const P3 a0 = vert(f0, e0), a1 = vert(f0, e0 == 2 ? 0 : e0 + 1), a2 = vert(f0, e0 == 0 ? 2 : e0 - 1);
+        const P3 b2 = vert(fi, j == 0 ? 2 : j - 1);
+        if (!(same(a0, pk) && same(a1, pj) && !same(a2, b2)) || f0 == fi) continue;
+        open_edges.erase(it);
+        const DevWall& wf = walls[f0]; const DevWall& wb = walls[fi];
+        const int i = e0, jj = i + 1 == 3 ? 0 : i + 1;
+        const P3 wf0 = vert(f0, 0), wfi = vert(f0, i), wfj = vert(f0, jj), wb0 = vert(fi, 0);
+        const P3 fu = {wf.ux, wf.uy, wf.uz}, fv = {wf.vx, wf.vy, wf.vz}, bu = {wb.ux, wb.uy, wb.uz}, bv = {wb.vx, wb.vy, wb.vz};
+        const P3 di0 = sub(wfi, wf0);
+        const double Ofu = dotp(di0, fu), Ofv = dotp(di0, fv);
+        const P3 dj0 = sub(wfj, wf0);
+        const double tfu = dotp(dj0, fu) - Ofu, tfv = dotp(dj0, fv) - Ofv;
+        const double d_f = 1 / std::sqrt(tfu * tfu + tfv * tfv);
+        const double efu = tfu * d_f, efv = tfv * d_f, ffu = -efv, ffv = efu;
+        const P3 dib = sub(wfi, wb0);
+        const double Obu = dotp(dib, bu), Obv = dotp(dib, bv);
+        const P3 djb = sub(wfj, wb0);
+        const double tbu = dotp(djb, bu) - Obu, tbv = dotp(djb, bv) - Obv;
+        const double d_b = 1 / std::sqrt(tbu * tbu + tbv * tbv);
+        const double ebu = tbu * d_b, ebv = tbv * d_b, fbu = -ebv, fbv = ebu;
+        const double m00 = efu * ebu + ffu * fbu, m01 = efv * ebu + ffv * fbu;
+        const double m10 = efu * ebv + ffu * fbv, m11 = efv * ebv + ffv * fbv;
+        double qu = Obu, qv = Obv;
+        qu -= m00 * Ofu + m01 * Ofv;
+        qv -= m10 * Ofu + m11 * Ofv;
+        out[3 * f0 + e0] = DevEdge{m00, m01, qu, qv, (uint32_t)fi, 1u, {0, 0}};
+        out[3 * fi + j] = DevEdge{m00, m01, qu, qv, (uint32_t)f0, 0u, {0, 0}};
+      }
+    }
+    first = last;
+  }
 }
 
 }  // namespace mcxg

@@ -9,6 +9,10 @@ struct GridSpec { double ox, oy, oz, sp_len, sp_rcp, R; int n_sp; bool use_expan
 void wall_constants(const double* verts, const uint32_t* tri, uint64_t n_walls, std::vector<DevWall>& out);
 // surface grids (Grid::initialize, src4/wall.cpp:38-74); tile_start = exclusive prefix of num_tiles; returns the total
 uint64_t grid_constants(const double* verts, const uint32_t* tri, const std::vector<DevWall>& walls, std::vector<DevGrid>& out);
+// triangle sides shared by two walls of one object (surface_net, src4/geometry.cpp:258-356) and the transform across
+// them (Edge::reinit_edge_constants, src4/wall.cpp:134-235); wall_object may be null (one object)
+void edge_constants(const double* verts, const uint32_t* tri, const std::vector<DevWall>& walls, const uint32_t* wall_object,
+                    std::vector<DevEdge>& out);
 // host helpers behind mcx_grid_num_tiles / mcx_grid2uv / mcx_xyz2grid (one triangle given by its 9 coordinates)
 uint32_t tri_num_tiles(const double* v9);
 void tri_grid2uv(const double* v9, uint32_t tile, double* uv2);

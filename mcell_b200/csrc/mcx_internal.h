@@ -35,6 +35,9 @@ struct DevClass { double max_fixed_p; uint32_t kind, r0, r1, first_pathway, n_pa
 struct DevPathway { double cum_prob; uint32_t n_products, products[MCX_MAX_PRODUCTS], keep_mask, rule_id; int prod_orient[MCX_MAX_PRODUCTS]; uint32_t pad; };
 
 // per-wall surface grid (Grid::initialize, src4/wall.cpp:38-74) + the wall's first entry in the tile table
+// one side of a triangle (src4/wall.h:32-90 Edge): the wall across it and the flattening transform between the uv frames
+struct __align__(16) DevEdge { double cos_t, sin_t, tu, tv; uint32_t nb_wall; uint32_t forward; uint32_t pad[2]; };
+
 struct __align__(16) DevGrid {
   double strip_width_rcp, vert2_slope, fullslope, binding_factor, vert0_u, vert0_v;
   int n_axis;
@@ -110,6 +113,8 @@ struct DevParams {
   uint32_t *swallA, *swallB;    // s.wall_index (or creation wall of a DF_CREATED_ON_SURF volume product)
   uint32_t *stileA, *stileB;    // s.grid_tile_index (or creation tile)
   double2 *suvA, *suvB;         // s.pos
+  const DevEdge* edges;         // 3 per wall
+  unsigned long long* tile_claim;  // per tile: (epoch << 32) | ~id of the best mover claiming it
   // rng
   unsigned long long seed, iteration;
   int rng_mode;

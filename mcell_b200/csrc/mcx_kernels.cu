@@ -115,13 +115,22 @@ __device__ __forceinline__ void raise_error(const DevParams& p, int err, uint32_
 }
 
 // result record of a molecule that stays alive: write to B and bin it for the next snapshot
+// surf: where a surface molecule's cold fields come from — nullptr: unchanged (copy A -> B); an Outcome that moved:
+// its new wall / tile / uv; SURF_FIELDS_IN_B: the proposal already wrote them to B
+#define SURF_FIELDS_IN_B ((const Outcome*)1)
 __device__ __forceinline__ void finalize_alive(const DevParams& p, uint32_t slot, D3 pos, uint32_t id, uint32_t species,
-                                               uint32_t flags, double t_now, double unimol_time) {
+                                               uint32_t flags, double t_now, double unimol_time, const Outcome* surf = nullptr) {
   if (!owned_z(p, pos.z)) { p.rank[slot] = MCX_NONE; return; }  // multi-GPU: the rank owning the new position keeps it
   uint32_t sf = species | (flags & ~(DF_HAS_UNIMOL | DF_DEAD));
   if (unimol_time != MCX_TIME_INVALID) { sf |= DF_HAS_UNIMOL; p.tuniB[slot] = unimol_time; }
   if (sf & DF_PARTIAL) p.tschedB[slot] = t_now;
-  if (sf & DF_SURF) { p.swallB[slot] = p.swallA[slot]; p.stileB[slot] = p.stileA[slot]; p.suvB[slot] = p.suvA[slot]; }
+  if (sf & DF_SURF) {
+    if (surf == nullptr || (surf != SURF_FIELDS_IN_B && !surf->surf_moved)) {
+      p.swallB[slot] = p.swallA[slot]; p.stileB[slot] = p.stileA[slot]; p.suvB[slot] = p.suvA[slot];
+    } else if (surf != SURF_FIELDS_IN_B) {
+      p.swallB[slot] = surf->s_wall; p.stileB[slot] = surf->s_tile; p.suvB[slot] = make_double2(surf->s_u, surf->s_v);
+    }
+  }
   store_rec(p.recB, slot, pos, id, sf);
   uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
   p.rank[slot] = atomicAdd(&p.cs_next[cell], 1u);
@@ -145,6 +154,10 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
   // products are created by the rank owning the event position; reactants are marked DEAD everywhere
   const bool own_event = owned_z(p, pos.z);
   const bool track = p.world == 1;  // incremental species counts (multi-GPU recounts during the scatter)
+  if (kind == MCX_OUT_SURFMOVE) {  // the mover won its new tile: it stays alive there (cold fields already in B)
+    finalize_alive(p, slot, pos, id, species, flags, t_now, unimol_time, SURF_FIELDS_IN_B);
+    return;
+  }
   if (kind == MCX_OUT_ABSORBED) {
     atomicOr(&p.recA[slot].sf, DF_DEAD);
     if (own_event) agg_add(&c->absorptions, 1u);
@@ -249,6 +262,10 @@ __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot
   unsigned long long key = claim_key(epoch, id);
   atomicMax(&p.claim[slot], key);
   if (partner_is_consumed(p, o.kind, o.rxn_class, o.pathway, species)) atomicMax(&p.claim[o.partner_slot], key);
+  if (o.kind == MCX_OUT_SURFMOVE) {
+    p.swallB[slot] = o.s_wall; p.stileB[slot] = o.s_tile; p.suvB[slot] = make_double2(o.s_u, o.s_v);
+    atomicMax(&p.tile_claim[p.grids[o.s_wall].tile_start + o.s_tile], key);
+  }
   if (list >= 0) {
     uint32_t k = agg_reserve(&p.ctr->n_pend[list], 1u);
     p.pend[list][k] = slot;
@@ -319,7 +336,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
     const uint32_t species = m.sf & SF_SPECIES_MASK;
     const uint32_t flags = m.sf & ~SF_SPECIES_MASK;
     const DevSpecies sp = p.species[species];
-    bool simple = live && !(m.sf & (DF_PARTIAL | DF_SCHED_UNIMOL)) && (sp.flags & MCX_SP_CAN_DIFFUSE) && sp.time_step == 1.0;
+    bool simple = live && !(m.sf & (DF_PARTIAL | DF_SCHED_UNIMOL | DF_SURF)) && (sp.flags & MCX_SP_CAN_DIFFUSE) && sp.time_step == 1.0;
     // scheduled unimolecular time: a predicated index keeps the load unconditional (no warp split) without
     // touching the cold array for molecules that have none
     const bool has_uni = (m.sf & DF_HAS_UNIMOL) != 0;
@@ -455,8 +472,10 @@ __global__ void __launch_bounds__(TPB, 2) k_diffuse_slow(const __grid_constant__
     const bool own_start = owned_z(p, m.z);
     LocalStats mls = {0, 0, 0, 0, 0, 0};  // statistics of redundantly evaluated halo molecules are not counted
     const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
+    SurfState ss = {MCX_NONE, MCX_NONE, 0.0, 0.0};
+    if (m.sf & DF_SURF) { const double2 uv = p.suvA[i]; ss.wall = p.swallA[i]; ss.tile = p.stileA[i]; ss.u = uv.x; ss.v = uv.y; }
     evaluate_iteration<false, WITH_DISK>(p, m, t_sched, t_uni, guard ? p.swallA[i] : MCX_NONE, guard ? p.stileA[i] : MCX_NONE,
-                                         rs, false, o, mls, tc, err);
+                                         ss, epoch, rs, false, o, mls, tc, err);
     if (!WITH_DISK && err == MCX_INTERNAL_NEEDS_DISK) {  // re-evaluated from scratch by the WITH_DISK launch
       if (tc.tr) tc.tr->rounds--;
       p.pend[1][agg_reserve(&p.ctr->n_pend[1], 1u)] = i;
@@ -470,7 +489,7 @@ __global__ void __launch_bounds__(TPB, 2) k_diffuse_slow(const __grid_constant__
     }
     trace_end(tc, o, rs);
     if (err && (own_start || err != MCX_ERR_ESCAPED)) raise_error(p, err, m.id);
-    if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time);
+    if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time, &o);
     else if (o.kind == MCX_OUT_NONE) p.rank[i] = MCX_NONE;
     else write_proposal(p, i, o, m.id, species, epoch, 0);
   }
@@ -493,6 +512,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(const __grid_constant__ DevPara
     unsigned long long key = claim_key(epoch, e.id);
     bool ok = p.claim[slot] == key;
     if (ok && partner_is_consumed(p, kind, rxn_class, pathway, species)) ok = p.claim[partner] == key;
+    if (ok && kind == MCX_OUT_SURFMOVE) ok = p.tile_claim[p.grids[p.swallB[slot]].tile_start + p.stileB[slot]] == key;
     if (ok) {
       commit_event(p, slot, kind, rxn_class, pathway, partner, p.prop_t[slot], D3{e.x, e.y, e.z}, e.id, species,
                    e.sf & ~SF_SPECIES_MASK, p.tschedB[slot], p.tuniB[slot], orient_bits);
@@ -534,11 +554,13 @@ __global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevPar
     Outcome o; int err = 0;
     LocalStats halo_ls = {0, 0, 0, 0, 0, 0};
     const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
+    SurfState ss = {MCX_NONE, MCX_NONE, 0.0, 0.0};
+    if (m.sf & DF_SURF) { const double2 uv = p.suvA[i]; ss.wall = p.swallA[i]; ss.tile = p.stileA[i]; ss.u = uv.x; ss.v = uv.y; }
     evaluate_iteration<true, true>(p, m, t_sched, t_uni, guard ? p.swallA[i] : MCX_NONE, guard ? p.stileA[i] : MCX_NONE,
-                                   rs, forced != 0, o, own_start ? ls : halo_ls, tc, err);
+                                   ss, epoch, rs, forced != 0, o, own_start ? ls : halo_ls, tc, err);
     trace_end(tc, o, rs);
     if (err) raise_error(p, err, m.id);
-    if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time);
+    if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time, &o);
     else if (o.kind == MCX_OUT_NONE) p.rank[i] = MCX_NONE;
     else if (forced) {  // only self-claims can occur without partners: commit directly
       p.rank[i] = MCX_NONE;

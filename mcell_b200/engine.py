@@ -82,7 +82,7 @@ class Engine:
                                           C.cast(t.pathways, C.c_void_p), t.n_pathways))
         self._ck(self.L.mcx_set_surface_classes(self.h, C.cast(t.surf_rules, C.c_void_p), t.n_surf_rules))
         self._ck(self.L.mcx_set_geometry(self.h, _vp(t.vertices), len(t.vertices), _vp(t.tri), len(t.tri),
-                                         _vp(t.wall_surf_class), None))
+                                         _vp(t.wall_surf_class), _vp(getattr(t, "wall_object", None))))
         if getattr(t, "n_counted_volumes", 0) > 1:
             self._ck(self.L.mcx_set_counted_volumes(self.h, t.n_counted_volumes, _vp(t.wall_cv_front), _vp(t.wall_cv_back)))
 

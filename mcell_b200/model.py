@@ -45,7 +45,7 @@ class Species:
     name: str
     diffusion_constant_3d: float = 0.0
     target_only: bool = False
-    surface: bool = False          # surface molecule (diffusion_constant_2d = 0: receptors, pumps)
+    surface: bool = False          # surface molecule; diffusion_constant_3d then holds diffusion_constant_2d
 
 
 def _parse_oriented(name):
@@ -156,8 +156,6 @@ class Model:
 
     # -- subsystem ------------------------------------------------------------------------
     def add_species(self, name, D, target_only=False, surface=False):
-        if surface and D != 0:
-            raise ValueError("surface diffusion is not built: surface species must have D = 0")
         self.species.append(Species(name, D, target_only, surface))
         return len(self.species) - 1
 

@@ -44,6 +44,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <map>
 #include <vector>
 
 #include "../include/mcx.h"
@@ -100,6 +101,11 @@ struct Wall {  // src4/wall.h Wall subset; constants per Wall::initialize_wall_c
   double distance_to_origin, uv_vert1_u, uv_vert2_u, uv_vert2_v, area;
   uint32_t surf_class, object;
   uint8_t cv_front = 0, cv_back = 0;  // counted volume on the normal side / on the other side
+  // src4/wall.h:32-90 Edge, one per triangle side: the neighbouring wall across it (MCX_NONE: free edge) and the
+  // flattening transform between the two uv frames; is_forward: this wall is Edge::forward_index
+  uint32_t nb_wall[3] = {MCX_NONE, MCX_NONE, MCX_NONE};
+  bool edge_forward[3] = {false, false, false};
+  double edge_cos[3] = {0, 0, 0}, edge_sin[3] = {0, 0, 0}, edge_tu[3] = {0, 0, 0}, edge_tv[3] = {0, 0, 0};
 };
 
 struct Mol {  // src4/molecule.h:52-260
@@ -136,7 +142,8 @@ static inline uint64_t hash_ev(uint64_t h, uint32_t a, uint32_t b) {
   return h;
 }
 enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
-       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u, EV_BLOCKED = 0xB10C0000u, EV_DISK = 0xD1500000u };
+       EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u, EV_BLOCKED = 0xB10C0000u, EV_DISK = 0xD1500000u,
+       EV_SURFMOVE = 0x3E000000u };
 
 struct Stats {
   uint64_t molecule_steps = 0, ray_polygon_tests = 0, ray_polygon_colls = 0, reflections = 0,
@@ -158,6 +165,7 @@ struct Outcome {
   bool initiator_is_reactant0 = true;
   uint32_t orient_bits = 0;       // bit k: random orientation drawn for products[k] (1 = up)
   uint32_t cvi = 0;               // counted volume of the molecule at the end of the evaluation / at the event
+  uint32_t wall = MCX_NONE, tile = MCX_NONE; double u = 0, v = 0;  // surface molecule: where it is after the evaluation
 };
 
 struct World {
@@ -178,6 +186,7 @@ struct World {
   std::vector<Grid> grids;       // per wall
   std::vector<std::vector<uint32_t>> tiles;  // per wall: molecule id per tile (Grid::molecules_per_tile); empty =
                                              // grid not initialized (wall.h:339-346)
+  std::vector<uint32_t> tile_start;          // first global tile of every wall (+ total)
   std::vector<mcx_surf_class_rxn> surf_rules;
   std::vector<Mol> mols;
   std::vector<uint32_t> id_to_index;  // molecule_id_to_index_mapping
@@ -312,6 +321,194 @@ static V3 uv2xyz(const World& w, const Wall& f, double u, double v) {
   V3 v0 = w.verts[f.vi[0]];
   return {u * f.unit_u.x + v * f.unit_v.x + v0.x, u * f.unit_u.y + v * f.unit_v.y + v0.y,
           u * f.unit_u.z + v * f.unit_v.z + v0.z};
+}
+
+// surface_net (src4/geometry.cpp:258-356) + Edge::reinit_edge_constants (src4/wall.cpp:134-235): pair the sides of the
+// triangles of one object that join the same two points in opposite directions; the face that comes first is the
+// edge's forward wall and the transform is set up from its side.  (Manifold meshes: exactly two faces per edge.)
+static void init_edges(World& w, uint32_t first_wall, uint32_t n_faces) {
+  struct Key { double a[6]; bool operator<(const Key& o) const { return std::lexicographical_compare(a, a + 6, o.a, o.a + 6); } };
+  std::map<Key, std::pair<uint32_t, int>> open_edges;  // undirected edge -> (face, side) of the first face seen
+  auto key_of = [](V3 p, V3 q) {
+    Key k;
+    bool swap = std::lexicographical_compare(&q.x, &q.x + 3, &p.x, &p.x + 3);
+    V3 lo = swap ? q : p, hi = swap ? p : q;
+    k.a[0] = lo.x; k.a[1] = lo.y; k.a[2] = lo.z; k.a[3] = hi.x; k.a[4] = hi.y; k.a[5] = hi.z;
+    return k;
+  };
+  auto same = [](V3 p, V3 q) { return p.x == q.x && p.y == q.y && p.z == q.z; };
+  for (uint32_t fi = 0; fi < n_faces; fi++) {
+    Wall& wb = w.walls[first_wall + fi];
+    for (int j = 0; j < 3; j++) {
+      int k = j + 1 < 3 ? j + 1 : 0;
+      V3 pj = w.verts[wb.vi[j]], pk = w.verts[wb.vi[k]];
+      Key key = key_of(pj, pk);
+      auto it = open_edges.find(key);
+      if (it == open_edges.end()) { open_edges[key] = {first_wall + fi, j}; continue; }
+      uint32_t f0 = it->second.first; int e0 = it->second.second;
+      Wall& wf = w.walls[f0];
+      // compatible_edges (geometry.cpp:50-96): traversed in opposite directions, third vertices differ
+      V3 a0 = w.verts[wf.vi[e0]], a1 = w.verts[wf.vi[e0 == 2 ? 0 : e0 + 1]], a2 = w.verts[wf.vi[e0 == 0 ? 2 : e0 - 1]];
+      V3 b2 = w.verts[wb.vi[j == 0 ? 2 : j - 1]];
+      if (!(same(a0, pk) && same(a1, pj) && !same(a2, b2)) || f0 == first_wall + fi) continue;
+      open_edges.erase(it);
+      // Edge::reinit_edge_constants with forward = f0, backward = this face, edge_num_used_for_init = e0
+      int i = e0, jj = i + 1 == 3 ? 0 : i + 1;
+      V3 wf0 = w.verts[wf.vi[0]], wfi = w.verts[wf.vi[i]], wfj = w.verts[wf.vi[jj]], wb0 = w.verts[wb.vi[0]];
+      V3 di0 = wfi - wf0;
+      double Ofu = dot(di0, wf.unit_u), Ofv = dot(di0, wf.unit_v);
+      V3 dj0 = wfj - wf0;
+      double tfu = dot(dj0, wf.unit_u) - Ofu, tfv = dot(dj0, wf.unit_v) - Ofv;
+      double d_f = 1 / sqrt(tfu * tfu + tfv * tfv);
+      double efu = tfu * d_f, efv = tfv * d_f, ffu = -efv, ffv = efu;
+      V3 dib = wfi - wb0;
+      double Obu = dot(dib, wb.unit_u), Obv = dot(dib, wb.unit_v);
+      V3 djb = wfj - wb0;
+      double tbu = dot(djb, wb.unit_u) - Obu, tbv = dot(djb, wb.unit_v) - Obv;
+      double d_b = 1 / sqrt(tbu * tbu + tbv * tbv);
+      double ebu = tbu * d_b, ebv = tbv * d_b, fbu = -ebv, fbv = ebu;
+      double m00 = efu * ebu + ffu * fbu, m01 = efv * ebu + ffv * fbu;
+      double m10 = efu * ebv + ffu * fbv, m11 = efv * ebv + ffv * fbv;
+      double qu = Obu, qv = Obv;
+      qu -= m00 * Ofu + m01 * Ofv;
+      qv -= m10 * Ofu + m11 * Ofv;
+      wf.nb_wall[e0] = first_wall + fi; wf.edge_forward[e0] = true;
+      wb.nb_wall[j] = f0; wb.edge_forward[j] = false;
+      wf.edge_cos[e0] = wb.edge_cos[j] = m00; wf.edge_sin[e0] = wb.edge_sin[j] = m01;
+      wf.edge_tu[e0] = wb.edge_tu[j] = qu; wf.edge_tv[e0] = wb.edge_tv[j] = qv;
+    }
+  }
+}
+// distinguishable_vec2, src4/defines.h:733-764
+static bool distinguishable_vec2(double au, double av, double bu, double bv, double eps) {
+  double c = fabs(au), cc, d;
+  d = fabs(av); if (d > c) c = d;
+  d = fabs(bu); if (d > c) c = d;
+  d = fabs(bv); if (d > c) c = d;
+  cc = fabs(au - bu);
+  d = fabs(av - bv); if (d > cc) cc = d;
+  if (c < eps) c = eps;
+  return c * eps < cc;
+}
+// GridUtils::uv2grid_tile_index, src4/grid_utils.inl:119-190
+static uint32_t uv2grid(const Wall& f, const Grid& g, double u, double v) {
+  if (g.n_tiles == 1) return 0;
+  uint32_t tile_idx_mid = g.n_tiles - 2 * (uint32_t)g.n_axis + 1, tile_idx_last = g.n_tiles - 1;
+  if (!distinguishable_vec2(u, v, 0, 0, POS_EPS)) return tile_idx_mid;
+  if (!distinguishable_vec2(u, v, f.uv_vert1_u, 0, POS_EPS)) return 0;
+  if (!distinguishable_vec2(u, v, f.uv_vert2_u, f.uv_vert2_v, POS_EPS)) return tile_idx_last;
+  double i = u, j = v;
+  double striploc = j * g.strip_width_rcp;
+  int strip = (int)striploc;
+  double striprem = striploc - strip;
+  strip = g.n_axis - strip - 1;
+  double u0 = j * g.vert2_slope;
+  double u1_u0 = f.uv_vert1_u - j * g.fullslope;
+  double stripeloc = ((i - u0) / u1_u0) * (strip + (1 - striprem));
+  int stripe = (int)stripeloc;
+  double striperem = stripeloc - stripe;
+  int flip = (striperem < 1 - striprem) ? 0 : 1;
+  int idx = strip * strip + 2 * stripe + flip;
+  if (idx < 0 || (uint32_t)idx >= g.n_tiles) return MCX_NONE;  // the reference raises an internal error
+  return (uint32_t)idx;
+}
+// GeometryUtils::find_edge_point, src4/geometry_utils.inl:222-291.  0,1,2: edge hit; 3: stays within the wall; 4: cannot tell
+enum { EDGE_WITHIN_WALL = 3, EDGE_CANNOT_TELL = 4 };
+static int find_edge_point(const Wall& here, double lu, double lv, double du, double dv, double& eu, double& ev) {
+  double lxd = lu * dv - lv * du;
+  double lxc1 = -lv * here.uv_vert1_u;
+  double dxc1 = -dv * here.uv_vert1_u;
+  double f, s, t;
+  if (dxc1 < -POS_EPS || dxc1 > POS_EPS) {
+    f = 1 / dxc1;
+    s = -lxd * f;
+    if (0 < s && s < 1 && f > 0) {
+      t = -lxc1 * f;
+      if (POS_EPS < t && t < 1) { eu = lu + t * du; ev = lv + t * dv; return 0; }
+      else if (t > 1 + POS_EPS) return EDGE_WITHIN_WALL;
+    }
+  }
+  double lxc2 = lu * here.uv_vert2_v - lv * here.uv_vert2_u;
+  double dxc2 = du * here.uv_vert2_v - dv * here.uv_vert2_u;
+  if (dxc2 < -POS_EPS || dxc2 > POS_EPS) {
+    f = 1 / dxc2;
+    s = 1 + lxd * f;
+    if (0 < s && s < 1 && f < 0) {
+      t = -lxc2 * f;
+      if (POS_EPS < t && t < 1) { eu = lu + t * du; ev = lv + t * dv; return 2; }
+      else if (t > 1 + POS_EPS) return EDGE_WITHIN_WALL;
+    }
+  }
+  f = dxc2 - dxc1;
+  if (f < -POS_EPS || f > POS_EPS) {
+    f = 1 / f;
+    s = -(lxd + dxc1) * f;
+    if (0 < s && s < 1 && f > 0) {
+      t = (here.uv_vert1_u * here.uv_vert2_v + lxc1 - lxc2) * f;
+      if (POS_EPS < t && t < 1) { eu = lu + t * du; ev = lv + t * dv; return 1; }
+      else if (t > 1 + POS_EPS) return EDGE_WITHIN_WALL;
+    }
+  }
+  return EDGE_CANNOT_TELL;
+}
+// GeometryUtils::traverse_surface, src4/geometry_utils.inl:305-342
+static uint32_t traverse_surface(const Wall& here, double lu, double lv, int which, double& nu, double& nv) {
+  if (here.nb_wall[which] == MCX_NONE) return MCX_NONE;
+  double c = here.edge_cos[which], sn = here.edge_sin[which], tu = here.edge_tu[which], tv = here.edge_tv[which];
+  if (here.edge_forward[which]) {
+    double ru = c * lu + sn * lv, rv = -sn * lu + c * lv;
+    nu = ru + tu; nv = rv + tv;
+  } else {
+    double ru = lu - tu, rv = lv - tv;
+    nu = c * ru - sn * rv;
+    nv = sn * ru + c * rv;
+  }
+  return here.nb_wall[which];
+}
+// ray_trace_surf, src4/diffuse_react_event.cpp:1578-1725 (no region borders: species.can_interact_with_border() is
+// false).  Returns the wall the move ends on (MCX_NONE: ambiguous edge hit, pick another displacement) and the
+// end point in that wall's frame.
+static uint32_t ray_trace_surf(const World& w, uint32_t wall_index, double pu, double pv, double du, double dv,
+                               double& out_u, double& out_v) {
+  const Wall* this_wall = &w.walls[wall_index];
+  uint32_t this_index = wall_index;
+  double this_u = pu, this_v = pv, disp_u = du, disp_v = dv;
+  for (int guard = 0; guard < 10000; guard++) {
+    double bu = 0, bv = 0;
+    int edge = find_edge_point(*this_wall, this_u, this_v, disp_u, disp_v, bu, bv);
+    if (edge == EDGE_CANNOT_TELL) return MCX_NONE;
+    if (edge == EDGE_WITHIN_WALL) { out_u = this_u + disp_u; out_v = this_v + disp_v; return this_index; }
+    double old_u = this_u, old_v = this_v;
+    double nu, nv;
+    uint32_t target = traverse_surface(*this_wall, old_u, old_v, edge, nu, nv);
+    if (target != MCX_NONE) {
+      this_u = nu; this_v = nv;
+      double su = old_u + disp_u, sv = old_v + disp_v;
+      double tu2, tv2;
+      traverse_surface(*this_wall, su, sv, edge, tu2, tv2);
+      disp_u = tu2 - this_u; disp_v = tv2 - this_v;
+      this_wall = &w.walls[target]; this_index = target;
+      continue;
+    }
+    // free edge: reflect
+    double ndu = disp_u - (bu - old_u), ndv = disp_v - (bv - old_v);
+    if (edge == 0) ndv *= -1.0;
+    else if (edge == 1) {
+      double ru = -this_wall->uv_vert2_v, rv = this_wall->uv_vert2_u - this_wall->uv_vert1_u;
+      double f = 1.0 / sqrt(ru * ru + rv * rv);
+      ru *= f; rv *= f;
+      f = 2.0 * (ndu * ru + ndv * rv);
+      ndu -= f * ru; ndv -= f * rv;
+    } else {
+      double ru = this_wall->uv_vert2_v, rv = -this_wall->uv_vert2_u;
+      double f = 1.0 / sqrt(ru * ru + rv * rv);
+      ru *= f; rv *= f;
+      f = 2.0 * (ndu * ru + ndv * rv);
+      ndu -= f * ru; ndv -= f * rv;
+    }
+    this_u = bu; this_v = bv; disp_u = ndu; disp_v = ndv;
+  }
+  return MCX_NONE;
 }
 
 static inline bool point_in_box(V3 p, V3 llf, V3 urb) {
@@ -600,6 +797,8 @@ struct Eval {
   const std::vector<Mol>* frozen;    // snapshot mode: start-of-iteration molecules (w.mols itself)
   const std::vector<uint8_t>* dead;  // snapshot mode: consumed flags by index
   bool no_partners = false;          // forced-final pass
+  const std::vector<uint8_t>* tile_claimed = nullptr;  // snapshot mode: per global tile, claimed by a mover in an earlier round
+  const std::vector<uint32_t>* tile_start = nullptr;   // first global tile of every wall
   mcx_trace_rec* tr = nullptr;
   uint32_t words_base = 0;
   uint64_t h = 0xcbf29ce484222325ULL;
@@ -939,7 +1138,8 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
 static void seq_set_defunct(World& w, Mol& m);
 
 struct MolState { V3 pos; uint32_t subpart; double t_now; uint32_t flags; double unimol_time;
-                  uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE; uint32_t cvi = 0; };
+                  uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE; uint32_t cvi = 0;
+                  uint32_t wall = MCX_NONE, tile = MCX_NONE; double u = 0, v = 0; };
 
 static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply, bool& again) {
   World& w = E.w;
@@ -950,7 +1150,10 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
   std::vector<Collision> colls;
   mcx_trace_rec* tr = E.tr;
   const mcx_species sp = w.species[m_species];
-  auto fill_event = [&](Outcome& o) { o.t_now = s.t_now; o.flags = s.flags; o.unimol_time = s.unimol_time; o.cvi = s.cvi; };
+  auto fill_event = [&](Outcome& o) {
+    o.t_now = s.t_now; o.flags = s.flags; o.unimol_time = s.unimol_time; o.cvi = s.cvi;
+    o.wall = s.wall; o.tile = s.tile; o.u = s.u; o.v = s.v;
+  };
 
   // -- unimolecular firing (diffuse_single_molecule :215-223 -> react_unimol_single_molecule :1764-1826)
   if (s.unimol_time != TIME_INVALID && s.unimol_time <= s.t_now) {
@@ -986,7 +1189,78 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
   if (s.unimol_time != TIME_INVALID && s.unimol_time < s.t_now + max_time) max_time = s.unimol_time - s.t_now;
 
   bool destroyed = false;
-  if (sp.flags & MCX_SP_CAN_DIFFUSE) {
+  bool surf_tile_changed = false;
+  if ((sp.flags & MCX_SP_CAN_DIFFUSE) && s.wall != MCX_NONE) {
+    // ---- diffuse_surf_molecule (:1071-1246)
+    double t_steps = sp.time_step > max_time ? max_time : sp.time_step;
+    double steps;
+    if (sp.time_step > max_time) {
+      steps = max_time / sp.time_step;
+      if (steps < EPS) { t_steps = EPS * sp.time_step; steps = EPS; }
+    } else steps = 1.0;
+    const double space_factor = steps == 1.0 ? sp.space_step : sp.space_step * sqrt(steps);
+    const uint32_t original_wall = s.wall;
+    auto available = [&](uint32_t wi, uint32_t ti) {
+      if (!w.tiles[wi].empty() && w.tiles[wi][ti] != MCX_NONE) return false;
+      if (E.snapshot) {
+        if (E.no_partners) return false;                       // forced-final pass: no new tile claims
+        if ((*E.tile_claimed)[(*E.tile_start)[wi] + ti]) return false;  // a mover of an earlier round took it
+      }
+      return true;
+    };
+    for (int find_new_position = 11; find_new_position > 0; find_new_position--) {  // SURFACE_DIFFUSION_RETRIES + 1
+      // pick_surf_displacement (diffusion_utils.inl:60-96): Marsaglia polar method on one 32-bit word
+      double au, av, f;
+      do {
+        uint32_t n = E.rs.next();
+        au = 2 * 1.52587890625e-5 * (n & 0xFFFF) - 1;
+        av = 2 * 1.52587890625e-5 * (n >> 16) - 1;
+        f = au * au + av * av;
+      } while ((f < POS_EPS) || (f > 1));
+      const double normal_factor = sqrt(-log(f) / f);
+      const double du = au * (normal_factor * space_factor), dv = av * (normal_factor * space_factor);
+      double nu, nv;
+      uint32_t new_wall = ray_trace_surf(w, s.wall, s.u, s.v, du, dv, nu, nv);
+      if (new_wall == MCX_NONE) continue;  // ambiguous edge hit: try again
+      uint32_t new_tile = uv2grid(w.walls[new_wall], w.grids[new_wall], nu, nv);
+      if (new_tile == MCX_NONE) continue;
+      if (new_wall == s.wall) {  // move_sm_on_same_triangle (diffusion_utils.inl:453-485)
+        if (new_tile != s.tile) {
+          if (!available(new_wall, new_tile)) continue;
+          surf_tile_changed = true;
+        }
+      } else {  // move_sm_to_new_triangle (:504-548)
+        if (!available(new_wall, new_tile)) continue;
+        surf_tile_changed = true;
+        // reschedule the unimolecular reaction of a molecule that changed wall (:1170-1186)
+        double time_until_unimol = s.unimol_time - t_steps - s.t_now;
+        time_until_unimol = (time_until_unimol < 0) ? 0 : time_until_unimol;
+        if (s.unimol_time == TIME_INVALID || (time_until_unimol > EPS || time_until_unimol > EPS * (s.t_now + t_steps))) {
+          s.unimol_time = TIME_INVALID;
+          s.flags |= MCX_MOL_SCHEDULE_UNIMOL;
+        }
+      }
+      if (apply && surf_tile_changed) {  // Grid::reset_molecule_tile / set_molecule_tile
+        if (w.tiles[new_wall].empty()) w.tiles[new_wall].assign(w.grids[new_wall].n_tiles, MCX_NONE);
+        w.tiles[s.wall][s.tile] = MCX_NONE;
+        w.tiles[new_wall][new_tile] = m_id;
+      }
+      s.wall = new_wall; s.tile = new_tile; s.u = nu; s.v = nv;
+      s.pos = uv2xyz(w, w.walls[new_wall], nu, nv);
+      s.subpart = w.subpart_index(s.pos);
+      break;
+    }
+    // MCell3 compatibility rule at the end of diffuse_surf_molecule (:1226-1236)
+    if (s.wall != original_wall && s.unimol_time >= t_end) {
+      s.unimol_time = TIME_INVALID;
+      s.flags |= MCX_MOL_SCHEDULE_UNIMOL;
+    }
+    max_time = t_steps;
+    if (apply) {
+      Mol& mm = w.mols[index];
+      mm.wall = s.wall; mm.tile = s.tile; mm.u = s.u; mm.v = s.v; mm.pos = s.pos;
+    }
+  } else if (sp.flags & MCX_SP_CAN_DIFFUSE) {
     // ---- diffuse_vol_molecule (:367-618)
     V3 remaining; double r_rate_factor, t_steps;
     E.compute_vol_displacement(sp, max_time, remaining, r_rate_factor, t_steps);
@@ -1151,6 +1425,14 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
   }
   out.kind = (sp.flags & MCX_SP_CAN_DIFFUSE) ? MCX_OUT_MOVED : MCX_OUT_STATIC;
   out.pos = s.pos; fill_event(out);
+  if (surf_tile_changed && !apply) {
+    // SNAPSHOT: taking a new tile is a claiming event; the evaluation ends here and what is left of the iteration
+    // is taken lazily next iteration (like a kept initiator)
+    out.kind = MCX_OUT_SURFMOVE;
+    out.flags = again ? (out.flags | MCX_MOL_PARTIAL) : (out.flags & ~MCX_MOL_PARTIAL);
+    E.ev(EV_SURFMOVE | (s.tile & 0xFFFFFFu), s.wall);
+    again = false;
+  }
   return out;
 }
 
@@ -1160,6 +1442,7 @@ static MolState load_state(const World& w, const Mol& m) {
   s.t_now = (m.flags & MCX_MOL_PARTIAL) ? m.diffusion_time : (double)w.iteration;
   s.flags = m.flags; s.unimol_time = m.unimol_rxn_time;
   s.created_wall = m.created_wall; s.created_tile = m.created_tile; s.cvi = m.cvi;
+  s.wall = m.wall; s.tile = m.tile; s.u = m.u; s.v = m.v;
   return s;
 }
 
@@ -1354,6 +1637,10 @@ static void step_snapshot(World& w, const SnapStreams& st) {
   }
   std::vector<Outcome> outs(n0);
   std::vector<uint32_t> claim(n0, MCX_NONE);
+  // surface tiles: claims of the movers of the running round, and the tiles claimed in earlier rounds
+  std::unordered_map<uint32_t, uint32_t> tile_claim;
+  std::vector<uint8_t> tile_claimed(w.tile_start.empty() ? 1 : w.tile_start.back() + 1, 0);
+  std::vector<uint32_t> tiles_of_round;
   std::vector<uint32_t> pending;
   struct NewMol { ProductSpec ps; double t; uint32_t id; };
   std::vector<NewMol> born;
@@ -1370,13 +1657,15 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     }
     Eval E(w, rs);
     E.snapshot = true; E.dead = &dead; E.no_partners = forced;
+    E.tile_claimed = &tile_claimed; E.tile_start = &w.tile_start;
     trace_begin(w, E, m);
     outs[i] = evaluate_iteration(E, i);
     trace_end(w, E, outs[i]);
   };
   auto is_claiming = [](const Outcome& o) {
-    return o.kind == MCX_OUT_REACTED || o.kind == MCX_OUT_ABSORBED || o.kind == MCX_OUT_UNIMOL;
+    return o.kind == MCX_OUT_REACTED || o.kind == MCX_OUT_ABSORBED || o.kind == MCX_OUT_UNIMOL || o.kind == MCX_OUT_SURFMOVE;
   };
+  auto gtile_of = [&](const Outcome& o) { return w.tile_start[o.wall] + o.tile; };
   // does the claiming event consume the partner? (kept reactants are not claimed)
   auto partner_consumed = [&](uint32_t i) {
     const Outcome& o = outs[i];
@@ -1390,11 +1679,18 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     uint32_t prio = w.mols[i].id;
     claim[i] = std::min(claim[i], prio);
     if (partner_consumed(i)) { uint32_t j = outs[i].partner_index; claim[j] = std::min(claim[j], prio); }
+    if (outs[i].kind == MCX_OUT_SURFMOVE) {
+      uint32_t gt = gtile_of(outs[i]);
+      auto it = tile_claim.find(gt);
+      if (it == tile_claim.end()) tile_claim[gt] = prio; else it->second = std::min(it->second, prio);
+      tiles_of_round.push_back(gt);
+    }
   };
   auto commit = [&](uint32_t i) {  // accepted claiming event
     Outcome& o = outs[i];
     const Mol& m = w.mols[i];
     if (o.kind == MCX_OUT_ABSORBED) { dead[i] = 1; w.stats.absorptions++; w.species_count[m.species]--; return; }
+    if (o.kind == MCX_OUT_SURFMOVE) { o.kind = MCX_OUT_MOVED; return; }  // stays alive on its new tile
     const mcx_rxn_class& c = w.classes[o.rxn_class];
     const mcx_pathway& pw = w.pathways[c.first_pathway + o.pathway];
     w.rxn_count[pw.rxn_rule_id]++;
@@ -1445,9 +1741,16 @@ static void step_snapshot(World& w, const SnapStreams& st) {
       uint32_t prio = w.mols[i].id;
       bool ok = claim[i] == prio;
       if (ok && partner_consumed(i)) ok = claim[outs[i].partner_index] == prio;
+      if (ok && outs[i].kind == MCX_OUT_SURFMOVE) ok = tile_claim[gtile_of(outs[i])] == prio;
       (ok ? accepted : still).push_back(i);
     }
-    for (uint32_t i : accepted) commit(i);
+    // tiles claimed in this round stay unavailable for the movers of later rounds, whoever won them
+    for (uint32_t gt : tiles_of_round) tile_claimed[gt] = 1;
+    tiles_of_round.clear(); tile_claim.clear();
+    for (uint32_t i : accepted) {
+      commit(i);
+      if (!dead[i]) claim[i] = MCX_NONE;  // a survivor (kept initiator, surface mover) can be claimed again in later rounds
+    }
     // reset claims of the losers, then re-evaluate them against the updated dead set
     for (uint32_t i : still) { claim[i] = MCX_NONE; if (partner_consumed(i)) claim[outs[i].partner_index] = MCX_NONE; }
     pending.clear();
@@ -1479,6 +1782,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     m.pos = o.pos; m.flags = o.flags; m.diffusion_time = o.t_now; m.unimol_rxn_time = o.unimol_time;
     m.subpart = w.subpart_index(m.pos);
     m.created_wall = m.created_tile = MCX_NONE; m.cvi = o.cvi;
+    if (m.wall != MCX_NONE) { m.wall = o.wall; m.tile = o.tile; m.u = o.u; m.v = o.v; }
   }
   // compaction + products (the product's per-iteration sort does both)
   std::vector<Mol> keep; keep.reserve(w.mols.size() + born.size());
@@ -1495,7 +1799,10 @@ static void step_snapshot(World& w, const SnapStreams& st) {
   w.mols.swap(keep);
   // tile occupancy of the next snapshot (the product's scatter rebuilds it the same way)
   for (auto& t : w.tiles) std::fill(t.begin(), t.end(), MCX_NONE);
-  for (auto& m : w.mols) if (m.wall != MCX_NONE) w.tiles[m.wall][m.tile] = m.id;
+  for (auto& m : w.mols) if (m.wall != MCX_NONE) {
+    if (w.tiles[m.wall].empty()) w.tiles[m.wall].assign(w.grids[m.wall].n_tiles, MCX_NONE);
+    w.tiles[m.wall][m.tile] = m.id;
+  }
   w.lists.clear();
   if (w.id_to_index.size() < w.next_id) w.id_to_index.resize(w.next_id, MCX_NONE);
   std::fill(w.id_to_index.begin(), w.id_to_index.end(), MCX_NONE);
@@ -1545,6 +1852,15 @@ int orc_set_geometry(void* h, const double* v, uint64_t nv, const uint32_t* tri,
   w.grids.resize(nw);
   for (uint64_t i = 0; i < nw; i++) grid_init(w, w.walls[i], w.grids[i]);
   w.tiles.assign(nw, {});
+  w.tile_start.assign(nw + 1, 0);
+  for (uint64_t i = 0; i < nw; i++) w.tile_start[i + 1] = w.tile_start[i] + w.grids[i].n_tiles;
+  // Geometry objects are contiguous runs of walls with the same object id (one object when none is given)
+  for (uint64_t i = 0; i < nw;) {
+    uint64_t j = i;
+    while (j < nw && w.walls[j].object == w.walls[i].object) j++;
+    init_edges(w, (uint32_t)i, (uint32_t)(j - i));
+    i = j;
+  }
   finalize_walls(w);
   return 0;
 }

@@ -89,7 +89,7 @@ class Oracle:
         self.L.orc_set_reactions(self.h, t.classes, C.c_uint32(t.n_classes), t.pathways, C.c_uint32(t.n_pathways))
         self.L.orc_set_surface_classes(self.h, t.surf_rules, C.c_uint32(t.n_surf_rules))
         self.L.orc_set_geometry(self.h, self._v(t.vertices), C.c_uint64(len(t.vertices)), self._v(t.tri),
-                                C.c_uint64(len(t.tri)), self._v(t.wall_surf_class), None)
+                                C.c_uint64(len(t.tri)), self._v(t.wall_surf_class), self._v(getattr(t, "wall_object", None)))
         if getattr(t, "n_counted_volumes", 0) > 1:
             self.L.orc_set_counted_volumes(self.h, C.c_uint32(t.n_counted_volumes), self._v(t.wall_cv_front), self._v(t.wall_cv_back))
 

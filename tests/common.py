@@ -130,6 +130,32 @@ def ligand_receptor_sphere(n_lig=6000, n_rec=1500, n_pump=600, radius_um=0.25, s
     return t, MolArrays.concat([vol, surf])
 
 
+def diffusing_receptors(n_rec=3000, n_lig=8000, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8, D_surf=1e-7,
+                        rng_mode=abi.MCX_RNG_PHILOX, p_bind=0.5, k_off=1e5, with_ligand=True):
+    """Surface diffusion: receptors R diffuse on an icosphere (diffuse_surf_molecule, ray_trace_surf
+    across triangle edges, one molecule per tile), ligand L binds them from outside, LR' -> R' keeps ids deterministic."""
+    import math
+    from mcell_b200.model import N_AV, MY_PI
+    m = Model(Config(seed=seed))
+    L = m.add_species("L", 1e-6)
+    R = m.add_species("R", D_surf, surface=True)
+    LR = m.add_species("LR", D_surf * 0.5, surface=True)
+    pb = 2.0 * 1.0e11 * m.config.surface_grid_density / (2.0 * N_AV) * math.sqrt(MY_PI * m.config.time_step / 1e-6)
+    if with_ligand:
+        m.add_reaction_rule(["L'", "R'"], ["LR'"], p_bind / pb)
+        m.add_reaction_rule(["LR'"], ["R'"], k_off)
+    sv, sf = create_icosphere(radius_um, subdivisions)
+    m.add_geometry_object(sv, sf)
+    bv, bf = create_box(box_um)
+    m.add_geometry_object(bv, bf)
+    t = m.build(max_molecules=2 * (n_rec + n_lig) + 64, rng_mode=rng_mode)
+    rng = np.random.default_rng(seed)
+    pos = release_uniform_box(rng, n_lig, box_um, t.length_unit, margin=1e-3)
+    vol = MolArrays.from_positions(pos, L, schedule_unimol=True)
+    surf = release_on_walls(rng, t, np.arange(len(sf), dtype=np.uint32), n_rec, R, orientation=1, first_id=n_lig)
+    return t, MolArrays.concat([vol, surf])
+
+
 def counted_spheres(n=12000, seed=1, box_um=0.8, rng_mode=abi.MCX_RNG_PHILOX, p_target=0.4):
     """Counted volumes: two nested transparent icospheres, both counted, inside a counted
     reflective box; A + B -> C everywhere.  Volumes: {box}, {box, outer}, {box, outer, inner} (+ the empty set)."""

@@ -206,6 +206,37 @@ def test_philox_surface_unbinding_two_products():
     assert cm.rel_close(ka[:, 1:4], kb[:, 1:4], POS_TOL).all()
 
 
+def test_philox_surface_diffusion_with_binding():
+    """Surface diffusion (diffuse_surf_molecule, ray_trace_surf across triangle edges, tile claims between movers)
+    together with ligand binding on the moving receptors: traces (incl. the tile every mover takes), conflict
+    rounds, counts and the whole population over many iterations."""
+    t, mols = cm.diffusing_receptors(n_rec=3000, n_lig=16000, seed=8)
+    n = mols.n
+    o = _oracle(t)
+    o.upload(mols)
+    e = _engine(t)
+    e.upload(mols)
+    moved = retries = rx = 0
+    for it in range(12):
+        tr_o, st_o = o.trace_step(1, n)
+        tr_g, st_g = e.trace_step(n)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "unimol_rxns", "resolve_retries", "unresolved_conflicts", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        moved += int((tr_g["outcome"][live] == abi.MCX_OUT_SURFMOVE).sum())
+        retries += st_g.resolve_retries
+        rx += st_g.bimol_rxns
+        assert (e.counts()[0] == o.counts()[0]).all(), it
+    assert moved > 5000 and retries > 20 and rx > 50, (moved, retries, rx)
+    a, b = o.download().sorted_by_id(), e.download().sorted_by_id()
+    _assert_same_population(a, b)
+    s = b.wall != abi.MCX_NONE
+    assert len(np.unique(np.stack([b.wall[s], b.tile[s]], 1), axis=0)) == 3000
+
+
 def test_philox_counted_volumes_nested_spheres():
     """Counted volumes: the index switches on transparent crossings of two nested counted spheres, products inherit
     it, and per-volume molecule / reaction counts (MolOrRxnCountEvent terms restricted to a volume) match."""

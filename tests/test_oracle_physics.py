@@ -298,3 +298,57 @@ def test_counted_volume_index_follows_the_geometry(mode):
     assert (mc[:, 1:] > 0).all() and (rc[0, 1:] > 0).all() and mc[:, 0].sum() == 0
     for cv in range(t.n_counted_volumes):
         assert (np.bincount(m.species[m.counted_volume == cv], minlength=3) == mc[:, cv]).all()
+
+
+# ---- surface diffusion --------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1])
+def test_surface_diffusion_msd_tiles_and_edges(mode):
+    """diffuse_surf_molecule / ray_trace_surf / traverse_surface: molecules stay on the mesh, keep one molecule per
+    tile, cross triangle edges, and at low occupancy their mean square displacement per step is space_step^2
+    (pick_surf_displacement: E|d|^2 = scale^2), measured over a few steps where the sphere is still locally flat."""
+    t, mols = cm.diffusing_receptors(n_rec=400, n_lig=10, D_surf=2e-8, with_ligand=False, seed=5)
+    o = O.Oracle(t)
+    o.upload(mols)
+    a = o.download().sorted_by_id()
+    steps = 6
+    o.step(steps, mode)
+    b = o.download().sorted_by_id()
+    s = a.wall != 0xFFFFFFFF
+    assert (b.wall != 0xFFFFFFFF).sum() == 400 and (a.id == b.id).all()
+    d2 = ((b.x - a.x) ** 2 + (b.y - a.y) ** 2 + (b.z - a.z) ** 2)[s]
+    want = steps * t.species[1].space_step ** 2
+    assert abs(d2.mean() - want) < 0.12 * want, (d2.mean(), want)
+    assert ((b.wall != a.wall) & s).sum() > 40                                 # edges were crossed
+    tiles = np.stack([b.wall[s], b.tile[s]], 1)
+    assert len(np.unique(tiles, axis=0)) == 400
+    # every molecule lies on its triangle: uv2xyz(u, v) is its position and the point is inside the wall
+    tri = t.vertices[t.tri[b.wall[s]]]
+    e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    p = np.c_[b.x, b.y, b.z][s] - tri[:, 0]
+    n = np.cross(e1, e2)
+    assert np.abs((p * n).sum(1) / np.linalg.norm(n, axis=1)).max() < 1e-9
+    den = (e1 * e1).sum(1) * (e2 * e2).sum(1) - (e1 * e2).sum(1) ** 2
+    bu = ((p * e1).sum(1) * (e2 * e2).sum(1) - (p * e2).sum(1) * (e1 * e2).sum(1)) / den
+    bv = ((p * e2).sum(1) * (e1 * e1).sum(1) - (p * e1).sum(1) * (e1 * e2).sum(1)) / den
+    assert (bu > -1e-9).all() and (bv > -1e-9).all() and (bu + bv < 1 + 1e-9).all()
+
+
+def test_surface_diffusion_crowded_with_binding_agrees_between_semantics():
+    """Crowded surface (38 % of the tiles taken) with ligand binding: sequential (reference) and snapshot semantics
+    agree statistically on bound receptors; tiles stay exclusive in both."""
+    seq, snap = [], []
+    for seed in range(1, 7):
+        t, mols = cm.diffusing_receptors(n_rec=3000, n_lig=8000, seed=seed)
+        for mode, acc in ((0, seq), (1, snap)):
+            o = O.Oracle(t)
+            o.upload(mols)
+            st = o.step(20, mode)
+            m = o.download()
+            s = m.wall != 0xFFFFFFFF
+            assert len(np.unique(np.stack([m.wall[s], m.tile[s]], 1), axis=0)) == 3000
+            acc.append(float(o.counts()[1][0]))
+            if mode == 1:
+                assert st.unresolved_conflicts == 0
+    seq, snap = np.array(seq), np.array(snap)
+    se = math.sqrt(seq.var(ddof=1) / len(seq) + snap.var(ddof=1) / len(snap))
+    assert abs(seq.mean() - snap.mean()) < 3 * se + 0.03 * seq.mean(), (seq.mean(), snap.mean(), se)
