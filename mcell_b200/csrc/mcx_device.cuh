@@ -929,7 +929,9 @@ __device__ uint32_t ray_trace_surf(const DevParams& p, uint32_t wall_index, doub
 // exact_disk (3.5 KB of per-thread pool, 300 more bytes of spills) out of the common generic pass saves a third of
 // its run time (profiles/r01_g).
 #define MCX_INTERNAL_NEEDS_DISK 1000
-template <bool RETRY, bool WITH_DISK>
+// SURF == false compiles the surface-molecule code out (models without surface species: the launcher picks the
+// instantiation from DevParams::has_surf), which gives the registers back to the volume path.
+template <bool RETRY, bool WITH_DISK, bool SURF>
 __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t_sched, double t_unimol_in,
                                    uint32_t created_wall, uint32_t created_tile, SurfState ss, unsigned int epoch,
                                    Stream& rs, bool forced, Outcome& out, LocalStats& ls, Tracer& tc, int& err) {
@@ -967,7 +969,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
         }
         pathway = match > A[min_idx].cum_prob ? max_idx : min_idx;
       }
-      if (flags & DF_SURF) out.orient_bits = draw_orientation_bits(p.pathways[cl.first_pathway + pathway], rs);
+      if (SURF && (flags & DF_SURF)) out.orient_bits = draw_orientation_bits(p.pathways[cl.first_pathway + pathway], rs);
       tc.ev(EV_UNIMOL | (uint32_t)pathway, (uint32_t)rc);
       if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->t_event = unimol_time; }
       out.kind = MCX_OUT_UNIMOL; out.pos = pos; out.rxn_class = rc; out.pathway = pathway; out.t_event = unimol_time;
@@ -991,7 +993,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
       double max_time = t_end - t_now;
       if (unimol_time != MCX_TIME_INVALID && unimol_time < t_now + max_time) max_time = unimol_time - t_now;
 
-      if (can_diffuse && (flags & DF_SURF)) {
+      if (SURF && can_diffuse && (flags & DF_SURF)) {
         // ---- diffuse_surf_molecule (:1071-1246)
         double t_steps = sp.time_step > max_time ? max_time : sp.time_step;
         double steps;
@@ -1165,7 +1167,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
             }
             // ---- collide_and_react_with_surf_mol (:845-975): the surface molecule on the tile under the hit point
             bool surf_reacted = false;
-            if (sp.can_vol_surf && p.n_tiles) {
+            if (SURF && sp.can_vol_surf && p.n_tiles) {
               const DevGrid& g = p.grids[wh.wall];
               const uint32_t j = xyz2grid(p, wh.pos, wh.wall);
               const uint32_t occ = p.tile_slot[g.tile_start + j];
@@ -1255,7 +1257,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
             if (unimol_time < t_end) again = true;
           } else t_now = MCX_TIME_FOREVER;
         }
-        if (surf_tile_changed) {
+        if (SURF && surf_tile_changed) {
           // taking a new tile is a claiming event: the evaluation ends here, what is left of the iteration is taken
           // lazily next iteration (like a kept initiator)
           out.kind = MCX_OUT_SURFMOVE; out.pos = pos; out.t_now = t_now; out.unimol_time = unimol_time;

@@ -327,7 +327,14 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
   const unsigned int n = p.ctr->n_slots;
   const double t_end = (double)p.iteration + 1.0;
   unsigned int msteps = 0, n_tests = 0, n_coll = 0;
+#ifdef MCX_FAST_BLOCKED
+  // each block walks one contiguous chunk of the sorted snapshot (neighbouring rows are re-read by the same SM)
+  const unsigned int chunk = (((n + gridDim.x - 1) / gridDim.x) + blockDim.x - 1) / blockDim.x * blockDim.x;
+  const unsigned int chunk_end = min(n, (blockIdx.x + 1) * chunk);
+  for (unsigned int base = blockIdx.x * chunk; base < chunk_end; base += blockDim.x) {
+#else
   for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+#endif
     const unsigned int i = base + threadIdx.x;
     const bool in_range = i < n;
     const unsigned int ii = in_range ? i : base;  // a valid slot for every lane
@@ -447,8 +454,11 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
 // k_diffuse_slow: the generic evaluation (evaluate_iteration) for the slots k_diffuse_fast deferred.
 // WITH_DISK == false reads slow_list and hands the few molecules whose collision disk is cut by a wall on to the
 // WITH_DISK == true launch through pend[1] (free until the conflict rounds start).
-template <bool WITH_DISK>
-__global__ void __launch_bounds__(TPB, 2) k_diffuse_slow(const __grid_constant__ DevParams p) {
+#ifndef MCX_SLOW_MINBLOCKS
+#define MCX_SLOW_MINBLOCKS 4
+#endif
+template <bool WITH_DISK, bool SURF>
+__global__ void __launch_bounds__(TPB, MCX_SLOW_MINBLOCKS) k_diffuse_slow(const __grid_constant__ DevParams p) {
   __shared__ ZigShared zig;
   zig_load(&zig);
   __syncthreads();
@@ -473,9 +483,9 @@ __global__ void __launch_bounds__(TPB, 2) k_diffuse_slow(const __grid_constant__
     LocalStats mls = {0, 0, 0, 0, 0, 0};  // statistics of redundantly evaluated halo molecules are not counted
     const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
     SurfState ss = {MCX_NONE, MCX_NONE, 0.0, 0.0};
-    if (m.sf & DF_SURF) { const double2 uv = p.suvA[i]; ss.wall = p.swallA[i]; ss.tile = p.stileA[i]; ss.u = uv.x; ss.v = uv.y; }
-    evaluate_iteration<false, WITH_DISK>(p, m, t_sched, t_uni, guard ? p.swallA[i] : MCX_NONE, guard ? p.stileA[i] : MCX_NONE,
-                                         ss, epoch, rs, false, o, mls, tc, err);
+    if (SURF && (m.sf & DF_SURF)) { const double2 uv = p.suvA[i]; ss.wall = p.swallA[i]; ss.tile = p.stileA[i]; ss.u = uv.x; ss.v = uv.y; }
+    evaluate_iteration<false, WITH_DISK, SURF>(p, m, t_sched, t_uni, (SURF && guard) ? p.swallA[i] : MCX_NONE,
+                                               (SURF && guard) ? p.stileA[i] : MCX_NONE, ss, epoch, rs, false, o, mls, tc, err);
     if (!WITH_DISK && err == MCX_INTERNAL_NEEDS_DISK) {  // re-evaluated from scratch by the WITH_DISK launch
       if (tc.tr) tc.tr->rounds--;
       p.pend[1][agg_reserve(&p.ctr->n_pend[1], 1u)] = i;
@@ -525,6 +535,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(const __grid_constant__ DevPara
 
 // losers of round r are re-evaluated against the updated snapshot flags; their new proposals go back
 // to list `cur` for round r+1
+template <bool SURF>
 __global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevParams p, unsigned int round, int forced) {
   __shared__ ZigShared zig;
   zig_load(&zig);
@@ -555,9 +566,10 @@ __global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevPar
     LocalStats halo_ls = {0, 0, 0, 0, 0, 0};
     const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
     SurfState ss = {MCX_NONE, MCX_NONE, 0.0, 0.0};
-    if (m.sf & DF_SURF) { const double2 uv = p.suvA[i]; ss.wall = p.swallA[i]; ss.tile = p.stileA[i]; ss.u = uv.x; ss.v = uv.y; }
-    evaluate_iteration<true, true>(p, m, t_sched, t_uni, guard ? p.swallA[i] : MCX_NONE, guard ? p.stileA[i] : MCX_NONE,
-                                   ss, epoch, rs, forced != 0, o, own_start ? ls : halo_ls, tc, err);
+    if (SURF && (m.sf & DF_SURF)) { const double2 uv = p.suvA[i]; ss.wall = p.swallA[i]; ss.tile = p.stileA[i]; ss.u = uv.x; ss.v = uv.y; }
+    evaluate_iteration<true, true, SURF>(p, m, t_sched, t_uni, (SURF && guard) ? p.swallA[i] : MCX_NONE,
+                                         (SURF && guard) ? p.stileA[i] : MCX_NONE, ss, epoch, rs, forced != 0, o,
+                                         own_start ? ls : halo_ls, tc, err);
     trace_end(tc, o, rs);
     if (err) raise_error(p, err, m.id);
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time, &o);
@@ -852,8 +864,13 @@ void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t 
   if (plan.prof) cudaEventRecord(plan.prof[0], s);
   k_diffuse_fast<<<plan.sm_count * 2 * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
   if (plan.prof) cudaEventRecord(plan.prof[4], s);
-  k_diffuse_slow<false><<<plan.sm_count * 4, TPB, 0, s>>>(p);
-  k_diffuse_slow<true><<<plan.sm_count, TPB, 0, s>>>(p);
+  if (p.has_surf) {
+    k_diffuse_slow<false, true><<<plan.sm_count * 2 * MCX_SLOW_MINBLOCKS, TPB, 0, s>>>(p);
+    k_diffuse_slow<true, true><<<plan.sm_count, TPB, 0, s>>>(p);
+  } else {
+    k_diffuse_slow<false, false><<<plan.sm_count * 2 * MCX_SLOW_MINBLOCKS, TPB, 0, s>>>(p);
+    k_diffuse_slow<true, false><<<plan.sm_count, TPB, 0, s>>>(p);
+  }
   if (plan.prof) cudaEventRecord(plan.prof[1], s);
   count_launches(plan, 3);
   if (plan.has_claims) {
@@ -863,7 +880,8 @@ void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t 
       k_round_begin<<<1, 1, 0, s>>>(p, r);
       k_resolve<<<small_grid, TPB, 0, s>>>(p, r);
       k_round_mid<<<1, 1, 0, s>>>(p, r);
-      k_retry<<<small_grid, TPB, 0, s>>>(p, r, r + 1 == p.max_rounds ? 1 : 0);
+      if (p.has_surf) k_retry<true><<<small_grid, TPB, 0, s>>>(p, r, r + 1 == p.max_rounds ? 1 : 0);
+      else k_retry<false><<<small_grid, TPB, 0, s>>>(p, r, r + 1 == p.max_rounds ? 1 : 0);
     }
   }
   if (plan.prof) cudaEventRecord(plan.prof[2], s);
