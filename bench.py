@@ -28,6 +28,7 @@ DENSITY_PER_LU3 = 1.0e6 / 200.0 ** 3     # config 2: 1e6 molecules in a (2 um)^3
 ITERS_PER_CALL = 10                      # "counts every 10 iterations": barrier window of one plugin call
 B_ALG_DIFFUSE = 92.0                     # 32 read + 32 write + 28 neighbour staging
 B_ALG_STEP = 160.0                       # + 68 B per-step sort
+WORKLOAD = "reactive box, 4 species / 6 reactions, 1.25e5 molecules/um^3 = config 2's density (BASELINE configs[4])"
 
 
 def build_model(n_total, seed=1, rank=0, world=1, cap_factor=1.25, cell_edge=0.0):
@@ -168,31 +169,85 @@ def _peaks():
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
+# The CPU arm is the mcell4-equivalent oracle in sequential (reference) semantics.  Its cost per molecule-step is set
+# by the number of molecules per default 0.5 um subpartition (15.6k at this density: every molecule is tested against
+# all of them, collision_utils.inl:520-552), so the bounded sample is a box of a x b x c WHOLE subpartitions of the
+# same chemistry and density: what one core spends per molecule-step there is what it would spend in the 1e8 box.
+SUBPART_UM = 0.5
+MOLS_PER_SUBPART = DENSITY_PER_LU3 * (SUBPART_UM * 100.0) ** 3      # 15 625
+
+
+def build_cpu_sample(dims, seed):
+    """Reactive-box chemistry in a box of dims = (a, b, c) whole default subpartitions (faces 1 nm inside the
+    subpartition boundaries)."""
+    from mcell_b200.model import Model, Config, create_box, N_AV, MY_PI
+    m = Model(Config(seed=seed))
+    for name in "ABCD":
+        m.add_species(name, 1e-6)
+    lu, ts = m.length_unit, m.config.time_step
+    eff = 2 * m.space_step(1e-6) * lu / ts
+    R = m.rxn_radius_um
+    pb = 1.0 / (2.0 * math.sqrt(MY_PI) * R * R * eff) * 1.0e15 / N_AV
+    k_bi = 0.1 / pb
+    m.add_reaction_rule(["A", "B"], ["C"], k_bi)
+    m.add_reaction_rule(["C"], ["A", "B"], 1.0e4)
+    m.add_reaction_rule(["A", "C"], ["D"], k_bi)
+    m.add_reaction_rule(["D"], ["A", "C"], 1.0e4)
+    m.add_reaction_rule(["B", "D"], ["C", "C"], k_bi)
+    m.add_reaction_rule(["C", "C"], ["B", "D"], k_bi)
+    v, f = create_box(1.0)                                   # unit cube centred at 0
+    inset = 0.001
+    size = np.array([d * SUBPART_UM - 2 * inset for d in dims])
+    lo = np.array([-(d // 2) * SUBPART_UM + inset for d in dims])   # subpartition boundaries are multiples of 0.5 um
+    v = (v + 0.5) * size + lo
+    m.add_geometry_object(v, f)
+    n = int(round(MOLS_PER_SUBPART * dims[0] * dims[1] * dims[2]))
+    t = m.build(max_molecules=2 * n + 1024)
+    return t, n, lo, size
+
+
+def make_cpu_molecules(t, n, lo, size, seed):
+    from mcell_b200.model import MolArrays
+    rng = np.random.default_rng(seed)
+    pos = (lo + size * (1e-6 + (1 - 2e-6) * rng.uniform(size=(n, 3)))) / t.length_unit
+    r = rng.integers(0, 10, n)
+    species = np.select([r < 4, r < 8, r < 9], [0, 1, 2], 3).astype(np.uint32)
+    return MolArrays.from_positions(pos, species, schedule_unimol=True)
+
+
 def _cpu_worker(args):
     """One independent seed of the bounded CPU sample (the reference's only scaling mode:
-    utils/mcell4_runner/mcell4_runner.py:203-212)."""
-    n_sample, seed, iters = args
+    utils/mcell4_runner/mcell4_runner.py:203-212): `warmup` untimed then `steps` timed iterations."""
+    dims, seed, steps, warmup = args
     from oracle import oracle_py as O
-    t, edge_um = build_model(n_sample, seed=seed)
-    mols = make_molecules(n_sample, edge_um, t.length_unit, seed, None, pinned=False)
+    t, n, lo, size = build_cpu_sample(dims, seed)
+    mols = make_cpu_molecules(t, n, lo, size, seed)
     o = O.Oracle(t)
     o.upload(mols)
+    if warmup:
+        o.step(warmup, 0)
     t0 = time.perf_counter()
-    st = o.step(iters, 0)
+    st = o.step(steps, 0)
     dt = time.perf_counter() - t0
     return st.molecule_steps, dt
 
 
-def cpu_sample(n_sample, iters, cores):
+def cpu_sample(dims, steps, warmup, cores):
+    """-> (aggregate molecule-steps/s, molecule-steps, slowest worker's seconds)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(n_sample, 100 + i, iters) for i in range(cores)])
-    wall = time.perf_counter() - t0
-    steps = sum(r[0] for r in res)
+        res = pool.map(_cpu_worker, [(dims, 100 + i, steps, warmup) for i in range(cores)])
+    total = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
-    return steps / busy, steps, busy, wall
+    return total / busy, total, busy
+
+
+def _sample_text(dims, cores, steps):
+    n = int(round(MOLS_PER_SUBPART * dims[0] * dims[1] * dims[2]))
+    return ("%d independent seeds x %d molecules (%dx%dx%d whole default 0.5 um subpartitions, 15 625 molecules each) x %d "
+            "iteration(s), same chemistry and density as the 1e8 box, sequential reference semantics" %
+            (cores, n, dims[0], dims[1], dims[2], steps))
 
 
 def run_reference(args):
@@ -202,29 +257,26 @@ def run_reference(args):
     from oracle import oracle_py as O
     O.build()
     cores = os.cpu_count() or 1
-    n_sample, iters = args.cpu_sample, 1
-    vals = []
-    for _ in range(args.warmup_cpu):
-        cpu_sample(n_sample, iters, cores)
-    t_all = 0.0
-    for _ in range(args.steps_cpu):
-        v, steps, busy, wall = cpu_sample(n_sample, iters, cores)
-        vals.append(v)
-        t_all += busy
-    value = float(np.mean(vals))
-    sample = ("%d independent seeds x %d molecules x %d iteration(s) of the same reactive-box "
-              "chemistry and density, default 0.5 um subpartitions, sequential reference semantics" % (cores, n_sample, iters))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # one iteration costs ~2.5 s of one core per subpartition of the sample: size the sample so that the whole
+    # --steps/--warmup run stays within ~2.5 minutes
+    per_subpart_s = 2.6
+    budget = 150.0
+    n_sub = budget / ((steps + warmup) * per_subpart_s)
+    dims = (2, 2, 2) if n_sub >= 8 else (1, 2, 2) if n_sub >= 4 else (1, 1, 2) if n_sub >= 2 else (1, 1, 1)
+    value, total, busy = cpu_sample(dims, steps, warmup, cores)
+    sample = _sample_text(dims, cores, steps)
     line = {
         "impl": "reference", "metric": "molecule_steps_per_sec", "value": value, "unit": "molecule-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps_cpu, "warmup": args.warmup_cpu,
-        "ms_per_step": 1e3 * t_all / max(1, args.steps_cpu), "higher_is_better": True, "scaling": "strong",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * busy / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "reactive box, 4 species / 6 reactions, 1.25e5 molecules/um^3 = config 2's density (BASELINE configs[4])",
-                   "molecules": args.molecules, "cpu_sample_molecules_per_core": n_sample},
+        "config": {"workload": WORKLOAD, "molecules": args.molecules,
+                   "cpu_sample_molecules_per_core": int(round(MOLS_PER_SUBPART * dims[0] * dims[1] * dims[2]))},
         "cpu_baseline": {"value": value, "unit": "molecule-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "molecule-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "mcell4-equivalent CPU oracle (oracle/), not the upstream binary: the reference cannot be built here",
+        "note": "mcell4-equivalent CPU oracle (oracle/), not the upstream binary: the reference cannot be built here (DESIGN.md 8)",
     }
     print(json.dumps(line))
 
@@ -344,15 +396,14 @@ def run_ours(args):
             from oracle import oracle_py as O
             O.build()
             cores = os.cpu_count() or 1
-            v, steps, busy, wall = cpu_sample(args.cpu_sample, 1, cores)
+            v, steps, busy = cpu_sample((2, 2, 2), 1, 0, cores)
             cpu = {"value": v, "unit": "molecule-steps/s", "cores": cores, "kind": "port",
-                   "sample": "%d independent seeds x %d molecules x 1 iteration (2x2x2 full default subpartitions), same chemistry/density, "
-                             "sequential reference semantics, %.1f s of CPU work per core" % (cores, args.cpu_sample, busy)}
+                   "sample": _sample_text((2, 2, 2), cores, 1) + ", %.1f s of CPU work per core" % busy}
         line = {
             "metric": "molecule_steps_per_sec", "value": value, "unit": "molecule-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / max(1, args.steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "reactive box, 4 species / 6 reactions, 1.25e5 molecules/um^3 = config 2's density (BASELINE configs[4])",
+            "config": {"workload": WORKLOAD,
                        "molecules": n_total, "box_edge_um": edge_um, "iterations_per_plugin_call": ITERS_PER_CALL,
                        "l2": "inputs (>=3 GB at 1e8 molecules) larger than L2; no flush",
                        "parallelism": "z-slabs x%d, NCCL halo refresh per iteration" % world, "rng": "philox4x32-10 per molecule"},
@@ -396,9 +447,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--molecules", type=int, default=100_000_000)
     ap.add_argument("--e2e-calls", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=125_000, help="molecules per CPU core in the bounded CPU sample")
-    ap.add_argument("--steps-cpu", type=int, default=2)
-    ap.add_argument("--warmup-cpu", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cell-edge", type=float, default=0.0, help="device neighbour-cell edge in length units (0 = auto)")
     args = ap.parse_args()
