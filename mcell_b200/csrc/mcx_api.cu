@@ -196,6 +196,8 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   rc |= dev_alloc(h, &p.prop_partner, cap); rc |= dev_alloc(h, &p.prop_info, cap); rc |= dev_alloc(h, &p.prop_t, cap);
   rc |= dev_alloc(h, &p.pend[0], cap); rc |= dev_alloc(h, &p.pend[1], cap);
   rc |= dev_alloc(h, &p.slow_list, cap);
+  rc |= dev_alloc(h, &p.second_list, cap);
+  rc |= dev_alloc(h, &p.slow2_list, cap);
   rc |= dev_alloc(h, &h->cs[0], (size_t)p.n_cells + 8); rc |= dev_alloc(h, &h->cs[1], (size_t)p.n_cells + 8);
   rc |= dev_alloc(h, &h->scan_sums, (size_t)(p.n_cells + 1) / 4096 + 16);
   p.scan_sums = h->scan_sums;

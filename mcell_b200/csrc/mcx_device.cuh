@@ -56,6 +56,19 @@ __device__ __forceinline__ unsigned int round_epoch0(const DevParams& p) {
   return (unsigned int)(p.iteration * (unsigned long long)(p.max_rounds + 1) + 1);
 }
 
+// Rare-path helpers kept out of line: every inlined copy of exp / log / log1p or of the ten Philox rounds costs
+// 100-300 SASS instructions, and the diffuse kernels instantiate the stream code at many sites (43 % of
+// k_diffuse_fast's code and 29 % of k_diffuse_slow's were such copies; both kernels stalled on instruction fetch,
+// profiles/r01_l).  Same functions, same roundings: results are unchanged.
+__device__ __noinline__ double mcx_exp(double x) { return exp(x); }
+__device__ __noinline__ double mcx_log(double x) { return log(x); }
+__device__ __noinline__ double mcx_log1p(double x) { return log1p(x); }
+__device__ __noinline__ uint4 philox_block_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  uint32_t o[4];
+  philox4x32_10(c0, c1, c2, c3, k0, k1, o);
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // ---- per-molecule word stream: Philox (production) or tape slice (replay) ----------------------
 struct Stream {
   const uint32_t* tape; unsigned long long tape_left;
@@ -74,6 +87,8 @@ struct Stream {
       tape = nullptr; tape_left = 0;
       k0 = (uint32_t)p.seed; k1 = (uint32_t)(p.seed >> 32);
       it_lo = (uint32_t)p.iteration; it_hi = (uint32_t)(p.iteration >> 32);
+      // block 0 is generated here, in line (every evaluation draws from it); later blocks out of line in next()
+      uint32_t o[4]; philox4x32_10(0u, it_lo, it_hi, id, k0, k1, o); b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
     }
   }
   __device__ __forceinline__ uint32_t next() {
@@ -81,7 +96,7 @@ struct Stream {
     if (tape) w = used < tape_left ? tape[used] : 0u;
     else {
       const uint32_t k = used & 3u;
-      if (k == 0u) { uint32_t o[4]; philox4x32_10(used >> 2, it_lo, it_hi, id, k0, k1, o); b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3]; }
+      if (k == 0u && used != 0u) { const uint4 o = philox_block_call(used >> 2, it_lo, it_hi, id, k0, k1); b0 = o.x; b1 = o.y; b2 = o.z; b3 = o.w; }
       w = k == 0u ? b0 : (k == 1u ? b1 : (k == 2u ? b2 : b3));
     }
     used++;
@@ -104,10 +119,10 @@ struct Stream {
         y = yB + yR * dbl();
       } else {
         const double R = MCX_ZIG_R;
-        x = R - log1p(-dbl()) * (1.0 / R);
-        y = exp(-R * (x - 0.5 * R)) * dbl();
+        x = R - mcx_log1p(-dbl()) * (1.0 / R);
+        y = mcx_exp(-R * (x - 0.5 * R)) * dbl();
       }
-      if (!(y >= exp(-0.5 * x * x))) break;
+      if (!(y >= mcx_exp(-0.5 * x * x))) break;
     }
     return sign * x;
   }
@@ -187,7 +202,7 @@ __device__ __forceinline__ bool owned_z(const DevParams& p, double z) {
 struct SpSet { uint32_t v[MCX_MAX_SP_MOLS]; int n; bool overflow; };
 struct SpList { uint32_t v[MCX_MAX_SP_WALLS]; int n; };
 
-__device__ __forceinline__ void spset_insert(SpSet& s, uint32_t sp) {
+__device__ __noinline__ void spset_insert(SpSet& s, uint32_t sp) {
   for (int i = 0; i < s.n; i++) if (s.v[i] == sp) return;
   if (s.n < MCX_MAX_SP_MOLS) s.v[s.n++] = sp; else s.overflow = true;
 }
@@ -713,6 +728,7 @@ __device__ __forceinline__ bool all_walls_plane_rejected(const DevParams& p, boo
                                                          unsigned int& n_tests, double& min_dist) {
   const uint32_t w0 = __ldg(p.spw_start + subpart), w1 = enabled ? __ldg(p.spw_start + subpart + 1) : w0;
   bool all = true;
+#pragma unroll 1
   for (uint32_t k = w0; k < w1; k++) {
     const DevWall& f = p.walls[__ldg(p.spw_list + k)];
     const D3 n = {f.nx, f.ny, f.nz};
@@ -985,7 +1001,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
         else {
           double k_tot = p.classes[rc].max_fixed_p;
           double pr = rs.dbl();
-          double from_now = (k_tot <= 0 || !distinguishable_d(pr, 0, MCX_EPS)) ? MCX_TIME_FOREVER : -log(pr) / k_tot;
+          double from_now = (k_tot <= 0 || !distinguishable_d(pr, 0, MCX_EPS)) ? MCX_TIME_FOREVER : -mcx_log(pr) / k_tot;
           unimol_time = t_now + from_now;
         }
       }
@@ -1014,7 +1030,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
             av = 2 * 1.52587890625e-5 * (n >> 16) - 1;
             f = au * au + av * av;
           } while ((f < MCX_EPS) || (f > 1));
-          const double normal_factor = sqrt(-log(f) / f);
+          const double normal_factor = sqrt(-mcx_log(f) / f);
           const double du = au * (normal_factor * space_factor), dv = av * (normal_factor * space_factor);
           double nu, nv;
           const uint32_t new_wall = ray_trace_surf(p, ss.wall, ss.u, ss.v, du, dv, nu, nv);

@@ -65,7 +65,8 @@ struct Counters {
   unsigned int n_emigrants[2]; // multi-GPU: records leaving through the low/high slab face
   unsigned int n_slow;         // entries of slow_list this iteration
   unsigned int n_send[2];      // multi-GPU: halo records packed for the low / high neighbour
-  unsigned int pad[2];
+  unsigned int n_second;       // entries of second_list this iteration
+  unsigned int n_slow2;        // entries of slow2_list this iteration
   // statistics (SimulationStats mirror)
   unsigned long long molecule_steps, ray_polygon_tests, ray_polygon_colls, reflections, transparent,
       absorptions, volvol_collisions, bimol_rxns, unimol_rxns, redos, retries, unresolved, products, deferred;
@@ -137,6 +138,8 @@ struct DevParams {
   double* prop_t;              // per slot: absolute event time
   uint32_t* pend[2];           // pending lists (slot indices)
   uint32_t* slow_list;         // slots the fast diffuse pass deferred to the generic evaluation
+  uint32_t* second_list;       // slots k_diffuse_fast<1> evaluates (two sub-steps)
+  uint32_t* slow2_list;        // slots k_diffuse_fast<1> deferred to the generic evaluation
   unsigned int capacity;
   unsigned int max_rounds;
   Counters* ctr;

@@ -312,138 +312,204 @@ __device__ __forceinline__ void trace_end(Tracer& tc, const Outcome& o, const St
 #ifndef MCX_FAST_MINBLOCKS
 #define MCX_FAST_MINBLOCKS 4
 #endif
+// PASS 0 walks every slot of the snapshot and finishes the whole-step molecules.  Molecules that start the iteration
+// at a fractional diffusion_time (newborn products, kept initiators: DF_PARTIAL / DF_SCHED_UNIMOL) take two
+// sub-steps — one whole step, then the rest of the iteration (diffuse_single_molecule's reschedule loop, :283-336);
+// they were 47 % of what the generic pass had to evaluate, at two partner scans each.  PASS 0 appends them to
+// second_list and PASS 1 runs the same flat body over that list, twice per molecule, with full warps of them.
+// Whatever turns out not to be simple in either pass goes to slow_list and is restarted from the snapshot there.
+template <int PASS>
 __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const __grid_constant__ DevParams p) {
   __shared__ ZigShared zig;
-  __shared__ uint32_t s_slow[TPB / 32][WL_CAP], s_prop[TPB / 32][WL_CAP];
+  __shared__ uint32_t s_slow[TPB / 32][WL_CAP], s_prop[TPB / 32][WL_CAP], s_second[PASS == 0 ? TPB / 32 : 1][WL_CAP];
   __shared__ unsigned int s_reason[TPB / 32][8];
   __shared__ WarpProbe s_probe[TPB / 32];
   zig_load(&zig);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane < 8) s_reason[warp][lane] = 0;
   __syncthreads();
-  WarpList slow_wl, prop_wl;
+  WarpList slow_wl, prop_wl, second_wl;
   slow_wl.init(s_slow[warp]);
   prop_wl.init(s_prop[warp]);
-  const unsigned int n = p.ctr->n_slots;
-  const double t_end = (double)p.iteration + 1.0;
+  second_wl.init(s_second[PASS == 0 ? warp : 0]);
+  const unsigned int n = PASS == 0 ? p.ctr->n_slots : p.ctr->n_second;
+  // PASS 1's own deferrals go to a list of their own (a small second launch of the generic pass takes them)
+  unsigned int* const n_slow_ctr = PASS == 0 ? &p.ctr->n_slow : &p.ctr->n_slow2;
+  uint32_t* const slow_out = PASS == 0 ? p.slow_list : p.slow2_list;
+  const double it = (double)p.iteration, t_end = it + 1.0;
   unsigned int msteps = 0, n_tests = 0, n_coll = 0;
-#ifdef MCX_FAST_BLOCKED
-  // each block walks one contiguous chunk of the sorted snapshot (neighbouring rows are re-read by the same SM)
-  const unsigned int chunk = (((n + gridDim.x - 1) / gridDim.x) + blockDim.x - 1) / blockDim.x * blockDim.x;
-  const unsigned int chunk_end = min(n, (blockIdx.x + 1) * chunk);
-  for (unsigned int base = blockIdx.x * chunk; base < chunk_end; base += blockDim.x) {
-#else
   for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-#endif
-    const unsigned int i = base + threadIdx.x;
-    const bool in_range = i < n;
-    const unsigned int ii = in_range ? i : base;  // a valid slot for every lane
-    const MolRec m = load_rec(p.recA, ii);
+    const unsigned int k = base + threadIdx.x;
+    const bool in_range = k < n;
+    const unsigned int kk = in_range ? k : base;  // a valid entry for every lane
+    const unsigned int i = PASS == 0 ? kk : __ldg(p.second_list + kk);
+    const MolRec m = load_rec(p.recA, i);
     const bool live = in_range && !(m.sf & (DF_DEAD | DF_GHOST));
     const uint32_t species = m.sf & SF_SPECIES_MASK;
-    const uint32_t flags = m.sf & ~SF_SPECIES_MASK;
+    uint32_t flags = m.sf & ~SF_SPECIES_MASK;
     const DevSpecies sp = p.species[species];
-    bool simple = live && !(m.sf & (DF_PARTIAL | DF_SCHED_UNIMOL | DF_SURF)) && (sp.flags & MCX_SP_CAN_DIFFUSE) && sp.time_step == 1.0;
-    // scheduled unimolecular time: a predicated index keeps the load unconditional (no warp split) without
-    // touching the cold array for molecules that have none
+    const bool vol_diffuser = live && !(m.sf & (DF_SURF | DF_CREATED_ON_SURF)) && (sp.flags & MCX_SP_CAN_DIFFUSE) && sp.time_step == 1.0;
+    const bool fractional = (m.sf & (DF_PARTIAL | DF_SCHED_UNIMOL)) != 0;
+    const bool to_second = PASS == 0 && vol_diffuser && fractional;
+    bool simple = vol_diffuser && (PASS == 1 || !fractional);
+    // cold fields: a predicated index keeps the loads unconditional (no warp split) without touching the arrays
+    // for molecules that have nothing there
     const bool has_uni = (m.sf & DF_HAS_UNIMOL) != 0;
-    const bool idle_candidate = live && !(sp.flags & MCX_SP_CAN_DIFFUSE) && !(m.sf & (DF_PARTIAL | DF_SCHED_UNIMOL));
-    const double t_uni_raw = __ldg(p.tuniA + (((simple || idle_candidate) && has_uni) ? ii : 0u));
-    const double t_uni = has_uni ? t_uni_raw : MCX_TIME_INVALID;
-    simple = simple && !(has_uni && t_uni < t_end);  // fires or splits the step inside this iteration -> generic path
+    const bool idle_candidate = PASS == 0 && live && !(sp.flags & MCX_SP_CAN_DIFFUSE) && !fractional;
+    const double t_uni_raw = __ldg(p.tuniA + (((simple || idle_candidate) && has_uni) ? i : 0u));
+    double t_uni = has_uni ? t_uni_raw : MCX_TIME_INVALID;
+    double t_now = it;
+    if (PASS == 1) {
+      const double t_sched_raw = __ldg(p.tschedA + ((m.sf & DF_PARTIAL) ? i : 0u));
+      if (m.sf & DF_PARTIAL) t_now = t_sched_raw;
+    }
     // a non-diffusing molecule with nothing scheduled inside this iteration (receptors, pumps): the generic
     // evaluation would return MCX_OUT_STATIC without drawing a number (diffuse_react_event.cpp:318-335)
     const bool idle = idle_candidate && !(has_uni && t_uni < t_end);
-    int reason = simple ? -1 : MCX_DEFER_TIMING;
-
-    // compute_vol_displacement with steps == 1 (diffusion_utils.inl:366-432); drawn by every lane
     Stream rs; rs.init(p, m.id, &zig);
-    D3 disp;
-    disp.x = sp.space_step * rs.gauss() * 0.70710678118654752440;
-    disp.y = sp.space_step * rs.gauss() * 0.70710678118654752440;
-    disp.z = sp.space_step * rs.gauss() * 0.70710678118654752440;
-    const D3 pos = {m.x, m.y, m.z};
-    const D3 dest = pos + disp;
-    simple = simple && in_partition(p, dest);
-    if (!simple && reason < 0) reason = MCX_DEFER_GEOMETRY;
-    int s0[3], s1[3];
-    subpart_3d(p, pos, s0);
-    subpart_3d(p, dest, s1);
-    const int dx = s1[0] - s0[0], dy = s1[1] - s0[1], dz = s1[2] - s0[2];
-    const uint32_t own = simple ? subpart_from_3d(p, s0[0], s0[1], s0[2]) : 0u;
-    const uint8_t f = __ldg(p.sp_flags + own);
-    const bool same = (dx | dy | dz) == 0;
-    const bool near = dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1;
-    // one subpartition face crossed: the DDA visits exactly {start, end} (collision_utils_subparts.inl:127-300)
-    const bool single = near && ((dx != 0) + (dy != 0) + (dz != 0)) == 1;
-    const uint32_t dest_sp = (simple && single) ? subpart_from_3d(p, s1[0], s1[1], s1[2]) : 0u;
-    const uint8_t fd = __ldg(p.sp_flags + dest_sp);
-    unsigned int n_wall_tests = 0, n_wall_tests_dest = 0;
-    const bool walls_own = simple && (same || single) && (f & 1);
-    const bool walls_dest = simple && single && (fd & 1);
-    double wall_dist = 1e300;
-    const bool rejected_own = all_walls_plane_rejected(p, walls_own, own, pos, disp, n_wall_tests, wall_dist);
-    const bool rejected_dest = all_walls_plane_rejected(p, walls_dest, dest_sp, pos, disp, n_wall_tests_dest, wall_dist);
-    n_wall_tests += n_wall_tests_dest;
-    simple = simple && ((same || single) ? ((!walls_own || rejected_own) && (!walls_dest || rejected_dest)) : (near && !(f & 2)));
-    if (!simple && reason < 0) reason = (same || single) ? MCX_DEFER_WALL : MCX_DEFER_GEOMETRY;
-
-    // partner probe: none -> move; exactly one, in the molecule's own subpartition (always a collected one)
-    // -> the single collision is evaluated below; anything else -> generic path
-    PartnerHit ph;
-    const bool probing = simple && sp.can_vol_react;
-    bool overflow;
-    const int n_hits = probe_partners_flat(p, probing, pos, disp, m.id, species, ph, overflow, &s_probe[warp]);
-    // a collision next to walls needs exact_disk (walls of the collision subpartition): generic path
-    // (every wall plane of the crossed subpartitions farther than R from the whole segment: the factor is 1)
-    const bool disk_walls = n_hits == 1 && wall_dist < p.R;
-    simple = simple && !overflow && (n_hits == 0 || (n_hits == 1 && ph.in_own_subpart && !disk_walls));
-    if (!simple && reason < 0)
-      reason = overflow ? MCX_DEFER_PROBE_SHAPE : (n_hits > 1 ? MCX_DEFER_MULTI_HIT : (disk_walls ? MCX_DEFER_DISK : MCX_DEFER_FOREIGN_HIT));
-
-    bool proposed = false;
-    if (simple) {
-      Tracer tc; trace_begin(p, tc, m.id);
-      Outcome o; o.kind = MCX_OUT_MOVED; o.pos = dest;
-      if (n_hits == 1) {
-        if (!(ph.t < MCX_EPS)) {  // is_immediate_collision (collision_utils.inl:814-816)
-          // collide_and_react_with_vol_mol (:786-829) with scaling = factor(1) * r_rate_factor(1)
-          tc.ev(EV_COLL, ph.id);
-          if (tc.tr) { tc.tr->partner[0] = ph.id; tc.tr->n_collisions = 1; }
-          const int pathway = test_bimolecular(p, p.classes[ph.rxn_class], 1.0, rs);
-          if (pathway >= 0) {
-            const double abs_t = (double)p.iteration + 1.0 * ph.t;
-            tc.ev(EV_RXN | (uint32_t)pathway, (uint32_t)ph.rxn_class);
-            if (tc.tr) { tc.tr->rxn_class = ph.rxn_class; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = ph.id; tc.tr->t_event = abs_t; }
-            o.kind = MCX_OUT_REACTED; o.pos = pos + disp * ph.t;
-            o.rxn_class = ph.rxn_class; o.pathway = pathway; o.partner_slot = ph.slot; o.partner_id = ph.id;
-            o.t_event = abs_t; o.t_now = (double)p.iteration; o.flags = flags; o.unimol_time = t_uni;
-          }
+    Tracer tc; tc.h = 0xcbf29ce484222325ULL; tc.tr = nullptr;
+    if (PASS == 1) {
+      // unimolecular firing comes first (diffuse_react_event.cpp:215-223): generic path
+      simple = simple && !(t_uni != MCX_TIME_INVALID && t_uni <= t_now);
+      // newbie lifetime (:232-236 -> pick_unimol_rxn_class_and_set_rxn_time :1731-1758): one draw
+      if (simple && (flags & DF_SCHED_UNIMOL)) {
+        flags &= ~DF_SCHED_UNIMOL;
+        const int rc = p.unimol[species];
+        if (rc < 0) t_uni = MCX_TIME_INVALID;
+        else {
+          const double k_tot = p.classes[rc].max_fixed_p;
+          const double pr = rs.dbl();
+          const double from_now = (k_tot <= 0 || !distinguishable_d(pr, 0, MCX_EPS)) ? MCX_TIME_FOREVER : -mcx_log(pr) / k_tot;
+          t_uni = t_now + from_now;
         }
       }
-      trace_end(tc, o, rs);
-      if (o.kind == MCX_OUT_MOVED) finalize_alive(p, i, dest, m.id, species, flags, t_end, t_uni);
-      else { write_proposal(p, i, o, m.id, species, round_epoch(p, 0), -1); proposed = true; }
-      if (owned_z(p, pos.z)) { msteps++; n_tests += n_wall_tests; n_coll += n_hits == 1 ? 1u : 0u; }
+      if (simple) trace_begin(p, tc, m.id);
     }
-    if (in_range && !live) p.rank[i] = MCX_NONE;
+    // a lifetime ending inside this iteration splits a step or fires (get_max_time :164-198): generic path
+    simple = simple && !(t_uni != MCX_TIME_INVALID && t_uni < t_end);
+    int reason = simple ? -1 : MCX_DEFER_TIMING;
+    const bool own_start = owned_z(p, m.z);
+    D3 pos = {m.x, m.y, m.z};
+    unsigned int my_tests = 0, my_coll = 0;
+    bool running = simple, proposed = false;  // running: this lane's evaluation is simple so far and not finished
+    bool slow = live && !idle && !to_second && !simple;
+
+#pragma unroll 1
+    for (int sub = 0; sub < (PASS == 0 ? 1 : 2); sub++) {
+      simple = running;
+      // compute_vol_displacement (diffusion_utils.inl:366-432) with time_step == 1; drawn by every lane
+      double t_steps = 1.0, scale = sp.space_step, r_rate_factor = 1.0, t_new = t_end;
+      bool again = false;
+      if (PASS == 1) {
+        const double max_time = t_end - t_now;
+        double steps = 1.0;
+        if (t_steps > max_time) { t_steps = max_time; steps = max_time / sp.time_step; }
+        simple = simple && !(steps < MCX_EPS) && !(t_uni != MCX_TIME_INVALID && t_uni < t_now + max_time);
+        if (steps != 1.0) { const double rate_factor = sqrt(steps); r_rate_factor = 1.0 / rate_factor; scale = rate_factor * sp.space_step; }
+        // reschedule (:283-336): does the molecule need another sub-step after this one?
+        t_new = t_now + t_steps;
+        again = t_new < t_end && !cmp_eq_d(t_new, t_end, MCX_EPS);
+        simple = simple && !(again && sub == 1);
+        if (!simple && reason < 0) reason = MCX_DEFER_TIMING;
+      }
+      D3 disp;
+      disp.x = scale * rs.gauss() * 0.70710678118654752440;
+      disp.y = scale * rs.gauss() * 0.70710678118654752440;
+      disp.z = scale * rs.gauss() * 0.70710678118654752440;
+      const D3 dest = pos + disp;
+      simple = simple && in_partition(p, dest);
+      if (!simple && reason < 0) reason = MCX_DEFER_GEOMETRY;
+      int s0[3], s1[3];
+      subpart_3d(p, pos, s0);
+      subpart_3d(p, dest, s1);
+      const int dx = s1[0] - s0[0], dy = s1[1] - s0[1], dz = s1[2] - s0[2];
+      const uint32_t own = simple ? subpart_from_3d(p, s0[0], s0[1], s0[2]) : 0u;
+      const uint8_t f = __ldg(p.sp_flags + own);
+      const bool same = (dx | dy | dz) == 0;
+      const bool near = dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1;
+      // one subpartition face crossed: the DDA visits exactly {start, end} (collision_utils_subparts.inl:127-300)
+      const bool single = near && ((dx != 0) + (dy != 0) + (dz != 0)) == 1;
+      const uint32_t dest_sp = (simple && single) ? subpart_from_3d(p, s1[0], s1[1], s1[2]) : 0u;
+      const uint8_t fd = __ldg(p.sp_flags + dest_sp);
+      unsigned int n_wall_tests = 0, n_wall_tests_dest = 0;
+      const bool walls_own = simple && (same || single) && (f & 1);
+      const bool walls_dest = simple && single && (fd & 1);
+      double wall_dist = 1e300;
+      const bool rejected_own = all_walls_plane_rejected(p, walls_own, own, pos, disp, n_wall_tests, wall_dist);
+      const bool rejected_dest = all_walls_plane_rejected(p, walls_dest, dest_sp, pos, disp, n_wall_tests_dest, wall_dist);
+      n_wall_tests += n_wall_tests_dest;
+      simple = simple && ((same || single) ? ((!walls_own || rejected_own) && (!walls_dest || rejected_dest)) : (near && !(f & 2)));
+      if (!simple && reason < 0) reason = (same || single) ? MCX_DEFER_WALL : MCX_DEFER_GEOMETRY;
+
+      // partner probe: none -> move; exactly one, in the molecule's own subpartition (always a collected one)
+      // -> the single collision is evaluated below; anything else -> generic path
+      PartnerHit ph;
+      const bool probing = simple && sp.can_vol_react;
+      bool overflow;
+      const int n_hits = probe_partners_flat(p, probing, pos, disp, m.id, species, ph, overflow, &s_probe[warp]);
+      // a collision next to walls needs exact_disk (walls of the collision subpartition): generic path
+      // (every wall plane of the crossed subpartitions farther than R from the whole segment: the factor is 1)
+      const bool disk_walls = n_hits == 1 && wall_dist < p.R;
+      simple = simple && !overflow && (n_hits == 0 || (n_hits == 1 && ph.in_own_subpart && !disk_walls));
+      if (!simple && reason < 0)
+        reason = overflow ? MCX_DEFER_PROBE_SHAPE : (n_hits > 1 ? MCX_DEFER_MULTI_HIT : (disk_walls ? MCX_DEFER_DISK : MCX_DEFER_FOREIGN_HIT));
+
+      if (simple) {
+        if (PASS == 0) trace_begin(p, tc, m.id);
+        Outcome o; o.kind = MCX_OUT_MOVED; o.pos = dest;
+        if (n_hits == 1) {
+          if (!(ph.t < MCX_EPS)) {  // is_immediate_collision (collision_utils.inl:814-816)
+            // collide_and_react_with_vol_mol (:786-829) with scaling = factor(1) * r_rate_factor
+            tc.ev(EV_COLL, ph.id);
+            if (tc.tr) { if (tc.tr->n_collisions < MCX_TRACE_K) tc.tr->partner[tc.tr->n_collisions] = ph.id; tc.tr->n_collisions++; }
+            const int pathway = test_bimolecular(p, p.classes[ph.rxn_class], r_rate_factor, rs);
+            if (pathway >= 0) {
+              const double abs_t = t_now + t_steps * ph.t;
+              tc.ev(EV_RXN | (uint32_t)pathway, (uint32_t)ph.rxn_class);
+              if (tc.tr) { tc.tr->rxn_class = ph.rxn_class; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = ph.id; tc.tr->t_event = abs_t; }
+              o.kind = MCX_OUT_REACTED; o.pos = pos + disp * ph.t;
+              o.rxn_class = ph.rxn_class; o.pathway = pathway; o.partner_slot = ph.slot; o.partner_id = ph.id;
+              o.t_event = abs_t; o.t_now = t_now; o.flags = flags; o.unimol_time = t_uni; o.orient_bits = 0;
+            }
+          }
+        }
+        my_tests += n_wall_tests; my_coll += n_hits == 1 ? 1u : 0u;
+        if (PASS == 1 && o.kind == MCX_OUT_MOVED && again) {  // first sub-step done
+          pos = dest; t_now = t_new;
+        } else {
+          trace_end(tc, o, rs);
+          if (o.kind == MCX_OUT_MOVED) {
+            if (PASS == 1) { const double r = round(t_new); if (cmp_eq_d(t_new, r, MCX_SQRT_EPS)) t_new = r; }
+            finalize_alive(p, i, dest, m.id, species, flags & ~DF_PARTIAL, t_new, t_uni);
+          } else { write_proposal(p, i, o, m.id, species, round_epoch(p, 0), -1); proposed = true; }
+          if (own_start) { msteps++; n_tests += my_tests; n_coll += my_coll; }
+          running = false;
+        }
+      } else if (running) {
+        running = false;
+        slow = true;
+      }
+    }
+    if (PASS == 0 && in_range && !live) p.rank[i] = MCX_NONE;
     if (idle) {
       if (p.trace && m.id < p.n_trace) {
-        Tracer tc; trace_begin(p, tc, m.id);
+        trace_begin(p, tc, m.id);
         Outcome o; o.kind = MCX_OUT_STATIC; o.pos = pos;
         trace_end(tc, o, rs);
         tc.tr->n_words = 0;
       }
       finalize_alive(p, i, pos, m.id, species, flags, 0.0, t_uni);
     }
-    const bool slow = live && !simple && !idle;
+    if (PASS == 1 && slow && tc.tr) tc.tr->rounds--;  // the generic pass starts it over (and counts the evaluation)
     // staged appends (loop bounds are warp-uniform: all 32 lanes arrive here)
     if (slow) atomicAdd(&s_reason[warp][reason & 7], 1u);
-    slow_wl.push(slow, i, &p.ctr->n_slow, p.slow_list);
+    slow_wl.push(slow, i, n_slow_ctr, slow_out);
     prop_wl.push(proposed, i, &p.ctr->n_pend[0], p.pend[0]);
+    if (PASS == 0) second_wl.push(to_second, i, &p.ctr->n_second, p.second_list);
   }
-  slow_wl.flush(&p.ctr->n_slow, p.slow_list);
+  slow_wl.flush(n_slow_ctr, slow_out);
   prop_wl.flush(&p.ctr->n_pend[0], p.pend[0]);
+  if (PASS == 0) second_wl.flush(&p.ctr->n_second, p.second_list);
   __syncwarp();
   if (lane == 0 && slow_wl.total) atomicAdd(&p.ctr->deferred, (unsigned long long)slow_wl.total);
   if (lane < 8 && s_reason[warp][lane]) atomicAdd(&p.ctr->defer_reason[lane], (unsigned long long)s_reason[warp][lane]);
@@ -458,12 +524,13 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
 #define MCX_SLOW_MINBLOCKS 4
 #endif
 template <bool WITH_DISK, bool SURF>
-__global__ void __launch_bounds__(TPB, MCX_SLOW_MINBLOCKS) k_diffuse_slow(const __grid_constant__ DevParams p) {
+__global__ void __launch_bounds__(TPB, MCX_SLOW_MINBLOCKS) k_diffuse_slow(const __grid_constant__ DevParams p, int second) {
   __shared__ ZigShared zig;
   zig_load(&zig);
   __syncthreads();
-  const unsigned int n = WITH_DISK ? p.ctr->n_pend[1] : p.ctr->n_slow;
-  const uint32_t* list = WITH_DISK ? p.pend[1] : p.slow_list;
+  // second: the deferrals of k_diffuse_fast<1> instead of those of k_diffuse_fast<0>
+  const unsigned int n = WITH_DISK ? p.ctr->n_pend[1] : (second ? p.ctr->n_slow2 : p.ctr->n_slow);
+  const uint32_t* list = WITH_DISK ? p.pend[1] : (second ? p.slow2_list : p.slow_list);
   const unsigned int epoch = round_epoch(p, 0);
   LocalStats ls = {0, 0, 0, 0, 0, 0};
   unsigned int msteps = 0;
@@ -689,7 +756,7 @@ __global__ void k_end_iteration(const __grid_constant__ DevParams p) {
   Counters* c = p.ctr;
   if (threadIdx.x == 0) {
     c->n_slots = c->n_next;
-    c->n_prod = 0; c->n_pend[0] = 0; c->n_pend[1] = 0; c->n_slow = 0; c->n_send[0] = 0; c->n_send[1] = 0;
+    c->n_prod = 0; c->n_pend[0] = 0; c->n_pend[1] = 0; c->n_slow = 0; c->n_second = 0; c->n_slow2 = 0; c->n_send[0] = 0; c->n_send[1] = 0;
   }
   if (p.world > 1) { c->species_count[threadIdx.x] = c->species_next[threadIdx.x]; c->species_next[threadIdx.x] = 0; }
 }
@@ -862,23 +929,27 @@ void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
 void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
   cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
   if (plan.prof) cudaEventRecord(plan.prof[0], s);
-  k_diffuse_fast<<<plan.sm_count * 2 * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
+  k_diffuse_fast<0><<<plan.sm_count * 2 * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
   if (plan.prof) cudaEventRecord(plan.prof[4], s);
+  k_diffuse_fast<1><<<plan.sm_count * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
+  const int g_slow = plan.sm_count * 2 * MCX_SLOW_MINBLOCKS;
+  if (p.has_surf) k_diffuse_slow<false, true><<<g_slow, TPB, 0, s>>>(p, 0);
+  else k_diffuse_slow<false, false><<<g_slow, TPB, 0, s>>>(p, 0);
   if (p.has_surf) {
-    k_diffuse_slow<false, true><<<plan.sm_count * 2 * MCX_SLOW_MINBLOCKS, TPB, 0, s>>>(p);
-    k_diffuse_slow<true, true><<<plan.sm_count, TPB, 0, s>>>(p);
+    k_diffuse_slow<false, true><<<plan.sm_count, TPB, 0, s>>>(p, 1);
+    k_diffuse_slow<true, true><<<plan.sm_count, TPB, 0, s>>>(p, 0);
   } else {
-    k_diffuse_slow<false, false><<<plan.sm_count * 2 * MCX_SLOW_MINBLOCKS, TPB, 0, s>>>(p);
-    k_diffuse_slow<true, false><<<plan.sm_count, TPB, 0, s>>>(p);
+    k_diffuse_slow<false, false><<<plan.sm_count, TPB, 0, s>>>(p, 1);
+    k_diffuse_slow<true, false><<<plan.sm_count, TPB, 0, s>>>(p, 0);
   }
   if (plan.prof) cudaEventRecord(plan.prof[1], s);
-  count_launches(plan, 3);
+  count_launches(plan, 5);
   if (plan.has_claims) {
     count_launches(plan, 4 * p.max_rounds);
     const int small_grid = plan.sm_count * 2;
     for (unsigned int r = 0; r < p.max_rounds; r++) {
       k_round_begin<<<1, 1, 0, s>>>(p, r);
-      k_resolve<<<small_grid, TPB, 0, s>>>(p, r);
+      k_resolve<<<r == 0 ? 2 * small_grid : small_grid, TPB, 0, s>>>(p, r);  // round 0 holds ~99 % of the proposals
       k_round_mid<<<1, 1, 0, s>>>(p, r);
       if (p.has_surf) k_retry<true><<<small_grid, TPB, 0, s>>>(p, r, r + 1 == p.max_rounds ? 1 : 0);
       else k_retry<false><<<small_grid, TPB, 0, s>>>(p, r, r + 1 == p.max_rounds ? 1 : 0);
