@@ -633,6 +633,7 @@ __device__ __forceinline__ int probe_partners(const DevParams& p, bool enabled, 
 // pairs of the warp's 32 molecules are concatenated and dealt to the lanes 32 at a time, so the trip count is
 // ceil(sum / 32): every lane tests one candidate of SOME lane's molecule per trip, the owner's move is read from
 // shared memory, and the (rare) hits are reported back through shared-memory atomics.  Warp-collective.
+#define MCX_FAST_MAX_HITS 4
 struct __align__(16) WarpProbe {
   double4 a[32];          // pos.x, pos.y, pos.z, movelen2
   double4 b[32];          // disp.x, disp.y, disp.z, bits(id | species << 32)
@@ -641,10 +642,10 @@ struct __align__(16) WarpProbe {
   uint32_t off[32];       // compacted owners: first pair index
   uint32_t owner[32];     // compacted owners: lane
   uint32_t hits[32];      // per owner lane: number of eligible collisions
-  uint32_t hit_slot[32];  // per owner lane: slot of one of them
+  uint32_t hit_slot[32][MCX_FAST_MAX_HITS];  // per owner lane: slots of the first few of them
 };
 __device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enabled, D3 pos, D3 disp, uint32_t self_id,
-                                                   uint32_t self_species, PartnerHit& first, bool& overflow, WarpProbe* sm) {
+                                                   uint32_t self_species, bool& overflow, WarpProbe* sm) {
   const int lane = threadIdx.x & 31;
   const double movelen2 = dot3(disp, disp);
   const double R2 = p.R * p.R;
@@ -687,37 +688,52 @@ __device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enab
     if (q < W) {
       const uint32_t o = sm->owner[k];
       const uint32_t kk = q - sm->off[k];
+      // row of pair kk = number of row ends at or below it (branch-free: the nested selects this replaces were
+      // compiled into divergent branches, 12-20 of 32 lanes active, profiles/r01_l)
       const uint4 c03 = *reinterpret_cast<const uint4*>(&sm->cum[o][0]);
-      const uint2 c45 = *reinterpret_cast<const uint2*>(&sm->cum[o][4]);
-      const uint4 l03 = *reinterpret_cast<const uint4*>(&sm->lo[o][0]);
-      const uint2 l45 = *reinterpret_cast<const uint2*>(&sm->lo[o][4]);
-      const uint32_t lo_r = kk < c03.z ? (kk < c03.x ? l03.x : (kk < c03.y ? l03.y : l03.z))
-                                       : (kk < c03.w ? l03.w : (kk < c45.x ? l45.x : l45.y));
-      const uint32_t j = lo_r + kk;
+      const uint32_t c4 = sm->cum[o][4];
+      const uint32_t r = (kk >= c03.x) + (kk >= c03.y) + (kk >= c03.z) + (kk >= c03.w) + (kk >= c4);
+      const uint32_t j = sm->lo[o][r] + kk;
       const MolRec c = load_rec(p.recA, j);
       const double4 oa = sm->a[o], ob = sm->b[o];
       const unsigned long long ids = (unsigned long long)__double_as_longlong(ob.w);
       double d;
       if (collide_mol_hit(c, D3{oa.x, oa.y, oa.z}, D3{ob.x, ob.y, ob.z}, oa.w, oa.w * R2, (uint32_t)ids, d)) {
         const int rc = p.bimol[(uint32_t)(ids >> 32) * p.n_species + (c.sf & SF_SPECIES_MASK)];
-        if (rc >= 0) { atomicAdd(&sm->hits[o], 1u); sm->hit_slot[o] = j; }
+        if (rc >= 0) { const uint32_t h = atomicAdd(&sm->hits[o], 1u); if (h < MCX_FAST_MAX_HITS) sm->hit_slot[o][h] = j; }
       }
     }
   }
   __syncwarp();
   const int found = (int)sm->hits[lane];
-  first.slot = MCX_NONE; first.in_own_subpart = false; first.t = 0; first.id = 0; first.species = 0; first.rxn_class = 0;
-  if (found == 1) {
-    const uint32_t j = sm->hit_slot[lane];
+  __syncwarp();  // the buffers are reused by the next trip of the caller's loop
+  return found;    // the slots of the first MCX_FAST_MAX_HITS of them are in sm->hit_slot[lane]
+}
+
+// Next collision of the probe's hit list in sort_collisions_by_time order (time ascending, vol-vol ties by
+// descending partner id, diffuse_react_event.cpp:341-364) strictly after (t_last, id_last); false when none is left.
+// all_own: every hit examined lies in the molecule's own subpartition (always a collected one).
+__device__ __forceinline__ bool next_probe_hit(const DevParams& p, const WarpProbe* sm, int n_hits, D3 pos, D3 disp, uint32_t self_species,
+                                               double t_last, uint32_t id_last, PartnerHit& best, bool& all_own) {
+  const int lane = threadIdx.x & 31;
+  const double movelen2 = dot3(disp, disp);
+  const uint32_t own = subpart_index(p, pos);
+  bool any = false;
+  best.t = MCX_TIME_FOREVER; best.id = 0; best.slot = MCX_NONE; best.species = 0; best.rxn_class = 0; best.in_own_subpart = true;
+  for (int h = 0; h < n_hits; h++) {
+    const uint32_t j = sm->hit_slot[lane][h];
     const MolRec c = load_rec(p.recA, j);
     const D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
-    const uint32_t csp = c.sf & SF_SPECIES_MASK;
-    first.t = dot3(dir, disp) / movelen2; first.slot = j; first.id = c.id; first.species = csp;
-    first.rxn_class = p.bimol[self_species * p.n_species + csp];
-    first.in_own_subpart = subpart_index(p, D3{c.x, c.y, c.z}) == subpart_index(p, pos);
+    const double t = dot3(dir, disp) / movelen2;
+    all_own = all_own && subpart_index(p, D3{c.x, c.y, c.z}) == own;
+    if (t < t_last || (t == t_last && c.id >= id_last)) continue;
+    if (!any || t < best.t || (t == best.t && c.id > best.id)) {
+      const uint32_t csp = c.sf & SF_SPECIES_MASK;
+      best.t = t; best.id = c.id; best.slot = j; best.species = csp; best.rxn_class = p.bimol[self_species * p.n_species + csp];
+      any = true;
+    }
   }
-  __syncwarp();  // the buffers are reused by the next trip of the caller's loop
-  return found;
+  return any;
 }
 
 // Plane-rejection stage of collide_wall (collision_utils.inl:664-683) for every wall of one subpartition:

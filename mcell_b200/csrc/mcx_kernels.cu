@@ -441,23 +441,31 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       simple = simple && ((same || single) ? ((!walls_own || rejected_own) && (!walls_dest || rejected_dest)) : (near && !(f & 2)));
       if (!simple && reason < 0) reason = (same || single) ? MCX_DEFER_WALL : MCX_DEFER_GEOMETRY;
 
-      // partner probe: none -> move; exactly one, in the molecule's own subpartition (always a collected one)
-      // -> the single collision is evaluated below; anything else -> generic path
-      PartnerHit ph;
+      // partner probe: none -> move; up to MCX_FAST_MAX_HITS, all in the molecule's own subpartition (always a
+      // collected one) -> evaluated below in collision order; anything else -> generic path
       const bool probing = simple && sp.can_vol_react;
       bool overflow;
-      const int n_hits = probe_partners_flat(p, probing, pos, disp, m.id, species, ph, overflow, &s_probe[warp]);
+      const int n_hits = probe_partners_flat(p, probing, pos, disp, m.id, species, overflow, &s_probe[warp]);
       // a collision next to walls needs exact_disk (walls of the collision subpartition): generic path
       // (every wall plane of the crossed subpartitions farther than R from the whole segment: the factor is 1)
-      const bool disk_walls = n_hits == 1 && wall_dist < p.R;
-      simple = simple && !overflow && (n_hits == 0 || (n_hits == 1 && ph.in_own_subpart && !disk_walls));
+      const bool disk_walls = n_hits > 0 && wall_dist < p.R;
+      simple = simple && !overflow && n_hits <= MCX_FAST_MAX_HITS && !disk_walls;
       if (!simple && reason < 0)
-        reason = overflow ? MCX_DEFER_PROBE_SHAPE : (n_hits > 1 ? MCX_DEFER_MULTI_HIT : (disk_walls ? MCX_DEFER_DISK : MCX_DEFER_FOREIGN_HIT));
+        reason = overflow ? MCX_DEFER_PROBE_SHAPE : (disk_walls ? MCX_DEFER_DISK : MCX_DEFER_MULTI_HIT);
+      // the first collision and whether every hit lies in the own subpartition (rare lanes: 12 % have a hit at all)
+      PartnerHit ph;
+      bool all_own = true;
+      bool have = simple && n_hits > 0 && next_probe_hit(p, &s_probe[warp], n_hits, pos, disp, species, -1.0, 0u, ph, all_own);
+      simple = simple && all_own;
+      if (!simple && reason < 0) reason = MCX_DEFER_FOREIGN_HIT;
 
       if (simple) {
         if (PASS == 0) trace_begin(p, tc, m.id);
         Outcome o; o.kind = MCX_OUT_MOVED; o.pos = dest;
-        if (n_hits == 1) {
+        unsigned int colls = 0;
+        // sort_collisions_by_time realised as repeated selection, like the generic pass (evaluate_iteration)
+        while (have) {
+          colls++;
           if (!(ph.t < MCX_EPS)) {  // is_immediate_collision (collision_utils.inl:814-816)
             // collide_and_react_with_vol_mol (:786-829) with scaling = factor(1) * r_rate_factor
             tc.ev(EV_COLL, ph.id);
@@ -470,10 +478,14 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
               o.kind = MCX_OUT_REACTED; o.pos = pos + disp * ph.t;
               o.rxn_class = ph.rxn_class; o.pathway = pathway; o.partner_slot = ph.slot; o.partner_id = ph.id;
               o.t_event = abs_t; o.t_now = t_now; o.flags = flags; o.unimol_time = t_uni; o.orient_bits = 0;
+              break;
             }
           }
+          if ((int)colls >= n_hits) break;
+          const double t_last = ph.t; const uint32_t id_last = ph.id;
+          have = next_probe_hit(p, &s_probe[warp], n_hits, pos, disp, species, t_last, id_last, ph, all_own);
         }
-        my_tests += n_wall_tests; my_coll += n_hits == 1 ? 1u : 0u;
+        my_tests += n_wall_tests; my_coll += colls;
         if (PASS == 1 && o.kind == MCX_OUT_MOVED && again) {  // first sub-step done
           pos = dest; t_now = t_new;
         } else {
