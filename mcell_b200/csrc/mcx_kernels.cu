@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
     const DevSpecies sp = p.species[species];
     const bool vol_diffuser = live && !(m.sf & (DF_SURF | DF_CREATED_ON_SURF)) && (sp.flags & MCX_SP_CAN_DIFFUSE) && sp.time_step == 1.0;
     const bool fractional = (m.sf & (DF_PARTIAL | DF_SCHED_UNIMOL)) != 0;
-    const bool to_second = PASS == 0 && vol_diffuser && fractional;
+    bool to_second = PASS == 0 && vol_diffuser && fractional;
     bool simple = vol_diffuser && (PASS == 1 || !fractional);
     // cold fields: a predicated index keeps the loads unconditional (no warp split) without touching the arrays
     // for molecules that have nothing there
@@ -441,29 +441,32 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       simple = simple && ((same || single) ? ((!walls_own || rejected_own) && (!walls_dest || rejected_dest)) : (near && !(f & 2)));
       if (!simple && reason < 0) reason = (same || single) ? MCX_DEFER_WALL : MCX_DEFER_GEOMETRY;
 
-      // partner probe: none -> move; up to MCX_FAST_MAX_HITS, all in the molecule's own subpartition (always a
-      // collected one) -> evaluated below in collision order; anything else -> generic path
+      // partner probe: none -> move; one hit in the molecule's own subpartition (always a collected one) -> evaluated
+      // below; 2..MCX_FAST_MAX_HITS hits -> PASS 1, which evaluates them in collision order; anything else -> generic
       const bool probing = simple && sp.can_vol_react;
       bool overflow;
       const int n_hits = probe_partners_flat(p, probing, pos, disp, m.id, species, overflow, &s_probe[warp]);
       // a collision next to walls needs exact_disk (walls of the collision subpartition): generic path
       // (every wall plane of the crossed subpartitions farther than R from the whole segment: the factor is 1)
       const bool disk_walls = n_hits > 0 && wall_dist < p.R;
-      simple = simple && !overflow && n_hits <= MCX_FAST_MAX_HITS && !disk_walls;
+      const bool several = PASS == 0 && simple && !overflow && !disk_walls && n_hits > 1 && n_hits <= MCX_FAST_MAX_HITS;
+      simple = simple && !overflow && n_hits <= (PASS == 0 ? 1 : MCX_FAST_MAX_HITS) && !disk_walls;
       if (!simple && reason < 0)
         reason = overflow ? MCX_DEFER_PROBE_SHAPE : (disk_walls ? MCX_DEFER_DISK : MCX_DEFER_MULTI_HIT);
-      // the first collision and whether every hit lies in the own subpartition (rare lanes: 12 % have a hit at all)
+      // the first collision, and whether every hit lies in the own subpartition
       PartnerHit ph;
       bool all_own = true;
       bool have = simple && n_hits > 0 && next_probe_hit(p, &s_probe[warp], n_hits, pos, disp, species, -1.0, 0u, ph, all_own);
       simple = simple && all_own;
       if (!simple && reason < 0) reason = MCX_DEFER_FOREIGN_HIT;
+      if (several) { to_second = true; slow = false; running = false; }
 
       if (simple) {
         if (PASS == 0) trace_begin(p, tc, m.id);
         Outcome o; o.kind = MCX_OUT_MOVED; o.pos = dest;
         unsigned int colls = 0;
-        // sort_collisions_by_time realised as repeated selection, like the generic pass (evaluate_iteration)
+        // sort_collisions_by_time realised as repeated selection, like the generic pass (evaluate_iteration);
+        // PASS 0 has at most one
         while (have) {
           colls++;
           if (!(ph.t < MCX_EPS)) {  // is_immediate_collision (collision_utils.inl:814-816)
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
               break;
             }
           }
-          if ((int)colls >= n_hits) break;
+          if (PASS == 0 || (int)colls >= n_hits) break;
           const double t_last = ph.t; const uint32_t id_last = ph.id;
           have = next_probe_hit(p, &s_probe[warp], n_hits, pos, disp, species, t_last, id_last, ph, all_own);
         }
