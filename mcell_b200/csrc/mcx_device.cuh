@@ -710,14 +710,39 @@ __device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enab
   return found;    // the slots of the first MCX_FAST_MAX_HITS of them are in sm->hit_slot[lane]
 }
 
+// Direction (-1 / 0 / +1 per axis) in which collect_neighboring_subparts (collision_utils_subparts.inl:38-122) adds
+// neighbours of the subpartition si around position q: the subpartitions it inserts are si + (a, b, c) with each
+// component either 0 or that direction, not all 0.
+__device__ __forceinline__ void neighbor_dirs(const DevParams& p, D3 q, const int si[3], double rr, int d[3]) {
+  const double sp_len = p.sp_len, part_len = p.part_len;
+  const D3 rel = {q.x - p.ox, q.y - p.oy, q.z - p.oz};
+  const D3 plus = {rel.x + rr, rel.y + rr, rel.z + rr};
+  const D3 minus = {rel.x - rr, rel.y - rr, rel.z - rr};
+  const D3 boundary = {si[0] * sp_len, si[1] * sp_len, si[2] * sp_len};
+  d[0] = (minus.x < boundary.x && minus.x > 0.0) ? -1 : ((plus.x > boundary.x + sp_len && plus.x < part_len) ? 1 : 0);
+  d[1] = (minus.y < boundary.y && minus.y > 0.0) ? -1 : ((plus.y > boundary.y + sp_len && plus.y < part_len) ? 1 : 0);
+  d[2] = (minus.z < boundary.z && minus.z > 0.0) ? -1 : ((plus.z > boundary.z + sp_len && plus.z < part_len) ? 1 : 0);
+}
+__device__ __forceinline__ bool in_neighbor_dirs(const int delta[3], const int d[3]) {
+  return (delta[0] == 0 || delta[0] == d[0]) && (delta[1] == 0 || delta[1] == d[1]) && (delta[2] == 0 || delta[2] == d[2]);
+}
+
 // Next collision of the probe's hit list in sort_collisions_by_time order (time ascending, vol-vol ties by
 // descending partner id, diffuse_react_event.cpp:341-364) strictly after (t_last, id_last); false when none is left.
-// all_own: every hit examined lies in the molecule's own subpartition (always a collected one).
-__device__ __forceinline__ bool next_probe_hit(const DevParams& p, const WarpProbe* sm, int n_hits, D3 pos, D3 disp, uint32_t self_species,
-                                               double t_last, uint32_t id_last, PartnerHit& best, bool& all_own) {
+// A hit counts only if its subpartition is one the reference collects for this move (ray_trace_vol :698-722):
+// the molecule's own one and, when the move crosses a single subpartition face, the one it ends in (s1); for a
+// move that stays inside its subpartition (stays == true) also the neighbours collect_neighboring_subparts adds
+// around the start and the end point (DECIDE_FOREIGN; the expanded list is in use whenever volume-volume
+// reactions exist).  decided = false: a hit in a foreign subpartition whose
+// membership this function does not work out (the caller hands the molecule to the generic pass).
+template <bool DECIDE_FOREIGN>
+__device__ __forceinline__ bool next_probe_hit(const DevParams& p, const WarpProbe* sm, int n_hits, D3 pos, D3 disp, bool stays,
+                                               bool single, const int s1[3], uint32_t self_species, double t_last,
+                                               uint32_t id_last, PartnerHit& best, bool& decided) {
   const int lane = threadIdx.x & 31;
   const double movelen2 = dot3(disp, disp);
-  const uint32_t own = subpart_index(p, pos);
+  int s0[3];
+  subpart_3d(p, pos, s0);
   bool any = false;
   best.t = MCX_TIME_FOREVER; best.id = 0; best.slot = MCX_NONE; best.species = 0; best.rxn_class = 0; best.in_own_subpart = true;
   for (int h = 0; h < n_hits; h++) {
@@ -725,7 +750,22 @@ __device__ __forceinline__ bool next_probe_hit(const DevParams& p, const WarpPro
     const MolRec c = load_rec(p.recA, j);
     const D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
     const double t = dot3(dir, disp) / movelen2;
-    all_own = all_own && subpart_index(p, D3{c.x, c.y, c.z}) == own;
+    int sc[3];
+    subpart_3d(p, D3{c.x, c.y, c.z}, sc);
+    const int delta[3] = {sc[0] - s0[0], sc[1] - s0[1], sc[2] - s0[2]};
+    // own subpartition, or the one a single face crossing leads into (s1): crossed subpartitions are collected
+    if ((delta[0] | delta[1] | delta[2]) != 0 && !(single && sc[0] == s1[0] && sc[1] == s1[1] && sc[2] == s1[2])) {
+      if (!DECIDE_FOREIGN || !stays) { decided = false; continue; }
+      bool member = false;
+      if (p.use_expanded) {
+        const double rr = p.R * MCX_POS_SQRT2;
+        int d[3];
+        neighbor_dirs(p, pos, s0, rr, d);
+        member = in_neighbor_dirs(delta, d);
+        if (!member) { neighbor_dirs(p, pos + disp, s0, rr, d); member = in_neighbor_dirs(delta, d); }
+      }
+      if (!member) continue;  // not a molecule of a collected subpartition: the reference does not see it
+    }
     if (t < t_last || (t == t_last && c.id >= id_last)) continue;
     if (!any || t < best.t || (t == best.t && c.id > best.id)) {
       const uint32_t csp = c.sf & SF_SPECIES_MASK;

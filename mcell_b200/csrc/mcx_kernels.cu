@@ -453,13 +453,16 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       simple = simple && !overflow && n_hits <= (PASS == 0 ? 1 : MCX_FAST_MAX_HITS) && !disk_walls;
       if (!simple && reason < 0)
         reason = overflow ? MCX_DEFER_PROBE_SHAPE : (disk_walls ? MCX_DEFER_DISK : MCX_DEFER_MULTI_HIT);
-      // the first collision, and whether every hit lies in the own subpartition
+      // the first collision; a hit in a foreign subpartition counts only if the reference collects that
+      // subpartition for this move: PASS 1 works that out for moves that stay inside their subpartition
       PartnerHit ph;
-      bool all_own = true;
-      bool have = simple && n_hits > 0 && next_probe_hit(p, &s_probe[warp], n_hits, pos, disp, species, -1.0, 0u, ph, all_own);
-      simple = simple && all_own;
+      bool decided = true;
+      bool have = simple && n_hits > 0 &&
+                  next_probe_hit<PASS == 1>(p, &s_probe[warp], n_hits, pos, disp, same, single, s1, species, -1.0, 0u, ph, decided);
+      const bool foreign = PASS == 0 && simple && !decided && same;
+      simple = simple && decided;
       if (!simple && reason < 0) reason = MCX_DEFER_FOREIGN_HIT;
-      if (several) { to_second = true; slow = false; running = false; }
+      if (several || foreign) { to_second = true; slow = false; running = false; }
 
       if (simple) {
         if (PASS == 0) trace_begin(p, tc, m.id);
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
           }
           if (PASS == 0 || (int)colls >= n_hits) break;
           const double t_last = ph.t; const uint32_t id_last = ph.id;
-          have = next_probe_hit(p, &s_probe[warp], n_hits, pos, disp, species, t_last, id_last, ph, all_own);
+          have = next_probe_hit<PASS == 1>(p, &s_probe[warp], n_hits, pos, disp, same, single, s1, species, t_last, id_last, ph, decided);
         }
         my_tests += n_wall_tests; my_coll += colls;
         if (PASS == 1 && o.kind == MCX_OUT_MOVED && again) {  // first sub-step done
