@@ -51,6 +51,40 @@ __device__ __forceinline__ unsigned int agg_reserve(unsigned int* addr, unsigned
 }
 
 
+// ---- per-block tallies of the counters every committed event touches ------------------------------------------------
+// k_resolve commits ~1.3e6 events per iteration at 1e8 molecules and each one used to issue 6-8 warp-aggregated
+// global atomics (a __match_any_sync each) on a handful of addresses.  The block counts in shared memory instead
+// and flushes once; commit_event falls back to the global atomics when no tally is given (forced commits of k_retry).
+struct BlockTally {
+  int species[256];            // signed change of the per-species population
+  unsigned int rxn[256];       // per reaction rule
+  unsigned int bimol, unimol, products, absorptions;
+};
+__device__ __forceinline__ void tally_clear(BlockTally* t) {
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) { t->species[k] = 0; t->rxn[k] = 0; }
+  if (threadIdx.x == 0) { t->bimol = 0; t->unimol = 0; t->products = 0; t->absorptions = 0; }
+  __syncthreads();
+}
+__device__ __forceinline__ void tally_flush(const BlockTally* t, Counters* c) {
+  __syncthreads();
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+    if (t->species[k]) atomicAdd(&c->species_count[k], (unsigned long long)(long long)t->species[k]);
+    if (t->rxn[k]) atomicAdd(&c->rxn_count[k], (unsigned long long)t->rxn[k]);
+  }
+  if (threadIdx.x == 0) {
+    if (t->bimol) atomicAdd(&c->bimol_rxns, (unsigned long long)t->bimol);
+    if (t->unimol) atomicAdd(&c->unimol_rxns, (unsigned long long)t->unimol);
+    if (t->products) atomicAdd(&c->products, (unsigned long long)t->products);
+    if (t->absorptions) atomicAdd(&c->absorptions, (unsigned long long)t->absorptions);
+  }
+}
+// one shared atomic per converged group of lanes for a counter they all hit
+__device__ __forceinline__ void tally_inc(unsigned int* ctr) {
+  const unsigned int m = __activemask();
+  if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(ctr, (unsigned int)__popc(m));
+}
+
+
 // ---- per-warp staging of slot indices appended to a global list --------------------------------------------------
 // Every warp of k_diffuse_fast used to reserve its deferred slots with one RETURNING atomicAdd on a single
 // address (Counters::n_slow): 2.4e5 same-address round trips per iteration at 1e7 molecules, 55 % of the
@@ -148,7 +182,7 @@ __device__ __forceinline__ bool partner_is_consumed(const DevParams& p, int kind
 // accepted claiming event: consume reactants, create products, count
 __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rxn_class, int pathway, uint32_t partner_slot,
                              double t_event, D3 pos, uint32_t id, uint32_t species, uint32_t flags, double t_now,
-                             double unimol_time, uint32_t orient_bits) {
+                             double unimol_time, uint32_t orient_bits, BlockTally* bt = nullptr) {
   Counters* c = p.ctr;
   // multi-GPU: halo molecules are evaluated redundantly (identically on both sides); an event is counted and its
   // products are created by the rank owning the event position; reactants are marked DEAD everywhere
@@ -160,34 +194,34 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
   }
   if (kind == MCX_OUT_ABSORBED) {
     atomicOr(&p.recA[slot].sf, DF_DEAD);
-    if (own_event) agg_add(&c->absorptions, 1u);
-    if (track) agg_sub(&c->species_count[species], 1u);
+    if (own_event) { if (bt) tally_inc(&bt->absorptions); else agg_add(&c->absorptions, 1u); }
+    if (track) { if (bt) atomicSub(&bt->species[species], 1); else agg_sub(&c->species_count[species], 1u); }
     return;
   }
   const DevClass& cl = p.classes[rxn_class];
   const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
-  if (own_event) agg_add(&c->rxn_count[pw.rule_id & 255u], 1u);
+  if (own_event) { if (bt) atomicAdd(&bt->rxn[pw.rule_id & 255u], 1u); else agg_add(&c->rxn_count[pw.rule_id & 255u], 1u); }
   if (own_event && p.wall_cv) agg_add(&p.rxn_count_cv[(pw.rule_id & 255u) * p.n_cv + (flags >> SF_CVI_SHIFT)], 1u);
   bool keepA, keepB = true;
   uint32_t reuse[2]; int n_reuse = 0;
   if (kind == MCX_OUT_REACTED) {
-    if (own_event) agg_add(&c->bimol_rxns, 1u);
+    if (own_event) { if (bt) tally_inc(&bt->bimol); else agg_add(&c->bimol_rxns, 1u); }
     bool a_is_r0 = species == cl.r0;
     keepA = (pw.keep_mask >> (a_is_r0 ? 0 : 1)) & 1u;
     keepB = (pw.keep_mask >> (a_is_r0 ? 1 : 0)) & 1u;
   } else {
-    if (own_event) agg_add(&c->unimol_rxns, 1u);
+    if (own_event) { if (bt) tally_inc(&bt->unimol); else agg_add(&c->unimol_rxns, 1u); }
     keepA = pw.keep_mask & 1u;
   }
   if (!keepA) {
     atomicOr(&p.recA[slot].sf, DF_DEAD);
-    if (track) agg_sub(&c->species_count[species], 1u);
+    if (track) { if (bt) atomicSub(&bt->species[species], 1); else agg_sub(&c->species_count[species], 1u); }
     reuse[n_reuse++] = id;
   }
   if (!keepB) {
     uint32_t old = atomicOr(&p.recA[partner_slot].sf, DF_DEAD);
     atomicOr(&p.recB[partner_slot].sf, DF_DEAD);
-    if (track) agg_sub(&c->species_count[old & SF_SPECIES_MASK], 1u);
+    if (track) { if (bt) atomicSub(&bt->species[old & SF_SPECIES_MASK], 1); else agg_sub(&c->species_count[old & SF_SPECIES_MASK], 1u); }
     uint32_t pid = p.recA[partner_slot].id;
     reuse[n_reuse++] = pid;
     if (p.trace && pid < p.n_trace) p.trace[pid].outcome = MCX_OUT_CONSUMED;
@@ -236,8 +270,8 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
     store_rec(p.recB, ns, pos, nid, psp | pflags);
     uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
     p.rank[ns] = atomicAdd(&p.cs_next[cell], 1u);
-    if (track) agg_add(&c->species_count[psp], 1u);
-    agg_add(&c->products, 1u);
+    if (track) { if (bt) atomicAdd(&bt->species[psp], 1); else agg_add(&c->species_count[psp], 1u); }
+    if (bt) tally_inc(&bt->products); else agg_add(&c->products, 1u);
   }
   if (keepA) {
     // kept initiator stops at the event and takes the rest of its step lazily next iteration
@@ -593,6 +627,8 @@ __global__ void __launch_bounds__(TPB, MCX_SLOW_MINBLOCKS) k_diffuse_slow(const 
 
 // round r: decide every pending proposal on the claims as they stand
 __global__ void __launch_bounds__(TPB) k_resolve(const __grid_constant__ DevParams p, unsigned int round) {
+  __shared__ BlockTally tally;
+  tally_clear(&tally);
   const int cur = 0, nxt = 1;  // list 0: proposals, list 1: rejected
   const unsigned int n = p.ctr->n_pend[cur];
   const unsigned int epoch = round_epoch(p, round);
@@ -610,12 +646,13 @@ __global__ void __launch_bounds__(TPB) k_resolve(const __grid_constant__ DevPara
     if (ok && kind == MCX_OUT_SURFMOVE) ok = p.tile_claim[p.grids[p.swallB[slot]].tile_start + p.stileB[slot]] == key;
     if (ok) {
       commit_event(p, slot, kind, rxn_class, pathway, partner, p.prop_t[slot], D3{e.x, e.y, e.z}, e.id, species,
-                   e.sf & ~SF_SPECIES_MASK, p.tschedB[slot], p.tuniB[slot], orient_bits);
+                   e.sf & ~SF_SPECIES_MASK, p.tschedB[slot], p.tuniB[slot], orient_bits, &tally);
     } else {
       uint32_t q = agg_reserve(&p.ctr->n_pend[nxt], 1u);
       p.pend[nxt][q] = slot;
     }
   }
+  tally_flush(&tally, p.ctr);
 }
 
 // losers of round r are re-evaluated against the updated snapshot flags; their new proposals go back
