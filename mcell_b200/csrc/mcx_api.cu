@@ -42,7 +42,7 @@ struct mcx_handle {
   // table device pointers that get replaced on re-set
   void *d_species = nullptr, *d_bimol = nullptr, *d_unimol = nullptr, *d_classes = nullptr, *d_pathways = nullptr,
        *d_surf = nullptr, *d_walls = nullptr, *d_tri = nullptr, *d_verts = nullptr, *d_wclass = nullptr,
-       *d_spw_start = nullptr, *d_spw_list = nullptr, *d_sp_flags = nullptr, *d_grids = nullptr, *d_volsurf = nullptr,
+       *d_spw_start = nullptr, *d_spw_list = nullptr, *d_fw_start = nullptr, *d_fw_list = nullptr, *d_sp_flags = nullptr, *d_grids = nullptr, *d_volsurf = nullptr,
        *d_tile_slot = nullptr, *d_exd_skip = nullptr, *d_wall_cv = nullptr, *d_rxn_count_cv = nullptr,
        *d_mol_count_cv = nullptr, *d_edges = nullptr, *d_tile_claim = nullptr;
   uint32_t n_cv = 1; uint32_t* st_cv = nullptr;
@@ -208,6 +208,7 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   std::vector<uint32_t> zero_start((size_t)p.n_sp * p.n_sp * p.n_sp + 1, 0);
   if (dev_replace(h, &h->d_spw_start, zero_start.data(), zero_start.size())) return fail(MCX_ERR_CUDA);
   p.spw_start = (const uint32_t*)h->d_spw_start;
+  p.fw_start = p.spw_start; p.fw_list = nullptr; p.fw_K = 1; p.fw_rcp = p.sp_rcp;
   std::vector<uint8_t> zero_flags(zero_start.size(), 0);
   if (dev_replace(h, &h->d_sp_flags, zero_flags.data(), zero_flags.size())) return fail(MCX_ERR_CUDA);
   p.sp_flags = (const uint8_t*)h->d_sp_flags;
@@ -249,6 +250,16 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   rc |= dev_replace(h, &h->d_wclass, h->wall_class_host.data(), h->wall_class_host.size());
   rc |= dev_replace(h, &h->d_spw_start, start.data(), start.size());
   rc |= dev_replace(h, &h->d_spw_list, list.data(), list.size());
+  // fine wall grid: K^3 cells per subpartition (K == 1: the subpartition lists themselves)
+  h->p.fw_K = mcxg::fine_wall_factor(g, vertices, tri, n_walls, start);
+  if (const char* e = getenv("MCX_FINE_WALL_K")) h->p.fw_K = std::max(1, std::min(16, atoi(e)));  // tuning knob (profiles/)
+  h->p.fw_rcp = (double)h->p.fw_K / h->p.sp_len;
+  if (h->p.fw_K > 1) {
+    std::vector<uint32_t> fstart, flist;
+    mcxg::bin_walls_fine(g, vertices, tri, start, list, h->p.fw_K, MCX_FW_MARGIN, fstart, flist);
+    rc |= dev_replace(h, &h->d_fw_start, fstart.data(), fstart.size());
+    rc |= dev_replace(h, &h->d_fw_list, flist.data(), flist.size());
+  }
   // surface grids of every wall and the tile table (Grid::molecules_per_tile, one entry per tile of every wall)
   std::vector<DevGrid> grids;
   const uint64_t n_tiles = mcxg::grid_constants(vertices, tri, walls, grids);
@@ -292,6 +303,8 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   DevParams& p = h->p;
   p.walls = (const DevWall*)h->d_walls; p.wall_tri = (const uint32_t*)h->d_tri; p.verts = (const double*)h->d_verts;
   p.wall_class = (const uint32_t*)h->d_wclass; p.spw_start = (const uint32_t*)h->d_spw_start;
+  p.fw_start = p.fw_K > 1 ? (const uint32_t*)h->d_fw_start : (const uint32_t*)h->d_spw_start;
+  p.fw_list = p.fw_K > 1 ? (const uint32_t*)h->d_fw_list : (const uint32_t*)h->d_spw_list;
   p.spw_list = (const uint32_t*)h->d_spw_list; p.n_walls = (int)n_walls; p.sp_flags = (const uint8_t*)h->d_sp_flags;
   h->n_walls_host = n_walls;
   h->has_geometry = true;

@@ -368,24 +368,91 @@ __device__ int collide_wall(const DevParams& p, D3 pos, uint32_t wi, Stream& rs,
   return W_MISS;
 }
 
+// ---- fine wall grid (mcx_geom.cpp: bin_walls_fine) -------------------------------------------------------------------
+// Cells of subpartition S under the box [lo, hi] (the caller has padded it by at least MCX_FW_MARGIN).
+struct FwRange { int x0, x1, y0, y1, z0, z1; uint32_t base; };
+__device__ __forceinline__ FwRange fw_range(const DevParams& p, uint32_t S, D3 lo, D3 hi) {
+  const int K = p.fw_K, n = p.n_sp;
+  const int sx = (int)(S % (uint32_t)n), sy = (int)((S / (uint32_t)n) % (uint32_t)n), sz = (int)(S / (uint32_t)(n * n));
+  const double ox = p.ox + sx * p.sp_len, oy = p.oy + sy * p.sp_len, oz = p.oz + sz * p.sp_len;
+  auto cell = [&](double v, double o) { const int c = (int)floor((v - o) * p.fw_rcp); return c < 0 ? 0 : (c >= K ? K - 1 : c); };
+  FwRange r;
+  r.x0 = cell(lo.x, ox); r.x1 = cell(hi.x, ox);
+  r.y0 = cell(lo.y, oy); r.y1 = cell(hi.y, oy);
+  r.z0 = cell(lo.z, oz); r.z1 = cell(hi.z, oz);
+  r.base = S * (uint32_t)(K * K * K);
+  return r;
+}
+__device__ __forceinline__ void segment_box(D3 pos, D3 move, double pad, D3& lo, D3& hi) {
+  lo = D3{fmin(pos.x, pos.x + move.x) - pad, fmin(pos.y, pos.y + move.y) - pad, fmin(pos.z, pos.z + move.z) - pad};
+  hi = D3{fmax(pos.x, pos.x + move.x) + pad, fmax(pos.y, pos.y + move.y) + pad, fmax(pos.z, pos.z + move.z) + pad};
+}
+// position of wall wi in the (ascending) list of its subpartition, MCX_NONE if it is not there
+__device__ __forceinline__ uint32_t spw_position(const DevParams& p, uint32_t w0, uint32_t w1, uint32_t wi) {
+  uint32_t a = w0, b = w1;
+  while (a < b) { const uint32_t mid = (a + b) >> 1; if (__ldg(p.spw_list + mid) < wi) a = mid + 1; else b = mid; }
+  return (a < w1 && __ldg(p.spw_list + a) == wi) ? a : MCX_NONE;
+}
+// Walk over the walls of subpartition S near a box in the order of the subpartition's own list (ascending wall index),
+// each wall once: a merge of the (ascending) lists of the at most 8 cells under the box.  Larger boxes, and fw_K == 1,
+// walk the whole subpartition list, which is always correct.
+struct WallWalk {
+  uint32_t cur[8], end[8];
+  int n;
+  uint32_t last, k, k1;
+  bool whole, have_last;
+  __device__ void init(const DevParams& p, uint32_t S, D3 lo, D3 hi) {
+    whole = true; k = p.spw_start[S]; k1 = p.spw_start[S + 1]; n = 0; have_last = false; last = 0;
+    if (p.fw_K == 1 || k == k1) return;
+    const FwRange r = fw_range(p, S, lo, hi);
+    if ((r.x1 - r.x0 + 1) * (r.y1 - r.y0 + 1) * (r.z1 - r.z0 + 1) > 8) return;
+    whole = false;
+    const int K = p.fw_K;
+    for (int z = r.z0; z <= r.z1; z++)
+      for (int y = r.y0; y <= r.y1; y++)
+        for (int x = r.x0; x <= r.x1; x++) {
+          const uint32_t c = r.base + (uint32_t)((z * K + y) * K + x);
+          cur[n] = __ldg(p.fw_start + c); end[n] = __ldg(p.fw_start + c + 1);
+          if (cur[n] < end[n]) n++;
+        }
+  }
+  __device__ uint32_t next(const DevParams& p) {  // MCX_NONE when exhausted
+    if (whole) return k < k1 ? p.spw_list[k++] : MCX_NONE;
+    uint32_t best = MCX_NONE;
+    for (int i = 0; i < n; i++) {
+      while (cur[i] < end[i] && have_last && __ldg(p.fw_list + cur[i]) <= last) cur[i]++;
+      if (cur[i] < end[i]) { const uint32_t w = __ldg(p.fw_list + cur[i]); if (w < best) best = w; }
+    }
+    if (best != MCX_NONE) { last = best; have_last = true; }
+    return best;
+  }
+};
+
 struct WallHit { int side; double t; D3 pos; uint32_t wall; };
 
-// get_closest_wall_collision, collision_utils.inl:819-914
+// get_closest_wall_collision, collision_utils.inl:819-914.  The walk leaves out walls of the list whose bounding box
+// the move cannot reach (they would be COLLIDE_MISS without a random draw); ray_polygon_tests still counts the whole
+// list like the reference does, from the list positions.
 __device__ bool closest_wall_collision(const DevParams& p, D3 pos, uint32_t subpart, uint32_t last_hit_wall,
                                        Stream& rs, D3& disp, D3& up_to_wall, WallHit& best, LocalStats& ls, Tracer& tc) {
   const uint32_t w0 = p.spw_start[subpart], w1 = p.spw_start[subpart + 1];
   if (w0 == w1) return false;
+  const bool last_in_list = last_hit_wall != MCX_NONE && spw_position(p, w0, w1, last_hit_wall) != MCX_NONE;
   int guard = 0;
 restart:
   bool found = false;
   double closest = MCX_TIME_FOREVER;
-  for (uint32_t k = w0; k < w1; k++) {
-    uint32_t wi = p.spw_list[k];
+  D3 lo, hi;
+  segment_box(pos, disp, MCX_FW_MARGIN, lo, hi);
+  WallWalk ww;
+  ww.init(p, subpart, lo, hi);
+  for (uint32_t wi = ww.next(p); wi != MCX_NONE; wi = ww.next(p)) {
     if (wi == last_hit_wall) continue;
     double t; D3 hit;
-    ls.ray_polygon_tests++;
     int ct = collide_wall(p, pos, wi, rs, disp, t, hit);
     if (ct == W_REDO) {
+      // the reference had tested the list up to this wall
+      ls.ray_polygon_tests += spw_position(p, w0, w1, wi) - w0 + 1 - ((last_in_list && last_hit_wall < wi) ? 1u : 0u);
       ls.redos++; tc.ev(EV_REDO, wi);
       if (tc.tr) tc.tr->n_redo++;
       if (++guard > 64) return false;
@@ -396,6 +463,7 @@ restart:
       if (t < closest) { found = true; closest = t; best.side = ct; best.t = t; best.pos = hit; best.wall = wi; }
     }
   }
+  ls.ray_polygon_tests += w1 - w0 - (last_in_list ? 1u : 0u);
   if (found) up_to_wall = best.pos - pos;
   return found;
 }
@@ -783,27 +851,61 @@ __device__ __forceinline__ bool next_probe_hit(const DevParams& p, const WarpPro
 __device__ __forceinline__ bool all_walls_plane_rejected(const DevParams& p, bool enabled, uint32_t subpart, D3 pos, D3 move,
                                                          unsigned int& n_tests, double& min_dist) {
   const uint32_t w0 = __ldg(p.spw_start + subpart), w1 = enabled ? __ldg(p.spw_start + subpart + 1) : w0;
+  n_tests = w1 - w0;  // what the reference's scan of the list counts
   bool all = true;
+  if (p.fw_K == 1) {  // short lists (warp-uniform branch): one flat predicated loop keeps the warp converged
 #pragma unroll 1
-  for (uint32_t k = w0; k < w1; k++) {
-    const DevWall& f = p.walls[__ldg(p.spw_list + k)];
-    const D3 n = {f.nx, f.ny, f.nz};
-    const double dp = dot3(n, pos), dv = dot3(n, move), dd = dp - f.dist;
-    double d_eps;
-    bool miss;
-    if (dd > 0) {
-      d_eps = MCX_EPS;
-      if (dd < d_eps) d_eps = 0.5 * dd;
-      miss = dd + dv > d_eps;
-    } else {
-      d_eps = -MCX_EPS;
-      if (dd > d_eps) d_eps = 0.5 * dd;
-      miss = dd < 0 && dd + dv < d_eps;
+    for (uint32_t k = w0; k < w1; k++) {
+      const DevWall& f = p.walls[__ldg(p.spw_list + k)];
+      const D3 n = {f.nx, f.ny, f.nz};
+      const double dp = dot3(n, pos), dv = dot3(n, move), dd = dp - f.dist;
+      double d_eps;
+      bool miss;
+      if (dd > 0) {
+        d_eps = MCX_EPS;
+        if (dd < d_eps) d_eps = 0.5 * dd;
+        miss = dd + dv > d_eps;
+      } else {
+        d_eps = -MCX_EPS;
+        if (dd > d_eps) d_eps = 0.5 * dd;
+        miss = dd < 0 && dd + dv < d_eps;
+      }
+      all = all && miss;
+      min_dist = fmin(min_dist, fmin(fabs(dd), fabs(dd + dv)));
     }
-    all = all && miss;
-    min_dist = fmin(min_dist, fmin(fabs(dd), fabs(dd + dv)));
+  } else if (w1 > w0) {
+    // only walls whose bounding box comes within the interaction radius of the move can be hit or can cut the
+    // interaction disk of a collision on it (exact_disk's own box test, exact_disk_utils.inl:905-925); the test has
+    // no side effect, so the duplicates of walls that span several cells are harmless
+    D3 lo, hi;
+    segment_box(pos, move, p.R * (1.0 + 1e-9) + MCX_FW_MARGIN, lo, hi);
+    const FwRange r = fw_range(p, subpart, lo, hi);
+    const int K = p.fw_K;
+    for (int z = r.z0; z <= r.z1; z++)
+      for (int y = r.y0; y <= r.y1; y++) {
+        const uint32_t row = r.base + (uint32_t)((z * K + y) * K);  // the cells of one x-run are consecutive in the table
+        const uint32_t e0 = __ldg(p.fw_start + row + r.x0), e1 = __ldg(p.fw_start + row + r.x1 + 1);
+#pragma unroll 1
+        for (uint32_t e = e0; e < e1; e++) {
+          const DevWall& f = p.walls[__ldg(p.fw_list + e)];
+          const D3 n = {f.nx, f.ny, f.nz};
+          const double dp = dot3(n, pos), dv = dot3(n, move), dd = dp - f.dist;
+          double d_eps;
+          bool miss;
+          if (dd > 0) {
+            d_eps = MCX_EPS;
+            if (dd < d_eps) d_eps = 0.5 * dd;
+            miss = dd + dv > d_eps;
+          } else {
+            d_eps = -MCX_EPS;
+            if (dd > d_eps) d_eps = 0.5 * dd;
+            miss = dd < 0 && dd + dv < d_eps;
+          }
+          all = all && miss;
+          min_dist = fmin(min_dist, fmin(fabs(dd), fabs(dd + dv)));
+        }
+      }
   }
-  n_tests = w1 - w0;
   return all;
 }
 

@@ -317,17 +317,27 @@ __device__ __noinline__ double exd_area_multiple_edges(ExdPool& P, double R2) {
 // wall is farther from the collision point than the disk reaches, i.e. exact_disk would return 1.
 __device__ __forceinline__ bool exd_any_wall_in_reach(const DevParams& p, D3 loc, D3 mv) {
   const uint32_t sub = subpart_index(p, loc);
-  const uint32_t w0 = __ldg(p.spw_start + sub), w1 = __ldg(p.spw_start + sub + 1);
+  if (__ldg(p.spw_start + sub) == __ldg(p.spw_start + sub + 1)) return false;
   const double R2 = p.R * p.R;
   const double m2_i = 1 / dot3(mv, mv);
   bool any = false;
-  for (uint32_t k = w0; k < w1; k++) {
-    const DevWall& f = p.walls[__ldg(p.spw_list + k)];
-    const D3 n = {f.nx, f.ny, f.nz};
-    const double d = f.dist - dot3(loc, n);
-    const double m_n = dot3(mv, n);
-    any = any || !(d * d >= R2 * (1 - m2_i * m_n * m_n));
-  }
+  // walls whose bounding box is farther than R from loc fail exact_disk's box test (:905-925) whatever their plane:
+  // only the cells under the box loc +- R are looked at (no side effects: duplicates are harmless)
+  const double pad = p.R * (1.0 + 1e-9) + MCX_FW_MARGIN;
+  const FwRange r = fw_range(p, sub, D3{loc.x - pad, loc.y - pad, loc.z - pad}, D3{loc.x + pad, loc.y + pad, loc.z + pad});
+  const int K = p.fw_K;
+  for (int z = r.z0; z <= r.z1; z++)
+    for (int y = r.y0; y <= r.y1; y++) {
+      const uint32_t row = r.base + (uint32_t)((z * K + y) * K);
+      const uint32_t e0 = __ldg(p.fw_start + row + r.x0), e1 = __ldg(p.fw_start + row + r.x1 + 1);
+      for (uint32_t e = e0; e < e1; e++) {
+        const DevWall& f = p.walls[__ldg(p.fw_list + e)];
+        const D3 n = {f.nx, f.ny, f.nz};
+        const double d = f.dist - dot3(loc, n);
+        const double m_n = dot3(mv, n);
+        any = any || !(d * d >= R2 * (1 - m2_i * m_n * m_n));
+      }
+    }
   return any;
 }
 
@@ -353,8 +363,13 @@ __device__ __noinline__ double exact_disk(const DevParams& p, D3 loc, D3 mv, uin
     sm.r2 = sm.u * sm.u + sm.v * sm.v;
     sm.zeta = exd_zetize(sm.v, sm.u);
   }
-  for (uint32_t k = w0; k < w1; k++) {
-    const uint32_t wi = p.spw_list[k];
+  // the walls of the collision subpartition in list order; those outside the box loc +- R fail the box test below
+  WallWalk ww;
+  {
+    const double pad = p.R * (1.0 + 1e-9) + MCX_FW_MARGIN;
+    ww.init(p, sub, D3{loc.x - pad, loc.y - pad, loc.z - pad}, D3{loc.x + pad, loc.y + pad, loc.z + pad});
+  }
+  for (uint32_t wi = ww.next(p); wi != MCX_NONE; wi = ww.next(p)) {
     const DevWall& f = p.walls[wi];
     const D3 n = {f.nx, f.ny, f.nz};
     const double l_n = dot3(loc, n);

@@ -170,6 +170,81 @@ void bin_walls(const GridSpec& g, const double* verts, const uint32_t* tri, cons
 }
 
 
+// ---- fine wall grid -----------------------------------------------------------------------------------------
+// The reference tests a move against every wall of each subpartition it crosses (get_closest_wall_collision,
+// collision_utils.inl:819-914); with the default 0.5 um subpartitions a membrane mesh puts hundreds of triangles
+// into one list.  libmcx subdivides every subpartition into K^3 cells and lists, per cell, the walls OF THAT
+// SUBPARTITION whose bounding box (inflated by `margin`) overlaps the cell, in the subpartition list's own
+// (ascending wall index) order.  A wall a move can hit inside the subpartition has the hit point inside its bounding
+// box and inside the move's bounding box, so walking the cells under the move's bounding box visits every wall that
+// can matter and skipping the others changes nothing: they are COLLIDE_MISS without a random draw.
+int fine_wall_factor(const GridSpec& g, const double* verts, const uint32_t* tri, uint64_t n_walls,
+                     const std::vector<uint32_t>& start) {
+  uint32_t longest = 0;
+  for (size_t s = 0; s + 1 < start.size(); s++) longest = std::max(longest, start[s + 1] - start[s]);
+  if (longest <= 24 || n_walls == 0) return 1;  // short lists: the subpartition list is the cell list
+  double extent = 0;
+  for (uint64_t wi = 0; wi < n_walls; wi++) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int k = 0; k < 3; k++) {
+      const double* q = verts + 3 * tri[3 * wi + k];
+      for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], q[a]); hi[a] = std::max(hi[a], q[a]); }
+    }
+    extent += std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+  }
+  extent /= (double)n_walls;
+  // cells about 1.5 wall extents wide, between 1/10 of a subpartition and a whole one, and a table of at most
+  // 2^25 cell starts
+  int K = (int)std::floor(g.sp_len / std::max(1.5 * extent, g.sp_len / 10.0));
+  K = std::max(1, std::min(10, K));
+  const double ns3 = (double)g.n_sp * g.n_sp * g.n_sp;
+  while (K > 1 && ns3 * K * K * K > 33554432.0) K--;
+  return K;
+}
+
+void bin_walls_fine(const GridSpec& g, const double* verts, const uint32_t* tri, const std::vector<uint32_t>& start,
+                    const std::vector<uint32_t>& list, int K, double margin, std::vector<uint32_t>& fstart,
+                    std::vector<uint32_t>& flist) {
+  const size_t ns3 = (size_t)g.n_sp * g.n_sp * g.n_sp, K3 = (size_t)K * K * K;
+  const double rcp = (double)K / g.sp_len;
+  fstart.assign(ns3 * K3 + 1, 0);
+  auto cell_range = [&](uint32_t wi, size_t s, int lo[3], int hi[3]) {
+    const int sx = (int)(s % g.n_sp), sy = (int)((s / g.n_sp) % g.n_sp), sz = (int)(s / ((size_t)g.n_sp * g.n_sp));
+    const double o[3] = {g.ox + sx * g.sp_len, g.oy + sy * g.sp_len, g.oz + sz * g.sp_len};
+    double blo[3] = {1e300, 1e300, 1e300}, bhi[3] = {-1e300, -1e300, -1e300};
+    for (int k = 0; k < 3; k++) {
+      const double* q = verts + 3 * tri[3 * wi + k];
+      for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], q[a]); bhi[a] = std::max(bhi[a], q[a]); }
+    }
+    for (int a = 0; a < 3; a++) {
+      lo[a] = std::max(0, std::min(K - 1, (int)std::floor((blo[a] - margin - o[a]) * rcp)));
+      hi[a] = std::max(0, std::min(K - 1, (int)std::floor((bhi[a] + margin - o[a]) * rcp)));
+    }
+  };
+  for (int pass = 0; pass < 2; pass++) {
+    std::vector<uint32_t> cursor;
+    if (pass == 1) {  // counts -> exclusive starts
+      uint64_t total = 0;
+      for (size_t c = 0; c < ns3 * K3; c++) { const uint32_t n = fstart[c]; fstart[c] = (uint32_t)total; total += n; }
+      fstart[ns3 * K3] = (uint32_t)total;
+      flist.assign(total, 0);
+      cursor.assign(fstart.begin(), fstart.end() - 1);
+    }
+    for (size_t s = 0; s < ns3; s++)
+      for (uint32_t k = start[s]; k < start[s + 1]; k++) {  // ascending wall index: every cell list is ascending too
+        int lo[3], hi[3];
+        cell_range(list[k], s, lo, hi);
+        for (int z = lo[2]; z <= hi[2]; z++)
+          for (int y = lo[1]; y <= hi[1]; y++)
+            for (int x = lo[0]; x <= hi[0]; x++) {
+              const size_t c = s * K3 + ((size_t)z * K + y) * K + x;
+              if (pass == 0) fstart[c]++; else flist[cursor[c]++] = list[k];
+            }
+      }
+  }
+}
+
+
 // ---- surface grids ------------------------------------------------------------------------------------------
 static double tri_area(const double* a, const double* b, const double* c) {
   P3 v0 = {a[0], a[1], a[2]}, v1 = {b[0], b[1], b[2]}, v2 = {c[0], c[1], c[2]};

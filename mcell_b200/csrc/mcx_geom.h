@@ -19,4 +19,8 @@ void tri_grid2uv(const double* v9, uint32_t tile, double* uv2);
 uint32_t tri_xyz2grid(const double* v9, const double* xyz3);
 void bin_walls(const GridSpec& g, const double* verts, const uint32_t* tri, const std::vector<DevWall>& walls,
                std::vector<uint32_t>& start, std::vector<uint32_t>& list);
+// fine wall grid (mcx_geom.cpp): subdivision factor K of a subpartition edge and the per-cell wall lists
+int fine_wall_factor(const GridSpec& g, const double* verts, const uint32_t* tri, uint64_t n_walls, const std::vector<uint32_t>& start);
+void bin_walls_fine(const GridSpec& g, const double* verts, const uint32_t* tri, const std::vector<uint32_t>& start,
+                    const std::vector<uint32_t>& list, int K, double margin, std::vector<uint32_t>& fstart, std::vector<uint32_t>& flist);
 }  // namespace mcxg

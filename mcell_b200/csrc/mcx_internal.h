@@ -76,6 +76,7 @@ struct Counters {
   unsigned long long rxn_count[256];
 };
 #define MCX_MAX_CV 256
+#define MCX_FW_MARGIN 1e-6        // inflation of wall and query boxes of the fine wall grid, in length units
 
 struct DevParams {
   // partition / subpartition grid (reference semantics)
@@ -92,6 +93,12 @@ struct DevParams {
   const uint32_t* wall_class;
   const uint32_t* spw_start;
   const uint32_t* spw_list;
+  // fine wall grid: every subpartition split into fw_K^3 cells; per cell the walls of that subpartition whose
+  // bounding box (+ MCX_FW_MARGIN) overlaps it, ascending like spw_list (fw_K == 1: the subpartition lists)
+  const uint32_t* fw_start;
+  const uint32_t* fw_list;
+  int fw_K;
+  double fw_rcp;                // fw_K / sp_len
   const uint8_t* sp_flags;      // per subpartition: bit0 = holds walls, bit1 = any of its 3x3x3 neighbours holds walls
   const DevSpecies* species;
   const int* bimol;
