@@ -31,17 +31,22 @@ def run(name, t, mols, iters, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", type=int, default=0, help="run one config (1-4)")
     a = ap.parse_args()
     import common as cm
     import test_gpu_fullsize as fs
-    t, mols = cm.free_diffusion_box(n=100000, seed=1, cap_factor=1.25)
-    run("1: free diffusion, 1e5 molecules, 1 um reflective cube", t, mols, a.iters)
-    t, mols = cm.reactive_box(n=1_000_000, edge_um=2.0, seed=2, p_target=0.1, cap_factor=1.25)
-    run("2: A+B->C, 1e6 molecules, 2 um box", t, mols, a.iters)
-    t, mols, _ = fs._config3(400_000, 8_000, seed=3)
-    run("3: ligand-receptor icosphere, 20 480 triangles", t, mols, a.iters)
-    t, mols, _, _ = fs._config4(10_000_000, seed=4)
-    run("4: synapse-like, 163 840 triangles, 1e7 molecules", t, mols, a.iters)
+    if a.only in (0, 1):
+        t, mols = cm.free_diffusion_box(n=100000, seed=1, cap_factor=1.25)
+        run("1: free diffusion, 1e5 molecules, 1 um reflective cube", t, mols, a.iters)
+    if a.only in (0, 2):
+        t, mols = cm.reactive_box(n=1_000_000, edge_um=2.0, seed=2, p_target=0.1, cap_factor=1.25)
+        run("2: A+B->C, 1e6 molecules, 2 um box", t, mols, a.iters)
+    if a.only in (0, 3):
+        t, mols, _ = fs._config3(400_000, 8_000, seed=3)
+        run("3: ligand-receptor icosphere, 20 480 triangles", t, mols, a.iters)
+    if a.only in (0, 4):
+        t, mols, _, _ = fs._config4(10_000_000, seed=4)
+        run("4: synapse-like, 163 840 triangles, 1e7 molecules", t, mols, a.iters)
 
 
 if __name__ == "__main__":
