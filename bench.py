@@ -161,6 +161,20 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def _traffic(kernel, molecules):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this same command
+    (profiles/traffic.json, written by tools/ncu_summary.py traffic); None when there is no capture at this size."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        e = t.get(kernel)
+        if e and int(e.get("molecules", 0)) == int(molecules):
+            return float(e["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -349,9 +363,9 @@ def run_ours(args):
     fast_bytes = mol_per_launch * 60.0 + (mol_per_launch - deferred_per_launch) * 32.0
     slow_bytes = deferred_per_launch * B_ALG_DIFFUSE
     if fast_ms >= slow_ms:
-        top_kernel, diffuse_ms, top_bytes = "k_diffuse_fast", fast_ms, fast_bytes
+        top_kernel, diffuse_ms, top_bytes = "k_diffuse_fast<0>", fast_ms, fast_bytes
     else:
-        top_kernel, diffuse_ms, top_bytes = "k_diffuse_slow", slow_ms, slow_bytes
+        top_kernel, diffuse_ms, top_bytes = "k_diffuse_fast<1> + k_diffuse_slow", slow_ms, slow_bytes
     achieved = top_bytes / (diffuse_ms * 1e-3) / 1e9 if diffuse_ms > 0 else 0.0
 
     # ---- end to end through the C ABI with HOST buffers: upload -> ITERS_PER_CALL iterations -> download
@@ -408,7 +422,8 @@ def run_ours(args):
                        "l2": "inputs (>=3 GB at 1e8 molecules) larger than L2; no flush",
                        "parallelism": "z-slabs x%d, NCCL halo refresh per iteration" % world, "rng": "philox4x32-10 per molecule"},
             "roofline": {"bound": "hbm", "kernel": top_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak if peak else None, "traffic": _traffic(top_kernel, n_total) if world == 1 else None,
+                         "peak_source": peak_src,
                          "alg_bytes_per_launch": top_bytes, "kernel_ms": diffuse_ms,
                          "kernel_share_of_step": diffuse_ms / (ms_total / max(1, args.steps)),
                          "whole_step_frac_at_160B": value / world * B_ALG_STEP / 1e9 / peak,

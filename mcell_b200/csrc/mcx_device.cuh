@@ -492,31 +492,29 @@ __device__ int test_bimolecular(const DevParams& p, const DevClass& rc, double s
   return prob > A[min_idx].cum_prob ? max_idx : min_idx;
 }
 
-__device__ __forceinline__ MolRec load_rec(const MolRec* a, uint32_t i) {
-  // two 128-bit loads of one 32-byte sector
-  const double2* q = reinterpret_cast<const double2*>(a + i);
-  double2 lo = __ldg(q);
-  double2 hi = __ldg(q + 1);
-  MolRec r; r.x = lo.x; r.y = lo.y; r.z = hi.x;
-  unsigned long long m = (unsigned long long)__double_as_longlong(hi.y);
+// A record is one 32-byte sector: sm_100 moves it with ONE 256-bit access (LDG.E.256 / STG.E.256; two 128-bit
+// accesses before) — half the load instructions of the candidate probe and full-sector stores in the scatter.
+__device__ __forceinline__ MolRec rec_from(double x, double y, double z, double w) {
+  MolRec r; r.x = x; r.y = y; r.z = z;
+  const unsigned long long m = (unsigned long long)__double_as_longlong(w);
   r.id = (uint32_t)m; r.sf = (uint32_t)(m >> 32);
   return r;
+}
+__device__ __forceinline__ MolRec load_rec(const MolRec* a, uint32_t i) {
+  double x, y, z, w;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(a + i));
+  return rec_from(x, y, z, w);
 }
 // snapshot records may receive DEAD flags while retry kernels run: read through L2, not the nc path
 __device__ __forceinline__ MolRec load_rec_volatile(const MolRec* a, uint32_t i) {
-  const double2* q = reinterpret_cast<const double2*>(a + i);
-  double2 lo = __ldcg(q);
-  double2 hi = __ldcg(q + 1);
-  MolRec r; r.x = lo.x; r.y = lo.y; r.z = hi.x;
-  unsigned long long m = (unsigned long long)__double_as_longlong(hi.y);
-  r.id = (uint32_t)m; r.sf = (uint32_t)(m >> 32);
-  return r;
+  double x, y, z, w;
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(a + i) : "memory");
+  return rec_from(x, y, z, w);
 }
 __device__ __forceinline__ void store_rec(MolRec* a, uint32_t i, D3 pos, uint32_t id, uint32_t sf) {
-  double2* q = reinterpret_cast<double2*>(a + i);
-  unsigned long long m = ((unsigned long long)sf << 32) | id;
-  q[0] = make_double2(pos.x, pos.y);
-  q[1] = make_double2(pos.z, __longlong_as_double((long long)m));
+  const unsigned long long m = ((unsigned long long)sf << 32) | id;
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(a + i), "d"(pos.x), "d"(pos.y), "d"(pos.z),
+               "d"(__longlong_as_double((long long)m)) : "memory");
 }
 
 // Cell range overlapped by the swept volume of a move (segment inflated by R, padded against rounding).

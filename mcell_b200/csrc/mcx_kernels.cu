@@ -569,6 +569,17 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
   flush_stats(p, ls, msteps);
 }
 
+// The generic evaluation is one long divergent path per molecule: a warp of 32 different molecules runs close to 32
+// evaluations back to back (2.4 of 32 lanes active on the mesh configs, profiles/r01_p).  When a launch has fewer
+// molecules than the machine has threads, spreading them out — one molecule per 2, 4 or 8 lanes, the other lanes
+// idle — shortens every warp's serial chain by that factor at no cost (the launch is latency bound, SMs are idle).
+__device__ __forceinline__ unsigned int lanes_per_molecule(unsigned int n) {
+  const unsigned long long threads = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned int lpm = 1;
+  while (lpm < 8 && (unsigned long long)n * (lpm * 2) <= threads) lpm *= 2;
+  return lpm;
+}
+
 // k_diffuse_slow: the generic evaluation (evaluate_iteration) for the slots k_diffuse_fast deferred.
 // WITH_DISK == false reads slow_list and hands the few molecules whose collision disk is cut by a wall on to the
 // WITH_DISK == true launch through pend[1] (free until the conflict rounds start).
@@ -587,9 +598,10 @@ __global__ void __launch_bounds__(TPB, MCX_SLOW_MINBLOCKS) k_diffuse_slow(const 
   LocalStats ls = {0, 0, 0, 0, 0, 0};
   unsigned int msteps = 0;
   // all lanes of a warp iterate together so the warp-level stat flush sees full warps
-  for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    const unsigned int k = base + threadIdx.x;
-    if (k >= n) continue;
+  const unsigned int lpm = lanes_per_molecule(n);
+  for (unsigned int base = blockIdx.x * blockDim.x; base < n * lpm; base += gridDim.x * blockDim.x) {
+    const unsigned int t = base + threadIdx.x, k = t / lpm;
+    if (t % lpm != 0 || k >= n) continue;
     const unsigned int i = list[k];
     MolRec m = load_rec(p.recA, i);
     const uint32_t species = m.sf & SF_SPECIES_MASK;
@@ -666,9 +678,10 @@ __global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevPar
   const unsigned int n = p.ctr->n_pend[nxt];
   const unsigned int epoch = round_epoch(p, round + 1);
   LocalStats ls = {0, 0, 0, 0, 0, 0};
-  for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    unsigned int k = base + threadIdx.x;
-    if (k >= n) continue;
+  const unsigned int lpm = lanes_per_molecule(n);
+  for (unsigned int base = blockIdx.x * blockDim.x; base < n * lpm; base += gridDim.x * blockDim.x) {
+    const unsigned int t = base + threadIdx.x, k = t / lpm;
+    if (t % lpm != 0 || k >= n) continue;
     uint32_t i = p.pend[nxt][k];
     MolRec m = load_rec_volatile(p.recA, i);
     if (m.sf & DF_DEAD) {  // consumed as somebody's partner in this round
@@ -786,13 +799,13 @@ __global__ void __launch_bounds__(TPB) k_scatter(const __grid_constant__ DevPara
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t r = p.rank[i];
     if (r == MCX_NONE) continue;
-    const double2* q = reinterpret_cast<const double2*>(p.recB + i);
-    double2 lo = q[0], hi = q[1];
-    uint32_t sf = (uint32_t)((unsigned long long)__double_as_longlong(hi.y) >> 32);
-    uint32_t cell = cell_of(p, lo.x, lo.y, hi.x);
+    double rx, ry, rz, rw;  // one 256-bit load, one 256-bit store per record
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(rx), "=d"(ry), "=d"(rz), "=d"(rw) : "l"(p.recB + i) : "memory");
+    const double2 hi = make_double2(rz, rw);
+    uint32_t sf = (uint32_t)((unsigned long long)__double_as_longlong(rw) >> 32);
+    uint32_t cell = cell_of(p, rx, ry, rz);
     uint32_t dst = p.cs_next[cell] + r;
-    double2* d = reinterpret_cast<double2*>(p.recA + dst);
-    d[0] = lo; d[1] = hi;
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p.recA + dst), "d"(rx), "d"(ry), "d"(rz), "d"(rw) : "memory");
     if (sf & DF_PARTIAL) p.tschedA[dst] = p.tschedB[i];
     if (sf & DF_HAS_UNIMOL) p.tuniA[dst] = p.tuniB[i];
     if (sf & (DF_SURF | DF_CREATED_ON_SURF)) {
@@ -991,11 +1004,11 @@ void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t 
   if (p.has_surf) k_diffuse_slow<false, true><<<g_slow, TPB, 0, s>>>(p, 0);
   else k_diffuse_slow<false, false><<<g_slow, TPB, 0, s>>>(p, 0);
   if (p.has_surf) {
-    k_diffuse_slow<false, true><<<plan.sm_count, TPB, 0, s>>>(p, 1);
-    k_diffuse_slow<true, true><<<plan.sm_count, TPB, 0, s>>>(p, 0);
+    k_diffuse_slow<false, true><<<g_slow, TPB, 0, s>>>(p, 1);
+    k_diffuse_slow<true, true><<<g_slow, TPB, 0, s>>>(p, 0);
   } else {
-    k_diffuse_slow<false, false><<<plan.sm_count, TPB, 0, s>>>(p, 1);
-    k_diffuse_slow<true, false><<<plan.sm_count, TPB, 0, s>>>(p, 0);
+    k_diffuse_slow<false, false><<<g_slow, TPB, 0, s>>>(p, 1);
+    k_diffuse_slow<true, false><<<g_slow, TPB, 0, s>>>(p, 0);
   }
   if (plan.prof) cudaEventRecord(plan.prof[1], s);
   count_launches(plan, 5);

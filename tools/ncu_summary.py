@@ -113,8 +113,31 @@ def hot_lines(rep, symbol):
         print("%-26s %7.1f%% %12.1f %8.1f%%" % ("%s:%s" % k if k else "?", 100 * a[0] / tot, a[1] / max(1, a[0]), 100 * a[2] / max(1, tots)))
 
 
+def traffic(rep, molecules):
+    """profiles/traffic.json: DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of every kernel of a
+    --set full capture, keyed by kernel name; bench.py reports it as roofline.traffic for the same workload size."""
+    import json
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    ik = hdr.index("Kernel Name")
+    ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    out = {}
+    for r in rows[2:]:
+        name = re.sub(r"^void ", "", r[ik]).split("(")[0]
+        b = float(r[ir]) * sc[units[ir]] + float(r[iw]) * sc[units[iw]]
+        e = out.setdefault(name, {"molecules": int(molecules), "dram_bytes_per_launch": 0.0, "launches": 0})
+        if b > e["dram_bytes_per_launch"]:
+            e["dram_bytes_per_launch"] = b  # the largest launch of that name (the others are the near-empty rounds)
+        e["launches"] += 1
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3])
     else:
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
