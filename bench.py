@@ -53,7 +53,12 @@ def build_model(n_total, seed=1, rank=0, world=1, cap_factor=1.25, cell_edge=0.0
     m.add_reaction_rule(["C", "C"], ["B", "D"], k_bi)
     v, f = create_box(edge_um)
     m.add_geometry_object(v, f)
-    per_rank = int(n_total / world * cap_factor * (1.6 if world > 1 else 1.0)) + 1024
+    # slab ranks hold their own z-layers plus a halo on each side (3x the one-step reach, mcx_api.cu configure_slab),
+    # and the halo refresh of an iteration is appended behind the results that still include the old halo copies:
+    # own * (1 + 4 * halo / slab) slots, times the product headroom
+    halo_lu = 3.0 * (m.rxn_radius_um / m.length_unit + 6.993 * m.space_step(1e-6)) + 2.0 * 3.5
+    slab_lu = edge_lu / world
+    per_rank = int(n_total / world * cap_factor * (1.0 + 4.0 * halo_lu / slab_lu if world > 1 else 1.0)) + 1024
     t = m.build(max_molecules=per_rank, rank=rank, world_size=world, cell_edge=cell_edge)
     return t, edge_um
 

@@ -12,6 +12,8 @@
 #include "mcx_comm.h"
 
 #include <nccl.h>
+#include <unistd.h>
+#include <cstring>
 
 struct McxComm {
   ncclComm_t comm = nullptr;
@@ -24,7 +26,22 @@ struct McxComm {
   unsigned int* h_counts = nullptr;   // pinned mirror
   unsigned long long* d_red = nullptr;
   int red_cap = 0;
+  // peer-memory halo path: the pack kernel stores straight into the neighbour's buffers over NVLink
+  bool p2p = false;
+  char* block = nullptr;                 // my receive block: [side low|high][parity 0|1] record buffers + 4 flag words
+  char* peer_base[2] = {nullptr, nullptr};   // the low / high neighbour's block as mapped here
+  bool peer_ipc[2] = {false, false};
+  unsigned int* d_done = nullptr;        // block counter of the pack kernel
+  unsigned int xchg = 0;                 // exchanges so far (same on every rank): flag tag and buffer parity
 };
+static size_t side_bytes(unsigned int cap) { return 2 * sizeof(HaloRec) * (size_t)cap; }
+static size_t block_bytes(unsigned int cap) { return 2 * side_bytes(cap) + 256; }
+static HaloRec* block_recv(char* base, unsigned int cap, int side, int parity) {
+  return (HaloRec*)(base + side * side_bytes(cap) + parity * sizeof(HaloRec) * (size_t)cap);
+}
+static unsigned long long* block_flag(char* base, unsigned int cap, int side, int parity) {
+  return (unsigned long long*)(base + 2 * side_bytes(cap)) + (side * 2 + parity);
+}
 
 #define NCK(call)                                                                         \
   do {                                                                                    \
@@ -43,6 +60,65 @@ extern "C" int mcx_comm_unique_id(void* out, uint32_t bytes) {
   if (ncclGetUniqueId(&id) != ncclSuccess) return MCX_ERR_COMM;
   memcpy(out, &id, sizeof(id));
   return (int)sizeof(id);
+}
+
+
+// ---- peer-memory setup ------------------------------------------------------------------------------------------------
+// Every rank allocates one receive block and hands it to both neighbours: as a CUDA IPC handle (one process per GPU,
+// the torchrun layout) or, when the ranks are threads of one process (tests/test_multi_gpu.py), as the pointer itself
+// with peer access enabled.  The handles travel over the NCCL communicator that exists anyway.
+struct PeerBlob { cudaIpcMemHandle_t handle; unsigned long long pid, ptr; int device, ok; char pad[128 - sizeof(cudaIpcMemHandle_t) - 24]; };
+static_assert(sizeof(PeerBlob) == 128, "PeerBlob layout");
+
+static void setup_p2p(McxComm* c) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool ok = cudaMalloc((void**)&c->block, block_bytes(c->cap)) == cudaSuccess;
+  ok = ok && cudaMemset(c->block, 0, block_bytes(c->cap)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&c->d_done, sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaMemset(c->d_done, 0, sizeof(unsigned int)) == cudaSuccess;
+  PeerBlob mine;
+  memset(&mine, 0, sizeof(mine));
+  ok = ok && cudaIpcGetMemHandle(&mine.handle, c->block) == cudaSuccess;
+  mine.pid = (unsigned long long)getpid(); mine.ptr = (unsigned long long)(uintptr_t)c->block; mine.device = dev; mine.ok = ok ? 1 : 0;
+  PeerBlob* d_blob = nullptr;  // [0] mine, [1] from the low neighbour, [2] from the high neighbour
+  if (cudaMalloc((void**)&d_blob, 3 * sizeof(PeerBlob)) != cudaSuccess) return;
+  cudaMemset(d_blob, 0, 3 * sizeof(PeerBlob));
+  cudaMemcpy(d_blob, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+  const bool lo = c->rank > 0, hi = c->rank < c->world - 1;
+  ncclGroupStart();
+  if (lo) { ncclSend(d_blob, sizeof(PeerBlob), ncclChar, c->rank - 1, c->comm, 0); ncclRecv(d_blob + 1, sizeof(PeerBlob), ncclChar, c->rank - 1, c->comm, 0); }
+  if (hi) { ncclSend(d_blob, sizeof(PeerBlob), ncclChar, c->rank + 1, c->comm, 0); ncclRecv(d_blob + 2, sizeof(PeerBlob), ncclChar, c->rank + 1, c->comm, 0); }
+  ncclGroupEnd();
+  cudaStreamSynchronize(0);
+  PeerBlob got[3];
+  cudaMemcpy(got, d_blob, sizeof(got), cudaMemcpyDeviceToHost);
+  cudaFree(d_blob);
+  for (int side = 0; side < 2 && ok; side++) {
+    if (!(side == 0 ? lo : hi)) continue;
+    const PeerBlob& b = got[1 + side];
+    if (!b.ok) { ok = false; break; }
+    if (b.pid == mine.pid) {  // same process: the pointer is valid here once peer access is on
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, dev, b.device);
+      cudaError_t e = can ? cudaDeviceEnablePeerAccess(b.device, 0) : cudaErrorInvalidDevice;
+      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      ok = e == cudaSuccess;
+      c->peer_base[side] = (char*)(uintptr_t)b.ptr;
+    } else {
+      void* q = nullptr;
+      ok = cudaIpcOpenMemHandle(&q, b.handle, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      c->peer_base[side] = (char*)q; c->peer_ipc[side] = ok;
+    }
+  }
+  if (!ok) cudaGetLastError();
+  // all ranks take the same path
+  unsigned long long v = ok ? 1ull : 0ull;
+  cudaMemcpy(c->d_red, &v, sizeof(v), cudaMemcpyHostToDevice);
+  ncclAllReduce(c->d_red, c->d_red, 1, ncclUint64, ncclMin, c->comm, 0);
+  cudaStreamSynchronize(0);
+  cudaMemcpy(&v, c->d_red, sizeof(v), cudaMemcpyDeviceToHost);
+  c->p2p = v == 1ull;
 }
 
 McxComm* mcx_comm_create(const void* nccl_unique_id, uint32_t id_bytes, int rank, int world_size, unsigned int halo_capacity,
@@ -66,6 +142,7 @@ McxComm* mcx_comm_create(const void* nccl_unique_id, uint32_t id_bytes, int rank
   ok = ok && cudaMalloc((void**)&c->d_red, sizeof(unsigned long long) * c->red_cap) == cudaSuccess;
   if (!ok) { err = "halo buffer allocation failed"; mcx_comm_destroy(c); return nullptr; }
   cudaMemset(c->d_counts, 0, 4 * sizeof(unsigned int));
+  if (!getenv("MCX_HALO_NCCL")) setup_p2p(c);  // falls back to the NCCL send/recv path when peer memory is not available
   return c;
 }
 
@@ -75,13 +152,39 @@ void mcx_comm_destroy(McxComm* c) {
   if (c->d_counts) cudaFree(c->d_counts);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->d_red) cudaFree(c->d_red);
+  for (int k = 0; k < 2; k++) if (c->peer_ipc[k] && c->peer_base[k]) cudaIpcCloseMemHandle(c->peer_base[k]);
+  if (c->block) cudaFree(c->block);
+  if (c->d_done) cudaFree(c->d_done);
   if (c->comm) ncclCommDestroy(c->comm);
   delete c;
 }
 const char* mcx_comm_error(McxComm* c) { return c ? c->err.c_str() : ""; }
 
 // halo refresh: pack -> counts -> payload -> unpack (appended behind the local results in B)
+// halo refresh over peer memory: ONE kernel selects the records, stores them into the neighbours' receive buffers over
+// NVLink (32 bytes per record, 48 when it carries cold fields) and publishes the counts with a release store; the
+// unpack kernel of the receiving rank acquires the flag and bins the records.  No NCCL call, no host round trip: the
+// host keeps enqueueing iterations.  Buffers alternate with the parity of the exchange: a rank can be at most one
+// exchange ahead of its neighbour (its unpack waits for the neighbour's pack), so two buffers never collide.
+static int exchange_halo_p2p(McxComm* c, DevParams& p, cudaStream_t s) {
+  c->xchg++;
+  const int parity = (int)(c->xchg & 1u);
+  HaloP2P L;
+  L.tag = c->xchg; L.cap = c->cap; L.done = c->d_done;
+  for (int side = 0; side < 2; side++) {
+    const bool has = side == 0 ? p.has_low != 0 : p.has_high != 0;
+    // I am the high-side neighbour of my low neighbour: my records land in ITS high-side buffers, and vice versa
+    L.peer_recv[side] = has ? block_recv(c->peer_base[side], c->cap, 1 - side, parity) : nullptr;
+    L.peer_flag[side] = has ? block_flag(c->peer_base[side], c->cap, 1 - side, parity) : nullptr;
+    L.my_recv[side] = block_recv(c->block, c->cap, side, parity);
+    L.my_flag[side] = block_flag(c->block, c->cap, side, parity);
+  }
+  mcx_launch_halo_p2p(p, L, s);
+  return MCX_OK;
+}
+
 static int exchange_halo(McxComm* c, DevParams& p, cudaStream_t s) {
+  if (c->p2p) return exchange_halo_p2p(c, p, s);
   const bool lo = p.has_low != 0, hi = p.has_high != 0;
   mcx_launch_pack_halo(p, c->send[0], c->send[1], c->cap, s);
   CCK(cudaMemcpyAsync(c->d_counts, &p.ctr->n_send[0], 2 * sizeof(unsigned int), cudaMemcpyDeviceToDevice, s));

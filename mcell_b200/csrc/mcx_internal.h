@@ -164,6 +164,16 @@ struct DevParams {
 struct HaloRec { MolRec rec; double tsched, tuni, pad_[2]; };  // 64 B (MolRec is 32-byte aligned)
 static_assert(sizeof(HaloRec) == 64, "HaloRec layout");
 
+// peer-memory halo exchange (mcx_comm.cu): where this rank's pack kernel writes and where its unpack kernel reads
+struct HaloP2P {
+  HaloRec* peer_recv[2];             // low / high neighbour's receive buffer for my records (peer memory, null: no neighbour)
+  unsigned long long* peer_flag[2];  // its flag word: (tag << 32) | count, release-stored after the records
+  const HaloRec* my_recv[2];         // my receive buffers (local memory) the neighbours write into
+  unsigned long long* my_flag[2];
+  unsigned int tag, cap;
+  unsigned int* done;                // pack kernel block counter (zero between launches)
+};
+
 // kernels / launchers implemented in mcx_kernels.cu
 struct StepPlan {
   int sm_count;
@@ -180,6 +190,7 @@ void mcx_launch_rebin(const DevParams& p, const StepPlan& plan, cudaStream_t s);
 void mcx_launch_pack_halo(const DevParams& p, HaloRec* send_low, HaloRec* send_high, unsigned int cap, cudaStream_t s);
 void mcx_launch_unpack_halo(const DevParams& p, const HaloRec* recv, unsigned int n, unsigned int offset, cudaStream_t s);
 void mcx_launch_add_received(const DevParams& p, unsigned int n, cudaStream_t s);
+void mcx_launch_halo_p2p(const DevParams& p, const HaloP2P& link, cudaStream_t s);  // pack+store to peers, acquire+unpack
 void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
 void mcx_launch_count_by_volume(const DevParams& p, cudaStream_t s);
 // device staging of the surface part of mcx_mol_soa (all null: volume molecules only)

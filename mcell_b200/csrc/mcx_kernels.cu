@@ -403,10 +403,9 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
     Stream rs; rs.init(p, m.id, &zig);
     Tracer tc; tc.h = 0xcbf29ce484222325ULL; tc.tr = nullptr;
     if (PASS == 1) {
-      // unimolecular firing comes first (diffuse_react_event.cpp:215-223): generic path
-      simple = simple && !(t_uni != MCX_TIME_INVALID && t_uni <= t_now);
-      // newbie lifetime (:232-236 -> pick_unimol_rxn_class_and_set_rxn_time :1731-1758): one draw
-      if (simple && (flags & DF_SCHED_UNIMOL)) {
+      // newbie lifetime (:232-236 -> pick_unimol_rxn_class_and_set_rxn_time :1731-1758): one draw; a unimolecular
+      // reaction that is due comes first (:215-223, the firing below)
+      if (simple && (flags & DF_SCHED_UNIMOL) && !(t_uni != MCX_TIME_INVALID && t_uni <= t_now)) {
         flags &= ~DF_SCHED_UNIMOL;
         const int rc = p.unimol[species];
         if (rc < 0) t_uni = MCX_TIME_INVALID;
@@ -418,9 +417,11 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
         }
       }
       if (simple) trace_begin(p, tc, m.id);
+    } else {
+      // a lifetime ending inside this iteration splits the step and fires (get_max_time :164-198): PASS 1
+      const bool timed = simple && t_uni != MCX_TIME_INVALID && t_uni < t_end;
+      if (timed) { to_second = true; simple = false; }
     }
-    // a lifetime ending inside this iteration splits a step or fires (get_max_time :164-198): generic path
-    simple = simple && !(t_uni != MCX_TIME_INVALID && t_uni < t_end);
     int reason = simple ? -1 : MCX_DEFER_TIMING;
     const bool own_start = owned_z(p, m.z);
     D3 pos = {m.x, m.y, m.z};
@@ -430,19 +431,49 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
 
 #pragma unroll 1
     for (int sub = 0; sub < (PASS == 0 ? 1 : 2); sub++) {
+      if (PASS == 1) {
+        // unimolecular firing (diffuse_react_event.cpp:215-223, :1764-1826) ends the evaluation with a claiming event
+        const bool fire = running && t_uni != MCX_TIME_INVALID && t_uni <= t_now;
+        if (fire) {
+          const int rc = p.unimol[species];
+          const DevClass& cl = p.classes[rc];
+          int pathway = 0;
+          if (cl.n_pathways > 1) {  // which_unimolecular, rxn_utils.inl:774-783
+            const double match = rs.dbl() * cl.max_fixed_p;
+            int min_idx = 0, max_idx = (int)cl.n_pathways - 1;
+            const DevPathway* A = p.pathways + cl.first_pathway;
+            while (max_idx - min_idx > 1) {
+              const int mid = (max_idx + min_idx) / 2;
+              if (match > A[mid].cum_prob) min_idx = mid; else max_idx = mid;
+            }
+            pathway = match > A[min_idx].cum_prob ? max_idx : min_idx;
+          }
+          tc.ev(EV_UNIMOL | (uint32_t)pathway, (uint32_t)rc);
+          if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->t_event = t_uni; }
+          Outcome o; o.kind = MCX_OUT_UNIMOL; o.pos = pos; o.rxn_class = rc; o.pathway = pathway; o.t_event = t_uni;
+          o.t_now = t_now; o.flags = flags; o.unimol_time = t_uni; o.partner_slot = MCX_NONE; o.partner_id = MCX_NONE; o.orient_bits = 0;
+          trace_end(tc, o, rs);
+          write_proposal(p, i, o, m.id, species, round_epoch(p, 0), -1);
+          proposed = true;
+          if (own_start) { msteps++; n_tests += my_tests; n_coll += my_coll; }
+          running = false;
+        }
+      }
       simple = running;
       // compute_vol_displacement (diffusion_utils.inl:366-432) with time_step == 1; drawn by every lane
       double t_steps = 1.0, scale = sp.space_step, r_rate_factor = 1.0, t_new = t_end;
       bool again = false;
       if (PASS == 1) {
-        const double max_time = t_end - t_now;
+        // get_max_time (:164-198): up to the end of the iteration or to the scheduled unimolecular reaction
+        double max_time = t_end - t_now;
+        if (t_uni != MCX_TIME_INVALID && t_uni < t_now + max_time) max_time = t_uni - t_now;
         double steps = 1.0;
         if (t_steps > max_time) { t_steps = max_time; steps = max_time / sp.time_step; }
-        simple = simple && !(steps < MCX_EPS) && !(t_uni != MCX_TIME_INVALID && t_uni < t_now + max_time);
+        simple = simple && !(steps < MCX_EPS);
         if (steps != 1.0) { const double rate_factor = sqrt(steps); r_rate_factor = 1.0 / rate_factor; scale = rate_factor * sp.space_step; }
-        // reschedule (:283-336): does the molecule need another sub-step after this one?
+        // reschedule (:283-336): does the molecule need another sub-step (or fire) after this one?
         t_new = t_now + t_steps;
-        again = t_new < t_end && !cmp_eq_d(t_new, t_end, MCX_EPS);
+        again = (t_uni != MCX_TIME_INVALID && t_uni < t_end) || (t_new < t_end && !cmp_eq_d(t_new, t_end, MCX_EPS));
         simple = simple && !(again && sub == 1);
         if (!simple && reason < 0) reason = MCX_DEFER_TIMING;
       }
@@ -918,6 +949,106 @@ __global__ void __launch_bounds__(TPB) k_unpack_halo(const __grid_constant__ Dev
 }
 __global__ void k_add_received(const __grid_constant__ DevParams p, unsigned int n) { p.ctr->n_prod += n; }
 
+// ---- halo refresh over peer memory (mcx_comm.cu: exchange_halo_p2p) ---------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* q) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* q, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// k_pack_halo's selection, but every selected record is stored straight into the neighbour's receive buffer (remote
+// stores over NVLink: one 256-bit store, plus one 128-bit store when the record carries cold fields).  The block that
+// finishes last publishes the two counts: a system-scope release store of (tag << 32 | count) into the neighbour's
+// flag word, ordered after every block's records by the fence + block-counter chain.
+__global__ void __launch_bounds__(TPB) k_halo_pack_p2p(const __grid_constant__ DevParams p, const HaloP2P L) {
+  const unsigned int n = p.ctr->n_slots + p.ctr->n_prod;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (p.rank[i] == MCX_NONE) continue;
+    const MolRec m = load_rec_volatile(p.recB, i);
+    if (m.sf & DF_DEAD) continue;  // tombstone of a consumed partner: dropped by everybody next iteration
+    const int cz = cell_z(p, m.z);
+    const bool to_low = p.has_low && cz < p.own_lo + p.halo_layers;
+    const bool to_high = p.has_high && cz >= p.own_hi - p.halo_layers;
+    if (!to_low && !to_high) continue;
+    const bool cold = (m.sf & (DF_PARTIAL | DF_HAS_UNIMOL)) != 0;
+    const double2 tt = cold ? make_double2((m.sf & DF_PARTIAL) ? p.tschedB[i] : 0.0, (m.sf & DF_HAS_UNIMOL) ? p.tuniB[i] : MCX_TIME_INVALID)
+                            : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      if (!(side == 0 ? to_low : to_high)) continue;
+      const unsigned int k = agg_reserve(&p.ctr->n_send[side], 1u);
+      if (k >= L.cap) { raise_error(p, MCX_ERR_CAPACITY, m.id); continue; }
+      HaloRec* dst = L.peer_recv[side] + k;
+      store_rec(&dst->rec, 0, D3{m.x, m.y, m.z}, m.id, m.sf);
+      if (cold) *reinterpret_cast<double2*>(&dst->tsched) = tt;
+    }
+  }
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = atomicAdd(L.done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int side = 0; side < 2; side++) {
+      if (!L.peer_flag[side]) continue;
+      const unsigned int cnt = min(atomicAdd(&p.ctr->n_send[side], 0u), L.cap);
+      st_release_sys(L.peer_flag[side], ((unsigned long long)L.tag << 32) | cnt);
+    }
+    *L.done = 0;
+  }
+}
+// the receiving side: wait for both neighbours' counts (acquire), then append their records behind the local results
+// and bin them like products; the last block adds them to the population
+__global__ void __launch_bounds__(TPB) k_halo_unpack_p2p(const __grid_constant__ DevParams p, const HaloP2P L) {
+  __shared__ unsigned int s_n[2];
+  if (threadIdx.x < 2) {
+    const int side = threadIdx.x;
+    unsigned int cnt = 0;
+    if (side == 0 ? p.has_low : p.has_high) {
+      const unsigned long long t0 = global_ns();
+      for (;;) {
+        const unsigned long long v = ld_acquire_sys(L.my_flag[side]);
+        if ((unsigned int)(v >> 32) == L.tag) { cnt = (unsigned int)v; break; }
+        if (global_ns() - t0 > 20000000000ull) { raise_error(p, MCX_ERR_COMM, 0); break; }  // 20 s: the neighbour is gone
+        __nanosleep(200);
+      }
+    }
+    s_n[side] = cnt;
+  }
+  __syncthreads();
+  const unsigned int n0 = s_n[0], n1 = s_n[1];
+  const unsigned int base = p.ctr->n_slots + p.ctr->n_prod;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n0 + n1; k += gridDim.x * blockDim.x) {
+    const HaloRec* src = k < n0 ? L.my_recv[0] + k : L.my_recv[1] + (k - n0);
+    const unsigned int i = base + k;
+    const MolRec m = load_rec_volatile(&src->rec, 0);
+    if (i >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, m.id); continue; }
+    store_rec(p.recB, i, D3{m.x, m.y, m.z}, m.id, m.sf);
+    if (m.sf & (DF_PARTIAL | DF_HAS_UNIMOL)) {
+      const double2 tt = __ldcg(reinterpret_cast<const double2*>(&src->tsched));
+      if (m.sf & DF_PARTIAL) p.tschedB[i] = tt.x;
+      if (m.sf & DF_HAS_UNIMOL) p.tuniB[i] = tt.y;
+    }
+    p.rank[i] = atomicAdd(&p.cs_next[cell_of(p, m.x, m.y, m.z)], 1u);
+  }
+}
+__global__ void k_halo_add_p2p(const __grid_constant__ DevParams p, const HaloP2P L) {
+  unsigned int n = 0;
+  if (p.has_low) n += (unsigned int)ld_acquire_sys(L.my_flag[0]);
+  if (p.has_high) n += (unsigned int)ld_acquire_sys(L.my_flag[1]);
+  p.ctr->n_prod += n;
+}
+
 // ---- SoA <-> record conversion at the ABI boundary ---------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_pack_soa(const __grid_constant__ DevParams p, const double* x, const double* y, const double* z,
                                                   const uint32_t* id, const uint32_t* species, const uint32_t* flags,
@@ -1054,6 +1185,11 @@ void mcx_launch_unpack_halo(const DevParams& p, const HaloRec* recv, unsigned in
   k_unpack_halo<<<grid, TPB, 0, s>>>(p, recv, n, offset);
 }
 void mcx_launch_add_received(const DevParams& p, unsigned int n, cudaStream_t s) { k_add_received<<<1, 1, 0, s>>>(p, n); }
+void mcx_launch_halo_p2p(const DevParams& p, const HaloP2P& link, cudaStream_t s) {
+  k_halo_pack_p2p<<<148 * 8, TPB, 0, s>>>(p, link);
+  k_halo_unpack_p2p<<<148 * 4, TPB, 0, s>>>(p, link);
+  k_halo_add_p2p<<<1, 1, 0, s>>>(p, link);
+}
 
 void mcx_launch_pack_soa(const DevParams& p, const double* x, const double* y, const double* z, const uint32_t* id,
                          const uint32_t* species, const uint32_t* flags, const double* tsched, const double* tuni,
