@@ -76,3 +76,18 @@ def test_layer_ranges_tile_the_grid():
     z = np.array([-1e30, -3.0, 0.0, 2.999, 3.0, 1e30])
     assert comm.layer_of(z, 0.0, 1.0 / 3.0, 10).tolist() == [0, 0, 0, 0, 1, 9]
     assert comm.rank_of(z, (0.0, 1.0 / 3.0, 10), world=2).tolist() == [0, 0, 0, 0, 0, 1]
+
+
+def test_bench_capacity_covers_the_halo_copies_of_every_rank_count():
+    """A slab rank holds its own layers, a halo on each side (3x the one-step reach, configure_slab) and — between the
+    halo refresh and the sort — the refreshed copies as well; bench.py must size max_molecules for that at every N the
+    driver runs (N = 4 and 8 once ran out of slots with a fixed factor)."""
+    import bench
+    n = 100_000_000
+    for world in (2, 4, 8):
+        t, edge_um = bench.build_model(n, world=world, rank=1)
+        edge_lu = edge_um / t.length_unit
+        reach = t.cfg.rxn_radius_3d + 6.993 * max(sp.space_step for sp in t.species)
+        halo = 3.0 * reach + 3.5                      # + one cell layer of rounding
+        need = n / world * (1.0 + 4.0 * halo / (edge_lu / world)) * 1.05   # + products of one iteration
+        assert t.cfg.max_molecules >= need, (world, t.cfg.max_molecules, need)
