@@ -477,7 +477,6 @@ int mcx_set_counted_volumes(mcx_handle* h, uint32_t n_counted_volumes, const uin
   if (!h || !wall_cv_front || !wall_cv_back) { if (h) h->err = "null counted-volume arrays"; return MCX_ERR_INVALID_ARG; }
   if (!h->has_geometry) { h->err = "mcx_set_geometry must precede mcx_set_counted_volumes"; return MCX_ERR_STATE; }
   if (n_counted_volumes == 0 || n_counted_volumes > MCX_MAX_CV) { h->err = "1..256 counted volumes are supported"; return MCX_ERR_INVALID_ARG; }
-  if (h->cfg.world_size > 1) { h->err = "counted volumes are not supported with world_size > 1 yet"; return MCX_ERR_INVALID_ARG; }
   CK(cudaSetDevice(h->cfg.device));
   std::vector<uint16_t> cv(std::max<uint64_t>(h->n_walls_host, 1), 0);
   for (uint64_t i = 0; i < h->n_walls_host; i++) {
@@ -513,6 +512,21 @@ int mcx_counts_by_volume(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_coun
     CK(cudaMemcpyAsync(rxn_counts, h->p.rxn_count_cv, sizeof(uint64_t) * (size_t)n_rules * h->n_cv, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
+  if (h->comm) {  // every rank counted its own molecules and the events it owns: sum over the ranks
+    auto reduce = [&](uint64_t* a, size_t n) -> int {
+      for (size_t at = 0; at < n; at += 1024) {
+        int rc = mcx_comm_allreduce_u64(h->comm, (unsigned long long*)(a + at), (int)std::min<size_t>(1024, n - at), h->stream);
+        if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+      }
+      return MCX_OK;
+    };
+    if (mol_counts) { int rc = reduce(mol_counts, h->species.size() * h->n_cv); if (rc) return rc; }
+    if (rxn_counts) {
+      uint32_t n_rules = 0;
+      for (const auto& pw : h->pathways) n_rules = std::max(n_rules, pw.rxn_rule_id + 1);
+      int rc = reduce(rxn_counts, (size_t)n_rules * h->n_cv); if (rc) return rc;
+    }
+  }
   return MCX_OK;
 }
 
@@ -554,7 +568,6 @@ static int ensure_staging(mcx_handle* h) {
 static int ensure_surface_arrays(mcx_handle* h) {
   h->p.has_surf = h->has_surf ? 1 : 0;
   if (!h->has_surf || h->surf_allocated) return MCX_OK;
-  if (h->cfg.world_size > 1) { h->err = "surface molecules are not supported with world_size > 1 yet"; return MCX_ERR_INVALID_ARG; }
   const size_t cap = h->p.capacity;
   DevParams& p = h->p;
   int rc = MCX_OK;

@@ -132,17 +132,19 @@ McxComm* mcx_comm_create(const void* nccl_unique_id, uint32_t id_bytes, int rank
   ncclResult_t r = ncclCommInitRank(&c->comm, world_size, id, rank);
   if (r != ncclSuccess) { err = std::string("ncclCommInitRank: ") + ncclGetErrorString(r); delete c; return nullptr; }
   bool ok = true;
-  for (int k = 0; k < 2; k++) {
-    ok = ok && cudaMalloc((void**)&c->send[k], sizeof(HaloRec) * (size_t)halo_capacity) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&c->recv[k], sizeof(HaloRec) * (size_t)halo_capacity) == cudaSuccess;
-  }
   ok = ok && cudaMalloc((void**)&c->d_counts, 4 * sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&c->h_counts, 4 * sizeof(unsigned int)) == cudaSuccess;
   c->red_cap = 1024;
   ok = ok && cudaMalloc((void**)&c->d_red, sizeof(unsigned long long) * c->red_cap) == cudaSuccess;
+  if (ok) cudaMemset(c->d_counts, 0, 4 * sizeof(unsigned int));
+  if (ok && !getenv("MCX_HALO_NCCL")) setup_p2p(c);  // falls back to NCCL send/recv when peer memory is not available
+  if (ok && !c->p2p) {  // staging buffers of the NCCL path
+    for (int k = 0; k < 2; k++) {
+      ok = ok && cudaMalloc((void**)&c->send[k], sizeof(HaloRec) * (size_t)halo_capacity) == cudaSuccess;
+      ok = ok && cudaMalloc((void**)&c->recv[k], sizeof(HaloRec) * (size_t)halo_capacity) == cudaSuccess;
+    }
+  }
   if (!ok) { err = "halo buffer allocation failed"; mcx_comm_destroy(c); return nullptr; }
-  cudaMemset(c->d_counts, 0, 4 * sizeof(unsigned int));
-  if (!getenv("MCX_HALO_NCCL")) setup_p2p(c);  // falls back to the NCCL send/recv path when peer memory is not available
   return c;
 }
 

@@ -161,8 +161,11 @@ struct DevParams {
 };
 
 // multi-GPU halo record: what a neighbour needs to evaluate a molecule exactly like its owner does
-struct HaloRec { MolRec rec; double tsched, tuni, pad_[2]; };  // 64 B (MolRec is 32-byte aligned)
-static_assert(sizeof(HaloRec) == 64, "HaloRec layout");
+// rec (32 B) | tsched, tuni (16 B, records with DF_PARTIAL / DF_HAS_UNIMOL) | Molecule::s of surface molecules and the
+// creation wall / tile of DF_CREATED_ON_SURF volume products (32 B); the peer-memory path stores only the parts a
+// record has, the NCCL fallback moves whole records
+struct HaloRec { MolRec rec; double tsched, tuni; uint32_t swall, stile; uint32_t pad_[2]; double su, sv; double pad2_[2]; };
+static_assert(sizeof(HaloRec) == 96, "HaloRec layout (MolRec is 32-byte aligned)");
 
 // peer-memory halo exchange (mcx_comm.cu): where this rank's pack kernel writes and where its unpack kernel reads
 struct HaloP2P {

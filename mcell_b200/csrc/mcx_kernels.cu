@@ -912,6 +912,7 @@ __global__ void __launch_bounds__(TPB) k_rebin(const __grid_constant__ DevParams
     store_rec(p.recB, i, D3{m.x, m.y, m.z}, m.id, m.sf);
     if (m.sf & DF_PARTIAL) p.tschedB[i] = p.tschedA[i];
     if (m.sf & DF_HAS_UNIMOL) p.tuniB[i] = p.tuniA[i];
+    if (m.sf & (DF_SURF | DF_CREATED_ON_SURF)) { p.swallB[i] = p.swallA[i]; p.stileB[i] = p.stileA[i]; if (m.sf & DF_SURF) p.suvB[i] = p.suvA[i]; }
     p.rank[i] = atomicAdd(&p.cs_next[cell_of(p, m.x, m.y, m.z)], 1u);
   }
 }
@@ -932,6 +933,11 @@ __global__ void __launch_bounds__(TPB) k_pack_halo(const __grid_constant__ DevPa
     h.rec = m;
     h.tsched = (m.sf & DF_PARTIAL) ? p.tschedB[i] : 0.0;
     h.tuni = (m.sf & DF_HAS_UNIMOL) ? p.tuniB[i] : MCX_TIME_INVALID;
+    h.swall = h.stile = MCX_NONE; h.su = h.sv = 0.0;
+    if (m.sf & (DF_SURF | DF_CREATED_ON_SURF)) {
+      h.swall = p.swallB[i]; h.stile = p.stileB[i];
+      if (m.sf & DF_SURF) { const double2 uv = p.suvB[i]; h.su = uv.x; h.sv = uv.y; }
+    }
     if (to_low) {
       unsigned int k = agg_reserve(&p.ctr->n_send[0], 1u);
       if (k < cap) send_low[k] = h; else raise_error(p, MCX_ERR_CAPACITY, m.id);
@@ -953,6 +959,7 @@ __global__ void __launch_bounds__(TPB) k_unpack_halo(const __grid_constant__ Dev
     store_rec(p.recB, i, D3{h.rec.x, h.rec.y, h.rec.z}, h.rec.id, h.rec.sf);
     if (h.rec.sf & DF_PARTIAL) p.tschedB[i] = h.tsched;
     if (h.rec.sf & DF_HAS_UNIMOL) p.tuniB[i] = h.tuni;
+    if (h.rec.sf & (DF_SURF | DF_CREATED_ON_SURF)) { p.swallB[i] = h.swall; p.stileB[i] = h.stile; if (h.rec.sf & DF_SURF) p.suvB[i] = make_double2(h.su, h.sv); }
     p.rank[i] = atomicAdd(&p.cs_next[cell_of(p, h.rec.x, h.rec.y, h.rec.z)], 1u);
   }
 }
@@ -989,6 +996,10 @@ __global__ void __launch_bounds__(TPB) k_halo_pack_p2p(const __grid_constant__ D
     const bool cold = (m.sf & (DF_PARTIAL | DF_HAS_UNIMOL)) != 0;
     const double2 tt = cold ? make_double2((m.sf & DF_PARTIAL) ? p.tschedB[i] : 0.0, (m.sf & DF_HAS_UNIMOL) ? p.tuniB[i] : MCX_TIME_INVALID)
                             : make_double2(0.0, 0.0);
+    const bool surf = (m.sf & (DF_SURF | DF_CREATED_ON_SURF)) != 0;  // Molecule::s, or where a volume product was created
+    uint2 wt = make_uint2(MCX_NONE, MCX_NONE);
+    double2 uv = make_double2(0.0, 0.0);
+    if (surf) { wt = make_uint2(p.swallB[i], p.stileB[i]); if (m.sf & DF_SURF) uv = p.suvB[i]; }
 #pragma unroll
     for (int side = 0; side < 2; side++) {
       if (!(side == 0 ? to_low : to_high)) continue;
@@ -997,6 +1008,7 @@ __global__ void __launch_bounds__(TPB) k_halo_pack_p2p(const __grid_constant__ D
       HaloRec* dst = L.peer_recv[side] + k;
       store_rec(&dst->rec, 0, D3{m.x, m.y, m.z}, m.id, m.sf);
       if (cold) *reinterpret_cast<double2*>(&dst->tsched) = tt;
+      if (surf) { *reinterpret_cast<uint2*>(&dst->swall) = wt; *reinterpret_cast<double2*>(&dst->su) = uv; }
     }
   }
   __shared__ bool last;
@@ -1047,6 +1059,11 @@ __global__ void __launch_bounds__(TPB) k_halo_unpack_p2p(const __grid_constant__
       const double2 tt = __ldcg(reinterpret_cast<const double2*>(&src->tsched));
       if (m.sf & DF_PARTIAL) p.tschedB[i] = tt.x;
       if (m.sf & DF_HAS_UNIMOL) p.tuniB[i] = tt.y;
+    }
+    if (m.sf & (DF_SURF | DF_CREATED_ON_SURF)) {
+      const uint2 wt = __ldcg(reinterpret_cast<const uint2*>(&src->swall));
+      p.swallB[i] = wt.x; p.stileB[i] = wt.y;
+      if (m.sf & DF_SURF) p.suvB[i] = __ldcg(reinterpret_cast<const double2*>(&src->su));
     }
     p.rank[i] = atomicAdd(&p.cs_next[cell_of(p, m.x, m.y, m.z)], 1u);
   }

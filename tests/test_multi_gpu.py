@@ -35,7 +35,8 @@ def _run_ranks(tables_fn, mols, n_iter, world=2, halo_width=0.0):
             e.comm_init(uid)
             e.upload(mols)                      # every rank uploads everything; foreign slabs are dropped
             stats = [e.step(1) for _ in range(n_iter)]
-            out[rank] = (e.download(), stats, e.counts(), e.slab_info())
+            by_volume = e.counts_by_volume() if len(t.counted_volume_sets) > 1 else None
+            out[rank] = (e.download(), stats, e.counts(), e.slab_info(), by_volume)
             e.close()
         except Exception as ex:                 # noqa: BLE001
             errs.append((rank, ex))
@@ -85,3 +86,48 @@ def test_two_ranks_match_single_gpu(scenario):
     for it in range(n_iter):
         for k in ("molecule_steps", "bimol_rxns", "mol_wall_reflections", "vol_mol_vol_mol_collisions"):
             assert sum(getattr(r[1][it], k) for r in res) == getattr(st1[it], k), (it, k)
+
+
+@pytest.mark.skipif(_n_devices() < 2, reason="needs 2 CUDA devices")
+@pytest.mark.parametrize("scenario", ["receptors", "surface_diffusion", "counted_volumes"])
+def test_two_ranks_match_single_gpu_surface_and_counted(scenario):
+    """Surface molecules (tiles, binding, unbinding, 2-D diffusion across the slab face) and counted volumes with two
+    ranks: the halo records carry Molecule::s and the creation wall / tile of surface-born volume products, the counted
+    volume rides in the record flags; the population and the per-volume counts equal the single-GPU run bit for bit."""
+    from mcell_b200 import Engine
+    n_iter = 8
+    if scenario == "receptors":
+        make = lambda: cm.ligand_receptor_sphere(n_lig=30000, n_rec=3000, n_pump=1500, radius_um=0.5, subdivisions=4,  # noqa: E731
+                                                 box_um=1.6, seed=6, release_products=False)
+        halo = 62.0   # 3 x (R + 6.993 * space_step of Ca, D = 2e-6)
+    elif scenario == "surface_diffusion":
+        make = lambda: cm.diffusing_receptors(n_rec=4000, n_lig=20000, radius_um=0.5, subdivisions=4, box_um=1.6, seed=7)  # noqa: E731
+        halo = 45.0
+    else:
+        make = lambda: cm.counted_spheres(n=30000, seed=8, box_um=1.2)  # noqa: E731
+        halo = 45.0
+    t, mols = make()
+    single = Engine(t)
+    single.upload(mols)
+    st1 = [single.step(1) for _ in range(n_iter)]
+    ref = single.download().sorted_by_id()
+    ref_counts = single.counts()
+    ref_by_volume = single.counts_by_volume() if len(t.counted_volume_sets) > 1 else None
+    res = _run_ranks(lambda: make()[0], mols, n_iter, halo_width=halo)
+    parts = [r[0] for r in res]
+    ids = np.concatenate([p.id[:p.n] for p in parts])
+    assert len(ids) == ref.n and len(np.unique(ids)) == ref.n
+    o = np.argsort(ids, kind="stable")
+    for k in ("id", "species", "x", "y", "z", "flags", "diffusion_time", "unimol_rxn_time", "wall", "tile", "orientation",
+              "u", "v", "counted_volume"):
+        got = np.concatenate([getattr(p, k)[:p.n] for p in parts])[o]
+        assert (got == getattr(ref, k)[:ref.n]).all(), k
+    assert (res[0][2][0] == ref_counts[0]).all() and (res[1][2][0] == ref_counts[0]).all()
+    assert (res[0][2][1] == ref_counts[1]).all()
+    for it in range(n_iter):
+        for k in ("molecule_steps", "bimol_rxns", "unimol_rxns", "mol_wall_reflections", "mol_wall_transparent"):
+            assert sum(getattr(r[1][it], k) for r in res) == getattr(st1[it], k), (it, k)
+    assert sum(getattr(s_, "bimol_rxns") for s_ in st1) > 20
+    if ref_by_volume is not None:
+        for r in res:
+            assert (r[4][0] == ref_by_volume[0]).all() and (r[4][1] == ref_by_volume[1]).all()
