@@ -328,6 +328,8 @@ def run_ours(args):
         from mcell_b200 import comm as mcomm
         eng.comm_init(mcomm.broadcast_unique_id(dist, rank, device="cuda"))
         slab = eng.slab_info()
+    halo_text = {0: "one device, no halo", 1: "NCCL send/recv halo refresh per iteration",
+                 2: "peer-memory halo refresh per iteration (NVLink stores + release/acquire flags)"}[eng.halo_path()]
     mols = make_molecules(n_total, edge_um, t.length_unit, 1, slab)
     eng.upload(mols)
 
@@ -425,7 +427,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD,
                        "molecules": n_total, "box_edge_um": edge_um, "iterations_per_plugin_call": ITERS_PER_CALL,
                        "l2": "inputs (>=3 GB at 1e8 molecules) larger than L2; no flush",
-                       "parallelism": "z-slabs x%d, NCCL halo refresh per iteration" % world, "rng": "philox4x32-10 per molecule"},
+                       "parallelism": "z-slabs x%d, %s" % (world, halo_text), "rng": "philox4x32-10 per molecule"},
             "roofline": {"bound": "hbm", "kernel": top_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": _traffic(top_kernel, n_total) if world == 1 else None,
                          "peak_source": peak_src,

@@ -291,9 +291,11 @@ int mcx_counts_by_volume(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_coun
  * molecules of other slabs are dropped), mcx_step.  Slabs are z-layers of the device cell grid. */
 int mcx_comm_init(mcx_handle* h, const void* nccl_unique_id, uint32_t id_bytes);
 /* Slab layout of this rank after mcx_comm_init: z-layers of the global device cell grid.  A position z belongs to
- * layer clamp(floor((z - grid_origin_z) * layer_rcp), 0, n_layers - 1); rank r owns layers
- * [n_layers * r / world, n_layers * (r + 1) / world).  Hosts that distribute molecules use exactly this
- * arithmetic (IEEE double) so that host and device agree on every molecule. */
+ * layer clamp(floor((z - grid_origin_z) * layer_rcp), 0, n_layers - 1); rank r owns layers [b(r), b(r + 1)) with
+ * b(0) = 0, b(world) = n_layers and b(k) = halo_layers + (n_layers - 2 * halo_layers) * k / world in between (integer
+ * division): the two outermost ranks have one halo only and own halo_layers more, so that every rank evaluates the
+ * same number of layers.  Hosts that distribute molecules use exactly this arithmetic (IEEE double for the layer)
+ * so that host and device agree on every molecule. */
 typedef struct mcx_slab_info {
   double   grid_origin_z;          /* length units */
   double   layer_rcp;              /* 1 / layer thickness */
@@ -303,6 +305,9 @@ typedef struct mcx_slab_info {
   int32_t  rank, world_size;
 } mcx_slab_info;
 int mcx_slab_info_get(mcx_handle* h, mcx_slab_info* out);
+/* How the halo refresh of this handle moves its records: 0 = single device (no exchange), 1 = NCCL send/recv,
+ * 2 = stores into the neighbours' memory over NVLink (peer memory).  Negative on error. */
+int mcx_comm_halo_path(mcx_handle* h);
 /* Rank 0 creates the id (ncclGetUniqueId) that every rank passes to mcx_comm_init; returns the number of bytes
  * written (<= bytes) or a negative error. */
 int mcx_comm_unique_id(void* out, uint32_t bytes);

@@ -40,19 +40,30 @@ def layer_of(z, grid_origin_z, layer_rcp, n_layers):
     return np.clip(c, 0, n_layers - 1).astype(np.int64)   # clamp first: the device conversion saturates
 
 
-def layer_range(n_layers, rank, world):
-    """Layers [lo, hi) owned by `rank` (configure_slab in csrc/mcx_api.cu)."""
-    return (n_layers * rank) // world, (n_layers * (rank + 1)) // world
+def layer_range(n_layers, rank, world, halo_layers=0):
+    """Layers [lo, hi) owned by `rank` (configure_slab in csrc/mcx_api.cu): the two outermost ranks, which have one
+    halo only, own `halo_layers` more than the inner ones so that every rank evaluates the same number of layers."""
+    def bound(k):
+        if k <= 0:
+            return 0
+        if k >= world:
+            return n_layers
+        return halo_layers + ((n_layers - 2 * halo_layers) * k) // world
+    return bound(rank), bound(rank + 1)
 
 
 def rank_of(z, info_or_tuple, world=None):
     """Owning rank of every position."""
+    halo = 0
     if isinstance(info_or_tuple, abi.mcx_slab_info):
         g0, rcp, n, world = info_or_tuple.grid_origin_z, info_or_tuple.layer_rcp, info_or_tuple.n_layers, info_or_tuple.world_size
+        halo = info_or_tuple.halo_layers
     else:
-        g0, rcp, n = info_or_tuple
+        g0, rcp, n = info_or_tuple[:3]
+        if len(info_or_tuple) > 3:
+            halo = info_or_tuple[3]
     lay = layer_of(z, g0, rcp, n)
-    bounds = np.array([layer_range(n, r, world)[1] for r in range(world)], dtype=np.int64)
+    bounds = np.array([layer_range(n, r, world, halo)[1] for r in range(world)], dtype=np.int64)
     return np.searchsorted(bounds, lay, side="right")
 
 

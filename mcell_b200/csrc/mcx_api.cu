@@ -838,7 +838,13 @@ static int configure_slab(mcx_handle* h) {
   const double ez = 1.0 / p.cell_rcp_z;
   const int H = (int)std::ceil(width / ez);
   const int g = h->ncz_global;
-  const int g_lo = (int)((long long)g * rank / world), g_hi = (int)((long long)g * (rank + 1) / world);
+  // Balanced slabs: every rank EVALUATES its owned layers plus a halo towards each neighbour, and the two outermost
+  // ranks have one neighbour only — they own H layers more, so that all ranks evaluate (g - 2H) / world + 2H layers
+  // (equal slabs left the inner ranks with 7 % more work at N = 4 and 8, and everybody waits for them in the halo
+  // refresh).  Mirrored by comm.layer_range() on the host.
+  auto bound = [&](int k) -> int { return k <= 0 ? 0 : (k >= world ? g : H + (int)((long long)(g - 2 * H) * k / world)); };
+  if (g <= 2 * H) { h->err = "slab thinner than the halo: fewer ranks or a narrower halo_width"; return MCX_ERR_INVALID_ARG; }
+  const int g_lo = bound(rank), g_hi = bound(rank + 1);
   if (g_hi - g_lo < H) { h->err = "slab thinner than the halo: fewer ranks or a narrower halo_width"; return MCX_ERR_INVALID_ARG; }
   const int z_off = std::max(0, g_lo - H), z_end = std::min(g, g_hi + H);
   p.z_off = z_off; p.ncz = z_end - z_off;
@@ -870,6 +876,11 @@ int mcx_slab_info_get(mcx_handle* h, mcx_slab_info* out) {
   out->layer_lo = (uint32_t)(p.own_lo + p.z_off); out->layer_hi = (uint32_t)(p.own_hi + p.z_off);
   out->halo_layers = (uint32_t)p.halo_layers; out->rank = h->cfg.rank; out->world_size = p.world;
   return MCX_OK;
+}
+
+int mcx_comm_halo_path(mcx_handle* h) {
+  if (!h) return MCX_ERR_INVALID_ARG;
+  return h->comm ? (mcx_comm_is_p2p(h->comm) ? 2 : 1) : 0;
 }
 
 int mcx_set_profiling(mcx_handle* h, int enabled) {

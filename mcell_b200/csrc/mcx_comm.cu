@@ -161,6 +161,7 @@ void mcx_comm_destroy(McxComm* c) {
   delete c;
 }
 const char* mcx_comm_error(McxComm* c) { return c ? c->err.c_str() : ""; }
+bool mcx_comm_is_p2p(const McxComm* c) { return c && c->p2p; }
 
 // halo refresh: pack -> counts -> payload -> unpack (appended behind the local results in B)
 // halo refresh over peer memory: ONE kernel selects the records, stores them into the neighbours' receive buffers over

@@ -14,3 +14,5 @@ int mcx_comm_iteration(McxComm* c, DevParams& p, const StepPlan& plan, cudaStrea
 // after an upload: align fresh-id ranges across ranks and fetch the neighbours' halo molecules (no evaluation)
 int mcx_comm_refresh(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_t s);
 int mcx_comm_allreduce_u64(McxComm* c, unsigned long long* host_buf, int n, cudaStream_t s);
+// true when the halo refresh goes through the neighbours' peer memory (NVLink stores), false on the NCCL path
+bool mcx_comm_is_p2p(const McxComm* c);

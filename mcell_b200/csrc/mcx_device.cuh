@@ -511,6 +511,13 @@ __device__ __forceinline__ MolRec load_rec_volatile(const MolRec* a, uint32_t i)
   asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(a + i) : "memory");
   return rec_from(x, y, z, w);
 }
+// result records are written once and next read by the scatter, a whole pass later: stored with the streaming
+// (evict-first) policy they do not push the snapshot records the probes gather out of L2
+__device__ __forceinline__ void store_rec_stream(MolRec* a, uint32_t i, D3 pos, uint32_t id, uint32_t sf) {
+  const unsigned long long m = ((unsigned long long)sf << 32) | id;
+  asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(a + i), "d"(pos.x), "d"(pos.y), "d"(pos.z),
+               "d"(__longlong_as_double((long long)m)) : "memory");
+}
 __device__ __forceinline__ void store_rec(MolRec* a, uint32_t i, D3 pos, uint32_t id, uint32_t sf) {
   const unsigned long long m = ((unsigned long long)sf << 32) | id;
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(a + i), "d"(pos.x), "d"(pos.y), "d"(pos.z),
@@ -745,31 +752,57 @@ __device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enab
   if (total > 0) { const int k = __popc(ne & ((1u << lane) - 1u)); sm->off[k] = incl - total; sm->owner[k] = lane; }
   __syncwarp();
   const uint32_t my_off = lane < __popc(ne) ? sm->off[lane] : 0xFFFFFFFFu;
-  for (uint32_t B = 0; B < W; B += 32) {
+  // pair q of the concatenation -> (owner lane o, candidate slot j); warp-collective (ballots), valid = q < W
+  auto locate = [&](uint32_t B, uint32_t& o, uint32_t& j) -> bool {
     const uint32_t q = B + lane;
     const unsigned int below = __ballot_sync(0xffffffffu, my_off <= B);
     const unsigned int bit = (my_off > B && my_off - B < 32u) ? (1u << (my_off - B)) : 0u;
     const unsigned int mask = __reduce_or_sync(0xffffffffu, bit);
     const int k = __popc(below) - 1 + __popc(mask & ((2u << lane) - 1u));
-    if (q < W) {
-      const uint32_t o = sm->owner[k];
+    const bool valid = q < W;
+    o = 0; j = 0;
+    if (valid) {
+      o = sm->owner[k];
       const uint32_t kk = q - sm->off[k];
       // row of pair kk = number of row ends at or below it (branch-free: the nested selects this replaces were
       // compiled into divergent branches, 12-20 of 32 lanes active, profiles/r01_l)
       const uint4 c03 = *reinterpret_cast<const uint4*>(&sm->cum[o][0]);
       const uint32_t c4 = sm->cum[o][4];
       const uint32_t r = (kk >= c03.x) + (kk >= c03.y) + (kk >= c03.z) + (kk >= c03.w) + (kk >= c4);
-      const uint32_t j = sm->lo[o][r] + kk;
-      const MolRec c = load_rec(p.recA, j);
-      const double4 oa = sm->a[o], ob = sm->b[o];
-      const unsigned long long ids = (unsigned long long)__double_as_longlong(ob.w);
-      double d;
-      if (collide_mol_hit(c, D3{oa.x, oa.y, oa.z}, D3{ob.x, ob.y, ob.z}, oa.w, oa.w * R2, (uint32_t)ids, d)) {
-        const int rc = p.bimol[(uint32_t)(ids >> 32) * p.n_species + (c.sf & SF_SPECIES_MASK)];
-        if (rc >= 0) { const uint32_t h = atomicAdd(&sm->hits[o], 1u); if (h < MCX_FAST_MAX_HITS) sm->hit_slot[o][h] = j; }
-      }
+      j = sm->lo[o][r] + kk;
     }
+    return valid;
+  };
+  // collide_mol (collision_utils.inl:464-515) of candidate record c against owner o's move
+  auto test = [&](bool valid, uint32_t o, uint32_t j, const MolRec& c) {
+    if (!valid) return;
+    const double4 oa = sm->a[o], ob = sm->b[o];
+    const unsigned long long ids = (unsigned long long)__double_as_longlong(ob.w);
+    double d;
+    if (collide_mol_hit(c, D3{oa.x, oa.y, oa.z}, D3{ob.x, ob.y, ob.z}, oa.w, oa.w * R2, (uint32_t)ids, d)) {
+      const int rc = p.bimol[(uint32_t)(ids >> 32) * p.n_species + (c.sf & SF_SPECIES_MASK)];
+      if (rc >= 0) { const uint32_t h = atomicAdd(&sm->hits[o], 1u); if (h < MCX_FAST_MAX_HITS) sm->hit_slot[o][h] = j; }
+    }
+  };
+#ifdef MCX_PROBE_UNROLL2
+  // two batches of 32 pairs per trip: both gathers are in flight before either is tested (the wait for a gathered
+  // record was 23 % of the kernel's stall samples with one load per trip, profiles/r01_s)
+  for (uint32_t B = 0; B < W; B += 64) {
+    uint32_t o0, j0, o1, j1;
+    const bool v0 = locate(B, o0, j0);
+    const bool v1 = locate(B + 32, o1, j1);
+    const MolRec c0 = load_rec(p.recA, j0);
+    const MolRec c1 = load_rec(p.recA, j1);
+    test(v0, o0, j0, c0);
+    test(v1, o1, j1, c1);
   }
+#else
+  for (uint32_t B = 0; B < W; B += 32) {
+    uint32_t o, j;
+    const bool v = locate(B, o, j);
+    if (v) { const MolRec c = load_rec(p.recA, j); test(v, o, j, c); }
+  }
+#endif
   __syncwarp();
   const int found = (int)sm->hits[lane];
   __syncwarp();  // the buffers are reused by the next trip of the caller's loop

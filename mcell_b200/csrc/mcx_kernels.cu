@@ -11,6 +11,7 @@
 //
 // All population sizes live in device memory (Counters); kernels are grid-stride over them so that an
 // iteration needs no host round trip.
+#include <cstdlib>
 #include <cstdio>
 #include "mcx_device.cuh"
 
@@ -165,9 +166,15 @@ __device__ __forceinline__ void finalize_alive(const DevParams& p, uint32_t slot
       p.swallB[slot] = surf->s_wall; p.stileB[slot] = surf->s_tile; p.suvB[slot] = make_double2(surf->s_u, surf->s_v);
     }
   }
+#ifdef MCX_STREAM_STORES
+  store_rec_stream(p.recB, slot, pos, id, sf);
+  uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
+  __stcs(p.rank + slot, atomicAdd(&p.cs_next[cell], 1u));
+#else
   store_rec(p.recB, slot, pos, id, sf);
   uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
   p.rank[slot] = atomicAdd(&p.cs_next[cell], 1u);
+#endif
 }
 
 __device__ __forceinline__ bool partner_is_consumed(const DevParams& p, int kind, int rxn_class, int pathway,
@@ -1153,6 +1160,14 @@ void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
 // cell histogram reset + fast/slow diffuse + conflict rounds: results sit in B with their ranks
 void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
   cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
+  static const bool carveout_set = [] {  // tuning knob (profiles/): shared-memory carveout of the fast pass in percent
+    if (const char* e = getenv("MCX_FAST_CARVEOUT")) {
+      cudaFuncSetAttribute(k_diffuse_fast<0>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+      cudaFuncSetAttribute(k_diffuse_fast<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+    }
+    return true;
+  }();
+  (void)carveout_set;
   if (plan.prof) cudaEventRecord(plan.prof[0], s);
   k_diffuse_fast<0><<<plan.sm_count * 2 * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
   if (plan.prof) cudaEventRecord(plan.prof[4], s);

@@ -12,7 +12,8 @@ from . import abi
 from .model import MolArrays
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcx.so")
+# MCX_LIB: another build of the same library (tuning variants, tools/build_variants.sh)
+LIB_PATH = os.environ.get("MCX_LIB") or os.path.join(_HERE, "libmcx.so")
 _lib = None
 
 
@@ -51,6 +52,7 @@ def load_library():
     L.mcx_comm_init.argtypes = [H, C.c_void_p, C.c_uint32]
     L.mcx_comm_unique_id.argtypes = [C.c_void_p, C.c_uint32]
     L.mcx_slab_info_get.argtypes = [H, C.POINTER(abi.mcx_slab_info)]
+    L.mcx_comm_halo_path.argtypes = [H]
     L.mcx_set_profiling.argtypes = [H, C.c_int]
     L.mcx_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
     L.mcx_philox_block.restype = None
@@ -104,6 +106,10 @@ class Engine:
     def comm_init(self, unique_id_bytes):
         buf = C.create_string_buffer(bytes(unique_id_bytes), len(unique_id_bytes))
         self._ck(self.L.mcx_comm_init(self.h, C.cast(buf, C.c_void_p), len(unique_id_bytes)))
+
+    def halo_path(self):
+        """0 = single device, 1 = NCCL send/recv, 2 = peer-memory stores over NVLink (mcx_comm_halo_path)."""
+        return int(self.L.mcx_comm_halo_path(self.h))
 
     def slab_info(self):
         info = abi.mcx_slab_info()

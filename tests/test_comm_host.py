@@ -73,6 +73,16 @@ def test_layer_ranges_tile_the_grid():
             assert edges[0][0] == 0 and edges[-1][1] == n_layers
             for a, b in zip(edges, edges[1:]):
                 assert a[1] == b[0]
+    # balanced slabs: with a halo of H layers per neighbour every rank evaluates the same thickness (+-1 layer)
+    for n_layers, halo in ((334, 17), (2738, 40)):
+        for world in (2, 4, 8):
+            edges = [comm.layer_range(n_layers, r, world, halo) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n_layers
+            for a, b in zip(edges, edges[1:]):
+                assert a[1] == b[0]
+            work = [(hi - lo) + halo * ((r > 0) + (r < world - 1)) for r, (lo, hi) in enumerate(edges)]
+            assert max(work) - min(work) <= 1, (n_layers, halo, world, work)
+            assert min(hi - lo for lo, hi in edges) >= halo
     z = np.array([-1e30, -3.0, 0.0, 2.999, 3.0, 1e30])
     assert comm.layer_of(z, 0.0, 1.0 / 3.0, 10).tolist() == [0, 0, 0, 0, 1, 9]
     assert comm.rank_of(z, (0.0, 1.0 / 3.0, 10), world=2).tolist() == [0, 0, 0, 0, 0, 1]

@@ -1,0 +1,8 @@
+#!/bin/bash
+# 4 GPUs of one box: strong-scaling bench at N=4 over the peer-memory halo path (ranks with two neighbours), then N=2
+set -x
+mkdir -p gpurun_out
+python -m mcell_b200.build > gpurun_out/mg4_build.log 2>&1
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 4 --steps 10 --warmup 3 --no-cpu > gpurun_out/mg4_bench_4gpu.json 2> gpurun_out/mg4_bench_4gpu.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu > gpurun_out/mg4_bench_2gpu.json 2> gpurun_out/mg4_bench_2gpu.err
+tail -1 gpurun_out/mg4_bench_4gpu.json | cut -c1-2000; tail -3 gpurun_out/mg4_bench_4gpu.err; tail -1 gpurun_out/mg4_bench_2gpu.json | cut -c1-600
