@@ -1267,9 +1267,11 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
         if (steps == 1.0) { scale = sp.space_step; r_rate_factor = 1.0; }
         else { double rate_factor = sqrt(steps); r_rate_factor = 1.0 / rate_factor; scale = rate_factor * sp.space_step; }
         D3 remaining;
-        remaining.x = scale * rs.gauss() * 0.70710678118654752440;
-        remaining.y = scale * rs.gauss() * 0.70710678118654752440;
-        remaining.z = scale * rs.gauss() * 0.70710678118654752440;
+#pragma unroll 1
+        for (int axis = 0; axis < 3; axis++) {  // one copy of the Ziggurat code (instruction-cache footprint)
+          const double g = scale * rs.gauss() * 0.70710678118654752440;
+          if (axis == 0) remaining.x = g; else if (axis == 1) remaining.y = g; else remaining.z = g;
+        }
         max_time = t_steps;
 
         uint32_t last_hit_wall = MCX_NONE;

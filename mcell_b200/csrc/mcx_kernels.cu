@@ -104,6 +104,7 @@ struct WarpList {
     unsigned int at = 0;
     if (lane == 0) at = atomicAdd(ctr, n);
     at = __shfl_sync(0xffffffffu, at, 0);
+#pragma unroll 1
     for (unsigned int k = lane; k < n; k += 32) list[at + k] = buf[k];
     __syncwarp();
     total += n;
@@ -507,8 +508,13 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       const bool walls_own = simple && (same || single) && (f & 1);
       const bool walls_dest = simple && single && (fd & 1);
       double wall_dist = 1e300;
-      const bool rejected_own = all_walls_plane_rejected(p, walls_own, own, pos, disp, n_wall_tests, wall_dist);
-      const bool rejected_dest = all_walls_plane_rejected(p, walls_dest, dest_sp, pos, disp, n_wall_tests_dest, wall_dist);
+      bool rejected_own = true, rejected_dest = true;
+#pragma unroll 1
+      for (int w = 0; w < 2; w++) {  // one copy of the wall loops for both subpartitions (instruction-cache footprint)
+        unsigned int nt = 0;
+        const bool r = all_walls_plane_rejected(p, w == 0 ? walls_own : walls_dest, w == 0 ? own : dest_sp, pos, disp, nt, wall_dist);
+        if (w == 0) { rejected_own = r; n_wall_tests = nt; } else { rejected_dest = r; n_wall_tests_dest = nt; }
+      }
       n_wall_tests += n_wall_tests_dest;
       simple = simple && ((same || single) ? ((!walls_own || rejected_own) && (!walls_dest || rejected_dest)) : (near && !(f & 2)));
       if (!simple && reason < 0) reason = (same || single) ? MCX_DEFER_WALL : MCX_DEFER_GEOMETRY;
