@@ -193,4 +193,101 @@ void GpuMolOrRxnCountEvent::step() {
   }
 }
 
+// ---- VizOutputWriter / GpuVizOutputEvent (src4/viz_output_event.cpp) ---------------------------------------------
+std::string VizOutputWriter::iterations_to_string(uint64_t current_iteration, uint64_t total_iterations) {
+  // :65-76 — as many digits as total_iterations has, zero padded
+  uint64_t lli = 10;
+  int ndigits;
+  for (ndigits = 1; lli <= total_iterations && ndigits < 20; ndigits++) lli *= 10;
+  char buf[48];
+  snprintf(buf, sizeof(buf), "%0*llu", ndigits, (unsigned long long)current_iteration);
+  return buf;
+}
+
+std::string VizOutputWriter::file_name(const std::string& prefix, viz_mode_t mode, uint64_t current_iteration,
+                                       uint64_t total_iterations) {
+  return prefix + "." + (mode == ASCII_MODE ? "ascii" : "cellbin") + "." +
+         iterations_to_string(current_iteration, total_iterations) + ".dat";  // :79-101
+}
+
+void VizOutputWriter::compute_where_and_norm(const Molecule& m, const VizSpeciesInfo& sp, const std::vector<VizWallFrame>* walls,
+                                             double length_unit, Vec3& where, Vec3& norm) {
+  if (!sp.is_surf) {
+    where = m.v.pos;
+    norm = Vec3{0, 0, 0};
+  } else {
+    if (!walls || m.s.wall_index >= walls->size())
+      throw McxFatalError(MCX_ERR_INVALID_ARG, "viz output: surface molecule on an unknown wall");
+    const VizWallFrame& w = (*walls)[m.s.wall_index];
+    // GeometryUtils::uv2xyz (geometry_utils.h:29-31): u * unit_u + v * unit_v + vert0, in this order
+    where = Vec3{m.s.pos.u * w.unit_u.x + m.s.pos.v * w.unit_v.x + w.v0.x,
+                 m.s.pos.u * w.unit_u.y + m.s.pos.v * w.unit_v.y + w.v0.y,
+                 m.s.pos.u * w.unit_u.z + m.s.pos.v * w.unit_v.z + w.v0.z};
+    const double o = (double)m.s.orientation;
+    norm = Vec3{o * w.normal.x, o * w.normal.y, o * w.normal.z};
+  }
+  where.x *= length_unit; where.y *= length_unit; where.z *= length_unit;
+}
+
+bool VizOutputWriter::write(const std::string& path, viz_mode_t mode, const std::vector<Molecule>& molecules,
+                            const std::vector<VizSpeciesInfo>& species, const std::vector<VizWallFrame>* walls, double length_unit,
+                            const std::vector<species_id_t>& species_to_visualize) {
+  if (mode == NO_VIZ_MODE) return true;
+  std::vector<char> shown(species.size(), species_to_visualize.empty() ? 1 : 0);
+  for (species_id_t s : species_to_visualize) if (s < shown.size()) shown[s] = 1;
+  FILE* f = fopen(path.c_str(), mode == ASCII_MODE ? "w" : "wb");
+  if (!f) return false;
+  Vec3 where, norm;
+  if (mode == ASCII_MODE) {  // output_ascii_molecules :132-170
+    for (const Molecule& m : molecules) {
+      if (m.is_defunct() || m.species_id >= species.size() || !shown[m.species_id]) continue;
+      compute_where_and_norm(m, species[m.species_id], walls, length_unit, where, norm);
+      fprintf(f, "%s %u %.9g %.9g %.9g %.9g %.9g %.9g\n", species[m.species_id].name.c_str(), m.id, where.x, where.y, where.z,
+              norm.x, norm.y, norm.z);
+    }
+  } else {  // output_cellblender_molecules :173-265
+    std::vector<std::vector<const Molecule*>> by_species(species.size());
+    for (const Molecule& m : molecules) {
+      if (m.is_defunct() || m.species_id >= species.size() || !shown[m.species_id]) continue;
+      by_species[m.species_id].push_back(&m);
+    }
+    const uint32_t ver = mode == CELLBLENDER_MODE_V2 ? 2 : 1;
+    fwrite(&ver, sizeof(uint32_t), 1, f);
+    std::vector<float> pos, nrm;
+    for (size_t si = 0; si < species.size(); si++) {
+      const std::vector<const Molecule*>& mols = by_species[si];
+      if (mols.empty()) continue;
+      const std::string& name = species[si].name;
+      if (ver == 1) { const unsigned char len = (unsigned char)name.size(); fwrite(&len, 1, 1, f); }
+      else { const uint32_t len = (uint32_t)name.size(); fwrite(&len, sizeof(uint32_t), 1, f); }
+      fwrite(name.data(), 1, name.size(), f);
+      const unsigned char type = species[si].is_surf ? 1 : 0;
+      fwrite(&type, 1, 1, f);
+      const uint32_t count = (uint32_t)(ver == 1 ? 3 * mols.size() : mols.size());
+      fwrite(&count, sizeof(uint32_t), 1, f);
+      if (ver == 2) for (const Molecule* m : mols) fwrite(&m->id, sizeof(uint32_t), 1, f);
+      pos.clear(); nrm.clear();
+      for (const Molecule* m : mols) {
+        compute_where_and_norm(*m, species[si], walls, length_unit, where, norm);
+        pos.push_back((float)where.x); pos.push_back((float)where.y); pos.push_back((float)where.z);
+        if (species[si].is_surf) { nrm.push_back((float)norm.x); nrm.push_back((float)norm.y); nrm.push_back((float)norm.z); }
+      }
+      fwrite(pos.data(), sizeof(float), pos.size(), f);
+      fwrite(nrm.data(), sizeof(float), nrm.size(), f);
+    }
+  }
+  const bool ok = ferror(f) == 0;
+  return fclose(f) == 0 && ok;
+}
+
+void GpuVizOutputEvent::step() {
+  if (viz_mode == NO_VIZ_MODE) return;
+  if (diffuse) diffuse->sync_to_host();
+  const uint64_t it = (uint64_t)std::llround(event_time);
+  last_file = VizOutputWriter::file_name(file_prefix_name, viz_mode, it, total_iterations);
+  if (!VizOutputWriter::write(last_file, viz_mode, p->molecules, species, walls.empty() ? nullptr : &walls, length_unit,
+                              species_ids_to_visualize))
+    throw McxFatalError(MCX_ERR_STATE, "Could not write viz output file " + last_file);
+}
+
 }  // namespace MCell

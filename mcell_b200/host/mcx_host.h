@@ -74,9 +74,9 @@ struct Molecule {
       uint32_t grid_tile_index;
     } s;
   };
-  Molecule() { memset(this, 0, sizeof(*this)); id = MOLECULE_ID_INVALID; diffusion_time = TIME_INVALID; unimol_rxn_time = TIME_FOREVER; birthday = TIME_INVALID; }
+  Molecule() { memset((void*)this, 0, sizeof(*this)); id = MOLECULE_ID_INVALID; diffusion_time = TIME_INVALID; unimol_rxn_time = TIME_FOREVER; birthday = TIME_INVALID; }
   Molecule(molecule_id_t id_, species_id_t sp, const Vec3& pos_, double birthday_) {
-    memset(this, 0, sizeof(*this));
+    memset((void*)this, 0, sizeof(*this));
     id = id_; species_id = sp; flags = MOLECULE_FLAG_VOL;
     diffusion_time = TIME_INVALID; unimol_rxn_time = TIME_INVALID; birthday = birthday_;
     v.pos = pos_; v.subpart_index = v.reactant_subpart_index = v.counted_volume_index = v.previous_wall_index = INDEX_INVALID32;
@@ -231,6 +231,59 @@ public:
 private:
   GpuDiffuseReactEvent* diffuse;
   double time_unit;
+};
+
+// ---- visualization output: VizOutputEvent (src4/viz_output_event.cpp:65-280) -------------------------------------
+// Molecule dumps in the reference's two formats, byte for byte:
+//   ASCII       "<species name> <id> <x> <y> <z> <nx> <ny> <nz>\n" with %.9g doubles (viz_output_event.cpp:132-170),
+//               molecules in Partition::get_molecules() order;
+//   CELLBLENDER binary: u32 version (1 or 2), then per species with at least one molecule, in species-id order:
+//               name length (u8 in v1, u32 in v2), name bytes, u8 species type (1 = surface), u32 count (3 * n floats
+//               in v1, n molecules in v2), [v2: n u32 ids], n * 3 float32 positions, and for surface species
+//               n * 3 float32 normals (viz_output_event.cpp:173-265).
+// Positions are in micrometres (internal position * length_unit); a volume molecule's normal is 0, a surface
+// molecule's is orientation * wall normal and its position uv2xyz(s.pos) (compute_where_and_norm :104-129).
+// File name: <prefix>.<ascii|cellbin>.<iteration, zero-padded to the digits of total_iterations>.dat (:65-101).
+enum viz_mode_t { NO_VIZ_MODE = 0, ASCII_MODE = 1, CELLBLENDER_MODE_V1 = 2, CELLBLENDER_MODE_V2 = 3 };
+
+struct VizSpeciesInfo { std::string name; bool is_surf; };
+// per wall: vertex 0, unit_u, unit_v, normal (3 doubles each, internal length units) — what uv2xyz and the normal need
+struct VizWallFrame { Vec3 v0, unit_u, unit_v, normal; };
+
+class VizOutputWriter {
+public:
+  static std::string iterations_to_string(uint64_t current_iteration, uint64_t total_iterations);
+  static std::string file_name(const std::string& prefix, viz_mode_t mode, uint64_t current_iteration, uint64_t total_iterations);
+  // where (micrometres) and normal of one molecule; walls may be null when the model has no surface molecules
+  static void compute_where_and_norm(const Molecule& m, const VizSpeciesInfo& sp, const std::vector<VizWallFrame>* walls,
+                                     double length_unit, Vec3& where, Vec3& norm);
+  // writes every non-defunct molecule of the listed species (all when species_to_visualize is empty); false on I/O error
+  static bool write(const std::string& path, viz_mode_t mode, const std::vector<Molecule>& molecules,
+                    const std::vector<VizSpeciesInfo>& species, const std::vector<VizWallFrame>* walls, double length_unit,
+                    const std::vector<species_id_t>& species_to_visualize = std::vector<species_id_t>());
+};
+
+// Drop-in for VizOutputEvent: a barrier event (the diffuse event stops at it), pulls the population from the device
+// only when it fires.
+class GpuVizOutputEvent : public BaseEvent {
+public:
+  GpuVizOutputEvent(GpuDiffuseReactEvent* diffuse_, PartitionMolecules* partition, viz_mode_t mode, const std::string& prefix,
+                    uint64_t total_iterations_, double length_unit_)
+    : BaseEvent(300 /* EVENT_TYPE_INDEX_VIZ_OUTPUT, base_event.h:33-56 */), viz_mode(mode), file_prefix_name(prefix),
+      total_iterations(total_iterations_), length_unit(length_unit_), diffuse(diffuse_), p(partition) {}
+  bool is_barrier() const override { return true; }
+  void step() override;
+  viz_mode_t viz_mode;
+  std::string file_prefix_name;
+  uint64_t total_iterations;
+  double length_unit;
+  std::vector<VizSpeciesInfo> species;
+  std::vector<VizWallFrame> walls;                  // empty: volume molecules only
+  std::vector<species_id_t> species_ids_to_visualize;  // empty: all
+  std::string last_file;
+private:
+  GpuDiffuseReactEvent* diffuse;
+  PartitionMolecules* p;
 };
 
 }  // namespace MCell

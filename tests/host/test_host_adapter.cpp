@@ -111,6 +111,27 @@ int main() {
     ev2.step();
     ev2.get_counts(sp, rx);
     if (sp[0] + sp[2] != (uint64_t)n / 2 + 100) { printf("release not seen\n"); return 1; }
+    // viz dump at a barrier: the event pulls the population from the device itself (no sync_to_host by the caller)
+    {
+      GpuVizOutputEvent viz(&ev2, &p2, CELLBLENDER_MODE_V2, "/tmp/mcx_host_adapter_viz", 100, 0.01);
+      viz.species = {{"A", false}, {"B", false}, {"C", false}};
+      viz.event_time = ev2.event_time;
+      viz.step();
+      FILE* f = fopen(viz.last_file.c_str(), "rb");
+      if (!f) { printf("viz file missing\n"); return 1; }
+      uint32_t ver = 0; size_t got = fread(&ver, 4, 1, f);
+      uint64_t total = 0;
+      for (int k = 0; k < 3 && got == 1; k++) {   // per species: name length, name, type, count, ids, positions
+        uint32_t len = 0, cnt = 0; unsigned char type = 9; char name[8] = {0};
+        if (fread(&len, 4, 1, f) != 1 || len != 1 || fread(name, 1, 1, f) != 1 || fread(&type, 1, 1, f) != 1 || fread(&cnt, 4, 1, f) != 1) break;
+        if (name[0] != "ABC"[k] || type != 0 || cnt != sp[k]) { printf("viz species block %d wrong: %s %u\n", k, name, cnt); return 1; }
+        fseek(f, (long)cnt * 16, SEEK_CUR);
+        total += cnt;
+      }
+      const long end = ftell(f); fseek(f, 0, SEEK_END);
+      if (ver != 2 || total != sp[0] + sp[1] + sp[2] || end != ftell(f)) { printf("viz file wrong\n"); return 1; }
+      fclose(f); remove(viz.last_file.c_str());
+    }
     printf("host adapter ok: MSD %.4f, C after 30 iterations %llu\n", msd, (unsigned long long)last_c);
     return 0;
   } catch (const McxFatalError& e) {

@@ -37,6 +37,21 @@ def test_count_buffer_text_formats(tmp_path):
     assert "count buffer ok" in r.stdout
 
 
+def test_viz_output_formats(tmp_path):
+    """VizOutputWriter / GpuVizOutputEvent of the host adapter: ASCII (%.9g) and CellBlender binary v1/v2 molecule dumps,
+    file naming and species grouping as in src4/viz_output_event.cpp:65-265."""
+    exe = os.path.join(ROOT, "tests", "host", "test_viz_output")
+    srcs = [os.path.join(ROOT, "tests", "host", "test_viz_output.cpp"), os.path.join(ROOT, "mcell_b200", "host", "mcx_host.cpp")]
+    from mcell_b200 import build as b
+    b.build()
+    libdir = os.path.join(ROOT, "mcell_b200")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-o", exe] + srcs +
+                   ["-L" + libdir, "-l:libmcx.so", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "viz output ok" in r.stdout
+
+
 def _has_gpu():
     try:
         import torch
