@@ -284,6 +284,32 @@ int mcx_set_counted_volumes(mcx_handle* h, uint32_t n_counted_volumes, const uin
  * mol_counts[species * n_counted_volumes + cv], rxn_counts[rxn_rule * n_counted_volumes + cv]; either may be NULL. */
 int mcx_counts_by_volume(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_counts);
 
+/* ---- release on the device (new; ReleaseEvent::release_ellipsoid_or_rectcuboid, src4/release_event.cpp:953-1003) --- */
+/* The reference releases molecules on the host, sequentially from its one random stream; 1e8 molecules cannot be
+ * pushed through that (or through PCIe as a 52-byte SoA) quickly.  mcx_release_volume_molecules creates `number`
+ * volume molecules of one species on the device with the reference's arithmetic per molecule — CUBIC: pos = rng_dbl
+ * - 0.5 per axis; SPHERICAL: the same, redrawn while |pos|^2 >= 0.25; SPHERICAL_SHELL: then pos /= 2 |pos| ((0, 0,
+ * 0.5) when |pos| == 0); location = pos * diameter + location — each molecule drawing from its OWN Philox stream
+ * (seed, molecule id, iteration | 2^63: a domain disjoint from the diffusion streams).  New molecules get the ids
+ * first_id .. first_id + number - 1, MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN, diffusion_time = release_time (which must lie
+ * in [iteration, iteration + 1)) and the given counted-volume index.  Needs rng_mode == MCX_RNG_PHILOX and a previous
+ * mcx_upload_molecules (which may be empty).  With several ranks every rank makes the same call and keeps the molecules
+ * of its own slab. */
+#define MCX_RELEASE_CUBIC 0
+#define MCX_RELEASE_SPHERICAL 1
+#define MCX_RELEASE_SPHERICAL_SHELL 2
+typedef struct mcx_release {
+  uint32_t species;
+  uint32_t shape;                  /* MCX_RELEASE_* */
+  uint64_t number;
+  double   location[3];            /* length units */
+  double   diameter[3];            /* length units */
+  double   release_time;           /* iterations; 0 = start of the current iteration */
+  uint32_t counted_volume_index;   /* Molecule::v.counted_volume_index of the released molecules (0 = outside all) */
+  uint32_t reserved;
+} mcx_release;
+int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* first_id_out);
+
 /* ---- multi-GPU (new: the reference has a single partition, world.cpp:147,277) --------- */
 /* nccl_unique_id: the 128-byte ncclUniqueId created by rank 0 and broadcast by the host
  * plumbing (torch.distributed).  Call order on every rank: mcx_create (rank/world_size in the config),

@@ -37,6 +37,14 @@ class mcx_config(C.Structure):
     ]
 
 
+MCX_RELEASE_CUBIC, MCX_RELEASE_SPHERICAL, MCX_RELEASE_SPHERICAL_SHELL = 0, 1, 2
+
+
+class mcx_release(C.Structure):
+    _fields_ = [("species", c_u32), ("shape", c_u32), ("number", c_u64), ("location", c_f64 * 3), ("diameter", c_f64 * 3),
+                ("release_time", c_f64), ("counted_volume_index", c_u32), ("reserved", c_u32)]
+
+
 class mcx_slab_info(C.Structure):
     _fields_ = [("grid_origin_z", c_f64), ("layer_rcp", c_f64), ("n_layers", c_u32), ("layer_lo", c_u32),
                 ("layer_hi", c_u32), ("halo_layers", c_u32), ("rank", c_i32), ("world_size", c_i32)]
@@ -109,7 +117,7 @@ EXPORTED_SYMBOLS = [
     "mcx_set_species", "mcx_set_reactions", "mcx_set_surface_classes", "mcx_upload_molecules",
     "mcx_download_molecules", "mcx_num_molecules", "mcx_step", "mcx_replay_step", "mcx_trace_step",
     "mcx_counts", "mcx_comm_init", "mcx_comm_unique_id", "mcx_slab_info_get", "mcx_comm_halo_path", "mcx_philox_block", "mcx_set_profiling",
-    "mcx_grid_num_tiles", "mcx_grid2uv", "mcx_xyz2grid", "mcx_set_counted_volumes", "mcx_counts_by_volume",
+    "mcx_grid_num_tiles", "mcx_grid2uv", "mcx_xyz2grid", "mcx_set_counted_volumes", "mcx_counts_by_volume", "mcx_release_volume_molecules",
 ]
 
 

@@ -638,6 +638,52 @@ int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
   return MCX_OK;
 }
 
+// Release on the device: re-bin the snapshot (A -> B), append the new molecules behind it, sort.  DESIGN.md §3.
+int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* first_id_out) {
+  if (!h || !r) return MCX_ERR_INVALID_ARG;
+  if (!h->uploaded) { h->err = "mcx_release_volume_molecules needs a previous mcx_upload_molecules (it may be empty)"; return MCX_ERR_STATE; }
+  if (h->p.rng_mode != MCX_RNG_PHILOX) { h->err = "device release needs rng_mode == MCX_RNG_PHILOX (a replay releases on the host)"; return MCX_ERR_STATE; }
+  if (r->species >= h->species.size() || !(h->species[r->species].flags & MCX_SP_VOL)) { h->err = "release: not a volume species"; return MCX_ERR_INVALID_ARG; }
+  if (r->shape > MCX_RELEASE_SPHERICAL_SHELL) { h->err = "release: unknown shape"; return MCX_ERR_INVALID_ARG; }
+  if (r->counted_volume_index >= h->n_cv) { h->err = "release: counted_volume_index out of range"; return MCX_ERR_INVALID_ARG; }
+  const double it = (double)h->iteration;
+  if (r->release_time != 0 && !(r->release_time >= it && r->release_time < it + 1.0)) { h->err = "release_time outside the current iteration"; return MCX_ERR_INVALID_ARG; }
+  if (r->number > (uint64_t)h->p.capacity) { h->err = "release larger than max_molecules"; return MCX_ERR_CAPACITY; }
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->stream;
+  Counters hc;
+  int rc = check_device_error(h, &hc);
+  if (rc) return rc;
+  unsigned long long base = hc.next_id;
+  if (h->comm) {  // the same first id on every rank: the maximum over ranks
+    std::vector<unsigned long long> v((size_t)h->cfg.world_size, 0ull);
+    v[(size_t)h->cfg.rank] = base;
+    rc = mcx_comm_allreduce_u64(h->comm, v.data(), (int)v.size(), s);
+    if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+    for (unsigned long long x : v) base = std::max(base, x);
+  }
+  if (base + r->number >= 0xFFFFFFF0ull) { h->err = "molecule ids exhausted"; return MCX_ERR_OVERFLOW; }
+  bind_iteration(h);
+  mcx_launch_rebin(h->p, h->plan, s);
+  mcx_launch_release(h->p, *r, (uint32_t)base, s);
+  const unsigned int next_id = (unsigned int)(base + r->number);
+  CK(cudaMemcpyAsync(&h->p.ctr->next_id, &next_id, sizeof(next_id), cudaMemcpyHostToDevice, s));
+  mcx_launch_sort(h->p, h->plan, s);
+  h->launches += 2;
+  h->cs_cur ^= 1;
+  if (h->comm) {  // hand the neighbours their halo copies of the new molecules
+    bind_iteration(h);
+    rc = mcx_comm_refresh(h->comm, h->p, h->plan, s);
+    if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+    h->cs_cur ^= 1;
+  }
+  rc = check_device_error(h, &hc);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  if (first_id_out) *first_id_out = (uint32_t)base;
+  return MCX_OK;
+}
+
 uint64_t mcx_num_molecules(mcx_handle* h) {
   if (!h || !h->uploaded) return 0;
   cudaSetDevice(h->cfg.device);
@@ -901,6 +947,7 @@ int mcx_sizeof(int which) {
     case 6: return (int)sizeof(mcx_step_stats);
     case 7: return (int)sizeof(mcx_trace_rec);
     case 8: return (int)sizeof(mcx_slab_info);
+    case 9: return (int)sizeof(mcx_release);
     default: return -1;
   }
 }

@@ -91,6 +91,13 @@ struct Stream {
       uint32_t o[4]; philox4x32_10(0u, it_lo, it_hi, id, k0, k1, o); b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
     }
   }
+  // a stream of the release domain (iteration | 2^63): disjoint from every diffusion stream of the same molecule
+  __device__ __forceinline__ void init_release(const DevParams& p, uint32_t mol_id, const ZigShared* z) {
+    zig = z; used = 0; id = mol_id; tape = nullptr; tape_left = 0;
+    k0 = (uint32_t)p.seed; k1 = (uint32_t)(p.seed >> 32);
+    it_lo = (uint32_t)p.iteration; it_hi = (uint32_t)(p.iteration >> 32) | 0x80000000u;
+    uint32_t o[4]; philox4x32_10(0u, it_lo, it_hi, id, k0, k1, o); b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
+  }
   __device__ __forceinline__ uint32_t next() {
     uint32_t w;
     if (tape) w = used < tape_left ? tape[used] : 0u;

@@ -189,6 +189,7 @@ void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t
 void mcx_launch_initial_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
 // multi-GPU pieces of an iteration (mcx_comm.cu drives them around the NCCL exchange)
 void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t s);   // memset + diffuse + resolve rounds
+void mcx_launch_release(const DevParams& p, const mcx_release& r, uint32_t first_id, cudaStream_t s);  // appends behind a re-binned population
 void mcx_launch_rebin(const DevParams& p, const StepPlan& plan, cudaStream_t s);      // A -> B unchanged (halo refresh without a step)
 void mcx_launch_pack_halo(const DevParams& p, HaloRec* send_low, HaloRec* send_high, unsigned int cap, cudaStream_t s);
 void mcx_launch_unpack_halo(const DevParams& p, const HaloRec* recv, unsigned int n, unsigned int offset, cudaStream_t s);

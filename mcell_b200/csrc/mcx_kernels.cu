@@ -485,10 +485,19 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
         simple = simple && !(again && sub == 1);
         if (!simple && reason < 0) reason = MCX_DEFER_TIMING;
       }
+#ifdef MCX_ROLL_GAUSS
+      D3 disp = {0.0, 0.0, 0.0};
+#pragma unroll 1
+      for (int axis = 0; axis < 3; axis++) {  // one copy of the Ziggurat code
+        const double g = scale * rs.gauss() * 0.70710678118654752440;
+        if (axis == 0) disp.x = g; else if (axis == 1) disp.y = g; else disp.z = g;
+      }
+#else
       D3 disp;
       disp.x = scale * rs.gauss() * 0.70710678118654752440;
       disp.y = scale * rs.gauss() * 0.70710678118654752440;
       disp.z = scale * rs.gauss() * 0.70710678118654752440;
+#endif
       const D3 dest = pos + disp;
       simple = simple && in_partition(p, dest);
       if (!simple && reason < 0) reason = MCX_DEFER_GEOMETRY;
@@ -508,6 +517,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       const bool walls_own = simple && (same || single) && (f & 1);
       const bool walls_dest = simple && single && (fd & 1);
       double wall_dist = 1e300;
+#ifndef MCX_NO_ROLL_WALLS
       bool rejected_own = true, rejected_dest = true;
 #pragma unroll 1
       for (int w = 0; w < 2; w++) {  // one copy of the wall loops for both subpartitions (instruction-cache footprint)
@@ -515,6 +525,10 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
         const bool r = all_walls_plane_rejected(p, w == 0 ? walls_own : walls_dest, w == 0 ? own : dest_sp, pos, disp, nt, wall_dist);
         if (w == 0) { rejected_own = r; n_wall_tests = nt; } else { rejected_dest = r; n_wall_tests_dest = nt; }
       }
+#else
+      const bool rejected_own = all_walls_plane_rejected(p, walls_own, own, pos, disp, n_wall_tests, wall_dist);
+      const bool rejected_dest = all_walls_plane_rejected(p, walls_dest, dest_sp, pos, disp, n_wall_tests_dest, wall_dist);
+#endif
       n_wall_tests += n_wall_tests_dest;
       simple = simple && ((same || single) ? ((!walls_own || rejected_own) && (!walls_dest || rejected_dest)) : (near && !(f & 2)));
       if (!simple && reason < 0) reason = (same || single) ? MCX_DEFER_WALL : MCX_DEFER_GEOMETRY;
@@ -913,6 +927,48 @@ __global__ void __launch_bounds__(TPB) k_count_by_volume(const __grid_constant__
 void mcx_launch_count_by_volume(const DevParams& p, cudaStream_t s) {
   cudaMemsetAsync(p.mol_count_cv, 0, sizeof(unsigned long long) * (size_t)p.n_species * p.n_cv, s);
   k_count_by_volume<<<148 * 8, TPB, 0, s>>>(p);
+}
+
+// ---- release on the device (ReleaseEvent::release_ellipsoid_or_rectcuboid, src4/release_event.cpp:953-1003) --------
+// One thread per new molecule: its own Philox stream (release domain), the reference's rejection loop and scaling,
+// appended behind the re-binned population like a product.  Multi-GPU: every rank walks all ids, keeps its own slab.
+__global__ void __launch_bounds__(TPB) k_release(const __grid_constant__ DevParams p, const mcx_release r, uint32_t first_id) {
+  Counters* c = p.ctr;
+  const bool spheroidal = r.shape == MCX_RELEASE_SPHERICAL || r.shape == MCX_RELEASE_SPHERICAL_SHELL;
+  const double t_rel = r.release_time > (double)p.iteration ? r.release_time : (double)p.iteration;
+  const uint32_t base_flags = DF_SCHED_UNIMOL | (t_rel > (double)p.iteration ? DF_PARTIAL : 0u) |
+                              ((r.counted_volume_index << SF_CVI_SHIFT) & SF_CVI_MASK);
+  for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < r.number;
+       k += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t id = first_id + (uint32_t)k;
+    Stream rs; rs.init_release(p, id, nullptr);
+    D3 q;
+    do {  // "Pick values in unit square, toss if not in unit circle"
+      q.x = rs.dbl() - 0.5;
+      q.y = rs.dbl() - 0.5;
+      q.z = rs.dbl() - 0.5;
+    } while (spheroidal && dot3(q, q) >= 0.25);
+    if (r.shape == MCX_RELEASE_SPHERICAL_SHELL) {
+      const double rad = sqrt(dot3(q, q)) * 2;
+      if (rad == 0) q = D3{0.0, 0.0, 0.5};
+      else q = D3{q.x / rad, q.y / rad, q.z / rad};
+    }
+    const D3 pos = {q.x * r.diameter[0] + r.location[0], q.y * r.diameter[1] + r.location[1], q.z * r.diameter[2] + r.location[2]};
+    if (!in_partition(p, pos)) { raise_error(p, MCX_ERR_ESCAPED, id); continue; }
+    if (!owned_z(p, pos.z)) continue;
+    const uint32_t ns = c->n_slots + agg_reserve(&c->n_prod, 1u);
+    if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); continue; }
+    if (base_flags & DF_PARTIAL) p.tschedB[ns] = t_rel;
+    store_rec(p.recB, ns, pos, id, r.species | base_flags);
+    p.rank[ns] = atomicAdd(&p.cs_next[cell_of(p, pos.x, pos.y, pos.z)], 1u);
+    if (p.world == 1) agg_add(&c->species_count[r.species], 1u);
+  }
+}
+void mcx_launch_release(const DevParams& p, const mcx_release& r, uint32_t first_id, cudaStream_t s) {
+  unsigned long long grid = (r.number + TPB - 1) / TPB;
+  if (grid == 0) grid = 1;
+  if (grid > 148ull * 16ull) grid = 148ull * 16ull;
+  k_release<<<(unsigned int)grid, TPB, 0, s>>>(p, r, first_id);
 }
 
 // ---- multi-GPU halo refresh (driven by mcx_comm.cu) --------------------------------------------------------------

@@ -53,6 +53,7 @@ def load_library():
     L.mcx_comm_unique_id.argtypes = [C.c_void_p, C.c_uint32]
     L.mcx_slab_info_get.argtypes = [H, C.POINTER(abi.mcx_slab_info)]
     L.mcx_comm_halo_path.argtypes = [H]
+    L.mcx_release_volume_molecules.argtypes = [H, C.POINTER(abi.mcx_release), C.POINTER(C.c_uint32)]
     L.mcx_set_profiling.argtypes = [H, C.c_int]
     L.mcx_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
     L.mcx_philox_block.restype = None
@@ -122,6 +123,18 @@ class Engine:
     def upload(self, mols):
         v = mols.view()
         self._ck(self.L.mcx_upload_molecules(self.h, C.byref(v)))
+
+    def release(self, species, number, location, diameter, shape=abi.MCX_RELEASE_CUBIC, release_time=0.0, counted_volume_index=0):
+        """ReleaseEvent::release_ellipsoid_or_rectcuboid on the device (mcx_release_volume_molecules); returns the first
+        id of the new molecules.  location / diameter in length units."""
+        r = abi.mcx_release()
+        r.species, r.shape, r.number = int(species), int(shape), int(number)
+        r.location[:] = [float(v) for v in location]
+        r.diameter[:] = [float(v) for v in diameter]
+        r.release_time, r.counted_volume_index = float(release_time), int(counted_volume_index)
+        first = C.c_uint32(0)
+        self._ck(self.L.mcx_release_volume_molecules(self.h, C.byref(r), C.byref(first)))
+        return int(first.value)
 
     def num_molecules(self):
         return int(self.L.mcx_num_molecules(self.h))

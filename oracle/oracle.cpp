@@ -1922,6 +1922,54 @@ int orc_upload_molecules(void* h, const mcx_mol_soa* s) {
   w.next_id = max_id + 1;
   return 0;
 }
+// ReleaseEvent::release_ellipsoid_or_rectcuboid (src4/release_event.cpp:953-1003) with the product's random-number
+// contract (include/mcx.h: mcx_release): molecule id draws from its own Philox stream of the release domain
+// (iteration | 2^63) instead of the reference's one sequential stream; the arithmetic per molecule is the reference's:
+//   do { pos = rng_dbl - 0.5 per axis } while (spheroidal && len3_squared(pos) >= 0.25);      :965-971
+//   SPHERICAL_SHELL: r = sqrt(len3_squared(pos)) * 2; pos = r == 0 ? (0, 0, 0.5) : pos / r;      :973-980
+//   location = pos * diameter + location;                                                       :982-991
+// new molecules: MOLECULE_FLAG_VOL | MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN (:996-997), diffusion_time = release time.
+int orc_release_volume_molecules(void* h, const mcx_release* r, uint32_t* first_id_out) {
+  World& w = *(World*)h;
+  if (r->species >= w.species.size() || !(w.species[r->species].flags & MCX_SP_VOL)) { w.err = "release: not a volume species"; return MCX_ERR_INVALID_ARG; }
+  if (r->shape > MCX_RELEASE_SPHERICAL_SHELL) { w.err = "release: unknown shape"; return MCX_ERR_INVALID_ARG; }
+  if (r->counted_volume_index >= w.n_cv) { w.err = "release: counted_volume_index out of range"; return MCX_ERR_INVALID_ARG; }
+  const double it = (double)w.iteration;
+  if (r->release_time != 0 && !(r->release_time >= it && r->release_time < it + 1.0)) { w.err = "release_time outside the current iteration"; return MCX_ERR_INVALID_ARG; }
+  const bool spheroidal = r->shape == MCX_RELEASE_SPHERICAL || r->shape == MCX_RELEASE_SPHERICAL_SHELL;
+  const double t_rel = r->release_time > it ? r->release_time : it;
+  const uint32_t first = w.next_id;
+  for (uint64_t k = 0; k < r->number; k++) {
+    WordSource ws; ws.kind = WordSource::PHILOX; ws.seed = w.cfg.seed; ws.mol_id = first + (uint32_t)k;
+    ws.iteration = w.iteration | 0x8000000000000000ull;
+    V3 pos;
+    do {
+      pos.x = ws.dbl() - 0.5;
+      pos.y = ws.dbl() - 0.5;
+      pos.z = ws.dbl() - 0.5;
+    } while (spheroidal && pos.x * pos.x + pos.y * pos.y + pos.z * pos.z >= 0.25);
+    if (r->shape == MCX_RELEASE_SPHERICAL_SHELL) {
+      const double rad = sqrt(pos.x * pos.x + pos.y * pos.y + pos.z * pos.z) * 2;
+      if (rad == 0) pos = {0.0, 0.0, 0.5};
+      else pos = {pos.x / rad, pos.y / rad, pos.z / rad};
+    }
+    Mol n{};
+    n.pos = {pos.x * r->diameter[0] + r->location[0], pos.y * r->diameter[1] + r->location[1], pos.z * r->diameter[2] + r->location[2]};
+    if (!w.in_this_partition(n.pos)) { w.err = "released molecule outside partition"; return MCX_ERR_ESCAPED; }
+    n.id = w.next_id++; n.species = r->species;
+    n.flags = MCX_MOL_SCHEDULE_UNIMOL | (t_rel > it ? MCX_MOL_PARTIAL : 0u);
+    n.diffusion_time = t_rel; n.unimol_rxn_time = TIME_INVALID;
+    n.subpart = w.subpart_index(n.pos); n.cvi = r->counted_volume_index;
+    w.mols.push_back(n);
+    if (w.id_to_index.size() <= n.id) w.id_to_index.resize((size_t)n.id + 1, MCX_NONE);
+    w.id_to_index[n.id] = (uint32_t)w.mols.size() - 1;
+    w.sched_ids.push_back(n.id);
+    list_insert(w, w.mols.back());
+    w.species_count[n.species]++;
+  }
+  if (first_id_out) *first_id_out = first;
+  return 0;
+}
 uint64_t orc_num_molecules(void* h) {
   World& w = *(World*)h; uint64_t n = 0;
   for (auto& m : w.mols) n += !(m.flags & MCX_MOL_DEFUNCT);

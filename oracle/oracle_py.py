@@ -113,6 +113,18 @@ class Oracle:
         if rc:
             raise RuntimeError(self.error())
 
+    def release(self, species, number, location, diameter, shape=0, release_time=0.0, counted_volume_index=0):
+        r = abi.mcx_release()
+        r.species, r.shape, r.number = int(species), int(shape), int(number)
+        r.location[:] = [float(v) for v in location]
+        r.diameter[:] = [float(v) for v in diameter]
+        r.release_time, r.counted_volume_index = float(release_time), int(counted_volume_index)
+        first = C.c_uint32(0)
+        rc = self.L.orc_release_volume_molecules(self.h, C.byref(r), C.byref(first))
+        if rc:
+            raise RuntimeError(self.error())
+        return int(first.value)
+
     def num_molecules(self):
         return int(self.L.orc_num_molecules(self.h))
 
