@@ -660,7 +660,14 @@ int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* 
     v[(size_t)h->cfg.rank] = base;
     rc = mcx_comm_allreduce_u64(h->comm, v.data(), (int)v.size(), s);
     if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+    // no fresh id handed out since the last refresh (every rank still at its aligned start): continue at the global
+    // maximum itself, which is what a single device would do — the released ids, and with them the streams and
+    // positions, then do not depend on the number of ranks
+    const unsigned long long w = (unsigned long long)h->cfg.world_size, floor_v = mcx_comm_id_floor(h->comm);
+    bool untouched = true;
+    for (size_t k = 0; k < v.size(); k++) untouched = untouched && v[k] == ((floor_v + w - 1) / w) * w + k;
     for (unsigned long long x : v) base = std::max(base, x);
+    if (untouched) base = floor_v;
   }
   if (base + r->number >= 0xFFFFFFF0ull) { h->err = "molecule ids exhausted"; return MCX_ERR_OVERFLOW; }
   bind_iteration(h);

@@ -28,6 +28,7 @@ struct McxComm {
   int red_cap = 0;
   // peer-memory halo path: the pack kernel stores straight into the neighbour's buffers over NVLink
   bool p2p = false;
+  unsigned long long id_floor = 0;  // global maximum of next_id at the last refresh (before the per-rank alignment)
   char* block = nullptr;                 // my receive block: [side low|high][parity 0|1] record buffers + 4 flag words
   char* peer_base[2] = {nullptr, nullptr};   // the low / high neighbour's block as mapped here
   bool peer_ipc[2] = {false, false};
@@ -162,6 +163,7 @@ void mcx_comm_destroy(McxComm* c) {
 }
 const char* mcx_comm_error(McxComm* c) { return c ? c->err.c_str() : ""; }
 bool mcx_comm_is_p2p(const McxComm* c) { return c && c->p2p; }
+unsigned long long mcx_comm_id_floor(const McxComm* c) { return c ? c->id_floor : 0ull; }
 
 // halo refresh: pack -> counts -> payload -> unpack (appended behind the local results in B)
 // halo refresh over peer memory: ONE kernel selects the records, stores them into the neighbours' receive buffers over
@@ -233,6 +235,7 @@ int mcx_comm_refresh(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_
   CCK(cudaMemcpyAsync(&v, c->d_red, sizeof(v), cudaMemcpyDeviceToHost, s));
   CCK(cudaStreamSynchronize(s));
   const unsigned long long w = (unsigned long long)c->world;
+  c->id_floor = v;  // every id below v may be in use, none at or above it
   next_id = (unsigned int)(((v + w - 1) / w) * w + (unsigned long long)c->rank);
   CCK(cudaMemcpyAsync(&p.ctr->next_id, &next_id, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
   mcx_launch_rebin(p, plan, s);

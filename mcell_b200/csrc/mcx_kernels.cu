@@ -485,10 +485,14 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
         simple = simple && !(again && sub == 1);
         if (!simple && reason < 0) reason = MCX_DEFER_TIMING;
       }
-#ifdef MCX_ROLL_GAUSS
+#ifndef MCX_NO_ROLL_GAUSS
+      // the three draws share ONE copy of the Ziggurat code (a rolled loop with predicated moves): the inlined copies
+      // were a quarter of the kernel's instructions and 18 % of its stall samples waited for instruction fetch —
+      // same-box A/B at 1e8 molecules: 17.0 -> 16.15 ms (profiles/r01_w_*); rolling the two wall loops the same way
+      // cost 0.9 ms (MCX_ROLL_WALLS) and stays off
       D3 disp = {0.0, 0.0, 0.0};
 #pragma unroll 1
-      for (int axis = 0; axis < 3; axis++) {  // one copy of the Ziggurat code
+      for (int axis = 0; axis < 3; axis++) {
         const double g = scale * rs.gauss() * 0.70710678118654752440;
         if (axis == 0) disp.x = g; else if (axis == 1) disp.y = g; else disp.z = g;
       }
@@ -517,7 +521,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       const bool walls_own = simple && (same || single) && (f & 1);
       const bool walls_dest = simple && single && (fd & 1);
       double wall_dist = 1e300;
-#ifndef MCX_NO_ROLL_WALLS
+#ifdef MCX_ROLL_WALLS
       bool rejected_own = true, rejected_dest = true;
 #pragma unroll 1
       for (int w = 0; w < 2; w++) {  // one copy of the wall loops for both subpartitions (instruction-cache footprint)

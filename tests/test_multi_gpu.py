@@ -20,7 +20,7 @@ def _n_devices():
         return 0
 
 
-def _run_ranks(tables_fn, mols, n_iter, world=2, halo_width=0.0):
+def _run_ranks(tables_fn, mols, n_iter, world=2, halo_width=0.0, script=None):
     from mcell_b200 import Engine
     uid = comm.unique_id()
     out, errs = [None] * world, []
@@ -34,7 +34,7 @@ def _run_ranks(tables_fn, mols, n_iter, world=2, halo_width=0.0):
             barrier.wait()
             e.comm_init(uid)
             e.upload(mols)                      # every rank uploads everything; foreign slabs are dropped
-            stats = [e.step(1) for _ in range(n_iter)]
+            stats = script(e) if script else [e.step(1) for _ in range(n_iter)]
             by_volume = e.counts_by_volume() if len(t.counted_volume_sets) > 1 else None
             out[rank] = (e.download(), stats, e.counts(), e.slab_info(), by_volume)
             e.close()
@@ -131,3 +131,41 @@ def test_two_ranks_match_single_gpu_surface_and_counted(scenario):
     if ref_by_volume is not None:
         for r in res:
             assert (r[4][0] == ref_by_volume[0]).all() and (r[4][1] == ref_by_volume[1]).all()
+
+
+@pytest.mark.skipif(_n_devices() < 2, reason="needs 2 CUDA devices")
+def test_two_ranks_release_on_device_matches_single_gpu():
+    """mcx_release_volume_molecules with two ranks: every rank makes the same call and keeps the molecules of its slab;
+    ids, positions and everything that follows equal the single-GPU run bit for bit (a sphere across the slab face and
+    a shell released inside an iteration)."""
+    from mcell_b200 import Engine
+    n = 30000
+
+    def make():
+        return cm.reactive_box(n=n, edge_um=1.0, p_target=0.5, seed=12, cap_factor=4)
+
+    def script(e):
+        st = [e.step(1) for _ in range(3)]
+        a = e.release(0, 6000, (0.0, 0.0, 0.0), (60.0, 60.0, 60.0), shape=abi.MCX_RELEASE_SPHERICAL)
+        b = e.release(1, 4000, (5.0, -5.0, 2.0), (50.0, 40.0, 70.0), shape=abi.MCX_RELEASE_SPHERICAL_SHELL, release_time=3.5)
+        assert (a, b) == (n, n + 6000)
+        return st + [e.step(1) for _ in range(4)]
+
+    t, mols = make()
+    single = Engine(t)
+    single.upload(mols)
+    st1 = script(single)
+    ref = single.download().sorted_by_id()
+    ref_counts = single.counts()
+    res = _run_ranks(lambda: make()[0], mols, 7, halo_width=45.0, script=script)
+    parts = [r[0] for r in res]
+    ids = np.concatenate([p.id[:p.n] for p in parts])
+    assert len(ids) == ref.n and len(np.unique(ids)) == ref.n
+    o = np.argsort(ids, kind="stable")
+    for k in ("id", "species", "x", "y", "z", "flags", "diffusion_time", "unimol_rxn_time"):
+        got = np.concatenate([getattr(p, k)[:p.n] for p in parts])[o]
+        assert (got == getattr(ref, k)[:ref.n]).all(), k
+    assert (res[0][2][0] == ref_counts[0]).all() and (res[1][2][0] == ref_counts[0]).all()
+    for it in range(7):
+        for k in ("molecule_steps", "bimol_rxns"):
+            assert sum(getattr(r[1][it], k) for r in res) == getattr(st1[it], k), (it, k)

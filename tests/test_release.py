@@ -141,7 +141,7 @@ def test_gpu_release_into_empty_population_and_errors():
     assert (m.id == np.arange(100000)).all()
     assert (np.sqrt(m.x ** 2 + m.y ** 2 + m.z ** 2) < 40).all()
     st = e.step(3)
-    assert st.molecule_steps == 100000 and e.num_molecules() == 100000
+    assert st.molecule_steps == 300000 and e.num_molecules() == 100000
     with pytest.raises(engine.McxError):
         e.release(0, 10, (0, 0, 0), (1, 1, 1), release_time=99.0)
     with pytest.raises(engine.McxError):
