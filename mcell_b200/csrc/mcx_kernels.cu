@@ -1057,32 +1057,58 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // finishes last publishes the two counts: a system-scope release store of (tag << 32 | count) into the neighbour's
 // flag word, ordered after every block's records by the fence + block-counter chain.
 __global__ void __launch_bounds__(TPB) k_halo_pack_p2p(const __grid_constant__ DevParams p, const HaloP2P L) {
+  // Slots in the neighbour's buffer are reserved once per block and trip: the halo zones are contiguous runs of the
+  // sorted snapshot, so one warp-aggregated atomic per warp still put 3e5 returning atomics per side on ONE address
+  // (the L2 atomic unit serialises them: ~1.5 ms of the 3.3 ms sort + halo phase at N = 4, profiles/r01_mg4b).
+  __shared__ unsigned int s_cnt[2], s_base[2];
   const unsigned int n = p.ctr->n_slots + p.ctr->n_prod;
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (p.rank[i] == MCX_NONE) continue;
-    const MolRec m = load_rec_volatile(p.recB, i);
-    if (m.sf & DF_DEAD) continue;  // tombstone of a consumed partner: dropped by everybody next iteration
-    const int cz = cell_z(p, m.z);
-    const bool to_low = p.has_low && cz < p.own_lo + p.halo_layers;
-    const bool to_high = p.has_high && cz >= p.own_hi - p.halo_layers;
-    if (!to_low && !to_high) continue;
-    const bool cold = (m.sf & (DF_PARTIAL | DF_HAS_UNIMOL)) != 0;
-    const double2 tt = cold ? make_double2((m.sf & DF_PARTIAL) ? p.tschedB[i] : 0.0, (m.sf & DF_HAS_UNIMOL) ? p.tuniB[i] : MCX_TIME_INVALID)
-                            : make_double2(0.0, 0.0);
-    const bool surf = (m.sf & (DF_SURF | DF_CREATED_ON_SURF)) != 0;  // Molecule::s, or where a volume product was created
-    uint2 wt = make_uint2(MCX_NONE, MCX_NONE);
-    double2 uv = make_double2(0.0, 0.0);
-    if (surf) { wt = make_uint2(p.swallB[i], p.stileB[i]); if (m.sf & DF_SURF) uv = p.suvB[i]; }
+  const int lane = threadIdx.x & 31;
+  for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const unsigned int i = base + threadIdx.x;
+    bool to_side[2] = {false, false};
+    MolRec m = {};
+    if (i < n && p.rank[i] != MCX_NONE) {
+      m = load_rec_volatile(p.recB, i);
+      if (!(m.sf & DF_DEAD)) {  // a tombstone of a consumed partner is dropped by everybody next iteration
+        const int cz = cell_z(p, m.z);
+        to_side[0] = p.has_low && cz < p.own_lo + p.halo_layers;
+        to_side[1] = p.has_high && cz >= p.own_hi - p.halo_layers;
+      }
+    }
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int off[2] = {0, 0};
 #pragma unroll
     for (int side = 0; side < 2; side++) {
-      if (!(side == 0 ? to_low : to_high)) continue;
-      const unsigned int k = agg_reserve(&p.ctr->n_send[side], 1u);
-      if (k >= L.cap) { raise_error(p, MCX_ERR_CAPACITY, m.id); continue; }
-      HaloRec* dst = L.peer_recv[side] + k;
-      store_rec(&dst->rec, 0, D3{m.x, m.y, m.z}, m.id, m.sf);
-      if (cold) *reinterpret_cast<double2*>(&dst->tsched) = tt;
-      if (surf) { *reinterpret_cast<uint2*>(&dst->swall) = wt; *reinterpret_cast<double2*>(&dst->su) = uv; }
+      const unsigned int mask = __ballot_sync(0xffffffffu, to_side[side]);
+      unsigned int wbase = 0;
+      if (lane == 0 && mask) wbase = atomicAdd(&s_cnt[side], (unsigned int)__popc(mask));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      off[side] = wbase + __popc(mask & ((1u << lane) - 1u));
     }
+    __syncthreads();
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&p.ctr->n_send[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (to_side[0] || to_side[1]) {
+      const bool cold = (m.sf & (DF_PARTIAL | DF_HAS_UNIMOL)) != 0;
+      const double2 tt = cold ? make_double2((m.sf & DF_PARTIAL) ? p.tschedB[i] : 0.0, (m.sf & DF_HAS_UNIMOL) ? p.tuniB[i] : MCX_TIME_INVALID)
+                              : make_double2(0.0, 0.0);
+      const bool surf = (m.sf & (DF_SURF | DF_CREATED_ON_SURF)) != 0;  // Molecule::s, or where a volume product was created
+      uint2 wt = make_uint2(MCX_NONE, MCX_NONE);
+      double2 uv = make_double2(0.0, 0.0);
+      if (surf) { wt = make_uint2(p.swallB[i], p.stileB[i]); if (m.sf & DF_SURF) uv = p.suvB[i]; }
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        if (!to_side[side]) continue;
+        const unsigned int k = s_base[side] + off[side];
+        if (k >= L.cap) { raise_error(p, MCX_ERR_CAPACITY, m.id); continue; }
+        HaloRec* dst = L.peer_recv[side] + k;
+        store_rec(&dst->rec, 0, D3{m.x, m.y, m.z}, m.id, m.sf);
+        if (cold) *reinterpret_cast<double2*>(&dst->tsched) = tt;
+        if (surf) { *reinterpret_cast<uint2*>(&dst->swall) = wt; *reinterpret_cast<double2*>(&dst->su) = uv; }
+      }
+    }
+    __syncthreads();  // s_cnt / s_base are reused by the next trip
   }
   __shared__ bool last;
   __syncthreads();
