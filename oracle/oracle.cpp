@@ -2096,6 +2096,33 @@ static void unit_world(World& w, const double* v9) {
   w.walls[0].surf_class = MCX_NONE; w.walls[0].object = 0;
   init_wall_constants(w, w.walls[0]);
 }
+// CollisionUtils::collect_crossed_subparts (collision_utils_subparts.inl:127-300) for one move; same outputs as
+// oracle/ref_mcell4_shim.cpp's ref4_collect_crossed_subparts (out_mols in insertion order here, a set there)
+unsigned orc_unit_collect_crossed_subparts(const double* origin3, double partition_edge_length, unsigned n_subparts_per_edge,
+                                           int use_expanded_list, double rxn_radius, const double* pos3, const double* disp3,
+                                           int collect_for_molecules, int collect_for_walls, unsigned* out_walls,
+                                           unsigned* n_walls, unsigned* out_mols, unsigned* n_mols, unsigned cap) {
+  World w;
+  memset(&w.cfg, 0, sizeof(w.cfg));
+  for (int k = 0; k < 3; k++) w.cfg.origin[k] = origin3[k];
+  w.cfg.partition_edge_length = partition_edge_length;
+  w.cfg.num_subparts_per_edge = n_subparts_per_edge;
+  w.cfg.use_expanded_list = use_expanded_list ? 1 : 0;
+  w.cfg.rxn_radius_3d = rxn_radius;
+  w.n_sp = n_subparts_per_edge;
+  w.sp_len = partition_edge_length / n_subparts_per_edge;
+  w.sp_rcp = 1.0 / w.sp_len;
+  WordSource ws;
+  Eval e(w, ws);
+  const V3 pos = {pos3[0], pos3[1], pos3[2]};
+  std::vector<uint32_t> sw, sm;
+  const uint32_t dest = e.collect_crossed_subparts(pos, w.subpart_index(pos), V3{disp3[0], disp3[1], disp3[2]},
+                                                   collect_for_molecules != 0, collect_for_walls != 0, sw, sm);
+  for (size_t k = 0; k < sw.size() && k < cap; k++) out_walls[k] = sw[k];
+  for (size_t k = 0; k < sm.size() && k < cap; k++) out_mols[k] = sm[k];
+  *n_walls = (unsigned)sw.size(); *n_mols = (unsigned)sm.size();
+  return dest;
+}
 void orc_unit_wall_constants(const double* v9, double* out16) {
   World w; unit_world(w, v9);
   const Wall& f = w.walls[0];

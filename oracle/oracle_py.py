@@ -218,6 +218,47 @@ def ref_mcell3_lib():
     return L
 
 
+_DDA_ARGS = [C.c_void_p, C.c_double, C.c_uint, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+
+
+def ref_mcell4_lib():
+    """MCell4's own subpartition walk (src4/collision_utils_subparts.inl) compiled unmodified into
+    oracle/_ref/libmcell4ref.so by `make -C oracle ref` (oracle/ref_mcell4_shim.cpp); None where it is absent."""
+    path = os.path.join(_HERE, "_ref", "libmcell4ref.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref4_collect_crossed_subparts.restype = C.c_uint
+    L.ref4_collect_crossed_subparts.argtypes = _DDA_ARGS
+    return L
+
+
+def _collect(fn, grid, pos, disp, for_mols, for_walls, cap):
+    origin, edge, n, expanded, radius = grid
+    o = np.ascontiguousarray(origin, np.float64)
+    pos = np.ascontiguousarray(pos, np.float64); disp = np.ascontiguousarray(disp, np.float64)
+    w = np.zeros(cap, np.uint32); m = np.zeros(cap, np.uint32)
+    nw, nm = C.c_uint(0), C.c_uint(0)
+    d = fn(C.c_void_p(o.ctypes.data), float(edge), int(n), int(expanded), float(radius), C.c_void_p(pos.ctypes.data),
+           C.c_void_p(disp.ctypes.data), int(for_mols), int(for_walls), C.c_void_p(w.ctypes.data), C.byref(nw),
+           C.c_void_p(m.ctypes.data), C.byref(nm), cap)
+    return int(d), w[:nw.value].copy(), m[:nm.value].copy()
+
+
+def ref4_collect(L4, grid, pos, disp, for_mols, for_walls, cap=512):
+    """(destination subpartition, ordered wall list, molecule set ascending) from the reference's compiled walk."""
+    return _collect(L4.ref4_collect_crossed_subparts, grid, pos, disp, for_mols, for_walls, cap)
+
+
+def orc_collect(grid, pos, disp, for_mols, for_walls, cap=512):
+    """The same call on the oracle's restatement (molecule set in insertion order)."""
+    L = lib()
+    L.orc_unit_collect_crossed_subparts.restype = C.c_uint
+    L.orc_unit_collect_crossed_subparts.argtypes = _DDA_ARGS
+    return _collect(L.orc_unit_collect_crossed_subparts, grid, pos, disp, for_mols, for_walls, cap)
+
+
 def unit_lib():
     """Typed access to the oracle's single-function entry points (orc_unit_*)."""
     L = lib()
