@@ -262,6 +262,13 @@ def cpu_sample(dims, steps, warmup, cores):
     return total / busy, total, busy
 
 
+def cpu_single(dims, steps):
+    """The same sample on ONE core with the others idle (BASELINE.json: the CPU column is quoted both single-threaded
+    and as independent seeds on all cores) -> (molecule-steps/s, seconds)."""
+    n_steps, dt = _cpu_worker((dims, 100, steps, 0))
+    return n_steps / dt, dt
+
+
 def _sample_text(dims, cores, steps):
     n = int(round(MOLS_PER_SUBPART * dims[0] * dims[1] * dims[2]))
     return ("%d independent seeds x %d molecules (%dx%dx%d whole default 0.5 um subpartitions, 15 625 molecules each) x %d "
@@ -284,6 +291,7 @@ def run_reference(args):
     n_sub = budget / ((steps + warmup) * per_subpart_s)
     dims = (2, 2, 2) if n_sub >= 8 else (1, 2, 2) if n_sub >= 4 else (1, 1, 2) if n_sub >= 2 else (1, 1, 1)
     value, total, busy = cpu_sample(dims, steps, warmup, cores)
+    single, single_s = cpu_single(dims, 1)
     sample = _sample_text(dims, cores, steps)
     line = {
         "impl": "reference", "metric": "molecule_steps_per_sec", "value": value, "unit": "molecule-steps/s",
@@ -292,7 +300,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "molecules": args.molecules,
                    "cpu_sample_molecules_per_core": int(round(MOLS_PER_SUBPART * dims[0] * dims[1] * dims[2]))},
-        "cpu_baseline": {"value": value, "unit": "molecule-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "molecule-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "single_thread": {"value": single, "cores": 1,
+                                           "sample": "one of those seeds alone on the box, 1 iteration, %.1f s" % single_s}},
         "e2e": {"value": value, "unit": "molecule-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "mcell4-equivalent CPU oracle (oracle/), not the upstream binary: the reference cannot be built here (DESIGN.md 8)",
@@ -418,8 +428,11 @@ def run_ours(args):
             O.build()
             cores = os.cpu_count() or 1
             v, steps, busy = cpu_sample((2, 2, 2), 1, 0, cores)
+            single, single_s = cpu_single((2, 2, 2), 1)
             cpu = {"value": v, "unit": "molecule-steps/s", "cores": cores, "kind": "port",
-                   "sample": _sample_text((2, 2, 2), cores, 1) + ", %.1f s of CPU work per core" % busy}
+                   "sample": _sample_text((2, 2, 2), cores, 1) + ", %.1f s of CPU work per core" % busy,
+                   "single_thread": {"value": single, "cores": 1,
+                                     "sample": "one of those seeds alone on the box, 1 iteration, %.1f s" % single_s}}
         line = {
             "metric": "molecule_steps_per_sec", "value": value, "unit": "molecule-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / max(1, args.steps),

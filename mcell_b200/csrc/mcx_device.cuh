@@ -518,13 +518,6 @@ __device__ __forceinline__ MolRec load_rec_volatile(const MolRec* a, uint32_t i)
   asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(a + i) : "memory");
   return rec_from(x, y, z, w);
 }
-// result records are written once and next read by the scatter, a whole pass later: stored with the streaming
-// (evict-first) policy they do not push the snapshot records the probes gather out of L2
-__device__ __forceinline__ void store_rec_stream(MolRec* a, uint32_t i, D3 pos, uint32_t id, uint32_t sf) {
-  const unsigned long long m = ((unsigned long long)sf << 32) | id;
-  asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(a + i), "d"(pos.x), "d"(pos.y), "d"(pos.z),
-               "d"(__longlong_as_double((long long)m)) : "memory");
-}
 __device__ __forceinline__ void store_rec(MolRec* a, uint32_t i, D3 pos, uint32_t id, uint32_t sf) {
   const unsigned long long m = ((unsigned long long)sf << 32) | id;
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(a + i), "d"(pos.x), "d"(pos.y), "d"(pos.z),
@@ -791,25 +784,11 @@ __device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enab
       if (rc >= 0) { const uint32_t h = atomicAdd(&sm->hits[o], 1u); if (h < MCX_FAST_MAX_HITS) sm->hit_slot[o][h] = j; }
     }
   };
-#ifdef MCX_PROBE_UNROLL2
-  // two batches of 32 pairs per trip: both gathers are in flight before either is tested (the wait for a gathered
-  // record was 23 % of the kernel's stall samples with one load per trip, profiles/r01_s)
-  for (uint32_t B = 0; B < W; B += 64) {
-    uint32_t o0, j0, o1, j1;
-    const bool v0 = locate(B, o0, j0);
-    const bool v1 = locate(B + 32, o1, j1);
-    const MolRec c0 = load_rec(p.recA, j0);
-    const MolRec c1 = load_rec(p.recA, j1);
-    test(v0, o0, j0, c0);
-    test(v1, o1, j1, c1);
-  }
-#else
   for (uint32_t B = 0; B < W; B += 32) {
     uint32_t o, j;
     const bool v = locate(B, o, j);
     if (v) { const MolRec c = load_rec(p.recA, j); test(v, o, j, c); }
   }
-#endif
   __syncwarp();
   const int found = (int)sm->hits[lane];
   __syncwarp();  // the buffers are reused by the next trip of the caller's loop

@@ -167,15 +167,9 @@ __device__ __forceinline__ void finalize_alive(const DevParams& p, uint32_t slot
       p.swallB[slot] = surf->s_wall; p.stileB[slot] = surf->s_tile; p.suvB[slot] = make_double2(surf->s_u, surf->s_v);
     }
   }
-#ifdef MCX_STREAM_STORES
-  store_rec_stream(p.recB, slot, pos, id, sf);
-  uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
-  __stcs(p.rank + slot, atomicAdd(&p.cs_next[cell], 1u));
-#else
   store_rec(p.recB, slot, pos, id, sf);
   uint32_t cell = cell_of(p, pos.x, pos.y, pos.z);
   p.rank[slot] = atomicAdd(&p.cs_next[cell], 1u);
-#endif
 }
 
 __device__ __forceinline__ bool partner_is_consumed(const DevParams& p, int kind, int rxn_class, int pathway,
@@ -485,23 +479,16 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
         simple = simple && !(again && sub == 1);
         if (!simple && reason < 0) reason = MCX_DEFER_TIMING;
       }
-#ifndef MCX_NO_ROLL_GAUSS
       // the three draws share ONE copy of the Ziggurat code (a rolled loop with predicated moves): the inlined copies
       // were a quarter of the kernel's instructions and 18 % of its stall samples waited for instruction fetch —
       // same-box A/B at 1e8 molecules: 17.0 -> 16.15 ms (profiles/r01_w_*); rolling the two wall loops the same way
-      // cost 0.9 ms (MCX_ROLL_WALLS) and stays off
+      // cost 0.9 ms and was not kept
       D3 disp = {0.0, 0.0, 0.0};
 #pragma unroll 1
       for (int axis = 0; axis < 3; axis++) {
         const double g = scale * rs.gauss() * 0.70710678118654752440;
         if (axis == 0) disp.x = g; else if (axis == 1) disp.y = g; else disp.z = g;
       }
-#else
-      D3 disp;
-      disp.x = scale * rs.gauss() * 0.70710678118654752440;
-      disp.y = scale * rs.gauss() * 0.70710678118654752440;
-      disp.z = scale * rs.gauss() * 0.70710678118654752440;
-#endif
       const D3 dest = pos + disp;
       simple = simple && in_partition(p, dest);
       if (!simple && reason < 0) reason = MCX_DEFER_GEOMETRY;
@@ -521,18 +508,8 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       const bool walls_own = simple && (same || single) && (f & 1);
       const bool walls_dest = simple && single && (fd & 1);
       double wall_dist = 1e300;
-#ifdef MCX_ROLL_WALLS
-      bool rejected_own = true, rejected_dest = true;
-#pragma unroll 1
-      for (int w = 0; w < 2; w++) {  // one copy of the wall loops for both subpartitions (instruction-cache footprint)
-        unsigned int nt = 0;
-        const bool r = all_walls_plane_rejected(p, w == 0 ? walls_own : walls_dest, w == 0 ? own : dest_sp, pos, disp, nt, wall_dist);
-        if (w == 0) { rejected_own = r; n_wall_tests = nt; } else { rejected_dest = r; n_wall_tests_dest = nt; }
-      }
-#else
       const bool rejected_own = all_walls_plane_rejected(p, walls_own, own, pos, disp, n_wall_tests, wall_dist);
       const bool rejected_dest = all_walls_plane_rejected(p, walls_dest, dest_sp, pos, disp, n_wall_tests_dest, wall_dist);
-#endif
       n_wall_tests += n_wall_tests_dest;
       simple = simple && ((same || single) ? ((!walls_own || rejected_own) && (!walls_dest || rejected_dest)) : (near && !(f & 2)));
       if (!simple && reason < 0) reason = (same || single) ? MCX_DEFER_WALL : MCX_DEFER_GEOMETRY;
