@@ -2096,6 +2096,58 @@ static void unit_world(World& w, const double* v9) {
   w.walls[0].surf_class = MCX_NONE; w.walls[0].object = 0;
   init_wall_constants(w, w.walls[0]);
 }
+// a mesh without a partition: wall constants and edge pairing only (surface_net + Edge::reinit_edge_constants)
+static void unit_mesh(World& w, const double* verts, unsigned nv, const unsigned* tri, unsigned nw) {
+  w.cfg = mcx_config{};
+  w.cfg.partition_edge_length = 1000; w.cfg.num_subparts_per_edge = 1;
+  w.n_sp = 1; w.sp_len = 1000; w.sp_rcp = 1e-3;
+  w.verts.resize(nv);
+  for (unsigned i = 0; i < nv; i++) w.verts[i] = {verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]};
+  w.walls.resize(nw);
+  for (unsigned i = 0; i < nw; i++) {
+    Wall& f = w.walls[i];
+    f.vi[0] = tri[3 * i]; f.vi[1] = tri[3 * i + 1]; f.vi[2] = tri[3 * i + 2];
+    f.surf_class = MCX_NONE; f.object = 0;
+    init_wall_constants(w, f);
+  }
+  init_edges(w, 0, nw);
+}
+// same outputs as oracle/ref_mcell3_shim.cpp: ref3_mesh_edges / ref3_find_edge_point / ref3_traverse_surface
+int orc_unit_mesh_edges(const double* verts, unsigned n_verts, const unsigned* tri, unsigned n_walls, int* nb_wall_out,
+                        int* forward_out, double* transform_out) {
+  World w; unit_mesh(w, verts, n_verts, tri, n_walls);
+  for (unsigned i = 0; i < n_walls; i++)
+    for (int k = 0; k < 3; k++) {
+      const Wall& f = w.walls[i];
+      const bool paired = f.nb_wall[k] != MCX_NONE;
+      nb_wall_out[3 * i + k] = paired ? (int)f.nb_wall[k] : -1;
+      forward_out[3 * i + k] = paired && f.edge_forward[k] ? 1 : 0;
+      double* t = transform_out + 4 * (3 * i + k);
+      t[0] = paired ? f.edge_cos[k] : 0; t[1] = paired ? f.edge_sin[k] : 0;
+      t[2] = paired ? f.edge_tu[k] : 0; t[3] = paired ? f.edge_tv[k] : 0;
+    }
+  return 0;
+}
+// MCell3's codes: 0..2 edge, -1 stays inside the wall, -2 cannot tell (src/wall_util.c:579-654)
+int orc_unit_find_edge_point(const double* v9, const double* loc2, const double* disp2, double* edgept2) {
+  World w; unit_world(w, v9);
+  double eu = 0, ev = 0;
+  const int r = find_edge_point(w.walls[0], loc2[0], loc2[1], disp2[0], disp2[1], eu, ev);
+  edgept2[0] = eu; edgept2[1] = ev;
+  return r == 3 ? -1 : (r == 4 ? -2 : r);
+}
+int orc_unit_traverse_surface(const double* verts, unsigned n_verts, const unsigned* tri, unsigned n_walls,
+                              const unsigned* q_wall, const int* q_side, const double* q_uv, unsigned n_q, int* wall_out,
+                              double* uv_out) {
+  World w; unit_mesh(w, verts, n_verts, tri, n_walls);
+  for (unsigned q = 0; q < n_q; q++) {
+    double nu = 0, nv = 0;
+    const uint32_t there = traverse_surface(w.walls[q_wall[q]], q_uv[2 * q], q_uv[2 * q + 1], q_side[q], nu, nv);
+    wall_out[q] = there == MCX_NONE ? -1 : (int)there;
+    uv_out[2 * q] = nu; uv_out[2 * q + 1] = nv;
+  }
+  return 0;
+}
 // CollisionUtils::collect_crossed_subparts (collision_utils_subparts.inl:127-300) for one move; same outputs as
 // oracle/ref_mcell4_shim.cpp's ref4_collect_crossed_subparts (out_mols in insertion order here, a set there)
 unsigned orc_unit_collect_crossed_subparts(const double* origin3, double partition_edge_length, unsigned n_subparts_per_edge,

@@ -218,6 +218,37 @@ def ref_mcell3_lib():
     return L
 
 
+def mesh_edges(fn, verts, tris):
+    """(neighbour wall per side or -1, is-forward flag, [cos, sin, tu, tv] per side) from ref3_mesh_edges or
+    orc_unit_mesh_edges."""
+    verts = np.ascontiguousarray(verts, np.float64); tris = np.ascontiguousarray(tris, np.uint32)
+    nw = len(tris)
+    nb = np.zeros(3 * nw, np.int32); fw = np.zeros(3 * nw, np.int32); tr = np.zeros((3 * nw, 4))
+    rc = fn(C.c_void_p(verts.ctypes.data), C.c_uint(len(verts)), C.c_void_p(tris.ctypes.data), C.c_uint(nw),
+            C.c_void_p(nb.ctypes.data), C.c_void_p(fw.ctypes.data), C.c_void_p(tr.ctypes.data))
+    assert rc == 0
+    return nb, fw, tr
+
+
+def traverse_surface(fn, verts, tris, q_wall, q_side, q_uv):
+    verts = np.ascontiguousarray(verts, np.float64); tris = np.ascontiguousarray(tris, np.uint32)
+    q_wall = np.ascontiguousarray(q_wall, np.uint32); q_side = np.ascontiguousarray(q_side, np.int32)
+    q_uv = np.ascontiguousarray(q_uv, np.float64)
+    w = np.zeros(len(q_wall), np.int32); uv = np.zeros((len(q_wall), 2))
+    rc = fn(C.c_void_p(verts.ctypes.data), C.c_uint(len(verts)), C.c_void_p(tris.ctypes.data), C.c_uint(len(tris)),
+            C.c_void_p(q_wall.ctypes.data), C.c_void_p(q_side.ctypes.data), C.c_void_p(q_uv.ctypes.data), C.c_uint(len(q_wall)),
+            C.c_void_p(w.ctypes.data), C.c_void_p(uv.ctypes.data))
+    assert rc == 0
+    return w, uv
+
+
+def find_edge_point(fn, v9, loc, disp):
+    v9 = np.ascontiguousarray(v9, np.float64); loc = np.ascontiguousarray(loc, np.float64); disp = np.ascontiguousarray(disp, np.float64)
+    pt = np.zeros(2)
+    code = fn(C.c_void_p(v9.ctypes.data), C.c_void_p(loc.ctypes.data), C.c_void_p(disp.ctypes.data), C.c_void_p(pt.ctypes.data))
+    return int(code), pt
+
+
 _DDA_ARGS = [C.c_void_p, C.c_double, C.c_uint, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
 

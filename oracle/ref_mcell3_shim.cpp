@@ -228,3 +228,81 @@ EXPORT double ref3_exact_disk(const double* loc3, const double* mv3, double R, c
   for (auto* w : walls) delete w;
   return r;
 }
+
+// ---- meshes: edge pairing and flattening transforms, edge crossing of a 2-D move ---------------------------------
+//   surface_net          src/wall_util.c:265   (== Geometry surface_net, src4/geometry.cpp:258-356)
+//   init_edge_transform  src/wall_util.c:360   (== Edge::reinit_edge_constants, src4/wall.cpp:134-235)
+//   find_edge_point      src/wall_util.c:579   (== GeometryUtils::find_edge_point, src4/geometry_utils.inl:222-291)
+//   traverse_surface     src/wall_util.c:656   (== GeometryUtils::traverse_surface, src4/geometry_utils.inl:305-342)
+namespace {
+struct RefMesh {
+  std::vector<struct vector3> verts;
+  std::vector<struct wall> walls;
+  std::vector<struct wall*> faces;
+  struct geom_object obj;
+  struct storage store;
+  bool ok = false;
+  RefMesh(const double* v, unsigned nv, const unsigned* tri, unsigned nw) : verts(nv), walls(nw), faces(nw) {
+    memset(&obj, 0, sizeof(obj));
+    memset(&store, 0, sizeof(store));
+    for (unsigned i = 0; i < nv; i++) { verts[i].x = v[3 * i]; verts[i].y = v[3 * i + 1]; verts[i].z = v[3 * i + 2]; }
+    memset(walls.data(), 0, sizeof(struct wall) * nw);
+    obj.walls = walls.data();
+    obj.n_walls = (int)nw;
+    store.join = create_mem(sizeof(struct edge), 4096);
+    for (unsigned i = 0; i < nw; i++) {
+      init_tri_wall(&obj, (int)i, &verts[tri[3 * i]], &verts[tri[3 * i + 1]], &verts[tri[3 * i + 2]]);
+      walls[i].birthplace = &store;
+      faces[i] = &walls[i];
+    }
+    ok = store.join != NULL && surface_net(faces.data(), (int)nw) != 1;
+  }
+  ~RefMesh() { if (store.join) delete_mem(store.join); }
+};
+}  // namespace
+
+// per (wall, side): neighbour wall (or -1), 1 when this wall is the edge's forward wall, and the transform
+// (cos, sin, translate u, translate v); rows of walls without a partner on that side keep -1 / zeros
+EXPORT int ref3_mesh_edges(const double* verts, unsigned n_verts, const unsigned* tri, unsigned n_walls, int* nb_wall_out,
+                           int* forward_out, double* transform_out) {
+  RefMesh m(verts, n_verts, tri, n_walls);
+  if (!m.ok) return 1;
+  for (unsigned i = 0; i < n_walls; i++)
+    for (int k = 0; k < 3; k++) {
+      const struct wall* w = &m.walls[i];
+      const struct edge* e = w->edges[k];
+      const bool paired = w->nb_walls[k] != NULL && e != NULL && e->backward != NULL;
+      nb_wall_out[3 * i + k] = paired ? (int)(w->nb_walls[k] - m.walls.data()) : -1;
+      forward_out[3 * i + k] = paired && e->forward == w ? 1 : 0;
+      double* t = transform_out + 4 * (3 * i + k);
+      t[0] = paired ? e->cos_theta : 0; t[1] = paired ? e->sin_theta : 0;
+      t[2] = paired ? e->translate.u : 0; t[3] = paired ? e->translate.v : 0;
+    }
+  return 0;
+}
+
+// find_edge_point of a single triangle: returns the reference's code (0..2 edge, -1 stays inside, -2 cannot tell)
+EXPORT int ref3_find_edge_point(const double* v9, const double* loc2, const double* disp2, double* edgept2) {
+  RefWall rw(v9);
+  struct vector2 loc = {loc2[0], loc2[1]}, disp = {disp2[0], disp2[1]}, pt = {0, 0};
+  const int r = find_edge_point(&rw.w, &loc, &disp, &pt);
+  edgept2[0] = pt.u; edgept2[1] = pt.v;
+  return r;
+}
+
+// traverse_surface for a batch of (wall, side, uv) queries on one mesh: neighbour wall index (-1: none) and new uv
+EXPORT int ref3_traverse_surface(const double* verts, unsigned n_verts, const unsigned* tri, unsigned n_walls,
+                                 const unsigned* q_wall, const int* q_side, const double* q_uv, unsigned n_q, int* wall_out,
+                                 double* uv_out) {
+  RefMesh m(verts, n_verts, tri, n_walls);
+  if (!m.ok) return 1;
+  for (unsigned q = 0; q < n_q; q++) {
+    struct vector2 loc = {q_uv[2 * q], q_uv[2 * q + 1]}, nl = {0, 0};
+    struct wall* there = traverse_surface(&m.walls[q_wall[q]], &loc, q_side[q], &nl);
+    wall_out[q] = there ? (int)(there - m.walls.data()) : -1;
+    if (!there) nl.u = nl.v = 0;  // free edge: the reference leaves newloc to an unset transform, callers ignore it
+    uv_out[2 * q] = nl.u; uv_out[2 * q + 1] = nl.v;
+  }
+  return 0;
+}
+

@@ -1,0 +1,35 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/mcell3_surface_vectors.npz from the REFERENCE's own compiled code (oracle/_ref/libmcell3ref.so:
+surface_net, init_edge_transform, find_edge_point, traverse_surface of src/wall_util.c, built unmodified by
+`make -C oracle ref`) on the cases of mcell3_surface_cases.py.  Build container only; the .npz is committed."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+import mcell3_surface_cases as sc  # noqa: E402
+from oracle import oracle_py as O  # noqa: E402
+
+O.build()
+R3 = O.ref_mcell3_lib()
+assert R3 is not None
+out = {}
+for name, (v, f) in sc.meshes().items():
+    nb, fw, tr = O.mesh_edges(R3.ref3_mesh_edges, v, f)
+    qw, qs, quv = sc.traverse_queries(len(f))
+    tw, tuv = O.traverse_surface(R3.ref3_traverse_surface, v, f, qw, qs, quv)
+    out[name + "_nb"], out[name + "_fw"], out[name + "_tr"], out[name + "_tw"], out[name + "_tuv"] = nb, fw, tr, tw, tuv
+    print(name, "walls", len(f), "paired sides", int((nb >= 0).sum()), "free", int((nb < 0).sum()))
+tris = sc.triangles()
+moves = sc.edge_moves(tris)
+code = np.zeros(len(moves), np.int32)
+pt = np.zeros((len(moves), 2))
+for i, (ti, loc, disp) in enumerate(moves):
+    code[i], pt[i] = O.find_edge_point(R3.ref3_find_edge_point, tris[ti], loc, disp)
+out["fep_code"], out["fep_pt"] = code, pt
+print("find_edge_point codes", {int(c): int((code == c).sum()) for c in np.unique(code)})
+np.savez_compressed(os.path.join(HERE, "mcell3_surface_vectors.npz"), **out)
