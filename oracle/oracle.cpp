@@ -2148,6 +2148,18 @@ int orc_unit_traverse_surface(const double* verts, unsigned n_verts, const unsig
   }
   return 0;
 }
+// ray_trace_surf for a batch of (wall, uv, displacement) queries on one mesh; same outputs as ref3_ray_trace_2d
+int orc_unit_ray_trace_surf(const double* verts, unsigned n_verts, const unsigned* tri, unsigned n_walls, const unsigned* q_wall,
+                            const double* q_uv, const double* q_disp, unsigned n_q, int* wall_out, double* uv_out) {
+  World w; unit_mesh(w, verts, n_verts, tri, n_walls);
+  for (unsigned q = 0; q < n_q; q++) {
+    double ou = 0, ov = 0;
+    const uint32_t there = ray_trace_surf(w, q_wall[q], q_uv[2 * q], q_uv[2 * q + 1], q_disp[2 * q], q_disp[2 * q + 1], ou, ov);
+    wall_out[q] = there == MCX_NONE ? -1 : (int)there;
+    uv_out[2 * q] = there == MCX_NONE ? 0 : ou; uv_out[2 * q + 1] = there == MCX_NONE ? 0 : ov;
+  }
+  return 0;
+}
 // CollisionUtils::collect_crossed_subparts (collision_utils_subparts.inl:127-300) for one move; same outputs as
 // oracle/ref_mcell4_shim.cpp's ref4_collect_crossed_subparts (out_mols in insertion order here, a set there)
 unsigned orc_unit_collect_crossed_subparts(const double* origin3, double partition_edge_length, unsigned n_subparts_per_edge,

@@ -242,6 +242,19 @@ def traverse_surface(fn, verts, tris, q_wall, q_side, q_uv):
     return w, uv
 
 
+def ray_trace_surf(fn, verts, tris, q_wall, q_uv, q_disp):
+    """(end wall or -1, end uv) per query from ref3_ray_trace_2d or orc_unit_ray_trace_surf."""
+    verts = np.ascontiguousarray(verts, np.float64); tris = np.ascontiguousarray(tris, np.uint32)
+    q_wall = np.ascontiguousarray(q_wall, np.uint32)
+    q_uv = np.ascontiguousarray(q_uv, np.float64); q_disp = np.ascontiguousarray(q_disp, np.float64)
+    w = np.zeros(len(q_wall), np.int32); uv = np.zeros((len(q_wall), 2))
+    rc = fn(C.c_void_p(verts.ctypes.data), C.c_uint(len(verts)), C.c_void_p(tris.ctypes.data), C.c_uint(len(tris)),
+            C.c_void_p(q_wall.ctypes.data), C.c_void_p(q_uv.ctypes.data), C.c_void_p(q_disp.ctypes.data), C.c_uint(len(q_wall)),
+            C.c_void_p(w.ctypes.data), C.c_void_p(uv.ctypes.data))
+    assert rc == 0
+    return w, uv
+
+
 def find_edge_point(fn, v9, loc, disp):
     v9 = np.ascontiguousarray(v9, np.float64); loc = np.ascontiguousarray(loc, np.float64); disp = np.ascontiguousarray(disp, np.float64)
     pt = np.zeros(2)

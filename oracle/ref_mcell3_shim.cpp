@@ -306,3 +306,46 @@ EXPORT int ref3_traverse_surface(const double* verts, unsigned n_verts, const un
   return 0;
 }
 
+// Own stand-ins for four engine functions that ray_trace_2D references only on its periodic-box and region-border
+// branches (src/vol_util.c, src/count_util.c are not part of this build): reaching one of them is a harness error.
+#include <cstdlib>
+struct subvolume* next_subvol(struct vector3*, struct vector3*, struct subvolume*, double*, double*, double*, int, int) { abort(); }
+struct subvolume* find_subvolume(struct volume*, struct vector3*, struct subvolume*) { abort(); }
+struct wall* find_closest_wall(struct volume*, struct vector3*, double, struct vector2*, int*, struct species*, const char*,
+                               struct string_buffer*, struct string_buffer*) { abort(); }
+void update_hit_data(struct hit_data**, struct wall*, struct wall*, struct surface_molecule*, struct vector2, int, int) { abort(); }
+
+// ray_trace_2D (src/diffuse.c; == DiffuseReactEvent::ray_trace_surf, src4/diffuse_react_event.cpp:1578-1725) for a
+// surface molecule of a species without region-border reactions, no periodic box: the walk across triangle edges with
+// reflection at free edges.  Returns the wall the move ends on (-1: ambiguous edge hit, the caller picks another
+// displacement) and the end point in that wall's frame.
+EXPORT int ref3_ray_trace_2d(const double* verts, unsigned n_verts, const unsigned* tri, unsigned n_walls,
+                             const unsigned* q_wall, const double* q_uv, const double* q_disp, unsigned n_q, int* wall_out,
+                             double* uv_out) {
+  RefMesh m(verts, n_verts, tri, n_walls);
+  if (!m.ok) return 1;
+  static struct volume world;   // zero-initialised: no periodic box, nothing else is read on this path
+  struct species sp;
+  memset(&sp, 0, sizeof(sp));
+  struct periodic_image box = {0, 0, 0};
+  for (unsigned q = 0; q < n_q; q++) {
+    struct surface_grid grid;
+    memset(&grid, 0, sizeof(grid));
+    grid.surface = &m.walls[q_wall[q]];
+    struct surface_molecule sm;
+    memset(&sm, 0, sizeof(sm));
+    sm.properties = &sp;
+    sm.grid = &grid;
+    sm.s_pos.u = q_uv[2 * q]; sm.s_pos.v = q_uv[2 * q + 1];
+    sm.periodic_box = &box;
+    struct vector2 disp = {q_disp[2 * q], q_disp[2 * q + 1]}, pos = {0, 0};
+    int kill_me = 0;
+    struct rxn* rx = NULL;
+    struct hit_data* hd = NULL;
+    struct wall* w = ray_trace_2D(&world, &sm, &disp, &pos, &kill_me, &rx, &hd);
+    wall_out[q] = w ? (int)(w - m.walls.data()) : -1;
+    uv_out[2 * q] = w ? pos.u : 0; uv_out[2 * q + 1] = w ? pos.v : 0;
+  }
+  return 0;
+}
+

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Generate tests/golden/mcell3_surface_vectors.npz from the REFERENCE's own compiled code (oracle/_ref/libmcell3ref.so:
-surface_net, init_edge_transform, find_edge_point, traverse_surface of src/wall_util.c, built unmodified by
+surface_net, init_edge_transform, find_edge_point, traverse_surface of src/wall_util.c and ray_trace_2D of
+src/diffuse.c, built unmodified by
 `make -C oracle ref`) on the cases of mcell3_surface_cases.py.  Build container only; the .npz is committed."""
 import ctypes as C
 import os
@@ -23,6 +24,8 @@ for name, (v, f) in sc.meshes().items():
     qw, qs, quv = sc.traverse_queries(len(f))
     tw, tuv = O.traverse_surface(R3.ref3_traverse_surface, v, f, qw, qs, quv)
     out[name + "_nb"], out[name + "_fw"], out[name + "_tr"], out[name + "_tw"], out[name + "_tuv"] = nb, fw, tr, tw, tuv
+    rw, ruv, rdisp = sc.ray_queries(v, f)
+    out[name + "_rayw"], out[name + "_rayuv"] = O.ray_trace_surf(R3.ref3_ray_trace_2d, v, f, rw, ruv, rdisp)
     print(name, "walls", len(f), "paired sides", int((nb >= 0).sum()), "free", int((nb < 0).sum()))
 tris = sc.triangles()
 moves = sc.edge_moves(tris)

@@ -71,3 +71,23 @@ def traverse_queries(n_walls, seed=11, n=400):
     rng = np.random.default_rng(seed)
     return (rng.integers(0, n_walls, n).astype(np.uint32), rng.integers(0, 3, n).astype(np.int32),
             np.ascontiguousarray(rng.uniform(-5, 15, (n, 2))))
+
+
+def ray_queries(verts, tris, seed=12, n=1500):
+    """(wall, start uv inside that wall, 2-D displacement of 0.05 to 4 edge lengths): most moves cross several edges; on
+    the open mesh they reflect at free edges."""
+    rng = np.random.default_rng(seed)
+    qw = rng.integers(0, len(tris), n).astype(np.uint32)
+    p0, p1, p2 = verts[tris[qw, 0]], verts[tris[qw, 1]], verts[tris[qw, 2]]
+    u = (p1 - p0) / np.linalg.norm(p1 - p0, axis=1, keepdims=True)
+    nrm = np.cross(u, p2 - p0)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    v = np.cross(nrm, u)
+    b = np.stack([np.einsum("ij,ij->i", p1 - p0, u), np.zeros(n)], 1)
+    c = np.stack([np.einsum("ij,ij->i", p2 - p0, u), np.einsum("ij,ij->i", p2 - p0, v)], 1)
+    w = rng.dirichlet([1, 1, 1], n)
+    uv = w[:, 1:2] * b + w[:, 2:3] * c
+    size = np.linalg.norm(b, axis=1, keepdims=True)
+    disp = rng.normal(0, 1, (n, 2)) * size * rng.uniform(0.05, 4.0, (n, 1))
+    return qw, np.ascontiguousarray(uv), np.ascontiguousarray(disp)
+

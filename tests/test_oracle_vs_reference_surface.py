@@ -1,7 +1,8 @@
 """CPU tier: PINS the geometry of surface diffusion against the REFERENCE'S OWN compiled code.
 
 tests/golden/mcell3_surface_vectors.npz holds outputs of oracle/_ref/libmcell3ref.so — surface_net,
-init_edge_transform, find_edge_point and traverse_surface of the reference's src/wall_util.c compiled unmodified (the
+init_edge_transform, find_edge_point and traverse_surface of the reference's src/wall_util.c and ray_trace_2D of its
+src/diffuse.c, compiled unmodified (the
 MCell3 originals of src4/geometry.cpp:258-356, wall.cpp:134-235, geometry_utils.inl:222-342; oracle/Makefile: ref) —
 on the cases of tests/golden/mcell3_surface_cases.py: closed and open meshes (free edges), regular and irregular
 triangles, moves that stay inside, leave through each edge, start on an edge or a vertex, run along an edge or through
@@ -40,6 +41,22 @@ def test_traverse_surface_bit_exact():
         assert (tuv == G[name + "_tuv"]).all(), name
 
 
+def test_ray_trace_surf_bit_exact_against_compiled_ray_trace_2d():
+    """The whole walk of a 2-D move — find_edge_point, traverse_surface of position and displacement, reflection at free
+    edges, the loop around them — against the reference's ray_trace_2D (src/diffuse.c; species without region-border
+    reactions, no periodic box)."""
+    L = O.lib()
+    crossed = reflected_mesh = 0
+    for name, (v, f) in sc.meshes().items():
+        qw, quv, qdisp = sc.ray_queries(v, f)
+        w, uv = O.ray_trace_surf(L.orc_unit_ray_trace_surf, v, f, qw, quv, qdisp)
+        assert (w == G[name + "_rayw"]).all(), name
+        assert (uv == G[name + "_rayuv"]).all(), name
+        crossed += int((w != qw.astype(np.int32)).sum())
+        reflected_mesh += name == "open_box"
+    assert crossed > 5000 and reflected_mesh == 1
+
+
 def test_find_edge_point_bit_exact_all_outcomes():
     L = O.lib()
     tris = sc.triangles()
@@ -71,6 +88,10 @@ def test_surface_geometry_live_against_compiled_reference():
         ta = O.traverse_surface(R3.ref3_traverse_surface, v, f, qw, qs, quv)
         tb = O.traverse_surface(L.orc_unit_traverse_surface, v, f, qw, qs, quv)
         assert (ta[0] == tb[0]).all() and (ta[1] == tb[1]).all(), trial
+        rw, ruv, rdisp = sc.ray_queries(v, f, seed=200 + trial, n=2000)
+        ra = O.ray_trace_surf(R3.ref3_ray_trace_2d, v, f, rw, ruv, rdisp)
+        rb = O.ray_trace_surf(L.orc_unit_ray_trace_surf, v, f, rw, ruv, rdisp)
+        assert (ra[0] == rb[0]).all() and (ra[1] == rb[1]).all(), trial
     tris = sc.triangles(seed=31, n=40)
     for ti, loc, disp in sc.edge_moves(tris, seed=32, per_tri=30):
         ca, pa = O.find_edge_point(R3.ref3_find_edge_point, tris[ti], loc, disp)
