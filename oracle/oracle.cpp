@@ -2252,6 +2252,12 @@ void orc_unit_grid_constants(const double* v9, double* out8) {
   double t[8] = {(double)g.n_axis, g.strip_width_rcp, g.vert2_slope, g.fullslope, g.binding_factor, g.vert0_u, g.vert0_v, (double)g.n_tiles};
   memcpy(out8, t, sizeof(t));
 }
+int orc_unit_uv2grid(const double* v9, const double* uv2) {
+  World w; unit_world(w, v9);
+  Grid g; grid_init(w, w.walls[0], g);
+  const uint32_t t = uv2grid(w.walls[0], g, uv2[0], uv2[1]);
+  return t == MCX_NONE ? -1 : (int)t;
+}
 int orc_unit_xyz2grid(const double* v9, const double* xyz3) {
   World w; unit_world(w, v9);
   Grid g; grid_init(w, w.walls[0], g);

@@ -184,6 +184,13 @@ EXPORT int ref3_xyz2grid(const double* v9, const double* xyz3) {
   struct vector3 v = {xyz3[0], xyz3[1], xyz3[2]};
   return xyz2grid(&v, &rg.g);
 }
+// uv2grid (src/grid_util.c:134-204 == GridUtils::uv2grid_tile_index, src4/grid_utils.inl:119-190); the point must
+// lie inside the wall (the reference aborts otherwise)
+EXPORT int ref3_uv2grid(const double* v9, const double* uv2) {
+  RefGrid rg(v9);
+  struct vector2 v = {uv2[0], uv2[1]};
+  return uv2grid(&v, &rg.g);
+}
 EXPORT void ref3_grid2uv(const double* v9, int idx, double* uv2) {
   RefGrid rg(v9);
   struct vector2 r;

@@ -35,4 +35,8 @@ for i, (ti, loc, disp) in enumerate(moves):
     code[i], pt[i] = O.find_edge_point(R3.ref3_find_edge_point, tris[ti], loc, disp)
 out["fep_code"], out["fep_pt"] = code, pt
 print("find_edge_point codes", {int(c): int((code == c).sum()) for c in np.unique(code)})
+big = sc.triangles(seed=14, n=40) * 5.0      # larger walls: tens of tiles per side
+pts = sc.uv_points(big)
+out["uv2grid"] = np.array([R3.ref3_uv2grid(C.c_void_p(big[ti].ctypes.data), C.c_void_p(uv.ctypes.data)) for ti, uv in pts], np.int32)
+print("uv2grid tiles up to", int(out["uv2grid"].max()))
 np.savez_compressed(os.path.join(HERE, "mcell3_surface_vectors.npz"), **out)

@@ -91,3 +91,26 @@ def ray_queries(verts, tris, seed=12, n=1500):
     disp = rng.normal(0, 1, (n, 2)) * size * rng.uniform(0.05, 4.0, (n, 1))
     return qw, np.ascontiguousarray(uv), np.ascontiguousarray(disp)
 
+
+def uv_points(tris, seed=13, per_tri=60):
+    """(triangle index, uv) strictly inside the triangle or exactly at one of its vertices (uv2grid's special cases)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for ti, t in enumerate(tris):
+        p0, p1, p2 = t[:3], t[3:6], t[6:9]
+        u = (p1 - p0) / np.linalg.norm(p1 - p0)
+        nrm = np.cross(u, p2 - p0)
+        nrm /= np.linalg.norm(nrm)
+        v = np.cross(nrm, u)
+        b = np.array([np.dot(p1 - p0, u), 0.0])
+        c = np.array([np.dot(p2 - p0, u), np.dot(p2 - p0, v)])
+        for k in range(per_tri):
+            if k < 3:
+                w = np.eye(3)[k]
+                uv = w[1] * b + w[2] * c
+            else:
+                w = rng.dirichlet([1, 1, 1] if k % 4 else [0.2, 0.2, 0.2])     # also close to edges and corners
+                uv = (w[1] * b + w[2] * c) * (1 - 1e-9) + 1e-9 * (b + c) / 3
+            out.append((ti, np.ascontiguousarray(uv)))
+    return out
+

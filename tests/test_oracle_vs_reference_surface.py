@@ -57,6 +57,18 @@ def test_ray_trace_surf_bit_exact_against_compiled_ray_trace_2d():
     assert crossed > 5000 and reflected_mesh == 1
 
 
+def test_uv2grid_exact():
+    """Tile under a uv point (GridUtils::uv2grid_tile_index): where a surface molecule lands after a 2-D move."""
+    import ctypes as C
+    L = O.lib()
+    big = sc.triangles(seed=14, n=40) * 5.0
+    pts = sc.uv_points(big)
+    assert len(pts) == len(G["uv2grid"])
+    for i, (ti, uv) in enumerate(pts):
+        assert L.orc_unit_uv2grid(C.c_void_p(big[ti].ctypes.data), C.c_void_p(uv.ctypes.data)) == int(G["uv2grid"][i]), i
+    assert G["uv2grid"].max() > 200
+
+
 def test_find_edge_point_bit_exact_all_outcomes():
     L = O.lib()
     tris = sc.triangles()
