@@ -2226,6 +2226,30 @@ int orc_unit_wall_in_box(const double* v9, const double* llf3, const double* urb
 }
 int orc_unit_distinguishable(double a, double b, double eps) { return distinguishable(a, b, eps) ? 1 : 0; }
 // returns the pathway index or -1 (no reaction)
+// time_of_unimol (rxn_utils.inl:721-736) as pick_unimol_time uses it, from time 0; which_unimolecular (:774-783)
+double orc_unit_time_of_unimol(double k_tot, const uint32_t* words, uint64_t n_words) {
+  World w; w.cfg = mcx_config{};
+  mcx_rxn_class rc{}; rc.kind = MCX_RXN_UNIMOL; rc.first_pathway = 0; rc.n_pathways = 1; rc.max_fixed_p = k_tot;
+  w.classes.push_back(rc);
+  w.unimol.assign(1, 0);
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  Eval E(w, rs);
+  return E.pick_unimol_time(0, 0.0);
+}
+int orc_unit_which_unimolecular(const double* cum_probs, int n, const uint32_t* words, uint64_t n_words, long long* words_used) {
+  World w; w.cfg = mcx_config{};
+  w.pathways.resize(n);
+  for (int i = 0; i < n; i++) { w.pathways[i] = mcx_pathway{}; w.pathways[i].cum_prob = cum_probs[i]; }
+  mcx_rxn_class rc{}; rc.kind = MCX_RXN_UNIMOL; rc.first_pathway = 0; rc.n_pathways = n; rc.max_fixed_p = cum_probs[n - 1];
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  int pathway = 0;
+  if (rc.n_pathways > 1) {  // the lines of step_molecule's unimolecular firing
+    double match = rs.dbl() * rc.max_fixed_p;
+    pathway = pathway_for_probability(w, rc, match);
+  }
+  *words_used = rs.used;
+  return pathway;
+}
 int orc_unit_test_bimolecular(const double* cum_probs, int n, double scaling, const uint32_t* words, uint64_t n_words,
                               long long* words_used) {
   World w; w.cfg = mcx_config{};

@@ -121,6 +121,27 @@ EXPORT int ref3_test_intersect(double* cum_probs, int n, double scaling, unsigne
   *rng_words_used = rng_uses(&rng) - before;
   return r;
 }
+// timeof_unimolecular (src/react_cond.c; == RxnUtils::time_of_unimol, src4/rxn_utils.inl:721-736): the lifetime drawn
+// when a molecule with a unimolecular reaction class is created; FOREVER (1e20) when k_tot <= 0
+EXPORT double ref3_timeof_unimolecular(double k_tot, unsigned seed, unsigned skip) {
+  struct rxn rx;
+  memset(&rx, 0, sizeof(rx));
+  rx.max_fixed_p = k_tot;
+  struct rng_state rng;
+  seed_rng(&rng, seed, skip);
+  return timeof_unimolecular(&rx, NULL, &rng);
+}
+// which_unimolecular (src/react_cond.c; == rxn_utils.inl:774-783): pathway of a firing unimolecular class
+EXPORT int ref3_which_unimolecular(double* cum_probs, int n, unsigned seed, unsigned skip, long long* rng_words_used) {
+  struct rxn rx;
+  make_rxn(&rx, cum_probs, n);
+  struct rng_state rng;
+  seed_rng(&rng, seed, skip);
+  long long before = rng_uses(&rng);
+  int r = which_unimolecular(&rx, NULL, &rng);
+  *rng_words_used = rng_uses(&rng) - before;
+  return r;
+}
 EXPORT int ref3_binary_search_double(double* A, double match, int max_idx, double mult) {
   return binary_search_double(A, match, max_idx, mult);
 }

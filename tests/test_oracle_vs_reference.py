@@ -116,6 +116,28 @@ def test_test_bimolecular_and_intersect_draws():
     assert ref[k, 2] == 0 and ref[k, 3] == 2
 
 
+def test_unimolecular_lifetime_and_pathway_draws():
+    """timeof_unimolecular / which_unimolecular (src/react_cond.c == rxn_utils.inl:721-736, 774-783): the lifetime of a
+    newborn molecule bit for bit (incl. FOREVER for k <= 0), the pathway of a firing class and its word count."""
+    import gen_mcell3_unimol_golden as gu
+    Gu = np.load(os.path.join(HERE, "golden", "mcell3_unimol_vectors.npz"))
+    L = O.lib()
+    L.orc_unit_time_of_unimol.restype = C.c_double
+    L.orc_unit_time_of_unimol.argtypes = [C.c_double, C.c_void_p, C.c_uint64]
+    for i, (k, seed, skip) in enumerate(gu.cases()):
+        tape = ref_words(seed, skip + 4)[skip:]
+        assert L.orc_unit_time_of_unimol(k, vp(tape), len(tape)) == Gu["lifetime"][i], (i, k)
+    assert (Gu["lifetime"][:2] == 1e20).all() and (Gu["lifetime"][4:] < 1e20).all()
+    zero = np.zeros(4, np.uint32)          # a zero word: p == 0 is not distinguishable from 0 -> FOREVER
+    assert L.orc_unit_time_of_unimol(5.0, vp(zero), 4) == 1e20
+    for i, (cum, seed, skip) in enumerate(gu.pathway_cases()):
+        tape = ref_words(seed, skip + 4)[skip:]
+        used = C.c_longlong(0)
+        r = L.orc_unit_which_unimolecular(vp(cum), len(cum), vp(tape), len(tape), C.byref(used))
+        assert (r, used.value) == tuple(int(x) for x in Gu["pathway"][i]), i
+    assert Gu["pathway"][:, 0].max() >= 4
+
+
 def test_distinguishable_and_pb_factor():
     U = O.unit_lib()
     for (a, b, e), want in zip(G["dist_cases"], G["dist_out"]):
