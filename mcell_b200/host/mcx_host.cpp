@@ -112,6 +112,22 @@ void GpuDiffuseReactEvent::sync_to_host() {
   device_dirty = false;
 }
 
+molecule_id_t GpuDiffuseReactEvent::release_volume_molecules(species_id_t species, uint64_t number, uint32_t shape,
+                                                             const Vec3& location, const Vec3& diameter, double release_time,
+                                                             uint32_t counted_volume_index) {
+  if (host_dirty) upload_from_host();   // the device must hold the current population before molecules are added to it
+  mcx_release r{};
+  r.species = species; r.shape = shape; r.number = number;
+  r.location[0] = location.x; r.location[1] = location.y; r.location[2] = location.z;
+  r.diameter[0] = diameter.x; r.diameter[1] = diameter.y; r.diameter[2] = diameter.z;
+  r.release_time = release_time; r.counted_volume_index = counted_volume_index;
+  uint32_t first = 0;
+  check(mcx_release_volume_molecules(h, &r, &first), "mcx_release_volume_molecules");
+  device_dirty = true;
+  p->next_molecule_id = first + (molecule_id_t)number;
+  return first;
+}
+
 void GpuDiffuseReactEvent::get_counts(std::vector<uint64_t>& per_species, std::vector<uint64_t>& per_rxn_rule) {
   per_species.assign(n_species, 0);
   per_rxn_rule.assign(n_rules, 0);

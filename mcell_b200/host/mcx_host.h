@@ -158,6 +158,12 @@ public:
   // edits; viz/checkpoint/introspection paths call sync_to_host() before reading Partition::get_molecules()
   void mark_host_modified() { host_dirty = true; }
   void sync_to_host();
+  // ReleaseEvent::release_ellipsoid_or_rectcuboid on the device (release_event.cpp:953-1003):
+  // `number` molecules of a volume species in a cuboid / sphere / spherical shell (MCX_RELEASE_*) of the given centre
+  // and diameter (internal length units) at event_time; returns the first of the consecutive new ids.  The host
+  // container is stale afterwards until sync_to_host().
+  molecule_id_t release_volume_molecules(species_id_t species, uint64_t number, uint32_t shape, const Vec3& location,
+                                         const Vec3& diameter, double release_time = 0, uint32_t counted_volume_index = 0);
   // MolOrRxnCountEvent world-count fast path (mol_or_rxn_count_event.cpp:622-653)
   void get_counts(std::vector<uint64_t>& per_species, std::vector<uint64_t>& per_rxn_rule);
   const mcx_step_stats& last_stats() const { return stats; }
