@@ -239,6 +239,32 @@ private:
   double time_unit;
 };
 
+// ---- releases: the device-capable part of ReleaseEvent (src4/release_event.h, release_event.cpp:953-1003) -------------
+// One release of `release_number` molecules of a volume species in a cuboid, sphere or spherical shell at event_time
+// (EVENT_TYPE_INDEX_RELEASE = 200, so that it runs before the counts and the diffusion of its iteration, base_event.h:
+// 33-56).  Region, list and surface releases stay with the host's ReleaseEvent and reach the device through
+// Partition::add_volume_molecule + mark_host_modified().
+class GpuReleaseEvent : public BaseEvent {
+public:
+  GpuReleaseEvent(GpuDiffuseReactEvent* diffuse_, species_id_t species_id_, uint64_t release_number_, uint32_t shape_,
+                  const Vec3& location_, const Vec3& diameter_, uint32_t counted_volume_index_ = 0)
+    : BaseEvent(200), species_id(species_id_), release_number(release_number_), release_shape(shape_), location(location_),
+      diameter(diameter_), counted_volume_index(counted_volume_index_), diffuse(diffuse_) {}
+  bool is_barrier() const override { return true; }   // the diffuse event must stop at the release time
+  void step() override {
+    first_released_id = diffuse->release_volume_molecules(species_id, release_number, release_shape, location, diameter,
+                                                          event_time, counted_volume_index);
+  }
+  species_id_t species_id;
+  uint64_t release_number;
+  uint32_t release_shape;   // MCX_RELEASE_CUBIC / _SPHERICAL / _SPHERICAL_SHELL
+  Vec3 location, diameter;  // internal length units
+  uint32_t counted_volume_index;
+  molecule_id_t first_released_id = MOLECULE_ID_INVALID;
+private:
+  GpuDiffuseReactEvent* diffuse;
+};
+
 // ---- visualization output: VizOutputEvent (src4/viz_output_event.cpp:65-280) -------------------------------------
 // Molecule dumps in the reference's two formats, byte for byte:
 //   ASCII       "<species name> <id> <x> <y> <z> <nx> <ny> <nz>\n" with %.9g doubles (viz_output_event.cpp:132-170),
