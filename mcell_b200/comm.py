@@ -84,8 +84,11 @@ def select_owned(mols, info):
     r = rank_of(mols.z[:mols.n], info)
     keep = np.flatnonzero(r == info.rank)
     out = MolArrays(0)
-    for k in ("x", "y", "z", "id", "species", "flags", "diffusion_time", "unimol_rxn_time"):
-        setattr(out, k, np.ascontiguousarray(getattr(mols, k)[:mols.n][keep]))
+    for k in MolArrays.FIELDS:   # incl. Molecule::s (wall, tile, orientation, u, v) and counted_volume
+        a = getattr(mols, k)
+        if a is None or len(a) < mols.n:   # an array the source does not carry (MolArrays.view() omits it too)
+            continue
+        setattr(out, k, np.ascontiguousarray(a[:mols.n][keep]))
     out.n = len(keep)
     return out
 

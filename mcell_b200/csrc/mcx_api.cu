@@ -213,6 +213,7 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   if (dev_replace(h, &h->d_sp_flags, zero_flags.data(), zero_flags.size())) return fail(MCX_ERR_CUDA);
   p.sp_flags = (const uint8_t*)h->d_sp_flags;
   h->plan.sm_count = h->sm_count;
+  p.sm_count = h->sm_count;
   h->plan.launches = &h->launches;
   *out = h;
   return MCX_OK;
@@ -306,6 +307,10 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   p.fw_start = p.fw_K > 1 ? (const uint32_t*)h->d_fw_start : (const uint32_t*)h->d_spw_start;
   p.fw_list = p.fw_K > 1 ? (const uint32_t*)h->d_fw_list : (const uint32_t*)h->d_spw_list;
   p.spw_list = (const uint32_t*)h->d_spw_list; p.n_walls = (int)n_walls; p.sp_flags = (const uint8_t*)h->d_sp_flags;
+  if (h->p.wall_cv && h->n_walls_host != n_walls) {
+    // the per-wall counted-volume table belongs to the previous geometry: drop it (mcx_set_counted_volumes again)
+    h->p.wall_cv = nullptr; h->p.n_cv = 1; h->n_cv = 1;
+  }
   h->n_walls_host = n_walls;
   h->has_geometry = true;
   return MCX_OK;
@@ -323,7 +328,7 @@ static int rebuild_tables(mcx_handle* h) {
   std::vector<DevPathway> dp(h->pathways.size());
   for (size_t c = 0; c < h->classes.size(); c++) {
     const mcx_rxn_class& rc = h->classes[c];
-    if (rc.first_pathway + rc.n_pathways > h->pathways.size() || rc.n_pathways == 0 || rc.n_pathways > 4095) {
+    if ((uint64_t)rc.first_pathway + (uint64_t)rc.n_pathways > (uint64_t)h->pathways.size() || rc.n_pathways == 0 || rc.n_pathways > 4095) {
       h->err = "reaction class pathway range invalid"; return MCX_ERR_INVALID_ARG;
     }
     if (rc.reactants[0] >= ns || (rc.kind != MCX_RXN_UNIMOL && rc.reactants[1] >= ns)) {
@@ -446,9 +451,12 @@ static int rebuild_tables(mcx_handle* h) {
 int mcx_set_species(mcx_handle* h, const mcx_species* species, uint32_t n_species) {
   if (!h || !species || n_species == 0) { if (h) h->err = "no species"; return MCX_ERR_INVALID_ARG; }
   CK(cudaSetDevice(h->cfg.device));
+  std::vector<mcx_species> previous = h->species;
   h->species.assign(species, species + n_species);
+  const int rc = rebuild_tables(h);
+  if (rc != MCX_OK) { h->species.swap(previous); return rc; }  // the device still holds the tables of `previous`
   h->has_species = true;
-  return rebuild_tables(h);
+  return MCX_OK;
 }
 
 int mcx_set_reactions(mcx_handle* h, const mcx_rxn_class* classes, uint32_t n_classes, const mcx_pathway* pathways,
@@ -456,21 +464,28 @@ int mcx_set_reactions(mcx_handle* h, const mcx_rxn_class* classes, uint32_t n_cl
   if (!h || (n_classes && (!classes || !pathways))) { if (h) h->err = "bad reaction arrays"; return MCX_ERR_INVALID_ARG; }
   if (!h->has_species) { h->err = "mcx_set_species must precede mcx_set_reactions"; return MCX_ERR_STATE; }
   CK(cudaSetDevice(h->cfg.device));
+  for (uint32_t k = 0; k < n_pathways; k++)
+    if (pathways[k].rxn_rule_id >= 256) { h->err = "rxn_rule_id >= 256 not supported by the device counters"; return MCX_ERR_INVALID_ARG; }
+  std::vector<mcx_rxn_class> prev_classes = h->classes;
+  std::vector<mcx_pathway> prev_pathways = h->pathways;
   h->classes.assign(classes, classes + n_classes);
   h->pathways.assign(pathways, pathways + n_pathways);
-  for (const auto& pw : h->pathways)
-    if (pw.rxn_rule_id >= 256) { h->err = "rxn_rule_id >= 256 not supported by the device counters"; return MCX_ERR_INVALID_ARG; }
-  return rebuild_tables(h);
+  const int rc = rebuild_tables(h);
+  if (rc != MCX_OK) { h->classes.swap(prev_classes); h->pathways.swap(prev_pathways); }
+  return rc;
 }
 
 int mcx_set_surface_classes(mcx_handle* h, const mcx_surf_class_rxn* rules, uint32_t n_rules) {
   if (!h || (n_rules && !rules)) { if (h) h->err = "bad surface class arrays"; return MCX_ERR_INVALID_ARG; }
   if (!h->has_species) { h->err = "mcx_set_species must precede mcx_set_surface_classes"; return MCX_ERR_STATE; }
   CK(cudaSetDevice(h->cfg.device));
+  for (uint32_t k = 0; k < n_rules; k++)
+    if (rules[k].surf_class >= 4096 || rules[k].type > MCX_SURF_ABSORPTIVE) { h->err = "bad surface class rule"; return MCX_ERR_INVALID_ARG; }
+  std::vector<mcx_surf_class_rxn> previous = h->surf_rules;
   h->surf_rules.assign(rules, rules + n_rules);
-  for (const auto& r : h->surf_rules)
-    if (r.surf_class >= 4096 || r.type > MCX_SURF_ABSORPTIVE) { h->err = "bad surface class rule"; return MCX_ERR_INVALID_ARG; }
-  return rebuild_tables(h);
+  const int rc = rebuild_tables(h);
+  if (rc != MCX_OK) h->surf_rules.swap(previous);
+  return rc;
 }
 
 int mcx_set_counted_volumes(mcx_handle* h, uint32_t n_counted_volumes, const uint8_t* wall_cv_front, const uint8_t* wall_cv_back) {
@@ -614,10 +629,10 @@ int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
   if (m->flags) CK(cudaMemcpyAsync(h->st_fl, m->flags, n * 4, cudaMemcpyHostToDevice, s));
   if (m->diffusion_time) CK(cudaMemcpyAsync(h->st_ts, m->diffusion_time, n * 8, cudaMemcpyHostToDevice, s));
   if (m->unimol_rxn_time) CK(cudaMemcpyAsync(h->st_tu, m->unimol_rxn_time, n * 8, cudaMemcpyHostToDevice, s));
-  Counters zero;
-  memset(&zero, 0, sizeof(zero));
-  zero.n_slots = (unsigned int)n;
-  CK(cudaMemcpyAsync(h->p.ctr, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
+  // only the population fields start over: reaction counts, SimulationStats counters and next_id are cumulative over
+  // the run (the reference's MolOrRxnCountEvent reports reactions since t = 0, and ids of dead molecules must not
+  // be handed out again); k_pack_soa raises next_id above every uploaded id
+  mcx_launch_reset_population(h->p, (unsigned int)n, s);
   bind_iteration(h);
   mcx_launch_pack_soa(h->p, h->st_x, h->st_y, h->st_z, h->st_id, h->st_sp, m->flags ? h->st_fl : nullptr,
                       m->diffusion_time ? h->st_ts : nullptr, m->unimol_rxn_time ? h->st_tu : nullptr, sv, (unsigned int)n, s);

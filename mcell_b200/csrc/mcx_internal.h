@@ -158,6 +158,7 @@ struct DevParams {
   int z_off;                    // global z-layer index of local layer 0 (cgz stays the GLOBAL grid origin, so every
                                 // rank computes the same global layer for a position before subtracting its offset)
   int has_low, has_high;        // a neighbour rank exists below / above
+  int sm_count;                 // multiprocessors of this device: every grid is sized in multiples of it
 };
 
 // multi-GPU halo record: what a neighbour needs to evaluate a molecule exactly like its owner does
@@ -197,6 +198,7 @@ void mcx_launch_add_received(const DevParams& p, unsigned int n, cudaStream_t s)
 void mcx_launch_halo_p2p(const DevParams& p, const HaloP2P& link, cudaStream_t s);  // pack+store to peers, acquire+unpack
 void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
 void mcx_launch_count_by_volume(const DevParams& p, cudaStream_t s);
+void mcx_launch_reset_population(const DevParams& p, unsigned int n_slots, cudaStream_t s);  // before an upload
 // device staging of the surface part of mcx_mol_soa (all null: volume molecules only)
 struct SurfSoa { const uint32_t* wall; const uint32_t* tile; const int32_t* orientation; const double* u; const double* v; const uint32_t* cv; };
 struct SurfSoaOut { uint32_t* wall; uint32_t* tile; int32_t* orientation; double* u; double* v; uint32_t* cv; };

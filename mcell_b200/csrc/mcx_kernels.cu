@@ -877,6 +877,17 @@ __global__ void k_end_iteration(const __grid_constant__ DevParams p) {
   if (p.world > 1) { c->species_count[threadIdx.x] = c->species_next[threadIdx.x]; c->species_next[threadIdx.x] = 0; }
 }
 
+// a new upload replaces the population, nothing else: cumulative reaction counts, statistics and next_id stay
+__global__ void k_reset_population(const __grid_constant__ DevParams p, unsigned int n_slots) {
+  Counters* c = p.ctr;
+  if (threadIdx.x == 0) {
+    c->n_slots = n_slots; c->n_prod = 0; c->n_pend[0] = 0; c->n_pend[1] = 0; c->n_next = 0; c->error = 0; c->error_id = 0;
+    c->n_emigrants[0] = 0; c->n_emigrants[1] = 0; c->n_slow = 0; c->n_send[0] = 0; c->n_send[1] = 0; c->n_second = 0; c->n_slow2 = 0;
+  }
+  c->species_count[threadIdx.x] = 0; c->species_next[threadIdx.x] = 0;
+}
+void mcx_launch_reset_population(const DevParams& p, unsigned int n_slots, cudaStream_t s) { k_reset_population<<<1, 256, 0, s>>>(p, n_slots); }
+
 // initial binning of uploaded records (they sit in B, slots [0, n_slots))
 __global__ void __launch_bounds__(TPB) k_bin_initial(const __grid_constant__ DevParams p) {
   const unsigned int n = p.ctr->n_slots;
@@ -907,7 +918,7 @@ __global__ void __launch_bounds__(TPB) k_count_by_volume(const __grid_constant__
 }
 void mcx_launch_count_by_volume(const DevParams& p, cudaStream_t s) {
   cudaMemsetAsync(p.mol_count_cv, 0, sizeof(unsigned long long) * (size_t)p.n_species * p.n_cv, s);
-  k_count_by_volume<<<148 * 8, TPB, 0, s>>>(p);
+  k_count_by_volume<<<p.sm_count * 8, TPB, 0, s>>>(p);
 }
 
 // ---- release on the device (ReleaseEvent::release_ellipsoid_or_rectcuboid, src4/release_event.cpp:953-1003) --------
@@ -948,7 +959,7 @@ __global__ void __launch_bounds__(TPB) k_release(const __grid_constant__ DevPara
 void mcx_launch_release(const DevParams& p, const mcx_release& r, uint32_t first_id, cudaStream_t s) {
   unsigned long long grid = (r.number + TPB - 1) / TPB;
   if (grid == 0) grid = 1;
-  if (grid > 148ull * 16ull) grid = 148ull * 16ull;
+  if (grid > (unsigned long long)p.sm_count * 16ull) grid = (unsigned long long)p.sm_count * 16ull;
   k_release<<<(unsigned int)grid, TPB, 0, s>>>(p, r, first_id);
 }
 
@@ -1286,18 +1297,18 @@ void mcx_launch_rebin(const DevParams& p, const StepPlan& plan, cudaStream_t s) 
   count_launches(plan, 1);
 }
 void mcx_launch_pack_halo(const DevParams& p, HaloRec* send_low, HaloRec* send_high, unsigned int cap, cudaStream_t s) {
-  k_pack_halo<<<148 * 8, TPB, 0, s>>>(p, send_low, send_high, cap);
+  k_pack_halo<<<p.sm_count * 8, TPB, 0, s>>>(p, send_low, send_high, cap);
 }
 void mcx_launch_unpack_halo(const DevParams& p, const HaloRec* recv, unsigned int n, unsigned int offset, cudaStream_t s) {
   if (n == 0) return;
   unsigned int grid = (n + TPB - 1) / TPB;
-  if (grid > 148u * 16u) grid = 148u * 16u;
+  if (grid > (unsigned int)p.sm_count * 16u) grid = (unsigned int)p.sm_count * 16u;
   k_unpack_halo<<<grid, TPB, 0, s>>>(p, recv, n, offset);
 }
 void mcx_launch_add_received(const DevParams& p, unsigned int n, cudaStream_t s) { k_add_received<<<1, 1, 0, s>>>(p, n); }
 void mcx_launch_halo_p2p(const DevParams& p, const HaloP2P& link, cudaStream_t s) {
-  k_halo_pack_p2p<<<148 * 8, TPB, 0, s>>>(p, link);
-  k_halo_unpack_p2p<<<148 * 4, TPB, 0, s>>>(p, link);
+  k_halo_pack_p2p<<<p.sm_count * 8, TPB, 0, s>>>(p, link);
+  k_halo_unpack_p2p<<<p.sm_count * 4, TPB, 0, s>>>(p, link);
   k_halo_add_p2p<<<1, 1, 0, s>>>(p, link);
 }
 
@@ -1312,5 +1323,5 @@ void mcx_launch_pack_soa(const DevParams& p, const double* x, const double* y, c
 void mcx_launch_unpack_soa(const DevParams& p, double* x, double* y, double* z, uint32_t* id, uint32_t* species,
                            uint32_t* flags, double* tsched, double* tuni, SurfSoaOut sv, unsigned int* n_out, cudaStream_t s) {
   cudaMemsetAsync(n_out, 0, sizeof(unsigned int), s);
-  k_unpack_soa<<<148 * 8, TPB, 0, s>>>(p, x, y, z, id, species, flags, tsched, tuni, sv, n_out);
+  k_unpack_soa<<<p.sm_count * 8, TPB, 0, s>>>(p, x, y, z, id, species, flags, tsched, tuni, sv, n_out);
 }

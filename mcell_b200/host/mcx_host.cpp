@@ -56,6 +56,13 @@ void GpuDiffuseReactEvent::set_barrier_time_for_next_execution(const double t) {
   time_up_to_next_barrier = t;
 }
 
+void GpuDiffuseReactEvent::mark_host_modified() {
+  if (device_dirty)
+    throw McxFatalError(MCX_ERR_STATE, "mark_host_modified(): the device holds newer molecule state than the host container; "
+                                       "call sync_to_host() before editing molecules on the host");
+  host_dirty = true;
+}
+
 void GpuDiffuseReactEvent::upload_from_host() {
   const size_t n = p->molecules.size();
   x.resize(n); y.resize(n); z.resize(n); tdiff.resize(n); tuni.resize(n); id.resize(n); species.resize(n); flags.resize(n);

@@ -154,9 +154,12 @@ public:
   double get_max_time_up_to_next_barrier() const override { return DIFFUSION_TIME_UPPER_LIMIT; }
   void set_barrier_time_for_next_execution(const double t) override;
 
-  // host <-> device population sync (dirty flags): the host calls mark_host_modified() after releases or API
-  // edits; viz/checkpoint/introspection paths call sync_to_host() before reading Partition::get_molecules()
-  void mark_host_modified() { host_dirty = true; }
+  // host <-> device population sync.  The two dirty flags are mutually exclusive: after a step() the device holds
+  // the newer state, so a host-side edit (ReleaseEvent::step with a region / list / surface release, Model API
+  // edits) goes  sync_to_host(); <edit Partition>; mark_host_modified();  — mark_host_modified() on a stale host
+  // container throws instead of silently replacing the device population with it.  viz / checkpoint / introspection
+  // paths call sync_to_host() before reading Partition::get_molecules().
+  void mark_host_modified();
   void sync_to_host();
   // ReleaseEvent::release_ellipsoid_or_rectcuboid on the device (release_event.cpp:953-1003):
   // `number` molecules of a volume species in a cuboid / sphere / spherical shell (MCX_RELEASE_*) of the given centre

@@ -241,6 +241,13 @@ class Model:
         for r_id, r in enumerate(self.rules):
             key = tuple(sorted(idx[_parse_oriented(x)[0]] for x in r.reactants))
             groups.setdefault(key, []).append((r_id, r))
+        # the reference keeps one reaction class per reactant geometry; the device tables hold one class per species
+        # pair, so rules of one pair must agree in their reactant orientations
+        for key, rules in groups.items():
+            geoms = {tuple(sorted((idx[n], o) for n, o in (_parse_oriented(x) for x in r.reactants))) for _, r in rules}
+            if len(geoms) > 1:
+                raise ValueError("rules on the species pair %s differ in reactant orientation (separate reaction classes "
+                                 "per geometry are not built)" % (tuple(self.species[k].name for k in key),))
         classes = (abi.mcx_rxn_class * max(1, len(groups)))()
         n_path = sum(len(v) for v in groups.values())
         pathways = (abi.mcx_pathway * max(1, n_path))()

@@ -102,15 +102,29 @@ int main() {
       last_c = sp[2];
     }
     if (last_c < 100) { printf("too few reactions: %llu\n", (unsigned long long)last_c); return 1; }
+    // a host edit on a stale container must be refused, not silently uploaded over the newer device state
+    {
+      bool refused = false;
+      try { ev2.mark_host_modified(); } catch (const McxFatalError& e) { refused = e.code == MCX_ERR_STATE; }
+      if (!refused) { printf("mark_host_modified() accepted a stale host container\n"); return 1; }
+    }
     ev2.sync_to_host();
     if (p2.molecules.size() != sp[0] + sp[1] + sp[2]) return 1;
     // host edits the population (a "release"), marks it dirty, continues
+    const uint64_t rx_before = rx[0], c_before = sp[2];
+    const molecule_id_t next_before = p2.next_molecule_id;
     for (int i = 0; i < 100; i++) p2.add_volume_molecule(0, Vec3{0, 0, 0}, ev2.event_time);
     ev2.mark_host_modified();
     ev2.set_barrier_time_for_next_execution(1);
     ev2.step();
     ev2.get_counts(sp, rx);
     if (sp[0] + sp[2] != (uint64_t)n / 2 + 100) { printf("release not seen\n"); return 1; }
+    // reaction counts are cumulative over the run (MolOrRxnCountEvent): the re-upload must not restart them
+    if (rx[0] < rx_before || rx[0] - rx_before != sp[2] - c_before) {
+      printf("reaction count restarted by the re-upload: %llu -> %llu\n", (unsigned long long)rx_before, (unsigned long long)rx[0]); return 1;
+    }
+    ev2.sync_to_host();
+    if (p2.next_molecule_id < next_before + 100) { printf("next id went backwards\n"); return 1; }
     // viz dump at a barrier: the event pulls the population from the device itself (no sync_to_host by the caller)
     {
       GpuVizOutputEvent viz(&ev2, &p2, CELLBLENDER_MODE_V2, "/tmp/mcx_host_adapter_viz", 100, 0.01);

@@ -101,3 +101,46 @@ def test_bench_capacity_covers_the_halo_copies_of_every_rank_count():
         halo = 3.0 * reach + 3.5                      # + one cell layer of rounding
         need = n / world * (1.0 + 4.0 * halo / (edge_lu / world)) * 1.05   # + products of one iteration
         assert t.cfg.max_molecules >= need, (world, t.cfg.max_molecules, need)
+
+
+def test_select_owned_carries_surface_and_counted_volume_fields():
+    """comm.select_owned hands a rank its molecules with EVERY field of the record: Molecule::s (wall, tile,
+    orientation, uv) of surface molecules and the counted-volume index of volume molecules (a view() of arrays shorter
+    than n silently drops them, which reset counted volumes to 0 and made surface uploads fail)."""
+    from mcell_b200 import abi
+    from mcell_b200.model import MolArrays
+    n = 1000
+    rng = np.random.default_rng(3)
+    m = MolArrays(n)
+    m.z[:] = rng.uniform(0, 30, n)
+    m.id[:] = np.arange(n)
+    m.species[:] = rng.integers(0, 4, n)
+    m.counted_volume[:] = rng.integers(0, 5, n)
+    surf = rng.random(n) < 0.3
+    m.wall[surf] = rng.integers(0, 50, surf.sum())
+    m.tile[surf] = rng.integers(0, 9, surf.sum())
+    m.orientation[surf] = rng.choice([-1, 1], surf.sum())
+    m.u[:] = rng.random(n)
+    m.v[:] = rng.random(n)
+    info = abi.mcx_slab_info()
+    info.grid_origin_z, info.layer_rcp, info.n_layers, info.world_size, info.halo_layers = 0.0, 1.0 / 3.0, 10, 2, 0
+    got = []
+    for rank in range(2):
+        info.rank = rank
+        part = comm.select_owned(m, info)
+        keep = np.flatnonzero(comm.rank_of(m.z, info) == rank)
+        assert part.n == len(keep) > 0
+        for k in MolArrays.FIELDS:
+            assert len(getattr(part, k)) == part.n, k
+            assert (getattr(part, k) == getattr(m, k)[keep]).all(), k
+        v = part.view()
+        assert v.wall and v.counted_volume          # the ABI view carries them (non-null pointers)
+        got.append(part.n)
+    assert sum(got) == n
+    # a source without the optional arrays (bench.make_molecules) still works
+    lean = MolArrays(0)
+    for k in ("x", "y", "z", "id", "species", "flags", "diffusion_time", "unimol_rxn_time"):
+        setattr(lean, k, getattr(m, k))
+    lean.n = n
+    info.rank = 0
+    assert comm.select_owned(lean, info).n == got[0]

@@ -112,3 +112,21 @@ def test_box_is_closed_and_outward():
     n = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
     assert (np.einsum("ij,ij->i", v[f].mean(1), n) > 0).all()
     assert 0.5 * np.linalg.norm(n, axis=1).sum() == pytest.approx(6 * 4.0)
+
+
+def test_rules_of_one_pair_with_different_orientations_are_refused():
+    """The reference keeps one reaction class per reactant geometry (A' + R' and A, + R' are different classes); the
+    device tables hold one class per species pair, so the table builder refuses such a model instead of merging the
+    rules under the first rule's orientation."""
+    import pytest
+    from mcell_b200.model import Model, Config, create_icosphere
+    m = Model(Config(seed=1))
+    m.add_species("A", 1e-6)
+    m.add_species("R", 0.0, surface=True)
+    m.add_species("AR", 0.0, surface=True)
+    m.add_reaction_rule(["A'", "R'"], ["AR'"], 1e7)
+    m.add_reaction_rule(["A,", "R'"], ["AR'"], 2e7)
+    v, f = create_icosphere(0.2, 1)
+    m.add_geometry_object(v, f)
+    with pytest.raises(ValueError, match="orientation"):
+        m.build(max_molecules=100)
