@@ -106,6 +106,24 @@ def make_molecules(n_total, edge_um, length_unit, seed, slab=None, pinned=True):
     return m
 
 
+def populate_by_release(eng, n_total, edge_um, length_unit):
+    """The benchmark population, released ON the device (mcx_release_volume_molecules = ReleaseEvent::
+    release_ellipsoid_or_rectcuboid): species A:B:C:D = 4:4:1:1 uniformly in the box, ids 0..n-1.  Every molecule's
+    position comes from its own Philox stream of the release domain, so the population does not depend on the number
+    of ranks (each rank keeps the molecules of its slab).  Returns the per-species numbers."""
+    from mcell_b200 import abi
+    from mcell_b200.model import MolArrays
+    eng.upload(MolArrays(0))
+    d = edge_um / length_unit * (1 - 1e-9)
+    shares = [0.4, 0.4, 0.1, 0.1]
+    numbers = [int(round(n_total * f)) for f in shares]
+    numbers[0] += n_total - sum(numbers)
+    for sp, k in enumerate(numbers):
+        if k:
+            eng.release(sp, k, (0.0, 0.0, 0.0), (d, d, d), shape=abi.MCX_RELEASE_CUBIC)
+    return numbers
+
+
 _PINNED_KEEP = []
 
 
@@ -237,11 +255,12 @@ def make_cpu_molecules(t, n, lo, size, seed):
 def _cpu_worker(args):
     """One independent seed of the bounded CPU sample (the reference's only scaling mode:
     utils/mcell4_runner/mcell4_runner.py:203-212): `warmup` untimed then `steps` timed iterations."""
-    dims, seed, steps, warmup = args
+    dims, seed, steps, warmup = args[:4]
+    native = len(args) > 4 and args[4]
     from oracle import oracle_py as O
     t, n, lo, size = build_cpu_sample(dims, seed)
     mols = make_cpu_molecules(t, n, lo, size, seed)
-    o = O.Oracle(t)
+    o = O.Oracle(t, native=native)
     o.upload(mols)
     if warmup:
         o.step(warmup, 0)
@@ -251,12 +270,13 @@ def _cpu_worker(args):
     return st.molecule_steps, dt
 
 
-def cpu_sample(dims, steps, warmup, cores):
-    """-> (aggregate molecule-steps/s, molecule-steps, slowest worker's seconds)."""
+def cpu_sample(dims, steps, warmup, cores, native=False):
+    """-> (aggregate molecule-steps/s, molecule-steps, slowest worker's seconds).  native: the -O3 -march=native build
+    of the oracle instead of the reference's release flags (-O3 -march=core2, CMakeLists.txt:58)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(dims, 100 + i, steps, warmup) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(dims, 100 + i, steps, warmup, native) for i in range(cores)])
     total = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
     return total / busy, total, busy
@@ -330,7 +350,16 @@ def run_ours(args):
         dist.barrier()
 
     n_total = args.molecules
-    t, edge_um = build_model(n_total, seed=1, rank=rank, world=world, cell_edge=args.cell_edge)
+    host_mols = None
+    workload = WORKLOAD
+    b_alg_step = B_ALG_STEP
+    if args.config == 5:
+        t, edge_um = build_model(n_total, seed=1, rank=rank, world=world, cell_edge=args.cell_edge)
+    else:
+        if world > 1:
+            raise SystemExit("bench.py: configs 1-4 are single-GPU parity-test configurations (config 5 is the scaling workload)")
+        t, host_mols, workload, b_alg_step, edge_um = build_small_config(args.config)
+        n_total = int(host_mols.n)
     t.cfg.device = local_rank
     eng = Engine(t)
     slab = None
@@ -340,8 +369,10 @@ def run_ours(args):
         slab = eng.slab_info()
     halo_text = {0: "one device, no halo", 1: "NCCL send/recv halo refresh per iteration",
                  2: "peer-memory halo refresh per iteration (NVLink stores + release/acquire flags)"}[eng.halo_path()]
-    mols = make_molecules(n_total, edge_um, t.length_unit, 1, slab)
-    eng.upload(mols)
+    if host_mols is None:
+        populate_by_release(eng, n_total, edge_um, t.length_unit)
+    else:
+        eng.upload(host_mols)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -368,6 +399,10 @@ def run_ours(args):
     mol_steps = float(steps_done.item())
     value = mol_steps / (ms_total * 1e-3)
     launches = int(st.kernel_launches)
+    # global counts after warmup + steps iterations (summed over ranks by the library): the same population evolves
+    # at every N, so these are directly comparable between the lines of a scaling run
+    counts_species, counts_rules = eng.counts()
+    iterations_done = args.warmup + args.steps
     prof_it = max(1, int(st.profiled_iterations))
     fast_ms = st.ms_diffuse / prof_it
     slow_ms = st.ms_diffuse_slow / prof_it
@@ -394,11 +429,18 @@ def run_ours(args):
     out.x, out.y, out.z = _pinned_alloc(cap, np.float64), _pinned_alloc(cap, np.float64), _pinned_alloc(cap, np.float64)
     out.id, out.species, out.flags = _pinned_alloc(cap, np.uint32), _pinned_alloc(cap, np.uint32), _pinned_alloc(cap, np.uint32)
     out.diffusion_time, out.unimol_rxn_time = _pinned_alloc(cap, np.float64), _pinned_alloc(cap, np.float64)
+    bytes_per_mol = 52
+    has_surf = host_mols is not None and bool((host_mols.wall[:host_mols.n] != 0xFFFFFFFF).any())
+    if has_surf:  # Molecule::s travels too: wall, tile, orientation, u, v (+ counted volume)
+        out.wall, out.tile, out.counted_volume = _pinned_alloc(cap, np.uint32), _pinned_alloc(cap, np.uint32), _pinned_alloc(cap, np.uint32)
+        out.orientation = _pinned_alloc(cap, np.uint32).view(np.int32)
+        out.u, out.v = _pinned_alloc(cap, np.float64), _pinned_alloc(cap, np.float64)
+        bytes_per_mol += 32
     out.n = cap
-    cur = mols
     h2d = d2h = 0
     e2e_calls = max(1, args.e2e_calls)
-    eng.upload(cur)
+    n_live = eng.download_into(out)
+    eng.upload(_view(out, n_live))
     eng.step(ITERS_PER_CALL)  # warm the path once
     n_live = eng.download_into(out)
     sync_all()
@@ -406,12 +448,12 @@ def run_ours(args):
     for _ in range(e2e_calls):
         src = _view(out, n_live)
         eng.upload(src)
-        h2d += n_live * 52
+        h2d += n_live * bytes_per_mol
         s2 = eng.step(ITERS_PER_CALL)
         e2e_steps += s2.molecule_steps
         n_live = eng.download_into(out)
         counts = eng.counts()
-        d2h += n_live * 52 + 8 * (len(counts[0]) + len(counts[1]))
+        d2h += n_live * bytes_per_mol + 8 * (len(counts[0]) + len(counts[1]))
     sync_all()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     e2e_total = torch.tensor([e2e_steps], dtype=torch.float64, device="cuda")
@@ -423,21 +465,29 @@ def run_ours(args):
 
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.config == 5:
             from oracle import oracle_py as O
             O.build()
             cores = os.cpu_count() or 1
             v, steps, busy = cpu_sample((2, 2, 2), 1, 0, cores)
             single, single_s = cpu_single((2, 2, 2), 1)
             cpu = {"value": v, "unit": "molecule-steps/s", "cores": cores, "kind": "port",
+                   "build": "-O3 -march=core2 -ffp-contract=off (the reference's release flags, CMakeLists.txt:58)",
                    "sample": _sample_text((2, 2, 2), cores, 1) + ", %.1f s of CPU work per core" % busy,
                    "single_thread": {"value": single, "cores": 1,
                                      "sample": "one of those seeds alone on the box, 1 iteration, %.1f s" % single_s}}
+            try:   # BASELINE.md 3 build (b): the same sample with -O3 -march=native, compiled on this box
+                O.build(native=True, force=True)
+                vn, _, busy_n = cpu_sample((2, 2, 2), 1, 0, cores, native=True)
+                cpu["march_native"] = {"value": vn, "cores": cores, "build": "-O3 -march=native -ffp-contract=off",
+                                       "sample": "same sample, %.1f s of CPU work per core" % busy_n}
+            except Exception as ex:   # noqa: BLE001
+                cpu["march_native"] = {"unavailable": str(ex)[:200]}
         line = {
             "metric": "molecule_steps_per_sec", "value": value, "unit": "molecule-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / max(1, args.steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
+            "config": {"workload": workload, "baseline_config": args.config,
                        "molecules": n_total, "box_edge_um": edge_um, "iterations_per_plugin_call": ITERS_PER_CALL,
                        "l2": "inputs (>=3 GB at 1e8 molecules) larger than L2; no flush",
                        "parallelism": "z-slabs x%d, %s" % (world, halo_text), "rng": "philox4x32-10 per molecule"},
@@ -446,13 +496,18 @@ def run_ours(args):
                          "peak_source": peak_src,
                          "alg_bytes_per_launch": top_bytes, "kernel_ms": diffuse_ms,
                          "kernel_share_of_step": diffuse_ms / (ms_total / max(1, args.steps)),
-                         "whole_step_frac_at_160B": value / world * B_ALG_STEP / 1e9 / peak,
+                         "whole_step_frac": value / world * b_alg_step / 1e9 / peak, "whole_step_alg_bytes_per_molecule": b_alg_step,
                          "ms_diffuse_fast": fast_ms, "ms_diffuse_slow": slow_ms,
                          "deferred_fraction": deferred_per_launch / max(1.0, mol_per_launch),
                          "deferred_by_reason": [int(x) for x in st.deferred_by_reason],
                          "ms_resolve": st.ms_resolve / prof_it, "ms_sort": st.ms_sort / prof_it},
-            "e2e": {"value": e2e_value, "unit": "molecule-steps/s", "h2d_bytes_per_step": h2d / e2e_calls,
-                    "d2h_bytes_per_step": d2h / e2e_calls, "iterations_per_call": ITERS_PER_CALL},
+            # one plugin call = upload + ITERS_PER_CALL iterations (= bench steps) + download + counts
+            "e2e": {"value": e2e_value, "unit": "molecule-steps/s",
+                    "h2d_bytes_per_step": h2d / e2e_calls / ITERS_PER_CALL, "d2h_bytes_per_step": d2h / e2e_calls / ITERS_PER_CALL,
+                    "h2d_bytes_per_call": h2d / e2e_calls, "d2h_bytes_per_call": d2h / e2e_calls,
+                    "iterations_per_call": ITERS_PER_CALL},
+            "counts": {"after_iterations": iterations_done, "species": [int(x) for x in counts_species],
+                       "rules": [int(x) for x in counts_rules]},
             "gpu_launches": launches, "clocks": clocks,
             "stats": {k: int(getattr(st, k)) for k in ("bimol_rxns", "unimol_rxns", "vol_mol_vol_mol_collisions",
                                                         "mol_wall_reflections", "resolve_retries", "unresolved_conflicts", "n_live")},
@@ -465,11 +520,37 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def build_small_config(which):
+    """BASELINE.json configs 1-4 (the parity-test configurations) as bench workloads: -> (tables, molecules, workload
+    text, algorithmic bytes per molecule-step of the whole step, box edge in um).  The scenario builders
+    are the ones the GPU tests use (tests/common.py, tests/test_gpu_fullsize.py)."""
+    tests_dir = os.path.join(ROOT, "tests")
+    if tests_dir not in sys.path:
+        sys.path.insert(0, tests_dir)
+    import common as cm
+    if which == 1:
+        t, mols = cm.free_diffusion_box(n=100000, seed=1, cap_factor=1.25)
+        return t, mols, "free diffusion of 1e5 volume molecules (D=1e-6 cm^2/s) in a reflective 1 um cube (BASELINE configs[0])", 64.0, 1.0
+    if which == 2:
+        t, mols = cm.reactive_box(n=1_000_000, edge_um=2.0, seed=2, p_target=0.1, cap_factor=1.25)
+        return t, mols, "A+B->C in a 2 um box, 1e6 molecules, default subpartition grid (BASELINE configs[1])", 160.0, 2.0
+    import test_gpu_fullsize as fs
+    if which == 3:
+        t, mols, _ = fs._config3(400_000, 8_000, seed=3)
+        return t, mols, "ligand-receptor on an icosphere of 20 480 triangles, absorptive/transparent classes (BASELINE configs[2])", 64.0, 1.6
+    if which == 4:
+        t, mols, _, _ = fs._config4(10_000_000, seed=4)
+        return t, mols, "synapse-like nested meshes, 163 840 triangles, Ca/calbindin/pumps, 1e7 molecules (BASELINE configs[3])", 160.0, 4.0
+    raise SystemExit("bench.py: --config must be 1..5")
+
+
 def _view(m, n):
     from mcell_b200.model import MolArrays
     v = MolArrays(0)
-    for k in ("x", "y", "z", "id", "species", "flags", "diffusion_time", "unimol_rxn_time"):
-        setattr(v, k, getattr(m, k)[:n])
+    for k in MolArrays.FIELDS:
+        a = getattr(m, k)
+        if a is not None and len(a) >= n and len(a) > 0:
+            setattr(v, k, a[:n])
     v.n = n
     return v
 
@@ -481,6 +562,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--molecules", type=int, default=100_000_000)
+    ap.add_argument("--config", type=int, default=5, help="BASELINE.json config 1-5 (5 = the headline reactive box; 1-4 single GPU)")
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cell-edge", type=float, default=0.0, help="device neighbour-cell edge in length units (0 = auto)")

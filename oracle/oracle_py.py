@@ -16,9 +16,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
-def build(native=False):
+def build(native=False, force=False):
+    """force: rebuild even when up to date (-march=native code must be compiled on the machine that runs it)."""
     target = "liboracle_native.so" if native else "liboracle.so"
-    subprocess.run(["make", "-s", "-C", _HERE, target], check=True)
+    subprocess.run(["make", "-s", "-C", _HERE] + (["-B"] if force else []) + [target], check=True)
     if os.path.isdir("/root/reference/src"):
         subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
     return os.path.join(_HERE, target)

@@ -19,12 +19,12 @@ def free_diffusion_box(n=20000, edge_um=1.0, seed=1, D=1e-6, rng_mode=abi.MCX_RN
 
 
 def reactive_box(n=20000, edge_um=0.5, seed=1, p_target=0.3, rng_mode=abi.MCX_RNG_PHILOX, density_scale=1.0,
-                 subpartition_dimension=0.5, cap_factor=2, products=("C",), max_resolve_rounds=0, cell_edge=0.0):
+                 subpartition_dimension=0.5, cap_factor=2, products=("C",), max_resolve_rounds=0, cell_edge=0.0, D=1e-6):
     """BASELINE config 2 shape: A + B -> C in a reflective box (rate chosen so max_fixed_p = p_target)."""
     m = Model(Config(seed=seed, subpartition_dimension=subpartition_dimension))
-    m.add_species("A", 1e-6)
-    m.add_species("B", 1e-6)
-    m.add_species("C", 0.5e-6)
+    m.add_species("A", D)
+    m.add_species("B", D)
+    m.add_species("C", 0.5 * D)
     pb = _pb_factor(m, 0, 1)
     m.add_reaction_rule(["A", "B"], list(products), p_target / pb)
     v, f = create_box(edge_um)

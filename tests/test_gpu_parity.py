@@ -334,3 +334,66 @@ def test_errors_are_reported_not_fatal():
     with pytest.raises(McxError) as ei:
         e.upload(mols)
     assert ei.value.code == abi.MCX_ERR_ESCAPED
+
+
+def test_benchmark_chemistry_matches_oracle():
+    """The chemistry bench.py times (config 5: 4 species, 6 reactions incl. the same-species class C + C -> B + D, the
+    two-product bimolecular B + D -> C + C and two two-product unimoleculars), at bench.py's density, built by
+    bench.build_model and populated by the same device release: every iteration starts from a common state and is
+    compared bit for bit — traces of every molecule alive at the start, statistics, per-rule reaction counts — and the
+    resulting populations as (species, position, times) multisets, because second products take fresh ids from device
+    atomics.  Molecules whose id does not depend on that order are also compared by id."""
+    import bench
+    n = 20000
+    t, edge_um = bench.build_model(n, seed=5, cap_factor=2.0)
+    e, o = _engine(t), _oracle(t)
+    assert bench.populate_by_release(e, n, edge_um, t.length_unit) == bench.populate_by_release(o, n, edge_um, t.length_unit)
+    a, b = o.download().sorted_by_id(), e.download().sorted_by_id()
+    _assert_same_population(a, b)                     # the released population itself is identical
+    assert (np.bincount(a.species, minlength=4) == [8000, 8000, 2000, 2000]).all()
+    nA0 = 8000 + 2000 + 2 * 2000                      # A + C + 2 D  (C = AB, D = A2B)
+    nB0 = 8000 + 2000 + 2000                          # B + C + D
+    rules_seen = np.zeros(6, np.int64)
+
+    def key(m):
+        arr = np.c_[m.species[:m.n].astype(float), m.x[:m.n], m.y[:m.n], m.z[:m.n], m.diffusion_time[:m.n],
+                    m.unimol_rxn_time[:m.n], m.flags[:m.n].astype(float)]
+        return arr[np.lexsort(arr.T[::-1])]
+
+    state = a
+    for it in range(12):
+        # a common start: the oracle's population (the engines keep their own iteration counters and cumulative counts)
+        n_ids = int(state.id.max()) + 1
+        r_before_o, r_before_g = o.counts()[1].astype(np.int64), e.counts()[1].astype(np.int64)
+        if it:
+            e.upload(state)
+            o.upload(state)
+        tr_o, st_o = o.trace_step(1, n_ids)
+        tr_g, st_g = e.trace_step(n_ids)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        assert set(live.tolist()) == set(state.id.tolist()), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "unimol_rxns", "vol_mol_vol_mol_collisions", "resolve_retries", "unresolved_conflicts",
+                  "products_created", "mol_wall_reflections", "molecule_steps", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        d_o, d_g = o.counts()[1].astype(np.int64) - r_before_o, e.counts()[1].astype(np.int64) - r_before_g
+        assert (d_o == d_g).all(), (it, d_o, d_g)
+        rules_seen += d_g
+        assert (o.counts()[0] == e.counts()[0]).all(), it
+        c = e.counts()[0].astype(np.int64)
+        assert c[0] + c[2] + 2 * c[3] == nA0 and c[1] + c[2] + c[3] == nB0, (it, c)
+        a, b = o.download(), e.download()
+        assert a.n == b.n
+        ka, kb = key(a), key(b)
+        assert (ka[:, 0] == kb[:, 0]).all() and (ka[:, 6] == kb[:, 6]).all(), it
+        assert cm.rel_close(ka[:, 1:6], kb[:, 1:6], POS_TOL).all(), it
+        # ids handed out before this iteration belong to the same molecules on both sides
+        sa, sb = a.sorted_by_id(), b.sorted_by_id()
+        old_a, old_b = sa.id < n_ids, sb.id < n_ids
+        assert (sa.id[old_a] == sb.id[old_b]).all() and (sa.species[old_a] == sb.species[old_b]).all(), it
+        assert cm.rel_close(np.c_[sa.x, sa.y, sa.z][old_a], np.c_[sb.x, sb.y, sb.z][old_b], POS_TOL).all(), it
+        state = sa
+    assert (rules_seen > 0).all(), rules_seen          # every one of the six rules fired, incl. C + C and B + D -> C + C
+    assert st_g.unresolved_conflicts == 0

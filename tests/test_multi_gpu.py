@@ -169,3 +169,40 @@ def test_two_ranks_release_on_device_matches_single_gpu():
     for it in range(7):
         for k in ("molecule_steps", "bimol_rxns"):
             assert sum(getattr(r[1][it], k) for r in res) == getattr(st1[it], k), (it, k)
+
+
+@pytest.mark.parametrize("world", [3, 4])
+def test_interior_ranks_match_single_gpu(world):
+    """Three and four ranks: the inner ranks have a neighbour on BOTH sides (two halos, both receive buffers, both
+    parities of the exchange), which two ranks never exercise.  Slow species (D = 1e-7: reach 5 lu, halo 15 lu) keep
+    every slab of the 1 um box thicker than its halo.  Population, counts and per-iteration statistics equal the
+    single-GPU run bit for bit over 10 iterations."""
+    if _n_devices() < world:
+        pytest.skip("needs %d CUDA devices" % world)
+    from mcell_b200 import Engine
+    n, n_iter = 120000, 10
+    make = lambda: cm.reactive_box(n=n, edge_um=1.0, p_target=0.7, seed=9, cap_factor=3, D=1e-7)  # noqa: E731
+    t, mols = make()
+    single = Engine(t)
+    single.upload(mols)
+    st1 = [single.step(1) for _ in range(n_iter)]
+    ref = single.download().sorted_by_id()
+    ref_counts = single.counts()
+    assert sum(s_.bimol_rxns for s_ in st1) > 300
+    res = _run_ranks(lambda: make()[0], mols, n_iter, world=world)
+    infos = [r[3] for r in res]
+    assert all(i.halo_layers > 0 for i in infos)
+    assert all(infos[k].layer_hi == infos[k + 1].layer_lo for k in range(world - 1))
+    parts = [r[0] for r in res]
+    assert all(p.n > 0 for p in parts)
+    ids = np.concatenate([p.id[:p.n] for p in parts])
+    assert len(ids) == ref.n and len(np.unique(ids)) == ref.n
+    o = np.argsort(ids, kind="stable")
+    for k in ("id", "species", "x", "y", "z", "flags", "diffusion_time", "unimol_rxn_time"):
+        got = np.concatenate([getattr(p, k)[:p.n] for p in parts])[o]
+        assert (got == getattr(ref, k)[:ref.n]).all(), k
+    for r in res:
+        assert (r[2][0] == ref_counts[0]).all() and (r[2][1] == ref_counts[1]).all()
+    for it in range(n_iter):
+        for k in ("molecule_steps", "bimol_rxns", "mol_wall_reflections", "vol_mol_vol_mol_collisions"):
+            assert sum(getattr(r[1][it], k) for r in res) == getattr(st1[it], k), (it, k)
