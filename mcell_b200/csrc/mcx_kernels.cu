@@ -516,7 +516,11 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
 
       // partner probe: none -> move; one hit in the molecule's own subpartition (always a collected one) -> evaluated
       // below; 2..MCX_FAST_MAX_HITS hits -> PASS 1, which evaluates them in collision order; anything else -> generic
+#ifdef MCX_EXPERIMENT_NO_PROBE   // timing experiment only (profiles/): what the fast pass costs without its partner probe
+      const bool probing = false;
+#else
       const bool probing = simple && sp.can_vol_react;
+#endif
       bool overflow;
       const int n_hits = probe_partners_flat(p, probing, pos, disp, m.id, species, overflow, &s_probe[warp]);
       // a collision next to walls needs exact_disk (walls of the collision subpartition): generic path

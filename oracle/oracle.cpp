@@ -1919,7 +1919,7 @@ int orc_upload_molecules(void* h, const mcx_mol_soa* s) {
     w.id_to_index[m.id] = (uint32_t)i;
     if (!(m.flags & MCX_MOL_DEFUNCT)) { w.sched_ids.push_back(m.id); list_insert(w, w.mols.back()); w.species_count[m.species]++; }
   }
-  w.next_id = std::max(w.next_id, max_id + 1);  // ids of molecules that died before this upload are not handed out again
+  if (s->n) w.next_id = std::max(w.next_id, max_id + 1);  // ids of molecules that died before this upload are not handed out again
   return 0;
 }
 // ReleaseEvent::release_ellipsoid_or_rectcuboid (src4/release_event.cpp:953-1003) with the product's random-number
