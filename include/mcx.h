@@ -334,6 +334,11 @@ int mcx_slab_info_get(mcx_handle* h, mcx_slab_info* out);
 /* How the halo refresh of this handle moves its records: 0 = single device (no exchange), 1 = NCCL send/recv,
  * 2 = stores into the neighbours' memory over NVLink (peer memory).  Negative on error. */
 int mcx_comm_halo_path(mcx_handle* h);
+/* Which kernel evaluated the whole-step molecules in the last mcx_step / mcx_replay_step / mcx_trace_step call:
+ * 0 = the gather walk over the cell-sorted snapshot (k_diffuse_fast), 1 = shared-memory tiles staged with bulk copies
+ * (k_diffuse_tile; selected with the environment variable MCX_TILE=1 when the cell grid allows it).  Both compute
+ * DiffuseReactEvent::diffuse_molecules (src4/diffuse_react_event.cpp:67-161) with identical results. */
+int mcx_fast_pass_kind(mcx_handle* h);
 /* Rank 0 creates the id (ncclGetUniqueId) that every rank passes to mcx_comm_init; returns the number of bytes
  * written (<= bytes) or a negative error. */
 int mcx_comm_unique_id(void* out, uint32_t bytes);

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcx.so")
 SOURCES = ["mcx_api.cu", "mcx_kernels.cu", "mcx_comm.cu", "mcx_geom.cpp"]
-HEADERS = ["mcx_internal.h", "mcx_device.cuh", "mcx_geom.h", "mcx_comm.h", "mcx_philox.h", "zig_tables.inc", "../../include/mcx.h"]
+HEADERS = ["mcx_internal.h", "mcx_device.cuh", "mcx_tile.cuh", "mcx_geom.h", "mcx_comm.h", "mcx_philox.h", "zig_tables.inc", "../../include/mcx.h"]
 # -fmad=false: fp64 expressions must round like the reference's -march=core2 build (no FMA contraction)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "--expt-relaxed-constexpr"]

@@ -105,6 +105,14 @@ void mcx_philox_block(uint64_t seed, uint32_t mol_id, uint64_t iteration, uint32
   philox4x32_10(block, (uint32_t)iteration, (uint32_t)(iteration >> 32), mol_id, (uint32_t)seed, (uint32_t)(seed >> 32), out);
 }
 
+// cells of the local grid incl. the padding of the (y, z) row blocks (row_index(), mcx_device.cuh)
+static void set_cell_count(DevParams& p) {
+  const int B = 1 << p.rb_log2;
+  p.nby = (p.ncy + B - 1) / B;
+  const int nbz = (p.ncz + B - 1) / B;
+  p.n_cells = (unsigned int)((size_t)p.ncx * ((size_t)p.nby * B) * ((size_t)nbz * B));
+}
+
 int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return MCX_ERR_INVALID_ARG; }
   if (cfg->abi_version != MCX_ABI_VERSION) { g_create_error = "ABI version mismatch"; return MCX_ERR_INVALID_ARG; }
@@ -182,7 +190,9 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   p.ncx = (int)std::ceil((hi[0] - p.cgx) / ex) + 1;
   p.ncy = (int)std::ceil((hi[1] - p.cgy) / ey) + 1;
   p.ncz = (int)std::ceil((hi[2] - p.cgz) / ez) + 1;
-  p.n_cells = (unsigned int)((size_t)p.ncx * p.ncy * p.ncz);
+  p.rb_log2 = 3;
+  if (const char* e = getenv("MCX_ROW_BLOCK_LOG2")) p.rb_log2 = std::max(0, std::min(6, atoi(e)));  // tuning knob (profiles/)
+  set_cell_count(p);
   p.own_lo = 0; p.own_hi = p.ncz; p.world = 1; p.halo_layers = 0; p.z_off = 0; p.has_low = 0; p.has_high = 0;
   h->ncz_global = p.ncz;
 
@@ -787,6 +797,7 @@ static int run_iterations(mcx_handle* h, uint32_t n_iterations, mcx_step_stats* 
   Counters before;
   CK(cudaMemcpyAsync(&before, h->p.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  mcx_plan_tiles(h->p, before.n_slots);
   CK(cudaEventRecord(h->ev0, h->stream));
   const uint32_t n_prof = h->profiling ? std::min<uint32_t>(n_iterations, 256) : 0;
   if (h->prof_events.size() < 5ull * n_prof) {
@@ -919,7 +930,7 @@ static int configure_slab(mcx_handle* h) {
   p.own_lo = g_lo - z_off; p.own_hi = g_hi - z_off;
   p.world = world; p.halo_layers = H;
   p.has_low = rank > 0; p.has_high = rank < world - 1;
-  p.n_cells = (unsigned int)((size_t)p.ncx * p.ncy * p.ncz);
+  set_cell_count(p);
   return MCX_OK;
 }
 
@@ -950,6 +961,8 @@ int mcx_comm_halo_path(mcx_handle* h) {
   if (!h) return MCX_ERR_INVALID_ARG;
   return h->comm ? (mcx_comm_is_p2p(h->comm) ? 2 : 1) : 0;
 }
+
+int mcx_fast_pass_kind(mcx_handle* h) { return h ? h->p.tile.enabled : MCX_ERR_INVALID_ARG; }
 
 int mcx_set_profiling(mcx_handle* h, int enabled) {
   if (!h) return MCX_ERR_INVALID_ARG;

@@ -194,11 +194,20 @@ __device__ __forceinline__ int cell_z(const DevParams& p, double z) {
   int c = (int)floor((z - p.cgz) * p.cell_rcp_z) - p.z_off;
   return c < 0 ? 0 : (c >= p.ncz ? p.ncz - 1 : c);
 }
+// Order of the cell rows in the sorted snapshot.  The records of one x-row of cells are contiguous; the rows themselves
+// are stored in blocks of 2^rb x 2^rb (y, z) rows, so that the rows above and below a row (z -+ 1) lie within one block
+// (a few MB) instead of a whole z-layer (12 MB at 1e8 molecules) away: with the plain (y, z) order every record was
+// fetched from DRAM three times per iteration, once per z-layer that probes it (profiles/r02_a: 18.3 GB for 8.3 GB).
+__device__ __forceinline__ uint32_t row_index(const DevParams& p, int cy, int cz) {
+  const int b = p.rb_log2, m = (1 << b) - 1;
+  return (uint32_t)((((((cz >> b) * p.nby + (cy >> b)) << b) | (cz & m)) << b) | (cy & m));
+}
+__device__ __forceinline__ uint32_t row_base(const DevParams& p, int cy, int cz) { return (uint32_t)p.ncx * row_index(p, cy, cz); }
 __device__ __forceinline__ uint32_t cell_of(const DevParams& p, double x, double y, double z) {
   int cx = cell_coord(x, p.cgx, p.cell_rcp_x, p.ncx);
   int cy = cell_coord(y, p.cgy, p.cell_rcp_y, p.ncy);
   int cz = cell_z(p, z);
-  return (uint32_t)(cx + p.ncx * (cy + p.ncy * cz));
+  return (uint32_t)cx + row_base(p, cy, cz);
 }
 // multi-GPU ownership: a position belongs to the rank whose owned z-layers contain it
 __device__ __forceinline__ bool owned_z(const DevParams& p, double z) {
@@ -557,7 +566,7 @@ struct CandWalkT {
     if (j >= jend) {
       if (SKIP_2X2) { while (row < nrows && ry < 2 && rz < 2) next_row(); }  // rows the 2x2 probe already covered
       if (row >= nrows) return false;
-      const uint32_t base = (uint32_t)(p.ncx * ((cy0 + ry) + p.ncy * (cz0 + rz)));
+      const uint32_t base = row_base(p, cy0 + ry, cz0 + rz);
       j = __ldg(p.cs_cur + base + cx0);
       jend = __ldg(p.cs_cur + base + cx1 + 1);
       next_row();
@@ -571,7 +580,7 @@ struct CandWalkT {
   __device__ __forceinline__ bool step2(const DevParams& p, bool& has0, uint32_t& slot0, bool& has1, uint32_t& slot1) {
     if (j >= jend) {
       if (row >= nrows) return false;
-      const uint32_t base = (uint32_t)(p.ncx * ((cy0 + ry) + p.ncy * (cz0 + rz)));
+      const uint32_t base = row_base(p, cy0 + ry, cz0 + rz);
       j = __ldg(p.cs_cur + base + cx0);
       jend = __ldg(p.cs_cur + base + cx1 + 1);
       next_row();
@@ -663,7 +672,7 @@ __device__ __forceinline__ int probe_partners(const DevParams& p, bool enabled, 
   for (int r = 0; r < 6; r++) {
     const int ry = tall ? (r & 1) : (r % 3), rz = tall ? (r >> 1) : (r / 3);
     const bool valid = en && ry < ny && rz < nz;
-    const uint32_t base = (uint32_t)(p.ncx * ((b.cy0 + ry) + p.ncy * (b.cz0 + rz)));
+    const uint32_t base = row_base(p, b.cy0 + ry, b.cz0 + rz);
     const uint32_t a = __ldg(p.cs_cur + (valid ? base + b.cx0 : 0u));
     const uint32_t e = __ldg(p.cs_cur + (valid ? base + b.cx1 + 1 : 0u));
     lo[r] = a - total;   // slot of candidate k in row r is lo[r] + k  (k counted over the concatenation)
@@ -732,7 +741,7 @@ __device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enab
   for (int r = 0; r < 6; r++) {
     const int ry = tall ? (r & 1) : (r % 3), rz = tall ? (r >> 1) : (r / 3);
     const bool valid = en && ry < ny && rz < nz;
-    const uint32_t base = (uint32_t)(p.ncx * ((bx.cy0 + ry) + p.ncy * (bx.cz0 + rz)));
+    const uint32_t base = row_base(p, bx.cy0 + ry, bx.cz0 + rz);
     const uint32_t a = __ldg(p.cs_cur + (valid ? base + bx.cx0 : 0u));
     const uint32_t e = __ldg(p.cs_cur + (valid ? base + bx.cx1 + 1 : 0u));
     sm->lo[lane][r] = a - total;
@@ -821,17 +830,17 @@ __device__ __forceinline__ bool in_neighbor_dirs(const int delta[3], const int d
 // reactions exist).  decided = false: a hit in a foreign subpartition whose
 // membership this function does not work out (the caller hands the molecule to the generic pass).
 template <bool DECIDE_FOREIGN>
-__device__ __forceinline__ bool next_probe_hit(const DevParams& p, const WarpProbe* sm, int n_hits, D3 pos, D3 disp, bool stays,
-                                               bool single, const int s1[3], uint32_t self_species, double t_last,
-                                               uint32_t id_last, PartnerHit& best, bool& decided) {
-  const int lane = threadIdx.x & 31;
+// hit_slots[h * hit_stride], h < n_hits: the snapshot slots the probe reported for this molecule.
+__device__ __forceinline__ bool next_probe_hit(const DevParams& p, const uint32_t* hit_slots, int hit_stride, int n_hits, D3 pos,
+                                               D3 disp, bool stays, bool single, const int s1[3], uint32_t self_species,
+                                               double t_last, uint32_t id_last, PartnerHit& best, bool& decided) {
   const double movelen2 = dot3(disp, disp);
   int s0[3];
   subpart_3d(p, pos, s0);
   bool any = false;
   best.t = MCX_TIME_FOREVER; best.id = 0; best.slot = MCX_NONE; best.species = 0; best.rxn_class = 0; best.in_own_subpart = true;
   for (int h = 0; h < n_hits; h++) {
-    const uint32_t j = sm->hit_slot[lane][h];
+    const uint32_t j = hit_slots[h * hit_stride];
     const MolRec c = load_rec(p.recA, j);
     const D3 dir = {c.x - pos.x, c.y - pos.y, c.z - pos.z};
     const double t = dot3(dir, disp) / movelen2;

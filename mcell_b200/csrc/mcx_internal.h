@@ -78,6 +78,23 @@ struct Counters {
 #define MCX_MAX_CV 256
 #define MCX_FW_MARGIN 1e-6        // inflation of wall and query boxes of the fine wall grid, in length units
 
+// Shared-memory tiles of the fast pass (k_diffuse_tile, mcx_tile.cuh): a thread block owns the records of TX x TY x TZ
+// cells and stages them plus a halo (hx cells in x, one cell row in y and z) with one bulk copy per cell row; the
+// staged records are re-binned in shared memory into a finer grid (rows split 2^lsy x 2^lsz) of fp32 positions
+// relative to the tile, which the partner probe pre-filters before the exact fp64 test.  Planned on the host from the
+// population density (mcx_api.cu: plan_tiles); enabled == 0: the flat gather kernel runs instead.
+struct TileGeom {
+  int enabled;
+  int TX, TY, TZ, hx;          // owned cells per tile; x halo in cells
+  int ntx, nty, ntz;           // tiles per axis of the local cell grid
+  unsigned int n_tiles;
+  int lsy, lsz;                // log2 of the fine sub-rows per cell row in y / z
+  int nfx, nfy, nfz;           // fine grid of the staged region: TX + 2 hx, (TY + 2) << lsy, (TZ + 2) << lsz
+  unsigned int cap;            // staged records that fit
+  float tol_d, r2p;            // slacks of the fp32 pre-filter: along the move (absolute) and the inflated R^2
+  unsigned int smem_bytes;     // dynamic shared memory of the launch
+};
+
 struct DevParams {
   // partition / subpartition grid (reference semantics)
   double ox, oy, oz, part_len, sp_len, sp_rcp, R;
@@ -85,7 +102,8 @@ struct DevParams {
   // device neighbour-cell grid
   double cgx, cgy, cgz, cell_rcp_x, cell_rcp_y, cell_rcp_z;  // cells are short in x (rows are contiguous), long in y/z
   int ncx, ncy, ncz;
-  unsigned int n_cells;
+  int rb_log2, nby;             // cell rows are stored in blocks of 2^rb_log2 x 2^rb_log2 (y, z) rows; nby = blocks per layer of blocks
+  unsigned int n_cells;         // ncx * rows incl. the padding of the row blocks
   // immutable tables
   const DevWall* walls;
   const uint32_t* wall_tri;
@@ -159,6 +177,7 @@ struct DevParams {
                                 // rank computes the same global layer for a position before subtracting its offset)
   int has_low, has_high;        // a neighbour rank exists below / above
   int sm_count;                 // multiprocessors of this device: every grid is sized in multiples of it
+  TileGeom tile;
 };
 
 // multi-GPU halo record: what a neighbour needs to evaluate a molecule exactly like its owner does
@@ -186,6 +205,7 @@ struct StepPlan {
   bool has_claims;   // model can produce reactions / absorptions (conflict rounds needed)
   bool trace;
 };
+void mcx_plan_tiles(DevParams& p, unsigned long long n_records);  // fills p.tile for a population of n_records
 void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t s);
 void mcx_launch_initial_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
 // multi-GPU pieces of an iteration (mcx_comm.cu drives them around the NCCL exchange)

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include "mcx_device.cuh"
+#include "mcx_tile.cuh"
 
 #define TPB 256
 
@@ -354,31 +355,31 @@ __device__ __forceinline__ void trace_end(Tracer& tc, const Outcome& o, const St
 // they were 47 % of what the generic pass had to evaluate, at two partner scans each.  PASS 0 appends them to
 // second_list and PASS 1 runs the same flat body over that list, twice per molecule, with full warps of them.
 // Whatever turns out not to be simple in either pass goes to slow_list and is restarted from the snapshot there.
-template <int PASS>
-__global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const __grid_constant__ DevParams p) {
-  __shared__ ZigShared zig;
-  __shared__ uint32_t s_slow[TPB / 32][WL_CAP], s_prop[TPB / 32][WL_CAP], s_second[PASS == 0 ? TPB / 32 : 1][WL_CAP];
-  __shared__ unsigned int s_reason[TPB / 32][8];
-  __shared__ WarpProbe s_probe[TPB / 32];
-  zig_load(&zig);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane < 8) s_reason[warp][lane] = 0;
-  __syncthreads();
+// The per-molecule body of the fast passes (see k_diffuse_fast below).  Warp-collective: all 32 lanes call it
+// together (lanes without a molecule pass in_range == false and a valid slot).  Probe is the partner probe of the
+// launch: the warp-flattened gather walk (FlatProbe) or the shared-memory tile (TileProbe, mcx_tile.cuh).
+struct FastCtx {
+  const ZigShared* zig;
   WarpList slow_wl, prop_wl, second_wl;
-  slow_wl.init(s_slow[warp]);
-  prop_wl.init(s_prop[warp]);
-  second_wl.init(s_second[PASS == 0 ? warp : 0]);
-  const unsigned int n = PASS == 0 ? p.ctr->n_slots : p.ctr->n_second;
-  // PASS 1's own deferrals go to a list of their own (a small second launch of the generic pass takes them)
-  unsigned int* const n_slow_ctr = PASS == 0 ? &p.ctr->n_slow : &p.ctr->n_slow2;
-  uint32_t* const slow_out = PASS == 0 ? p.slow_list : p.slow2_list;
+  unsigned int* n_slow_ctr;
+  uint32_t* slow_out;
+  unsigned int* reason_row;   // this warp's deferral-reason counters (shared memory)
+  unsigned int msteps, n_tests, n_coll;
+};
+struct FlatProbe {
+  static constexpr int HIT_STRIDE = 1;
+  WarpProbe* sm;
+  __device__ __forceinline__ int run(const DevParams& p, bool probing, D3 pos, D3 disp, uint32_t id, uint32_t species, uint32_t,
+                                     bool& overflow, bool& outside) {
+    outside = false;
+    return probe_partners_flat(p, probing, pos, disp, id, species, overflow, sm);
+  }
+  __device__ __forceinline__ const uint32_t* hit_slots() const { return &sm->hit_slot[threadIdx.x & 31][0]; }
+};
+
+template <int PASS, class Probe>
+__device__ __forceinline__ void fast_molecule(const DevParams& p, FastCtx& cx, Probe& probe, const bool in_range, const unsigned int i) {
   const double it = (double)p.iteration, t_end = it + 1.0;
-  unsigned int msteps = 0, n_tests = 0, n_coll = 0;
-  for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    const unsigned int k = base + threadIdx.x;
-    const bool in_range = k < n;
-    const unsigned int kk = in_range ? k : base;  // a valid entry for every lane
-    const unsigned int i = PASS == 0 ? kk : __ldg(p.second_list + kk);
     const MolRec m = load_rec(p.recA, i);
     const bool live = in_range && !(m.sf & (DF_DEAD | DF_GHOST));
     const uint32_t species = m.sf & SF_SPECIES_MASK;
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
     // a non-diffusing molecule with nothing scheduled inside this iteration (receptors, pumps): the generic
     // evaluation would return MCX_OUT_STATIC without drawing a number (diffuse_react_event.cpp:318-335)
     const bool idle = idle_candidate && !(has_uni && t_uni < t_end);
-    Stream rs; rs.init(p, m.id, &zig);
+    Stream rs; rs.init(p, m.id, cx.zig);
     Tracer tc; tc.h = 0xcbf29ce484222325ULL; tc.tr = nullptr;
     if (PASS == 1) {
       // newbie lifetime (:232-236 -> pick_unimol_rxn_class_and_set_rxn_time :1731-1758): one draw; a unimolecular
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
           trace_end(tc, o, rs);
           write_proposal(p, i, o, m.id, species, round_epoch(p, 0), -1);
           proposed = true;
-          if (own_start) { msteps++; n_tests += my_tests; n_coll += my_coll; }
+          if (own_start) { cx.msteps++; cx.n_tests += my_tests; cx.n_coll += my_coll; }
           running = false;
         }
       }
@@ -521,8 +522,9 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
 #else
       const bool probing = simple && sp.can_vol_react;
 #endif
-      bool overflow;
-      const int n_hits = probe_partners_flat(p, probing, pos, disp, m.id, species, overflow, &s_probe[warp]);
+      // outside (tile probe only): the swept box leaves the staged tile — PASS 1 probes it with the gather walk
+      bool overflow, outside;
+      const int n_hits = probe.run(p, probing, pos, disp, m.id, species, i, overflow, outside);
       // a collision next to walls needs exact_disk (walls of the collision subpartition): generic path
       // (every wall plane of the crossed subpartitions farther than R from the whole segment: the factor is 1)
       const bool disk_walls = n_hits > 0 && wall_dist < p.R;
@@ -535,11 +537,13 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
       PartnerHit ph;
       bool decided = true;
       bool have = simple && n_hits > 0 &&
-                  next_probe_hit<PASS == 1>(p, &s_probe[warp], n_hits, pos, disp, same, single, s1, species, -1.0, 0u, ph, decided);
+                  next_probe_hit<PASS == 1>(p, probe.hit_slots(), Probe::HIT_STRIDE, n_hits, pos, disp, same, single, s1, species, -1.0, 0u, ph, decided);
       const bool foreign = PASS == 0 && simple && !decided && same;
       simple = simple && decided;
       if (!simple && reason < 0) reason = MCX_DEFER_FOREIGN_HIT;
-      if (several || foreign) { to_second = true; slow = false; running = false; }
+      const bool elsewhere = PASS == 0 && simple && outside;
+      simple = simple && !outside;
+      if (several || foreign || elsewhere) { to_second = true; slow = false; running = false; }
 
       if (simple) {
         if (PASS == 0) trace_begin(p, tc, m.id);
@@ -566,7 +570,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
           }
           if (PASS == 0 || (int)colls >= n_hits) break;
           const double t_last = ph.t; const uint32_t id_last = ph.id;
-          have = next_probe_hit<PASS == 1>(p, &s_probe[warp], n_hits, pos, disp, same, single, s1, species, t_last, id_last, ph, decided);
+          have = next_probe_hit<PASS == 1>(p, probe.hit_slots(), Probe::HIT_STRIDE, n_hits, pos, disp, same, single, s1, species, t_last, id_last, ph, decided);
         }
         my_tests += n_wall_tests; my_coll += colls;
         if (PASS == 1 && o.kind == MCX_OUT_MOVED && again) {  // first sub-step done
@@ -577,7 +581,7 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
             if (PASS == 1) { const double r = round(t_new); if (cmp_eq_d(t_new, r, MCX_SQRT_EPS)) t_new = r; }
             finalize_alive(p, i, dest, m.id, species, flags & ~DF_PARTIAL, t_new, t_uni);
           } else { write_proposal(p, i, o, m.id, species, round_epoch(p, 0), -1); proposed = true; }
-          if (own_start) { msteps++; n_tests += my_tests; n_coll += my_coll; }
+          if (own_start) { cx.msteps++; cx.n_tests += my_tests; cx.n_coll += my_coll; }
           running = false;
         }
       } else if (running) {
@@ -597,19 +601,167 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
     }
     if (PASS == 1 && slow && tc.tr) tc.tr->rounds--;  // the generic pass starts it over (and counts the evaluation)
     // staged appends (loop bounds are warp-uniform: all 32 lanes arrive here)
-    if (slow) atomicAdd(&s_reason[warp][reason & 7], 1u);
-    slow_wl.push(slow, i, n_slow_ctr, slow_out);
-    prop_wl.push(proposed, i, &p.ctr->n_pend[0], p.pend[0]);
-    if (PASS == 0) second_wl.push(to_second, i, &p.ctr->n_second, p.second_list);
-  }
-  slow_wl.flush(n_slow_ctr, slow_out);
-  prop_wl.flush(&p.ctr->n_pend[0], p.pend[0]);
-  if (PASS == 0) second_wl.flush(&p.ctr->n_second, p.second_list);
+    if (slow) atomicAdd(&cx.reason_row[reason & 7], 1u);
+    cx.slow_wl.push(slow, i, cx.n_slow_ctr, cx.slow_out);
+    cx.prop_wl.push(proposed, i, &p.ctr->n_pend[0], p.pend[0]);
+    if (PASS == 0) cx.second_wl.push(to_second, i, &p.ctr->n_second, p.second_list);
+}
+
+// end of a fast-pass kernel: flush the staged list appends and the warp's statistics
+template <int PASS>
+__device__ __forceinline__ void fast_finish(const DevParams& p, FastCtx& cx, int lane) {
+  cx.slow_wl.flush(cx.n_slow_ctr, cx.slow_out);
+  cx.prop_wl.flush(&p.ctr->n_pend[0], p.pend[0]);
+  if (PASS == 0) cx.second_wl.flush(&p.ctr->n_second, p.second_list);
   __syncwarp();
-  if (lane == 0 && slow_wl.total) atomicAdd(&p.ctr->deferred, (unsigned long long)slow_wl.total);
-  if (lane < 8 && s_reason[warp][lane]) atomicAdd(&p.ctr->defer_reason[lane], (unsigned long long)s_reason[warp][lane]);
-  LocalStats ls = {n_tests, 0, 0, 0, n_coll, 0};
-  flush_stats(p, ls, msteps);
+  if (lane == 0 && cx.slow_wl.total) atomicAdd(&p.ctr->deferred, (unsigned long long)cx.slow_wl.total);
+  if (lane < 8 && cx.reason_row[lane]) atomicAdd(&p.ctr->defer_reason[lane], (unsigned long long)cx.reason_row[lane]);
+  LocalStats ls = {cx.n_tests, 0, 0, 0, cx.n_coll, 0};
+  flush_stats(p, ls, cx.msteps);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const __grid_constant__ DevParams p) {
+  __shared__ ZigShared zig;
+  __shared__ uint32_t s_slow[TPB / 32][WL_CAP], s_prop[TPB / 32][WL_CAP], s_second[PASS == 0 ? TPB / 32 : 1][WL_CAP];
+  __shared__ unsigned int s_reason[TPB / 32][8];
+  __shared__ WarpProbe s_probe[TPB / 32];
+  zig_load(&zig);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < 8) s_reason[warp][lane] = 0;
+  __syncthreads();
+  FastCtx cx;
+  cx.zig = &zig;
+  cx.slow_wl.init(s_slow[warp]);
+  cx.prop_wl.init(s_prop[warp]);
+  cx.second_wl.init(s_second[PASS == 0 ? warp : 0]);
+  const unsigned int n = PASS == 0 ? p.ctr->n_slots : p.ctr->n_second;
+  // PASS 1's own deferrals go to a list of their own (a small second launch of the generic pass takes them)
+  cx.n_slow_ctr = PASS == 0 ? &p.ctr->n_slow : &p.ctr->n_slow2;
+  cx.slow_out = PASS == 0 ? p.slow_list : p.slow2_list;
+  cx.reason_row = s_reason[warp];
+  cx.msteps = 0; cx.n_tests = 0; cx.n_coll = 0;
+  FlatProbe probe{&s_probe[warp]};
+  for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const unsigned int k = base + threadIdx.x;
+    const bool in_range = k < n;
+    const unsigned int kk = in_range ? k : base;  // a valid entry for every lane
+    const unsigned int i = PASS == 0 ? kk : __ldg(p.second_list + kk);
+    fast_molecule<PASS>(p, cx, probe, in_range, i);
+  }
+  fast_finish<PASS>(p, cx, lane);
+}
+
+// dynamic shared memory a tile block may use: what the multiprocessor has (227 KB, 1 KB reserved per block) shared by
+// the resident blocks, minus the static arrays of the kernel
+#define TILE_SMEM_DYN_MAX ((TILE_TPB == 1024 ? 232448 : 115712) - 28 * TILE_TPB - 2048)
+// PASS 0 over shared-memory tiles (mcx_tile.cuh): one persistent block per multiprocessor walks the tiles of the cell
+// grid; the same per-molecule body as k_diffuse_fast<0>, with the partner probe served from the staged tile.
+__global__ void __launch_bounds__(TILE_TPB, TILE_BLOCKS_PER_SM) k_diffuse_tile(const __grid_constant__ DevParams p) {
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  __shared__ ZigShared zig;
+  __shared__ uint32_t s_slow[TILE_TPB / 32][WL_CAP], s_prop[TILE_TPB / 32][WL_CAP], s_second[TILE_TPB / 32][WL_CAP];
+  __shared__ unsigned int s_reason[TILE_TPB / 32][8];
+  TileSmem ts;
+  tile_smem_layout(p.tile, tile_smem, ts);
+  zig_load(&zig);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < 8) s_reason[warp][lane] = 0;
+  if (threadIdx.x < 32) {
+    uint32_t mask = 0;
+    if ((int)threadIdx.x < p.n_species && p.n_species <= 32)
+      for (int sp = 0; sp < p.n_species; sp++) if (p.bimol[threadIdx.x * p.n_species + sp] >= 0) mask |= 1u << sp;
+    ts.rmask[threadIdx.x] = mask;
+  }
+  if (threadIdx.x == 0) { mbar_init(ts.bar, 1); fence_proxy_async(); }
+  __syncthreads();
+  FastCtx cx;
+  cx.zig = &zig;
+  cx.slow_wl.init(s_slow[warp]);
+  cx.prop_wl.init(s_prop[warp]);
+  cx.second_wl.init(s_second[warp]);
+  cx.n_slow_ctr = &p.ctr->n_slow;
+  cx.slow_out = p.slow_list;
+  cx.reason_row = s_reason[warp];
+  cx.msteps = 0; cx.n_tests = 0; cx.n_coll = 0;
+  const unsigned int n_tiles = p.tile.n_tiles;
+  const int n_rows = (p.tile.TY + 2) * (p.tile.TZ + 2);
+  unsigned int parity = 0;
+  int cur = 0;
+  if (warp == 0 && blockIdx.x < n_tiles) tile_issue(p, ts, blockIdx.x, &ts.tab[0]);
+  for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, cur ^= 1) {
+    const TileTab* tab = &ts.tab[cur];
+    mbar_wait(ts.bar, parity);  // the tile's records are in shared memory, its tables are visible (release / acquire)
+    parity ^= 1u;
+    if (!tab->overflow) tile_bin(p, ts, tab); else __syncthreads();
+    // the staging buffer is free again: the next tile's bulk copies run under this tile's evaluation
+    const unsigned int next = tile + gridDim.x;
+    if (warp == 0 && next < n_tiles) { fence_proxy_async(); tile_issue(p, ts, next, &ts.tab[cur ^ 1]); }
+    const unsigned int n_owned = tab->n_owned;
+    for (unsigned int kb = warp * 32; kb < n_owned; kb += TILE_TPB) {  // warp-uniform bounds
+      const unsigned int k = kb + lane;
+      const bool in_range = k < n_owned;
+      const unsigned int kk = in_range ? k : kb;
+      int lo = 0, hi = n_rows;  // row of owned molecule kk: last row whose owned prefix is <= kk
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tab->own_pref[mid] <= kk) lo = mid; else hi = mid; }
+      const uint32_t own_idx = tab->own_lo[lo] + (kk - tab->own_pref[lo]);
+      const uint32_t slot = tab->row_src[lo] + (own_idx - tab->row_off[lo]);
+      TileProbe probe{&ts, tab, own_idx};
+      fast_molecule<0>(p, cx, probe, in_range, slot);
+    }
+    __syncthreads();  // the fine grid and the tables of this tile are dead
+  }
+  fast_finish<0>(p, cx, lane);
+}
+
+// Tile geometry for a population of n_records in the local cell grid (called whenever stepping starts).  TY = TZ = 4
+// owned cell rows and one halo row each side; the x extent from the staging capacity, the size of the fine-cell table
+// and ~0.9 owned molecules per thread; fp32 slacks from the staged extent (see TileProbe::run).
+void mcx_plan_tiles(DevParams& p, unsigned long long n_records) {
+  TileGeom g{};
+  p.tile = g;
+  // opt-in: measured slower than the gather walk so far (profiles/r02_c..f)
+  const char* on = getenv("MCX_TILE");
+  if (!on || atoi(on) == 0 || n_records == 0 || p.n_cells == 0) return;
+  const double ex = 1.0 / p.cell_rcp_x, ey = 1.0 / p.cell_rcp_y, ez = 1.0 / p.cell_rcp_z;
+  const double lambda = (double)n_records / (double)p.n_cells;
+  g.TY = p.ncy < 4 ? p.ncy : 4; g.TZ = p.ncz < 4 ? p.ncz : 4;
+  g.lsy = g.lsz = 1;
+  if (const char* e = getenv("MCX_TILE_LS")) g.lsy = g.lsz = atoi(e);
+  g.hx = (int)ceil(fmax(ey, ez) / ex);
+  if (g.hx < 1) g.hx = 1;
+  if (g.hx > 16) return;
+  g.nfy = (g.TY + 2) << g.lsy; g.nfz = (g.TZ + 2) << g.lsz;
+  g.cap = TILE_TPB == 1024 ? 3328 : 1664;
+  if (const char* e = getenv("MCX_TILE_CAP")) g.cap = (unsigned int)atoi(e);
+  if (g.cap > TILE_TPB * TILE_REC_PER_THREAD) g.cap = TILE_TPB * TILE_REC_PER_THREAD;
+  const int rows = (g.TY + 2) * (g.TZ + 2);
+  double sx = TILE_NF_MAX / (double)(g.nfy * g.nfz);
+  sx = fmin(sx, 0.82 * g.cap / (rows * lambda));
+  double tx = fmin(sx - 2 * g.hx, 0.9 * TILE_TPB / (g.TY * g.TZ * lambda));
+  if (const char* e = getenv("MCX_TILE_TX")) tx = atof(e);
+  g.TX = (int)floor(tx);
+  if (g.TX > p.ncx) g.TX = p.ncx;
+  if (g.TX < 4) return;
+  g.nfx = g.TX + 2 * g.hx;
+  if ((long long)g.nfx * g.nfy * g.nfz > TILE_NF_MAX) return;
+  g.ntx = (p.ncx + g.TX - 1) / g.TX; g.nty = (p.ncy + g.TY - 1) / g.TY; g.ntz = (p.ncz + g.TZ - 1) / g.TZ;
+  const unsigned long long nt = (unsigned long long)g.ntx * g.nty * g.ntz;
+  if (nt > 0xFFFFFFF0ull) return;
+  g.n_tiles = (unsigned int)nt;
+  // fp32 slacks: coordinates relative to the tile are below S, so each carries an absolute error below eps_c
+  const double S = fmax(g.nfx * ex, fmax((g.TY + 2) * ey, (g.TZ + 2) * ez)) * 1.01, D = S * 1.7320508;
+  const double eps_c = S * ldexp(1.0, -23);
+  const double tol_d = 4.0 * (2.0 * eps_c * 1.7320508 * D + D * D * ldexp(1.0, -22));
+  const double bound_v = 4.0 * D * 2.0 * eps_c * 1.7320508 + 8.0 * D * D * ldexp(1.0, -24);
+  const double r2 = p.R * p.R, r2p = r2 * 1.0625 + 2.0 * bound_v;
+  if (!(r2p < 2.0 * r2)) return;  // boxes too large for an fp32 pre-filter: the gather walk runs
+  g.tol_d = (float)tol_d; g.r2p = (float)r2p;
+  TileSmem ts;
+  g.smem_bytes = tile_smem_layout(g, nullptr, ts);
+  if (g.smem_bytes > TILE_SMEM_DYN_MAX) return;
+  g.enabled = 1;
+  p.tile = g;
 }
 
 // The generic evaluation is one long divergent path per molecule: a warp of 32 different molecules runs close to 32
@@ -1253,7 +1405,16 @@ void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t 
   }();
   (void)carveout_set;
   if (plan.prof) cudaEventRecord(plan.prof[0], s);
-  k_diffuse_fast<0><<<plan.sm_count * 2 * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
+  if (p.tile.enabled) {
+    static const bool smem_set = [] {
+      cudaFuncSetAttribute(k_diffuse_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_DYN_MAX);
+      return true;
+    }();
+    (void)smem_set;
+    k_diffuse_tile<<<plan.sm_count * TILE_BLOCKS_PER_SM, TILE_TPB, p.tile.smem_bytes, s>>>(p);
+  } else {
+    k_diffuse_fast<0><<<plan.sm_count * 2 * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
+  }
   if (plan.prof) cudaEventRecord(plan.prof[4], s);
   k_diffuse_fast<1><<<plan.sm_count * MCX_FAST_MINBLOCKS, TPB, 0, s>>>(p);
   const int g_slow = plan.sm_count * 2 * MCX_SLOW_MINBLOCKS;

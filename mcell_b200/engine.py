@@ -53,6 +53,7 @@ def load_library():
     L.mcx_comm_unique_id.argtypes = [C.c_void_p, C.c_uint32]
     L.mcx_slab_info_get.argtypes = [H, C.POINTER(abi.mcx_slab_info)]
     L.mcx_comm_halo_path.argtypes = [H]
+    L.mcx_fast_pass_kind.argtypes = [H]
     L.mcx_release_volume_molecules.argtypes = [H, C.POINTER(abi.mcx_release), C.POINTER(C.c_uint32)]
     L.mcx_set_profiling.argtypes = [H, C.c_int]
     L.mcx_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
@@ -111,6 +112,10 @@ class Engine:
     def halo_path(self):
         """0 = single device, 1 = NCCL send/recv, 2 = peer-memory stores over NVLink (mcx_comm_halo_path)."""
         return int(self.L.mcx_comm_halo_path(self.h))
+
+    def fast_pass_kind(self):
+        """0 = gather walk, 1 = shared-memory tiles (mcx_fast_pass_kind), for the last stepping call."""
+        return int(self.L.mcx_fast_pass_kind(self.h))
 
     def slab_info(self):
         info = abi.mcx_slab_info()

@@ -27,7 +27,8 @@ for stage in "$@"; do
                  -s ${NCU_SKIP:-60} -c ${NCU_COUNT:-16} -o ${O}_prof -f python bench.py --steps 3 --warmup 3 --e2e-calls 1 --no-cpu > ${O}_ncu.log 2>&1; tail -3 ${O}_ncu.log ;;
     ab:*)      for v in $(echo ${stage#ab:} | tr ',' ' '); do
                  lib=mcell_b200/libmcx_$v.so; [ "$v" = head ] && lib=mcell_b200/libmcx.so
-                 for rep in 1 2; do MCX_LIB=$PWD/$lib timeout 600 python bench.py --no-cpu --e2e-calls 1 ${AB_ARGS} > ${O}_ab_${v}_$rep.json 2>> ${O}_ab.err
+                 extra_env=""; case $v in env_*) lib=mcell_b200/libmcx.so; extra_env="$(echo ${v#env_} | tr '+' ' ')";; esac   # env_VAR=1+VAR2=x: HEAD with tuning variables
+                 for rep in 1 2; do env $extra_env MCX_LIB=$PWD/$lib timeout 600 python bench.py --no-cpu --e2e-calls 1 ${AB_ARGS} > ${O}_ab_${v}_$rep.json 2>> ${O}_ab.err
                    python - <<EOF
 import json; d=json.load(open("${O}_ab_${v}_$rep.json")); r=d["roofline"]
 print("AB $v rep $rep: ms/step %.3f fast %.3f slow %.3f resolve %.3f sort %.3f value %.4g" % (d["ms_per_step"], r["ms_diffuse_fast"], r["ms_diffuse_slow"], r["ms_resolve"], r["ms_sort"], d["value"]))
