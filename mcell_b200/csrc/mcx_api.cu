@@ -150,6 +150,7 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   p.rng_mode = (int)cfg->rng_mode;
   p.capacity = (unsigned int)cfg->max_molecules;
   p.max_rounds = cfg->max_resolve_rounds ? cfg->max_resolve_rounds : 8;
+  if (p.max_rounds > MCX_ROUNDS_MAX) p.max_rounds = MCX_ROUNDS_MAX;
   h->iteration = cfg->initial_iteration;
 
   // device neighbour-cell grid over the active box

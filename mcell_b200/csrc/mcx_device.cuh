@@ -444,13 +444,54 @@ struct WallWalk {
   }
 };
 
+// A group of G lanes (G = 1: one lane, or an aligned group of 8 lanes of a warp) that evaluates ONE molecule together: the
+// lanes run the same evaluation on the same inputs — same control flow, same random stream — and split the two loops
+// that dominate it, the wall list of get_closest_wall_collision and the candidate records of the partner scan.
+// One molecule per lane spent its time in chains of dependent loads, one wall or candidate after the other, with 3 of
+// 32 lanes active (profiles/r01_x); the group issues 8 of those loads at once.
+struct Group {
+  unsigned int mask;  // lanes of the group in the warp
+  int G, sub, base;   // lanes per group (1, 2, 4, 8, 16 or 32), this lane's position in the group, first lane of the group
+};
+__device__ __forceinline__ Group group_of(int G) {
+  Group g;
+  const int lane = threadIdx.x & 31;
+  g.G = G;
+  g.base = lane & ~(G - 1);
+  g.sub = lane - g.base;
+  g.mask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << g.base;
+  return g;
+}
+
+// first stage of collide_wall (collision_utils.inl:664-683): the move stays on one side of the wall's plane — COLLIDE_MISS
+// without a random draw
+__device__ __forceinline__ bool wall_plane_rejected(const DevParams& p, uint32_t wi, D3 pos, D3 move) {
+  const DevWall& f = p.walls[wi];
+  const D3 n = {f.nx, f.ny, f.nz};
+  const double dp = dot3(n, pos), dv = dot3(n, move), dd = dp - f.dist;
+  double d_eps;
+  if (dd > 0) {
+    d_eps = MCX_EPS;
+    if (dd < d_eps) d_eps = 0.5 * dd;
+    return dd + dv > d_eps;
+  }
+  d_eps = -MCX_EPS;
+  if (dd > d_eps) d_eps = 0.5 * dd;
+  return dd < 0 && dd + dv < d_eps;
+}
+
 struct WallHit { int side; double t; D3 pos; uint32_t wall; };
+#define MCX_WALL_CAND_MAX 12
 
 // get_closest_wall_collision, collision_utils.inl:819-914.  The walk leaves out walls of the list whose bounding box
 // the move cannot reach (they would be COLLIDE_MISS without a random draw); ray_polygon_tests still counts the whole
 // list like the reference does, from the list positions.
+// G > 1: the lanes of the group first deal the list entries among themselves and drop the walls whose plane the move
+// does not reach (no side effects, so neither the order nor duplicates matter); what is left — a handful of walls — goes
+// through collide_wall in ascending wall order on every lane, exactly like the sequential walk (same draws, same REDOs).
 __device__ bool closest_wall_collision(const DevParams& p, D3 pos, uint32_t subpart, uint32_t last_hit_wall,
-                                       Stream& rs, D3& disp, D3& up_to_wall, WallHit& best, LocalStats& ls, Tracer& tc) {
+                                       Stream& rs, D3& disp, D3& up_to_wall, WallHit& best, LocalStats& ls, Tracer& tc,
+                                       const Group& grp) {
   const uint32_t w0 = p.spw_start[subpart], w1 = p.spw_start[subpart + 1];
   if (w0 == w1) return false;
   const bool last_in_list = last_hit_wall != MCX_NONE && spw_position(p, w0, w1, last_hit_wall) != MCX_NONE;
@@ -462,7 +503,39 @@ restart:
   segment_box(pos, disp, MCX_FW_MARGIN, lo, hi);
   WallWalk ww;
   ww.init(p, subpart, lo, hi);
-  for (uint32_t wi = ww.next(p); wi != MCX_NONE; wi = ww.next(p)) {
+  uint32_t cand[MCX_WALL_CAND_MAX];
+  int nc = 0, ic = 0;
+  const int G = grp.G;
+  bool sequential = G == 1;
+  if (G > 1) {
+    // plane pre-pass over the entries of the walk's lists
+    const int n_ranges = ww.whole ? 1 : ww.n;
+    for (int r = 0; r < n_ranges && !sequential; r++) {
+      const uint32_t e0 = ww.whole ? ww.k : ww.cur[r], e1 = ww.whole ? ww.k1 : ww.end[r];
+      const uint32_t* list = ww.whole ? p.spw_list : p.fw_list;
+      for (uint32_t e = e0; e < e1 && !sequential; e += G) {
+        const uint32_t mine = e + (uint32_t)grp.sub;
+        const uint32_t wi = mine < e1 ? __ldg(list + mine) : MCX_NONE;
+        const bool keep = wi != MCX_NONE && wi != last_hit_wall && !wall_plane_rejected(p, wi, pos, disp);
+        unsigned int bal = (__ballot_sync(grp.mask, keep) & grp.mask) >> grp.base;
+        while (bal) {
+          const int l = __ffs(bal) - 1;
+          bal &= bal - 1;
+          const uint32_t w = __shfl_sync(grp.mask, wi, grp.base + l);
+          int at = 0;  // sorted insert, duplicates dropped (a wall can sit in several cells of the fine grid)
+          while (at < nc && cand[at] < w) at++;
+          if (at < nc && cand[at] == w) continue;
+          if (nc == MCX_WALL_CAND_MAX) { sequential = true; break; }
+          for (int q = nc; q > at; q--) cand[q] = cand[q - 1];
+          cand[at] = w; nc++;
+        }
+      }
+    }
+  }
+  for (;;) {
+    uint32_t wi;
+    if (sequential) wi = ww.next(p); else wi = ic < nc ? cand[ic++] : MCX_NONE;
+    if (wi == MCX_NONE) break;
     if (wi == last_hit_wall) continue;
     double t; D3 hit;
     int ct = collide_wall(p, pos, wi, rs, disp, t, hit);
@@ -611,12 +684,12 @@ struct PartnerHit { double t; uint32_t slot, id, species; int rxn_class; bool in
 template <bool VOLATILE_SNAPSHOT>
 __device__ int scan_partners(const DevParams& p, D3 pos, D3 disp, uint32_t self_id, uint32_t self_species,
                              const SpSet& spm, bool need_sp_filter, double t_last, uint32_t id_last, double t_limit,
-                             PartnerHit& best) {
+                             PartnerHit& best, const Group& grp) {
   const double movelen2 = dot3(disp, disp);
   const double rhs = movelen2 * (p.R * p.R);
   const int* bimol_row = p.bimol + self_species * p.n_species;
   int count = 0;
-  best.t = MCX_TIME_FOREVER; best.id = 0; best.slot = MCX_NONE;
+  best.t = MCX_TIME_FOREVER; best.id = 0; best.slot = MCX_NONE; best.species = 0; best.rxn_class = 0;
   // one candidate: collide_mol (collision_utils.inl:464-515) + eligibility + (time asc, id desc) selection
   auto consider = [&](const MolRec& c, uint32_t j) {
     double d;
@@ -634,15 +707,41 @@ __device__ int scan_partners(const DevParams& p, D3 pos, D3 disp, uint32_t self_
       best.t = t; best.id = c.id; best.slot = j; best.species = csp; best.rxn_class = rc;
     }
   };
-  CandWalk cw; cw.init(swept_cells(p, pos, disp));
-  bool has0, has1; uint32_t j0, j1;
-  // two candidates per trip, both record loads issued before any arithmetic (the walk is latency bound)
-  while (cw.step2(p, has0, j0, has1, j1)) {
-    if (!has0) continue;
-    const MolRec c0 = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j0) : load_rec(p.recA, j0);
-    const MolRec c1 = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j1) : load_rec(p.recA, j1);
-    consider(c0, j0);
-    if (has1) consider(c1, j1);
+  const int G = grp.G;
+  if (G == 1) {
+    CandWalk cw; cw.init(swept_cells(p, pos, disp));
+    bool has0, has1; uint32_t j0, j1;
+    // two candidates per trip, both record loads issued before any arithmetic (the walk is latency bound)
+    while (cw.step2(p, has0, j0, has1, j1)) {
+      if (!has0) continue;
+      const MolRec c0 = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j0) : load_rec(p.recA, j0);
+      const MolRec c1 = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j1) : load_rec(p.recA, j1);
+      consider(c0, j0);
+      if (has1) consider(c1, j1);
+    }
+    return count;
+  }
+  // the group deals the records of every cell row among its lanes (the order of the tests does not matter: the
+  // selection is a minimum over (time, -id) and the count a sum), then combines
+  const CellBox b = swept_cells(p, pos, disp);
+  for (int cz = b.cz0; cz <= b.cz1; cz++)
+    for (int cy = b.cy0; cy <= b.cy1; cy++) {
+      const uint32_t base = row_base(p, cy, cz);
+      const uint32_t j0 = __ldg(p.cs_cur + base + b.cx0), j1 = __ldg(p.cs_cur + base + b.cx1 + 1);
+      for (uint32_t j = j0 + (uint32_t)grp.sub; j < j1; j += G) {
+        const MolRec c = VOLATILE_SNAPSHOT ? load_rec_volatile(p.recA, j) : load_rec(p.recA, j);
+        consider(c, j);
+      }
+    }
+  for (int o = 1; o < G; o <<= 1) {
+    count += __shfl_xor_sync(grp.mask, count, o);
+    const double ot = __shfl_xor_sync(grp.mask, best.t, o);
+    const uint32_t oid = __shfl_xor_sync(grp.mask, best.id, o), oslot = __shfl_xor_sync(grp.mask, best.slot, o);
+    const uint32_t osp = __shfl_xor_sync(grp.mask, best.species, o);
+    const int orc = __shfl_xor_sync(grp.mask, best.rxn_class, o);
+    if (oslot != MCX_NONE && (best.slot == MCX_NONE || ot < best.t || (ot == best.t && oid > best.id))) {
+      best.t = ot; best.id = oid; best.slot = oslot; best.species = osp; best.rxn_class = orc;
+    }
   }
   return count;
 }
@@ -1131,10 +1230,11 @@ __device__ uint32_t ray_trace_surf(const DevParams& p, uint32_t wall_index, doub
 #define MCX_INTERNAL_NEEDS_DISK 1000
 // SURF == false compiles the surface-molecule code out (models without surface species: the launcher picks the
 // instantiation from DevParams::has_surf), which gives the registers back to the volume path.
+// grp: the lanes that evaluate this molecule together (Group above); all of them pass identical arguments.
 template <bool RETRY, bool WITH_DISK, bool SURF>
 __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t_sched, double t_unimol_in,
                                    uint32_t created_wall, uint32_t created_tile, SurfState ss, unsigned int epoch,
-                                   Stream& rs, bool forced, Outcome& out, LocalStats& ls, Tracer& tc, int& err) {
+                                   Stream& rs, bool forced, Outcome& out, LocalStats& ls, Tracer& tc, int& err, const Group& grp) {
   const uint32_t species = m.sf & SF_SPECIES_MASK;
   const DevSpecies sp = p.species[species];
   const double it = (double)p.iteration, t_end = it + 1;
@@ -1284,7 +1384,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
           bool hit = false, hit_in_last = false;
           WallHit wh;
           for (int k = 0; k < spw.n && !hit; k++) {
-            if (closest_wall_collision(p, pos, spw.v[k], last_hit_wall, rs, remaining, up_to_wall, wh, ls, tc)) {
+            if (closest_wall_collision(p, pos, spw.v[k], last_hit_wall, rs, remaining, up_to_wall, wh, ls, tc, grp)) {
               hit = true; hit_in_last = last_subpart == spw.v[k];
             }
           }
@@ -1312,7 +1412,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
             bool scanning = true;
             while (scanning) {
               PartnerHit ph;
-              int cnt = scan_partners<RETRY>(p, pos, remaining, m.id, species, spm, filter, t_last, id_last, t_limit, ph);
+              int cnt = scan_partners<RETRY>(p, pos, remaining, m.id, species, spm, filter, t_last, id_last, t_limit, ph, grp);
               if (cnt == 0) scanning = false;
               else {
                 t_last = ph.t; id_last = ph.id;

@@ -53,11 +53,12 @@ struct __align__(16) DevWall {
   double v0x, v0y, v0z;           // vertex 0
 };
 
+#define MCX_ROUNDS_MAX 32        // upper bound of mcx_config::max_resolve_rounds
 struct Counters {
   // population
   unsigned int n_slots;        // records in the current snapshot buffer (incl. tombstones/ghosts)
   unsigned int n_prod;         // products appended behind n_slots this iteration
-  unsigned int n_pend[2];      // pending-proposal list sizes (ping-pong)
+  unsigned int n_disk;         // molecules handed to the exact_disk launch of the generic pass (list in pend[1])
   unsigned int n_next;         // records binned for the next snapshot
   int error;                   // first MCX_ERR_* raised on the device
   unsigned int error_id;       // molecule id that raised it
@@ -74,6 +75,8 @@ struct Counters {
   unsigned long long species_count[256];
   unsigned long long species_next[256];  // multi-GPU: recount of owned molecules during the scatter
   unsigned long long rxn_count[256];
+  // conflict rounds: proposals entering round r (list pend[0]) and losers of round r (list pend[1])
+  unsigned int n_prop[MCX_ROUNDS_MAX + 1], n_lose[MCX_ROUNDS_MAX + 1];
 };
 #define MCX_MAX_CV 256
 #define MCX_FW_MARGIN 1e-6        // inflation of wall and query boxes of the fine wall grid, in length units

@@ -13,6 +13,7 @@
 // iteration needs no host round trip.
 #include <cstdlib>
 #include <cstdio>
+#include <cooperative_groups.h>
 #include "mcx_device.cuh"
 #include "mcx_tile.cuh"
 
@@ -285,9 +286,10 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
   }
 }
 
-// list < 0: the caller appends the slot to the pending list itself (WarpList)
+// n_list: counter of the proposal list (pend[0]) of the round the proposal joins; nullptr: the caller appends the slot
+// itself (WarpList)
 __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot, const Outcome& o, uint32_t id,
-                                               uint32_t species, unsigned int epoch, int list) {
+                                               uint32_t species, unsigned int epoch, unsigned int* n_list) {
   store_rec(p.recB, slot, o.pos, id, species | (o.flags & ~DF_DEAD));
   p.tschedB[slot] = o.t_now;
   p.tuniB[slot] = o.unimol_time;
@@ -303,9 +305,9 @@ __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot
     p.swallB[slot] = o.s_wall; p.stileB[slot] = o.s_tile; p.suvB[slot] = make_double2(o.s_u, o.s_v);
     atomicMax(&p.tile_claim[p.grids[o.s_wall].tile_start + o.s_tile], key);
   }
-  if (list >= 0) {
-    uint32_t k = agg_reserve(&p.ctr->n_pend[list], 1u);
-    p.pend[list][k] = slot;
+  if (n_list) {
+    uint32_t k = agg_reserve(n_list, 1u);
+    p.pend[0][k] = slot;
   }
 }
 
@@ -456,7 +458,7 @@ __device__ __forceinline__ void fast_molecule(const DevParams& p, FastCtx& cx, P
           Outcome o; o.kind = MCX_OUT_UNIMOL; o.pos = pos; o.rxn_class = rc; o.pathway = pathway; o.t_event = t_uni;
           o.t_now = t_now; o.flags = flags; o.unimol_time = t_uni; o.partner_slot = MCX_NONE; o.partner_id = MCX_NONE; o.orient_bits = 0;
           trace_end(tc, o, rs);
-          write_proposal(p, i, o, m.id, species, round_epoch(p, 0), -1);
+          write_proposal(p, i, o, m.id, species, round_epoch(p, 0), nullptr);
           proposed = true;
           if (own_start) { cx.msteps++; cx.n_tests += my_tests; cx.n_coll += my_coll; }
           running = false;
@@ -580,7 +582,7 @@ __device__ __forceinline__ void fast_molecule(const DevParams& p, FastCtx& cx, P
           if (o.kind == MCX_OUT_MOVED) {
             if (PASS == 1) { const double r = round(t_new); if (cmp_eq_d(t_new, r, MCX_SQRT_EPS)) t_new = r; }
             finalize_alive(p, i, dest, m.id, species, flags & ~DF_PARTIAL, t_new, t_uni);
-          } else { write_proposal(p, i, o, m.id, species, round_epoch(p, 0), -1); proposed = true; }
+          } else { write_proposal(p, i, o, m.id, species, round_epoch(p, 0), nullptr); proposed = true; }
           if (own_start) { cx.msteps++; cx.n_tests += my_tests; cx.n_coll += my_coll; }
           running = false;
         }
@@ -603,7 +605,7 @@ __device__ __forceinline__ void fast_molecule(const DevParams& p, FastCtx& cx, P
     // staged appends (loop bounds are warp-uniform: all 32 lanes arrive here)
     if (slow) atomicAdd(&cx.reason_row[reason & 7], 1u);
     cx.slow_wl.push(slow, i, cx.n_slow_ctr, cx.slow_out);
-    cx.prop_wl.push(proposed, i, &p.ctr->n_pend[0], p.pend[0]);
+    cx.prop_wl.push(proposed, i, &p.ctr->n_prop[0], p.pend[0]);
     if (PASS == 0) cx.second_wl.push(to_second, i, &p.ctr->n_second, p.second_list);
 }
 
@@ -611,7 +613,7 @@ __device__ __forceinline__ void fast_molecule(const DevParams& p, FastCtx& cx, P
 template <int PASS>
 __device__ __forceinline__ void fast_finish(const DevParams& p, FastCtx& cx, int lane) {
   cx.slow_wl.flush(cx.n_slow_ctr, cx.slow_out);
-  cx.prop_wl.flush(&p.ctr->n_pend[0], p.pend[0]);
+  cx.prop_wl.flush(&p.ctr->n_prop[0], p.pend[0]);
   if (PASS == 0) cx.second_wl.flush(&p.ctr->n_second, p.second_list);
   __syncwarp();
   if (lane == 0 && cx.slow_wl.total) atomicAdd(&p.ctr->deferred, (unsigned long long)cx.slow_wl.total);
@@ -626,6 +628,8 @@ __global__ void __launch_bounds__(TPB, MCX_FAST_MINBLOCKS) k_diffuse_fast(const 
   __shared__ uint32_t s_slow[TPB / 32][WL_CAP], s_prop[TPB / 32][WL_CAP], s_second[PASS == 0 ? TPB / 32 : 1][WL_CAP];
   __shared__ unsigned int s_reason[TPB / 32][8];
   __shared__ WarpProbe s_probe[TPB / 32];
+  // an empty launch costs its blocks nothing but this test (small models are launch bound: profiles/r02_i_configs)
+  if ((PASS == 0 ? p.ctr->n_slots : p.ctr->n_second) <= blockIdx.x * blockDim.x) return;
   zig_load(&zig);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane < 8) s_reason[warp][lane] = 0;
@@ -764,46 +768,56 @@ void mcx_plan_tiles(DevParams& p, unsigned long long n_records) {
   p.tile = g;
 }
 
-// The generic evaluation is one long divergent path per molecule: a warp of 32 different molecules runs close to 32
-// evaluations back to back (2.4 of 32 lanes active on the mesh configs, profiles/r01_p).  When a launch has fewer
-// molecules than the machine has threads, spreading them out — one molecule per 2, 4 or 8 lanes, the other lanes
-// idle — shortens every warp's serial chain by that factor at no cost (the launch is latency bound, SMs are idle).
-__device__ __forceinline__ unsigned int lanes_per_molecule(unsigned int n) {
-  const unsigned long long threads = (unsigned long long)gridDim.x * blockDim.x;
-  unsigned int lpm = 1;
-  while (lpm < 8 && (unsigned long long)n * (lpm * 2) <= threads) lpm *= 2;
-  return lpm;
-}
-
-// k_diffuse_slow: the generic evaluation (evaluate_iteration) for the slots k_diffuse_fast deferred.
-// WITH_DISK == false reads slow_list and hands the few molecules whose collision disk is cut by a wall on to the
-// WITH_DISK == true launch through pend[1] (free until the conflict rounds start).
+// The generic evaluation is one long path per molecule.  A group of G lanes evaluates one molecule together (Group,
+// mcx_device.cuh): identical control flow on all of them, the wall lists and candidate records dealt among them, lane 0
+// of the group writes the result.  G is chosen per launch: as many lanes per molecule as the launch has threads for —
+// big lists keep one molecule per lane (the redundant part of a group's work would cost throughput there: 1e8
+// molecules, 5.7e5 deferred: 4.0 ms with G = 1, 6.4 ms with G = 8, profiles/r02_k), short lists get short chains.
 #ifndef MCX_SLOW_MINBLOCKS
 #define MCX_SLOW_MINBLOCKS 4
 #endif
+#ifndef MCX_GROUP_FILL
+#define MCX_GROUP_FILL 1   // lanes per molecule are doubled while n * G <= MCX_GROUP_FILL * threads of the launch
+#endif
+__device__ __forceinline__ int lanes_per_molecule(unsigned int n) {
+  const unsigned long long threads = (unsigned long long)gridDim.x * blockDim.x * MCX_GROUP_FILL;
+  int g = 1;
+  while (g < 8 && (unsigned long long)n * (g * 2) <= threads) g *= 2;
+  return g;
+}
+
 template <bool WITH_DISK, bool SURF>
 __global__ void __launch_bounds__(TPB, MCX_SLOW_MINBLOCKS) k_diffuse_slow(const __grid_constant__ DevParams p, int second) {
   __shared__ ZigShared zig;
+  // second: the deferrals of k_diffuse_fast<1> instead of those of k_diffuse_fast<0>
+  const unsigned int n = WITH_DISK ? p.ctr->n_disk : (second ? p.ctr->n_slow2 : p.ctr->n_slow);
+  if (n == 0) return;
   zig_load(&zig);
   __syncthreads();
-  // second: the deferrals of k_diffuse_fast<1> instead of those of k_diffuse_fast<0>
-  const unsigned int n = WITH_DISK ? p.ctr->n_pend[1] : (second ? p.ctr->n_slow2 : p.ctr->n_slow);
   const uint32_t* list = WITH_DISK ? p.pend[1] : (second ? p.slow2_list : p.slow_list);
   const unsigned int epoch = round_epoch(p, 0);
   LocalStats ls = {0, 0, 0, 0, 0, 0};
   unsigned int msteps = 0;
+  const int G = lanes_per_molecule(n);
+  const Group grp = group_of(G);
+  const bool lead = grp.sub == 0;
   // all lanes of a warp iterate together so the warp-level stat flush sees full warps
-  const unsigned int lpm = lanes_per_molecule(n);
-  for (unsigned int base = blockIdx.x * blockDim.x; base < n * lpm; base += gridDim.x * blockDim.x) {
-    const unsigned int t = base + threadIdx.x, k = t / lpm;
-    if (t % lpm != 0 || k >= n) continue;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < (unsigned long long)n * G;
+       base += (unsigned long long)gridDim.x * blockDim.x) {
+    unsigned long long k = (base + threadIdx.x) / G;
+    if (k >= n) continue;  // whole groups leave together
+    // the list is in snapshot order: neighbours in space — the long evaluations next to a complicated piece of mesh —
+    // sit in the same warp, which then runs them back to back; a stride permutation spreads them over the launch
+    // (config 4: 6.40 -> 6.08 ms for the generic launches, profiles/r02_o)
+    if (G == 1) { const unsigned long long P = (n % 1000003ull) ? 1000003ull : 999983ull; k = (k * P) % n; }
     const unsigned int i = list[k];
     MolRec m = load_rec(p.recA, i);
     const uint32_t species = m.sf & SF_SPECIES_MASK;
     double t_sched = (m.sf & DF_PARTIAL) ? p.tschedA[i] : 0.0;
     double t_uni = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;
     Stream rs; rs.init(p, m.id, &zig);
-    Tracer tc; trace_begin(p, tc, m.id);
+    Tracer tc; tc.h = 0xcbf29ce484222325ULL; tc.tr = nullptr;
+    if (lead) trace_begin(p, tc, m.id);
     Outcome o; int err = 0;
     const bool own_start = owned_z(p, m.z);
     LocalStats mls = {0, 0, 0, 0, 0, 0};  // statistics of redundantly evaluated halo molecules are not counted
@@ -811,10 +825,11 @@ __global__ void __launch_bounds__(TPB, MCX_SLOW_MINBLOCKS) k_diffuse_slow(const 
     SurfState ss = {MCX_NONE, MCX_NONE, 0.0, 0.0};
     if (SURF && (m.sf & DF_SURF)) { const double2 uv = p.suvA[i]; ss.wall = p.swallA[i]; ss.tile = p.stileA[i]; ss.u = uv.x; ss.v = uv.y; }
     evaluate_iteration<false, WITH_DISK, SURF>(p, m, t_sched, t_uni, (SURF && guard) ? p.swallA[i] : MCX_NONE,
-                                               (SURF && guard) ? p.stileA[i] : MCX_NONE, ss, epoch, rs, false, o, mls, tc, err);
+                                               (SURF && guard) ? p.stileA[i] : MCX_NONE, ss, epoch, rs, false, o, mls, tc, err, grp);
+    if (!lead) continue;
     if (!WITH_DISK && err == MCX_INTERNAL_NEEDS_DISK) {  // re-evaluated from scratch by the WITH_DISK launch
       if (tc.tr) tc.tr->rounds--;
-      p.pend[1][agg_reserve(&p.ctr->n_pend[1], 1u)] = i;
+      p.pend[1][agg_reserve(&p.ctr->n_disk, 1u)] = i;
       continue;
     }
     if (own_start) {
@@ -827,71 +842,72 @@ __global__ void __launch_bounds__(TPB, MCX_SLOW_MINBLOCKS) k_diffuse_slow(const 
     if (err && (own_start || err != MCX_ERR_ESCAPED)) raise_error(p, err, m.id);
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time, &o);
     else if (o.kind == MCX_OUT_NONE) p.rank[i] = MCX_NONE;
-    else write_proposal(p, i, o, m.id, species, epoch, 0);
+    else write_proposal(p, i, o, m.id, species, epoch, &p.ctr->n_prop[0]);
   }
   flush_stats(p, ls, msteps);
 }
 
-// round r: decide every pending proposal on the claims as they stand
-__global__ void __launch_bounds__(TPB) k_resolve(const __grid_constant__ DevParams p, unsigned int round) {
-  __shared__ BlockTally tally;
-  tally_clear(&tally);
-  const int cur = 0, nxt = 1;  // list 0: proposals, list 1: rejected
-  const unsigned int n = p.ctr->n_pend[cur];
+// Conflict rounds.  Round r decides the proposals of list 0 (n_prop[r] entries) on the claims as they stand: winners
+// commit, losers go to list 1 (n_lose[r]); the losers are re-evaluated against the updated DEAD flags and their new
+// proposals form list 0 of round r + 1 (n_prop[r + 1]).  Every round has its own two counters, so nothing has to be
+// reset between the phases (the four launches per round of round 1 became two phases of one kernel).
+__device__ __forceinline__ void resolve_round(const DevParams& p, unsigned int round, BlockTally* tally) {
+  tally_clear(tally);
+  const unsigned int n = *(volatile unsigned int*)&p.ctr->n_prop[round];
   const unsigned int epoch = round_epoch(p, round);
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    uint32_t slot = p.pend[cur][k];
+    uint32_t slot = __ldcg(p.pend[0] + k);
     MolRec e = load_rec_volatile(p.recB, slot);  // event position + identity
     uint32_t species = e.sf & SF_SPECIES_MASK;
-    uint32_t info = p.prop_info[slot];
+    uint32_t info = __ldcg(p.prop_info + slot);
     int kind = info & 15, pathway = (info >> 4) & 0xFF, rxn_class = info >> 16;
     const uint32_t orient_bits = (info >> 12) & 0xFu;
-    uint32_t partner = p.prop_partner[slot];
+    uint32_t partner = __ldcg(p.prop_partner + slot);
     unsigned long long key = claim_key(epoch, e.id);
-    bool ok = p.claim[slot] == key;
-    if (ok && partner_is_consumed(p, kind, rxn_class, pathway, species)) ok = p.claim[partner] == key;
-    if (ok && kind == MCX_OUT_SURFMOVE) ok = p.tile_claim[p.grids[p.swallB[slot]].tile_start + p.stileB[slot]] == key;
+    bool ok = __ldcg(p.claim + slot) == key;
+    if (ok && partner_is_consumed(p, kind, rxn_class, pathway, species)) ok = __ldcg(p.claim + partner) == key;
+    if (ok && kind == MCX_OUT_SURFMOVE) ok = __ldcg(p.tile_claim + p.grids[__ldcg(p.swallB + slot)].tile_start + __ldcg(p.stileB + slot)) == key;
     if (ok) {
-      commit_event(p, slot, kind, rxn_class, pathway, partner, p.prop_t[slot], D3{e.x, e.y, e.z}, e.id, species,
-                   e.sf & ~SF_SPECIES_MASK, p.tschedB[slot], p.tuniB[slot], orient_bits, &tally);
+      commit_event(p, slot, kind, rxn_class, pathway, partner, __ldcg(p.prop_t + slot), D3{e.x, e.y, e.z}, e.id, species,
+                   e.sf & ~SF_SPECIES_MASK, __ldcg(p.tschedB + slot), __ldcg(p.tuniB + slot), orient_bits, tally);
     } else {
-      uint32_t q = agg_reserve(&p.ctr->n_pend[nxt], 1u);
-      p.pend[nxt][q] = slot;
+      uint32_t q = agg_reserve(&p.ctr->n_lose[round], 1u);
+      p.pend[1][q] = slot;
     }
   }
-  tally_flush(&tally, p.ctr);
+  tally_flush(tally, p.ctr);
 }
 
-// losers of round r are re-evaluated against the updated snapshot flags; their new proposals go back
-// to list `cur` for round r+1
 template <bool SURF>
-__global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevParams p, unsigned int round, int forced) {
-  __shared__ ZigShared zig;
-  zig_load(&zig);
-  __syncthreads();
-  const int cur = 0, nxt = 1;
-  const unsigned int n = p.ctr->n_pend[nxt];
+__device__ __forceinline__ void retry_round(const DevParams& p, unsigned int round, int forced, const ZigShared* zig) {
+  const unsigned int n = *(volatile unsigned int*)&p.ctr->n_lose[round];
   const unsigned int epoch = round_epoch(p, round + 1);
   LocalStats ls = {0, 0, 0, 0, 0, 0};
-  const unsigned int lpm = lanes_per_molecule(n);
-  for (unsigned int base = blockIdx.x * blockDim.x; base < n * lpm; base += gridDim.x * blockDim.x) {
-    const unsigned int t = base + threadIdx.x, k = t / lpm;
-    if (t % lpm != 0 || k >= n) continue;
-    uint32_t i = p.pend[nxt][k];
+  const int G = lanes_per_molecule(n);
+  const Group grp = group_of(G);
+  const bool lead = grp.sub == 0;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < (unsigned long long)n * G;
+       base += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long k = (base + threadIdx.x) / G;
+    if (k >= n) continue;  // whole groups leave together
+    uint32_t i = __ldcg(p.pend[1] + k);
     MolRec m = load_rec_volatile(p.recA, i);
     if (m.sf & DF_DEAD) {  // consumed as somebody's partner in this round
-      p.rank[i] = MCX_NONE;
-      if (p.trace && m.id < p.n_trace) p.trace[m.id].outcome = MCX_OUT_CONSUMED;
+      if (lead) {
+        p.rank[i] = MCX_NONE;
+        if (p.trace && m.id < p.n_trace) p.trace[m.id].outcome = MCX_OUT_CONSUMED;
+      }
       continue;
     }
     const bool own_start = owned_z(p, m.z);  // statistics of redundantly evaluated halo molecules are not counted
-    if (own_start) agg_add(&p.ctr->retries, 1u);
-    if (forced && own_start) agg_add(&p.ctr->unresolved, 1u);
+    if (lead && own_start) agg_add(&p.ctr->retries, 1u);
+    if (lead && forced && own_start) agg_add(&p.ctr->unresolved, 1u);
     const uint32_t species = m.sf & SF_SPECIES_MASK;
     double t_sched = (m.sf & DF_PARTIAL) ? p.tschedA[i] : 0.0;
     double t_uni = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;
-    Stream rs; rs.init(p, m.id, &zig);
-    Tracer tc; trace_begin(p, tc, m.id);
+    Stream rs; rs.init(p, m.id, zig);
+    Tracer tc; tc.h = 0xcbf29ce484222325ULL; tc.tr = nullptr;
+    if (lead) trace_begin(p, tc, m.id);
     Outcome o; int err = 0;
     LocalStats halo_ls = {0, 0, 0, 0, 0, 0};
     const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
@@ -899,7 +915,8 @@ __global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevPar
     if (SURF && (m.sf & DF_SURF)) { const double2 uv = p.suvA[i]; ss.wall = p.swallA[i]; ss.tile = p.stileA[i]; ss.u = uv.x; ss.v = uv.y; }
     evaluate_iteration<true, true, SURF>(p, m, t_sched, t_uni, (SURF && guard) ? p.swallA[i] : MCX_NONE,
                                          (SURF && guard) ? p.stileA[i] : MCX_NONE, ss, epoch, rs, forced != 0, o,
-                                         own_start ? ls : halo_ls, tc, err);
+                                         (own_start && lead) ? ls : halo_ls, tc, err, grp);
+    if (!lead) continue;
     trace_end(tc, o, rs);
     if (err) raise_error(p, err, m.id);
     if (o.kind == MCX_OUT_MOVED || o.kind == MCX_OUT_STATIC) finalize_alive(p, i, o.pos, m.id, species, o.flags, o.t_now, o.unimol_time, &o);
@@ -908,18 +925,39 @@ __global__ void __launch_bounds__(TPB, 2) k_retry(const __grid_constant__ DevPar
       p.rank[i] = MCX_NONE;
       commit_event(p, i, o.kind, o.rxn_class, o.pathway, o.partner_slot, o.t_event, o.pos, m.id, species, o.flags, o.t_now,
                    o.unimol_time, o.orient_bits);
-    } else write_proposal(p, i, o, m.id, species, epoch, cur);
+    } else write_proposal(p, i, o, m.id, species, epoch, &p.ctr->n_prop[round + 1]);
   }
   flush_stats(p, ls, 0);
 }
 
-__global__ void k_round_begin(const __grid_constant__ DevParams p, unsigned int round) {
-  // before k_resolve(round): the list it fills (nxt) must be empty
-  p.ctr->n_pend[1] = 0;
+// round 0 holds ~99 % of the proposals (1.3e6 at 1e8 molecules): its own launch with a grid sized for them
+__global__ void __launch_bounds__(TPB) k_resolve0(const __grid_constant__ DevParams p) {
+  __shared__ BlockTally tally;
+  if (p.ctr->n_prop[0] <= blockIdx.x * blockDim.x) return;
+  resolve_round(p, 0, &tally);
 }
-__global__ void k_round_mid(const __grid_constant__ DevParams p, unsigned int round) {
-  // before k_retry(round): list cur was consumed by k_resolve and is refilled by k_retry
-  p.ctr->n_pend[0] = 0;
+// everything after it in ONE cooperative launch: retry(r), grid barrier, resolve(r + 1), grid barrier, ... until a
+// round leaves no losers — the launches of an iteration no longer depend on max_resolve_rounds and an iteration
+// without conflicts pays one nearly empty kernel (32 launches of mostly empty kernels before, profiles/r02_a_launches)
+template <bool SURF>
+__global__ void __launch_bounds__(TPB, 2) k_rounds(const __grid_constant__ DevParams p) {
+  __shared__ ZigShared zig;
+  __shared__ BlockTally tally;
+  if (*(volatile unsigned int*)&p.ctr->n_lose[0] == 0) return;  // no conflicts at all: every block leaves at once
+  zig_load(&zig);
+  __syncthreads();
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  for (unsigned int r = 0; r < p.max_rounds; r++) {
+    if (*(volatile unsigned int*)&p.ctr->n_lose[r] == 0) break;  // same value in every block: final since the last barrier
+    retry_round<SURF>(p, r, r + 1 == p.max_rounds ? 1 : 0, &zig);
+    if (r + 1 == p.max_rounds) break;
+    __threadfence();
+    grid.sync();
+    if (*(volatile unsigned int*)&p.ctr->n_prop[r + 1] == 0) break;
+    resolve_round(p, r + 1, &tally);
+    __threadfence();
+    grid.sync();
+  }
 }
 
 // ---- exclusive scan of the cell histogram (3 phases, 4096 cells per block) ---------------------------
@@ -1028,8 +1066,9 @@ __global__ void k_end_iteration(const __grid_constant__ DevParams p) {
   Counters* c = p.ctr;
   if (threadIdx.x == 0) {
     c->n_slots = c->n_next;
-    c->n_prod = 0; c->n_pend[0] = 0; c->n_pend[1] = 0; c->n_slow = 0; c->n_second = 0; c->n_slow2 = 0; c->n_send[0] = 0; c->n_send[1] = 0;
+    c->n_prod = 0; c->n_disk = 0; c->n_slow = 0; c->n_second = 0; c->n_slow2 = 0; c->n_send[0] = 0; c->n_send[1] = 0;
   }
+  if (threadIdx.x <= MCX_ROUNDS_MAX) { c->n_prop[threadIdx.x] = 0; c->n_lose[threadIdx.x] = 0; }
   if (p.world > 1) { c->species_count[threadIdx.x] = c->species_next[threadIdx.x]; c->species_next[threadIdx.x] = 0; }
 }
 
@@ -1037,10 +1076,11 @@ __global__ void k_end_iteration(const __grid_constant__ DevParams p) {
 __global__ void k_reset_population(const __grid_constant__ DevParams p, unsigned int n_slots) {
   Counters* c = p.ctr;
   if (threadIdx.x == 0) {
-    c->n_slots = n_slots; c->n_prod = 0; c->n_pend[0] = 0; c->n_pend[1] = 0; c->n_next = 0; c->error = 0; c->error_id = 0;
+    c->n_slots = n_slots; c->n_prod = 0; c->n_disk = 0; c->n_next = 0; c->error = 0; c->error_id = 0;
     c->n_emigrants[0] = 0; c->n_emigrants[1] = 0; c->n_slow = 0; c->n_send[0] = 0; c->n_send[1] = 0; c->n_second = 0; c->n_slow2 = 0;
   }
   c->species_count[threadIdx.x] = 0; c->species_next[threadIdx.x] = 0;
+  if (threadIdx.x <= MCX_ROUNDS_MAX) { c->n_prop[threadIdx.x] = 0; c->n_lose[threadIdx.x] = 0; }
 }
 void mcx_launch_reset_population(const DevParams& p, unsigned int n_slots, cudaStream_t s) { k_reset_population<<<1, 256, 0, s>>>(p, n_slots); }
 
@@ -1430,15 +1470,12 @@ void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t 
   if (plan.prof) cudaEventRecord(plan.prof[1], s);
   count_launches(plan, 5);
   if (plan.has_claims) {
-    count_launches(plan, 4 * p.max_rounds);
-    const int small_grid = plan.sm_count * 2;
-    for (unsigned int r = 0; r < p.max_rounds; r++) {
-      k_round_begin<<<1, 1, 0, s>>>(p, r);
-      k_resolve<<<r == 0 ? 2 * small_grid : small_grid, TPB, 0, s>>>(p, r);  // round 0 holds ~99 % of the proposals
-      k_round_mid<<<1, 1, 0, s>>>(p, r);
-      if (p.has_surf) k_retry<true><<<small_grid, TPB, 0, s>>>(p, r, r + 1 == p.max_rounds ? 1 : 0);
-      else k_retry<false><<<small_grid, TPB, 0, s>>>(p, r, r + 1 == p.max_rounds ? 1 : 0);
-    }
+    count_launches(plan, 2);
+    k_resolve0<<<plan.sm_count * 8, TPB, 0, s>>>(p);
+    // cooperative launch: all blocks resident (two per multiprocessor, the kernel's launch bounds)
+    void* args[] = {(void*)&p};
+    if (p.has_surf) cudaLaunchCooperativeKernel((const void*)k_rounds<true>, dim3(plan.sm_count * 2), dim3(TPB), args, 0, s);
+    else cudaLaunchCooperativeKernel((const void*)k_rounds<false>, dim3(plan.sm_count * 2), dim3(TPB), args, 0, s);
   }
   if (plan.prof) cudaEventRecord(plan.prof[2], s);
 }
