@@ -347,6 +347,13 @@ int mcx_comm_unique_id(void* out, uint32_t bytes);
 /* Surface grid of one triangle for host-side placement of surface molecules (release stays on the host):
  * v9 = three vertices; returns num_tiles = ceil(sqrt(area))^2 (Grid::initialize, src4/wall.cpp:38-74). */
 uint32_t mcx_grid_num_tiles(const double* v9);
+/* The subpartition wall lists the device walks, built exactly as mcx_set_geometry builds them (host only): CSR over the
+ * n^3 subpartitions, start_out[n^3 + 1], ascending wall indices in list_out (up to cap entries); returns the number of
+ * entries.  Replaces Partition::finalize_walls -> GeometryUtils::wall_subparts_collision_test -> WallUtils::wall_in_box
+ * (src4/partition.cpp:91-118, geometry_utils.inl:110-207, wall_utils.inl:326-504). */
+uint64_t mcx_walls_per_subpart(const double* origin3, double partition_edge_length, uint32_t n_subparts_per_edge,
+                               double rxn_radius_3d, uint32_t use_expanded_list, const double* vertices, uint64_t n_vertices,
+                               const uint32_t* tri, uint64_t n_walls, uint32_t* start_out, uint32_t* list_out, uint64_t cap);
 /* Centre of a tile in the wall's uv frame (GridUtils::grid2uv, src4/grid_utils.inl:233-253). */
 void mcx_grid2uv(const double* v9, uint32_t tile, double* uv2);
 /* Tile under a point of the wall (GridUtils::xyz2grid_tile_index, src4/grid_utils.inl:48-118). */

@@ -98,6 +98,20 @@ int mcx_abi_version(void) { return MCX_ABI_VERSION; }
 uint32_t mcx_grid_num_tiles(const double* v9) { return mcxg::tri_num_tiles(v9); }
 void mcx_grid2uv(const double* v9, uint32_t tile, double* uv2) { mcxg::tri_grid2uv(v9, tile, uv2); }
 uint32_t mcx_xyz2grid(const double* v9, const double* xyz3) { return mcxg::tri_xyz2grid(v9, xyz3); }
+uint64_t mcx_walls_per_subpart(const double* origin3, double partition_edge_length, uint32_t n_subparts_per_edge,
+                               double rxn_radius_3d, uint32_t use_expanded_list, const double* vertices, uint64_t n_vertices,
+                               const uint32_t* tri, uint64_t n_walls, uint32_t* start_out, uint32_t* list_out, uint64_t cap) {
+  (void)n_vertices;
+  std::vector<DevWall> walls;
+  mcxg::wall_constants(vertices, tri, n_walls, walls);
+  const double sp_len = partition_edge_length / n_subparts_per_edge;
+  mcxg::GridSpec g{origin3[0], origin3[1], origin3[2], sp_len, 1.0 / sp_len, rxn_radius_3d, (int)n_subparts_per_edge, use_expanded_list != 0};
+  std::vector<uint32_t> start, list;
+  mcxg::bin_walls(g, vertices, tri, walls, start, list);
+  for (size_t i = 0; i < start.size(); i++) start_out[i] = start[i];
+  for (size_t i = 0; i < list.size() && i < cap; i++) list_out[i] = list[i];
+  return list.size();
+}
 
 const char* mcx_last_error(const mcx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 

@@ -790,6 +790,25 @@ static ProductSpec product_spec(const World& w, const mcx_rxn_class& c, const mc
 }
 
 // ---- the evaluation context ---------------------------------------------------------------
+// pick_surf_displacement (diffusion_utils.inl:60-96): Marsaglia polar method on one 32-bit word
+static inline void pick_surf_displacement(WordSource& rs, double scale, double& du, double& dv) {
+  double au, av, f;
+  do {
+    uint32_t n = rs.next();
+    au = 2 * 1.52587890625e-5 * (n & 0xFFFF) - 1;
+    av = 2 * 1.52587890625e-5 * (n >> 16) - 1;
+    f = au * au + av * av;
+  } while ((f < POS_EPS) || (f > 1));
+  const double normal_factor = sqrt(-log(f) / f);
+  du = au * (normal_factor * scale); dv = av * (normal_factor * scale);
+}
+
+// the displacement left after a reflection, CollisionUtils::reflect_from_wall (collision_utils.inl:1735-1744)
+static inline V3 reflected_displacement(V3 displacement, V3 normal, double t_reflect) {
+  const double reflect_factor = -2.0 * dot(displacement, normal);
+  return (displacement + normal * reflect_factor) * (1.0 - t_reflect);
+}
+
 struct Eval {
   World& w;
   WordSource& rs;
@@ -1209,16 +1228,8 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
       return true;
     };
     for (int find_new_position = 11; find_new_position > 0; find_new_position--) {  // SURFACE_DIFFUSION_RETRIES + 1
-      // pick_surf_displacement (diffusion_utils.inl:60-96): Marsaglia polar method on one 32-bit word
-      double au, av, f;
-      do {
-        uint32_t n = E.rs.next();
-        au = 2 * 1.52587890625e-5 * (n & 0xFFFF) - 1;
-        av = 2 * 1.52587890625e-5 * (n >> 16) - 1;
-        f = au * au + av * av;
-      } while ((f < POS_EPS) || (f > 1));
-      const double normal_factor = sqrt(-log(f) / f);
-      const double du = au * (normal_factor * space_factor), dv = av * (normal_factor * space_factor);
+      double du, dv;
+      pick_surf_displacement(E.rs, space_factor, du, dv);
       double nu, nv;
       uint32_t new_wall = ray_trace_surf(w, s.wall, s.u, s.v, du, dv, nu, nv);
       if (new_wall == MCX_NONE) continue;  // ambiguous edge hit: try again
@@ -1390,8 +1401,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
             s.pos = c.pos; s.subpart = w.subpart_index(s.pos);
             t_steps *= (1.0 - c.time);
             last_hit_wall = c.wall;
-            double reflect_factor = -2.0 * dot(remaining, wall.normal);
-            remaining = (remaining + wall.normal * reflect_factor) * (1.0 - c.time);
+            remaining = reflected_displacement(remaining, wall.normal, c.time);
           }
           break;  // exactly one wall per trace, then re-trace (:566)
         }
@@ -2208,6 +2218,40 @@ int orc_unit_collide_wall(const double* point3, double* move3, const double* v9,
   *t = tt; hit3[0] = hit.x; hit3[1] = hit.y; hit3[2] = hit.z;
   *words_used = rs.used;
   return r == WALL_MISS ? 0 : r == WALL_FRONT ? 1 : r == WALL_BACK ? 2 : -1;
+}
+// get_closest_wall_collision over a whole mesh held by ONE subpartition, then reflect_from_wall (collision_utils.inl:
+// 819-914, 1711-1747); same outputs as oracle/ref_mcell4_leaf_shim.cpp: ref4_closest_wall_and_reflect
+int orc_unit_closest_wall_and_reflect(const double* verts, unsigned n_verts, const unsigned* tri, unsigned n_walls,
+                                      const double* pos3, double* move3, unsigned last_hit_wall, const uint32_t* words,
+                                      uint64_t n_words, unsigned* wall, int* side, double* t, double* hit3, double* pos_after3,
+                                      double* disp_after3, double* t_steps_io, long long* words_used,
+                                      unsigned long long* ray_polygon_tests) {
+  World w; unit_mesh(w, verts, n_verts, tri, n_walls);
+  w.walls_per_subpart.assign(1, {});
+  for (unsigned i = 0; i < n_walls; i++) w.walls_per_subpart[0].push_back(i);
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  Eval E(w, rs);
+  V3 disp = {move3[0], move3[1], move3[2]}, up_to_wall = {0, 0, 0};
+  const V3 pos = {pos3[0], pos3[1], pos3[2]};
+  Collision c;
+  const bool found = E.closest_wall_collision(pos, 0, last_hit_wall, disp, up_to_wall, c);
+  move3[0] = disp.x; move3[1] = disp.y; move3[2] = disp.z;
+  *words_used = rs.used;
+  *ray_polygon_tests = w.stats.ray_polygon_tests;
+  if (!found) return 0;
+  *wall = c.wall; *side = c.type == COLL_WALL_FRONT ? 1 : 2; *t = c.time;
+  hit3[0] = c.pos.x; hit3[1] = c.pos.y; hit3[2] = c.pos.z;
+  *t_steps_io *= (1.0 - c.time);
+  const V3 after = reflected_displacement(disp, w.walls[c.wall].normal, c.time);
+  pos_after3[0] = c.pos.x; pos_after3[1] = c.pos.y; pos_after3[2] = c.pos.z;
+  disp_after3[0] = after.x; disp_after3[1] = after.y; disp_after3[2] = after.z;
+  return 1;
+}
+// pick_surf_displacement on a tape of words; returns the words drawn
+long long orc_unit_pick_surf_displacement(double scale, const uint32_t* words, uint64_t n_words, double* out2) {
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  pick_surf_displacement(rs, scale, out2[0], out2[1]);
+  return (long long)rs.used;
 }
 // returns COLLIDE_VOL_M (3) on hit, COLLIDE_MISS (0) otherwise
 int orc_unit_collide_mol(const double* point3, const double* move3, const double* target3, double R, double* t,

@@ -279,6 +279,52 @@ def ref_mcell4_lib():
     return L
 
 
+_CWR_ARGS = None
+
+
+def ref_mcell4_leaf_lib():
+    """MCell4's own collide_mol / jump_away_line / collide_wall / get_closest_wall_collision / reflect_from_wall and
+    Wall::initialize_wall_constants compiled unmodified into oracle/_ref/libmcell4leaf.so (oracle/ref_mcell4_leaf_shim.cpp);
+    None where it is absent."""
+    path = os.path.join(_HERE, "_ref", "libmcell4leaf.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref4_collide_wall.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref4_collide_mol.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    L.ref4_wall_constants.argtypes = [C.c_void_p, C.c_void_p]
+    return L
+
+
+def _cwr(fn, mesh, pos, move, last, tail_args):
+    """common driver of ref4_closest_wall_and_reflect / orc_unit_closest_wall_and_reflect -> 19 numbers:
+    found, wall, side, t, hit(3), pos_after(3), disp_after(3), t_steps, move_out(3), words, ray_polygon_tests"""
+    v, f = mesh
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    move = np.ascontiguousarray(move, np.float64).copy()
+    pos = np.ascontiguousarray(pos, np.float64)
+    wall, side, t = C.c_uint(0), C.c_int(0), C.c_double(0)
+    hit, pa, da = np.zeros(3), np.zeros(3), np.zeros(3)
+    ts, used, tests = C.c_double(1.0), C.c_longlong(0), C.c_ulonglong(0)
+    found = fn(vp(v), C.c_uint(len(v)), vp(f), C.c_uint(len(f)), vp(pos), vp(move), C.c_uint(last), *tail_args,
+               C.byref(wall), C.byref(side), C.byref(t), vp(hit), vp(pa), vp(da), C.byref(ts), C.byref(used), C.byref(tests))
+    if not found:
+        return [0.0] + [0.0] * 12 + [1.0] + list(move) + [float(used.value), float(tests.value)]
+    return [1.0, float(wall.value), float(side.value), t.value] + list(hit) + list(pa) + list(da) + [ts.value] + list(move) + \
+           [float(used.value), float(tests.value)]
+
+
+def ref4_closest_wall_and_reflect(L, mesh, pos, move, last, seed, skip):
+    L.ref4_closest_wall_and_reflect.restype = C.c_int
+    return _cwr(L.ref4_closest_wall_and_reflect, mesh, pos, move, last, (C.c_uint(seed), C.c_uint(skip)))
+
+
+def orc_closest_wall_and_reflect(mesh, pos, move, last, words):
+    L = lib()
+    L.orc_unit_closest_wall_and_reflect.restype = C.c_int
+    return _cwr(L.orc_unit_closest_wall_and_reflect, mesh, pos, move, last, (C.c_void_p(words.ctypes.data), C.c_uint64(len(words))))
+
+
 def _collect(fn, grid, pos, disp, for_mols, for_walls, cap):
     origin, edge, n, expanded, radius = grid
     o = np.ascontiguousarray(origin, np.float64)
