@@ -125,6 +125,8 @@ static void set_cell_count(DevParams& p) {
   p.nby = (p.ncy + B - 1) / B;
   const int nbz = (p.ncz + B - 1) / B;
   p.n_cells = (unsigned int)((size_t)p.ncx * ((size_t)p.nby * B) * ((size_t)nbz * B));
+  p.grp_x = (unsigned int)((p.ncx + 15) / 16);
+  p.n_groups = (unsigned int)((size_t)p.n_cells / (size_t)p.ncx * p.grp_x);
 }
 
 int mcx_create(const mcx_config* cfg, mcx_handle** out) {
@@ -205,7 +207,9 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   p.ncx = (int)std::ceil((hi[0] - p.cgx) / ex) + 1;
   p.ncy = (int)std::ceil((hi[1] - p.cgy) / ey) + 1;
   p.ncz = (int)std::ceil((hi[2] - p.cgz) / ez) + 1;
-  p.rb_log2 = 3;
+  // plain (y, z) row order: blocks of rows bought nothing (profiles/r02_g) and the order of the fresh molecule ids
+  // (FreshEvent) must not depend on the local grid of a rank
+  p.rb_log2 = 0;
   if (const char* e = getenv("MCX_ROW_BLOCK_LOG2")) p.rb_log2 = std::max(0, std::min(6, atoi(e)));  // tuning knob (profiles/)
   set_cell_count(p);
   p.own_lo = 0; p.own_hi = p.ncz; p.world = 1; p.halo_layers = 0; p.z_off = 0; p.has_low = 0; p.has_high = 0;
@@ -227,6 +231,10 @@ int mcx_create(const mcx_config* cfg, mcx_handle** out) {
   rc |= dev_alloc(h, &h->scan_sums, (size_t)(p.n_cells + 1) / 4096 + 16);
   p.scan_sums = h->scan_sums;
   rc |= dev_alloc(h, &p.ctr, 1);
+  p.fresh_cap = (unsigned int)std::max<size_t>(1u << 16, cap / 8);
+  rc |= dev_alloc(h, &p.fresh_list, p.fresh_cap);
+  rc |= dev_alloc(h, &p.fresh_head, (size_t)p.n_groups + 8); rc |= dev_alloc(h, &p.fresh_pref, (size_t)p.n_groups + 8);
+  p.rank_fresh = nullptr; p.my_rank = cfg->rank;
   rc |= dev_alloc(h, &h->d_n_out, 4);
   if (rc) return fail(MCX_ERR_CUDA);
   // empty wall tables until geometry arrives
@@ -470,6 +478,14 @@ static int rebuild_tables(mcx_handle* h) {
   p.classes = (const DevClass*)h->d_classes; p.pathways = (const DevPathway*)h->d_pathways;
   p.surf_action = (const uint8_t*)h->d_surf; p.n_species = (int)ns; p.n_surf_classes = (int)nsc;
   h->plan.has_claims = !h->classes.empty() || absorbing;
+  h->plan.has_fresh = false;
+  for (const mcx_rxn_class& rc : h->classes)
+    for (uint32_t q = 0; q < rc.n_pathways; q++) {
+      const mcx_pathway& pw = h->pathways[rc.first_pathway + q];
+      const uint32_t n_react = rc.kind == MCX_RXN_UNIMOL ? 1u : 2u;
+      const uint32_t kept = (uint32_t)__builtin_popcount(pw.keep_reactant_mask & ((1u << n_react) - 1u));
+      if (pw.n_products > n_react - kept) h->plan.has_fresh = true;
+    }
   return MCX_OK;
 }
 
@@ -700,14 +716,7 @@ int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* 
     v[(size_t)h->cfg.rank] = base;
     rc = mcx_comm_allreduce_u64(h->comm, v.data(), (int)v.size(), s);
     if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
-    // no fresh id handed out since the last refresh (every rank still at its aligned start): continue at the global
-    // maximum itself, which is what a single device would do — the released ids, and with them the streams and
-    // positions, then do not depend on the number of ranks
-    const unsigned long long w = (unsigned long long)h->cfg.world_size, floor_v = mcx_comm_id_floor(h->comm);
-    bool untouched = true;
-    for (size_t k = 0; k < v.size(); k++) untouched = untouched && v[k] == ((floor_v + w - 1) / w) * w + k;
-    for (unsigned long long x : v) base = std::max(base, x);
-    if (untouched) base = floor_v;
+    for (unsigned long long x : v) base = std::max(base, x);  // next_id is global (k_assign_ids): equal on every rank
   }
   if (base + r->number >= 0xFFFFFFF0ull) { h->err = "molecule ids exhausted"; return MCX_ERR_OVERFLOW; }
   bind_iteration(h);
@@ -960,6 +969,7 @@ int mcx_comm_init(mcx_handle* h, const void* nccl_unique_id, uint32_t id_bytes) 
   const unsigned int halo_cap = std::max<unsigned int>(1u << 16, h->p.capacity / 3);
   h->comm = mcx_comm_create(nccl_unique_id, id_bytes, h->cfg.rank, h->cfg.world_size, halo_cap, err);
   if (!h->comm) { h->err = err; return MCX_ERR_COMM; }
+  h->p.rank_fresh = mcx_comm_rank_fresh(h->comm);
   return MCX_OK;
 }
 

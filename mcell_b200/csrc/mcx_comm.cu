@@ -26,6 +26,7 @@ struct McxComm {
   unsigned int* h_counts = nullptr;   // pinned mirror
   unsigned long long* d_red = nullptr;
   int red_cap = 0;
+  unsigned int* d_fresh = nullptr;    // [world] fresh molecule ids of every rank this iteration (all-gathered), [world]: mine
   // peer-memory halo path: the pack kernel stores straight into the neighbour's buffers over NVLink
   bool p2p = false;
   unsigned long long id_floor = 0;  // global maximum of next_id at the last refresh (before the per-rank alignment)
@@ -137,6 +138,8 @@ McxComm* mcx_comm_create(const void* nccl_unique_id, uint32_t id_bytes, int rank
   ok = ok && cudaMallocHost((void**)&c->h_counts, 4 * sizeof(unsigned int)) == cudaSuccess;
   c->red_cap = 1024;
   ok = ok && cudaMalloc((void**)&c->d_red, sizeof(unsigned long long) * c->red_cap) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&c->d_fresh, sizeof(unsigned int) * (size_t)(world_size + 1)) == cudaSuccess;
+  if (ok) cudaMemset(c->d_fresh, 0, sizeof(unsigned int) * (size_t)(world_size + 1));
   if (ok) cudaMemset(c->d_counts, 0, 4 * sizeof(unsigned int));
   if (ok && !getenv("MCX_HALO_NCCL")) setup_p2p(c);  // falls back to NCCL send/recv when peer memory is not available
   if (ok && !c->p2p) {  // staging buffers of the NCCL path
@@ -155,6 +158,7 @@ void mcx_comm_destroy(McxComm* c) {
   if (c->d_counts) cudaFree(c->d_counts);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->d_red) cudaFree(c->d_red);
+  if (c->d_fresh) cudaFree(c->d_fresh);
   for (int k = 0; k < 2; k++) if (c->peer_ipc[k] && c->peer_base[k]) cudaIpcCloseMemHandle(c->peer_base[k]);
   if (c->block) cudaFree(c->block);
   if (c->d_done) cudaFree(c->d_done);
@@ -163,6 +167,7 @@ void mcx_comm_destroy(McxComm* c) {
 }
 const char* mcx_comm_error(McxComm* c) { return c ? c->err.c_str() : ""; }
 bool mcx_comm_is_p2p(const McxComm* c) { return c && c->p2p; }
+const uint32_t* mcx_comm_rank_fresh(const McxComm* c) { return c ? c->d_fresh : nullptr; }
 unsigned long long mcx_comm_id_floor(const McxComm* c) { return c ? c->id_floor : 0ull; }
 
 // halo refresh: pack -> counts -> payload -> unpack (appended behind the local results in B)
@@ -216,6 +221,15 @@ static int exchange_halo(McxComm* c, DevParams& p, cudaStream_t s) {
 
 int mcx_comm_iteration(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_t s) {
   mcx_launch_evaluate(p, plan, s);
+  if (plan.has_fresh) {
+    // fresh molecule ids are global: every rank learns how many each rank hands out this iteration (FreshEvent order:
+    // the ranks own consecutive ranges of cell groups), then writes its own into the product records before the halo
+    // refresh copies them to the neighbours
+    CCK(cudaMemcpyAsync(c->d_fresh + c->world, &p.ctr->n_fresh_ids, sizeof(unsigned int), cudaMemcpyDeviceToDevice, s));
+    NCK(ncclAllGather(c->d_fresh + c->world, c->d_fresh, 1, ncclUint32, c->comm, s));
+    mcx_launch_fresh_scan(p, plan, s);
+    mcx_launch_assign_ids(p, plan, s);
+  }
   int rc = exchange_halo(c, p, s);
   if (rc) return rc;
   if (plan.launches) *plan.launches += 4;
@@ -225,7 +239,7 @@ int mcx_comm_iteration(McxComm* c, DevParams& p, const StepPlan& plan, cudaStrea
 }
 
 int mcx_comm_refresh(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_t s) {
-  // fresh molecule ids: rank r hands out ids congruent to r modulo world above the global maximum
+  // fresh molecule ids start above the global maximum on every rank
   unsigned int next_id = 0;
   CCK(cudaMemcpyAsync(&next_id, &p.ctr->next_id, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
   CCK(cudaStreamSynchronize(s));
@@ -234,9 +248,8 @@ int mcx_comm_refresh(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_
   NCK(ncclAllReduce(c->d_red, c->d_red, 1, ncclUint64, ncclMax, c->comm, s));
   CCK(cudaMemcpyAsync(&v, c->d_red, sizeof(v), cudaMemcpyDeviceToHost, s));
   CCK(cudaStreamSynchronize(s));
-  const unsigned long long w = (unsigned long long)c->world;
   c->id_floor = v;  // every id below v may be in use, none at or above it
-  next_id = (unsigned int)(((v + w - 1) / w) * w + (unsigned long long)c->rank);
+  next_id = (unsigned int)v;  // the same on every rank: fresh ids are handed out in one global order (k_assign_ids)
   CCK(cudaMemcpyAsync(&p.ctr->next_id, &next_id, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
   mcx_launch_rebin(p, plan, s);
   int rc = exchange_halo(c, p, s);

@@ -16,5 +16,7 @@ int mcx_comm_refresh(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_
 int mcx_comm_allreduce_u64(McxComm* c, unsigned long long* host_buf, int n, cudaStream_t s);
 // true when the halo refresh goes through the neighbours' peer memory (NVLink stores), false on the NCCL path
 bool mcx_comm_is_p2p(const McxComm* c);
+// device array [world]: fresh molecule ids every rank hands out in the current iteration (filled by mcx_comm_iteration)
+const uint32_t* mcx_comm_rank_fresh(const McxComm* c);
 // global maximum of next_id at the last mcx_comm_refresh, before the ranks were moved to their congruence classes
 unsigned long long mcx_comm_id_floor(const McxComm* c);

@@ -58,6 +58,7 @@ struct Counters {
   // population
   unsigned int n_slots;        // records in the current snapshot buffer (incl. tombstones/ghosts)
   unsigned int n_prod;         // products appended behind n_slots this iteration
+  unsigned int n_fresh_events, n_fresh_ids;  // events of this iteration that need fresh molecule ids / how many ids
   unsigned int n_disk;         // molecules handed to the exact_disk launch of the generic pass (list in pend[1])
   unsigned int n_next;         // records binned for the next snapshot
   int error;                   // first MCX_ERR_* raised on the device
@@ -97,6 +98,11 @@ struct TileGeom {
   float tol_d, r2p;            // slacks of the fp32 pre-filter: along the move (absolute) and the inflated R^2
   unsigned int smem_bytes;     // dynamic shared memory of the launch
 };
+
+// An event that creates more products than it frees reactant ids (mcx_kernels.cu: k_assign_ids).  Fresh ids are handed
+// out AFTER the conflict rounds, in the order (cell group of the event position, id of the initiator) — a function of the
+// events only, so a run is reproducible and does not depend on the number of ranks.
+struct FreshEvent { uint32_t first_slot, n, init_id, next, group; };
 
 struct DevParams {
   // partition / subpartition grid (reference semantics)
@@ -181,6 +187,14 @@ struct DevParams {
   int has_low, has_high;        // a neighbour rank exists below / above
   int sm_count;                 // multiprocessors of this device: every grid is sized in multiples of it
   TileGeom tile;
+  // fresh molecule ids (FreshEvent): event list, per cell group (16 x-cells of one cell row) the head of its chain of
+  // events and the number of fresh ids (exclusive prefix after the scan)
+  FreshEvent* fresh_list;
+  uint32_t* fresh_head;
+  uint32_t* fresh_pref;
+  unsigned int fresh_cap, n_groups, grp_x;
+  const uint32_t* rank_fresh;   // multi-GPU: fresh ids of every rank this iteration (all-gathered), null on one device
+  int my_rank;
 };
 
 // multi-GPU halo record: what a neighbour needs to evaluate a molecule exactly like its owner does
@@ -206,6 +220,7 @@ struct StepPlan {
   unsigned long long* launches;  // host-side counter of kernels launched (may be null)
   cudaEvent_t* prof;             // 5 events for this iteration (null = no per-kernel timing)
   bool has_claims;   // model can produce reactions / absorptions (conflict rounds needed)
+  bool has_fresh;    // some pathway creates more products than it consumes reactants (fresh molecule ids needed)
   bool trace;
 };
 void mcx_plan_tiles(DevParams& p, unsigned long long n_records);  // fills p.tile for a population of n_records
@@ -213,6 +228,8 @@ void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t
 void mcx_launch_initial_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
 // multi-GPU pieces of an iteration (mcx_comm.cu drives them around the NCCL exchange)
 void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t s);   // memset + diffuse + resolve rounds
+void mcx_launch_fresh_scan(const DevParams& p, const StepPlan& plan, cudaStream_t s);  // prefix of the fresh ids per cell group
+void mcx_launch_assign_ids(const DevParams& p, const StepPlan& plan, cudaStream_t s);  // fresh ids into the product records
 void mcx_launch_release(const DevParams& p, const mcx_release& r, uint32_t first_id, cudaStream_t s);  // appends behind a re-binned population
 void mcx_launch_rebin(const DevParams& p, const StepPlan& plan, cudaStream_t s);      // A -> B unchanged (halo refresh without a step)
 void mcx_launch_pack_halo(const DevParams& p, HaloRec* send_low, HaloRec* send_high, unsigned int cap, cudaStream_t s);

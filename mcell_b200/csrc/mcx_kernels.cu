@@ -183,6 +183,12 @@ __device__ __forceinline__ bool partner_is_consumed(const DevParams& p, int kind
   return !((pw.keep_mask >> (a_is_r0 ? 1 : 0)) & 1u);
 }
 
+// cell group of a position: 16 x-cells of one cell row (the unit of the fresh-id order, FreshEvent)
+__device__ __forceinline__ uint32_t group_of(const DevParams& p, D3 q) {
+  const int cx = cell_coord(q.x, p.cgx, p.cell_rcp_x, p.ncx), cy = cell_coord(q.y, p.cgy, p.cell_rcp_y, p.ncy), cz = cell_z(p, q.z);
+  return row_index(p, cy, cz) * p.grp_x + (uint32_t)(cx >> 4);
+}
+
 // accepted claiming event: consume reactants, create products, count
 __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rxn_class, int pathway, uint32_t partner_slot,
                              double t_event, D3 pos, uint32_t id, uint32_t species, uint32_t flags, double t_now,
@@ -241,10 +247,24 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
   const uint32_t n_new = own_event ? pw.n_products : 0u;
   const uint32_t first_slot = n_new ? c->n_slots + agg_reserve(&c->n_prod, n_new) : 0u;
   const D3 event_pos = pos;
+  // products beyond the reactant ids this event frees take fresh ids, assigned after the conflict rounds (k_assign_ids)
+  if (n_new > (uint32_t)n_reuse && first_slot + n_new <= p.capacity) {
+    const uint32_t e = agg_reserve(&c->n_fresh_events, 1u);
+    if (e >= p.fresh_cap) raise_error(p, MCX_ERR_CAPACITY, id);
+    else {
+      const uint32_t g = group_of(p, event_pos);
+      const uint32_t nf = n_new - (uint32_t)n_reuse;
+      FreshEvent ev; ev.first_slot = first_slot + (uint32_t)n_reuse; ev.n = nf; ev.init_id = id; ev.group = g;
+      ev.next = atomicExch(&p.fresh_head[g], e);
+      p.fresh_list[e] = ev;
+      atomicAdd(&p.fresh_pref[g], nf);
+      atomicAdd(&c->n_fresh_ids, nf);
+    }
+  }
   for (uint32_t k = 0; k < n_new; k++) {
     uint32_t ns = first_slot + k;
     if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
-    uint32_t nid = (int)k < n_reuse ? reuse[k] : atomicAdd(&c->next_id, (unsigned int)p.world) ;  // fresh ids: strided by rank
+    uint32_t nid = (int)k < n_reuse ? reuse[k] : MCX_NONE;  // fresh id: filled in by k_assign_ids
     uint32_t psp = pw.products[k];
     uint32_t pflags = DF_SCHED_UNIMOL | DF_PARTIAL | (flags & SF_CVI_MASK);  // products inherit the counted volume
     pos = event_pos;
@@ -1008,7 +1028,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_sums(unsigned int* sums, unsi
     if (threadIdx.x == 0) carry += total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) { *out_total = carry; ctr->n_next = carry; }
+  if (threadIdx.x == 0) { *out_total = carry; if (ctr) ctr->n_next = carry; }
 }
 __global__ void __launch_bounds__(SCAN_TPB) k_scan_apply(uint32_t* __restrict__ cnt, unsigned int n, const unsigned int* __restrict__ sums) {
   __shared__ unsigned int smem[32];
@@ -1062,10 +1082,27 @@ __global__ void __launch_bounds__(TPB) k_scatter(const __grid_constant__ DevPara
       if (s_species[k]) atomicAdd(&p.ctr->species_next[k], (unsigned long long)s_species[k]);
   }
 }
+// Fresh molecule ids: event e of cell group g gets next_id + (fresh ids of the lower ranks) + (fresh ids of the lower
+// groups: fresh_pref after the scan) + (fresh ids of the events of g whose initiator has a smaller id: chain of g).
+__global__ void __launch_bounds__(TPB) k_assign_ids(const __grid_constant__ DevParams p) {
+  const unsigned int n = min(p.ctr->n_fresh_events, p.fresh_cap);
+  unsigned int base = p.ctr->next_id;
+  if (p.rank_fresh) for (int r = 0; r < p.my_rank; r++) base += p.rank_fresh[r];
+  for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const FreshEvent ev = p.fresh_list[e];
+    unsigned int before = p.fresh_pref[ev.group];
+    for (uint32_t q = p.fresh_head[ev.group]; q != MCX_NONE; q = p.fresh_list[q].next)
+      if (p.fresh_list[q].init_id < ev.init_id) before += p.fresh_list[q].n;
+    for (uint32_t k = 0; k < ev.n; k++) p.recB[ev.first_slot + k].id = base + before + k;
+  }
+}
 __global__ void k_end_iteration(const __grid_constant__ DevParams p) {
   Counters* c = p.ctr;
   if (threadIdx.x == 0) {
     c->n_slots = c->n_next;
+    unsigned int fresh = c->n_fresh_ids;
+    if (p.rank_fresh) { fresh = 0; for (int r = 0; r < p.world; r++) fresh += p.rank_fresh[r]; }
+    c->next_id += fresh; c->n_fresh_events = 0; c->n_fresh_ids = 0;
     c->n_prod = 0; c->n_disk = 0; c->n_slow = 0; c->n_second = 0; c->n_slow2 = 0; c->n_send[0] = 0; c->n_send[1] = 0;
   }
   if (threadIdx.x <= MCX_ROUNDS_MAX) { c->n_prop[threadIdx.x] = 0; c->n_lose[threadIdx.x] = 0; }
@@ -1076,7 +1113,7 @@ __global__ void k_end_iteration(const __grid_constant__ DevParams p) {
 __global__ void k_reset_population(const __grid_constant__ DevParams p, unsigned int n_slots) {
   Counters* c = p.ctr;
   if (threadIdx.x == 0) {
-    c->n_slots = n_slots; c->n_prod = 0; c->n_disk = 0; c->n_next = 0; c->error = 0; c->error_id = 0;
+    c->n_slots = n_slots; c->n_prod = 0; c->n_disk = 0; c->n_next = 0; c->n_fresh_events = 0; c->n_fresh_ids = 0; c->error = 0; c->error_id = 0;
     c->n_emigrants[0] = 0; c->n_emigrants[1] = 0; c->n_slow = 0; c->n_send[0] = 0; c->n_send[1] = 0; c->n_second = 0; c->n_slow2 = 0;
   }
   c->species_count[threadIdx.x] = 0; c->species_next[threadIdx.x] = 0;
@@ -1436,6 +1473,10 @@ void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
 // cell histogram reset + fast/slow diffuse + conflict rounds: results sit in B with their ranks
 void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
   cudaMemsetAsync(p.cs_next, 0, sizeof(uint32_t) * (size_t)(p.n_cells + 1), s);
+  if (plan.has_fresh) {
+    cudaMemsetAsync(p.fresh_pref, 0, sizeof(uint32_t) * (size_t)(p.n_groups + 1), s);
+    cudaMemsetAsync(p.fresh_head, 0xFF, sizeof(uint32_t) * (size_t)p.n_groups, s);
+  }
   static const bool carveout_set = [] {  // tuning knob (profiles/): shared-memory carveout of the fast pass in percent
     if (const char* e = getenv("MCX_FAST_CARVEOUT")) {
       cudaFuncSetAttribute(k_diffuse_fast<0>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
@@ -1480,8 +1521,25 @@ void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t 
   if (plan.prof) cudaEventRecord(plan.prof[2], s);
 }
 
+void mcx_launch_fresh_scan(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
+  if (!plan.has_fresh) return;
+  count_launches(plan, 3);
+  const unsigned int n = p.n_groups + 1;
+  const unsigned int nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_reduce<<<nblocks, SCAN_TPB, 0, s>>>(p.fresh_pref, n, p.scan_sums);
+  k_scan_sums<<<1, SCAN_TPB, 0, s>>>(p.scan_sums, nblocks, p.scan_sums + nblocks, nullptr);
+  k_scan_apply<<<nblocks, SCAN_TPB, 0, s>>>(p.fresh_pref, n, p.scan_sums);
+}
+void mcx_launch_assign_ids(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
+  if (!plan.has_fresh) return;
+  count_launches(plan, 1);
+  k_assign_ids<<<plan.sm_count * 2, TPB, 0, s>>>(p);
+}
+
 void mcx_launch_iteration(const DevParams& p, const StepPlan& plan, cudaStream_t s) {
   mcx_launch_evaluate(p, plan, s);
+  mcx_launch_fresh_scan(p, plan, s);
+  mcx_launch_assign_ids(p, plan, s);
   mcx_launch_sort(p, plan, s);
   if (plan.prof) cudaEventRecord(plan.prof[3], s);
 }
