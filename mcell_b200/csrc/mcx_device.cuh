@@ -892,7 +892,11 @@ __device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enab
       if (rc >= 0) { const uint32_t h = atomicAdd(&sm->hits[o], 1u); if (h < MCX_FAST_MAX_HITS) sm->hit_slot[o][h] = j; }
     }
   };
+#ifdef MCX_EXPERIMENT_NO_PAIRS   // timing experiment only: the probe's set-up without its pair loop
+  for (uint32_t B = W; B < W; B += 32) {
+#else
   for (uint32_t B = 0; B < W; B += 32) {
+#endif
     uint32_t o, j;
     const bool v = locate(B, o, j);
     if (v) { const MolRec c = load_rec(p.recA, j); test(v, o, j, c); }

@@ -546,7 +546,11 @@ __device__ __forceinline__ void fast_molecule(const DevParams& p, FastCtx& cx, P
 #endif
       // outside (tile probe only): the swept box leaves the staged tile — PASS 1 probes it with the gather walk
       bool overflow, outside;
+#ifdef MCX_EXPERIMENT_IGNORE_HITS   // timing experiment only: the probe runs, what it finds is dropped (cost of the hit handling)
+      const int n_hits = probe.run(p, probing, pos, disp, m.id, species, i, overflow, outside) & 0;
+#else
       const int n_hits = probe.run(p, probing, pos, disp, m.id, species, i, overflow, outside);
+#endif
       // a collision next to walls needs exact_disk (walls of the collision subpartition): generic path
       // (every wall plane of the crossed subpartitions farther than R from the whole segment: the factor is 1)
       const bool disk_walls = n_hits > 0 && wall_dist < p.R;
