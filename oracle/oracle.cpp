@@ -175,6 +175,7 @@ struct World {
   std::vector<V3> verts;
   std::vector<Wall> walls;
   std::vector<std::vector<uint32_t>> walls_per_subpart;  // ascending wall indices (uint_set order)
+  uint32_t sample_stride = 0, sample_offset = 0;  // > 0: step_snapshot only evaluates molecules with id % stride == offset, once, and changes nothing
   std::vector<mcx_species> species;
   std::vector<mcx_rxn_class> classes;
   std::vector<mcx_pathway> pathways;
@@ -1643,7 +1644,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
   std::vector<uint8_t> dead(n0, 0);
   for (size_t i = 0; i < n0; i++) {
     dead[i] = (w.mols[i].flags & MCX_MOL_DEFUNCT) ? 1 : 0;
-    if (!dead[i] && (w.species[w.mols[i].species].flags & MCX_SP_CAN_DIFFUSE)) w.stats.molecule_steps++;
+    if (!w.sample_stride && !dead[i] && (w.species[w.mols[i].species].flags & MCX_SP_CAN_DIFFUSE)) w.stats.molecule_steps++;
   }
   std::vector<Outcome> outs(n0);
   std::vector<uint32_t> claim(n0, MCX_NONE);
@@ -1738,6 +1739,11 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     }
   };
 
+  if (w.sample_stride) {  // a sample of first evaluations against the snapshot (test_gpu_fullsize.py): no claims, no commits
+    for (uint32_t i = 0; i < n0; i++)
+      if (!dead[i] && w.mols[i].id % w.sample_stride == w.sample_offset) eval_one(i, false);
+    return;
+  }
   // round 0: everyone
   for (uint32_t i = 0; i < n0; i++) {
     if (dead[i]) { outs[i].kind = MCX_OUT_NONE; continue; }
@@ -2050,6 +2056,22 @@ int orc_trace_step(void* h, int mode, const uint32_t* words, uint64_t n_words, c
   w.tracing = false;
   for (uint64_t i = 0; i < n_trace && i < w.trace.size(); i++) trace_out[i] = w.trace[i];
   fill_stats(w, stats, 1, 0);
+  return w.err.empty() ? 0 : MCX_ERR_ESCAPED;
+}
+// First evaluation (round 0 of the snapshot semantics) of the molecules with id % stride == offset only, against the
+// current state, which stays untouched: what lets a test compare a full-size configuration with the oracle in seconds
+// (the evaluation of one molecule depends on the snapshot alone).  Philox streams.
+int orc_trace_sample(void* h, uint32_t stride, uint32_t offset, mcx_trace_rec* trace_out, uint64_t n_trace) {
+  World& w = *(World*)h;
+  const Stats keep = w.stats;
+  w.tracing = true; w.trace.clear();
+  mcx_trace_rec z{}; z.rxn_class = z.rxn_pathway = z.rxn_partner = MCX_NONE;
+  w.trace.assign(std::max<uint64_t>(n_trace, w.next_id), z);
+  w.sample_stride = stride ? stride : 1; w.sample_offset = offset;
+  SnapStreams st{MCX_RNG_PHILOX, nullptr, 0, nullptr, 0};
+  step_snapshot(w, st);
+  w.sample_stride = 0; w.tracing = false; w.stats = keep;
+  for (uint64_t i = 0; i < n_trace && i < w.trace.size(); i++) trace_out[i] = w.trace[i];
   return w.err.empty() ? 0 : MCX_ERR_ESCAPED;
 }
 // tape recorded by the last sequential traced iteration

@@ -157,6 +157,15 @@ class Oracle:
             raise RuntimeError(self.error())
         return tr, st
 
+    def trace_sample(self, stride, offset, n_trace):
+        """First evaluation of the molecules with id % stride == offset against the current state (Philox streams); the
+        state is not changed (orc_trace_sample)."""
+        tr = np.zeros(n_trace, dtype=abi.TRACE_DTYPE)
+        rc = self.L.orc_trace_sample(self.h, C.c_uint32(stride), C.c_uint32(offset), C.c_void_p(tr.ctypes.data), C.c_uint64(n_trace))
+        if rc:
+            raise RuntimeError(self.error())
+        return tr
+
     def tape(self, n_ids):
         n = int(self.L.orc_tape_size(self.h))
         words = np.zeros(max(n, 1), np.uint32)

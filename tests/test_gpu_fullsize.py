@@ -204,3 +204,51 @@ def test_config4_synapse_like_mesh_160k_triangles_1e7_molecules():
         n_in0 = float((buf0 & (r0 < inner)).sum())
         n_in1 = float((buf1 & (r1 < inner)).sum())
         assert abs(n_in1 - n_in0) < 12 * math.sqrt(n_in0) + 4e-4 * 3 * n_in0, (radius, n_in0, n_in1)
+
+
+# ---- oracle comparison AT FULL SIZE ------------------------------------------------------------------------------------
+# The oracle cannot run a whole iteration of these configurations in seconds, but the evaluation of ONE molecule depends
+# on the start-of-iteration snapshot only.  So the device runs the full population — a few iterations to
+# get products, fractional first steps and scheduled lifetimes into the state, then one traced iteration — and the
+# oracle evaluates a sample of the molecules (every stride-th id) against the same state (orc_trace_sample).  Every
+# sampled molecule that the device evaluated once (no conflict retry, not consumed as somebody's partner) must have the
+# oracle's trace: event hash, partners, walls, reaction, words drawn bit for bit, position to 1e-12.
+def _compare_full_size_sample(t, mols, stride, offset, warm_iterations):
+    from oracle import oracle_py as O
+    e = _engine(t)
+    e.upload(mols)
+    if warm_iterations:
+        e.step(warm_iterations)
+    state = e.download()
+    n_ids = int(state.id[:state.n].max()) + 1
+    e2 = _engine(t)
+    e2.upload(state)                       # common state: ids, positions, times as the oracle gets them
+    o = O.Oracle(t)
+    o.upload(state)
+    tr_g, st_g = e2.trace_step(n_ids)
+    tr_o = o.trace_sample(stride, offset, n_ids)
+    sampled = np.flatnonzero(tr_o["rounds"] > 0)
+    once = sampled[(tr_g["rounds"][sampled] == 1) & (tr_g["outcome"][sampled] != abi.MCX_OUT_CONSUMED)]
+    assert len(once) > 0.9 * len(sampled) and len(sampled) > 10000
+    bad = cm.compare_traces(tr_o, tr_g, once)
+    assert not bad, bad[:5]
+    return tr_o[once], st_g
+
+
+def test_config2_full_size_sample_matches_oracle():
+    t, mols = cm.reactive_box(n=1_000_000, edge_um=2.0, seed=21, p_target=0.1, cap_factor=1.25)
+    tr, st = _compare_full_size_sample(t, mols, stride=32, offset=5, warm_iterations=3)
+    assert (tr["n_collisions"] > 0).sum() > 2000 and (tr["rxn_class"] != abi.MCX_NONE).sum() > 100
+    assert st.bimol_rxns > 5000
+
+
+def test_config3_full_size_sample_matches_oracle():
+    t, mols, _ = _config3(400_000, 8_000, seed=3)
+    tr, st = _compare_full_size_sample(t, mols, stride=4, offset=1, warm_iterations=3)
+    assert (tr["n_wall_hits"] > 0).sum() > 1000
+
+
+def test_config4_full_size_sample_matches_oracle():
+    t, mols, _, _ = _config4(10_000_000, seed=4)
+    tr, st = _compare_full_size_sample(t, mols, stride=512, offset=7, warm_iterations=2)
+    assert (tr["n_wall_hits"] > 0).sum() > 100 and (tr["n_collisions"] > 0).sum() > 500
