@@ -815,11 +815,15 @@ __device__ __forceinline__ int probe_partners(const DevParams& p, bool enabled, 
 // ceil(sum / 32): every lane tests one candidate of SOME lane's molecule per trip, the owner's move is read from
 // shared memory, and the (rare) hits are reported back through shared-memory atomics.  Warp-collective.
 #define MCX_FAST_MAX_HITS 4
+// Layout: every table is indexed [field][owner lane], so that the 32 lanes of a warp store to 32 consecutive words
+// (one wavefront of the shared-memory pipe per store) and a trip, whose 32 pairs belong to 2-3 owners, reads 2-3 words of
+// different banks per load (one wavefront).  With [owner][field] rows of 32 bytes the table stores were 8-way bank
+// conflicts and the 128-bit loads of the owner's move took 2.9 wavefronts each: 1.3e9 shared-memory wavefronts per launch,
+// the largest share of the busiest unit of the kernel (L1TEX data pipe 64 % busy, profiles/r02_y; r3c for the change).
 struct __align__(16) WarpProbe {
-  double4 a[32];          // pos.x, pos.y, pos.z, movelen2
-  double4 b[32];          // disp.x, disp.y, disp.z, bits(id | species << 32)
-  uint32_t cum[32][8];    // inclusive row ends over the concatenation of the owner's rows (6 used)
-  uint32_t lo[32][8];     // slot of candidate k in row r = lo[r] + k
+  double m[8][32];        // per owner lane: pos.x, pos.y, pos.z, movelen2, disp.x, disp.y, disp.z, bits(id | species << 32)
+  uint32_t cum[6][32];    // inclusive row ends over the concatenation of the owner's rows
+  uint32_t lo[6][32];     // slot of candidate k in row r = lo[r] + k
   uint32_t off[32];       // compacted owners: first pair index
   uint32_t owner[32];     // compacted owners: lane
   uint32_t hits[32];      // per owner lane: number of eligible collisions
@@ -843,13 +847,13 @@ __device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enab
     const uint32_t base = row_base(p, bx.cy0 + ry, bx.cz0 + rz);
     const uint32_t a = __ldg(p.cs_cur + (valid ? base + bx.cx0 : 0u));
     const uint32_t e = __ldg(p.cs_cur + (valid ? base + bx.cx1 + 1 : 0u));
-    sm->lo[lane][r] = a - total;
+    sm->lo[r][lane] = a - total;
     total += e - a;
-    sm->cum[lane][r] = total;
+    sm->cum[r][lane] = total;
   }
-  sm->a[lane] = make_double4(pos.x, pos.y, pos.z, movelen2);
-  sm->b[lane] = make_double4(disp.x, disp.y, disp.z,
-                             __longlong_as_double((long long)(((unsigned long long)self_species << 32) | self_id)));
+  sm->m[0][lane] = pos.x; sm->m[1][lane] = pos.y; sm->m[2][lane] = pos.z; sm->m[3][lane] = movelen2;
+  sm->m[4][lane] = disp.x; sm->m[5][lane] = disp.y; sm->m[6][lane] = disp.z;
+  sm->m[7][lane] = __longlong_as_double((long long)(((unsigned long long)self_species << 32) | self_id));
   sm->hits[lane] = 0;
   // exclusive prefix of the totals; owners with candidates are compacted so that their offsets strictly increase
   uint32_t incl = total;
@@ -874,20 +878,20 @@ __device__ __forceinline__ int probe_partners_flat(const DevParams& p, bool enab
       const uint32_t kk = q - sm->off[k];
       // row of pair kk = number of row ends at or below it (branch-free: the nested selects this replaces were
       // compiled into divergent branches, 12-20 of 32 lanes active, profiles/r01_l)
-      const uint4 c03 = *reinterpret_cast<const uint4*>(&sm->cum[o][0]);
-      const uint32_t c4 = sm->cum[o][4];
-      const uint32_t r = (kk >= c03.x) + (kk >= c03.y) + (kk >= c03.z) + (kk >= c03.w) + (kk >= c4);
-      j = sm->lo[o][r] + kk;
+      const uint32_t r = (kk >= sm->cum[0][o]) + (kk >= sm->cum[1][o]) + (kk >= sm->cum[2][o]) + (kk >= sm->cum[3][o]) +
+                         (kk >= sm->cum[4][o]);
+      j = sm->lo[r][o] + kk;
     }
     return valid;
   };
   // collide_mol (collision_utils.inl:464-515) of candidate record c against owner o's move
   auto test = [&](bool valid, uint32_t o, uint32_t j, const MolRec& c) {
     if (!valid) return;
-    const double4 oa = sm->a[o], ob = sm->b[o];
-    const unsigned long long ids = (unsigned long long)__double_as_longlong(ob.w);
+    const double ml2 = sm->m[3][o];
+    const unsigned long long ids = (unsigned long long)__double_as_longlong(sm->m[7][o]);
     double d;
-    if (collide_mol_hit(c, D3{oa.x, oa.y, oa.z}, D3{ob.x, ob.y, ob.z}, oa.w, oa.w * R2, (uint32_t)ids, d)) {
+    if (collide_mol_hit(c, D3{sm->m[0][o], sm->m[1][o], sm->m[2][o]}, D3{sm->m[4][o], sm->m[5][o], sm->m[6][o]}, ml2, ml2 * R2,
+                        (uint32_t)ids, d)) {
       const int rc = p.bimol[(uint32_t)(ids >> 32) * p.n_species + (c.sf & SF_SPECIES_MASK)];
       if (rc >= 0) { const uint32_t h = atomicAdd(&sm->hits[o], 1u); if (h < MCX_FAST_MAX_HITS) sm->hit_slot[o][h] = j; }
     }
