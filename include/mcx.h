@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MCX_ABI_VERSION 2
+#define MCX_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define MCX_OK 0
@@ -100,12 +100,24 @@ typedef struct mcx_pathway {
   double   cum_prob;               /* cumulative probability (src/mcell_reactions.c:2932-2933) */
   uint32_t n_products;             /* newly created products (kept reactants are NOT listed) */
   uint32_t products[MCX_MAX_PRODUCTS];
-  uint32_t keep_reactant_mask;     /* bit r: rule reactant r appears unchanged on both sides */
+  uint32_t keep_reactant_mask;     /* bit r: rule reactant r appears on both sides (is_simple_cplx_reactant_on_both_
+                                      sides_of_rxn_w_identical_compartments, diffuse_react_event.cpp:2558-2565) */
   uint32_t rxn_rule_id;            /* slot of the per-reaction occurrence counter */
-  uint32_t reserved;
+  uint32_t kept_info;              /* kept reactants among the rule's products (diffuse_react_event.cpp:2618-2716):
+                                      MCX_KEPT_VALID | rule product order, one nibble per rule product (0-3 =
+                                      products[k], 8 + r = kept reactant r, 0xF = end) | product-side orientation of
+                                      kept reactant r in bits 24 + 2 r (0 none, 1 = up ', 2 = down ,).  The order is the
+                                      order of the orientation draws; a kept volume reactant of a volume-surface
+                                      reaction whose product-side orientation differs from its reactant-side one
+                                      passes through the wall (RX_FLIP, :945-970), a kept surface reactant takes its
+                                      product-side orientation.  0 (not valid): kept reactants stay as they are */
   int32_t  product_orientation[MCX_MAX_PRODUCTS]; /* rule orientation of products[k]; 0 = none: one random bit
                                       when a surface is involved (diffuse_react_event.cpp:2622-2627) */
 } mcx_pathway;
+
+#define MCX_KEPT_VALID (1u << 31)
+#define MCX_KEPT_ORDER_END 0xFu
+#define MCX_KEPT_ORDER_REACTANT 8u   /* nibble value 8 + r: kept reactant r */
 
 /* ---- surface classes (mcell4_converter.cpp:515-622; rxn_utils.inl:263-287) ----------- */
 enum { MCX_SURF_REFLECTIVE = 0, MCX_SURF_TRANSPARENT = 1, MCX_SURF_ABSORPTIVE = 2 };

@@ -2,7 +2,7 @@
 field for field; tests/test_abi.py checks sizes against the library's own sizeof table."""
 import ctypes as C
 
-MCX_ABI_VERSION = 2
+MCX_ABI_VERSION = 3
 MCX_OK = 0
 MCX_ERR_INVALID_ARG, MCX_ERR_CUDA, MCX_ERR_CAPACITY, MCX_ERR_ESCAPED = -1, -2, -3, -4
 MCX_ERR_STATE, MCX_ERR_OVERFLOW, MCX_ERR_COMM = -5, -6, -7
@@ -18,6 +18,7 @@ MCX_SP_VOL, MCX_SP_CAN_DIFFUSE, MCX_SP_CANT_INITIATE = 1, 2, 4
 MCX_RXN_UNIMOL, MCX_RXN_BIMOL_VOLVOL, MCX_RXN_BIMOL_VOLSURF = 1, 2, 3
 MCX_SURF_REFLECTIVE, MCX_SURF_TRANSPARENT, MCX_SURF_ABSORPTIVE = 0, 1, 2
 MCX_MOL_DEFUNCT, MCX_MOL_SCHEDULE_UNIMOL, MCX_MOL_PARTIAL = 1, 2, 4
+MCX_KEPT_VALID, MCX_KEPT_ORDER_END, MCX_KEPT_ORDER_REACTANT = 1 << 31, 0xF, 8
 MCX_OUT_NONE, MCX_OUT_MOVED, MCX_OUT_REACTED, MCX_OUT_ABSORBED = 0, 1, 2, 3
 MCX_OUT_UNIMOL, MCX_OUT_CONSUMED, MCX_OUT_STATIC, MCX_OUT_SURFMOVE = 4, 5, 6, 7
 
@@ -62,7 +63,7 @@ class mcx_rxn_class(C.Structure):
 
 class mcx_pathway(C.Structure):
     _fields_ = [("cum_prob", c_f64), ("n_products", c_u32), ("products", c_u32 * MCX_MAX_PRODUCTS),
-                ("keep_reactant_mask", c_u32), ("rxn_rule_id", c_u32), ("reserved", c_u32),
+                ("keep_reactant_mask", c_u32), ("rxn_rule_id", c_u32), ("kept_info", c_u32),
                 ("product_orientation", c_i32 * MCX_MAX_PRODUCTS)]
 
 

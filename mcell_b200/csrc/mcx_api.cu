@@ -357,6 +357,7 @@ static int rebuild_tables(mcx_handle* h) {
   std::vector<int> bimol(ns * ns, -1), unimol(ns, -1), volsurf(ns * ns, -1);
   bool any_surf = false;
   for (size_t a = 0; a < ns; a++) any_surf = any_surf || !(h->species[a].flags & MCX_SP_VOL);
+  if (h->classes.size() > 8191) { h->err = "more than 8191 reaction classes (proposal word)"; return MCX_ERR_INVALID_ARG; }
   std::vector<DevClass> dc(h->classes.size());
   std::vector<DevPathway> dp(h->pathways.size());
   for (size_t c = 0; c < h->classes.size(); c++) {
@@ -395,8 +396,15 @@ static int rebuild_tables(mcx_handle* h) {
         if (n_surf_products > 1 || (n_surf_products == 1 && surf_kept)) {
           h->err = "surface products beyond the recycled tile of the surface reactant are not supported"; return MCX_ERR_INVALID_ARG;
         }
-        if (rc.kind == MCX_RXN_BIMOL_VOLSURF && (pw.keep_reactant_mask & 1u)) {
-          h->err = "vol-surf pathways that keep the volume reactant (RX_FLIP / catalytic) are not supported"; return MCX_ERR_INVALID_ARG;
+        // a kept surface partner is not claimed by the event (several molecules may react with it in one iteration),
+        // so it cannot change its orientation there: it has to carry the mark of the class on both sides
+        if (rc.kind == MCX_RXN_BIMOL_VOLSURF && surf_kept && (pw.kept_info & MCX_KEPT_VALID)) {
+          const uint32_t code = (pw.kept_info >> 26) & 3u;
+          const int o = code == 1u ? 1 : (code == 2u ? -1 : 0);
+          if (rc.reactant_orientation[1] == 0 ? o != 0 : o != rc.reactant_orientation[1]) {
+            h->err = "a kept surface reactant of a volume-surface reaction that changes its orientation is not supported";
+            return MCX_ERR_INVALID_ARG;
+          }
         }
       }
     }
@@ -406,6 +414,7 @@ static int rebuild_tables(mcx_handle* h) {
     if (pw.n_products > MCX_MAX_PRODUCTS) { h->err = "too many products"; return MCX_ERR_INVALID_ARG; }
     DevPathway d{};
     d.cum_prob = pw.cum_prob; d.n_products = pw.n_products; d.keep_mask = pw.keep_reactant_mask; d.rule_id = pw.rxn_rule_id;
+    d.kept_info = pw.kept_info;
     for (uint32_t q = 0; q < pw.n_products; q++) {
       if (pw.products[q] >= ns) { h->err = "product references an unknown species"; return MCX_ERR_INVALID_ARG; }
       d.products[q] = pw.products[q];

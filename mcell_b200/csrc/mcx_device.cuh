@@ -143,7 +143,8 @@ struct Outcome {
   uint32_t flags;         // device flag bits (DF_*)
   int rxn_class, pathway;
   uint32_t partner_slot, partner_id;
-  uint32_t orient_bits;   // bit k: random orientation drawn for products[k] (1 = up)
+  uint32_t orient_bits;   // bit k: random orientation drawn for products[k] (1 = up); bit 4 + r: for kept reactant r;
+                          // ORIENT_BIT_FRONT: a volume-surface reaction whose initiator hit the FRONT of the wall
   uint32_t s_wall, s_tile; double s_u, s_v;  // surface molecule that diffused: where it is now (Molecule::s)
   bool surf_moved;        // the surface fields above differ from the snapshot's
 };
@@ -1090,11 +1091,37 @@ __device__ __forceinline__ bool orientations_match(const DevClass& rc, int orien
   return orientA != 0 && orientA * orientB * geomA * geomB > 0;
 }
 // one random bit per product with rule orientation NONE (outcome_products_random, diffuse_react_event.cpp:2618-2627)
+// With kept_info (include/mcx.h) the draws follow the order of the rule's products, kept reactants included.
+#define ORIENT_BIT_FRONT 64u
+#define ORIENT_BITS_MASK 127u
+__device__ __forceinline__ int kept_code(const DevPathway& pw, int r) {
+  const uint32_t c = (pw.kept_info >> (24 + 2 * r)) & 3u;
+  return c == 1u ? 1 : (c == 2u ? -1 : 0);
+}
 __device__ __forceinline__ uint32_t draw_orientation_bits(const DevPathway& pw, Stream& rs) {
   uint32_t bits = 0;
-  for (uint32_t k = 0; k < pw.n_products; k++)
-    if (pw.prod_orient[k] == 0 && (rs.next() & 1u)) bits |= 1u << k;
+  if (!(pw.kept_info & MCX_KEPT_VALID)) {
+    for (uint32_t k = 0; k < pw.n_products; k++)
+      if (pw.prod_orient[k] == 0 && (rs.next() & 1u)) bits |= 1u << k;
+    return bits;
+  }
+  for (int q = 0; q < 6; q++) {
+    const uint32_t nib = (pw.kept_info >> (4 * q)) & 0xFu;
+    if (nib == MCX_KEPT_ORDER_END) break;
+    if (nib >= MCX_KEPT_ORDER_REACTANT) {
+      const int r = (int)(nib & 1u);
+      if (kept_code(pw, r) == 0 && (rs.next() & 1u)) bits |= 1u << (4 + r);
+    } else if (nib < pw.n_products && pw.prod_orient[nib] == 0 && (rs.next() & 1u)) bits |= 1u << nib;
+  }
   return bits;
+}
+// product-side orientation of kept reactant r (outcome_products_random :2618-2652); 0: the table does not say
+__device__ __forceinline__ int kept_orientation(const DevClass& c, const DevPathway& pw, int r, uint32_t orient_bits, int surf_orient) {
+  if (!(pw.kept_info & MCX_KEPT_VALID)) return 0;
+  int o = kept_code(pw, r);
+  if (o == 0) return ((orient_bits >> (4 + r)) & 1u) ? 1 : -1;
+  if (c.kind == MCX_RXN_BIMOL_VOLSURF && c.geom1 != 0 && surf_orient != c.geom1) o = -o;
+  return o;
 }
 
 // ---- surface diffusion -------------------------------------------------------------------------------------------
@@ -1503,7 +1530,8 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
                   if (tc.tr) { if (tc.tr->n_collisions < MCX_TRACE_K) tc.tr->partner[tc.tr->n_collisions] = sm.id; tc.tr->n_collisions++; }
                   const int pathway = test_bimolecular(p, p.classes[rc], scaling, rs);
                   if (pathway >= 0) {
-                    out.orient_bits = draw_orientation_bits(p.pathways[p.classes[rc].first_pathway + pathway], rs);
+                    out.orient_bits = draw_orientation_bits(p.pathways[p.classes[rc].first_pathway + pathway], rs) |
+                                      (coll_orient > 0 ? ORIENT_BIT_FRONT : 0u);
                     tc.ev(EV_RXN | (uint32_t)pathway, (uint32_t)rc);
                     if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = sm.id; tc.tr->t_event = abs_t; }
                     out.kind = MCX_OUT_REACTED; out.pos = wh.pos;

@@ -32,7 +32,7 @@ enum : uint32_t {
 
 struct DevSpecies { double space_step, time_step; uint32_t flags; uint32_t can_vol_react; uint32_t can_vol_surf; uint32_t pad; };
 struct DevClass { double max_fixed_p; uint32_t kind, r0, r1, first_pathway, n_pathways; int geom0, geom1; uint32_t pad; };
-struct DevPathway { double cum_prob; uint32_t n_products, products[MCX_MAX_PRODUCTS], keep_mask, rule_id; int prod_orient[MCX_MAX_PRODUCTS]; uint32_t pad; };
+struct DevPathway { double cum_prob; uint32_t n_products, products[MCX_MAX_PRODUCTS], keep_mask, rule_id; int prod_orient[MCX_MAX_PRODUCTS]; uint32_t kept_info; };
 
 // per-wall surface grid (Grid::initialize, src4/wall.cpp:38-74) + the wall's first entry in the tile table
 // one side of a triangle (src4/wall.h:32-90 Edge): the wall across it and the flattening transform between the uv frames
@@ -168,7 +168,7 @@ struct DevParams {
   unsigned int* scan_sums;  // scratch of the cell-histogram scan
   unsigned long long* claim;   // per slot: (epoch << 32) | ~priority
   uint32_t* prop_partner;      // per slot: partner slot of the pending proposal
-  uint32_t* prop_info;         // per slot: kind(4) | pathway(12) | class(16)
+  uint32_t* prop_info;         // per slot: kind(4) | pathway(8) | orientation bits(7) | class(13)
   double* prop_t;              // per slot: absolute event time
   uint32_t* pend[2];           // pending lists (slot indices)
   uint32_t* slow_list;         // slots the fast diffuse pass deferred to the generic evaluation

@@ -301,8 +301,34 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
     // kept initiator stops at the event and takes the rest of its step lazily next iteration
     uint32_t f = flags | DF_PARTIAL;
     double ut = unimol_time;
-    if (cl.kind == MCX_RXN_UNIMOL) { f |= DF_SCHED_UNIMOL; ut = MCX_TIME_INVALID; }
-    finalize_alive(p, slot, event_pos, id, species, f, t_event, ut);
+    D3 kept_pos = event_pos;
+    if (cl.kind == MCX_RXN_UNIMOL) {
+      f |= DF_SCHED_UNIMOL; ut = MCX_TIME_INVALID;
+      if (surf_slot != MCX_NONE) {  // a kept surface molecule takes its product-side orientation (:2706-2709)
+        const int ko = kept_orientation(cl, pw, 0, orient_bits, (flags & DF_ORIENT_UP) ? 1 : -1);
+        if (ko != 0) f = (f & ~DF_ORIENT_UP) | (ko > 0 ? DF_ORIENT_UP : 0u);
+      }
+    } else if (cl.kind == MCX_RXN_BIMOL_VOLSURF && surf_slot != MCX_NONE) {
+      // kept volume initiator of a surface reaction (:945-975, :2694-2716): it stays on the side it came from, or passes
+      // through the wall when its product-side orientation differs from the reactant-side one (RX_FLIP).  Like a
+      // volume product of the reaction it waits 2*16*EPS off the wall on that side, guarded against rebinding on
+      // the same tile once (the rest of its step is taken next iteration)
+      const int ko = kept_orientation(cl, pw, 0, orient_bits, (surf_sf & DF_ORIENT_UP) ? 1 : -1);
+      const bool flip = ko != 0 && cl.geom0 != ko;
+      const int coll_side = (orient_bits & ORIENT_BIT_FRONT) ? 1 : -1;
+      const int side = flip ? -coll_side : coll_side;
+      const uint32_t wi = p.swallA[surf_slot];
+      const DevWall& fw = p.walls[wi];
+      if (flip && p.wall_cv) {  // update_counted_volume_id_when_crossing_wall: a FRONT hit goes to the back side
+        const uint32_t cv = __ldg(p.wall_cv + wi);
+        f = (f & ~SF_CVI_MASK) | ((coll_side > 0 ? (cv >> 8) : (cv & 0xFFu)) << SF_CVI_SHIFT);
+      }
+      const double bump = (side > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
+      kept_pos = D3{event_pos.x + (2 * bump) * fw.nx, event_pos.y + (2 * bump) * fw.ny, event_pos.z + (2 * bump) * fw.nz};
+      f |= DF_CREATED_ON_SURF;
+      p.swallB[slot] = wi; p.stileB[slot] = p.stileA[surf_slot];
+    }
+    finalize_alive(p, slot, kept_pos, id, species, f, t_event, ut);
   }
 }
 
@@ -314,8 +340,8 @@ __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot
   p.tschedB[slot] = o.t_now;
   p.tuniB[slot] = o.unimol_time;
   p.prop_partner[slot] = o.partner_slot;
-  p.prop_info[slot] = (uint32_t)o.kind | (((uint32_t)o.pathway & 0xFFu) << 4) | ((o.orient_bits & 0xFu) << 12) |
-                      ((uint32_t)o.rxn_class << 16);
+  p.prop_info[slot] = (uint32_t)o.kind | (((uint32_t)o.pathway & 0xFFu) << 4) | ((o.orient_bits & ORIENT_BITS_MASK) << 12) |
+                      ((uint32_t)o.rxn_class << 19);
   p.prop_t[slot] = o.t_event;
   p.rank[slot] = MCX_NONE;
   unsigned long long key = claim_key(epoch, id);
@@ -884,8 +910,8 @@ __device__ __forceinline__ void resolve_round(const DevParams& p, unsigned int r
     MolRec e = load_rec_volatile(p.recB, slot);  // event position + identity
     uint32_t species = e.sf & SF_SPECIES_MASK;
     uint32_t info = __ldcg(p.prop_info + slot);
-    int kind = info & 15, pathway = (info >> 4) & 0xFF, rxn_class = info >> 16;
-    const uint32_t orient_bits = (info >> 12) & 0xFu;
+    int kind = info & 15, pathway = (info >> 4) & 0xFF, rxn_class = info >> 19;
+    const uint32_t orient_bits = (info >> 12) & ORIENT_BITS_MASK;
     uint32_t partner = __ldcg(p.prop_partner + slot);
     unsigned long long key = claim_key(epoch, e.id);
     bool ok = __ldcg(p.claim + slot) == key;

@@ -309,19 +309,34 @@ class Model:
                 prods = [idx[n] for n, _ in pparsed]
                 porient = [o for _, o in pparsed]
                 keep = 0
+                kept_at = {}   # position among the rule's products -> kept reactant (class order)
                 for k, rs in enumerate(r_idx):
-                    if rs in prods:
-                        at = prods.index(rs)
-                        prods.pop(at)
-                        porient.pop(at)
-                        keep |= 1 << k
-                if len(prods) > abi.MCX_MAX_PRODUCTS:
+                    for q, ps in enumerate(prods):
+                        if ps == rs and q not in kept_at:
+                            kept_at[q] = k
+                            keep |= 1 << k
+                            break
+                new_at = [q for q in range(len(prods)) if q not in kept_at]
+                if len(new_at) > abi.MCX_MAX_PRODUCTS:
                     raise ValueError("too many products")
-                pw.n_products = len(prods)
-                for k, p in enumerate(prods):
-                    pw.products[k] = p
-                    pw.product_orientation[k] = porient[k]
+                pw.n_products = len(new_at)
+                for k, q in enumerate(new_at):
+                    pw.products[k] = prods[q]
+                    pw.product_orientation[k] = porient[q]
                 pw.keep_reactant_mask = keep
+                # rule order of the products (= order of the orientation draws, diffuse_react_event.cpp:2618-2627) and the
+                # product-side orientation of the kept reactants (:2689-2716)
+                info = abi.MCX_KEPT_VALID
+                for q in range(6):
+                    if q >= len(prods):
+                        nib = abi.MCX_KEPT_ORDER_END
+                    elif q in kept_at:
+                        nib = abi.MCX_KEPT_ORDER_REACTANT + kept_at[q]
+                        info |= {0: 0, 1: 1, -1: 2}[porient[q]] << (24 + 2 * kept_at[q])
+                    else:
+                        nib = new_at.index(q)
+                    info |= nib << (4 * q)
+                pw.kept_info = info
                 pw.rxn_rule_id = r_id
                 pi += 1
             rc.max_fixed_p = cum

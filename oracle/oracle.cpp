@@ -166,6 +166,8 @@ struct Outcome {
   uint32_t orient_bits = 0;       // bit k: random orientation drawn for products[k] (1 = up)
   uint32_t cvi = 0;               // counted volume of the molecule at the end of the evaluation / at the event
   uint32_t wall = MCX_NONE, tile = MCX_NONE; double u = 0, v = 0;  // surface molecule: where it is after the evaluation
+  int coll_side = 0;              // volume-surface reaction: +1 the initiator hit the wall's front, -1 its back
+  uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE;  // SNAPSHOT, kept initiator of a surface reaction: rebinding guard
 };
 
 struct World {
@@ -743,12 +745,42 @@ static bool orientations_match(const mcx_rxn_class& rc, int orientA, int orientB
 }
 // one random bit per product whose rule orientation is NONE, drawn from the main stream right after the pathway
 // is chosen (outcome_products_random, diffuse_react_event.cpp:2618-2627); only when a surface is involved
+// With pw.kept_info the draws follow the order of the rule's products, kept reactants included (bit 4 + r belongs to
+// kept reactant r); without it (older tables) only the new products draw.
+static inline int kept_code(const mcx_pathway& pw, int r) {  // product-side orientation of kept reactant r: 0 none, +1, -1
+  const uint32_t c = (pw.kept_info >> (24 + 2 * r)) & 3u;
+  return c == 1 ? 1 : (c == 2 ? -1 : 0);
+}
 template <class RS>
 static uint32_t draw_orientation_bits(const mcx_pathway& pw, RS& rs) {
   uint32_t bits = 0;
-  for (uint32_t k = 0; k < pw.n_products; k++)
-    if (pw.product_orientation[k] == 0 && (rs.next() & 1)) bits |= 1u << k;
+  if (!(pw.kept_info & MCX_KEPT_VALID)) {
+    for (uint32_t k = 0; k < pw.n_products; k++)
+      if (pw.product_orientation[k] == 0 && (rs.next() & 1)) bits |= 1u << k;
+    return bits;
+  }
+  for (int q = 0; q < 6; q++) {
+    const uint32_t nib = (pw.kept_info >> (4 * q)) & 0xFu;
+    if (nib == MCX_KEPT_ORDER_END) break;
+    if (nib >= MCX_KEPT_ORDER_REACTANT) {
+      const int r = (int)(nib & 1u);
+      if (kept_code(pw, r) == 0 && (rs.next() & 1)) bits |= 1u << (4 + r);
+    } else if (nib < pw.n_products && pw.product_orientation[nib] == 0 && (rs.next() & 1)) bits |= 1u << nib;
+  }
   return bits;
+}
+// Product-side orientation of kept reactant r (outcome_products_random :2618-2652): the rule's mark, a drawn bit when
+// the rule has none, flipped when the surface reactant of a volume-surface reaction lies the other way round than
+// the rule states.  0: the table does not say (kept reactants stay as they are).
+static inline int kept_orientation(const mcx_rxn_class& c, const mcx_pathway& pw, int r, uint32_t orient_bits, int surf_orient) {
+  if (!(pw.kept_info & MCX_KEPT_VALID)) return 0;
+  int o = kept_code(pw, r);
+  if (o == 0) return ((orient_bits >> (4 + r)) & 1u) ? 1 : -1;
+  if (c.kind == MCX_RXN_BIMOL_VOLSURF) {
+    const int gB = c.reactant_orientation[1];
+    if (gB != 0 && surf_orient != gB) o = -o;
+  }
+  return o;
 }
 struct ProductSpec {
   uint32_t species; V3 pos;
@@ -1153,7 +1185,7 @@ struct Eval {
 //                 firing) ends the evaluation and is returned as a proposal.
 // ================================================================================================
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
-                            uint32_t orient_bits, bool& a_destroyed);
+                            uint32_t orient_bits, bool& a_destroyed, bool* flip = nullptr);
 static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed);
 static void seq_set_defunct(World& w, Mol& m);
 
@@ -1354,15 +1386,30 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
                   if (!apply) {
                     out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.rxn_class = rc; out.pathway = pathway;
                     out.partner_index = occ_index; out.partner_id = sm.id; out.t_event = abs_t; out.orient_bits = obits;
+                    out.coll_side = coll_orient;
                     fill_event(out);
                     return out;
                   }
-                  bool a_destroyed = false;
+                  bool a_destroyed = false, flip = false;
                   w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart; w.mols[index].cvi = s.cvi;
-                  seq_apply_bimol(w, index, occ_index, rc, pathway, c.pos, abs_t, obits, a_destroyed);
-                  // kept volume initiators are rejected at table set-up: the molecule is gone (collide_res == 1)
-                  destroyed = true; out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.t_event = abs_t;
-                  break;
+                  seq_apply_bimol(w, index, occ_index, rc, pathway, c.pos, abs_t, obits, a_destroyed, &flip);
+                  if (a_destroyed) {  // collide_res == 1
+                    destroyed = true; out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.t_event = abs_t;
+                    break;
+                  }
+                  last_hit_wall = c.wall;
+                  if (flip) {
+                    // RX_FLIP (:945-970): the kept initiator goes through the wall at the hit point and carries on
+                    s.pos = c.pos; s.subpart = w.subpart_index(s.pos);
+                    s.cvi = c.type == COLL_WALL_FRONT ? wall.cv_back : wall.cv_front;
+                    const double t_smash = c.time;
+                    remaining = remaining * (1.0 - t_smash);
+                    elapsed += t_steps * t_smash;
+                    t_steps *= (1.0 - t_smash);
+                    if (t_steps < EPS) t_steps = EPS;
+                    break;
+                  }
+                  // RX_A_OK with the initiator kept (:972-975): on to the wall's surface class, else it reflects
                 }
               }
             }
@@ -1502,7 +1549,7 @@ static std::vector<uint32_t>* g_new_actions = nullptr;  // new_diffuse_actions F
 // outcome_bimolecular / outcome_products_random (:1833-1895, :2446-2933): two volume reactants, or a volume
 // initiator and the surface molecule it hit
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
-                            uint32_t orient_bits, bool& a_destroyed) {
+                            uint32_t orient_bits, bool& a_destroyed, bool* flip) {
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
@@ -1524,6 +1571,17 @@ static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc
   if (!keepA) seq_set_defunct(w, w.mols[a_index]);
   if (!keepB) seq_set_defunct(w, w.mols[b_index]);
   a_destroyed = !keepA;
+  // kept reactants of a surface reaction (:2689-2716; class order is (volume, surface)): a kept surface molecule takes
+  // its product-side orientation; a kept volume initiator whose product-side orientation differs from the rule's
+  // reactant-side one passes through the wall (RX_FLIP)
+  if (flip) *flip = false;
+  if (surf_rxn && c.kind == MCX_RXN_BIMOL_VOLSURF) {
+    if (keepB) { const int o = kept_orientation(c, pw, 1, orient_bits, surf_copy.orient); if (o != 0) w.mols[b_index].orient = o; }
+    if (keepA && flip) {
+      const int o = kept_orientation(c, pw, 0, orient_bits, surf_copy.orient);
+      *flip = o != 0 && c.reactant_orientation[0] != o;
+    }
+  }
 }
 // outcome_unimolecular (:2939-3003)
 static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed) {
@@ -1544,6 +1602,7 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
   }
   if (!keep) seq_set_defunct(w, w.mols[index]);
   destroyed = !keep;
+  if (surf_rxn && keep) { const int o = kept_orientation(c, pw, 0, orient_bits, surf_copy.orient); if (o != 0) w.mols[index].orient = o; }
 }
 
 static void trace_begin(World& w, Eval& E, const Mol& m) {
@@ -1736,6 +1795,24 @@ static void step_snapshot(World& w, const SnapStreams& st) {
       // (catalytic initiators are rare; documented deviation: remaining sub-step is taken lazily)
       o.kind = MCX_OUT_MOVED; o.t_now = o.t_event; o.flags |= MCX_MOL_PARTIAL;
       if (c.kind == MCX_RXN_UNIMOL) { o.flags |= MCX_MOL_SCHEDULE_UNIMOL; o.unimol_time = TIME_INVALID; }
+      if (c.kind == MCX_RXN_UNIMOL && surf) {  // a kept surface molecule takes its product-side orientation (:2706-2709)
+        const int ko = kept_orientation(c, pw, 0, o.orient_bits, surf->orient);
+        if (ko != 0) w.mols[i].orient = ko;
+      }
+      if (c.kind == MCX_RXN_BIMOL_VOLSURF && surf) {
+        // kept volume initiator of a surface reaction (:945-975, :2694-2716): it stays on the side it came from, or
+        // passes through the wall when its product-side orientation differs from the reactant-side one (RX_FLIP).
+        // SNAPSHOT: like a volume product of the reaction it waits 2*16*EPS off the wall on that side, guarded
+        // against rebinding on the same tile once, and takes the rest of its step next iteration
+        const int ko = kept_orientation(c, pw, 0, o.orient_bits, surf->orient);
+        const bool flip = ko != 0 && c.reactant_orientation[0] != ko;
+        const Wall& f = w.walls[surf->wall];
+        const int side = flip ? -o.coll_side : o.coll_side;
+        if (flip) o.cvi = o.coll_side > 0 ? f.cv_back : f.cv_front;  // update_counted_volume_id_when_crossing_wall
+        const double bump = (side > 0) ? 16 * POS_EPS : -16 * POS_EPS;
+        o.pos = o.pos + V3{(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
+        o.created_wall = surf->wall; o.created_tile = surf->tile;
+      }
     }
   };
 
@@ -1797,7 +1874,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     Mol& m = w.mols[i];
     m.pos = o.pos; m.flags = o.flags; m.diffusion_time = o.t_now; m.unimol_rxn_time = o.unimol_time;
     m.subpart = w.subpart_index(m.pos);
-    m.created_wall = m.created_tile = MCX_NONE; m.cvi = o.cvi;
+    m.created_wall = o.created_wall; m.created_tile = o.created_tile; m.cvi = o.cvi;
     if (m.wall != MCX_NONE) { m.wall = o.wall; m.tile = o.tile; m.u = o.u; m.v = o.v; }
   }
   // compaction + products (the product's per-iteration sort does both)

@@ -130,6 +130,45 @@ def ligand_receptor_sphere(n_lig=6000, n_rec=1500, n_pump=600, radius_um=0.25, s
     return t, MolArrays.concat([vol, surf])
 
 
+def transporter_sphere(n_vol=20000, n_trans=2500, n_enz=1500, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8,
+                       rng_mode=abi.MCX_RNG_PHILOX, p_react=0.5, enzyme=True):
+    """Kept volume reactants of surface reactions (diffuse_react_event.cpp:945-975, 2689-2716) on a counted
+    icosphere inside a reflective box:
+       A' + T' -> A, + T'          transporter: A hits T from the front and passes through the wall (RX_FLIP)
+       S' + E' -> S' + E' + Pr'    enzyme: S and E are kept, the product is released in front of the wall; S reflects"""
+    import math
+    from mcell_b200.model import N_AV, MY_PI
+    m = Model(Config(seed=seed))
+    A = m.add_species("A", 1e-6)
+    S = m.add_species("S", 1e-6)
+    Pr = m.add_species("Pr", 2e-6)
+    T = m.add_species("T", 0.0, surface=True)
+    E = m.add_species("E", 0.0, surface=True)
+
+    def k_for(p, D):
+        pb = 2.0 * 1.0e11 * m.config.surface_grid_density / (2.0 * N_AV) * math.sqrt(MY_PI * m.config.time_step / D)
+        return p / pb
+
+    m.add_reaction_rule(["A'", "T'"], ["A,", "T'"], k_for(p_react, 1e-6))
+    if enzyme:   # its product takes a fresh id; without it molecule ids stay deterministic
+        m.add_reaction_rule(["S'", "E'"], ["S'", "E'", "Pr'"], k_for(p_react, 1e-6))
+    sv, sf = create_icosphere(radius_um, subdivisions)
+    m.add_geometry_object(sv, sf, counted=True)
+    bv, bf = create_box(box_um)
+    m.add_geometry_object(bv, bf, counted=True)
+    n_total = n_vol + n_trans + n_enz
+    t = m.build(max_molecules=3 * n_total + 64, rng_mode=rng_mode)
+    rng = np.random.default_rng(seed)
+    pos = release_uniform_box(rng, n_vol, box_um, t.length_unit, margin=1e-3)
+    vol = MolArrays.from_positions(pos, (np.arange(n_vol) % 2).astype(np.uint32) * S + (1 - np.arange(n_vol) % 2).astype(np.uint32) * A,
+                                   schedule_unimol=True)
+    vol.counted_volume[:] = counted_volume_of(t, pos)
+    sphere_walls = np.arange(len(sf), dtype=np.uint32)
+    surf = release_on_walls(rng, t, sphere_walls, n_trans + n_enz, T, orientation=1, first_id=n_vol)
+    surf.species[n_trans:] = E
+    return t, MolArrays.concat([vol, surf])
+
+
 def diffusing_receptors(n_rec=3000, n_lig=8000, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8, D_surf=1e-7,
                         rng_mode=abi.MCX_RNG_PHILOX, p_bind=0.5, k_off=1e5, with_ligand=True):
     """Surface diffusion: receptors R diffuse on an icosphere (diffuse_surf_molecule, ray_trace_surf

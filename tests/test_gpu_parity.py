@@ -206,6 +206,86 @@ def test_philox_surface_unbinding_two_products():
     assert cm.rel_close(ka[:, 1:4], kb[:, 1:4], POS_TOL).all()
 
 
+def test_philox_transporter_flips_volume_reactant_through_the_wall():
+    """SURVEY 8 a17, RX_FLIP (diffuse_react_event.cpp:945-970, 2694-2716): A' + T' -> A, + T' keeps both reactants and
+    takes A through the wall of a counted sphere.  No new molecules, so ids stay deterministic: traces, statistics,
+    per-volume counts and the whole population (incl. the counted volume of every molecule and the rebinding guard of
+    the kept initiator, which shows in the next iteration's trace) are compared over many iterations."""
+    t, mols = cm.transporter_sphere(n_vol=24000, n_trans=3500, n_enz=500, seed=5, enzyme=False)
+    n = mols.n
+    o = _oracle(t)
+    o.upload(mols)
+    e = _engine(t)
+    e.upload(mols)
+    flips = 0
+    for it in range(14):
+        tr_o, st_o = o.trace_step(1, n)
+        tr_g, st_g = e.trace_step(n)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "products_created", "mol_wall_reflections", "resolve_retries", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        flips += st_g.bimol_rxns
+        assert st_g.products_created == 0
+        mo, ro = o.counts_by_volume()
+        mg, rg = e.counts_by_volume()
+        assert (mo == mg).all() and (ro == rg).all(), it
+    assert flips > 150, flips
+    a, b = o.download().sorted_by_id(), e.download().sorted_by_id()
+    _assert_same_population(a, b)
+    assert (a.counted_volume == b.counted_volume).all()
+    vol = b.wall == abi.MCX_NONE
+    pos = np.stack([b.x, b.y, b.z], 1)[vol]
+    assert (b.counted_volume[vol] == cm.counted_volume_of(t, pos)).all()   # the index follows the molecule through the wall
+    assert e.counts()[1][0] == flips
+
+
+def test_philox_enzyme_keeps_volume_and_surface_reactant():
+    """S' + E' -> S' + E' + Pr' next to the transporter rule: both reactants are kept (the volume
+    reactant waits in front of the wall for the rest of its step), the product takes a fresh id — so every
+    iteration starts from a common state and is compared bit for bit (traces, statistics, counts), the populations as
+    multisets."""
+    t, mols = cm.transporter_sphere(n_vol=24000, n_trans=2500, n_enz=2500, seed=6)
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+
+    def key(m):
+        arr = np.c_[m.species[:m.n].astype(float), m.x[:m.n], m.y[:m.n], m.z[:m.n], m.diffusion_time[:m.n],
+                    m.flags[:m.n].astype(float), m.counted_volume[:m.n].astype(float), m.wall[:m.n].astype(float),
+                    m.tile[:m.n].astype(float)]
+        return arr[np.lexsort(arr.T[::-1])]
+
+    made = 0
+    state = mols
+    for it in range(8):
+        n_ids = int(state.id[:state.n].max()) + 1
+        if it:
+            e.upload(state)
+            o.upload(state)
+        tr_o, st_o = o.trace_step(1, n_ids)
+        tr_g, st_g = e.trace_step(n_ids)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "products_created", "mol_wall_reflections", "resolve_retries", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        made += st_g.products_created
+        assert (o.counts()[0] == e.counts()[0]).all(), it
+        a, b = o.download(), e.download()
+        assert a.n == b.n
+        ka, kb = key(a), key(b)
+        assert (ka[:, 0] == kb[:, 0]).all() and (ka[:, 4:] == kb[:, 4:]).all(), it
+        assert cm.rel_close(ka[:, 1:4], kb[:, 1:4], POS_TOL).all(), it
+        state = a
+    assert made > 100, made
+    c = e.counts()[0]
+    assert c[0] + c[1] == 24000 and c[3] == 2500 and c[4] == 2500
+
+
 def test_philox_surface_diffusion_with_binding():
     """Surface diffusion (diffuse_surf_molecule, ray_trace_surf across triangle edges, tile claims between movers)
     together with ligand binding on the moving receptors: traces (incl. the tile every mover takes), conflict

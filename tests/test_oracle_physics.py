@@ -352,3 +352,60 @@ def test_surface_diffusion_crowded_with_binding_agrees_between_semantics():
     seq, snap = np.array(seq), np.array(snap)
     se = math.sqrt(seq.var(ddof=1) / len(seq) + snap.var(ddof=1) / len(snap))
     assert abs(seq.mean() - snap.mean()) < 3 * se + 0.03 * seq.mean(), (seq.mean(), snap.mean(), se)
+
+
+def _inside(t, m, species):
+    """(molecules of a volume species inside the sphere of transporter_sphere by a fresh ray cast, all of them)"""
+    sel = (m.species[:m.n] == species) & (m.wall[:m.n] == abi.MCX_NONE)
+    pos = np.stack([m.x[:m.n], m.y[:m.n], m.z[:m.n]], 1)[sel]
+    inner = [i for i, s_ in enumerate(t.counted_volume_sets) if 0 in s_][0]
+    return int((cm.counted_volume_of(t, pos) == inner).sum()), int(sel.sum())
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_kept_volume_reactants_of_surface_reactions(mode):
+    """SURVEY 8 a17 (diffuse_react_event.cpp:945-975, 2689-2716): A' + T' -> A, + T' takes A through the wall (RX_FLIP:
+    the molecule goes on behind the wall and its counted volume switches), S' + E' -> S' + E' + Pr' keeps both
+    reactants (S reflects) and releases Pr in front.  The sphere is reflective otherwise, so A only ever enters, S and
+    Pr never do; mode 0 = reference semantics, 1 = snapshot semantics."""
+    t, mols = cm.transporter_sphere(n_vol=6000, n_trans=2500, n_enz=1500, seed=11)
+    A, S, Pr, T, E = 0, 1, 2, 3, 4
+    o = O.Oracle(t)
+    o.upload(mols)
+    a_in0, a_tot = _inside(t, mols, A)
+    s_in0, s_tot = _inside(t, mols, S)
+    prev = a_in0
+    for it in range(8):
+        o.step(2, mode)
+        m = o.download()
+        a_in, a_n = _inside(t, m, A)
+        s_in, s_n = _inside(t, m, S)
+        pr_in, pr_n = _inside(t, m, Pr)
+        assert a_n == a_tot and s_n == s_tot                      # kept reactants are never consumed
+        assert a_in >= prev and s_in == s_in0 and pr_in == 0       # one-way transport; S and Pr stay outside
+        prev = a_in
+        sp, rx = o.counts()
+        assert sp[T] == 2500 and sp[E] == 1500 and sp[Pr] == rx[1] == pr_n
+        assert rx[0] == a_in - a_in0                               # every transport event moved one A inside
+        # counted volume index of every volume molecule == a fresh ray cast (SURVEY A.2)
+        vol = m.wall[:m.n] == abi.MCX_NONE
+        pos = np.stack([m.x[:m.n], m.y[:m.n], m.z[:m.n]], 1)[vol]
+        assert (m.counted_volume[:m.n][vol] == cm.counted_volume_of(t, pos)).all()
+    assert prev - a_in0 > 25 and rx[1] > 25, (prev - a_in0, rx)
+
+
+def test_kept_volume_reactants_snapshot_matches_reference_semantics():
+    """transport and turnover counts of the two execution modes agree statistically"""
+    res = []
+    for mode in (0, 1):
+        tot = np.zeros(2)
+        for seed in range(3):
+            t, mols = cm.transporter_sphere(n_vol=8000, n_trans=2500, n_enz=1500, seed=20 + seed)
+            o = O.Oracle(t)
+            o.upload(mols)
+            o.step(16, mode)
+            tot += o.counts()[1][:2]
+        res.append(tot)
+    for k in range(2):
+        a, b = res[0][k], res[1][k]
+        assert abs(a - b) < 5 * math.sqrt(a + b), (k, res)
