@@ -296,6 +296,17 @@ int mcx_set_counted_volumes(mcx_handle* h, uint32_t n_counted_volumes, const uin
  * mol_counts[species * n_counted_volumes + cv], rxn_counts[rxn_rule * n_counted_volumes + cv]; either may be NULL. */
 int mcx_counts_by_volume(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_counts);
 
+/* Counted surface regions (MolOrRxnCountEvent terms CountType::PresentOnSurfaceRegion and RxnCountOnSurfaceRegion,
+ * src4/mol_or_rxn_count_event.cpp:528-534, 588-600; the reference keeps reaction counts per wall,
+ * Partition::inc_rxn_on_surface_occured_count, diffuse_react_event.cpp:2513-2521).  The host numbers the distinct sets of
+ * counted regions a wall can belong to (set 0 = none) and hands over one index per wall; a region expression is then
+ * evaluated per set on the host (wall_matches_region_expr_recursively).  Call after mcx_set_geometry;
+ * n_region_sets <= 256.  Reactions are counted from this call on. */
+int mcx_set_surface_regions(mcx_handle* h, uint32_t n_region_sets, const uint8_t* wall_region_set);
+/* mol_counts[species * n_region_sets + set]: surface molecules on the walls of each set;
+ * rxn_counts[rxn_rule * n_region_sets + set]: reactions whose initiator was a surface molecule there; either may be NULL. */
+int mcx_counts_by_surface_region(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_counts);
+
 /* ---- release on the device (new; ReleaseEvent::release_ellipsoid_or_rectcuboid, src4/release_event.cpp:953-1003) --- */
 /* The reference releases molecules on the host, sequentially from its one random stream; 1e8 molecules cannot be
  * pushed through that (or through PCIe as a 52-byte SoA) quickly.  mcx_release_volume_molecules creates `number`

@@ -46,6 +46,7 @@ struct mcx_handle {
        *d_tile_slot = nullptr, *d_exd_skip = nullptr, *d_wall_cv = nullptr, *d_rxn_count_cv = nullptr,
        *d_mol_count_cv = nullptr, *d_edges = nullptr, *d_tile_claim = nullptr;
   uint32_t n_cv = 1; uint32_t* st_cv = nullptr;
+  void *d_wall_rs = nullptr, *d_rxn_count_rs = nullptr, *d_mol_count_rs = nullptr; uint32_t n_rs = 0;
   uint64_t n_walls_host = 0;
   bool has_surf = false, surf_allocated = false;
   uint32_t *st_wall = nullptr, *st_tile = nullptr; int32_t* st_orient = nullptr; double *st_u = nullptr, *st_v = nullptr;
@@ -344,6 +345,7 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
     // the per-wall counted-volume table belongs to the previous geometry: drop it (mcx_set_counted_volumes again)
     h->p.wall_cv = nullptr; h->p.n_cv = 1; h->n_cv = 1;
   }
+  if (h->p.wall_rs && h->n_walls_host != n_walls) { h->p.wall_rs = nullptr; h->p.n_rs = 0; h->n_rs = 0; }  // likewise
   h->n_walls_host = n_walls;
   h->has_geometry = true;
   return MCX_OK;
@@ -591,6 +593,55 @@ int mcx_counts_by_volume(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_coun
       for (const auto& pw : h->pathways) n_rules = std::max(n_rules, pw.rxn_rule_id + 1);
       int rc = reduce(rxn_counts, (size_t)n_rules * h->n_cv); if (rc) return rc;
     }
+  }
+  return MCX_OK;
+}
+
+int mcx_set_surface_regions(mcx_handle* h, uint32_t n_region_sets, const uint8_t* wall_region_set) {
+  if (!h || !wall_region_set) { if (h) h->err = "null surface-region array"; return MCX_ERR_INVALID_ARG; }
+  if (!h->has_geometry) { h->err = "mcx_set_geometry must precede mcx_set_surface_regions"; return MCX_ERR_STATE; }
+  if (n_region_sets == 0 || n_region_sets > 256) { h->err = "1..256 surface-region sets are supported"; return MCX_ERR_INVALID_ARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  for (uint64_t i = 0; i < h->n_walls_host; i++)
+    if (wall_region_set[i] >= n_region_sets) { h->err = "surface-region set index out of range"; return MCX_ERR_INVALID_ARG; }
+  std::vector<unsigned long long> zero((size_t)256 * n_region_sets, 0);
+  int rc = MCX_OK;
+  rc |= dev_replace(h, &h->d_wall_rs, wall_region_set, std::max<uint64_t>(h->n_walls_host, 1));
+  rc |= dev_replace(h, &h->d_rxn_count_rs, zero.data(), zero.size());
+  rc |= dev_replace(h, &h->d_mol_count_rs, zero.data(), zero.size());
+  if (rc) return MCX_ERR_CUDA;
+  h->n_rs = n_region_sets;
+  h->p.wall_rs = (const uint8_t*)h->d_wall_rs; h->p.rxn_count_rs = (unsigned long long*)h->d_rxn_count_rs;
+  h->p.mol_count_rs = (unsigned long long*)h->d_mol_count_rs; h->p.n_rs = n_region_sets;
+  return MCX_OK;
+}
+
+int mcx_counts_by_surface_region(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_counts) {
+  if (!h) return MCX_ERR_INVALID_ARG;
+  if (!h->uploaded) { h->err = "nothing uploaded"; return MCX_ERR_STATE; }
+  if (!h->p.wall_rs) { h->err = "mcx_set_surface_regions was not called"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  h->p.cs_cur = h->cs[h->cs_cur]; h->p.cs_next = h->cs[h->cs_cur ^ 1]; h->p.iteration = h->iteration;
+  uint32_t n_rules = 0;
+  for (const auto& pw : h->pathways) n_rules = std::max(n_rules, pw.rxn_rule_id + 1);
+  if (mol_counts) {
+    mcx_launch_count_by_surface_region(h->p, h->stream);
+    h->launches += 1;
+    CK(cudaMemcpyAsync(mol_counts, h->p.mol_count_rs, sizeof(uint64_t) * h->species.size() * h->n_rs, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (rxn_counts)
+    CK(cudaMemcpyAsync(rxn_counts, h->p.rxn_count_rs, sizeof(uint64_t) * (size_t)n_rules * h->n_rs, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->comm) {  // every rank counted its own molecules and the events it owns: sum over the ranks
+    auto reduce = [&](uint64_t* a, size_t n) -> int {
+      for (size_t at = 0; at < n; at += 1024) {
+        int rc = mcx_comm_allreduce_u64(h->comm, (unsigned long long*)(a + at), (int)std::min<size_t>(1024, n - at), h->stream);
+        if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+      }
+      return MCX_OK;
+    };
+    if (mol_counts) { int rc = reduce(mol_counts, h->species.size() * h->n_rs); if (rc) return rc; }
+    if (rxn_counts) { int rc = reduce(rxn_counts, (size_t)n_rules * h->n_rs); if (rc) return rc; }
   }
   return MCX_OK;
 }

@@ -138,6 +138,10 @@ struct DevParams {
   unsigned long long* rxn_count_cv;  // [rule * n_cv + cv]
   unsigned long long* mol_count_cv;  // [species * n_cv + cv], filled by mcx_counts_by_volume
   unsigned int n_cv;
+  const uint8_t* wall_rs;       // per wall: index of the set of counted surface regions it belongs to; null = none
+  unsigned long long* rxn_count_rs;  // [rule * n_rs + region set]: reactions whose initiator was a surface molecule there
+  unsigned long long* mol_count_rs;  // [species * n_rs + region set], filled by mcx_counts_by_surface_region
+  unsigned int n_rs;
   int n_species, n_surf_classes, n_walls;
   // surface molecules: tile table of the current snapshot and per-slot cold fields
   const DevGrid* grids;         // per wall
@@ -238,6 +242,7 @@ void mcx_launch_add_received(const DevParams& p, unsigned int n, cudaStream_t s)
 void mcx_launch_halo_p2p(const DevParams& p, const HaloP2P& link, cudaStream_t s);  // pack+store to peers, acquire+unpack
 void mcx_launch_sort(const DevParams& p, const StepPlan& plan, cudaStream_t s);
 void mcx_launch_count_by_volume(const DevParams& p, cudaStream_t s);
+void mcx_launch_count_by_surface_region(const DevParams& p, cudaStream_t s);
 void mcx_launch_reset_population(const DevParams& p, unsigned int n_slots, cudaStream_t s);  // before an upload
 // device staging of the surface part of mcx_mol_soa (all null: volume molecules only)
 struct SurfSoa { const uint32_t* wall; const uint32_t* tile; const int32_t* orientation; const double* u; const double* v; const uint32_t* cv; };

@@ -211,7 +211,10 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
   const DevClass& cl = p.classes[rxn_class];
   const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
   if (own_event) { if (bt) atomicAdd(&bt->rxn[pw.rule_id & 255u], 1u); else agg_add(&c->rxn_count[pw.rule_id & 255u], 1u); }
-  if (own_event && p.wall_cv) agg_add(&p.rxn_count_cv[(pw.rule_id & 255u) * p.n_cv + (flags >> SF_CVI_SHIFT)], 1u);
+  // outcome_products_random :2513-2521: a volume initiator counts the reaction in its counted volume, a surface
+  // initiator on its wall (here: in the wall's set of counted surface regions)
+  if (own_event && p.wall_cv && !(flags & DF_SURF)) agg_add(&p.rxn_count_cv[(pw.rule_id & 255u) * p.n_cv + (flags >> SF_CVI_SHIFT)], 1u);
+  if (own_event && p.wall_rs && (flags & DF_SURF)) agg_add(&p.rxn_count_rs[(pw.rule_id & 255u) * p.n_rs + __ldg(p.wall_rs + p.swallA[slot])], 1u);
   bool keepA, keepB = true;
   uint32_t reuse[2]; int n_reuse = 0;
   if (kind == MCX_OUT_REACTED) {
@@ -1178,6 +1181,22 @@ __global__ void __launch_bounds__(TPB) k_count_by_volume(const __grid_constant__
     const unsigned int peers = __match_any_sync(__activemask(), key);
     if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.mol_count_cv[key], (unsigned long long)__popc(peers));
   }
+}
+// CountType::PresentOnSurfaceRegion (mol_or_rxn_count_event.cpp:528-534): surface molecules per (species, set of
+// counted surface regions of their wall)
+__global__ void __launch_bounds__(TPB) k_count_by_surface_region(const __grid_constant__ DevParams p) {
+  const unsigned int n = p.ctr->n_slots;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const MolRec m = load_rec_volatile(p.recA, i);
+    if ((m.sf & DF_DEAD) || !(m.sf & DF_SURF) || !owned_z(p, m.z)) continue;
+    const unsigned int key = (m.sf & SF_SPECIES_MASK) * p.n_rs + __ldg(p.wall_rs + p.swallA[i]);
+    const unsigned int peers = __match_any_sync(__activemask(), key);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.mol_count_rs[key], (unsigned long long)__popc(peers));
+  }
+}
+void mcx_launch_count_by_surface_region(const DevParams& p, cudaStream_t s) {
+  cudaMemsetAsync(p.mol_count_rs, 0, sizeof(unsigned long long) * (size_t)p.n_species * p.n_rs, s);
+  if (p.has_surf) k_count_by_surface_region<<<p.sm_count * 8, TPB, 0, s>>>(p);
 }
 void mcx_launch_count_by_volume(const DevParams& p, cudaStream_t s) {
   cudaMemsetAsync(p.mol_count_cv, 0, sizeof(unsigned long long) * (size_t)p.n_species * p.n_cv, s);

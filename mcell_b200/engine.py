@@ -60,6 +60,8 @@ def load_library():
     L.mcx_philox_block.restype = None
     L.mcx_set_counted_volumes.argtypes = [H, C.c_uint32, C.c_void_p, C.c_void_p]
     L.mcx_counts_by_volume.argtypes = [H, C.c_void_p, C.c_void_p]
+    L.mcx_set_surface_regions.argtypes = [H, C.c_uint32, C.c_void_p]
+    L.mcx_counts_by_surface_region.argtypes = [H, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -89,6 +91,8 @@ class Engine:
                                          _vp(t.wall_surf_class), _vp(getattr(t, "wall_object", None))))
         if getattr(t, "n_counted_volumes", 0) > 1:
             self._ck(self.L.mcx_set_counted_volumes(self.h, t.n_counted_volumes, _vp(t.wall_cv_front), _vp(t.wall_cv_back)))
+        if getattr(t, "n_region_sets", 0) > 1:
+            self._ck(self.L.mcx_set_surface_regions(self.h, t.n_region_sets, _vp(t.wall_region_set)))
 
     def _ck(self, rc):
         if rc:
@@ -193,6 +197,25 @@ def _counts_by_volume(self):
 
 
 Engine.counts_by_volume = _counts_by_volume
+
+
+def _counts_by_surface_region(self):
+    """(surface molecules[species, region set], reactions initiated by surface molecules[rule, region set]); a region
+    expression is evaluated over Tables.region_sets (region_count below)."""
+    nrs = max(1, getattr(self.t, "n_region_sets", 1))
+    m = np.zeros((max(1, self.t.n_species), nrs), np.uint64)
+    r = np.zeros((max(1, self.t.n_rules), nrs), np.uint64)
+    self._ck(self.L.mcx_counts_by_surface_region(self.h, _vp(m), _vp(r)))
+    return m, r
+
+
+Engine.counts_by_surface_region = _counts_by_surface_region
+
+
+def region_count(tables, per_set, region_index):
+    """Sum of a [row, region set] count table over the sets that contain one region: the count 'on region R'."""
+    cols = [k for k, s_ in enumerate(tables.region_sets) if region_index in s_]
+    return per_set[:, cols].sum(axis=1)
 
 
 def philox_block(seed, mol_id, iteration, block):

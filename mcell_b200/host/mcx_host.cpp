@@ -45,6 +45,15 @@ GpuDiffuseReactEvent::GpuDiffuseReactEvent(const GpuModelTables& t, PartitionMol
                          t.wall_vertex_indices.size() / 3, t.wall_surf_class.empty() ? nullptr : t.wall_surf_class.data(),
                          nullptr), "mcx_set_geometry");
   for (const mcx_pathway& pw : t.pathways) n_rules = std::max<size_t>(n_rules, pw.rxn_rule_id + 1);
+  for (const mcx_species& sp : t.species) has_surface_species = has_surface_species || !(sp.flags & MCX_SP_VOL);
+  if (!t.wall_cv_front.empty()) {
+    check(mcx_set_counted_volumes(h, t.n_counted_volumes, t.wall_cv_front.data(), t.wall_cv_back.data()), "mcx_set_counted_volumes");
+    n_cv = t.n_counted_volumes;
+  }
+  if (!t.wall_region_set.empty()) {
+    check(mcx_set_surface_regions(h, t.n_region_sets, t.wall_region_set.data()), "mcx_set_surface_regions");
+    n_rs = t.n_region_sets;
+  }
 }
 
 GpuDiffuseReactEvent::~GpuDiffuseReactEvent() { mcx_destroy(h); }
@@ -66,10 +75,22 @@ void GpuDiffuseReactEvent::mark_host_modified() {
 void GpuDiffuseReactEvent::upload_from_host() {
   const size_t n = p->molecules.size();
   x.resize(n); y.resize(n); z.resize(n); tdiff.resize(n); tuni.resize(n); id.resize(n); species.resize(n); flags.resize(n);
+  cvi.resize(n);
+  if (has_surface_species) { su.resize(n); sv.resize(n); swall.resize(n); stile.resize(n); sorient.resize(n); }
   size_t k = 0;
   for (const Molecule& m : p->molecules) {
-    if (m.is_defunct() || !m.is_vol()) continue;  // surface molecules: not on the device path yet
-    x[k] = m.v.pos.x; y[k] = m.v.pos.y; z[k] = m.v.pos.z; id[k] = m.id; species[k] = m.species_id;
+    if (m.is_defunct()) continue;
+    if (!m.is_vol() && !has_surface_species)
+      throw McxFatalError(MCX_ERR_INVALID_ARG, "surface molecule of a model without surface species");
+    id[k] = m.id; species[k] = m.species_id;
+    if (m.is_vol()) {
+      x[k] = m.v.pos.x; y[k] = m.v.pos.y; z[k] = m.v.pos.z;
+      cvi[k] = m.v.counted_volume_index == INDEX_INVALID32 ? 0u : m.v.counted_volume_index;
+      if (has_surface_species) { swall[k] = MCX_NONE; stile[k] = MCX_NONE; sorient[k] = 0; su[k] = sv[k] = 0; }
+    } else {  // Molecule::s; the device derives the 3-D position from (wall, uv) like Partition::add_surface_molecule
+      x[k] = y[k] = z[k] = 0; cvi[k] = 0;
+      swall[k] = m.s.wall_index; stile[k] = m.s.grid_tile_index; sorient[k] = m.s.orientation; su[k] = m.s.pos.u; sv[k] = m.s.pos.v;
+    }
     uint32_t f = 0;
     if (m.flags & MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN) f |= MCX_MOL_SCHEDULE_UNIMOL;
     const bool partial = m.diffusion_time != TIME_INVALID && m.diffusion_time > event_time + 1e-12;
@@ -82,6 +103,8 @@ void GpuDiffuseReactEvent::upload_from_host() {
   mcx_mol_soa v{};
   v.n = k; v.x = x.data(); v.y = y.data(); v.z = z.data(); v.id = id.data(); v.species = species.data(); v.flags = flags.data();
   v.diffusion_time = tdiff.data(); v.unimol_rxn_time = tuni.data();
+  if (n_cv > 1) v.counted_volume = cvi.data();
+  if (has_surface_species) { v.wall = swall.data(); v.tile = stile.data(); v.orientation = sorient.data(); v.u = su.data(); v.v = sv.data(); }
   check(mcx_upload_molecules(h, &v), "mcx_upload_molecules");
   host_dirty = false;
 }
@@ -99,16 +122,22 @@ void GpuDiffuseReactEvent::sync_to_host() {
   if (!device_dirty) return;
   const size_t cap = (size_t)mcx_num_molecules(h) + 16;
   x.resize(cap); y.resize(cap); z.resize(cap); tdiff.resize(cap); tuni.resize(cap); id.resize(cap); species.resize(cap); flags.resize(cap);
+  cvi.resize(cap);
+  if (has_surface_species) { su.resize(cap); sv.resize(cap); swall.resize(cap); stile.resize(cap); sorient.resize(cap); }
   mcx_mol_soa v{};
   v.x = x.data(); v.y = y.data(); v.z = z.data(); v.id = id.data(); v.species = species.data(); v.flags = flags.data();
   v.diffusion_time = tdiff.data(); v.unimol_rxn_time = tuni.data();
+  if (n_cv > 1) v.counted_volume = cvi.data();
+  if (has_surface_species) { v.wall = swall.data(); v.tile = stile.data(); v.orientation = sorient.data(); v.u = su.data(); v.v = sv.data(); }
   check(mcx_download_molecules(h, &v, cap), "mcx_download_molecules");
   std::vector<Molecule> keep;
   keep.reserve(v.n);
-  for (const Molecule& m : p->molecules)
-    if (!m.is_vol() && !m.is_defunct()) keep.push_back(m);  // host-resident (surface) molecules stay as they are
   for (uint64_t k = 0; k < v.n; k++) {
     Molecule m(id[k], species[k], Vec3{x[k], y[k], z[k]}, TIME_INVALID);
+    if (has_surface_species && swall[k] != MCX_NONE) {  // Molecule::s
+      m.flags = MOLECULE_FLAG_SURF;
+      m.s.pos = Vec2{su[k], sv[k]}; m.s.orientation = sorient[k]; m.s.wall_index = swall[k]; m.s.grid_tile_index = stile[k];
+    } else if (n_cv > 1) m.v.counted_volume_index = cvi[k];
     if (flags[k] & MCX_MOL_SCHEDULE_UNIMOL) m.flags |= MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN;
     m.diffusion_time = tdiff[k];
     m.unimol_rxn_time = tuni[k];
@@ -140,6 +169,18 @@ void GpuDiffuseReactEvent::get_counts(std::vector<uint64_t>& per_species, std::v
   per_rxn_rule.assign(n_rules, 0);
   check(mcx_counts(h, per_species.data(), (uint32_t)n_species, per_rxn_rule.empty() ? nullptr : per_rxn_rule.data(),
                    (uint32_t)n_rules), "mcx_counts");
+}
+
+void GpuDiffuseReactEvent::get_counts_by_volume(std::vector<uint64_t>& per_species, std::vector<uint64_t>& per_rxn_rule) {
+  per_species.assign(n_species * n_cv, 0);
+  per_rxn_rule.assign(std::max<size_t>(n_rules, 1) * n_cv, 0);
+  check(mcx_counts_by_volume(h, per_species.data(), per_rxn_rule.data()), "mcx_counts_by_volume");
+}
+
+void GpuDiffuseReactEvent::get_counts_by_surface_region(std::vector<uint64_t>& per_species, std::vector<uint64_t>& per_rxn_rule) {
+  per_species.assign(n_species * n_rs, 0);
+  per_rxn_rule.assign(std::max<size_t>(n_rules, 1) * n_rs, 0);
+  check(mcx_counts_by_surface_region(h, per_species.data(), per_rxn_rule.data()), "mcx_counts_by_surface_region");
 }
 
 // ---- CountBuffer --------------------------------------------------------------------------------------------
@@ -204,13 +245,32 @@ void CountBuffer::flush_and_close() {
 }
 
 void GpuMolOrRxnCountEvent::step() {
-  std::vector<uint64_t> per_species, per_rxn;
+  std::vector<uint64_t> per_species, per_rxn, cv_species, cv_rxn, rs_species, rs_rxn;
   diffuse->get_counts(per_species, per_rxn);
+  bool need_cv = false, need_rs = false;
+  for (const MolOrRxnCountItem& item : items)
+    for (const MolOrRxnCountTerm& t : item.terms) {
+      need_cv = need_cv || t.where == CountWhere::VolumeRegion;
+      need_rs = need_rs || t.where == CountWhere::SurfaceRegion;
+    }
+  if (need_cv) diffuse->get_counts_by_volume(cv_species, cv_rxn);
+  if (need_rs) diffuse->get_counts_by_surface_region(rs_species, rs_rxn);
   for (const MolOrRxnCountItem& item : items) {
     double v = 0;
     for (const MolOrRxnCountTerm& t : item.terms) {
-      const std::vector<uint64_t>& src = t.is_rxn ? per_rxn : per_species;
-      if (t.index < src.size()) v += t.multiplier * (double)src[t.index];
+      if (t.where == CountWhere::World) {
+        const std::vector<uint64_t>& src = t.is_rxn ? per_rxn : per_species;
+        if (t.index < src.size()) v += t.multiplier * (double)src[t.index];
+        continue;
+      }
+      // a term restricted to a region: sum over the counted volumes / region sets its expression holds for
+      const bool vol = t.where == CountWhere::VolumeRegion;
+      const std::vector<uint64_t>& src = vol ? (t.is_rxn ? cv_rxn : cv_species) : (t.is_rxn ? rs_rxn : rs_species);
+      const size_t n_sets = vol ? diffuse->num_counted_volumes() : diffuse->num_region_sets();
+      for (uint32_t set : t.sets) {
+        const size_t at = (size_t)t.index * n_sets + set;
+        if (set < n_sets && at < src.size()) v += t.multiplier * (double)src[at];
+      }
     }
     buffers.at(item.buffer)->add(item.column, CountItem{event_time * time_unit, v});
   }

@@ -135,6 +135,12 @@ struct GpuModelTables {
   std::vector<double> vertices;        // 3 per vertex, length units
   std::vector<uint32_t> wall_vertex_indices;  // 3 per wall
   std::vector<uint32_t> wall_surf_class;      // per wall or empty
+  // counted volumes (World::init_counted_volumes): per wall the counted-volume index in front of / behind it; empty = none
+  uint32_t n_counted_volumes = 1;
+  std::vector<uint8_t> wall_cv_front, wall_cv_back;
+  // counted surface regions: per wall the index of the set of counted regions it belongs to (set 0 = none); empty = none
+  uint32_t n_region_sets = 1;
+  std::vector<uint8_t> wall_region_set;
 };
 
 // Drop-in for DiffuseReactEvent (src4/diffuse_react_event.h:108-154) running on the GPU through libmcx.
@@ -169,6 +175,12 @@ public:
                                          const Vec3& diameter, double release_time = 0, uint32_t counted_volume_index = 0);
   // MolOrRxnCountEvent world-count fast path (mol_or_rxn_count_event.cpp:622-653)
   void get_counts(std::vector<uint64_t>& per_species, std::vector<uint64_t>& per_rxn_rule);
+  // count terms restricted to a volume / a surface region (mol_or_rxn_count_event.cpp:519-534, 571-600):
+  // per_species[species * n_sets + set], per_rxn_rule[rule * n_sets + set]
+  void get_counts_by_volume(std::vector<uint64_t>& per_species, std::vector<uint64_t>& per_rxn_rule);
+  void get_counts_by_surface_region(std::vector<uint64_t>& per_species, std::vector<uint64_t>& per_rxn_rule);
+  uint32_t num_counted_volumes() const { return n_cv; }
+  uint32_t num_region_sets() const { return n_rs; }
   const mcx_step_stats& last_stats() const { return stats; }
 
 private:
@@ -177,6 +189,8 @@ private:
   mcx_handle* h = nullptr;
   PartitionMolecules* p;
   size_t n_species, n_rules;
+  uint32_t n_cv = 1, n_rs = 1;
+  bool has_surface_species = false;
   double time_up_to_next_barrier;
   double iterations_last_step = 1;
   bool host_dirty = true, device_dirty = false;
@@ -184,6 +198,10 @@ private:
   // SoA staging (host side of the ABI)
   std::vector<double> x, y, z, tdiff, tuni;
   std::vector<uint32_t> id, species, flags;
+  // Molecule::s and v.counted_volume_index
+  std::vector<double> su, sv;
+  std::vector<uint32_t> swall, stile, cvi;
+  std::vector<int32_t> sorient;
 };
 
 // ---- observables output: CountBuffer / CountItem (src4/count_buffer.h:24-123, count_buffer.cpp:30-129) -----------
@@ -226,7 +244,16 @@ private:
 // The world-count part of MolOrRxnCountEvent (mol_or_rxn_count_event.cpp:622-653): every `periodicity` iterations
 // one row per observable; species counts and reaction counts come from the device (mcx_counts), so a count
 // iteration costs no molecule download.
-struct MolOrRxnCountTerm { bool is_rxn; uint32_t index; double multiplier; };   // species id or rxn rule id
+// CountType of MolOrRxnCountTerm (mol_or_rxn_count_event.h): where the molecules / reactions of a term are counted
+enum class CountWhere { World, VolumeRegion, SurfaceRegion };
+// index: species id or rxn rule id.  sets (VolumeRegion: counted-volume indices, SurfaceRegion: region-set indices):
+// the sets for which the term's region expression holds, evaluated once by the host
+// (counted_volume_matches_region_expr_recursively / wall_matches_region_expr_recursively)
+struct MolOrRxnCountTerm {
+  bool is_rxn; uint32_t index; double multiplier;
+  CountWhere where = CountWhere::World;
+  std::vector<uint32_t> sets;
+};
 struct MolOrRxnCountItem { size_t buffer, column; std::vector<MolOrRxnCountTerm> terms; };
 
 class GpuMolOrRxnCountEvent : public BaseEvent {

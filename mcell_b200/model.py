@@ -141,6 +141,11 @@ class Tables:
     wall_cv_back: np.ndarray = None
     wall_object: np.ndarray = None
     counted_volume_sets: list = field(default_factory=lambda: [frozenset()])
+    # counted surface regions (MolOrRxnCountTerm region expressions over wall regions): set 0 = no counted region
+    n_region_sets: int = 1
+    wall_region_set: np.ndarray = None
+    region_sets: list = field(default_factory=lambda: [frozenset()])
+    region_names: list = field(default_factory=list)
 
 
 class Model:
@@ -153,6 +158,7 @@ class Model:
         self._tris = []
         self._wall_class = []
         self._counted = []
+        self._regions = []   # (name, object index, face indices of that object)
 
     # -- subsystem ------------------------------------------------------------------------
     def add_species(self, name, D, target_only=False, surface=False):
@@ -176,6 +182,12 @@ class Model:
         self._tris.append(np.asarray(faces, dtype=np.uint32) + np.uint32(base))
         sc = np.broadcast_to(np.asarray(surf_class, dtype=np.uint32), (len(faces),)).copy()
         self._wall_class.append(sc)
+
+    def add_surface_region(self, name, object_index, faces):
+        """A named surface region = some faces of one geometry object (Region, src4/region.h); used by surface-region
+        counts (CountType::PresentOnSurfaceRegion / RxnCountOnSurfaceRegion).  Returns the region's index."""
+        self._regions.append((name, int(object_index), np.asarray(faces, dtype=np.int64)))
+        return len(self._regions) - 1
 
     # -- derived units ----------------------------------------------------------------------
     @property
@@ -381,6 +393,25 @@ class Model:
         t.wall_object = np.concatenate([np.full(len(f), k, np.uint32) for k, f in enumerate(self._tris)]) if self._tris else np.zeros(0, np.uint32)
         if any(self._counted):
             _assign_counted_volumes(t, self._counted)
+        if self._regions:
+            # every distinct set of regions a wall belongs to gets one index (set 0 = none), as Partition keeps the
+            # regions of a wall (wall_matches_region_expr_recursively, mol_or_rxn_count_event.cpp)
+            first_wall = np.cumsum([0] + [len(f) for f in self._tris])
+            member = [set() for _ in range(len(tri))]
+            for k, (_, obj, faces) in enumerate(self._regions):
+                for f in faces:
+                    member[first_wall[obj] + int(f)].add(k)
+            sets = [frozenset()]
+            wrs = np.zeros(len(tri), np.uint8)
+            for wi, ms in enumerate(member):
+                fs = frozenset(ms)
+                if fs not in sets:
+                    sets.append(fs)
+                wrs[wi] = sets.index(fs)
+            if len(sets) > 256:
+                raise ValueError("more than 256 distinct sets of surface regions")
+            t.region_sets, t.n_region_sets, t.wall_region_set = sets, len(sets), wrs
+            t.region_names = [r[0] for r in self._regions]
         t.n_species, t.n_classes, t.n_pathways = len(self.species), len(groups), n_path
         t.n_surf_rules = len(self.surface_properties)
         t.n_rules = len(self.rules)

@@ -203,6 +203,9 @@ struct World {
   std::vector<uint64_t> species_count, rxn_count;
   uint32_t n_cv = 1;                       // counted volumes (index 0 = outside all)
   std::vector<uint64_t> rxn_count_cv;      // [rule * n_cv + cv] (inc_rxn_in_volume_occured_count)
+  std::vector<uint8_t> wall_rs;            // per wall: set of counted surface regions (mcx_set_surface_regions); empty = none
+  uint32_t n_rs = 0;
+  std::vector<uint64_t> rxn_count_rs;      // [rule * n_rs + set] (inc_rxn_on_surface_occured_count, summed per region set)
   std::vector<mcx_trace_rec> trace;  // by id, when tracing
   bool tracing = false;
   std::string err;
@@ -1548,12 +1551,18 @@ static std::vector<uint32_t>* g_new_actions = nullptr;  // new_diffuse_actions F
 
 // outcome_bimolecular / outcome_products_random (:1833-1895, :2446-2933): two volume reactants, or a volume
 // initiator and the surface molecule it hit
+// outcome_products_random :2513-2521: a volume initiator counts the reaction in its counted volume, a surface initiator
+// on its wall
+static inline void count_rxn_where(World& w, uint32_t rule, const Mol& initiator, uint32_t cvi) {
+  if (initiator.wall == MCX_NONE) w.rxn_count_cv[rule * w.n_cv + cvi]++;
+  else if (w.n_rs) w.rxn_count_rs[rule * w.n_rs + w.wall_rs[initiator.wall]]++;
+}
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
                             uint32_t orient_bits, bool& a_destroyed, bool* flip) {
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
-  w.rxn_count_cv[pw.rxn_rule_id * w.n_cv + w.mols[a_index].cvi]++;
+  count_rxn_where(w, pw.rxn_rule_id, w.mols[a_index], w.mols[a_index].cvi);
   w.stats.bimol_rxns++;
   // reactant ordering vs rule (:2541-2554)
   bool a_is_r0 = w.mols[a_index].species == c.reactants[0];
@@ -1588,7 +1597,7 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
-  w.rxn_count_cv[pw.rxn_rule_id * w.n_cv + w.mols[index].cvi]++;
+  count_rxn_where(w, pw.rxn_rule_id, w.mols[index], w.mols[index].cvi);
   w.stats.unimol_rxns++;
   V3 pos = w.mols[index].pos;
   bool keep = pw.keep_reactant_mask & 1;
@@ -1764,7 +1773,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     const mcx_rxn_class& c = w.classes[o.rxn_class];
     const mcx_pathway& pw = w.pathways[c.first_pathway + o.pathway];
     w.rxn_count[pw.rxn_rule_id]++;
-    w.rxn_count_cv[pw.rxn_rule_id * w.n_cv + o.cvi]++;
+    count_rxn_where(w, pw.rxn_rule_id, m, o.cvi);
     bool keepA, keepB = true;
     uint32_t reuse[2]; int n_reuse = 0;
     if (o.kind == MCX_OUT_REACTED) {
@@ -1971,6 +1980,25 @@ int orc_set_counted_volumes(void* h, uint32_t n_cv, const uint8_t* front, const 
   w.n_cv = n_cv ? n_cv : 1;
   for (size_t i = 0; i < w.walls.size(); i++) { w.walls[i].cv_front = front[i]; w.walls[i].cv_back = back[i]; }
   build_lookups(w);
+  return 0;
+}
+int orc_set_surface_regions(void* h, uint32_t n_region_sets, const uint8_t* wall_region_set) {
+  World& w = *(World*)h;
+  w.n_rs = n_region_sets;
+  w.wall_rs.assign(wall_region_set, wall_region_set + w.walls.size());
+  uint32_t max_rule = 1;
+  for (auto& pw : w.pathways) max_rule = std::max(max_rule, pw.rxn_rule_id + 1);
+  w.rxn_count_rs.assign((size_t)max_rule * w.n_rs, 0);
+  return 0;
+}
+int orc_counts_by_surface_region(void* h, uint64_t* mol_counts, uint64_t* rxn_counts) {
+  World& w = *(World*)h;
+  if (!w.n_rs) return MCX_ERR_STATE;
+  if (mol_counts) {
+    std::fill(mol_counts, mol_counts + w.species.size() * w.n_rs, 0);
+    for (auto& m : w.mols) if (!(m.flags & MCX_MOL_DEFUNCT) && m.wall != MCX_NONE) mol_counts[m.species * w.n_rs + w.wall_rs[m.wall]]++;
+  }
+  if (rxn_counts) std::copy(w.rxn_count_rs.begin(), w.rxn_count_rs.end(), rxn_counts);
   return 0;
 }
 int orc_counts_by_volume(void* h, uint64_t* mol_counts, uint64_t* rxn_counts) {

@@ -93,6 +93,8 @@ class Oracle:
                                 C.c_uint64(len(t.tri)), self._v(t.wall_surf_class), self._v(getattr(t, "wall_object", None)))
         if getattr(t, "n_counted_volumes", 0) > 1:
             self.L.orc_set_counted_volumes(self.h, C.c_uint32(t.n_counted_volumes), self._v(t.wall_cv_front), self._v(t.wall_cv_back))
+        if getattr(t, "n_region_sets", 0) > 1:
+            self.L.orc_set_surface_regions(self.h, C.c_uint32(t.n_region_sets), self._v(t.wall_region_set))
 
     def close(self):
         if self.h:
@@ -188,6 +190,16 @@ class Oracle:
         m = np.zeros((max(1, self.t.n_species), ncv), np.uint64)
         r = np.zeros((max(1, self.t.n_rules), ncv), np.uint64)
         self.L.orc_counts_by_volume(self.h, C.c_void_p(m.ctypes.data), C.c_void_p(r.ctypes.data))
+        return m, r
+
+    def counts_by_surface_region(self):
+        """(surface molecules[species, region set], reactions initiated by surface molecules[rule, region set])"""
+        nrs = max(1, getattr(self.t, "n_region_sets", 1))
+        m = np.zeros((max(1, self.t.n_species), nrs), np.uint64)
+        r = np.zeros((max(1, self.t.n_rules), nrs), np.uint64)
+        rc = self.L.orc_counts_by_surface_region(self.h, C.c_void_p(m.ctypes.data), C.c_void_p(r.ctypes.data))
+        if rc:
+            raise RuntimeError("orc_counts_by_surface_region: %d" % rc)
         return m, r
 
     def subpart_walls(self, subpart):

@@ -88,7 +88,7 @@ def reversible_box(n=20000, edge_um=0.5, seed=1, rng_mode=abi.MCX_RNG_PHILOX, k_
 
 
 def ligand_receptor_sphere(n_lig=6000, n_rec=1500, n_pump=600, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8,
-                           rng_mode=abi.MCX_RNG_PHILOX, p_bind=0.5, k_off=1e5, k_pump=2e5, release_products=True):
+                           rng_mode=abi.MCX_RNG_PHILOX, p_bind=0.5, k_off=1e5, k_pump=2e5, release_products=True, regions=False):
     """BASELINE config 3/4 surface chemistry on an icosphere inside a reflective box:
        L' + R' -> LR'        ligand binds receptors from the outside (front) only
        LR'     -> L' + R'    unbinding releases the ligand on the outside
@@ -118,6 +118,10 @@ def ligand_receptor_sphere(n_lig=6000, n_rec=1500, n_pump=600, radius_um=0.25, s
     m.add_geometry_object(sv, sf)
     bv, bf = create_box(box_um)
     m.add_geometry_object(bv, bf)
+    if regions:   # two overlapping counted surface regions of the sphere: walls fall into the sets {}, {north}, {band}, {north, band}
+        cz = np.asarray(sv)[np.asarray(sf)].mean(axis=1)[:, 2]
+        m.add_surface_region("north", 0, np.flatnonzero(cz > 0))
+        m.add_surface_region("band", 0, np.flatnonzero(np.abs(cz) < 0.4 * radius_um))
     n_total = n_lig + n_rec + n_pump
     t = m.build(max_molecules=2 * n_total + 64, rng_mode=rng_mode)
     rng = np.random.default_rng(seed)

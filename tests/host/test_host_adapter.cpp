@@ -146,6 +146,93 @@ int main() {
       if (ver != 2 || total != sp[0] + sp[1] + sp[2] || end != ftell(f)) { printf("viz file wrong\n"); return 1; }
       fclose(f); remove(viz.last_file.c_str());
     }
+    // ---- surface molecules through the adapter, counts restricted to counted volumes and to surface regions:
+    // L (volume) + R (surface, on the box faces) -> LR;  LR -> R (initiated by a surface molecule: counted on its wall)
+    {
+      const double hb = half * 0.3;
+      GpuModelTables t3 = box_model(hb, false, 4 * n);
+      t3.species.clear();
+      t3.species.push_back(mcx_species{2.0, 1.0, MCX_SP_VOL | MCX_SP_CAN_DIFFUSE, 0});  // L
+      t3.species.push_back(mcx_species{0.0, 1.0, 0, 0});                                  // R  (surface, static)
+      t3.species.push_back(mcx_species{0.0, 1.0, 0, 0});                                  // LR (surface, static)
+      mcx_rxn_class bind{}; bind.kind = MCX_RXN_BIMOL_VOLSURF; bind.reactants[0] = 0; bind.reactants[1] = 1;
+      bind.first_pathway = 0; bind.n_pathways = 1; bind.max_fixed_p = 0.5;
+      mcx_pathway pb{}; pb.cum_prob = 0.5; pb.n_products = 1; pb.products[0] = 2; pb.product_orientation[0] = 1; pb.rxn_rule_id = 0;
+      mcx_rxn_class unb{}; unb.kind = MCX_RXN_UNIMOL; unb.reactants[0] = 2; unb.reactants[1] = MCX_NONE;
+      unb.first_pathway = 1; unb.n_pathways = 1; unb.max_fixed_p = 0.2;
+      mcx_pathway pu{}; pu.cum_prob = 0.2; pu.n_products = 1; pu.products[0] = 1; pu.product_orientation[0] = 1; pu.rxn_rule_id = 1;
+      t3.rxn_classes = {bind, unb};
+      t3.pathways = {pb, pu};
+      // the box is a counted volume (index 1 inside = behind its outward-facing walls); walls 0-5 are region "low",
+      // walls 6-11 region "high": region sets {}, {low}, {high}
+      t3.n_counted_volumes = 2; t3.wall_cv_front.assign(12, 0); t3.wall_cv_back.assign(12, 1);
+      t3.n_region_sets = 3; t3.wall_region_set.resize(12);
+      for (int w = 0; w < 12; w++) t3.wall_region_set[w] = w < 6 ? 1 : 2;
+      PartitionMolecules p3;
+      for (int i = 0; i < n; i++) {
+        Molecule& m = p3.add_volume_molecule(0, Vec3{U(gen) * 0.3, U(gen) * 0.3, U(gen) * 0.3}, 0.0);
+        m.v.counted_volume_index = 1;
+      }
+      // receptors: every third tile of every wall, at the tile centre (Partition::add_surface_molecule)
+      uint64_t n_rec = 0, n_low = 0;
+      for (uint32_t w = 0; w < 12; w++) {
+        double v9[9];
+        for (int c = 0; c < 3; c++) for (int k = 0; k < 3; k++) v9[3 * c + k] = t3.vertices[3 * t3.wall_vertex_indices[3 * w + c] + k];
+        const uint32_t nt = mcx_grid_num_tiles(v9);
+        for (uint32_t tile = 0; tile < nt; tile += 3) {
+          double uv[2]; mcx_grid2uv(v9, tile, uv);
+          Molecule m; m.id = p3.next_molecule_id++; m.species_id = 1; m.flags = MOLECULE_FLAG_SURF | MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN;
+          m.diffusion_time = 0; m.unimol_rxn_time = TIME_INVALID; m.birthday = 0;
+          m.s.pos = Vec2{uv[0], uv[1]}; m.s.orientation = 1; m.s.wall_index = w; m.s.grid_tile_index = tile;
+          p3.molecules.push_back(m);
+          n_rec++; if (w < 6) n_low++;
+        }
+      }
+      p3.rebuild_mapping();
+      GpuDiffuseReactEvent ev3(t3, &p3);
+      ev3.event_time = 0;
+      GpuMolOrRxnCountEvent cnt3(&ev3, 1e-6);
+      CountBuffer buf("/tmp/mcx_host_adapter_counts.gdat", {"LR", "LR_low", "LR_high", "unbind_low", "unbind_high", "bind_in_box", "L_in_box"},
+                      100, CountOutputFormat::GDAT);
+      cnt3.buffers = {&buf};
+      cnt3.items = {
+        {0, 0, {{false, 2, 1.0}}},
+        {0, 1, {{false, 2, 1.0, CountWhere::SurfaceRegion, {1}}}},
+        {0, 2, {{false, 2, 1.0, CountWhere::SurfaceRegion, {2}}}},
+        {0, 3, {{true, 1, 1.0, CountWhere::SurfaceRegion, {1}}}},
+        {0, 4, {{true, 1, 1.0, CountWhere::SurfaceRegion, {2}}}},
+        {0, 5, {{true, 0, 1.0, CountWhere::VolumeRegion, {1}}}},
+        {0, 6, {{false, 0, 1.0, CountWhere::VolumeRegion, {1}}}}};
+      std::vector<uint64_t> rs_sp, rs_rx, cv_sp, cv_rx;
+      for (int window = 0; window < 3; window++) {
+        ev3.set_barrier_time_for_next_execution(10);
+        ev3.step();
+        ev3.update_event_time_for_next_scheduled_time();
+        cnt3.event_time = ev3.event_time;
+        cnt3.step();
+        ev3.get_counts(sp, rx);
+        ev3.get_counts_by_surface_region(rs_sp, rs_rx);
+        ev3.get_counts_by_volume(cv_sp, cv_rx);
+        if (sp[1] + sp[2] != n_rec || sp[0] + sp[2] + rx[1] != (uint64_t)n) { printf("surface count identity broken\n"); return 1; }
+        if (rs_sp[2 * 3 + 1] + rs_sp[2 * 3 + 2] != sp[2] || rs_sp[2 * 3 + 0] != 0) { printf("LR per region != LR\n"); return 1; }
+        if (rs_sp[1 * 3 + 1] + rs_sp[2 * 3 + 1] != n_low) { printf("receptors of region low moved\n"); return 1; }
+        if (rs_rx[1 * 3 + 1] + rs_rx[1 * 3 + 2] != rx[1] || rs_rx[0 * 3 + 1] + rs_rx[0 * 3 + 2] != 0) { printf("unbinding per region != unbinding\n"); return 1; }
+        if (cv_rx[0 * 2 + 1] != rx[0] || cv_rx[1 * 2 + 0] + cv_rx[1 * 2 + 1] != 0) { printf("binding in the box != binding\n"); return 1; }
+        if (cv_sp[0 * 2 + 1] != sp[0]) { printf("L in the box != L\n"); return 1; }
+      }
+      if (rx[0] < 50 || rx[1] < 5) { printf("too few surface reactions: %llu %llu\n", (unsigned long long)rx[0], (unsigned long long)rx[1]); return 1; }
+      buf.flush_and_close();
+      ev3.sync_to_host();
+      uint64_t surf_back = 0;
+      for (const Molecule& m : p3.molecules) if (!m.is_vol()) { surf_back++; if (m.s.wall_index >= 12) return 1; }
+      if (surf_back != n_rec) { printf("surface molecules lost in the download: %llu of %llu\n", (unsigned long long)surf_back, (unsigned long long)n_rec); return 1; }
+      FILE* f = fopen("/tmp/mcx_host_adapter_counts.gdat", "r");
+      if (!f) { printf("count file missing\n"); return 1; }
+      int lines = 0; char line[512];
+      while (fgets(line, sizeof(line), f)) lines++;
+      fclose(f); remove("/tmp/mcx_host_adapter_counts.gdat");
+      if (lines != 4) { printf("count file has %d lines\n", lines); return 1; }
+    }
     printf("host adapter ok: MSD %.4f, C after 30 iterations %llu\n", msd, (unsigned long long)last_c);
     return 0;
   } catch (const McxFatalError& e) {

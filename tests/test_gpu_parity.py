@@ -286,6 +286,25 @@ def test_philox_enzyme_keeps_volume_and_surface_reactant():
     assert c[0] + c[1] == 24000 and c[3] == 2500 and c[4] == 2500
 
 
+def test_philox_surface_region_counts():
+    """surface molecules per set of counted surface regions and the reactions initiated by surface
+    molecules there (mcx_counts_by_surface_region) against the oracle, every iteration."""
+    t, mols = cm.ligand_receptor_sphere(n_lig=24000, n_rec=3000, n_pump=1500, seed=12, k_off=3e5, k_pump=4e5,
+                                        release_products=False, regions=True)
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+    for it in range(10):
+        o.step(1, 1)
+        e.step(1)
+        mo, ro = o.counts_by_surface_region()
+        mg, rg = e.counts_by_surface_region()
+        assert (mo == mg).all() and (ro == rg).all(), it
+        assert (o.counts()[1] == e.counts()[1]).all(), it
+    assert rg.sum() > 30 and (rg.sum(axis=1)[[1, 3]] == e.counts()[1][[1, 3]]).all()
+    assert mg.sum() == 4500
+
+
 def test_philox_surface_diffusion_with_binding():
     """Surface diffusion (diffuse_surf_molecule, ray_trace_surf across triangle edges, tile claims between movers)
     together with ligand binding on the moving receptors: traces (incl. the tile every mover takes), conflict

@@ -409,3 +409,32 @@ def test_kept_volume_reactants_snapshot_matches_reference_semantics():
     for k in range(2):
         a, b = res[0][k], res[1][k]
         assert abs(a - b) < 5 * math.sqrt(a + b), (k, res)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_surface_region_counts(mode):
+    """SURVEY 8 f2 (mol_or_rxn_count_event.cpp:528-534, 588-600; diffuse_react_event.cpp:2513-2521): surface molecules per
+    set of counted regions == a count over the downloaded walls; reactions initiated by surface molecules (the
+    unimolecular LR -> R, CaP -> P) are counted on their wall, reactions initiated by volume molecules in their volume."""
+    from mcell_b200.engine import region_count
+    t, mols = cm.ligand_receptor_sphere(n_lig=8000, n_rec=2500, n_pump=1200, seed=9, k_off=3e5, k_pump=4e5,
+                                        release_products=False, regions=True)
+    assert t.n_region_sets == 4 and set(t.region_sets) == {frozenset(), frozenset({0}), frozenset({1}), frozenset({0, 1})}
+    o = O.Oracle(t)
+    o.upload(mols)
+    for it in range(4):
+        o.step(5, mode)
+        m = o.download()
+        mc, rc = o.counts_by_surface_region()
+        surf = m.wall[:m.n] != abi.MCX_NONE
+        ref = np.zeros_like(mc)
+        np.add.at(ref, (m.species[:m.n][surf], t.wall_region_set[m.wall[:m.n][surf]]), 1)
+        assert (mc == ref).all()
+        sp, rx = o.counts()
+        assert (mc.sum(axis=1)[2:] == sp[2:]).all() and (mc[:2] == 0).all()       # every surface molecule is on some set
+        assert (rc.sum(axis=1)[[1, 3]] == rx[[1, 3]]).all() and (rc[[0, 2]] == 0).all()
+        north = region_count(t, mc, 0)
+        band = region_count(t, mc, 1)
+        both = mc[:, t.region_sets.index(frozenset({0, 1}))]
+        assert (north + band - both <= sp).all()
+    assert rx[1] > 20 and rx[3] > 10
