@@ -321,6 +321,15 @@ int mcx_counts_by_surface_region(mcx_handle* h, uint64_t* mol_counts, uint64_t* 
 #define MCX_RELEASE_CUBIC 0
 #define MCX_RELEASE_SPHERICAL 1
 #define MCX_RELEASE_SPHERICAL_SHELL 2
+/* MCX_RELEASE_REGION: ReleaseEvent::release_inside_regions (release_event.cpp:904-951) — uniform in the box (location =
+ * centre, diameter = edges of the region's bounding box, region_llf / region_urb), a point is kept when it lies inside
+ * every closed object of region_in and outside every object of region_out (bit k = geometry object k of
+ * mcx_set_geometry's wall_object, k < 32: the INTERSECT / DIFFERENCE operators of the release's region expression;
+ * a UNION is released as separate calls over disjoint pieces), redrawn from the molecule's own stream otherwise.  The
+ * test is a ray cast through the subpartition wall lists (Region::is_point_inside, geometry.cpp:1048-1086); the
+ * counted volume of each molecule comes from the same ray (compute_counted_volume_for_pos, collision_utils.inl:
+ * 1515-1566) and counted_volume_index is ignored. */
+#define MCX_RELEASE_REGION 3
 typedef struct mcx_release {
   uint32_t species;
   uint32_t shape;                  /* MCX_RELEASE_* */
@@ -330,8 +339,40 @@ typedef struct mcx_release {
   double   release_time;           /* iterations; 0 = start of the current iteration */
   uint32_t counted_volume_index;   /* Molecule::v.counted_volume_index of the released molecules (0 = outside all) */
   uint32_t reserved;
+  uint32_t region_in, region_out;  /* MCX_RELEASE_REGION: object masks (see above) */
 } mcx_release;
 int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* first_id_out);
+/* ReleaseEvent::release_list (release_event.cpp:1008-1040), volume molecules: one molecule of species[k] at
+ * (x[k], y[k], z[k]) (length units) with counted_volume[k] (may be NULL: 0), ids first_id .. first_id + n - 1 in list
+ * order, added to the resident population without a download / upload round trip.  Same call on every rank. */
+int mcx_release_list(mcx_handle* h, uint64_t n, const uint32_t* species, const double* x, const double* y, const double* z,
+                     const uint32_t* counted_volume, double release_time, uint32_t* first_id_out);
+
+/* Surface molecules onto regions (ReleaseEvent::release_onto_regions, release_event.cpp:640-760): `number` molecules of a
+ * surface species on vacant tiles of the listed walls (the walls of the release's surface region(s), in the order of
+ * cumm_area_and_pwall_index_pairs), each tile chosen like the reference does — A = rng_dbl * total_area, the wall by
+ * bisection of the cumulative areas, tile = num_tiles * (A - area before the wall) / wall.area — and taken only if it
+ * is vacant.  The reference places one molecule after the other from its one random stream; here every molecule draws
+ * from its OWN Philox stream (release domain) and the placement runs in rounds: a tile goes to the lowest id that
+ * picked it, the others (and those that picked an occupied tile) draw again next round; whoever is still without a tile
+ * after MCX_SURFACE_RELEASE_ROUNDS rounds takes the first vacant tiles in wall-list order, lowest id first (the
+ * reference's fall-back, :702-744).  MCX_ERR_CAPACITY when the walls have fewer vacant tiles than `number`.
+ * Position on the tile: random (GridUtils::grid2uv_random, config.randomize_smol_pos) or the tile centre (grid2uv);
+ * orientation 0 draws one bit per molecule (place_single_molecule_onto_grid, grid_utils.inl:2097-2166).  New molecules
+ * get ids first_id .. first_id + number - 1 and MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN.  One device only (a rank knows
+ * the occupancy of its own slab alone). */
+#define MCX_SURFACE_RELEASE_ROUNDS 64
+typedef struct mcx_surface_release {
+  uint32_t species;
+  int32_t  orientation;            /* +1, -1, or 0 = random */
+  uint64_t number;
+  double   release_time;           /* iterations; 0 = start of the current iteration */
+  const uint32_t* walls;           /* wall indices */
+  uint64_t n_walls;
+  uint32_t randomize_pos;          /* config.randomize_smol_pos */
+  uint32_t reserved;
+} mcx_surface_release;
+int mcx_release_surface_molecules(mcx_handle* h, const mcx_surface_release* r, uint32_t* first_id_out);
 
 /* ---- multi-GPU (new: the reference has a single partition, world.cpp:147,277) --------- */
 /* nccl_unique_id: the 128-byte ncclUniqueId created by rank 0 and broadcast by the host

@@ -38,12 +38,18 @@ class mcx_config(C.Structure):
     ]
 
 
-MCX_RELEASE_CUBIC, MCX_RELEASE_SPHERICAL, MCX_RELEASE_SPHERICAL_SHELL = 0, 1, 2
+MCX_RELEASE_CUBIC, MCX_RELEASE_SPHERICAL, MCX_RELEASE_SPHERICAL_SHELL, MCX_RELEASE_REGION = 0, 1, 2, 3
 
 
 class mcx_release(C.Structure):
     _fields_ = [("species", c_u32), ("shape", c_u32), ("number", c_u64), ("location", c_f64 * 3), ("diameter", c_f64 * 3),
-                ("release_time", c_f64), ("counted_volume_index", c_u32), ("reserved", c_u32)]
+                ("release_time", c_f64), ("counted_volume_index", c_u32), ("reserved", c_u32),
+                ("region_in", c_u32), ("region_out", c_u32)]
+
+
+class mcx_surface_release(C.Structure):
+    _fields_ = [("species", c_u32), ("orientation", c_i32), ("number", c_u64), ("release_time", c_f64),
+                ("walls", C.c_void_p), ("n_walls", c_u64), ("randomize_pos", c_u32), ("reserved", c_u32)]
 
 
 class mcx_slab_info(C.Structure):
@@ -119,6 +125,7 @@ EXPORTED_SYMBOLS = [
     "mcx_download_molecules", "mcx_num_molecules", "mcx_step", "mcx_replay_step", "mcx_trace_step",
     "mcx_counts", "mcx_comm_init", "mcx_comm_unique_id", "mcx_slab_info_get", "mcx_comm_halo_path", "mcx_philox_block", "mcx_set_profiling",
     "mcx_grid_num_tiles", "mcx_grid2uv", "mcx_xyz2grid", "mcx_set_counted_volumes", "mcx_counts_by_volume", "mcx_release_volume_molecules", "mcx_fast_pass_kind", "mcx_walls_per_subpart",
+    "mcx_set_surface_regions", "mcx_counts_by_surface_region", "mcx_release_list", "mcx_release_surface_molecules",
 ]
 
 

@@ -46,6 +46,8 @@ struct mcx_handle {
        *d_tile_slot = nullptr, *d_exd_skip = nullptr, *d_wall_cv = nullptr, *d_rxn_count_cv = nullptr,
        *d_mol_count_cv = nullptr, *d_edges = nullptr, *d_tile_claim = nullptr;
   uint32_t n_cv = 1; uint32_t* st_cv = nullptr;
+  void *d_wall_obj = nullptr;
+  std::vector<double> wall_area_host;
   void *d_wall_rs = nullptr, *d_rxn_count_rs = nullptr, *d_mol_count_rs = nullptr; uint32_t n_rs = 0;
   uint64_t n_walls_host = 0;
   bool has_surf = false, surf_allocated = false;
@@ -276,6 +278,7 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   mcxg::GridSpec g{h->p.ox, h->p.oy, h->p.oz, h->p.sp_len, h->p.sp_rcp, h->p.R, h->p.n_sp, h->p.use_expanded != 0};
   std::vector<uint32_t> start, list;
   mcxg::bin_walls(g, vertices, tri, walls, start, list);
+  mcxg::wall_areas(vertices, tri, n_walls, h->wall_area_host);
   h->wall_class_host.assign(n_walls, MCX_NONE);
   if (wall_surf_class) h->wall_class_host.assign(wall_surf_class, wall_surf_class + n_walls);
   int rc = MCX_OK;
@@ -283,6 +286,11 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   rc |= dev_replace(h, &h->d_tri, tri, 3 * n_walls);
   rc |= dev_replace(h, &h->d_verts, vertices, 3 * n_vertices);
   rc |= dev_replace(h, &h->d_wclass, h->wall_class_host.data(), h->wall_class_host.size());
+  {
+    std::vector<uint32_t> wobj(std::max<uint64_t>(n_walls, 1), 0u);
+    if (wall_object) wobj.assign(wall_object, wall_object + n_walls);
+    rc |= dev_replace(h, &h->d_wall_obj, wobj.data(), wobj.size());
+  }
   rc |= dev_replace(h, &h->d_spw_start, start.data(), start.size());
   rc |= dev_replace(h, &h->d_spw_list, list.data(), list.size());
   // fine wall grid: K^3 cells per subpartition (K == 1: the subpartition lists themselves)
@@ -338,6 +346,7 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   DevParams& p = h->p;
   p.walls = (const DevWall*)h->d_walls; p.wall_tri = (const uint32_t*)h->d_tri; p.verts = (const double*)h->d_verts;
   p.wall_class = (const uint32_t*)h->d_wclass; p.spw_start = (const uint32_t*)h->d_spw_start;
+  p.wall_obj = (const uint32_t*)h->d_wall_obj;
   p.fw_start = p.fw_K > 1 ? (const uint32_t*)h->d_fw_start : (const uint32_t*)h->d_spw_start;
   p.fw_list = p.fw_K > 1 ? (const uint32_t*)h->d_fw_list : (const uint32_t*)h->d_spw_list;
   p.spw_list = (const uint32_t*)h->d_spw_list; p.n_walls = (int)n_walls; p.sp_flags = (const uint8_t*)h->d_sp_flags;
@@ -760,7 +769,11 @@ int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* 
   if (!h->uploaded) { h->err = "mcx_release_volume_molecules needs a previous mcx_upload_molecules (it may be empty)"; return MCX_ERR_STATE; }
   if (h->p.rng_mode != MCX_RNG_PHILOX) { h->err = "device release needs rng_mode == MCX_RNG_PHILOX (a replay releases on the host)"; return MCX_ERR_STATE; }
   if (r->species >= h->species.size() || !(h->species[r->species].flags & MCX_SP_VOL)) { h->err = "release: not a volume species"; return MCX_ERR_INVALID_ARG; }
-  if (r->shape > MCX_RELEASE_SPHERICAL_SHELL) { h->err = "release: unknown shape"; return MCX_ERR_INVALID_ARG; }
+  if (r->shape > MCX_RELEASE_REGION) { h->err = "release: unknown shape"; return MCX_ERR_INVALID_ARG; }
+  if (r->shape == MCX_RELEASE_REGION) {
+    if (!h->has_geometry) { h->err = "region release needs mcx_set_geometry"; return MCX_ERR_STATE; }
+    if (r->region_in == 0 || (r->region_in & r->region_out)) { h->err = "region release: region_in must name an object and be disjoint from region_out"; return MCX_ERR_INVALID_ARG; }
+  }
   if (r->counted_volume_index >= h->n_cv) { h->err = "release: counted_volume_index out of range"; return MCX_ERR_INVALID_ARG; }
   const double it = (double)h->iteration;
   if (r->release_time != 0 && !(r->release_time >= it && r->release_time < it + 1.0)) { h->err = "release_time outside the current iteration"; return MCX_ERR_INVALID_ARG; }
@@ -794,6 +807,158 @@ int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* 
     h->cs_cur ^= 1;
   }
   rc = check_device_error(h, &hc);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  if (first_id_out) *first_id_out = (uint32_t)base;
+  return MCX_OK;
+}
+
+// ReleaseEvent::release_list for volume molecules: appended behind the re-binned snapshot like the other releases
+int mcx_release_list(mcx_handle* h, uint64_t n, const uint32_t* species, const double* x, const double* y, const double* z,
+                     const uint32_t* counted_volume, double release_time, uint32_t* first_id_out) {
+  if (!h || (n && (!species || !x || !y || !z))) { if (h) h->err = "release list: null arrays"; return MCX_ERR_INVALID_ARG; }
+  if (!h->uploaded) { h->err = "mcx_release_list needs a previous mcx_upload_molecules (it may be empty)"; return MCX_ERR_STATE; }
+  const double it = (double)h->iteration;
+  if (release_time != 0 && !(release_time >= it && release_time < it + 1.0)) { h->err = "release_time outside the current iteration"; return MCX_ERR_INVALID_ARG; }
+  if (n > (uint64_t)h->p.capacity) { h->err = "release larger than max_molecules"; return MCX_ERR_CAPACITY; }
+  CK(cudaSetDevice(h->cfg.device));
+  if (ensure_staging(h)) return MCX_ERR_CUDA;
+  cudaStream_t s = h->stream;
+  Counters hc;
+  int rc = check_device_error(h, &hc);
+  if (rc) return rc;
+  unsigned long long base = hc.next_id;
+  if (h->comm) {
+    std::vector<unsigned long long> v((size_t)h->cfg.world_size, 0ull);
+    v[(size_t)h->cfg.rank] = base;
+    rc = mcx_comm_allreduce_u64(h->comm, v.data(), (int)v.size(), s);
+    if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+    for (unsigned long long q : v) base = std::max(base, q);
+  }
+  if (base + n >= 0xFFFFFFF0ull) { h->err = "molecule ids exhausted"; return MCX_ERR_OVERFLOW; }
+  CK(cudaMemcpyAsync(h->st_x, x, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->st_y, y, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->st_z, z, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->st_sp, species, n * 4, cudaMemcpyHostToDevice, s));
+  const bool with_cv = counted_volume && h->p.wall_cv;
+  if (with_cv) CK(cudaMemcpyAsync(h->st_cv, counted_volume, n * 4, cudaMemcpyHostToDevice, s));
+  bind_iteration(h);
+  mcx_launch_rebin(h->p, h->plan, s);
+  mcx_launch_release_list(h->p, h->st_x, h->st_y, h->st_z, h->st_sp, with_cv ? h->st_cv : nullptr, n, release_time, (uint32_t)base, s);
+  const unsigned int next_id = (unsigned int)(base + n);
+  CK(cudaMemcpyAsync(&h->p.ctr->next_id, &next_id, sizeof(next_id), cudaMemcpyHostToDevice, s));
+  mcx_launch_sort(h->p, h->plan, s);
+  h->launches += 2;
+  h->cs_cur ^= 1;
+  if (h->comm) {
+    bind_iteration(h);
+    rc = mcx_comm_refresh(h->comm, h->p, h->plan, s);
+    if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+    h->cs_cur ^= 1;
+  }
+  rc = check_device_error(h, &hc);
+  if (rc) { if (rc == MCX_ERR_INVALID_ARG) h->err += " (not a volume species, or counted volume out of range)"; return rc; }
+  CK(cudaGetLastError());
+  if (first_id_out) *first_id_out = (uint32_t)base;
+  return MCX_OK;
+}
+
+// ReleaseEvent::release_onto_regions on the device (include/mcx.h): rounds of pick / bid / settle, then the fall-back fill
+int mcx_release_surface_molecules(mcx_handle* h, const mcx_surface_release* r, uint32_t* first_id_out) {
+  if (!h || !r) return MCX_ERR_INVALID_ARG;
+  if (!h->uploaded) { h->err = "mcx_release_surface_molecules needs a previous mcx_upload_molecules (it may be empty)"; return MCX_ERR_STATE; }
+  if (h->p.rng_mode != MCX_RNG_PHILOX) { h->err = "device release needs rng_mode == MCX_RNG_PHILOX"; return MCX_ERR_STATE; }
+  if (h->comm || h->cfg.world_size > 1) { h->err = "surface release on the device needs one device (a rank knows the tiles of its own slab only)"; return MCX_ERR_STATE; }
+  if (r->species >= h->species.size() || (h->species[r->species].flags & MCX_SP_VOL)) { h->err = "surface release: not a surface species"; return MCX_ERR_INVALID_ARG; }
+  if (!h->has_geometry || !h->p.has_surf || !h->p.n_tiles) { h->err = "surface release needs geometry and an upload after the surface species were set"; return MCX_ERR_STATE; }
+  if (!r->walls || r->n_walls == 0 || r->n_walls > 0xFFFFFFF0ull) { h->err = "surface release: empty wall list"; return MCX_ERR_INVALID_ARG; }
+  if (r->orientation < -1 || r->orientation > 1) { h->err = "surface release: orientation must be -1, 0 or +1"; return MCX_ERR_INVALID_ARG; }
+  const double it = (double)h->iteration;
+  if (r->release_time != 0 && !(r->release_time >= it && r->release_time < it + 1.0)) { h->err = "release_time outside the current iteration"; return MCX_ERR_INVALID_ARG; }
+  if (r->number > (uint64_t)h->p.capacity) { h->err = "release larger than max_molecules"; return MCX_ERR_CAPACITY; }
+  std::vector<double> cum(r->n_walls), area(r->n_walls);
+  double total = 0;
+  {
+    std::vector<uint8_t> seen(h->n_walls_host, 0);
+    for (uint64_t a = 0; a < r->n_walls; a++) {
+      const uint32_t wi = r->walls[a];
+      if (wi >= h->n_walls_host || seen[wi]) { h->err = "surface release: wall index out of range or listed twice"; return MCX_ERR_INVALID_ARG; }
+      seen[wi] = 1;
+      area[a] = h->wall_area_host[wi];
+      total += area[a];
+      cum[a] = total;   // cumm_area_and_pwall_index_pairs
+    }
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->stream;
+  Counters hc;
+  int rc = check_device_error(h, &hc);
+  if (rc) return rc;
+  const unsigned long long base = hc.next_id;
+  if (base + r->number >= 0xFFFFFFF0ull) { h->err = "molecule ids exhausted"; return MCX_ERR_OVERFLOW; }
+  const size_t n = (size_t)r->number;
+  uint32_t *d_walls = nullptr, *d_claim = nullptr, *d_choice = nullptr, *d_cwall = nullptr, *d_pa = nullptr, *d_pb = nullptr;
+  double *d_cum = nullptr, *d_area = nullptr;
+  unsigned int* d_ctr = nullptr;
+  auto release_tmp = [&]() { cudaFree(d_walls); cudaFree(d_claim); cudaFree(d_choice); cudaFree(d_cwall); cudaFree(d_pa); cudaFree(d_pb);
+                             cudaFree(d_cum); cudaFree(d_area); cudaFree(d_ctr); };
+  bool ok = cudaMalloc(&d_walls, r->n_walls * 4) == cudaSuccess && cudaMalloc(&d_cum, r->n_walls * 8) == cudaSuccess &&
+            cudaMalloc(&d_area, r->n_walls * 8) == cudaSuccess && cudaMalloc(&d_claim, (size_t)h->p.n_tiles * 4) == cudaSuccess &&
+            cudaMalloc(&d_choice, std::max<size_t>(n, 1) * 4) == cudaSuccess && cudaMalloc(&d_cwall, std::max<size_t>(n, 1) * 4) == cudaSuccess &&
+            cudaMalloc(&d_pa, std::max<size_t>(n, 1) * 4) == cudaSuccess && cudaMalloc(&d_pb, std::max<size_t>(n, 1) * 4) == cudaSuccess &&
+            cudaMalloc(&d_ctr, 16) == cudaSuccess;
+  if (!ok) { release_tmp(); h->err = "surface release: out of device memory"; return MCX_ERR_CUDA; }
+  cudaMemcpyAsync(d_walls, r->walls, r->n_walls * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_cum, cum.data(), r->n_walls * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_area, area.data(), r->n_walls * 8, cudaMemcpyHostToDevice, s);
+  cudaMemsetAsync(d_claim, 0xFF, (size_t)h->p.n_tiles * 4, s);
+  SurfRelease sr{};
+  sr.walls = d_walls; sr.cum_area = d_cum; sr.area = d_area; sr.n_walls = (unsigned int)r->n_walls; sr.total_area = total;
+  sr.species = r->species; sr.orientation = r->orientation; sr.randomize_pos = r->randomize_pos; sr.release_time = r->release_time;
+  sr.first_id = (uint32_t)base; sr.claim = d_claim; sr.choice = d_choice; sr.choice_wall = d_cwall;
+  bind_iteration(h);
+  unsigned int host_n = 0;
+  mcx_launch_surface_release_count_vacant(h->p, sr, d_ctr, s);
+  cudaMemcpyAsync(&host_n, d_ctr, 4, cudaMemcpyDeviceToHost, s);
+  if (cudaStreamSynchronize(s) != cudaSuccess) { release_tmp(); h->err = cudaGetErrorString(cudaGetLastError()); return MCX_ERR_CUDA; }
+  if ((uint64_t)host_n < r->number) {
+    release_tmp();
+    h->err = "surface release: " + std::to_string(r->number) + " molecules for " + std::to_string(host_n) + " vacant tiles";
+    return MCX_ERR_CAPACITY;
+  }
+  mcx_launch_rebin(h->p, h->plan, s);
+  unsigned int n_pend = (unsigned int)n;
+  const uint32_t* pend_in = nullptr;
+  uint32_t* bufs[2] = {d_pa, d_pb};
+  int which = 0;
+  for (unsigned int round = 0; round < MCX_SURFACE_RELEASE_ROUNDS && n_pend > 0; round++) {
+    mcx_launch_surface_release_round(h->p, sr, pend_in, n_pend, bufs[which], d_ctr, round, s);
+    h->launches += 3;
+    cudaMemcpyAsync(&host_n, d_ctr, 4, cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) { release_tmp(); h->err = cudaGetErrorString(cudaGetLastError()); return MCX_ERR_CUDA; }
+    n_pend = host_n;
+    pend_in = bufs[which];
+    which ^= 1;
+  }
+  if (n_pend > 0) {  // the reference's fall-back: first vacant tiles in list order, lowest id first
+    std::vector<uint32_t> left(n_pend);
+    cudaMemcpyAsync(left.data(), pend_in, (size_t)n_pend * 4, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    std::sort(left.begin(), left.end());
+    cudaMemcpyAsync(bufs[which], left.data(), (size_t)n_pend * 4, cudaMemcpyHostToDevice, s);
+    mcx_launch_surface_release_fill(h->p, sr, bufs[which], n_pend, d_ctr, s);
+    h->launches += 1;
+    cudaMemcpyAsync(&host_n, d_ctr, 4, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    if (host_n != 0) { release_tmp(); h->err = "surface release: ran out of vacant tiles"; return MCX_ERR_CAPACITY; }
+  }
+  const unsigned int next_id = (unsigned int)(base + r->number);
+  cudaMemcpyAsync(&h->p.ctr->next_id, &next_id, sizeof(next_id), cudaMemcpyHostToDevice, s);
+  mcx_launch_sort(h->p, h->plan, s);
+  h->launches += 2;
+  h->cs_cur ^= 1;
+  rc = check_device_error(h, &hc);
+  release_tmp();
   if (rc) return rc;
   CK(cudaGetLastError());
   if (first_id_out) *first_id_out = (uint32_t)base;
@@ -1068,6 +1233,7 @@ int mcx_sizeof(int which) {
     case 7: return (int)sizeof(mcx_trace_rec);
     case 8: return (int)sizeof(mcx_slab_info);
     case 9: return (int)sizeof(mcx_release);
+    case 10: return (int)sizeof(mcx_surface_release);
     default: return -1;
   }
 }

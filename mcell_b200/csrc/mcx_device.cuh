@@ -385,6 +385,76 @@ __device__ int collide_wall(const DevParams& p, D3 pos, uint32_t wi, Stream& rs,
   return W_MISS;
 }
 
+// ---- point location by a ray cast (region releases; the reference's Region::is_point_inside, geometry.cpp:1048-1086,
+// and compute_counted_volume_for_pos, collision_utils.inl:1515-1566, count the walls crossed on the way to a far point).
+// One ray from pos towards -x (skewed in y and z) up to the partition boundary, walked through the subpartitions it
+// crosses with the arithmetic of collect_crossed_subparts; every wall it crosses is counted once, in the subpartition
+// that holds the crossing point.  inside_mask: bit k = odd number of crossings of object k's walls (k < 32);
+// first_wall / first_side: the nearest crossing (the counted volume of pos is the one on that side of that wall).
+struct RayScan { uint32_t inside_mask; uint32_t first_wall; int first_side; bool redo; };
+__device__ void scan_ray(const DevParams& p, D3 pos, Stream& rs, RayScan& out) {
+  out.inside_mask = 0; out.first_wall = MCX_NONE; out.first_side = W_MISS; out.redo = false;
+  const D3 raw = {-p.part_len, p.part_len * (1.0 / 11.0), p.part_len * (1.0 / 22.0)};
+  const D3 disp = displacement_up_to_partition_boundary(p, pos, raw);
+  if (disp.x == 0 && disp.y == 0 && disp.z == 0) return;  // on the partition boundary: outside everything
+  double first_t = 2.0;
+  auto visit = [&](uint32_t S) -> bool {
+    const uint32_t w0 = p.spw_start[S], w1 = p.spw_start[S + 1];
+    for (uint32_t k = w0; k < w1; k++) {
+      const uint32_t wi = p.spw_list[k];
+      D3 move = disp, hit; double t;
+      const int ct = collide_wall(p, pos, wi, rs, move, t, hit);
+      if (ct == W_REDO) { out.redo = true; return false; }
+      if ((ct == W_FRONT || ct == W_BACK) && subpart_index(p, hit) == S) {
+        const uint32_t obj = p.wall_obj ? p.wall_obj[wi] : 0u;
+        if (obj < 32u) out.inside_mask ^= 1u << obj;
+        if (t < first_t) { first_t = t; out.first_wall = wi; out.first_side = ct; }
+      }
+    }
+    return true;
+  };
+  // the walk of collect_crossed_subparts (for walls), streamed
+  const double sp_len = p.sp_len;
+  uint32_t cur_subpart = subpart_index(p, pos);
+  if (!visit(cur_subpart)) return;
+  D3 dest = pos + disp;
+  D3 dnz = disp;
+  if (dnz.x == 0) dnz.x = FLT_MIN;
+  if (dnz.y == 0) dnz.y = FLT_MIN;
+  if (dnz.z == 0) dnz.z = FLT_MIN;
+  int dir[3] = {dnz.x > 0 ? 1 : 0, dnz.y > 0 ? 1 : 0, dnz.z > 0 ? 1 : 0};
+  int src[3], dst[3];
+  src[0] = cur_subpart % p.n_sp; src[1] = (cur_subpart / p.n_sp) % p.n_sp; src[2] = (cur_subpart / (p.n_sp * p.n_sp)) % p.n_sp;
+  subpart_3d(p, dest, dst);
+  const uint32_t dest_subpart = subpart_from_3d(p, dst[0], dst[1], dst[2]);
+  if (cur_subpart == dest_subpart) return;
+  int add[3] = {dir[0] ? 1 : -1, dir[1] ? 1 : -1, dir[2] ? 1 : -1};
+  D3 cur = pos;
+  int ci[3] = {src[0], src[1], src[2]};
+  uint32_t cs;
+  D3 rcp = {1.0 / dnz.x, 1.0 / dnz.y, 1.0 / dnz.z};
+  int guard = 0;
+  do {
+    D3 edges = {p.ox + ci[0] * sp_len + dir[0] * sp_len, p.oy + ci[1] * sp_len + dir[1] * sp_len,
+                p.oz + ci[2] * sp_len + dir[2] * sp_len};
+    D3 diff = edges - cur;
+    D3 ct = {diff.x * rcp.x, diff.y * rcp.y, diff.z * rcp.z};
+    if (ct.x < ct.y && ct.x <= ct.z) {
+      cur = cur + disp * ct.x; ci[0] += add[0];
+      if (!idx_in_range(p, ci[0])) break;
+    } else if (ct.y <= ct.z) {
+      cur = cur + disp * ct.y; ci[1] += add[1];
+      if (!idx_in_range(p, ci[1])) break;
+    } else {
+      cur = cur + disp * ct.z; ci[2] += add[2];
+      if (!idx_in_range(p, ci[2])) break;
+    }
+    cs = subpart_from_3d(p, ci[0], ci[1], ci[2]);
+    if (!visit(cs)) return;
+    if (++guard > 4096) break;
+  } while (cs != dest_subpart);
+}
+
 // ---- fine wall grid (mcx_geom.cpp: bin_walls_fine) -------------------------------------------------------------------
 // Cells of subpartition S under the box [lo, hi] (the caller has padded it by at least MCX_FW_MARGIN).
 struct FwRange { int x0, x1, y0, y1, z0, z1; uint32_t base; };

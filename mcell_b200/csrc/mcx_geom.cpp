@@ -274,6 +274,10 @@ uint64_t grid_constants(const double* verts, const uint32_t* tri, const std::vec
   }
   return total;
 }
+void wall_areas(const double* verts, const uint32_t* tri, uint64_t n_walls, std::vector<double>& out) {
+  out.resize(n_walls);
+  for (uint64_t i = 0; i < n_walls; i++) out[i] = tri_area(verts + 3 * tri[3 * i], verts + 3 * tri[3 * i + 1], verts + 3 * tri[3 * i + 2]);
+}
 static void one_triangle(const double* v9, DevWall& w, DevGrid& g) {
   const uint32_t t[3] = {0, 1, 2};
   std::vector<DevWall> ws;

@@ -9,6 +9,8 @@ struct GridSpec { double ox, oy, oz, sp_len, sp_rcp, R; int n_sp; bool use_expan
 void wall_constants(const double* verts, const uint32_t* tri, uint64_t n_walls, std::vector<DevWall>& out);
 // surface grids (Grid::initialize, src4/wall.cpp:38-74); tile_start = exclusive prefix of num_tiles; returns the total
 uint64_t grid_constants(const double* verts, const uint32_t* tri, const std::vector<DevWall>& walls, std::vector<DevGrid>& out);
+// Wall::area (src4/wall.cpp:304) of every wall, the value Grid::initialize sizes the tile grid with
+void wall_areas(const double* verts, const uint32_t* tri, uint64_t n_walls, std::vector<double>& out);
 // triangle sides shared by two walls of one object (surface_net, src4/geometry.cpp:258-356) and the transform across
 // them (Edge::reinit_edge_constants, src4/wall.cpp:134-235); wall_object may be null (one object)
 void edge_constants(const double* verts, const uint32_t* tri, const std::vector<DevWall>& walls, const uint32_t* wall_object,

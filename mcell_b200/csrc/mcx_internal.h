@@ -138,6 +138,7 @@ struct DevParams {
   unsigned long long* rxn_count_cv;  // [rule * n_cv + cv]
   unsigned long long* mol_count_cv;  // [species * n_cv + cv], filled by mcx_counts_by_volume
   unsigned int n_cv;
+  const uint32_t* wall_obj;     // per wall: geometry object index (mcx_set_geometry's wall_object; null = one object)
   const uint8_t* wall_rs;       // per wall: index of the set of counted surface regions it belongs to; null = none
   unsigned long long* rxn_count_rs;  // [rule * n_rs + region set]: reactions whose initiator was a surface molecule there
   unsigned long long* mol_count_rs;  // [species * n_rs + region set], filled by mcx_counts_by_surface_region
@@ -234,7 +235,22 @@ void mcx_launch_initial_sort(const DevParams& p, const StepPlan& plan, cudaStrea
 void mcx_launch_evaluate(const DevParams& p, const StepPlan& plan, cudaStream_t s);   // memset + diffuse + resolve rounds
 void mcx_launch_fresh_scan(const DevParams& p, const StepPlan& plan, cudaStream_t s);  // prefix of the fresh ids per cell group
 void mcx_launch_assign_ids(const DevParams& p, const StepPlan& plan, cudaStream_t s);  // fresh ids into the product records
-void mcx_launch_release(const DevParams& p, const mcx_release& r, uint32_t first_id, cudaStream_t s);  // appends behind a re-binned population
+void mcx_launch_release(const DevParams& p, const mcx_release& r, uint32_t first_id, cudaStream_t s);
+// surface release (mcx_release_surface_molecules): one placement round / the fall-back fill
+struct SurfRelease {
+  const uint32_t* walls; const double* cum_area; const double* area; unsigned int n_walls; double total_area;
+  uint32_t species; int orientation; uint32_t randomize_pos; double release_time; uint32_t first_id;
+  uint32_t* claim;        // per tile: lowest molecule index (k) that picked it, 0xFFFFFFFF = nobody yet
+  uint32_t* choice;       // per molecule index: tile picked this round (global tile index) or MCX_NONE
+  uint32_t* choice_wall;  // ... and its wall
+};
+void mcx_launch_surface_release_round(const DevParams& p, const SurfRelease& r, const uint32_t* pend_in, unsigned int n_pend,
+                                      uint32_t* pend_out, unsigned int* n_out, unsigned int round, cudaStream_t s);
+void mcx_launch_surface_release_count_vacant(const DevParams& p, const SurfRelease& r, unsigned int* n_vacant, cudaStream_t s);
+void mcx_launch_surface_release_fill(const DevParams& p, const SurfRelease& r, const uint32_t* pend_sorted, unsigned int n_pend,
+                                     unsigned int* n_left, cudaStream_t s);
+void mcx_launch_release_list(const DevParams& p, const double* x, const double* y, const double* z, const uint32_t* species,
+                             const uint32_t* cv, uint64_t n, double release_time, uint32_t first_id, cudaStream_t s);  // appends behind a re-binned population
 void mcx_launch_rebin(const DevParams& p, const StepPlan& plan, cudaStream_t s);      // A -> B unchanged (halo refresh without a step)
 void mcx_launch_pack_halo(const DevParams& p, HaloRec* send_low, HaloRec* send_high, unsigned int cap, cudaStream_t s);
 void mcx_launch_unpack_halo(const DevParams& p, const HaloRec* recv, unsigned int n, unsigned int offset, cudaStream_t s);

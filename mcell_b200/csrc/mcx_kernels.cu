@@ -1227,16 +1227,208 @@ __global__ void __launch_bounds__(TPB) k_release(const __grid_constant__ DevPara
       if (rad == 0) q = D3{0.0, 0.0, 0.5};
       else q = D3{q.x / rad, q.y / rad, q.z / rad};
     }
-    const D3 pos = {q.x * r.diameter[0] + r.location[0], q.y * r.diameter[1] + r.location[1], q.z * r.diameter[2] + r.location[2]};
+    D3 pos = {q.x * r.diameter[0] + r.location[0], q.y * r.diameter[1] + r.location[1], q.z * r.diameter[2] + r.location[2]};
+    uint32_t flags_k = base_flags;
+    if (r.shape == MCX_RELEASE_REGION) {
+      // ReleaseEvent::release_inside_regions (release_event.cpp:904-951): uniform in the bounding box, kept when the
+      // point lies inside the region expression — here inside every object of region_in and outside every object
+      // of region_out, found by one ray cast (scan_ray); the molecule's counted volume comes from the same ray
+      int tries = 0;
+      bool ok = false;
+      for (;;) {
+        bool inb = in_partition(p, pos);
+        RayScan sc;
+        if (inb) scan_ray(p, pos, rs, sc);
+        if (inb && !sc.redo && (sc.inside_mask & r.region_in) == r.region_in && (sc.inside_mask & r.region_out) == 0u) {
+          if (p.wall_cv) {
+            uint32_t cvi = 0;
+            if (sc.first_wall != MCX_NONE) { const uint32_t cv = __ldg(p.wall_cv + sc.first_wall); cvi = sc.first_side == W_FRONT ? (cv & 0xFFu) : (cv >> 8); }
+            flags_k = (flags_k & ~SF_CVI_MASK) | (cvi << SF_CVI_SHIFT);
+          }
+          ok = true;
+          break;
+        }
+        if (++tries >= 100000) break;
+        q.x = rs.dbl() - 0.5; q.y = rs.dbl() - 0.5; q.z = rs.dbl() - 0.5;
+        pos = D3{q.x * r.diameter[0] + r.location[0], q.y * r.diameter[1] + r.location[1], q.z * r.diameter[2] + r.location[2]};
+      }
+      if (!ok) { raise_error(p, MCX_ERR_INVALID_ARG, id); continue; }  // the region holds (almost) nothing of its box
+    }
     if (!in_partition(p, pos)) { raise_error(p, MCX_ERR_ESCAPED, id); continue; }
     if (!owned_z(p, pos.z)) continue;
     const uint32_t ns = c->n_slots + agg_reserve(&c->n_prod, 1u);
     if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); continue; }
     if (base_flags & DF_PARTIAL) p.tschedB[ns] = t_rel;
-    store_rec(p.recB, ns, pos, id, r.species | base_flags);
+    store_rec(p.recB, ns, pos, id, r.species | flags_k);
     p.rank[ns] = atomicAdd(&p.cs_next[cell_of(p, pos.x, pos.y, pos.z)], 1u);
     if (p.world == 1) agg_add(&c->species_count[r.species], 1u);
   }
+}
+// ---- surface molecules onto regions (ReleaseEvent::release_onto_regions, release_event.cpp:640-760; include/mcx.h) ----
+// GridUtils::grid2uv (grid_utils.inl:233-253) and grid2uv_random (:256-288)
+__device__ __forceinline__ void tile_uv(const DevParams& p, uint32_t wi, uint32_t tile, bool random, Stream& rs, double& u, double& v) {
+  const DevWall& f = p.walls[wi];
+  const DevGrid& g = p.grids[wi];
+  const int root = (int)(sqrt((double)tile));
+  const int rootrem = (int)tile - root * root;
+  const int k = g.n_axis - root - 1;
+  const int j = rootrem / 2;
+  const int i = rootrem - 2 * j;
+  if (!random) {
+    const double over3n = 1 / (double)(3 * g.n_axis);
+    u = ((double)(3 * j + i + 1)) * over3n * f.uv1u + ((double)(3 * k + i + 1)) * over3n * f.uv2u;
+    v = ((double)(3 * k + i + 1)) * over3n * f.uv2v;
+    return;
+  }
+  const double over_n = 1 / (double)(g.n_axis);
+  const double u_ran = rs.dbl();
+  const double v_ran = 1 - sqrt(rs.dbl());
+  u = ((double)(j + i) + (1 - 2 * i) * (1 - v_ran) * u_ran) * over_n * f.uv1u + ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv2u;
+  v = ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv2v;
+}
+// the new surface molecule on (wall, tile): appended behind the re-binned population like a product
+__device__ void place_surface_molecule(const DevParams& p, const SurfRelease& r, uint32_t k, uint32_t wi, uint32_t tile) {
+  Counters* c = p.ctr;
+  const uint32_t id = r.first_id + k;
+  Stream rs; rs.init_release(p, id, nullptr);
+  rs.it_hi |= 0x40000000u;   // placement draws: a domain of their own (the tile picks use the release domain)
+  { uint32_t o[4]; philox4x32_10(0u, rs.it_lo, rs.it_hi, rs.id, rs.k0, rs.k1, o); rs.b0 = o[0]; rs.b1 = o[1]; rs.b2 = o[2]; rs.b3 = o[3]; }
+  double u, v;
+  tile_uv(p, wi, tile, r.randomize_pos != 0, rs, u, v);
+  int orient = r.orientation;
+  if (orient == 0) orient = (rs.next() & 1u) ? 1 : -1;
+  const DevWall& f = p.walls[wi];
+  const D3 pos = {u * f.ux + v * f.vx + f.v0x, u * f.uy + v * f.vy + f.v0y, u * f.uz + v * f.vz + f.v0z};
+  const double t_rel = r.release_time > (double)p.iteration ? r.release_time : (double)p.iteration;
+  const uint32_t ns = c->n_slots + agg_reserve(&c->n_prod, 1u);
+  if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
+  const uint32_t flags = DF_SURF | DF_SCHED_UNIMOL | (orient > 0 ? DF_ORIENT_UP : 0u) | (t_rel > (double)p.iteration ? DF_PARTIAL : 0u);
+  if (flags & DF_PARTIAL) p.tschedB[ns] = t_rel;
+  p.swallB[ns] = wi; p.stileB[ns] = tile; p.suvB[ns] = make_double2(u, v);
+  store_rec(p.recB, ns, pos, id, r.species | flags);
+  p.rank[ns] = atomicAdd(&p.cs_next[cell_of(p, pos.x, pos.y, pos.z)], 1u);
+  agg_add(&c->species_count[r.species], 1u);
+}
+// phase 0: every molecule without a tile picks one (draw number `round` of its stream) and bids for it with its index
+__global__ void __launch_bounds__(TPB) k_srel_pick(const __grid_constant__ DevParams p, const SurfRelease r, const uint32_t* pend, unsigned int n_pend,
+                                                   unsigned int round) {
+  for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pend; q += gridDim.x * blockDim.x) {
+    const uint32_t k = pend ? pend[q] : q;
+    Stream rs; rs.init_release(p, r.first_id + k, nullptr);
+    for (unsigned int d = 0; d < round; d++) (void)rs.next();
+    double A = rs.dbl() * r.total_area;
+    // cum_area_bisect_high (release_event.cpp:60-81)
+    size_t low = 0, hi = r.n_walls - 1, mid;
+    while (hi - low > 1) { mid = (hi + low) / 2; if (r.cum_area[mid] > A) hi = mid; else low = mid; }
+    const size_t at = r.cum_area[low] > A ? low : hi;
+    const uint32_t wi = r.walls[at];
+    const double area = r.area[at];
+    if (at != 0) A -= r.cum_area[at - 1];
+    const DevGrid& g = p.grids[wi];
+    const uint32_t nt = (uint32_t)(g.n_axis * g.n_axis);
+    uint32_t tile = (uint32_t)((double)(g.n_axis * g.n_axis) * (A / area));
+    if (tile >= nt) tile = nt - 1;
+    const uint32_t gt = g.tile_start + tile;
+    uint32_t pick = MCX_NONE;
+    if (p.tile_slot[gt] == MCX_NONE && *(volatile uint32_t*)&r.claim[gt] == MCX_NONE) pick = gt;  // vacant in the snapshot and in earlier rounds
+    r.choice[k] = pick; r.choice_wall[k] = wi;
+  }
+}
+__global__ void __launch_bounds__(TPB) k_srel_bid(const __grid_constant__ DevParams p, const SurfRelease r, const uint32_t* pend, unsigned int n_pend) {
+  for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pend; q += gridDim.x * blockDim.x) {
+    const uint32_t k = pend ? pend[q] : q;
+    const uint32_t gt = r.choice[k];
+    if (gt != MCX_NONE) atomicMin(&r.claim[gt], k);
+  }
+}
+// phase 1: the lowest bidder of a tile is placed there, everybody else goes on to the next round
+__global__ void __launch_bounds__(TPB) k_srel_settle(const __grid_constant__ DevParams p, const SurfRelease r, const uint32_t* pend, unsigned int n_pend,
+                                                     uint32_t* pend_out, unsigned int* n_out) {
+  for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pend; q += gridDim.x * blockDim.x) {
+    const uint32_t k = pend ? pend[q] : q;
+    const uint32_t gt = r.choice[k];
+    if (gt != MCX_NONE && r.claim[gt] == k) {
+      const uint32_t wi = r.choice_wall[k];
+      place_surface_molecule(p, r, k, wi, gt - p.grids[wi].tile_start);
+    } else pend_out[agg_reserve(n_out, 1u)] = k;
+  }
+}
+void mcx_launch_surface_release_round(const DevParams& p, const SurfRelease& r, const uint32_t* pend_in, unsigned int n_pend,
+                                      uint32_t* pend_out, unsigned int* n_out, unsigned int round, cudaStream_t s) {
+  unsigned int grid = (n_pend + TPB - 1) / TPB;
+  if (grid == 0) grid = 1;
+  if (grid > (unsigned int)p.sm_count * 16u) grid = (unsigned int)p.sm_count * 16u;
+  cudaMemsetAsync(n_out, 0, sizeof(unsigned int), s);
+  k_srel_pick<<<grid, TPB, 0, s>>>(p, r, pend_in, n_pend, round);
+  k_srel_bid<<<grid, TPB, 0, s>>>(p, r, pend_in, n_pend);
+  k_srel_settle<<<grid, TPB, 0, s>>>(p, r, pend_in, n_pend, pend_out, n_out);
+}
+// fall-back (release_event.cpp:702-744): the first vacant tiles in wall-list order, lowest index first
+__global__ void k_srel_fill(const __grid_constant__ DevParams p, const SurfRelease r, const uint32_t* pend_sorted, unsigned int n_pend,
+                            unsigned int* n_left) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  unsigned int q = 0;
+  for (unsigned int a = 0; a < r.n_walls && q < n_pend; a++) {
+    const uint32_t wi = r.walls[a];
+    const DevGrid& g = p.grids[wi];
+    const uint32_t nt = (uint32_t)(g.n_axis * g.n_axis);
+    for (uint32_t tile = 0; tile < nt && q < n_pend; tile++) {
+      const uint32_t gt = g.tile_start + tile;
+      if (p.tile_slot[gt] != MCX_NONE || r.claim[gt] != MCX_NONE) continue;
+      r.claim[gt] = pend_sorted[q];
+      place_surface_molecule(p, r, pend_sorted[q], wi, tile);
+      q++;
+    }
+  }
+  *n_left = n_pend - q;
+}
+__global__ void __launch_bounds__(TPB) k_srel_count_vacant(const __grid_constant__ DevParams p, const SurfRelease r, unsigned int* n_vacant) {
+  unsigned int mine = 0;
+  for (unsigned int a = blockIdx.x; a < r.n_walls; a += gridDim.x) {
+    const DevGrid& g = p.grids[r.walls[a]];
+    const uint32_t nt = (uint32_t)(g.n_axis * g.n_axis);
+    for (uint32_t tile = threadIdx.x; tile < nt; tile += blockDim.x) mine += p.tile_slot[g.tile_start + tile] == MCX_NONE ? 1u : 0u;
+  }
+  if (mine) atomicAdd(n_vacant, mine);
+}
+void mcx_launch_surface_release_count_vacant(const DevParams& p, const SurfRelease& r, unsigned int* n_vacant, cudaStream_t s) {
+  cudaMemsetAsync(n_vacant, 0, sizeof(unsigned int), s);
+  k_srel_count_vacant<<<std::max(1u, std::min(r.n_walls, (unsigned int)p.sm_count * 8u)), TPB, 0, s>>>(p, r, n_vacant);
+}
+void mcx_launch_surface_release_fill(const DevParams& p, const SurfRelease& r, const uint32_t* pend_sorted, unsigned int n_pend,
+                                     unsigned int* n_left, cudaStream_t s) {
+  k_srel_fill<<<1, 32, 0, s>>>(p, r, pend_sorted, n_pend, n_left);
+}
+
+// ReleaseEvent::release_list (release_event.cpp:1008-1040), volume molecules: one molecule per listed position
+__global__ void __launch_bounds__(TPB) k_release_list(const __grid_constant__ DevParams p, const double* x, const double* y, const double* z,
+                                                      const uint32_t* species, const uint32_t* cv, unsigned long long n, double release_time,
+                                                      uint32_t first_id) {
+  Counters* c = p.ctr;
+  const double t_rel = release_time > (double)p.iteration ? release_time : (double)p.iteration;
+  for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+       k += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t id = first_id + (uint32_t)k;
+    const uint32_t sp = species[k];
+    if (sp >= (uint32_t)p.n_species || !(p.species[sp].flags & MCX_SP_VOL) || (cv && cv[k] >= p.n_cv)) { raise_error(p, MCX_ERR_INVALID_ARG, id); continue; }
+    const D3 pos = {x[k], y[k], z[k]};
+    if (!in_partition(p, pos)) { raise_error(p, MCX_ERR_ESCAPED, id); continue; }
+    if (!owned_z(p, pos.z)) continue;
+    const uint32_t ns = c->n_slots + agg_reserve(&c->n_prod, 1u);
+    if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); continue; }
+    const uint32_t flags = DF_SCHED_UNIMOL | (t_rel > (double)p.iteration ? DF_PARTIAL : 0u) | (cv ? (cv[k] << SF_CVI_SHIFT) & SF_CVI_MASK : 0u);
+    if (flags & DF_PARTIAL) p.tschedB[ns] = t_rel;
+    store_rec(p.recB, ns, pos, id, sp | flags);
+    p.rank[ns] = atomicAdd(&p.cs_next[cell_of(p, pos.x, pos.y, pos.z)], 1u);
+    if (p.world == 1) agg_add(&c->species_count[sp], 1u);
+  }
+}
+void mcx_launch_release_list(const DevParams& p, const double* x, const double* y, const double* z, const uint32_t* species,
+                             const uint32_t* cv, uint64_t n, double release_time, uint32_t first_id, cudaStream_t s) {
+  unsigned long long grid = (n + TPB - 1) / TPB;
+  if (grid == 0) grid = 1;
+  if (grid > (unsigned long long)p.sm_count * 16ull) grid = (unsigned long long)p.sm_count * 16ull;
+  k_release_list<<<(unsigned int)grid, TPB, 0, s>>>(p, x, y, z, species, cv, n, release_time, first_id);
 }
 void mcx_launch_release(const DevParams& p, const mcx_release& r, uint32_t first_id, cudaStream_t s) {
   unsigned long long grid = (r.number + TPB - 1) / TPB;

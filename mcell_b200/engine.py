@@ -55,6 +55,8 @@ def load_library():
     L.mcx_comm_halo_path.argtypes = [H]
     L.mcx_fast_pass_kind.argtypes = [H]
     L.mcx_release_volume_molecules.argtypes = [H, C.POINTER(abi.mcx_release), C.POINTER(C.c_uint32)]
+    L.mcx_release_list.argtypes = [H, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_uint32)]
+    L.mcx_release_surface_molecules.argtypes = [H, C.POINTER(abi.mcx_surface_release), C.POINTER(C.c_uint32)]
     L.mcx_set_profiling.argtypes = [H, C.c_int]
     L.mcx_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
     L.mcx_philox_block.restype = None
@@ -133,7 +135,7 @@ class Engine:
         v = mols.view()
         self._ck(self.L.mcx_upload_molecules(self.h, C.byref(v)))
 
-    def release(self, species, number, location, diameter, shape=abi.MCX_RELEASE_CUBIC, release_time=0.0, counted_volume_index=0):
+    def release(self, species, number, location, diameter, shape=abi.MCX_RELEASE_CUBIC, release_time=0.0, counted_volume_index=0, region_in=0, region_out=0):
         """ReleaseEvent::release_ellipsoid_or_rectcuboid on the device (mcx_release_volume_molecules); returns the first
         id of the new molecules.  location / diameter in length units."""
         r = abi.mcx_release()
@@ -141,8 +143,32 @@ class Engine:
         r.location[:] = [float(v) for v in location]
         r.diameter[:] = [float(v) for v in diameter]
         r.release_time, r.counted_volume_index = float(release_time), int(counted_volume_index)
+        r.region_in, r.region_out = int(region_in), int(region_out)
         first = C.c_uint32(0)
         self._ck(self.L.mcx_release_volume_molecules(self.h, C.byref(r), C.byref(first)))
+        return int(first.value)
+
+    def release_surface(self, species, number, walls, orientation=1, release_time=0.0, randomize_pos=True):
+        """ReleaseEvent::release_onto_regions on the device (mcx_release_surface_molecules): `number` molecules of a
+        surface species on vacant tiles of the listed walls; returns the first id."""
+        wl = np.ascontiguousarray(walls, np.uint32)
+        r = abi.mcx_surface_release()
+        r.species, r.orientation, r.number, r.release_time = int(species), int(orientation), int(number), float(release_time)
+        r.walls, r.n_walls, r.randomize_pos = wl.ctypes.data, len(wl), 1 if randomize_pos else 0
+        first = C.c_uint32(0)
+        self._ck(self.L.mcx_release_surface_molecules(self.h, C.byref(r), C.byref(first)))
+        return int(first.value)
+
+    def release_list(self, species, positions, counted_volume=None, release_time=0.0):
+        """ReleaseEvent::release_list for volume molecules on the device (mcx_release_list): one molecule of species[k]
+        at positions[k] (length units); returns the first id."""
+        sp = np.ascontiguousarray(species, np.uint32)
+        pos = np.asarray(positions, np.float64)
+        x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+        cv = None if counted_volume is None else np.ascontiguousarray(counted_volume, np.uint32)
+        first = C.c_uint32(0)
+        self._ck(self.L.mcx_release_list(self.h, C.c_uint64(len(sp)), _vp(sp), _vp(x), _vp(y), _vp(z), _vp(cv) if cv is not None else None,
+                                         C.c_double(release_time), C.byref(first)))
         return int(first.value)
 
     def num_molecules(self):

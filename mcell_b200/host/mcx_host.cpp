@@ -150,15 +150,45 @@ void GpuDiffuseReactEvent::sync_to_host() {
 
 molecule_id_t GpuDiffuseReactEvent::release_volume_molecules(species_id_t species, uint64_t number, uint32_t shape,
                                                              const Vec3& location, const Vec3& diameter, double release_time,
-                                                             uint32_t counted_volume_index) {
+                                                             uint32_t counted_volume_index, uint32_t region_in, uint32_t region_out) {
   if (host_dirty) upload_from_host();   // the device must hold the current population before molecules are added to it
   mcx_release r{};
   r.species = species; r.shape = shape; r.number = number;
   r.location[0] = location.x; r.location[1] = location.y; r.location[2] = location.z;
   r.diameter[0] = diameter.x; r.diameter[1] = diameter.y; r.diameter[2] = diameter.z;
   r.release_time = release_time; r.counted_volume_index = counted_volume_index;
+  r.region_in = region_in; r.region_out = region_out;
   uint32_t first = 0;
   check(mcx_release_volume_molecules(h, &r, &first), "mcx_release_volume_molecules");
+  device_dirty = true;
+  p->next_molecule_id = first + (molecule_id_t)number;
+  return first;
+}
+
+molecule_id_t GpuDiffuseReactEvent::release_list(const std::vector<species_id_t>& sp, const std::vector<Vec3>& positions,
+                                                 const std::vector<uint32_t>* counted_volume, double release_time) {
+  if (sp.size() != positions.size() || (counted_volume && counted_volume->size() != sp.size()))
+    throw McxFatalError(MCX_ERR_INVALID_ARG, "release_list: array lengths differ");
+  if (host_dirty) upload_from_host();
+  const size_t n = sp.size();
+  std::vector<double> lx(n), ly(n), lz(n);
+  for (size_t k = 0; k < n; k++) { lx[k] = positions[k].x; ly[k] = positions[k].y; lz[k] = positions[k].z; }
+  uint32_t first = 0;
+  check(mcx_release_list(h, n, sp.data(), lx.data(), ly.data(), lz.data(), counted_volume ? counted_volume->data() : nullptr,
+                         release_time, &first), "mcx_release_list");
+  device_dirty = true;
+  p->next_molecule_id = first + (molecule_id_t)n;
+  return first;
+}
+
+molecule_id_t GpuDiffuseReactEvent::release_surface_molecules(species_id_t species, uint64_t number, const std::vector<wall_index_t>& walls,
+                                                              int32_t orientation, double release_time, bool randomize_pos) {
+  if (host_dirty) upload_from_host();
+  mcx_surface_release r{};
+  r.species = species; r.orientation = orientation; r.number = number; r.release_time = release_time;
+  r.walls = walls.data(); r.n_walls = walls.size(); r.randomize_pos = randomize_pos ? 1u : 0u;
+  uint32_t first = 0;
+  check(mcx_release_surface_molecules(h, &r, &first), "mcx_release_surface_molecules");
   device_dirty = true;
   p->next_molecule_id = first + (molecule_id_t)number;
   return first;

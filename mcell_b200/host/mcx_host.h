@@ -172,7 +172,16 @@ public:
   // and diameter (internal length units) at event_time; returns the first of the consecutive new ids.  The host
   // container is stale afterwards until sync_to_host().
   molecule_id_t release_volume_molecules(species_id_t species, uint64_t number, uint32_t shape, const Vec3& location,
-                                         const Vec3& diameter, double release_time = 0, uint32_t counted_volume_index = 0);
+                                         const Vec3& diameter, double release_time = 0, uint32_t counted_volume_index = 0,
+                                         uint32_t region_in = 0, uint32_t region_out = 0);
+  // ReleaseEvent::release_list (release_event.cpp:1008-1040) for volume molecules, on the device: one molecule of
+  // species[k] at positions[k] (internal length units); returns the first of the consecutive new ids
+  molecule_id_t release_list(const std::vector<species_id_t>& species, const std::vector<Vec3>& positions,
+                             const std::vector<uint32_t>* counted_volume = nullptr, double release_time = 0);
+  // ReleaseEvent::release_onto_regions (release_event.cpp:640-760) on the device: `number` molecules of a surface
+  // species on vacant tiles of the listed walls (the walls of the release's surface regions); orientation 0 = random
+  molecule_id_t release_surface_molecules(species_id_t species, uint64_t number, const std::vector<wall_index_t>& walls,
+                                          int32_t orientation, double release_time = 0, bool randomize_pos = true);
   // MolOrRxnCountEvent world-count fast path (mol_or_rxn_count_event.cpp:622-653)
   void get_counts(std::vector<uint64_t>& per_species, std::vector<uint64_t>& per_rxn_rule);
   // count terms restricted to a volume / a surface region (mol_or_rxn_count_event.cpp:519-534, 571-600):
@@ -272,8 +281,10 @@ private:
 // ---- releases: the device-capable part of ReleaseEvent (src4/release_event.h, release_event.cpp:953-1003) -------------
 // One release of `release_number` molecules of a volume species in a cuboid, sphere or spherical shell at event_time
 // (EVENT_TYPE_INDEX_RELEASE = 200, so that it runs before the counts and the diffusion of its iteration, base_event.h:
-// 33-56).  Region, list and surface releases stay with the host's ReleaseEvent and reach the device through
-// Partition::add_volume_molecule + mark_host_modified().
+// 33-56).  release_shape MCX_RELEASE_REGION releases inside closed objects (release_inside_regions, :904-951; location /
+// diameter = the region's bounding box, region_in / region_out = object masks); lists go through
+// GpuDiffuseReactEvent::release_list.  Surface releases stay with the host's ReleaseEvent and reach the device through
+// Partition::add_surface_molecule + mark_host_modified().
 class GpuReleaseEvent : public BaseEvent {
 public:
   GpuReleaseEvent(GpuDiffuseReactEvent* diffuse_, species_id_t species_id_, uint64_t release_number_, uint32_t shape_,
@@ -283,11 +294,12 @@ public:
   bool is_barrier() const override { return true; }   // the diffuse event must stop at the release time
   void step() override {
     first_released_id = diffuse->release_volume_molecules(species_id, release_number, release_shape, location, diameter,
-                                                          event_time, counted_volume_index);
+                                                          event_time, counted_volume_index, region_in, region_out);
   }
+  uint32_t region_in = 0, region_out = 0;   // MCX_RELEASE_REGION: objects the molecules must be inside / outside of
   species_id_t species_id;
   uint64_t release_number;
-  uint32_t release_shape;   // MCX_RELEASE_CUBIC / _SPHERICAL / _SPHERICAL_SHELL
+  uint32_t release_shape;   // MCX_RELEASE_CUBIC / _SPHERICAL / _SPHERICAL_SHELL / _REGION
   Vec3 location, diameter;  // internal length units
   uint32_t counted_volume_index;
   molecule_id_t first_released_id = MOLECULE_ID_INVALID;

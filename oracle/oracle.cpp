@@ -1062,6 +1062,34 @@ struct Eval {
     return true;
   }
 
+  // Point location by a ray cast (region releases; Region::is_point_inside, geometry.cpp:1048-1086, and
+  // compute_counted_volume_for_pos, collision_utils.inl:1515-1566, count the walls crossed on the way to a far point):
+  // one ray from pos towards -x (skewed in y and z) up to the partition boundary through the subpartitions it crosses;
+  // every wall it crosses is counted once, in the subpartition that holds the crossing point.
+  struct RayScan { uint32_t inside_mask = 0; uint32_t first_wall = MCX_NONE; int first_side = WALL_MISS; bool redo = false; };
+  RayScan scan_ray(V3 pos) {
+    RayScan out;
+    const double pl = w.cfg.partition_edge_length;
+    const V3 raw = {-pl, pl * (1.0 / 11.0), pl * (1.0 / 22.0)};
+    const V3 disp = displacement_up_to_partition_boundary(pos, raw);
+    if (disp.x == 0 && disp.y == 0 && disp.z == 0) return out;
+    std::vector<uint32_t> sp_walls, sp_mols;
+    collect_crossed_subparts(pos, w.subpart_index(pos), disp, false, true, sp_walls, sp_mols);
+    double first_t = 2.0;
+    for (uint32_t S : sp_walls)
+      for (uint32_t wi : w.walls_per_subpart[S]) {
+        V3 move = disp, hit; double t;
+        const int ct = collide_wall(pos, wi, move, t, hit);
+        if (ct == WALL_REDO) { out.redo = true; return out; }
+        if ((ct == WALL_FRONT || ct == WALL_BACK) && w.subpart_index(hit) == S) {
+          const uint32_t obj = w.walls[wi].object;
+          if (obj < 32u) out.inside_mask ^= 1u << obj;
+          if (t < first_t) { first_t = t; out.first_wall = wi; out.first_side = ct; }
+        }
+      }
+    return out;
+  }
+
   // ray_trace_vol, diffuse_react_event.cpp:627-780.  Returns true if a wall was hit.
   // pos/subpart are the molecule's current position; on FINISHED the caller moves it.
   bool ray_trace_vol(V3 pos, uint32_t subpart, uint32_t self_id, uint32_t species, bool can_vol_react,
@@ -2053,7 +2081,8 @@ int orc_upload_molecules(void* h, const mcx_mol_soa* s) {
 int orc_release_volume_molecules(void* h, const mcx_release* r, uint32_t* first_id_out) {
   World& w = *(World*)h;
   if (r->species >= w.species.size() || !(w.species[r->species].flags & MCX_SP_VOL)) { w.err = "release: not a volume species"; return MCX_ERR_INVALID_ARG; }
-  if (r->shape > MCX_RELEASE_SPHERICAL_SHELL) { w.err = "release: unknown shape"; return MCX_ERR_INVALID_ARG; }
+  if (r->shape > MCX_RELEASE_REGION) { w.err = "release: unknown shape"; return MCX_ERR_INVALID_ARG; }
+  if (r->shape == MCX_RELEASE_REGION && (r->region_in == 0 || (r->region_in & r->region_out))) { w.err = "region release: bad object masks"; return MCX_ERR_INVALID_ARG; }
   if (r->counted_volume_index >= w.n_cv) { w.err = "release: counted_volume_index out of range"; return MCX_ERR_INVALID_ARG; }
   const double it = (double)w.iteration;
   if (r->release_time != 0 && !(r->release_time >= it && r->release_time < it + 1.0)) { w.err = "release_time outside the current iteration"; return MCX_ERR_INVALID_ARG; }
@@ -2076,11 +2105,165 @@ int orc_release_volume_molecules(void* h, const mcx_release* r, uint32_t* first_
     }
     Mol n{};
     n.pos = {pos.x * r->diameter[0] + r->location[0], pos.y * r->diameter[1] + r->location[1], pos.z * r->diameter[2] + r->location[2]};
+    uint32_t cvi_k = r->counted_volume_index;
+    if (r->shape == MCX_RELEASE_REGION) {
+      // release_inside_regions (release_event.cpp:904-951): redrawn until the point lies inside the region
+      Eval E(w, ws);
+      int tries = 0; bool ok = false;
+      for (;;) {
+        const bool inb = w.in_this_partition(n.pos);
+        Eval::RayScan sc;
+        if (inb) sc = E.scan_ray(n.pos);
+        if (inb && !sc.redo && (sc.inside_mask & r->region_in) == r->region_in && (sc.inside_mask & r->region_out) == 0u) {
+          cvi_k = 0;
+          if (sc.first_wall != MCX_NONE) cvi_k = sc.first_side == WALL_FRONT ? w.walls[sc.first_wall].cv_front : w.walls[sc.first_wall].cv_back;
+          ok = true;
+          break;
+        }
+        if (++tries >= 100000) break;
+        pos.x = ws.dbl() - 0.5; pos.y = ws.dbl() - 0.5; pos.z = ws.dbl() - 0.5;
+        n.pos = {pos.x * r->diameter[0] + r->location[0], pos.y * r->diameter[1] + r->location[1], pos.z * r->diameter[2] + r->location[2]};
+      }
+      if (!ok) { w.err = "region release: no point of the box lies inside the region"; return MCX_ERR_INVALID_ARG; }
+    }
     if (!w.in_this_partition(n.pos)) { w.err = "released molecule outside partition"; return MCX_ERR_ESCAPED; }
     n.id = w.next_id++; n.species = r->species;
     n.flags = MCX_MOL_SCHEDULE_UNIMOL | (t_rel > it ? MCX_MOL_PARTIAL : 0u);
     n.diffusion_time = t_rel; n.unimol_rxn_time = TIME_INVALID;
-    n.subpart = w.subpart_index(n.pos); n.cvi = r->counted_volume_index;
+    n.subpart = w.subpart_index(n.pos); n.cvi = cvi_k;
+    w.mols.push_back(n);
+    if (w.id_to_index.size() <= n.id) w.id_to_index.resize((size_t)n.id + 1, MCX_NONE);
+    w.id_to_index[n.id] = (uint32_t)w.mols.size() - 1;
+    w.sched_ids.push_back(n.id);
+    list_insert(w, w.mols.back());
+    w.species_count[n.species]++;
+  }
+  if (first_id_out) *first_id_out = first;
+  return 0;
+}
+// ReleaseEvent::release_onto_regions (release_event.cpp:640-760) in the product's parallel form (include/mcx.h,
+// mcx_release_surface_molecules): every molecule picks tiles from its own stream, rounds of pick / lowest index wins,
+// then the reference's fall-back fill.  grid2uv_random: grid_utils.inl:256-288.
+static void grid2uv_random(const Wall& f, const Grid& g, uint32_t tile_index, WordSource& rs, double& u, double& v) {
+  int root = (int)(sqrt((double)tile_index));
+  int rootrem = (int)tile_index - root * root;
+  int k = g.n_axis - root - 1;
+  int j = rootrem / 2;
+  int i = rootrem - 2 * j;
+  double over_n = 1 / (double)(g.n_axis);
+  double u_ran = rs.dbl();
+  double v_ran = 1 - sqrt(rs.dbl());
+  u = ((double)(j + i) + (1 - 2 * i) * (1 - v_ran) * u_ran) * over_n * f.uv_vert1_u + ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv_vert2_u;
+  v = ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv_vert2_v;
+}
+int orc_release_surface_molecules(void* h, const mcx_surface_release* r, uint32_t* first_id_out) {
+  World& w = *(World*)h;
+  if (r->species >= w.species.size() || (w.species[r->species].flags & MCX_SP_VOL)) { w.err = "surface release: not a surface species"; return MCX_ERR_INVALID_ARG; }
+  if (!r->walls || r->n_walls == 0) { w.err = "surface release: empty wall list"; return MCX_ERR_INVALID_ARG; }
+  const double it = (double)w.iteration;
+  if (r->release_time != 0 && !(r->release_time >= it && r->release_time < it + 1.0)) { w.err = "release_time outside the current iteration"; return MCX_ERR_INVALID_ARG; }
+  const double t_rel = r->release_time > it ? r->release_time : it;
+  std::vector<double> cum(r->n_walls), area(r->n_walls);
+  double total = 0;
+  uint64_t vacant = 0;
+  for (uint64_t a = 0; a < r->n_walls; a++) {
+    const uint32_t wi = r->walls[a];
+    if (wi >= w.walls.size()) { w.err = "surface release: wall index out of range"; return MCX_ERR_INVALID_ARG; }
+    area[a] = w.walls[wi].area; total += area[a]; cum[a] = total;
+    if (w.tiles[wi].empty()) w.tiles[wi].assign(w.grids[wi].n_tiles, MCX_NONE);
+    for (uint32_t occ : w.tiles[wi]) vacant += occ == MCX_NONE;
+  }
+  if (vacant < r->number) { w.err = "surface release: more molecules than vacant tiles"; return MCX_ERR_CAPACITY; }
+  const uint32_t first = w.next_id;
+  const size_t n = (size_t)r->number;
+  // claim per (wall, tile): index of the molecule that holds it
+  std::vector<std::vector<uint32_t>> claim(w.walls.size());
+  for (uint64_t a = 0; a < r->n_walls; a++) claim[r->walls[a]].assign(w.grids[r->walls[a]].n_tiles, MCX_NONE);
+  std::vector<uint32_t> got_wall(n, MCX_NONE), got_tile(n, MCX_NONE);
+  std::vector<uint32_t> pend(n), next;
+  for (size_t k = 0; k < n; k++) pend[k] = (uint32_t)k;
+  for (unsigned int round = 0; round < MCX_SURFACE_RELEASE_ROUNDS && !pend.empty(); round++) {
+    std::vector<uint32_t> pw(pend.size(), MCX_NONE), pt(pend.size(), MCX_NONE);
+    for (size_t q = 0; q < pend.size(); q++) {
+      WordSource ws; ws.kind = WordSource::PHILOX; ws.seed = w.cfg.seed; ws.mol_id = first + pend[q];
+      ws.iteration = w.iteration | 0x8000000000000000ull;
+      for (unsigned int d = 0; d < round; d++) (void)ws.next();
+      double A = ws.dbl() * total;
+      size_t low = 0, hi = r->n_walls - 1, mid;   // cum_area_bisect_high (release_event.cpp:60-81)
+      while (hi - low > 1) { mid = (hi + low) / 2; if (cum[mid] > A) hi = mid; else low = mid; }
+      const size_t at = cum[low] > A ? low : hi;
+      const uint32_t wi = r->walls[at];
+      if (at != 0) A -= cum[at - 1];
+      const Grid& g = w.grids[wi];
+      uint32_t tile = (uint32_t)((double)(g.n_axis * g.n_axis) * (A / area[at]));
+      if (tile >= g.n_tiles) tile = g.n_tiles - 1;
+      if (w.tiles[wi][tile] == MCX_NONE && claim[wi][tile] == MCX_NONE) { pw[q] = wi; pt[q] = tile; }
+    }
+    // lowest index wins a tile
+    std::vector<std::vector<uint32_t>> bid = claim;
+    for (size_t q = 0; q < pend.size(); q++) if (pw[q] != MCX_NONE) bid[pw[q]][pt[q]] = std::min(bid[pw[q]][pt[q]], pend[q]);
+    next.clear();
+    for (size_t q = 0; q < pend.size(); q++) {
+      if (pw[q] != MCX_NONE && bid[pw[q]][pt[q]] == pend[q]) { got_wall[pend[q]] = pw[q]; got_tile[pend[q]] = pt[q]; claim[pw[q]][pt[q]] = pend[q]; }
+      else next.push_back(pend[q]);
+    }
+    pend.swap(next);
+  }
+  if (!pend.empty()) {
+    std::sort(pend.begin(), pend.end());
+    size_t q = 0;
+    for (uint64_t a = 0; a < r->n_walls && q < pend.size(); a++) {
+      const uint32_t wi = r->walls[a];
+      for (uint32_t tile = 0; tile < w.grids[wi].n_tiles && q < pend.size(); tile++) {
+        if (w.tiles[wi][tile] != MCX_NONE || claim[wi][tile] != MCX_NONE) continue;
+        claim[wi][tile] = pend[q]; got_wall[pend[q]] = wi; got_tile[pend[q]] = tile; q++;
+      }
+    }
+    if (q != pend.size()) { w.err = "surface release: ran out of vacant tiles"; return MCX_ERR_CAPACITY; }
+  }
+  for (size_t k = 0; k < n; k++) {
+    const uint32_t wi = got_wall[k], tile = got_tile[k];
+    WordSource ws; ws.kind = WordSource::PHILOX; ws.seed = w.cfg.seed; ws.mol_id = first + (uint32_t)k;
+    ws.iteration = w.iteration | 0xC000000000000000ull;   // placement draws: a domain of their own
+    Mol m{};
+    if (r->randomize_pos) grid2uv_random(w.walls[wi], w.grids[wi], tile, ws, m.u, m.v);
+    else grid2uv(w.walls[wi], w.grids[wi], tile, m.u, m.v);
+    m.orient = r->orientation ? r->orientation : ((ws.next() & 1) ? 1 : -1);
+    m.pos = uv2xyz(w, w.walls[wi], m.u, m.v);
+    m.id = w.next_id++; m.species = r->species;
+    m.flags = MCX_MOL_SCHEDULE_UNIMOL | (t_rel > it ? MCX_MOL_PARTIAL : 0u);
+    m.diffusion_time = t_rel; m.unimol_rxn_time = TIME_INVALID;
+    m.subpart = w.subpart_index(m.pos); m.cvi = 0;
+    m.wall = wi; m.tile = tile; m.created_wall = m.created_tile = MCX_NONE;
+    w.mols.push_back(m);
+    if (w.id_to_index.size() <= m.id) w.id_to_index.resize((size_t)m.id + 1, MCX_NONE);
+    w.id_to_index[m.id] = (uint32_t)w.mols.size() - 1;
+    w.sched_ids.push_back(m.id);
+    list_insert(w, w.mols.back());
+    w.tiles[wi][tile] = m.id;
+    w.species_count[m.species]++;
+  }
+  if (first_id_out) *first_id_out = first;
+  return 0;
+}
+// ReleaseEvent::release_list (release_event.cpp:1008-1040), volume molecules
+int orc_release_list(void* h, uint64_t n_list, const uint32_t* species, const double* x, const double* y, const double* z,
+                     const uint32_t* counted_volume, double release_time, uint32_t* first_id_out) {
+  World& w = *(World*)h;
+  const double it = (double)w.iteration;
+  if (release_time != 0 && !(release_time >= it && release_time < it + 1.0)) { w.err = "release_time outside the current iteration"; return MCX_ERR_INVALID_ARG; }
+  const double t_rel = release_time > it ? release_time : it;
+  const uint32_t first = w.next_id;
+  for (uint64_t k = 0; k < n_list; k++) {
+    if (species[k] >= w.species.size() || !(w.species[species[k]].flags & MCX_SP_VOL)) { w.err = "release list: not a volume species"; return MCX_ERR_INVALID_ARG; }
+    Mol n{};
+    n.pos = {x[k], y[k], z[k]};
+    if (!w.in_this_partition(n.pos)) { w.err = "released molecule outside partition"; return MCX_ERR_ESCAPED; }
+    n.id = w.next_id++; n.species = species[k];
+    n.flags = MCX_MOL_SCHEDULE_UNIMOL | (t_rel > it ? MCX_MOL_PARTIAL : 0u);
+    n.diffusion_time = t_rel; n.unimol_rxn_time = TIME_INVALID;
+    n.subpart = w.subpart_index(n.pos); n.cvi = counted_volume ? counted_volume[k] : 0;
+    n.wall = n.tile = MCX_NONE; n.created_wall = n.created_tile = MCX_NONE;
     w.mols.push_back(n);
     if (w.id_to_index.size() <= n.id) w.id_to_index.resize((size_t)n.id + 1, MCX_NONE);
     w.id_to_index[n.id] = (uint32_t)w.mols.size() - 1;

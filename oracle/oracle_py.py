@@ -116,14 +116,40 @@ class Oracle:
         if rc:
             raise RuntimeError(self.error())
 
-    def release(self, species, number, location, diameter, shape=0, release_time=0.0, counted_volume_index=0):
+    def release(self, species, number, location, diameter, shape=0, release_time=0.0, counted_volume_index=0, region_in=0, region_out=0):
         r = abi.mcx_release()
         r.species, r.shape, r.number = int(species), int(shape), int(number)
         r.location[:] = [float(v) for v in location]
         r.diameter[:] = [float(v) for v in diameter]
         r.release_time, r.counted_volume_index = float(release_time), int(counted_volume_index)
+        r.region_in, r.region_out = int(region_in), int(region_out)
         first = C.c_uint32(0)
         rc = self.L.orc_release_volume_molecules(self.h, C.byref(r), C.byref(first))
+        if rc:
+            raise RuntimeError(self.error())
+        return int(first.value)
+
+    def release_surface(self, species, number, walls, orientation=1, release_time=0.0, randomize_pos=True):
+        """ReleaseEvent::release_onto_regions on the device (mcx_release_surface_molecules): `number` molecules of a
+        surface species on vacant tiles of the listed walls; returns the first id."""
+        wl = np.ascontiguousarray(walls, np.uint32)
+        r = abi.mcx_surface_release()
+        r.species, r.orientation, r.number, r.release_time = int(species), int(orientation), int(number), float(release_time)
+        r.walls, r.n_walls, r.randomize_pos = wl.ctypes.data, len(wl), 1 if randomize_pos else 0
+        first = C.c_uint32(0)
+        rc = self.L.orc_release_surface_molecules(self.h, C.byref(r), C.byref(first))
+        if rc:
+            raise RuntimeError(self.error())
+        return int(first.value)
+
+    def release_list(self, species, positions, counted_volume=None, release_time=0.0):
+        sp = np.ascontiguousarray(species, np.uint32)
+        pos = np.asarray(positions, np.float64)
+        x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+        cv = None if counted_volume is None else np.ascontiguousarray(counted_volume, np.uint32)
+        first = C.c_uint32(0)
+        rc = self.L.orc_release_list(self.h, C.c_uint64(len(sp)), self._v(sp), self._v(x), self._v(y), self._v(z),
+                                     self._v(cv) if cv is not None else None, C.c_double(release_time), C.byref(first))
         if rc:
             raise RuntimeError(self.error())
         return int(first.value)

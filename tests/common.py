@@ -199,7 +199,7 @@ def diffusing_receptors(n_rec=3000, n_lig=8000, radius_um=0.25, subdivisions=3, 
     return t, MolArrays.concat([vol, surf])
 
 
-def counted_spheres(n=12000, seed=1, box_um=0.8, rng_mode=abi.MCX_RNG_PHILOX, p_target=0.4):
+def counted_spheres(n=12000, seed=1, box_um=0.8, rng_mode=abi.MCX_RNG_PHILOX, p_target=0.4, max_molecules=None):
     """Counted volumes: two nested transparent icospheres, both counted, inside a counted
     reflective box; A + B -> C everywhere.  Volumes: {box}, {box, outer}, {box, outer, inner} (+ the empty set)."""
     m = Model(Config(seed=seed))
@@ -215,7 +215,7 @@ def counted_spheres(n=12000, seed=1, box_um=0.8, rng_mode=abi.MCX_RNG_PHILOX, p_
     bv, bf = create_box(box_um)
     m.add_geometry_object(bv, bf, counted=True)
     m.add_surface_property(0, abi.MCX_SURF_TRANSPARENT, species=None)
-    t = m.build(max_molecules=2 * n + 64, rng_mode=rng_mode)
+    t = m.build(max_molecules=max_molecules or 2 * n + 64, rng_mode=rng_mode)
     rng = np.random.default_rng(seed)
     pos = release_uniform_box(rng, n, box_um, t.length_unit, margin=1e-3)
     mols = MolArrays.from_positions(pos, (np.arange(n) % 2).astype(np.uint32))

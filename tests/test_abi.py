@@ -33,7 +33,8 @@ def test_struct_layouts_match_library():
     L = engine.load_library()
     L.mcx_sizeof.restype = C.c_int
     structs = [abi.mcx_config, abi.mcx_species, abi.mcx_rxn_class, abi.mcx_pathway, abi.mcx_surf_class_rxn,
-               abi.mcx_mol_soa, abi.mcx_step_stats, abi.mcx_trace_rec, abi.mcx_slab_info, abi.mcx_release]
+               abi.mcx_mol_soa, abi.mcx_step_stats, abi.mcx_trace_rec, abi.mcx_slab_info, abi.mcx_release,
+               abi.mcx_surface_release]
     for i, s in enumerate(structs):
         assert L.mcx_sizeof(i) == C.sizeof(s), s.__name__
     assert L.mcx_sizeof(99) == -1
