@@ -86,7 +86,14 @@ typedef struct mcx_species {
 
 /* ---- reactions: RxnClass / pathway tables ------------------------------ */
 enum { MCX_RXN_UNIMOL = 1, MCX_RXN_BIMOL_VOLVOL = 2,
-       MCX_RXN_BIMOL_VOLSURF = 3 /* reactants[0] = volume species, reactants[1] = surface species */ };
+       MCX_RXN_BIMOL_VOLSURF = 3, /* reactants[0] = volume species, reactants[1] = surface species */
+       MCX_RXN_BIMOL_VOLWALL = 4  /* reactants[0] = volume species (or MCX_ALL_*), reactants[1] = surface class: a
+                                     Standard reaction of a volume molecule with a reactive surface
+                                     (collide_and_react_with_walls -> test_intersect -> outcome_intersect,
+                                     diffuse_react_event.cpp:991-1067, 1916-1988); reached through a
+                                     mcx_surf_class_rxn of type MCX_SURF_STANDARD.  Products are volume species; a kept
+                                     reactant 0 reflects, or crosses the wall when kept_info gives it another
+                                     orientation (RX_FLIP) */ };
 typedef struct mcx_rxn_class {
   uint32_t kind;                   /* MCX_RXN_* */
   uint32_t reactants[2];           /* species ids in rule order; [1] = MCX_NONE for unimol */
@@ -120,12 +127,14 @@ typedef struct mcx_pathway {
 #define MCX_KEPT_ORDER_REACTANT 8u   /* nibble value 8 + r: kept reactant r */
 
 /* ---- surface classes (mcell4_converter.cpp:515-622; rxn_utils.inl:263-287) ----------- */
-enum { MCX_SURF_REFLECTIVE = 0, MCX_SURF_TRANSPARENT = 1, MCX_SURF_ABSORPTIVE = 2 };
+enum { MCX_SURF_REFLECTIVE = 0, MCX_SURF_TRANSPARENT = 1, MCX_SURF_ABSORPTIVE = 2,
+       MCX_SURF_STANDARD = 3 /* a finite-rate reaction: rxn_class names a MCX_RXN_BIMOL_VOLWALL class */ };
 typedef struct mcx_surf_class_rxn {
   uint32_t species;                /* species id, MCX_ALL_MOLECULES or MCX_ALL_VOLUME_MOLECULES */
   uint32_t surf_class;             /* value used in wall_surf_class[] */
   int32_t  orientation;            /* 0: both sides; +1: hits on the FRONT only; -1: BACK only */
   uint32_t type;                   /* MCX_SURF_* */
+  uint32_t rxn_class;              /* MCX_SURF_STANDARD: index of the reaction class */
 } mcx_surf_class_rxn;
 
 /* ---- molecules: SoA view of Partition::molecules (src4/molecule.h:52-260) ------------ */
@@ -195,7 +204,8 @@ enum {
 enum {
   MCX_OUT_NONE = 0, MCX_OUT_MOVED = 1, MCX_OUT_REACTED = 2, MCX_OUT_ABSORBED = 3,
   MCX_OUT_UNIMOL = 4, MCX_OUT_CONSUMED = 5, MCX_OUT_STATIC = 6,
-  MCX_OUT_SURFMOVE = 7  /* surface molecule took a new tile (move_sm_on_same_triangle / move_sm_to_new_triangle) */
+  MCX_OUT_SURFMOVE = 7, /* surface molecule took a new tile (move_sm_on_same_triangle / move_sm_to_new_triangle) */
+  MCX_OUT_WALLRXN = 8   /* reacted with the surface class of a wall (MCX_RXN_BIMOL_VOLWALL) */
 };
 typedef struct mcx_trace_rec {
   uint32_t id;

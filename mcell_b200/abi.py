@@ -15,12 +15,12 @@ MCX_TIME_INVALID = -256.0
 MCX_TIME_FOREVER = 1e20
 MCX_RNG_PHILOX, MCX_RNG_TAPE = 0, 1
 MCX_SP_VOL, MCX_SP_CAN_DIFFUSE, MCX_SP_CANT_INITIATE = 1, 2, 4
-MCX_RXN_UNIMOL, MCX_RXN_BIMOL_VOLVOL, MCX_RXN_BIMOL_VOLSURF = 1, 2, 3
-MCX_SURF_REFLECTIVE, MCX_SURF_TRANSPARENT, MCX_SURF_ABSORPTIVE = 0, 1, 2
+MCX_RXN_UNIMOL, MCX_RXN_BIMOL_VOLVOL, MCX_RXN_BIMOL_VOLSURF, MCX_RXN_BIMOL_VOLWALL = 1, 2, 3, 4
+MCX_SURF_REFLECTIVE, MCX_SURF_TRANSPARENT, MCX_SURF_ABSORPTIVE, MCX_SURF_STANDARD = 0, 1, 2, 3
 MCX_MOL_DEFUNCT, MCX_MOL_SCHEDULE_UNIMOL, MCX_MOL_PARTIAL = 1, 2, 4
 MCX_KEPT_VALID, MCX_KEPT_ORDER_END, MCX_KEPT_ORDER_REACTANT = 1 << 31, 0xF, 8
 MCX_OUT_NONE, MCX_OUT_MOVED, MCX_OUT_REACTED, MCX_OUT_ABSORBED = 0, 1, 2, 3
-MCX_OUT_UNIMOL, MCX_OUT_CONSUMED, MCX_OUT_STATIC, MCX_OUT_SURFMOVE = 4, 5, 6, 7
+MCX_OUT_UNIMOL, MCX_OUT_CONSUMED, MCX_OUT_STATIC, MCX_OUT_SURFMOVE, MCX_OUT_WALLRXN = 4, 5, 6, 7, 8
 
 c_u32, c_u64, c_i32, c_f64 = C.c_uint32, C.c_uint64, C.c_int32, C.c_double
 P = C.POINTER
@@ -74,7 +74,7 @@ class mcx_pathway(C.Structure):
 
 
 class mcx_surf_class_rxn(C.Structure):
-    _fields_ = [("species", c_u32), ("surf_class", c_u32), ("orientation", c_i32), ("type", c_u32)]
+    _fields_ = [("species", c_u32), ("surf_class", c_u32), ("orientation", c_i32), ("type", c_u32), ("rxn_class", c_u32)]
 
 
 class mcx_mol_soa(C.Structure):

@@ -46,7 +46,7 @@ struct mcx_handle {
        *d_tile_slot = nullptr, *d_exd_skip = nullptr, *d_wall_cv = nullptr, *d_rxn_count_cv = nullptr,
        *d_mol_count_cv = nullptr, *d_edges = nullptr, *d_tile_claim = nullptr;
   uint32_t n_cv = 1; uint32_t* st_cv = nullptr;
-  void *d_wall_obj = nullptr;
+  void *d_wall_obj = nullptr, *d_surf_rxn = nullptr;
   std::vector<double> wall_area_host;
   void *d_wall_rs = nullptr, *d_rxn_count_rs = nullptr, *d_mol_count_rs = nullptr; uint32_t n_rs = 0;
   uint64_t n_walls_host = 0;
@@ -376,7 +376,11 @@ static int rebuild_tables(mcx_handle* h) {
     if ((uint64_t)rc.first_pathway + (uint64_t)rc.n_pathways > (uint64_t)h->pathways.size() || rc.n_pathways == 0 || rc.n_pathways > 4095) {
       h->err = "reaction class pathway range invalid"; return MCX_ERR_INVALID_ARG;
     }
-    if (rc.reactants[0] >= ns || (rc.kind != MCX_RXN_UNIMOL && rc.reactants[1] >= ns)) {
+    if (rc.kind == MCX_RXN_BIMOL_VOLWALL) {
+      // reactants[0]: a volume species or MCX_ALL_*; reactants[1]: a surface class (the class is reached through the
+      // surface-class rules, not through the species tables)
+      if (rc.reactants[0] < ns && !(h->species[rc.reactants[0]].flags & MCX_SP_VOL)) { h->err = "vol-wall class: reactant 0 must be a volume species"; return MCX_ERR_INVALID_ARG; }
+    } else if (rc.reactants[0] >= ns || (rc.kind != MCX_RXN_UNIMOL && rc.reactants[1] >= ns)) {
       h->err = "reaction class references an unknown species"; return MCX_ERR_INVALID_ARG;
     }
     if (rc.n_pathways > 255) { h->err = "more than 255 pathways in one reaction class"; return MCX_ERR_INVALID_ARG; }
@@ -392,6 +396,15 @@ static int rebuild_tables(mcx_handle* h) {
       volsurf[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
       any_surf = true;
     } else if (rc.kind == MCX_RXN_UNIMOL) unimol[rc.reactants[0]] = (int)c;
+    else if (rc.kind == MCX_RXN_BIMOL_VOLWALL) {
+      for (uint32_t q = 0; q < rc.n_pathways; q++) {
+        const mcx_pathway& pw = h->pathways[rc.first_pathway + q];
+        if (pw.keep_reactant_mask & ~1u) { h->err = "vol-wall pathway: only reactant 0 can be kept (the surface always is)"; return MCX_ERR_INVALID_ARG; }
+        for (uint32_t k = 0; k < pw.n_products && k < MCX_MAX_PRODUCTS; k++)
+          if (pw.products[k] < ns && !is_vol(pw.products[k])) { h->err = "vol-wall pathway: surface products are not supported"; return MCX_ERR_INVALID_ARG; }
+      }
+      continue;
+    }
     else { h->err = "unknown reaction kind"; return MCX_ERR_INVALID_ARG; }
     // supported product placement (SURVEY A.2 fast cases; the general find_surf_product_positions branch is not built)
     const bool surf_reactant = rc.kind == MCX_RXN_BIMOL_VOLSURF || (rc.kind == MCX_RXN_UNIMOL && !is_vol(rc.reactants[0]));
@@ -449,6 +462,11 @@ static int rebuild_tables(mcx_handle* h) {
   for (uint32_t c : h->wall_class_host) if (c != MCX_NONE) nsc = std::max(nsc, c + 1);
   h->n_surf_classes = nsc;
   std::vector<uint8_t> act(std::max<size_t>(1, ns * nsc * 2), MCX_SURF_REFLECTIVE);
+  std::vector<int> act_rxn(std::max<size_t>(1, ns * nsc * 2), -1);
+  for (const auto& r : h->surf_rules)
+    if (r.type == MCX_SURF_STANDARD && (r.rxn_class >= h->classes.size() || h->classes[r.rxn_class].kind != MCX_RXN_BIMOL_VOLWALL)) {
+      h->err = "surface-class rule of type MCX_SURF_STANDARD needs a MCX_RXN_BIMOL_VOLWALL reaction class"; return MCX_ERR_INVALID_ARG;
+    }
   bool absorbing = false;
   for (size_t a = 0; a < ns; a++)
     for (uint32_t c = 0; c < nsc; c++)
@@ -460,6 +478,7 @@ static int rebuild_tables(mcx_handle* h) {
           for (const auto& r : h->surf_rules)
             if (r.species == order[o] && r.surf_class == c && (r.orientation == 0 || r.orientation == orient)) {
               act[(a * nsc + c) * 2 + side] = (uint8_t)r.type;
+              act_rxn[(a * nsc + c) * 2 + side] = r.type == MCX_SURF_STANDARD ? (int)r.rxn_class : -1;
               absorbing = absorbing || r.type == MCX_SURF_ABSORPTIVE;
               done = true;
               break;
@@ -488,6 +507,7 @@ static int rebuild_tables(mcx_handle* h) {
   rc |= dev_replace(h, &h->d_classes, dc.data(), dc.size());
   rc |= dev_replace(h, &h->d_pathways, dp.data(), dp.size());
   rc |= dev_replace(h, &h->d_surf, act.data(), act.size());
+  rc |= dev_replace(h, &h->d_surf_rxn, act_rxn.data(), act_rxn.size());
   rc |= dev_replace(h, &h->d_volsurf, volsurf.data(), volsurf.size());
   if (rc) return MCX_ERR_CUDA;
   DevParams& p = h->p;
@@ -496,13 +516,14 @@ static int rebuild_tables(mcx_handle* h) {
   h->has_surf = any_surf;
   p.species = (const DevSpecies*)h->d_species; p.bimol = (const int*)h->d_bimol; p.unimol = (const int*)h->d_unimol;
   p.classes = (const DevClass*)h->d_classes; p.pathways = (const DevPathway*)h->d_pathways;
+  p.surf_rxn = (const int*)h->d_surf_rxn;
   p.surf_action = (const uint8_t*)h->d_surf; p.n_species = (int)ns; p.n_surf_classes = (int)nsc;
   h->plan.has_claims = !h->classes.empty() || absorbing;
   h->plan.has_fresh = false;
   for (const mcx_rxn_class& rc : h->classes)
     for (uint32_t q = 0; q < rc.n_pathways; q++) {
       const mcx_pathway& pw = h->pathways[rc.first_pathway + q];
-      const uint32_t n_react = rc.kind == MCX_RXN_UNIMOL ? 1u : 2u;
+      const uint32_t n_react = (rc.kind == MCX_RXN_UNIMOL || rc.kind == MCX_RXN_BIMOL_VOLWALL) ? 1u : 2u;
       const uint32_t kept = (uint32_t)__builtin_popcount(pw.keep_reactant_mask & ((1u << n_react) - 1u));
       if (pw.n_products > n_react - kept) h->plan.has_fresh = true;
     }
@@ -541,7 +562,7 @@ int mcx_set_surface_classes(mcx_handle* h, const mcx_surf_class_rxn* rules, uint
   if (!h->has_species) { h->err = "mcx_set_species must precede mcx_set_surface_classes"; return MCX_ERR_STATE; }
   CK(cudaSetDevice(h->cfg.device));
   for (uint32_t k = 0; k < n_rules; k++)
-    if (rules[k].surf_class >= 4096 || rules[k].type > MCX_SURF_ABSORPTIVE) { h->err = "bad surface class rule"; return MCX_ERR_INVALID_ARG; }
+    if (rules[k].surf_class >= 4096 || rules[k].type > MCX_SURF_STANDARD) { h->err = "bad surface class rule"; return MCX_ERR_INVALID_ARG; }
   std::vector<mcx_surf_class_rxn> previous = h->surf_rules;
   h->surf_rules.assign(rules, rules + n_rules);
   const int rc = rebuild_tables(h);

@@ -161,7 +161,7 @@ struct Tracer {
 };
 enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
        EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u, EV_BLOCKED = 0xB10C0000u, EV_DISK = 0xD1500000u,
-       EV_SURFMOVE = 0x3E000000u };
+       EV_SURFMOVE = 0x3E000000u, EV_WALLRXN = 0x9A000000u };
 
 struct LocalStats {
   unsigned int ray_polygon_tests, ray_polygon_colls, reflections, transparent, volvol_collisions, redos;
@@ -650,6 +650,21 @@ __device__ int test_bimolecular(const DevParams& p, const DevClass& rc, double s
     if (prob > A[mid].cum_prob) min_idx = mid; else max_idx = mid;
   }
   return prob > A[min_idx].cum_prob ? max_idx : min_idx;
+}
+
+// test_intersect, rxn_utils.inl:593-626 (a Standard reaction with a reactive surface): -1 = no reaction
+__device__ int test_intersect(const DevParams& p, const DevClass& rc, double scaling, Stream& rs) {
+  const double max_prob = rc.max_fixed_p;
+  if (max_prob > scaling) (void)(rs.dbl() * max_prob);
+  else { const double pr = rs.dbl() * scaling; if (pr > max_prob) return -1; }
+  const double match = rs.dbl() * max_prob;
+  int min_idx = 0, max_idx = (int)rc.n_pathways - 1;
+  const DevPathway* A = p.pathways + rc.first_pathway;
+  while (max_idx - min_idx > 1) {
+    int mid = (max_idx + min_idx) / 2;
+    if (match > A[mid].cum_prob) min_idx = mid; else max_idx = mid;
+  }
+  return match > A[min_idx].cum_prob ? max_idx : min_idx;
 }
 
 // A record is one 32-byte sector: sm_100 moves it with ONE 256-bit access (LDG.E.256 / STG.E.256; two 128-bit
@@ -1567,7 +1582,8 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
             const int side = wh.side;  // W_FRONT / W_BACK
             const uint32_t wclass = p.wall_class[wh.wall];
             int action = MCX_SURF_REFLECTIVE;
-            if (wclass != MCX_NONE) action = p.surf_action[(species * p.n_surf_classes + wclass) * 2 + (side == W_FRONT ? 0 : 1)];
+            const uint32_t action_at = (species * p.n_surf_classes + wclass) * 2 + (side == W_FRONT ? 0 : 1);
+            if (wclass != MCX_NONE) action = p.surf_action[action_at];
             if (tc.tr) {
               if (tc.tr->n_wall_hits < MCX_TRACE_K) { tc.tr->wall[tc.tr->n_wall_hits] = wh.wall; tc.tr->wall_side[tc.tr->n_wall_hits] = side; }
               tc.tr->n_wall_hits++;
@@ -1610,6 +1626,25 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
                     surf_reacted = true; decided = true; tracing = false;
                   }
                 }
+              }
+            }
+            if (!surf_reacted && action == MCX_SURF_STANDARD) {
+              // collide_and_react_with_walls (:1034-1066): test_intersect of the one matching class; a reaction is a
+              // claiming event (the proposal's partner word carries the wall), no reaction reflects
+              const int wrc = p.surf_rxn[action_at];
+              const int pathway = test_intersect(p, p.classes[wrc], r_rate_factor, rs);
+              action = MCX_SURF_REFLECTIVE;
+              if (pathway >= 0) {
+                const double abs_t = elapsed + t_steps * wh.t;
+                out.orient_bits = draw_orientation_bits(p.pathways[p.classes[wrc].first_pathway + pathway], rs) |
+                                  (side == W_FRONT ? ORIENT_BIT_FRONT : 0u);
+                tc.ev(EV_WALLRXN | (uint32_t)side, wh.wall);
+                tc.ev(EV_RXN | (uint32_t)pathway, (uint32_t)wrc);
+                if (tc.tr) { tc.tr->rxn_class = wrc; tc.tr->rxn_pathway = pathway; tc.tr->t_event = abs_t; }
+                out.kind = MCX_OUT_WALLRXN; out.pos = wh.pos; out.rxn_class = wrc; out.pathway = pathway;
+                out.partner_slot = wh.wall; out.partner_id = MCX_NONE;
+                out.t_event = abs_t; out.t_now = t_now; out.flags = flags; out.unimol_time = unimol_time;
+                surf_reacted = true; decided = true; tracing = false;
               }
             }
             if (surf_reacted) {

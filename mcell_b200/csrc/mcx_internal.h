@@ -133,6 +133,7 @@ struct DevParams {
   const DevClass* classes;
   const DevPathway* pathways;
   const uint8_t* surf_action;   // [species][surf_class][side(0 front,1 back)]
+  const int* surf_rxn;          // same index: the MCX_RXN_BIMOL_VOLWALL class of a MCX_SURF_STANDARD entry
   const uint8_t* exd_skip;      // [species][surf_class]: exact_disk ignores the wall (the species travels through it)
   const uint16_t* wall_cv;      // per wall: counted volume on the front side | on the back side << 8; null = none
   unsigned long long* rxn_count_cv;  // [rule * n_cv + cv]

@@ -210,6 +210,76 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
   }
   const DevClass& cl = p.classes[rxn_class];
   const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
+  if (kind == MCX_OUT_WALLRXN) {
+    // Standard reaction with a reactive surface (outcome_intersect :1916-1988; partner_slot carries the wall): volume
+    // products at the hit point, bumped 2*16*EPS off the wall to the side their orientation names, with the counted
+    // volume of that side and the tile under the hit point remembered; the molecule is consumed, or kept — then it
+    // waits on its own side or behind the wall (RX_FLIP) for the rest of its step
+    const uint32_t wi = partner_slot;
+    const DevWall& fw = p.walls[wi];
+    const DevGrid& g = p.grids[wi];
+    if (own_event) { if (bt) atomicAdd(&bt->rxn[pw.rule_id & 255u], 1u); else agg_add(&c->rxn_count[pw.rule_id & 255u], 1u); }
+    if (own_event && p.wall_cv) agg_add(&p.rxn_count_cv[(pw.rule_id & 255u) * p.n_cv + (flags >> SF_CVI_SHIFT)], 1u);
+    if (own_event) { if (bt) tally_inc(&bt->bimol); else agg_add(&c->bimol_rxns, 1u); }
+    const bool keep = pw.keep_mask & 1u;
+    const double hu = pos.x * fw.ux + pos.y * fw.uy + pos.z * fw.uz - g.vert0_u;   // GeometryUtils::xyz2uv
+    const double hv = pos.x * fw.vx + pos.y * fw.vy + pos.z * fw.vz - g.vert0_v;
+    const uint32_t hit_tile = uv2grid(p, wi, hu, hv);
+    if (!keep) {
+      atomicOr(&p.recA[slot].sf, DF_DEAD);
+      if (track) { if (bt) atomicSub(&bt->species[species], 1); else agg_sub(&c->species_count[species], 1u); }
+    }
+    const uint32_t n_new = own_event ? pw.n_products : 0u;
+    const uint32_t n_reuse = keep ? 0u : 1u;
+    const uint32_t first_slot = n_new ? c->n_slots + agg_reserve(&c->n_prod, n_new) : 0u;
+    if (n_new > n_reuse && first_slot + n_new <= p.capacity) {
+      const uint32_t e = agg_reserve(&c->n_fresh_events, 1u);
+      if (e >= p.fresh_cap) raise_error(p, MCX_ERR_CAPACITY, id);
+      else {
+        const uint32_t grp = group_of(p, pos);
+        const uint32_t nf = n_new - n_reuse;
+        FreshEvent ev; ev.first_slot = first_slot + n_reuse; ev.n = nf; ev.init_id = id; ev.group = grp;
+        ev.next = atomicExch(&p.fresh_head[grp], e);
+        p.fresh_list[e] = ev;
+        atomicAdd(&p.fresh_pref[grp], nf);
+        atomicAdd(&c->n_fresh_ids, nf);
+      }
+    }
+    for (uint32_t k = 0; k < n_new; k++) {
+      const uint32_t ns = first_slot + k;
+      if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
+      int o = pw.prod_orient[k];
+      if (o == 0) o = ((orient_bits >> k) & 1u) ? 1 : -1;
+      const double bump = (o > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
+      const D3 ppos = {pos.x + (2 * bump) * fw.nx, pos.y + (2 * bump) * fw.ny, pos.z + (2 * bump) * fw.nz};
+      uint32_t pflags = DF_SCHED_UNIMOL | DF_PARTIAL;
+      if (p.has_surf) { pflags |= DF_CREATED_ON_SURF; p.swallB[ns] = wi; p.stileB[ns] = hit_tile; }
+      if (p.wall_cv) { const uint32_t cv = __ldg(p.wall_cv + wi); pflags |= (o > 0 ? (cv & 0xFFu) : (cv >> 8)) << SF_CVI_SHIFT; }
+      const uint32_t psp = pw.products[k];
+      p.tschedB[ns] = t_event;
+      store_rec(p.recB, ns, ppos, (k == 0 && !keep) ? id : MCX_NONE, psp | pflags);
+      p.rank[ns] = atomicAdd(&p.cs_next[cell_of(p, ppos.x, ppos.y, ppos.z)], 1u);
+      if (track) { if (bt) atomicAdd(&bt->species[psp], 1); else agg_add(&c->species_count[psp], 1u); }
+      if (bt) tally_inc(&bt->products); else agg_add(&c->products, 1u);
+    }
+    if (keep) {
+      int ko = 0;
+      if (pw.kept_info & MCX_KEPT_VALID) { ko = kept_code(pw, 0); if (ko == 0) ko = ((orient_bits >> 4) & 1u) ? 1 : -1; }
+      const bool flip = ko != 0 && cl.geom0 != ko;
+      const int coll_side = (orient_bits & ORIENT_BIT_FRONT) ? 1 : -1;
+      const int side = flip ? -coll_side : coll_side;
+      uint32_t f = flags | DF_PARTIAL;
+      if (flip && p.wall_cv) {
+        const uint32_t cv = __ldg(p.wall_cv + wi);
+        f = (f & ~SF_CVI_MASK) | ((coll_side > 0 ? (cv >> 8) : (cv & 0xFFu)) << SF_CVI_SHIFT);
+      }
+      const double bump = (side > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
+      const D3 kpos = {pos.x + (2 * bump) * fw.nx, pos.y + (2 * bump) * fw.ny, pos.z + (2 * bump) * fw.nz};
+      if (p.has_surf) { f |= DF_CREATED_ON_SURF; p.swallB[slot] = wi; p.stileB[slot] = hit_tile; }
+      finalize_alive(p, slot, kpos, id, species, f, t_event, unimol_time);
+    }
+    return;
+  }
   if (own_event) { if (bt) atomicAdd(&bt->rxn[pw.rule_id & 255u], 1u); else agg_add(&c->rxn_count[pw.rule_id & 255u], 1u); }
   // outcome_products_random :2513-2521: a volume initiator counts the reaction in its counted volume, a surface
   // initiator on its wall (here: in the wall's set of counted surface regions)

@@ -159,6 +159,7 @@ class Model:
         self._wall_class = []
         self._counted = []
         self._regions = []   # (name, object index, face indices of that object)
+        self.wall_rules = []  # (surf class, reactant, products, rate, name): finite-rate surface-class reactions
 
     # -- subsystem ------------------------------------------------------------------------
     def add_species(self, name, D, target_only=False, surface=False):
@@ -171,6 +172,15 @@ class Model:
 
     def add_surface_property(self, surf_class, type_, species=None, orientation=0):
         self.surface_properties.append(SurfaceProperty(surf_class, type_, species, orientation))
+
+    def add_surface_class_reaction(self, surf_class, reactant, products, fwd_rate, name=""):
+        """A finite-rate reaction of a volume species with a surface class (MCell's "A' @ sc -> ...": a Standard reaction
+        with a reactive surface, collide_and_react_with_walls / test_intersect / outcome_intersect).  reactant: "A'"
+        (hits on the front), "A," (back) or "A" (both sides); products: volume species with orientation marks — the
+        side of the wall they appear on; the reactant itself among the products is kept: with its own mark it
+        reflects, with the other one it crosses the wall."""
+        self.wall_rules.append((int(surf_class), reactant, list(products), float(fwd_rate),
+                                name or (reactant + "@sc%d->" % surf_class + "+".join(products))))
 
     # -- instantiation --------------------------------------------------------------------
     def add_geometry_object(self, vertices_um, faces, surf_class=abi.MCX_NONE, counted=False):
@@ -260,8 +270,13 @@ class Model:
             if len(geoms) > 1:
                 raise ValueError("rules on the species pair %s differ in reactant orientation (separate reaction classes "
                                  "per geometry are not built)" % (tuple(self.species[k].name for k in key),))
-        classes = (abi.mcx_rxn_class * max(1, len(groups)))()
-        n_path = sum(len(v) for v in groups.values())
+        # finite-rate surface-class reactions: one class per (species, side, surface class), behind the ordinary classes
+        wall_groups = {}
+        for w_id, (sc, reactant, prods, rate, _) in enumerate(self.wall_rules):
+            rn, ro = _parse_oriented(reactant)
+            wall_groups.setdefault((idx[rn], ro, sc), []).append((len(self.rules) + w_id, prods, rate))
+        classes = (abi.mcx_rxn_class * max(1, len(groups) + len(wall_groups)))()
+        n_path = sum(len(v) for v in groups.values()) + sum(len(v) for v in wall_groups.values())
         pathways = (abi.mcx_pathway * max(1, n_path))()
         pi = 0
         has_bimol = False
@@ -353,10 +368,61 @@ class Model:
                 pi += 1
             rc.max_fixed_p = cum
 
-        rules = (abi.mcx_surf_class_rxn * max(1, len(self.surface_properties)))()
+        wall_class_rules = []
+        for wi, ((sp_i, ro, sc), wrules) in enumerate(wall_groups.items()):
+            ci = len(groups) + wi
+            rc = classes[ci]
+            rc.kind = abi.MCX_RXN_BIMOL_VOLWALL
+            rc.reactants[0], rc.reactants[1] = sp_i, sc
+            rc.reactant_orientation[0], rc.reactant_orientation[1] = ro, 1
+            # src/react_util.c:110-157: the vol-wall factor; doubled when the molecule carries the mark of the surface class
+            D_tot = self.species[sp_i].diffusion_constant_3d
+            pb_factor = 0.0 if D_tot <= 0 else 1.0e11 * c.surface_grid_density / (2.0 * N_AV) * math.sqrt(MY_PI * c.time_step / D_tot)
+            if ro != 0:
+                pb_factor *= 2.0
+            rc.first_pathway, rc.n_pathways = pi, len(wrules)
+            cum = 0.0
+            for r_id, prods_s, rate in wrules:
+                pw = pathways[pi]
+                cum += pb_factor * rate
+                pw.cum_prob = cum
+                pparsed = [_parse_oriented(x) for x in prods_s]
+                prods = [idx[n] for n, _ in pparsed]
+                porient = [o for _, o in pparsed]
+                if any(self.species[q].surface for q in prods):
+                    raise ValueError("surface products of a surface-class reaction are not built")
+                kept_q = prods.index(sp_i) if sp_i in prods else None
+                new_at = [q for q in range(len(prods)) if q != kept_q]
+                if len(new_at) > abi.MCX_MAX_PRODUCTS:
+                    raise ValueError("too many products")
+                pw.n_products = len(new_at)
+                for k, q in enumerate(new_at):
+                    pw.products[k] = prods[q]
+                    pw.product_orientation[k] = porient[q]
+                pw.keep_reactant_mask = 0 if kept_q is None else 1
+                info = abi.MCX_KEPT_VALID
+                for q in range(6):
+                    if q >= len(prods):
+                        nib = abi.MCX_KEPT_ORDER_END
+                    elif q == kept_q:
+                        nib = abi.MCX_KEPT_ORDER_REACTANT
+                        info |= {0: 0, 1: 1, -1: 2}[porient[q]] << 24
+                    else:
+                        nib = new_at.index(q)
+                    info |= nib << (4 * q)
+                pw.kept_info = info
+                pw.rxn_rule_id = r_id
+                pi += 1
+            rc.max_fixed_p = cum
+            wall_class_rules.append((sp_i, sc, ro, ci))
+
+        rules = (abi.mcx_surf_class_rxn * max(1, len(self.surface_properties) + len(wall_class_rules)))()
         for i, s in enumerate(self.surface_properties):
             rules[i].species = abi.MCX_ALL_MOLECULES if s.species is None else idx[s.species]
             rules[i].surf_class, rules[i].orientation, rules[i].type = s.surf_class, s.orientation, s.type
+        for k, (sp_i, sc, ro, ci) in enumerate(wall_class_rules):
+            r_ = rules[len(self.surface_properties) + k]
+            r_.species, r_.surf_class, r_.orientation, r_.type, r_.rxn_class = sp_i, sc, ro, abi.MCX_SURF_STANDARD, ci
 
         if self._verts:
             verts = np.concatenate(self._verts) / lu   # mcell4_converter.cpp:921-923
@@ -389,7 +455,7 @@ class Model:
             raise ValueError("reaction radius too large for the subpartition size")
         t = Tables(cfg, sp, classes, pathways, rules, np.ascontiguousarray(verts, np.float64),
                    np.ascontiguousarray(tri, np.uint32), np.ascontiguousarray(wsc, np.uint32),
-                   names, [r.name for r in self.rules], lu, c.time_step)
+                   names, [r.name for r in self.rules] + [w_[4] for w_ in self.wall_rules], lu, c.time_step)
         t.wall_object = np.concatenate([np.full(len(f), k, np.uint32) for k, f in enumerate(self._tris)]) if self._tris else np.zeros(0, np.uint32)
         if any(self._counted):
             _assign_counted_volumes(t, self._counted)
@@ -412,9 +478,9 @@ class Model:
                 raise ValueError("more than 256 distinct sets of surface regions")
             t.region_sets, t.n_region_sets, t.wall_region_set = sets, len(sets), wrs
             t.region_names = [r[0] for r in self._regions]
-        t.n_species, t.n_classes, t.n_pathways = len(self.species), len(groups), n_path
-        t.n_surf_rules = len(self.surface_properties)
-        t.n_rules = len(self.rules)
+        t.n_species, t.n_classes, t.n_pathways = len(self.species), len(groups) + len(wall_groups), n_path
+        t.n_surf_rules = len(self.surface_properties) + len(wall_class_rules)
+        t.n_rules = len(self.rules) + len(self.wall_rules)
         return t
 
 

@@ -143,7 +143,7 @@ static inline uint64_t hash_ev(uint64_t h, uint32_t a, uint32_t b) {
 }
 enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
        EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u, EV_BLOCKED = 0xB10C0000u, EV_DISK = 0xD1500000u,
-       EV_SURFMOVE = 0x3E000000u };
+       EV_SURFMOVE = 0x3E000000u, EV_WALLRXN = 0x9A000000u };
 
 struct Stats {
   uint64_t molecule_steps = 0, ray_polygon_tests = 0, ray_polygon_colls = 0, reflections = 0,
@@ -166,7 +166,8 @@ struct Outcome {
   uint32_t orient_bits = 0;       // bit k: random orientation drawn for products[k] (1 = up)
   uint32_t cvi = 0;               // counted volume of the molecule at the end of the evaluation / at the event
   uint32_t wall = MCX_NONE, tile = MCX_NONE; double u = 0, v = 0;  // surface molecule: where it is after the evaluation
-  int coll_side = 0;              // volume-surface reaction: +1 the initiator hit the wall's front, -1 its back
+  int coll_side = 0;              // volume-surface / volume-wall reaction: +1 the initiator hit the wall's front, -1 its back
+  uint32_t hit_wall = MCX_NONE;   // volume-wall reaction: the wall
   uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE;  // SNAPSHOT, kept initiator of a surface reaction: rebinding guard
 };
 
@@ -701,14 +702,16 @@ static void build_lookups(World& w) {
 
 // surface class lookup: first matching rule in the reference's order
 // (species-specific, then ALL_MOLECULES, then ALL_VOLUME_MOLECULES; rxn_utils.inl:182-244)
-static int surf_action(const World& w, uint32_t species, uint32_t surf_class, int side /*COLL_WALL_*/) {
+static int surf_action(const World& w, uint32_t species, uint32_t surf_class, int side /*COLL_WALL_*/, int* rxn_class = nullptr) {
   if (surf_class == MCX_NONE) return MCX_SURF_REFLECTIVE;
   int orient = side == COLL_WALL_FRONT ? 1 : -1;  // FRONT -> ORIENTATION_UP (diffuse_react_event.cpp:1009)
   const uint32_t order[3] = {species, MCX_ALL_MOLECULES, MCX_ALL_VOLUME_MOLECULES};
   for (int o = 0; o < 3; o++)
     for (const auto& r : w.surf_rules)
-      if (r.species == order[o] && r.surf_class == surf_class && (r.orientation == 0 || r.orientation == orient))
+      if (r.species == order[o] && r.surf_class == surf_class && (r.orientation == 0 || r.orientation == orient)) {
+        if (rxn_class) *rxn_class = (int)r.rxn_class;
         return (int)r.type;
+      }
   return MCX_SURF_REFLECTIVE;
 }
 
@@ -825,6 +828,31 @@ static ProductSpec product_spec(const World& w, const mcx_rxn_class& c, const mc
   return ps;
 }
 
+// Volume product k of a reaction with a reactive surface (outcome_products_random :2739-2806 with a wall collision): at the
+// hit point, bumped off the wall to the side its orientation names, counted volume of that side, remembered with the
+// tile under the hit point (xyz2uv + uv2grid_tile_index, :2768-2776)
+static ProductSpec wall_product_spec(const World& w, const mcx_pathway& pw, uint32_t k, V3 pos, uint32_t orient_bits, uint32_t wall) {
+  ProductSpec ps;
+  ps.species = pw.products[k];
+  int o = pw.product_orientation[k];
+  if (o == 0) o = ((orient_bits >> k) & 1) ? 1 : -1;
+  const Wall& f = w.walls[wall];
+  const Grid& g = w.grids[wall];
+  ps.cvi = o > 0 ? f.cv_front : f.cv_back;
+  const double bump = (o > 0) ? 16 * POS_EPS : -16 * POS_EPS;
+  ps.pos = pos + V3{(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
+  const double hu = pos.x * f.unit_u.x + pos.y * f.unit_u.y + pos.z * f.unit_u.z - g.vert0_u;   // GeometryUtils::xyz2uv
+  const double hv = pos.x * f.unit_v.x + pos.y * f.unit_v.y + pos.z * f.unit_v.z - g.vert0_v;
+  ps.created_wall = wall; ps.created_tile = uv2grid(f, g, hu, hv);
+  return ps;
+}
+// does the kept volume reactant of a reaction with a reactive surface cross the wall? (RX_FLIP, :2694-2716)
+static inline bool wallrxn_flips(const mcx_rxn_class& c, const mcx_pathway& pw, uint32_t orient_bits) {
+  if (!(pw.keep_reactant_mask & 1u) || !(pw.kept_info & MCX_KEPT_VALID)) return false;
+  int o = kept_code(pw, 0);
+  if (o == 0) o = ((orient_bits >> 4) & 1u) ? 1 : -1;
+  return c.reactant_orientation[0] != o;
+}
 // ---- the evaluation context ---------------------------------------------------------------
 // pick_surf_displacement (diffusion_utils.inl:60-96): Marsaglia polar method on one 32-bit word
 static inline void pick_surf_displacement(WordSource& rs, double scale, double& du, double& dv) {
@@ -1218,6 +1246,8 @@ struct Eval {
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
                             uint32_t orient_bits, bool& a_destroyed, bool* flip = nullptr);
 static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed);
+static void seq_apply_wallrxn(World& w, uint32_t index, int rc, int pathway, V3 pos, double t, uint32_t orient_bits, uint32_t wall,
+                              uint32_t cvi, bool& destroyed);
 static void seq_set_defunct(World& w, Mol& m);
 
 struct MolState { V3 pos; uint32_t subpart; double t_now; uint32_t flags; double unimol_time;
@@ -1383,7 +1413,8 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
         } else {
           // ---- wall collision (:476-567)
           const Wall& wall = w.walls[c.wall];
-          int action = surf_action(w, m_species, wall.surf_class, c.type);
+          int wall_rc = -1;
+          int action = surf_action(w, m_species, wall.surf_class, c.type, &wall_rc);
           if (tr) {
             if (tr->n_wall_hits < MCX_TRACE_K) { tr->wall[tr->n_wall_hits] = c.wall; tr->wall_side[tr->n_wall_hits] = c.type; }
             tr->n_wall_hits++;
@@ -1443,6 +1474,38 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
                   // RX_A_OK with the initiator kept (:972-975): on to the wall's surface class, else it reflects
                 }
               }
+            }
+          }
+          if (action == MCX_SURF_STANDARD) {
+            // collide_and_react_with_walls (:1034-1066): test_intersect (rxn_utils.inl:593-626) of the one matching class
+            const mcx_rxn_class& wc = w.classes[wall_rc];
+            const double scaling = r_rate_factor, max_prob = wc.max_fixed_p;
+            double pr;
+            bool reacts = true;
+            if (max_prob > scaling) pr = E.rs.dbl() * max_prob;
+            else { pr = E.rs.dbl() * scaling; if (pr > max_prob) reacts = false; }
+            action = MCX_SURF_REFLECTIVE;   // no reaction: it reflects (:1066)
+            if (reacts) {
+              const double match = E.rs.dbl() * max_prob;
+              const int pathway = pathway_for_probability(w, wc, match);
+              const mcx_pathway& pw = w.pathways[wc.first_pathway + pathway];
+              const uint32_t obits = draw_orientation_bits(pw, E.rs);
+              const double abs_t = elapsed + t_steps * c.time;
+              E.ev(EV_WALLRXN | (uint32_t)c.type, c.wall);
+              E.ev(EV_RXN | (uint32_t)pathway, (uint32_t)wall_rc);
+              if (tr) { tr->rxn_class = wall_rc; tr->rxn_pathway = pathway; tr->t_event = abs_t; }
+              if (!apply) {
+                out.kind = MCX_OUT_WALLRXN; out.pos = c.pos; out.rxn_class = wall_rc; out.pathway = pathway; out.t_event = abs_t;
+                out.orient_bits = obits; out.coll_side = c.type == COLL_WALL_FRONT ? 1 : -1; out.hit_wall = c.wall;
+                fill_event(out);
+                return out;
+              }
+              bool gone = false;
+              w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart; w.mols[index].cvi = s.cvi;
+              seq_apply_wallrxn(w, index, wall_rc, pathway, c.pos, abs_t, obits, c.wall, s.cvi, gone);
+              if (gone) { destroyed = true; out.kind = MCX_OUT_WALLRXN; out.pos = c.pos; out.t_event = abs_t; break; }
+              // RX_FLIP -> WallRxnResult::TRANSPARENT, RX_A_OK -> REFLECT (:1048-1056)
+              action = wallrxn_flips(wc, pw, obits) ? MCX_SURF_TRANSPARENT : MCX_SURF_REFLECTIVE;
             }
           }
           if (action == MCX_SURF_TRANSPARENT) {
@@ -1642,6 +1705,24 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
   if (surf_rxn && keep) { const int o = kept_orientation(c, pw, 0, orient_bits, surf_copy.orient); if (o != 0) w.mols[index].orient = o; }
 }
 
+// outcome_intersect (:1916-1988) of a Standard reaction with a reactive surface; the surface is always kept
+static void seq_apply_wallrxn(World& w, uint32_t index, int rc, int pathway, V3 pos, double t, uint32_t orient_bits, uint32_t wall,
+                              uint32_t cvi, bool& destroyed) {
+  const mcx_rxn_class& c = w.classes[rc];
+  const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
+  w.rxn_count[pw.rxn_rule_id]++;
+  count_rxn_where(w, pw.rxn_rule_id, w.mols[index], cvi);
+  w.stats.bimol_rxns++;
+  for (uint32_t k = 0; k < pw.n_products; k++) {
+    ProductSpec ps = wall_product_spec(w, pw, k, pos, orient_bits, wall);
+    uint32_t nid = seq_add_molecule(w, ps, t);
+    if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
+  }
+  const bool keep = pw.keep_reactant_mask & 1u;
+  if (!keep) seq_set_defunct(w, w.mols[index]);
+  destroyed = !keep;
+}
+
 static void trace_begin(World& w, Eval& E, const Mol& m) {
   if (!w.tracing) return;
   if (w.trace.size() <= m.id) {
@@ -1770,7 +1851,8 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     trace_end(w, E, outs[i]);
   };
   auto is_claiming = [](const Outcome& o) {
-    return o.kind == MCX_OUT_REACTED || o.kind == MCX_OUT_ABSORBED || o.kind == MCX_OUT_UNIMOL || o.kind == MCX_OUT_SURFMOVE;
+    return o.kind == MCX_OUT_REACTED || o.kind == MCX_OUT_ABSORBED || o.kind == MCX_OUT_UNIMOL || o.kind == MCX_OUT_SURFMOVE ||
+           o.kind == MCX_OUT_WALLRXN;
   };
   auto gtile_of = [&](const Outcome& o) { return w.tile_start[o.wall] + o.tile; };
   // does the claiming event consume the partner? (kept reactants are not claimed)
@@ -1798,6 +1880,38 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     const Mol& m = w.mols[i];
     if (o.kind == MCX_OUT_ABSORBED) { dead[i] = 1; w.stats.absorptions++; w.species_count[m.species]--; return; }
     if (o.kind == MCX_OUT_SURFMOVE) { o.kind = MCX_OUT_MOVED; return; }  // stays alive on its new tile
+    if (o.kind == MCX_OUT_WALLRXN) {
+      // Standard reaction with a reactive surface (outcome_intersect :1916-1988): products in front of / behind the wall;
+      // the molecule is consumed, or kept — then it stays on its side or crosses (RX_FLIP), waiting 2*16*EPS off the wall,
+      // guarded against an immediate surface-molecule reaction on the tile under the hit point, for the rest of its step
+      const mcx_rxn_class& c = w.classes[o.rxn_class];
+      const mcx_pathway& pw = w.pathways[c.first_pathway + o.pathway];
+      w.rxn_count[pw.rxn_rule_id]++;
+      count_rxn_where(w, pw.rxn_rule_id, m, o.cvi);
+      w.stats.bimol_rxns++;
+      const bool keep = pw.keep_reactant_mask & 1u;
+      const V3 hit = o.pos;
+      if (!keep) { dead[i] = 1; w.species_count[m.species]--; }
+      for (uint32_t k = 0; k < pw.n_products; k++) {
+        NewMol nm; nm.ps = wall_product_spec(w, pw, k, hit, o.orient_bits, o.hit_wall); nm.t = o.t_event;
+        nm.id = (k == 0 && !keep) ? m.id : MCX_NONE;
+        born.push_back(nm);
+        w.species_count[nm.ps.species]++;
+        w.stats.products++;
+      }
+      if (keep) {
+        const bool flip = wallrxn_flips(c, pw, o.orient_bits);
+        const Wall& f = w.walls[o.hit_wall];
+        const int side = flip ? -o.coll_side : o.coll_side;
+        if (flip) o.cvi = o.coll_side > 0 ? f.cv_back : f.cv_front;
+        const double bump = (side > 0) ? 16 * POS_EPS : -16 * POS_EPS;
+        o.pos = hit + V3{(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
+        ProductSpec g = wall_product_spec(w, pw, 0, hit, 0, o.hit_wall);   // for the tile under the hit point
+        o.created_wall = o.hit_wall; o.created_tile = g.created_tile;
+        o.kind = MCX_OUT_MOVED; o.t_now = o.t_event; o.flags |= MCX_MOL_PARTIAL;
+      }
+      return;
+    }
     const mcx_rxn_class& c = w.classes[o.rxn_class];
     const mcx_pathway& pw = w.pathways[c.first_pathway + o.pathway];
     w.rxn_count[pw.rxn_rule_id]++;
@@ -1902,7 +2016,8 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     if (dead[i]) {
       if (!(w.mols[i].flags & MCX_MOL_DEFUNCT)) {
         w.mols[i].flags |= MCX_MOL_DEFUNCT;
-        if (w.tracing && outs[i].kind != MCX_OUT_REACTED && outs[i].kind != MCX_OUT_ABSORBED && outs[i].kind != MCX_OUT_UNIMOL)
+        if (w.tracing && outs[i].kind != MCX_OUT_REACTED && outs[i].kind != MCX_OUT_ABSORBED && outs[i].kind != MCX_OUT_UNIMOL &&
+            outs[i].kind != MCX_OUT_WALLRXN)
           w.trace[w.mols[i].id].outcome = MCX_OUT_CONSUMED;
       }
       continue;

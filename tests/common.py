@@ -88,7 +88,8 @@ def reversible_box(n=20000, edge_um=0.5, seed=1, rng_mode=abi.MCX_RNG_PHILOX, k_
 
 
 def ligand_receptor_sphere(n_lig=6000, n_rec=1500, n_pump=600, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8,
-                           rng_mode=abi.MCX_RNG_PHILOX, p_bind=0.5, k_off=1e5, k_pump=2e5, release_products=True, regions=False):
+                           rng_mode=abi.MCX_RNG_PHILOX, p_bind=0.5, k_off=1e5, k_pump=2e5, release_products=True, regions=False,
+                           max_molecules=None):
     """BASELINE config 3/4 surface chemistry on an icosphere inside a reflective box:
        L' + R' -> LR'        ligand binds receptors from the outside (front) only
        LR'     -> L' + R'    unbinding releases the ligand on the outside
@@ -123,7 +124,7 @@ def ligand_receptor_sphere(n_lig=6000, n_rec=1500, n_pump=600, radius_um=0.25, s
         m.add_surface_region("north", 0, np.flatnonzero(cz > 0))
         m.add_surface_region("band", 0, np.flatnonzero(np.abs(cz) < 0.4 * radius_um))
     n_total = n_lig + n_rec + n_pump
-    t = m.build(max_molecules=2 * n_total + 64, rng_mode=rng_mode)
+    t = m.build(max_molecules=max_molecules or 2 * n_total + 64, rng_mode=rng_mode)
     rng = np.random.default_rng(seed)
     pos = release_uniform_box(rng, n_lig, box_um, t.length_unit, margin=1e-3)
     vol = MolArrays.from_positions(pos, (np.arange(n_lig) % 2).astype(np.uint32) * Ca + (1 - np.arange(n_lig) % 2).astype(np.uint32) * L,
@@ -171,6 +172,45 @@ def transporter_sphere(n_vol=20000, n_trans=2500, n_enz=1500, radius_um=0.25, su
     surf = release_on_walls(rng, t, sphere_walls, n_trans + n_enz, T, orientation=1, first_id=n_vol)
     surf.species[n_trans:] = E
     return t, MolArrays.concat([vol, surf])
+
+
+def permeable_sphere(n=20000, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8, rng_mode=abi.MCX_RNG_PHILOX,
+                     p_in=0.3, p_out=0.15, products=True):
+    """Finite-rate reactions with a surface class (collide_and_react_with_walls -> test_intersect ->
+    outcome_intersect) on a counted icosphere of surface class 0 inside a reflective box:
+       A' @ sc -> A,          A crosses inwards with probability p_in per hit from outside (RX_FLIP)
+       A, @ sc -> A'          ... and outwards with p_out per hit from inside
+       B' @ sc -> C' + D,     (products=True) B is consumed; C appears outside, D inside
+       E' @ sc -> E' + F,     E is kept (reflects), F appears inside"""
+    import math
+    from mcell_b200.model import N_AV, MY_PI
+    m = Model(Config(seed=seed))
+    for name in ("A", "B", "C", "D", "E", "F"):
+        m.add_species(name, 1e-6)
+
+    def k_for(p):   # marked reactant: doubled factor (src/react_util.c:145-157)
+        pb = 2.0 * 1.0e11 * m.config.surface_grid_density / (2.0 * N_AV) * math.sqrt(MY_PI * m.config.time_step / 1e-6)
+        return p / pb
+
+    m.add_surface_class_reaction(0, "A'", ["A,"], k_for(p_in))
+    m.add_surface_class_reaction(0, "A,", ["A'"], k_for(p_out))
+    if products:
+        m.add_surface_class_reaction(0, "B'", ["C'", "D,"], k_for(0.4))
+        m.add_surface_class_reaction(0, "E'", ["E'", "F,"], k_for(0.25))
+    sv, sf = create_icosphere(radius_um, subdivisions)
+    m.add_geometry_object(sv, sf, surf_class=0, counted=True)
+    bv, bf = create_box(box_um)
+    m.add_geometry_object(bv, bf, counted=True)
+    t = m.build(max_molecules=3 * n + 64, rng_mode=rng_mode)
+    rng = np.random.default_rng(seed)
+    pos = release_uniform_box(rng, n, box_um, t.length_unit, margin=1e-3)
+    sp = np.zeros(n, np.uint32)
+    if products:
+        sp = (np.arange(n) % 3).astype(np.uint32) * 0 + np.where(np.arange(n) % 3 == 1, 1, 0).astype(np.uint32) + \
+            np.where(np.arange(n) % 3 == 2, 4, 0).astype(np.uint32)     # A, B, E in equal parts
+    mols = MolArrays.from_positions(pos, sp, schedule_unimol=True)
+    mols.counted_volume[:] = counted_volume_of(t, pos)
+    return t, mols
 
 
 def diffusing_receptors(n_rec=3000, n_lig=8000, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8, D_surf=1e-7,

@@ -305,6 +305,78 @@ def test_philox_surface_region_counts():
     assert mg.sum() == 4500
 
 
+def test_philox_surface_class_permeation():
+    """SURVEY 8 a18, finite-rate reactions with a surface class (collide_and_react_with_walls -> test_intersect ->
+    outcome_intersect): A crosses a reactive sphere in both directions with different probabilities (kept reactant,
+    RX_FLIP).  Ids stay deterministic: traces, statistics, per-volume counts and the whole population over many
+    iterations."""
+    t, mols = cm.permeable_sphere(n=30000, seed=7, products=False)
+    n = mols.n
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+    crossed = 0
+    for it in range(14):
+        tr_o, st_o = o.trace_step(1, n)
+        tr_g, st_g = e.trace_step(n)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "products_created", "mol_wall_reflections", "resolve_retries", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        crossed += st_g.bimol_rxns
+        mo, ro = o.counts_by_volume()
+        mg, rg = e.counts_by_volume()
+        assert (mo == mg).all() and (ro == rg).all(), it
+        assert (o.counts()[1] == e.counts()[1]).all(), it
+    assert crossed > 300 and int((tr_g["outcome"][live] == abi.MCX_OUT_WALLRXN).sum()) > 5, crossed
+    a, b = o.download().sorted_by_id(), e.download().sorted_by_id()
+    _assert_same_population(a, b)
+    pos = np.stack([b.x, b.y, b.z], 1)
+    assert (b.counted_volume == cm.counted_volume_of(t, pos)).all()
+
+
+def test_philox_surface_class_reactions_with_products():
+    """... and the consuming (B' @ sc -> C' + D,) and catalytic (E' @ sc -> E' + F,) wall reactions, whose products take
+    fresh ids: every iteration starts from a common state; traces, statistics and counts bit for bit, populations as
+    multisets."""
+    t, mols = cm.permeable_sphere(n=30000, seed=8)
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+
+    def key(m):
+        arr = np.c_[m.species[:m.n].astype(float), m.x[:m.n], m.y[:m.n], m.z[:m.n], m.diffusion_time[:m.n],
+                    m.flags[:m.n].astype(float), m.counted_volume[:m.n].astype(float)]
+        return arr[np.lexsort(arr.T[::-1])]
+
+    made = 0
+    state = mols
+    for it in range(8):
+        n_ids = int(state.id[:state.n].max()) + 1
+        if it:
+            e.upload(state)
+            o.upload(state)
+        tr_o, st_o = o.trace_step(1, n_ids)
+        tr_g, st_g = e.trace_step(n_ids)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "products_created", "mol_wall_reflections", "resolve_retries", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        made += st_g.products_created
+        assert (o.counts()[0] == e.counts()[0]).all(), it
+        a, b = o.download(), e.download()
+        assert a.n == b.n
+        ka, kb = key(a), key(b)
+        assert (ka[:, 0] == kb[:, 0]).all() and (ka[:, 4:] == kb[:, 4:]).all(), it
+        assert cm.rel_close(ka[:, 1:4], kb[:, 1:4], POS_TOL).all(), it
+        state = a
+    assert made > 200, made
+
+
 def test_philox_surface_diffusion_with_binding():
     """Surface diffusion (diffuse_surf_molecule, ray_trace_surf across triangle edges, tile claims between movers)
     together with ligand binding on the moving receptors: traces (incl. the tile every mover takes), conflict

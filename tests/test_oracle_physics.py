@@ -438,3 +438,53 @@ def test_surface_region_counts(mode):
         both = mc[:, t.region_sets.index(frozenset({0, 1}))]
         assert (north + band - both <= sp).all()
     assert rx[1] > 20 and rx[3] > 10
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_finite_rate_surface_class_reactions(mode):
+    """SURVEY 8 a18 (diffuse_react_event.cpp:991-1067, 1916-1988; rxn_utils.inl:593-626): permeation through a reactive
+    surface in both directions, a consuming and a catalytic wall reaction.  Conservation, the side every product appears
+    on, counted volumes against fresh ray casts, reaction counts against population changes."""
+    t, mols = cm.permeable_sphere(n=9000, seed=13)
+    A, B, Cc, D, E, F = range(6)
+    inner = [i for i, s_ in enumerate(t.counted_volume_sets) if 0 in s_][0]
+    o = O.Oracle(t)
+    o.upload(mols)
+    n0 = np.bincount(mols.species[:mols.n], minlength=6)
+    for it in range(6):
+        o.step(3, mode)
+        m = o.download()
+        sp, rx = o.counts()
+        pos = np.stack([m.x[:m.n], m.y[:m.n], m.z[:m.n]], 1)
+        cv = cm.counted_volume_of(t, pos)
+        assert (m.counted_volume[:m.n] == cv).all()
+        assert sp[A] == n0[A] and sp[E] == n0[E]                                  # kept reactants
+        assert sp[B] + sp[Cc] == n0[B] and sp[Cc] == sp[D] == rx[2] and sp[F] == rx[3]
+        s_ = m.species[:m.n]
+        assert (cv[s_ == Cc] != inner).all() and (cv[s_ == D] == inner).all()      # C outside, D inside
+        assert (cv[s_ == F] == inner).all() and (cv[s_ == E] != inner).sum() + (cv[s_ == E] == inner).sum() == n0[E]
+        a_in = int((cv[s_ == A] == inner).sum())
+    a_in0 = int((cm.counted_volume_of(t, np.stack([mols.x, mols.y, mols.z], 1)[mols.species == A]) == inner).sum())
+    assert rx[0] - rx[1] == a_in - a_in0                                            # net inward crossings
+    assert rx[0] > 60 and rx[1] > 10 and rx[2] > 60 and rx[3] > 40, rx
+    e_in0 = int((cm.counted_volume_of(t, np.stack([mols.x, mols.y, mols.z], 1)[mols.species == E]) == inner).sum())
+    assert int((cv[s_ == E] == inner).sum()) == e_in0                               # E never crosses
+
+
+def test_surface_class_permeation_ratio_and_mode_agreement():
+    """Hits from outside cross with p_in, hits from inside with p_out: the crossing / hit ratios of both directions
+    follow the probabilities, and the two execution modes agree statistically."""
+    res = []
+    for mode in (0, 1):
+        tot = np.zeros(2)
+        for seed in range(3):
+            t, mols = cm.permeable_sphere(n=9000, seed=30 + seed, products=False)
+            o = O.Oracle(t)
+            o.upload(mols)
+            o.step(14, mode)
+            tot += o.counts()[1][:2]
+        res.append(tot)
+    for k in range(2):
+        a, b = res[0][k], res[1][k]
+        assert abs(a - b) < 5 * math.sqrt(a + b), (k, res)
+    assert res[0][0] > 200

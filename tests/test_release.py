@@ -251,7 +251,7 @@ def test_gpu_region_and_list_release_match_oracle_and_step_on():
 
 def _surface_case(seed=3, n_rec=1500):
     """ligand_receptor_sphere: 1280 sphere walls (object 0) with receptors / pumps already on some tiles"""
-    t, mols = cm.ligand_receptor_sphere(n_lig=4000, n_rec=n_rec, n_pump=500, seed=seed, release_products=False)
+    t, mols = cm.ligand_receptor_sphere(n_lig=4000, n_rec=n_rec, n_pump=500, seed=seed, release_products=False, max_molecules=40000)
     tri = t.vertices[t.tri]
     cz = tri.mean(axis=1)[:, 2]
     north = np.flatnonzero((t.wall_object == 0) & (cz > 0)).astype(np.uint32)
