@@ -40,6 +40,7 @@ extern "C" {
 /* Pseudo species for surface-class rules (libmcell/api/model.cpp:95, rxn_utils.inl:192-203) */
 #define MCX_ALL_MOLECULES 0xFFFFFFF0u
 #define MCX_ALL_VOLUME_MOLECULES 0xFFFFFFF1u
+#define MCX_ALL_SURFACE_MOLECULES 0xFFFFFFF2u
 
 /* time sentinels (src4/defines.h:178-179) */
 #define MCX_TIME_INVALID (-256.0)
@@ -130,7 +131,7 @@ typedef struct mcx_pathway {
 enum { MCX_SURF_REFLECTIVE = 0, MCX_SURF_TRANSPARENT = 1, MCX_SURF_ABSORPTIVE = 2,
        MCX_SURF_STANDARD = 3 /* a finite-rate reaction: rxn_class names a MCX_RXN_BIMOL_VOLWALL class */ };
 typedef struct mcx_surf_class_rxn {
-  uint32_t species;                /* species id, MCX_ALL_MOLECULES or MCX_ALL_VOLUME_MOLECULES */
+  uint32_t species;                /* species id, MCX_ALL_MOLECULES, MCX_ALL_VOLUME_MOLECULES or MCX_ALL_SURFACE_MOLECULES */
   uint32_t surf_class;             /* value used in wall_surf_class[] */
   int32_t  orientation;            /* 0: both sides; +1: hits on the FRONT only; -1: BACK only */
   uint32_t type;                   /* MCX_SURF_* */
@@ -305,6 +306,14 @@ int mcx_set_counted_volumes(mcx_handle* h, uint32_t n_counted_volumes, const uin
  * and Partition::inc_rxn_in_volume_occured_count (partition.h:1036-1077).
  * mol_counts[species * n_counted_volumes + cv], rxn_counts[rxn_rule * n_counted_volumes + cv]; either may be NULL. */
 int mcx_counts_by_volume(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_counts);
+
+/* Region borders for surface molecules (ray_trace_surf, diffuse_react_event.cpp:1627-1665; reflect_absorb_inside_out /
+ * outside_in, diffusion_utils.inl:598-700): wall_edge_border[w] bit e = edge e of wall w (0: v0-v1, 1: v1-v2, 2: v2-v0) is
+ * a border of a reactive region the wall belongs to (WallUtils::is_wall_edge_region_border with
+ * region_must_be_reactive).  A surface molecule that reaches such an edge — leaving the region or entering it — turns
+ * back when the wall's surface class is MCX_SURF_REFLECTIVE for its species and orientation, is destroyed when it is
+ * MCX_SURF_ABSORPTIVE (absorptive region border), passes otherwise.  NULL removes the borders. */
+int mcx_set_region_borders(mcx_handle* h, const uint8_t* wall_edge_border);
 
 /* Counted surface regions (MolOrRxnCountEvent terms CountType::PresentOnSurfaceRegion and RxnCountOnSurfaceRegion,
  * src4/mol_or_rxn_count_event.cpp:528-534, 588-600; the reference keeps reaction counts per wall,

@@ -11,6 +11,7 @@ MCX_MAX_PRODUCTS = 4
 MCX_TRACE_K = 4
 MCX_ALL_MOLECULES = 0xFFFFFFF0
 MCX_ALL_VOLUME_MOLECULES = 0xFFFFFFF1
+MCX_ALL_SURFACE_MOLECULES = 0xFFFFFFF2
 MCX_TIME_INVALID = -256.0
 MCX_TIME_FOREVER = 1e20
 MCX_RNG_PHILOX, MCX_RNG_TAPE = 0, 1
@@ -125,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "mcx_download_molecules", "mcx_num_molecules", "mcx_step", "mcx_replay_step", "mcx_trace_step",
     "mcx_counts", "mcx_comm_init", "mcx_comm_unique_id", "mcx_slab_info_get", "mcx_comm_halo_path", "mcx_philox_block", "mcx_set_profiling",
     "mcx_grid_num_tiles", "mcx_grid2uv", "mcx_xyz2grid", "mcx_set_counted_volumes", "mcx_counts_by_volume", "mcx_release_volume_molecules", "mcx_fast_pass_kind", "mcx_walls_per_subpart",
-    "mcx_set_surface_regions", "mcx_counts_by_surface_region", "mcx_release_list", "mcx_release_surface_molecules",
+    "mcx_set_surface_regions", "mcx_counts_by_surface_region", "mcx_release_list", "mcx_release_surface_molecules", "mcx_set_region_borders",
 ]
 
 

@@ -46,7 +46,7 @@ struct mcx_handle {
        *d_tile_slot = nullptr, *d_exd_skip = nullptr, *d_wall_cv = nullptr, *d_rxn_count_cv = nullptr,
        *d_mol_count_cv = nullptr, *d_edges = nullptr, *d_tile_claim = nullptr;
   uint32_t n_cv = 1; uint32_t* st_cv = nullptr;
-  void *d_wall_obj = nullptr, *d_surf_rxn = nullptr;
+  void *d_wall_obj = nullptr, *d_surf_rxn = nullptr, *d_surf_border = nullptr, *d_wall_border = nullptr;
   std::vector<double> wall_area_host;
   void *d_wall_rs = nullptr, *d_rxn_count_rs = nullptr, *d_mol_count_rs = nullptr; uint32_t n_rs = 0;
   uint64_t n_walls_host = 0;
@@ -354,6 +354,7 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
     // the per-wall counted-volume table belongs to the previous geometry: drop it (mcx_set_counted_volumes again)
     h->p.wall_cv = nullptr; h->p.n_cv = 1; h->n_cv = 1;
   }
+  if (h->p.wall_border && h->n_walls_host != n_walls) h->p.wall_border = nullptr;   // likewise
   if (h->p.wall_rs && h->n_walls_host != n_walls) { h->p.wall_rs = nullptr; h->p.n_rs = 0; h->n_rs = 0; }  // likewise
   h->n_walls_host = n_walls;
   h->has_geometry = true;
@@ -484,6 +485,24 @@ static int rebuild_tables(mcx_handle* h) {
               break;
             }
       }
+  // region borders for surface molecules (reflect_absorb_check_wall, diffusion_utils.inl:598-628): the first REFLECTIVE or
+  // ABSORPTIVE rule in the order species, ALL_MOLECULES, ALL_SURFACE_MOLECULES; nothing = it passes
+  std::vector<uint8_t> border(std::max<size_t>(1, ns * nsc * 2), MCX_SURF_TRANSPARENT);
+  for (size_t a = 0; a < ns; a++)
+    for (uint32_t c = 0; c < nsc; c++)
+      for (int side = 0; side < 2; side++) {
+        const int orient = side == 0 ? 1 : -1;
+        const uint32_t order[3] = {(uint32_t)a, MCX_ALL_MOLECULES, MCX_ALL_SURFACE_MOLECULES};
+        bool done = false;
+        for (int o = 0; o < 3 && !done; o++)
+          for (const auto& r : h->surf_rules)
+            if (r.species == order[o] && r.surf_class == c && (r.orientation == 0 || r.orientation == orient) &&
+                (r.type == MCX_SURF_REFLECTIVE || r.type == MCX_SURF_ABSORPTIVE)) {
+              border[(a * nsc + c) * 2 + side] = (uint8_t)r.type;
+              done = true;
+              break;
+            }
+      }
   // exact_disk ignores walls the moving molecule travels through (exact_disk_utils.inl:957-975): trigger_intersect
   // with ORIENTATION_NONE matches the orientation-independent classes (rxn_utils.inl:149-158); the wall is ignored
   // when there is at least one and all of them are transparent
@@ -508,6 +527,7 @@ static int rebuild_tables(mcx_handle* h) {
   rc |= dev_replace(h, &h->d_pathways, dp.data(), dp.size());
   rc |= dev_replace(h, &h->d_surf, act.data(), act.size());
   rc |= dev_replace(h, &h->d_surf_rxn, act_rxn.data(), act_rxn.size());
+  rc |= dev_replace(h, &h->d_surf_border, border.data(), border.size());
   rc |= dev_replace(h, &h->d_volsurf, volsurf.data(), volsurf.size());
   if (rc) return MCX_ERR_CUDA;
   DevParams& p = h->p;
@@ -516,7 +536,7 @@ static int rebuild_tables(mcx_handle* h) {
   h->has_surf = any_surf;
   p.species = (const DevSpecies*)h->d_species; p.bimol = (const int*)h->d_bimol; p.unimol = (const int*)h->d_unimol;
   p.classes = (const DevClass*)h->d_classes; p.pathways = (const DevPathway*)h->d_pathways;
-  p.surf_rxn = (const int*)h->d_surf_rxn;
+  p.surf_rxn = (const int*)h->d_surf_rxn; p.surf_border = (const uint8_t*)h->d_surf_border;
   p.surf_action = (const uint8_t*)h->d_surf; p.n_species = (int)ns; p.n_surf_classes = (int)nsc;
   h->plan.has_claims = !h->classes.empty() || absorbing;
   h->plan.has_fresh = false;
@@ -624,6 +644,16 @@ int mcx_counts_by_volume(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_coun
       int rc = reduce(rxn_counts, (size_t)n_rules * h->n_cv); if (rc) return rc;
     }
   }
+  return MCX_OK;
+}
+
+int mcx_set_region_borders(mcx_handle* h, const uint8_t* wall_edge_border) {
+  if (!h) return MCX_ERR_INVALID_ARG;
+  if (!h->has_geometry) { h->err = "mcx_set_geometry must precede mcx_set_region_borders"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  if (!wall_edge_border) { h->p.wall_border = nullptr; return MCX_OK; }
+  if (dev_replace(h, &h->d_wall_border, wall_edge_border, std::max<uint64_t>(h->n_walls_host, 1))) return MCX_ERR_CUDA;
+  h->p.wall_border = (const uint8_t*)h->d_wall_border;
   return MCX_OK;
 }
 

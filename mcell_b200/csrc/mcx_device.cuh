@@ -1299,10 +1299,17 @@ __device__ __forceinline__ uint32_t traverse_surface(const DevParams& p, uint32_
 }
 // ray_trace_surf, src4/diffuse_react_event.cpp:1578-1725 (no region borders).  Returns the wall the move ends on
 // (MCX_NONE: ambiguous side hit) and the end point in that wall's frame.
+// Region borders (species.can_interact_with_border(), :1627-1665; reflect_absorb_inside_out / outside_in, diffusion_utils.inl:
+// 598-700): an edge that is a border of a reactive region — of the wall the molecule leaves or of the one it enters —
+// turns the molecule back (REFLECTIVE class), takes it (ABSORPTIVE: absorbed = true, MCX_NONE) or lets it pass.
 __device__ uint32_t ray_trace_surf(const DevParams& p, uint32_t wall_index, double pu, double pv, double du, double dv,
-                                   double& out_u, double& out_v) {
+                                   double& out_u, double& out_v, uint32_t sm_species, int sm_orient, bool& absorbed) {
   uint32_t this_index = wall_index;
   double this_u = pu, this_v = pv, disp_u = du, disp_v = dv;
+  absorbed = false;
+  const bool borders = p.wall_border != nullptr;
+  const uint32_t act_base = sm_species * (uint32_t)p.n_surf_classes;
+  const uint32_t act_side = sm_orient > 0 ? 0u : 1u;
   for (int guard = 0; guard < 10000; guard++) {
     const DevWall& tw = p.walls[this_index];
     double bu = 0, bv = 0;
@@ -1311,7 +1318,24 @@ __device__ uint32_t ray_trace_surf(const DevParams& p, uint32_t wall_index, doub
     if (edge == 3) { out_u = this_u + disp_u; out_v = this_v + disp_v; return this_index; }
     const double old_u = this_u, old_v = this_v;
     double nu, nv;
-    const uint32_t target = traverse_surface(p, this_index, old_u, old_v, edge, nu, nv);
+    bool reflect_now = false;
+    if (borders && ((p.wall_border[this_index] >> edge) & 1u)) {   // inside out
+      const uint32_t wc = p.wall_class[this_index];
+      const int act = wc == MCX_NONE ? MCX_SURF_TRANSPARENT : p.surf_border[(act_base + wc) * 2 + act_side];
+      if (act == MCX_SURF_ABSORPTIVE) { absorbed = true; return MCX_NONE; }
+      reflect_now = act == MCX_SURF_REFLECTIVE;
+    }
+    uint32_t target = reflect_now ? MCX_NONE : traverse_surface(p, this_index, old_u, old_v, edge, nu, nv);
+    if (target != MCX_NONE && borders) {   // outside in: the shared edge in the neighbour's numbering
+      int te = -1;
+      for (int e2 = 0; e2 < 3; e2++) if (p.edges[3 * target + e2].nb_wall == this_index) te = e2;
+      if (te >= 0 && ((p.wall_border[target] >> te) & 1u)) {
+        const uint32_t wc = p.wall_class[target];
+        const int act = wc == MCX_NONE ? MCX_SURF_TRANSPARENT : p.surf_border[(act_base + wc) * 2 + act_side];
+        if (act == MCX_SURF_ABSORPTIVE) { absorbed = true; return MCX_NONE; }
+        if (act == MCX_SURF_REFLECTIVE) target = MCX_NONE;
+      }
+    }
     if (target != MCX_NONE) {
       this_u = nu; this_v = nv;
       double tu2, tv2;
@@ -1437,8 +1461,17 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
           const double normal_factor = sqrt(-mcx_log(f) / f);
           const double du = au * (normal_factor * space_factor), dv = av * (normal_factor * space_factor);
           double nu, nv;
-          const uint32_t new_wall = ray_trace_surf(p, ss.wall, ss.u, ss.v, du, dv, nu, nv);
-          bool ok = new_wall != MCX_NONE;
+          bool absorbed_at_border;
+          const uint32_t new_wall = ray_trace_surf(p, ss.wall, ss.u, ss.v, du, dv, nu, nv, species, (flags & DF_ORIENT_UP) ? 1 : -1,
+                                                   absorbed_at_border);
+          if (absorbed_at_border) {  // absorptive region border (:1152-1160): destroyed at the start of the step, no products
+            tc.ev(EV_ABSORB, ss.wall);
+            if (tc.tr) tc.tr->t_event = t_now;
+            out.kind = MCX_OUT_ABSORBED; out.pos = pos; out.t_event = t_now; out.t_now = t_now; out.flags = flags;
+            out.unimol_time = unimol_time;
+            decided = true; placed = true;
+          }
+          bool ok = !absorbed_at_border && new_wall != MCX_NONE;
           uint32_t new_tile = MCX_NONE;
           if (ok) { new_tile = uv2grid(p, new_wall, nu, nv); ok = new_tile != MCX_NONE; }
           bool changes_tile = false;

@@ -133,6 +133,8 @@ struct DevParams {
   const DevClass* classes;
   const DevPathway* pathways;
   const uint8_t* surf_action;   // [species][surf_class][side(0 front,1 back)]
+  const uint8_t* surf_border;   // same index, side = orientation of a surface molecule (0 up, 1 down): what a region border of that class does
+  const uint8_t* wall_border;   // per wall: bit e = edge e is a border of a reactive region (mcx_set_region_borders); null = none
   const int* surf_rxn;          // same index: the MCX_RXN_BIMOL_VOLWALL class of a MCX_SURF_STANDARD entry
   const uint8_t* exd_skip;      // [species][surf_class]: exact_disk ignores the wall (the species travels through it)
   const uint16_t* wall_cv;      // per wall: counted volume on the front side | on the back side << 8; null = none

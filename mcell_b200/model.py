@@ -146,6 +146,7 @@ class Tables:
     wall_region_set: np.ndarray = None
     region_sets: list = field(default_factory=lambda: [frozenset()])
     region_names: list = field(default_factory=list)
+    wall_edge_border: np.ndarray = None   # per wall: bit e = edge e is a border of a reactive region
 
 
 class Model:
@@ -159,6 +160,7 @@ class Model:
         self._wall_class = []
         self._counted = []
         self._regions = []   # (name, object index, face indices of that object)
+        self._region_class = []
         self.wall_rules = []  # (surf class, reactant, products, rate, name): finite-rate surface-class reactions
 
     # -- subsystem ------------------------------------------------------------------------
@@ -193,10 +195,16 @@ class Model:
         sc = np.broadcast_to(np.asarray(surf_class, dtype=np.uint32), (len(faces),)).copy()
         self._wall_class.append(sc)
 
-    def add_surface_region(self, name, object_index, faces):
+    def add_surface_region(self, name, object_index, faces, surf_class=None):
         """A named surface region = some faces of one geometry object (Region, src4/region.h); used by surface-region
-        counts (CountType::PresentOnSurfaceRegion / RxnCountOnSurfaceRegion).  Returns the region's index."""
-        self._regions.append((name, int(object_index), np.asarray(faces, dtype=np.int64)))
+        counts (CountType::PresentOnSurfaceRegion / RxnCountOnSurfaceRegion).  surf_class: the region is reactive — its
+        faces get that surface class and its outline becomes a region border for surface molecules
+        (Region::is_edge, WallUtils::is_wall_edge_region_border).  Returns the region's index."""
+        faces = np.asarray(faces, dtype=np.int64)
+        self._regions.append((name, int(object_index), faces))
+        self._region_class.append(surf_class)
+        if surf_class is not None:
+            self._wall_class[int(object_index)][faces] = np.uint32(surf_class)
         return len(self._regions) - 1
 
     # -- derived units ----------------------------------------------------------------------
@@ -478,6 +486,25 @@ class Model:
                 raise ValueError("more than 256 distinct sets of surface regions")
             t.region_sets, t.n_region_sets, t.wall_region_set = sets, len(sets), wrs
             t.region_names = [r[0] for r in self._regions]
+            # borders of the reactive regions: an edge (e: v_e - v_{e+1}) of a region wall whose neighbour across it is not
+            # in the region (or that has none)
+            if any(c_ is not None for c_ in self._region_class):
+                border = np.zeros(len(tri), np.uint8)
+                for k, (_, obj, faces) in enumerate(self._regions):
+                    if self._region_class[k] is None:
+                        continue
+                    walls = [int(first_wall[obj] + f) for f in faces]
+                    count = {}
+                    for wi in walls:
+                        for e in range(3):
+                            key = tuple(sorted((int(tri[wi][e]), int(tri[wi][(e + 1) % 3]))))
+                            count[key] = count.get(key, 0) + 1
+                    for wi in walls:
+                        for e in range(3):
+                            key = tuple(sorted((int(tri[wi][e]), int(tri[wi][(e + 1) % 3]))))
+                            if count[key] == 1:
+                                border[wi] |= 1 << e
+                t.wall_edge_border = border
         t.n_species, t.n_classes, t.n_pathways = len(self.species), len(groups) + len(wall_groups), n_path
         t.n_surf_rules = len(self.surface_properties) + len(wall_class_rules)
         t.n_rules = len(self.rules) + len(self.wall_rules)

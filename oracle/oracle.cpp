@@ -204,6 +204,7 @@ struct World {
   std::vector<uint64_t> species_count, rxn_count;
   uint32_t n_cv = 1;                       // counted volumes (index 0 = outside all)
   std::vector<uint64_t> rxn_count_cv;      // [rule * n_cv + cv] (inc_rxn_in_volume_occured_count)
+  std::vector<uint8_t> wall_border;        // per wall: bit e = edge e is a border of a reactive region (mcx_set_region_borders); empty = none
   std::vector<uint8_t> wall_rs;            // per wall: set of counted surface regions (mcx_set_surface_regions); empty = none
   uint32_t n_rs = 0;
   std::vector<uint64_t> rxn_count_rs;      // [rule * n_rs + set] (inc_rxn_on_surface_occured_count, summed per region set)
@@ -475,8 +476,14 @@ static uint32_t traverse_surface(const Wall& here, double lu, double lv, int whi
 // ray_trace_surf, src4/diffuse_react_event.cpp:1578-1725 (no region borders: species.can_interact_with_border() is
 // false).  Returns the wall the move ends on (MCX_NONE: ambiguous edge hit, pick another displacement) and the
 // end point in that wall's frame.
+static int border_action(const World& w, uint32_t species, uint32_t surf_class, int orient);
+// Region borders (species.can_interact_with_border(), :1627-1665): sm_species != MCX_NONE checks the edges that are borders of
+// a reactive region — leaving it (reflect_absorb_inside_out) and entering one (reflect_absorb_outside_in, diffusion_utils.inl:
+// 632-700): a REFLECTIVE class turns the molecule back at the edge, an ABSORPTIVE one takes it (*absorbed = true, MCX_NONE).
 static uint32_t ray_trace_surf(const World& w, uint32_t wall_index, double pu, double pv, double du, double dv,
-                               double& out_u, double& out_v) {
+                               double& out_u, double& out_v, uint32_t sm_species = MCX_NONE, int sm_orient = 0, bool* absorbed = nullptr) {
+  const bool borders = sm_species != MCX_NONE && !w.wall_border.empty();
+  if (absorbed) *absorbed = false;
   const Wall* this_wall = &w.walls[wall_index];
   uint32_t this_index = wall_index;
   double this_u = pu, this_v = pv, disp_u = du, disp_v = dv;
@@ -487,7 +494,23 @@ static uint32_t ray_trace_surf(const World& w, uint32_t wall_index, double pu, d
     if (edge == EDGE_WITHIN_WALL) { out_u = this_u + disp_u; out_v = this_v + disp_v; return this_index; }
     double old_u = this_u, old_v = this_v;
     double nu, nv;
-    uint32_t target = traverse_surface(*this_wall, old_u, old_v, edge, nu, nv);
+    bool reflect_now = false;
+    if (borders && ((w.wall_border[this_index] >> edge) & 1)) {   // inside out
+      const int act = border_action(w, sm_species, this_wall->surf_class, sm_orient);
+      if (act == MCX_SURF_ABSORPTIVE) { if (absorbed) *absorbed = true; return MCX_NONE; }
+      reflect_now = act == MCX_SURF_REFLECTIVE;
+    }
+    uint32_t target = reflect_now ? MCX_NONE : traverse_surface(*this_wall, old_u, old_v, edge, nu, nv);
+    if (target != MCX_NONE && borders) {   // outside in: the shared edge in the neighbour's numbering
+      const Wall& tw = w.walls[target];
+      int te = -1;
+      for (int e2 = 0; e2 < 3; e2++) if (tw.nb_wall[e2] == this_index) te = e2;
+      if (te >= 0 && ((w.wall_border[target] >> te) & 1)) {
+        const int act = border_action(w, sm_species, tw.surf_class, sm_orient);
+        if (act == MCX_SURF_ABSORPTIVE) { if (absorbed) *absorbed = true; return MCX_NONE; }
+        if (act == MCX_SURF_REFLECTIVE) target = MCX_NONE;
+      }
+    }
     if (target != MCX_NONE) {
       this_u = nu; this_v = nv;
       double su = old_u + disp_u, sv = old_v + disp_v;
@@ -713,6 +736,20 @@ static int surf_action(const World& w, uint32_t species, uint32_t surf_class, in
         return (int)r.type;
       }
   return MCX_SURF_REFLECTIVE;
+}
+// reflect_absorb_check_wall (diffusion_utils.inl:598-628): what the border of the wall's reactive region does to a surface
+// molecule of this species and orientation — MCX_SURF_REFLECTIVE, MCX_SURF_ABSORPTIVE (absorptive region border), or
+// MCX_SURF_TRANSPARENT (nothing: it passes).  Lookup order of find_mol_reactions_with_surf_classes: the species, ALL_MOLECULES,
+// ALL_SURFACE_MOLECULES.
+static int border_action(const World& w, uint32_t species, uint32_t surf_class, int orient) {
+  if (surf_class == MCX_NONE) return MCX_SURF_TRANSPARENT;
+  const uint32_t order[3] = {species, MCX_ALL_MOLECULES, MCX_ALL_SURFACE_MOLECULES};
+  for (int o = 0; o < 3; o++)
+    for (const auto& r : w.surf_rules)
+      if (r.species == order[o] && r.surf_class == surf_class && (r.orientation == 0 || r.orientation == orient) &&
+          (r.type == MCX_SURF_REFLECTIVE || r.type == MCX_SURF_ABSORPTIVE))
+        return (int)r.type;
+  return MCX_SURF_TRANSPARENT;
 }
 
 // exact_disk ignores a wall the moving molecule can travel through (exact_disk_utils.inl:957-975):
@@ -1325,7 +1362,18 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
       double du, dv;
       pick_surf_displacement(E.rs, space_factor, du, dv);
       double nu, nv;
-      uint32_t new_wall = ray_trace_surf(w, s.wall, s.u, s.v, du, dv, nu, nv);
+      bool absorbed_at_border = false;
+      uint32_t new_wall = ray_trace_surf(w, s.wall, s.u, s.v, du, dv, nu, nv, m_species, w.mols[index].orient, &absorbed_at_border);
+      if (absorbed_at_border) {
+        // absorptive region border (:1152-1160): outcome_unimolecular of the border's class at the start of the step, no products
+        E.ev(EV_ABSORB, s.wall);
+        if (tr) tr->t_event = s.t_now;
+        if (!apply) { out.kind = MCX_OUT_ABSORBED; out.pos = s.pos; out.t_event = s.t_now; fill_event(out); return out; }
+        w.stats.absorptions++;
+        destroyed = true; out.kind = MCX_OUT_ABSORBED; out.pos = s.pos; out.t_event = s.t_now;
+        seq_set_defunct(w, w.mols[index]);
+        return out;
+      }
       if (new_wall == MCX_NONE) continue;  // ambiguous edge hit: try again
       uint32_t new_tile = uv2grid(w.walls[new_wall], w.grids[new_wall], nu, nv);
       if (new_tile == MCX_NONE) continue;
@@ -2123,6 +2171,11 @@ int orc_set_counted_volumes(void* h, uint32_t n_cv, const uint8_t* front, const 
   w.n_cv = n_cv ? n_cv : 1;
   for (size_t i = 0; i < w.walls.size(); i++) { w.walls[i].cv_front = front[i]; w.walls[i].cv_back = back[i]; }
   build_lookups(w);
+  return 0;
+}
+int orc_set_region_borders(void* h, const uint8_t* wall_edge_border) {
+  World& w = *(World*)h;
+  if (wall_edge_border) w.wall_border.assign(wall_edge_border, wall_edge_border + w.walls.size()); else w.wall_border.clear();
   return 0;
 }
 int orc_set_surface_regions(void* h, uint32_t n_region_sets, const uint8_t* wall_region_set) {

@@ -214,7 +214,7 @@ def permeable_sphere(n=20000, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8
 
 
 def diffusing_receptors(n_rec=3000, n_lig=8000, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8, D_surf=1e-7,
-                        rng_mode=abi.MCX_RNG_PHILOX, p_bind=0.5, k_off=1e5, with_ligand=True):
+                        rng_mode=abi.MCX_RNG_PHILOX, p_bind=0.5, k_off=1e5, with_ligand=True, border=None):
     """Surface diffusion: receptors R diffuse on an icosphere (diffuse_surf_molecule, ray_trace_surf
     across triangle edges, one molecule per tile), ligand L binds them from outside, LR' -> R' keeps ids deterministic."""
     import math
@@ -231,6 +231,12 @@ def diffusing_receptors(n_rec=3000, n_lig=8000, radius_um=0.25, subdivisions=3, 
     m.add_geometry_object(sv, sf)
     bv, bf = create_box(box_um)
     m.add_geometry_object(bv, bf)
+    if border is not None:
+        # a reactive region "cap" (surface class 1) whose outline R cannot cross: abi.MCX_SURF_REFLECTIVE turns it back,
+        # abi.MCX_SURF_ABSORPTIVE (absorptive region border) takes it; LR is not affected
+        cz = np.asarray(sv)[np.asarray(sf)].mean(axis=1)[:, 2]
+        m.add_surface_region("cap", 0, np.flatnonzero(cz > 0.3 * radius_um), surf_class=1)
+        m.add_surface_property(1, border, species="R")
     t = m.build(max_molecules=2 * (n_rec + n_lig) + 64, rng_mode=rng_mode)
     rng = np.random.default_rng(seed)
     pos = release_uniform_box(rng, n_lig, box_um, t.length_unit, margin=1e-3)

@@ -408,6 +408,38 @@ def test_philox_surface_diffusion_with_binding():
     assert len(np.unique(np.stack([b.wall[s], b.tile[s]], 1), axis=0)) == 3000
 
 
+@pytest.mark.parametrize("border", [abi.MCX_SURF_REFLECTIVE, abi.MCX_SURF_ABSORPTIVE])
+def test_philox_region_borders_for_surface_molecules(border):
+    """SURVEY 8 a22, region borders: receptors diffusing on a sphere with a reactive region whose outline reflects or
+    absorbs them, ligands binding on both sides: traces (every reflection changes the tile a mover takes, every
+    absorption ends its trace), conflict rounds, counts and the whole population over many iterations."""
+    t, mols = cm.diffusing_receptors(n_rec=3000, n_lig=12000, seed=9, D_surf=4e-7, border=border)
+    n = mols.n
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+    absorbed = moved = 0
+    for it in range(12):
+        tr_o, st_o = o.trace_step(1, n)
+        tr_g, st_g = e.trace_step(n)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "unimol_rxns", "mol_wall_absorptions", "resolve_retries", "unresolved_conflicts", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        absorbed += st_g.mol_wall_absorptions
+        moved += int((tr_g["outcome"][live] == abi.MCX_OUT_SURFMOVE).sum())
+        assert (e.counts()[0] == o.counts()[0]).all(), it
+    a, b = o.download().sorted_by_id(), e.download().sorted_by_id()
+    _assert_same_population(a, b)
+    assert moved > 5000
+    if border == abi.MCX_SURF_ABSORPTIVE:
+        assert absorbed > 20 and e.counts()[0][1] + e.counts()[0][2] == 3000 - absorbed
+    else:
+        assert absorbed == 0 and e.counts()[0][1] + e.counts()[0][2] == 3000
+
+
 def test_philox_counted_volumes_nested_spheres():
     """Counted volumes: the index switches on transparent crossings of two nested counted spheres, products inherit
     it, and per-volume molecule / reaction counts (MolOrRxnCountEvent terms restricted to a volume) match."""

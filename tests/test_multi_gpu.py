@@ -89,7 +89,7 @@ def test_two_ranks_match_single_gpu(scenario):
 
 
 @pytest.mark.skipif(_n_devices() < 2, reason="needs 2 CUDA devices")
-@pytest.mark.parametrize("scenario", ["receptors", "surface_diffusion", "counted_volumes"])
+@pytest.mark.parametrize("scenario", ["receptors", "surface_diffusion", "counted_volumes", "transporter", "permeable", "region_border"])
 def test_two_ranks_match_single_gpu_surface_and_counted(scenario):
     """Surface molecules (tiles, binding, unbinding, 2-D diffusion across the slab face) and counted volumes with two
     ranks: the halo records carry Molecule::s and the creation wall / tile of surface-born volume products, the counted
@@ -102,6 +102,17 @@ def test_two_ranks_match_single_gpu_surface_and_counted(scenario):
         halo = 62.0   # 3 x (R + 6.993 * space_step of Ca, D = 2e-6)
     elif scenario == "surface_diffusion":
         make = lambda: cm.diffusing_receptors(n_rec=4000, n_lig=20000, radius_um=0.5, subdivisions=4, box_um=1.6, seed=7)  # noqa: E731
+        halo = 45.0
+    elif scenario == "transporter":   # kept volume reactant passing through the wall (RX_FLIP): the kept molecule's guard travels in the halo
+        make = lambda: cm.transporter_sphere(n_vol=30000, n_trans=4000, n_enz=500, radius_um=0.5, subdivisions=4, box_um=1.6,  # noqa: E731
+                                             seed=6, enzyme=False)
+        halo = 45.0
+    elif scenario == "permeable":     # finite-rate reactions with a surface class, both directions
+        make = lambda: cm.permeable_sphere(n=30000, radius_um=0.5, subdivisions=4, box_um=1.6, seed=6, products=False)  # noqa: E731
+        halo = 45.0
+    elif scenario == "region_border":
+        make = lambda: cm.diffusing_receptors(n_rec=4000, n_lig=20000, radius_um=0.5, subdivisions=4, box_um=1.6, seed=7,  # noqa: E731
+                                              D_surf=4e-7, border=abi.MCX_SURF_REFLECTIVE)
         halo = 45.0
     else:
         make = lambda: cm.counted_spheres(n=30000, seed=8, box_um=1.2)  # noqa: E731

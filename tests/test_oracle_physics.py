@@ -488,3 +488,39 @@ def test_surface_class_permeation_ratio_and_mode_agreement():
         a, b = res[0][k], res[1][k]
         assert abs(a - b) < 5 * math.sqrt(a + b), (k, res)
     assert res[0][0] > 200
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_region_borders_for_surface_molecules(mode):
+    """SURVEY 8 a22, region borders (ray_trace_surf :1627-1665; reflect_absorb_inside_out / outside_in, diffusion_utils.inl:
+    598-700): a REFLECTIVE class keeps surface molecules on their side of the outline of a reactive region, in both
+    directions; an ABSORPTIVE one (absorptive region border) takes whoever reaches it; without the class they mix."""
+    def run(border):
+        t, mols = cm.diffusing_receptors(n_rec=3000, n_lig=0, seed=21, D_surf=4e-7, with_ligand=False, border=border)
+        cap = None
+        if border is not None:
+            cap = np.flatnonzero(t.wall_region_set == t.region_sets.index(frozenset({0})))
+            assert 0 < len(cap) < len(t.wall_region_set) and (t.wall_edge_border[cap] != 0).any()
+            assert (t.wall_edge_border[np.setdiff1d(np.arange(len(t.wall_region_set)), cap)] == 0).all()
+        o = O.Oracle(t)
+        o.upload(mols)
+        a = mols.sorted_by_id()
+        o.step(40, mode)
+        b = o.download().sorted_by_id()
+        return t, cap, a, b
+    # control: some receptors cross the outline
+    t, _, a, b = run(None)
+    t2, cap, _, _ = run(abi.MCX_SURF_REFLECTIVE)
+    in0, in1 = np.isin(a.wall, cap), np.isin(b.wall, cap)
+    assert b.n == a.n and (in0 != in1).sum() > 20
+    # reflective border: nobody crosses, in either direction
+    _, cap, a, b = run(abi.MCX_SURF_REFLECTIVE)
+    assert b.n == a.n and (b.id == a.id).all()
+    in0, in1 = np.isin(a.wall, cap), np.isin(b.wall, cap)
+    assert (in0 == in1).all() and in0.sum() > 100 and (~in0).sum() > 100
+    assert ((a.wall != b.wall) | (a.tile != b.tile)).sum() > 1000      # they do move
+    # absorptive border: those that reach it are gone, the others stay on their side
+    _, cap, a, b = run(abi.MCX_SURF_ABSORPTIVE)
+    assert 20 < a.n - b.n < a.n // 2
+    keep = np.isin(a.id, b.id)
+    assert (np.isin(a.wall[keep], cap) == np.isin(b.wall, cap)).all()
