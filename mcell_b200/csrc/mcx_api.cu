@@ -365,7 +365,7 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
 static int rebuild_tables(mcx_handle* h) {
   const size_t ns = h->species.size();
   if (ns == 0) return MCX_OK;
-  if (ns > 256) { h->err = "more than 256 species are not supported by the device counters"; return MCX_ERR_INVALID_ARG; }
+  if (ns > MCX_MAX_COUNTED) { h->err = "more than 1024 species are not supported by the device counters"; return MCX_ERR_INVALID_ARG; }
   std::vector<int> bimol(ns * ns, -1), unimol(ns, -1), volsurf(ns * ns, -1);
   bool any_surf = false;
   for (size_t a = 0; a < ns; a++) any_surf = any_surf || !(h->species[a].flags & MCX_SP_VOL);
@@ -567,7 +567,7 @@ int mcx_set_reactions(mcx_handle* h, const mcx_rxn_class* classes, uint32_t n_cl
   if (!h->has_species) { h->err = "mcx_set_species must precede mcx_set_reactions"; return MCX_ERR_STATE; }
   CK(cudaSetDevice(h->cfg.device));
   for (uint32_t k = 0; k < n_pathways; k++)
-    if (pathways[k].rxn_rule_id >= 256) { h->err = "rxn_rule_id >= 256 not supported by the device counters"; return MCX_ERR_INVALID_ARG; }
+    if (pathways[k].rxn_rule_id >= MCX_MAX_COUNTED) { h->err = "rxn_rule_id >= 1024 not supported by the device counters"; return MCX_ERR_INVALID_ARG; }
   std::vector<mcx_rxn_class> prev_classes = h->classes;
   std::vector<mcx_pathway> prev_pathways = h->pathways;
   h->classes.assign(classes, classes + n_classes);
@@ -600,7 +600,7 @@ int mcx_set_counted_volumes(mcx_handle* h, uint32_t n_counted_volumes, const uin
     if (wall_cv_front[i] >= n_counted_volumes || wall_cv_back[i] >= n_counted_volumes) { h->err = "counted volume index out of range"; return MCX_ERR_INVALID_ARG; }
     cv[i] = (uint16_t)(wall_cv_front[i] | (wall_cv_back[i] << 8));
   }
-  std::vector<unsigned long long> zero_r((size_t)256 * n_counted_volumes, 0), zero_m((size_t)256 * n_counted_volumes, 0);
+  std::vector<unsigned long long> zero_r((size_t)MCX_MAX_COUNTED * n_counted_volumes, 0), zero_m((size_t)MCX_MAX_COUNTED * n_counted_volumes, 0);
   int rc = MCX_OK;
   rc |= dev_replace(h, &h->d_wall_cv, cv.data(), cv.size());
   rc |= dev_replace(h, &h->d_rxn_count_cv, zero_r.data(), zero_r.size());
@@ -664,7 +664,7 @@ int mcx_set_surface_regions(mcx_handle* h, uint32_t n_region_sets, const uint8_t
   CK(cudaSetDevice(h->cfg.device));
   for (uint64_t i = 0; i < h->n_walls_host; i++)
     if (wall_region_set[i] >= n_region_sets) { h->err = "surface-region set index out of range"; return MCX_ERR_INVALID_ARG; }
-  std::vector<unsigned long long> zero((size_t)256 * n_region_sets, 0);
+  std::vector<unsigned long long> zero((size_t)MCX_MAX_COUNTED * n_region_sets, 0);
   int rc = MCX_OK;
   rc |= dev_replace(h, &h->d_wall_rs, wall_region_set, std::max<uint64_t>(h->n_walls_host, 1));
   rc |= dev_replace(h, &h->d_rxn_count_rs, zero.data(), zero.size());
@@ -1191,14 +1191,16 @@ int mcx_counts(mcx_handle* h, uint64_t* per_species, uint32_t n_species, uint64_
   CK(cudaSetDevice(h->cfg.device));
   Counters hc;
   CK(cudaMemcpy(&hc, h->p.ctr, sizeof(hc), cudaMemcpyDeviceToHost));
-  std::vector<unsigned long long> buf(512, 0);
-  for (uint32_t i = 0; i < 256; i++) { buf[i] = hc.species_count[i]; buf[256 + i] = hc.rxn_count[i]; }
+  std::vector<unsigned long long> buf(2 * MCX_MAX_COUNTED, 0);
+  for (uint32_t i = 0; i < MCX_MAX_COUNTED; i++) { buf[i] = hc.species_count[i]; buf[MCX_MAX_COUNTED + i] = hc.rxn_count[i]; }
   if (h->comm) {
-    int rc = mcx_comm_allreduce_u64(h->comm, buf.data(), 512, h->stream);
-    if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+    for (size_t at = 0; at < buf.size(); at += 1024) {
+      int rc = mcx_comm_allreduce_u64(h->comm, buf.data() + at, 1024, h->stream);
+      if (rc) { h->err = mcx_comm_error(h->comm); return rc; }
+    }
   }
-  for (uint32_t i = 0; i < n_species && per_species; i++) per_species[i] = i < 256 ? buf[i] : 0;
-  for (uint32_t i = 0; i < n_rxn_rules && per_rxn_rule; i++) per_rxn_rule[i] = i < 256 ? buf[256 + i] : 0;
+  for (uint32_t i = 0; i < n_species && per_species; i++) per_species[i] = i < MCX_MAX_COUNTED ? buf[i] : 0;
+  for (uint32_t i = 0; i < n_rxn_rules && per_rxn_rule; i++) per_rxn_rule[i] = i < MCX_MAX_COUNTED ? buf[MCX_MAX_COUNTED + i] : 0;
   return MCX_OK;
 }
 

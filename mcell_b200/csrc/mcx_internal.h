@@ -53,6 +53,7 @@ struct __align__(16) DevWall {
   double v0x, v0y, v0z;           // vertex 0
 };
 
+#define MCX_MAX_COUNTED 1024      // species and reaction rules the device counters hold (a power of two)
 #define MCX_ROUNDS_MAX 32        // upper bound of mcx_config::max_resolve_rounds
 struct Counters {
   // population
@@ -73,9 +74,9 @@ struct Counters {
   unsigned long long molecule_steps, ray_polygon_tests, ray_polygon_colls, reflections, transparent,
       absorptions, volvol_collisions, bimol_rxns, unimol_rxns, redos, retries, unresolved, products, deferred;
   unsigned long long defer_reason[8];  // why the fast pass deferred a molecule (MCX_DEFER_*)
-  unsigned long long species_count[256];
-  unsigned long long species_next[256];  // multi-GPU: recount of owned molecules during the scatter
-  unsigned long long rxn_count[256];
+  unsigned long long species_count[MCX_MAX_COUNTED];
+  unsigned long long species_next[MCX_MAX_COUNTED];  // multi-GPU: recount of owned molecules during the scatter
+  unsigned long long rxn_count[MCX_MAX_COUNTED];
   // conflict rounds: proposals entering round r (list pend[0]) and losers of round r (list pend[1])
   unsigned int n_prop[MCX_ROUNDS_MAX + 1], n_lose[MCX_ROUNDS_MAX + 1];
 };

@@ -59,18 +59,18 @@ __device__ __forceinline__ unsigned int agg_reserve(unsigned int* addr, unsigned
 // global atomics (a __match_any_sync each) on a handful of addresses.  The block counts in shared memory instead
 // and flushes once; commit_event falls back to the global atomics when no tally is given (forced commits of k_retry).
 struct BlockTally {
-  int species[256];            // signed change of the per-species population
-  unsigned int rxn[256];       // per reaction rule
+  int species[MCX_MAX_COUNTED];            // signed change of the per-species population
+  unsigned int rxn[MCX_MAX_COUNTED];       // per reaction rule
   unsigned int bimol, unimol, products, absorptions;
 };
 __device__ __forceinline__ void tally_clear(BlockTally* t) {
-  for (int k = threadIdx.x; k < 256; k += blockDim.x) { t->species[k] = 0; t->rxn[k] = 0; }
+  for (int k = threadIdx.x; k < MCX_MAX_COUNTED; k += blockDim.x) { t->species[k] = 0; t->rxn[k] = 0; }
   if (threadIdx.x == 0) { t->bimol = 0; t->unimol = 0; t->products = 0; t->absorptions = 0; }
   __syncthreads();
 }
 __device__ __forceinline__ void tally_flush(const BlockTally* t, Counters* c) {
   __syncthreads();
-  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+  for (int k = threadIdx.x; k < MCX_MAX_COUNTED; k += blockDim.x) {
     if (t->species[k]) atomicAdd(&c->species_count[k], (unsigned long long)(long long)t->species[k]);
     if (t->rxn[k]) atomicAdd(&c->rxn_count[k], (unsigned long long)t->rxn[k]);
   }
@@ -218,8 +218,8 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
     const uint32_t wi = partner_slot;
     const DevWall& fw = p.walls[wi];
     const DevGrid& g = p.grids[wi];
-    if (own_event) { if (bt) atomicAdd(&bt->rxn[pw.rule_id & 255u], 1u); else agg_add(&c->rxn_count[pw.rule_id & 255u], 1u); }
-    if (own_event && p.wall_cv) agg_add(&p.rxn_count_cv[(pw.rule_id & 255u) * p.n_cv + (flags >> SF_CVI_SHIFT)], 1u);
+    if (own_event) { if (bt) atomicAdd(&bt->rxn[pw.rule_id & (MCX_MAX_COUNTED - 1u)], 1u); else agg_add(&c->rxn_count[pw.rule_id & (MCX_MAX_COUNTED - 1u)], 1u); }
+    if (own_event && p.wall_cv) agg_add(&p.rxn_count_cv[(pw.rule_id & (MCX_MAX_COUNTED - 1u)) * p.n_cv + (flags >> SF_CVI_SHIFT)], 1u);
     if (own_event) { if (bt) tally_inc(&bt->bimol); else agg_add(&c->bimol_rxns, 1u); }
     const bool keep = pw.keep_mask & 1u;
     const double hu = pos.x * fw.ux + pos.y * fw.uy + pos.z * fw.uz - g.vert0_u;   // GeometryUtils::xyz2uv
@@ -280,11 +280,11 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
     }
     return;
   }
-  if (own_event) { if (bt) atomicAdd(&bt->rxn[pw.rule_id & 255u], 1u); else agg_add(&c->rxn_count[pw.rule_id & 255u], 1u); }
+  if (own_event) { if (bt) atomicAdd(&bt->rxn[pw.rule_id & (MCX_MAX_COUNTED - 1u)], 1u); else agg_add(&c->rxn_count[pw.rule_id & (MCX_MAX_COUNTED - 1u)], 1u); }
   // outcome_products_random :2513-2521: a volume initiator counts the reaction in its counted volume, a surface
   // initiator on its wall (here: in the wall's set of counted surface regions)
-  if (own_event && p.wall_cv && !(flags & DF_SURF)) agg_add(&p.rxn_count_cv[(pw.rule_id & 255u) * p.n_cv + (flags >> SF_CVI_SHIFT)], 1u);
-  if (own_event && p.wall_rs && (flags & DF_SURF)) agg_add(&p.rxn_count_rs[(pw.rule_id & 255u) * p.n_rs + __ldg(p.wall_rs + p.swallA[slot])], 1u);
+  if (own_event && p.wall_cv && !(flags & DF_SURF)) agg_add(&p.rxn_count_cv[(pw.rule_id & (MCX_MAX_COUNTED - 1u)) * p.n_cv + (flags >> SF_CVI_SHIFT)], 1u);
+  if (own_event && p.wall_rs && (flags & DF_SURF)) agg_add(&p.rxn_count_rs[(pw.rule_id & (MCX_MAX_COUNTED - 1u)) * p.n_rs + __ldg(p.wall_rs + p.swallA[slot])], 1u);
   bool keepA, keepB = true;
   uint32_t reuse[2]; int n_reuse = 0;
   if (kind == MCX_OUT_REACTED) {
@@ -1153,8 +1153,8 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_apply(uint32_t* __restrict__ 
 __global__ void __launch_bounds__(TPB) k_scatter(const __grid_constant__ DevParams p) {
   // multi-GPU: the owned population is recounted here, per block in shared memory (one global atomic per record on
   // the same four words serialised the whole kernel in the L2 atomic unit: +1.5 ms at 5e7 records, profiles/r01_r)
-  __shared__ unsigned int s_species[256];
-  if (p.world > 1) { for (int k = threadIdx.x; k < 256; k += blockDim.x) s_species[k] = 0; __syncthreads(); }
+  __shared__ unsigned int s_species[MCX_MAX_COUNTED];
+  if (p.world > 1) { for (int k = threadIdx.x; k < MCX_MAX_COUNTED; k += blockDim.x) s_species[k] = 0; __syncthreads(); }
   const unsigned int n = p.ctr->n_slots + p.ctr->n_prod;
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t r = p.rank[i];
@@ -1177,7 +1177,7 @@ __global__ void __launch_bounds__(TPB) k_scatter(const __grid_constant__ DevPara
       }
     }
     // multi-GPU: recount the owned population (halo copies are not this rank's molecules)
-    if (p.world > 1 && !(sf & DF_DEAD) && owned_z(p, hi.x)) atomicAdd(&s_species[(sf & SF_SPECIES_MASK) & 255u], 1u);
+    if (p.world > 1 && !(sf & DF_DEAD) && owned_z(p, hi.x)) atomicAdd(&s_species[(sf & SF_SPECIES_MASK) & (MCX_MAX_COUNTED - 1u)], 1u);
   }
   if (p.world > 1) {
     __syncthreads();
@@ -1209,7 +1209,7 @@ __global__ void k_end_iteration(const __grid_constant__ DevParams p) {
     c->n_prod = 0; c->n_disk = 0; c->n_slow = 0; c->n_second = 0; c->n_slow2 = 0; c->n_send[0] = 0; c->n_send[1] = 0;
   }
   if (threadIdx.x <= MCX_ROUNDS_MAX) { c->n_prop[threadIdx.x] = 0; c->n_lose[threadIdx.x] = 0; }
-  if (p.world > 1) { c->species_count[threadIdx.x] = c->species_next[threadIdx.x]; c->species_next[threadIdx.x] = 0; }
+  if (p.world > 1) for (int k = threadIdx.x; k < MCX_MAX_COUNTED; k += blockDim.x) { c->species_count[k] = c->species_next[k]; c->species_next[k] = 0; }
 }
 
 // a new upload replaces the population, nothing else: cumulative reaction counts, statistics and next_id stay
@@ -1219,7 +1219,7 @@ __global__ void k_reset_population(const __grid_constant__ DevParams p, unsigned
     c->n_slots = n_slots; c->n_prod = 0; c->n_disk = 0; c->n_next = 0; c->n_fresh_events = 0; c->n_fresh_ids = 0; c->error = 0; c->error_id = 0;
     c->n_emigrants[0] = 0; c->n_emigrants[1] = 0; c->n_slow = 0; c->n_send[0] = 0; c->n_send[1] = 0; c->n_second = 0; c->n_slow2 = 0;
   }
-  c->species_count[threadIdx.x] = 0; c->species_next[threadIdx.x] = 0;
+  for (int k = threadIdx.x; k < MCX_MAX_COUNTED; k += blockDim.x) { c->species_count[k] = 0; c->species_next[k] = 0; }
   if (threadIdx.x <= MCX_ROUNDS_MAX) { c->n_prop[threadIdx.x] = 0; c->n_lose[threadIdx.x] = 0; }
 }
 void mcx_launch_reset_population(const DevParams& p, unsigned int n_slots, cudaStream_t s) { k_reset_population<<<1, 256, 0, s>>>(p, n_slots); }

@@ -440,6 +440,35 @@ def test_philox_region_borders_for_surface_molecules(border):
         assert absorbed == 0 and e.counts()[0][1] + e.counts()[0][2] == 3000
 
 
+def test_more_than_256_species_and_rules():
+    """The device counters hold 1024 species and 1024 reaction rules (the reference has no such limit; round 1 stopped at
+    256): a chain of 600 species with one unimolecular rule each, populations and per-rule counts against the oracle."""
+    from mcell_b200.model import Model, Config, MolArrays, create_box, release_uniform_box
+    ns, n = 600, 30000
+    m = Model(Config(seed=5))
+    for k in range(ns):
+        m.add_species("S%d" % k, 1e-6)
+    for k in range(ns):
+        m.add_reaction_rule(["S%d" % k], ["S%d" % ((k + 1) % ns)], 2e5 + 500.0 * k)
+    bv, bf = create_box(0.5)
+    m.add_geometry_object(bv, bf)
+    t = m.build(max_molecules=2 * n + 64)
+    rng = np.random.default_rng(5)
+    pos = release_uniform_box(rng, n, 0.5, t.length_unit, margin=1e-3)
+    mols = MolArrays.from_positions(pos, (np.arange(n) % ns).astype(np.uint32), schedule_unimol=True)
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+    for it in range(6):
+        st_o, st_g = o.step(1, 1), e.step(1)
+        assert st_g.unimol_rxns == st_o.unimol_rxns, it
+    co, cg = o.counts(), e.counts()
+    assert len(cg[0]) == ns and len(cg[1]) == ns
+    assert (co[0] == cg[0]).all() and (co[1] == cg[1]).all()
+    assert cg[1][300:].sum() > 500 and cg[0].sum() == n
+    _assert_same_population(o.download().sorted_by_id(), e.download().sorted_by_id())
+
+
 def test_philox_counted_volumes_nested_spheres():
     """Counted volumes: the index switches on transparent crossings of two nested counted spheres, products inherit
     it, and per-volume molecule / reaction counts (MolOrRxnCountEvent terms restricted to a volume) match."""
