@@ -142,7 +142,11 @@ typedef struct mcx_surf_class_rxn {
 enum {
   MCX_MOL_DEFUNCT = 1u << 0,          /* MOLECULE_FLAG_DEFUNCT */
   MCX_MOL_SCHEDULE_UNIMOL = 1u << 1,  /* MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN: lifetime not drawn yet */
-  MCX_MOL_PARTIAL = 1u << 2           /* diffusion_time is fractional (born mid-iteration) */
+  MCX_MOL_PARTIAL = 1u << 2,          /* diffusion_time is fractional (born mid-iteration) */
+  MCX_MOL_CVI_PENDING = 1u << 3       /* v.counted_volume_index is a guess: it is recomputed by a ray cast when the molecule
+                                         is next evaluated (Partition::add_volume_molecule does that for
+                                         COUNTED_VOLUME_INDEX_INVALID, partition.h:572-576); needs
+                                         mcx_set_counted_volume_objects */
 };
 typedef struct mcx_mol_soa {
   uint64_t  n;
@@ -306,6 +310,15 @@ int mcx_set_counted_volumes(mcx_handle* h, uint32_t n_counted_volumes, const uin
  * and Partition::inc_rxn_in_volume_occured_count (partition.h:1036-1077).
  * mol_counts[species * n_counted_volumes + cv], rxn_counts[rxn_rule * n_counted_volumes + cv]; either may be NULL. */
 int mcx_counts_by_volume(mcx_handle* h, uint64_t* mol_counts, uint64_t* rxn_counts);
+/* Counted objects that intersect each other (the reference recomputes the counted volume from waypoints then,
+ * update_counted_volume_id_when_crossing_wall / compute_counted_volume_using_waypoints, collision_utils.inl:1568-1694):
+ * a wall of such an object has no single volume in front of and behind it.  cv_object_mask[cv] = the set of counted
+ * objects that enclose counted volume cv (bit k = geometry object k, k < 32; every set that can occur must be listed);
+ * a molecule that crosses a wall of an object named in intersecting_objects toggles that object's bit in its set
+ * instead of reading the wall's pair; volume products of unimolecular surface reactions on such walls and molecules
+ * flagged MCX_MOL_CVI_PENDING get their set from a ray cast at their next evaluation; releases inside regions read it off
+ * their ray.  Call after mcx_set_counted_volumes; NULL switches it off. */
+int mcx_set_counted_volume_objects(mcx_handle* h, const uint32_t* cv_object_mask, uint32_t intersecting_objects);
 
 /* Region borders for surface molecules (ray_trace_surf, diffuse_react_event.cpp:1627-1665; reflect_absorb_inside_out /
  * outside_in, diffusion_utils.inl:598-700): wall_edge_border[w] bit e = edge e of wall w (0: v0-v1, 1: v1-v2, 2: v2-v0) is

@@ -18,7 +18,7 @@ MCX_RNG_PHILOX, MCX_RNG_TAPE = 0, 1
 MCX_SP_VOL, MCX_SP_CAN_DIFFUSE, MCX_SP_CANT_INITIATE = 1, 2, 4
 MCX_RXN_UNIMOL, MCX_RXN_BIMOL_VOLVOL, MCX_RXN_BIMOL_VOLSURF, MCX_RXN_BIMOL_VOLWALL = 1, 2, 3, 4
 MCX_SURF_REFLECTIVE, MCX_SURF_TRANSPARENT, MCX_SURF_ABSORPTIVE, MCX_SURF_STANDARD = 0, 1, 2, 3
-MCX_MOL_DEFUNCT, MCX_MOL_SCHEDULE_UNIMOL, MCX_MOL_PARTIAL = 1, 2, 4
+MCX_MOL_DEFUNCT, MCX_MOL_SCHEDULE_UNIMOL, MCX_MOL_PARTIAL, MCX_MOL_CVI_PENDING = 1, 2, 4, 8
 MCX_KEPT_VALID, MCX_KEPT_ORDER_END, MCX_KEPT_ORDER_REACTANT = 1 << 31, 0xF, 8
 MCX_OUT_NONE, MCX_OUT_MOVED, MCX_OUT_REACTED, MCX_OUT_ABSORBED = 0, 1, 2, 3
 MCX_OUT_UNIMOL, MCX_OUT_CONSUMED, MCX_OUT_STATIC, MCX_OUT_SURFMOVE, MCX_OUT_WALLRXN = 4, 5, 6, 7, 8
@@ -126,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "mcx_download_molecules", "mcx_num_molecules", "mcx_step", "mcx_replay_step", "mcx_trace_step",
     "mcx_counts", "mcx_comm_init", "mcx_comm_unique_id", "mcx_slab_info_get", "mcx_comm_halo_path", "mcx_philox_block", "mcx_set_profiling",
     "mcx_grid_num_tiles", "mcx_grid2uv", "mcx_xyz2grid", "mcx_set_counted_volumes", "mcx_counts_by_volume", "mcx_release_volume_molecules", "mcx_fast_pass_kind", "mcx_walls_per_subpart",
-    "mcx_set_surface_regions", "mcx_counts_by_surface_region", "mcx_release_list", "mcx_release_surface_molecules", "mcx_set_region_borders",
+    "mcx_set_surface_regions", "mcx_counts_by_surface_region", "mcx_release_list", "mcx_release_surface_molecules", "mcx_set_region_borders", "mcx_set_counted_volume_objects",
 ]
 
 

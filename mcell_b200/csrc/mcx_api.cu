@@ -46,6 +46,7 @@ struct mcx_handle {
        *d_tile_slot = nullptr, *d_exd_skip = nullptr, *d_wall_cv = nullptr, *d_rxn_count_cv = nullptr,
        *d_mol_count_cv = nullptr, *d_edges = nullptr, *d_tile_claim = nullptr;
   uint32_t n_cv = 1; uint32_t* st_cv = nullptr;
+  void *d_cv_mask = nullptr;
   void *d_wall_obj = nullptr, *d_surf_rxn = nullptr, *d_surf_border = nullptr, *d_wall_border = nullptr;
   std::vector<double> wall_area_host;
   void *d_wall_rs = nullptr, *d_rxn_count_rs = nullptr, *d_mol_count_rs = nullptr; uint32_t n_rs = 0;
@@ -352,7 +353,7 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   p.spw_list = (const uint32_t*)h->d_spw_list; p.n_walls = (int)n_walls; p.sp_flags = (const uint8_t*)h->d_sp_flags;
   if (h->p.wall_cv && h->n_walls_host != n_walls) {
     // the per-wall counted-volume table belongs to the previous geometry: drop it (mcx_set_counted_volumes again)
-    h->p.wall_cv = nullptr; h->p.n_cv = 1; h->n_cv = 1;
+    h->p.wall_cv = nullptr; h->p.n_cv = 1; h->n_cv = 1; h->p.cv_mask = nullptr; h->p.cv_xor = 0; h->p.cv_all = 0;
   }
   if (h->p.wall_border && h->n_walls_host != n_walls) h->p.wall_border = nullptr;   // likewise
   if (h->p.wall_rs && h->n_walls_host != n_walls) { h->p.wall_rs = nullptr; h->p.n_rs = 0; h->n_rs = 0; }  // likewise
@@ -607,8 +608,25 @@ int mcx_set_counted_volumes(mcx_handle* h, uint32_t n_counted_volumes, const uin
   rc |= dev_replace(h, &h->d_mol_count_cv, zero_m.data(), zero_m.size());
   if (rc) return MCX_ERR_CUDA;
   h->n_cv = n_counted_volumes;
+  h->p.cv_mask = nullptr; h->p.cv_xor = 0; h->p.cv_all = 0;   // belongs to the previous table (mcx_set_counted_volume_objects again)
   h->p.wall_cv = (const uint16_t*)h->d_wall_cv; h->p.rxn_count_cv = (unsigned long long*)h->d_rxn_count_cv;
   h->p.mol_count_cv = (unsigned long long*)h->d_mol_count_cv; h->p.n_cv = n_counted_volumes;
+  return MCX_OK;
+}
+
+int mcx_set_counted_volume_objects(mcx_handle* h, const uint32_t* cv_object_mask, uint32_t intersecting_objects) {
+  if (!h) return MCX_ERR_INVALID_ARG;
+  if (!h->p.wall_cv) { h->err = "mcx_set_counted_volumes must precede mcx_set_counted_volume_objects"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  if (!cv_object_mask) { h->p.cv_mask = nullptr; h->p.cv_xor = 0; h->p.cv_all = 0; return MCX_OK; }
+  uint32_t all = 0;
+  for (uint32_t k = 0; k < h->n_cv; k++) {
+    all |= cv_object_mask[k];
+    for (uint32_t q = 0; q < k; q++) if (cv_object_mask[q] == cv_object_mask[k]) { h->err = "two counted volumes with the same set of objects"; return MCX_ERR_INVALID_ARG; }
+  }
+  if (intersecting_objects & ~all) { h->err = "intersecting_objects names an object that encloses no counted volume"; return MCX_ERR_INVALID_ARG; }
+  if (dev_replace(h, &h->d_cv_mask, cv_object_mask, h->n_cv)) return MCX_ERR_CUDA;
+  h->p.cv_mask = (const uint32_t*)h->d_cv_mask; h->p.cv_xor = intersecting_objects; h->p.cv_all = all;
   return MCX_OK;
 }
 

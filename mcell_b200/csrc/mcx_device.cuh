@@ -385,6 +385,24 @@ __device__ int collide_wall(const DevParams& p, D3 pos, uint32_t wi, Stream& rs,
   return W_MISS;
 }
 
+// ---- counted volumes of intersecting objects (include/mcx.h: mcx_set_counted_volume_objects) ------------------------
+__device__ __forceinline__ uint32_t cv_lookup(const DevParams& p, uint32_t mask) {
+  for (uint32_t k = 0; k < p.n_cv; k++) if (__ldg(p.cv_mask + k) == mask) return k;
+  return MCX_NONE;
+}
+__device__ __forceinline__ bool cv_uses_xor(const DevParams& p, uint32_t wall) {
+  if (!p.cv_mask) return false;
+  const uint32_t obj = p.wall_obj[wall];
+  return obj < 32u && ((p.cv_xor >> obj) & 1u);
+}
+// update_counted_volume_id_when_crossing_wall (collision_utils.inl:1637-1694): the volume behind a wall hit on its front,
+// in front of one hit on its back; a wall of an intersecting object toggles its object in the molecule's set instead.
+// MCX_NONE: the resulting set is not in the table.
+__device__ __forceinline__ uint32_t cv_cross(const DevParams& p, uint32_t cvi, uint32_t wall, bool hit_front) {
+  if (!cv_uses_xor(p, wall)) { const uint32_t cv = __ldg(p.wall_cv + wall); return hit_front ? (cv >> 8) : (cv & 0xFFu); }
+  return cv_lookup(p, __ldg(p.cv_mask + cvi) ^ (1u << p.wall_obj[wall]));
+}
+
 // ---- point location by a ray cast (region releases; the reference's Region::is_point_inside, geometry.cpp:1048-1086,
 // and compute_counted_volume_for_pos, collision_utils.inl:1515-1566, count the walls crossed on the way to a far point).
 // One ray from pos towards -x (skewed in y and z) up to the partition boundary, walked through the subpartitions it
@@ -1394,6 +1412,16 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
   out.surf_moved = false; out.s_wall = ss.wall; out.s_tile = ss.tile; out.s_u = ss.u; out.s_v = ss.v;
   bool surf_tile_changed = false;
   bool decided = false;  // a claiming event or an error ended the evaluation; `out` is complete
+  // a counted volume that is only a guess: Partition::add_volume_molecule's ray cast (partition.h:572-576 ->
+  // compute_counted_volume_using_waypoints), done when the molecule is first evaluated
+  if (flags & DF_CVI_PENDING) {
+    flags &= ~DF_CVI_PENDING;
+    if (!(flags & DF_SURF) && p.cv_mask) {
+      RayScan sc;
+      scan_ray(p, pos, rs, sc);
+      if (!sc.redo) { const uint32_t kq = cv_lookup(p, sc.inside_mask & p.cv_all); if (kq != MCX_NONE) flags = (flags & ~SF_CVI_MASK) | (kq << SF_CVI_SHIFT); }
+    }
+  }
 
   bool again = true;
   for (int sub_guard = 0; again && !decided && sub_guard < 1000; sub_guard++) {
@@ -1686,8 +1714,9 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
               ls.transparent++;
               pos = wh.pos; subpart = subpart_index(p, pos);
               if (p.wall_cv) {  // update_counted_volume_id_when_crossing_wall (collision_utils.inl:1637-1694)
-                const uint32_t cv = __ldg(p.wall_cv + wh.wall);
-                flags = (flags & ~SF_CVI_MASK) | ((side == W_FRONT ? (cv >> 8) : (cv & 0xFFu)) << SF_CVI_SHIFT);
+                const uint32_t nc = cv_cross(p, flags >> SF_CVI_SHIFT, wh.wall, side == W_FRONT);
+                if (nc == MCX_NONE) err = MCX_ERR_STATE;   // a set of counted objects the host did not list
+                else flags = (flags & ~SF_CVI_MASK) | (nc << SF_CVI_SHIFT);
               }
               remaining = remaining * (1.0 - wh.t);
               elapsed += t_steps * wh.t;

@@ -20,7 +20,7 @@ enum : uint32_t {
   DF_SCHED_UNIMOL = 1u << 17,  // MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN
   DF_PARTIAL = 1u << 18,     // cold t_sched[] holds a fractional diffusion_time
   DF_HAS_UNIMOL = 1u << 19,  // cold t_unimol[] holds a scheduled unimolecular time
-  DF_GHOST = 1u << 20,       // reserved
+  DF_CVI_PENDING = 1u << 20, // MCX_MOL_CVI_PENDING: the counted volume is a guess, a ray cast at the next evaluation replaces it
   DF_SURF = 1u << 21,        // surface molecule: cold swall/stile/suv hold Molecule::s (src4/molecule.h)
   DF_ORIENT_UP = 1u << 22,   // s.orientation == ORIENTATION_UP (else DOWN)
   DF_CREATED_ON_SURF = 1u << 23,  // volume product of a surface reaction: cold swall/stile hold where it was created
@@ -142,6 +142,8 @@ struct DevParams {
   unsigned long long* rxn_count_cv;  // [rule * n_cv + cv]
   unsigned long long* mol_count_cv;  // [species * n_cv + cv], filled by mcx_counts_by_volume
   unsigned int n_cv;
+  const uint32_t* cv_mask;      // per counted volume: the counted objects enclosing it (mcx_set_counted_volume_objects); null = off
+  uint32_t cv_xor, cv_all;      // objects whose walls toggle membership instead of naming a pair of volumes; all counted objects
   const uint32_t* wall_obj;     // per wall: geometry object index (mcx_set_geometry's wall_object; null = one object)
   const uint8_t* wall_rs;       // per wall: index of the set of counted surface regions it belongs to; null = none
   unsigned long long* rxn_count_rs;  // [rule * n_rs + region set]: reactions whose initiator was a surface molecule there

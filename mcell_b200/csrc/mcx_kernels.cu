@@ -254,7 +254,16 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
       const D3 ppos = {pos.x + (2 * bump) * fw.nx, pos.y + (2 * bump) * fw.ny, pos.z + (2 * bump) * fw.nz};
       uint32_t pflags = DF_SCHED_UNIMOL | DF_PARTIAL;
       if (p.has_surf) { pflags |= DF_CREATED_ON_SURF; p.swallB[ns] = wi; p.stileB[ns] = hit_tile; }
-      if (p.wall_cv) { const uint32_t cv = __ldg(p.wall_cv + wi); pflags |= (o > 0 ? (cv & 0xFFu) : (cv >> 8)) << SF_CVI_SHIFT; }
+      if (p.wall_cv) {
+        const uint32_t cv = __ldg(p.wall_cv + wi);
+        uint32_t pc = o > 0 ? (cv & 0xFFu) : (cv >> 8);
+        if (cv_uses_xor(p, wi)) {   // the initiator's set, its object toggled for a product behind the wall
+          const bool front = (orient_bits & ORIENT_BIT_FRONT) != 0;
+          pc = (o > 0) == front ? (flags >> SF_CVI_SHIFT) : cv_cross(p, flags >> SF_CVI_SHIFT, wi, front);
+          if (pc == MCX_NONE) { raise_error(p, MCX_ERR_STATE, id); pc = flags >> SF_CVI_SHIFT; }
+        }
+        pflags |= pc << SF_CVI_SHIFT;
+      }
       const uint32_t psp = pw.products[k];
       p.tschedB[ns] = t_event;
       store_rec(p.recB, ns, ppos, (k == 0 && !keep) ? id : MCX_NONE, psp | pflags);
@@ -270,8 +279,9 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
       const int side = flip ? -coll_side : coll_side;
       uint32_t f = flags | DF_PARTIAL;
       if (flip && p.wall_cv) {
-        const uint32_t cv = __ldg(p.wall_cv + wi);
-        f = (f & ~SF_CVI_MASK) | ((coll_side > 0 ? (cv >> 8) : (cv & 0xFFu)) << SF_CVI_SHIFT);
+        uint32_t nc = cv_cross(p, flags >> SF_CVI_SHIFT, wi, coll_side > 0);
+        if (nc == MCX_NONE) { raise_error(p, MCX_ERR_STATE, id); nc = flags >> SF_CVI_SHIFT; }
+        f = (f & ~SF_CVI_MASK) | (nc << SF_CVI_SHIFT);
       }
       const double bump = (side > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
       const D3 kpos = {pos.x + (2 * bump) * fw.nx, pos.y + (2 * bump) * fw.ny, pos.z + (2 * bump) * fw.nz};
@@ -359,7 +369,15 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
         pflags |= DF_CREATED_ON_SURF;
         if (p.wall_cv) {  // released to the front (up) or to the back side of the wall
           const uint32_t cv = __ldg(p.wall_cv + wi);
-          pflags = (pflags & ~SF_CVI_MASK) | ((o > 0 ? (cv & 0xFFu) : (cv >> 8)) << SF_CVI_SHIFT);
+          uint32_t pc = o > 0 ? (cv & 0xFFu) : (cv >> 8);
+          if (cv_uses_xor(p, wi)) {
+            if (kind == MCX_OUT_REACTED) {  // the volume initiator's set, its object toggled for a product behind the wall
+              const bool front = (orient_bits & ORIENT_BIT_FRONT) != 0;
+              pc = (o > 0) == front ? (flags >> SF_CVI_SHIFT) : cv_cross(p, flags >> SF_CVI_SHIFT, wi, front);
+              if (pc == MCX_NONE) { raise_error(p, MCX_ERR_STATE, id); pc = flags >> SF_CVI_SHIFT; }
+            } else pflags |= DF_CVI_PENDING;  // no volume reactant to go by: a ray cast at its first evaluation
+          }
+          pflags = (pflags & ~SF_CVI_MASK) | (pc << SF_CVI_SHIFT);
         } else pflags &= ~SF_CVI_MASK;
       }
     }
@@ -393,8 +411,9 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
       const uint32_t wi = p.swallA[surf_slot];
       const DevWall& fw = p.walls[wi];
       if (flip && p.wall_cv) {  // update_counted_volume_id_when_crossing_wall: a FRONT hit goes to the back side
-        const uint32_t cv = __ldg(p.wall_cv + wi);
-        f = (f & ~SF_CVI_MASK) | ((coll_side > 0 ? (cv >> 8) : (cv & 0xFFu)) << SF_CVI_SHIFT);
+        uint32_t nc = cv_cross(p, flags >> SF_CVI_SHIFT, wi, coll_side > 0);
+        if (nc == MCX_NONE) { raise_error(p, MCX_ERR_STATE, id); nc = flags >> SF_CVI_SHIFT; }
+        f = (f & ~SF_CVI_MASK) | (nc << SF_CVI_SHIFT);
       }
       const double bump = (side > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
       kept_pos = D3{event_pos.x + (2 * bump) * fw.nx, event_pos.y + (2 * bump) * fw.ny, event_pos.z + (2 * bump) * fw.nz};
@@ -502,18 +521,18 @@ template <int PASS, class Probe>
 __device__ __forceinline__ void fast_molecule(const DevParams& p, FastCtx& cx, Probe& probe, const bool in_range, const unsigned int i) {
   const double it = (double)p.iteration, t_end = it + 1.0;
     const MolRec m = load_rec(p.recA, i);
-    const bool live = in_range && !(m.sf & (DF_DEAD | DF_GHOST));
+    const bool live = in_range && !(m.sf & DF_DEAD);
     const uint32_t species = m.sf & SF_SPECIES_MASK;
     uint32_t flags = m.sf & ~SF_SPECIES_MASK;
     const DevSpecies sp = p.species[species];
-    const bool vol_diffuser = live && !(m.sf & (DF_SURF | DF_CREATED_ON_SURF)) && (sp.flags & MCX_SP_CAN_DIFFUSE) && sp.time_step == 1.0;
+    const bool vol_diffuser = live && !(m.sf & (DF_SURF | DF_CREATED_ON_SURF | DF_CVI_PENDING)) && (sp.flags & MCX_SP_CAN_DIFFUSE) && sp.time_step == 1.0;
     const bool fractional = (m.sf & (DF_PARTIAL | DF_SCHED_UNIMOL)) != 0;
     bool to_second = PASS == 0 && vol_diffuser && fractional;
     bool simple = vol_diffuser && (PASS == 1 || !fractional);
     // cold fields: a predicated index keeps the loads unconditional (no warp split) without touching the arrays
     // for molecules that have nothing there
     const bool has_uni = (m.sf & DF_HAS_UNIMOL) != 0;
-    const bool idle_candidate = PASS == 0 && live && !(sp.flags & MCX_SP_CAN_DIFFUSE) && !fractional;
+    const bool idle_candidate = PASS == 0 && live && !(sp.flags & MCX_SP_CAN_DIFFUSE) && !fractional && !(m.sf & DF_CVI_PENDING);
     const double t_uni_raw = __ldg(p.tuniA + (((simple || idle_candidate) && has_uni) ? i : 0u));
     double t_uni = has_uni ? t_uni_raw : MCX_TIME_INVALID;
     double t_now = it;
@@ -1313,6 +1332,7 @@ __global__ void __launch_bounds__(TPB) k_release(const __grid_constant__ DevPara
           if (p.wall_cv) {
             uint32_t cvi = 0;
             if (sc.first_wall != MCX_NONE) { const uint32_t cv = __ldg(p.wall_cv + sc.first_wall); cvi = sc.first_side == W_FRONT ? (cv & 0xFFu) : (cv >> 8); }
+            if (p.cv_mask) { const uint32_t kq = cv_lookup(p, sc.inside_mask & p.cv_all); if (kq != MCX_NONE) cvi = kq; }
             flags_k = (flags_k & ~SF_CVI_MASK) | (cvi << SF_CVI_SHIFT);
           }
           ok = true;
@@ -1734,6 +1754,7 @@ __global__ void __launch_bounds__(TPB) k_pack_soa(const __grid_constant__ DevPar
     }
     if (hf & MCX_MOL_DEFUNCT) sf |= DF_DEAD;
     if (hf & MCX_MOL_SCHEDULE_UNIMOL) sf |= DF_SCHED_UNIMOL;
+    if ((hf & MCX_MOL_CVI_PENDING) && !is_surf) sf |= DF_CVI_PENDING;
     if ((hf & MCX_MOL_PARTIAL) && tsched) { sf |= DF_PARTIAL; p.tschedB[i] = tsched[i]; }
     if (tuni && tuni[i] != MCX_TIME_INVALID) { sf |= DF_HAS_UNIMOL; p.tuniB[i] = tuni[i]; }
     store_rec(p.recB, i, pos, id[i], sf);
@@ -1751,6 +1772,7 @@ __global__ void __launch_bounds__(TPB) k_unpack_soa(const __grid_constant__ DevP
     uint32_t hf = 0;
     if (m.sf & DF_SCHED_UNIMOL) hf |= MCX_MOL_SCHEDULE_UNIMOL;
     if (m.sf & DF_PARTIAL) hf |= MCX_MOL_PARTIAL;
+    if (m.sf & DF_CVI_PENDING) hf |= MCX_MOL_CVI_PENDING;
     if (flags) flags[k] = hf;
     if (tsched) tsched[k] = (m.sf & DF_PARTIAL) ? p.tschedA[i] : (double)p.iteration;
     if (tuni) tuni[k] = (m.sf & DF_HAS_UNIMOL) ? p.tuniA[i] : MCX_TIME_INVALID;

@@ -64,6 +64,7 @@ def load_library():
     L.mcx_counts_by_volume.argtypes = [H, C.c_void_p, C.c_void_p]
     L.mcx_set_surface_regions.argtypes = [H, C.c_uint32, C.c_void_p]
     L.mcx_set_region_borders.argtypes = [H, C.c_void_p]
+    L.mcx_set_counted_volume_objects.argtypes = [H, C.c_void_p, C.c_uint32]
     L.mcx_counts_by_surface_region.argtypes = [H, C.c_void_p, C.c_void_p]
     _lib = L
     return L
@@ -94,6 +95,8 @@ class Engine:
                                          _vp(t.wall_surf_class), _vp(getattr(t, "wall_object", None))))
         if getattr(t, "n_counted_volumes", 0) > 1:
             self._ck(self.L.mcx_set_counted_volumes(self.h, t.n_counted_volumes, _vp(t.wall_cv_front), _vp(t.wall_cv_back)))
+        if getattr(t, "cv_intersecting", 0) and t.cv_object_mask is not None:
+            self._ck(self.L.mcx_set_counted_volume_objects(self.h, _vp(t.cv_object_mask), t.cv_intersecting))
         if getattr(t, "n_region_sets", 0) > 1:
             self._ck(self.L.mcx_set_surface_regions(self.h, t.n_region_sets, _vp(t.wall_region_set)))
         if getattr(t, "wall_edge_border", None) is not None:

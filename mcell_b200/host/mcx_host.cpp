@@ -49,6 +49,8 @@ GpuDiffuseReactEvent::GpuDiffuseReactEvent(const GpuModelTables& t, PartitionMol
   if (!t.wall_cv_front.empty()) {
     check(mcx_set_counted_volumes(h, t.n_counted_volumes, t.wall_cv_front.data(), t.wall_cv_back.data()), "mcx_set_counted_volumes");
     n_cv = t.n_counted_volumes;
+    if (!t.cv_object_mask.empty())
+      check(mcx_set_counted_volume_objects(h, t.cv_object_mask.data(), t.intersecting_objects), "mcx_set_counted_volume_objects");
   }
   if (!t.wall_region_set.empty()) {
     check(mcx_set_surface_regions(h, t.n_region_sets, t.wall_region_set.data()), "mcx_set_surface_regions");

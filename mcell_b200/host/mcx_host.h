@@ -138,6 +138,10 @@ struct GpuModelTables {
   // counted volumes (World::init_counted_volumes): per wall the counted-volume index in front of / behind it; empty = none
   uint32_t n_counted_volumes = 1;
   std::vector<uint8_t> wall_cv_front, wall_cv_back;
+  // counted objects that intersect (Partition waypoints): per counted volume the set of enclosing objects (bit k = object
+  // k), and the objects whose walls toggle membership instead of naming a pair of volumes; empty = none intersect
+  std::vector<uint32_t> cv_object_mask;
+  uint32_t intersecting_objects = 0;
   // counted surface regions: per wall the index of the set of counted regions it belongs to (set 0 = none); empty = none
   uint32_t n_region_sets = 1;
   std::vector<uint8_t> wall_region_set;

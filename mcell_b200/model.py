@@ -141,6 +141,8 @@ class Tables:
     wall_cv_back: np.ndarray = None
     wall_object: np.ndarray = None
     counted_volume_sets: list = field(default_factory=lambda: [frozenset()])
+    cv_object_mask: np.ndarray = None      # per counted volume: bit k = counted object k encloses it
+    cv_intersecting: int = 0               # counted objects that intersect another counted object
     # counted surface regions (MolOrRxnCountTerm region expressions over wall regions): set 0 = no counted region
     n_region_sets: int = 1
     wall_region_set: np.ndarray = None
@@ -565,6 +567,22 @@ def _assign_counted_volumes(t, counted):
     t.n_counted_volumes = len(sets)
     t.wall_cv_front = np.array([index[s_] for s_ in fs], np.uint8)
     t.wall_cv_back = np.array([index[s_] for s_ in bs], np.uint8)
+    # counted objects that intersect another one: some of their vertices lie inside, some outside of it; their walls have no
+    # single volume in front of / behind them (mcx_set_counted_volume_objects: membership toggles instead)
+    t.cv_object_mask = np.array([sum(1 << k for k in s_) for s_ in sets], np.uint32) if len(counted) <= 32 else None
+    inter = 0
+    if t.cv_object_mask is not None:
+        for a in range(len(counted)):
+            if not counted[a]:
+                continue
+            va = np.unique(t.tri[t.wall_object == a])
+            for b in range(len(counted)):
+                if a == b or not counted[b]:
+                    continue
+                ins = points_inside_mesh(t.vertices[va], tri[t.wall_object == b])
+                if ins.any() and not ins.all():
+                    inter |= (1 << a) | (1 << b)
+    t.cv_intersecting = inter
 
 
 def counted_volume_of(t, positions):

@@ -204,6 +204,8 @@ struct World {
   std::vector<uint64_t> species_count, rxn_count;
   uint32_t n_cv = 1;                       // counted volumes (index 0 = outside all)
   std::vector<uint64_t> rxn_count_cv;      // [rule * n_cv + cv] (inc_rxn_in_volume_occured_count)
+  std::vector<uint32_t> cv_mask;           // per counted volume: the counted objects that enclose it (mcx_set_counted_volume_objects); empty = off
+  uint32_t cv_xor = 0, cv_all = 0;         // objects whose walls toggle membership instead of naming a pair of volumes; all counted objects
   std::vector<uint8_t> wall_border;        // per wall: bit e = edge e is a border of a reactive region (mcx_set_region_borders); empty = none
   std::vector<uint8_t> wall_rs;            // per wall: set of counted surface regions (mcx_set_surface_regions); empty = none
   uint32_t n_rs = 0;
@@ -688,6 +690,24 @@ static void list_erase(World& w, Mol& m) {
   v.pop_back();
 }
 
+// ---- counted volumes of intersecting objects (include/mcx.h: mcx_set_counted_volume_objects) -------------------------
+static inline uint32_t cv_lookup(const World& w, uint32_t mask) {
+  for (size_t k = 0; k < w.cv_mask.size(); k++) if (w.cv_mask[k] == mask) return (uint32_t)k;
+  return MCX_NONE;
+}
+static inline bool cv_uses_xor(const World& w, uint32_t wall) {
+  return !w.cv_mask.empty() && w.walls[wall].object < 32 && ((w.cv_xor >> w.walls[wall].object) & 1u);
+}
+// update_counted_volume_id_when_crossing_wall (collision_utils.inl:1637-1694): the volume behind a wall hit on its front,
+// in front of one hit on its back; walls of intersecting objects toggle their object in the molecule's set instead
+static inline uint32_t cv_cross(World& w, uint32_t cvi, uint32_t wall, bool hit_front) {
+  const Wall& f = w.walls[wall];
+  if (!cv_uses_xor(w, wall)) return hit_front ? f.cv_back : f.cv_front;
+  const uint32_t k = cv_lookup(w, w.cv_mask[cvi] ^ (1u << f.object));
+  if (k == MCX_NONE) { w.err = "counted volume set not registered (mcx_set_counted_volume_objects)"; return cvi; }
+  return k;
+}
+
 // ---- model table helpers ------------------------------------------------------------------
 static void build_lookups(World& w) {
   size_t ns = w.species.size();
@@ -830,6 +850,7 @@ struct ProductSpec {
   uint32_t wall = MCX_NONE, tile = MCX_NONE; int orient = 0; double u = 0, v = 0;
   uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE;
   uint32_t cvi = 0;
+  bool cvi_pending = false;   // on a wall of an intersecting counted object without a volume reactant to go by: ray cast later
 };
 // Where and how product k of a pathway is created (outcome_products_random :2446-2933, the cases of SURVEY A.2):
 //  * no surface reactant: volume product at the event position;
@@ -839,8 +860,9 @@ struct ProductSpec {
 //    omitted: another wall within 3.2e-11 length units of the position), remembered for the rebinding guard.
 // cvi: counted volume of the initiator at the event; a volume product of a surface reaction takes the volume on the
 // side of the wall it is released to (outcome_products_random :2757-2760)
-static ProductSpec product_spec(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw, uint32_t k, V3 pos,
-                                uint32_t orient_bits, const Mol* surf, uint32_t cvi) {
+// init_side: the side of the wall the volume initiator (whose counted volume is cvi) was on, 0 = there is none
+static ProductSpec product_spec(World& w, const mcx_rxn_class& c, const mcx_pathway& pw, uint32_t k, V3 pos,
+                                uint32_t orient_bits, const Mol* surf, uint32_t cvi, int init_side = 0) {
   ProductSpec ps;
   ps.species = pw.products[k]; ps.pos = pos; ps.cvi = cvi;
   if (!surf) return ps;
@@ -857,6 +879,10 @@ static ProductSpec product_spec(const World& w, const mcx_rxn_class& c, const mc
     ps.cvi = 0;
   } else {
     ps.cvi = o > 0 ? f.cv_front : f.cv_back;
+    if (cv_uses_xor(w, surf->wall)) {
+      if (init_side != 0) ps.cvi = (o > 0) == (init_side > 0) ? cvi : cv_cross(w, cvi, surf->wall, init_side > 0);
+      else ps.cvi_pending = true;
+    }
     double bump = (o > 0) ? 16 * POS_EPS : -16 * POS_EPS;
     V3 d = {(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
     ps.pos = pos + d;
@@ -868,7 +894,8 @@ static ProductSpec product_spec(const World& w, const mcx_rxn_class& c, const mc
 // Volume product k of a reaction with a reactive surface (outcome_products_random :2739-2806 with a wall collision): at the
 // hit point, bumped off the wall to the side its orientation names, counted volume of that side, remembered with the
 // tile under the hit point (xyz2uv + uv2grid_tile_index, :2768-2776)
-static ProductSpec wall_product_spec(const World& w, const mcx_pathway& pw, uint32_t k, V3 pos, uint32_t orient_bits, uint32_t wall) {
+static ProductSpec wall_product_spec(World& w, const mcx_pathway& pw, uint32_t k, V3 pos, uint32_t orient_bits, uint32_t wall,
+                                     uint32_t cvi_init = 0, int init_side = 0) {
   ProductSpec ps;
   ps.species = pw.products[k];
   int o = pw.product_orientation[k];
@@ -876,6 +903,7 @@ static ProductSpec wall_product_spec(const World& w, const mcx_pathway& pw, uint
   const Wall& f = w.walls[wall];
   const Grid& g = w.grids[wall];
   ps.cvi = o > 0 ? f.cv_front : f.cv_back;
+  if (cv_uses_xor(w, wall) && init_side != 0) ps.cvi = (o > 0) == (init_side > 0) ? cvi_init : cv_cross(w, cvi_init, wall, init_side > 0);
   const double bump = (o > 0) ? 16 * POS_EPS : -16 * POS_EPS;
   ps.pos = pos + V3{(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
   const double hu = pos.x * f.unit_u.x + pos.y * f.unit_u.y + pos.z * f.unit_u.z - g.vert0_u;   // GeometryUtils::xyz2uv
@@ -1281,10 +1309,10 @@ struct Eval {
 //                 firing) ends the evaluation and is returned as a proposal.
 // ================================================================================================
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
-                            uint32_t orient_bits, bool& a_destroyed, bool* flip = nullptr);
+                            uint32_t orient_bits, bool& a_destroyed, bool* flip = nullptr, int coll_side = 0);
 static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed);
 static void seq_apply_wallrxn(World& w, uint32_t index, int rc, int pathway, V3 pos, double t, uint32_t orient_bits, uint32_t wall,
-                              uint32_t cvi, bool& destroyed);
+                              uint32_t cvi, bool& destroyed, int coll_side);
 static void seq_set_defunct(World& w, Mol& m);
 
 struct MolState { V3 pos; uint32_t subpart; double t_now; uint32_t flags; double unimol_time;
@@ -1305,6 +1333,15 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
     o.wall = s.wall; o.tile = s.tile; o.u = s.u; o.v = s.v;
   };
 
+  // -- a counted volume that is only a guess (MCX_MOL_CVI_PENDING): Partition::add_volume_molecule's ray cast
+  // (partition.h:572-576 -> compute_counted_volume_using_waypoints), done when the molecule is first evaluated
+  if (s.flags & MCX_MOL_CVI_PENDING) {
+    s.flags &= ~MCX_MOL_CVI_PENDING;
+    if (w.mols[index].wall == MCX_NONE && !w.cv_mask.empty()) {
+      const Eval::RayScan sc = E.scan_ray(s.pos);
+      if (!sc.redo) { const uint32_t kq = cv_lookup(w, sc.inside_mask & w.cv_all); if (kq != MCX_NONE) s.cvi = kq; }
+    }
+  }
   // -- unimolecular firing (diffuse_single_molecule :215-223 -> react_unimol_single_molecule :1764-1826)
   if (s.unimol_time != TIME_INVALID && s.unimol_time <= s.t_now) {
     int rc = w.unimol[m_species];
@@ -1502,7 +1539,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
                   }
                   bool a_destroyed = false, flip = false;
                   w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart; w.mols[index].cvi = s.cvi;
-                  seq_apply_bimol(w, index, occ_index, rc, pathway, c.pos, abs_t, obits, a_destroyed, &flip);
+                  seq_apply_bimol(w, index, occ_index, rc, pathway, c.pos, abs_t, obits, a_destroyed, &flip, coll_orient);
                   if (a_destroyed) {  // collide_res == 1
                     destroyed = true; out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.t_event = abs_t;
                     break;
@@ -1511,7 +1548,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
                   if (flip) {
                     // RX_FLIP (:945-970): the kept initiator goes through the wall at the hit point and carries on
                     s.pos = c.pos; s.subpart = w.subpart_index(s.pos);
-                    s.cvi = c.type == COLL_WALL_FRONT ? wall.cv_back : wall.cv_front;
+                    s.cvi = cv_cross(w, s.cvi, c.wall, c.type == COLL_WALL_FRONT);
                     const double t_smash = c.time;
                     remaining = remaining * (1.0 - t_smash);
                     elapsed += t_steps * t_smash;
@@ -1550,7 +1587,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
               }
               bool gone = false;
               w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart; w.mols[index].cvi = s.cvi;
-              seq_apply_wallrxn(w, index, wall_rc, pathway, c.pos, abs_t, obits, c.wall, s.cvi, gone);
+              seq_apply_wallrxn(w, index, wall_rc, pathway, c.pos, abs_t, obits, c.wall, s.cvi, gone, c.type == COLL_WALL_FRONT ? 1 : -1);
               if (gone) { destroyed = true; out.kind = MCX_OUT_WALLRXN; out.pos = c.pos; out.t_event = abs_t; break; }
               // RX_FLIP -> WallRxnResult::TRANSPARENT, RX_A_OK -> REFLECT (:1048-1056)
               action = wallrxn_flips(wc, pw, obits) ? MCX_SURF_TRANSPARENT : MCX_SURF_REFLECTIVE;
@@ -1562,7 +1599,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
             w.stats.transparent++;
             s.pos = c.pos; s.subpart = w.subpart_index(s.pos);
             // update_counted_volume_id_when_crossing_wall (collision_utils.inl:1637-1694): a FRONT hit goes inside
-            s.cvi = c.type == COLL_WALL_FRONT ? wall.cv_back : wall.cv_front;
+            s.cvi = cv_cross(w, s.cvi, c.wall, c.type == COLL_WALL_FRONT);
             double t_smash = c.time;
             remaining = remaining * (1.0 - t_smash);
             elapsed += t_steps * t_smash;
@@ -1671,7 +1708,7 @@ static void seq_set_defunct(World& w, Mol& m) {  // Partition::set_molecule_as_d
 static uint32_t seq_add_molecule(World& w, const ProductSpec& ps, double t) {  // add_volume_molecule / add_surface_molecule
   Mol n{};
   n.pos = ps.pos; n.id = w.next_id++; n.species = ps.species;
-  n.flags = MCX_MOL_SCHEDULE_UNIMOL | MCX_MOL_PARTIAL;
+  n.flags = MCX_MOL_SCHEDULE_UNIMOL | MCX_MOL_PARTIAL | (ps.cvi_pending ? MCX_MOL_CVI_PENDING : 0u);
   n.diffusion_time = t; n.unimol_rxn_time = TIME_INVALID;
   n.subpart = w.subpart_index(ps.pos);
   n.wall = ps.wall; n.tile = ps.tile; n.orient = ps.orient; n.u = ps.u; n.v = ps.v;
@@ -1697,7 +1734,7 @@ static inline void count_rxn_where(World& w, uint32_t rule, const Mol& initiator
   else if (w.n_rs) w.rxn_count_rs[rule * w.n_rs + w.wall_rs[initiator.wall]]++;
 }
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
-                            uint32_t orient_bits, bool& a_destroyed, bool* flip) {
+                            uint32_t orient_bits, bool& a_destroyed, bool* flip, int coll_side) {
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
@@ -1712,7 +1749,7 @@ static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc
   // tiles that are going to be reused are freed first (:2606-2615)
   if (surf_rxn && !keepB) w.tiles[surf_copy.wall][surf_copy.tile] = MCX_NONE;
   for (uint32_t k = 0; k < pw.n_products; k++) {
-    ProductSpec ps = product_spec(w, c, pw, k, pos, orient_bits, surf_rxn ? &surf_copy : nullptr, w.mols[a_index].cvi);
+    ProductSpec ps = product_spec(w, c, pw, k, pos, orient_bits, surf_rxn ? &surf_copy : nullptr, w.mols[a_index].cvi, coll_side);
     uint32_t nid = seq_add_molecule(w, ps, t);
     if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
   }
@@ -1755,14 +1792,14 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
 
 // outcome_intersect (:1916-1988) of a Standard reaction with a reactive surface; the surface is always kept
 static void seq_apply_wallrxn(World& w, uint32_t index, int rc, int pathway, V3 pos, double t, uint32_t orient_bits, uint32_t wall,
-                              uint32_t cvi, bool& destroyed) {
+                              uint32_t cvi, bool& destroyed, int coll_side) {
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
   count_rxn_where(w, pw.rxn_rule_id, w.mols[index], cvi);
   w.stats.bimol_rxns++;
   for (uint32_t k = 0; k < pw.n_products; k++) {
-    ProductSpec ps = wall_product_spec(w, pw, k, pos, orient_bits, wall);
+    ProductSpec ps = wall_product_spec(w, pw, k, pos, orient_bits, wall, cvi, coll_side);
     uint32_t nid = seq_add_molecule(w, ps, t);
     if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
   }
@@ -1941,7 +1978,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
       const V3 hit = o.pos;
       if (!keep) { dead[i] = 1; w.species_count[m.species]--; }
       for (uint32_t k = 0; k < pw.n_products; k++) {
-        NewMol nm; nm.ps = wall_product_spec(w, pw, k, hit, o.orient_bits, o.hit_wall); nm.t = o.t_event;
+        NewMol nm; nm.ps = wall_product_spec(w, pw, k, hit, o.orient_bits, o.hit_wall, o.cvi, o.coll_side); nm.t = o.t_event;
         nm.id = (k == 0 && !keep) ? m.id : MCX_NONE;
         born.push_back(nm);
         w.species_count[nm.ps.species]++;
@@ -1951,7 +1988,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
         const bool flip = wallrxn_flips(c, pw, o.orient_bits);
         const Wall& f = w.walls[o.hit_wall];
         const int side = flip ? -o.coll_side : o.coll_side;
-        if (flip) o.cvi = o.coll_side > 0 ? f.cv_back : f.cv_front;
+        if (flip) o.cvi = cv_cross(w, o.cvi, o.hit_wall, o.coll_side > 0);
         const double bump = (side > 0) ? 16 * POS_EPS : -16 * POS_EPS;
         o.pos = hit + V3{(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
         ProductSpec g = wall_product_spec(w, pw, 0, hit, 0, o.hit_wall);   // for the tile under the hit point
@@ -1983,7 +2020,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     else if (o.kind == MCX_OUT_UNIMOL && m.wall != MCX_NONE) surf = &m;
     // product ids: consumed reactants' ids are recycled first (initiator, then partner), then fresh ids
     for (uint32_t k = 0; k < pw.n_products; k++) {
-      NewMol nm; nm.ps = product_spec(w, c, pw, k, o.pos, o.orient_bits, surf, o.cvi); nm.t = o.t_event;
+      NewMol nm; nm.ps = product_spec(w, c, pw, k, o.pos, o.orient_bits, surf, o.cvi, o.kind == MCX_OUT_REACTED ? o.coll_side : 0); nm.t = o.t_event;
       nm.id = (int)k < n_reuse ? reuse[k] : MCX_NONE;
       born.push_back(nm);
       w.species_count[nm.ps.species]++;
@@ -2007,7 +2044,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
         const bool flip = ko != 0 && c.reactant_orientation[0] != ko;
         const Wall& f = w.walls[surf->wall];
         const int side = flip ? -o.coll_side : o.coll_side;
-        if (flip) o.cvi = o.coll_side > 0 ? f.cv_back : f.cv_front;  // update_counted_volume_id_when_crossing_wall
+        if (flip) o.cvi = cv_cross(w, o.cvi, surf->wall, o.coll_side > 0);  // update_counted_volume_id_when_crossing_wall
         const double bump = (side > 0) ? 16 * POS_EPS : -16 * POS_EPS;
         o.pos = o.pos + V3{(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
         o.created_wall = surf->wall; o.created_tile = surf->tile;
@@ -2083,7 +2120,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
   for (auto& nm : born) {
     Mol n{};
     n.pos = nm.ps.pos; n.species = nm.ps.species; n.id = nm.id != MCX_NONE ? nm.id : w.next_id++;
-    n.flags = MCX_MOL_SCHEDULE_UNIMOL | MCX_MOL_PARTIAL;
+    n.flags = MCX_MOL_SCHEDULE_UNIMOL | MCX_MOL_PARTIAL | (nm.ps.cvi_pending ? MCX_MOL_CVI_PENDING : 0u);
     n.diffusion_time = nm.t; n.unimol_rxn_time = TIME_INVALID; n.subpart = w.subpart_index(nm.ps.pos);
     n.wall = nm.ps.wall; n.tile = nm.ps.tile; n.orient = nm.ps.orient; n.u = nm.ps.u; n.v = nm.ps.v;
     n.created_wall = nm.ps.created_wall; n.created_tile = nm.ps.created_tile; n.cvi = nm.ps.cvi;
@@ -2171,6 +2208,15 @@ int orc_set_counted_volumes(void* h, uint32_t n_cv, const uint8_t* front, const 
   w.n_cv = n_cv ? n_cv : 1;
   for (size_t i = 0; i < w.walls.size(); i++) { w.walls[i].cv_front = front[i]; w.walls[i].cv_back = back[i]; }
   build_lookups(w);
+  return 0;
+}
+int orc_set_counted_volume_objects(void* h, const uint32_t* cv_object_mask, uint32_t intersecting_objects) {
+  World& w = *(World*)h;
+  w.cv_mask.clear(); w.cv_xor = 0; w.cv_all = 0;
+  if (!cv_object_mask) return 0;
+  w.cv_mask.assign(cv_object_mask, cv_object_mask + w.n_cv);
+  w.cv_xor = intersecting_objects;
+  for (uint32_t m_ : w.cv_mask) w.cv_all |= m_;
   return 0;
 }
 int orc_set_region_borders(void* h, const uint8_t* wall_edge_border) {
@@ -2285,6 +2331,7 @@ int orc_release_volume_molecules(void* h, const mcx_release* r, uint32_t* first_
         if (inb && !sc.redo && (sc.inside_mask & r->region_in) == r->region_in && (sc.inside_mask & r->region_out) == 0u) {
           cvi_k = 0;
           if (sc.first_wall != MCX_NONE) cvi_k = sc.first_side == WALL_FRONT ? w.walls[sc.first_wall].cv_front : w.walls[sc.first_wall].cv_back;
+          if (!w.cv_mask.empty()) { const uint32_t kq = cv_lookup(w, sc.inside_mask & w.cv_all); if (kq != MCX_NONE) cvi_k = kq; }
           ok = true;
           break;
         }

@@ -269,6 +269,44 @@ def counted_spheres(n=12000, seed=1, box_um=0.8, rng_mode=abi.MCX_RNG_PHILOX, p_
     return t, mols
 
 
+def intersecting_counted_spheres(n=12000, n_rec=0, seed=1, box_um=0.8, rng_mode=abi.MCX_RNG_PHILOX, p_target=0.4, k_off=3e5):
+    """Counted objects that intersect (the waypoint case of update_counted_volume_id_when_crossing_wall,
+    collision_utils.inl:1568-1694): two transparent, counted icospheres of radius 0.2 um whose centres are 0.2 um
+    apart, inside a counted reflective box; A + B -> C everywhere.  Volumes: {box}, {box, S0}, {box, S1},
+    {box, S0, S1}.  n_rec > 0: receptors on sphere 0 bind A from both sides and release it again (L R -> A + R: a volume
+    product of a unimolecular surface reaction, on a wall that lies partly inside sphere 1)."""
+    import math
+    from mcell_b200.model import N_AV, MY_PI
+    m = Model(Config(seed=seed))
+    m.add_species("A", 1e-6)
+    m.add_species("B", 1e-6)
+    m.add_species("C", 0.5e-6)
+    pb = _pb_factor(m, 0, 1)
+    m.add_reaction_rule(["A", "B"], ["C"], p_target / pb)
+    if n_rec:
+        R = m.add_species("R", 0.0, surface=True)
+        m.add_species("AR", 0.0, surface=True)
+        pbs = 1.0e11 * m.config.surface_grid_density / (2.0 * N_AV) * math.sqrt(MY_PI * m.config.time_step / 1e-6)
+        m.add_reaction_rule(["A", "R"], ["AR'"], 0.5 / pbs)
+        m.add_reaction_rule(["AR'"], ["A,", "R'"], k_off)
+    v0, f0 = create_icosphere(0.2, 3)
+    v1, f1 = create_icosphere(0.2, 3)
+    m.add_geometry_object(np.asarray(v0) + [-0.1, 0.0, 0.0], f0, surf_class=0, counted=True)
+    m.add_geometry_object(np.asarray(v1) + [0.1, 0.013, 0.007], f1, surf_class=0, counted=True)
+    bv, bf = create_box(box_um)
+    m.add_geometry_object(bv, bf, counted=True)
+    m.add_surface_property(0, abi.MCX_SURF_TRANSPARENT, species=None)
+    t = m.build(max_molecules=2 * (n + n_rec) + 64, rng_mode=rng_mode)
+    rng = np.random.default_rng(seed)
+    pos = release_uniform_box(rng, n, box_um, t.length_unit, margin=1e-3)
+    mols = MolArrays.from_positions(pos, (np.arange(n) % 2).astype(np.uint32), schedule_unimol=True)
+    mols.counted_volume[:] = counted_volume_of(t, pos)
+    if n_rec:
+        surf = release_on_walls(rng, t, np.arange(len(f0), dtype=np.uint32), n_rec, R, orientation=1, first_id=n)
+        mols = MolArrays.concat([mols, surf])
+    return t, mols
+
+
 def isaac_slices(seed, n_ids, words_per_mol):
     """Per-molecule tapes cut from one ISAAC64 stream of the reference RNG restatement."""
     import ctypes as C

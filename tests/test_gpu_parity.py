@@ -440,6 +440,56 @@ def test_philox_region_borders_for_surface_molecules(border):
         assert absorbed == 0 and e.counts()[0][1] + e.counts()[0][2] == 3000
 
 
+def test_philox_intersecting_counted_objects():
+    """SURVEY 8 a20, counted objects that intersect: membership toggling on crossings, the lazy ray cast of surface-born
+    volume products (MCX_MOL_CVI_PENDING) — every iteration from a common state (the second product of the unbinding
+    takes a fresh id): traces, statistics, per-volume counts bit for bit, populations as multisets incl. the counted
+    volume and the pending flag; and the device's counted volumes against an independent ray cast in numpy."""
+    t, mols = cm.intersecting_counted_spheres(n=24000, n_rec=3000, seed=19)
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+
+    def key(m):
+        arr = np.c_[m.species[:m.n].astype(float), m.x[:m.n], m.y[:m.n], m.z[:m.n], m.diffusion_time[:m.n],
+                    m.flags[:m.n].astype(float), m.counted_volume[:m.n].astype(float), m.wall[:m.n].astype(float),
+                    m.tile[:m.n].astype(float)]
+        return arr[np.lexsort(arr.T[::-1])]
+
+    crossings = pending = 0
+    state = mols
+    for it in range(10):
+        n_ids = int(state.id[:state.n].max()) + 1
+        if it:
+            e.upload(state)
+            o.upload(state)
+        tr_o, st_o = o.trace_step(1, n_ids)
+        tr_g, st_g = e.trace_step(n_ids)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "unimol_rxns", "products_created", "mol_wall_transparent", "resolve_retries", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        crossings += st_g.mol_wall_transparent
+        mo, ro = o.counts_by_volume()
+        mg, rg = e.counts_by_volume()
+        assert (mo == mg).all(), it
+        a, b = o.download(), e.download()
+        assert a.n == b.n
+        ka, kb = key(a), key(b)
+        assert (ka[:, 0] == kb[:, 0]).all() and (ka[:, 4:] == kb[:, 4:]).all(), it
+        assert cm.rel_close(ka[:, 1:4], kb[:, 1:4], POS_TOL).all(), it
+        vol = b.wall[:b.n] == abi.MCX_NONE
+        pend = (b.flags[:b.n] & abi.MCX_MOL_CVI_PENDING) != 0
+        pending += int(pend.sum())
+        ok = vol & ~pend
+        pos = np.stack([b.x[:b.n], b.y[:b.n], b.z[:b.n]], 1)[ok]
+        assert (b.counted_volume[:b.n][ok] == cm.counted_volume_of(t, pos)).all(), it
+        state = a
+    assert crossings > 3000 and pending > 10, (crossings, pending)
+
+
 def test_more_than_256_species_and_rules():
     """The device counters hold 1024 species and 1024 reaction rules (the reference has no such limit; round 1 stopped at
     256): a chain of 600 species with one unimolecular rule each, populations and per-rule counts against the oracle."""

@@ -524,3 +524,36 @@ def test_region_borders_for_surface_molecules(mode):
     assert 20 < a.n - b.n < a.n // 2
     keep = np.isin(a.id, b.id)
     assert (np.isin(a.wall[keep], cap) == np.isin(b.wall, cap)).all()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_intersecting_counted_objects(mode):
+    """SURVEY 8 a20, counted objects that intersect (the waypoint case of update_counted_volume_id_when_crossing_wall,
+    collision_utils.inl:1568-1694): crossing a wall of such an object toggles the object in the molecule's set of
+    enclosing objects; volume products of unimolecular surface reactions on such walls get theirs from a ray cast at
+    their first evaluation (MCX_MOL_CVI_PENDING until then).  Invariant: the counted volume of every volume molecule
+    equals an independent ray cast in numpy, in all four volumes."""
+    t, mols = cm.intersecting_counted_spheres(n=8000, n_rec=1500, seed=17)
+    assert t.cv_intersecting == 0b011 and t.n_counted_volumes == 5
+    o = O.Oracle(t)
+    o.upload(mols)
+    seen, crossings, pending_seen = set(), 0, 0
+    for it in range(10):
+        st = o.step(2, mode)
+        crossings += st.mol_wall_transparent
+        m = o.download()
+        vol = m.wall[:m.n] == abi.MCX_NONE
+        pend = (m.flags[:m.n] & abi.MCX_MOL_CVI_PENDING) != 0
+        pending_seen += int(pend.sum())
+        pos = np.stack([m.x[:m.n], m.y[:m.n], m.z[:m.n]], 1)
+        ok = vol & ~pend
+        cv = cm.counted_volume_of(t, pos[ok])
+        assert (m.counted_volume[:m.n][ok] == cv).all(), it
+        seen |= set(np.unique(cv).tolist())
+        assert not (pend & ~vol).any()
+    assert seen == {1, 2, 3, 4} and crossings > 2000
+    sp, rx = o.counts()
+    assert rx[2] > 30                                 # unbinding on the straddling walls happened ...
+    assert pending_seen > 0 or mode == 0              # ... and was resolved later (the sequential mode evaluates products at once)
+    mo, _ = o.counts_by_volume()
+    assert mo[:3].sum() == sp[:3].sum()
