@@ -2861,6 +2861,14 @@ void orc_unit_grid2uv(const double* v9, int idx, double* uv2) {
   Grid g; grid_init(w, w.walls[0], g);
   grid2uv(w.walls[0], g, (uint32_t)idx, uv2[0], uv2[1]);
 }
+// grid2uv_random of tile idx of one triangle on a tape of words; returns the words drawn
+long long orc_unit_grid2uv_random(const double* v9, int idx, const uint32_t* words, uint64_t n_words, double* uv2) {
+  World w; unit_world(w, v9);
+  Grid g; grid_init(w, w.walls[0], g);
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  grid2uv_random(w.walls[0], g, (uint32_t)idx, rs, uv2[0], uv2[1]);
+  return (long long)rs.used;
+}
 void orc_unit_uv2xyz(const double* v9, const double* uv2, double* xyz3) {
   World w; unit_world(w, v9);
   V3 r = uv2xyz(w, w.walls[0], uv2[0], uv2[1]);

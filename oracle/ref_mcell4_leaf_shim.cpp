@@ -10,7 +10,7 @@
 //   Wall::initialize_wall_constants           src4/wall.cpp:281-342
 //   DiffusionUtils::pick_surf_displacement    src4/diffusion_utils.inl:60-93
 //   Grid::initialize                          src4/wall.cpp:38-74
-//   GridUtils::xyz2grid_tile_index, uv2grid_tile_index, grid2uv   src4/grid_utils.inl:48-118, 120-191, 233-253
+//   GridUtils::xyz2grid_tile_index, uv2grid_tile_index, grid2uv, grid2uv_random   src4/grid_utils.inl:48-118, 120-191, 233-253, 256-286
 //   GeometryUtils::find_edge_point            src4/geometry_utils.inl:222-291
 //   WallUtils::wall_in_box                    src4/wall_utils.inl:326-504
 //   GeometryUtils::wall_subparts_collision_test   src4/geometry_utils.inl:110-207 (Partition::finalize_walls' distribution of
@@ -363,6 +363,15 @@ EXPORT void ref4_grid2uv(const double* v9, int idx, double* uv2) {
   Partition p; fill_with_grid(p, v9);
   const Vec2 r = GridUtils::grid2uv(p.walls[0], (tile_index_t)idx);
   uv2[0] = r.u; uv2[1] = r.v;
+}
+// GridUtils::grid2uv_random (src4/grid_utils.inl:256-286): a random point inside a tile; returns the words drawn
+EXPORT long long ref4_grid2uv_random(const double* v9, int idx, unsigned seed, unsigned skip, double* uv2) {
+  Partition p; fill_with_grid(p, v9);
+  rng_state rng; seed_rng(&rng, seed, skip);
+  const long long before = rng_uses(&rng);
+  const Vec2 r = GridUtils::grid2uv_random(p.walls[0], (tile_index_t)idx, rng);
+  uv2[0] = r.u; uv2[1] = r.v;
+  return rng_uses(&rng) - before;
 }
 EXPORT int ref4_find_edge_point(const double* v9, const double* loc2, const double* disp2, double* edgept2) {
   const unsigned tri[3] = {0, 1, 2};

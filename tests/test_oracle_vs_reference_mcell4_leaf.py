@@ -254,3 +254,32 @@ def test_oracle_wall_lists_match_mcell4_wall_distribution():
         assert 0 < na <= cap
         for s in np.flatnonzero(np.diff(sa.astype(np.int64)) > 0):
             assert np.array_equal(o.subpart_walls(int(s)), la[sa[s]:sa[s + 1]]), s
+
+
+def test_grid2uv_random_matches_compiled_mcell4():
+    """GridUtils::grid2uv_random (src4/grid_utils.inl:256-286), the position of a released surface molecule inside its tile
+    (mcx_release_surface_molecules, place_single_molecule_onto_grid with config.randomize_smol_pos): the oracle's
+    restatement against MCell4's own compiled function, golden vectors on every box and live where oracle/_ref is."""
+    import gen_mcell4_grid2uv_random_golden as gg
+    L = O.lib()
+    L.orc_unit_grid2uv_random.restype = C.c_longlong
+    L.orc_unit_grid2uv_random.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+    ref = np.load(os.path.join(HERE, "golden", "mcell4_grid2uv_random_vectors.npz"))["out"]
+    tris = mc.triangles()
+    cases = gg.cases()
+    assert len(cases) == len(ref) > 2000
+    R4 = O.ref_mcell4_leaf_lib()
+    if R4 is not None:
+        R4.ref4_grid2uv_random.restype = C.c_longlong
+        R4.ref4_grid2uv_random.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
+    for i, (ti, tile, seed, skip) in enumerate(cases):
+        tape = ref_words(seed, skip + 4)[skip:]
+        uv = np.zeros(2)
+        used = L.orc_unit_grid2uv_random(vp(tris[ti]), tile, vp(tape), len(tape), vp(uv))
+        assert uv[0] == ref[i, 0] and uv[1] == ref[i, 1] and used == int(ref[i, 2]) == 2, i
+        if R4 is not None and i % 9 == 0:   # live, other seeds
+            uv_r, uv_o = np.zeros(2), np.zeros(2)
+            tape2 = ref_words(seed + 100, skip + 4)[skip:]
+            assert R4.ref4_grid2uv_random(vp(tris[ti]), tile, seed + 100, skip, vp(uv_r)) == 2
+            L.orc_unit_grid2uv_random(vp(tris[ti]), tile, vp(tape2), len(tape2), vp(uv_o))
+            assert (uv_r == uv_o).all(), i
