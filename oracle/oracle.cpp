@@ -1269,6 +1269,17 @@ struct Eval {
     return pathway_for_probability(w, rc, prob);
   }
 
+  // RxnUtils::test_intersect, rxn_utils.inl:593-626 (a Standard reaction with a reactive surface): pathway or -1
+  int test_intersect(const mcx_rxn_class& rc, double scaling) {
+    const double max_prob = rc.max_fixed_p;
+    double pr;
+    if (max_prob > scaling) pr = rs.dbl() * max_prob;
+    else { pr = rs.dbl() * scaling; if (pr > max_prob) return -1; }
+    if (pr > rc.max_fixed_p) return -1;
+    const double match = rs.dbl() * rc.max_fixed_p;
+    return pathway_for_probability(w, rc, match);
+  }
+
   // compute_vol_displacement + pick_vol_displacement, diffusion_utils.inl:366-432,113-119
   void compute_vol_displacement(const mcx_species& sp, double& max_time, V3& disp, double& r_rate_factor,
                                 double& t_steps) {
@@ -1564,15 +1575,9 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
           if (action == MCX_SURF_STANDARD) {
             // collide_and_react_with_walls (:1034-1066): test_intersect (rxn_utils.inl:593-626) of the one matching class
             const mcx_rxn_class& wc = w.classes[wall_rc];
-            const double scaling = r_rate_factor, max_prob = wc.max_fixed_p;
-            double pr;
-            bool reacts = true;
-            if (max_prob > scaling) pr = E.rs.dbl() * max_prob;
-            else { pr = E.rs.dbl() * scaling; if (pr > max_prob) reacts = false; }
+            const int pathway = E.test_intersect(wc, r_rate_factor);
             action = MCX_SURF_REFLECTIVE;   // no reaction: it reflects (:1066)
-            if (reacts) {
-              const double match = E.rs.dbl() * max_prob;
-              const int pathway = pathway_for_probability(w, wc, match);
+            if (pathway >= 0) {
               const mcx_pathway& pw = w.pathways[wc.first_pathway + pathway];
               const uint32_t obits = draw_orientation_bits(pw, E.rs);
               const double abs_t = elapsed + t_steps * c.time;
@@ -2828,6 +2833,18 @@ int orc_unit_test_bimolecular(const double* cum_probs, int n, double scaling, co
   WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
   Eval E(w, rs);
   int r = E.test_bimolecular(rc, scaling);
+  *words_used = rs.used;
+  return r;
+}
+int orc_unit_test_intersect(const double* cum_probs, int n, double scaling, const uint32_t* words, uint64_t n_words,
+                            long long* words_used) {
+  World w; w.cfg = mcx_config{};
+  w.pathways.resize(n);
+  for (int i = 0; i < n; i++) { w.pathways[i] = mcx_pathway{}; w.pathways[i].cum_prob = cum_probs[i]; }
+  mcx_rxn_class rc{}; rc.kind = MCX_RXN_BIMOL_VOLWALL; rc.first_pathway = 0; rc.n_pathways = n; rc.max_fixed_p = cum_probs[n - 1];
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  Eval E(w, rs);
+  int r = E.test_intersect(rc, scaling);
   *words_used = rs.used;
   return r;
 }

@@ -106,6 +106,7 @@ typedef std::vector<wall_index_t> WallsInSubpart;
 }  // namespace MCell
 namespace BNG {
 const int PATHWAY_INDEX_NO_RXN = -1;
+typedef int rxn_class_pathway_index_t;   // libbng: the index of a pathway in its reaction class
 class RxnContainer;
 class RxnClass;
 typedef std::vector<RxnClass*> RxnClassesVector;
@@ -218,6 +219,7 @@ namespace DiffusionUtils {
 }
 namespace RxnUtils {
 #include "gen/mcell4_test_bimolecular.inl"  // src4/rxn_utils.inl:336-414
+#include "gen/mcell4_test_intersect.inl"    // src4/rxn_utils.inl:593-626
 }
 
 }  // namespace MCell
@@ -332,6 +334,17 @@ EXPORT int ref4_test_bimolecular(const double* cum_probs, int n, double scaling,
   const long long before = rng_uses(&rng);
   Molecule a, b;
   const int r = RxnUtils::test_bimolecular(p, &rc, rng, a, b, scaling, 0.0, 0.0);
+  *rng_words_used = rng_uses(&rng) - before;
+  return r;
+}
+
+// RxnUtils::test_intersect (src4/rxn_utils.inl:593-626), a Standard reaction with a reactive surface: pathway index or -1
+EXPORT int ref4_test_intersect(const double* cum_probs, int n, double scaling, unsigned seed, unsigned skip, long long* rng_words_used) {
+  BNG::RxnClass rc;
+  rc.cum_probs.assign(cum_probs, cum_probs + n);
+  rng_state rng; seed_rng(&rng, seed, skip);
+  const long long before = rng_uses(&rng);
+  const int r = RxnUtils::test_intersect(&rc, scaling, 0.0, rng);
   *rng_words_used = rng_uses(&rng) - before;
   return r;
 }

@@ -283,3 +283,32 @@ def test_grid2uv_random_matches_compiled_mcell4():
             assert R4.ref4_grid2uv_random(vp(tris[ti]), tile, seed + 100, skip, vp(uv_r)) == 2
             L.orc_unit_grid2uv_random(vp(tris[ti]), tile, vp(tape2), len(tape2), vp(uv_o))
             assert (uv_r == uv_o).all(), i
+
+
+def test_test_intersect_matches_compiled_mcell4():
+    """RxnUtils::test_intersect (src4/rxn_utils.inl:593-626), the test of a finite-rate reaction with a surface class
+    (SURVEY a18): pathway and number of words drawn against MCell4's own compiled function — reactions that happen
+    (two draws), that do not (one), the GIGANTIC rate of an absorptive class."""
+    L = O.lib()
+    L.orc_unit_test_intersect.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_uint64, C.c_void_p]
+    ref = np.load(os.path.join(HERE, "golden", "mcell4_test_intersect_vectors.npz"))["out"]
+    R4 = O.ref_mcell4_leaf_lib()
+    if R4 is not None:
+        R4.ref4_test_intersect.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint, C.c_uint, C.c_void_p]
+    reacted = missed = 0
+    for i, (cum, scaling, seed, skip) in enumerate(mc.rxn_cases()):
+        cum = np.ascontiguousarray(cum, dtype=np.float64)
+        tape = ref_words(seed, skip + 8)[skip:]
+        used = C.c_longlong(0)
+        r = L.orc_unit_test_intersect(vp(cum), len(cum), scaling, vp(tape), len(tape), C.byref(used))
+        assert r == int(ref[i, 0]) and used.value == int(ref[i, 1]), (i, r, used.value, ref[i])
+        assert used.value == (2 if r >= 0 else 1)
+        reacted += r >= 0
+        missed += r < 0
+        if R4 is not None and i % 5 == 0:   # live, other seeds
+            u1, u2 = C.c_longlong(0), C.c_longlong(0)
+            tape2 = ref_words(seed + 7, skip + 8)[skip:]
+            a = R4.ref4_test_intersect(vp(cum), len(cum), scaling, seed + 7, skip, C.byref(u1))
+            b = L.orc_unit_test_intersect(vp(cum), len(cum), scaling, vp(tape2), len(tape2), C.byref(u2))
+            assert a == b and u1.value == u2.value, i
+    assert reacted > 50 and missed > 50
