@@ -95,7 +95,7 @@ class Engine:
                                          _vp(t.wall_surf_class), _vp(getattr(t, "wall_object", None))))
         if getattr(t, "n_counted_volumes", 0) > 1:
             self._ck(self.L.mcx_set_counted_volumes(self.h, t.n_counted_volumes, _vp(t.wall_cv_front), _vp(t.wall_cv_back)))
-        if getattr(t, "cv_intersecting", 0) and t.cv_object_mask is not None:
+        if getattr(t, "n_counted_volumes", 0) > 1 and getattr(t, "cv_object_mask", None) is not None:
             self._ck(self.L.mcx_set_counted_volume_objects(self.h, _vp(t.cv_object_mask), t.cv_intersecting))
         if getattr(t, "n_region_sets", 0) > 1:
             self._ck(self.L.mcx_set_surface_regions(self.h, t.n_region_sets, _vp(t.wall_region_set)))

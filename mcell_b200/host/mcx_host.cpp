@@ -49,8 +49,10 @@ GpuDiffuseReactEvent::GpuDiffuseReactEvent(const GpuModelTables& t, PartitionMol
   if (!t.wall_cv_front.empty()) {
     check(mcx_set_counted_volumes(h, t.n_counted_volumes, t.wall_cv_front.data(), t.wall_cv_back.data()), "mcx_set_counted_volumes");
     n_cv = t.n_counted_volumes;
-    if (!t.cv_object_mask.empty())
+    if (!t.cv_object_mask.empty()) {
       check(mcx_set_counted_volume_objects(h, t.cv_object_mask.data(), t.intersecting_objects), "mcx_set_counted_volume_objects");
+      has_cv_masks = true;
+    }
   }
   if (!t.wall_region_set.empty()) {
     check(mcx_set_surface_regions(h, t.n_region_sets, t.wall_region_set.data()), "mcx_set_surface_regions");
@@ -95,6 +97,9 @@ void GpuDiffuseReactEvent::upload_from_host() {
     }
     uint32_t f = 0;
     if (m.flags & MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN) f |= MCX_MOL_SCHEDULE_UNIMOL;
+    // COUNTED_VOLUME_INDEX_INVALID: Partition::add_volume_molecule computes it (partition.h:572-576) — here the device does,
+    // by a ray cast when the molecule is first evaluated
+    if (m.is_vol() && has_cv_masks && m.v.counted_volume_index == INDEX_INVALID32) f |= MCX_MOL_CVI_PENDING;
     const bool partial = m.diffusion_time != TIME_INVALID && m.diffusion_time > event_time + 1e-12;
     if (partial) f |= MCX_MOL_PARTIAL;
     flags[k] = f;

@@ -203,6 +203,7 @@ private:
   PartitionMolecules* p;
   size_t n_species, n_rules;
   uint32_t n_cv = 1, n_rs = 1;
+  bool has_cv_masks = false;   // the device can compute a counted volume by a ray cast (MCX_MOL_CVI_PENDING)
   bool has_surface_species = false;
   double time_up_to_next_barrier;
   double iterations_last_step = 1;

@@ -93,7 +93,7 @@ class Oracle:
                                 C.c_uint64(len(t.tri)), self._v(t.wall_surf_class), self._v(getattr(t, "wall_object", None)))
         if getattr(t, "n_counted_volumes", 0) > 1:
             self.L.orc_set_counted_volumes(self.h, C.c_uint32(t.n_counted_volumes), self._v(t.wall_cv_front), self._v(t.wall_cv_back))
-        if getattr(t, "cv_intersecting", 0) and t.cv_object_mask is not None:
+        if getattr(t, "n_counted_volumes", 0) > 1 and getattr(t, "cv_object_mask", None) is not None:
             self.L.orc_set_counted_volume_objects(self.h, self._v(t.cv_object_mask), C.c_uint32(t.cv_intersecting))
         if getattr(t, "n_region_sets", 0) > 1:
             self.L.orc_set_surface_regions(self.h, C.c_uint32(t.n_region_sets), self._v(t.wall_region_set))

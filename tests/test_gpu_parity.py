@@ -490,6 +490,31 @@ def test_philox_intersecting_counted_objects():
     assert crossings > 3000 and pending > 10, (crossings, pending)
 
 
+def test_counted_volume_computed_for_uploaded_molecules():
+    """Molecules uploaded with MCX_MOL_CVI_PENDING (the host does not know their counted volume): the device ray-casts it at
+    their first evaluation; traces and populations against the oracle, counted volumes against numpy."""
+    t, mols = cm.counted_spheres(n=16000, seed=23)
+    mols.counted_volume[:] = 0
+    mols.flags[:] |= abi.MCX_MOL_CVI_PENDING
+    n = mols.n
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+    for it in range(3):
+        tr_o, st_o = o.trace_step(1, n)
+        tr_g, st_g = e.trace_step(n)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        mo, ro = o.counts_by_volume()
+        mg, rg = e.counts_by_volume()
+        assert (mo == mg).all() and (ro == rg).all(), it
+    b = e.download()
+    assert not (b.flags[:b.n] & abi.MCX_MOL_CVI_PENDING).any()
+    pos = np.stack([b.x[:b.n], b.y[:b.n], b.z[:b.n]], 1)
+    assert (b.counted_volume[:b.n] == cm.counted_volume_of(t, pos)).all()
+
+
 def test_more_than_256_species_and_rules():
     """The device counters hold 1024 species and 1024 reaction rules (the reference has no such limit; round 1 stopped at
     256): a chain of 600 species with one unimolecular rule each, populations and per-rule counts against the oracle."""

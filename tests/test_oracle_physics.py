@@ -557,3 +557,21 @@ def test_intersecting_counted_objects(mode):
     assert pending_seen > 0 or mode == 0              # ... and was resolved later (the sequential mode evaluates products at once)
     mo, _ = o.counts_by_volume()
     assert mo[:3].sum() == sp[:3].sum()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_counted_volume_computed_for_uploaded_molecules(mode):
+    """Partition::add_volume_molecule computes the counted volume of a molecule that comes without one (partition.h:572-576);
+    here such molecules are uploaded with MCX_MOL_CVI_PENDING and get it from a ray cast when they are first evaluated."""
+    t, mols = cm.counted_spheres(n=6000, seed=23)
+    truth = mols.counted_volume.copy()
+    mols.counted_volume[:] = 0
+    mols.flags[:] |= abi.MCX_MOL_CVI_PENDING
+    assert (truth != 0).sum() > 4000 and len(np.unique(truth)) == 3
+    o = O.Oracle(t)
+    o.upload(mols)
+    o.step(1, mode)
+    m = o.download()
+    assert not (m.flags[:m.n] & abi.MCX_MOL_CVI_PENDING).any()
+    pos = np.stack([m.x[:m.n], m.y[:m.n], m.z[:m.n]], 1)
+    assert (m.counted_volume[:m.n] == cm.counted_volume_of(t, pos)).all()
