@@ -374,6 +374,12 @@ typedef struct mcx_release {
   uint32_t region_in, region_out;  /* MCX_RELEASE_REGION: object masks (see above) */
 } mcx_release;
 int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* first_id_out);
+/* Partition::next_molecule_id (partition.h): the id the next new molecule takes.  mcx_upload_molecules raises it above
+ * every uploaded id; a run resumed from a checkpoint restores the saved value with mcx_set_next_molecule_id (ids of
+ * molecules that no longer exist must not be handed out again, and the per-molecule random streams are keyed by id), which
+ * can only raise it.  Same call on every rank. */
+int mcx_get_next_molecule_id(mcx_handle* h, uint32_t* next_id_out);
+int mcx_set_next_molecule_id(mcx_handle* h, uint32_t next_id);
 /* ReleaseEvent::release_list (release_event.cpp:1008-1040), volume molecules: one molecule of species[k] at
  * (x[k], y[k], z[k]) (length units) with counted_volume[k] (may be NULL: 0), ids first_id .. first_id + n - 1 in list
  * order, added to the resident population without a download / upload round trip.  Same call on every rank. */

@@ -1034,6 +1034,31 @@ int mcx_release_surface_molecules(mcx_handle* h, const mcx_surface_release* r, u
   return MCX_OK;
 }
 
+int mcx_get_next_molecule_id(mcx_handle* h, uint32_t* next_id_out) {
+  if (!h || !next_id_out) return MCX_ERR_INVALID_ARG;
+  if (!h->uploaded) { h->err = "nothing uploaded"; return MCX_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  Counters hc;
+  int rc = check_device_error(h, &hc);
+  if (rc) return rc;
+  *next_id_out = hc.next_id;
+  return MCX_OK;
+}
+int mcx_set_next_molecule_id(mcx_handle* h, uint32_t next_id) {
+  if (!h) return MCX_ERR_INVALID_ARG;
+  if (!h->uploaded) { h->err = "mcx_set_next_molecule_id follows mcx_upload_molecules"; return MCX_ERR_STATE; }
+  if (next_id >= 0xFFFFFFF0u) { h->err = "molecule ids exhausted"; return MCX_ERR_OVERFLOW; }
+  CK(cudaSetDevice(h->cfg.device));
+  Counters hc;
+  int rc = check_device_error(h, &hc);
+  if (rc) return rc;
+  if (next_id > hc.next_id) {
+    CK(cudaMemcpyAsync(&h->p.ctr->next_id, &next_id, sizeof(next_id), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return MCX_OK;
+}
+
 uint64_t mcx_num_molecules(mcx_handle* h) {
   if (!h || !h->uploaded) return 0;
   cudaSetDevice(h->cfg.device);

@@ -57,6 +57,8 @@ def load_library():
     L.mcx_release_volume_molecules.argtypes = [H, C.POINTER(abi.mcx_release), C.POINTER(C.c_uint32)]
     L.mcx_release_list.argtypes = [H, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_uint32)]
     L.mcx_release_surface_molecules.argtypes = [H, C.POINTER(abi.mcx_surface_release), C.POINTER(C.c_uint32)]
+    L.mcx_get_next_molecule_id.argtypes = [H, C.POINTER(C.c_uint32)]
+    L.mcx_set_next_molecule_id.argtypes = [H, C.c_uint32]
     L.mcx_set_profiling.argtypes = [H, C.c_int]
     L.mcx_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
     L.mcx_philox_block.restype = None
@@ -176,6 +178,14 @@ class Engine:
         self._ck(self.L.mcx_release_list(self.h, C.c_uint64(len(sp)), _vp(sp), _vp(x), _vp(y), _vp(z), _vp(cv) if cv is not None else None,
                                          C.c_double(release_time), C.byref(first)))
         return int(first.value)
+
+    def next_molecule_id(self, set_to=None):
+        """Partition::next_molecule_id: query, or (checkpoint resume) raise it to the saved value."""
+        if set_to is not None:
+            self._ck(self.L.mcx_set_next_molecule_id(self.h, C.c_uint32(int(set_to))))
+        out = C.c_uint32(0)
+        self._ck(self.L.mcx_get_next_molecule_id(self.h, C.byref(out)))
+        return int(out.value)
 
     def num_molecules(self):
         return int(self.L.mcx_num_molecules(self.h))

@@ -113,6 +113,7 @@ void GpuDiffuseReactEvent::upload_from_host() {
   if (n_cv > 1) v.counted_volume = cvi.data();
   if (has_surface_species) { v.wall = swall.data(); v.tile = stile.data(); v.orientation = sorient.data(); v.u = su.data(); v.v = sv.data(); }
   check(mcx_upload_molecules(h, &v), "mcx_upload_molecules");
+  check(mcx_set_next_molecule_id(h, p->next_molecule_id), "mcx_set_next_molecule_id");   // e.g. restored from a checkpoint
   host_dirty = false;
 }
 
@@ -152,6 +153,11 @@ void GpuDiffuseReactEvent::sync_to_host() {
   }
   p->molecules.swap(keep);
   p->rebuild_mapping();
+  {  // Partition::next_molecule_id follows the device (products took fresh ids there); a checkpoint stores it
+    uint32_t next = 0;
+    check(mcx_get_next_molecule_id(h, &next), "mcx_get_next_molecule_id");
+    if (next > p->next_molecule_id) p->next_molecule_id = next;
+  }
   device_dirty = false;
 }
 

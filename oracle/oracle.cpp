@@ -2494,6 +2494,8 @@ int orc_release_list(void* h, uint64_t n_list, const uint32_t* species, const do
   if (first_id_out) *first_id_out = first;
   return 0;
 }
+int orc_get_next_molecule_id(void* h, uint32_t* out) { *out = ((World*)h)->next_id; return 0; }
+int orc_set_next_molecule_id(void* h, uint32_t next_id) { World& w = *(World*)h; if (next_id > w.next_id) w.next_id = next_id; return 0; }
 uint64_t orc_num_molecules(void* h) {
   World& w = *(World*)h; uint64_t n = 0;
   for (auto& m : w.mols) n += !(m.flags & MCX_MOL_DEFUNCT);

@@ -158,6 +158,13 @@ class Oracle:
             raise RuntimeError(self.error())
         return int(first.value)
 
+    def next_molecule_id(self, set_to=None):
+        if set_to is not None:
+            self.L.orc_set_next_molecule_id(self.h, C.c_uint32(int(set_to)))
+        out = C.c_uint32(0)
+        self.L.orc_get_next_molecule_id(self.h, C.byref(out))
+        return int(out.value)
+
     def num_molecules(self):
         return int(self.L.orc_num_molecules(self.h))
 

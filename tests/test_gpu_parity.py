@@ -515,6 +515,16 @@ def test_counted_volume_computed_for_uploaded_molecules():
     assert (b.counted_volume[:b.n] == cm.counted_volume_of(t, pos)).all()
 
 
+def test_checkpoint_resume_is_exact_on_the_device():
+    """download at iteration k, a new handle with Config.initial_iteration = k, upload, restore
+    next_molecule_id, go on — bit for bit the run that never stopped (streams are keyed by seed, molecule id, iteration)."""
+    import test_oracle_physics as top
+    ref, ref_counts, got, counts, saved_counts = top._run_resume(lambda t: _engine(t))
+    _assert_same_population(ref, got)
+    assert (ref_counts[0] == counts[0]).all()
+    assert (ref_counts[1] == counts[1] + saved_counts[1]).all() and ref_counts[1].sum() > 50
+
+
 def test_more_than_256_species_and_rules():
     """The device counters hold 1024 species and 1024 reaction rules (the reference has no such limit; round 1 stopped at
     256): a chain of 600 species with one unimolecular rule each, populations and per-rule counts against the oracle."""

@@ -575,3 +575,46 @@ def test_counted_volume_computed_for_uploaded_molecules(mode):
     assert not (m.flags[:m.n] & abi.MCX_MOL_CVI_PENDING).any()
     pos = np.stack([m.x[:m.n], m.y[:m.n], m.z[:m.n]], 1)
     assert (m.counted_volume[:m.n] == cm.counted_volume_of(t, pos)).all()
+
+
+def _resume_case():
+    return cm.reversible_box(n=6000, edge_um=0.4, seed=31)
+
+
+def _run_resume(make_engine, total=8, stop=3):
+    """run `total` iterations at once, and `stop` iterations + download + a NEW engine at initial_iteration = stop +
+    upload + the rest: both ends of the checkpoint must give the same population"""
+    t, mols = _resume_case()
+    a = make_engine(t)
+    a.upload(mols)
+    for _ in range(total):
+        a.step(1) if not hasattr(a, "SNAPSHOT") else a.step(1, 1)
+    ref = a.download().sorted_by_id()
+    ref_counts = a.counts()
+    b = make_engine(t)
+    b.upload(mols)
+    for _ in range(stop):
+        b.step(1) if not hasattr(b, "SNAPSHOT") else b.step(1, 1)
+    saved, saved_counts, saved_next = b.download(), b.counts(), b.next_molecule_id()
+    t2, _ = _resume_case()
+    t2.cfg.initial_iteration = stop
+    c = make_engine(t2)
+    c.upload(saved)
+    assert c.next_molecule_id(set_to=saved_next) == saved_next     # ids of molecules that are gone are not handed out again
+    for _ in range(total - stop):
+        c.step(1) if not hasattr(c, "SNAPSHOT") else c.step(1, 1)
+    got = c.download().sorted_by_id()
+    return ref, ref_counts, got, c.counts(), saved_counts
+
+
+def test_checkpoint_resume_is_exact():
+    """SURVEY 5.4 (checkpoint / resume): the per-molecule Philox streams are keyed by (seed, molecule id, iteration), so a
+    run resumed from a downloaded population at Config.initial_iteration continues bit for bit; reaction counts of the
+    two legs add up (the host adds initial_reactions_count like MolOrRxnCountTerm does)."""
+    ref, ref_counts, got, counts, saved_counts = _run_resume(lambda t: O.Oracle(t))
+    assert ref.n == got.n and (ref.id == got.id).all() and (ref.species == got.species).all()
+    for k in ("x", "y", "z", "diffusion_time", "unimol_rxn_time"):
+        assert (getattr(ref, k) == getattr(got, k)).all(), k
+    assert (ref.flags == got.flags).all()
+    assert (ref_counts[0] == counts[0]).all()
+    assert (ref_counts[1] == counts[1] + saved_counts[1]).all() and ref_counts[1].sum() > 50
