@@ -399,6 +399,7 @@ static int rebuild_tables(mcx_handle* h) {
       any_surf = true;
     } else if (rc.kind == MCX_RXN_UNIMOL) unimol[rc.reactants[0]] = (int)c;
     else if (rc.kind == MCX_RXN_BIMOL_VOLWALL) {
+      any_surf = true;   // kept reactants and products remember the wall of their event: the cold surface arrays are needed
       for (uint32_t q = 0; q < rc.n_pathways; q++) {
         const mcx_pathway& pw = h->pathways[rc.first_pathway + q];
         if (pw.keep_reactant_mask & ~1u) { h->err = "vol-wall pathway: only reactant 0 can be kept (the surface always is)"; return MCX_ERR_INVALID_ARG; }

@@ -1551,6 +1551,18 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
         max_time = t_steps;
 
         uint32_t last_hit_wall = MCX_NONE;
+        if (created_tile == MCX_KEPT_AT_WALL) {
+          // a KEPT reactant of a surface / wall reaction carries on from the wall of its event like the reference's does
+          // within the same step (last_hit_wall_index = wall, the remaining displacement leads away from it,
+          // diffuse_react_event.cpp:945-975, reflect_from_wall): the first displacement is mirrored away from that wall
+          // if it points into it, and the first trace skips the wall
+          const DevWall& kw = p.walls[created_wall];
+          const D3 kn = {kw.nx, kw.ny, kw.nz};
+          const double dd = dot3(kn, pos) - kw.dist, dn = dot3(remaining, kn);
+          if (dd > 0 ? dn < 0 : dn > 0) remaining = remaining + kn * (-2.0 * dn);
+          last_hit_wall = created_wall;
+          created_wall = created_tile = MCX_NONE;
+        }
         double elapsed = t_now;
         // ---- diffuse_vol_molecule loop (:423-572)
         bool tracing = true;

@@ -53,6 +53,7 @@ struct __align__(16) DevWall {
   double v0x, v0y, v0z;           // vertex 0
 };
 
+#define MCX_KEPT_AT_WALL 0xFFFFFFFEu  // stile of a DF_CREATED_ON_SURF record that is a KEPT reactant, not a product (mcx_device.cuh)
 #define MCX_MAX_COUNTED 1024      // species and reaction rules the device counters hold (a power of two)
 #define MCX_ROUNDS_MAX 32        // upper bound of mcx_config::max_resolve_rounds
 struct Counters {

@@ -285,7 +285,7 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
       }
       const double bump = (side > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
       const D3 kpos = {pos.x + (2 * bump) * fw.nx, pos.y + (2 * bump) * fw.ny, pos.z + (2 * bump) * fw.nz};
-      if (p.has_surf) { f |= DF_CREATED_ON_SURF; p.swallB[slot] = wi; p.stileB[slot] = hit_tile; }
+      if (p.has_surf) { f |= DF_CREATED_ON_SURF; p.swallB[slot] = wi; p.stileB[slot] = MCX_KEPT_AT_WALL; }
       finalize_alive(p, slot, kpos, id, species, f, t_event, unimol_time);
     }
     return;
@@ -418,7 +418,7 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
       const double bump = (side > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
       kept_pos = D3{event_pos.x + (2 * bump) * fw.nx, event_pos.y + (2 * bump) * fw.ny, event_pos.z + (2 * bump) * fw.nz};
       f |= DF_CREATED_ON_SURF;
-      p.swallB[slot] = wi; p.stileB[slot] = p.stileA[surf_slot];
+      p.swallB[slot] = wi; p.stileB[slot] = MCX_KEPT_AT_WALL;
     }
     finalize_alive(p, slot, kept_pos, id, species, f, t_event, ut);
   }

@@ -130,6 +130,11 @@ struct Grid {  // src4/wall.h:101-193, constants per Grid::initialize (wall.cpp:
 };
 
 enum { COLL_VOLMOL = 0, COLL_WALL_FRONT = 1, COLL_WALL_BACK = 2 };
+// created_tile of a KEPT reactant of a surface / wall reaction (SNAPSHOT): not a rebinding guard — the molecule carries on
+// from created_wall like the reference's does within the same step (last_hit_wall_index = wall, remaining displacement
+// leading away from it, diffuse_react_event.cpp:945-975, reflect_from_wall): its first displacement is mirrored
+// away from that wall if it points into it, and the first trace skips the wall
+static const uint32_t KEPT_AT_WALL = 0xFFFFFFFEu;
 struct Collision {  // src4/collision_structs.h:29-243
   int type; double time; V3 pos; uint32_t partner_id; uint32_t partner_index; int rxn_class; uint32_t wall;
 };
@@ -1466,6 +1471,13 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
     V3 remaining; double r_rate_factor, t_steps;
     E.compute_vol_displacement(sp, max_time, remaining, r_rate_factor, t_steps);
     uint32_t last_hit_wall = MCX_NONE;
+    if (s.created_tile == KEPT_AT_WALL) {  // a kept reactant carries on from the wall of its event (see KEPT_AT_WALL)
+      const Wall& kw = w.walls[s.created_wall];
+      const double dd = dot(kw.normal, s.pos) - kw.distance_to_origin, dn = dot(remaining, kw.normal);
+      if (dd > 0 ? dn < 0 : dn > 0) remaining = remaining + kw.normal * (-2.0 * dn);
+      last_hit_wall = s.created_wall;
+      s.created_wall = s.created_tile = MCX_NONE;
+    }
     double elapsed = s.t_now;
     bool can_vol_react = w.can_vol_react[m_species] != 0;
     bool hit;
@@ -1996,8 +2008,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
         if (flip) o.cvi = cv_cross(w, o.cvi, o.hit_wall, o.coll_side > 0);
         const double bump = (side > 0) ? 16 * POS_EPS : -16 * POS_EPS;
         o.pos = hit + V3{(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
-        ProductSpec g = wall_product_spec(w, pw, 0, hit, 0, o.hit_wall);   // for the tile under the hit point
-        o.created_wall = o.hit_wall; o.created_tile = g.created_tile;
+        o.created_wall = o.hit_wall; o.created_tile = KEPT_AT_WALL;
         o.kind = MCX_OUT_MOVED; o.t_now = o.t_event; o.flags |= MCX_MOL_PARTIAL;
       }
       return;
@@ -2052,7 +2063,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
         if (flip) o.cvi = cv_cross(w, o.cvi, surf->wall, o.coll_side > 0);  // update_counted_volume_id_when_crossing_wall
         const double bump = (side > 0) ? 16 * POS_EPS : -16 * POS_EPS;
         o.pos = o.pos + V3{(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
-        o.created_wall = surf->wall; o.created_tile = surf->tile;
+        o.created_wall = surf->wall; o.created_tile = KEPT_AT_WALL;
       }
     }
   };
