@@ -372,7 +372,16 @@ typedef struct mcx_release {
   uint32_t counted_volume_index;   /* Molecule::v.counted_volume_index of the released molecules (0 = outside all) */
   uint32_t reserved;
   uint32_t region_in, region_out;  /* MCX_RELEASE_REGION: object masks (see above) */
+  /* MCX_RELEASE_REGION, general region expressions (RegionExprNode trees, is_point_inside_region_expr_recursively,
+   * release_event.cpp:787-813): region_expr_len > 0 replaces the two masks by a postfix program of region_expr_len
+   * bytes — k < 32 pushes "inside geometry object k", MCX_REGION_UNION / _INTERSECT / _DIFFERENCE pop two values
+   * (left below right) and push the result; the point is kept when the one value left is true */
+  uint32_t region_expr_len;
+  uint8_t  region_expr[28];
 } mcx_release;
+#define MCX_REGION_UNION 0x80
+#define MCX_REGION_INTERSECT 0x81
+#define MCX_REGION_DIFFERENCE 0x82
 int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* first_id_out);
 /* Partition::next_molecule_id (partition.h): the id the next new molecule takes.  mcx_upload_molecules raises it above
  * every uploaded id; a run resumed from a checkpoint restores the saved value with mcx_set_next_molecule_id (ids of

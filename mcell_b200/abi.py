@@ -40,12 +40,13 @@ class mcx_config(C.Structure):
 
 
 MCX_RELEASE_CUBIC, MCX_RELEASE_SPHERICAL, MCX_RELEASE_SPHERICAL_SHELL, MCX_RELEASE_REGION = 0, 1, 2, 3
+MCX_REGION_UNION, MCX_REGION_INTERSECT, MCX_REGION_DIFFERENCE = 0x80, 0x81, 0x82
 
 
 class mcx_release(C.Structure):
     _fields_ = [("species", c_u32), ("shape", c_u32), ("number", c_u64), ("location", c_f64 * 3), ("diameter", c_f64 * 3),
                 ("release_time", c_f64), ("counted_volume_index", c_u32), ("reserved", c_u32),
-                ("region_in", c_u32), ("region_out", c_u32)]
+                ("region_in", c_u32), ("region_out", c_u32), ("region_expr_len", c_u32), ("region_expr", C.c_uint8 * 28)]
 
 
 class mcx_surface_release(C.Structure):

@@ -842,7 +842,18 @@ int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* 
   if (r->shape > MCX_RELEASE_REGION) { h->err = "release: unknown shape"; return MCX_ERR_INVALID_ARG; }
   if (r->shape == MCX_RELEASE_REGION) {
     if (!h->has_geometry) { h->err = "region release needs mcx_set_geometry"; return MCX_ERR_STATE; }
-    if (r->region_in == 0 || (r->region_in & r->region_out)) { h->err = "region release: region_in must name an object and be disjoint from region_out"; return MCX_ERR_INVALID_ARG; }
+    if (r->region_expr_len == 0 && (r->region_in == 0 || (r->region_in & r->region_out))) { h->err = "region release: region_in must name an object and be disjoint from region_out"; return MCX_ERR_INVALID_ARG; }
+    {  // a well-formed postfix program: never pops an empty stack, leaves exactly one value
+      bool ok = r->region_expr_len <= sizeof(r->region_expr);
+      int depth = 0;
+      for (uint32_t q = 0; ok && q < r->region_expr_len; q++) {
+        const uint8_t op = r->region_expr[q];
+        if (op < 32) ok = ++depth <= 24;
+        else if (op == MCX_REGION_UNION || op == MCX_REGION_INTERSECT || op == MCX_REGION_DIFFERENCE) { ok = depth >= 2; depth--; }
+        else ok = false;
+      }
+      if (!ok || (r->region_expr_len && depth != 1)) { h->err = "region release: malformed region expression"; return MCX_ERR_INVALID_ARG; }
+    }
   }
   if (r->counted_volume_index >= h->n_cv) { h->err = "release: counted_volume_index out of range"; return MCX_ERR_INVALID_ARG; }
   const double it = (double)h->iteration;

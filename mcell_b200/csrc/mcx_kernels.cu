@@ -1292,6 +1292,20 @@ void mcx_launch_count_by_volume(const DevParams& p, cudaStream_t s) {
   k_count_by_volume<<<p.sm_count * 8, TPB, 0, s>>>(p);
 }
 
+// is_point_inside_region_expr_recursively (release_event.cpp:787-813) on the membership mask of one ray cast: the two
+// masks, or the postfix program of mcx_release::region_expr
+__device__ __forceinline__ bool region_accepts(const mcx_release& r, uint32_t inside_mask) {
+  if (r.region_expr_len == 0) return (inside_mask & r.region_in) == r.region_in && (inside_mask & r.region_out) == 0u;
+  uint32_t stack = 0; int depth = 0;   // a stack of booleans, top = bit 0
+  for (uint32_t q = 0; q < r.region_expr_len; q++) {
+    const uint8_t op = r.region_expr[q];
+    if (op < 32) { stack = (stack << 1) | ((inside_mask >> op) & 1u); depth++; continue; }
+    const uint32_t b = stack & 1u, a = (stack >> 1) & 1u;
+    const uint32_t v = op == MCX_REGION_UNION ? (a | b) : (op == MCX_REGION_INTERSECT ? (a & b) : (a & ~b & 1u));
+    stack = ((stack >> 2) << 1) | v; depth--;
+  }
+  return depth == 1 && (stack & 1u);
+}
 // ---- release on the device (ReleaseEvent::release_ellipsoid_or_rectcuboid, src4/release_event.cpp:953-1003) --------
 // One thread per new molecule: its own Philox stream (release domain), the reference's rejection loop and scaling,
 // appended behind the re-binned population like a product.  Multi-GPU: every rank walks all ids, keeps its own slab.
@@ -1328,7 +1342,7 @@ __global__ void __launch_bounds__(TPB) k_release(const __grid_constant__ DevPara
         bool inb = in_partition(p, pos);
         RayScan sc;
         if (inb) scan_ray(p, pos, rs, sc);
-        if (inb && !sc.redo && (sc.inside_mask & r.region_in) == r.region_in && (sc.inside_mask & r.region_out) == 0u) {
+        if (inb && !sc.redo && region_accepts(r, sc.inside_mask)) {
           if (p.wall_cv) {
             uint32_t cvi = 0;
             if (sc.first_wall != MCX_NONE) { const uint32_t cv = __ldg(p.wall_cv + sc.first_wall); cvi = sc.first_side == W_FRONT ? (cv & 0xFFu) : (cv >> 8); }

@@ -143,7 +143,7 @@ class Engine:
         v = mols.view()
         self._ck(self.L.mcx_upload_molecules(self.h, C.byref(v)))
 
-    def release(self, species, number, location, diameter, shape=abi.MCX_RELEASE_CUBIC, release_time=0.0, counted_volume_index=0, region_in=0, region_out=0):
+    def release(self, species, number, location, diameter, shape=abi.MCX_RELEASE_CUBIC, release_time=0.0, counted_volume_index=0, region_in=0, region_out=0, region_expr=()):
         """ReleaseEvent::release_ellipsoid_or_rectcuboid on the device (mcx_release_volume_molecules); returns the first
         id of the new molecules.  location / diameter in length units."""
         r = abi.mcx_release()
@@ -152,6 +152,9 @@ class Engine:
         r.diameter[:] = [float(v) for v in diameter]
         r.release_time, r.counted_volume_index = float(release_time), int(counted_volume_index)
         r.region_in, r.region_out = int(region_in), int(region_out)
+        r.region_expr_len = len(region_expr)   # postfix: object index, abi.MCX_REGION_UNION / _INTERSECT / _DIFFERENCE
+        for q, op in enumerate(region_expr):
+            r.region_expr[q] = int(op)
         first = C.c_uint32(0)
         self._ck(self.L.mcx_release_volume_molecules(self.h, C.byref(r), C.byref(first)))
         return int(first.value)

@@ -163,7 +163,8 @@ void GpuDiffuseReactEvent::sync_to_host() {
 
 molecule_id_t GpuDiffuseReactEvent::release_volume_molecules(species_id_t species, uint64_t number, uint32_t shape,
                                                              const Vec3& location, const Vec3& diameter, double release_time,
-                                                             uint32_t counted_volume_index, uint32_t region_in, uint32_t region_out) {
+                                                             uint32_t counted_volume_index, uint32_t region_in, uint32_t region_out,
+                                                             const std::vector<uint8_t>* region_expr) {
   if (host_dirty) upload_from_host();   // the device must hold the current population before molecules are added to it
   mcx_release r{};
   r.species = species; r.shape = shape; r.number = number;
@@ -171,6 +172,11 @@ molecule_id_t GpuDiffuseReactEvent::release_volume_molecules(species_id_t specie
   r.diameter[0] = diameter.x; r.diameter[1] = diameter.y; r.diameter[2] = diameter.z;
   r.release_time = release_time; r.counted_volume_index = counted_volume_index;
   r.region_in = region_in; r.region_out = region_out;
+  if (region_expr) {
+    if (region_expr->size() > sizeof(r.region_expr)) throw McxFatalError(MCX_ERR_INVALID_ARG, "region expression longer than 28 bytes");
+    r.region_expr_len = (uint32_t)region_expr->size();
+    memcpy(r.region_expr, region_expr->data(), region_expr->size());
+  }
   uint32_t first = 0;
   check(mcx_release_volume_molecules(h, &r, &first), "mcx_release_volume_molecules");
   device_dirty = true;

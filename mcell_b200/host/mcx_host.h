@@ -177,7 +177,8 @@ public:
   // container is stale afterwards until sync_to_host().
   molecule_id_t release_volume_molecules(species_id_t species, uint64_t number, uint32_t shape, const Vec3& location,
                                          const Vec3& diameter, double release_time = 0, uint32_t counted_volume_index = 0,
-                                         uint32_t region_in = 0, uint32_t region_out = 0);
+                                         uint32_t region_in = 0, uint32_t region_out = 0,
+                                         const std::vector<uint8_t>* region_expr = nullptr);
   // ReleaseEvent::release_list (release_event.cpp:1008-1040) for volume molecules, on the device: one molecule of
   // species[k] at positions[k] (internal length units); returns the first of the consecutive new ids
   molecule_id_t release_list(const std::vector<species_id_t>& species, const std::vector<Vec3>& positions,
@@ -299,9 +300,11 @@ public:
   bool is_barrier() const override { return true; }   // the diffuse event must stop at the release time
   void step() override {
     first_released_id = diffuse->release_volume_molecules(species_id, release_number, release_shape, location, diameter,
-                                                          event_time, counted_volume_index, region_in, region_out);
+                                                          event_time, counted_volume_index, region_in, region_out,
+                                                          region_expr.empty() ? nullptr : &region_expr);
   }
   uint32_t region_in = 0, region_out = 0;   // MCX_RELEASE_REGION: objects the molecules must be inside / outside of
+  std::vector<uint8_t> region_expr;         // ... or the release's RegionExprNode tree in postfix (include/mcx.h)
   species_id_t species_id;
   uint64_t release_number;
   uint32_t release_shape;   // MCX_RELEASE_CUBIC / _SPHERICAL / _SPHERICAL_SHELL / _REGION

@@ -2308,11 +2308,38 @@ int orc_upload_molecules(void* h, const mcx_mol_soa* s) {
 //   SPHERICAL_SHELL: r = sqrt(len3_squared(pos)) * 2; pos = r == 0 ? (0, 0, 0.5) : pos / r;      :973-980
 //   location = pos * diameter + location;                                                       :982-991
 // new molecules: MOLECULE_FLAG_VOL | MOLECULE_FLAG_SCHEDULE_UNIMOL_RXN (:996-997), diffusion_time = release time.
+// a well-formed postfix program: never pops an empty stack, leaves exactly one value, at most 28 bytes / 24 deep
+static inline bool region_expr_ok(const mcx_release& r) {
+  if (r.region_expr_len > sizeof(r.region_expr)) return false;
+  int depth = 0;
+  for (uint32_t q = 0; q < r.region_expr_len; q++) {
+    const uint8_t op = r.region_expr[q];
+    if (op < 32) { if (++depth > 24) return false; }
+    else if (op == MCX_REGION_UNION || op == MCX_REGION_INTERSECT || op == MCX_REGION_DIFFERENCE) { if (depth < 2) return false; depth--; }
+    else return false;
+  }
+  return r.region_expr_len == 0 || depth == 1;
+}
+// is_point_inside_region_expr_recursively (release_event.cpp:787-813) on the membership mask of one ray cast: the two
+// masks, or the postfix program of mcx_release::region_expr
+static inline bool region_accepts(const mcx_release& r, uint32_t inside_mask) {
+  if (r.region_expr_len == 0) return (inside_mask & r.region_in) == r.region_in && (inside_mask & r.region_out) == 0u;
+  uint32_t stack = 0; int depth = 0;   // a stack of booleans, top = bit 0
+  for (uint32_t q = 0; q < r.region_expr_len; q++) {
+    const uint8_t op = r.region_expr[q];
+    if (op < 32) { stack = (stack << 1) | ((inside_mask >> op) & 1u); depth++; continue; }
+    const uint32_t b = stack & 1u, a = (stack >> 1) & 1u;
+    const uint32_t v = op == MCX_REGION_UNION ? (a | b) : (op == MCX_REGION_INTERSECT ? (a & b) : (a & ~b & 1u));
+    stack = ((stack >> 2) << 1) | v; depth--;
+  }
+  return depth == 1 && (stack & 1u);
+}
 int orc_release_volume_molecules(void* h, const mcx_release* r, uint32_t* first_id_out) {
   World& w = *(World*)h;
   if (r->species >= w.species.size() || !(w.species[r->species].flags & MCX_SP_VOL)) { w.err = "release: not a volume species"; return MCX_ERR_INVALID_ARG; }
   if (r->shape > MCX_RELEASE_REGION) { w.err = "release: unknown shape"; return MCX_ERR_INVALID_ARG; }
-  if (r->shape == MCX_RELEASE_REGION && (r->region_in == 0 || (r->region_in & r->region_out))) { w.err = "region release: bad object masks"; return MCX_ERR_INVALID_ARG; }
+  if (r->shape == MCX_RELEASE_REGION && r->region_expr_len == 0 && (r->region_in == 0 || (r->region_in & r->region_out))) { w.err = "region release: bad object masks"; return MCX_ERR_INVALID_ARG; }
+  if (r->shape == MCX_RELEASE_REGION && !region_expr_ok(*r)) { w.err = "region release: malformed region expression"; return MCX_ERR_INVALID_ARG; }
   if (r->counted_volume_index >= w.n_cv) { w.err = "release: counted_volume_index out of range"; return MCX_ERR_INVALID_ARG; }
   const double it = (double)w.iteration;
   if (r->release_time != 0 && !(r->release_time >= it && r->release_time < it + 1.0)) { w.err = "release_time outside the current iteration"; return MCX_ERR_INVALID_ARG; }
@@ -2344,7 +2371,7 @@ int orc_release_volume_molecules(void* h, const mcx_release* r, uint32_t* first_
         const bool inb = w.in_this_partition(n.pos);
         Eval::RayScan sc;
         if (inb) sc = E.scan_ray(n.pos);
-        if (inb && !sc.redo && (sc.inside_mask & r->region_in) == r->region_in && (sc.inside_mask & r->region_out) == 0u) {
+        if (inb && !sc.redo && region_accepts(*r, sc.inside_mask)) {
           cvi_k = 0;
           if (sc.first_wall != MCX_NONE) cvi_k = sc.first_side == WALL_FRONT ? w.walls[sc.first_wall].cv_front : w.walls[sc.first_wall].cv_back;
           if (!w.cv_mask.empty()) { const uint32_t kq = cv_lookup(w, sc.inside_mask & w.cv_all); if (kq != MCX_NONE) cvi_k = kq; }

@@ -120,13 +120,16 @@ class Oracle:
         if rc:
             raise RuntimeError(self.error())
 
-    def release(self, species, number, location, diameter, shape=0, release_time=0.0, counted_volume_index=0, region_in=0, region_out=0):
+    def release(self, species, number, location, diameter, shape=0, release_time=0.0, counted_volume_index=0, region_in=0, region_out=0, region_expr=()):
         r = abi.mcx_release()
         r.species, r.shape, r.number = int(species), int(shape), int(number)
         r.location[:] = [float(v) for v in location]
         r.diameter[:] = [float(v) for v in diameter]
         r.release_time, r.counted_volume_index = float(release_time), int(counted_volume_index)
         r.region_in, r.region_out = int(region_in), int(region_out)
+        r.region_expr_len = len(region_expr)   # postfix: object index, abi.MCX_REGION_UNION / _INTERSECT / _DIFFERENCE
+        for q, op in enumerate(region_expr):
+            r.region_expr[q] = int(op)
         first = C.c_uint32(0)
         rc = self.L.orc_release_volume_molecules(self.h, C.byref(r), C.byref(first))
         if rc:

@@ -359,3 +359,54 @@ def test_gpu_surface_release_matches_oracle_and_steps_on():
         assert st_g.bimol_rxns == st_o.bimol_rxns and st_g.unimol_rxns == st_o.unimol_rxns, it
     assert (e.counts()[0] == o.counts()[0]).all()
     gp._assert_same_population(o.download().sorted_by_id(), e.download().sorted_by_id())
+
+
+def _expr_cases():
+    U, I, D = abi.MCX_REGION_UNION, abi.MCX_REGION_INTERSECT, abi.MCX_REGION_DIFFERENCE
+    # intersecting_counted_spheres: objects 0 and 1 = the two overlapping spheres, 2 = the box
+    return [("union", (0, 1, U), lambda a, b: a | b), ("lens", (0, 1, I), lambda a, b: a & b),
+            ("difference", (0, 1, D), lambda a, b: a & ~b), ("box minus both", (2, 0, D, 1, D), lambda a, b: ~a & ~b),
+            ("symmetric difference", (0, 1, D, 1, 0, D, U), lambda a, b: a ^ b)]
+
+
+def test_oracle_region_release_with_region_expressions():
+    """Region expressions of a release (RegionExprNode trees: UNION / INTERSECT / DIFFERENCE of closed objects,
+    release_event.cpp:787-813) as postfix programs over the memberships one ray cast gives: every released molecule lies
+    where the expression says (independent point-in-mesh test in numpy), counted volumes included — the two spheres
+    intersect, so the counted volume comes from the set of enclosing objects."""
+    t, mols = cm.intersecting_counted_spheres(n=500, seed=3)
+    lu = t.length_unit
+    box = ((0.0, 0.0, 0.0), (0.62 / lu,) * 3)
+    o = _oracle(t)
+    o.upload(mols)
+    for name, expr, where in _expr_cases():
+        first = o.release(2, 1500, box[0], box[1], shape=abi.MCX_RELEASE_REGION, region_expr=expr)
+        m = o.download().sorted_by_id()
+        new = m.id >= first
+        pos = np.stack([m.x, m.y, m.z], 1)[new]
+        a, b = _inside(t, pos, 0), _inside(t, pos, 1)
+        assert new.sum() == 1500 and where(a, b).all(), name
+        assert (m.counted_volume[new] == cm.counted_volume_of(t, pos)).all(), name
+    for bad in ((0, abi.MCX_REGION_UNION), (0, 1), (0, 1, 0x90), (40, 1, abi.MCX_REGION_UNION)):
+        with pytest.raises(RuntimeError):
+            o.release(2, 10, box[0], box[1], shape=abi.MCX_RELEASE_REGION, region_expr=bad)
+
+
+@pytest.mark.gpu
+def test_gpu_region_release_with_region_expressions_matches_oracle():
+    import test_gpu_parity as gp
+    from mcell_b200 import Engine
+    t, mols = cm.intersecting_counted_spheres(n=500, seed=3)
+    t.cfg.max_molecules = 40000
+    lu = t.length_unit
+    box = ((0.0, 0.0, 0.0), (0.62 / lu,) * 3)
+    o = _oracle(t)
+    o.upload(mols)
+    e = Engine(t)
+    e.upload(mols)
+    for name, expr, _ in _expr_cases():
+        assert o.release(2, 4000, box[0], box[1], shape=abi.MCX_RELEASE_REGION, region_expr=expr) == \
+            e.release(2, 4000, box[0], box[1], shape=abi.MCX_RELEASE_REGION, region_expr=expr), name
+    gp._assert_same_population(o.download().sorted_by_id(), e.download().sorted_by_id())
+    with pytest.raises(engine.McxError):
+        e.release(2, 10, box[0], box[1], shape=abi.MCX_RELEASE_REGION, region_expr=(0, abi.MCX_REGION_UNION))
