@@ -42,6 +42,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <array>
+#include <deque>
 #include <string>
 #include <unordered_map>
 #include <map>
@@ -196,6 +198,7 @@ struct World {
   std::vector<std::vector<uint32_t>> tiles;  // per wall: molecule id per tile (Grid::molecules_per_tile); empty =
                                              // grid not initialized (wall.h:339-346)
   std::vector<uint32_t> tile_start;          // first global tile of every wall (+ total)
+  mutable std::vector<std::vector<uint32_t>> vertex_walls;  // Partition::walls_using_vertex_mapping, built on first use
   std::vector<mcx_surf_class_rxn> surf_rules;
   std::vector<Mol> mols;
   std::vector<uint32_t> id_to_index;  // molecule_id_to_index_mapping
@@ -394,6 +397,8 @@ static void init_edges(World& w, uint32_t first_wall, uint32_t n_faces) {
     }
   }
 }
+#include "oracle_tiles.h"  // find_neighbor_tiles (grid_utils.inl:296-1801)
+
 // distinguishable_vec2, src4/defines.h:733-764
 static bool distinguishable_vec2(double au, double av, double bu, double bv, double eps) {
   double c = fabs(au), cc, d;
@@ -2666,6 +2671,7 @@ void orc_tape_gauss(const uint32_t* words, uint64_t n_words, double* out, long n
 }
 // ---- unit entry points: one reference function each, for pinning against oracle/_ref/libmcell3ref.so
 //      (the reference's own compiled arithmetic) in tests/test_oracle_vs_reference.py -------------------------
+static inline bool grid_init_flag(const unsigned char* g, unsigned i) { return !g || g[i]; }
 static void unit_world(World& w, const double* v9) {
   w.cfg = mcx_config{};
   w.cfg.partition_edge_length = 1000; w.cfg.num_subparts_per_edge = 1;
@@ -2691,6 +2697,34 @@ static void unit_mesh(World& w, const double* verts, unsigned nv, const unsigned
     init_wall_constants(w, f);
   }
   init_edges(w, 0, nw);
+}
+// find_neighbor_tiles of every tile of every wall that has a grid, as a CSR of (wall, tile) pairs in list order (same
+// layout as ref4_neighbor_tile_table, oracle/ref_mcell4_tiles_shim.cpp); grid_init: per wall 0 = no grid yet, null = all
+unsigned long long orc_unit_neighbor_tile_table(const double* verts, unsigned n_verts, const unsigned* tri, unsigned n_walls,
+                                                const unsigned char* has_grid, unsigned* start, unsigned* out_pairs,
+                                                unsigned long long cap) {
+  World w; unit_mesh(w, verts, n_verts, tri, n_walls);
+  w.grids.resize(n_walls); w.tiles.resize(n_walls);
+  for (unsigned i = 0; i < n_walls; i++) {
+    grid_init(w, w.walls[i], w.grids[i]);
+    if (!grid_init_flag(has_grid, i)) continue;
+    w.tiles[i].assign(w.grids[i].n_tiles, MCX_NONE);
+  }
+  unsigned long long n = 0; unsigned gt = 0;
+  for (unsigned i = 0; i < n_walls; i++) {
+    if (w.tiles[i].empty()) continue;
+    for (uint32_t tile = 0; tile < w.grids[i].n_tiles; tile++) {
+      TileNeighbors nb;
+      find_neighbor_tiles(w, i, tile, nb);
+      start[gt++] = (unsigned)n;
+      for (const WallTile& t : nb) {
+        if (n < cap) { out_pairs[2 * n] = t.first; out_pairs[2 * n + 1] = t.second; }
+        n++;
+      }
+    }
+  }
+  start[gt] = (unsigned)n;
+  return n;
 }
 // same outputs as oracle/ref_mcell3_shim.cpp: ref3_mesh_edges / ref3_find_edge_point / ref3_traverse_surface
 int orc_unit_mesh_edges(const double* verts, unsigned n_verts, const unsigned* tri, unsigned n_walls, int* nb_wall_out,
