@@ -94,7 +94,19 @@ enum { MCX_RXN_UNIMOL = 1, MCX_RXN_BIMOL_VOLVOL = 2,
                                      diffuse_react_event.cpp:991-1067, 1916-1988); reached through a
                                      mcx_surf_class_rxn of type MCX_SURF_STANDARD.  Products are volume species; a kept
                                      reactant 0 reflects, or crosses the wall when kept_info gives it another
-                                     orientation (RX_FLIP) */ };
+                                     orientation (RX_FLIP) */,
+       MCX_RXN_BIMOL_SURFSURF = 5 /* both reactants are surface species (either order).  After its move a surface
+                                     molecule looks at the molecules on the tiles around its own (find_neighbor_tiles,
+                                     grid_utils.inl:1754-1801), tests the matching classes once with the local
+                                     probability factor 3 / (number of neighbour tiles) (react_2D_all_neighbors,
+                                     diffuse_react_event.cpp:1250-1393; test_bimolecular / test_many_bimolecular,
+                                     rxn_utils.inl:336-414, 475-580) and reacts with at most one of them.  Surface
+                                     products take the tiles of the consumed reactants (find_surf_product_positions,
+                                     :1993-2288, recycled positions); pathways that need more tiles than they free,
+                                     or fewer surface products than freed tiles next to a volume product, are
+                                     refused.  max_fixed_p / cum_prob hold the plain pathway probabilities
+                                     (rate / grid density scaling done by the table builder, as for the other
+                                     kinds) */ };
 typedef struct mcx_rxn_class {
   uint32_t kind;                   /* MCX_RXN_* */
   uint32_t reactants[2];           /* species ids in rule order; [1] = MCX_NONE for unimol */

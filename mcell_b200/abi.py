@@ -16,7 +16,7 @@ MCX_TIME_INVALID = -256.0
 MCX_TIME_FOREVER = 1e20
 MCX_RNG_PHILOX, MCX_RNG_TAPE = 0, 1
 MCX_SP_VOL, MCX_SP_CAN_DIFFUSE, MCX_SP_CANT_INITIATE = 1, 2, 4
-MCX_RXN_UNIMOL, MCX_RXN_BIMOL_VOLVOL, MCX_RXN_BIMOL_VOLSURF, MCX_RXN_BIMOL_VOLWALL = 1, 2, 3, 4
+MCX_RXN_UNIMOL, MCX_RXN_BIMOL_VOLVOL, MCX_RXN_BIMOL_VOLSURF, MCX_RXN_BIMOL_VOLWALL, MCX_RXN_BIMOL_SURFSURF = 1, 2, 3, 4, 5
 MCX_SURF_REFLECTIVE, MCX_SURF_TRANSPARENT, MCX_SURF_ABSORPTIVE, MCX_SURF_STANDARD = 0, 1, 2, 3
 MCX_MOL_DEFUNCT, MCX_MOL_SCHEDULE_UNIMOL, MCX_MOL_PARTIAL, MCX_MOL_CVI_PENDING = 1, 2, 4, 8
 MCX_KEPT_VALID, MCX_KEPT_ORDER_END, MCX_KEPT_ORDER_REACTANT = 1 << 31, 0xF, 8

@@ -310,7 +310,14 @@ class Model:
                 if (r_orient[0] + r_orient[1]) * (r_orient[0] - r_orient[1]) == 0 and r_orient[0] * r_orient[1] != 0:
                     pb_factor *= 2.0
             elif len(key) == 2 and n_surf_reactants == 2:
-                raise ValueError("surface-surface reactions are not built")
+                # two surface molecules (src/react_util.c:84-100): 3 neighbours, both molecules may initiate
+                rc.kind = abi.MCX_RXN_BIMOL_SURFSURF
+                rc.reactants[0], rc.reactants[1] = r_idx[0], r_idx[1]
+                rc.reactant_orientation[0], rc.reactant_orientation[1] = r_orient[0], r_orient[1]
+                sa, sb = self.species[r_idx[0]], self.species[r_idx[1]]
+                if sa.target_only and sb.target_only:
+                    raise ValueError("both reactants TARGET_ONLY")
+                pb_factor = c.time_step * c.surface_grid_density / (3.0 if (sa.target_only or sb.target_only) else 6.0)
             elif len(key) == 1:
                 rc.kind = abi.MCX_RXN_UNIMOL
                 rc.reactants[0], rc.reactants[1] = r_idx[0], abi.MCX_NONE

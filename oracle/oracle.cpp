@@ -150,7 +150,7 @@ static inline uint64_t hash_ev(uint64_t h, uint32_t a, uint32_t b) {
 }
 enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
        EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u, EV_BLOCKED = 0xB10C0000u, EV_DISK = 0xD1500000u,
-       EV_SURFMOVE = 0x3E000000u, EV_WALLRXN = 0x9A000000u };
+       EV_SURFMOVE = 0x3E000000u, EV_WALLRXN = 0x9A000000u, EV_SURFSURF = 0x55000000u };
 
 struct Stats {
   uint64_t molecule_steps = 0, ray_polygon_tests = 0, ray_polygon_colls = 0, reflections = 0,
@@ -176,6 +176,7 @@ struct Outcome {
   int coll_side = 0;              // volume-surface / volume-wall reaction: +1 the initiator hit the wall's front, -1 its back
   uint32_t hit_wall = MCX_NONE;   // volume-wall reaction: the wall
   uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE;  // SNAPSHOT, kept initiator of a surface reaction: rebinding guard
+  bool surf_moved = false;        // SNAPSHOT, surface-surface reaction: the initiator took a new tile first (claims it too)
 };
 
 struct World {
@@ -194,6 +195,8 @@ struct World {
   std::vector<uint8_t> can_vol_react;
   std::vector<int> volsurf;      // [vol*ns+surf] -> class or -1
   std::vector<uint8_t> can_vol_surf;   // SPECIES_FLAG_CAN_VOLSURF
+  std::vector<int> surfsurf;     // [a*ns+b] -> MCX_RXN_BIMOL_SURFSURF class or -1 (both orders)
+  std::vector<uint8_t> can_surf_surf;  // SPECIES_FLAG_CAN_SURFSURF: the species takes part in a surface-surface class
   std::vector<Grid> grids;       // per wall
   std::vector<std::vector<uint32_t>> tiles;  // per wall: molecule id per tile (Grid::molecules_per_tile); empty =
                                              // grid not initialized (wall.h:339-346)
@@ -726,8 +729,18 @@ static void build_lookups(World& w) {
   w.can_vol_react.assign(ns, 0);
   w.volsurf.assign(ns * ns, -1);
   w.can_vol_surf.assign(ns, 0);
+  w.surfsurf.assign(ns * ns, -1);
+  w.can_surf_surf.assign(ns, 0);
   for (size_t c = 0; c < w.classes.size(); c++) {
     const mcx_rxn_class& rc = w.classes[c];
+    if (rc.kind == MCX_RXN_BIMOL_SURFSURF) {
+      if (rc.reactants[0] < ns && rc.reactants[1] < ns) {
+        w.surfsurf[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
+        w.surfsurf[rc.reactants[1] * ns + rc.reactants[0]] = (int)c;
+        w.can_surf_surf[rc.reactants[0]] = w.can_surf_surf[rc.reactants[1]] = 1;
+      }
+      continue;
+    }
     if (rc.kind == MCX_RXN_BIMOL_VOLSURF) {
       if (rc.reactants[0] < ns && rc.reactants[1] < ns) {
         w.volsurf[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
@@ -798,14 +811,15 @@ static bool exd_passes_through(const World& w, uint32_t species, uint32_t surf_c
 }
 
 // binary_search_double, src4/rxn_utils.inl:301-320 (== src/react_cond.c:80-97)
-static int pathway_for_probability(const World& w, const mcx_rxn_class& rc, double match) {
+// mult: RxnClass::get_pathway_index_for_probability's local probability factor (1 except between surface molecules)
+static int pathway_for_probability(const World& w, const mcx_rxn_class& rc, double match, double mult = 1) {
   int min_idx = 0, max_idx = (int)rc.n_pathways - 1;
   const mcx_pathway* A = &w.pathways[rc.first_pathway];
   while (max_idx - min_idx > 1) {
     int mid = (max_idx + min_idx) / 2;
-    if (match > A[mid].cum_prob) min_idx = mid; else max_idx = mid;
+    if (match > A[mid].cum_prob * mult) min_idx = mid; else max_idx = mid;
   }
-  if (match > A[min_idx].cum_prob) return max_idx;
+  if (match > A[min_idx].cum_prob * mult) return max_idx;
   return min_idx;
 }
 
@@ -899,6 +913,107 @@ static ProductSpec product_spec(World& w, const mcx_rxn_class& c, const mcx_path
     ps.created_wall = surf->wall; ps.created_tile = surf->tile;
   }
   return ps;
+}
+
+// ---- surface-surface reactions (outcome_products_random :2446-2933 for a SURFMOL_SURFMOL collision) -----------------
+struct SurfSite { uint32_t wall, tile; double u, v; int orient; uint32_t species; };
+static inline SurfSite site_of(const Mol& m) { return SurfSite{m.wall, m.tile, m.u, m.v, m.orient, m.species}; }
+// Which pathways of a surface-surface class can be placed: every new surface product finds a tile a consumed reactant
+// frees (find_surf_product_positions :1993-2288 without its search for vacant neighbour tiles), and the reference's
+// assignment loop terminates (it hands out min(products, freed tiles) tiles to surface products only, :2155-2191)
+static const char* surfsurf_pathway_problem(const World& w, const mcx_pathway& pw) {
+  const int keep0 = pw.keep_reactant_mask & 1, keep1 = (pw.keep_reactant_mask >> 1) & 1;
+  int needed = 0;
+  for (uint32_t k = 0; k < pw.n_products; k++) needed += w.is_surf(pw.products[k]) ? 1 : 0;
+  const int freed = (keep0 ? 0 : 1) + (keep1 ? 0 : 1), actual = (int)pw.n_products + keep0 + keep1;
+  if (needed > freed) return "a surface-surface pathway with more new surface products than consumed reactants needs vacant neighbour tiles (find_surf_product_positions' general branch is not built)";
+  const int to_recycle = std::min(actual, freed);
+  if (needed != 0 && !(needed == 1 && to_recycle == 1) && needed < to_recycle)
+    return "a surface-surface pathway that frees more tiles than it has surface products, next to a volume product: the reference's tile assignment (diffuse_react_event.cpp:2155-2191) does not terminate";
+  return nullptr;
+}
+// find_surf_product_positions (:1993-2288) over recycled tiles: bit 8 + k = product k takes the second freed tile (freed
+// tiles in the order of the rule's reactants).  Draws from the stream like the reference (rng_uint % players, :2161)
+template <class RS>
+static uint32_t surfsurf_position_bits(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw, bool init_is_r0, RS& rs) {
+  const int keep0 = pw.keep_reactant_mask & 1, keep1 = (pw.keep_reactant_mask >> 1) & 1;
+  int needed = 0; uint32_t first_surf = MCX_NONE;
+  for (uint32_t k = 0; k < pw.n_products; k++) if (w.is_surf(pw.products[k])) { needed++; if (first_surf == MCX_NONE) first_surf = k; }
+  if (needed == 0) return 0;
+  const int freed = (keep0 ? 0 : 1) + (keep1 ? 0 : 1), actual = (int)pw.n_products + keep0 + keep1;
+  const int to_recycle = std::min(actual, freed);
+  if (needed == 1 && to_recycle == 1) {  // :2140-2154: the initiator's tile when it is consumed, else the one freed tile
+    const int ri = init_is_r0 ? 0 : 1;
+    const bool init_consumed = ri == 0 ? !keep0 : !keep1;
+    const int idx = (init_consumed && ri == 1 && !keep0) ? 1 : 0;
+    return idx ? (1u << (8 + first_surf)) : 0u;
+  }
+  uint32_t bits = 0, assigned = 0;
+  int next_available = 0;
+  const uint32_t num_players = (uint32_t)actual + 2;
+  int guard = 0;
+  while (next_available < to_recycle && ++guard < 100000) {  // :2159-2191
+    const uint32_t rnd = rs.next() % num_players;
+    if (rnd < 2) continue;
+    const uint32_t k = rnd - 2;
+    if (k >= pw.n_products || !w.is_surf(pw.products[k])) continue;
+    if ((assigned >> k) & 1u) continue;
+    assigned |= 1u << k;
+    if (next_available == 1) bits |= 1u << (8 + k);
+    next_available++;
+  }
+  return bits;
+}
+// the factor of :2640-2652: a product's rule orientation flips once for every surface reactant that lies the other way
+// round than the rule states
+static inline int surfsurf_match(const mcx_rxn_class& c, const SurfSite& r0, const SurfSite& r1) {
+  int m = 1;
+  if (c.reactant_orientation[0] != 0 && r0.orient != c.reactant_orientation[0]) m = -m;
+  if (c.reactant_orientation[1] != 0 && r1.orient != c.reactant_orientation[1]) m = -m;
+  return m;
+}
+// product-side orientation of kept reactant r of a surface-surface pathway (:2618-2652, 2689-2716); 0: the table does not say
+static inline int surfsurf_kept_orientation(const mcx_rxn_class& c, const mcx_pathway& pw, int r, uint32_t bits, const SurfSite& r0,
+                                            const SurfSite& r1) {
+  if (!(pw.kept_info & MCX_KEPT_VALID)) return 0;
+  const int o = kept_code(pw, r);
+  if (o == 0) return ((bits >> (4 + r)) & 1u) ? 1 : -1;
+  return o * surfsurf_match(c, r0, r1);
+}
+// The products of the pathway: surface products on the freed tiles at the uv of the reactant that left (REACA_UV /
+// REACB_UV, :2826-2846); volume products at the position of the rule's first reactant (collision without a position,
+// :2745-2750), bumped off the INITIATOR's wall to the side their orientation names and remembered with its tile (:2757-2762)
+static void surfsurf_products(World& w, const mcx_rxn_class& c, const mcx_pathway& pw, const SurfSite& init, const SurfSite& partner,
+                              uint32_t bits, std::vector<ProductSpec>& out) {
+  const bool init_is_r0 = init.species == c.reactants[0];
+  const SurfSite& r0 = init_is_r0 ? init : partner;
+  const SurfSite& r1 = init_is_r0 ? partner : init;
+  const SurfSite* freed[2]; int n_freed = 0;
+  if (!(pw.keep_reactant_mask & 1u)) freed[n_freed++] = &r0;
+  if (!(pw.keep_reactant_mask & 2u)) freed[n_freed++] = &r1;
+  const int match = surfsurf_match(c, r0, r1);
+  for (uint32_t k = 0; k < pw.n_products; k++) {
+    ProductSpec ps;
+    ps.species = pw.products[k];
+    int o = pw.product_orientation[k];
+    if (o == 0) o = ((bits >> k) & 1u) ? 1 : -1; else o *= match;
+    if (w.is_surf(ps.species)) {
+      const int which = std::min((int)((bits >> (8 + k)) & 1u), n_freed - 1);
+      const SurfSite& t = *freed[which < 0 ? 0 : which];
+      ps.wall = t.wall; ps.tile = t.tile; ps.u = t.u; ps.v = t.v; ps.orient = o;
+      ps.pos = uv2xyz(w, w.walls[t.wall], t.u, t.v);
+      ps.cvi = 0;
+    } else {
+      const Wall& f = w.walls[init.wall];
+      ps.cvi = o > 0 ? f.cv_front : f.cv_back;
+      if (cv_uses_xor(w, init.wall)) ps.cvi_pending = true;
+      const double bump = (o > 0) ? 16 * POS_EPS : -16 * POS_EPS;
+      const V3 from = uv2xyz(w, w.walls[r0.wall], r0.u, r0.v);
+      ps.pos = from + V3{(2 * bump) * f.normal.x, (2 * bump) * f.normal.y, (2 * bump) * f.normal.z};
+      ps.created_wall = init.wall; ps.created_tile = init.tile;
+    }
+    out.push_back(ps);
+  }
 }
 
 // Volume product k of a reaction with a reactive surface (outcome_products_random :2739-2806 with a wall collision): at the
@@ -1261,14 +1376,16 @@ struct Eval {
                                same, (int)wl.size(), tri.data(), plane.data(), skip.data());
   }
 
-  // RxnUtils::test_bimolecular, rxn_utils.inl:336-414 (local_prob_factor == 0)
-  int test_bimolecular(const mcx_rxn_class& rc, double scaling) {
+  // RxnUtils::test_bimolecular, rxn_utils.inl:336-414; local_prob_factor > 0 only between two surface molecules
+  int test_bimolecular(const mcx_rxn_class& rc, double scaling, double local_prob_factor = 0) {
     double max_fixed_p = rc.max_fixed_p, prob;
+    if (local_prob_factor != 0) max_fixed_p = rc.max_fixed_p * local_prob_factor;
     if (max_fixed_p < scaling) {
       prob = rs.dbl() * scaling;
       if (prob >= max_fixed_p) return -1;
     } else {
       float max_p = (float)rc.max_fixed_p;  // sic: float in the reference (rxn_utils.inl:369)
+      if (local_prob_factor > 0) max_p *= local_prob_factor;
       if (max_p >= scaling) {
         prob = rs.dbl() * max_p;  // skipped-reaction accounting omitted (stats only)
       } else {
@@ -1276,7 +1393,32 @@ struct Eval {
         if (prob >= max_p) return -1;
       }
     }
-    return pathway_for_probability(w, rc, prob);
+    return pathway_for_probability(w, rc, prob, local_prob_factor > 0 ? local_prob_factor : 1);
+  }
+  // RxnUtils::test_many_bimolecular with all_neighbors_flag (rxn_utils.inl:475-580): which of the n matching classes
+  // reacts (-1: none); pathway = chosen_pathway_index
+  int test_many_bimolecular(const std::vector<int>& rcs, const std::vector<double>& scaling, double local_prob_factor, int& pathway) {
+    const int n = (int)rcs.size();
+    if (n == 1) { pathway = test_bimolecular(w.classes[rcs[0]], scaling[0], local_prob_factor); return pathway; }  // sic: returns the pathway
+    std::vector<double> cum(2 * n, 0.0);  // sic: twice as long, the binary search below runs over the padded array
+    cum[0] = w.classes[rcs[0]].max_fixed_p * local_prob_factor / scaling[0];
+    for (int i = 1; i < n; i++) cum[i] = cum[i - 1] + w.classes[rcs[i]].max_fixed_p * local_prob_factor / scaling[i];
+    double prob;
+    if (cum[n - 1] > 1.0) prob = rs.dbl() * cum[n - 1];  // skipped-reaction accounting omitted (stats only)
+    else {
+      prob = rs.dbl();
+      if (prob > cum[n - 1]) return -1;
+    }
+    int min_idx = 0, max_idx = 2 * n - 1;  // binary_search_double(cum, prob, cum.size() - 1, 1), rxn_utils.inl:301-320
+    while (max_idx - min_idx > 1) {
+      const int mid = (max_idx + min_idx) / 2;
+      if (prob > cum[mid]) min_idx = mid; else max_idx = mid;
+    }
+    const int rxn_index = prob > cum[min_idx] ? max_idx : min_idx;
+    if (rxn_index > 0) prob = prob - cum[rxn_index - 1];
+    prob = prob * scaling[rxn_index];
+    pathway = pathway_for_probability(w, w.classes[rcs[rxn_index]], prob, local_prob_factor);
+    return rxn_index;
   }
 
   // RxnUtils::test_intersect, rxn_utils.inl:593-626 (a Standard reaction with a reactive surface): pathway or -1
@@ -1332,6 +1474,7 @@ struct Eval {
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
                             uint32_t orient_bits, bool& a_destroyed, bool* flip = nullptr, int coll_side = 0);
 static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed);
+static void seq_apply_surfsurf(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, double t, uint32_t bits, bool& a_destroyed);
 static void seq_apply_wallrxn(World& w, uint32_t index, int rc, int pathway, V3 pos, double t, uint32_t orient_bits, uint32_t wall,
                               uint32_t cvi, bool& destroyed, int coll_side);
 static void seq_set_defunct(World& w, Mol& m);
@@ -1398,7 +1541,11 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
 
   bool destroyed = false;
   bool surf_tile_changed = false;
-  if ((sp.flags & MCX_SP_CAN_DIFFUSE) && s.wall != MCX_NONE) {
+  // SPECIES_FLAG_CAN_SURFSURF: diffuse_surf_molecule runs for such a molecule even when it cannot diffuse (:274-283)
+  const bool can_ss = s.wall != MCX_NONE && w.can_surf_surf[m_species];
+  const bool surf_diffusible = (sp.flags & MCX_SP_CAN_DIFFUSE) != 0;
+  bool ss_fired = false;   // SNAPSHOT: a surface-surface reaction ended the evaluation (the outcome is completed at the end)
+  if (s.wall != MCX_NONE && (surf_diffusible || can_ss)) {
     // ---- diffuse_surf_molecule (:1071-1246)
     double t_steps = sp.time_step > max_time ? max_time : sp.time_step;
     double steps;
@@ -1416,7 +1563,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
       }
       return true;
     };
-    for (int find_new_position = 11; find_new_position > 0; find_new_position--) {  // SURFACE_DIFFUSION_RETRIES + 1
+    for (int find_new_position = surf_diffusible ? 11 : 0; find_new_position > 0; find_new_position--) {  // SURFACE_DIFFUSION_RETRIES + 1
       double du, dv;
       pick_surf_displacement(E.rs, space_factor, du, dv);
       double nu, nv;
@@ -1461,16 +1608,66 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
       s.subpart = w.subpart_index(s.pos);
       break;
     }
-    // MCell3 compatibility rule at the end of diffuse_surf_molecule (:1226-1236)
-    if (s.wall != original_wall && s.unimol_time >= t_end) {
-      s.unimol_time = TIME_INVALID;
-      s.flags |= MCX_MOL_SCHEDULE_UNIMOL;
-    }
-    max_time = t_steps;
     if (apply) {
       Mol& mm = w.mols[index];
       mm.wall = s.wall; mm.tile = s.tile; mm.u = s.u; mm.v = s.v; mm.pos = s.pos;
     }
+    // ---- react_2D_all_neighbors (:1250-1393): after its move the molecule tests the molecules on the tiles around its own
+    if (can_ss && !(sp.flags & MCX_SP_CANT_INITIATE) && !(E.snapshot && E.no_partners)) {
+      TileNeighbors nbt;
+      find_neighbor_tiles(w, s.wall, s.tile, nbt);
+      std::vector<int> m_rc; std::vector<double> m_factor; std::vector<uint32_t> m_index;
+      const size_t ns = w.species.size();
+      for (const WallTile& nt : nbt) {
+        const uint32_t nid = w.tiles[nt.first][nt.second];  // Grid::get_molecule_on_tile; the list only holds walls with a grid
+        if (nid == MCX_NONE || nid == m_id) continue;        // SNAPSHOT: the tile table still shows the mover on its old tile
+        const uint32_t j = w.id_to_index[nid];
+        if (E.snapshot && (*E.dead)[j]) continue;
+        const Mol& nsm = w.mols[j];
+        const int rc = w.surfsurf[m_species * ns + nsm.species];
+        // trigger_bimolecular_orientation_from_mols (rxn_utils.inl:58-97)
+        if (rc < 0 || !orientations_match(w.classes[rc], w.mols[index].orient, nsm.orient)) continue;
+        m_rc.push_back(rc); m_factor.push_back(t_steps / w.grids[nt.first].binding_factor); m_index.push_back(j);
+      }
+      if (!nbt.empty() && !m_rc.empty()) {
+        const double local_prob_factor = 3.0 / nbt.size();
+        int which, pathway;
+        if (m_rc.size() == 1) { pathway = E.test_bimolecular(w.classes[m_rc[0]], m_factor[0], local_prob_factor); which = 0; }
+        else {
+          which = E.test_many_bimolecular(m_rc, m_factor, local_prob_factor, pathway);
+          pathway = 0;  // sic (TODO_PATHWAYS, :1367): the first pathway of the chosen class
+        }
+        if (tr) for (uint32_t j : m_index) { if (tr->n_collisions < MCX_TRACE_K) tr->partner[tr->n_collisions] = w.mols[j].id; tr->n_collisions++; }
+        if (which >= 0 && pathway >= 0) {
+          const int rc = m_rc[which];
+          const uint32_t j = m_index[which];
+          const mcx_rxn_class& cl = w.classes[rc];
+          const mcx_pathway& pw = w.pathways[cl.first_pathway + pathway];
+          // random draws in the reference's order: tile assignment (find_surf_product_positions), then orientations
+          uint32_t bits = surfsurf_position_bits(w, cl, pw, m_species == cl.reactants[0], E.rs);
+          bits |= draw_orientation_bits(pw, E.rs);
+          const double t_rxn = s.t_now;  // collision_time = diffusion_start_time (:1343)
+          E.ev(EV_SURFSURF | (uint32_t)pathway, (uint32_t)rc);
+          E.ev(EV_RXN | (bits & 0xFFFFu), w.mols[j].id);
+          if (tr) { tr->rxn_class = rc; tr->rxn_pathway = pathway; tr->rxn_partner = w.mols[j].id; tr->t_event = t_rxn; }
+          if (!apply) {
+            out.rxn_class = rc; out.pathway = pathway; out.partner_index = j; out.partner_id = w.mols[j].id;
+            out.t_event = t_rxn; out.orient_bits = bits; out.surf_moved = surf_tile_changed;
+            ss_fired = true;
+          } else {
+            bool a_destroyed = false;
+            seq_apply_surfsurf(w, index, j, rc, pathway, t_rxn, bits, a_destroyed);
+            if (a_destroyed) { out.kind = MCX_OUT_REACTED; out.pos = s.pos; out.t_event = t_rxn; return out; }
+          }
+        }
+      }
+    }
+    // MCell3 compatibility rule at the end of diffuse_surf_molecule (:1222-1236)
+    if ((!surf_diffusible || s.wall != original_wall) && s.unimol_time >= t_end) {
+      s.unimol_time = TIME_INVALID;
+      s.flags |= MCX_MOL_SCHEDULE_UNIMOL;
+    }
+    max_time = t_steps;
   } else if (sp.flags & MCX_SP_CAN_DIFFUSE) {
     // ---- diffuse_vol_molecule (:367-618)
     V3 remaining; double r_rate_factor, t_steps;
@@ -1669,7 +1866,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
   if (destroyed) return out;
 
   // -- reschedule (diffuse_single_molecule :283-336)
-  if (sp.flags & MCX_SP_CAN_DIFFUSE) {
+  if ((sp.flags & MCX_SP_CAN_DIFFUSE) || can_ss) {
     s.t_now += max_time;
     if ((s.unimol_time != TIME_INVALID && s.unimol_time < t_end) || cmp_lt(s.t_now, t_end, EPS)) again = true;
     else {
@@ -1682,8 +1879,16 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
       if (s.unimol_time < t_end) again = true;
     } else s.t_now = TIME_FOREVER;
   }
-  out.kind = (sp.flags & MCX_SP_CAN_DIFFUSE) ? MCX_OUT_MOVED : MCX_OUT_STATIC;
+  out.kind = ((sp.flags & MCX_SP_CAN_DIFFUSE) || can_ss) ? MCX_OUT_MOVED : MCX_OUT_STATIC;
   out.pos = s.pos; fill_event(out);
+  if (ss_fired) {
+    // SNAPSHOT: the surface-surface reaction is a claiming event (the initiator, the partner it consumes, the tile it moved
+    // to); a kept initiator has used up its step like any other mover and takes what is left of the iteration lazily
+    out.kind = MCX_OUT_REACTED;
+    out.flags = again ? (out.flags | MCX_MOL_PARTIAL) : (out.flags & ~MCX_MOL_PARTIAL);
+    again = false;
+    return out;
+  }
   if (surf_tile_changed && !apply) {
     // SNAPSHOT: taking a new tile is a claiming event; the evaluation ends here and what is left of the iteration
     // is taken lazily next iteration (like a kept initiator)
@@ -1810,6 +2015,34 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
   if (!keep) seq_set_defunct(w, w.mols[index]);
   destroyed = !keep;
   if (surf_rxn && keep) { const int o = kept_orientation(c, pw, 0, orient_bits, surf_copy.orient); if (o != 0) w.mols[index].orient = o; }
+}
+
+// outcome_bimolecular (:1833-1895) -> outcome_products_random for two surface molecules
+static void seq_apply_surfsurf(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, double t, uint32_t bits, bool& a_destroyed) {
+  const mcx_rxn_class& c = w.classes[rc];
+  const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
+  w.rxn_count[pw.rxn_rule_id]++;
+  count_rxn_where(w, pw.rxn_rule_id, w.mols[a_index], 0);
+  w.stats.bimol_rxns++;
+  const SurfSite init = site_of(w.mols[a_index]), partner = site_of(w.mols[b_index]);
+  const bool a_is_r0 = init.species == c.reactants[0];
+  const bool keepA = (pw.keep_reactant_mask >> (a_is_r0 ? 0 : 1)) & 1, keepB = (pw.keep_reactant_mask >> (a_is_r0 ? 1 : 0)) & 1;
+  // tiles that are going to be reused are freed first (:2606-2615)
+  if (!keepA) w.tiles[init.wall][init.tile] = MCX_NONE;
+  if (!keepB) w.tiles[partner.wall][partner.tile] = MCX_NONE;
+  std::vector<ProductSpec> prods;
+  surfsurf_products(w, c, pw, init, partner, bits, prods);
+  for (const ProductSpec& ps : prods) {
+    uint32_t nid = seq_add_molecule(w, ps, t);
+    if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
+  }
+  // kept reactants take their product-side orientation (:2689-2716)
+  const SurfSite& r0 = a_is_r0 ? init : partner; const SurfSite& r1 = a_is_r0 ? partner : init;
+  if (keepA) { const int o = surfsurf_kept_orientation(c, pw, a_is_r0 ? 0 : 1, bits, r0, r1); if (o != 0) w.mols[a_index].orient = o; }
+  if (keepB) { const int o = surfsurf_kept_orientation(c, pw, a_is_r0 ? 1 : 0, bits, r0, r1); if (o != 0) w.mols[b_index].orient = o; }
+  if (!keepA) seq_set_defunct(w, w.mols[a_index]);
+  if (!keepB) seq_set_defunct(w, w.mols[b_index]);
+  a_destroyed = !keepA;
 }
 
 // outcome_intersect (:1916-1988) of a Standard reaction with a reactive surface; the surface is always kept
@@ -1939,6 +2172,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
   std::vector<uint32_t> pending;
   struct NewMol { ProductSpec ps; double t; uint32_t id; };
   std::vector<NewMol> born;
+  std::vector<std::pair<uint32_t, int>> orient_updates;  // kept initiators of surface-surface reactions: (index, new orientation)
 
   auto eval_one = [&](uint32_t i, bool forced) {
     const Mol& m = w.mols[i];
@@ -1975,7 +2209,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     uint32_t prio = w.mols[i].id;
     claim[i] = std::min(claim[i], prio);
     if (partner_consumed(i)) { uint32_t j = outs[i].partner_index; claim[j] = std::min(claim[j], prio); }
-    if (outs[i].kind == MCX_OUT_SURFMOVE) {
+    if (outs[i].kind == MCX_OUT_SURFMOVE || (outs[i].kind == MCX_OUT_REACTED && outs[i].surf_moved)) {
       uint32_t gt = gtile_of(outs[i]);
       auto it = tile_claim.find(gt);
       if (it == tile_claim.end()) tile_claim[gt] = prio; else it->second = std::min(it->second, prio);
@@ -2021,6 +2255,33 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     const mcx_rxn_class& c = w.classes[o.rxn_class];
     const mcx_pathway& pw = w.pathways[c.first_pathway + o.pathway];
     w.rxn_count[pw.rxn_rule_id]++;
+    if (o.kind == MCX_OUT_REACTED && c.kind == MCX_RXN_BIMOL_SURFSURF) {
+      // surface-surface reaction (react_2D_all_neighbors -> outcome_bimolecular): counted on the wall the initiator moved to
+      if (w.n_rs) w.rxn_count_rs[pw.rxn_rule_id * w.n_rs + w.wall_rs[o.wall]]++;
+      w.stats.bimol_rxns++;
+      const uint32_t j = o.partner_index;
+      const SurfSite init{o.wall, o.tile, o.u, o.v, m.orient, m.species}, partner = site_of(w.mols[j]);
+      const bool a_is_r0 = m.species == c.reactants[0];
+      const bool keepA = (pw.keep_reactant_mask >> (a_is_r0 ? 0 : 1)) & 1, keepB = (pw.keep_reactant_mask >> (a_is_r0 ? 1 : 0)) & 1;
+      uint32_t reuse[2]; int n_reuse = 0;
+      if (!keepA) { dead[i] = 1; w.species_count[m.species]--; reuse[n_reuse++] = m.id; }
+      if (!keepB) { dead[j] = 1; w.species_count[w.mols[j].species]--; reuse[n_reuse++] = w.mols[j].id; }
+      std::vector<ProductSpec> prods;
+      surfsurf_products(w, c, pw, init, partner, o.orient_bits, prods);
+      for (uint32_t k = 0; k < prods.size(); k++) {
+        NewMol nm; nm.ps = prods[k]; nm.t = o.t_event; nm.id = (int)k < n_reuse ? reuse[k] : MCX_NONE;
+        born.push_back(nm);
+        w.species_count[nm.ps.species]++;
+        w.stats.products++;
+      }
+      if (keepA) {  // stays on the tile it moved to, its step used up; takes its product-side orientation (:2706-2709)
+        o.kind = MCX_OUT_MOVED;
+        const SurfSite& r0 = a_is_r0 ? init : partner; const SurfSite& r1 = a_is_r0 ? partner : init;
+        const int ko = surfsurf_kept_orientation(c, pw, a_is_r0 ? 0 : 1, o.orient_bits, r0, r1);
+        if (ko != 0) orient_updates.push_back({i, ko});  // visible from the next snapshot on, like its new tile
+      }
+      return;
+    }
     count_rxn_where(w, pw.rxn_rule_id, m, o.cvi);
     bool keepA, keepB = true;
     uint32_t reuse[2]; int n_reuse = 0;
@@ -2091,7 +2352,8 @@ static void step_snapshot(World& w, const SnapStreams& st) {
       uint32_t prio = w.mols[i].id;
       bool ok = claim[i] == prio;
       if (ok && partner_consumed(i)) ok = claim[outs[i].partner_index] == prio;
-      if (ok && outs[i].kind == MCX_OUT_SURFMOVE) ok = tile_claim[gtile_of(outs[i])] == prio;
+      if (ok && (outs[i].kind == MCX_OUT_SURFMOVE || (outs[i].kind == MCX_OUT_REACTED && outs[i].surf_moved)))
+        ok = tile_claim[gtile_of(outs[i])] == prio;
       (ok ? accepted : still).push_back(i);
     }
     // tiles claimed in this round stay unavailable for the movers of later rounds, whoever won them
@@ -2117,6 +2379,7 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     }
     // claims of re-evaluated molecules compete only among themselves and with accepted ones (consumed)
   }
+  for (auto& u : orient_updates) w.mols[u.first].orient = u.second;
   // finalize survivors
   for (uint32_t i = 0; i < n0; i++) {
     if (dead[i]) {
@@ -2219,7 +2482,12 @@ int orc_set_species(void* h, const mcx_species* s, uint32_t n) {
   World& w = *(World*)h; w.species.assign(s, s + n); build_lookups(w); return 0;
 }
 int orc_set_reactions(void* h, const mcx_rxn_class* c, uint32_t nc, const mcx_pathway* p, uint32_t np) {
-  World& w = *(World*)h; w.classes.assign(c, c + nc); w.pathways.assign(p, p + np); build_lookups(w); return 0;
+  World& w = *(World*)h; w.classes.assign(c, c + nc); w.pathways.assign(p, p + np); build_lookups(w);
+  for (const mcx_rxn_class& rc : w.classes)
+    if (rc.kind == MCX_RXN_BIMOL_SURFSURF)
+      for (uint32_t q = 0; q < rc.n_pathways; q++)
+        if (const char* why = surfsurf_pathway_problem(w, w.pathways[rc.first_pathway + q])) { w.err = why; return -1; }
+  return 0;
 }
 int orc_set_surface_classes(void* h, const mcx_surf_class_rxn* r, uint32_t n) {
   World& w = *(World*)h; w.surf_rules.assign(r, r + n); return 0;

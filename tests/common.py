@@ -245,6 +245,41 @@ def diffusing_receptors(n_rec=3000, n_lig=8000, radius_um=0.25, subdivisions=3, 
     return t, MolArrays.concat([vol, surf])
 
 
+def surface_reactions(n_a=1500, n_b=1500, n_e=300, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8, D_surf=2e-7,
+                      rng_mode=abi.MCX_RNG_PHILOX, p=0.3, k_off=2e5, static_b=False, max_molecules=None):
+    """Surface-surface reactions (react_2D_all_neighbors): A' + B' -> C' (both consumed, C on the initiator's
+    tile), C' -> A' + V' would need a second tile and is not part of it: C' -> A' keeps ids deterministic; A' + E' -> D' + E'
+    (catalytic: E kept), D' + D' -> A' + B' (same species, two surface products over the two freed tiles: the random tile
+    assignment), B' + E, -> V, (orientation classes that never match the release: E is released up).  static_b: B cannot
+    diffuse but still initiates reactions (SPECIES_FLAG_CAN_SURFSURF molecules are diffused every step)."""
+    m = Model(Config(seed=seed))
+    A = m.add_species("A", D_surf, surface=True)
+    B = m.add_species("B", 0.0 if static_b else D_surf * 0.5, surface=True)
+    Cc = m.add_species("C", D_surf * 0.5, surface=True)
+    D = m.add_species("D", D_surf, surface=True)
+    E = m.add_species("E", D_surf * 0.25, surface=True)
+    V = m.add_species("V", 1e-6)
+    pb = m.config.time_step * m.config.surface_grid_density / 6.0
+    m.add_reaction_rule(["A'", "B'"], ["C'"], p / pb)
+    m.add_reaction_rule(["C'"], ["A'"], k_off)
+    m.add_reaction_rule(["A'", "E'"], ["D'", "E'"], 0.5 * p / pb)
+    m.add_reaction_rule(["D'", "D'"], ["A'", "B'"], 2 * p / pb)
+    m.add_reaction_rule(["B'", "E,"], ["V,"], p / pb)
+    sv, sf = create_icosphere(radius_um, subdivisions)
+    m.add_geometry_object(sv, sf)
+    bv, bf = create_box(box_um)
+    m.add_geometry_object(bv, bf)
+    n = n_a + n_b + n_e
+    t = m.build(max_molecules=max_molecules or 2 * n + 64, rng_mode=rng_mode)
+    rng = np.random.default_rng(seed)
+    walls = np.arange(len(sf), dtype=np.uint32)
+    # one draw of distinct tiles for all three species (release_on_walls keeps the tiles of one call distinct)
+    allm = release_on_walls(rng, t, walls, n, A, orientation=1, first_id=0)
+    allm.species[n_a:n_a + n_b] = B
+    allm.species[n_a + n_b:] = E
+    return t, allm
+
+
 def counted_spheres(n=12000, seed=1, box_um=0.8, rng_mode=abi.MCX_RNG_PHILOX, p_target=0.4, max_molecules=None):
     """Counted volumes: two nested transparent icospheres, both counted, inside a counted
     reflective box; A + B -> C everywhere.  Volumes: {box}, {box, outer}, {box, outer, inner} (+ the empty set)."""
