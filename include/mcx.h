@@ -477,6 +477,14 @@ uint32_t mcx_grid_num_tiles(const double* v9);
 uint64_t mcx_walls_per_subpart(const double* origin3, double partition_edge_length, uint32_t n_subparts_per_edge,
                                double rxn_radius_3d, uint32_t use_expanded_list, const double* vertices, uint64_t n_vertices,
                                const uint32_t* tri, uint64_t n_walls, uint32_t* start_out, uint32_t* list_out, uint64_t cap);
+/* The neighbour tiles of every tile of every wall, built exactly as the device table of the surface-surface partner search
+ * is (host only): CSR over all tiles in wall order (tile_start of a wall = sum of the tiles of the walls before it),
+ * start_out[total tiles + 1], (wall, tile) pairs in list_out (up to cap pairs) in the order the reference walks its list;
+ * returns the number of pairs.  Every wall is taken to have a grid; at run time the entries of walls without one are
+ * skipped.  Replaces GridUtils::find_neighbor_tiles and everything under it (src4/grid_utils.inl:296-1801), which the
+ * reference runs per molecule and step from react_2D_all_neighbors (src4/diffuse_react_event.cpp:1267). */
+uint64_t mcx_tile_neighbor_table(const double* vertices, uint64_t n_vertices, const uint32_t* tri, uint64_t n_walls,
+                                 const uint32_t* wall_object, uint32_t* start_out, uint32_t* list_out, uint64_t cap);
 /* Centre of a tile in the wall's uv frame (GridUtils::grid2uv, src4/grid_utils.inl:233-253). */
 void mcx_grid2uv(const double* v9, uint32_t tile, double* uv2);
 /* Tile under a point of the wall (GridUtils::xyz2grid_tile_index, src4/grid_utils.inl:48-118). */

@@ -52,6 +52,11 @@ struct mcx_handle {
   void *d_wall_rs = nullptr, *d_rxn_count_rs = nullptr, *d_mol_count_rs = nullptr; uint32_t n_rs = 0;
   uint64_t n_walls_host = 0;
   bool has_surf = false, surf_allocated = false;
+  // surface-surface reactions: host copy of the mesh (the neighbour-tile table is built when a table with such classes and
+  // a geometry are both there) and the device tables
+  bool has_surfsurf = false;
+  std::vector<double> geom_verts; std::vector<uint32_t> geom_tri, geom_wall_object;
+  void *d_surfsurf = nullptr, *d_tn_start = nullptr, *d_tn_list = nullptr, *d_wall_has_grid = nullptr;
   uint32_t *st_wall = nullptr, *st_tile = nullptr; int32_t* st_orient = nullptr; double *st_u = nullptr, *st_v = nullptr;
   McxComm* comm = nullptr;
   int ncz_global = 0;
@@ -115,6 +120,19 @@ uint64_t mcx_walls_per_subpart(const double* origin3, double partition_edge_leng
   for (size_t i = 0; i < start.size(); i++) start_out[i] = start[i];
   for (size_t i = 0; i < list.size() && i < cap; i++) list_out[i] = list[i];
   return list.size();
+}
+
+uint64_t mcx_tile_neighbor_table(const double* vertices, uint64_t n_vertices, const uint32_t* tri, uint64_t n_walls,
+                                 const uint32_t* wall_object, uint32_t* start_out, uint32_t* list_out, uint64_t cap) {
+  std::vector<DevWall> walls; std::vector<DevGrid> grids; std::vector<DevEdge> edges;
+  mcxg::wall_constants(vertices, tri, n_walls, walls);
+  const uint64_t n_tiles = mcxg::grid_constants(vertices, tri, walls, grids);
+  mcxg::edge_constants(vertices, tri, walls, wall_object, edges);
+  std::vector<uint32_t> start, list;
+  mcxg::tile_neighbor_table(vertices, n_vertices, tri, walls, grids, edges, start, list);
+  for (uint64_t i = 0; i <= n_tiles; i++) start_out[i] = start[i];
+  for (size_t i = 0; i < list.size() && i < 2 * cap; i++) list_out[i] = list[i];
+  return list.size() / 2;
 }
 
 const char* mcx_last_error(const mcx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -267,6 +285,8 @@ void mcx_destroy(mcx_handle* h) {
   delete h;
 }
 
+static int build_tile_neighbors(mcx_handle* h);
+
 int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices, const uint32_t* tri, uint64_t n_walls,
                      const uint32_t* wall_surf_class, const uint32_t* wall_object) {
   if (!h) return MCX_ERR_INVALID_ARG;
@@ -359,15 +379,47 @@ int mcx_set_geometry(mcx_handle* h, const double* vertices, uint64_t n_vertices,
   if (h->p.wall_rs && h->n_walls_host != n_walls) { h->p.wall_rs = nullptr; h->p.n_rs = 0; h->n_rs = 0; }  // likewise
   h->n_walls_host = n_walls;
   h->has_geometry = true;
+  h->geom_verts.assign(vertices, vertices + 3 * n_vertices);
+  h->geom_tri.assign(tri, tri + 3 * n_walls);
+  h->geom_wall_object.clear();
+  if (wall_object) h->geom_wall_object.assign(wall_object, wall_object + n_walls);
+  {
+    // Wall::has_initialized_grid per wall (a wall gets its grid with its first surface molecule): set by the scatter
+    std::vector<uint8_t> none(std::max<uint64_t>(n_walls, 1), 0);
+    if (dev_replace(h, &h->d_wall_has_grid, none.data(), none.size())) return MCX_ERR_CUDA;
+    h->p.wall_has_grid = (uint8_t*)h->d_wall_has_grid;
+  }
+  { const int trc = build_tile_neighbors(h); if (trc != MCX_OK) return trc; }
   return MCX_OK;
 }
 
 // (re)build every table that depends on species x reactions x surface classes
+// neighbour tiles of every tile for react_2D_all_neighbors (mcx_geom.cpp: tile_neighbor_table), built once per geometry
+static int build_tile_neighbors(mcx_handle* h) {
+  h->p.tn_start = nullptr; h->p.tn_list = nullptr;
+  if (!h->has_surfsurf || !h->has_geometry || h->n_walls_host == 0) return MCX_OK;
+  const uint64_t n_walls = h->n_walls_host;
+  std::vector<DevWall> walls; std::vector<DevGrid> grids; std::vector<DevEdge> edges;
+  mcxg::wall_constants(h->geom_verts.data(), h->geom_tri.data(), n_walls, walls);
+  mcxg::grid_constants(h->geom_verts.data(), h->geom_tri.data(), walls, grids);
+  mcxg::edge_constants(h->geom_verts.data(), h->geom_tri.data(), walls, h->geom_wall_object.empty() ? nullptr : h->geom_wall_object.data(), edges);
+  std::vector<uint32_t> start, list;
+  mcxg::tile_neighbor_table(h->geom_verts.data(), h->geom_verts.size() / 3, h->geom_tri.data(), walls, grids, edges, start, list);
+  if (list.empty()) list.assign(2, MCX_NONE);
+  int rc = MCX_OK;
+  rc |= dev_replace(h, &h->d_tn_start, start.data(), start.size());
+  rc |= dev_replace(h, &h->d_tn_list, list.data(), list.size());
+  if (rc) return MCX_ERR_CUDA;
+  h->p.tn_start = (const uint32_t*)h->d_tn_start; h->p.tn_list = (const uint2*)h->d_tn_list;
+  return MCX_OK;
+}
+
 static int rebuild_tables(mcx_handle* h) {
   const size_t ns = h->species.size();
   if (ns == 0) return MCX_OK;
   if (ns > MCX_MAX_COUNTED) { h->err = "more than 1024 species are not supported by the device counters"; return MCX_ERR_INVALID_ARG; }
-  std::vector<int> bimol(ns * ns, -1), unimol(ns, -1), volsurf(ns * ns, -1);
+  std::vector<int> bimol(ns * ns, -1), unimol(ns, -1), volsurf(ns * ns, -1), surfsurf(ns * ns, -1);
+  bool any_surfsurf = false;
   bool any_surf = false;
   for (size_t a = 0; a < ns; a++) any_surf = any_surf || !(h->species[a].flags & MCX_SP_VOL);
   if (h->classes.size() > 8191) { h->err = "more than 8191 reaction classes (proposal word)"; return MCX_ERR_INVALID_ARG; }
@@ -398,6 +450,31 @@ static int rebuild_tables(mcx_handle* h) {
       volsurf[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
       any_surf = true;
     } else if (rc.kind == MCX_RXN_UNIMOL) unimol[rc.reactants[0]] = (int)c;
+    else if (rc.kind == MCX_RXN_BIMOL_SURFSURF) {
+      // two surface molecules (react_2D_all_neighbors): surface products go to the tiles the consumed reactants free
+      if (is_vol(rc.reactants[0]) || is_vol(rc.reactants[1])) { h->err = "surf-surf class with a volume reactant"; return MCX_ERR_INVALID_ARG; }
+      if (h->p.wall_border) { h->err = "surface-surface classes together with region borders are not supported (restricted regions of the neighbour search)"; return MCX_ERR_INVALID_ARG; }
+      surfsurf[rc.reactants[0] * ns + rc.reactants[1]] = (int)c;
+      surfsurf[rc.reactants[1] * ns + rc.reactants[0]] = (int)c;
+      any_surf = any_surfsurf = true;
+      for (uint32_t q = 0; q < rc.n_pathways; q++) {
+        const mcx_pathway& pw = h->pathways[rc.first_pathway + q];
+        const int keep0 = pw.keep_reactant_mask & 1u, keep1 = (pw.keep_reactant_mask >> 1) & 1u;
+        int needed = 0;
+        for (uint32_t k = 0; k < pw.n_products && k < MCX_MAX_PRODUCTS; k++) needed += (pw.products[k] < ns && !is_vol(pw.products[k])) ? 1 : 0;
+        const int freed = 2 - keep0 - keep1, actual = (int)pw.n_products + keep0 + keep1;
+        if (needed > freed) {
+          h->err = "a surface-surface pathway with more new surface products than consumed reactants needs vacant neighbour tiles (not supported)";
+          return MCX_ERR_INVALID_ARG;
+        }
+        const int to_recycle = std::min(actual, freed);
+        if (needed != 0 && !(needed == 1 && to_recycle == 1) && needed < to_recycle) {
+          h->err = "a surface-surface pathway that frees more tiles than it has surface products next to a volume product is not supported (the reference's tile assignment does not terminate)";
+          return MCX_ERR_INVALID_ARG;
+        }
+      }
+      continue;
+    }
     else if (rc.kind == MCX_RXN_BIMOL_VOLWALL) {
       any_surf = true;   // kept reactants and products remember the wall of their event: the cold surface arrays are needed
       for (uint32_t q = 0; q < rc.n_pathways; q++) {
@@ -455,8 +532,10 @@ static int rebuild_tables(mcx_handle* h) {
     for (size_t b = 0; b < ns; b++) any = any || bimol[a * ns + b] >= 0;
     bool vs = false;
     for (size_t b = 0; b < ns; b++) vs = vs || volsurf[a * ns + b] >= 0;
+    bool ss = false;   // SPECIES_FLAG_CAN_SURFSURF
+    for (size_t b = 0; b < ns; b++) ss = ss || surfsurf[a * ns + b] >= 0;
     ds[a] = DevSpecies{h->species[a].space_step, h->species[a].time_step, h->species[a].flags,
-                       (any && !(h->species[a].flags & MCX_SP_CANT_INITIATE)) ? 1u : 0u, vs ? 1u : 0u, 0u};
+                       (any && !(h->species[a].flags & MCX_SP_CANT_INITIATE)) ? 1u : 0u, vs ? 1u : 0u, ss ? 1u : 0u};
   }
   // surface-class action table; lookup order as in find_mol_reactions_with_surf_classes
   // (rxn_utils.inl:182-244): species-specific, ALL_MOLECULES, ALL_VOLUME_MOLECULES
@@ -531,9 +610,16 @@ static int rebuild_tables(mcx_handle* h) {
   rc |= dev_replace(h, &h->d_surf_rxn, act_rxn.data(), act_rxn.size());
   rc |= dev_replace(h, &h->d_surf_border, border.data(), border.size());
   rc |= dev_replace(h, &h->d_volsurf, volsurf.data(), volsurf.size());
+  rc |= dev_replace(h, &h->d_surfsurf, surfsurf.data(), surfsurf.size());
   if (rc) return MCX_ERR_CUDA;
   DevParams& p = h->p;
   p.volsurf = (const int*)h->d_volsurf;
+  p.surfsurf = any_surfsurf ? (const int*)h->d_surfsurf : nullptr;
+  if (any_surfsurf != h->has_surfsurf || (any_surfsurf && !p.tn_start)) {
+    h->has_surfsurf = any_surfsurf;
+    const int trc = build_tile_neighbors(h);
+    if (trc != MCX_OK) return trc;
+  }
   p.exd_skip = (const uint8_t*)h->d_exd_skip;
   h->has_surf = any_surf;
   p.species = (const DevSpecies*)h->d_species; p.bimol = (const int*)h->d_bimol; p.unimol = (const int*)h->d_unimol;
@@ -545,7 +631,7 @@ static int rebuild_tables(mcx_handle* h) {
   for (const mcx_rxn_class& rc : h->classes)
     for (uint32_t q = 0; q < rc.n_pathways; q++) {
       const mcx_pathway& pw = h->pathways[rc.first_pathway + q];
-      const uint32_t n_react = (rc.kind == MCX_RXN_UNIMOL || rc.kind == MCX_RXN_BIMOL_VOLWALL) ? 1u : 2u;
+      const uint32_t n_react = (rc.kind == MCX_RXN_UNIMOL || rc.kind == MCX_RXN_BIMOL_VOLWALL) ? 1u : 2u;  // surf-surf: 2
       const uint32_t kept = (uint32_t)__builtin_popcount(pw.keep_reactant_mask & ((1u << n_react) - 1u));
       if (pw.n_products > n_react - kept) h->plan.has_fresh = true;
     }
@@ -671,6 +757,7 @@ int mcx_set_region_borders(mcx_handle* h, const uint8_t* wall_edge_border) {
   if (!h->has_geometry) { h->err = "mcx_set_geometry must precede mcx_set_region_borders"; return MCX_ERR_STATE; }
   CK(cudaSetDevice(h->cfg.device));
   if (!wall_edge_border) { h->p.wall_border = nullptr; return MCX_OK; }
+  if (h->has_surfsurf) { h->err = "region borders together with surface-surface classes are not supported (restricted regions of the neighbour search)"; return MCX_ERR_INVALID_ARG; }
   if (dev_replace(h, &h->d_wall_border, wall_edge_border, std::max<uint64_t>(h->n_walls_host, 1))) return MCX_ERR_CUDA;
   h->p.wall_border = (const uint8_t*)h->d_wall_border;
   return MCX_OK;
@@ -813,6 +900,8 @@ int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
   // the run (the reference's MolOrRxnCountEvent reports reactions since t = 0, and ids of dead molecules must not
   // be handed out again); k_pack_soa raises next_id above every uploaded id
   mcx_launch_reset_population(h->p, (unsigned int)n, s);
+  // Wall::has_initialized_grid starts over with the uploaded population (the scatter marks the walls that hold molecules)
+  if (h->p.wall_has_grid && h->n_walls_host) CK(cudaMemsetAsync(h->p.wall_has_grid, 0, h->n_walls_host, s));
   bind_iteration(h);
   mcx_launch_pack_soa(h->p, h->st_x, h->st_y, h->st_z, h->st_id, h->st_sp, m->flags ? h->st_fl : nullptr,
                       m->diffusion_time ? h->st_ts : nullptr, m->unimol_rxn_time ? h->st_tu : nullptr, sv, (unsigned int)n, s);

@@ -161,7 +161,7 @@ struct Tracer {
 };
 enum { EV_WALL = 0x57000000u, EV_COLL = 0xC0000000u, EV_RXN = 0xAE000000u, EV_ABSORB = 0xAB000000u,
        EV_REDO = 0x4ED00000u, EV_UNIMOL = 0x11000000u, EV_TRANSP = 0x7A000000u, EV_SURFMOL = 0x5F000000u, EV_BLOCKED = 0xB10C0000u, EV_DISK = 0xD1500000u,
-       EV_SURFMOVE = 0x3E000000u, EV_WALLRXN = 0x9A000000u };
+       EV_SURFMOVE = 0x3E000000u, EV_WALLRXN = 0x9A000000u, EV_SURFSURF = 0x55000000u };
 
 struct LocalStats {
   unsigned int ray_polygon_tests, ray_polygon_colls, reflections, transparent, volvol_collisions, redos;
@@ -647,27 +647,34 @@ restart:
 }
 
 // test_bimolecular, rxn_utils.inl:336-414 (local_prob_factor == 0)
-__device__ int test_bimolecular(const DevParams& p, const DevClass& rc, double scaling, Stream& rs) {
+// RxnClass::get_pathway_index_for_probability: binary_search_double (rxn_utils.inl:301-320) over the cumulative pathway
+// probabilities times mult (the local probability factor between two surface molecules, else 1)
+__device__ __forceinline__ int pathway_for_probability(const DevParams& p, const DevClass& rc, double prob, double mult) {
+  int min_idx = 0, max_idx = (int)rc.n_pathways - 1;
+  const DevPathway* A = p.pathways + rc.first_pathway;
+  while (max_idx - min_idx > 1) {
+    int mid = (max_idx + min_idx) / 2;
+    if (prob > A[mid].cum_prob * mult) min_idx = mid; else max_idx = mid;
+  }
+  return prob > A[min_idx].cum_prob * mult ? max_idx : min_idx;
+}
+// local_prob_factor > 0 only between two surface molecules (react_2D_all_neighbors: 3 / number of neighbour tiles)
+__device__ int test_bimolecular(const DevParams& p, const DevClass& rc, double scaling, Stream& rs, double local_prob_factor = 0) {
   double max_fixed_p = rc.max_fixed_p, prob;
+  if (local_prob_factor != 0) max_fixed_p = rc.max_fixed_p * local_prob_factor;
   if (max_fixed_p < scaling) {
     prob = rs.dbl() * scaling;
     if (prob >= max_fixed_p) return -1;
   } else {
     float max_p = (float)rc.max_fixed_p;  // sic (rxn_utils.inl:369)
+    if (local_prob_factor > 0) max_p = (float)((double)max_p * local_prob_factor);  // float *= double
     if (max_p >= scaling) prob = rs.dbl() * max_p;
     else {
       prob = rs.dbl() * scaling;
       if (prob >= max_p) return -1;
     }
   }
-  // binary_search_double, rxn_utils.inl:301-320
-  int min_idx = 0, max_idx = (int)rc.n_pathways - 1;
-  const DevPathway* A = p.pathways + rc.first_pathway;
-  while (max_idx - min_idx > 1) {
-    int mid = (max_idx + min_idx) / 2;
-    if (prob > A[mid].cum_prob) min_idx = mid; else max_idx = mid;
-  }
-  return prob > A[min_idx].cum_prob ? max_idx : min_idx;
+  return pathway_for_probability(p, rc, prob, local_prob_factor > 0 ? local_prob_factor : 1.0);
 }
 
 // test_intersect, rxn_utils.inl:593-626 (a Standard reaction with a reactive surface): -1 = no reaction
@@ -1227,6 +1234,48 @@ __device__ __forceinline__ int kept_orientation(const DevClass& c, const DevPath
   return o;
 }
 
+// ---- surface-surface reactions (react_2D_all_neighbors, diffuse_react_event.cpp:1250-1393) --------------------------
+#define SURFSURF_SWAP 64u   // bit 6 of the orientation bits: the first surface product takes the SECOND freed tile
+#define SURFSURF_MAX_MATCHES 32
+// find_surf_product_positions (:1993-2288) over the tiles the consumed reactants free (in the order of the rule's
+// reactants): the one surface product of a pathway takes the initiator's tile when the initiator is consumed, else
+// the one freed tile (:2140-2154); two surface products draw for the two tiles like the reference (:2155-2191)
+__device__ __forceinline__ uint32_t surfsurf_position_bits(const DevParams& p, const DevPathway& pw, bool init_is_r0, Stream& rs) {
+  const int keep0 = pw.keep_mask & 1u, keep1 = (pw.keep_mask >> 1) & 1u;
+  int needed = 0; uint32_t first_surf = MCX_NONE;
+  for (uint32_t k = 0; k < pw.n_products; k++)
+    if (!(p.species[pw.products[k]].flags & MCX_SP_VOL)) { needed++; if (first_surf == MCX_NONE) first_surf = k; }
+  if (needed == 0) return 0;
+  const int freed = 2 - keep0 - keep1, actual = (int)pw.n_products + keep0 + keep1;
+  const int to_recycle = actual < freed ? actual : freed;
+  if (needed == 1 && to_recycle == 1) {
+    const int ri = init_is_r0 ? 0 : 1;
+    const bool init_consumed = ri == 0 ? !keep0 : !keep1;
+    return (init_consumed && ri == 1 && !keep0) ? SURFSURF_SWAP : 0u;
+  }
+  uint32_t bits = 0, assigned = 0;
+  int next_available = 0;
+  const uint32_t num_players = (uint32_t)actual + 2u;
+  for (int guard = 0; next_available < to_recycle && guard < 100000; guard++) {
+    const uint32_t rnd = rs.next() % num_players;
+    if (rnd < 2) continue;
+    const uint32_t k = rnd - 2;
+    if (k >= pw.n_products || (p.species[pw.products[k]].flags & MCX_SP_VOL)) continue;
+    if ((assigned >> k) & 1u) continue;
+    assigned |= 1u << k;
+    if ((next_available == 1) == (k == first_surf)) bits |= SURFSURF_SWAP;
+    next_available++;
+  }
+  return bits;
+}
+// :2640-2652: a rule orientation flips once for every surface reactant that lies the other way round than the rule states
+__device__ __forceinline__ int surfsurf_match(const DevClass& c, int orient_r0, int orient_r1) {
+  int m = 1;
+  if (c.geom0 != 0 && orient_r0 != c.geom0) m = -m;
+  if (c.geom1 != 0 && orient_r1 != c.geom1) m = -m;
+  return m;
+}
+
 // ---- surface diffusion -------------------------------------------------------------------------------------------
 // distinguishable_vec2, src4/defines.h:733-764
 __device__ __forceinline__ bool distinguishable_vec2_d(double au, double av, double bu, double bv, double eps) {
@@ -1407,6 +1456,9 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
   double unimol_time = (flags & DF_HAS_UNIMOL) ? t_unimol_in : MCX_TIME_INVALID;
   const bool can_diffuse = (sp.flags & MCX_SP_CAN_DIFFUSE) != 0;
   const bool can_vol_react = sp.can_vol_react != 0 && !forced;
+  // SPECIES_FLAG_CAN_SURFSURF: diffuse_surf_molecule runs for such a molecule even when it cannot diffuse (:274-283)
+  const bool can_ss = SURF && (flags & DF_SURF) && sp.can_surf_surf != 0 && p.surfsurf != nullptr;
+  bool ss_fired = false;
   out.rxn_class = -1; out.pathway = -1; out.partner_slot = MCX_NONE; out.partner_id = MCX_NONE; out.t_event = 0;
   out.kind = MCX_OUT_NONE; out.orient_bits = 0;
   out.surf_moved = false; out.s_wall = ss.wall; out.s_tile = ss.tile; out.s_u = ss.u; out.s_v = ss.v;
@@ -1465,7 +1517,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
       double max_time = t_end - t_now;
       if (unimol_time != MCX_TIME_INVALID && unimol_time < t_now + max_time) max_time = unimol_time - t_now;
 
-      if (SURF && can_diffuse && (flags & DF_SURF)) {
+      if (SURF && (flags & DF_SURF) && (can_diffuse || can_ss)) {
         // ---- diffuse_surf_molecule (:1071-1246)
         double t_steps = sp.time_step > max_time ? max_time : sp.time_step;
         double steps;
@@ -1477,7 +1529,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
         const uint32_t original_wall = ss.wall;
         const unsigned int epoch_first = round_epoch0(p);
         bool placed = false;
-        for (int find_new_position = 11; find_new_position > 0 && !placed; find_new_position--) {  // SURFACE_DIFFUSION_RETRIES + 1
+        for (int find_new_position = can_diffuse ? 11 : 0; find_new_position > 0 && !placed; find_new_position--) {  // SURFACE_DIFFUSION_RETRIES + 1
           // pick_surf_displacement (diffusion_utils.inl:60-96)
           double au, av, f;
           do {
@@ -1529,7 +1581,74 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
             placed = true;
           }
         }
-        if (ss.wall != original_wall && unimol_time >= t_end) {  // MCell3 compatibility rule (:1226-1236)
+        // ---- react_2D_all_neighbors (:1250-1393): after its move the molecule tests the molecules on the tiles around its
+        // own; the lists are static (tn_start / tn_list, built on the host), walls without a grid are left out here
+        if (can_ss && !decided && !forced && !(sp.flags & MCX_SP_CANT_INITIATE) && p.tn_start) {
+          const uint32_t gt0 = p.grids[ss.wall].tile_start + ss.tile;
+          const uint32_t qb = __ldg(p.tn_start + gt0), qe = __ldg(p.tn_start + gt0 + 1);
+          int m_rc[SURFSURF_MAX_MATCHES]; double m_factor[SURFSURF_MAX_MATCHES]; uint32_t m_slot[SURFSURF_MAX_MATCHES], m_id[SURFSURF_MAX_MATCHES];
+          int n_match = 0; uint32_t n_nb = 0;
+          const int my_orient = (flags & DF_ORIENT_UP) ? 1 : -1;
+          for (uint32_t q = qb; q < qe; q++) {
+            const uint2 wt = __ldg(p.tn_list + q);
+            if (!p.wall_has_grid[wt.x]) continue;  // Wall::has_initialized_grid (grid_utils.inl:1243, 783-790)
+            n_nb++;
+            const DevGrid& ng = p.grids[wt.x];
+            const uint32_t occ = p.tile_slot[ng.tile_start + wt.y];
+            if (occ == MCX_NONE) continue;
+            const MolRec nsm = load_rec_volatile(p.recA, occ);
+            if (nsm.id == m.id || (nsm.sf & DF_DEAD)) continue;  // the tile table still shows the mover on its old tile
+            const int rc = p.surfsurf[species * p.n_species + (nsm.sf & SF_SPECIES_MASK)];
+            if (rc < 0 || !orientations_match(p.classes[rc], my_orient, (nsm.sf & DF_ORIENT_UP) ? 1 : -1)) continue;
+            if (n_match >= SURFSURF_MAX_MATCHES) { err = MCX_ERR_STATE; break; }
+            m_rc[n_match] = rc; m_factor[n_match] = t_steps / ng.binding_factor; m_slot[n_match] = occ; m_id[n_match] = nsm.id;
+            n_match++;
+          }
+          if (n_nb != 0 && n_match != 0) {
+            const double local_prob_factor = 3.0 / (double)n_nb;
+            int which = 0, pathway;
+            if (n_match == 1) pathway = test_bimolecular(p, p.classes[m_rc[0]], m_factor[0], rs, local_prob_factor);
+            else {
+              // RxnUtils::test_many_bimolecular with all_neighbors_flag (rxn_utils.inl:475-580)
+              double cum[SURFSURF_MAX_MATCHES];
+              cum[0] = p.classes[m_rc[0]].max_fixed_p * local_prob_factor / m_factor[0];
+              for (int i = 1; i < n_match; i++) cum[i] = cum[i - 1] + p.classes[m_rc[i]].max_fixed_p * local_prob_factor / m_factor[i];
+              double prob;
+              which = -1;
+              bool none = false;
+              if (cum[n_match - 1] > 1.0) prob = rs.dbl() * cum[n_match - 1];
+              else { prob = rs.dbl(); none = prob > cum[n_match - 1]; }
+              if (!none) {
+                // binary_search_double over the reference's zero-padded array of 2 n entries (:559)
+                int min_idx = 0, max_idx = 2 * n_match - 1;
+                while (max_idx - min_idx > 1) {
+                  const int mid = (max_idx + min_idx) / 2;
+                  if (prob > (mid < n_match ? cum[mid] : 0.0)) min_idx = mid; else max_idx = mid;
+                }
+                which = prob > (min_idx < n_match ? cum[min_idx] : 0.0) ? max_idx : min_idx;
+                if (which >= n_match) which = n_match - 1;
+              }
+              pathway = 0;  // sic (TODO_PATHWAYS, :1367): the first pathway of the chosen class
+            }
+            if (tc.tr) for (int i = 0; i < n_match; i++) { if (tc.tr->n_collisions < MCX_TRACE_K) tc.tr->partner[tc.tr->n_collisions] = m_id[i]; tc.tr->n_collisions++; }
+            if (which >= 0 && pathway >= 0) {
+              const int rc = m_rc[which];
+              const DevClass& cl = p.classes[rc];
+              const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
+              // random draws in the reference's order: tile assignment (find_surf_product_positions), then orientations
+              uint32_t bits = surfsurf_position_bits(p, pw, species == cl.r0, rs);
+              bits |= draw_orientation_bits(pw, rs);
+              tc.ev(EV_SURFSURF | (uint32_t)pathway, (uint32_t)rc);
+              tc.ev(EV_RXN | (bits & 0x7Fu), m_id[which]);
+              if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = m_id[which]; tc.tr->t_event = t_now; }
+              out.rxn_class = rc; out.pathway = pathway; out.partner_slot = m_slot[which]; out.partner_id = m_id[which];
+              out.t_event = t_now;  // collision_time = diffusion_start_time (:1343)
+              out.orient_bits = bits;
+              ss_fired = true;
+            }
+          }
+        }
+        if ((!can_diffuse || ss.wall != original_wall) && unimol_time >= t_end) {  // MCell3 compatibility rule (:1222-1236)
           unimol_time = MCX_TIME_INVALID;
           flags |= DF_SCHED_UNIMOL;
         }
@@ -1761,7 +1880,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
       created_wall = created_tile = MCX_NONE;  // the guard belongs to the first DiffuseAction only (:116-129)
       if (!decided) {
         // -- reschedule (:283-336)
-        if (can_diffuse) {
+        if (can_diffuse || can_ss) {
           t_now += max_time;
           if ((unimol_time != MCX_TIME_INVALID && unimol_time < t_end) || (t_now < t_end && !cmp_eq_d(t_now, t_end, MCX_EPS))) again = true;
           else {
@@ -1774,7 +1893,13 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
             if (unimol_time < t_end) again = true;
           } else t_now = MCX_TIME_FOREVER;
         }
-        if (SURF && surf_tile_changed) {
+        if (SURF && ss_fired) {
+          // the surface-surface reaction is a claiming event (the initiator, the partner it consumes, the tile it moved to);
+          // a kept initiator has used up its step like any other mover
+          out.kind = MCX_OUT_REACTED; out.pos = pos; out.t_now = t_now; out.unimol_time = unimol_time;
+          out.flags = again ? (flags | DF_PARTIAL) : (flags & ~DF_PARTIAL);
+          decided = true; again = false;
+        } else if (SURF && surf_tile_changed) {
           // taking a new tile is a claiming event: the evaluation ends here, what is left of the iteration is taken
           // lazily next iteration (like a kept initiator)
           out.kind = MCX_OUT_SURFMOVE; out.pos = pos; out.t_now = t_now; out.unimol_time = unimol_time;
@@ -1786,7 +1911,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
     }
   }
   if (!decided) {
-    out.kind = can_diffuse ? MCX_OUT_MOVED : MCX_OUT_STATIC;
+    out.kind = (can_diffuse || can_ss) ? MCX_OUT_MOVED : MCX_OUT_STATIC;
     out.pos = pos; out.t_now = t_now; out.flags = flags & ~DF_PARTIAL; out.unimol_time = unimol_time;
   }
 }

@@ -402,4 +402,255 @@ void edge_constants(const double* verts, const uint32_t* tri, const std::vector<
   }
 }
 
+
+// ---- neighbour tiles (react_2D_all_neighbors' partner search) ----------------------------------------------
+// The reference finds the tiles around a tile anew for every surface molecule and step (GridUtils::find_neighbor_tiles,
+// src4/grid_utils.inl:1754-1801): twelve tiles of the own grid for a tile in the interior (:1657-1737), for a tile on
+// the rim the own tiles next to it plus the tiles of the walls across the sides it touches whose border vertices fall
+// inside its own span of the shared side (:1285-1640, 946-1240), and for a corner tile one corner tile of every wall
+// that meets it in that vertex alone (:743-868).  None of this depends on the molecules, so libmcx works the lists out
+// ONCE on the host, for every tile, and the device only gathers (tn_start / tn_list).  What does depend on the state
+// — a neighbouring wall whose grid does not exist yet contributes nothing (:1243, :783-790) — is a per-wall filter the
+// device applies to the entries (every entry names its wall; leaving a wall out does not change the others).  The
+// reference builds its list by pushing to the front; the table is stored front to back, i.e. in the order
+// react_2D_all_neighbors walks it.
+namespace {
+struct TileAddr { int strip, stripe, flip; };  // strip counted from the side v0-v1, stripe from the side v0-v2
+inline TileAddr tile_addr(int n_axis, uint32_t t) {
+  const int root = (int)std::sqrt((double)t), rem = (int)t - root * root;
+  return TileAddr{n_axis - root - 1, rem / 2, rem & 1};
+}
+inline bool interior_tile(int n_axis, uint32_t t) {  // :296-319
+  const TileAddr a = tile_addr(n_axis, t);
+  if (a.strip == 0 || a.stripe == 0 || a.strip + a.stripe == n_axis - 1) return false;
+  return !(a.strip + a.stripe == n_axis - 2 && a.flip == 1);
+}
+inline int strip_above(int n_axis, uint32_t t) {  // move_strip_up :523-536
+  const int root = (int)std::sqrt((double)t) + 1;
+  return n_axis == root ? -1 : (int)t + 2 * root;
+}
+inline int strip_below(int n_axis, uint32_t t) {  // move_strip_down :551-590
+  const TileAddr a = tile_addr(n_axis, t);
+  const int per_strip = 2 * n_axis - 2 * a.strip - 1;
+  const uint32_t n_tiles = (uint32_t)(n_axis * n_axis);
+  bool ok;
+  if (interior_tile(n_axis, t)) ok = true;
+  else if (a.strip == 0 && a.stripe > 0) ok = t != n_tiles - 1;
+  else ok = a.flip != 0;
+  return ok ? (int)t - per_strip + 1 : -1;
+}
+struct Mesh {
+  const double* verts; const uint32_t* tri; const std::vector<DevWall>* walls; const std::vector<DevGrid>* grids;
+  const std::vector<DevEdge>* edges; std::vector<std::vector<uint32_t>> vertex_walls;
+  P3 vtx(uint32_t w, int k) const { const double* q = verts + 3 * tri[3 * w + k]; return P3{q[0], q[1], q[2]}; }
+  int n_axis(uint32_t w) const { return (*grids)[w].n_axis; }
+  uint32_t across(uint32_t w, int e) const { return (*edges)[3 * w + e].nb_wall; }
+};
+// collected in push order; the reference's list reads back to front
+struct Pushed {
+  std::vector<uint32_t> wt;
+  void add(uint32_t w, int t) { wt.push_back(w); wt.push_back((uint32_t)t); }
+  void add_once(uint32_t w, int t) {
+    for (size_t i = 0; i < wt.size(); i += 2) if (wt[i] == w && wt[i + 1] == (uint32_t)t) return;
+    add(w, t);
+  }
+};
+// the tiles of wall `other` along the side it shares with wall `w` that touch the start tile (:946-1240)
+void across_side(const Mesh& m, uint32_t w, TileAddr a, P3 from, P3 to, int side, uint32_t other, Pushed& out) {
+  const int N = m.n_axis(w), M = m.n_axis(other);
+  const double dx = from.x - to.x, dy = from.y - to.y, dz = from.z - to.z;
+  const double len = std::sqrt(dx * dx + dy * dy + dz * dz);
+  double p1 = -1, p2 = -1;  // the start tile's vertices on the shared side, as distances from `from`
+  auto span = [&](int k) { p1 = k * len / N; p2 = (k + 1) * len / N; };
+  auto point = [&](int k) { p1 = k * len / N; };
+  if (a.stripe == 0) {
+    if (a.strip > 0) { if (!a.flip) span(a.strip); else point(a.strip + 1); }
+    else if (side == 0) { if (!a.flip) span(a.stripe); else point(a.stripe + 1); }
+    else if (side == 1) { if (!a.flip) point(a.strip); else span(a.strip); }
+    else { if (!a.flip) span(a.strip); else point(a.strip + 1); }
+  }
+  if (a.strip == 0 && a.stripe > 0) {
+    const bool at_end = a.stripe == N - 1 || (a.stripe == N - 2 && a.flip == 1);
+    if (!at_end || side == 0) { if (!a.flip) span(a.stripe); else point(a.stripe + 1); }
+    else if (side == 1) { if (!a.flip) span(a.strip); else point(a.strip + 1); }
+  }
+  if (a.strip > 0 && a.stripe > 0) { if (!a.flip) span(a.strip); else point(a.strip + 1); }
+  // which two vertices of the other wall lie on the shared side (:682-728), and which of them is `from`
+  int s1 = -1, s2 = -1;
+  for (int k = 0; k < 3; k++) {
+    const P3 q = m.vtx(other, k);
+    bool shared = false;
+    for (int j = 0; j < 3; j++) shared |= !distinguishable_vec3(q, m.vtx(w, j), 1e-12);
+    if (!shared) continue;
+    if (k == 0 || s1 < 0) s1 = k; else s2 = k;
+  }
+  const bool from_is_s1 = !distinguishable_vec3(from, m.vtx(other, s1), 1e-12);
+  const int i_from = from_is_s1 ? s1 : s2, i_to = from_is_s1 ? s2 : s1;
+  if (i_from > i_to) { p1 = len - p1; if (p2 > 0) p2 = len - p2; }
+  const int other_side = (s1 + s2 == 1) ? 0 : (s1 + s2 == 2) ? 2 : 1;
+  // border tiles of the other wall, grouped by the border vertex they meet in
+  const int n_pos = M + 1;
+  std::vector<double> pos(n_pos);
+  std::vector<int> grp(3 * n_pos, -1);
+  for (int i = 0; i < n_pos; i++) pos[i] = i * len / M;
+  const int corner0 = M * M - 2 * M + 1;
+  int last = other_side == 1 ? M * M - 1 : corner0;
+  grp[2] = last;
+  for (int i = 1; i < n_pos - 1; i++) {
+    if (other_side == 0) { for (int k = 0; k < 3; k++) grp[3 * i + k] = last + k; last += 2; }
+    else {
+      grp[3 * i] = last; grp[3 * i + 1] = other_side == 1 ? last - 1 : last + 1;
+      last = grp[3 * i + 2] = strip_below(M, (uint32_t)grp[3 * i + 1]);
+    }
+  }
+  grp[3 * (n_pos - 1)] = last;
+  // bisect / bisect_high (:871-915)
+  auto below = [&](double v) { int lo = 0, hi = n_pos; while (hi - lo > 1) { const int mid = (hi + lo) / 2; if (pos[mid] > v) hi = mid; else lo = mid; } return lo; };
+  auto above = [&](double v) { int lo = 0, hi = n_pos - 1; while (hi - lo > 1) { const int mid = (hi + lo) / 2; if (pos[mid] > v) hi = mid; else lo = mid; } return pos[lo] > v ? lo : hi; };
+  const double hi_pos = p1 > p2 ? p1 : p2, lo_pos = p1 > p2 ? p2 : p1;
+  const int i_hi = above(hi_pos);
+  const int i_lo = lo_pos > 0 ? below(lo_pos) : -1;
+  if (i_lo >= 0) {
+    for (int i = i_lo + 1; i < i_hi; i++)
+      for (int k = 0; k < 3; k++) out.add_once(other, grp[3 * i + k]);
+  } else out.add_once(other, grp[3 * i_hi]);
+}
+void rim_tile(const Mesh& m, uint32_t w, uint32_t t, Pushed& out) {  // :1285-1640
+  const int N = m.n_axis(w), ti = (int)t, n_tiles = N * N;
+  const TileAddr a = tile_addr(N, t);
+  const P3 v0 = m.vtx(w, 0), v1 = m.vtx(w, 1), v2 = m.vtx(w, 2);
+  auto side = [&](int e, int as_side) {
+    const uint32_t o = m.across(w, e);
+    if (o == MCX_NONE) return;
+    const P3 from = e == 1 ? v1 : v0, to = e == 0 ? v1 : v2;
+    across_side(m, w, a, from, to, as_side, o, out);
+  };
+  auto own = [&](int q) { out.add(w, q); };
+  if (a.stripe == 0) {
+    if (a.flip) {
+      own(ti - 1); own(ti + 1);
+      if (a.strip < N - 2) own(ti + 2);
+      int q = strip_below(N, t);
+      own(q);
+      if (a.strip < N - 2) { own(q + 1); own(q + 2); }
+      if (a.strip > 0) { q = strip_above(N, t); own(q); own(q - 1); own(q + 1); }
+      side(2, 2);
+      if (a.strip == 0) side(0, 0);
+      if (a.strip == N - 2) side(1, 0);  // the reference passes side index 0 here (:1408)
+    } else if (t == 0) {
+      if (n_tiles > 1) { const int q = strip_above(N, t); own(q); own(q - 1); own(q + 1); }
+      else side(0, 0);
+      side(1, 1); side(2, 2);
+    } else {
+      own(ti + 1); own(ti + 2);
+      int q = strip_below(N, t + 1);
+      own(q);
+      if (a.strip > 0) { q = strip_above(N, t); own(q); own(q - 1); own(q + 1); own(q + 2); }
+      else { side(0, 0); side(2, 2); }
+    }
+  } else if (a.strip == 0) {
+    own(ti - 1); own(ti - 2);
+    if (a.stripe < N - 2 || (a.stripe == N - 2 && !a.flip)) { own(ti + 1); own(ti + 2); }
+    else if (a.stripe == N - 2) own(ti + 1);
+    if (a.flip) {
+      const int q = strip_below(N, t);
+      own(q); own(q - 1); own(q - 2);
+      if (a.stripe < N - 2) { own(q + 1); own(q + 2); }
+    } else if (ti < n_tiles - 1) { const int q = strip_below(N, t); own(q); own(q - 1); own(q + 1); }
+    else own(strip_below(N, t - 1));
+    side(0, 0);
+    if (ti >= n_tiles - 2) side(1, 1);
+  } else {
+    if (a.flip) {
+      own(ti - 1); own(ti - 2); own(ti + 1);
+      int q = strip_above(N, t); own(q); own(q - 1); own(q + 1);
+      q = strip_below(N, t); own(q); own(q - 1); own(q - 2);
+    } else {
+      own(ti - 1); own(ti - 2);
+      const int q = strip_above(N, t); own(q); own(q - 1); own(q - 2); own(q + 1);
+      own(strip_below(N, t - 1));
+    }
+    side(1, 1);
+  }
+}
+void interior(const Mesh& m, uint32_t w, uint32_t t, Pushed& out) {  // :1657-1737 with grid_neighbors :414-470
+  const int N = m.n_axis(w), ti = (int)t;
+  const int root = (int)std::sqrt((double)t), rem = ti - root * root, j = rem / 2, i = rem & 1;
+  const int cand[3] = {i ? 2 * j + (root - 1) * (root - 1) : 1 + 2 * j + (root + 1) * (root + 1), ti + 1, ti - 1};
+  int other_row = -1;
+  for (int k = 0; k < 3; k++) if (cand[k] != ti - 1 && cand[k] != ti + 1) { other_row = cand[k]; break; }
+  auto own = [&](int q) { out.add(w, q); };
+  own(ti - 1); own(ti - 2); own(ti + 1); own(ti + 2);
+  // tile_orientation (:483-510) of the tile's centre (grid2uv :233-253)
+  const DevWall& f = (*m.walls)[w];
+  const DevGrid& g = (*m.grids)[w];
+  const int k3 = N - root - 1;
+  const double over3n = 1 / (double)(3 * N);
+  const double cu = ((double)(3 * j + i + 1)) * over3n * f.uv1u + ((double)(3 * k3 + i + 1)) * over3n * f.uv2u;
+  const double cv = ((double)(3 * k3 + i + 1)) * over3n * f.uv2v;
+  const double striploc = cv * g.strip_width_rcp;
+  int strip = (int)striploc;
+  const double striprem = striploc - strip;
+  strip = N - strip - 1;
+  const double stripeloc = ((cu - cv * g.vert2_slope) / (f.uv1u - cv * g.fullslope)) * (((double)strip) + (1 - striprem));
+  const double striperem = stripeloc - (int)stripeloc;
+  const bool upright = striperem < 1 - striprem;
+  auto five = [&]() { own(other_row); own(other_row - 1); own(other_row - 2); own(other_row + 1); own(other_row + 2); };
+  if (upright) { five(); const int q = strip_below(N, t); own(q); own(q - 1); own(q + 1); }
+  else { const int q = strip_above(N, t); own(q); own(q - 1); own(q + 1); five(); }
+}
+}  // namespace
+
+void tile_neighbor_table(const double* verts, uint64_t n_verts, const uint32_t* tri, const std::vector<DevWall>& walls,
+                         const std::vector<DevGrid>& grids, const std::vector<DevEdge>& edges, std::vector<uint32_t>& start,
+                         std::vector<uint32_t>& list) {
+  Mesh m{verts, tri, &walls, &grids, &edges, {}};
+  m.vertex_walls.resize(n_verts);
+  for (uint32_t w = 0; w < walls.size(); w++)
+    for (int k = 0; k < 3; k++) m.vertex_walls[tri[3 * w + k]].push_back(w);
+  start.clear(); list.clear();
+  for (uint32_t w = 0; w < walls.size(); w++) {
+    const int N = grids[w].n_axis;
+    const uint32_t n_tiles = (uint32_t)(N * N);
+    for (uint32_t t = 0; t < n_tiles; t++) {
+      start.push_back((uint32_t)(list.size() / 2));
+      Pushed out;
+      if (interior_tile(N, t)) interior(m, w, t, out);
+      else {
+        const int corner_of = t == n_tiles - 2 * (uint32_t)N + 1 ? 0 : t == n_tiles - 1 ? 1 : t == 0 ? 2 : -1;  // is_corner_tile :329-342
+        // a 1-tile grid is all three corners at once (:624-670 test every vertex)
+        for (int c = 0; c < 3 && corner_of >= 0; c++) {
+          const bool here = (c == 0 && t == n_tiles - 2 * (uint32_t)N + 1) || (c == 1 && t == n_tiles - 1) || (c == 2 && t == 0);
+          if (!here) continue;
+          const uint32_t v = tri[3 * w + c];
+          bool used_across = false;  // neighboring_wall_uses_this_vertex :605-622
+          for (int e = 0; e < 3; e++) {
+            const uint32_t o = m.across(w, e);
+            if (o != MCX_NONE) for (int k = 0; k < 3; k++) used_across |= tri[3 * o + k] == v;
+          }
+          if (!used_across) continue;
+          for (uint32_t o : m.vertex_walls[v]) {  // find_nbr_walls_shared_one_vertex (wall_utils.inl:79-104)
+            if (o == w) continue;
+            int same = 0;  // walls_share_full_edge (wall_utils.inl:50-65)
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) same += !distinguishable_vec3(m.vtx(w, a), m.vtx(o, b), 1e-12);
+            if (same == 2) continue;
+            // the corner tile of that wall (:743-868): under the LAST vertex index the two walls have in common
+            int t_other;
+            if (n_tiles == 1) t_other = 0;
+            else {
+              uint32_t common = MCX_NONE;
+              for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) if (tri[3 * w + a] == tri[3 * o + b]) { common = tri[3 * o + b]; break; }
+              const int M = grids[o].n_axis;
+              t_other = common == tri[3 * o] ? M * M - 2 * M + 1 : common == tri[3 * o + 1] ? M * M - 1 : 0;
+            }
+            out.add(o, t_other);
+          }
+        }
+        rim_tile(m, w, t, out);
+      }
+      for (size_t q = out.wt.size(); q >= 2; q -= 2) { list.push_back(out.wt[q - 2]); list.push_back(out.wt[q - 1]); }
+    }
+  }
+  start.push_back((uint32_t)(list.size() / 2));
+}
 }  // namespace mcxg

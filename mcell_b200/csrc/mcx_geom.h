@@ -25,4 +25,9 @@ void bin_walls(const GridSpec& g, const double* verts, const uint32_t* tri, cons
 int fine_wall_factor(const GridSpec& g, const double* verts, const uint32_t* tri, uint64_t n_walls, const std::vector<uint32_t>& start);
 void bin_walls_fine(const GridSpec& g, const double* verts, const uint32_t* tri, const std::vector<uint32_t>& start,
                     const std::vector<uint32_t>& list, int K, double margin, std::vector<uint32_t>& fstart, std::vector<uint32_t>& flist);
+// neighbour tiles of every tile (GridUtils::find_neighbor_tiles, src4/grid_utils.inl:296-1801, with every grid present):
+// start has total tiles + 1 entries, list holds (wall, tile) pairs in the order react_2D_all_neighbors walks them
+void tile_neighbor_table(const double* verts, uint64_t n_verts, const uint32_t* tri, const std::vector<DevWall>& walls,
+                         const std::vector<DevGrid>& grids, const std::vector<DevEdge>& edges, std::vector<uint32_t>& start,
+                         std::vector<uint32_t>& list);
 }  // namespace mcxg

@@ -30,7 +30,7 @@ enum : uint32_t {
   SF_CVI_MASK = 0xFF000000u
 };
 
-struct DevSpecies { double space_step, time_step; uint32_t flags; uint32_t can_vol_react; uint32_t can_vol_surf; uint32_t pad; };
+struct DevSpecies { double space_step, time_step; uint32_t flags; uint32_t can_vol_react; uint32_t can_vol_surf; uint32_t can_surf_surf; };
 struct DevClass { double max_fixed_p; uint32_t kind, r0, r1, first_pathway, n_pathways; int geom0, geom1; uint32_t pad; };
 struct DevPathway { double cum_prob; uint32_t n_products, products[MCX_MAX_PRODUCTS], keep_mask, rule_id; int prod_orient[MCX_MAX_PRODUCTS]; uint32_t kept_info; };
 
@@ -162,6 +162,12 @@ struct DevParams {
   double2 *suvA, *suvB;         // s.pos
   const DevEdge* edges;         // 3 per wall
   unsigned long long* tile_claim;  // per tile: (epoch << 32) | ~id of the best mover claiming it
+  // surface-surface reactions (react_2D_all_neighbors): class table, the neighbour tiles of every tile as (wall, tile)
+  // pairs in the reference's list order (mcx_geom.cpp: tile_neighbor_table), and which walls have a grid yet
+  const int* surfsurf;          // [surface species][surface species] -> class or -1; null = no such class
+  const uint32_t* tn_start;     // per tile (+ 1)
+  const uint2* tn_list;
+  uint8_t* wall_has_grid;       // Wall::has_initialized_grid: the wall has held a surface molecule since the last upload
   // rng
   unsigned long long seed, iteration;
   int rng_mode;

@@ -290,6 +290,113 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
     }
     return;
   }
+  if (kind == MCX_OUT_REACTED && cl.kind == MCX_RXN_BIMOL_SURFSURF) {
+    // Two surface molecules (react_2D_all_neighbors -> outcome_bimolecular -> outcome_products_random): the initiator
+    // sits where its move took it (surface fields already in B), the partner on its tile of the snapshot.  Surface
+    // products take the tiles the consumed reactants free, at the uv of the reactant that left (:2826-2846); volume
+    // products start at the position of the rule's first reactant, bumped off the INITIATOR's wall to the side their
+    // orientation names and remembered with its tile (:2745-2762)
+    const uint32_t iw = p.swallB[slot], itile = p.stileB[slot];
+    const double2 iuv = p.suvB[slot];
+    if (own_event) { if (bt) atomicAdd(&bt->rxn[pw.rule_id & (MCX_MAX_COUNTED - 1u)], 1u); else agg_add(&c->rxn_count[pw.rule_id & (MCX_MAX_COUNTED - 1u)], 1u); }
+    if (own_event && p.wall_rs) agg_add(&p.rxn_count_rs[(pw.rule_id & (MCX_MAX_COUNTED - 1u)) * p.n_rs + __ldg(p.wall_rs + iw)], 1u);
+    if (own_event) { if (bt) tally_inc(&bt->bimol); else agg_add(&c->bimol_rxns, 1u); }
+    const MolRec pr = load_rec_volatile(p.recA, partner_slot);
+    const uint32_t pw_wall = p.swallA[partner_slot], pw_tile = p.stileA[partner_slot];
+    const double2 puv = p.suvA[partner_slot];
+    const bool a_is_r0 = species == cl.r0;
+    const bool keepA = (pw.keep_mask >> (a_is_r0 ? 0 : 1)) & 1u, keepB = (pw.keep_mask >> (a_is_r0 ? 1 : 0)) & 1u;
+    const int oi = (flags & DF_ORIENT_UP) ? 1 : -1, op = (pr.sf & DF_ORIENT_UP) ? 1 : -1;
+    const int match = surfsurf_match(cl, a_is_r0 ? oi : op, a_is_r0 ? op : oi);
+    uint32_t reuse[2]; int n_reuse = 0;
+    if (!keepA) {
+      atomicOr(&p.recA[slot].sf, DF_DEAD);
+      if (track) { if (bt) atomicSub(&bt->species[species], 1); else agg_sub(&c->species_count[species], 1u); }
+      reuse[n_reuse++] = id;
+    }
+    if (!keepB) {
+      const uint32_t old = atomicOr(&p.recA[partner_slot].sf, DF_DEAD);
+      atomicOr(&p.recB[partner_slot].sf, DF_DEAD);
+      if (track) { if (bt) atomicSub(&bt->species[old & SF_SPECIES_MASK], 1); else agg_sub(&c->species_count[old & SF_SPECIES_MASK], 1u); }
+      reuse[n_reuse++] = pr.id;
+      if (p.trace && pr.id < p.n_trace) p.trace[pr.id].outcome = MCX_OUT_CONSUMED;
+    }
+    // freed tiles in the order of the rule's reactants: 0 = initiator's, 1 = partner's site
+    int freed[2]; int n_freed = 0;
+    const bool keep0 = pw.keep_mask & 1u, keep1 = (pw.keep_mask & 2u) != 0;
+    if (!keep0) freed[n_freed++] = a_is_r0 ? 0 : 1;
+    if (!keep1) freed[n_freed++] = a_is_r0 ? 1 : 0;
+    uint32_t first_surf = MCX_NONE;
+    for (uint32_t k = 0; k < pw.n_products && first_surf == MCX_NONE; k++) if (!(p.species[pw.products[k]].flags & MCX_SP_VOL)) first_surf = k;
+    const uint32_t n_new = own_event ? pw.n_products : 0u;
+    const uint32_t first_slot = n_new ? c->n_slots + agg_reserve(&c->n_prod, n_new) : 0u;
+    if (n_new > (uint32_t)n_reuse && first_slot + n_new <= p.capacity) {
+      const uint32_t e = agg_reserve(&c->n_fresh_events, 1u);
+      if (e >= p.fresh_cap) raise_error(p, MCX_ERR_CAPACITY, id);
+      else {
+        const uint32_t g = group_of(p, pos);
+        const uint32_t nf = n_new - (uint32_t)n_reuse;
+        FreshEvent ev; ev.first_slot = first_slot + (uint32_t)n_reuse; ev.n = nf; ev.init_id = id; ev.group = g;
+        ev.next = atomicExch(&p.fresh_head[g], e);
+        p.fresh_list[e] = ev;
+        atomicAdd(&p.fresh_pref[g], nf);
+        atomicAdd(&c->n_fresh_ids, nf);
+      }
+    }
+    const DevWall& fi = p.walls[iw];
+    for (uint32_t k = 0; k < n_new; k++) {
+      const uint32_t ns = first_slot + k;
+      if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
+      const uint32_t psp = pw.products[k];
+      int o = pw.prod_orient[k];
+      if (o == 0) o = ((orient_bits >> k) & 1u) ? 1 : -1; else o *= match;
+      uint32_t pflags = DF_SCHED_UNIMOL | DF_PARTIAL;
+      D3 ppos;
+      if (!(p.species[psp].flags & MCX_SP_VOL)) {
+        const bool swap = (orient_bits & SURFSURF_SWAP) != 0;
+        int which = ((k == first_surf) == swap) ? 1 : 0;
+        if (which > n_freed - 1) which = n_freed - 1;
+        const bool at_init = freed[which < 0 ? 0 : which] == 0;
+        const uint32_t tw = at_init ? iw : pw_wall;
+        const double2 tuv = at_init ? iuv : puv;
+        p.swallB[ns] = tw; p.stileB[ns] = at_init ? itile : pw_tile; p.suvB[ns] = tuv;
+        const DevWall& f = p.walls[tw];
+        ppos = D3{tuv.x * f.ux + tuv.y * f.vx + f.v0x, tuv.x * f.uy + tuv.y * f.vy + f.v0y, tuv.x * f.uz + tuv.y * f.vz + f.v0z};
+        pflags |= DF_SURF | (o > 0 ? DF_ORIENT_UP : 0u);
+      } else {
+        const uint32_t rw = a_is_r0 ? iw : pw_wall;       // the rule's first reactant
+        const double2 ruv = a_is_r0 ? iuv : puv;
+        const DevWall& f = p.walls[rw];
+        const D3 from = {ruv.x * f.ux + ruv.y * f.vx + f.v0x, ruv.x * f.uy + ruv.y * f.vy + f.v0y, ruv.x * f.uz + ruv.y * f.vz + f.v0z};
+        const double bump = (o > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
+        ppos = D3{from.x + (2 * bump) * fi.nx, from.y + (2 * bump) * fi.ny, from.z + (2 * bump) * fi.nz};
+        pflags |= DF_CREATED_ON_SURF;
+        p.swallB[ns] = iw; p.stileB[ns] = itile;
+        if (p.wall_cv) {
+          const uint32_t cv = __ldg(p.wall_cv + iw);
+          const uint32_t pc = o > 0 ? (cv & 0xFFu) : (cv >> 8);
+          if (cv_uses_xor(p, iw)) pflags |= DF_CVI_PENDING;  // no volume reactant to go by: a ray cast at its first evaluation
+          pflags |= pc << SF_CVI_SHIFT;
+        }
+      }
+      p.tschedB[ns] = t_event;
+      store_rec(p.recB, ns, ppos, (int)k < n_reuse ? reuse[k] : MCX_NONE, psp | pflags);
+      p.rank[ns] = atomicAdd(&p.cs_next[cell_of(p, ppos.x, ppos.y, ppos.z)], 1u);
+      if (track) { if (bt) atomicAdd(&bt->species[psp], 1); else agg_add(&c->species_count[psp], 1u); }
+      if (bt) tally_inc(&bt->products); else agg_add(&c->products, 1u);
+    }
+    if (keepA) {  // stays on the tile it moved to, its step used up; takes its product-side orientation (:2706-2709)
+      uint32_t f = flags;
+      if (pw.kept_info & MCX_KEPT_VALID) {
+        const int r = a_is_r0 ? 0 : 1;
+        int ko = kept_code(pw, r);
+        if (ko == 0) ko = ((orient_bits >> (4 + r)) & 1u) ? 1 : -1; else ko *= match;
+        f = (f & ~DF_ORIENT_UP) | (ko > 0 ? DF_ORIENT_UP : 0u);
+      }
+      finalize_alive(p, slot, pos, id, species, f, t_now, unimol_time, SURF_FIELDS_IN_B);
+    }
+    return;
+  }
   if (own_event) { if (bt) atomicAdd(&bt->rxn[pw.rule_id & (MCX_MAX_COUNTED - 1u)], 1u); else agg_add(&c->rxn_count[pw.rule_id & (MCX_MAX_COUNTED - 1u)], 1u); }
   // outcome_products_random :2513-2521: a volume initiator counts the reaction in its counted volume, a surface
   // initiator on its wall (here: in the wall's set of counted surface regions)
@@ -442,6 +549,10 @@ __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot
   if (o.kind == MCX_OUT_SURFMOVE) {
     p.swallB[slot] = o.s_wall; p.stileB[slot] = o.s_tile; p.suvB[slot] = make_double2(o.s_u, o.s_v);
     atomicMax(&p.tile_claim[p.grids[o.s_wall].tile_start + o.s_tile], key);
+  } else if (o.kind == MCX_OUT_REACTED && p.classes[o.rxn_class].kind == MCX_RXN_BIMOL_SURFSURF) {
+    // surface-surface reaction: where the initiator is after its move; the tile is claimed when it is a new one
+    p.swallB[slot] = o.s_wall; p.stileB[slot] = o.s_tile; p.suvB[slot] = make_double2(o.s_u, o.s_v);
+    if (o.s_wall != p.swallA[slot] || o.s_tile != p.stileA[slot]) atomicMax(&p.tile_claim[p.grids[o.s_wall].tile_start + o.s_tile], key);
   }
   if (n_list) {
     uint32_t k = agg_reserve(n_list, 1u);
@@ -532,7 +643,8 @@ __device__ __forceinline__ void fast_molecule(const DevParams& p, FastCtx& cx, P
     // cold fields: a predicated index keeps the loads unconditional (no warp split) without touching the arrays
     // for molecules that have nothing there
     const bool has_uni = (m.sf & DF_HAS_UNIMOL) != 0;
-    const bool idle_candidate = PASS == 0 && live && !(sp.flags & MCX_SP_CAN_DIFFUSE) && !fractional && !(m.sf & DF_CVI_PENDING);
+    const bool idle_candidate = PASS == 0 && live && !(sp.flags & MCX_SP_CAN_DIFFUSE) && !fractional && !(m.sf & DF_CVI_PENDING) &&
+                                !sp.can_surf_surf;  // surface molecules with surface-surface classes test their neighbours every step
     const double t_uni_raw = __ldg(p.tuniA + (((simple || idle_candidate) && has_uni) ? i : 0u));
     double t_uni = has_uni ? t_uni_raw : MCX_TIME_INVALID;
     double t_now = it;
@@ -1009,6 +1121,10 @@ __device__ __forceinline__ void resolve_round(const DevParams& p, unsigned int r
     bool ok = __ldcg(p.claim + slot) == key;
     if (ok && partner_is_consumed(p, kind, rxn_class, pathway, species)) ok = __ldcg(p.claim + partner) == key;
     if (ok && kind == MCX_OUT_SURFMOVE) ok = __ldcg(p.tile_claim + p.grids[__ldcg(p.swallB + slot)].tile_start + __ldcg(p.stileB + slot)) == key;
+    if (ok && kind == MCX_OUT_REACTED && p.classes[rxn_class].kind == MCX_RXN_BIMOL_SURFSURF) {  // the initiator took a new tile first
+      const uint32_t nw = __ldcg(p.swallB + slot), nt = __ldcg(p.stileB + slot);
+      if (nw != p.swallA[slot] || nt != p.stileA[slot]) ok = __ldcg(p.tile_claim + p.grids[nw].tile_start + nt) == key;
+    }
     if (ok) {
       commit_event(p, slot, kind, rxn_class, pathway, partner, __ldcg(p.prop_t + slot), D3{e.x, e.y, e.z}, e.id, species,
                    e.sf & ~SF_SPECIES_MASK, __ldcg(p.tschedB + slot), __ldcg(p.tuniB + slot), orient_bits, tally);
@@ -1193,6 +1309,7 @@ __global__ void __launch_bounds__(TPB) k_scatter(const __grid_constant__ DevPara
       if (sf & DF_SURF) {
         p.suvA[dst] = p.suvB[i];
         if (!(sf & DF_DEAD)) p.tile_slot[p.grids[wi].tile_start + ti] = dst;  // Grid::molecules_per_tile of the next snapshot
+        if (p.surfsurf && !p.wall_has_grid[wi]) p.wall_has_grid[wi] = 1;       // Wall::has_initialized_grid from now on
       }
     }
     // multi-GPU: recount the owned population (halo copies are not this rank's molecules)

@@ -932,8 +932,10 @@ static const char* surfsurf_pathway_problem(const World& w, const mcx_pathway& p
     return "a surface-surface pathway that frees more tiles than it has surface products, next to a volume product: the reference's tile assignment (diffuse_react_event.cpp:2155-2191) does not terminate";
   return nullptr;
 }
-// find_surf_product_positions (:1993-2288) over recycled tiles: bit 8 + k = product k takes the second freed tile (freed
-// tiles in the order of the rule's reactants).  Draws from the stream like the reference (rng_uint % players, :2161)
+// find_surf_product_positions (:1993-2288) over recycled tiles: SURFSURF_SWAP = the first surface product takes the second
+// freed tile (freed tiles in the order of the rule's reactants) and the other one, if there is one, the first.  Draws
+// from the stream like the reference (rng_uint % players, :2161)
+static const uint32_t SURFSURF_SWAP = 64u;  // bit 6 of the orientation bits (bits 0-3: products, 4-5: kept reactants)
 template <class RS>
 static uint32_t surfsurf_position_bits(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw, bool init_is_r0, RS& rs) {
   const int keep0 = pw.keep_reactant_mask & 1, keep1 = (pw.keep_reactant_mask >> 1) & 1;
@@ -946,7 +948,7 @@ static uint32_t surfsurf_position_bits(const World& w, const mcx_rxn_class& c, c
     const int ri = init_is_r0 ? 0 : 1;
     const bool init_consumed = ri == 0 ? !keep0 : !keep1;
     const int idx = (init_consumed && ri == 1 && !keep0) ? 1 : 0;
-    return idx ? (1u << (8 + first_surf)) : 0u;
+    return idx ? SURFSURF_SWAP : 0u;
   }
   uint32_t bits = 0, assigned = 0;
   int next_available = 0;
@@ -959,7 +961,7 @@ static uint32_t surfsurf_position_bits(const World& w, const mcx_rxn_class& c, c
     if (k >= pw.n_products || !w.is_surf(pw.products[k])) continue;
     if ((assigned >> k) & 1u) continue;
     assigned |= 1u << k;
-    if (next_available == 1) bits |= 1u << (8 + k);
+    if ((next_available == 1) == (k == first_surf)) bits |= SURFSURF_SWAP;  // each of the two assignments says the same
     next_available++;
   }
   return bits;
@@ -992,13 +994,16 @@ static void surfsurf_products(World& w, const mcx_rxn_class& c, const mcx_pathwa
   if (!(pw.keep_reactant_mask & 1u)) freed[n_freed++] = &r0;
   if (!(pw.keep_reactant_mask & 2u)) freed[n_freed++] = &r1;
   const int match = surfsurf_match(c, r0, r1);
+  uint32_t first_surf = MCX_NONE;
+  for (uint32_t k = 0; k < pw.n_products && first_surf == MCX_NONE; k++) if (w.is_surf(pw.products[k])) first_surf = k;
   for (uint32_t k = 0; k < pw.n_products; k++) {
     ProductSpec ps;
     ps.species = pw.products[k];
     int o = pw.product_orientation[k];
     if (o == 0) o = ((bits >> k) & 1u) ? 1 : -1; else o *= match;
     if (w.is_surf(ps.species)) {
-      const int which = std::min((int)((bits >> (8 + k)) & 1u), n_freed - 1);
+      const bool swap = (bits & SURFSURF_SWAP) != 0;
+      const int which = std::min((k == first_surf) == swap ? 1 : 0, n_freed - 1);
       const SurfSite& t = *freed[which < 0 ? 0 : which];
       ps.wall = t.wall; ps.tile = t.tile; ps.u = t.u; ps.v = t.v; ps.orient = o;
       ps.pos = uv2xyz(w, w.walls[t.wall], t.u, t.v);
@@ -1648,7 +1653,7 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
           bits |= draw_orientation_bits(pw, E.rs);
           const double t_rxn = s.t_now;  // collision_time = diffusion_start_time (:1343)
           E.ev(EV_SURFSURF | (uint32_t)pathway, (uint32_t)rc);
-          E.ev(EV_RXN | (bits & 0xFFFFu), w.mols[j].id);
+          E.ev(EV_RXN | (bits & 0x7Fu), w.mols[j].id);
           if (tr) { tr->rxn_class = rc; tr->rxn_pathway = pathway; tr->rxn_partner = w.mols[j].id; tr->t_event = t_rxn; }
           if (!apply) {
             out.rxn_class = rc; out.pathway = pathway; out.partner_index = j; out.partner_id = w.mols[j].id;
@@ -3176,6 +3181,38 @@ int orc_unit_test_bimolecular(const double* cum_probs, int n, double scaling, co
   Eval E(w, rs);
   int r = E.test_bimolecular(rc, scaling);
   *words_used = rs.used;
+  return r;
+}
+// test_bimolecular with a local probability factor / test_many_bimolecular (react_2D_all_neighbors); same outputs as
+// ref4_test_bimolecular_lpf / ref4_test_many_bimolecular (oracle/ref_mcell4_tiles_shim.cpp)
+int orc_unit_test_bimolecular_lpf(const double* cum_probs, int n, double scaling, double local_prob_factor, const uint32_t* words,
+                                  uint64_t n_words, long long* words_used) {
+  World w; w.cfg = mcx_config{};
+  w.pathways.resize(n);
+  for (int i = 0; i < n; i++) { w.pathways[i] = mcx_pathway{}; w.pathways[i].cum_prob = cum_probs[i]; }
+  mcx_rxn_class rc{}; rc.kind = MCX_RXN_BIMOL_SURFSURF; rc.first_pathway = 0; rc.n_pathways = n; rc.max_fixed_p = cum_probs[n - 1];
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  Eval E(w, rs);
+  int r = E.test_bimolecular(rc, scaling, local_prob_factor);
+  *words_used = rs.used;
+  return r;
+}
+int orc_unit_test_many_bimolecular(const double* cum_probs, const int* n_pathways, int n, const double* scaling, double local_prob_factor,
+                                   const uint32_t* words, uint64_t n_words, int* pathway, long long* words_used) {
+  World w; w.cfg = mcx_config{};
+  std::vector<int> rcs; std::vector<double> sc(scaling, scaling + n);
+  int q = 0;
+  for (int i = 0; i < n; i++) {
+    mcx_rxn_class rc{}; rc.kind = MCX_RXN_BIMOL_SURFSURF; rc.first_pathway = (uint32_t)w.pathways.size(); rc.n_pathways = (uint32_t)n_pathways[i];
+    for (int k = 0; k < n_pathways[i]; k++) { mcx_pathway pw{}; pw.cum_prob = cum_probs[q++]; w.pathways.push_back(pw); }
+    rc.max_fixed_p = w.pathways.back().cum_prob;
+    w.classes.push_back(rc); rcs.push_back(i);
+  }
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  Eval E(w, rs);
+  int pw_out = -7;
+  const int r = E.test_many_bimolecular(rcs, sc, local_prob_factor, pw_out);
+  *pathway = pw_out; *words_used = rs.used;
   return r;
 }
 int orc_unit_test_intersect(const double* cum_probs, int n, double scaling, const uint32_t* words, uint64_t n_words,

@@ -1,0 +1,62 @@
+"""Generates tests/golden/mcell4_tiles_vectors.npz from oracle/_ref/libmcell4tiles.so — MCell4's own find_neighbor_tiles
+(src4/grid_utils.inl:296-1801), test_bimolecular with a local probability factor and test_many_bimolecular
+(src4/rxn_utils.inl:336-414, 475-580), cut out of the reference files by line range and compiled unmodified
+(oracle/ref_mcell4_tiles_shim.cpp, `make -C oracle ref`).  Run in the build container (needs /root/reference):
+    python tests/golden/gen_mcell4_tiles_golden.py"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+sys.path.insert(0, HERE)
+import mcell4_tiles_cases as tc  # noqa: E402
+
+
+def vp(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def ref_table(L, V, T, mask):
+    per = np.zeros(len(T), np.uint32)
+    nt = L.ref4_tiles_num_tiles(vp(V), len(V), vp(T), len(T), vp(per))
+    start = np.zeros(nt + 1, np.uint32)
+    out = np.zeros(2 * 48 * nt, np.uint32)
+    n = L.ref4_neighbor_tile_table(vp(V), len(V), vp(T), len(T), vp(mask), vp(start), vp(out), C.c_ulonglong(48 * nt))
+    ntl = int(per[mask.astype(bool)].sum()) if mask is not None else nt
+    return per, start[:ntl + 1].copy(), out[:2 * n].copy()
+
+
+def main():
+    L = C.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libmcell4tiles.so"))
+    L.ref4_neighbor_tile_table.restype = C.c_ulonglong
+    out = {}
+    for k, (V, T) in enumerate(tc.meshes()):
+        for q, mask in enumerate(tc.grid_masks(len(T), k)):
+            per, start, pairs = ref_table(L, V, T, mask)
+            out["per_%d" % k] = per
+            out["start_%d_%d" % (k, q)] = start
+            out["pairs_%d_%d" % (k, q)] = pairs
+    L.ref4_test_bimolecular_lpf.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_uint, C.c_uint, C.c_void_p]
+    rows = []
+    for cum, scaling, lpf, seed, skip in tc.lpf_cases():
+        used = C.c_longlong(0)
+        r = L.ref4_test_bimolecular_lpf(vp(np.ascontiguousarray(cum)), len(cum), scaling, lpf, seed, skip, C.byref(used))
+        rows.append((r, used.value))
+    out["lpf_out"] = np.array(rows, np.int64)
+    L.ref4_test_many_bimolecular.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
+    rows = []
+    for cums, scaling, lpf, seed, skip in tc.many_cases():
+        flat = np.ascontiguousarray(np.concatenate(cums)); npw = np.array([len(c) for c in cums], np.int32)
+        pw = C.c_int(0); used = C.c_longlong(0)
+        r = L.ref4_test_many_bimolecular(vp(flat), vp(npw), len(cums), vp(np.ascontiguousarray(scaling)), lpf, seed, skip, C.byref(pw), C.byref(used))
+        rows.append((r, pw.value, used.value))
+    out["many_out"] = np.array(rows, np.int64)
+    np.savez_compressed(os.path.join(HERE, "mcell4_tiles_vectors.npz"), **out)
+    print("wrote", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

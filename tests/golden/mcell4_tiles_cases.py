@@ -1,0 +1,60 @@
+"""Cases of the neighbour-tile pins (tests/test_oracle_vs_reference_mcell4_tiles.py, gen_mcell4_tiles_golden.py): closed
+icospheres with perturbed vertices (walls with 1 to ~50 tiles, so neighbouring grids differ in size), an open fan of
+triangles around one vertex (free edges, a vertex shared by many walls) and a flat strip; with every wall holding a grid
+and with a random subset of the grids missing.  Reaction cases for test_bimolecular with a local probability factor and
+test_many_bimolecular."""
+import numpy as np
+
+from mcell_b200.model import create_icosphere
+
+
+def meshes():
+    rng = np.random.default_rng(5)
+    out = []
+    for sub, scale in ((1, 40), (1, 120), (1, 60), (2, 200), (2, 90), (1, 25), (3, 300), (1, 8)):
+        v, t = create_icosphere(0.05, sub)
+        V = np.ascontiguousarray(np.asarray(v, np.float64) * scale)
+        V = V * (1 + 0.25 * rng.random(V.shape))
+        out.append((V, np.ascontiguousarray(np.asarray(t), np.uint32)))
+    # a fan of 7 triangles around vertex 0 (open: the rim edges are free)
+    n = 7
+    ang = np.linspace(0, 1.7 * np.pi, n + 1)
+    V = np.zeros((n + 2, 3)); V[1:, 0] = 5.5 * np.cos(ang) * (1 + 0.2 * rng.random(n + 1)); V[1:, 1] = 5.5 * np.sin(ang); V[1:, 2] = 0.3 * rng.random(n + 1)
+    T = np.array([[0, i + 1, i + 2] for i in range(n)], np.uint32)
+    out.append((np.ascontiguousarray(V), T))
+    # a flat strip of 6 triangles with vertex orders rotated (every side of a wall gets to be the shared one)
+    V = np.array([[0, 0, 0], [4, 0, 0], [0.5, 3.7, 0], [4.4, 3.9, 0], [8.1, 0.2, 0], [8.6, 4.2, 0], [12.2, 0.1, 0], [12.0, 4.0, 0]], np.float64)
+    T = np.array([[0, 1, 2], [2, 1, 3], [3, 1, 4], [4, 5, 3], [6, 5, 4], [5, 6, 7]], np.uint32)
+    out.append((V, T))
+    return out
+
+
+def grid_masks(n_walls, k):
+    rng = np.random.default_rng(100 + k)
+    return [None, (rng.random(n_walls) < 0.7).astype(np.uint8), (rng.random(n_walls) < 0.3).astype(np.uint8)]
+
+
+def lpf_cases():
+    """(cumulative pathway probabilities, scaling, local probability factor, seed, skip)"""
+    rng = np.random.default_rng(11)
+    out = []
+    for i in range(400):
+        npw = int(rng.integers(1, 5))
+        cum = np.cumsum(rng.random(npw) * 10 ** rng.uniform(-3, 0.3))
+        scaling = float(10 ** rng.uniform(-2, 1))
+        lpf = 3.0 / float(rng.integers(1, 16))
+        out.append((cum, scaling, lpf, int(rng.integers(1, 1000)), int(rng.integers(0, 50))))
+    return out
+
+
+def many_cases():
+    """(list of cumulative pathway probabilities per class, scaling per class, local probability factor, seed, skip)"""
+    rng = np.random.default_rng(12)
+    out = []
+    for i in range(400):
+        n = int(rng.integers(2, 7))
+        cums = [np.cumsum(rng.random(int(rng.integers(1, 4))) * 10 ** rng.uniform(-3, 0.2)) for _ in range(n)]
+        scaling = 10 ** rng.uniform(-1.5, 1, n)
+        lpf = 3.0 / float(rng.integers(1, 16))
+        out.append((cums, scaling, lpf, int(rng.integers(1, 1000)), int(rng.integers(0, 50))))
+    return out

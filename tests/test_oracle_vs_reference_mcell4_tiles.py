@@ -1,0 +1,153 @@
+"""CPU tier: PINS the neighbour-tile search and the reaction test of surface-surface reactions against
+MCell4's OWN compiled code.
+
+tests/golden/mcell4_tiles_vectors.npz holds the outputs of oracle/_ref/libmcell4tiles.so — the reference's
+GridUtils::find_neighbor_tiles and everything under it (src4/grid_utils.inl:296-1801), RxnUtils::test_bimolecular with a
+local probability factor and test_many_bimolecular (src4/rxn_utils.inl:336-414, 475-580), cut out of the reference files
+by line range at build time and compiled unmodified (oracle/ref_mcell4_tiles_shim.cpp, oracle/Makefile: ref) — on the
+cases of tests/golden/mcell4_tiles_cases.py.  Three statements: the oracle's restatement (oracle/oracle_tiles.h)
+reproduces MCell4 entry for entry, with every grid present and with grids missing; so does the PRODUCT's table
+(mcx_tile_neighbor_table, the host code behind the device's tn_start / tn_list) once the entries of walls without a grid
+are left out the way the device leaves them out; and, where the compiled code is present, the same on fresh cases."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import mcell4_tiles_cases as tc  # noqa: E402
+from oracle import oracle_py as O  # noqa: E402
+from test_oracle_vs_reference import ref_words, vp  # noqa: E402
+
+G = np.load(os.path.join(HERE, "golden", "mcell4_tiles_vectors.npz"))
+
+
+def _vp(a):
+    return None if a is None else vp(a)
+
+
+def oracle_table(V, T, mask, per):
+    L = O.lib()
+    L.orc_unit_neighbor_tile_table.restype = C.c_ulonglong
+    nt = int(per.sum())
+    start = np.zeros(nt + 1, np.uint32)
+    out = np.zeros(2 * 48 * nt, np.uint32)
+    n = L.orc_unit_neighbor_tile_table(vp(V), len(V), vp(T), len(T), _vp(mask), vp(start), vp(out), C.c_ulonglong(48 * nt))
+    ntl = int(per[mask.astype(bool)].sum()) if mask is not None else nt
+    return start[:ntl + 1].copy(), out[:2 * n].copy()
+
+
+def product_table(V, T, per):
+    from mcell_b200.engine import load_library
+    L = load_library()
+    L.mcx_tile_neighbor_table.restype = C.c_uint64
+    L.mcx_tile_neighbor_table.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    nt = int(per.sum())
+    start = np.zeros(nt + 1, np.uint32)
+    out = np.zeros(2 * 48 * nt, np.uint32)
+    n = L.mcx_tile_neighbor_table(vp(V), len(V), vp(T), len(T), None, vp(start), vp(out), 48 * nt)
+    return start, out[:2 * n].reshape(-1, 2)
+
+
+def filtered(start, pairs, mask, per):
+    """What the device does with the static table (mcx_device.cuh: react_2D block): tiles of walls without a grid do not
+    exist, entries that name such a wall are skipped."""
+    first = np.concatenate([[0], np.cumsum(per)])
+    s_out, p_out = [0], []
+    for w in range(len(per)):
+        if mask is not None and not mask[w]:
+            continue
+        for t in range(int(per[w])):
+            g = int(first[w]) + t
+            e = pairs[start[g]:start[g + 1]]
+            if mask is not None:
+                e = e[mask[e[:, 0]].astype(bool)]
+            p_out.append(e)
+            s_out.append(s_out[-1] + len(e))
+    return np.array(s_out, np.uint32), (np.concatenate(p_out) if p_out else np.zeros((0, 2), np.uint32)).reshape(-1)
+
+
+def test_oracle_find_neighbor_tiles_equals_compiled_mcell4():
+    n_tiles = n_entries = 0
+    sizes = set()
+    for k, (V, T) in enumerate(tc.meshes()):
+        per = G["per_%d" % k]
+        sizes |= set(per.tolist())
+        for q, mask in enumerate(tc.grid_masks(len(T), k)):
+            start, pairs = oracle_table(V, T, mask, per)
+            assert np.array_equal(start, G["start_%d_%d" % (k, q)]), (k, q)
+            assert np.array_equal(pairs, G["pairs_%d_%d" % (k, q)]), (k, q)
+            n_tiles += len(start) - 1; n_entries += len(pairs) // 2
+    assert n_tiles > 15000 and n_entries > 120000 and {1, 4, 9, 16, 25, 36} <= sizes
+
+
+def test_product_neighbor_tile_table_equals_compiled_mcell4():
+    """The table libmcx builds once per geometry, filtered per wall like the device filters it, is MCell4's list for every
+    tile — in the reference's order, which decides which partner a molecule with several candidates reacts with."""
+    longest = 0
+    for k, (V, T) in enumerate(tc.meshes()):
+        per = G["per_%d" % k]
+        start, pairs = product_table(V, T, per)
+        longest = max(longest, int(np.diff(start).max()))
+        for q, mask in enumerate(tc.grid_masks(len(T), k)):
+            s, p = filtered(start, pairs, mask, per)
+            assert np.array_equal(s, G["start_%d_%d" % (k, q)]), (k, q)
+            assert np.array_equal(p, G["pairs_%d_%d" % (k, q)]), (k, q)
+    assert 12 <= longest <= 32   # the device holds up to 32 matching neighbours (SURFSURF_MAX_MATCHES)
+
+
+def test_test_bimolecular_with_local_prob_factor_and_test_many_bimolecular_match_compiled_mcell4():
+    L = O.lib()
+    L.orc_unit_test_bimolecular_lpf.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_uint64, C.c_void_p]
+    ref = G["lpf_out"]
+    reacted = 0
+    for i, (cum, scaling, lpf, seed, skip) in enumerate(tc.lpf_cases()):
+        tape = ref_words(seed, skip + 8)[skip:]
+        used = C.c_longlong(0)
+        r = L.orc_unit_test_bimolecular_lpf(vp(np.ascontiguousarray(cum)), len(cum), scaling, lpf, vp(tape), len(tape), C.byref(used))
+        assert r == int(ref[i, 0]) and used.value == int(ref[i, 1]) == 1, (i, r, ref[i])
+        reacted += r >= 0
+    assert 40 < reacted < 360
+    L.orc_unit_test_many_bimolecular.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    ref = G["many_out"]
+    chosen = set()
+    for i, (cums, scaling, lpf, seed, skip) in enumerate(tc.many_cases()):
+        flat = np.ascontiguousarray(np.concatenate(cums)); npw = np.array([len(c) for c in cums], np.int32)
+        tape = ref_words(seed, skip + 8)[skip:]
+        pw = C.c_int(0); used = C.c_longlong(0)
+        r = L.orc_unit_test_many_bimolecular(vp(flat), vp(npw), len(cums), vp(np.ascontiguousarray(scaling)), lpf, vp(tape), len(tape),
+                                             C.byref(pw), C.byref(used))
+        assert r == int(ref[i, 0]) and used.value == int(ref[i, 2]) == 1, (i, r, ref[i])
+        if r >= 0:
+            assert pw.value == int(ref[i, 1]), (i, pw.value, ref[i])
+        chosen.add(r)
+    assert {-1, 0, 1, 2} <= chosen
+
+
+def test_live_mcell4_on_fresh_meshes():
+    path = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libmcell4tiles.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libmcell4tiles.so is not built here (needs the reference tree)")
+    R = C.CDLL(path)
+    R.ref4_neighbor_tile_table.restype = C.c_ulonglong
+    from mcell_b200.model import create_icosphere
+    rng = np.random.default_rng(77)
+    for sub, scale in ((1, 80), (2, 140), (3, 420)):
+        v, t = create_icosphere(0.05, sub)
+        V = np.ascontiguousarray(np.asarray(v, np.float64) * scale * (1 + 0.3 * rng.random((len(v), 3))))
+        T = np.ascontiguousarray(np.asarray(t), np.uint32)
+        T = np.ascontiguousarray(np.stack([np.roll(row, int(rng.integers(0, 3))) for row in T]))   # rotate vertex orders
+        per = np.zeros(len(T), np.uint32)
+        nt = R.ref4_tiles_num_tiles(vp(V), len(V), vp(T), len(T), vp(per))
+        for mask in (None, (rng.random(len(T)) < 0.6).astype(np.uint8)):
+            start = np.zeros(nt + 1, np.uint32); out = np.zeros(2 * 48 * nt, np.uint32)
+            n = R.ref4_neighbor_tile_table(vp(V), len(V), vp(T), len(T), _vp(mask), vp(start), vp(out), C.c_ulonglong(48 * nt))
+            ntl = int(per[mask.astype(bool)].sum()) if mask is not None else nt
+            s_o, p_o = oracle_table(V, T, mask, per)
+            assert np.array_equal(s_o, start[:ntl + 1]) and np.array_equal(p_o, out[:2 * n])
+            s_p, p_p = product_table(V, T, per)
+            s_f, p_f = filtered(s_p, p_p, mask, per)
+            assert np.array_equal(s_f, start[:ntl + 1]) and np.array_equal(p_f, out[:2 * n])
