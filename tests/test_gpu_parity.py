@@ -714,3 +714,43 @@ def test_benchmark_chemistry_matches_oracle():
         state = sa
     assert (rules_seen > 0).all(), rules_seen          # every one of the six rules fired, incl. C + C and B + D -> C + C
     assert st_g.unresolved_conflicts == 0
+
+
+@pytest.mark.parametrize("static_b", [False, True])
+def test_philox_surface_surface_reactions(static_b):
+    """SURVEY 8 a23, react_2D_all_neighbors: surface molecules that react with the molecules on the tiles around their own —
+    after their move, over the neighbour tiles of the static table (walls without a grid left out), one test with the
+    local probability factor, several candidates through test_many_bimolecular; both consumed (product on the initiator's
+    tile), catalytic (partner kept), two surface products over the two freed tiles (the random assignment), a class whose
+    orientations never match.  static_b: a species that cannot diffuse but initiates.  Traces (partners in list order,
+    class, pathway, orientation / tile bits in the event hash), conflict rounds, counts, the whole population."""
+    t, mols = cm.surface_reactions(seed=4, static_b=static_b)
+    n = mols.n
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+    rx = retries = moved = 0
+    for it in range(14):
+        tr_o, st_o = o.trace_step(1, n)
+        tr_g, st_g = e.trace_step(n)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "unimol_rxns", "resolve_retries", "unresolved_conflicts", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        rx += st_g.bimol_rxns
+        retries += st_g.resolve_retries
+        moved += int((tr_g["outcome"][live] == abi.MCX_OUT_SURFMOVE).sum())
+        co, cg = o.counts(), e.counts()
+        assert (cg[0] == co[0]).all() and (cg[1] == co[1]).all(), it
+    assert rx > 150 and retries > 5 and moved > 3000, (rx, retries, moved)
+    sp, rule = e.counts()
+    assert rule[0] > 100 and rule[2] > 20 and rule[3] > 3 and rule[4] == 0, rule
+    # every rule moved the species counts the way it says (A, B, C, D, E, V)
+    assert sp[1] == 1500 - rule[0] + rule[3] and sp[2] == rule[0] - rule[1] and sp[3] == rule[2] - 2 * rule[3] and sp[4] == 300
+    assert sp[0] == 1500 - rule[0] + rule[1] - rule[2] + rule[3]
+    a, b = o.download().sorted_by_id(), e.download().sorted_by_id()
+    _assert_same_population(a, b)
+    s = b.wall != abi.MCX_NONE
+    assert len(np.unique(np.stack([b.wall[s], b.tile[s]], 1), axis=0)) == int(s.sum())
