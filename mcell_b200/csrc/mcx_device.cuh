@@ -1591,7 +1591,9 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
           const int my_orient = (flags & DF_ORIENT_UP) ? 1 : -1;
           for (uint32_t q = qb; q < qe; q++) {
             const uint2 wt = __ldg(p.tn_list + q);
-            if (!p.wall_has_grid[wt.x]) continue;  // Wall::has_initialized_grid (grid_utils.inl:1243, 783-790)
+            // Wall::has_initialized_grid (grid_utils.inl:1243, 783-790); the molecule's own wall always counts (a wall it
+            // has just moved to gets its grid with it)
+            if (wt.x != ss.wall && !p.wall_has_grid[wt.x]) continue;
             n_nb++;
             const DevGrid& ng = p.grids[wt.x];
             const uint32_t occ = p.tile_slot[ng.tile_start + wt.y];

@@ -22,6 +22,11 @@
 __device__ __forceinline__ unsigned long long claim_key(unsigned int epoch, uint32_t id) {
   return ((unsigned long long)epoch << 32) | (unsigned long long)(~id);
 }
+// A surface molecule that only takes a new tile claims itself and the tile WEAKLY: any reaction that consumes it, or that
+// needs the tile for its initiator, comes first (ids stay below 2^31, so bit 31 of ~id is set in every strong key).
+// Otherwise a reaction whose partner happens to move in the same iteration would be dropped half of the time — the
+// partner's own move would win the partner — and the re-evaluated initiator draws a new, independent reaction test.
+__device__ __forceinline__ unsigned long long weak_key(unsigned long long key) { return key & ~0x80000000ull; }
 // ---- warp-aggregated atomics: lanes of the (possibly divergent) warp that target the same address combine
 // into one atomic.  Counters and list cursors are hit by every committing thread; without this the L2 atomic
 // unit serialises them (profiles/r01_a: k_resolve 0.5 ms for 1.4e5 proposals).
@@ -544,6 +549,7 @@ __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot
   p.prop_t[slot] = o.t_event;
   p.rank[slot] = MCX_NONE;
   unsigned long long key = claim_key(epoch, id);
+  if (o.kind == MCX_OUT_SURFMOVE) key = weak_key(key);
   atomicMax(&p.claim[slot], key);
   if (partner_is_consumed(p, o.kind, o.rxn_class, o.pathway, species)) atomicMax(&p.claim[o.partner_slot], key);
   if (o.kind == MCX_OUT_SURFMOVE) {
@@ -1118,6 +1124,7 @@ __device__ __forceinline__ void resolve_round(const DevParams& p, unsigned int r
     const uint32_t orient_bits = (info >> 12) & ORIENT_BITS_MASK;
     uint32_t partner = __ldcg(p.prop_partner + slot);
     unsigned long long key = claim_key(epoch, e.id);
+    if (kind == MCX_OUT_SURFMOVE) key = weak_key(key);
     bool ok = __ldcg(p.claim + slot) == key;
     if (ok && partner_is_consumed(p, kind, rxn_class, pathway, species)) ok = __ldcg(p.claim + partner) == key;
     if (ok && kind == MCX_OUT_SURFMOVE) ok = __ldcg(p.tile_claim + p.grids[__ldcg(p.swallB + slot)].tile_start + __ldcg(p.stileB + slot)) == key;

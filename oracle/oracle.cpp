@@ -1624,7 +1624,10 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
       std::vector<int> m_rc; std::vector<double> m_factor; std::vector<uint32_t> m_index;
       const size_t ns = w.species.size();
       for (const WallTile& nt : nbt) {
-        const uint32_t nid = w.tiles[nt.first][nt.second];  // Grid::get_molecule_on_tile; the list only holds walls with a grid
+        // Grid::get_molecule_on_tile; the list only holds walls with a grid and the molecule's own wall (SNAPSHOT: a
+        // wall it has just moved to gets its grid at the end of the iteration; nobody else is on it yet)
+        if (w.tiles[nt.first].empty()) continue;
+        const uint32_t nid = w.tiles[nt.first][nt.second];
         if (nid == MCX_NONE || nid == m_id) continue;        // SNAPSHOT: the tile table still shows the mover on its old tile
         const uint32_t j = w.id_to_index[nid];
         if (E.snapshot && (*E.dead)[j]) continue;
@@ -2210,8 +2213,11 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     bool a_is_r0 = w.mols[i].species == c.reactants[0];
     return !((pw.keep_reactant_mask >> (a_is_r0 ? 1 : 0)) & 1);
   };
+  // a surface molecule that only takes a new tile claims itself and the tile WEAKLY: a reaction that consumes it, or
+  // that needs the tile for its initiator, comes first (see mcx_kernels.cu: weak_key)
+  auto prio_of = [&](uint32_t i) { return outs[i].kind == MCX_OUT_SURFMOVE ? (w.mols[i].id | 0x80000000u) : w.mols[i].id; };
   auto make_claims = [&](uint32_t i) {
-    uint32_t prio = w.mols[i].id;
+    uint32_t prio = prio_of(i);
     claim[i] = std::min(claim[i], prio);
     if (partner_consumed(i)) { uint32_t j = outs[i].partner_index; claim[j] = std::min(claim[j], prio); }
     if (outs[i].kind == MCX_OUT_SURFMOVE || (outs[i].kind == MCX_OUT_REACTED && outs[i].surf_moved)) {
@@ -2345,16 +2351,19 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     return;
   }
   // round 0: everyone
+  int dbg_prop0 = 0;
   for (uint32_t i = 0; i < n0; i++) {
     if (dead[i]) { outs[i].kind = MCX_OUT_NONE; continue; }
     eval_one(i, false);
     if (is_claiming(outs[i])) { pending.push_back(i); make_claims(i); }
+    if (outs[i].kind == MCX_OUT_REACTED) dbg_prop0++;
   }
+  if (getenv("ORC_DEBUG")) fprintf(stderr, "round0 REACTED proposals %d\n", dbg_prop0);
   for (uint32_t round = 0; round < max_rounds && !pending.empty(); round++) {
     // resolve: decisions use the claims as they stand; commits become visible afterwards
     std::vector<uint32_t> still, accepted;
     for (uint32_t i : pending) {
-      uint32_t prio = w.mols[i].id;
+      uint32_t prio = prio_of(i);
       bool ok = claim[i] == prio;
       if (ok && partner_consumed(i)) ok = claim[outs[i].partner_index] == prio;
       if (ok && (outs[i].kind == MCX_OUT_SURFMOVE || (outs[i].kind == MCX_OUT_REACTED && outs[i].surf_moved)))

@@ -275,8 +275,11 @@ def surface_reactions(n_a=1500, n_b=1500, n_e=300, radius_um=0.25, subdivisions=
     walls = np.arange(len(sf), dtype=np.uint32)
     # one draw of distinct tiles for all three species (release_on_walls keeps the tiles of one call distinct)
     allm = release_on_walls(rng, t, walls, n, A, orientation=1, first_id=0)
-    allm.species[n_a:n_a + n_b] = B
-    allm.species[n_a + n_b:] = E
+    # release_on_walls hands the molecules out wall by wall: mix the species over the sphere
+    sp = np.full(n, A, dtype=allm.species.dtype)
+    sp[n_a:n_a + n_b] = B
+    sp[n_a + n_b:] = E
+    allm.species[:] = rng.permutation(sp)
     return t, allm
 
 

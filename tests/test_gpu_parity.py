@@ -745,7 +745,7 @@ def test_philox_surface_surface_reactions(static_b):
         co, cg = o.counts(), e.counts()
         assert (cg[0] == co[0]).all() and (cg[1] == co[1]).all(), it
     assert rx > 150 and retries > 5 and moved > 3000, (rx, retries, moved)
-    sp, rule = e.counts()
+    sp, rule = (np.asarray(a, dtype=np.int64) for a in e.counts())
     assert rule[0] > 100 and rule[2] > 20 and rule[3] > 3 and rule[4] == 0, rule
     # every rule moved the species counts the way it says (A, B, C, D, E, V)
     assert sp[1] == 1500 - rule[0] + rule[3] and sp[2] == rule[0] - rule[1] and sp[3] == rule[2] - 2 * rule[3] and sp[4] == 300

@@ -1,6 +1,7 @@
 """CPU tier: the oracle (restatement of the reference algorithm) against analytic expectations and structural
 identities (the reference tree holds no golden vectors for the geometry/collision/reaction path),
 and the oracle's two execution modes against each other."""
+import ctypes as C
 import math
 
 import numpy as np
@@ -618,3 +619,84 @@ def test_checkpoint_resume_is_exact():
     assert (ref.flags == got.flags).all()
     assert (ref_counts[0] == counts[0]).all()
     assert (ref_counts[1] == counts[1] + saved_counts[1]).all() and ref_counts[1].sum() > 50
+
+
+# ---- surface-surface reactions -------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("static_b", [False, True])
+def test_surface_surface_reactions_bookkeeping(mode, static_b):
+    """react_2D_all_neighbors in both semantics: every rule moves the species counts the way it says, one molecule per
+    tile throughout, every surface molecule lies on the tile its uv names, products of A' + B' -> C' and D' + D' -> A' + B'
+    sit on tiles the reactants freed (no tile is gained or lost: surface molecules = tiles in use), the class whose
+    orientations cannot match never fires, and a species that cannot diffuse still takes part (static_b)."""
+    t, mols = cm.surface_reactions(seed=6, static_b=static_b)
+    o = O.Oracle(t)
+    o.upload(mols)
+    for _ in range(4):
+        o.step(10, mode)
+        sp, rule = (np.asarray(a, dtype=np.int64) for a in o.counts())
+        assert sp[1] == 1500 - rule[0] + rule[3] and sp[2] == rule[0] - rule[1] and sp[3] == rule[2] - 2 * rule[3] and sp[4] == 300
+        assert sp[0] == 1500 - rule[0] + rule[1] - rule[2] + rule[3] and sp[5] == 0 and rule[4] == 0
+        d = o.download()
+        s = d.wall != 0xFFFFFFFF
+        assert s.sum() == sp[:5].sum()
+        assert len(np.unique(np.stack([d.wall[s], d.tile[s]], 1), axis=0)) == s.sum()
+        L = load_library_for_grid()
+        for i in np.flatnonzero(s)[::37]:
+            v9 = np.ascontiguousarray(t.vertices[t.tri[d.wall[i]]].reshape(9))
+            xyz = np.array([d.x[i], d.y[i], d.z[i]])
+            assert L.mcx_xyz2grid(v9.ctypes.data_as(C.c_void_p), xyz.ctypes.data_as(C.c_void_p)) == d.tile[i]
+    assert rule[0] > 150 and rule[2] > 40 and rule[3] > 5, rule
+
+
+def load_library_for_grid():
+    from mcell_b200.engine import load_library
+    L = load_library()
+    L.mcx_xyz2grid.restype = C.c_uint32
+    L.mcx_xyz2grid.argtypes = [C.c_void_p, C.c_void_p]
+    return L
+
+
+def test_surface_surface_rate_is_mass_action_in_both_semantics():
+    """A' + B' -> C' alone at low coverage: each A tests the B's on its ~12 neighbour tiles with the local probability
+    factor 3 / (number of neighbour tiles) and vice versa, which adds up to the 2-D mass-action rate k [A][B] per area:
+    reactions per step = k dt n_A n_B / area.  Sequential (reference) and snapshot semantics both give it."""
+    from mcell_b200.model import Model, Config, create_icosphere, create_box, release_on_walls
+    k_rate, steps = None, 20
+    got = {0: 0, 1: 0}
+    want = 0.0
+    for seed in range(1, 7):
+        m = Model(Config(seed=seed))
+        A = m.add_species("A", 2e-7, surface=True)
+        m.add_species("B", 1e-7, surface=True)
+        m.add_species("C", 1e-7, surface=True)
+        pb = m.config.time_step * m.config.surface_grid_density / 6.0
+        k_rate = 0.03 / pb
+        m.add_reaction_rule(["A'", "B'"], ["C'"], k_rate)
+        sv, sf = create_icosphere(0.25, 3)
+        m.add_geometry_object(sv, sf)
+        bv, bf = create_box(0.8)
+        m.add_geometry_object(bv, bf)
+        n_a = n_b = 800
+        t = m.build(max_molecules=4 * n_a)
+        rng = np.random.default_rng(seed)
+        mols = release_on_walls(rng, t, np.arange(len(sf), dtype=np.uint32), n_a + n_b, A, orientation=1, first_id=0)
+        mols.species[:] = rng.permutation(np.r_[np.zeros(n_a, np.uint32), np.ones(n_b, np.uint32)]).astype(mols.species.dtype)
+        tri = np.asarray(sv)[np.asarray(sf)]
+        area_um2 = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1).sum()
+        for mode in (0, 1):
+            o = O.Oracle(t)
+            o.upload(mols)
+            na, nb = float(n_a), float(n_b)
+            exp = 0.0
+            for _ in range(steps):
+                o.step(1, mode)
+                sp, rule = o.counts()
+                exp += k_rate * m.config.time_step * na * nb / area_um2
+                na, nb = float(sp[0]), float(sp[1])
+            got[mode] += int(rule[0])
+            if mode == 0:
+                want += exp
+    for mode in (0, 1):
+        assert abs(got[mode] - want) < 4 * np.sqrt(want) + 0.06 * want, (mode, got, want)
+    assert abs(got[0] - got[1]) < 4 * np.sqrt(got[0] + got[1])
