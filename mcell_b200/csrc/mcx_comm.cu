@@ -219,6 +219,15 @@ static int exchange_halo(McxComm* c, DevParams& p, cudaStream_t s) {
   return MCX_OK;
 }
 
+// Wall::has_initialized_grid is a property of the whole mesh: a wall has its grid as soon as ANY rank holds a surface
+// molecule on it (the scatter marks the walls of the records a rank sees; the neighbour search of the surface-surface
+// reactions must not depend on where the slabs are cut).  One byte per wall, models with surface-surface classes only.
+static int share_wall_grids(McxComm* c, DevParams& p, cudaStream_t s) {
+  if (!p.surfsurf || !p.wall_has_grid || p.n_walls <= 0) return MCX_OK;
+  NCK(ncclAllReduce(p.wall_has_grid, p.wall_has_grid, (size_t)p.n_walls, ncclUint8, ncclMax, c->comm, s));
+  return MCX_OK;
+}
+
 int mcx_comm_iteration(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_t s) {
   mcx_launch_evaluate(p, plan, s);
   if (plan.has_fresh) {
@@ -235,7 +244,7 @@ int mcx_comm_iteration(McxComm* c, DevParams& p, const StepPlan& plan, cudaStrea
   if (plan.launches) *plan.launches += 4;
   mcx_launch_sort(p, plan, s);
   if (plan.prof) cudaEventRecord(plan.prof[3], s);
-  return MCX_OK;
+  return share_wall_grids(c, p, s);
 }
 
 int mcx_comm_refresh(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_t s) {
@@ -255,7 +264,7 @@ int mcx_comm_refresh(McxComm* c, DevParams& p, const StepPlan& plan, cudaStream_
   int rc = exchange_halo(c, p, s);
   if (rc) return rc;
   mcx_launch_sort(p, plan, s);
-  return MCX_OK;
+  return share_wall_grids(c, p, s);
 }
 
 int mcx_comm_allreduce_u64(McxComm* c, unsigned long long* host_buf, int n, cudaStream_t s) {

@@ -89,7 +89,8 @@ def test_two_ranks_match_single_gpu(scenario):
 
 
 @pytest.mark.skipif(_n_devices() < 2, reason="needs 2 CUDA devices")
-@pytest.mark.parametrize("scenario", ["receptors", "surface_diffusion", "counted_volumes", "transporter", "permeable", "region_border"])
+@pytest.mark.parametrize("scenario", ["receptors", "surface_diffusion", "counted_volumes", "transporter", "permeable", "region_border",
+                                      "surface_surface"])
 def test_two_ranks_match_single_gpu_surface_and_counted(scenario):
     """Surface molecules (tiles, binding, unbinding, 2-D diffusion across the slab face) and counted volumes with two
     ranks: the halo records carry Molecule::s and the creation wall / tile of surface-born volume products, the counted
@@ -109,6 +110,9 @@ def test_two_ranks_match_single_gpu_surface_and_counted(scenario):
         halo = 45.0
     elif scenario == "permeable":     # finite-rate reactions with a surface class, both directions
         make = lambda: cm.permeable_sphere(n=30000, radius_um=0.5, subdivisions=4, box_um=1.6, seed=6, products=False)  # noqa: E731
+        halo = 45.0
+    elif scenario == "surface_surface":   # react_2D_all_neighbors across the slab face; Wall::has_initialized_grid shared by the ranks
+        make = lambda: cm.surface_reactions(n_a=3000, n_b=3000, n_e=600, radius_um=0.5, subdivisions=4, box_um=1.6, seed=6)  # noqa: E731
         halo = 45.0
     elif scenario == "region_border":
         make = lambda: cm.diffusing_receptors(n_rec=4000, n_lig=20000, radius_um=0.5, subdivisions=4, box_um=1.6, seed=7,  # noqa: E731
