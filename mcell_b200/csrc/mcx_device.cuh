@@ -1442,6 +1442,82 @@ __device__ uint32_t ray_trace_surf(const DevParams& p, uint32_t wall_index, doub
 // SURF == false compiles the surface-molecule code out (models without surface species: the launcher picks the
 // instantiation from DevParams::has_surf), which gives the registers back to the volume path.
 // grp: the lanes that evaluate this molecule together (Group above); all of them pass identical arguments.
+// ---- react_2D_all_neighbors (diffuse_react_event.cpp:1250-1393): the molecules on the tiles around the tile of a surface
+// molecule (after its move); the lists are static (tn_start / tn_list, built on the host), walls without a grid are
+// left out here.  Out of line: its candidate arrays stay out of the stack frame of the common path.  Returns true when
+// a reaction fired (out: class, pathway, partner, time, orientation / tile bits).
+__device__ __noinline__ bool react_2d_all_neighbors(const DevParams& p, uint32_t self_id, uint32_t species, uint32_t flags,
+                                                    const SurfState& ss, double t_steps, double t_now, Stream& rs, Tracer& tc,
+                                                    Outcome& out, int& err) {
+  bool fired = false;
+  const uint32_t gt0 = p.grids[ss.wall].tile_start + ss.tile;
+  const uint32_t qb = __ldg(p.tn_start + gt0), qe = __ldg(p.tn_start + gt0 + 1);
+  int m_rc[SURFSURF_MAX_MATCHES]; double m_factor[SURFSURF_MAX_MATCHES]; uint32_t m_slot[SURFSURF_MAX_MATCHES], m_id[SURFSURF_MAX_MATCHES];
+  int n_match = 0; uint32_t n_nb = 0;
+  const int my_orient = (flags & DF_ORIENT_UP) ? 1 : -1;
+  for (uint32_t q = qb; q < qe; q++) {
+    const uint2 wt = __ldg(p.tn_list + q);
+    // Wall::has_initialized_grid (grid_utils.inl:1243, 783-790); the molecule's own wall always counts (a wall it
+    // has just moved to gets its grid with it)
+    if (wt.x != ss.wall && !p.wall_has_grid[wt.x]) continue;
+    n_nb++;
+    const DevGrid& ng = p.grids[wt.x];
+    const uint32_t occ = p.tile_slot[ng.tile_start + wt.y];
+    if (occ == MCX_NONE) continue;
+    const MolRec nsm = load_rec_volatile(p.recA, occ);
+    if (nsm.id == self_id || (nsm.sf & DF_DEAD)) continue;  // the tile table still shows the mover on its old tile
+    const int rc = p.surfsurf[species * p.n_species + (nsm.sf & SF_SPECIES_MASK)];
+    if (rc < 0 || !orientations_match(p.classes[rc], my_orient, (nsm.sf & DF_ORIENT_UP) ? 1 : -1)) continue;
+    if (n_match >= SURFSURF_MAX_MATCHES) { err = MCX_ERR_STATE; break; }
+    m_rc[n_match] = rc; m_factor[n_match] = t_steps / ng.binding_factor; m_slot[n_match] = occ; m_id[n_match] = nsm.id;
+    n_match++;
+  }
+  if (n_nb != 0 && n_match != 0) {
+    const double local_prob_factor = 3.0 / (double)n_nb;
+    int which = 0, pathway;
+    if (n_match == 1) pathway = test_bimolecular(p, p.classes[m_rc[0]], m_factor[0], rs, local_prob_factor);
+    else {
+      // RxnUtils::test_many_bimolecular with all_neighbors_flag (rxn_utils.inl:475-580)
+      double cum[SURFSURF_MAX_MATCHES];
+      cum[0] = p.classes[m_rc[0]].max_fixed_p * local_prob_factor / m_factor[0];
+      for (int i = 1; i < n_match; i++) cum[i] = cum[i - 1] + p.classes[m_rc[i]].max_fixed_p * local_prob_factor / m_factor[i];
+      double prob;
+      which = -1;
+      bool none = false;
+      if (cum[n_match - 1] > 1.0) prob = rs.dbl() * cum[n_match - 1];
+      else { prob = rs.dbl(); none = prob > cum[n_match - 1]; }
+      if (!none) {
+        // binary_search_double over the reference's zero-padded array of 2 n entries (:559)
+        int min_idx = 0, max_idx = 2 * n_match - 1;
+        while (max_idx - min_idx > 1) {
+          const int mid = (max_idx + min_idx) / 2;
+          if (prob > (mid < n_match ? cum[mid] : 0.0)) min_idx = mid; else max_idx = mid;
+        }
+        which = prob > (min_idx < n_match ? cum[min_idx] : 0.0) ? max_idx : min_idx;
+        if (which >= n_match) which = n_match - 1;
+      }
+      pathway = 0;  // sic (TODO_PATHWAYS, :1367): the first pathway of the chosen class
+    }
+    if (tc.tr) for (int i = 0; i < n_match; i++) { if (tc.tr->n_collisions < MCX_TRACE_K) tc.tr->partner[tc.tr->n_collisions] = m_id[i]; tc.tr->n_collisions++; }
+    if (which >= 0 && pathway >= 0) {
+      const int rc = m_rc[which];
+      const DevClass& cl = p.classes[rc];
+      const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
+      // random draws in the reference's order: tile assignment (find_surf_product_positions), then orientations
+      uint32_t bits = surfsurf_position_bits(p, pw, species == cl.r0, rs);
+      bits |= draw_orientation_bits(pw, rs);
+      tc.ev(EV_SURFSURF | (uint32_t)pathway, (uint32_t)rc);
+      tc.ev(EV_RXN | (bits & 0x7Fu), m_id[which]);
+      if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = m_id[which]; tc.tr->t_event = t_now; }
+      out.rxn_class = rc; out.pathway = pathway; out.partner_slot = m_slot[which]; out.partner_id = m_id[which];
+      out.t_event = t_now;  // collision_time = diffusion_start_time (:1343)
+      out.orient_bits = bits;
+      fired = true;
+    }
+  }
+  return fired;
+}
+
 template <bool RETRY, bool WITH_DISK, bool SURF>
 __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t_sched, double t_unimol_in,
                                    uint32_t created_wall, uint32_t created_tile, SurfState ss, unsigned int epoch,
@@ -1581,75 +1657,9 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
             placed = true;
           }
         }
-        // ---- react_2D_all_neighbors (:1250-1393): after its move the molecule tests the molecules on the tiles around its
-        // own; the lists are static (tn_start / tn_list, built on the host), walls without a grid are left out here
-        if (can_ss && !decided && !forced && !(sp.flags & MCX_SP_CANT_INITIATE) && p.tn_start) {
-          const uint32_t gt0 = p.grids[ss.wall].tile_start + ss.tile;
-          const uint32_t qb = __ldg(p.tn_start + gt0), qe = __ldg(p.tn_start + gt0 + 1);
-          int m_rc[SURFSURF_MAX_MATCHES]; double m_factor[SURFSURF_MAX_MATCHES]; uint32_t m_slot[SURFSURF_MAX_MATCHES], m_id[SURFSURF_MAX_MATCHES];
-          int n_match = 0; uint32_t n_nb = 0;
-          const int my_orient = (flags & DF_ORIENT_UP) ? 1 : -1;
-          for (uint32_t q = qb; q < qe; q++) {
-            const uint2 wt = __ldg(p.tn_list + q);
-            // Wall::has_initialized_grid (grid_utils.inl:1243, 783-790); the molecule's own wall always counts (a wall it
-            // has just moved to gets its grid with it)
-            if (wt.x != ss.wall && !p.wall_has_grid[wt.x]) continue;
-            n_nb++;
-            const DevGrid& ng = p.grids[wt.x];
-            const uint32_t occ = p.tile_slot[ng.tile_start + wt.y];
-            if (occ == MCX_NONE) continue;
-            const MolRec nsm = load_rec_volatile(p.recA, occ);
-            if (nsm.id == m.id || (nsm.sf & DF_DEAD)) continue;  // the tile table still shows the mover on its old tile
-            const int rc = p.surfsurf[species * p.n_species + (nsm.sf & SF_SPECIES_MASK)];
-            if (rc < 0 || !orientations_match(p.classes[rc], my_orient, (nsm.sf & DF_ORIENT_UP) ? 1 : -1)) continue;
-            if (n_match >= SURFSURF_MAX_MATCHES) { err = MCX_ERR_STATE; break; }
-            m_rc[n_match] = rc; m_factor[n_match] = t_steps / ng.binding_factor; m_slot[n_match] = occ; m_id[n_match] = nsm.id;
-            n_match++;
-          }
-          if (n_nb != 0 && n_match != 0) {
-            const double local_prob_factor = 3.0 / (double)n_nb;
-            int which = 0, pathway;
-            if (n_match == 1) pathway = test_bimolecular(p, p.classes[m_rc[0]], m_factor[0], rs, local_prob_factor);
-            else {
-              // RxnUtils::test_many_bimolecular with all_neighbors_flag (rxn_utils.inl:475-580)
-              double cum[SURFSURF_MAX_MATCHES];
-              cum[0] = p.classes[m_rc[0]].max_fixed_p * local_prob_factor / m_factor[0];
-              for (int i = 1; i < n_match; i++) cum[i] = cum[i - 1] + p.classes[m_rc[i]].max_fixed_p * local_prob_factor / m_factor[i];
-              double prob;
-              which = -1;
-              bool none = false;
-              if (cum[n_match - 1] > 1.0) prob = rs.dbl() * cum[n_match - 1];
-              else { prob = rs.dbl(); none = prob > cum[n_match - 1]; }
-              if (!none) {
-                // binary_search_double over the reference's zero-padded array of 2 n entries (:559)
-                int min_idx = 0, max_idx = 2 * n_match - 1;
-                while (max_idx - min_idx > 1) {
-                  const int mid = (max_idx + min_idx) / 2;
-                  if (prob > (mid < n_match ? cum[mid] : 0.0)) min_idx = mid; else max_idx = mid;
-                }
-                which = prob > (min_idx < n_match ? cum[min_idx] : 0.0) ? max_idx : min_idx;
-                if (which >= n_match) which = n_match - 1;
-              }
-              pathway = 0;  // sic (TODO_PATHWAYS, :1367): the first pathway of the chosen class
-            }
-            if (tc.tr) for (int i = 0; i < n_match; i++) { if (tc.tr->n_collisions < MCX_TRACE_K) tc.tr->partner[tc.tr->n_collisions] = m_id[i]; tc.tr->n_collisions++; }
-            if (which >= 0 && pathway >= 0) {
-              const int rc = m_rc[which];
-              const DevClass& cl = p.classes[rc];
-              const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
-              // random draws in the reference's order: tile assignment (find_surf_product_positions), then orientations
-              uint32_t bits = surfsurf_position_bits(p, pw, species == cl.r0, rs);
-              bits |= draw_orientation_bits(pw, rs);
-              tc.ev(EV_SURFSURF | (uint32_t)pathway, (uint32_t)rc);
-              tc.ev(EV_RXN | (bits & 0x7Fu), m_id[which]);
-              if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = m_id[which]; tc.tr->t_event = t_now; }
-              out.rxn_class = rc; out.pathway = pathway; out.partner_slot = m_slot[which]; out.partner_id = m_id[which];
-              out.t_event = t_now;  // collision_time = diffusion_start_time (:1343)
-              out.orient_bits = bits;
-              ss_fired = true;
-            }
-          }
-        }
+        // ---- react_2D_all_neighbors (:1250-1393): after its move the molecule tests the molecules on the tiles around its own
+        if (can_ss && !decided && !forced && !(sp.flags & MCX_SP_CANT_INITIATE) && p.tn_start)
+          ss_fired = react_2d_all_neighbors(p, m.id, species, flags, ss, t_steps, t_now, rs, tc, out, err);
         if ((!can_diffuse || ss.wall != original_wall) && unimol_time >= t_end) {  // MCell3 compatibility rule (:1222-1236)
           unimol_time = MCX_TIME_INVALID;
           flags |= DF_SCHED_UNIMOL;
