@@ -2351,14 +2351,11 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     return;
   }
   // round 0: everyone
-  int dbg_prop0 = 0;
   for (uint32_t i = 0; i < n0; i++) {
     if (dead[i]) { outs[i].kind = MCX_OUT_NONE; continue; }
     eval_one(i, false);
     if (is_claiming(outs[i])) { pending.push_back(i); make_claims(i); }
-    if (outs[i].kind == MCX_OUT_REACTED) dbg_prop0++;
   }
-  if (getenv("ORC_DEBUG")) fprintf(stderr, "round0 REACTED proposals %d\n", dbg_prop0);
   for (uint32_t round = 0; round < max_rounds && !pending.empty(); round++) {
     // resolve: decisions use the claims as they stand; commits become visible afterwards
     std::vector<uint32_t> still, accepted;
