@@ -541,7 +541,13 @@ def build_small_config(which):
     if which == 4:
         t, mols, _, _ = fs._config4(10_000_000, seed=4)
         return t, mols, "synapse-like nested meshes, 163 840 triangles, Ca/calbindin/pumps, 1e7 molecules (BASELINE configs[3])", 160.0, 4.0
-    raise SystemExit("bench.py: --config must be 1..5")
+    if which == 6:
+        # not a BASELINE config: the surface-surface path (react_2D_all_neighbors) at a size where it is measured
+        t, mols = cm.surface_reactions(n_a=450_000, n_b=450_000, n_e=100_000, radius_um=5.0, subdivisions=6, box_um=10.4, seed=6,
+                                       p=0.1, max_molecules=1_300_000)
+        return t, mols, ("surface-surface reactions: 1e6 surface molecules of 5 species diffusing on an icosphere of 20 480 triangles "
+                         "(3.5e6 tiles), A+B->C, C->A, A+E->D+E, D+D->A+B (extension, not in BASELINE.json)"), 160.0, 10.4
+    raise SystemExit("bench.py: --config must be 1..6")
 
 
 def _view(m, n):
@@ -562,7 +568,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--molecules", type=int, default=100_000_000)
-    ap.add_argument("--config", type=int, default=5, help="BASELINE.json config 1-5 (5 = the headline reactive box; 1-4 single GPU)")
+    ap.add_argument("--config", type=int, default=5, help="BASELINE.json config 1-5 (5 = the headline reactive box; 1-4 single GPU); 6 = surface-surface extension")
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cell-edge", type=float, default=0.0, help="device neighbour-cell edge in length units (0 = auto)")
