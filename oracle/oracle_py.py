@@ -87,7 +87,8 @@ class Oracle:
         t = tables
         self._v = lambda x: C.c_void_p(x.ctypes.data) if x is not None and x.size else None
         self.L.orc_set_species(self.h, t.species, C.c_uint32(t.n_species))
-        self.L.orc_set_reactions(self.h, t.classes, C.c_uint32(t.n_classes), t.pathways, C.c_uint32(t.n_pathways))
+        if self.L.orc_set_reactions(self.h, t.classes, C.c_uint32(t.n_classes), t.pathways, C.c_uint32(t.n_pathways)):
+            raise RuntimeError(self.error())   # a table the oracle (like the product) refuses
         self.L.orc_set_surface_classes(self.h, t.surf_rules, C.c_uint32(t.n_surf_rules))
         self.L.orc_set_geometry(self.h, self._v(t.vertices), C.c_uint64(len(t.vertices)), self._v(t.tri),
                                 C.c_uint64(len(t.tri)), self._v(t.wall_surf_class), self._v(getattr(t, "wall_object", None)))

@@ -174,6 +174,32 @@ EXPORT double ref3_compute_pb_factor_volvol(double time_unit, double length_unit
   return compute_pb_factor(time_unit, length_unit, grid_density, rx_radius_3d, &rf, &shared, &rx, 0);
 }
 
+// compute_pb_factor (src/react_util.c:45-183) for two surface molecules: time_unit * grid_density / 6, or / 3 when one of the
+// two cannot initiate
+EXPORT double ref3_compute_pb_factor_surfsurf(double time_unit, double length_unit, double grid_density, int a_cant_initiate,
+                                              int b_cant_initiate) {
+  struct species sa, sb;
+  memset(&sa, 0, sizeof(sa)); memset(&sb, 0, sizeof(sb));
+  sa.flags = ON_GRID; sb.flags = ON_GRID;
+  sa.D = 1; sb.D = 1;
+  if (a_cant_initiate) sa.flags |= CANT_INITIATE;
+  if (b_cant_initiate) sb.flags |= CANT_INITIATE;
+  struct species* players[2] = {&sa, &sb};
+  short geom[2] = {1, 1};
+  struct rxn rx;
+  memset(&rx, 0, sizeof(rx));
+  rx.n_reactants = 2;
+  rx.players = players;
+  rx.geometries = geom;
+  rx.get_reactant_diffusion = rxn_get_standard_diffusion;
+  rx.get_reactant_time_step = rxn_get_standard_time_step;
+  rx.get_reactant_space_step = rxn_get_standard_space_step;
+  struct reaction_flags rf;
+  memset(&rf, 0, sizeof(rf));
+  int shared = 0;
+  return compute_pb_factor(time_unit, length_unit, grid_density, 0.0, &rf, &shared, &rx, 0);
+}
+
 // ---- surface grids: src/grid_util.c (== Grid::initialize src4/wall.cpp:38-74, GridUtils::xyz2grid_tile_index /
 // grid2uv src4/grid_utils.inl:48-118,233-253) -------------------------------------------------------------------
 #include "grid_util.h"

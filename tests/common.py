@@ -283,6 +283,23 @@ def surface_reactions(n_a=1500, n_b=1500, n_e=300, radius_um=0.25, subdivisions=
     return t, allm
 
 
+def unsupported_surface_surface_tables():
+    """Surface-surface pathways outside the supported set: (what, tables).  Both the oracle and libmcx must
+    refuse them instead of approximating."""
+    out = []
+    for what, products in (("needs a vacant neighbour tile", ["C'", "D'", "A'"]),
+                           ("frees two tiles, fills one, next to a volume product", ["C'", "V,"])):
+        m = Model(Config(seed=1))
+        for n in ("A", "B", "C", "D"):
+            m.add_species(n, 1e-7, surface=True)
+        m.add_species("V", 1e-6)
+        m.add_reaction_rule(["A'", "B'"], products, 1e4)
+        sv, sf = create_icosphere(0.1, 1)
+        m.add_geometry_object(sv, sf)
+        out.append((what, m.build(max_molecules=16)))
+    return out
+
+
 def counted_spheres(n=12000, seed=1, box_um=0.8, rng_mode=abi.MCX_RNG_PHILOX, p_target=0.4, max_molecules=None):
     """Counted volumes: two nested transparent icospheres, both counted, inside a counted
     reflective box; A + B -> C everywhere.  Volumes: {box}, {box, outer}, {box, outer, inner} (+ the empty set)."""

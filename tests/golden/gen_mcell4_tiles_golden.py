@@ -54,6 +54,13 @@ def main():
         r = L.ref4_test_many_bimolecular(vp(flat), vp(npw), len(cums), vp(np.ascontiguousarray(scaling)), lpf, seed, skip, C.byref(pw), C.byref(used))
         rows.append((r, pw.value, used.value))
     out["many_out"] = np.array(rows, np.int64)
+    # compute_pb_factor of MCell3 (src/react_util.c:84-100, libmcell3ref.so) for two surface molecules: (time_unit,
+    # grid_density, a TARGET_ONLY, b TARGET_ONLY) -> factor
+    L3 = C.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libmcell3ref.so"))
+    L3.ref3_compute_pb_factor_surfsurf.restype = C.c_double
+    L3.ref3_compute_pb_factor_surfsurf.argtypes = [C.c_double] * 3 + [C.c_int] * 2
+    out["pb_surfsurf"] = np.array([[tu, gd, a, b, L3.ref3_compute_pb_factor_surfsurf(tu, 1 / np.sqrt(gd), gd, a, b)]
+                                   for tu, gd in ((1e-6, 1e4), (5e-7, 1.5e4)) for a, b in ((0, 0), (1, 0), (0, 1))])
     np.savez_compressed(os.path.join(HERE, "mcell4_tiles_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -754,3 +754,13 @@ def test_philox_surface_surface_reactions(static_b):
     _assert_same_population(a, b)
     s = b.wall != abi.MCX_NONE
     assert len(np.unique(np.stack([b.wall[s], b.tile[s]], 1), axis=0)) == int(s.sum())
+
+
+def test_unsupported_surface_surface_pathways_are_refused():
+    """mcx_set_reactions refuses surface-surface pathways it cannot place (products on vacant neighbour tiles; the
+    reference's non-terminating tile assignment) and the combination with region borders, with a message."""
+    from mcell_b200 import McxError
+    for what, t in cm.unsupported_surface_surface_tables():
+        with pytest.raises(McxError) as ei:
+            _engine(t)
+        assert "surface-surface" in str(ei.value), (what, str(ei.value))

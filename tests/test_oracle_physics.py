@@ -700,3 +700,9 @@ def test_surface_surface_rate_is_mass_action_in_both_semantics():
     for mode in (0, 1):
         assert abs(got[mode] - want) < 4 * np.sqrt(want) + 0.06 * want, (mode, got, want)
     assert abs(got[0] - got[1]) < 4 * np.sqrt(got[0] + got[1])
+
+
+def test_oracle_refuses_unsupported_surface_surface_pathways():
+    for what, t in cm.unsupported_surface_surface_tables():
+        with pytest.raises(RuntimeError):
+            O.Oracle(t)

@@ -127,6 +127,37 @@ def test_test_bimolecular_with_local_prob_factor_and_test_many_bimolecular_match
     assert {-1, 0, 1, 2} <= chosen
 
 
+def test_table_builder_surface_surface_classes_use_the_reference_pb_factor():
+    """mcell_b200/model.py builds MCX_RXN_BIMOL_SURFSURF classes with MCell3's compute_pb_factor for two surface molecules
+    (src/react_util.c:84-100, compiled in libmcell3ref.so: time_unit * grid_density / 6, / 3 when one reactant is
+    TARGET_ONLY), rule order of the reactants, orientations, kept reactants and the order of the rule's products."""
+    from mcell_b200 import abi
+    from mcell_b200.model import Model, Config, create_icosphere
+    for tu, gd, a_t, b_t, want in G["pb_surfsurf"]:
+        m = Model(Config(time_step=float(tu), surface_grid_density=float(gd)))
+        m.add_species("A", 1e-7, surface=True, target_only=bool(a_t))
+        m.add_species("B", 1e-7, surface=True, target_only=bool(b_t))
+        m.add_species("C", 1e-7, surface=True)
+        m.add_species("V", 1e-6)
+        m.add_reaction_rule(["B,", "A'"], ["C'", "V,"], 7.0)
+        m.add_reaction_rule(["B,", "A'"], ["B,", "C"], 3.0)
+        sv, sf = create_icosphere(0.1, 1)
+        m.add_geometry_object(sv, sf)
+        t = m.build(max_molecules=8)
+        c = t.classes[0]
+        assert c.kind == abi.MCX_RXN_BIMOL_SURFSURF and (c.reactants[0], c.reactants[1]) == (1, 0)
+        assert (c.reactant_orientation[0], c.reactant_orientation[1]) == (-1, 1) and c.n_pathways == 2
+        p0, p1 = t.pathways[c.first_pathway], t.pathways[c.first_pathway + 1]
+        assert p0.cum_prob == pytest.approx(7.0 * want, rel=1e-15) and p1.cum_prob == pytest.approx(10.0 * want, rel=1e-15)
+        assert c.max_fixed_p == p1.cum_prob
+        assert p0.keep_reactant_mask == 0 and p0.n_products == 2 and (p0.products[0], p0.products[1]) == (2, 3)
+        assert p1.keep_reactant_mask == 1 and p1.n_products == 1 and p1.products[0] == 2 and p1.product_orientation[0] == 0
+        # rule order of the products of pathway 1: kept reactant 0 (B, down), then product 0
+        assert p1.kept_info & abi.MCX_KEPT_VALID
+        assert (p1.kept_info & 0xF) == abi.MCX_KEPT_ORDER_REACTANT and ((p1.kept_info >> 4) & 0xF) == 0
+        assert ((p1.kept_info >> 24) & 3) == 2
+
+
 def test_live_mcell4_on_fresh_meshes():
     path = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libmcell4tiles.so")
     if not os.path.exists(path):
