@@ -252,3 +252,40 @@ def test_config4_full_size_sample_matches_oracle():
     t, mols, _, _ = _config4(10_000_000, seed=4)
     tr, st = _compare_full_size_sample(t, mols, stride=512, offset=7, warm_iterations=2)
     assert (tr["n_wall_hits"] > 0).sum() > 100 and (tr["n_collisions"] > 0).sum() > 500
+
+
+def test_config6_surface_surface_1e6_whole_iterations_match_oracle():
+    """Surface-surface reactions at the size bench.py --config 6 times (1e6 surface molecules on 20 480 triangles, 3.5e6
+    tiles): the oracle finishes an iteration of this in seconds, so WHOLE iterations are compared — traces of all
+    molecules (tiles taken, partners in list order, class, pathway, tile / orientation bits, conflict rounds), statistics,
+    species and rule counts — and the populations at the end."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from oracle import oracle_py as O
+    t, mols, _, _, _ = bench.build_small_config(6)
+    n = mols.n
+    e, o = _engine(t), O.Oracle(t)
+    e.upload(mols)
+    o.upload(mols)
+    rx = 0
+    for it in range(3):
+        tr_o, st_o = o.trace_step(1, n)
+        tr_g, st_g = e.trace_step(n)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad[:3])
+        for k in ("bimol_rxns", "unimol_rxns", "resolve_retries", "unresolved_conflicts", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        co, cg = o.counts(), e.counts()
+        assert (np.asarray(cg[0]) == np.asarray(co[0])).all() and (np.asarray(cg[1]) == np.asarray(co[1])).all(), it
+        rx += st_g.bimol_rxns
+    assert rx > 50000 and st_g.unresolved_conflicts == 0
+    a, b = o.download().sorted_by_id(), e.download().sorted_by_id()
+    assert a.n == b.n and (a.id == b.id).all() and (a.species == b.species).all()
+    assert (a.wall == b.wall).all() and (a.tile == b.tile).all() and (a.orientation == b.orientation).all()
+    assert cm.rel_close(a.u, b.u, 1e-12).all() and cm.rel_close(a.v, b.v, 1e-12).all()
+    s = b.wall != abi.MCX_NONE
+    assert len(np.unique(np.stack([b.wall[s], b.tile[s]], 1), axis=0)) == int(s.sum())
