@@ -2495,6 +2495,10 @@ int orc_set_species(void* h, const mcx_species* s, uint32_t n) {
 int orc_set_reactions(void* h, const mcx_rxn_class* c, uint32_t nc, const mcx_pathway* p, uint32_t np) {
   World& w = *(World*)h; w.classes.assign(c, c + nc); w.pathways.assign(p, p + np); build_lookups(w);
   for (const mcx_rxn_class& rc : w.classes)
+    if (rc.kind == MCX_RXN_BIMOL_SURFSURF && !w.wall_border.empty()) {
+      w.err = "surface-surface classes together with region borders are not supported (restricted regions of the neighbour search)"; return -1;
+    }
+  for (const mcx_rxn_class& rc : w.classes)
     if (rc.kind == MCX_RXN_BIMOL_SURFSURF)
       for (uint32_t q = 0; q < rc.n_pathways; q++)
         if (const char* why = surfsurf_pathway_problem(w, w.pathways[rc.first_pathway + q])) { w.err = why; return -1; }
@@ -2521,7 +2525,11 @@ int orc_set_counted_volume_objects(void* h, const uint32_t* cv_object_mask, uint
 }
 int orc_set_region_borders(void* h, const uint8_t* wall_edge_border) {
   World& w = *(World*)h;
-  if (wall_edge_border) w.wall_border.assign(wall_edge_border, wall_edge_border + w.walls.size()); else w.wall_border.clear();
+  if (wall_edge_border) {
+    for (uint8_t c : w.can_surf_surf)
+      if (c) { w.err = "region borders together with surface-surface classes are not supported (restricted regions of the neighbour search)"; return -1; }
+    w.wall_border.assign(wall_edge_border, wall_edge_border + w.walls.size());
+  } else w.wall_border.clear();
   return 0;
 }
 int orc_set_surface_regions(void* h, uint32_t n_region_sets, const uint8_t* wall_region_set) {

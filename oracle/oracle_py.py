@@ -99,7 +99,8 @@ class Oracle:
         if getattr(t, "n_region_sets", 0) > 1:
             self.L.orc_set_surface_regions(self.h, C.c_uint32(t.n_region_sets), self._v(t.wall_region_set))
         if getattr(t, "wall_edge_border", None) is not None:
-            self.L.orc_set_region_borders(self.h, self._v(t.wall_edge_border))
+            if self.L.orc_set_region_borders(self.h, self._v(t.wall_edge_border)):
+                raise RuntimeError(self.error())
 
     def close(self):
         if self.h:

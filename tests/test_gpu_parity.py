@@ -764,3 +764,28 @@ def test_unsupported_surface_surface_pathways_are_refused():
         with pytest.raises(McxError) as ei:
             _engine(t)
         assert "surface-surface" in str(ei.value), (what, str(ei.value))
+
+
+def test_replay_surface_surface_reactions():
+    """The surface-surface scenario with per-molecule ISAAC64 tape slices (replay mode): the draws of the neighbour test,
+    the tile assignment and the orientations come off the replayed stream in the reference's order on both sides."""
+    t, mols = cm.surface_reactions(seed=11, rng_mode=abi.MCX_RNG_TAPE)
+    n = mols.n
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+    rx = 0
+    for it in range(5):
+        words, off = cm.isaac_slices(300 + it, n, 64)
+        tr_o, st_o = o.trace_step(2, n, words, off)
+        tr_g, st_g = e.replay_step(words, off)
+        live = np.flatnonzero(tr_o["rounds"] > 0)
+        assert (np.flatnonzero(tr_g["rounds"] > 0) == live).all(), it
+        bad = cm.compare_traces(tr_o, tr_g, live, check_rounds=True)
+        assert not bad, (it, bad)
+        for k in ("bimol_rxns", "unimol_rxns", "resolve_retries", "unresolved_conflicts", "n_live"):
+            assert getattr(st_g, k) == getattr(st_o, k), (it, k)
+        rx += st_g.bimol_rxns
+        assert (np.asarray(e.counts()[1]) == np.asarray(o.counts()[1])).all(), it
+    assert rx > 300, rx
+    _assert_same_population(o.download().sorted_by_id(), e.download().sorted_by_id())
