@@ -401,6 +401,14 @@ int mcx_release_volume_molecules(mcx_handle* h, const mcx_release* r, uint32_t* 
  * can only raise it.  Same call on every rank. */
 int mcx_get_next_molecule_id(mcx_handle* h, uint32_t* next_id_out);
 int mcx_set_next_molecule_id(mcx_handle* h, uint32_t next_id);
+/* Replaces: Wall::has_initialized_grid of every wall (src4/wall.h:339-346) as part of a checkpoint.  A wall gets its grid
+ * with its first surface molecule and keeps it; the neighbour search of the surface-surface reactions skips walls without
+ * one (src4/grid_utils.inl:1243, 783-790), so the flags belong to the state of a model with MCX_RXN_BIMOL_SURFSURF
+ * classes.  mcx_upload_molecules never takes a grid away (the host may add and remove molecules between steps, the
+ * reference's walls keep their grids); mcx_set_geometry starts over.  A run resumed on a new handle restores the saved
+ * flags with mcx_set_wall_grids after the upload (they are OR-ed in).  One byte per wall, 0 / 1. */
+int mcx_get_wall_grids(mcx_handle* h, uint8_t* has_grid_out, uint64_t n_walls);
+int mcx_set_wall_grids(mcx_handle* h, const uint8_t* has_grid, uint64_t n_walls);
 /* ReleaseEvent::release_list (release_event.cpp:1008-1040), volume molecules: one molecule of species[k] at
  * (x[k], y[k], z[k]) (length units) with counted_volume[k] (may be NULL: 0), ids first_id .. first_id + n - 1 in list
  * order, added to the resident population without a download / upload round trip.  Same call on every rank. */

@@ -127,7 +127,7 @@ EXPORTED_SYMBOLS = [
     "mcx_download_molecules", "mcx_num_molecules", "mcx_step", "mcx_replay_step", "mcx_trace_step",
     "mcx_counts", "mcx_comm_init", "mcx_comm_unique_id", "mcx_slab_info_get", "mcx_comm_halo_path", "mcx_philox_block", "mcx_set_profiling",
     "mcx_grid_num_tiles", "mcx_grid2uv", "mcx_xyz2grid", "mcx_set_counted_volumes", "mcx_counts_by_volume", "mcx_release_volume_molecules", "mcx_fast_pass_kind", "mcx_walls_per_subpart",
-    "mcx_set_surface_regions", "mcx_counts_by_surface_region", "mcx_release_list", "mcx_release_surface_molecules", "mcx_set_region_borders", "mcx_set_counted_volume_objects", "mcx_get_next_molecule_id", "mcx_set_next_molecule_id", "mcx_tile_neighbor_table",
+    "mcx_set_surface_regions", "mcx_counts_by_surface_region", "mcx_release_list", "mcx_release_surface_molecules", "mcx_set_region_borders", "mcx_set_counted_volume_objects", "mcx_get_next_molecule_id", "mcx_set_next_molecule_id", "mcx_tile_neighbor_table", "mcx_get_wall_grids", "mcx_set_wall_grids",
 ]
 
 

@@ -900,8 +900,8 @@ int mcx_upload_molecules(mcx_handle* h, const mcx_mol_soa* m) {
   // the run (the reference's MolOrRxnCountEvent reports reactions since t = 0, and ids of dead molecules must not
   // be handed out again); k_pack_soa raises next_id above every uploaded id
   mcx_launch_reset_population(h->p, (unsigned int)n, s);
-  // Wall::has_initialized_grid starts over with the uploaded population (the scatter marks the walls that hold molecules)
-  if (h->p.wall_has_grid && h->n_walls_host) CK(cudaMemsetAsync(h->p.wall_has_grid, 0, h->n_walls_host, s));
+  // Wall::has_initialized_grid is NOT reset: the reference's walls keep their grids when molecules are added or taken away
+  // on the host; the scatter marks the walls the uploaded population sits on (mcx_set_wall_grids restores a checkpoint)
   bind_iteration(h);
   mcx_launch_pack_soa(h->p, h->st_x, h->st_y, h->st_z, h->st_id, h->st_sp, m->flags ? h->st_fl : nullptr,
                       m->diffusion_time ? h->st_ts : nullptr, m->unimol_rxn_time ? h->st_tu : nullptr, sv, (unsigned int)n, s);
@@ -1157,6 +1157,28 @@ int mcx_set_next_molecule_id(mcx_handle* h, uint32_t next_id) {
     CK(cudaMemcpyAsync(&h->p.ctr->next_id, &next_id, sizeof(next_id), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
+  return MCX_OK;
+}
+
+int mcx_get_wall_grids(mcx_handle* h, uint8_t* has_grid_out, uint64_t n_walls) {
+  if (!h || !has_grid_out) { if (h) h->err = "null wall-grid array"; return MCX_ERR_INVALID_ARG; }
+  if (!h->has_geometry || n_walls != h->n_walls_host) { h->err = "mcx_get_wall_grids: wall count differs from the geometry"; return MCX_ERR_INVALID_ARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (n_walls) CK(cudaMemcpy(has_grid_out, h->p.wall_has_grid, n_walls, cudaMemcpyDeviceToHost));
+  return MCX_OK;
+}
+
+int mcx_set_wall_grids(mcx_handle* h, const uint8_t* has_grid, uint64_t n_walls) {
+  if (!h || !has_grid) { if (h) h->err = "null wall-grid array"; return MCX_ERR_INVALID_ARG; }
+  if (!h->has_geometry || n_walls != h->n_walls_host) { h->err = "mcx_set_wall_grids: wall count differs from the geometry"; return MCX_ERR_INVALID_ARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  // grids are never taken away: the saved flags are OR-ed into what the uploaded population has set already
+  std::vector<uint8_t> cur(std::max<uint64_t>(n_walls, 1), 0);
+  if (n_walls) CK(cudaMemcpy(cur.data(), h->p.wall_has_grid, n_walls, cudaMemcpyDeviceToHost));
+  for (uint64_t i = 0; i < n_walls; i++) cur[i] = (cur[i] || has_grid[i]) ? 1 : 0;
+  if (n_walls) CK(cudaMemcpy(h->p.wall_has_grid, cur.data(), n_walls, cudaMemcpyHostToDevice));
   return MCX_OK;
 }
 

@@ -59,6 +59,8 @@ def load_library():
     L.mcx_release_surface_molecules.argtypes = [H, C.POINTER(abi.mcx_surface_release), C.POINTER(C.c_uint32)]
     L.mcx_get_next_molecule_id.argtypes = [H, C.POINTER(C.c_uint32)]
     L.mcx_set_next_molecule_id.argtypes = [H, C.c_uint32]
+    L.mcx_get_wall_grids.argtypes = [H, C.c_void_p, C.c_uint64]
+    L.mcx_set_wall_grids.argtypes = [H, C.c_void_p, C.c_uint64]
     L.mcx_set_profiling.argtypes = [H, C.c_int]
     L.mcx_philox_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
     L.mcx_philox_block.restype = None
@@ -189,6 +191,16 @@ class Engine:
         out = C.c_uint32(0)
         self._ck(self.L.mcx_get_next_molecule_id(self.h, C.byref(out)))
         return int(out.value)
+
+    def wall_grids(self, set_to=None):
+        """Wall::has_initialized_grid of every wall (one byte each): query, or (checkpoint resume) OR the saved flags in."""
+        n = len(self.t.tri)
+        if set_to is not None:
+            a = np.ascontiguousarray(set_to, dtype=np.uint8)
+            self._ck(self.L.mcx_set_wall_grids(self.h, C.c_void_p(a.ctypes.data), n))
+        out = np.zeros(max(n, 1), np.uint8)
+        self._ck(self.L.mcx_get_wall_grids(self.h, C.c_void_p(out.ctypes.data), n))
+        return out[:n]
 
     def num_molecules(self):
         return int(self.L.mcx_num_molecules(self.h))

@@ -44,6 +44,7 @@ GpuDiffuseReactEvent::GpuDiffuseReactEvent(const GpuModelTables& t, PartitionMol
   check(mcx_set_geometry(h, t.vertices.data(), t.vertices.size() / 3, t.wall_vertex_indices.data(),
                          t.wall_vertex_indices.size() / 3, t.wall_surf_class.empty() ? nullptr : t.wall_surf_class.data(),
                          nullptr), "mcx_set_geometry");
+  n_walls = t.wall_vertex_indices.size() / 3;
   for (const mcx_pathway& pw : t.pathways) n_rules = std::max<size_t>(n_rules, pw.rxn_rule_id + 1);
   for (const mcx_species& sp : t.species) has_surface_species = has_surface_species || !(sp.flags & MCX_SP_VOL);
   if (!t.wall_cv_front.empty()) {
@@ -114,6 +115,8 @@ void GpuDiffuseReactEvent::upload_from_host() {
   if (has_surface_species) { v.wall = swall.data(); v.tile = stile.data(); v.orientation = sorient.data(); v.u = su.data(); v.v = sv.data(); }
   check(mcx_upload_molecules(h, &v), "mcx_upload_molecules");
   check(mcx_set_next_molecule_id(h, p->next_molecule_id), "mcx_set_next_molecule_id");   // e.g. restored from a checkpoint
+  if (has_surface_species && n_walls && p->wall_has_grid.size() == n_walls)              // likewise: walls keep their grids
+    check(mcx_set_wall_grids(h, p->wall_has_grid.data(), n_walls), "mcx_set_wall_grids");
   host_dirty = false;
 }
 
@@ -157,6 +160,10 @@ void GpuDiffuseReactEvent::sync_to_host() {
     uint32_t next = 0;
     check(mcx_get_next_molecule_id(h, &next), "mcx_get_next_molecule_id");
     if (next > p->next_molecule_id) p->next_molecule_id = next;
+  }
+  if (has_surface_species && n_walls) {  // Wall::has_initialized_grid follows the device too
+    p->wall_has_grid.resize(n_walls);
+    check(mcx_get_wall_grids(h, p->wall_has_grid.data(), n_walls), "mcx_get_wall_grids");
   }
   device_dirty = false;
 }

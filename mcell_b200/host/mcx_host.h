@@ -111,6 +111,9 @@ struct PartitionMolecules {
   std::vector<Molecule> molecules;
   std::vector<uint32_t> molecule_id_to_index_mapping;
   molecule_id_t next_molecule_id = 0;
+  // Wall::has_initialized_grid of every wall (src4/wall.h:339-346), one byte each; empty = not tracked.  Part of a checkpoint
+  // of a model with surface-surface reactions: sync_to_host() fills it, the adapter's upload restores it
+  std::vector<uint8_t> wall_has_grid;
 
   // Partition::add_volume_molecule (partition.h:555-611): assigns the id, marks a newborn
   Molecule& add_volume_molecule(species_id_t species, const Vec3& pos, double birthday);
@@ -206,6 +209,7 @@ private:
   uint32_t n_cv = 1, n_rs = 1;
   bool has_cv_masks = false;   // the device can compute a counted volume by a ray cast (MCX_MOL_CVI_PENDING)
   bool has_surface_species = false;
+  uint64_t n_walls = 0;
   double time_up_to_next_barrier;
   double iterations_last_step = 1;
   bool host_dirty = true, device_dirty = false;

@@ -2476,6 +2476,7 @@ int orc_set_geometry(void* h, const double* v, uint64_t nv, const uint32_t* tri,
   }
   w.grids.resize(nw);
   for (uint64_t i = 0; i < nw; i++) grid_init(w, w.walls[i], w.grids[i]);
+  w.tiles.assign(nw, {});  // a new geometry starts without grids
   w.tiles.assign(nw, {});
   w.tile_start.assign(nw + 1, 0);
   for (uint64_t i = 0; i < nw; i++) w.tile_start[i + 1] = w.tile_start[i] + w.grids[i].n_tiles;
@@ -2563,7 +2564,10 @@ int orc_counts_by_volume(void* h, uint64_t* mol_counts, uint64_t* rxn_counts) {
 int orc_upload_molecules(void* h, const mcx_mol_soa* s) {
   World& w = *(World*)h;
   w.mols.clear(); w.lists.clear(); w.sched_ids.clear(); w.id_to_index.clear();
-  w.tiles.assign(w.walls.size(), {});
+  // the walls keep their grids (Wall::has_initialized_grid) across uploads like the reference's walls do when the host adds or
+  // removes molecules; only the occupancy starts over
+  if (w.tiles.size() != w.walls.size()) w.tiles.assign(w.walls.size(), {});
+  for (auto& tl : w.tiles) std::fill(tl.begin(), tl.end(), MCX_NONE);
   std::fill(w.species_count.begin(), w.species_count.end(), 0);
   uint32_t max_id = 0;
   for (uint64_t i = 0; i < s->n; i++) max_id = std::max(max_id, s->id[i]);
@@ -2826,6 +2830,18 @@ int orc_release_list(void* h, uint64_t n_list, const uint32_t* species, const do
 }
 int orc_get_next_molecule_id(void* h, uint32_t* out) { *out = ((World*)h)->next_id; return 0; }
 int orc_set_next_molecule_id(void* h, uint32_t next_id) { World& w = *(World*)h; if (next_id > w.next_id) w.next_id = next_id; return 0; }
+int orc_get_wall_grids(void* h, uint8_t* out, uint64_t n_walls) {
+  World& w = *(World*)h;
+  for (uint64_t i = 0; i < n_walls && i < w.walls.size(); i++) out[i] = (i < w.tiles.size() && !w.tiles[i].empty()) ? 1 : 0;
+  return 0;
+}
+int orc_set_wall_grids(void* h, const uint8_t* in, uint64_t n_walls) {
+  World& w = *(World*)h;
+  if (w.tiles.size() != w.walls.size()) w.tiles.resize(w.walls.size());
+  for (uint64_t i = 0; i < n_walls && i < w.walls.size(); i++)
+    if (in[i] && w.tiles[i].empty()) w.tiles[i].assign(w.grids[i].n_tiles, MCX_NONE);
+  return 0;
+}
 uint64_t orc_num_molecules(void* h) {
   World& w = *(World*)h; uint64_t n = 0;
   for (auto& m : w.mols) n += !(m.flags & MCX_MOL_DEFUNCT);

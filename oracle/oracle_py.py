@@ -170,6 +170,15 @@ class Oracle:
         self.L.orc_get_next_molecule_id(self.h, C.byref(out))
         return int(out.value)
 
+    def wall_grids(self, set_to=None):
+        n = len(self.t.tri)
+        if set_to is not None:
+            a = np.ascontiguousarray(set_to, dtype=np.uint8)
+            self.L.orc_set_wall_grids(self.h, C.c_void_p(a.ctypes.data), C.c_uint64(n))
+        out = np.zeros(max(n, 1), np.uint8)
+        self.L.orc_get_wall_grids(self.h, C.c_void_p(out.ctypes.data), C.c_uint64(n))
+        return out[:n]
+
     def num_molecules(self):
         return int(self.L.orc_num_molecules(self.h))
 

@@ -525,6 +525,24 @@ def test_checkpoint_resume_is_exact_on_the_device():
     assert (ref_counts[1] == counts[1] + saved_counts[1]).all() and ref_counts[1].sum() > 50
 
 
+def test_checkpoint_resume_with_surface_surface_reactions_on_the_device():
+    """The same with surface-surface reactions: Wall::has_initialized_grid travels with the checkpoint
+    (mcx_get_wall_grids / mcx_set_wall_grids); the device's flags equal the oracle's."""
+    import test_oracle_physics as top
+    ref, ref_counts, got, counts, saved_counts = top._run_resume(lambda t: _engine(t), total=10, stop=5,
+                                                                 case=top._resume_case_surface_surface)
+    _assert_same_population(ref, got)
+    assert (ref_counts[1] == counts[1] + saved_counts[1]).all() and ref_counts[1].sum() > 20
+    t, mols = top._resume_case_surface_surface()
+    o, e = _oracle(t), _engine(t)
+    o.upload(mols)
+    e.upload(mols)
+    assert (o.wall_grids() == e.wall_grids()).all()
+    o.step(5, 1)
+    e.step(5)
+    assert (o.wall_grids() == e.wall_grids()).all() and e.wall_grids().sum() > 0
+
+
 def test_more_than_256_species_and_rules():
     """The device counters hold 1024 species and 1024 reaction rules (the reference has no such limit; round 1 stopped at
     256): a chain of 600 species with one unimolecular rule each, populations and per-rule counts against the oracle."""

@@ -582,9 +582,15 @@ def _resume_case():
     return cm.reversible_box(n=6000, edge_um=0.4, seed=31)
 
 
-def _run_resume(make_engine, total=8, stop=3):
+def _resume_case_surface_surface():
+    # few molecules per wall, so that walls gain their grids while the run goes on: Wall::has_initialized_grid is state
+    return cm.surface_reactions(n_a=220, n_b=220, n_e=60, radius_um=0.25, subdivisions=3, seed=33, D_surf=6e-7)
+
+
+def _run_resume(make_engine, total=8, stop=3, case=None, restore_wall_grids=True):
     """run `total` iterations at once, and `stop` iterations + download + a NEW engine at initial_iteration = stop +
     upload + the rest: both ends of the checkpoint must give the same population"""
+    _resume_case = case or globals()["_resume_case"]
     t, mols = _resume_case()
     a = make_engine(t)
     a.upload(mols)
@@ -597,11 +603,14 @@ def _run_resume(make_engine, total=8, stop=3):
     for _ in range(stop):
         b.step(1) if not hasattr(b, "SNAPSHOT") else b.step(1, 1)
     saved, saved_counts, saved_next = b.download(), b.counts(), b.next_molecule_id()
+    saved_grids = b.wall_grids()
     t2, _ = _resume_case()
     t2.cfg.initial_iteration = stop
     c = make_engine(t2)
     c.upload(saved)
     assert c.next_molecule_id(set_to=saved_next) == saved_next     # ids of molecules that are gone are not handed out again
+    if restore_wall_grids:
+        assert (c.wall_grids(set_to=saved_grids) == saved_grids).all()   # walls that held a molecule once keep their grid
     for _ in range(total - stop):
         c.step(1) if not hasattr(c, "SNAPSHOT") else c.step(1, 1)
     got = c.download().sorted_by_id()
@@ -619,6 +628,29 @@ def test_checkpoint_resume_is_exact():
     assert (ref.flags == got.flags).all()
     assert (ref_counts[0] == counts[0]).all()
     assert (ref_counts[1] == counts[1] + saved_counts[1]).all() and ref_counts[1].sum() > 50
+
+
+def test_checkpoint_resume_with_surface_surface_reactions_needs_the_wall_grids():
+    """Wall::has_initialized_grid is part of the state of a model with surface-surface reactions (the neighbour search
+    skips walls without a grid, which also sets the probability factor): restored with the population the resumed run is
+    exact; the saved flags are a superset of the walls the saved population sits on."""
+    ref, ref_counts, got, counts, saved_counts = _run_resume(lambda t: O.Oracle(t), total=10, stop=5, case=_resume_case_surface_surface)
+    assert ref.n == got.n and (ref.id == got.id).all() and (ref.species == got.species).all()
+    for k in ("x", "y", "z", "diffusion_time", "unimol_rxn_time", "wall", "tile", "u", "v"):
+        assert (getattr(ref, k) == getattr(got, k)).all(), k
+    assert (ref_counts[1] == counts[1] + saved_counts[1]).all() and ref_counts[1].sum() > 20
+    # without the flags the resumed run is a different one
+    _, _, lost, _, _ = _run_resume(lambda t: O.Oracle(t), total=10, stop=5, case=_resume_case_surface_surface, restore_wall_grids=False)
+    assert lost.n != ref.n or not ((lost.wall == ref.wall).all() and (lost.tile == ref.tile).all() and (lost.species == ref.species).all())
+    t, mols = _resume_case_surface_surface()
+    o = O.Oracle(t)
+    o.upload(mols)
+    g0 = o.wall_grids()
+    o.step(5, 1)
+    g1 = o.wall_grids()
+    d = o.download()
+    on = np.zeros(len(t.tri), bool); on[d.wall[d.wall != 0xFFFFFFFF]] = True
+    assert (g1 >= g0).all() and g1.sum() > g0.sum() and (g1[on] == 1).all() and (g1.astype(bool) & ~on).sum() > 0
 
 
 # ---- surface-surface reactions (SURVEY 8 a23) -------------------------------------------------------------------------
