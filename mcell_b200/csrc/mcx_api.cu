@@ -55,6 +55,7 @@ struct mcx_handle {
   // surface-surface reactions: host copy of the mesh (the neighbour-tile table is built when a table with such classes and
   // a geometry are both there) and the device tables
   bool has_surfsurf = false;
+  bool has_general = false;   // some pathway puts surface products on vacant neighbour tiles (DevPathway::general)
   std::vector<double> geom_verts; std::vector<uint32_t> geom_tri, geom_wall_object;
   void *d_surfsurf = nullptr, *d_tn_start = nullptr, *d_tn_list = nullptr, *d_wall_has_grid = nullptr;
   uint32_t *st_wall = nullptr, *st_tile = nullptr; int32_t* st_orient = nullptr; double *st_u = nullptr, *st_v = nullptr;
@@ -425,6 +426,16 @@ static int rebuild_tables(mcx_handle* h) {
   if (h->classes.size() > 8191) { h->err = "more than 8191 reaction classes (proposal word)"; return MCX_ERR_INVALID_ARG; }
   std::vector<DevClass> dc(h->classes.size());
   std::vector<DevPathway> dp(h->pathways.size());
+  std::vector<uint8_t> general(h->pathways.size(), 0);
+  // a pathway that creates more surface products than it consumes surface reactants puts the extra ones on vacant
+  // neighbour tiles (find_surf_product_positions' general branch): what it needs from the table
+  auto check_general = [&](const mcx_rxn_class& rc, uint32_t q, int consumed_surf, int kept_surf) -> const char* {
+    const mcx_pathway& pw = h->pathways[rc.first_pathway + q];
+    if (!(pw.kept_info & MCX_KEPT_VALID)) return "a pathway with surface products on vacant neighbour tiles needs kept_info (the order of the rule's products)";
+    if (consumed_surf > 0 && kept_surf > 0) return "a pathway with surface products on vacant neighbour tiles that keeps one surface reactant and consumes another is not supported";
+    general[rc.first_pathway + q] = 1;
+    return nullptr;
+  };
   for (size_t c = 0; c < h->classes.size(); c++) {
     const mcx_rxn_class& rc = h->classes[c];
     if ((uint64_t)rc.first_pathway + (uint64_t)rc.n_pathways > (uint64_t)h->pathways.size() || rc.n_pathways == 0 || rc.n_pathways > 4095) {
@@ -464,8 +475,8 @@ static int rebuild_tables(mcx_handle* h) {
         for (uint32_t k = 0; k < pw.n_products && k < MCX_MAX_PRODUCTS; k++) needed += (pw.products[k] < ns && !is_vol(pw.products[k])) ? 1 : 0;
         const int freed = 2 - keep0 - keep1, actual = (int)pw.n_products + keep0 + keep1;
         if (needed > freed) {
-          h->err = "a surface-surface pathway with more new surface products than consumed reactants needs vacant neighbour tiles (not supported)";
-          return MCX_ERR_INVALID_ARG;
+          if (const char* why = check_general(rc, q, freed, keep0 + keep1)) { h->err = std::string("surface-surface pathway: ") + why; return MCX_ERR_INVALID_ARG; }
+          continue;
         }
         const int to_recycle = std::min(actual, freed);
         if (needed != 0 && !(needed == 1 && to_recycle == 1) && needed < to_recycle) {
@@ -498,7 +509,7 @@ static int rebuild_tables(mcx_handle* h) {
         const int surf_idx = rc.kind == MCX_RXN_BIMOL_VOLSURF ? 1 : 0;
         const bool surf_kept = (pw.keep_reactant_mask >> surf_idx) & 1u;
         if (n_surf_products > 1 || (n_surf_products == 1 && surf_kept)) {
-          h->err = "surface products beyond the recycled tile of the surface reactant are not supported"; return MCX_ERR_INVALID_ARG;
+          if (const char* why = check_general(rc, q, surf_kept ? 0 : 1, surf_kept ? 1 : 0)) { h->err = why; return MCX_ERR_INVALID_ARG; }
         }
         // a kept surface partner is not claimed by the event (several molecules may react with it in one iteration),
         // so it cannot change its orientation there: it has to carry the mark of the class on both sides
@@ -519,6 +530,7 @@ static int rebuild_tables(mcx_handle* h) {
     DevPathway d{};
     d.cum_prob = pw.cum_prob; d.n_products = pw.n_products; d.keep_mask = pw.keep_reactant_mask; d.rule_id = pw.rxn_rule_id;
     d.kept_info = pw.kept_info;
+    d.general = general[k];
     for (uint32_t q = 0; q < pw.n_products; q++) {
       if (pw.products[q] >= ns) { h->err = "product references an unknown species"; return MCX_ERR_INVALID_ARG; }
       d.products[q] = pw.products[q];
@@ -615,13 +627,19 @@ static int rebuild_tables(mcx_handle* h) {
   DevParams& p = h->p;
   p.volsurf = (const int*)h->d_volsurf;
   p.surfsurf = any_surfsurf ? (const int*)h->d_surfsurf : nullptr;
-  if (any_surfsurf != h->has_surfsurf || (any_surfsurf && !p.tn_start)) {
-    h->has_surfsurf = any_surfsurf;
-    const int trc = build_tile_neighbors(h);
-    if (trc != MCX_OK) return trc;
+  h->has_general = false;
+  for (uint8_t g : general) h->has_general = h->has_general || g != 0;
+  {  // the neighbour-tile table serves the partner search of surface-surface classes and the vacant tiles of general pathways
+    const bool need_tiles = any_surfsurf || h->has_general;
+    if (need_tiles != h->has_surfsurf || (need_tiles && !p.tn_start)) {
+      h->has_surfsurf = need_tiles;
+      const int trc = build_tile_neighbors(h);
+      if (trc != MCX_OK) return trc;
+    }
   }
   p.exd_skip = (const uint8_t*)h->d_exd_skip;
   h->has_surf = any_surf;
+
   p.species = (const DevSpecies*)h->d_species; p.bimol = (const int*)h->d_bimol; p.unimol = (const int*)h->d_unimol;
   p.classes = (const DevClass*)h->d_classes; p.pathways = (const DevPathway*)h->d_pathways;
   p.surf_rxn = (const int*)h->d_surf_rxn; p.surf_border = (const uint8_t*)h->d_surf_border;
@@ -849,6 +867,13 @@ static int ensure_staging(mcx_handle* h) {
 // cold per-slot surface fields and their staging: only models with surface species pay for them
 static int ensure_surface_arrays(mcx_handle* h) {
   h->p.has_surf = h->has_surf ? 1 : 0;
+  if (h->has_surf && h->has_general && !h->p.prop_pmask) {  // placements of the pending proposals (place_general)
+    int rcg = MCX_OK;
+    rcg |= dev_alloc(h, &h->p.prop_ptile, (size_t)h->p.capacity * MCX_MAX_PRODUCTS);
+    rcg |= dev_alloc(h, &h->p.prop_puv, (size_t)h->p.capacity * MCX_MAX_PRODUCTS);
+    rcg |= dev_alloc(h, &h->p.prop_pmask, (size_t)h->p.capacity);
+    if (rcg) return MCX_ERR_CUDA;
+  }
   if (!h->has_surf || h->surf_allocated) return MCX_OK;
   const size_t cap = h->p.capacity;
   DevParams& p = h->p;

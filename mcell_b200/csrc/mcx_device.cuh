@@ -1442,13 +1442,119 @@ __device__ uint32_t ray_trace_surf(const DevParams& p, uint32_t wall_index, doub
 // SURF == false compiles the surface-molecule code out (models without surface species: the launcher picks the
 // instantiation from DevParams::has_surf), which gives the registers back to the volume path.
 // grp: the lanes that evaluate this molecule together (Group above); all of them pass identical arguments.
+// GridUtils::grid2uv (grid_utils.inl:233-253) and grid2uv_random (:256-288)
+__device__ __forceinline__ void tile_uv(const DevParams& p, uint32_t wi, uint32_t tile, bool random, Stream& rs, double& u, double& v) {
+  const DevWall& f = p.walls[wi];
+  const DevGrid& g = p.grids[wi];
+  const int root = (int)(sqrt((double)tile));
+  const int rootrem = (int)tile - root * root;
+  const int k = g.n_axis - root - 1;
+  const int j = rootrem / 2;
+  const int i = rootrem - 2 * j;
+  if (!random) {
+    const double over3n = 1 / (double)(3 * g.n_axis);
+    u = ((double)(3 * j + i + 1)) * over3n * f.uv1u + ((double)(3 * k + i + 1)) * over3n * f.uv2u;
+    v = ((double)(3 * k + i + 1)) * over3n * f.uv2v;
+    return;
+  }
+  const double over_n = 1 / (double)(g.n_axis);
+  const double u_ran = rs.dbl();
+  const double v_ran = 1 - sqrt(rs.dbl());
+  u = ((double)(j + i) + (1 - 2 * i) * (1 - v_ran) * u_ran) * over_n * f.uv1u + ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv2u;
+  v = ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv2v;
+}
+
+// ---- products on vacant neighbour tiles: the general branch of find_surf_product_positions (:2060-2100, 2155-2285) ----
+// A pathway that creates more surface products than it frees tiles (DevPathway::general) puts the extra ones on vacant
+// tiles around the surface reactant — the row of the neighbour-tile table, every wall counting (create_grid_flag) — at a
+// random point of the tile (grid2uv_random).  The reference's bookkeeping is kept literally: positions are assigned per
+// entry of the rule's product list (kept reactants and volume products draw a tile too and waste it), the c-th CREATED
+// surface product takes the position of the c-th ENTRY (:2815-2818).  Draws in the reference's order: recycled tiles,
+// vacant tiles, orientations, random points.  The result goes to the proposal arrays of `slot` (all lanes of a group
+// write the same values).  Returns false when the reaction is blocked (RX_BLOCKED).
+// rec_*: the sites of the consumed surface reactants in the order of the rule's reactants.
+__device__ __noinline__ bool place_general(const DevParams& p, const DevClass& cl, const DevPathway& pw, uint32_t slot,
+                                           uint32_t reac_wall, uint32_t reac_tile, int n_rec, const uint32_t* rec_wall,
+                                           const uint32_t* rec_tile, const double2* rec_uv, bool forced, unsigned int epoch_first,
+                                           unsigned int epoch, bool retry, Stream& rs, uint32_t& orient_bits) {
+  // entries of the rule's product list (kept_info nibbles): bit 0 surface, bit 1 kept
+  int n_ent = 0; uint8_t ent[6];
+  for (int q = 0; q < 6; q++) {
+    const uint32_t nib = (pw.kept_info >> (4 * q)) & 0xFu;
+    if (nib == MCX_KEPT_ORDER_END) break;
+    if (nib >= MCX_KEPT_ORDER_REACTANT) {
+      const uint32_t sp = (nib & 1u) ? cl.r1 : cl.r0;
+      ent[n_ent++] = (uint8_t)(2u | ((sp < (uint32_t)p.n_species && !(p.species[sp].flags & MCX_SP_VOL)) ? 1u : 0u));
+    } else if (nib < pw.n_products) ent[n_ent++] = (uint8_t)((p.species[pw.products[nib]].flags & MCX_SP_VOL) ? 0u : 1u);
+  }
+  const int n_reactants = cl.kind == MCX_RXN_UNIMOL ? 1 : 2;
+  int needed = 0;
+  for (uint32_t k = 0; k < pw.n_products; k++) needed += (p.species[pw.products[k]].flags & MCX_SP_VOL) ? 0 : 1;
+  // vacant tiles around the surface reactant, from the back of the reference's list (:2090-2098)
+  const uint32_t gt0 = p.grids[reac_wall].tile_start + reac_tile;
+  const uint32_t qb = __ldg(p.tn_start + gt0), qe = __ldg(p.tn_start + gt0 + 1);
+  uint2 vacant[SURFSURF_MAX_MATCHES];
+  int n_vac = 0;
+  for (uint32_t q = qe; q > qb; q--) {
+    const uint2 wt = __ldg(p.tn_list + (q - 1));
+    const uint32_t gt = p.grids[wt.x].tile_start + wt.y;
+    const unsigned int ce = (unsigned int)(retry ? (__ldcg(p.tile_claim + gt) >> 32) : 0ull);
+    const bool ok = !forced && p.tile_slot[gt] == MCX_NONE && !(retry && ce >= epoch_first && ce < epoch);
+    if (ok && n_vac < SURFSURF_MAX_MATCHES) vacant[n_vac++] = wt;
+  }
+  if (n_vac + n_rec < needed) return false;
+  int assigned[6];   // -1 nothing, 0/1 recycled site, 2 + j vacant tile j
+  for (int e = 0; e < 6; e++) assigned[e] = -1;
+  const int to_recycle = n_ent < n_rec ? n_ent : n_rec;
+  int next_available = 0;
+  const uint32_t num_players = (uint32_t)(n_ent + n_reactants);
+  for (int guard = 0; next_available < to_recycle && guard < 100000; guard++) {  // :2159-2191
+    const uint32_t rnd = rs.next() % num_players;
+    if (rnd < (uint32_t)n_reactants) continue;
+    const int e = (int)rnd - n_reactants;
+    if (!(ent[e] & 1u)) continue;
+    if (assigned[e] >= 0) continue;
+    assigned[e] = next_available++;
+  }
+  uint32_t used = 0;
+  for (int e = 0; e < n_ent; e++) {  // :2232-2283: every entry without a position draws a vacant tile
+    if (assigned[e] >= 0) continue;
+    int attempts = 0; bool found = false;
+    while (!found && attempts < 10) {
+      const uint32_t rnd = rs.next() % (uint32_t)n_vac;
+      if ((used >> rnd) & 1u) { attempts++; continue; }
+      assigned[e] = 2 + (int)rnd; used |= 1u << rnd; found = true;
+    }
+    if (attempts >= 10) return false;
+  }
+  orient_bits = draw_orientation_bits(pw, rs);
+  int cnt = 0; uint32_t vac_mask = 0;
+  for (int e = 0; e < n_ent; e++) {
+    if (ent[e] != 1u) continue;   // created surface products only
+    const int a = assigned[cnt];
+    uint2 wt; double2 uv;
+    if (a >= 2) {
+      wt = vacant[a - 2]; vac_mask |= 1u << cnt;
+      tile_uv(p, wt.x, wt.y, true, rs, uv.x, uv.y);   // grid2uv_random (:2852-2855)
+    } else {
+      const int r = a < 0 ? 0 : a;
+      wt = make_uint2(rec_wall[r], rec_tile[r]); uv = rec_uv[r];
+    }
+    p.prop_ptile[slot * MCX_MAX_PRODUCTS + cnt] = wt;
+    p.prop_puv[slot * MCX_MAX_PRODUCTS + cnt] = uv;
+    cnt++;
+  }
+  p.prop_pmask[slot] = (uint32_t)cnt | (vac_mask << 4);
+  return true;
+}
+
 // ---- react_2D_all_neighbors (diffuse_react_event.cpp:1250-1393): the molecules on the tiles around the tile of a surface
 // molecule (after its move); the lists are static (tn_start / tn_list, built on the host), walls without a grid are
 // left out here.  Out of line: its candidate arrays stay out of the stack frame of the common path.  Returns true when
 // a reaction fired (out: class, pathway, partner, time, orientation / tile bits).
-__device__ __noinline__ bool react_2d_all_neighbors(const DevParams& p, uint32_t self_id, uint32_t species, uint32_t flags,
-                                                    const SurfState& ss, double t_steps, double t_now, Stream& rs, Tracer& tc,
-                                                    Outcome& out, int& err) {
+__device__ __noinline__ bool react_2d_all_neighbors(const DevParams& p, uint32_t self_id, uint32_t slot, uint32_t species, uint32_t flags,
+                                                    const SurfState& ss, double t_steps, double t_now, unsigned int epoch_first,
+                                                    unsigned int epoch, bool retry, Stream& rs, Tracer& tc, Outcome& out, int& err) {
   bool fired = false;
   const uint32_t gt0 = p.grids[ss.wall].tile_start + ss.tile;
   const uint32_t qb = __ldg(p.tn_start + gt0), qe = __ldg(p.tn_start + gt0 + 1);
@@ -1504,8 +1610,25 @@ __device__ __noinline__ bool react_2d_all_neighbors(const DevParams& p, uint32_t
       const DevClass& cl = p.classes[rc];
       const DevPathway& pw = p.pathways[cl.first_pathway + pathway];
       // random draws in the reference's order: tile assignment (find_surf_product_positions), then orientations
-      uint32_t bits = surfsurf_position_bits(p, pw, species == cl.r0, rs);
-      bits |= draw_orientation_bits(pw, rs);
+      uint32_t bits = 0;
+      bool blocked = false;
+      if (pw.general) {
+        const uint32_t ps = m_slot[which];
+        const bool me_r0 = species == cl.r0;
+        uint32_t rw[2], rt[2]; double2 ruv[2]; int n_rec = 0;
+        for (int r = 0; r < 2; r++) {
+          if ((pw.keep_mask >> r) & 1u) continue;
+          const bool mine = (r == 0) == me_r0;
+          rw[n_rec] = mine ? ss.wall : p.swallA[ps]; rt[n_rec] = mine ? ss.tile : p.stileA[ps];
+          ruv[n_rec] = mine ? make_double2(ss.u, ss.v) : p.suvA[ps];
+          n_rec++;
+        }
+        blocked = !place_general(p, cl, pw, slot, ss.wall, ss.tile, n_rec, rw, rt, ruv, false, epoch_first, epoch, retry, rs, bits);
+      } else {
+        bits = surfsurf_position_bits(p, pw, species == cl.r0, rs);
+        bits |= draw_orientation_bits(pw, rs);
+      }
+      if (blocked) { tc.ev(EV_BLOCKED, m_id[which]); return false; }   // RX_BLOCKED: the molecule survives (:1388-1392)
       tc.ev(EV_SURFSURF | (uint32_t)pathway, (uint32_t)rc);
       tc.ev(EV_RXN | (bits & 0x7Fu), m_id[which]);
       if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = m_id[which]; tc.tr->t_event = t_now; }
@@ -1519,7 +1642,7 @@ __device__ __noinline__ bool react_2d_all_neighbors(const DevParams& p, uint32_t
 }
 
 template <bool RETRY, bool WITH_DISK, bool SURF>
-__device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t_sched, double t_unimol_in,
+__device__ void evaluate_iteration(const DevParams& p, const MolRec& m, uint32_t slot, double t_sched, double t_unimol_in,
                                    uint32_t created_wall, uint32_t created_tile, SurfState ss, unsigned int epoch,
                                    Stream& rs, bool forced, Outcome& out, LocalStats& ls, Tracer& tc, int& err, const Group& grp) {
   const uint32_t species = m.sf & SF_SPECIES_MASK;
@@ -1569,12 +1692,26 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
         }
         pathway = match > A[min_idx].cum_prob ? max_idx : min_idx;
       }
-      if (SURF && (flags & DF_SURF)) out.orient_bits = draw_orientation_bits(p.pathways[cl.first_pathway + pathway], rs);
-      tc.ev(EV_UNIMOL | (uint32_t)pathway, (uint32_t)rc);
-      if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->t_event = unimol_time; }
-      out.kind = MCX_OUT_UNIMOL; out.pos = pos; out.rxn_class = rc; out.pathway = pathway; out.t_event = unimol_time;
-      out.t_now = t_now; out.flags = flags; out.unimol_time = unimol_time;
-      decided = true;
+      bool blocked = false;
+      if (SURF && (flags & DF_SURF)) {
+        const DevPathway& upw = p.pathways[cl.first_pathway + pathway];
+        if (upw.general) {
+          const double2 self_uv = make_double2(ss.u, ss.v);
+          blocked = !place_general(p, cl, upw, slot, ss.wall, ss.tile, (upw.keep_mask & 1u) ? 0 : 1, &ss.wall, &ss.tile, &self_uv, forced,
+                                   round_epoch0(p), epoch, RETRY, rs, out.orient_bits);
+        } else out.orient_bits = draw_orientation_bits(upw, rs);
+      }
+      if (blocked) {
+        // RX_BLOCKED (outcome_unimolecular :2976-2999): no room for the products; the molecule lives on and draws a new lifetime
+        tc.ev(EV_BLOCKED, (uint32_t)rc);
+        flags |= DF_SCHED_UNIMOL;
+      } else {
+        tc.ev(EV_UNIMOL | (uint32_t)pathway, (uint32_t)rc);
+        if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->t_event = unimol_time; }
+        out.kind = MCX_OUT_UNIMOL; out.pos = pos; out.rxn_class = rc; out.pathway = pathway; out.t_event = unimol_time;
+        out.t_now = t_now; out.flags = flags; out.unimol_time = unimol_time;
+        decided = true;
+      }
     }
     if (!decided) {
       // -- newbie lifetime (:232-236 -> pick_unimol_rxn_class_and_set_rxn_time :1731-1758, time_of_unimol)
@@ -1659,7 +1796,7 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
         }
         // ---- react_2D_all_neighbors (:1250-1393): after its move the molecule tests the molecules on the tiles around its own
         if (can_ss && !decided && !forced && !(sp.flags & MCX_SP_CANT_INITIATE) && p.tn_start)
-          ss_fired = react_2d_all_neighbors(p, m.id, species, flags, ss, t_steps, t_now, rs, tc, out, err);
+          ss_fired = react_2d_all_neighbors(p, m.id, slot, species, flags, ss, t_steps, t_now, round_epoch0(p), epoch, RETRY, rs, tc, out, err);
         if ((!can_diffuse || ss.wall != original_wall) && unimol_time >= t_end) {  // MCell3 compatibility rule (:1222-1236)
           unimol_time = MCX_TIME_INVALID;
           flags |= DF_SCHED_UNIMOL;
@@ -1818,10 +1955,23 @@ __device__ void evaluate_iteration(const DevParams& p, const MolRec& m, double t
                   const double abs_t = elapsed + t_steps * wh.t;
                   tc.ev(EV_SURFMOL | (uint32_t)side, sm.id);
                   if (tc.tr) { if (tc.tr->n_collisions < MCX_TRACE_K) tc.tr->partner[tc.tr->n_collisions] = sm.id; tc.tr->n_collisions++; }
-                  const int pathway = test_bimolecular(p, p.classes[rc], scaling, rs);
+                  int pathway = test_bimolecular(p, p.classes[rc], scaling, rs);
                   if (pathway >= 0) {
-                    out.orient_bits = draw_orientation_bits(p.pathways[p.classes[rc].first_pathway + pathway], rs) |
-                                      (coll_orient > 0 ? ORIENT_BIT_FRONT : 0u);
+                    const DevPathway& vpw = p.pathways[p.classes[rc].first_pathway + pathway];
+                    if (vpw.general) {
+                      const uint32_t pwall = p.swallA[occ], ptile = p.stileA[occ];
+                      const double2 puv = p.suvA[occ];
+                      uint32_t ob = 0;
+                      if (!place_general(p, p.classes[rc], vpw, slot, pwall, ptile, (vpw.keep_mask & 2u) ? 0 : 1, &pwall, &ptile, &puv, forced,
+                                         round_epoch0(p), epoch, RETRY, rs, ob)) {
+                        tc.ev(EV_BLOCKED, sm.id);   // RX_BLOCKED (:936-975): no reaction, the molecule goes on to the wall
+                        pathway = -1;
+                      }
+                      out.orient_bits = ob | (coll_orient > 0 ? ORIENT_BIT_FRONT : 0u);
+                    } else
+                    out.orient_bits = draw_orientation_bits(vpw, rs) | (coll_orient > 0 ? ORIENT_BIT_FRONT : 0u);
+                  }
+                  if (pathway >= 0) {
                     tc.ev(EV_RXN | (uint32_t)pathway, (uint32_t)rc);
                     if (tc.tr) { tc.tr->rxn_class = rc; tc.tr->rxn_pathway = pathway; tc.tr->rxn_partner = sm.id; tc.tr->t_event = abs_t; }
                     out.kind = MCX_OUT_REACTED; out.pos = wh.pos;

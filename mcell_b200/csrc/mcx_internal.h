@@ -32,7 +32,8 @@ enum : uint32_t {
 
 struct DevSpecies { double space_step, time_step; uint32_t flags; uint32_t can_vol_react; uint32_t can_vol_surf; uint32_t can_surf_surf; };
 struct DevClass { double max_fixed_p; uint32_t kind, r0, r1, first_pathway, n_pathways; int geom0, geom1; uint32_t pad; };
-struct DevPathway { double cum_prob; uint32_t n_products, products[MCX_MAX_PRODUCTS], keep_mask, rule_id; int prod_orient[MCX_MAX_PRODUCTS]; uint32_t kept_info; };
+struct DevPathway { double cum_prob; uint32_t n_products, products[MCX_MAX_PRODUCTS], keep_mask, rule_id; int prod_orient[MCX_MAX_PRODUCTS]; uint32_t kept_info;
+                    uint32_t general; };  // general: creates more surface products than it frees tiles (products on vacant neighbour tiles)
 
 // per-wall surface grid (Grid::initialize, src4/wall.cpp:38-74) + the wall's first entry in the tile table
 // one side of a triangle (src4/wall.h:32-90 Edge): the wall across it and the flattening transform between the uv frames
@@ -168,6 +169,11 @@ struct DevParams {
   const uint32_t* tn_start;     // per tile (+ 1)
   const uint2* tn_list;
   uint8_t* wall_has_grid;       // Wall::has_initialized_grid: the wall has held a surface molecule since the last upload
+  // products on vacant neighbour tiles (pathways flagged DevPathway::general; null without such a pathway): per slot, where
+  // the created surface products of the pending proposal go — written by the evaluation, read by the conflict rounds
+  uint2* prop_ptile;            // [slot * MCX_MAX_PRODUCTS + c]: wall, tile of created surface product c
+  double2* prop_puv;            // ... its uv
+  uint32_t* prop_pmask;         // [slot]: number of created surface products | (bit 4 + c: product c sits on a vacant tile the event claims)
   // rng
   unsigned long long seed, iteration;
   int rng_mode;

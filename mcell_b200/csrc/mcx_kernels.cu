@@ -188,6 +188,13 @@ __device__ __forceinline__ bool partner_is_consumed(const DevParams& p, int kind
   return !((pw.keep_mask >> (a_is_r0 ? 1 : 0)) & 1u);
 }
 
+// does the claiming event place surface products on vacant neighbour tiles (DevPathway::general)?
+__device__ __forceinline__ bool event_is_general(const DevParams& p, int kind, int rxn_class, int pathway) {
+  if (!p.prop_pmask || (kind != MCX_OUT_REACTED && kind != MCX_OUT_UNIMOL)) return false;
+  const DevClass& c = p.classes[rxn_class];
+  return p.pathways[c.first_pathway + pathway].general != 0;
+}
+
 // cell group of a position: 16 x-cells of one cell row (the unit of the fresh-id order, FreshEvent)
 __device__ __forceinline__ uint32_t group_of(const DevParams& p, D3 q) {
   const int cx = cell_coord(q.x, p.cgx, p.cell_rcp_x, p.ncx), cy = cell_coord(q.y, p.cgy, p.cell_rcp_y, p.ncy), cz = cell_z(p, q.z);
@@ -349,6 +356,7 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
       }
     }
     const DevWall& fi = p.walls[iw];
+    uint32_t n_placed = 0;
     for (uint32_t k = 0; k < n_new; k++) {
       const uint32_t ns = first_slot + k;
       if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
@@ -361,10 +369,15 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
         const bool swap = (orient_bits & SURFSURF_SWAP) != 0;
         int which = ((k == first_surf) == swap) ? 1 : 0;
         if (which > n_freed - 1) which = n_freed - 1;
-        const bool at_init = freed[which < 0 ? 0 : which] == 0;
-        const uint32_t tw = at_init ? iw : pw_wall;
-        const double2 tuv = at_init ? iuv : puv;
-        p.swallB[ns] = tw; p.stileB[ns] = at_init ? itile : pw_tile; p.suvB[ns] = tuv;
+        const bool at_init = n_freed == 0 || freed[which < 0 ? 0 : which] == 0;
+        uint32_t tw = at_init ? iw : pw_wall, tt = at_init ? itile : pw_tile;
+        double2 tuv = at_init ? iuv : puv;
+        if (pw.general && p.prop_pmask) {  // where place_general put the created surface product
+          const uint2 wt = p.prop_ptile[slot * MCX_MAX_PRODUCTS + n_placed];
+          tw = wt.x; tt = wt.y; tuv = p.prop_puv[slot * MCX_MAX_PRODUCTS + n_placed];
+          n_placed++;
+        }
+        p.swallB[ns] = tw; p.stileB[ns] = tt; p.suvB[ns] = tuv;
         const DevWall& f = p.walls[tw];
         ppos = D3{tuv.x * f.ux + tuv.y * f.vx + f.v0x, tuv.x * f.uy + tuv.y * f.vy + f.v0y, tuv.x * f.uz + tuv.y * f.vz + f.v0z};
         pflags |= DF_SURF | (o > 0 ? DF_ORIENT_UP : 0u);
@@ -456,6 +469,7 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
       atomicAdd(&c->n_fresh_ids, nf);
     }
   }
+  uint32_t n_placed_g = 0;
   for (uint32_t k = 0; k < n_new; k++) {
     uint32_t ns = first_slot + k;
     if (ns >= p.capacity) { raise_error(p, MCX_ERR_CAPACITY, id); return; }
@@ -471,9 +485,18 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
       p.swallB[ns] = wi; p.stileB[ns] = p.stileA[surf_slot];
       if (!(p.species[psp].flags & MCX_SP_VOL)) {
         pflags = (pflags & ~SF_CVI_MASK) | DF_SURF | (o > 0 ? DF_ORIENT_UP : 0u);
+        if (pw.general && p.prop_pmask) {  // where place_general put the created surface product
+          const uint2 wt = p.prop_ptile[slot * MCX_MAX_PRODUCTS + n_placed_g];
+          const double2 tuv = p.prop_puv[slot * MCX_MAX_PRODUCTS + n_placed_g];
+          n_placed_g++;
+          p.swallB[ns] = wt.x; p.stileB[ns] = wt.y; p.suvB[ns] = tuv;
+          const DevWall& f = p.walls[wt.x];
+          pos = D3{tuv.x * f.ux + tuv.y * f.vx + f.v0x, tuv.x * f.uy + tuv.y * f.vy + f.v0y, tuv.x * f.uz + tuv.y * f.vz + f.v0z};
+        } else {
         p.suvB[ns] = p.suvA[surf_slot];
         const MolRec sr = load_rec_volatile(p.recA, surf_slot);
         pos = D3{sr.x, sr.y, sr.z};
+        }
       } else {
         const DevWall& f = p.walls[wi];
         const double bump = (o > 0) ? 16 * MCX_EPS : -16 * MCX_EPS;
@@ -532,7 +555,8 @@ __device__ void commit_event(const DevParams& p, uint32_t slot, int kind, int rx
       f |= DF_CREATED_ON_SURF;
       p.swallB[slot] = wi; p.stileB[slot] = MCX_KEPT_AT_WALL;
     }
-    finalize_alive(p, slot, kept_pos, id, species, f, t_event, ut);
+    finalize_alive(p, slot, kept_pos, id, species, f, t_event, ut,
+                   (cl.kind == MCX_RXN_UNIMOL && (flags & DF_SURF)) ? SURF_FIELDS_IN_B : nullptr);
   }
 }
 
@@ -555,10 +579,22 @@ __device__ __forceinline__ void write_proposal(const DevParams& p, uint32_t slot
   if (o.kind == MCX_OUT_SURFMOVE) {
     p.swallB[slot] = o.s_wall; p.stileB[slot] = o.s_tile; p.suvB[slot] = make_double2(o.s_u, o.s_v);
     atomicMax(&p.tile_claim[p.grids[o.s_wall].tile_start + o.s_tile], key);
+  } else if (o.kind == MCX_OUT_UNIMOL && (o.flags & DF_SURF)) {
+    // a surface molecule may have moved inside its tile earlier in the iteration (a sub-step that ended at its lifetime):
+    // a kept reactant stays where it is now, not where the snapshot has it
+    p.swallB[slot] = o.s_wall; p.stileB[slot] = o.s_tile; p.suvB[slot] = make_double2(o.s_u, o.s_v);
   } else if (o.kind == MCX_OUT_REACTED && p.classes[o.rxn_class].kind == MCX_RXN_BIMOL_SURFSURF) {
     // surface-surface reaction: where the initiator is after its move; the tile is claimed when it is a new one
     p.swallB[slot] = o.s_wall; p.stileB[slot] = o.s_tile; p.suvB[slot] = make_double2(o.s_u, o.s_v);
     if (o.s_wall != p.swallA[slot] || o.s_tile != p.stileA[slot]) atomicMax(&p.tile_claim[p.grids[o.s_wall].tile_start + o.s_tile], key);
+  }
+  if (event_is_general(p, o.kind, o.rxn_class, o.pathway)) {  // products on vacant neighbour tiles claim them (place_general wrote them)
+    const uint32_t pm = p.prop_pmask[slot];
+    for (uint32_t c = 0; c < (pm & 15u); c++)
+      if ((pm >> (4 + c)) & 1u) {
+        const uint2 wt = p.prop_ptile[slot * MCX_MAX_PRODUCTS + c];
+        atomicMax(&p.tile_claim[p.grids[wt.x].tile_start + wt.y], key);
+      }
   }
   if (n_list) {
     uint32_t k = agg_reserve(n_list, 1u);
@@ -1084,7 +1120,7 @@ __global__ void __launch_bounds__(TPB, MCX_SLOW_MINBLOCKS) k_diffuse_slow(const 
     const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
     SurfState ss = {MCX_NONE, MCX_NONE, 0.0, 0.0};
     if (SURF && (m.sf & DF_SURF)) { const double2 uv = p.suvA[i]; ss.wall = p.swallA[i]; ss.tile = p.stileA[i]; ss.u = uv.x; ss.v = uv.y; }
-    evaluate_iteration<false, WITH_DISK, SURF>(p, m, t_sched, t_uni, (SURF && guard) ? p.swallA[i] : MCX_NONE,
+    evaluate_iteration<false, WITH_DISK, SURF>(p, m, i, t_sched, t_uni, (SURF && guard) ? p.swallA[i] : MCX_NONE,
                                                (SURF && guard) ? p.stileA[i] : MCX_NONE, ss, epoch, rs, false, o, mls, tc, err, grp);
     if (!lead) continue;
     if (!WITH_DISK && err == MCX_INTERNAL_NEEDS_DISK) {  // re-evaluated from scratch by the WITH_DISK launch
@@ -1132,6 +1168,14 @@ __device__ __forceinline__ void resolve_round(const DevParams& p, unsigned int r
       const uint32_t nw = __ldcg(p.swallB + slot), nt = __ldcg(p.stileB + slot);
       if (nw != p.swallA[slot] || nt != p.stileA[slot]) ok = __ldcg(p.tile_claim + p.grids[nw].tile_start + nt) == key;
     }
+    if (ok && event_is_general(p, kind, rxn_class, pathway)) {
+      const uint32_t pm = __ldcg(p.prop_pmask + slot);
+      for (uint32_t c = 0; ok && c < (pm & 15u); c++)
+        if ((pm >> (4 + c)) & 1u) {
+          const uint2 wt = p.prop_ptile[slot * MCX_MAX_PRODUCTS + c];
+          ok = __ldcg(p.tile_claim + p.grids[wt.x].tile_start + wt.y) == key;
+        }
+    }
     if (ok) {
       commit_event(p, slot, kind, rxn_class, pathway, partner, __ldcg(p.prop_t + slot), D3{e.x, e.y, e.z}, e.id, species,
                    e.sf & ~SF_SPECIES_MASK, __ldcg(p.tschedB + slot), __ldcg(p.tuniB + slot), orient_bits, tally);
@@ -1178,7 +1222,7 @@ __device__ __forceinline__ void retry_round(const DevParams& p, unsigned int rou
     const bool guard = (m.sf & DF_CREATED_ON_SURF) != 0;
     SurfState ss = {MCX_NONE, MCX_NONE, 0.0, 0.0};
     if (SURF && (m.sf & DF_SURF)) { const double2 uv = p.suvA[i]; ss.wall = p.swallA[i]; ss.tile = p.stileA[i]; ss.u = uv.x; ss.v = uv.y; }
-    evaluate_iteration<true, true, SURF>(p, m, t_sched, t_uni, (SURF && guard) ? p.swallA[i] : MCX_NONE,
+    evaluate_iteration<true, true, SURF>(p, m, i, t_sched, t_uni, (SURF && guard) ? p.swallA[i] : MCX_NONE,
                                          (SURF && guard) ? p.stileA[i] : MCX_NONE, ss, epoch, rs, forced != 0, o,
                                          (own_start && lead) ? ls : halo_ls, tc, err, grp);
     if (!lead) continue;
@@ -1493,27 +1537,6 @@ __global__ void __launch_bounds__(TPB) k_release(const __grid_constant__ DevPara
   }
 }
 // ---- surface molecules onto regions (ReleaseEvent::release_onto_regions, release_event.cpp:640-760; include/mcx.h) ----
-// GridUtils::grid2uv (grid_utils.inl:233-253) and grid2uv_random (:256-288)
-__device__ __forceinline__ void tile_uv(const DevParams& p, uint32_t wi, uint32_t tile, bool random, Stream& rs, double& u, double& v) {
-  const DevWall& f = p.walls[wi];
-  const DevGrid& g = p.grids[wi];
-  const int root = (int)(sqrt((double)tile));
-  const int rootrem = (int)tile - root * root;
-  const int k = g.n_axis - root - 1;
-  const int j = rootrem / 2;
-  const int i = rootrem - 2 * j;
-  if (!random) {
-    const double over3n = 1 / (double)(3 * g.n_axis);
-    u = ((double)(3 * j + i + 1)) * over3n * f.uv1u + ((double)(3 * k + i + 1)) * over3n * f.uv2u;
-    v = ((double)(3 * k + i + 1)) * over3n * f.uv2v;
-    return;
-  }
-  const double over_n = 1 / (double)(g.n_axis);
-  const double u_ran = rs.dbl();
-  const double v_ran = 1 - sqrt(rs.dbl());
-  u = ((double)(j + i) + (1 - 2 * i) * (1 - v_ran) * u_ran) * over_n * f.uv1u + ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv2u;
-  v = ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv2v;
-}
 // the new surface molecule on (wall, tile): appended behind the re-binned population like a product
 __device__ void place_surface_molecule(const DevParams& p, const SurfRelease& r, uint32_t k, uint32_t wi, uint32_t tile) {
   Counters* c = p.ctr;

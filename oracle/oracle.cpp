@@ -177,6 +177,9 @@ struct Outcome {
   uint32_t hit_wall = MCX_NONE;   // volume-wall reaction: the wall
   uint32_t created_wall = MCX_NONE, created_tile = MCX_NONE;  // SNAPSHOT, kept initiator of a surface reaction: rebinding guard
   bool surf_moved = false;        // SNAPSHOT, surface-surface reaction: the initiator took a new tile first (claims it too)
+  // SNAPSHOT, pathway with surface products on vacant neighbour tiles: where the created surface products go
+  bool pl_general = false; int pl_n = 0; uint32_t pl_wall[MCX_MAX_PRODUCTS], pl_tile[MCX_MAX_PRODUCTS], pl_vacant = 0;
+  double pl_u[MCX_MAX_PRODUCTS], pl_v[MCX_MAX_PRODUCTS];
 };
 
 struct World {
@@ -202,6 +205,7 @@ struct World {
                                              // grid not initialized (wall.h:339-346)
   std::vector<uint32_t> tile_start;          // first global tile of every wall (+ total)
   mutable std::vector<std::vector<uint32_t>> vertex_walls;  // Partition::walls_using_vertex_mapping, built on first use
+  mutable bool assume_all_grids = false;  // find_neighbor_tiles with create_grid_flag (product placement): every wall counts
   std::vector<mcx_surf_class_rxn> surf_rules;
   std::vector<Mol> mols;
   std::vector<uint32_t> id_to_index;  // molecule_id_to_index_mapping
@@ -915,9 +919,155 @@ static ProductSpec product_spec(World& w, const mcx_rxn_class& c, const mcx_path
   return ps;
 }
 
-// ---- surface-surface reactions (outcome_products_random :2446-2933 for a SURFMOL_SURFMOL collision) -----------------
 struct SurfSite { uint32_t wall, tile; double u, v; int orient; uint32_t species; };
 static inline SurfSite site_of(const Mol& m) { return SurfSite{m.wall, m.tile, m.u, m.v, m.orient, m.species}; }
+
+// ---- products on vacant neighbour tiles: the general branch of find_surf_product_positions (:2060-2100, 2155-2285) ----
+// A pathway that creates more surface products than it consumes surface reactants puts the extra ones on vacant tiles
+// around the surface reactant (find_neighbor_tiles with create_grid_flag, every wall counts), at a random point of the
+// tile (grid2uv_random, :2852-2855).  The reference's bookkeeping is restated literally, quirks included: positions are
+// assigned per entry of the rule's product list (kept reactants and volume products draw a tile too and waste it), and
+// the c-th CREATED surface product takes the position of the c-th ENTRY (:2815-2818).
+// Deviation: a unimolecular split into two surface products leaves the product that stays on the
+// reactant's tile at the reactant's uv; the reference moves it next to the other product's tile (find_closest_position).
+// GridUtils::grid2uv_random, src4/grid_utils.inl:256-286: a random point of a tile
+static void grid2uv_random(const Wall& f, const Grid& g, uint32_t tile_index, WordSource& rs, double& u, double& v) {
+  int root = (int)(sqrt((double)tile_index));
+  int rootrem = (int)tile_index - root * root;
+  int k = g.n_axis - root - 1;
+  int j = rootrem / 2;
+  int i = rootrem - 2 * j;
+  double over_n = 1 / (double)(g.n_axis);
+  double u_ran = rs.dbl();
+  double v_ran = 1 - sqrt(rs.dbl());
+  u = ((double)(j + i) + (1 - 2 * i) * (1 - v_ran) * u_ran) * over_n * f.uv_vert1_u + ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv_vert2_u;
+  v = ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv_vert2_v;
+}
+struct Placement {
+  bool general = false;
+  int n = 0;                       // created surface products
+  uint32_t wall[MCX_MAX_PRODUCTS], tile[MCX_MAX_PRODUCTS];
+  double u[MCX_MAX_PRODUCTS], v[MCX_MAX_PRODUCTS];
+  uint32_t vacant_mask = 0;        // bit c: created surface product c sits on a tile that was vacant (claimed by the event)
+};
+struct RuleEntry { bool kept; uint32_t idx; bool surf; };  // one entry of the rule's product list: new product idx / kept reactant idx
+static int rule_entries(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw, RuleEntry out[6]) {
+  int n = 0;
+  if (!(pw.kept_info & MCX_KEPT_VALID)) {  // older tables: the new products in their order, kept reactants behind them
+    for (uint32_t k = 0; k < pw.n_products; k++) out[n++] = RuleEntry{false, k, w.is_surf(pw.products[k])};
+    for (uint32_t r = 0; r < 2 && n < 6; r++)
+      if ((pw.keep_reactant_mask >> r) & 1u) out[n++] = RuleEntry{true, r, c.reactants[r] < w.species.size() && w.is_surf(c.reactants[r])};
+    return n;
+  }
+  for (int q = 0; q < 6; q++) {
+    const uint32_t nib = (pw.kept_info >> (4 * q)) & 0xFu;
+    if (nib == MCX_KEPT_ORDER_END) break;
+    if (nib >= MCX_KEPT_ORDER_REACTANT) { const uint32_t r = nib & 1u; out[n++] = RuleEntry{true, r, c.reactants[r] < w.species.size() && w.is_surf(c.reactants[r])}; }
+    else if (nib < pw.n_products) out[n++] = RuleEntry{false, nib, w.is_surf(pw.products[nib])};
+  }
+  return n;
+}
+static inline int n_surface_reactants(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw, bool kept) {
+  int n = 0;
+  const int nr = c.kind == MCX_RXN_UNIMOL ? 1 : 2;
+  if (c.kind == MCX_RXN_BIMOL_VOLWALL) return 0;
+  for (int r = 0; r < nr; r++)
+    if (c.reactants[r] < w.species.size() && w.is_surf(c.reactants[r]) && (((pw.keep_reactant_mask >> r) & 1u) != 0) == kept) n++;
+  return n;
+}
+static inline bool pathway_is_general(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw) {
+  if (c.kind != MCX_RXN_UNIMOL && c.kind != MCX_RXN_BIMOL_VOLSURF && c.kind != MCX_RXN_BIMOL_SURFSURF) return false;
+  if (n_surface_reactants(w, c, pw, false) + n_surface_reactants(w, c, pw, true) == 0) return false;
+  int created = 0;
+  for (uint32_t k = 0; k < pw.n_products; k++) created += w.is_surf(pw.products[k]) ? 1 : 0;
+  return created > n_surface_reactants(w, c, pw, false);
+}
+static const char* general_pathway_problem(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw) {
+  if (!(pw.kept_info & MCX_KEPT_VALID)) return "a pathway with surface products on vacant neighbour tiles needs kept_info (the order of the rule's products)";
+  if (n_surface_reactants(w, c, pw, false) > 0 && n_surface_reactants(w, c, pw, true) > 0)
+    return "a pathway with surface products on vacant neighbour tiles that keeps one surface reactant and consumes another is not supported";
+  return nullptr;
+}
+// recycled: the sites of the consumed surface reactants in the order of the rule's reactants; vacant(wall, tile) tells
+// whether a tile can be taken.  Returns false when the reaction is blocked (RX_BLOCKED).  Draws in the reference's order:
+// tile assignment, orientations, random points.
+template <class RS, class VacantFn>
+static bool place_general(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw, uint32_t reac_wall, uint32_t reac_tile,
+                          const SurfSite* recycled, int n_recycled, RS& rs, VacantFn is_vacant, Placement& pl, uint32_t& orient_bits) {
+  pl.general = true; pl.n = 0; pl.vacant_mask = 0;
+  RuleEntry ent[6];
+  const int n_ent = rule_entries(w, c, pw, ent);
+  const int n_reactants = c.kind == MCX_RXN_UNIMOL ? 1 : 2;
+  int needed = 0;
+  for (uint32_t k = 0; k < pw.n_products; k++) needed += w.is_surf(pw.products[k]) ? 1 : 0;
+  // vacant tiles around the surface reactant, from the back of the reference's list (:2090-2098)
+  TileNeighbors nbt;
+  w.assume_all_grids = true;
+  find_neighbor_tiles(w, reac_wall, reac_tile, nbt);
+  w.assume_all_grids = false;
+  std::vector<WallTile> vacant;
+  for (int i = (int)nbt.size() - 1; i >= 0; i--) if (is_vacant(nbt[i].first, nbt[i].second)) vacant.push_back(nbt[i]);
+  if ((int)vacant.size() + n_recycled < needed) return false;  // :2101-2105
+  int assigned[6];   // -1 nothing, 0/1 recycled site, 2 + j vacant tile j
+  for (int e = 0; e < 6; e++) assigned[e] = -1;
+  const int to_recycle = std::min(n_ent, n_recycled);
+  int next_available = 0, guard = 0;
+  const uint32_t num_players = (uint32_t)(n_ent + n_reactants);
+  while (next_available < to_recycle && ++guard < 100000) {  // :2159-2191
+    const uint32_t rnd = rs.next() % num_players;
+    if (rnd < (uint32_t)n_reactants) continue;
+    const int e = (int)rnd - n_reactants;
+    if (!ent[e].surf) continue;
+    if (assigned[e] >= 0) continue;
+    assigned[e] = next_available++;
+  }
+  std::vector<uint8_t> used(vacant.size(), 0);
+  for (int e = 0; e < n_ent; e++) {  // :2232-2283: every entry without a position draws a vacant tile
+    if (assigned[e] >= 0) continue;
+    int attempts = 0; bool found = false;
+    while (!found && attempts < 10) {  // SURFACE_DIFFUSION_RETRIES
+      const uint32_t rnd = rs.next() % (uint32_t)vacant.size();
+      if (used[rnd]) { attempts++; continue; }
+      assigned[e] = 2 + (int)rnd; used[rnd] = 1; found = true;
+    }
+    if (attempts >= 10) return false;
+  }
+  orient_bits = draw_orientation_bits(pw, rs);
+  int cnt = 0;   // current_surf_product_position_index
+  for (int e = 0; e < n_ent; e++) {
+    if (ent[e].kept || !ent[e].surf) continue;
+    const int a = assigned[cnt];
+    if (a >= 2) {
+      const WallTile t = vacant[a - 2];
+      pl.wall[cnt] = t.first; pl.tile[cnt] = t.second; pl.vacant_mask |= 1u << cnt;
+      grid2uv_random(w.walls[t.first], w.grids[t.first], t.second, rs, pl.u[cnt], pl.v[cnt]);   // :2852-2855
+    } else {
+      const SurfSite& r = recycled[a < 0 ? 0 : a];
+      pl.wall[cnt] = r.wall; pl.tile[cnt] = r.tile; pl.u[cnt] = r.u; pl.v[cnt] = r.v;
+    }
+    cnt++;
+  }
+  pl.n = cnt;
+  return true;
+}
+static inline void put_placement(Outcome& o, const Placement& pl) {
+  o.pl_general = pl.general; o.pl_n = pl.n; o.pl_vacant = pl.vacant_mask;
+  for (int k = 0; k < pl.n; k++) { o.pl_wall[k] = pl.wall[k]; o.pl_tile[k] = pl.tile[k]; o.pl_u[k] = pl.u[k]; o.pl_v[k] = pl.v[k]; }
+}
+static inline Placement get_placement(const Outcome& o) {
+  Placement pl; pl.general = o.pl_general; pl.n = o.pl_n; pl.vacant_mask = o.pl_vacant;
+  for (int k = 0; k < o.pl_n; k++) { pl.wall[k] = o.pl_wall[k]; pl.tile[k] = o.pl_tile[k]; pl.u[k] = o.pl_u[k]; pl.v[k] = o.pl_v[k]; }
+  return pl;
+}
+// a created surface product of a general pathway goes where the placement says (c counts the created surface products)
+static inline void apply_placement(const World& w, const Placement* pl, int& c, ProductSpec& ps) {
+  if (!pl || !pl->general || !w.is_surf(ps.species)) return;
+  ps.wall = pl->wall[c]; ps.tile = pl->tile[c]; ps.u = pl->u[c]; ps.v = pl->v[c];
+  ps.pos = uv2xyz(w, w.walls[ps.wall], ps.u, ps.v);
+  c++;
+}
+
+// ---- surface-surface reactions (outcome_products_random :2446-2933 for a SURFMOL_SURFMOL collision) -----------------
 // Which pathways of a surface-surface class can be placed: every new surface product finds a tile a consumed reactant
 // frees (find_surf_product_positions :1993-2288 without its search for vacant neighbour tiles), and the reference's
 // assignment loop terminates (it hands out min(products, freed tiles) tiles to surface products only, :2155-2191)
@@ -1004,7 +1154,7 @@ static void surfsurf_products(World& w, const mcx_rxn_class& c, const mcx_pathwa
     if (w.is_surf(ps.species)) {
       const bool swap = (bits & SURFSURF_SWAP) != 0;
       const int which = std::min((k == first_surf) == swap ? 1 : 0, n_freed - 1);
-      const SurfSite& t = *freed[which < 0 ? 0 : which];
+      const SurfSite& t = n_freed ? *freed[which < 0 ? 0 : which] : init;  // no freed tile: a general pathway places it (apply_placement)
       ps.wall = t.wall; ps.tile = t.tile; ps.u = t.u; ps.v = t.v; ps.orient = o;
       ps.pos = uv2xyz(w, w.walls[t.wall], t.u, t.v);
       ps.cvi = 0;
@@ -1477,9 +1627,11 @@ struct Eval {
 //                 firing) ends the evaluation and is returned as a proposal.
 // ================================================================================================
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
-                            uint32_t orient_bits, bool& a_destroyed, bool* flip = nullptr, int coll_side = 0);
-static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed);
-static void seq_apply_surfsurf(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, double t, uint32_t bits, bool& a_destroyed);
+                            uint32_t orient_bits, bool& a_destroyed, bool* flip = nullptr, int coll_side = 0, const Placement* pl = nullptr);
+static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed,
+                             const Placement* pl = nullptr);
+static void seq_apply_surfsurf(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, double t, uint32_t bits, bool& a_destroyed,
+                               const Placement* pl = nullptr);
 static void seq_apply_wallrxn(World& w, uint32_t index, int rc, int pathway, V3 pos, double t, uint32_t orient_bits, uint32_t wall,
                               uint32_t cvi, bool& destroyed, int coll_side);
 static void seq_set_defunct(World& w, Mol& m);
@@ -1502,6 +1654,15 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
     o.wall = s.wall; o.tile = s.tile; o.u = s.u; o.v = s.v;
   };
 
+  // a tile a product may take: vacant in the tile table; SNAPSHOT: and not claimed in an earlier conflict round, none in the forced pass
+  auto tile_is_vacant = [&](uint32_t wi, uint32_t ti) {
+    if (!w.tiles[wi].empty() && w.tiles[wi][ti] != MCX_NONE) return false;
+    if (E.snapshot) {
+      if (E.no_partners) return false;
+      if ((*E.tile_claimed)[(*E.tile_start)[wi] + ti]) return false;
+    }
+    return true;
+  };
   // -- a counted volume that is only a guess (MCX_MOL_CVI_PENDING): Partition::add_volume_molecule's ray cast
   // (partition.h:572-576 -> compute_counted_volume_using_waypoints), done when the molecule is first evaluated
   if (s.flags & MCX_MOL_CVI_PENDING) {
@@ -1520,19 +1681,31 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
       pathway = pathway_for_probability(w, w.classes[rc], match);
     }
     uint32_t obits = 0;
-    if (w.mols[index].wall != MCX_NONE)  // is_orientable: the reactant is a surface molecule (:2569)
-      obits = draw_orientation_bits(w.pathways[w.classes[rc].first_pathway + pathway], E.rs);
+    const mcx_pathway& upw = w.pathways[w.classes[rc].first_pathway + pathway];
+    Placement pl;
+    bool blocked = false;
+    if (w.mols[index].wall != MCX_NONE) {  // is_orientable: the reactant is a surface molecule (:2569)
+      if (pathway_is_general(w, w.classes[rc], upw)) {
+        const SurfSite self{s.wall, s.tile, s.u, s.v, w.mols[index].orient, m_species};
+        blocked = !place_general(w, w.classes[rc], upw, s.wall, s.tile, &self, (upw.keep_reactant_mask & 1u) ? 0 : 1, E.rs, tile_is_vacant, pl, obits);
+      } else obits = draw_orientation_bits(upw, E.rs);
+    }
+    if (blocked) {
+      // RX_BLOCKED (outcome_unimolecular :2976-2999): no room for the products; the molecule lives on and draws a new lifetime
+      E.ev(EV_BLOCKED, (uint32_t)rc);
+    } else {
     E.ev(EV_UNIMOL | (uint32_t)pathway, (uint32_t)rc);
     if (tr) { tr->rxn_class = rc; tr->rxn_pathway = pathway; tr->t_event = s.unimol_time; }
     if (!apply) {
       out.kind = MCX_OUT_UNIMOL; out.pos = s.pos; out.rxn_class = rc; out.pathway = pathway;
-      out.t_event = s.unimol_time; out.orient_bits = obits; fill_event(out);
+      out.t_event = s.unimol_time; out.orient_bits = obits; fill_event(out); put_placement(out, pl);
       return out;
     }
     bool destroyed = false;
     w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart; w.mols[index].cvi = s.cvi;
-    seq_apply_unimol(w, index, rc, pathway, s.unimol_time, obits, destroyed);
+    seq_apply_unimol(w, index, rc, pathway, s.unimol_time, obits, destroyed, &pl);
     if (destroyed) { out.kind = MCX_OUT_UNIMOL; out.pos = s.pos; out.t_event = s.unimol_time; return out; }
+    }
     s.flags |= MCX_MOL_SCHEDULE_UNIMOL;  // survivor re-draws its lifetime (outcome_unimolecular :2999)
   }
   // -- newbie lifetime (diffuse_single_molecule :232-236)
@@ -1652,20 +1825,36 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
           const mcx_rxn_class& cl = w.classes[rc];
           const mcx_pathway& pw = w.pathways[cl.first_pathway + pathway];
           // random draws in the reference's order: tile assignment (find_surf_product_positions), then orientations
-          uint32_t bits = surfsurf_position_bits(w, cl, pw, m_species == cl.reactants[0], E.rs);
-          bits |= draw_orientation_bits(pw, E.rs);
+          uint32_t bits = 0;
+          Placement pl;
+          bool blocked = false;
+          if (pathway_is_general(w, cl, pw)) {
+            const SurfSite me{s.wall, s.tile, s.u, s.v, w.mols[index].orient, m_species}, other = site_of(w.mols[j]);
+            const bool me_r0 = m_species == cl.reactants[0];
+            SurfSite rec[2]; int n_rec = 0;
+            if (!(pw.keep_reactant_mask & 1u)) rec[n_rec++] = me_r0 ? me : other;
+            if (!(pw.keep_reactant_mask & 2u)) rec[n_rec++] = me_r0 ? other : me;
+            blocked = !place_general(w, cl, pw, s.wall, s.tile, rec, n_rec, E.rs, tile_is_vacant, pl, bits);
+          } else {
+            bits = surfsurf_position_bits(w, cl, pw, m_species == cl.reactants[0], E.rs);
+            bits |= draw_orientation_bits(pw, E.rs);
+          }
           const double t_rxn = s.t_now;  // collision_time = diffusion_start_time (:1343)
+          if (blocked) E.ev(EV_BLOCKED, w.mols[j].id);   // RX_BLOCKED: the molecule survives (:1388-1392)
+          else {
           E.ev(EV_SURFSURF | (uint32_t)pathway, (uint32_t)rc);
           E.ev(EV_RXN | (bits & 0x7Fu), w.mols[j].id);
           if (tr) { tr->rxn_class = rc; tr->rxn_pathway = pathway; tr->rxn_partner = w.mols[j].id; tr->t_event = t_rxn; }
           if (!apply) {
             out.rxn_class = rc; out.pathway = pathway; out.partner_index = j; out.partner_id = w.mols[j].id;
             out.t_event = t_rxn; out.orient_bits = bits; out.surf_moved = surf_tile_changed;
+            put_placement(out, pl);
             ss_fired = true;
           } else {
             bool a_destroyed = false;
-            seq_apply_surfsurf(w, index, j, rc, pathway, t_rxn, bits, a_destroyed);
+            seq_apply_surfsurf(w, index, j, rc, pathway, t_rxn, bits, a_destroyed, &pl);
             if (a_destroyed) { out.kind = MCX_OUT_REACTED; out.pos = s.pos; out.t_event = t_rxn; return out; }
+          }
           }
         }
       }
@@ -1759,20 +1948,31 @@ static Outcome evaluate_substep(Eval& E, uint32_t index, MolState& s, bool apply
                 E.ev(EV_SURFMOL | (uint32_t)c.type, sm.id);
                 if (tr) { if (tr->n_collisions < MCX_TRACE_K) tr->partner[tr->n_collisions] = sm.id; tr->n_collisions++; }
                 int pathway = E.test_bimolecular(w.classes[rc], scaling);
+                Placement pl;
+                uint32_t obits = 0;
                 if (pathway >= 0) {
-                  uint32_t obits = draw_orientation_bits(w.pathways[w.classes[rc].first_pathway + pathway], E.rs);
+                  const mcx_pathway& vpw = w.pathways[w.classes[rc].first_pathway + pathway];
+                  if (pathway_is_general(w, w.classes[rc], vpw)) {
+                    const SurfSite partner = site_of(sm);
+                    if (!place_general(w, w.classes[rc], vpw, sm.wall, sm.tile, &partner, (vpw.keep_reactant_mask & 2u) ? 0 : 1, E.rs, tile_is_vacant, pl, obits)) {
+                      E.ev(EV_BLOCKED, sm.id);   // RX_BLOCKED (:936-975): no reaction, the molecule goes on to the wall
+                      pathway = -1;
+                    }
+                  } else obits = draw_orientation_bits(vpw, E.rs);
+                }
+                if (pathway >= 0) {
                   E.ev(EV_RXN | (uint32_t)pathway, (uint32_t)rc);
                   if (tr) { tr->rxn_class = rc; tr->rxn_pathway = pathway; tr->rxn_partner = sm.id; tr->t_event = abs_t; }
                   if (!apply) {
                     out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.rxn_class = rc; out.pathway = pathway;
                     out.partner_index = occ_index; out.partner_id = sm.id; out.t_event = abs_t; out.orient_bits = obits;
                     out.coll_side = coll_orient;
-                    fill_event(out);
+                    fill_event(out); put_placement(out, pl);
                     return out;
                   }
                   bool a_destroyed = false, flip = false;
                   w.mols[index].pos = s.pos; w.mols[index].subpart = s.subpart; w.mols[index].cvi = s.cvi;
-                  seq_apply_bimol(w, index, occ_index, rc, pathway, c.pos, abs_t, obits, a_destroyed, &flip, coll_orient);
+                  seq_apply_bimol(w, index, occ_index, rc, pathway, c.pos, abs_t, obits, a_destroyed, &flip, coll_orient, &pl);
                   if (a_destroyed) {  // collide_res == 1
                     destroyed = true; out.kind = MCX_OUT_REACTED; out.pos = c.pos; out.t_event = abs_t;
                     break;
@@ -1953,7 +2153,10 @@ static uint32_t seq_add_molecule(World& w, const ProductSpec& ps, double t) {  /
   w.id_to_index[n.id] = (uint32_t)w.mols.size() - 1;
   w.sched_ids.push_back(n.id);
   list_insert(w, w.mols.back());
-  if (n.wall != MCX_NONE) w.tiles[n.wall][n.tile] = n.id;  // Grid::set_molecule_tile (:2899)
+  if (n.wall != MCX_NONE) {
+    if (w.tiles[n.wall].empty()) w.tiles[n.wall].assign(w.grids[n.wall].n_tiles, MCX_NONE);  // Wall::initialize_grid
+    w.tiles[n.wall][n.tile] = n.id;  // Grid::set_molecule_tile (:2899)
+  }
   w.species_count[ps.species]++;
   w.stats.products++;
   return n.id;
@@ -1969,7 +2172,7 @@ static inline void count_rxn_where(World& w, uint32_t rule, const Mol& initiator
   else if (w.n_rs) w.rxn_count_rs[rule * w.n_rs + w.wall_rs[initiator.wall]]++;
 }
 static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, V3 pos, double t,
-                            uint32_t orient_bits, bool& a_destroyed, bool* flip, int coll_side) {
+                            uint32_t orient_bits, bool& a_destroyed, bool* flip, int coll_side, const Placement* pl) {
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
@@ -1983,8 +2186,10 @@ static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc
   const Mol surf_copy = w.mols[b_index];  // adding molecules may reallocate w.mols
   // tiles that are going to be reused are freed first (:2606-2615)
   if (surf_rxn && !keepB) w.tiles[surf_copy.wall][surf_copy.tile] = MCX_NONE;
+  int placed = 0;
   for (uint32_t k = 0; k < pw.n_products; k++) {
     ProductSpec ps = product_spec(w, c, pw, k, pos, orient_bits, surf_rxn ? &surf_copy : nullptr, w.mols[a_index].cvi, coll_side);
+    apply_placement(w, pl, placed, ps);
     uint32_t nid = seq_add_molecule(w, ps, t);
     if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
   }
@@ -2004,7 +2209,8 @@ static void seq_apply_bimol(World& w, uint32_t a_index, uint32_t b_index, int rc
   }
 }
 // outcome_unimolecular (:2939-3003)
-static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed) {
+static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, double t, uint32_t orient_bits, bool& destroyed,
+                             const Placement* pl) {
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
@@ -2015,8 +2221,10 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
   const bool surf_rxn = w.mols[index].wall != MCX_NONE;
   const Mol surf_copy = w.mols[index];
   if (surf_rxn && !keep) w.tiles[surf_copy.wall][surf_copy.tile] = MCX_NONE;
+  int placed = 0;
   for (uint32_t k = 0; k < pw.n_products; k++) {
     ProductSpec ps = product_spec(w, c, pw, k, pos, orient_bits, surf_rxn ? &surf_copy : nullptr, w.mols[index].cvi);
+    apply_placement(w, pl, placed, ps);
     uint32_t nid = seq_add_molecule(w, ps, t);
     if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
   }
@@ -2026,7 +2234,8 @@ static void seq_apply_unimol(World& w, uint32_t index, int rc, int pathway, doub
 }
 
 // outcome_bimolecular (:1833-1895) -> outcome_products_random for two surface molecules
-static void seq_apply_surfsurf(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, double t, uint32_t bits, bool& a_destroyed) {
+static void seq_apply_surfsurf(World& w, uint32_t a_index, uint32_t b_index, int rc, int pathway, double t, uint32_t bits, bool& a_destroyed,
+                               const Placement* pl) {
   const mcx_rxn_class& c = w.classes[rc];
   const mcx_pathway& pw = w.pathways[c.first_pathway + pathway];
   w.rxn_count[pw.rxn_rule_id]++;
@@ -2040,7 +2249,9 @@ static void seq_apply_surfsurf(World& w, uint32_t a_index, uint32_t b_index, int
   if (!keepB) w.tiles[partner.wall][partner.tile] = MCX_NONE;
   std::vector<ProductSpec> prods;
   surfsurf_products(w, c, pw, init, partner, bits, prods);
-  for (const ProductSpec& ps : prods) {
+  int placed = 0;
+  for (ProductSpec& ps : prods) {
+    apply_placement(w, pl, placed, ps);
     uint32_t nid = seq_add_molecule(w, ps, t);
     if (cmp_lt(t, (double)w.iteration + 1, EPS) && g_new_actions) g_new_actions->push_back(nid);
   }
@@ -2220,12 +2431,15 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     uint32_t prio = prio_of(i);
     claim[i] = std::min(claim[i], prio);
     if (partner_consumed(i)) { uint32_t j = outs[i].partner_index; claim[j] = std::min(claim[j], prio); }
-    if (outs[i].kind == MCX_OUT_SURFMOVE || (outs[i].kind == MCX_OUT_REACTED && outs[i].surf_moved)) {
-      uint32_t gt = gtile_of(outs[i]);
+    auto claim_tile = [&](uint32_t gt) {
       auto it = tile_claim.find(gt);
       if (it == tile_claim.end()) tile_claim[gt] = prio; else it->second = std::min(it->second, prio);
       tiles_of_round.push_back(gt);
-    }
+    };
+    if (outs[i].kind == MCX_OUT_SURFMOVE || (outs[i].kind == MCX_OUT_REACTED && outs[i].surf_moved)) claim_tile(gtile_of(outs[i]));
+    // products on vacant neighbour tiles claim them
+    for (int k = 0; k < outs[i].pl_n; k++)
+      if ((outs[i].pl_vacant >> k) & 1u) claim_tile(w.tile_start[outs[i].pl_wall[k]] + outs[i].pl_tile[k]);
   };
   auto commit = [&](uint32_t i) {  // accepted claiming event
     Outcome& o = outs[i];
@@ -2279,7 +2493,10 @@ static void step_snapshot(World& w, const SnapStreams& st) {
       if (!keepB) { dead[j] = 1; w.species_count[w.mols[j].species]--; reuse[n_reuse++] = w.mols[j].id; }
       std::vector<ProductSpec> prods;
       surfsurf_products(w, c, pw, init, partner, o.orient_bits, prods);
+      const Placement pl = get_placement(o);
+      int placed = 0;
       for (uint32_t k = 0; k < prods.size(); k++) {
+        apply_placement(w, &pl, placed, prods[k]);
         NewMol nm; nm.ps = prods[k]; nm.t = o.t_event; nm.id = (int)k < n_reuse ? reuse[k] : MCX_NONE;
         born.push_back(nm);
         w.species_count[nm.ps.species]++;
@@ -2312,8 +2529,11 @@ static void step_snapshot(World& w, const SnapStreams& st) {
     if (o.kind == MCX_OUT_REACTED && w.mols[o.partner_index].wall != MCX_NONE) surf = &w.mols[o.partner_index];
     else if (o.kind == MCX_OUT_UNIMOL && m.wall != MCX_NONE) surf = &m;
     // product ids: consumed reactants' ids are recycled first (initiator, then partner), then fresh ids
+    const Placement gpl = get_placement(o);
+    int placed = 0;
     for (uint32_t k = 0; k < pw.n_products; k++) {
       NewMol nm; nm.ps = product_spec(w, c, pw, k, o.pos, o.orient_bits, surf, o.cvi, o.kind == MCX_OUT_REACTED ? o.coll_side : 0); nm.t = o.t_event;
+      apply_placement(w, &gpl, placed, nm.ps);
       nm.id = (int)k < n_reuse ? reuse[k] : MCX_NONE;
       born.push_back(nm);
       w.species_count[nm.ps.species]++;
@@ -2365,6 +2585,8 @@ static void step_snapshot(World& w, const SnapStreams& st) {
       if (ok && partner_consumed(i)) ok = claim[outs[i].partner_index] == prio;
       if (ok && (outs[i].kind == MCX_OUT_SURFMOVE || (outs[i].kind == MCX_OUT_REACTED && outs[i].surf_moved)))
         ok = tile_claim[gtile_of(outs[i])] == prio;
+      for (int k = 0; ok && k < outs[i].pl_n; k++)
+        if ((outs[i].pl_vacant >> k) & 1u) ok = tile_claim[w.tile_start[outs[i].pl_wall[k]] + outs[i].pl_tile[k]] == prio;
       (ok ? accepted : still).push_back(i);
     }
     // tiles claimed in this round stay unavailable for the movers of later rounds, whoever won them
@@ -2500,9 +2722,14 @@ int orc_set_reactions(void* h, const mcx_rxn_class* c, uint32_t nc, const mcx_pa
       w.err = "surface-surface classes together with region borders are not supported (restricted regions of the neighbour search)"; return -1;
     }
   for (const mcx_rxn_class& rc : w.classes)
-    if (rc.kind == MCX_RXN_BIMOL_SURFSURF)
-      for (uint32_t q = 0; q < rc.n_pathways; q++)
-        if (const char* why = surfsurf_pathway_problem(w, w.pathways[rc.first_pathway + q])) { w.err = why; return -1; }
+    for (uint32_t q = 0; q < rc.n_pathways; q++) {
+      const mcx_pathway& pw = w.pathways[rc.first_pathway + q];
+      if (pathway_is_general(w, rc, pw)) {
+        if (const char* why = general_pathway_problem(w, rc, pw)) { w.err = why; return -1; }
+      } else if (rc.kind == MCX_RXN_BIMOL_SURFSURF) {
+        if (const char* why = surfsurf_pathway_problem(w, pw)) { w.err = why; return -1; }
+      }
+    }
   return 0;
 }
 int orc_set_surface_classes(void* h, const mcx_surf_class_rxn* r, uint32_t n) {
@@ -2698,18 +2925,6 @@ int orc_release_volume_molecules(void* h, const mcx_release* r, uint32_t* first_
 // ReleaseEvent::release_onto_regions (release_event.cpp:640-760) in the product's parallel form (include/mcx.h,
 // mcx_release_surface_molecules): every molecule picks tiles from its own stream, rounds of pick / lowest index wins,
 // then the reference's fall-back fill.  grid2uv_random: grid_utils.inl:256-288.
-static void grid2uv_random(const Wall& f, const Grid& g, uint32_t tile_index, WordSource& rs, double& u, double& v) {
-  int root = (int)(sqrt((double)tile_index));
-  int rootrem = (int)tile_index - root * root;
-  int k = g.n_axis - root - 1;
-  int j = rootrem / 2;
-  int i = rootrem - 2 * j;
-  double over_n = 1 / (double)(g.n_axis);
-  double u_ran = rs.dbl();
-  double v_ran = 1 - sqrt(rs.dbl());
-  u = ((double)(j + i) + (1 - 2 * i) * (1 - v_ran) * u_ran) * over_n * f.uv_vert1_u + ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv_vert2_u;
-  v = ((double)(k + i) + (1 - 2 * i) * v_ran) * over_n * f.uv_vert2_v;
-}
 int orc_release_surface_molecules(void* h, const mcx_surface_release* r, uint32_t* first_id_out) {
   World& w = *(World*)h;
   if (r->species >= w.species.size() || (w.species[r->species].flags & MCX_SP_VOL)) { w.err = "surface release: not a surface species"; return MCX_ERR_INVALID_ARG; }

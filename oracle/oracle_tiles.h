@@ -75,7 +75,7 @@ static const std::vector<uint32_t>& walls_using_vertex(const World& w, uint32_t 
   }
   return w.vertex_walls[v];
 }
-static inline bool wall_has_grid(const World& w, uint32_t wi) { return !w.tiles[wi].empty(); }  // Wall::has_initialized_grid
+static inline bool wall_has_grid(const World& w, uint32_t wi) { return w.assume_all_grids || !w.tiles[wi].empty(); }  // Wall::has_initialized_grid (create_grid_flag: every wall gets one)
 
 // neighboring_wall_uses_this_vertex, grid_utils.inl:605-622
 static bool neighboring_wall_uses_this_vertex(const World& w, const Wall& f, uint32_t vi) {

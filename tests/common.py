@@ -283,6 +283,43 @@ def surface_reactions(n_a=1500, n_b=1500, n_e=300, radius_um=0.25, subdivisions=
     return t, allm
 
 
+def vacant_tile_products(n_r=900, n_a=600, n_lig=6000, radius_um=0.25, subdivisions=3, seed=1, box_um=0.8, D_surf=2e-7,
+                         rng_mode=abi.MCX_RNG_PHILOX, max_molecules=None):
+    """Surface products on vacant neighbour tiles (find_surf_product_positions' general branch):
+    R' -> R' + A' (a kept reactant emits a surface molecule), L' + R' -> P' + A' (two surface products, one freed tile),
+    P' -> A' + A' (a split: one product stays, one takes a neighbour tile), A' + A' -> P' + A' + W' would need ... no:
+    A' + A' -> R' (keeps the population bounded), A' -> V, (leaves the surface)."""
+    import math
+    from mcell_b200.model import N_AV, MY_PI
+    m = Model(Config(seed=seed))
+    L = m.add_species("L", 1e-6)
+    R = m.add_species("R", D_surf, surface=True)
+    A = m.add_species("A", D_surf, surface=True)
+    P = m.add_species("P", D_surf * 0.5, surface=True)
+    V = m.add_species("V", 1e-6)
+    pb_vs = 2.0 * 1.0e11 * m.config.surface_grid_density / (2.0 * N_AV) * math.sqrt(MY_PI * m.config.time_step / 1e-6)
+    pb_ss = m.config.time_step * m.config.surface_grid_density / 6.0
+    m.add_reaction_rule(["R'"], ["R'", "A'"], 3e4)
+    m.add_reaction_rule(["L'", "R'"], ["P'", "A'"], 0.5 / pb_vs)
+    m.add_reaction_rule(["P'"], ["A'", "A'"], 1e5)
+    m.add_reaction_rule(["A'", "A'"], ["R'"], 0.2 / pb_ss)
+    m.add_reaction_rule(["A'"], ["V,"], 5e4)
+    sv, sf = create_icosphere(radius_um, subdivisions)
+    m.add_geometry_object(sv, sf)
+    bv, bf = create_box(box_um)
+    m.add_geometry_object(bv, bf)
+    n = n_r + n_a
+    t = m.build(max_molecules=max_molecules or 4 * (n + n_lig) + 64, rng_mode=rng_mode)
+    rng = np.random.default_rng(seed)
+    pos = release_uniform_box(rng, n_lig, box_um, t.length_unit, margin=1e-3)
+    vol = MolArrays.from_positions(pos, L, schedule_unimol=True)
+    surf = release_on_walls(rng, t, np.arange(len(sf), dtype=np.uint32), n, R, orientation=1, first_id=n_lig)
+    sp = np.full(n, R, dtype=surf.species.dtype)
+    sp[n_r:] = A
+    surf.species[:] = rng.permutation(sp)
+    return t, MolArrays.concat([vol, surf])
+
+
 def unsupported_surface_surface_tables():
     """Surface-surface pathways outside the supported set: (what, tables).  Both the oracle and libmcx must
     refuse them instead of approximating."""
