@@ -102,9 +102,10 @@ enum { MCX_RXN_UNIMOL = 1, MCX_RXN_BIMOL_VOLVOL = 2,
                                      diffuse_react_event.cpp:1250-1393; test_bimolecular / test_many_bimolecular,
                                      rxn_utils.inl:336-414, 475-580) and reacts with at most one of them.  Surface
                                      products take the tiles of the consumed reactants (find_surf_product_positions,
-                                     :1993-2288, recycled positions); pathways that need more tiles than they free,
-                                     or fewer surface products than freed tiles next to a volume product, are
-                                     refused.  max_fixed_p / cum_prob hold the plain pathway probabilities
+                                     :1993-2288, recycled positions) and, beyond those, vacant tiles around the
+                                     initiator (the general branch, kept_info required); pathways that free two tiles
+                                     but fill one next to a volume product, or keep one reactant and consume the
+                                     other while needing vacant tiles, are refused.  max_fixed_p / cum_prob hold the plain pathway probabilities
                                      (rate / grid density scaling done by the table builder, as for the other
                                      kinds) */ };
 typedef struct mcx_rxn_class {

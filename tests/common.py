@@ -324,7 +324,7 @@ def unsupported_surface_surface_tables():
     """Surface-surface pathways outside the supported set: (what, tables).  Both the oracle and libmcx must
     refuse them instead of approximating."""
     out = []
-    for what, products in (("needs a vacant neighbour tile", ["C'", "D'", "A'"]),
+    for what, products in (("needs vacant neighbour tiles while it keeps one surface reactant and consumes the other", ["C'", "D'", "A'"]),
                            ("frees two tiles, fills one, next to a volume product", ["C'", "V,"])):
         m = Model(Config(seed=1))
         for n in ("A", "B", "C", "D"):
