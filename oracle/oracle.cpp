@@ -993,7 +993,8 @@ static const char* general_pathway_problem(const World& w, const mcx_rxn_class& 
 // tile assignment, orientations, random points.
 template <class RS, class VacantFn>
 static bool place_general(const World& w, const mcx_rxn_class& c, const mcx_pathway& pw, uint32_t reac_wall, uint32_t reac_tile,
-                          const SurfSite* recycled, int n_recycled, RS& rs, VacantFn is_vacant, Placement& pl, uint32_t& orient_bits) {
+                          const SurfSite* recycled, int n_recycled, RS& rs, VacantFn is_vacant, Placement& pl, uint32_t& orient_bits,
+                          int* entry_kind = nullptr, WallTile* entry_pos = nullptr) {   // the last two: per-entry result for the pin test
   pl.general = true; pl.n = 0; pl.vacant_mask = 0;
   RuleEntry ent[6];
   const int n_ent = rule_entries(w, c, pw, ent);
@@ -1032,6 +1033,12 @@ static bool place_general(const World& w, const mcx_rxn_class& c, const mcx_path
     }
     if (attempts >= 10) return false;
   }
+  if (entry_kind)
+    for (int e = 0; e < n_ent; e++) {
+      entry_kind[e] = assigned[e] < 0 ? 0 : (assigned[e] >= 2 ? 2 : 1);   // 0 nothing, 1 recycled, 2 vacant
+      entry_pos[e] = assigned[e] >= 2 ? vacant[assigned[e] - 2]
+                                      : (assigned[e] >= 0 ? WallTile(recycled[assigned[e]].wall, recycled[assigned[e]].tile) : WallTile(MCX_NONE, MCX_NONE));
+    }
   orient_bits = draw_orientation_bits(pw, rs);
   int cnt = 0;   // current_surf_product_position_index
   for (int e = 0; e < n_ent; e++) {
@@ -3427,6 +3434,41 @@ int orc_unit_test_bimolecular(const double* cum_probs, int n, double scaling, co
   int r = E.test_bimolecular(rc, scaling);
   *words_used = rs.used;
   return r;
+}
+// place_general on a mesh with given occupied tiles; same per-entry outputs as ref4_find_surf_product_positions
+// (oracle/ref_mcell4_place_shim.cpp): kind per entry of the rule's product list (0 nothing, 1 a recycled tile, 2 a vacant
+// tile) with its wall and tile; returns 0, or -2 when the reaction is blocked; *words_used counts the words drawn for the
+// tiles only (the orientation draws and random points that follow are not part of find_surf_product_positions)
+int orc_unit_place_general(const double* verts, unsigned n_verts, const unsigned* tri, unsigned n_walls, const unsigned* occupied,
+                           unsigned n_occupied, int rxn_kind, const unsigned char* reactant_is_surf, unsigned keep_mask, unsigned kept_info,
+                           unsigned n_products, const unsigned char* product_is_surf, unsigned reac_wall, unsigned reac_tile,
+                           const unsigned* recycled_wall_tile, int n_recycled, const uint32_t* words, uint64_t n_words,
+                           int* entry_kind, unsigned* entry_wall, unsigned* entry_tile, long long* words_used) {
+  World w; unit_mesh(w, verts, n_verts, tri, n_walls);
+  w.grids.resize(n_walls); w.tiles.resize(n_walls);
+  for (unsigned i = 0; i < n_walls; i++) { grid_init(w, w.walls[i], w.grids[i]); w.tiles[i].assign(w.grids[i].n_tiles, MCX_NONE); }
+  for (unsigned i = 0; i < n_occupied; i++) w.tiles[occupied[2 * i]][occupied[2 * i + 1]] = 1000 + i;
+  w.species.resize(2); w.species[0] = mcx_species{}; w.species[0].flags = MCX_SP_VOL; w.species[1] = mcx_species{};
+  mcx_rxn_class c{}; c.kind = (uint32_t)rxn_kind; c.first_pathway = 0; c.n_pathways = 1;
+  c.reactants[0] = reactant_is_surf[0] ? 1 : 0; c.reactants[1] = rxn_kind == MCX_RXN_UNIMOL ? MCX_NONE : (reactant_is_surf[1] ? 1u : 0u);
+  mcx_pathway pw{}; pw.n_products = n_products; pw.keep_reactant_mask = keep_mask; pw.kept_info = kept_info;
+  for (unsigned k = 0; k < n_products; k++) { pw.products[k] = product_is_surf[k] ? 1 : 0; pw.product_orientation[k] = 1; }
+  SurfSite rec[2];
+  for (int r = 0; r < n_recycled && r < 2; r++) rec[r] = SurfSite{recycled_wall_tile[2 * r], recycled_wall_tile[2 * r + 1], 0, 0, 1, 1};
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  auto vacant = [&](uint32_t wi, uint32_t ti) { return w.tiles[wi][ti] == MCX_NONE; };
+  Placement pl; uint32_t obits = 0;
+  int kinds[6] = {0, 0, 0, 0, 0, 0}; WallTile pos[6];
+  // the words of the tile assignment alone: the orientation draws are skipped by giving every product an orientation, the
+  // random points are counted and subtracted
+  const bool ok = place_general(w, c, pw, reac_wall, reac_tile, rec, n_recycled, rs, vacant, pl, obits, kinds, pos);
+  long long used = (long long)rs.used;
+  if (ok) used -= 2LL * __builtin_popcount(pl.vacant_mask);   // grid2uv_random: two doubles of one word each
+  *words_used = used;
+  RuleEntry ent[6];
+  const int n_ent = rule_entries(w, c, pw, ent);
+  for (int e = 0; e < n_ent; e++) { entry_kind[e] = ok ? kinds[e] : 0; entry_wall[e] = ok ? pos[e].first : MCX_NONE; entry_tile[e] = ok ? pos[e].second : MCX_NONE; }
+  return ok ? 0 : -2;
 }
 // test_bimolecular with a local probability factor / test_many_bimolecular (react_2D_all_neighbors); same outputs as
 // ref4_test_bimolecular_lpf / ref4_test_many_bimolecular (oracle/ref_mcell4_tiles_shim.cpp)

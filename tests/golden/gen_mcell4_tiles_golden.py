@@ -29,6 +29,33 @@ def ref_table(L, V, T, mask):
     return per, start[:ntl + 1].copy(), out[:2 * n].copy()
 
 
+def ref_place(LP, ms, case):
+    """-> [rc, words, (kind, wall, tile) x 6] with kind 0 nothing / 1 recycled / 2 vacant"""
+    k, occ, si, sites, surf_reac, seed, skip = case
+    V, T = ms[k]
+    kind, surf_flags, entries = tc.PLACE_SHAPES[si]
+    ent = np.array([1 if (e == "S" or (e[0] == "K" and surf_flags[int(e[1])])) else 0 for e in entries], np.uint8)
+    keep = [("K%d" % r) in entries for r in range(2)]
+    def r5(site):
+        return np.array([0, 0, 0, 0, 0], np.float64) if site is None else np.array([1, site[0], site[1], 0.1, 0.1], np.float64)
+    a5 = r5(sites[0]); b5 = r5(sites[1]) if len(sites) > 1 else None
+    ot = np.zeros(6, np.int32); ow = np.zeros(6, np.uint32); otl = np.zeros(6, np.uint32)
+    nsp = C.c_uint(0); used = C.c_int(0); words = C.c_longlong(0)
+    LP.ref4_find_surf_product_positions.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_int, C.c_void_p, C.c_uint,
+                                                    C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = LP.ref4_find_surf_product_positions(vp(V), len(V), vp(T), len(T), vp(occ), len(occ), 1 if kind == 1 else 0, vp(ent), len(ent),
+                                             vp(a5), int(keep[0]), vp(b5), int(keep[1]), surf_reac, seed, skip, vp(ot), vp(ow), vp(otl),
+                                             C.byref(nsp), C.byref(used), C.byref(words))
+    row = [rc, words.value]
+    for e in range(6):
+        kk = 0
+        if rc == 0 and e < len(ent):
+            kk = 1 if ot[e] in (2, 3) else (2 if ot[e] == 5 else 0)
+        row += [kk, int(ow[e]) if kk else -1, int(otl[e]) if kk else -1]
+    return row
+
+
 def main():
     L = C.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libmcell4tiles.so"))
     L.ref4_neighbor_tile_table.restype = C.c_ulonglong
@@ -61,6 +88,13 @@ def main():
     L3.ref3_compute_pb_factor_surfsurf.argtypes = [C.c_double] * 3 + [C.c_int] * 2
     out["pb_surfsurf"] = np.array([[tu, gd, a, b, L3.ref3_compute_pb_factor_surfsurf(tu, 1 / np.sqrt(gd), gd, a, b)]
                                    for tu, gd in ((1e-6, 1e4), (5e-7, 1.5e4)) for a, b in ((0, 0), (1, 0), (0, 1))])
+    # find_surf_product_positions (src4/diffuse_react_event.cpp:1993-2288, libmcell4place.so)
+    LP = C.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libmcell4place.so"))
+    rows = []
+    ms = tc.meshes()
+    for case in tc.place_cases():
+        rows.append(ref_place(LP, ms, case))
+    out["place_out"] = np.array(rows, np.int64)
     np.savez_compressed(os.path.join(HERE, "mcell4_tiles_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

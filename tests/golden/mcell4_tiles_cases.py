@@ -58,3 +58,49 @@ def many_cases():
         lpf = 3.0 / float(rng.integers(1, 16))
         out.append((cums, scaling, lpf, int(rng.integers(1, 1000)), int(rng.integers(0, 50))))
     return out
+
+
+# ---- find_surf_product_positions (products on vacant neighbour tiles) ------------------------------------------------------
+# rule shapes: (kind, reactants are surface, entries of the rule's product list): 'S' new surface product, 'V' new volume
+# product, 'K0' / 'K1' kept reactant 0 / 1.  kind: 1 unimolecular, 3 volume-surface (reactant 0 volume, 1 surface),
+# 5 surface-surface.  All need more tiles than they free (the general branch).
+PLACE_SHAPES = [
+    (1, (1,), ("K0", "S")), (1, (1,), ("S", "K0")), (1, (1,), ("S", "S")), (1, (1,), ("S", "S", "S")), (1, (1,), ("S", "V", "S")),
+    (1, (1,), ("K0", "S", "S")), (1, (1,), ("V", "K0", "S")),
+    (3, (0, 1), ("S", "S")), (3, (0, 1), ("K1", "S")), (3, (0, 1), ("S", "K1")), (3, (0, 1), ("K0", "S", "S")), (3, (0, 1), ("S", "V", "S")),
+    (3, (0, 1), ("K0", "K1", "S")), (3, (0, 1), ("S", "S", "S")),
+    (5, (1, 1), ("S", "S", "S")), (5, (1, 1), ("K0", "K1", "S")), (5, (1, 1), ("S", "S", "S", "V")), (5, (1, 1), ("K1", "S", "K0")),
+    (5, (1, 1), ("S", "V", "S", "S")),
+]
+
+
+def place_cases(n_per_mesh=60):
+    """(mesh index, occupied (wall, tile) pairs, shape index, reactant sites [(wall, tile)] in rule order (None: volume),
+    surface reactant index, seed, skip)"""
+    rng = np.random.default_rng(21)
+    out = []
+    ms = meshes()
+    for k in (0, 2, 3, 5, 8, 9):
+        V, T = ms[k]
+        area = 0.5 * np.linalg.norm(np.cross(V[T[:, 1]] - V[T[:, 0]], V[T[:, 2]] - V[T[:, 0]]), axis=1)
+        n_axis = np.maximum(1, np.ceil(np.sqrt(area))).astype(int)
+        per = n_axis * n_axis
+        tiles = np.array([(w, t) for w in range(len(T)) for t in range(per[w])], np.uint32)
+        for _ in range(n_per_mesh):
+            frac = rng.choice([0.15, 0.5, 0.8, 0.93, 0.985])
+            occ_mask = rng.random(len(tiles)) < frac
+            si = int(rng.integers(0, len(PLACE_SHAPES)))
+            kind, surf_flags, entries = PLACE_SHAPES[si]
+            sites = []
+            for f in surf_flags:
+                if f:
+                    j = int(rng.integers(0, len(tiles)))
+                    occ_mask[j] = True
+                    sites.append((int(tiles[j][0]), int(tiles[j][1])))
+                else:
+                    sites.append(None)
+            if kind == 5 and sites[0] == sites[1]:
+                continue
+            surf_reac = 0 if kind == 1 else (1 if kind == 3 else int(rng.integers(0, 2)))
+            out.append((k, np.ascontiguousarray(tiles[occ_mask]), si, sites, surf_reac, int(rng.integers(1, 1000)), int(rng.integers(0, 40))))
+    return out

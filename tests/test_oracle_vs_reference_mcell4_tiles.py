@@ -158,6 +158,62 @@ def test_table_builder_surface_surface_classes_use_the_reference_pb_factor():
         assert ((p1.kept_info >> 24) & 3) == 2
 
 
+def _orc_place(case, ms):
+    """the oracle's place_general on one case of tc.place_cases(), in the layout of gen_mcell4_tiles_golden.ref_place"""
+    from mcell_b200 import abi
+    k, occ, si, sites, surf_reac, seed, skip = case
+    V, T = ms[k]
+    kind, surf_flags, entries = tc.PLACE_SHAPES[si]
+    new_at = [q for q, e in enumerate(entries) if e[0] != "K"]
+    keep_mask = sum(1 << r for r in range(2) if ("K%d" % r) in entries)
+    info = abi.MCX_KEPT_VALID | (1 << 24) | (1 << 26)        # kept reactants carry an orientation: no draws for them
+    for q in range(6):
+        if q >= len(entries):
+            nib = abi.MCX_KEPT_ORDER_END
+        elif entries[q][0] == "K":
+            nib = abi.MCX_KEPT_ORDER_REACTANT + int(entries[q][1])
+        else:
+            nib = new_at.index(q)
+        info |= nib << (4 * q)
+    prod_surf = np.array([1 if entries[q] == "S" else 0 for q in new_at] + [0] * 4, np.uint8)[:4]
+    rsurf = np.array(list(surf_flags) + [0], np.uint8)[:2]
+    rec = [sites[r] for r in range(len(sites)) if surf_flags[r] and not (keep_mask >> r) & 1]
+    rec_arr = np.array([x for s_ in rec for x in s_] + [0, 0, 0, 0], np.uint32)
+    rw, rt = sites[surf_reac]
+    tape = ref_words(seed, skip + 80)[skip:]
+    L = O.lib()
+    L.orc_unit_place_general.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_int, C.c_void_p, C.c_uint, C.c_uint,
+                                         C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    ek = np.zeros(6, np.int32); ew = np.zeros(6, np.uint32); et = np.zeros(6, np.uint32)
+    used = C.c_longlong(0)
+    rc = L.orc_unit_place_general(vp(V), len(V), vp(T), len(T), vp(occ), len(occ), kind, vp(rsurf), keep_mask, info, len(new_at), vp(prod_surf),
+                                  rw, rt, vp(rec_arr), len(rec), vp(tape), len(tape), vp(ek), vp(ew), vp(et), C.byref(used))
+    row = [rc, used.value]
+    for e in range(6):
+        kk = int(ek[e]) if (rc == 0 and e < len(entries)) else 0
+        row += [kk, int(ew[e]) if kk else -1, int(et[e]) if kk else -1]
+    return row
+
+
+def test_product_placement_on_vacant_tiles_equals_compiled_mcell4():
+    """find_surf_product_positions (src4/diffuse_react_event.cpp:1993-2288), MCell4's own function compiled unmodified
+    (oracle/_ref/libmcell4place.so), against the oracle's place_general on 359 cases: unimolecular, volume-surface and
+    surface-surface rule shapes with kept reactants and volume products in every position of the product list, on six
+    meshes at 15-98 % occupancy — which entry gets a recycled tile and which vacant tile each of the others draws (wall and
+    tile), RX_BLOCKED both ways (too few vacant tiles; ten failed attempts), and the number of words drawn."""
+    ms = tc.meshes()
+    ref = G["place_out"]
+    cases = tc.place_cases()
+    assert len(cases) == len(ref)
+    blocked_after_draws = 0
+    for i, case in enumerate(cases):
+        row = _orc_place(case, ms)
+        assert row == ref[i].tolist(), (i, tc.PLACE_SHAPES[case[2]], row, ref[i].tolist())
+        blocked_after_draws += row[0] == -2 and row[1] > 0
+    assert (ref[:, 0] == 0).sum() > 150 and (ref[:, 0] == -2).sum() > 50 and blocked_after_draws > 3
+
+
 def test_live_mcell4_on_fresh_meshes():
     path = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libmcell4tiles.so")
     if not os.path.exists(path):
