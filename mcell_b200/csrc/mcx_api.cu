@@ -479,6 +479,10 @@ static int rebuild_tables(mcx_handle* h) {
           continue;
         }
         const int to_recycle = std::min(actual, freed);
+        if (needed == 2 && to_recycle == 2 && actual > 2) {
+          h->err = "a surface-surface pathway with two surface products on the two freed tiles and a volume product is not supported (the reference draws a vacant tile for the volume entry from an empty list: a division by zero)";
+          return MCX_ERR_INVALID_ARG;
+        }
         if (needed != 0 && !(needed == 1 && to_recycle == 1) && needed < to_recycle) {
           h->err = "a surface-surface pathway that frees more tiles than it has surface products next to a volume product is not supported (the reference's tile assignment does not terminate)";
           return MCX_ERR_INVALID_ARG;

@@ -1085,6 +1085,8 @@ static const char* surfsurf_pathway_problem(const World& w, const mcx_pathway& p
   const int freed = (keep0 ? 0 : 1) + (keep1 ? 0 : 1), actual = (int)pw.n_products + keep0 + keep1;
   if (needed > freed) return "a surface-surface pathway with more new surface products than consumed reactants needs vacant neighbour tiles (find_surf_product_positions' general branch is not built)";
   const int to_recycle = std::min(actual, freed);
+  if (needed == 2 && to_recycle == 2 && actual > 2)
+    return "a surface-surface pathway with two surface products on the two freed tiles and a volume product: the reference draws a vacant tile for the volume entry from an empty list (diffuse_react_event.cpp:2232-2251, a division by zero)";
   if (needed != 0 && !(needed == 1 && to_recycle == 1) && needed < to_recycle)
     return "a surface-surface pathway that frees more tiles than it has surface products, next to a volume product: the reference's tile assignment (diffuse_react_event.cpp:2155-2191) does not terminate";
   return nullptr;
@@ -3434,6 +3436,19 @@ int orc_unit_test_bimolecular(const double* cum_probs, int n, double scaling, co
   int r = E.test_bimolecular(rc, scaling);
   *words_used = rs.used;
   return r;
+}
+// surfsurf_position_bits (the recycled branches of find_surf_product_positions for two surface reactants): SURFSURF_SWAP or 0
+unsigned orc_unit_surfsurf_position_bits(unsigned keep_mask, unsigned n_products, const unsigned char* product_is_surf, int init_is_r0,
+                                         const uint32_t* words, uint64_t n_words, long long* words_used) {
+  World w; w.cfg = mcx_config{};
+  w.species.resize(2); w.species[0] = mcx_species{}; w.species[0].flags = MCX_SP_VOL; w.species[1] = mcx_species{};
+  mcx_rxn_class c{}; c.kind = MCX_RXN_BIMOL_SURFSURF; c.reactants[0] = c.reactants[1] = 1;
+  mcx_pathway pw{}; pw.n_products = n_products; pw.keep_reactant_mask = keep_mask;
+  for (unsigned k = 0; k < n_products; k++) pw.products[k] = product_is_surf[k] ? 1 : 0;
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  const uint32_t bits = surfsurf_position_bits(w, c, pw, init_is_r0 != 0, rs);
+  *words_used = (long long)rs.used;
+  return bits;
 }
 // place_general on a mesh with given occupied tiles; same per-entry outputs as ref4_find_surf_product_positions
 // (oracle/ref_mcell4_place_shim.cpp): kind per entry of the rule's product list (0 nothing, 1 a recycled tile, 2 a vacant

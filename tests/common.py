@@ -325,7 +325,8 @@ def unsupported_surface_surface_tables():
     refuse them instead of approximating."""
     out = []
     for what, products in (("needs vacant neighbour tiles while it keeps one surface reactant and consumes the other", ["C'", "D'", "A'"]),
-                           ("frees two tiles, fills one, next to a volume product", ["C'", "V,"])):
+                           ("frees two tiles, fills one, next to a volume product", ["C'", "V,"]),
+                           ("two surface products on the two freed tiles and a volume product", ["C'", "D'", "V,"])):
         m = Model(Config(seed=1))
         for n in ("A", "B", "C", "D"):
             m.add_species(n, 1e-7, surface=True)

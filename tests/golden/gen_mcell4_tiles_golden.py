@@ -29,11 +29,11 @@ def ref_table(L, V, T, mask):
     return per, start[:ntl + 1].copy(), out[:2 * n].copy()
 
 
-def ref_place(LP, ms, case):
+def ref_place(LP, ms, case, shape=None):
     """-> [rc, words, (kind, wall, tile) x 6] with kind 0 nothing / 1 recycled / 2 vacant"""
     k, occ, si, sites, surf_reac, seed, skip = case
     V, T = ms[k]
-    kind, surf_flags, entries = tc.PLACE_SHAPES[si]
+    kind, surf_flags, entries = shape or tc.PLACE_SHAPES[si]
     ent = np.array([1 if (e == "S" or (e[0] == "K" and surf_flags[int(e[1])])) else 0 for e in entries], np.uint8)
     keep = [("K%d" % r) in entries for r in range(2)]
     def r5(site):
@@ -95,6 +95,14 @@ def main():
     for case in tc.place_cases():
         rows.append(ref_place(LP, ms, case))
     out["place_out"] = np.array(rows, np.int64)
+    # the recycled branches of the same function for two surface reactants
+    V, T = ms[2]
+    rows = []
+    for si, init_b, seed, skip in tc.recycle_cases():
+        entries = tc.RECYCLE_SHAPES[si]
+        case = (2, np.array([[0, 1], [3, 2]], np.uint32), None, [(0, 1), (3, 2)], init_b, seed, skip)
+        rows.append(ref_place(LP, ms, case, shape=(5, (1, 1), entries)))
+    out["recycle_out"] = np.array(rows, np.int64)
     np.savez_compressed(os.path.join(HERE, "mcell4_tiles_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

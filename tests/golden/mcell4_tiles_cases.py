@@ -104,3 +104,16 @@ def place_cases(n_per_mesh=60):
             surf_reac = 0 if kind == 1 else (1 if kind == 3 else int(rng.integers(0, 2)))
             out.append((k, np.ascontiguousarray(tiles[occ_mask]), si, sites, surf_reac, int(rng.integers(1, 1000)), int(rng.integers(0, 40))))
     return out
+
+
+# surface-surface rule shapes that fit on the tiles they free (the recycled branches): same notation
+# (two surface products next to a volume product — ("S", "S", "V") — make the reference divide by zero: after the two freed
+# tiles are handed out the volume entry draws from an empty list of vacant tiles, :2232-2251; such tables are refused)
+RECYCLE_SHAPES = [("S",), ("S", "S"), ("K0", "S"), ("S", "K1"), ("K1", "S", "V"), ("V", "K0", "S"), ("K0", "K1"), ("V",), ("K0", "V"), ("K1", "V", "S")]
+
+
+def recycle_cases(n=240):
+    """(shape index, initiator is reactant 1, seed, skip) on mesh 2 with the reactants on two fixed tiles"""
+    rng = np.random.default_rng(22)
+    return [(int(rng.integers(0, len(RECYCLE_SHAPES))), int(rng.integers(0, 2)), int(rng.integers(1, 1000)), int(rng.integers(0, 40)))
+            for _ in range(n)]

@@ -214,6 +214,35 @@ def test_product_placement_on_vacant_tiles_equals_compiled_mcell4():
     assert (ref[:, 0] == 0).sum() > 150 and (ref[:, 0] == -2).sum() > 50 and blocked_after_draws > 3
 
 
+def test_recycled_tiles_of_surface_surface_pathways_equal_compiled_mcell4():
+    """The recycled branches of find_surf_product_positions for two surface reactants (the initiator's tile for a single
+    surface product, :2140-2154; the random hand-out of two freed tiles, :2155-2191), compiled MCell4 against the oracle's
+    surfsurf_position_bits: which freed tile the c-th created surface product takes, and the words drawn."""
+    L = O.lib()
+    L.orc_unit_surfsurf_position_bits.restype = C.c_uint
+    L.orc_unit_surfsurf_position_bits.argtypes = [C.c_uint, C.c_uint, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+    ref = G["recycle_out"]
+    sites = [(0, 1), (3, 2)]          # reactant 0, reactant 1 (gen_mcell4_tiles_golden.py)
+    swapped = drew = 0
+    for i, (si, init_b, seed, skip) in enumerate(tc.recycle_cases()):
+        entries = tc.RECYCLE_SHAPES[si]
+        keep_mask = sum(1 << r for r in range(2) if ("K%d" % r) in entries)
+        new = [e for e in entries if e[0] != "K"]
+        prod_surf = np.array([1 if e == "S" else 0 for e in new] + [0] * 4, np.uint8)[:4]
+        tape = ref_words(seed, skip + 80)[skip:]
+        used = C.c_longlong(0)
+        bits = L.orc_unit_surfsurf_position_bits(keep_mask, len(new), vp(prod_surf), 0 if init_b else 1, vp(tape), len(tape), C.byref(used))
+        assert ref[i, 0] == 0 and used.value == ref[i, 1], (i, entries, used.value, ref[i, 1])
+        freed = [sites[r] for r in range(2) if not (keep_mask >> r) & 1]
+        n_created = int(prod_surf.sum())
+        swap = 1 if bits & 64 else 0
+        want = [freed[min(swap if c == 0 else 1 - swap, len(freed) - 1)] for c in range(n_created)]
+        got = [(int(ref[i, 2 + 3 * c + 1]), int(ref[i, 2 + 3 * c + 2])) for c in range(n_created)]
+        assert got == want and all(ref[i, 2 + 3 * c] == 1 for c in range(n_created)), (i, entries, init_b, got, want)
+        swapped += swap; drew += used.value > 0
+    assert swapped > 20 and drew > 10
+
+
 def test_live_mcell4_on_fresh_meshes():
     path = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libmcell4tiles.so")
     if not os.path.exists(path):
