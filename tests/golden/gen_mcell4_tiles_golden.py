@@ -56,6 +56,29 @@ def ref_place(LP, ms, case, shape=None):
     return row
 
 
+def ref_react2d(t, mols, seeds):
+    """per molecule: partner id (-1 none), class, pathway, words drawn — from the compiled reference function"""
+    LR = C.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libmcell4react2d.so"))
+    V = np.ascontiguousarray(t.vertices, np.float64); T = np.ascontiguousarray(t.tri, np.uint32)
+    n = mols.n
+    has_grid = np.zeros(len(T), np.uint8); has_grid[mols.wall[:n]] = 1
+    m4 = np.ascontiguousarray(np.stack([mols.wall[:n], mols.tile[:n], mols.species[:n], mols.orientation[:n]], 1).astype(np.int32))
+    ns = t.n_species
+    table = np.full(ns * ns, -1, np.int32); geom = []; npw = []; cum = []
+    for c in range(t.n_classes):
+        rc = t.classes[c]
+        table[rc.reactants[0] * ns + rc.reactants[1]] = c; table[rc.reactants[1] * ns + rc.reactants[0]] = c
+        geom += [rc.reactant_orientation[0], rc.reactant_orientation[1]]; npw.append(rc.n_pathways)
+        cum += [t.pathways[rc.first_pathway + q].cum_prob for q in range(rc.n_pathways)]
+    geom = np.array(geom, np.int32); npw = np.array(npw, np.int32); cum = np.array(cum, np.float64)
+    out4 = np.zeros(4 * n, np.int32)
+    LR.ref4_react_2d_all_neighbors.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p,
+                                               C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    LR.ref4_react_2d_all_neighbors(vp(V), len(V), vp(T), len(T), vp(has_grid), vp(m4), n, ns, vp(table), t.n_classes, vp(geom), vp(npw), vp(cum),
+                                   1.0, vp(np.ascontiguousarray(seeds)), vp(out4))
+    return out4.reshape(n, 4)
+
+
 def main():
     L = C.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libmcell4tiles.so"))
     L.ref4_neighbor_tile_table.restype = C.c_ulonglong
@@ -103,6 +126,9 @@ def main():
         case = (2, np.array([[0, 1], [3, 2]], np.uint32), None, [(0, 1), (3, 2)], init_b, seed, skip)
         rows.append(ref_place(LP, ms, case, shape=(5, (1, 1), entries)))
     out["recycle_out"] = np.array(rows, np.int64)
+    # react_2D_all_neighbors as a whole (src4/diffuse_react_event.cpp:1249-1393, libmcell4react2d.so)
+    for k, (t, mols, seeds) in enumerate(tc.react2d_models()):
+        out["react2d_%d" % k] = ref_react2d(t, mols, seeds)
     np.savez_compressed(os.path.join(HERE, "mcell4_tiles_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -117,3 +117,34 @@ def recycle_cases(n=240):
     rng = np.random.default_rng(22)
     return [(int(rng.integers(0, len(RECYCLE_SHAPES))), int(rng.integers(0, 2)), int(rng.integers(1, 1000)), int(rng.integers(0, 40)))
             for _ in range(n)]
+
+
+# ---- react_2D_all_neighbors as a whole -------------------------------------------------------------------------------------
+def react2d_models():
+    """Static surface molecules of four species on a sphere (nothing diffuses: an evaluation is the neighbour test alone),
+    surface-surface classes with and without orientation classes, with one and with several pathways; sparse and dense
+    populations (walls without a molecule have no grid).  -> list of (tables, molecules, seeds)"""
+    from mcell_b200.model import Model, Config, create_box, release_on_walls
+    out = []
+    for n, sub, radius, seed in ((700, 2, 0.12, 41), (2600, 3, 0.25, 42), (5200, 3, 0.25, 43)):
+        m = Model(Config(seed=seed))
+        for name in ("A", "B", "C", "D"):
+            m.add_species(name, 0.0, surface=True)
+        pb = m.config.time_step * m.config.surface_grid_density / 6.0
+        m.add_reaction_rule(["A'", "B'"], ["C'"], 0.9 / pb)
+        m.add_reaction_rule(["A'", "B'"], ["D'"], 0.6 / pb)           # second pathway of the same class
+        m.add_reaction_rule(["A", "C"], ["D"], 1.4 / pb)               # no orientation class
+        m.add_reaction_rule(["B'", "D,"], ["A'"], 2.5 / pb)            # opposite orientations
+        m.add_reaction_rule(["C'", "C'"], ["A'", "B'"], 0.5 / pb)      # same species
+        m.add_reaction_rule(["D'", "D'"], ["C'"], 4.0 / pb)            # probability above 1 with several partners
+        sv, sf = create_icosphere(radius, sub)
+        m.add_geometry_object(sv, sf)
+        bv, bf = create_box(4 * radius)
+        m.add_geometry_object(bv, bf)
+        t = m.build(max_molecules=2 * n + 16, rng_mode=1)              # abi.MCX_RNG_TAPE
+        rng = np.random.default_rng(seed)
+        mols = release_on_walls(rng, t, np.arange(len(sf), dtype=np.uint32), n, 0, orientation=1, first_id=0, schedule_unimol=False)
+        mols.species[:] = rng.integers(0, 4, n).astype(mols.species.dtype)
+        mols.orientation[:] = rng.choice([-1, 1], n).astype(mols.orientation.dtype)
+        out.append((t, mols, rng.integers(1, 100000, n).astype(np.uint32)))
+    return out

@@ -243,6 +243,40 @@ def test_recycled_tiles_of_surface_surface_pathways_equal_compiled_mcell4():
     assert swapped > 20 and drew > 10
 
 
+def test_react_2d_all_neighbors_as_a_whole_equals_compiled_mcell4():
+    """DiffuseReactEvent::react_2D_all_neighbors (src4/diffuse_react_event.cpp:1249-1393) compiled unmodified with
+    trigger_bimolecular (rxn_utils.inl:58-97), the neighbour-tile search and the reaction tests under it
+    (oracle/_ref/libmcell4react2d.so; outcome_bimolecular is a recorder) against the ORACLE'S WHOLE STEP in the product's
+    semantics: static surface molecules of four species (an evaluation is the neighbour test alone), every molecule
+    replaying the ISAAC64 stream the reference function was given.  For every molecule evaluated once: the partner it
+    reacts with, the class and the pathway are the reference's, and so is the number of words up to the decision — i.e. the
+    neighbour list and its order, walls without a grid, the orientation test, time / binding_factor, the local
+    probability factor, test_bimolecular vs test_many_bimolecular and the first-pathway quirk all agree."""
+    from mcell_b200 import abi
+    checked = reacted = many = 0
+    for k, (t, mols, seeds) in enumerate(tc.react2d_models()):
+        ref = G["react2d_%d" % k]
+        n = mols.n
+        per = 24
+        words = np.concatenate([ref_words(int(sd), per) for sd in seeds]).astype(np.uint32)
+        off = (np.arange(n, dtype=np.uint64) * per)
+        o = O.Oracle(t)
+        o.upload(mols)
+        tr, st = o.trace_step(2, n, words, off)
+        once = np.flatnonzero(tr["rounds"] == 1)
+        assert len(once) > 0.6 * n
+        got_partner = np.where(tr["rxn_partner"][once] == abi.MCX_NONE, -1, tr["rxn_partner"][once].astype(np.int64))
+        got_class = np.where(tr["rxn_class"][once] == abi.MCX_NONE, -1, tr["rxn_class"][once].astype(np.int64))
+        got_path = np.where(tr["rxn_pathway"][once] == abi.MCX_NONE, -1, tr["rxn_pathway"][once].astype(np.int64))
+        assert (got_partner == ref[once, 0]).all(), (k, np.flatnonzero(got_partner != ref[once, 0])[:5])
+        assert (got_class == ref[once, 1]).all() and (got_path == ref[once, 2]).all(), k
+        quiet = once[ref[once, 0] < 0]                     # no reaction: the words drawn are the test's alone
+        assert (tr["n_words"][quiet] == ref[quiet, 3]).all(), k
+        assert (tr["n_words"][once] >= ref[once, 3]).all(), k
+        checked += len(once); reacted += int((ref[once, 0] >= 0).sum()); many += int((tr["n_collisions"][once] > 1).sum())
+    assert checked > 5000 and reacted > 1500 and many > 1500
+
+
 def test_live_mcell4_on_fresh_meshes():
     path = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libmcell4tiles.so")
     if not os.path.exists(path):
