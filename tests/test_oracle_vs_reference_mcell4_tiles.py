@@ -277,6 +277,37 @@ def test_react_2d_all_neighbors_as_a_whole_equals_compiled_mcell4():
     assert checked > 5000 and reacted > 1500 and many > 1500
 
 
+def test_live_mcell4_placement_and_react_2d_on_fresh_cases():
+    """The same two comparisons against the compiled reference functions themselves, on cases that are not in the goldens
+    (other seeds, other occupancies); skipped where oracle/_ref is not built."""
+    ref_dir = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
+    if not (os.path.exists(os.path.join(ref_dir, "libmcell4place.so")) and os.path.exists(os.path.join(ref_dir, "libmcell4react2d.so"))):
+        pytest.skip("oracle/_ref/libmcell4place.so / libmcell4react2d.so are not built here (need the reference tree)")
+    import gen_mcell4_tiles_golden as gen
+    LP = C.CDLL(os.path.join(ref_dir, "libmcell4place.so"))
+    ms = tc.meshes()
+    rng = np.random.default_rng(1234)
+    n_ok = 0
+    for case in tc.place_cases(n_per_mesh=25):
+        k, occ, si, sites, surf_reac, seed, skip = case
+        case = (k, occ, si, sites, surf_reac, int(rng.integers(1000, 9000)), int(rng.integers(0, 30)))   # other streams
+        want = gen.ref_place(LP, ms, case)
+        assert _orc_place(case, ms) == want, (tc.PLACE_SHAPES[si], want)
+        n_ok += want[0] == 0
+    assert n_ok > 40
+    from mcell_b200 import abi
+    t, mols, _ = tc.react2d_models()[1]
+    seeds = rng.integers(200000, 900000, mols.n).astype(np.uint32)
+    ref = gen.ref_react2d(t, mols, seeds)
+    words = np.concatenate([ref_words(int(sd), 24) for sd in seeds]).astype(np.uint32)
+    o = O.Oracle(t)
+    o.upload(mols)
+    tr, _ = o.trace_step(2, mols.n, words, np.arange(mols.n, dtype=np.uint64) * 24)
+    once = np.flatnonzero(tr["rounds"] == 1)
+    got = np.where(tr["rxn_partner"][once] == abi.MCX_NONE, -1, tr["rxn_partner"][once].astype(np.int64))
+    assert (got == ref[once, 0]).all() and (ref[once, 0] >= 0).sum() > 500
+
+
 def test_live_mcell4_on_fresh_meshes():
     path = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libmcell4tiles.so")
     if not os.path.exists(path):
