@@ -3378,6 +3378,41 @@ int orc_unit_closest_wall_and_reflect(const double* verts, unsigned n_verts, con
   disp_after3[0] = after.x; disp_after3[1] = after.y; disp_after3[2] = after.z;
   return 1;
 }
+// ray_trace_vol as a whole (diffuse_react_event.cpp:627-780) for ONE molecule of the uploaded population moving by
+// disp3 (in/out: REDOs change it), then sort_collisions_by_time (:341-364) the way diffuse_vol_molecule calls it.
+// Same outputs as oracle/ref_mcell4_raytrace_shim.cpp: ref4_ray_trace_vol.  Returns 1 when a wall was hit, 0 for
+// FINISHED, -1 for an unknown id; type 0 = molecule (what = partner id), 1 / 2 = wall front / back (what = wall).
+int orc_unit_ray_trace_vol(void* h, uint32_t mol_id, double* disp3, uint32_t last_hit_wall, const uint32_t* words,
+                           uint64_t n_words, int cap, int* n_coll, int* type, double* time, double* pos3, uint32_t* what,
+                           long long* words_used) {
+  World& w = *(World*)h;
+  if (mol_id >= w.id_to_index.size() || w.id_to_index[mol_id] == MCX_NONE) return -1;
+  const Mol& m = w.mols[w.id_to_index[mol_id]];
+  WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;
+  Eval E(w, rs);
+  V3 remaining = {disp3[0], disp3[1], disp3[2]};
+  std::vector<Collision> colls;
+  const bool hit = E.ray_trace_vol(m.pos, m.subpart, m.id, m.species, w.can_vol_react[m.species] != 0, last_hit_wall,
+                                   remaining, colls);
+  if (colls.size() > 1) {
+    std::stable_sort(colls.begin(), colls.end(), [](const Collision& a, const Collision& b) {
+      if (a.time < b.time) return true;
+      if (a.time > b.time) return false;
+      if (a.type == COLL_VOLMOL && b.type == COLL_VOLMOL) return a.partner_id > b.partner_id;
+      return false;
+    });
+  }
+  disp3[0] = remaining.x; disp3[1] = remaining.y; disp3[2] = remaining.z;
+  *n_coll = (int)colls.size();
+  for (int k = 0; k < (int)colls.size() && k < cap; k++) {
+    const Collision& c = colls[k];
+    type[k] = c.type; time[k] = c.time;
+    pos3[3 * k] = c.pos.x; pos3[3 * k + 1] = c.pos.y; pos3[3 * k + 2] = c.pos.z;
+    what[k] = c.type == COLL_VOLMOL ? c.partner_id : c.wall;
+  }
+  *words_used = (long long)rs.used;
+  return hit ? 1 : 0;
+}
 // pick_surf_displacement on a tape of words; returns the words drawn
 long long orc_unit_pick_surf_displacement(double scale, const uint32_t* words, uint64_t n_words, double* out2) {
   WordSource rs; rs.kind = WordSource::TAPE; rs.tape = words; rs.tape_len = n_words;

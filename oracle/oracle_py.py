@@ -351,6 +351,96 @@ def ref_mcell4_lib():
     return L
 
 
+def ref_mcell4_raytrace_lib():
+    """MCell4's own ray_trace_vol (src4/diffuse_react_event.cpp:627-780) with sort_collisions_by_time and everything under
+    it compiled unmodified into oracle/_ref/libmcell4raytrace.so (oracle/ref_mcell4_raytrace_shim.cpp); None where absent."""
+    path = os.path.join(_HERE, "_ref", "libmcell4raytrace.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref4_ray_trace_vol.restype = C.c_int
+    return L
+
+
+class RayTraceScene:
+    """One population for ref4_ray_trace_vol / orc_unit_ray_trace_vol: the oracle's world (tables + molecules) and the
+    same data flattened for the reference shim (wall lists per subpartition taken from the oracle: that distribution is
+    pinned separately against MCell4's own wall_subparts_collision_test)."""
+
+    def __init__(self, tables, mols, cap=64):
+        self.t, self.mols, self.cap = tables, mols, cap
+        self.orc = Oracle(tables)
+        self.orc.upload(mols)
+        L = self.orc.L
+        L.orc_unit_ray_trace_vol.restype = C.c_int
+        cfg = tables.cfg
+        self.n_sp = int(cfg.num_subparts_per_edge) ** 3
+        lists = [self.orc.subpart_walls(s) for s in range(self.n_sp)]
+        self.wall_off = np.zeros(self.n_sp + 1, np.uint32)
+        self.wall_off[1:] = np.cumsum([len(x) for x in lists])
+        self.walls = np.concatenate(lists + [np.zeros(1, np.uint32)]).astype(np.uint32)
+        ns = int(tables.n_species)
+        self.reacts = np.zeros((ns, ns), np.uint8)
+        for k in range(int(tables.n_classes)):
+            c = tables.classes[k]
+            if c.kind == abi.MCX_RXN_BIMOL_VOLVOL:
+                self.reacts[c.reactants[0], c.reactants[1]] = self.reacts[c.reactants[1], c.reactants[0]] = 1
+        self.pos = np.ascontiguousarray(np.stack([mols.x, mols.y, mols.z], axis=1))
+        self.species = np.ascontiguousarray(mols.species.astype(np.uint32))
+        self.origin = np.array([cfg.origin[0], cfg.origin[1], cfg.origin[2]], np.float64)
+        self.verts = np.ascontiguousarray(tables.vertices, np.float64)
+        self.tri = np.ascontiguousarray(tables.tri, np.uint32)
+
+    def wall_near(self, mol_id):
+        """a wall of the molecule's own subpartition (MCX_NONE when it has none): a plausible last_hit_wall"""
+        cfg = self.t.cfg
+        rcp = cfg.num_subparts_per_edge / cfg.partition_edge_length
+        i = ((self.pos[mol_id] - self.origin) * rcp).astype(np.int64)
+        n = int(cfg.num_subparts_per_edge)
+        s = int(i[0] + i[1] * n + i[2] * n * n)
+        a, b = int(self.wall_off[s]), int(self.wall_off[s + 1])
+        return int(self.walls[a]) if b > a else 0xFFFFFFFF
+
+    def _out(self):
+        cap = self.cap
+        return (C.c_int(0), np.zeros(cap, np.int32), np.zeros(cap, np.float64), np.zeros(3 * cap, np.float64),
+                np.zeros(cap, np.uint32), C.c_longlong(0))
+
+    @staticmethod
+    def _row(rc, disp, n, typ, tim, pos, what, used):
+        k = n.value
+        return dict(hit=rc, disp=disp.copy(), n=k, type=typ[:k].copy(), time=tim[:k].copy(), pos=pos[:3 * k].copy(),
+                    what=what[:k].copy(), words=used.value)
+
+    def oracle(self, mol_id, disp, last_hit_wall, words):
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        d = np.array(disp, np.float64)
+        n, typ, tim, pos, what, used = self._out()
+        words = np.ascontiguousarray(words, np.uint32)
+        rc = self.orc.L.orc_unit_ray_trace_vol(self.orc.h, C.c_uint32(mol_id), vp(d), C.c_uint32(last_hit_wall), vp(words),
+                                               C.c_uint64(len(words)), C.c_int(self.cap), C.byref(n), vp(typ), vp(tim), vp(pos),
+                                               vp(what), C.byref(used))
+        return self._row(rc, d, n, typ, tim, pos, what, used)
+
+    def reference(self, R, mol_id, disp, last_hit_wall, seed, skip):
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        d = np.array(disp, np.float64)
+        n, typ, tim, pos, what, used = self._out()
+        after = np.zeros(3)
+        sp_after = C.c_uint(0)
+        cfg = self.t.cfg
+        rc = R.ref4_ray_trace_vol(vp(self.origin), C.c_double(cfg.partition_edge_length), C.c_uint(cfg.num_subparts_per_edge),
+                                  C.c_double(cfg.rxn_radius_3d), vp(self.verts), C.c_uint(len(self.verts)), vp(self.tri),
+                                  C.c_uint(len(self.tri)), vp(self.wall_off), vp(self.walls), vp(self.species), vp(self.pos),
+                                  C.c_uint(len(self.species)), vp(self.reacts), C.c_uint(self.reacts.shape[0]), C.c_uint(mol_id),
+                                  vp(d), C.c_uint(last_hit_wall), C.c_uint(seed), C.c_uint(skip), C.c_int(self.cap), C.byref(n),
+                                  vp(typ), vp(tim), vp(pos), vp(what), C.byref(used), vp(after), C.byref(sp_after))
+        row = self._row(rc, d, n, typ, tim, pos, what, used)
+        row["pos_after"] = after
+        row["subpart_after"] = sp_after.value
+        return row
+
+
 _CWR_ARGS = None
 
 
