@@ -4,20 +4,23 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library; the product (libmcx.so) never does.
 //
-// PARITY STATUS: pinned at function level, unpinned at whole-step level.
+// PARITY STATUS: pinned at function level and for the whole functions of diffuse_react_event.cpp that can be cut out of
+// the engine; the loop around them is unpinned (DESIGN.md section 4 has the full list).
 //   PINNED bit-for-bit against the reference's own compiled code (oracle/_ref, built by `make ref` from the
 //   sources where they lie; golden outputs committed in tests/golden/):
 //     * RNG: ISAAC64 + Ziggurat vs src/rng.c, src/isaac64.c           (tests/test_oracle_rng.py)
-//     * init_wall_constants, collide_wall incl. every REDO / jump_away_line path, collide_mol, wall_in_box,
-//       test_bimolecular, binary search of pathways, distinguishable, and the table builder's pb_factor vs
-//       MCell3's src/wall_util.c, react_cond.c, react_util.c, util.c — the originals MCell4's src4/*.inl
-//       functions were derived from and kept identical to (include/debug_config.h:36-37)
-//                                                                       (tests/test_oracle_vs_reference.py)
-//   UNPINNED: the composition of those functions into a whole diffuse_vol_molecule step (ray_trace_vol,
-//   subpartition DDA, collision ordering, rescheduling).  The reference tree holds no golden vectors for it and
-//   src4/ cannot be built here (absent libbng/nfsim/boost); it is a line-by-line restatement
-//   of the cited src4 functions, checked by analytic expectations (MSD, uniform density, mass action,
-//   exponential decay) in tests/test_oracle_physics.py.
+//     * MCell3 originals (src/wall_util.c, react_cond.c, react_util.c, util.c, diffuse.c, grid_util.c): wall constants,
+//       collide_wall incl. every REDO / jump_away_line path, collide_mol, wall_in_box, test_bimolecular, pathway search,
+//       distinguishable, pb_factor, unimolecular lifetimes, ray_trace_2D   (tests/test_oracle_vs_reference*.py)
+//     * MCell4's own src4/ code cut out by line range and compiled unmodified: the subpartition walk, the leaf
+//       arithmetic of the volume and surface path incl. exact_disk, the neighbour-tile search, and the whole functions
+//       ray_trace_vol + sort_collisions_by_time, react_2D_all_neighbors, find_surf_product_positions
+//                                                                       (tests/test_oracle_vs_reference_mcell4*.py)
+//   UNPINNED: the loop of diffuse_vol_molecule / diffuse_surf_molecule around those functions (what follows each
+//   collision, rescheduling).  The reference tree holds no golden vectors for it and diffuse_react_event.cpp as a whole
+//   cannot be built here (absent libbng/nfsim/boost); it is a line-by-line restatement of the cited
+//   src4 functions, checked by analytic expectations (MSD, uniform density, mass action, exponential decay) in
+//   tests/test_oracle_physics.py.
 //
 // Absent third-party arithmetic: libbng (github.com/mcellteam/libbng, version unpinned —
 // consumed as sibling checkout, CMakeLists.txt:146-148).  Restated from MCell3 originals:
@@ -32,8 +35,7 @@
 //                the start-of-iteration state with its own word stream (tape or Philox);
 //                reactions are proposals resolved in synchronous rounds.
 //
-// Not restated yet (documented gaps, identical in the product): exact_disk occlusion factor
-// (exact_disk_utils.inl:840-1145; factor := 1), surface molecules, counted volumes.
+// Gaps inside the path (identical in the product): DESIGN.md section 7.
 #include <algorithm>
 #include <cassert>
 #include <cfloat>

@@ -10,11 +10,12 @@ BOX_UM = 0.4
 CAP = 64
 
 
-def scene(seed=31, n=12000, subdivisions=2):
+def scene(seed=31, n=12000, subdivisions=2, interaction_radius=0.01, subpartition_dimension=0.042):
     """A + B -> A and A + A -> B react, N reacts with nothing; interaction radius 0.01 um against 0.04 um subpartitions,
     so that the neighbouring subpartitions of a move matter.  The partition is barely larger than the box: long moves
     of molecules next to the box end outside it (get_displacement_up_to_partition_boundary)."""
-    m = Model(Config(seed=seed, partition_dimension=0.42, subpartition_dimension=0.042, interaction_radius=0.01))
+    m = Model(Config(seed=seed, partition_dimension=0.42, subpartition_dimension=subpartition_dimension,
+                     interaction_radius=interaction_radius))
     m.add_species("A", 1e-6)
     m.add_species("B", 1e-6)
     m.add_species("N", 1e-6)

@@ -93,3 +93,24 @@ def test_ray_trace_vol_as_a_whole_equals_compiled_mcell4_live(scene):
         hits += r["hit"]
         several += r["n"] > 1
     assert hits > 200 and several > 400
+
+
+@pytest.mark.parametrize("radius,subpart,subdiv", [(0.014, 0.042, 1), (0.004, 0.021, 3)])
+def test_ray_trace_vol_other_granularities_live(radius, subpart, subdiv):
+    """the same comparison where the interaction radius is the largest the converter admits (mcell4_converter.cpp:121-127: neighbouring subpartitions collected on
+    almost every move) and where the subpartitions are small against the move (long walks, 1280 + 12 walls)"""
+    R = O.ref_mcell4_raytrace_lib()
+    if R is None:
+        pytest.skip("oracle/_ref/libmcell4raytrace.so not built here")
+    t, mols = rc.scene(seed=57, n=9000, subdivisions=subdiv, interaction_radius=radius, subpartition_dimension=subpart)
+    S = O.RayTraceScene(t, mols, 256)
+    hits = several = 0
+    for i, (mid, d, use_last, seed, skip) in enumerate(rc.moves(t, mols, n_cases=500, seed=777)):
+        last = S.wall_near(mid) if use_last else NONE
+        r = S.reference(R, mid, d, last, seed, skip)
+        assert r["n"] <= 256
+        o = S.oracle(mid, d, last, ref_words(seed, skip + 64)[skip:])
+        _same(o, r, i)
+        hits += r["hit"]
+        several += r["n"] > 1
+    assert hits > 50 and several > 15, (hits, several)
